@@ -1,0 +1,563 @@
+/*
+ * oracle/ref_shim.cpp -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Thin extern "C" probe around the UNMODIFIED reference (fraunhoferhhi/vvenc) library objects that
+ * oracle/Makefile.ref compiles in place from /root/reference.  It lets tests/ (ctypes) and bench.py's
+ * cpu_baseline / --impl reference legs call the reference's own scalar and SSE4.1/AVX2 kernels through the
+ * very function-pointer tables the encoder uses:
+ *
+ *   RdCost::m_afpDistortFunc / m_afpDistortFuncX5 / m_fxdWtdPredPtr  (CommonLib/RdCost.h:117-121)
+ *   TrQuant::xT + Quant::quant / Quant::xNeedRDOQ                    (CommonLib/TrQuant.cpp:481, Quant.cpp:735,835)
+ *   MCTF::m_motionErrorLumaInt8 / m_motionErrorLumaFrac8[2]          (CommonLib/MCTF.h:160-166)
+ *   AffineGradientSearch::m_*                                        (CommonLib/AffineGradientSearch.h:67-69)
+ *
+ * Nothing here re-implements codec arithmetic: every number returned is computed by reference code.
+ * The only logic of our own is argument marshalling, the ME full-search loop of
+ * InterSearch::xPatternSearch (EncoderLib/InterSearch.cpp:2209-2251; that member is private and bound to
+ * encoder state, so its 20-line loop is replayed here on top of the reference distFunc + MV-cost calls),
+ * and a std::thread fan-out used for the multi-core CPU baseline.
+ *
+ * "private/protected" are opened up below ONLY so that the probe can reach TrQuant::xT, Quant::xQuant,
+ * Quant::xNeedRDOQ and TransformUnit::m_coeffs; object layout is unaffected.
+ */
+#include <cstdint>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <array>
+#include <deque>
+#include <list>
+#include <map>
+#include <set>
+#include <string>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <atomic>
+#include <algorithm>
+#include <functional>
+#include <condition_variable>
+#include <chrono>
+#include <bitset>
+#include <limits>
+#include <numeric>
+#include <unordered_map>
+#include <future>
+#include <cassert>
+#include <cstdarg>
+#include <cstdio>
+#include <immintrin.h>
+
+#define private public
+#define protected public
+#include "vvenc/vvenc.h"
+#include "CommonLib/CommonDef.h"
+#include "CommonLib/Unit.h"
+#include "CommonLib/UnitTools.h"
+#include "CommonLib/Slice.h"
+#include "CommonLib/CodingStructure.h"
+#include "CommonLib/RdCost.h"
+#include "CommonLib/TrQuant.h"
+#include "CommonLib/TrQuant_EMT.h"
+#include "CommonLib/Quant.h"
+#include "CommonLib/DepQuant.h"
+#include "CommonLib/MCTF.h"
+#include "CommonLib/AffineGradientSearch.h"
+#include "CommonLib/Rom.h"
+#include "CommonLib/Contexts.h"
+#undef private
+#undef protected
+
+using namespace vvenc;
+
+namespace {
+
+struct RefCtx
+{
+  RdCost                 rdScalar, rdSimd;
+  TrQuant*               tq      = nullptr;
+  MCTF*                  mctf[2] = { nullptr, nullptr };
+  AffineGradientSearch*  ags[2]  = { nullptr, nullptr };
+  std::string            simd;
+};
+
+RefCtx* g_ctx = nullptr;
+std::mutex g_mtx;
+
+RefCtx& ctx()
+{
+  if( !g_ctx )
+  {
+    std::lock_guard<std::mutex> lk( g_mtx );
+    if( !g_ctx )
+    {
+      RefCtx* c = new RefCtx;
+      c->rdScalar.create( false );
+      c->rdSimd  .create( true );
+      c->tq      = new TrQuant;
+      c->tq->init( nullptr, 0, false, false, true, 8 );   // rdoq off, thrVal 8 (vvencCfg.cpp:971-973)
+      c->mctf[0] = new MCTF( false );
+      c->mctf[1] = new MCTF( true );
+      c->ags[0]  = new AffineGradientSearch( false );
+      c->ags[1]  = new AffineGradientSearch( true );
+      g_ctx = c;
+    }
+  }
+  return *g_ctx;
+}
+
+inline int ilog2( unsigned v ) { int r = 0; while( v > 1 ) { v >>= 1; r++; } return r; }
+
+// DFunc family (ours) -> reference table base (CommonLib/TypeDef.h:339-382)
+inline int familyBase( int family )
+{
+  switch( family )
+  {
+    case 0: return DF_SSE;
+    case 1: return DF_SAD;
+    case 2: return DF_HAD;
+    case 3: return DF_HAD_fast;
+    case 4: return DF_HAD_2SAD;
+    default: return -1;
+  }
+}
+
+inline FpDistFunc pickFunc( RdCost& rc, int family, int w, int bitDepth )
+{
+  const int row  = bitDepth > 10 ? 1 : 0;                      // RdCost.cpp:176,219
+  const int base = familyBase( family );
+  const int idx  = family == 4 ? base : base + ilog2( w );     // RdCost.cpp:211-215 (DF_HAD_2SAD has one slot)
+  return rc.m_afpDistortFunc[row][idx];
+}
+
+inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int bitDepth, int subShift )
+{
+  DistParam dp;
+  dp.org.buf = org; dp.org.stride = so; dp.org.width = w; dp.org.height = h;
+  dp.cur.buf = cur; dp.cur.stride = sc; dp.cur.width = w; dp.cur.height = h;
+  dp.bitDepth = bitDepth;
+  dp.subShift = subShift;
+  dp.compID   = COMP_Y;
+  dp.applyWeight = false;
+  dp.maximumDistortionForEarlyExit = MAX_DISTORTION;
+  dp.distFunc = pickFunc( rc, family, w, bitDepth );
+  return dp.distFunc( dp );
+}
+
+template<class F>
+void parallelFor( int n, int nthreads, F&& f )
+{
+  if( nthreads <= 1 || n < 2 * nthreads ) { f( 0, n, 0 ); return; }
+  std::vector<std::thread> th;
+  const int chunk = ( n + nthreads - 1 ) / nthreads;
+  for( int t = 0; t < nthreads; t++ )
+  {
+    const int b = t * chunk, e = std::min( n, b + chunk );
+    if( b >= e ) break;
+    th.emplace_back( [=,&f]{ f( b, e, t ); } );
+  }
+  for( auto& t : th ) t.join();
+}
+
+// A minimal TU that satisfies everything TrQuant::xT / Quant::quant / Quant::xNeedRDOQ dereference.
+struct TuRig
+{
+  XUCache          xuCache;
+  std::mutex       csMutex;
+  CodingStructure  cs;
+  SPS              sps;
+  PPS              pps;
+  Slice            slice;
+  CodingUnit       cu;
+  TransformUnit    tu;
+  std::vector<TCoeffSig> qcoef;
+  TCoeffSig*       coeffPtrs[MAX_NUM_TBLOCKS];
+
+  TuRig() : cs( xuCache, &csMutex ) {}
+
+  void setup( int w, int h, int bitDepth, int mtsIdx, bool intraSlice, bool intraCu, int qp )
+  {
+    sps.bitDepths.recon[CH_L] = bitDepth;
+    sps.bitDepths.recon[CH_C] = bitDepth;
+    sps.qpBDOffset[CH_L] = 6 * ( bitDepth - 8 );
+    sps.qpBDOffset[CH_C] = 6 * ( bitDepth - 8 );
+    sps.internalMinusInputBitDepth[CH_L] = 0;
+    sps.internalMinusInputBitDepth[CH_C] = 0;
+    sps.MTS = true; sps.MTSIntra = true; sps.MTSInter = true; sps.LFNST = false;
+    sps.chromaFormatIdc = CHROMA_400;
+    slice.sps = &sps; slice.pps = &pps;
+    slice.sliceType = intraSlice ? VVENC_I_SLICE : VVENC_B_SLICE;
+    slice.nalUnitType = intraSlice ? VVENC_NAL_UNIT_CODED_SLICE_IDR_W_RADL : VVENC_NAL_UNIT_CODED_SLICE_TRAIL;
+    slice.signDataHidingEnabled = false;
+    slice.depQuantEnabled = false;
+    slice.tsResidualCodingDisabled = false;
+    cs.sps = &sps; cs.pps = &pps; cs.slice = &slice;
+
+    const UnitArea ua( CHROMA_400, Area( 0, 0, w, h ) );
+    static_cast<UnitArea&>( cu ) = ua;
+    cu.cs = &cs; cu.slice = &slice; cu.chType = CH_L;
+    cu.predMode = intraCu ? MODE_INTRA : MODE_INTER;
+    cu.qp = qp; cu.lfnstIdx = 0; cu.ispMode = 0; cu.mipFlag = false; cu.sbtInfo = 0;
+    cu.bdpcmM[CH_L] = 0; cu.bdpcmM[CH_C] = 0; cu.colorTransform = false; cu.chromaQpAdj = 0;
+    cu.treeType = TREE_D; cu.modeType = MODE_TYPE_ALL;
+
+    static_cast<UnitArea&>( tu ) = ua;
+    tu.cu = &cu; tu.cs = &cs; tu.chType = CH_L; tu.depth = 0; tu.noResidual = false; tu.jointCbCr = 0;
+    for( int i = 0; i < MAX_NUM_TBLOCKS; i++ ) { tu.mtsIdx[i] = 0; tu.cbf[i] = 0; tu.lastPos[i] = -1; }
+    tu.mtsIdx[COMP_Y] = (uint8_t) mtsIdx;
+    tu.next = tu.prev = nullptr; tu.idx = 0; tu.chromaAdj = 0;
+    qcoef.assign( (size_t) w * h, 0 );
+    for( int i = 0; i < MAX_NUM_TBLOCKS; i++ ) coeffPtrs[i] = qcoef.data();
+    tu.init( coeffPtrs );
+  }
+};
+
+thread_local TuRig* t_rig = nullptr;
+TuRig& rig() { if( !t_rig ) t_rig = new TuRig; return *t_rig; }
+
+int mtsIdxFor( int trHor, int trVer )   // ours: 0 DCT2, 1 DCT8, 2 DST7 (reference enum TransType, TypeDef.h)
+{
+  if( trHor == 0 && trVer == 0 ) return MTS_DCT2_DCT2;
+  if( trHor == 0 || trVer == 0 ) return -1;          // mixed DCT2/MTS only arises via implicit MTS / SBT size rules
+  // TrQuant.cpp:470-475: indHor = (mtsIdx-2)&1 -> DCT8, indVer = (mtsIdx-2)>>1 -> DCT8
+  return MTS_DST7_DST7 + ( trHor == 1 ? 1 : 0 ) + ( trVer == 1 ? 2 : 0 );
+}
+
+} // namespace
+
+extern "C" {
+
+int refshim_version() { return 3; }
+
+// "SCALAR" | "SSE41" | "SSE42" | "AVX" | "AVX2"; rebuilds every probe object so that the per-instance pointers
+// are re-resolved (vvenc.cpp:412 -> VVEncImpl::setSIMDExtension, vvencimpl.cpp:800-866).
+const char* refshim_set_simd( const char* name )
+{
+  std::lock_guard<std::mutex> lk( g_mtx );
+  const char* r = vvenc_set_SIMD_extension( name );
+  if( g_ctx ) { /* leak the tiny old ctx on purpose: callers may still hold pointers */ g_ctx = nullptr; }
+  return r;
+}
+
+// opt: 0 = RdCost::create(false) scalar table, 1 = create(true) (SIMD per vvenc_set_SIMD_extension)
+uint64_t refshim_dist( int opt, int family, const int16_t* org, int orgStride, const int16_t* cur, int curStride,
+                       int w, int h, int bitDepth, int subShift )
+{
+  RefCtx& c = ctx();
+  return callDist( opt ? c.rdSimd : c.rdScalar, family, org, orgStride, cur, curStride, w, h, bitDepth, subShift );
+}
+
+// Pair list over two planes: desc[i] = { org_x, org_y, cur_x, cur_y, w, h } (plane coordinates, may be negative inside the margin).
+void refshim_dist_list( int opt, int family, const int16_t* orgPlane, int orgStride, const int16_t* curPlane, int curStride,
+                        const int32_t* desc, int n, int bitDepth, int subShift, uint64_t* out, int nthreads )
+{
+  RefCtx& c = ctx();
+  parallelFor( n, nthreads, [&]( int b, int e, int )
+  {
+    RdCost rc; rc.create( opt != 0 );     // one RdCost per worker, as EncSlice.cpp:142-147 does
+    for( int i = b; i < e; i++ )
+    {
+      const int32_t* d = desc + 6 * (size_t) i;
+      const int16_t* o = orgPlane + (ptrdiff_t) d[1] * orgStride + d[0];
+      const int16_t* u = curPlane + (ptrdiff_t) d[3] * curStride + d[2];
+      out[i] = callDist( rc, family, o, orgStride, u, curStride, d[4], d[5], bitDepth, subShift );
+    }
+  } );
+  (void) c;
+}
+
+uint64_t refshim_sad_mask( int opt, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h,
+                           const int16_t* mask, int maskStride, int stepX, int maskStride2, int bitDepth, int subShift )
+{
+  RefCtx& c = ctx();
+  RdCost& rc = opt ? c.rdSimd : c.rdScalar;
+  DistParam dp;
+  dp.org.buf = org; dp.org.stride = orgStride; dp.org.width = w; dp.org.height = h;
+  dp.cur.buf = cur; dp.cur.stride = curStride; dp.cur.width = w; dp.cur.height = h;
+  dp.mask = mask; dp.maskStride = maskStride; dp.stepX = stepX; dp.maskStride2 = maskStride2;
+  dp.bitDepth = bitDepth; dp.subShift = subShift; dp.compID = COMP_Y;
+  return rc.m_afpDistortFunc[0][DF_SAD_WITH_MASK]( dp );
+}
+
+void refshim_sad_x5( int opt, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h,
+                     int bitDepth, int subShift, int calcCentre, uint64_t* cost5 )
+{
+  RefCtx& c = ctx();
+  RdCost& rc = opt ? c.rdSimd : c.rdScalar;
+  DistParam dp = rc.setDistParam( org, cur, orgStride, curStride, bitDepth, COMP_Y, w, h, subShift, true );   // RdCost.cpp:228
+  Distortion tmp[5] = { 0, 0, 0, 0, 0 };
+  dp.dmvrSadX5( dp, tmp, calcCentre != 0 );
+  for( int i = 0; i < 5; i++ ) cost5[i] = tmp[i];
+}
+
+uint64_t refshim_fix_wsse( int opt, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h,
+                           int bitDepth, uint32_t fixedWeight )
+{
+  RefCtx& c = ctx();
+  RdCost& rc = opt ? c.rdSimd : c.rdScalar;
+  DistParam dp;
+  dp.org.buf = org; dp.org.stride = orgStride; dp.org.width = w; dp.org.height = h;
+  dp.cur.buf = cur; dp.cur.stride = curStride; dp.cur.width = w; dp.cur.height = h;
+  dp.bitDepth = bitDepth; dp.compID = COMP_Y;
+  return rc.m_fxdWtdPredPtr( dp, fixedWeight );
+}
+
+// MV rate (RdCost.h:181-203).  lambda is what RdCost::setLambda receives; motion lambda = sqrt(lambda).
+uint32_t refshim_mv_bits( int x, int y, int predHor, int predVer, int costScale, int imvShift )
+{
+  RdCost rc; rc.create( false );
+  rc.setPredictor( Mv( predHor, predVer ) );
+  rc.setCostScale( costScale );
+  return rc.getBitsOfVectorWithPredictor( x, y, imvShift );
+}
+
+uint64_t refshim_mv_cost( double lambda, int x, int y, int predHor, int predVer, int costScale, int imvShift )
+{
+  RdCost rc; rc.create( false );
+  BitDepths bd; bd.recon[CH_L] = 10; bd.recon[CH_C] = 10;
+  rc.setLambda( lambda, bd );
+  rc.selectMotionLambda();
+  rc.setPredictor( Mv( predHor, predVer ) );
+  rc.setCostScale( costScale );
+  return rc.getCostOfVectorWithPredictor( x, y, imvShift );
+}
+
+// Replay of InterSearch::xPatternSearch (InterSearch.cpp:2209-2251) for a list of blocks:
+// blk[i] = { x, y, w, h, left, right, top, bottom, predHor, predVer } ; search positions are integer offsets (dx,dy)
+// in [left..right]x[top..bottom] relative to the block position, cost = SAD(subShift) + floor(sqrt(lambda)*bits).
+// out[i] = { bestDx, bestDy, bestCost(lo32), bestCost(hi32) } ; optional full cost table (uint32 SAD only) per block.
+void refshim_full_search( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
+                          const int32_t* blk, int n, int bitDepth, int subShift, double lambda, int costScale, int imvShift,
+                          int32_t* out, uint32_t* sadTables, int tableStride, int nthreads )
+{
+  parallelFor( n, nthreads, [&]( int b, int e, int )
+  {
+    RdCost rc; rc.create( opt != 0 );
+    BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
+    rc.setLambda( lambda, bd );
+    rc.selectMotionLambda();
+    rc.setCostScale( costScale );
+    for( int i = b; i < e; i++ )
+    {
+      const int32_t* d = blk + 10 * (size_t) i;
+      const int x = d[0], y = d[1], w = d[2], h = d[3], l = d[4], r = d[5], t = d[6], bt = d[7];
+      rc.setPredictor( Mv( d[8], d[9] ) );
+      DistParam dp;
+      dp.org.buf = orgPlane + (ptrdiff_t) y * orgStride + x; dp.org.stride = orgStride; dp.org.width = w; dp.org.height = h;
+      dp.cur.stride = refStride; dp.cur.width = w; dp.cur.height = h;
+      dp.bitDepth = bitDepth; dp.subShift = subShift; dp.compID = COMP_Y;
+      dp.maximumDistortionForEarlyExit = MAX_DISTORTION;       // GPU always returns the full sum
+      dp.distFunc = pickFunc( rc, 1, w, bitDepth );
+      Distortion best = MAX_DISTORTION; int bx = 0, by = 0;
+      uint32_t* tab = sadTables ? sadTables + (size_t) i * tableStride : nullptr;
+      int k = 0;
+      for( int dy = t; dy <= bt; dy++ )
+      {
+        const int16_t* row = refPlane + (ptrdiff_t)( y + dy ) * refStride + x;
+        for( int dx = l; dx <= r; dx++, k++ )
+        {
+          dp.cur.buf = row + dx;
+          Distortion sad = dp.distFunc( dp );
+          if( tab ) tab[k] = (uint32_t) sad;
+          sad += rc.getCostOfVectorWithPredictor( dx, dy, imvShift );
+          if( sad < best ) { best = sad; bx = dx; by = dy; }
+        }
+      }
+      out[4*i+0] = bx; out[4*i+1] = by; out[4*i+2] = (int32_t)( best & 0xffffffffu ); out[4*i+3] = (int32_t)( best >> 32 );
+    }
+  } );
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Forward transform via TrQuant::xT (TrQuant.cpp:481-564).  trHor/trVer: 0 DCT2, 1 DCT8, 2 DST7.
+// Output: TCoeff[h][w] row-major.  Returns 0, or -1 for a combination the explicit-MTS syntax cannot express.
+int refshim_fwd_transform( int trHor, int trVer, const int16_t* resi, int stride, int w, int h, int bitDepth, int32_t* coef )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, false, true, 32 );
+  CPelBuf  resiBuf( resi, stride, w, h );
+  CoeffBuf dst( coef, w, w, h );
+  c.tq->xT( r.tu, COMP_Y, resiBuf, dst, w, h );
+  return 0;
+}
+
+// Bare 1-D core as the reference unit test exercises it (vvenc_unit_test.cpp:1085-1140): g_tCoeffOps.fastFwdCore_2D[log2N-2].
+void refshim_fwd_core( int trSize, const int16_t* tc, const int32_t* src, int32_t* dst, unsigned line, unsigned reducedLine, unsigned cutoff, int shift )
+{
+  ctx();
+  g_tCoeffOps.fastFwdCore_2D[ ilog2( trSize ) - 2 ]( tc, src, dst, line, reducedLine, cutoff, shift );
+}
+
+// Copies the reference transform matrix (CommonLib/RomTr.cpp:364-441) into out[N*N]; type 0 DCT2, 1 DCT8, 2 DST7.
+int refshim_tr_matrix( int type, int N, int16_t* out )
+{
+  const TMatrixCoeff* p = nullptr;
+  if( type == 0 ) { switch( N ) { case 2: p = g_trCoreDCT2P2[0][0]; break; case 4: p = g_trCoreDCT2P4[0][0]; break; case 8: p = g_trCoreDCT2P8[0][0]; break;
+                                  case 16: p = g_trCoreDCT2P16[0][0]; break; case 32: p = g_trCoreDCT2P32[0][0]; break; case 64: p = g_trCoreDCT2P64[0][0]; break; } }
+  if( type == 1 ) { switch( N ) { case 4: p = g_trCoreDCT8P4[0][0]; break; case 8: p = g_trCoreDCT8P8[0][0]; break; case 16: p = g_trCoreDCT8P16[0][0]; break; case 32: p = g_trCoreDCT8P32[0][0]; break; } }
+  if( type == 2 ) { switch( N ) { case 4: p = g_trCoreDST7P4[0][0]; break; case 8: p = g_trCoreDST7P8[0][0]; break; case 16: p = g_trCoreDST7P16[0][0]; break; case 32: p = g_trCoreDST7P32[0][0]; break; } }
+  if( !p ) return -1;
+  memcpy( out, p, sizeof( int16_t ) * N * N );
+  return 0;
+}
+
+// Scan order of the quantiser (ContextModelling.cpp:76 -> getScanOrder(SCAN_GROUPED_4x4,...), Rom.cpp:1620): raster index per scan position.
+int refshim_scan_order( int w, int h, int32_t* idx )
+{
+  const ScanElement* s = getScanOrder( SCAN_GROUPED_4x4, ilog2( w ), ilog2( h ) );
+  const int n = std::min( 32, w ) * std::min( 32, h );
+  for( int i = 0; i < n; i++ ) idx[i] = s[i].idx;
+  return n;
+}
+
+// Plain quantiser: Quant::quant (Quant.cpp:735-833) -> xQuant pointer (QuantCore / QuantCoreSIMD) + last-position trim.
+// coef: TCoeff[h][w]; out q: int16[h][w]; returns 0.  Sign-bit hiding off (slice.signDataHidingEnabled = false).
+int refshim_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int intraCu, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, MTS_DCT2_DCT2, isIRAP != 0, intraCu != 0, qp );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  alignas(64) static thread_local unsigned char ctxMem[ sizeof( Ctx ) ];   // unused by the plain quantiser
+  const Ctx& dummy = *reinterpret_cast<const Ctx*>( ctxMem );
+  static_cast<Quant*>( c.tq->m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum  = sum;
+  *lastPos = r.tu.lastPos[COMP_Y];
+  return 0;
+}
+
+// Quant::xNeedRDOQ (Quant.cpp:835-891) -> xNeedRdoq pointer (needRdoqCore / NeedRdoqSIMD)
+int refshim_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, MTS_DCT2_DCT2, false, false, qp );
+  r.slice.depQuantEnabled = depQuant != 0;
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  return static_cast<Quant*>( c.tq->m_quant )->xNeedRDOQ( r.tu, COMP_Y, src, qpp ) ? 1 : 0;
+}
+
+// Whole TU: xT then Quant::quant, as TrQuant::transformNxN does for LFNST-off, non-skip TUs (TrQuant.cpp:688-736).
+int refshim_transform_quant( int trHor, int trVer, const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP,
+                             int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, isIRAP != 0, true, qp );
+  CPelBuf  resiBuf( resi, stride, w, h );
+  CoeffBuf dst( coef, w, w, h );
+  c.tq->xT( r.tu, COMP_Y, resiBuf, dst, w, h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  alignas(64) static thread_local unsigned char ctxMem[ sizeof( Ctx ) ];
+  const Ctx& dummy = *reinterpret_cast<const Ctx*>( ctxMem );
+  static_cast<Quant*>( c.tq->m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  return 0;
+}
+
+// Batch of equal-shape TUs laid out back to back (resi: n * h * w int16, compact), threaded; used by the CPU baseline.
+void refshim_transform_quant_batch( int trHor, int trVer, const int16_t* resi, int n, int w, int h, int bitDepth, int qp, int isIRAP,
+                                    int16_t* q, int32_t* absSum, int32_t* lastPos, int nthreads )
+{
+  ctx();
+  parallelFor( n, nthreads, [&]( int b, int e, int )
+  {
+    std::vector<int32_t> coef( (size_t) w * h );
+    for( int i = b; i < e; i++ )
+      refshim_transform_quant( trHor, trVer, resi + (size_t) i * w * h, w, w, h, bitDepth, qp, isIRAP, coef.data(),
+                               q + (size_t) i * w * h, absSum + i, lastPos + i );
+  } );
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MCTF block-matching errors (MCTF.h:160-166).  besterror = INT_MAX as in vvenc_unit_test.cpp:1552.
+int refshim_mctf_err_int( int opt, const int16_t* org, int orgStride, const int16_t* buf, int bufStride, int w, int h, int besterror )
+{
+  RefCtx& c = ctx();
+  return c.mctf[opt?1:0]->m_motionErrorLumaInt8( org, orgStride, buf, bufStride, w, h, besterror );
+}
+
+// tap4: 0 -> 6-tap (m_interpolationFilter8 rows, taps 1..6), 1 -> 4-tap; fx, fy in 0..15 (MCTF.cpp:1138-1160)
+int refshim_mctf_err_frac( int opt, int tap4, const int16_t* org, int orgStride, const int16_t* buf, int bufStride, int w, int h,
+                           int fx, int fy, int bitDepth, int besterror )
+{
+  RefCtx& c = ctx();
+  const int16_t* xf = tap4 ? MCTF::m_interpolationFilter4[fx] : MCTF::m_interpolationFilter8[fx];
+  const int16_t* yf = tap4 ? MCTF::m_interpolationFilter4[fy] : MCTF::m_interpolationFilter8[fy];
+  return c.mctf[opt?1:0]->m_motionErrorLumaFrac8[tap4?1:0]( org, orgStride, buf, bufStride, w, h, xf, yf, bitDepth, besterror );
+}
+
+void refshim_mctf_filters( int16_t* f8 /*16x8*/, int16_t* f4 /*16x4*/ )
+{
+  memcpy( f8, MCTF::m_interpolationFilter8, sizeof( int16_t ) * 16 * 8 );
+  memcpy( f4, MCTF::m_interpolationFilter4, sizeof( int16_t ) * 16 * 4 );
+}
+
+// list form for the CPU baseline: desc[i] = { x, y, mvx, mvy (1/16 pel), w, h }
+void refshim_mctf_err_list( int opt, int tap4, const int16_t* orgPlane, int orgStride, const int16_t* bufPlane, int bufStride,
+                            const int32_t* desc, int n, int bitDepth, int32_t* out, int nthreads )
+{
+  RefCtx& c = ctx();
+  MCTF* m = c.mctf[opt?1:0];
+  parallelFor( n, nthreads, [&]( int b, int e, int )
+  {
+    for( int i = b; i < e; i++ )
+    {
+      const int32_t* d = desc + 6 * (size_t) i;
+      int dx = d[2], dy = d[3];
+      const int fx = dx & 15, fy = dy & 15;
+      const int16_t* org = orgPlane + (ptrdiff_t) d[1] * orgStride + d[0];
+      if( ( fx | fy ) == 0 )
+      {
+        dx /= 16; dy /= 16;
+        const int16_t* buf = bufPlane + (ptrdiff_t)( d[1] + dy ) * bufStride + d[0] + dx;
+        out[i] = m->m_motionErrorLumaInt8( org, orgStride, buf, bufStride, d[4], d[5], INT32_MAX );
+      }
+      else
+      {
+        dx >>= 4; dy >>= 4;
+        const int16_t* buf = bufPlane + (ptrdiff_t)( d[1] + dy ) * bufStride + d[0] + dx;
+        const int16_t* xf = tap4 ? MCTF::m_interpolationFilter4[fx] : MCTF::m_interpolationFilter8[fx];
+        const int16_t* yf = tap4 ? MCTF::m_interpolationFilter4[fy] : MCTF::m_interpolationFilter8[fy];
+        out[i] = m->m_motionErrorLumaFrac8[tap4?1:0]( org, orgStride, buf, bufStride, d[4], d[5], xf, yf, bitDepth, INT32_MAX );
+      }
+    }
+  } );
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Affine gradient helpers (AffineGradientSearch.h:67-69)
+void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )
+{
+  RefCtx& c = ctx();
+  AffineGradientSearch* a = c.ags[opt?1:0];
+  if( vertical ) a->m_VerticalSobelFilter  ( const_cast<Pel*>( pred ), predStride, deriv, derivStride, w, h );
+  else           a->m_HorizontalSobelFilter( const_cast<Pel*>( pred ), predStride, deriv, derivStride, w, h );
+}
+
+void refshim_equal_coeff( int opt, int sixParam, const int16_t* resi, int resiStride, const int16_t* dx, const int16_t* dy, int derivStride,
+                          int w, int h, int64_t* eq /*7x7, accumulated into*/ )
+{
+  RefCtx& c = ctx();
+  AffineGradientSearch* a = c.ags[opt?1:0];
+  Pel* d[2] = { const_cast<Pel*>( dx ), const_cast<Pel*>( dy ) };
+  a->m_EqualCoeffComputer[sixParam?1:0]( const_cast<Pel*>( resi ), resiStride, d, derivStride, w, h, reinterpret_cast<int64_t(*)[7]>( eq ) );
+}
+
+} // extern "C"
