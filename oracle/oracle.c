@@ -1,0 +1,527 @@
+/*
+ * oracle/oracle.c -- TEST INFRASTRUCTURE (CPU restatement), never shipped, never imported by the product.
+ *
+ * Plain-C restatement of the arithmetic of VVenC's block-cost hot path, written from the definitions
+ * (SURVEY.md section 8a), each function citing the reference file:line it follows.  It is pinned against the
+ * reference's own scalar and AVX2 kernels (oracle/_ref, built by oracle/Makefile.ref) by
+ * tests/test_oracle_vs_reference.py, and against the committed vectors in tests/golden/ everywhere else.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "vvc_tables.h"
+
+typedef int16_t Pel;
+
+static inline int iabs( int v ) { return v < 0 ? -v : v; }
+static inline int ilog2u( uint32_t v ) { int r = 0; while( v > 1 ) { v >>= 1; r++; } return r; }
+
+int orc_version( void ) { return 1; }
+
+/* ------------------------------------------------------------------------------------------------------
+ * SAD  (CommonLib/RdCost.cpp:300-335 xGetSAD; width-specialised :337-644 compute the same sum)
+ * rows visited with step 2^subShift, result << subShift.  Early exit is not modelled: callers of the
+ * reference use maximumDistortionForEarlyExit = MAX_DISTORTION for comparison (vvenc_unit_test.cpp:1957).
+ * ---------------------------------------------------------------------------------------------------- */
+uint64_t orc_sad( const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift )
+{
+  const int step = 1 << subShift;
+  uint64_t sum = 0;
+  for( int y = 0; y < h; y += step )
+    for( int x = 0; x < w; x++ )
+      sum += (uint64_t) iabs( org[y * so + x] - cur[y * sc + x] );
+  return sum << subShift;
+}
+
+/* SSE (CommonLib/RdCost.cpp:651-1000): sum of squared differences, no sub-sampling, 64-bit */
+uint64_t orc_sse( const Pel* org, int so, const Pel* cur, int sc, int w, int h )
+{
+  uint64_t sum = 0;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      const int d = org[y * so + x] - cur[y * sc + x];
+      sum += (uint64_t)( d * d );
+    }
+  return sum;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * SATD.  A tile's cost is sum|H_th * D * H_tw| with the DC term down-weighted, then a shape-dependent
+ * normalisation (CommonLib/RdCost.cpp: 2x2 :1006-1026, 4x4 :1028-1124, 8x8 :1225-1322, 16x8 :1324-1470,
+ * 8x16 :1472-1609, 4x8 :1611-1685, 8x4 :1687-1766, 16x16_fast :1126-1223).  The reference's butterfly order
+ * only permutes/negates Hadamard outputs, so sum|.| and |DC| are order independent.
+ * ---------------------------------------------------------------------------------------------------- */
+static void wht1d( int* v, int n, int stride )
+{
+  for( int len = 1; len < n; len <<= 1 )
+    for( int i = 0; i < n; i += len << 1 )
+      for( int j = i; j < i + len; j++ )
+      {
+        const int a = v[j * stride], b = v[( j + len ) * stride];
+        v[j * stride] = a + b; v[( j + len ) * stride] = a - b;
+      }
+}
+
+static uint64_t had_tile( const int* diff, int tw, int th )
+{
+  int m[16 * 16];
+  memcpy( m, diff, sizeof( int ) * tw * th );
+  for( int y = 0; y < th; y++ ) wht1d( m + y * tw, tw, 1 );
+  for( int x = 0; x < tw; x++ ) wht1d( m + x, th, tw );
+  int64_t sad = 0;
+  for( int i = 0; i < tw * th; i++ ) sad += iabs( m[i] );
+  const int dc = iabs( m[0] );
+  if( tw == 2 && th == 2 )                      /* :1020-1023: only the DC term is scaled, no final normalisation */
+    return (uint64_t)( sad - dc + ( dc >> 2 ) );
+  sad = sad - dc + ( dc >> 2 );
+  if( tw == 4 && th == 4 ) return (uint64_t)( ( sad + 1 ) >> 1 );                    /* :1121 */
+  if( tw == 8 && th == 8 ) return (uint64_t)( ( sad + 2 ) >> 2 );                    /* :1319 */
+  if( tw * th == 128 )     return (uint64_t)(int)( (int) sad / sqrt( 16.0 * 8 ) * 2 );  /* :1467,1606 */
+  if( tw * th == 32 )      return (uint64_t)(int)( (int) sad / sqrt( 4.0 * 8 ) * 2 );   /* :1682,1763 */
+  return 0;
+}
+
+static uint64_t had_tile_at( const Pel* org, int so, const Pel* cur, int sc, int tw, int th )
+{
+  int diff[16 * 16];
+  for( int y = 0; y < th; y++ )
+    for( int x = 0; x < tw; x++ )
+      diff[y * tw + x] = org[y * so + x] - cur[y * sc + x];
+  return had_tile( diff, tw, th );
+}
+
+/* 16x16 'fast': 2x2 rounded means of org and cur separately, 8x8 Hadamard, ((sad+2)>>2)<<2 (:1126-1223) */
+static uint64_t had_tile16_fast( const Pel* org, int so, const Pel* cur, int sc )
+{
+  int diff[64];
+  for( int y = 0; y < 8; y++ )
+    for( int x = 0; x < 8; x++ )
+    {
+      const Pel* o = org + 2 * y * so + 2 * x;
+      const Pel* c = cur + 2 * y * sc + 2 * x;
+      diff[y * 8 + x] = ( ( o[0] + o[1] + o[so] + o[so + 1] + 2 ) >> 2 ) - ( ( c[0] + c[1] + c[sc] + c[sc + 1] + 2 ) >> 2 );
+    }
+  return had_tile( diff, 8, 8 ) << 2;
+}
+
+/* tile choice: CommonLib/RdCost.cpp:1818-1938 (xGetHADs<fastHad>) */
+uint64_t orc_had( const Pel* org, int so, const Pel* cur, int sc, int w, int h, int fast )
+{
+  int tw, th, f16 = 0;
+  if(      w > h && ( h & 7 ) == 0 && ( w & 15 ) == 0 ) { tw = 16; th = 8; }
+  else if( w < h && ( w & 7 ) == 0 && ( h & 15 ) == 0 ) { tw = 8;  th = 16; }
+  else if( w > h && ( h & 3 ) == 0 && ( w & 7 ) == 0 )  { tw = 8;  th = 4; }
+  else if( w < h && ( w & 3 ) == 0 && ( h & 7 ) == 0 )  { tw = 4;  th = 8; }
+  else if( fast && ( h % 32 == 0 ) && ( w % 32 == 0 ) && w == h ) { tw = 16; th = 16; f16 = 1; }
+  else if( ( h % 8 == 0 ) && ( w % 8 == 0 ) ) { tw = 8; th = 8; }
+  else if( ( h % 4 == 0 ) && ( w % 4 == 0 ) ) { tw = 4; th = 4; }
+  else if( ( h % 2 == 0 ) && ( w % 2 == 0 ) ) { tw = 2; th = 2; }
+  else return UINT64_MAX;                       /* reference THROWs "Invalid size" */
+  uint64_t sum = 0;
+  for( int y = 0; y < h; y += th )
+    for( int x = 0; x < w; x += tw )
+      sum += f16 ? had_tile16_fast( org + y * so + x, so, cur + y * sc + x, sc )
+                 : had_tile_at( org + y * so + x, so, cur + y * sc + x, sc, tw, th );
+  return sum;
+}
+
+/* min(SATD, 2*SAD) (CommonLib/RdCost.cpp:1768-1816); the reference requires compact buffers, the value is
+ * defined for any stride */
+uint64_t orc_had2sad( const Pel* org, int so, const Pel* cur, int sc, int w, int h )
+{
+  const uint64_t had = orc_had( org, so, cur, sc, w, h, 0 );
+  const uint64_t sad = orc_sad( org, so, cur, sc, w, h, 0 );
+  return had < 2 * sad ? had : 2 * sad;
+}
+
+/* family: 0 SSE, 1 SAD, 2 HAD, 3 HAD_fast, 4 HAD_2SAD */
+uint64_t orc_dist( int family, const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift )
+{
+  switch( family )
+  {
+    case 0: return orc_sse( org, so, cur, sc, w, h );
+    case 1: return orc_sad( org, so, cur, sc, w, h, subShift );
+    case 2: return orc_had( org, so, cur, sc, w, h, 0 );
+    case 3: return orc_had( org, so, cur, sc, w, h, 1 );
+    case 4: return orc_had2sad( org, so, cur, sc, w, h );
+  }
+  return UINT64_MAX;
+}
+
+void orc_dist_list( int family, const Pel* orgPlane, int so, const Pel* curPlane, int sc, const int32_t* desc, int n, int subShift, uint64_t* out )
+{
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t* d = desc + 6 * (size_t) i;
+    out[i] = orc_dist( family, orgPlane + (ptrdiff_t) d[1] * so + d[0], so, curPlane + (ptrdiff_t) d[3] * sc + d[2], sc, d[4], d[5], subShift );
+  }
+}
+
+/* GEO mask-weighted SAD (CommonLib/RdCost.cpp:2062-2093) */
+uint64_t orc_sad_mask( const Pel* org, int so, const Pel* cur, int sc, int w, int h, const Pel* mask, int maskStride, int stepX, int maskStride2, int subShift )
+{
+  const int step = 1 << subShift;
+  uint64_t sum = 0;
+  for( int y = 0; y < h; y += step )
+  {
+    for( int x = 0; x < w; x++ ) { sum += (uint64_t)( iabs( org[x] - cur[x] ) * *mask ); mask += stepX; }
+    org += so * step; cur += sc * step; mask += maskStride * step; mask += maskStride2;
+  }
+  return sum << subShift;
+}
+
+/* DMVR row of five SADs (CommonLib/RdCost.cpp:1984-2034): position i uses org+i and cur-i, each >>1 */
+void orc_sad_x5( const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift, int calcCentre, uint64_t* cost5 )
+{
+  for( int i = 0; i < 5; i++ )
+  {
+    if( i == 2 && !calcCentre ) continue;
+    cost5[i] = orc_sad( org + i, so, cur - i, sc, w, h, subShift ) >> 1;
+  }
+}
+
+/* fixed-weight SSE (CommonLib/RdCost.cpp:1942-1982): sum((w*d*d + 2^15) >> 16), odd width only for w==1 */
+uint64_t orc_fix_wsse( const Pel* org, int so, const Pel* cur, int sc, int w, int h, uint32_t weight )
+{
+  uint64_t sum = 0;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      const int32_t d = org[y * so + x] - cur[y * sc + x];
+      sum += (uint64_t)(int32_t)( ( (int64_t) weight * ( d * d ) + ( 1 << 15 ) ) >> 16 );
+    }
+  return sum;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * MV rate (CommonLib/RdCost.h:181-203)
+ * ---------------------------------------------------------------------------------------------------- */
+static uint32_t eg_bits( int v )
+{
+  const uint32_t t = v <= 0 ? ( (uint32_t)( -v ) << 1 ) + 1 : (uint32_t) v << 1;
+  return 1 + ( (uint32_t) ilog2u( t ) << 1 );
+}
+
+uint32_t orc_mv_bits( int x, int y, int predHor, int predVer, int costScale, int imvShift )
+{
+  return eg_bits( ( x * ( 1 << costScale ) - predHor ) >> imvShift ) + eg_bits( ( y * ( 1 << costScale ) - predVer ) >> imvShift );
+}
+
+uint64_t orc_mv_cost( double lambda, int x, int y, int predHor, int predVer, int costScale, int imvShift )
+{
+  const double motionLambda = sqrt( lambda );       /* RdCost.cpp:73-78 */
+  return (uint64_t)( motionLambda * orc_mv_bits( x, y, predHor, predVer, costScale, imvShift ) );
+}
+
+/* Full search replay (EncoderLib/InterSearch.cpp:2209-2251): raster order, first strictly smaller wins.
+ * blk[i] = { x, y, w, h, left, right, top, bottom, predHor, predVer }; out[i] = { dx, dy, cost lo, cost hi } */
+void orc_full_search( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int subShift, double lambda,
+                      int costScale, int imvShift, int32_t* out, uint32_t* sadTables, int tableStride )
+{
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t* d = blk + 10 * (size_t) i;
+    const Pel* org = orgPlane + (ptrdiff_t) d[1] * so + d[0];
+    uint64_t best = UINT64_MAX; int bx = 0, by = 0, k = 0;
+    for( int dy = d[6]; dy <= d[7]; dy++ )
+      for( int dx = d[4]; dx <= d[5]; dx++, k++ )
+      {
+        uint64_t c = orc_sad( org, so, refPlane + (ptrdiff_t)( d[1] + dy ) * sr + d[0] + dx, sr, d[2], d[3], subShift );
+        if( sadTables ) sadTables[(size_t) i * tableStride + k] = (uint32_t) c;
+        c += orc_mv_cost( lambda, dx, dy, d[8], d[9], costScale, imvShift );
+        if( c < best ) { best = c; bx = dx; by = dy; }
+      }
+    out[4 * i] = bx; out[4 * i + 1] = by; out[4 * i + 2] = (int32_t)( best & 0xffffffffu ); out[4 * i + 3] = (int32_t)( best >> 32 );
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Forward 2-D transform (CommonLib/TrQuant.cpp:481-564 xT; TrQuant_EMT.cpp:366-421 _fastForwardMM and the
+ * B2/B4 butterflies :197-300,1106,1507 which equal the matrix product).  trHor/trVer: 0 DCT2, 1 DCT8, 2 DST7.
+ * ---------------------------------------------------------------------------------------------------- */
+static const int8_t* tr_matrix( int type, int N )
+{
+  const int off = vvc_tr_offset_host[type][ilog2u( N )];
+  return off < 0 ? NULL : vvc_tr_table_host + off;
+}
+
+int orc_fwd_transform( int trHor, int trVer, const Pel* resi, int stride, int w, int h, int bitDepth, int32_t* coef )
+{
+  const int8_t* th = tr_matrix( trHor, w );
+  const int8_t* tv = tr_matrix( trVer, h );
+  if( !th || !tv ) return -1;
+  const int skipW = ( trHor != 0 && w == 32 ) ? 16 : ( w > 32 ? w - 32 : 0 );    /* TrQuant.cpp:496-497 */
+  const int skipH = ( trVer != 0 && h == 32 ) ? 16 : ( h > 32 ? h - 32 : 0 );
+  const int s1 = ilog2u( w ) + bitDepth + 6 - 15;                                 /* :544 */
+  const int s2 = ilog2u( h ) + 6;                                                 /* :545 */
+  const int keepW = w - skipW, keepH = h - skipH;
+  int32_t* tmp = (int32_t*) malloc( sizeof( int32_t ) * w * h );
+  /* stage 1: tmp[j*h + i] = (sum_k resi[i][k] * Th[j][k] + rnd) >> s1, j < keepW  (stored transposed, 'line' = h) */
+  const int r1 = s1 > 0 ? 1 << ( s1 - 1 ) : 0;
+  for( int i = 0; i < h; i++ )
+    for( int j = 0; j < keepW; j++ )
+    {
+      int32_t sum = 0;
+      for( int k = 0; k < w; k++ ) sum += resi[i * stride + k] * th[j * w + k];
+      tmp[j * h + i] = ( sum + r1 ) >> s1;
+    }
+  /* stage 2: coef[j*w + i] = (sum_k tmp[i][k] * Tv[j][k] + rnd) >> s2 over i < keepW lines, j < keepH */
+  memset( coef, 0, sizeof( int32_t ) * w * h );
+  const int r2 = 1 << ( s2 - 1 );
+  for( int i = 0; i < keepW; i++ )
+    for( int j = 0; j < keepH; j++ )
+    {
+      int32_t sum = 0;
+      for( int k = 0; k < h; k++ ) sum += tmp[i * h + k] * tv[j * h + k];
+      coef[j * w + i] = ( sum + r2 ) >> s2;
+    }
+  free( tmp );
+  return 0;
+}
+
+/* bare 1-D core as unit-tested by the reference (TrQuant_EMT.cpp:1973-2000 fastFwdCore) */
+void orc_fwd_core( int trSize, const int16_t* tc, const int32_t* src, int32_t* dst, unsigned line, unsigned reducedLine, unsigned cutoff, int shift )
+{
+  const int rnd = 1 << ( shift - 1 );
+  for( unsigned i = 0; i < reducedLine; i++ )
+    for( unsigned j = 0; j < cutoff; j++ )
+    {
+      int32_t sum = 0;
+      for( int k = 0; k < trSize; k++ ) sum += src[i * trSize + k] * tc[j * trSize + k];
+      dst[j * line + i] = ( sum + rnd ) >> shift;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Coefficient scan (CommonLib/Rom.cpp:1098-1136 ScanGenerator, :1236-1284 grouped 4x4 up-right diagonal)
+ * for blocks with w,h >= 4: groups of 4x4 inside the min(32,w) x min(32,h) region.
+ * ---------------------------------------------------------------------------------------------------- */
+static void diag_scan( int bw, int bh, int* xs, int* ys )
+{
+  int line = 0, col = 0;
+  for( int i = 0; i < bw * bh; i++ )
+  {
+    xs[i] = col; ys[i] = line;
+    if( col == bw - 1 || line == 0 )
+    {
+      line += col + 1; col = 0;
+      if( line >= bh ) { col += line - ( bh - 1 ); line = bh - 1; }
+    }
+    else { col++; line--; }
+  }
+}
+
+int orc_scan_order( int w, int h, int32_t* idx )
+{
+  const int gw = ( w < 32 ? w : 32 ) >> 2, gh = ( h < 32 ? h : 32 ) >> 2;
+  int gx[64], gy[64], cx[16], cy[16];
+  diag_scan( gw, gh, gx, gy );
+  diag_scan( 4, 4, cx, cy );
+  for( int g = 0; g < gw * gh; g++ )
+    for( int c = 0; c < 16; c++ )
+      idx[g * 16 + c] = ( gy[g] * 4 + cy[c] ) * w + gx[g] * 4 + cx[c];
+  return gw * gh * 16;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Plain quantiser (CommonLib/Quant.cpp:132-230 QuantCore, wrapper :735-833 without sign-bit hiding).
+ * Luma, no scaling lists, no LFNST, no transform skip; maxLog2TrDynamicRange = 15 (Slice.h:776).
+ * qp is the CU QP (cu.qp); the quantiser uses qp + 6*(bitDepth-8) (Quant.cpp:99).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct { int scale, qbits; int64_t add; } QuantPar;
+
+static QuantPar quant_par( int w, int h, int bitDepth, int qp, int addNum )
+{
+  QuantPar p;
+  int baseQp = qp + 6 * ( bitDepth - 8 );
+  if( baseQp < 0 ) baseQp = 0;
+  if( baseQp > 63 + 6 * ( bitDepth - 8 ) ) baseQp = 63 + 6 * ( bitDepth - 8 );
+  const int per = baseQp / 6, rem = baseQp % 6;
+  const int sqrt2 = ( ilog2u( w ) + ilog2u( h ) ) & 1;                                  /* UnitTools.cpp:3616 */
+  const int trShift = 15 - bitDepth - ( ( ilog2u( w ) + ilog2u( h ) ) >> 1 ) - sqrt2;   /* Quant.h:69-72 */
+  p.scale = vvc_quant_scales_host[sqrt2][rem];
+  p.qbits = 14 + per + trShift;                                                         /* Quant.cpp:769 */
+  p.add   = (int64_t) addNum << ( p.qbits - 9 );
+  return p;
+}
+
+int orc_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  const QuantPar p = quant_par( w, h, bitDepth, qp, isIRAP ? 171 : 85 );               /* Quant.cpp:772 */
+  int32_t scan[1024];
+  const int nScan = orc_scan_order( w, h, scan );
+  int pos = nScan - 1;
+  for( ; pos > 0; pos-- ) if( coef[scan[pos]] ) break;                                 /* :160-165 */
+  const int thrVal = 8;                                                                /* vvencCfg.cpp:971-973 */
+  const int32_t thres = p.qbits ? (int32_t)( (int64_t) thrVal << ( p.qbits - 1 ) ) : (int32_t)( (int64_t)( thrVal >> 1 ) << p.qbits );
+  const int32_t useThres = thres / ( p.scale << 2 );                                   /* :180 */
+  for( int sub = pos >> 4; sub >= 1; sub-- )                                           /* :184-208 */
+  {
+    if( pos >= 16 )
+    {
+      const int inCg = pos & 15;
+      int allSmaller = 1;
+      for( int k = inCg, sp = pos; allSmaller && k >= 0; k--, sp-- ) allSmaller &= iabs( coef[scan[sp]] ) <= useThres;
+      if( allSmaller ) { pos -= inCg + 1; continue; }
+      else break;
+    }
+  }
+  memset( q, 0, sizeof( int16_t ) * w * h );
+  int32_t sum = 0;
+  for( int cp = 0; cp <= pos; cp++ )
+  {
+    const int32_t c = coef[scan[cp]];
+    const int64_t t = (int64_t) iabs( c ) * p.scale;
+    const int32_t mag = (int32_t)( ( t + p.add ) >> p.qbits );
+    sum += mag;
+    int32_t v = c < 0 ? -mag : mag;
+    if( v < -32768 ) v = -32768; if( v > 32767 ) v = 32767;
+    q[scan[cp]] = (int16_t) v;
+  }
+  int last = pos;
+  if( sum )                                                                            /* Quant.cpp:806-816 */
+    for( int sp = pos; sp >= 0; sp-- ) if( q[scan[sp]] ) { last = sp; break; }
+  *absSum = sum; *lastPos = last;
+  return 0;
+}
+
+/* needRdoqCore (CommonLib/Quant.cpp:264-278) through Quant::xNeedRDOQ (:835-891), luma */
+int orc_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant )
+{
+  const QuantPar p = quant_par( w, h, bitDepth, depQuant ? qp + 1 : qp, 171 );
+  const int n = w * ( h < 32 ? h : 32 );
+  for( int i = 0; i < n; i++ )
+  {
+    const int64_t t = (int64_t) iabs( coef[i] ) * p.scale;
+    if( (int32_t)( ( t + p.add ) >> p.qbits ) != 0 ) return 1;
+  }
+  return 0;
+}
+
+int orc_transform_quant( int trHor, int trVer, const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP,
+                         int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( orc_fwd_transform( trHor, trVer, resi, stride, w, h, bitDepth, coef ) ) return -1;
+  return orc_quant( coef, w, h, bitDepth, qp, isIRAP, q, absSum, lastPos );
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * MCTF block matching (CommonLib/MCTF.cpp:122-145 int, :147-203 6-tap, :205-257 4-tap); filters :72-110
+ * ---------------------------------------------------------------------------------------------------- */
+static const int16_t mctf_f8[16][8] = {
+  {0,0,0,64,0,0,0,0},{0,1,-3,64,4,-2,0,0},{0,1,-6,62,9,-3,1,0},{0,2,-8,60,14,-5,1,0},{0,2,-9,57,19,-7,2,0},{0,3,-10,53,24,-8,2,0},
+  {0,3,-11,50,29,-9,2,0},{0,3,-11,44,35,-10,3,0},{0,1,-7,38,38,-7,1,0},{0,3,-10,35,44,-11,3,0},{0,2,-9,29,50,-11,3,0},{0,2,-8,24,53,-10,3,0},
+  {0,2,-7,19,57,-9,2,0},{0,1,-5,14,60,-8,2,0},{0,1,-3,9,62,-6,1,0},{0,0,-2,4,64,-3,1,0} };
+static const int16_t mctf_f4[16][4] = {
+  {0,64,0,0},{-2,62,4,0},{-2,58,10,-2},{-4,56,14,-2},{-4,54,16,-2},{-6,52,20,-2},{-6,46,28,-4},{-4,42,30,-4},
+  {-4,36,36,-4},{-4,30,42,-4},{-4,28,46,-6},{-2,20,52,-6},{-2,16,54,-4},{-2,14,56,-4},{-2,10,58,-2},{0,4,62,-2} };
+
+void orc_mctf_filters( int16_t* f8, int16_t* f4 ) { memcpy( f8, mctf_f8, sizeof( mctf_f8 ) ); memcpy( f4, mctf_f4, sizeof( mctf_f4 ) ); }
+
+int32_t orc_mctf_err_int( const Pel* org, int so, const Pel* buf, int sb, int w, int h )
+{
+  int32_t e = 0;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ ) { const int d = org[y * so + x] - buf[y * sb + x]; e += d * d; }
+  return e;
+}
+
+int32_t orc_mctf_err_frac( int tap4, const Pel* org, int so, const Pel* buf, int sb, int w, int h, int fx, int fy, int bitDepth )
+{
+  const int maxv = ( 1 << bitDepth ) - 1;
+  const int taps = tap4 ? 4 : 6, first = tap4 ? 0 : 1, back = tap4 ? 1 : 2;   /* 6-tap uses entries 1..6 around x-3+1 */
+  const int16_t* xf = tap4 ? mctf_f4[fx] : mctf_f8[fx];
+  const int16_t* yf = tap4 ? mctf_f4[fy] : mctf_f8[fy];
+  int32_t e = 0;
+  int tmp[( 64 + 8 ) * 64];
+  const int rows = h + taps - 1;
+  for( int r = 0; r < rows; r++ )
+    for( int x = 0; x < w; x++ )
+    {
+      int sum = 0;
+      for( int t = 0; t < taps; t++ ) sum += xf[first + t] * buf[( r - back ) * sb + x - back + t];
+      sum = ( sum + 32 ) >> 6;
+      tmp[r * 64 + x] = sum < 0 ? 0 : ( sum > maxv ? maxv : sum );
+    }
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      int sum = 0;
+      for( int t = 0; t < taps; t++ ) sum += yf[first + t] * tmp[( y + t ) * 64 + x];
+      sum = ( sum + 32 ) >> 6;
+      sum = sum < 0 ? 0 : ( sum > maxv ? maxv : sum );
+      const int d = sum - org[y * so + x];
+      e += d * d;
+    }
+  return e;
+}
+
+/* MCTF::motionErrorLuma dispatch (CommonLib/MCTF.cpp:1099-1164); desc[i] = { x, y, mvx, mvy (1/16 pel), w, h } */
+void orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPlane, int sb, const int32_t* desc, int n, int bitDepth, int32_t* out )
+{
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t* d = desc + 6 * (size_t) i;
+    int dx = d[2], dy = d[3];
+    const int fx = dx & 15, fy = dy & 15;
+    const Pel* org = orgPlane + (ptrdiff_t) d[1] * so + d[0];
+    if( ( fx | fy ) == 0 )
+    {
+      dx /= 16; dy /= 16;
+      out[i] = orc_mctf_err_int( org, so, bufPlane + (ptrdiff_t)( d[1] + dy ) * sb + d[0] + dx, sb, d[4], d[5] );
+    }
+    else
+    {
+      dx >>= 4; dy >>= 4;
+      out[i] = orc_mctf_err_frac( tap4, org, so, bufPlane + (ptrdiff_t)( d[1] + dy ) * sb + d[0] + dx, sb, d[4], d[5], fx, fy, bitDepth );
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190)
+ * ---------------------------------------------------------------------------------------------------- */
+void orc_sobel( int vertical, const Pel* p, int ps, Pel* d, int ds, int w, int h )
+{
+  for( int j = 1; j < h - 1; j++ )
+    for( int k = 1; k < w - 1; k++ )
+    {
+      const Pel* c = p + j * ps + k;
+      int v;
+      if( !vertical ) v = c[1 - ps] - c[-1 - ps] + ( c[1] << 1 ) - ( c[-1] << 1 ) + c[1 + ps] - c[-1 + ps];
+      else            v = c[ps - 1] - c[-ps - 1] + ( c[ps] << 1 ) - ( c[-ps] << 1 ) + c[ps + 1] - c[-ps + 1];
+      d[j * ds + k] = (Pel) v;
+    }
+  /* border replication: edges copy their inner neighbour, corners copy the inner diagonal (:101-114) */
+  for( int j = 1; j < h - 1; j++ ) { d[j * ds] = d[j * ds + 1]; d[j * ds + w - 1] = d[j * ds + w - 2]; }
+  for( int k = 1; k < w - 1; k++ ) { d[k] = d[ds + k]; d[( h - 1 ) * ds + k] = d[( h - 2 ) * ds + k]; }
+  d[0] = d[ds + 1]; d[w - 1] = d[ds + w - 2];
+  d[( h - 1 ) * ds] = d[( h - 2 ) * ds + 1]; d[( h - 1 ) * ds + w - 1] = d[( h - 2 ) * ds + w - 2];
+}
+
+void orc_equal_coeff( int sixParam, const Pel* resi, int rs, const Pel* gx, const Pel* gy, int ds, int w, int h, int64_t* eq )
+{
+  const int np = sixParam ? 6 : 4;
+  for( int j = 0; j < h; j++ )
+  {
+    const int cy = ( ( j >> 2 ) << 2 ) + 2;
+    for( int k = 0; k < w; k++ )
+    {
+      const int cx = ( ( k >> 2 ) << 2 ) + 2;
+      const int a = gx[j * ds + k], b = gy[j * ds + k];
+      int c[6];
+      if( !sixParam ) { c[0] = a; c[1] = cx * a + cy * b; c[2] = b; c[3] = cy * a - cx * b; }
+      else            { c[0] = a; c[1] = cx * a; c[2] = b; c[3] = cx * b; c[4] = cy * a; c[5] = cy * b; }
+      for( int col = 0; col < np; col++ )
+      {
+        for( int row = 0; row < np; row++ ) eq[( col + 1 ) * 7 + row] += (int64_t) c[col] * c[row];
+        eq[( col + 1 ) * 7 + np] += ( (int64_t) c[col] * resi[j * rs + k] ) * 8;
+      }
+    }
+  }
+}

@@ -1,0 +1,169 @@
+"""Seeded parity cases shared by the golden-vector generator (tests/golden/make_golden.py), the oracle tests and
+the GPU parity tests.  Inputs come from numpy's frozen legacy MT19937 stream (np.random.RandomState), so a case
+is fully described by its parameter row + seed and the fixtures only need to carry the expected outputs.
+
+The matrix mirrors the reference's differential unit tests (test/vvenc_unit_test/vvenc_unit_test.cpp:1885-2180
+RdCost, :912-1211 TCoeffOps, :1441-1560 MCTF, :2182-2266 affine) and adds what they do not pin (DF_SSE*, real
+DCT/DST matrices through xT, QuantCore, needRdoq, Sobel) -- SURVEY.md section 8c.
+"""
+import numpy as np
+
+FAM_SSE, FAM_SAD, FAM_HAD, FAM_HAD_FAST, FAM_HAD_2SAD = range(5)
+
+
+def aligned(shape, dtype, align=64):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.zeros(n + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def pel_block(rs, h, stride, kind, bit_depth=10):
+    hi = (1 << bit_depth)
+    if kind == 0:
+        a = rs.randint(0, hi, size=(h, stride))
+    elif kind == 1:
+        a = np.full((h, stride), hi - 1)
+    elif kind == 2:
+        a = np.zeros((h, stride))
+    else:   # smooth-ish: small differences, exercises small SATD values / rounding
+        a = 512 + rs.randint(-6, 7, size=(h, stride))
+    out = aligned((h, stride), np.int16)
+    out[:] = a
+    return out
+
+
+def dist_cases():
+    """rows: family, w, h, org_stride, cur_stride, subShift, kind_org, kind_cur, bit_depth, seed"""
+    rows = []
+    rs = np.random.RandomState(1234)
+    seed = 1000
+    widths = [1, 2, 4, 8, 16, 32, 64, 128]
+    heights = [1, 2, 4, 6, 8, 12, 16, 24, 32, 64, 128]
+    for w in widths:
+        for h in heights:
+            for fam in range(5):
+                if fam >= FAM_HAD and (w < 2 or h % 2):
+                    continue
+                if fam == FAM_SSE and w == 1:
+                    continue          # RdCost::getDistPart routes w==1 to scalar xGetSSE (RdCost.cpp:275-278)
+                if fam == FAM_HAD_2SAD and (w < 4 or h % 4):
+                    continue          # RdCost.cpp:1783-1784 walks h/4 rows of 4*w pels; SIMD loads 16 at a time (RdCostX86.h:2585)
+                for rep in range(2 if w * h <= 1024 else 1):
+                    compact = fam == FAM_HAD_2SAD      # RdCost.cpp:1778 CHECKD: compact, aligned buffers
+                    so = w if compact else w + int(rs.randint(0, 40))
+                    sc = w if compact else w + int(rs.randint(0, 40))
+                    ss = int(rs.randint(0, 2)) if (fam == FAM_SAD and h >= 2 and h % 2 == 0) else 0
+                    kinds = [(0, 0), (1, 2), (3, 3), (0, 3)][(seed + rep) % 4]
+                    bd = 8 if (seed % 7 == 0) else 10
+                    rows.append([fam, w, h, so, sc, ss, kinds[0], kinds[1], bd, seed])
+                    seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def dist_inputs(row):
+    fam, w, h, so, sc, ss, ko, kc, bd, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    return pel_block(rs, h, so, ko, bd), pel_block(rs, h, sc, kc, bd)
+
+
+def tq_cases():
+    """rows: trHor, trVer, w, h, stride, amp, qp, isIRAP, bit_depth, seed   (tr: 0 DCT2, 1 DCT8, 2 DST7)"""
+    rows = []
+    seed = 5000
+    rs = np.random.RandomState(99)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            for (th, tv) in ((0, 0), (2, 2), (1, 2), (2, 1), (1, 1)):
+                if (th or tv) and (w > 32 or h > 32):
+                    continue
+                for amp in (1023, 200, 12):
+                    bd = 8 if seed % 5 == 0 else 10
+                    a = min(amp, (1 << bd) - 1)
+                    rows.append([th, tv, w, h, w + int(rs.randint(0, 6)), a, int(rs.randint(8, 52)), int(rs.randint(0, 2)), bd, seed])
+                    seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def tq_inputs(row):
+    th, tv, w, h, st, amp, qp, irap, bd, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    if seed % 11 == 0:
+        a = np.full((h, st), amp)
+    elif seed % 11 == 1:
+        a = np.where(rs.randint(0, 2, size=(h, st)) > 0, amp, -amp)
+    else:
+        a = rs.randint(-amp, amp + 1, size=(h, st))
+    return a.astype(np.int16)
+
+
+def mctf_cases():
+    """rows: w, h, mvx, mvy (1/16 pel), tap4, bit_depth, seed"""
+    rows = []
+    seed = 9000
+    rs = np.random.RandomState(7)
+    for (w, h) in ((8, 8), (16, 16), (16, 8), (32, 32), (64, 64), (24, 40), (8, 64)):
+        rows.append([w, h, 16 * int(rs.randint(-3, 4)), 16 * int(rs.randint(-3, 4)), 0, 10, seed]); seed += 1
+        for tap4 in (0, 1):
+            for k in range(10):
+                mvx = int(rs.randint(-64, 64)); mvy = int(rs.randint(-64, 64))
+                if (mvx | mvy) & 15 == 0:
+                    mvx += 5
+                rows.append([w, h, mvx, mvy, tap4, 8 if k == 9 else 10, seed]); seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+MCTF_MARGIN = 12
+
+
+def mctf_inputs(row):
+    w, h, mvx, mvy, tap4, bd, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    m = MCTF_MARGIN
+    org = rs.randint(0, 1 << bd, size=(h, w + 5)).astype(np.int16)
+    buf = rs.randint(0, 1 << bd, size=(h + 2 * m, w + 2 * m)).astype(np.int16)
+    return org, buf
+
+
+def affine_cases():
+    """rows: w, h, pred_stride, deriv_stride, six_param, seed"""
+    rows = []
+    seed = 12000
+    rs = np.random.RandomState(5)
+    for (w, h) in ((16, 16), (32, 16), (16, 32), (64, 64), (128, 64), (128, 128)):
+        for six in (0, 1):
+            rows.append([w, h, w + int(rs.randint(0, 9)), w + int(rs.randint(0, 9)), six, seed]); seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def affine_inputs(row):
+    w, h, ps, ds, six, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    pred = rs.randint(0, 1024, size=(h, ps)).astype(np.int16)
+    resi = rs.randint(-1023, 1024, size=(h, ps)).astype(np.int16)
+    if seed % 3 == 0:      # extremes, as the reference's MinMaxGenerator does (vvenc_unit_test.cpp:170-202)
+        gx = np.where(rs.randint(0, 2, size=(h, ds)) > 0, 4095, -4096).astype(np.int16)
+        gy = np.where(rs.randint(0, 2, size=(h, ds)) > 0, 4095, -4096).astype(np.int16)
+    else:
+        gx = rs.randint(-4096, 4096, size=(h, ds)).astype(np.int16)
+        gy = rs.randint(-4096, 4096, size=(h, ds)).astype(np.int16)
+    return pred, resi, gx, gy
+
+
+def search_case(seed=777, W=192, H=128, margin=48):
+    """one small picture pair + block list for the full-search replay; returns dict"""
+    rs = np.random.RandomState(seed)
+    S = W + 2 * margin
+    base = rs.randint(0, 1024, size=(H + 2 * margin + 8, S + 8))
+    # low-pass so that argmins are non-trivial, then pan by (3,-2) plus noise
+    sm = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4
+    org = sm[4:4 + H + 2 * margin, 4:4 + S].astype(np.int16)
+    ref = np.clip(sm[4 + 3:4 + 3 + H + 2 * margin, 4 - 2:4 - 2 + S] + rs.randint(-9, 10, size=org.shape), 0, 1023).astype(np.int16)
+    blks = []
+    for (bw, bh) in ((4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (64, 32), (128, 64)):
+        for k in range(3):
+            x = int(rs.randint(0, (W - bw) // 4 + 1)) * 4; y = int(rs.randint(0, (H - bh) // 4 + 1)) * 4
+            r = int(rs.randint(2, 17))
+            blks.append([x, y, bw, bh, -r, r, -r, r, int(rs.randint(-60, 60)), int(rs.randint(-60, 60))])
+    return dict(org=np.ascontiguousarray(org), ref=np.ascontiguousarray(ref), stride=S, margin=margin, W=W, H=H,
+                blk=np.array(blks, dtype=np.int32), lam=57.25, cost_scale=2, imv_shift=0)

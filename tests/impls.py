@@ -1,0 +1,165 @@
+"""Adapters that give the CPU oracle and the live reference probe one calling convention, so the same seeded case
+loops (tests/cases.py) drive: oracle-vs-golden, oracle-vs-reference and (tests/test_gpu_*.py) CUDA-vs-oracle."""
+import ctypes
+import numpy as np
+import cases as C
+from _libs import oracle, refshim, P, PO
+
+I32 = ctypes.c_int32
+
+
+class OracleImpl:
+    name = 'oracle'
+
+    def __init__(self):
+        self.L = oracle()
+
+    def dist(self, fam, o, so, c, sc, w, h, bd, ss):
+        return int(self.L.orc_dist(fam, P(o), so, P(c), sc, w, h, ss))
+
+    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap):
+        coef = np.zeros((h, w), dtype=np.int32); q = np.zeros((h, w), dtype=np.int16); s = I32(); lp = I32()
+        assert self.L.orc_transform_quant(th, tv, P(resi), st, w, h, bd, qp, irap, P(coef), P(q), ctypes.byref(s), ctypes.byref(lp)) == 0
+        return coef, q, s.value, lp.value
+
+    def need_rdoq(self, coef, w, h, bd, qp, dq):
+        return int(self.L.orc_need_rdoq(P(coef), w, h, bd, qp, dq))
+
+    def mctf_err(self, tap4, org, so, buf, sb, x, y, mvx, mvy, w, h, bd):
+        desc = np.array([[x, y, mvx, mvy, w, h]], dtype=np.int32); out = np.zeros(1, dtype=np.int32)
+        self.L.orc_mctf_err_list(tap4, PO(org, -(y * so + x)), so, P(buf), sb, P(desc), 1, bd, P(out))
+        return int(out[0])
+
+    def sobel(self, vert, pred, ps, ds, w, h):
+        d = np.zeros((h, ds), dtype=np.int16)
+        self.L.orc_sobel(vert, P(pred), ps, P(d), ds, w, h)
+        return d
+
+    def equal_coeff(self, six, resi, rs, gx, gy, ds, w, h):
+        e = np.zeros(49, dtype=np.int64)
+        self.L.orc_equal_coeff(six, P(resi), rs, P(gx), P(gy), ds, w, h, P(e))
+        return e
+
+    def full_search(self, sc, ss, want_table=False):
+        n = len(sc['blk']); S = sc['stride']; base = sc['margin'] * S + sc['margin']
+        out = np.zeros((n, 4), dtype=np.int32)
+        ts = int(max((b[5] - b[4] + 1) * (b[7] - b[6] + 1) for b in sc['blk']))
+        tab = np.zeros((n, ts), dtype=np.uint32) if want_table else None
+        self.L.orc_full_search(PO(sc['org'], base), S, PO(sc['ref'], base), S, P(sc['blk']), n, ss, sc['lam'], sc['cost_scale'], sc['imv_shift'],
+                               P(out), P(tab) if want_table else None, ts)
+        return (out, tab) if want_table else out
+
+    def mv_bits(self, *a):
+        return int(self.L.orc_mv_bits(*a))
+
+    def mv_cost(self, lam, *a):
+        return int(self.L.orc_mv_cost(lam, *a))
+
+
+class RefImpl(OracleImpl):
+    """the unmodified reference through oracle/_ref (opt=1: SIMD table, opt=0: scalar table)"""
+
+    def __init__(self, opt=1, simd=b'AVX2'):
+        self.L = refshim(); self.opt = opt; self.simd = simd
+        self.name = 'reference-%s' % (simd.decode() if opt else 'scalar')
+
+    def _simd(self):
+        self.L.refshim_set_simd(self.simd if self.opt else b'SCALAR')
+
+    def dist(self, fam, o, so, c, sc, w, h, bd, ss):
+        return int(self.L.refshim_dist(self.opt, fam, P(o), so, P(c), sc, w, h, bd, ss))
+
+    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap):
+        self._simd()
+        coef = np.zeros((h, w), dtype=np.int32); q = np.zeros((h, w), dtype=np.int16); s = I32(); lp = I32()
+        assert self.L.refshim_transform_quant(th, tv, P(resi), st, w, h, bd, qp, irap, P(coef), P(q), ctypes.byref(s), ctypes.byref(lp)) == 0
+        return coef, q, s.value, lp.value
+
+    def need_rdoq(self, coef, w, h, bd, qp, dq):
+        self._simd()
+        return int(self.L.refshim_need_rdoq(P(coef), w, h, bd, qp, dq))
+
+    def mctf_err(self, tap4, org, so, buf, sb, x, y, mvx, mvy, w, h, bd):
+        desc = np.array([[x, y, mvx, mvy, w, h]], dtype=np.int32); out = np.zeros(1, dtype=np.int32)
+        self.L.refshim_mctf_err_list(self.opt, tap4, PO(org, -(y * so + x)), so, P(buf), sb, P(desc), 1, bd, P(out), 1)
+        return int(out[0])
+
+    def sobel(self, vert, pred, ps, ds, w, h):
+        d = np.zeros((h, ds), dtype=np.int16)
+        self.L.refshim_sobel(self.opt, vert, P(pred), ps, P(d), ds, w, h)
+        return d
+
+    def equal_coeff(self, six, resi, rs, gx, gy, ds, w, h):
+        e = np.zeros(49, dtype=np.int64)
+        self.L.refshim_equal_coeff(self.opt, six, P(resi), rs, P(gx), P(gy), ds, w, h, P(e))
+        return e
+
+    def full_search(self, sc, ss, want_table=False):
+        n = len(sc['blk']); S = sc['stride']; base = sc['margin'] * S + sc['margin']
+        out = np.zeros((n, 4), dtype=np.int32)
+        ts = int(max((b[5] - b[4] + 1) * (b[7] - b[6] + 1) for b in sc['blk']))
+        tab = np.zeros((n, ts), dtype=np.uint32) if want_table else None
+        self.L.refshim_full_search(self.opt, PO(sc['org'], base), S, PO(sc['ref'], base), S, P(sc['blk']), n, 10, ss, sc['lam'], sc['cost_scale'],
+                                   sc['imv_shift'], P(out), P(tab) if want_table else None, ts, 2)
+        return (out, tab) if want_table else out
+
+    def mv_bits(self, *a):
+        return int(self.L.refshim_mv_bits(*a))
+
+    def mv_cost(self, lam, *a):
+        return int(self.L.refshim_mv_cost(lam, *a))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# case loops: each returns a list of mismatch descriptions (empty == parity)
+
+def run_dist(impl, rows, expect):
+    bad = []
+    for row, e in zip(rows, expect):
+        fam, w, h, so, sc, ss, ko, kc, bd, seed = [int(v) for v in row]
+        o, c = C.dist_inputs(row)
+        g = impl.dist(fam, o, so, c, sc, w, h, bd, ss)
+        if g != int(e):
+            bad.append(('dist', row.tolist(), g, int(e)))
+    return bad
+
+
+def run_tq(impl, rows, coef, q, meta):
+    bad = []; off = 0
+    for i, row in enumerate(rows):
+        th, tv, w, h, st, amp, qp, irap, bd, seed = [int(v) for v in row]
+        resi = C.tq_inputs(row)
+        c, qq, s, lp = impl.transform_quant(th, tv, resi, st, w, h, bd, qp, irap)
+        ec = coef[off:off + w * h].reshape(h, w); eq = q[off:off + w * h].reshape(h, w); off += w * h
+        nr = impl.need_rdoq(np.ascontiguousarray(ec), w, h, bd, qp, seed & 1)
+        if not (np.array_equal(c, ec) and np.array_equal(qq, eq) and s == meta[i][0] and lp == meta[i][1] and nr == meta[i][2]):
+            bad.append(('tq', row.tolist(), bool(np.array_equal(c, ec)), bool(np.array_equal(qq, eq)), s, lp, nr, meta[i].tolist()))
+    return bad
+
+
+def run_mctf(impl, rows, expect):
+    bad = []
+    m = C.MCTF_MARGIN
+    for row, e in zip(rows, expect):
+        w, h, mvx, mvy, tap4, bd, seed = [int(v) for v in row]
+        org, buf = C.mctf_inputs(row)
+        g = impl.mctf_err(tap4, org, org.shape[1], buf, buf.shape[1], m, m, mvx, mvy, w, h, bd)
+        if g != int(e):
+            bad.append(('mctf', row.tolist(), g, int(e)))
+    return bad
+
+
+def run_affine(impl, rows, sobel, eqs):
+    bad = []; off = 0
+    for i, row in enumerate(rows):
+        w, h, ps, ds, six, seed = [int(v) for v in row]
+        pred, resi, gx, gy = C.affine_inputs(row)
+        for vert in (0, 1):
+            d = impl.sobel(vert, pred, ps, ds, w, h)[:, :w]
+            e = sobel[off:off + w * h].reshape(h, w); off += w * h
+            if not np.array_equal(d, e):
+                bad.append(('sobel', row.tolist(), vert))
+        g = impl.equal_coeff(six, resi, ps, gx, gy, ds, w, h)
+        if not np.array_equal(g, eqs[i]):
+            bad.append(('equal_coeff', row.tolist()))
+    return bad

@@ -1,0 +1,44 @@
+"""CPU-only: the oracle (oracle/oracle.c) against the committed golden vectors, which were produced by the
+unmodified reference (scalar == AVX2 asserted at generation time, tests/golden/make_golden.py)."""
+import numpy as np
+import cases as C
+import impls
+
+
+def test_case_tables_match_fixture(golden):
+    # the fixture is only meaningful if the seeded case generators still produce the rows it was built from
+    assert np.array_equal(golden['dist_rows'], C.dist_cases())
+    assert np.array_equal(golden['tq_rows'], C.tq_cases())
+    assert np.array_equal(golden['mctf_rows'], C.mctf_cases())
+    assert np.array_equal(golden['aff_rows'], C.affine_cases())
+
+
+def test_oracle_dist_golden(golden):
+    assert impls.run_dist(impls.OracleImpl(), golden['dist_rows'], golden['dist_expect']) == []
+
+
+def test_oracle_transform_quant_golden(golden):
+    assert impls.run_tq(impls.OracleImpl(), golden['tq_rows'], golden['tq_coef'], golden['tq_q'], golden['tq_meta']) == []
+
+
+def test_oracle_mctf_golden(golden):
+    assert impls.run_mctf(impls.OracleImpl(), golden['mctf_rows'], golden['mctf_expect']) == []
+
+
+def test_oracle_affine_golden(golden):
+    assert impls.run_affine(impls.OracleImpl(), golden['aff_rows'], golden['aff_sobel'], golden['aff_eq']) == []
+
+
+def test_oracle_full_search_golden(golden):
+    sc = C.search_case()
+    O = impls.OracleImpl()
+    for ss in (0, 1):
+        assert np.array_equal(O.full_search(sc, ss), golden['search_best_ss%d' % ss])
+
+
+def test_oracle_mv_rate_golden(golden):
+    O = impls.OracleImpl()
+    for i, row in enumerate(golden['mv_rows']):
+        a = [int(v) for v in row]
+        assert O.mv_bits(*a) == int(golden['mv_bits'][i])
+        assert O.mv_cost(57.25 + i, *a) == int(golden['mv_cost'][i])

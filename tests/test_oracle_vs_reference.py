@@ -1,0 +1,116 @@
+"""CPU-only, build container only (skipped where oracle/_ref is absent): a wider random sweep of the oracle
+against the LIVE reference, scalar and AVX2, in the style of test/vvenc_unit_test (tolerance 0)."""
+import numpy as np
+import pytest
+import cases as C
+import impls
+from _libs import have_ref
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_dist_sweep(opt):
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    rs = np.random.RandomState(31 + opt)
+    n = 0
+    for w in (1, 2, 4, 8, 16, 32, 64, 128):
+        for h in (1, 2, 4, 6, 8, 12, 16, 24, 32, 48, 64, 128):
+            for fam in range(5):
+                if fam >= 2 and (w < 2 or h % 2): continue
+                if fam == 0 and w == 1 and opt: continue
+                if fam == 4 and (w < 4 or h % 4): continue
+                so = w if fam == 4 else w + int(rs.randint(0, 64)); sc = w if fam == 4 else w + int(rs.randint(0, 64))
+                o = C.pel_block(rs, h, so, 0); c = C.pel_block(rs, h, sc, int(rs.randint(0, 4)))
+                ss = int(rs.randint(0, 2)) if fam == 1 and h % 2 == 0 else 0
+                assert O.dist(fam, o, so, c, sc, w, h, 10, ss) == R.dist(fam, o, so, c, sc, w, h, 10, ss), (fam, w, h, ss)
+                n += 1
+    assert n > 300
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_transform_quant_sweep(opt):
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    rs = np.random.RandomState(77 + opt)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            for (th, tv) in ((0, 0), (2, 2), (1, 2), (2, 1), (1, 1)):
+                if (th or tv) and (w > 32 or h > 32): continue
+                amp = int(rs.choice([1023, 300, 20, 3])); st = w + int(rs.randint(0, 9))
+                resi = rs.randint(-amp, amp + 1, size=(h, st)).astype(np.int16)
+                qp = int(rs.randint(0, 64)); irap = int(rs.randint(0, 2))
+                a = O.transform_quant(th, tv, resi, st, w, h, 10, qp, irap); b = R.transform_quant(th, tv, resi, st, w, h, 10, qp, irap)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2:] == b[2:], (th, tv, w, h, qp, irap)
+                for dq in (0, 1):
+                    assert O.need_rdoq(a[0], w, h, 10, qp, dq) == R.need_rdoq(a[0], w, h, 10, qp, dq)
+
+
+def test_fwd_core_like_reference_unit_test():
+    # vvenc_unit_test.cpp:1085-1140: random 8-bit matrix, 11-bit signed src, random line/reducedLine/cutoff/shift
+    import ctypes
+    from _libs import oracle, refshim, P
+    O = oracle(); R = refshim()
+    rs = np.random.RandomState(5)
+    for tr in (4, 8, 16, 32, 64):
+        for rep in range(20):
+            line = int(rs.choice([4, 8, 16, 32, 64])); red = line - int(rs.choice([0, line // 2])) ; cut = tr - int(rs.choice([0, tr // 2]))
+            shift = int(rs.randint(1, 17))
+            tc = C.aligned((tr, tr), np.int16); tc[:] = rs.randint(-128, 128, size=(tr, tr))
+            src = C.aligned((line, tr), np.int32); src[:] = rs.randint(-1024, 1024, size=(line, tr))
+            d1 = C.aligned((tr, line), np.int32); d2 = C.aligned((tr, line), np.int32)
+            R.refshim_fwd_core(tr, P(tc), P(src), P(d1), line, red, cut, shift); O.orc_fwd_core(tr, P(tc), P(src), P(d2), line, red, cut, shift)
+            d1 = d1[:, :red]; d2 = d2[:, :red]      # columns past reducedLine are unspecified (vvenc_unit_test.cpp:1117-1119)
+            assert np.array_equal(d1, d2), (tr, line, red, cut, shift)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_mctf_all_phases(opt):
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    rs = np.random.RandomState(11)
+    m = C.MCTF_MARGIN
+    for (w, h) in ((8, 8), (16, 16), (32, 24), (64, 64)):
+        org = rs.randint(0, 1024, size=(h, w + 3)).astype(np.int16); buf = rs.randint(0, 1024, size=(h + 2 * m, w + 2 * m)).astype(np.int16)
+        for tap4 in (0, 1):
+            for fx in range(16):
+                for fy in range(16):
+                    mvx = 16 * int(rs.randint(-2, 3)) + fx; mvy = 16 * int(rs.randint(-2, 3)) + fy
+                    a = O.mctf_err(tap4, org, w + 3, buf, w + 2 * m, m, m, mvx, mvy, w, h, 10)
+                    b = R.mctf_err(tap4, org, w + 3, buf, w + 2 * m, m, m, mvx, mvy, w, h, 10)
+                    assert a == b, (w, h, tap4, mvx, mvy)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_affine(opt):
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    for row in C.affine_cases():
+        w, h, ps, ds, six, seed = [int(v) for v in row]
+        pred, resi, gx, gy = C.affine_inputs(row)
+        for vert in (0, 1):
+            assert np.array_equal(O.sobel(vert, pred, ps, ds, w, h), R.sobel(vert, pred, ps, ds, w, h))
+        assert np.array_equal(O.equal_coeff(six, resi, ps, gx, gy, ds, w, h), R.equal_coeff(six, resi, ps, gx, gy, ds, w, h))
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_full_search_with_tables(opt):
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    sc = C.search_case(seed=991)
+    for ss in (0, 1):
+        a, ta = O.full_search(sc, ss, True); b, tb = R.full_search(sc, ss, True)
+        assert np.array_equal(a, b) and np.array_equal(ta, tb)
+
+
+def test_tables_match_reference():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import gen_tables as g
+    from _libs import refshim, P
+    R = refshim()
+    for (t, N), m in g.matrices().items():
+        ref = np.zeros((N, N), dtype=np.int16)
+        assert R.refshim_tr_matrix(t, N, P(ref)) == 0
+        assert np.array_equal(ref, m), (t, N)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            a = np.zeros(1024, dtype=np.int32); b = np.zeros(1024, dtype=np.int32)
+            from _libs import oracle
+            assert R.refshim_scan_order(w, h, P(a)) == oracle().orc_scan_order(w, h, P(b)) and np.array_equal(a, b)
