@@ -1,0 +1,165 @@
+/*
+ * vvenc_b200.h -- C ABI of the B200-native block-cost path (drop-in boundary).
+ *
+ * Every entry point replaces one seam of the reference (fraunhoferhhi/vvenc); citations are
+ * /root/reference-relative file:line.  Conventions: int return (0 = VVB_OK), no exceptions across the ABI,
+ * plain pointers and sizes, no torch types.  A context owns one CUDA stream; calls on one context are
+ * serialised on that stream, different contexts may be driven from different encoder worker threads
+ * (the reference gives every worker its own RdCost/TrQuant, EncoderLib/EncSlice.cpp:142-147).
+ * There is no CPU fallback: every call fails with VVB_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Entry points without suffix take HOST buffers and copy in/out inside the call (the end-to-end path);
+ * `_dev` twins take DEVICE pointers, enqueue on the context stream and return without synchronising.
+ */
+#ifndef VVENC_B200_H
+#define VVENC_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VVB_OK               0
+#define VVB_ERR_ARG         -1   /* malformed argument (null pointer, negative size, unknown plane id)          */
+#define VVB_ERR_UNSUPPORTED -2   /* shape outside the reference's own domain (e.g. width not a power of two)    */
+#define VVB_ERR_CUDA        -3   /* CUDA runtime error, text in vvb_last_error()                                 */
+#define VVB_ERR_NOMEM       -4
+
+typedef struct vvb_ctx vvb_ctx;
+
+/* Distortion function family == reference enum DFunc base (CommonLib/TypeDef.h:339-382); the per-width slot
+ * (DF_SAD + log2 w etc.) is implied by the candidate's width exactly as RdCost::setDistParam does
+ * (CommonLib/RdCost.cpp:158-226). */
+enum vvb_dfunc
+{
+  VVB_DF_SSE      = 0,    /* xGetSSE*      CommonLib/RdCost.cpp:651-1000                        */
+  VVB_DF_SAD      = 1,    /* xGetSAD*      CommonLib/RdCost.cpp:300-644 (subShift honoured)     */
+  VVB_DF_HAD      = 2,    /* xGetHADs<0>   CommonLib/RdCost.cpp:1818-1938                       */
+  VVB_DF_HAD_FAST = 3,    /* xGetHADs<1>   (16x16_fast tiles for square multiples of 32)       */
+  VVB_DF_HAD_2SAD = 4     /* xGetHAD2SADs  CommonLib/RdCost.cpp:1768-1816                       */
+};
+
+/* ---- lifetime / errors -------------------------------------------------------------------------------- */
+int         vvb_create     ( vvb_ctx** out, int device );   /* replaces RdCost::create(true) + initRdCostX86 (RdCost.cpp:82-148), TCoeffOps::initTCoeffOps (TrQuant_EMT.cpp:2028) */
+void        vvb_destroy    ( vvb_ctx* ctx );
+const char* vvb_last_error ( const vvb_ctx* ctx );
+int         vvb_synchronize( vvb_ctx* ctx );
+void*       vvb_stream     ( vvb_ctx* ctx );                /* cudaStream_t of the context, for event timing / interop */
+int         vvb_launch_count( const vvb_ctx* ctx, uint64_t* kernels_launched );   /* kernels this context has launched so far */
+
+/* ---- pictures ("planes") ---------------------------------------------------------------------------------
+ * int16 sample planes (Pel, CommonLib/TypeDef.h:181) with a margin on all sides, like the encoder's padded
+ * reference pictures (CommonLib/Picture.cpp:461-501).  `origin` points at sample (0,0); rows -margin..height+margin-1
+ * and columns -margin..width+margin-1 must be readable.  Uploaded once per picture, referenced by id afterwards. */
+int vvb_plane_upload  ( vvb_ctx* ctx, int plane_id, const int16_t* origin, int stride, int width, int height, int margin, int bit_depth );
+int vvb_plane_bind_dev( vvb_ctx* ctx, int plane_id, const int16_t* dev_origin, int stride, int width, int height, int margin, int bit_depth );
+int vvb_plane_free    ( vvb_ctx* ctx, int plane_id );
+
+/* ---- pair-list regime: one cost per descriptor (FpDistFunc, CommonLib/RdCost.h:74) ------------------------- */
+typedef struct
+{
+  int32_t  org_plane, org_x, org_y;   /* DistParam::org (RdCost.h:85)                      */
+  int32_t  cur_plane, cur_x, cur_y;   /* DistParam::cur                                    */
+  uint16_t w, h;                      /* org.width / org.height                            */
+  uint8_t  dfunc;                     /* enum vvb_dfunc                                    */
+  uint8_t  sub_shift;                 /* DistParam::subShift (SAD only)                    */
+  uint8_t  pad[2];
+} vvb_cand;                           /* 32 bytes */
+
+int vvb_dist_batch    ( vvb_ctx* ctx, const vvb_cand* cands, int n, uint64_t* cost_out );
+int vvb_dist_batch_dev( vvb_ctx* ctx, const vvb_cand* dev_cands, int n, uint64_t* dev_cost_out );
+
+/* Single synchronous call with borrowed HOST blocks: the exact shape of FpDistFunc for parity tests and for a
+ * reference-side `RdCost::_initRdCostB200()`.  Returns the cost; *err receives VVB_*. */
+uint64_t vvb_dist_block( vvb_ctx* ctx, int dfunc, const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                         int w, int h, int bit_depth, int sub_shift, int* err );
+
+/* xGetSADwMask (RdCost.cpp:2062-2093), xGetSAD8X5/16X5 (RdCost.cpp:1984-2034), fixWeightedSSE (RdCost.cpp:1948-1982) */
+uint64_t vvb_sad_mask_block( vvb_ctx* ctx, const int16_t* org, int org_stride, const int16_t* cur, int cur_stride, int w, int h,
+                             const int16_t* mask, int mask_stride, int step_x, int mask_stride2, int sub_shift, int* err );
+int      vvb_sad_x5_block  ( vvb_ctx* ctx, const int16_t* org, int org_stride, const int16_t* cur, int cur_stride, int w, int h,
+                             int sub_shift, int calc_centre, uint64_t cost5[5] );
+uint64_t vvb_fix_wsse_block( vvb_ctx* ctx, const int16_t* org, int org_stride, const int16_t* cur, int cur_stride, int w, int h,
+                             uint32_t fixed_weight, int* err );
+
+/* ---- candidate-pool regime (RDO style): K candidate predictions per original block, each with its own
+ * compact w x h buffer: pool[(b*K + k)*w*h ...].  One cost per (block, candidate); HBM streaming. ---------- */
+typedef struct { int32_t x, y; } vvb_pos;
+int vvb_dist_pool    ( vvb_ctx* ctx, int dfunc, int org_plane, const vvb_pos* blocks, int n_blocks, int w, int h, int K,
+                       const int16_t* pool, int sub_shift, uint32_t* cost_out /* n_blocks*K */ );
+int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int org_plane, const vvb_pos* dev_blocks, int n_blocks, int w, int h, int K,
+                       const int16_t* dev_pool, int sub_shift, uint32_t* dev_cost_out );
+
+/* ---- motion-search regimes (EncoderLib/InterSearch.cpp) ----------------------------------------------------
+ * MV rate: cost += Distortion( sqrt(lambda) * bits ), bits = EG((x<<cost_scale) - pred_hor >> imv_shift) + EG(y...)
+ * (CommonLib/RdCost.h:181-203, RdCost.cpp:73-78). */
+typedef struct
+{
+  int32_t x, y;                        /* block position in the original plane                    */
+  int16_t left, right, top, bottom;    /* SearchRange (InterSearch.h:441-447), integer offsets    */
+  int16_t pred_hor, pred_ver;          /* RdCost::setPredictor, units of 1/(1<<cost_scale) pel    */
+  int16_t start_x, start_y;            /* pattern regime: centre of the fixed pattern              */
+} vvb_block;                           /* 24 bytes */
+
+typedef struct { int16_t dx, dy; uint32_t sad; uint64_t cost; } vvb_best;   /* 16 bytes; cost = sad + mv cost */
+
+typedef struct { double lambda; int32_t cost_scale, imv_shift, sub_shift; } vvb_me_par;
+
+/* Dense full search = InterSearch::xPatternSearch (InterSearch.cpp:2209-2251): every (dx,dy) in
+ * [left..right]x[top..bottom], raster order, first strictly smaller total cost wins.  Optional SAD table
+ * (uint32, row-major over the window, table_stride entries per block). */
+int vvb_sad_search    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, const vvb_me_par* par,
+                        uint32_t* sad_tables, int table_stride, vvb_best* best_out );
+/* max_nx / max_ny: largest (right-left+1) / (bottom-top+1) in the batch; the host sizes shared memory from them */
+int vvb_sad_search_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, const vvb_me_par* par,
+                        int max_nx, int max_ny, uint32_t* dev_sad_tables, int table_stride, vvb_best* dev_best_out );
+
+/* Fixed candidate set = the static point pattern of xTZ8PointDiamondSearch / raster scan
+ * (InterSearch.cpp:557-758, 2491-2497) around (start_x,start_y): pattern[k] = (dx,dy) offsets, clipped against the
+ * block's SearchRange (points outside are reported as UINT32_MAX and never win).  costs are SAD only;
+ * best_out applies the MV rate in list order (first strictly smaller wins). */
+typedef struct { int16_t dx, dy; } vvb_mv;
+int vvb_sad_pattern    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, const vvb_mv* pattern, int K,
+                         const vvb_me_par* par, uint32_t* sad_out /* n*K, nullable */, vvb_best* best_out /* nullable */ );
+int vvb_sad_pattern_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, const vvb_mv* dev_pattern, int K,
+                         const vvb_me_par* par, uint32_t* dev_sad_out, vvb_best* dev_best_out );
+
+/* ---- forward transform + quantise (TrQuant::transformNxN for LFNST-off, non-skip luma TUs; ---------------
+ * CommonLib/TrQuant.cpp:688-736 -> xT :481-564 -> Quant::quant CommonLib/Quant.cpp:735-833 -> QuantCore :132-230,
+ * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types. */
+typedef struct
+{
+  int32_t w, h;                /* TU size, each in {4,8,16,32,64}                               */
+  int32_t tr_hor, tr_ver;      /* 0 DCT-II, 1 DCT-VIII, 2 DST-VII (enum TransType)                */
+  int32_t bit_depth;           /* 8 or 10                                                         */
+  int32_t qp;                  /* CU QP (cu.qp); +6*(bit_depth-8) applied inside (Quant.cpp:99)   */
+  int32_t is_irap;             /* slice->isIRAP(): rounding offset 171 vs 85 (Quant.cpp:772)      */
+  int32_t dep_quant;           /* for need_rdoq only: slice->depQuantEnabled (Quant.cpp:852-855)  */
+} vvb_tu_par;
+
+/* resi: n compact residual blocks [n][h][w] (Pel); outputs (each nullable except q):
+ * coef [n][h][w] TCoeff (int32), q [n][h][w] TCoeffSig (int16), abs_sum[n], last_pos[n], need_rdoq[n] (0/1) */
+int vvb_fwd_trquant    ( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* resi, int n,
+                         int32_t* coef, int16_t* q, int32_t* abs_sum, int32_t* last_pos, uint8_t* need_rdoq );
+int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_resi, int n,
+                         int32_t* dev_coef, int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos, uint8_t* dev_need_rdoq );
+/* Residual formed on the device: resi = org(x,y) - pred(x+dx,y+dy) for each TU position (PelBuf::subtract, IntraSearch.cpp:1328) */
+int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int org_plane, int pred_plane, const vvb_block* dev_blocks, int n,
+                         int32_t* dev_coef, int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos, uint8_t* dev_need_rdoq );
+
+/* ---- MCTF block matching (CommonLib/MCTF.cpp:122-257 via MCTF::motionErrorLuma :1099-1164) ----------------- */
+typedef struct { int32_t x, y; int32_t mvx, mvy; /* 1/16 pel */ uint16_t w, h; } vvb_mctf_cand;   /* 20 bytes */
+int vvb_mctf_error_batch    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* cands, int n, int low_res_filter /* 4-tap */, int32_t* err_out );
+int vvb_mctf_error_batch_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* dev_cands, int n, int low_res_filter, int32_t* dev_err_out );
+
+/* ---- affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190) ---------------------------------- */
+int vvb_affine_sobel      ( vvb_ctx* ctx, int vertical, const int16_t* pred, int pred_stride, int16_t* deriv, int deriv_stride, int w, int h );
+int vvb_affine_equal_coeff( vvb_ctx* ctx, int six_param, const int16_t* resi, int resi_stride, const int16_t* deriv_x, const int16_t* deriv_y,
+                            int deriv_stride, int w, int h, int64_t eq_out[49] /* accumulated into, row stride 7 */ );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

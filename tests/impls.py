@@ -17,10 +17,10 @@ class OracleImpl:
     def dist(self, fam, o, so, c, sc, w, h, bd, ss):
         return int(self.L.orc_dist(fam, P(o), so, P(c), sc, w, h, ss))
 
-    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap):
+    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap, dq=0):
         coef = np.zeros((h, w), dtype=np.int32); q = np.zeros((h, w), dtype=np.int16); s = I32(); lp = I32()
         assert self.L.orc_transform_quant(th, tv, P(resi), st, w, h, bd, qp, irap, P(coef), P(q), ctypes.byref(s), ctypes.byref(lp)) == 0
-        return coef, q, s.value, lp.value
+        return coef, q, s.value, lp.value, self.need_rdoq(coef, w, h, bd, qp, dq)
 
     def need_rdoq(self, coef, w, h, bd, qp, dq):
         return int(self.L.orc_need_rdoq(P(coef), w, h, bd, qp, dq))
@@ -69,11 +69,11 @@ class RefImpl(OracleImpl):
     def dist(self, fam, o, so, c, sc, w, h, bd, ss):
         return int(self.L.refshim_dist(self.opt, fam, P(o), so, P(c), sc, w, h, bd, ss))
 
-    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap):
+    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap, dq=0):
         self._simd()
         coef = np.zeros((h, w), dtype=np.int32); q = np.zeros((h, w), dtype=np.int16); s = I32(); lp = I32()
         assert self.L.refshim_transform_quant(th, tv, P(resi), st, w, h, bd, qp, irap, P(coef), P(q), ctypes.byref(s), ctypes.byref(lp)) == 0
-        return coef, q, s.value, lp.value
+        return coef, q, s.value, lp.value, self.need_rdoq(coef, w, h, bd, qp, dq)
 
     def need_rdoq(self, coef, w, h, bd, qp, dq):
         self._simd()
@@ -129,9 +129,8 @@ def run_tq(impl, rows, coef, q, meta):
     for i, row in enumerate(rows):
         th, tv, w, h, st, amp, qp, irap, bd, seed = [int(v) for v in row]
         resi = C.tq_inputs(row)
-        c, qq, s, lp = impl.transform_quant(th, tv, resi, st, w, h, bd, qp, irap)
+        c, qq, s, lp, nr = impl.transform_quant(th, tv, resi, st, w, h, bd, qp, irap, seed & 1)
         ec = coef[off:off + w * h].reshape(h, w); eq = q[off:off + w * h].reshape(h, w); off += w * h
-        nr = impl.need_rdoq(np.ascontiguousarray(ec), w, h, bd, qp, seed & 1)
         if not (np.array_equal(c, ec) and np.array_equal(qq, eq) and s == meta[i][0] and lp == meta[i][1] and nr == meta[i][2]):
             bad.append(('tq', row.tolist(), bool(np.array_equal(c, ec)), bool(np.array_equal(qq, eq)), s, lp, nr, meta[i].tolist()))
     return bad
@@ -163,3 +162,63 @@ def run_affine(impl, rows, sobel, eqs):
         if not np.array_equal(g, eqs[i]):
             bad.append(('equal_coeff', row.tolist()))
     return bad
+
+
+class GpuImpl:
+    """the CUDA product through its C ABI (vvenc_b200.CostEngine); same calling convention as OracleImpl"""
+    name = 'gpu'
+
+    def __init__(self, device=0):
+        import vvenc_b200 as V
+        self.V = V
+        self.eng = V.CostEngine(device)
+
+    def dist(self, fam, o, so, c, sc, w, h, bd, ss):
+        return self.eng.dist_block(fam, o, so, c, sc, w, h, bd, ss)
+
+    def transform_quant(self, th, tv, resi, st, w, h, bd, qp, irap, dq=0):
+        par = self.eng.tu_par(w, h, th, tv, bd, qp, bool(irap), bool(dq))
+        r = self.eng.fwd_trquant(par, np.ascontiguousarray(resi[:, :w]).reshape(1, h, w))
+        return r['coef'][0], r['q'][0], int(r['abs_sum'][0]), int(r['last_pos'][0]), int(r['need_rdoq'][0])
+
+    def mctf_err(self, tap4, org, so, buf, sb, x, y, mvx, mvy, w, h, bd):
+        m = min(x, y)
+        orgp = np.zeros_like(buf)
+        orgp[y:y + h, x:x + w] = org[:h, :w]
+        self.eng.upload_plane(0, np.ascontiguousarray(orgp), buf.shape[1] - 2 * m, buf.shape[0] - 2 * m, m, bd)
+        self.eng.upload_plane(1, np.ascontiguousarray(buf), buf.shape[1] - 2 * m, buf.shape[0] - 2 * m, m, bd)
+        c = np.zeros(1, dtype=self.V.MCTF_DT)
+        c['x'] = x - m; c['y'] = y - m; c['mvx'] = mvx; c['mvy'] = mvy; c['w'] = w; c['h'] = h
+        return int(self.eng.mctf_error_batch(0, 1, c, bool(tap4))[0])
+
+    def sobel(self, vert, pred, ps, ds, w, h):
+        return self.eng.affine_sobel(vert, pred, ps, ds, w, h)
+
+    def equal_coeff(self, six, resi, rs, gx, gy, ds, w, h):
+        return self.eng.affine_equal_coeff(six, resi, rs, gx, gy, ds, w, h)
+
+    def upload_search_case(self, sc):
+        m = sc['margin']
+        self.eng.upload_plane(0, sc['org'], sc['W'], sc['H'], m, 10)
+        self.eng.upload_plane(1, sc['ref'], sc['W'], sc['H'], m, 10)
+
+    def full_search(self, sc, ss, want_table=False):
+        self.upload_search_case(sc)
+        blk = sc['blk']; n = len(blk)
+        out = np.zeros((n, 4), dtype=np.int32)
+        ts = int(max((b[5] - b[4] + 1) * (b[7] - b[6] + 1) for b in blk))
+        tab = np.zeros((n, ts), dtype=np.uint32)
+        par = self.eng.me_par(sc['lam'], sc['cost_scale'], sc['imv_shift'], ss)
+        # one launch per distinct block shape (the C ABI takes uniform-shape batches)
+        shapes = sorted(set((int(b[2]), int(b[3])) for b in blk))
+        for (w, h) in shapes:
+            idx = [i for i in range(n) if (int(blk[i][2]), int(blk[i][3])) == (w, h)]
+            B = np.zeros(len(idx), dtype=self.V.BLOCK_DT)
+            for k, i in enumerate(idx):
+                b = blk[i]
+                B[k] = (b[0], b[1], b[4], b[5], b[6], b[7], b[8], b[9], 0, 0)
+            best, t = self.eng.sad_search(0, 1, B, w, h, par, want_tables=True)
+            for k, i in enumerate(idx):
+                out[i] = (best[k]['dx'], best[k]['dy'], int(best[k]['cost']) & 0xffffffff, int(best[k]['cost']) >> 32)
+                tab[i, :t.shape[1]] = t[k]
+        return (out, tab) if want_table else out

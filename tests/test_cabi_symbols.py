@@ -1,0 +1,47 @@
+"""CPU-only: the C-ABI library is built, loads without a GPU, exports every symbol include/vvenc_b200.h declares,
+and refuses to create a context when no CUDA device exists (no CPU fallback)."""
+import os, re, subprocess, ctypes
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, 'include', 'vvenc_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(vvb_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import vvenc_b200._lib as L
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    names = _declared()
+    assert len(names) >= 25
+    out = subprocess.check_output(['nm', '-D', '--defined-only', L.LIB_PATH], text=True)
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    missing = [n for n in names if n not in exported]
+    assert missing == []
+    # and the ctypes table binds the same set
+    assert sorted(L.SYMBOLS) == names
+    L.load()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    import vvenc_b200 as V
+    with pytest.raises(V.VvbError):
+        V.CostEngine(0)
+
+
+def test_product_never_imports_oracle():
+    # the product package must not reference oracle/ (tests, smoke() and bench.py's cpu_baseline leg are the only users)
+    pkg = os.path.join(ROOT, 'vvenc_b200')
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dp, f), errors='ignore').read()
+                assert 'liboracle' not in txt and 'refshim' not in txt and 'oracle/' not in txt.replace('oracle/vvc_tables.h', ''), f

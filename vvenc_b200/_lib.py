@@ -1,0 +1,89 @@
+"""ctypes binding of the C-ABI shared library (include/vvenc_b200.h).  Fails loudly when the library is missing:
+there is no Python or CPU fallback for any entry point."""
+import ctypes, os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'csrc', 'libvvenc_b200.so')
+
+VVB_OK, VVB_ERR_ARG, VVB_ERR_UNSUPPORTED, VVB_ERR_CUDA, VVB_ERR_NOMEM = 0, -1, -2, -3, -4
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+
+
+class vvb_cand(ctypes.Structure):
+    _fields_ = [('org_plane', ctypes.c_int32), ('org_x', ctypes.c_int32), ('org_y', ctypes.c_int32),
+                ('cur_plane', ctypes.c_int32), ('cur_x', ctypes.c_int32), ('cur_y', ctypes.c_int32),
+                ('w', ctypes.c_uint16), ('h', ctypes.c_uint16), ('dfunc', ctypes.c_uint8), ('sub_shift', ctypes.c_uint8), ('pad', ctypes.c_uint8 * 2)]
+
+
+class vvb_me_par(ctypes.Structure):
+    _fields_ = [('lam', ctypes.c_double), ('cost_scale', ctypes.c_int32), ('imv_shift', ctypes.c_int32), ('sub_shift', ctypes.c_int32)]
+
+
+class vvb_tu_par(ctypes.Structure):
+    _fields_ = [('w', ctypes.c_int32), ('h', ctypes.c_int32), ('tr_hor', ctypes.c_int32), ('tr_ver', ctypes.c_int32), ('bit_depth', ctypes.c_int32),
+                ('qp', ctypes.c_int32), ('is_irap', ctypes.c_int32), ('dep_quant', ctypes.c_int32)]
+
+
+# numpy dtypes mirroring the packed C structs
+import numpy as np
+CAND_DT = np.dtype([('org_plane', '<i4'), ('org_x', '<i4'), ('org_y', '<i4'), ('cur_plane', '<i4'), ('cur_x', '<i4'), ('cur_y', '<i4'),
+                    ('w', '<u2'), ('h', '<u2'), ('dfunc', 'u1'), ('sub_shift', 'u1'), ('pad', 'u1', (2,))])
+POS_DT = np.dtype([('x', '<i4'), ('y', '<i4')])
+BLOCK_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('left', '<i2'), ('right', '<i2'), ('top', '<i2'), ('bottom', '<i2'),
+                     ('pred_hor', '<i2'), ('pred_ver', '<i2'), ('start_x', '<i2'), ('start_y', '<i2')])
+BEST_DT = np.dtype([('dx', '<i2'), ('dy', '<i2'), ('sad', '<u4'), ('cost', '<u8')])
+MV_DT = np.dtype([('dx', '<i2'), ('dy', '<i2')])
+MCTF_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('mvx', '<i4'), ('mvy', '<i4'), ('w', '<u2'), ('h', '<u2')])
+assert CAND_DT.itemsize == 32 and BLOCK_DT.itemsize == 24 and BEST_DT.itemsize == 16 and MCTF_DT.itemsize == 20
+
+# every symbol include/vvenc_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'vvb_create': (c_i, [ctypes.POINTER(c_p), c_i]),
+    'vvb_destroy': (None, [c_p]),
+    'vvb_last_error': (ctypes.c_char_p, [c_p]),
+    'vvb_synchronize': (c_i, [c_p]),
+    'vvb_stream': (c_p, [c_p]),
+    'vvb_launch_count': (c_i, [c_p, ctypes.POINTER(ctypes.c_uint64)]),
+    'vvb_plane_upload': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),
+    'vvb_plane_bind_dev': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),
+    'vvb_plane_free': (c_i, [c_p, c_i]),
+    'vvb_dist_batch': (c_i, [c_p, c_p, c_i, c_p]),
+    'vvb_dist_batch_dev': (c_i, [c_p, c_p, c_i, c_p]),
+    'vvb_dist_block': (ctypes.c_uint64, [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, ctypes.POINTER(c_i)]),
+    'vvb_sad_mask_block': (ctypes.c_uint64, [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, ctypes.POINTER(c_i)]),
+    'vvb_sad_x5_block': (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    'vvb_fix_wsse_block': (ctypes.c_uint64, [c_p, c_p, c_i, c_p, c_i, c_i, c_i, ctypes.c_uint32, ctypes.POINTER(c_i)]),
+    'vvb_dist_pool': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'vvb_dist_pool_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'vvb_sad_search': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, ctypes.POINTER(vvb_me_par), c_p, c_i, c_p]),
+    'vvb_sad_search_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_p, c_i, c_p]),
+    'vvb_sad_pattern': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
+    'vvb_sad_pattern_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
+    'vvb_fwd_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_fwd_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_mctf_error_batch': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'vvb_mctf_error_batch_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'vvb_affine_sobel': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i]),
+    'vvb_affine_equal_coeff': (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree CUDA library and bind every declared symbol; raises if it is absent (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('vvenc_b200: %s is missing -- run `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(nvcc, sm_100a); there is no CPU fallback' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(lib, name)          # AttributeError if the export is missing
+            f.restype = res
+            f.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,188 @@
+"""Host-side mirror of the reference's cost interfaces on top of the C ABI (include/vvenc_b200.h).
+
+`CostEngine` plays the role one `RdCost` + `TrQuant` pair plays for an encoder worker
+(EncoderLib/EncCu.h:265-272): it owns a context (one CUDA stream), resident pictures and exposes
+
+  getDistPart-like single calls .... dist_block / sad_mask_block / sad_x5_block / fix_wsse_block   (RdCost.h:74-75,117)
+  batched candidate evaluation ..... dist_batch (descriptor list), dist_pool (RDO candidate pools)
+  motion search .................... sad_search (xPatternSearch), sad_pattern (fixed TZ point set)
+  TU coding ........................ fwd_trquant (TrQuant::transformNxN: xT + Quant::quant + xNeedRDOQ)
+  pre-analysis ..................... mctf_error_batch (MCTF::motionErrorLuma)
+  affine ME ........................ affine_sobel / affine_equal_coeff
+
+numpy arrays are host buffers (copied inside the call: the end-to-end path).  The *_dev methods take raw device
+pointers (e.g. torch tensors' data_ptr()) and only enqueue work on the context stream.
+Errors surface as VvbError carrying the reference-style reason; nothing falls back to the CPU.
+"""
+import ctypes
+import numpy as np
+from . import _lib as L
+
+DF_SSE, DF_SAD, DF_HAD, DF_HAD_FAST, DF_HAD_2SAD = range(5)
+DCT2, DCT8, DST7 = 0, 1, 2
+
+
+class VvbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('vvenc_b200 error %d: %s' % (code, msg))
+        self.code = code
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _po(a, off):
+    return ctypes.c_void_p(a.ctypes.data + off * a.itemsize)
+
+
+class CostEngine:
+    def __init__(self, device=0):
+        self.lib = L.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.vvb_create(ctypes.byref(h), device)
+        if rc != L.VVB_OK:
+            raise VvbError(rc, 'vvb_create failed (no usable CUDA device?)')
+        self.h = h
+        self._planes = {}
+
+    # ---- lifetime
+    def close(self):
+        if self.h:
+            self.lib.vvb_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != L.VVB_OK:
+            raise VvbError(rc, self.lib.vvb_last_error(self.h).decode())
+
+    def synchronize(self):
+        self._chk(self.lib.vvb_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.vvb_stream(self.h)
+
+    @property
+    def launches(self):
+        n = ctypes.c_uint64()
+        self._chk(self.lib.vvb_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    # ---- pictures
+    def upload_plane(self, plane_id, padded, width, height, margin, bit_depth=10):
+        """padded: 2-D int16 array of shape (>= height + 2*margin, stride) whose sample (0,0) sits at [margin, margin]"""
+        assert padded.dtype == np.int16 and padded.ndim == 2 and padded.flags['C_CONTIGUOUS']
+        stride = padded.shape[1]
+        self._chk(self.lib.vvb_plane_upload(self.h, plane_id, _po(padded, margin * stride + margin), stride, width, height, margin, bit_depth))
+        self._planes[plane_id] = (width, height, margin, bit_depth)
+
+    def bind_plane_dev(self, plane_id, dev_origin_ptr, stride, width, height, margin, bit_depth=10):
+        self._chk(self.lib.vvb_plane_bind_dev(self.h, plane_id, ctypes.c_void_p(dev_origin_ptr), stride, width, height, margin, bit_depth))
+        self._planes[plane_id] = (width, height, margin, bit_depth)
+
+    def free_plane(self, plane_id):
+        self._chk(self.lib.vvb_plane_free(self.h, plane_id)); self._planes.pop(plane_id, None)
+
+    # ---- distortion
+    def dist_batch(self, cands):
+        cands = np.ascontiguousarray(cands, dtype=L.CAND_DT)
+        out = np.zeros(len(cands), dtype=np.uint64)
+        self._chk(self.lib.vvb_dist_batch(self.h, _p(cands), len(cands), _p(out)))
+        return out
+
+    def dist_block(self, dfunc, org, org_stride, cur, cur_stride, w, h, bit_depth=10, sub_shift=0):
+        err = ctypes.c_int(0)
+        v = self.lib.vvb_dist_block(self.h, dfunc, _p(org), org_stride, _p(cur), cur_stride, w, h, bit_depth, sub_shift, ctypes.byref(err))
+        self._chk(err.value)
+        return int(v)
+
+    def sad_mask_block(self, org, org_stride, cur, cur_stride, w, h, mask, mask_off, mask_stride, step_x, mask_stride2, sub_shift=0):
+        err = ctypes.c_int(0)
+        v = self.lib.vvb_sad_mask_block(self.h, _p(org), org_stride, _p(cur), cur_stride, w, h, _po(mask, mask_off), mask_stride, step_x, mask_stride2,
+                                        sub_shift, ctypes.byref(err))
+        self._chk(err.value)
+        return int(v)
+
+    def sad_x5_block(self, org, org_off, org_stride, cur, cur_off, cur_stride, w, h, sub_shift=1, calc_centre=True):
+        out = np.zeros(5, dtype=np.uint64)
+        self._chk(self.lib.vvb_sad_x5_block(self.h, _po(org, org_off), org_stride, _po(cur, cur_off), cur_stride, w, h, sub_shift, int(calc_centre), _p(out)))
+        return out
+
+    def fix_wsse_block(self, org, org_stride, cur, cur_stride, w, h, weight):
+        err = ctypes.c_int(0)
+        v = self.lib.vvb_fix_wsse_block(self.h, _p(org), org_stride, _p(cur), cur_stride, w, h, weight, ctypes.byref(err))
+        self._chk(err.value)
+        return int(v)
+
+    def dist_pool(self, dfunc, org_plane, blocks, w, h, K, pool, sub_shift=0):
+        blocks = np.ascontiguousarray(blocks, dtype=L.POS_DT)
+        pool = np.ascontiguousarray(pool, dtype=np.int16)
+        assert pool.size == len(blocks) * K * w * h
+        out = np.zeros(len(blocks) * K, dtype=np.uint32)
+        self._chk(self.lib.vvb_dist_pool(self.h, dfunc, org_plane, _p(blocks), len(blocks), w, h, K, _p(pool), sub_shift, _p(out)))
+        return out.reshape(len(blocks), K)
+
+    # ---- motion search
+    @staticmethod
+    def me_par(lam, cost_scale=2, imv_shift=0, sub_shift=0):
+        return L.vvb_me_par(float(lam), cost_scale, imv_shift, sub_shift)
+
+    def sad_search(self, org_plane, ref_plane, blocks, w, h, par, want_tables=False):
+        blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
+        n = len(blocks)
+        best = np.zeros(n, dtype=L.BEST_DT)
+        ts = 0; tab = None
+        if want_tables and n:
+            ts = int(((blocks['right'].astype(np.int64) - blocks['left'] + 1) * (blocks['bottom'].astype(np.int64) - blocks['top'] + 1)).max())
+            tab = np.zeros((n, ts), dtype=np.uint32)
+        self._chk(self.lib.vvb_sad_search(self.h, org_plane, ref_plane, _p(blocks), n, w, h, ctypes.byref(par), _p(tab), ts, _p(best)))
+        return (best, tab) if want_tables else best
+
+    def sad_pattern(self, org_plane, ref_plane, blocks, w, h, pattern, par, want_sad=True, want_best=True):
+        blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
+        pattern = np.ascontiguousarray(pattern, dtype=L.MV_DT)
+        n, K = len(blocks), len(pattern)
+        sad = np.zeros((n, K), dtype=np.uint32) if want_sad else None
+        best = np.zeros(n, dtype=L.BEST_DT) if want_best else None
+        self._chk(self.lib.vvb_sad_pattern(self.h, org_plane, ref_plane, _p(blocks), n, w, h, _p(pattern), K, ctypes.byref(par), _p(sad), _p(best)))
+        return sad, best
+
+    # ---- transform + quantise
+    @staticmethod
+    def tu_par(w, h, tr_hor=DCT2, tr_ver=DCT2, bit_depth=10, qp=32, is_irap=False, dep_quant=False):
+        return L.vvb_tu_par(w, h, tr_hor, tr_ver, bit_depth, qp, int(is_irap), int(dep_quant))
+
+    def fwd_trquant(self, par, resi, want_coef=True):
+        """resi: int16 [n][h][w] compact.  Returns dict(coef, q, abs_sum, last_pos, need_rdoq)."""
+        resi = np.ascontiguousarray(resi, dtype=np.int16)
+        n = resi.shape[0]
+        coef = np.zeros((n, par.h, par.w), dtype=np.int32) if want_coef else None
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        s = np.zeros(n, dtype=np.int32); lp = np.zeros(n, dtype=np.int32); nr = np.zeros(n, dtype=np.uint8)
+        self._chk(self.lib.vvb_fwd_trquant(self.h, ctypes.byref(par), _p(resi), n, _p(coef), _p(q), _p(s), _p(lp), _p(nr)))
+        return dict(coef=coef, q=q, abs_sum=s, last_pos=lp, need_rdoq=nr)
+
+    # ---- MCTF
+    def mctf_error_batch(self, org_plane, ref_plane, cands, low_res_filter=False):
+        cands = np.ascontiguousarray(cands, dtype=L.MCTF_DT)
+        out = np.zeros(len(cands), dtype=np.int32)
+        self._chk(self.lib.vvb_mctf_error_batch(self.h, org_plane, ref_plane, _p(cands), len(cands), int(low_res_filter), _p(out)))
+        return out
+
+    # ---- affine
+    def affine_sobel(self, vertical, pred, pred_stride, deriv_stride, w, h):
+        d = np.zeros((h, deriv_stride), dtype=np.int16)
+        self._chk(self.lib.vvb_affine_sobel(self.h, int(vertical), _p(pred), pred_stride, _p(d), deriv_stride, w, h))
+        return d
+
+    def affine_equal_coeff(self, six_param, resi, resi_stride, gx, gy, deriv_stride, w, h, eq=None):
+        if eq is None:
+            eq = np.zeros(49, dtype=np.int64)
+        self._chk(self.lib.vvb_affine_equal_coeff(self.h, int(six_param), _p(resi), resi_stride, _p(gx), _p(gy), deriv_stride, w, h, _p(eq)))
+        return eq

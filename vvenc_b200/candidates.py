@@ -1,0 +1,55 @@
+"""Host-side candidate enumerators -- the control logic that stays on the CPU.
+
+They restate WHICH integer positions the reference's motion search evaluates, so that a fixed candidate set can be
+sent to the GPU as one batch and the decisions replayed on the host afterwards:
+
+  * full_search_window : InterSearch::xSetSearchRange / xPatternSearch (EncoderLib/InterSearch.cpp:2183-2251)
+  * tz_diamond_pattern : the static point pattern of xTZ8PointDiamondSearch (InterSearch.cpp:557-758) for every
+                         distance 1, 2, 4 ... <= search range, plus the optional raster grid (:2491-2497)
+"""
+import numpy as np
+from ._lib import MV_DT
+
+
+def tz_diamond_points(dist, corners_at_dist1=False):
+    """offsets (dx, dy) relative to the start point, in the evaluation order of xTZ8PointDiamondSearch"""
+    d = dist
+    if d == 1:
+        if corners_at_dist1:       # InterSearch.cpp:576-620
+            return [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]
+        return [(0, -1), (-1, 0), (1, 0), (0, 1)]
+    if d <= 8:                     # :625-643: 4 axis points at d, 4 diagonal points at d/2
+        h = d >> 1
+        return [(0, -d), (-h, -h), (h, -h), (-d, 0), (d, 0), (-h, h), (h, h), (0, d)]
+    pts = [(0, -d), (-d, 0), (d, 0), (0, d)]          # :688-705: 16 points on the diamond
+    q = d >> 2
+    for i in range(1, 4):
+        pts += [(-q * i, -d + q * i), (q * i, -d + q * i), (-q * i, d - q * i), (q * i, d - q * i)]
+    return pts
+
+
+def tz_diamond_pattern(search_range, raster_step=0, include_centre=True, corners_at_dist1=False):
+    """The fixed TZ candidate set around a start vector: centre, diamonds at d = 1,2,4,.. <= search_range and (optionally) the
+    raster grid with the given step inside +-search_range (InterSearch.cpp:2491-2497).  Returns a MV_DT array."""
+    pts = [(0, 0)] if include_centre else []
+    d = 1
+    while d <= search_range:
+        pts += tz_diamond_points(d, corners_at_dist1)
+        d <<= 1
+    if raster_step:
+        for y in range(-search_range, search_range + 1, raster_step):
+            for x in range(-search_range, search_range + 1, raster_step):
+                pts.append((x, y))
+    out = np.zeros(len(pts), dtype=MV_DT)
+    out['dx'] = [p[0] for p in pts]; out['dy'] = [p[1] for p in pts]
+    return out
+
+
+def full_search_window(pred_x, pred_y, search_range, pic_w, pic_h, x, y, w, h, margin):
+    """SearchRange (left, right, top, bottom) in integer pels around an integer predictor, clipped so that every candidate
+    block stays inside the padded picture (xClipMvSearch / xSetSearchRange, InterSearch.cpp:2134-2207)."""
+    left = max(pred_x - search_range, -margin - x)
+    right = min(pred_x + search_range, pic_w + margin - w - x)
+    top = max(pred_y - search_range, -margin - y)
+    bottom = min(pred_y + search_range, pic_h + margin - h - y)
+    return left, right, top, bottom

@@ -1,0 +1,694 @@
+// capi.cu -- C ABI (include/vvenc_b200.h) of the B200 block-cost path: context, plane residency, launch logic.
+// There is deliberately no CPU fallback anywhere in this file: without a usable CUDA device every entry point fails.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <new>
+#include "common.cuh"
+#include "dist_kernels.cuh"
+#include "search_kernels.cuh"
+#include "trquant_kernels.cuh"
+#include "mctf_affine_kernels.cuh"
+#include "vvc_tables.h"
+
+using namespace vvb;
+
+namespace {
+
+int fail( vvb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess )
+{
+  if( c )
+  {
+    c->err = what;
+    if( e != cudaSuccess ) { c->err += ": "; c->err += cudaGetErrorString( e ); }
+  }
+  return code;
+}
+
+#define CU( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) return fail( ctx, VVB_ERR_CUDA, #call, e_ ); } while( 0 )
+#define CHECK_LAUNCH( name ) do { cudaError_t e_ = cudaGetLastError(); if( e_ != cudaSuccess ) return fail( ctx, VVB_ERR_CUDA, name, e_ ); ctx->launches++; } while( 0 )
+
+bool isPow2( int v ) { return v > 0 && ( v & ( v - 1 ) ) == 0; }
+int  ilog2h( int v ) { int r = 0; while( v > 1 ) { v >>= 1; r++; } return r; }
+
+int scratch( vvb_ctx* ctx, int slot, size_t bytes, void** out )
+{
+  if( bytes == 0 ) bytes = 16;
+  if( ctx->d_scratchSize[slot] < bytes )
+  {
+    if( ctx->d_scratch[slot] ) { cudaStreamSynchronize( ctx->stream ); cudaFree( ctx->d_scratch[slot] ); ctx->d_scratch[slot] = nullptr; ctx->d_scratchSize[slot] = 0; }
+    const size_t cap = bytes + bytes / 4 + 4096;
+    CU( cudaMalloc( &ctx->d_scratch[slot], cap ) );
+    ctx->d_scratchSize[slot] = cap;
+  }
+  *out = ctx->d_scratch[slot];
+  return VVB_OK;
+}
+
+bool validPlane( const vvb_ctx* ctx, int id ) { return id >= 0 && id < VVB_MAX_PLANES - 2 && ctx->planes.p[id].origin != nullptr; }
+
+// shape domain of the reference's distortion table: width a power of two (index = base + log2 w, RdCost.cpp:176-184)
+int checkDistShape( vvb_ctx* ctx, int fam, int w, int h, int subShift )
+{
+  if( fam < 0 || fam > 4 ) return fail( ctx, VVB_ERR_ARG, "unknown dfunc" );
+  if( !isPow2( w ) || w > 128 || h < 1 || h > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "block shape outside the reference's DFunc domain (w power of two <= 128, h <= 128)" );
+  if( fam == FAM_SAD && subShift && ( h & ( ( 1 << subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
+  if( fam >= FAM_HAD && ( w < 2 || ( h & 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "Hadamard needs even dimensions (RdCost.cpp:1933 THROW)" );
+  if( fam == FAM_HAD_2SAD && ( w < 4 || ( h & 3 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "HAD_2SAD needs w >= 4 and h % 4 == 0 (RdCost.cpp:1783-1784)" );
+  if( fam == FAM_SSE && w < 2 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "SSE of width 1 is routed to the scalar xGetSSE by the reference (RdCost.cpp:275)" );
+  return VVB_OK;
+}
+
+int makeMePar( vvb_ctx* ctx, const vvb_me_par* in, MePar& out )
+{
+  if( !in ) return fail( ctx, VVB_ERR_ARG, "null me_par" );
+  out.costScale = in->cost_scale; out.imvShift = in->imv_shift; out.subShift = in->sub_shift;
+  const double motionLambda = std::sqrt( in->lambda );                 // RdCost.cpp:77
+  for( int b = 0; b < VVB_MVCOST_ENTRIES; b++ )
+  {
+    const uint64_t c = (uint64_t)( motionLambda * (uint32_t) b );       // RdCost.h:181 Distortion( m_motionLambda * b )
+    if( c > 0xffffffffull ) return fail( ctx, VVB_ERR_UNSUPPORTED, "lambda too large for the 32-bit MV cost table" );
+    out.tab.cost[b] = (uint32_t) c;
+  }
+  return VVB_OK;
+}
+
+void buildScanTables( std::vector<int32_t>& inv )
+{
+  // grouped 4x4 up-right diagonal scan (Rom.cpp:1098-1136, 1236-1284); inv[shape][y*regionW + x] = scan position
+  inv.assign( 25 * 1024, 0 );
+  auto diag = []( int bw, int bh, std::vector<int>& xs, std::vector<int>& ys )
+  {
+    xs.resize( bw * bh ); ys.resize( bw * bh );
+    int line = 0, col = 0;
+    for( int i = 0; i < bw * bh; i++ )
+    {
+      xs[i] = col; ys[i] = line;
+      if( col == bw - 1 || line == 0 ) { line += col + 1; col = 0; if( line >= bh ) { col += line - ( bh - 1 ); line = bh - 1; } }
+      else { col++; line--; }
+    }
+  };
+  std::vector<int> cx, cy, gx, gy;
+  diag( 4, 4, cx, cy );
+  for( int lw = 2; lw <= 6; lw++ )
+    for( int lh = 2; lh <= 6; lh++ )
+    {
+      const int rw = std::min( 32, 1 << lw ), rh = std::min( 32, 1 << lh );
+      diag( rw >> 2, rh >> 2, gx, gy );
+      int32_t* t = inv.data() + ( ( lw - 2 ) * 5 + ( lh - 2 ) ) * 1024;
+      for( int g = 0; g < ( rw >> 2 ) * ( rh >> 2 ); g++ )
+        for( int c = 0; c < 16; c++ )
+          t[( gy[g] * 4 + cy[c] ) * rw + gx[g] * 4 + cx[c]] = g * 16 + c;
+    }
+}
+
+// single-block helper kernels (FpDistFunc-shaped calls)
+__global__ void sad_mask_kernel( const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, const int16_t* mask, int maskStride, int stepX, int maskStride2,
+                                 int subShift, unsigned long long* out )
+{
+  // RdCost.cpp:2062-2093: mask pointer walks stepX per sample, then maskStride*step + maskStride2 per visited row
+  const int step = 1 << subShift;
+  unsigned long long acc = 0;
+  const int rows = h >> subShift;
+  for( int i = threadIdx.x; i < rows * w; i += blockDim.x )
+  {
+    const int r = i / w, x = i - r * w, y = r * step;
+    const long long mpos = (long long) r * ( (long long) w * stepX + (long long) maskStride * step + maskStride2 ) + (long long) x * stepX;
+    acc += (unsigned long long)( abs( (int) org[y * so + x] - (int) cur[y * sc + x] ) * (int) mask[mpos] );
+  }
+  for( int m = 16; m > 0; m >>= 1 ) acc += __shfl_xor_sync( 0xffffffffu, acc, m );
+  if( threadIdx.x == 0 ) *out = acc << subShift;
+}
+
+__global__ void sad_x5_kernel( const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int subShift, unsigned long long* out5 )
+{
+  // RdCost.cpp:1984-2034: position i compares org+i with cur-i, each SAD >> 1
+  const int i5 = blockIdx.x;
+  const uint32_t s = group_sad<32>( org + i5, so, cur - i5, sc, w, h, subShift, threadIdx.x );
+  if( threadIdx.x == 0 ) out5[i5] = s >> 1;
+}
+
+__global__ void fix_wsse_kernel( const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, uint32_t weight, unsigned long long* out )
+{
+  unsigned long long acc = 0;
+  for( int i = threadIdx.x; i < w * h; i += blockDim.x )
+  {
+    const int y = i / w, x = i - y * w;
+    const int d = (int) org[y * so + x] - (int) cur[y * sc + x];
+    acc += (unsigned long long)(int)( ( (long long) weight * ( d * d ) + ( 1 << 15 ) ) >> 16 );     // RdCost.cpp:1942-1946
+  }
+  for( int m = 16; m > 0; m >>= 1 ) acc += __shfl_xor_sync( 0xffffffffu, acc, m );
+  if( threadIdx.x == 0 ) *out = acc;
+}
+
+// copy a strided host block into a compact device buffer (via pinned-less synchronous 2-D copy)
+int uploadBlock( vvb_ctx* ctx, int slot, const int16_t* host, int stride, int w, int h, int16_t** dev, int padBefore = 0, int padAfter = 0 )
+{
+  void* d = nullptr;
+  const int rowPels = w + padBefore + padAfter;
+  int rc = scratch( ctx, slot, (size_t) rowPels * h * sizeof( int16_t ) + 64, &d );
+  if( rc ) return rc;
+  CU( cudaMemcpy2DAsync( d, (size_t) rowPels * 2, host - padBefore, (size_t) stride * 2, (size_t) rowPels * 2, h, cudaMemcpyHostToDevice, ctx->stream ) );
+  *dev = reinterpret_cast<int16_t*>( d ) + padBefore;
+  return VVB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int vvb_create( vvb_ctx** out, int device )
+{
+  if( !out ) return VVB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount( &count );
+  if( e != cudaSuccess || count <= 0 || device < 0 || device >= count ) return VVB_ERR_CUDA;
+  vvb_ctx* ctx = new( std::nothrow ) vvb_ctx;
+  if( !ctx ) return VVB_ERR_NOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if( cudaSetDevice( device ) != cudaSuccess || cudaGetDeviceProperties( &prop, device ) != cudaSuccess ) { delete ctx; return VVB_ERR_CUDA; }
+  ctx->numSMs = prop.multiProcessorCount;
+  if( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) != cudaSuccess ) { delete ctx; return VVB_ERR_CUDA; }
+  std::vector<int32_t> inv;
+  buildScanTables( inv );
+  if( cudaMalloc( &ctx->d_trTable, VVC_TR_TABLE_SIZE ) != cudaSuccess || cudaMalloc( &ctx->d_scan, inv.size() * sizeof( int32_t ) ) != cudaSuccess ||
+      cudaMemcpy( ctx->d_trTable, vvc_tr_table_host, VVC_TR_TABLE_SIZE, cudaMemcpyHostToDevice ) != cudaSuccess ||
+      cudaMemcpy( ctx->d_scan, inv.data(), inv.size() * sizeof( int32_t ), cudaMemcpyHostToDevice ) != cudaSuccess )
+  {
+    vvb_destroy( ctx );
+    return VVB_ERR_CUDA;
+  }
+  cudaFuncSetAttribute( sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( fwd_trquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+  *out = ctx;
+  return VVB_OK;
+}
+
+void vvb_destroy( vvb_ctx* ctx )
+{
+  if( !ctx ) return;
+  cudaSetDevice( ctx->device );
+  if( ctx->stream ) cudaStreamSynchronize( ctx->stream );
+  for( int i = 0; i < VVB_MAX_PLANES; i++ ) if( ctx->owned[i] ) cudaFree( ctx->owned[i] );
+  for( int i = 0; i < 6; i++ ) if( ctx->d_scratch[i] ) cudaFree( ctx->d_scratch[i] );
+  if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
+  if( ctx->d_scan ) cudaFree( ctx->d_scan );
+  if( ctx->h_pinned ) cudaFreeHost( ctx->h_pinned );
+  if( ctx->stream ) cudaStreamDestroy( ctx->stream );
+  delete ctx;
+}
+
+const char* vvb_last_error( const vvb_ctx* ctx ) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vvb_synchronize( vvb_ctx* ctx )
+{
+  if( !ctx ) return VVB_ERR_ARG;
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+void* vvb_stream( vvb_ctx* ctx ) { return ctx ? (void*) ctx->stream : nullptr; }
+
+int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) return VVB_ERR_ARG; *k = ctx->launches; return VVB_OK; }
+
+// ---- planes --------------------------------------------------------------------------------------------------
+int vvb_plane_free( vvb_ctx* ctx, int id )
+{
+  if( !ctx || id < 0 || id >= VVB_MAX_PLANES - 2 ) return fail( ctx, VVB_ERR_ARG, "plane id out of range" );
+  if( ctx->owned[id] ) { cudaStreamSynchronize( ctx->stream ); cudaFree( ctx->owned[id] ); ctx->owned[id] = nullptr; }
+  ctx->planes.p[id] = Plane{};
+  return VVB_OK;
+}
+
+int vvb_plane_upload( vvb_ctx* ctx, int id, const int16_t* origin, int stride, int width, int height, int margin, int bitDepth )
+{
+  if( !ctx || !origin || id < 0 || id >= VVB_MAX_PLANES - 2 || width <= 0 || height <= 0 || margin < 0 || stride < width + 2 * margin )
+    return fail( ctx, VVB_ERR_ARG, "bad plane arguments" );
+  CU( cudaSetDevice( ctx->device ) );
+  vvb_plane_free( ctx, id );
+  const int dw = width + 2 * margin, dh = height + 2 * margin;
+  const int dstride = ( dw + 7 ) & ~7;                                 // rows 16-byte aligned
+  void* d = nullptr;
+  CU( cudaMalloc( &d, (size_t) dstride * dh * sizeof( int16_t ) + 256 ) );
+  const int16_t* src = origin - (ptrdiff_t) margin * stride - margin;
+  // margin rounded so that sample (0,0) keeps 16-byte alignment when margin % 8 == 0
+  CU( cudaMemcpy2DAsync( d, (size_t) dstride * 2, src, (size_t) stride * 2, (size_t) dw * 2, dh, cudaMemcpyHostToDevice, ctx->stream ) );
+  ctx->owned[id] = d;
+  Plane p; p.origin = reinterpret_cast<int16_t*>( d ) + (size_t) margin * dstride + margin; p.stride = dstride; p.width = width; p.height = height; p.margin = margin; p.bitDepth = bitDepth;
+  ctx->planes.p[id] = p;
+  CU( cudaStreamSynchronize( ctx->stream ) );                          // the host buffer is only borrowed for the call
+  return VVB_OK;
+}
+
+int vvb_plane_bind_dev( vvb_ctx* ctx, int id, const int16_t* devOrigin, int stride, int width, int height, int margin, int bitDepth )
+{
+  if( !ctx || !devOrigin || id < 0 || id >= VVB_MAX_PLANES - 2 ) return fail( ctx, VVB_ERR_ARG, "bad plane arguments" );
+  vvb_plane_free( ctx, id );
+  Plane p; p.origin = devOrigin; p.stride = stride; p.width = width; p.height = height; p.margin = margin; p.bitDepth = bitDepth;
+  ctx->planes.p[id] = p;
+  return VVB_OK;
+}
+
+// ---- pair list -------------------------------------------------------------------------------------------------
+int vvb_dist_batch_dev( vvb_ctx* ctx, const vvb_cand* dCands, int n, uint64_t* dOut )
+{
+  if( !ctx || !dCands || !dOut || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int warpsPerCta = 8;
+  const int grid = std::min( ( n + warpsPerCta - 1 ) / warpsPerCta, ctx->numSMs * 16 );
+  dist_list_kernel<<<grid, warpsPerCta * 32, 0, ctx->stream>>>( ctx->planes, dCands, n, reinterpret_cast<unsigned long long*>( dOut ) );
+  CHECK_LAUNCH( "dist_list_kernel" );
+  return VVB_OK;
+}
+
+int vvb_dist_batch( vvb_ctx* ctx, const vvb_cand* cands, int n, uint64_t* out )
+{
+  if( !ctx || !cands || !out || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  for( int i = 0; i < n; i++ )
+  {
+    const vvb_cand& c = cands[i];
+    if( !validPlane( ctx, c.org_plane ) || !validPlane( ctx, c.cur_plane ) ) return fail( ctx, VVB_ERR_ARG, "candidate refers to an unknown plane" );
+    int rc = checkDistShape( ctx, c.dfunc, c.w, c.h, c.sub_shift );
+    if( rc ) return rc;
+  }
+  if( n == 0 ) return VVB_OK;
+  void *dC, *dO;
+  int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_cand ), &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * 8, &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_dist_batch_dev( ctx, (const vvb_cand*) dC, n, (uint64_t*) dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( out, dO, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+uint64_t vvb_dist_block( vvb_ctx* ctx, int dfunc, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int bitDepth, int subShift, int* err )
+{
+  int rc = VVB_OK;
+  uint64_t result = 0;
+  do
+  {
+    if( !ctx || !org || !cur ) { rc = fail( ctx, VVB_ERR_ARG, "null pointer" ); break; }
+    if( ( rc = checkDistShape( ctx, dfunc, w, h, subShift ) ) ) break;
+    if( cudaSetDevice( ctx->device ) != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "cudaSetDevice" ); break; }
+    int16_t *dO, *dC; void *dCand, *dOut;
+    if( ( rc = uploadBlock( ctx, 2, org, orgStride, w, h, &dO ) ) || ( rc = uploadBlock( ctx, 3, cur, curStride, w, h, &dC ) ) ) break;
+    if( ( rc = scratch( ctx, 0, sizeof( vvb_cand ), &dCand ) ) || ( rc = scratch( ctx, 1, 8, &dOut ) ) ) break;
+    PlaneTable pt = ctx->planes;
+    pt.p[VVB_MAX_PLANES - 2] = Plane{ dO, w, w, h, 0, bitDepth };
+    pt.p[VVB_MAX_PLANES - 1] = Plane{ dC, w, w, h, 0, bitDepth };
+    vvb_cand c{}; c.org_plane = VVB_MAX_PLANES - 2; c.cur_plane = VVB_MAX_PLANES - 1; c.w = (uint16_t) w; c.h = (uint16_t) h; c.dfunc = (uint8_t) dfunc; c.sub_shift = (uint8_t) subShift;
+    if( cudaMemcpyAsync( dCand, &c, sizeof( c ), cudaMemcpyHostToDevice, ctx->stream ) != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "memcpy cand" ); break; }
+    dist_list_kernel<<<1, 32, 0, ctx->stream>>>( pt, (const vvb_cand*) dCand, 1, (unsigned long long*) dOut );
+    cudaError_t e = cudaGetLastError();
+    if( e != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "dist_list_kernel", e ); break; }
+    ctx->launches++;
+    e = cudaMemcpyAsync( &result, dOut, 8, cudaMemcpyDeviceToHost, ctx->stream );
+    if( e == cudaSuccess ) e = cudaStreamSynchronize( ctx->stream );
+    if( e != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "dist_block readback", e ); break; }
+  } while( 0 );
+  if( err ) *err = rc;
+  return result;
+}
+
+uint64_t vvb_sad_mask_block( vvb_ctx* ctx, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h,
+                             const int16_t* mask, int maskStride, int stepX, int maskStride2, int subShift, int* err )
+{
+  int rc = VVB_OK; uint64_t result = 0;
+  do
+  {
+    if( !ctx || !org || !cur || !mask || ( stepX != 1 && stepX != -1 ) ) { rc = fail( ctx, VVB_ERR_ARG, "bad arguments" ); break; }
+    if( w < 1 || h < 1 || w > 128 || h > 128 || ( h & ( ( 1 << subShift ) - 1 ) ) ) { rc = fail( ctx, VVB_ERR_UNSUPPORTED, "bad mask-SAD shape" ); break; }
+    cudaSetDevice( ctx->device );
+    int16_t *dO, *dC; void *dM, *dOut;
+    if( ( rc = uploadBlock( ctx, 2, org, orgStride, w, h, &dO ) ) || ( rc = uploadBlock( ctx, 3, cur, curStride, w, h, &dC ) ) ) break;
+    // the mask walk covers, per visited row r: start + r*rowAdv + x*stepX ; gather exactly those samples into a compact [rows][w] mask
+    const int step = 1 << subShift, rows = h >> subShift;
+    std::vector<int16_t> m( (size_t) rows * w );
+    for( int r = 0; r < rows; r++ )
+      for( int x = 0; x < w; x++ )
+        m[(size_t) r * w + x] = mask[(ptrdiff_t) r * ( (ptrdiff_t) w * stepX + (ptrdiff_t) maskStride * step + maskStride2 ) + (ptrdiff_t) x * stepX];
+    if( ( rc = scratch( ctx, 4, m.size() * 2, &dM ) ) || ( rc = scratch( ctx, 1, 8, &dOut ) ) ) break;
+    if( cudaMemcpyAsync( dM, m.data(), m.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "mask upload" ); break; }
+    // compact mask: stepX = +1, row advance = w  -> maskStride*step + maskStride2 = 0
+    sad_mask_kernel<<<1, 32, 0, ctx->stream>>>( dO, w, dC, w, w, h, (const int16_t*) dM, 0, 1, 0, subShift, (unsigned long long*) dOut );
+    cudaError_t e = cudaGetLastError();
+    if( e != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "sad_mask_kernel", e ); break; }
+    ctx->launches++;
+    e = cudaMemcpyAsync( &result, dOut, 8, cudaMemcpyDeviceToHost, ctx->stream );
+    if( e == cudaSuccess ) e = cudaStreamSynchronize( ctx->stream );
+    if( e != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "sad_mask readback", e ); break; }
+  } while( 0 );
+  if( err ) *err = rc;
+  return result;
+}
+
+int vvb_sad_x5_block( vvb_ctx* ctx, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int subShift, int calcCentre, uint64_t cost5[5] )
+{
+  if( !ctx || !org || !cur || !cost5 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( ( w != 8 && w != 16 ) || h < 1 || h > 128 || ( h & ( ( 1 << subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "SADX5 is defined for widths 8 and 16 (RdCost.cpp:131-132)" );
+  CU( cudaSetDevice( ctx->device ) );
+  int16_t *dO, *dC; void* dOut; int rc;
+  if( ( rc = uploadBlock( ctx, 2, org, orgStride, w, h, &dO, 0, 4 ) ) || ( rc = uploadBlock( ctx, 3, cur, curStride, w, h, &dC, 4, 0 ) ) ) return rc;
+  if( ( rc = scratch( ctx, 1, 40, &dOut ) ) ) return rc;
+  sad_x5_kernel<<<5, 32, 0, ctx->stream>>>( dO, w + 4, dC, w + 4, w, h, subShift, (unsigned long long*) dOut );
+  CHECK_LAUNCH( "sad_x5_kernel" );
+  uint64_t tmp[5];
+  CU( cudaMemcpyAsync( tmp, dOut, 40, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  for( int i = 0; i < 5; i++ ) if( i != 2 || calcCentre ) cost5[i] = tmp[i];
+  return VVB_OK;
+}
+
+uint64_t vvb_fix_wsse_block( vvb_ctx* ctx, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, uint32_t weight, int* err )
+{
+  int rc = VVB_OK; uint64_t result = 0;
+  do
+  {
+    if( !ctx || !org || !cur ) { rc = fail( ctx, VVB_ERR_ARG, "null pointer" ); break; }
+    if( w < 1 || h < 1 || w > 128 || h > 128 || ( ( w & 1 ) && w != 1 ) ) { rc = fail( ctx, VVB_ERR_UNSUPPORTED, "width must be even or 1 (RdCost.cpp:1966)" ); break; }
+    cudaSetDevice( ctx->device );
+    int16_t *dO, *dC; void* dOut;
+    if( ( rc = uploadBlock( ctx, 2, org, orgStride, w, h, &dO ) ) || ( rc = uploadBlock( ctx, 3, cur, curStride, w, h, &dC ) ) || ( rc = scratch( ctx, 1, 8, &dOut ) ) ) break;
+    fix_wsse_kernel<<<1, 32, 0, ctx->stream>>>( dO, w, dC, w, w, h, weight, (unsigned long long*) dOut );
+    cudaError_t e = cudaGetLastError();
+    if( e != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "fix_wsse_kernel", e ); break; }
+    ctx->launches++;
+    e = cudaMemcpyAsync( &result, dOut, 8, cudaMemcpyDeviceToHost, ctx->stream );
+    if( e == cudaSuccess ) e = cudaStreamSynchronize( ctx->stream );
+    if( e != cudaSuccess ) { rc = fail( ctx, VVB_ERR_CUDA, "fix_wsse readback", e ); break; }
+  } while( 0 );
+  if( err ) *err = rc;
+  return result;
+}
+
+// ---- candidate pool ----------------------------------------------------------------------------------------------
+int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* dBlocks, int nBlocks, int w, int h, int K, const int16_t* dPool, int subShift, uint32_t* dOut )
+{
+  if( !ctx || !dBlocks || !dPool || !dOut || nBlocks < 0 || K < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  int rc = checkDistShape( ctx, dfunc, w, h, subShift );
+  if( rc ) return rc;
+  if( nBlocks == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int G = pick_group( dfunc, w, h );
+  const long long total = (long long) nBlocks * K;
+  const long long threads = total * G;
+  const int block = 256;
+  const int grid = (int) std::min<long long>( ( threads + block - 1 ) / block, (long long) ctx->numSMs * 32 );
+  const Plane& op = ctx->planes.p[orgPlane];
+#define LAUNCH_POOL( GG ) dist_pool_kernel<GG><<<grid, block, 0, ctx->stream>>>( op, dBlocks, nBlocks, w, h, K, dfunc, subShift, dPool, dOut )
+  switch( G ) { case 4: LAUNCH_POOL( 4 ); break; case 8: LAUNCH_POOL( 8 ); break; case 16: LAUNCH_POOL( 16 ); break; default: LAUNCH_POOL( 32 ); break; }
+#undef LAUNCH_POOL
+  CHECK_LAUNCH( "dist_pool_kernel" );
+  return VVB_OK;
+}
+
+int vvb_dist_pool( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* blocks, int nBlocks, int w, int h, int K, const int16_t* pool, int subShift, uint32_t* out )
+{
+  if( !ctx || !blocks || !pool || !out || nBlocks < 0 || K < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( nBlocks == 0 ) return VVB_OK;
+  void *dB, *dP, *dO; int rc;
+  const size_t total = (size_t) nBlocks * K;
+  if( ( rc = scratch( ctx, 0, (size_t) nBlocks * sizeof( vvb_pos ), &dB ) ) || ( rc = scratch( ctx, 2, total * w * h * 2, &dP ) ) || ( rc = scratch( ctx, 1, total * 4, &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) nBlocks * sizeof( vvb_pos ), cudaMemcpyHostToDevice, ctx->stream ) );
+  CU( cudaMemcpyAsync( dP, pool, total * w * h * 2, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_dist_pool_dev( ctx, dfunc, orgPlane, (const vvb_pos*) dB, nBlocks, w, h, K, (const int16_t*) dP, subShift, (uint32_t*) dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( out, dO, total * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+// ---- motion search -----------------------------------------------------------------------------------------------
+static int checkSearchShape( vvb_ctx* ctx, int orgPlane, int refPlane, int w, int h )
+{
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( !isPow2( w ) || !isPow2( h ) || w < 4 || h < 4 || w > 128 || h > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search blocks are 4..128 powers of two" );
+  return VVB_OK;
+}
+
+} // extern "C"
+
+// host-known maximum window (nx, ny) variant used by both public entry points
+static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_me_par* par,
+                            int maxNx, int maxNy, uint32_t* dTables, int tableStride, vvb_best* dBest )
+{
+  int rc = checkSearchShape( ctx, orgPlane, refPlane, w, h );
+  if( rc ) return rc;
+  MePar mp;
+  if( ( rc = makeMePar( ctx, par, mp ) ) ) return rc;
+  if( mp.subShift && ( h & ( ( 1 << mp.subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int nStrips = ( maxNx + SS_STRIP - 1 ) / SS_STRIP;
+  const int ws = w + nStrips * SS_STRIP + 8, winH = h + maxNy - 1;
+  const size_t smem = ( (size_t) winH * ws + (size_t) w * h ) * sizeof( int16_t ) + 16;
+  if( smem > 220 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search window does not fit shared memory (reduce the range)" );
+  // block size: enough threads for the (ny x strips) items, rounded to warps, capped at 256
+  const int items = maxNy * nStrips;
+  int bd = 256;
+  if( items < 256 ) bd = std::max( 32, ( items + 31 ) & ~31 );
+  sad_search_kernel<<<n, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, w, h, mp, dTables, tableStride, dBest );
+  CHECK_LAUNCH( "sad_search_kernel" );
+  return VVB_OK;
+}
+
+extern "C" {
+
+// device-resident variant: the host states the largest window (max_nx x max_ny positions) in the batch, it sizes shared memory
+int vvb_sad_search_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_me_par* par,
+                        int maxNx, int maxNy, uint32_t* dTables, int tableStride, vvb_best* dBest )
+{
+  if( !ctx || !dBlocks || !dBest || n < 0 || maxNx < 1 || maxNy < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  return sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks, n, w, h, par, maxNx, maxNy, dTables, tableStride, dBest );
+}
+
+int vvb_sad_search( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_me_par* par,
+                    uint32_t* tables, int tableStride, vvb_best* best )
+{
+  if( !ctx || !blocks || !best || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  int maxNx = 1, maxNy = 1;
+  for( int i = 0; i < n; i++ )
+  {
+    const int nx = blocks[i].right - blocks[i].left + 1, ny = blocks[i].bottom - blocks[i].top + 1;
+    if( nx < 1 || ny < 1 ) return fail( ctx, VVB_ERR_ARG, "empty search range" );
+    if( tables && nx * ny > tableStride ) return fail( ctx, VVB_ERR_ARG, "table_stride smaller than the window" );
+    maxNx = std::max( maxNx, nx ); maxNy = std::max( maxNy, ny );
+  }
+  void *dB, *dT = nullptr, *dO; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * sizeof( vvb_best ), &dO ) ) ) return rc;
+  if( tables && ( rc = scratch( ctx, 2, (size_t) n * tableStride * 4, &dT ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, par, maxNx, maxNy, (uint32_t*) dT, tableStride, (vvb_best*) dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( tables ) CU( cudaMemcpyAsync( tables, dT, (size_t) n * tableStride * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+int vvb_sad_pattern_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_mv* dPattern, int K,
+                         const vvb_me_par* par, uint32_t* dSad, vvb_best* dBest )
+{
+  if( !ctx || !dBlocks || !dPattern || n < 0 || K < 1 || ( !dSad && !dBest ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  int rc = checkSearchShape( ctx, orgPlane, refPlane, w, h );
+  if( rc ) return rc;
+  MePar mp;
+  if( ( rc = makeMePar( ctx, par, mp ) ) ) return rc;
+  if( mp.subShift && ( h & ( ( 1 << mp.subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int G = pick_group( FAM_SAD, w, h >> mp.subShift );
+  const Plane &op = ctx->planes.p[orgPlane], &rp = ctx->planes.p[refPlane];
+#define LAUNCH_PAT( GG ) sad_pattern_kernel<GG><<<n, 128, 0, ctx->stream>>>( op, rp, dBlocks, w, h, dPattern, K, mp, dSad, dBest )
+  switch( G ) { case 4: LAUNCH_PAT( 4 ); break; case 8: LAUNCH_PAT( 8 ); break; case 16: LAUNCH_PAT( 16 ); break; default: LAUNCH_PAT( 32 ); break; }
+#undef LAUNCH_PAT
+  CHECK_LAUNCH( "sad_pattern_kernel" );
+  return VVB_OK;
+}
+
+int vvb_sad_pattern( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_mv* pattern, int K,
+                     const vvb_me_par* par, uint32_t* sadOut, vvb_best* best )
+{
+  if( !ctx || !blocks || !pattern || n < 0 || K < 1 || ( !sadOut && !best ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  void *dB, *dP, *dS = nullptr, *dO = nullptr; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 3, (size_t) K * sizeof( vvb_mv ), &dP ) ) ) return rc;
+  if( sadOut && ( rc = scratch( ctx, 2, (size_t) n * K * 4, &dS ) ) ) return rc;
+  if( best && ( rc = scratch( ctx, 1, (size_t) n * sizeof( vvb_best ), &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+  CU( cudaMemcpyAsync( dP, pattern, (size_t) K * sizeof( vvb_mv ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_sad_pattern_dev( ctx, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (const vvb_mv*) dP, K, par, (uint32_t*) dS, (vvb_best*) dO ) ) ) return rc;
+  if( sadOut ) CU( cudaMemcpyAsync( sadOut, dS, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( best ) CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+// ---- transform + quantise ----------------------------------------------------------------------------------------
+static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
+{
+  if( !in ) return fail( ctx, VVB_ERR_ARG, "null tu_par" );
+  const int w = in->w, h = in->h;
+  if( !isPow2( w ) || !isPow2( h ) || w < 4 || h < 4 || w > 64 || h > 64 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "TU sizes are 4..64" );
+  if( in->tr_hor < 0 || in->tr_hor > 2 || in->tr_ver < 0 || in->tr_ver > 2 ) return fail( ctx, VVB_ERR_ARG, "unknown transform type" );
+  if( ( in->tr_hor && w > 32 ) || ( in->tr_ver && h > 32 ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "DST-VII/DCT-VIII exist for 4..32 only (TrQuant.cpp:76-81)" );
+  if( in->bit_depth < 8 || in->bit_depth > 12 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth 8..12" );
+  p.w = w; p.h = h; p.lw = ilog2h( w ); p.lh = ilog2h( h );
+  p.trHor = in->tr_hor; p.trVer = in->tr_ver;
+  const int skipW = ( p.trHor != 0 && w == 32 ) ? 16 : ( w > 32 ? w - 32 : 0 );        // TrQuant.cpp:496
+  const int skipH = ( p.trVer != 0 && h == 32 ) ? 16 : ( h > 32 ? h - 32 : 0 );        // TrQuant.cpp:497
+  p.keepW = w - skipW; p.keepH = h - skipH;
+  p.s1 = p.lw + in->bit_depth + 6 - 15;                                                 // TrQuant.cpp:544
+  p.s2 = p.lh + 6;                                                                       // TrQuant.cpp:545
+  if( p.s1 < 0 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "negative first-stage shift (TrQuant.cpp:546 CHECK)" );
+  p.offH = vvc_tr_offset_host[p.trHor][p.lw]; p.offV = vvc_tr_offset_host[p.trVer][p.lh];
+  p.regionW = std::min( 32, w ); p.regionH = std::min( 32, h );
+  p.scanOff = ( ( p.lw - 2 ) * 5 + ( p.lh - 2 ) ) * 1024;
+  auto qpar = [&]( int qp, int addNum, int& scale, int& qbits, long long& add )
+  {
+    int baseQp = qp + 6 * ( in->bit_depth - 8 );                                         // Quant.cpp:99
+    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) );         // Quant.cpp:113
+    const int per = baseQp / 6, rem = baseQp % 6;
+    const int sqrt2 = ( p.lw + p.lh ) & 1;                                               // UnitTools.cpp:3616-3621
+    const int trShift = 15 - in->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;           // Quant.h:69-72, Quant.cpp:767
+    scale = vvc_quant_scales_host[sqrt2][rem];
+    qbits = 14 + per + trShift;                                                          // Quant.cpp:769
+    add   = (long long) addNum << ( qbits - 9 );                                         // Quant.cpp:772 / :879
+  };
+  qpar( in->qp, in->is_irap ? 171 : 85, p.scale, p.qbits, p.add );
+  qpar( in->dep_quant ? in->qp + 1 : in->qp, 171, p.scaleRdoq, p.qbitsRdoq, p.addRdoq );   // Quant.cpp:852-855, :879
+  if( p.qbits < 9 || p.qbitsRdoq < 9 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "quantiser shift below 9" );
+  const int thrVal = 8;                                                                  // vvencCfg.cpp:971-973
+  const int32_t thres = (int32_t)( (int64_t) thrVal << ( p.qbits - 1 ) );               // Quant.cpp:175-176 (TCoeff cast)
+  p.useThres = thres / ( p.scale << 2 );                                                 // Quant.cpp:180
+  int t = ( w * h ) / 4;
+  p.team = std::max( 4, std::min( 128, t ) );
+  return VVB_OK;
+}
+
+int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dResi, int n, int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
+{
+  if( !ctx || !dResi || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  TuPar p;
+  int rc = makeTuPar( ctx, par, p );
+  if( rc ) return rc;
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int nTeams = 128 / p.team;
+  const TeamSmem ts = team_smem( p );
+  const size_t smem = ( (size_t)( p.w >> 2 ) * p.keepW + (size_t)( p.h >> 2 ) * p.keepH + (size_t) nTeams * ts.total ) * 4;
+  const int ctasNeeded = ( n + nTeams - 1 ) / nTeams;
+  const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 16, ( 200 * 1024 ) / ( smem + 1024 ) ) );
+  const int grid = std::min( ctasNeeded, ctx->numSMs * perSM );
+  fwd_trquant_kernel<<<grid, 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+  CHECK_LAUNCH( "fwd_trquant_kernel" );
+  return VVB_OK;
+}
+
+int vvb_fwd_trquant( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* resi, int n, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, uint8_t* needRdoq )
+{
+  if( !ctx || !par || !resi || !q || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t area = (size_t) par->w * par->h;
+  void *dR, *dC = nullptr, *dQ, *dM; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * area * 2, &dR ) ) || ( rc = scratch( ctx, 1, (size_t) n * area * 2, &dQ ) ) || ( rc = scratch( ctx, 3, (size_t) n * 12, &dM ) ) ) return rc;
+  if( coef && ( rc = scratch( ctx, 2, (size_t) n * area * 4, &dC ) ) ) return rc;
+  int32_t* dSum = (int32_t*) dM; int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
+  CU( cudaMemcpyAsync( dR, resi, (size_t) n * area * 2, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_fwd_trquant_dev( ctx, par, (const int16_t*) dR, n, (int32_t*) dC, (int16_t*) dQ, dSum, dLast, dNr ) ) ) return rc;
+  CU( cudaMemcpyAsync( q, dQ, (size_t) n * area * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( coef )     CU( cudaMemcpyAsync( coef, dC, (size_t) n * area * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( absSum )   CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( lastPos )  CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, int predPlane, const vvb_block* dBlocks, int n,
+                                int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
+{
+  if( !ctx || !par || !dBlocks || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, predPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  void* dR; int rc;
+  const size_t area = (size_t) par->w * par->h;
+  if( ( rc = scratch( ctx, 5, (size_t) n * area * 2, &dR ) ) ) return rc;
+  const long long total = (long long) n * area;
+  const int grid = (int) std::min<long long>( ( total + 255 ) / 256, (long long) ctx->numSMs * 16 );
+  residual_from_planes_kernel<<<grid, 256, 0, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[predPlane], dBlocks, n, par->w, par->h, (int16_t*) dR );
+  CHECK_LAUNCH( "residual_from_planes_kernel" );
+  return vvb_fwd_trquant_dev( ctx, par, (const int16_t*) dR, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+}
+
+// ---- MCTF ----------------------------------------------------------------------------------------------------------
+int vvb_mctf_error_batch_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dCands, int n, int lowRes, int32_t* dErr )
+{
+  if( !ctx || !dCands || !dErr || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int grid = std::min( ( n + MCTF_WARPS - 1 ) / MCTF_WARPS, ctx->numSMs * 8 );
+  mctf_error_kernel<<<grid, MCTF_WARPS * 32, 0, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dCands, n, lowRes ? 1 : 0, dErr );
+  CHECK_LAUNCH( "mctf_error_kernel" );
+  return VVB_OK;
+}
+
+int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* cands, int n, int lowRes, int32_t* err )
+{
+  if( !ctx || !cands || !err || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  for( int i = 0; i < n; i++ )
+    if( cands[i].w < 8 || cands[i].h < 8 || cands[i].w > 64 || cands[i].h > 64 || ( cands[i].w & 7 ) || ( cands[i].h & 7 ) )
+      return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF blocks are multiples of 8 up to 64 (MCTF.cpp:1113-1118)" );
+  if( n == 0 ) return VVB_OK;
+  void *dC, *dE; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_mctf_cand ), &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * 4, &dE ) ) ) return rc;
+  CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_mctf_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_mctf_error_batch_dev( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, (int32_t*) dE ) ) ) return rc;
+  CU( cudaMemcpyAsync( err, dE, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+// ---- affine ---------------------------------------------------------------------------------------------------------
+int vvb_affine_sobel( vvb_ctx* ctx, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )
+{
+  if( !ctx || !pred || !deriv ) return fail( ctx, VVB_ERR_ARG, "null pointer" );
+  if( w < 4 || h < 4 || w > 128 || h > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "affine blocks are 4..128" );
+  CU( cudaSetDevice( ctx->device ) );
+  int16_t* dP; void* dD; int rc;
+  if( ( rc = uploadBlock( ctx, 2, pred, predStride, w, h, &dP ) ) || ( rc = scratch( ctx, 3, (size_t) w * h * 2, &dD ) ) ) return rc;
+  sobel_kernel<<<( w * h + 255 ) / 256, 256, 0, ctx->stream>>>( dP, w, (int16_t*) dD, w, w, h, vertical );
+  CHECK_LAUNCH( "sobel_kernel" );
+  CU( cudaMemcpy2DAsync( deriv, (size_t) derivStride * 2, dD, (size_t) w * 2, (size_t) w * 2, h, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+int vvb_affine_equal_coeff( vvb_ctx* ctx, int sixParam, const int16_t* resi, int resiStride, const int16_t* gx, const int16_t* gy, int derivStride, int w, int h, int64_t eq[49] )
+{
+  if( !ctx || !resi || !gx || !gy || !eq ) return fail( ctx, VVB_ERR_ARG, "null pointer" );
+  if( w < 4 || h < 4 || w > 128 || h > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "affine blocks are 4..128" );
+  CU( cudaSetDevice( ctx->device ) );
+  int16_t *dR, *dX, *dY; void* dE; int rc;
+  if( ( rc = uploadBlock( ctx, 2, resi, resiStride, w, h, &dR ) ) || ( rc = uploadBlock( ctx, 3, gx, derivStride, w, h, &dX ) ) || ( rc = uploadBlock( ctx, 4, gy, derivStride, w, h, &dY ) ) ||
+      ( rc = scratch( ctx, 1, 49 * 8, &dE ) ) ) return rc;
+  CU( cudaMemsetAsync( dE, 0, 49 * 8, ctx->stream ) );
+  const int grid = std::min( 16, ( w * h + 255 ) / 256 );
+  if( sixParam ) equal_coeff_kernel<6><<<grid, 256, 0, ctx->stream>>>( dR, w, dX, dY, w, w, h, (long long*) dE );
+  else           equal_coeff_kernel<4><<<grid, 256, 0, ctx->stream>>>( dR, w, dX, dY, w, w, h, (long long*) dE );
+  CHECK_LAUNCH( "equal_coeff_kernel" );
+  int64_t tmp[49];
+  CU( cudaMemcpyAsync( tmp, dE, 49 * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  for( int i = 0; i < 49; i++ ) eq[i] += tmp[i];
+  return VVB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,288 @@
+// trquant_kernels.cuh -- forward 2-D integer transform (DCT-II / DST-VII / DCT-VIII) + plain quantiser, fused.
+//
+// Replaces TrQuant::xT (CommonLib/TrQuant.cpp:481-564; 1-D cores CommonLib/TrQuant_EMT.cpp:366-421,1973-2000,
+// AVX2 CommonLib/x86/TrafoX86.h:310-640) followed by Quant::quant -> QuantCore (CommonLib/Quant.cpp:735-833,132-230)
+// and Quant::xNeedRDOQ -> needRdoqCore (:835-891,264-278) for luma TUs without LFNST / transform skip / scaling lists.
+//
+// Exactness: all sums are int32 exactly as the scalar reference.  Products run on IDP.2A (two int16 x int8 MACs per
+// instruction): stage 1 always (residuals are int16), stage 2 when every stage-1 output fits int16 (always true for
+// real video -- it is also the domain in which the AVX2 path, which saturates at TrafoX86.h:364, equals the scalar one);
+// otherwise stage 2 falls back to plain 32-bit IMAD so that the result still equals the scalar reference.
+//
+// One *team* of T threads (4..128) owns one TU; a 128-thread CTA runs 128/T teams in lock step.
+#pragma once
+#include "common.cuh"
+
+namespace vvb {
+
+struct TuPar
+{
+  int w, h, lw, lh;
+  int trHor, trVer;
+  int keepW, keepH;          // non-zeroed-out outputs (TrQuant.cpp:496-497)
+  int s1, s2;                // shifts (TrQuant.cpp:544-545)
+  int offH, offV;            // offsets of the two matrices inside the int8 table (row j, column k)
+  int scale, qbits;          // g_quantScales entry, iQBits (Quant.cpp:767-769)
+  long long add, addRdoq;    // (171|85) << (qbits-9) ; 171 << (qbitsRdoq-9)
+  int scaleRdoq, qbitsRdoq;
+  int useThres;              // thres / (scale << 2)   (Quant.cpp:173-180, thrVal = 8)
+  int scanOff;               // offset (entries) of this shape's raster->scanpos table
+  int regionW, regionH;      // min(32,w), min(32,h)
+  int team;                  // threads per TU
+};
+
+// shared-memory carve-up per team (all in 32-bit words)
+struct TeamSmem { int resiWords, tmpWords, coefWords, total; };
+
+static inline TeamSmem team_smem( const TuPar& p )
+{
+  TeamSmem s;
+  s.resiWords = ( p.w * p.h ) / 2;                       // int16 residual, later reused for the int16 levels
+  s.tmpWords  = p.keepW * p.h;                           // int32 or packed int16 stage-1 output [keepW][h]
+  s.coefWords = p.regionW * p.regionH;                   // int32 coefficients of the scanned region
+  s.total     = s.resiWords + s.tmpWords + s.coefWords + 8;
+  return s;
+}
+
+// Matrix staging: Mt[q][j] (32-bit word) = bytes T[j][4q..4q+3]; j fastest so that a thread's 4 consecutive j are one LDS.128
+__device__ __forceinline__ void stage_matrix( uint32_t* dst, const int8_t* __restrict__ table, int off, int N, int keep, int tid, int nthr )
+{
+  const int Q = N >> 2;
+  for( int i = tid; i < Q * keep; i += nthr )
+  {
+    const int q = i / keep, j = i - q * keep;
+    dst[i] = *reinterpret_cast<const uint32_t*>( table + off + j * N + 4 * q );
+  }
+}
+
+__global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
+                                                             const int16_t* __restrict__ resi, int n,
+                                                             int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
+                                                             int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
+{
+  extern __shared__ __align__( 16 ) uint32_t smem[];
+  const int T = par.team, nTeams = blockDim.x / T;
+  const int team = threadIdx.x / T, tt = threadIdx.x - team * T;
+  const int w = par.w, h = par.h;
+
+  // ---- matrices, shared by all teams of the CTA
+  uint32_t* MtH = smem;                                        // [w/4][keepW]
+  uint32_t* MtV = MtH + ( w >> 2 ) * par.keepW;                // [h/4][keepH]
+  uint32_t* teamBase = MtV + ( h >> 2 ) * par.keepH;
+  stage_matrix( MtH, trTable, par.offH, w, par.keepW, threadIdx.x, blockDim.x );
+  stage_matrix( MtV, trTable, par.offV, h, par.keepH, threadIdx.x, blockDim.x );
+
+  const int resiWords = ( w * h ) >> 1, tmpWords = par.keepW * h, coefWords = par.regionW * par.regionH;
+  uint32_t* myResi = teamBase + team * ( resiWords + tmpWords + coefWords + 8 );
+  uint32_t* myTmp  = myResi + resiWords;
+  int32_t*  myCoef = reinterpret_cast<int32_t*>( myTmp + tmpWords );
+  int*      myRed  = reinterpret_cast<int*>( myCoef + coefWords );     // [0] ovf, [1] lastNZ, [2] cgLo, [3] cgHi, [4] absSum, [5] lastQ, [6] rdoq
+
+  for( int base = blockIdx.x * nTeams; base < n; base += gridDim.x * nTeams )
+  {
+    const int tu = base + team;
+    const bool live = tu < n;
+    __syncthreads();                                           // previous iteration's smem fully consumed; matrices visible
+    if( tt < 8 ) myRed[tt] = 0;
+    // ---- load residual (compact [h][w]) as 32-bit words
+    if( live )
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>( resi + (size_t) tu * w * h );
+      for( int i = tt; i < resiWords; i += T ) myResi[i] = __ldg( src + i );
+    }
+    __syncthreads();
+
+    // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < h, j < keepW
+    {
+      const int jGroups = par.keepW >> 2, items = h * jGroups;
+      const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0;
+      const int Q = w >> 2;
+      int ovf = 0;
+      // pass A: compute and detect int16 overflow; results parked in registers for the common 1-item-per-thread case would
+      // complicate the code, so outputs go to smem as int32 first and are repacked in place when they fit.
+      for( int it = tt; live && it < items; it += T )
+      {
+        const int i = it / jGroups, j0 = ( it - i * jGroups ) << 2;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const uint2* rrow = reinterpret_cast<const uint2*>( myResi + i * ( w >> 1 ) );
+        for( int q = 0; q < Q; q++ )
+        {
+          const uint2 rv = rrow[q];
+          const uint4 m = *reinterpret_cast<const uint4*>( MtH + q * par.keepW + j0 );
+          a0 = __dp2a_lo( (int) rv.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) rv.y, (int) m.x, a0 );
+          a1 = __dp2a_lo( (int) rv.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) rv.y, (int) m.y, a1 );
+          a2 = __dp2a_lo( (int) rv.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) rv.y, (int) m.z, a2 );
+          a3 = __dp2a_lo( (int) rv.x, (int) m.w, a3 ); a3 = __dp2a_hi( (int) rv.y, (int) m.w, a3 );
+        }
+        a0 = ( a0 + r1 ) >> par.s1; a1 = ( a1 + r1 ) >> par.s1; a2 = ( a2 + r1 ) >> par.s1; a3 = ( a3 + r1 ) >> par.s1;
+        ovf |= ( a0 != (short) a0 ) | ( a1 != (short) a1 ) | ( a2 != (short) a2 ) | ( a3 != (short) a3 );
+        int32_t* t = reinterpret_cast<int32_t*>( myTmp );
+        t[( j0 + 0 ) * h + i] = a0; t[( j0 + 1 ) * h + i] = a1; t[( j0 + 2 ) * h + i] = a2; t[( j0 + 3 ) * h + i] = a3;
+      }
+      if( ovf ) atomicOr( &myRed[0], 1 );
+    }
+    __syncthreads();
+
+    // ---- stage 2: coef[j][i] = ( sum_k tmp[i][k] * Tv[j][k] + r2 ) >> s2   for i < keepW, j < keepH
+    {
+      const int jGroups = par.keepH >> 2, items = par.keepW * jGroups;
+      const int r2 = 1 << ( par.s2 - 1 );
+      const int Q = h >> 2;
+      const bool wide = myRed[0] != 0;
+      const int32_t* t32 = reinterpret_cast<const int32_t*>( myTmp );
+      for( int it = tt; live && it < items; it += T )
+      {
+        const int i = it / jGroups, j0 = ( it - i * jGroups ) << 2;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const int4* trow = reinterpret_cast<const int4*>( t32 + i * h );
+        if( !wide )
+        {
+          for( int q = 0; q < Q; q++ )
+          {
+            const int4 tv = trow[q];
+            const uint32_t p0 = ( (uint32_t) tv.x & 0xffffu ) | ( (uint32_t) tv.y << 16 );
+            const uint32_t p1 = ( (uint32_t) tv.z & 0xffffu ) | ( (uint32_t) tv.w << 16 );
+            const uint4 m = *reinterpret_cast<const uint4*>( MtV + q * par.keepH + j0 );
+            a0 = __dp2a_lo( (int) p0, (int) m.x, a0 ); a0 = __dp2a_hi( (int) p1, (int) m.x, a0 );
+            a1 = __dp2a_lo( (int) p0, (int) m.y, a1 ); a1 = __dp2a_hi( (int) p1, (int) m.y, a1 );
+            a2 = __dp2a_lo( (int) p0, (int) m.z, a2 ); a2 = __dp2a_hi( (int) p1, (int) m.z, a2 );
+            a3 = __dp2a_lo( (int) p0, (int) m.w, a3 ); a3 = __dp2a_hi( (int) p1, (int) m.w, a3 );
+          }
+        }
+        else
+        {
+          for( int q = 0; q < Q; q++ )
+          {
+            const int4 tv = trow[q];
+            const uint4 m = *reinterpret_cast<const uint4*>( MtV + q * par.keepH + j0 );
+#define VVB_MAC4( acc, mw ) acc += tv.x * (int)(signed char)( (mw) & 0xff ) + tv.y * (int)(signed char)( ( (mw) >> 8 ) & 0xff ) + tv.z * (int)(signed char)( ( (mw) >> 16 ) & 0xff ) + tv.w * (int)(signed char)( (mw) >> 24 )
+            VVB_MAC4( a0, m.x ); VVB_MAC4( a1, m.y ); VVB_MAC4( a2, m.z ); VVB_MAC4( a3, m.w );
+#undef VVB_MAC4
+          }
+        }
+        a0 = ( a0 + r2 ) >> par.s2; a1 = ( a1 + r2 ) >> par.s2; a2 = ( a2 + r2 ) >> par.s2; a3 = ( a3 + r2 ) >> par.s2;
+        myCoef[( j0 + 0 ) * par.regionW + i] = a0; myCoef[( j0 + 1 ) * par.regionW + i] = a1;
+        myCoef[( j0 + 2 ) * par.regionW + i] = a2; myCoef[( j0 + 3 ) * par.regionW + i] = a3;
+      }
+      // rows/columns of the scanned region that were zeroed out (MTS 32 -> 16)
+      if( live && ( par.keepW < par.regionW || par.keepH < par.regionH ) )
+        for( int i = tt; i < coefWords; i += T )
+        {
+          const int y = i / par.regionW, x = i - y * par.regionW;
+          if( x >= par.keepW || y >= par.keepH ) myCoef[i] = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- quantiser pass 1: last non-zero scan position, coefficient groups holding a value above the threshold, RDOQ pre-check
+    const int32_t* inv = scanTab + par.scanOff;                // raster (y*regionW + x) -> scan position
+    if( live )
+    {
+      int lastNZ = 0; uint32_t cgLo = 0, cgHi = 0; int rd = 0;
+      for( int i = tt; i < coefWords; i += T )
+      {
+        const int c = myCoef[i];
+        const int ac = abs( c );
+        if( c )
+        {
+          const int sp = __ldg( inv + i );
+          lastNZ = max( lastNZ, sp );
+          if( ac > par.useThres ) { const int cg = sp >> 4; if( cg < 32 ) cgLo |= 1u << cg; else cgHi |= 1u << ( cg - 32 ); }
+          if( (int)( ( (long long) ac * par.scaleRdoq + par.addRdoq ) >> par.qbitsRdoq ) != 0 ) rd = 1;
+        }
+      }
+      if( lastNZ ) atomicMax( &myRed[1], lastNZ );
+      if( cgLo ) atomicOr( reinterpret_cast<unsigned*>( &myRed[2] ), cgLo );
+      if( cgHi ) atomicOr( reinterpret_cast<unsigned*>( &myRed[3] ), cgHi );
+      if( rd ) atomicOr( &myRed[6], 1 );
+    }
+    __syncthreads();
+
+    // ---- final scan position after trailing-CG trimming (Quant.cpp:182-208)
+    int pos = myRed[1];
+    {
+      const int initCg = pos >> 4;
+      if( initCg >= 1 )
+      {
+        const unsigned long long mask = ( (unsigned long long)(unsigned) myRed[3] << 32 ) | (unsigned) myRed[2];
+        const unsigned long long m = mask & ( initCg >= 63 ? ~0ull : ( ( 1ull << ( initCg + 1 ) ) - 1ull ) ) & ~1ull;   // CGs 1..initCg
+        if( m == 0 ) pos = 15;
+        else { const int g = 63 - __clzll( (long long) m ); if( g != initCg ) pos = g * 16 + 15; }
+      }
+    }
+
+    // ---- quantise (Quant.cpp:211-227), write int16 levels into the residual buffer (reused), optional coef output
+    int16_t* qS = reinterpret_cast<int16_t*>( myResi );
+    if( live )
+    {
+      for( int i = tt; i < resiWords; i += T ) myResi[i] = 0u;
+    }
+    __syncthreads();
+    if( live )
+    {
+      int sum = 0, lastQ = -1;
+      for( int i = tt; i < coefWords; i += T )
+      {
+        const int c = myCoef[i];
+        if( c )
+        {
+          const int sp = __ldg( inv + i );
+          if( sp <= pos )
+          {
+            const long long t = (long long) abs( c ) * par.scale;
+            const int mag = (int)( ( t + par.add ) >> par.qbits );
+            sum += mag;
+            int v = c < 0 ? -mag : mag;
+            v = max( -32768, min( 32767, v ) );
+            const int y = i / par.regionW, x = i - y * par.regionW;
+            qS[y * w + x] = (int16_t) v;
+            if( v ) lastQ = max( lastQ, sp );
+          }
+        }
+      }
+      if( sum ) atomicAdd( &myRed[4], sum );
+      if( lastQ >= 0 ) atomicMax( &myRed[5], lastQ + 1 );     // stored +1 so that 0 means "none"
+    }
+    __syncthreads();
+    if( live )
+    {
+      uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * w * h );
+      for( int i = tt; i < resiWords; i += T ) dst[i] = myResi[i];
+      if( coefOut )
+      {
+        int32_t* cd = coefOut + (size_t) tu * w * h;
+        for( int i = tt; i < w * h; i += T )
+        {
+          const int y = i / w, x = i - y * w;
+          cd[i] = ( x < par.regionW && y < par.regionH ) ? myCoef[y * par.regionW + x] : 0;
+        }
+      }
+      if( tt == 0 )
+      {
+        const int sum = myRed[4];
+        if( absSumOut )   absSumOut[tu]   = sum;
+        if( lastPosOut )  lastPosOut[tu]  = sum ? myRed[5] - 1 : pos;      // Quant.cpp:806-816, :830
+        if( needRdoqOut ) needRdoqOut[tu] = (uint8_t) myRed[6];
+      }
+    }
+  }
+}
+
+// residual = org(x,y) - pred(x + start_x, y + start_y), written compactly so that fwd_trquant_kernel can consume it
+__global__ void residual_from_planes_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane,
+                                             const vvb_block* __restrict__ blocks, int n, int w, int h, int16_t* __restrict__ resi )
+{
+  const int area = w * h;
+  const long long total = (long long) n * area;
+  for( long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x )
+  {
+    const int b = (int)( i / area ), r = (int)( i - (long long) b * area );
+    const int y = r / w, x = r - y * w;
+    const vvb_block blk = blocks[b];
+    const int o = __ldg( orgPlane.origin + (ptrdiff_t)( blk.y + y ) * orgPlane.stride + blk.x + x );
+    const int p = __ldg( predPlane.origin + (ptrdiff_t)( blk.y + blk.start_y + y ) * predPlane.stride + blk.x + blk.start_x + x );
+    resi[i] = (int16_t)( o - p );
+  }
+}
+
+} // namespace vvb
