@@ -1,0 +1,496 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 block-cost path (contract: see DESIGN.md section "Measurement").
+
+Workload `2160p10_fullsearch_me_rdo` (BASELINE.json: candidate-blocks/s (SAD+SATD+DCT-quant) on 2160p10):
+one 3840x2160 10-bit luma picture against one reference picture; for every block of the quad-tree depths
+8x8, 16x16, 32x32, 64x64 tiling the picture
+    1. integer full search, +-32 window (4225 SAD candidates, MV rate, raster tie-break)   InterSearch::xPatternSearch
+    2. Hadamard (SATD) refinement over an 18-point ring pattern around the best vector      InterSearch.cpp:2582-2630 style
+    3. residual = org - pred(best), forward DCT-II + quantise + RDOQ pre-check              TrQuant::transformNxN
+A "step" is one picture; units = candidate-blocks = SAD candidates + SATD candidates + TUs.
+
+  value : whole-job candidate-blocks/s, inputs resident in HBM, K steps timed with CUDA events on the context stream
+  e2e   : same step through the host-buffer C ABI (pictures + block lists uploaded, costs / vectors / levels downloaded
+          every step), pinned host memory
+  --impl reference : the reference's own AVX2 path (oracle/_ref, else the oracle port) on the host cores, bounded sample
+
+N > 1 (torchrun): CTU-row bands -- every rank owns one 3840x2160 band of an N-times taller picture (weak scaling),
+one NCCL all-gather of the per-block best-vector tables per step.
+"""
+import argparse, ctypes, json, os, statistics, subprocess, sys, threading, time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, MARGIN, BITDEPTH = 3840, 2160, 80, 10
+SIZES = (8, 16, 32, 64)
+SEARCH_RANGE = 32
+QP = 32
+LAMBDA = 57.9          # ~ 0.57 * 2^((QP-12)/3), the encoder's lambda scale at QP 32
+N_PICTURE_SETS = 4     # rotated between steps: 4 x (org+ref) = 4 x 36.6 MB planes + outputs > 126 MB L2
+
+
+def refine_pattern():
+    # centre + 8 neighbours at distance 1 + 8 at distance 2 + centre again at the end (18 points, integer-pel Hadamard refinement)
+    pts = [(0, 0)] + [(dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if dx or dy] + [(dx, dy) for dy in (-2, 0, 2) for dx in (-2, 0, 2) if dx or dy] + [(0, 0)]
+    return pts
+
+
+def synth_picture_pair(seed, w=W, h=H, margin=MARGIN):
+    """natural-like 10-bit luma: low-pass noise, reference = panned copy + noise (SURVEY 8d distribution ii)"""
+    rs = np.random.RandomState(seed)
+    S = w + 2 * margin
+    Hh = h + 2 * margin
+    base = rs.randint(0, 1024, size=(Hh // 4 + 3, S // 4 + 3)).astype(np.float32)
+    up = np.kron(base, np.ones((4, 4), dtype=np.float32))[:Hh + 8, :S + 8]
+    sm = (up[:-4, :-4] + up[4:, :-4] + up[:-4, 4:] + up[4:, 4:] + 2 * up[2:-2, 2:-2]) / 6.0
+    sm = sm[:Hh + 4, :S + 4]
+    tex = rs.randint(-24, 25, size=sm.shape)
+    full = np.clip(sm + tex, 0, 1023)
+    org = full[2:2 + Hh, 2:2 + S].astype(np.int16)
+    ref = np.clip(full[2 + 1:2 + 1 + Hh, 2 - 2:2 - 2 + S] + rs.randint(-6, 7, size=org.shape), 0, 1023).astype(np.int16)
+    return np.ascontiguousarray(org), np.ascontiguousarray(ref), S
+
+
+def block_grid(n, w=W, h=H):
+    xs, ys = np.meshgrid(np.arange(0, w - n + 1, n), np.arange(0, h - n + 1, n))
+    return xs.ravel().astype(np.int32), ys.ravel().astype(np.int32)
+
+
+def units_per_step():
+    u = {'sad': 0, 'satd': 0, 'tu': 0}
+    K = len(refine_pattern())
+    for n in SIZES:
+        nb = len(block_grid(n)[0])
+        u['sad'] += nb * (2 * SEARCH_RANGE + 1) ** 2
+        u['satd'] += nb * K
+        u['tu'] += nb
+    return u
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index = index; self.proc = None; self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores (oracle/_ref), else the oracle port
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_arm(sample_budget_s=12.0, threads=None, quiet=False):
+    """times a bounded sample of the SAME workload on the host; returns dict(value cand-blocks/s, kind, cores, sample, per-leg rates)"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _libs import have_ref, refshim, oracle, P, PO
+    threads = threads or (os.cpu_count() or 1)
+    kind = 'reference' if have_ref() else 'port'
+    org, ref, S = synth_picture_pair(1234)
+    base = MARGIN * S + MARGIN
+    K = len(refine_pattern()); pat = refine_pattern()
+    legs = {}
+    R = refshim() if kind == 'reference' else None
+    O = oracle()
+    if kind == 'port':
+        threads = 1
+    u = units_per_step()
+    per_leg_budget = sample_budget_s / (3 * len(SIZES))
+    sample_desc = []
+    t_step = 0.0
+    for n in SIZES:
+        xs, ys = block_grid(n)
+        nb_all = len(xs)
+        # ---- SAD full search: calibrate on a few blocks, then size the sample to the budget
+        def run_search(idx):
+            blk = np.zeros((len(idx), 10), dtype=np.int32)
+            blk[:, 0] = xs[idx]; blk[:, 1] = ys[idx]; blk[:, 2] = n; blk[:, 3] = n
+            blk[:, 4] = -SEARCH_RANGE; blk[:, 5] = SEARCH_RANGE; blk[:, 6] = -SEARCH_RANGE; blk[:, 7] = SEARCH_RANGE
+            out = np.zeros((len(idx), 4), dtype=np.int32)
+            t0 = time.perf_counter()
+            if R is not None:
+                R.refshim_full_search(1, PO(org, base), S, PO(ref, base), S, P(blk), len(idx), BITDEPTH, 0, LAMBDA, 2, 0, P(out), None, 0, threads, 1)
+            else:
+                O.orc_full_search(PO(org, base), S, PO(ref, base), S, P(blk), len(idx), 0, LAMBDA, 2, 0, P(out), None, 0)
+            return time.perf_counter() - t0, out
+        rs = np.random.RandomState(n)
+        probe = rs.choice(nb_all, size=min(nb_all, 4 * threads), replace=False)
+        tp, _ = run_search(probe)
+        cnt = int(min(nb_all, max(len(probe), len(probe) * per_leg_budget / max(tp, 1e-6))))
+        idx = rs.choice(nb_all, size=cnt, replace=False)
+        ts, best = run_search(idx)
+        t_sad = ts / cnt * nb_all
+        # ---- SATD refinement around the best vectors of the sample
+        desc = np.zeros((cnt * K, 6), dtype=np.int32)
+        bx = np.repeat(xs[idx], K); by = np.repeat(ys[idx], K)
+        ddx = np.tile(np.array([p[0] for p in pat], dtype=np.int32), cnt) + np.repeat(best[:, 0], K)
+        ddy = np.tile(np.array([p[1] for p in pat], dtype=np.int32), cnt) + np.repeat(best[:, 1], K)
+        desc[:, 0] = bx; desc[:, 1] = by; desc[:, 2] = bx + ddx; desc[:, 3] = by + ddy; desc[:, 4] = n; desc[:, 5] = n
+        outc = np.zeros(cnt * K, dtype=np.uint64)
+        t0 = time.perf_counter()
+        if R is not None:
+            R.refshim_dist_list(1, 2, PO(org, base), S, PO(ref, base), S, P(desc), cnt * K, BITDEPTH, 0, P(outc), threads)
+        else:
+            O.orc_dist_list(2, PO(org, base), S, PO(ref, base), S, P(desc), cnt * K, 0, P(outc))
+        t_satd = (time.perf_counter() - t0) / cnt * nb_all
+        # ---- TU: residual of the best prediction, DCT-II + quantise
+        resi = np.zeros((cnt, n, n), dtype=np.int16)
+        for i in range(cnt):
+            x, y = int(xs[idx[i]]), int(ys[idx[i]]); mx, my = int(best[i, 0]), int(best[i, 1])
+            resi[i] = org[MARGIN + y:MARGIN + y + n, MARGIN + x:MARGIN + x + n] - ref[MARGIN + y + my:MARGIN + y + my + n, MARGIN + x + mx:MARGIN + x + mx + n]
+        q = np.zeros((cnt, n, n), dtype=np.int16); s = np.zeros(cnt, dtype=np.int32); lp = np.zeros(cnt, dtype=np.int32)
+        t0 = time.perf_counter()
+        if R is not None:
+            R.refshim_transform_quant_batch(0, 0, P(resi), cnt, n, n, BITDEPTH, QP, 0, P(q), P(s), P(lp), threads)
+        else:
+            coef = np.zeros((n, n), dtype=np.int32)
+            for i in range(cnt):
+                O.orc_transform_quant(0, 0, P(resi[i]), n, n, n, BITDEPTH, QP, 0, P(coef), P(q[i]), PO(s, i), PO(lp, i))
+        t_tu = (time.perf_counter() - t0) / cnt * nb_all
+        legs[n] = {'sad_s': t_sad, 'satd_s': t_satd, 'tu_s': t_tu, 'sample_blocks': cnt}
+        sample_desc.append('%dx%d:%d/%d blocks' % (n, n, cnt, nb_all))
+        t_step += t_sad + t_satd + t_tu
+    total_units = u['sad'] + u['satd'] + u['tu']
+    return {'value': total_units / t_step, 'unit': 'candidate-blocks/s', 'cores': threads, 'kind': kind,
+            'sample': 'random block sample per size, full-step time extrapolated per leg (' + ', '.join(sample_desc) + '); AVX2, early exit on' if kind == 'reference'
+                      else 'scalar oracle port, ' + ', '.join(sample_desc),
+            'cpu_s_per_step': t_step, 'legs': legs}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-budget', type=float, default=12.0)
+    ap.add_argument('--skip-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    u = units_per_step()
+    total_units = u['sad'] + u['satd'] + u['tu']
+    config = {'workload': '2160p10_fullsearch_me_rdo', 'picture': '%dx%d 10-bit luma, 1 reference picture' % (W, H), 'block_sizes': list(SIZES),
+              'search_range': SEARCH_RANGE, 'satd_points': len(refine_pattern()), 'tu': 'DCT-II + quant, one per block', 'qp': QP,
+              'units_per_step': u, 'l2': 'inputs rotated over %d picture sets (> L2)' % N_PICTURE_SETS,
+              'parallelism': 'ctu-row bands x%d' % max(1, args.gpus)}
+
+    # ------------------------------------------------------------------------------------------- reference arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        K, Wm = max(1, args.steps), max(0, args.warmup)
+        budget = max(2.0, min(12.0, 100.0 / (K + Wm)))
+        vals = []
+        for i in range(K + Wm):
+            r = cpu_arm(budget)
+            if i >= Wm:
+                vals.append(r)
+        v = statistics.mean(x['value'] for x in vals)
+        r = vals[-1]
+        line = {'impl': 'reference', 'metric': 'candidate-blocks/s (SAD+SATD+DCT-quant) on 2160p10', 'value': v, 'unit': 'candidate-blocks/s',
+                'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': 1e3 * total_units / v, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'int16/int32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': v, 'unit': 'candidate-blocks/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
+                'e2e': {'value': v, 'unit': 'candidate-blocks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line)); return 0
+
+    # ------------------------------------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import vvenc_b200 as V
+    import vvenc_b200._lib as L
+    eng = V.CostEngine(local)
+    lib = eng.lib
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', local))
+    hbm_peak, peak_src = measured_peaks()
+
+    pat_np = np.zeros(len(refine_pattern()), dtype=V.MV_DT)
+    pat_np['dx'] = [p[0] for p in refine_pattern()]; pat_np['dy'] = [p[1] for p in refine_pattern()]
+    KP = len(pat_np)
+    me = eng.me_par(LAMBDA, 2, 0, 0)
+    nx = 2 * SEARCH_RANGE + 1
+
+    def dev(a):
+        return torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy()).cuda()
+
+    # resident inputs: N_PICTURE_SETS picture pairs, per-size block lists
+    host_sets = []
+    dev_planes = []
+    for s in range(N_PICTURE_SETS):
+        org, ref, S = synth_picture_pair(1234 + 17 * s + 1000 * rank)
+        host_sets.append((org, ref, S))
+        dorg = torch.from_numpy(org).cuda(); dref = torch.from_numpy(ref).cuda()
+        dev_planes.append((dorg, dref))
+        base = (MARGIN * S + MARGIN) * 2
+        eng.bind_plane_dev(2 * s, dorg.data_ptr() + base, S, W, H, MARGIN, BITDEPTH)
+        eng.bind_plane_dev(2 * s + 1, dref.data_ptr() + base, S, W, H, MARGIN, BITDEPTH)
+    blocks_np, d_blocks, d_best, d_satd, d_q, d_sum, d_last, d_nr, tu_par = {}, {}, {}, {}, {}, {}, {}, {}, {}
+    d_pat = dev(pat_np)
+    for n in SIZES:
+        xs, ys = block_grid(n)
+        b = np.zeros(len(xs), dtype=V.BLOCK_DT)
+        b['x'] = xs; b['y'] = ys; b['left'] = -SEARCH_RANGE; b['right'] = SEARCH_RANGE; b['top'] = -SEARCH_RANGE; b['bottom'] = SEARCH_RANGE
+        blocks_np[n] = b
+        d_blocks[n] = dev(b)
+        nb = len(b)
+        d_best[n] = torch.empty(nb * 16, dtype=torch.uint8, device='cuda')
+        d_satd[n] = torch.empty(nb * KP, dtype=torch.int32, device='cuda')
+        d_q[n] = torch.empty(nb * n * n, dtype=torch.int16, device='cuda')
+        d_sum[n] = torch.empty(nb, dtype=torch.int32, device='cuda'); d_last[n] = torch.empty(nb, dtype=torch.int32, device='cuda')
+        d_nr[n] = torch.empty(nb, dtype=torch.uint8, device='cuda')
+        tu_par[n] = eng.tu_par(n, n, V.DCT2, V.DCT2, BITDEPTH, QP, False, False)
+    gather_buf = None
+    if world > 1:
+        nb16 = len(blocks_np[16])
+        gather_buf = torch.empty(world * nb16 * 16, dtype=torch.uint8, device='cuda')
+    torch.cuda.synchronize()
+
+    P_ = ctypes.c_void_p
+
+    def chk(rc):
+        if rc != 0:
+            raise RuntimeError('vvenc_b200: ' + lib.vvb_last_error(eng.h).decode())
+
+    def step_resident(i):
+        s = i % N_PICTURE_SETS
+        po, pr = 2 * s, 2 * s + 1
+        for n in SIZES:
+            nb = len(blocks_np[n])
+            chk(lib.vvb_sad_search_dev(eng.h, po, pr, P_(d_blocks[n].data_ptr()), nb, n, n, ctypes.byref(me), nx, nx, None, 0, P_(d_best[n].data_ptr())))
+            chk(lib.vvb_blocks_set_start_dev(eng.h, P_(d_blocks[n].data_ptr()), P_(d_best[n].data_ptr()), nb))
+            chk(lib.vvb_cost_pattern_dev(eng.h, V.DF_HAD, po, pr, P_(d_blocks[n].data_ptr()), nb, n, n, P_(d_pat.data_ptr()), KP, ctypes.byref(me),
+                                         P_(d_satd[n].data_ptr()), None))
+            chk(lib.vvb_fwd_trquant_planes_dev(eng.h, ctypes.byref(tu_par[n]), po, pr, P_(d_blocks[n].data_ptr()), nb, None, P_(d_q[n].data_ptr()),
+                                               P_(d_sum[n].data_ptr()), P_(d_last[n].data_ptr()), P_(d_nr[n].data_ptr())))
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(gather_buf, d_best[16])      # per-row best-vector tables of every band
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        eng.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = eng.launches
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record(ext)
+            for i in range(steps):
+                fn(warm + i)
+            e1.record(ext)
+        eng.synchronize(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.barrier()
+        return float(t.item()), eng.launches - l0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, max(3, args.warmup))
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = total_units * world / (ms_step * 1e-3)
+
+    # ------------------------------------------------------------------------------------------- per-kernel timing + rooflines (rank 0)
+    roofline = None; extra = {}
+    if rank == 0:
+        def time_launch(fn, reps=10):
+            fn(); eng.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ext):
+                e0.record(ext)
+                for _ in range(reps):
+                    fn()
+                e1.record(ext)
+            eng.synchronize(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        kt = {}
+        comp_bytes = 0; t_search = 0.0; pel_diffs = 0
+        for n in SIZES:
+            nb = len(blocks_np[n])
+            ctr = [0]
+            def f_search(n=n, nb=nb, ctr=ctr):
+                s = ctr[0] % N_PICTURE_SETS; ctr[0] += 1
+                chk(lib.vvb_sad_search_dev(eng.h, 2 * s, 2 * s + 1, P_(d_blocks[n].data_ptr()), nb, n, n, ctypes.byref(me), nx, nx, None, 0, P_(d_best[n].data_ptr())))
+            def f_satd(n=n, nb=nb, ctr=ctr):
+                s = ctr[0] % N_PICTURE_SETS; ctr[0] += 1
+                chk(lib.vvb_cost_pattern_dev(eng.h, V.DF_HAD, 2 * s, 2 * s + 1, P_(d_blocks[n].data_ptr()), nb, n, n, P_(d_pat.data_ptr()), KP, ctypes.byref(me),
+                                             P_(d_satd[n].data_ptr()), None))
+            def f_tu(n=n, nb=nb, ctr=ctr):
+                s = ctr[0] % N_PICTURE_SETS; ctr[0] += 1
+                chk(lib.vvb_fwd_trquant_planes_dev(eng.h, ctypes.byref(tu_par[n]), 2 * s, 2 * s + 1, P_(d_blocks[n].data_ptr()), nb, None, P_(d_q[n].data_ptr()),
+                                                   P_(d_sum[n].data_ptr()), P_(d_last[n].data_ptr()), P_(d_nr[n].data_ptr())))
+            kt[n] = {'sad_search_ms': time_launch(f_search), 'satd_pattern_ms': time_launch(f_satd), 'trquant_ms': time_launch(f_tu)}
+            t_search += kt[n]['sad_search_ms']
+            comp_bytes += nb * (2 * n * n + 2 * (n + 2 * SEARCH_RANGE) ** 2 + 16)            # compulsory bytes per block
+            pel_diffs += nb * nx * nx * n * n
+        # ALU ceiling for the packed-SAD instruction mix
+        ctas, iters = 148 * 8, 4096
+        t_probe = time_launch(lambda: chk(lib.vvb_alu_probe_dev(eng.h, ctas, iters)), reps=5)
+        alu_peak = ctas * 256 * iters * 16 / (t_probe * 1e-3)
+        ach = comp_bytes / (t_search * 1e-3) / 1e9
+        roofline = {'kernel': 'sad_search_kernel (4 launches per step: 8x8..64x64)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                    'note': 'dense +-32 search re-uses every reference pel up to 4225x from shared memory: integer-ALU bound by construction (SURVEY 8d W2); '
+                            'bytes = compulsory 2N^2 + 2(N+2R)^2 + 16 per block; see "alu" for the binding roof',
+                    'alu': {'achieved': pel_diffs / (t_search * 1e-3) / 1e12, 'peak': alu_peak / 1e12, 'unit': 'Tpel-diff/s', 'frac': pel_diffs / (t_search * 1e-3) / alu_peak,
+                            'peak_source': 'alu_probe_kernel: same 2xVIMNMX.S16x2 + 2xIDP.2A mix on register operands, measured in this run'},
+                    'share_of_step': t_search / ms_step}
+        extra['kernel_ms'] = kt
+        # HBM-streaming evidence: candidate-pool SAD / SATD, 16x16, pool >> L2 (2wh + 2wh/K + 8 bytes per candidate)
+        try:
+            n = 16; Kp = 32; nb = len(blocks_np[n])
+            pool = torch.randint(0, 1024, (nb * Kp * n * n,), dtype=torch.int16, device='cuda')
+            pos = np.zeros(nb, dtype=V.POS_DT); pos['x'] = blocks_np[n]['x']; pos['y'] = blocks_np[n]['y']
+            d_pos = dev(pos); d_out = torch.empty(nb * Kp, dtype=torch.int32, device='cuda')
+            sweep = {}
+            for fam, name in ((V.DF_SAD, 'sad'), (V.DF_HAD, 'satd'), (V.DF_SSE, 'sse')):
+                t = time_launch(lambda fam=fam: chk(lib.vvb_dist_pool_dev(eng.h, fam, 0, P_(d_pos.data_ptr()), nb, n, n, Kp, P_(pool.data_ptr()), 0, P_(d_out.data_ptr()))), reps=5)
+                byt = nb * Kp * (2 * n * n + 2 * n * n / Kp + 8)
+                sweep[name] = {'ms': t, 'GBps': byt / (t * 1e-3) / 1e9, 'frac_hbm': byt / (t * 1e-3) / 1e9 / hbm_peak, 'cand_per_s': nb * Kp / (t * 1e-3)}
+            extra['hbm_sweep_16x16_pool'] = {'pool_MB': pool.numel() * 2 / 1e6, 'K': Kp, **sweep}
+            del pool
+        except Exception as ex:     # the sweep is evidence, not part of the metric
+            extra['hbm_sweep_16x16_pool'] = {'error': str(ex)}
+
+    # ------------------------------------------------------------------------------------------- end-to-end through the host-buffer C ABI
+    e2e = None
+    if not args.skip_e2e:
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+        h_planes = []
+        for (org, ref, S) in host_sets:
+            po = pin(org.shape, torch.int16); pr = pin(ref.shape, torch.int16); po[:] = org; pr[:] = ref
+            h_planes.append((po, pr, S))
+        h_blocks = {n: pin((len(blocks_np[n]) * 24,), torch.uint8) for n in SIZES}
+        h_best = {n: pin((len(blocks_np[n]) * 16,), torch.uint8) for n in SIZES}
+        h_satd = {n: pin((len(blocks_np[n]) * KP,), torch.int32) for n in SIZES}
+        h_q = {n: pin((len(blocks_np[n]) * n * n,), torch.int16) for n in SIZES}
+        h_sum = {n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES}; h_last = {n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES}
+        h_nr = {n: pin((len(blocks_np[n]),), torch.uint8) for n in SIZES}
+        for n in SIZES:
+            h_blocks[n][:] = np.frombuffer(blocks_np[n].tobytes(), dtype=np.uint8)
+        PA = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        E0, E1 = 40, 41        # plane ids of the uploaded pictures
+        h2d = 0; d2h = 0
+        for n in SIZES:
+            nb = len(blocks_np[n])
+            h2d += 3 * nb * 24 + KP * 4
+            d2h += nb * 16 + nb * KP * 4 + nb * n * n * 2 + nb * 9
+        S0 = host_sets[0][2]
+        h2d += 2 * (H + 2 * MARGIN) * S0 * 2
+
+        def step_e2e(i):
+            po, pr, S = h_planes[i % N_PICTURE_SETS]
+            base = MARGIN * S + MARGIN
+            chk(lib.vvb_plane_upload(eng.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
+            chk(lib.vvb_plane_upload(eng.h, E1, ctypes.c_void_p(pr.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
+            for n in SIZES:
+                nb = len(blocks_np[n])
+                chk(lib.vvb_sad_search(eng.h, E0, E1, PA(h_blocks[n]), nb, n, n, ctypes.byref(me), None, 0, PA(h_best[n])))
+                # host logic between the calls: the best vector becomes the refinement centre / prediction offset
+                bv = h_best[n].view(V.BEST_DT); bl = h_blocks[n].view(V.BLOCK_DT)
+                bl['start_x'] = bv['dx']; bl['start_y'] = bv['dy']
+                chk(lib.vvb_cost_pattern(eng.h, V.DF_HAD, E0, E1, PA(h_blocks[n]), nb, n, n, PA(pat_np), KP, ctypes.byref(me), PA(h_satd[n]), None))
+                chk(lib.vvb_fwd_trquant_planes(eng.h, ctypes.byref(tu_par[n]), E0, E1, PA(h_blocks[n]), nb, None, PA(h_q[n]), PA(h_sum[n]), PA(h_last[n]), PA(h_nr[n])))
+
+        ke = max(3, min(args.steps, 10))
+        for i in range(2):
+            step_e2e(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            step_e2e(2 + i)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ke
+        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {'value': total_units * world / dt, 'unit': 'candidate-blocks/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'ms_per_step': dt * 1e3, 'steps': ke, 'timing': 'host wall clock around synchronous C-ABI calls (each call ends with a stream sync), max over ranks'}
+        # parity spot-check of what came back (device-resident and host paths must agree bit for bit)
+        bv = h_best[16].view(V.BEST_DT)
+        dv = np.frombuffer(d_best[16].cpu().numpy().tobytes(), dtype=V.BEST_DT)
+        extra['e2e_matches_resident'] = bool(np.array_equal(bv['cost'][:64], dv['cost'][:64])) if (2 + ke - 1) % N_PICTURE_SETS == (max(3, args.warmup) + args.steps - 1) % N_PICTURE_SETS else None
+
+    cpu = None
+    if rank == 0 and world == 1:
+        cpu = cpu_arm(args.cpu_budget)
+
+    if rank == 0:
+        line = {'metric': 'candidate-blocks/s (SAD+SATD+DCT-quant) on 2160p10', 'value': value, 'unit': 'candidate-blocks/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'int16 pels / int32 accumulation (exact)', 'data': 'synthetic', 'config': config, 'roofline': roofline,
+                'cpu_baseline': None if cpu is None else {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+                'e2e': e2e, 'clocks': clocks, 'gpu_launches': int(launches * world), 'extra': extra}
+        if cpu is not None:
+            line['extra']['cpu_s_per_step'] = cpu['cpu_s_per_step']; line['extra']['cpu_legs'] = cpu['legs']
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

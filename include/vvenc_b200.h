@@ -49,6 +49,9 @@ int         vvb_synchronize( vvb_ctx* ctx );
 void*       vvb_stream     ( vvb_ctx* ctx );                /* cudaStream_t of the context, for event timing / interop */
 int         vvb_launch_count( const vvb_ctx* ctx, uint64_t* kernels_launched );   /* kernels this context has launched so far */
 
+/* measurement aid (bench.py): issue-rate probe of the packed-SAD instruction mix; no reference counterpart */
+int         vvb_alu_probe_dev( vvb_ctx* ctx, int grid_ctas, int iters );
+
 /* ---- pictures ("planes") ---------------------------------------------------------------------------------
  * int16 sample planes (Pel, CommonLib/TypeDef.h:181) with a margin on all sides, like the encoder's padded
  * reference pictures (CommonLib/Picture.cpp:461-501).  `origin` points at sample (0,0); rows -margin..height+margin-1
@@ -126,6 +129,15 @@ int vvb_sad_pattern    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_b
 int vvb_sad_pattern_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, const vvb_mv* dev_pattern, int K,
                          const vvb_me_par* par, uint32_t* dev_sad_out, vvb_best* dev_best_out );
 
+/* Same candidate pattern with any distortion family (e.g. Hadamard integer refinement, InterSearch.cpp:2582,2630 and
+ * xPatternRefinement :760-972, which add the MV rate the same way); cost_out holds the distortion only. */
+int vvb_cost_pattern    ( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, const vvb_mv* pattern, int K,
+                          const vvb_me_par* par, uint32_t* cost_out /* n*K, nullable */, vvb_best* best_out /* nullable */ );
+int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, const vvb_mv* dev_pattern, int K,
+                          const vvb_me_par* par, uint32_t* dev_cost_out, vvb_best* dev_best_out );
+/* device-side chaining: blocks[i].start = best[i].(dx,dy) (start of a refinement pattern / offset of the prediction block) */
+int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dev_blocks, const vvb_best* dev_best, int n );
+
 /* ---- forward transform + quantise (TrQuant::transformNxN for LFNST-off, non-skip luma TUs; ---------------
  * CommonLib/TrQuant.cpp:688-736 -> xT :481-564 -> Quant::quant CommonLib/Quant.cpp:735-833 -> QuantCore :132-230,
  * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types. */
@@ -145,7 +157,9 @@ int vvb_fwd_trquant    ( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* res
                          int32_t* coef, int16_t* q, int32_t* abs_sum, int32_t* last_pos, uint8_t* need_rdoq );
 int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_resi, int n,
                          int32_t* dev_coef, int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos, uint8_t* dev_need_rdoq );
-/* Residual formed on the device: resi = org(x,y) - pred(x+dx,y+dy) for each TU position (PelBuf::subtract, IntraSearch.cpp:1328) */
+/* Residual formed on the device: resi = org(x,y) - pred(x+start_x, y+start_y) for each TU position (PelBuf::subtract, IntraSearch.cpp:1328) */
+int vvb_fwd_trquant_planes    ( vvb_ctx* ctx, const vvb_tu_par* par, int org_plane, int pred_plane, const vvb_block* blocks, int n,
+                         int32_t* coef, int16_t* q, int32_t* abs_sum, int32_t* last_pos, uint8_t* need_rdoq );
 int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int org_plane, int pred_plane, const vvb_block* dev_blocks, int n,
                          int32_t* dev_coef, int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos, uint8_t* dev_need_rdoq );
 

@@ -332,8 +332,10 @@ uint64_t refshim_mv_cost( double lambda, int x, int y, int predHor, int predVer,
 // out[i] = { bestDx, bestDy, bestCost(lo32), bestCost(hi32) } ; optional full cost table (uint32 SAD only) per block.
 void refshim_full_search( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
                           const int32_t* blk, int n, int bitDepth, int subShift, double lambda, int costScale, int imvShift,
-                          int32_t* out, uint32_t* sadTables, int tableStride, int nthreads )
+                          int32_t* out, uint32_t* sadTables, int tableStride, int nthreads, int earlyExit )
 {
+  // earlyExit != 0 reproduces m_cDistParam.maximumDistortionForEarlyExit = uiSad (InterSearch.cpp:2241): the reference's SIMD SAD may
+  // then return a partial sum for W >= 64 (RdCostX86.h:372-410) -- same decisions, used by the timed CPU baseline only.
   parallelFor( n, nthreads, [&]( int b, int e, int )
   {
     RdCost rc; rc.create( opt != 0 );
@@ -364,7 +366,7 @@ void refshim_full_search( int opt, const int16_t* orgPlane, int orgStride, const
           Distortion sad = dp.distFunc( dp );
           if( tab ) tab[k] = (uint32_t) sad;
           sad += rc.getCostOfVectorWithPredictor( dx, dy, imvShift );
-          if( sad < best ) { best = sad; bx = dx; by = dy; }
+          if( sad < best ) { best = sad; bx = dx; by = dy; if( earlyExit ) dp.maximumDistortionForEarlyExit = sad; }
         }
       }
       out[4*i+0] = bx; out[4*i+1] = by; out[4*i+2] = (int32_t)( best & 0xffffffffu ); out[4*i+3] = (int32_t)( best >> 32 );

@@ -78,7 +78,7 @@ def main():
         for opt in (0, 1):
             o = np.zeros((n, 4), dtype=np.int32)
             R.refshim_full_search(opt, PO(sc['org'], base), S, PO(sc['ref'], base), S, P(sc['blk']), n, 10, ss, sc['lam'], sc['cost_scale'],
-                                  sc['imv_shift'], P(o), None, 0, 1)
+                                  sc['imv_shift'], P(o), None, 0, 1, 0)
             res.append(o)
         assert np.array_equal(res[0], res[1])
         out['search_best_ss%d' % ss] = res[1]

@@ -100,7 +100,7 @@ class RefImpl(OracleImpl):
         ts = int(max((b[5] - b[4] + 1) * (b[7] - b[6] + 1) for b in sc['blk']))
         tab = np.zeros((n, ts), dtype=np.uint32) if want_table else None
         self.L.refshim_full_search(self.opt, PO(sc['org'], base), S, PO(sc['ref'], base), S, P(sc['blk']), n, 10, ss, sc['lam'], sc['cost_scale'],
-                                   sc['imv_shift'], P(out), P(tab) if want_table else None, ts, 2)
+                                   sc['imv_shift'], P(out), P(tab) if want_table else None, ts, 2, 0)
         return (out, tab) if want_table else out
 
     def mv_bits(self, *a):

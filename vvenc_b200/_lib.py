@@ -46,6 +46,7 @@ SYMBOLS = {
     'vvb_synchronize': (c_i, [c_p]),
     'vvb_stream': (c_p, [c_p]),
     'vvb_launch_count': (c_i, [c_p, ctypes.POINTER(ctypes.c_uint64)]),
+    'vvb_alu_probe_dev': (c_i, [c_p, c_i, c_i]),
     'vvb_plane_upload': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),
     'vvb_plane_bind_dev': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),
     'vvb_plane_free': (c_i, [c_p, c_i]),
@@ -61,8 +62,12 @@ SYMBOLS = {
     'vvb_sad_search_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_p, c_i, c_p]),
     'vvb_sad_pattern': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
     'vvb_sad_pattern_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
+    'vvb_cost_pattern': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
+    'vvb_cost_pattern_dev': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
+    'vvb_blocks_set_start_dev': (c_i, [c_p, c_p, c_p, c_i]),
     'vvb_fwd_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_fwd_trquant_planes': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_mctf_error_batch': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_mctf_error_batch_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),

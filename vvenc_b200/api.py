@@ -153,6 +153,16 @@ class CostEngine:
         self._chk(self.lib.vvb_sad_pattern(self.h, org_plane, ref_plane, _p(blocks), n, w, h, _p(pattern), K, ctypes.byref(par), _p(sad), _p(best)))
         return sad, best
 
+    def cost_pattern(self, dfunc, org_plane, ref_plane, blocks, w, h, pattern, par, want_cost=True, want_best=True):
+        """any distortion family over the fixed pattern (e.g. DF_HAD integer refinement around blocks['start_*'])"""
+        blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
+        pattern = np.ascontiguousarray(pattern, dtype=L.MV_DT)
+        n, K = len(blocks), len(pattern)
+        cost = np.zeros((n, K), dtype=np.uint32) if want_cost else None
+        best = np.zeros(n, dtype=L.BEST_DT) if want_best else None
+        self._chk(self.lib.vvb_cost_pattern(self.h, dfunc, org_plane, ref_plane, _p(blocks), n, w, h, _p(pattern), K, ctypes.byref(par), _p(cost), _p(best)))
+        return cost, best
+
     # ---- transform + quantise
     @staticmethod
     def tu_par(w, h, tr_hor=DCT2, tr_ver=DCT2, bit_depth=10, qp=32, is_irap=False, dep_quant=False):
@@ -166,6 +176,16 @@ class CostEngine:
         q = np.zeros((n, par.h, par.w), dtype=np.int16)
         s = np.zeros(n, dtype=np.int32); lp = np.zeros(n, dtype=np.int32); nr = np.zeros(n, dtype=np.uint8)
         self._chk(self.lib.vvb_fwd_trquant(self.h, ctypes.byref(par), _p(resi), n, _p(coef), _p(q), _p(s), _p(lp), _p(nr)))
+        return dict(coef=coef, q=q, abs_sum=s, last_pos=lp, need_rdoq=nr)
+
+    def fwd_trquant_planes(self, par, org_plane, pred_plane, blocks, want_coef=False):
+        """residual = org(x,y) - pred(x+start_x, y+start_y) formed on the device, then transformNxN"""
+        blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
+        n = len(blocks)
+        coef = np.zeros((n, par.h, par.w), dtype=np.int32) if want_coef else None
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        s = np.zeros(n, dtype=np.int32); lp = np.zeros(n, dtype=np.int32); nr = np.zeros(n, dtype=np.uint8)
+        self._chk(self.lib.vvb_fwd_trquant_planes(self.h, ctypes.byref(par), org_plane, pred_plane, _p(blocks), n, _p(coef), _p(q), _p(s), _p(lp), _p(nr)))
         return dict(coef=coef, q=q, abs_sum=s, last_pos=lp, need_rdoq=nr)
 
     # ---- MCTF

@@ -142,6 +142,24 @@ __global__ void fix_wsse_kernel( const int16_t* org, int so, const int16_t* cur,
   if( threadIdx.x == 0 ) *out = acc;
 }
 
+// Issue-rate probe for the packed-SAD instruction mix (2 x VIMNMX.S16x2 + 2 x IDP.2A per pel pair) on register operands:
+// the measured ceiling the dense search kernel is compared against (bench.py "alu" roofline).
+__global__ void __launch_bounds__( 256 ) alu_probe_kernel( int iters, uint32_t seed, uint32_t* out )
+{
+  uint32_t a[8], b[8]; int acc[8];
+#pragma unroll
+  for( int i = 0; i < 8; i++ ) { a[i] = seed * ( 2654435761u + i ) + threadIdx.x; b[i] = a[i] ^ ( 0x01230123u * ( i + 1 ) ); acc[i] = 0; }
+  for( int it = 0; it < iters; it++ )
+  {
+#pragma unroll
+    for( int i = 0; i < 8; i++ ) { acc[i] = sad2_acc( a[i], b[i], acc[i] ); a[i] += 0x00010001u; }
+  }
+  int s = 0;
+#pragma unroll
+  for( int i = 0; i < 8; i++ ) s += acc[i];
+  if( s == 0x7fffffff ) out[0] = (uint32_t) s;      // keeps the loop alive
+}
+
 // copy a strided host block into a compact device buffer (via pinned-less synchronous 2-D copy)
 int uploadBlock( vvb_ctx* ctx, int slot, const int16_t* host, int stride, int w, int h, int16_t** dev, int padBefore = 0, int padAfter = 0 )
 {
@@ -213,6 +231,18 @@ int vvb_synchronize( vvb_ctx* ctx )
 void* vvb_stream( vvb_ctx* ctx ) { return ctx ? (void*) ctx->stream : nullptr; }
 
 int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) return VVB_ERR_ARG; *k = ctx->launches; return VVB_OK; }
+
+// launches the ALU probe: grid_ctas CTAs x 256 threads x iters iterations x 8 packed SADs (16 pel differences) each
+int vvb_alu_probe_dev( vvb_ctx* ctx, int gridCtas, int iters )
+{
+  if( !ctx || gridCtas < 1 || iters < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  CU( cudaSetDevice( ctx->device ) );
+  void* d; int rc;
+  if( ( rc = scratch( ctx, 1, 64, &d ) ) ) return rc;
+  alu_probe_kernel<<<gridCtas, 256, 0, ctx->stream>>>( iters, 12345u, (uint32_t*) d );
+  CHECK_LAUNCH( "alu_probe_kernel" );
+  return VVB_OK;
+}
 
 // ---- planes --------------------------------------------------------------------------------------------------
 int vvb_plane_free( vvb_ctx* ctx, int id )
@@ -491,41 +521,64 @@ int vvb_sad_search( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* b
   return VVB_OK;
 }
 
-int vvb_sad_pattern_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_mv* dPattern, int K,
-                         const vvb_me_par* par, uint32_t* dSad, vvb_best* dBest )
+int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_mv* dPattern, int K,
+                          const vvb_me_par* par, uint32_t* dCost, vvb_best* dBest )
 {
-  if( !ctx || !dBlocks || !dPattern || n < 0 || K < 1 || ( !dSad && !dBest ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !ctx || !dBlocks || !dPattern || n < 0 || K < 1 || ( !dCost && !dBest ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   int rc = checkSearchShape( ctx, orgPlane, refPlane, w, h );
   if( rc ) return rc;
   MePar mp;
   if( ( rc = makeMePar( ctx, par, mp ) ) ) return rc;
-  if( mp.subShift && ( h & ( ( 1 << mp.subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
+  if( dfunc != FAM_SAD ) mp.subShift = 0;
+  if( ( rc = checkDistShape( ctx, dfunc, w, h, mp.subShift ) ) ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const int G = pick_group( FAM_SAD, w, h >> mp.subShift );
+  const int G = dfunc == FAM_SAD ? pick_group( FAM_SAD, w, h >> mp.subShift ) : pick_group( dfunc, w, h );
   const Plane &op = ctx->planes.p[orgPlane], &rp = ctx->planes.p[refPlane];
-#define LAUNCH_PAT( GG ) sad_pattern_kernel<GG><<<n, 128, 0, ctx->stream>>>( op, rp, dBlocks, w, h, dPattern, K, mp, dSad, dBest )
+#define LAUNCH_PAT( GG ) cost_pattern_kernel<GG><<<n, 128, 0, ctx->stream>>>( op, rp, dBlocks, w, h, dfunc, dPattern, K, mp, dCost, dBest )
   switch( G ) { case 4: LAUNCH_PAT( 4 ); break; case 8: LAUNCH_PAT( 8 ); break; case 16: LAUNCH_PAT( 16 ); break; default: LAUNCH_PAT( 32 ); break; }
 #undef LAUNCH_PAT
-  CHECK_LAUNCH( "sad_pattern_kernel" );
+  CHECK_LAUNCH( "cost_pattern_kernel" );
   return VVB_OK;
+}
+
+int vvb_cost_pattern( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_mv* pattern, int K,
+                      const vvb_me_par* par, uint32_t* costOut, vvb_best* best )
+{
+  if( !ctx || !blocks || !pattern || n < 0 || K < 1 || ( !costOut && !best ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  void *dB, *dP, *dS = nullptr, *dO = nullptr; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 3, (size_t) K * sizeof( vvb_mv ), &dP ) ) ) return rc;
+  if( costOut && ( rc = scratch( ctx, 2, (size_t) n * K * 4, &dS ) ) ) return rc;
+  if( best && ( rc = scratch( ctx, 1, (size_t) n * sizeof( vvb_best ), &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+  CU( cudaMemcpyAsync( dP, pattern, (size_t) K * sizeof( vvb_mv ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_cost_pattern_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (const vvb_mv*) dP, K, par, (uint32_t*) dS, (vvb_best*) dO ) ) ) return rc;
+  if( costOut ) CU( cudaMemcpyAsync( costOut, dS, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( best ) CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+int vvb_sad_pattern_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_mv* dPattern, int K,
+                         const vvb_me_par* par, uint32_t* dSad, vvb_best* dBest )
+{
+  return vvb_cost_pattern_dev( ctx, FAM_SAD, orgPlane, refPlane, dBlocks, n, w, h, dPattern, K, par, dSad, dBest );
 }
 
 int vvb_sad_pattern( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_mv* pattern, int K,
                      const vvb_me_par* par, uint32_t* sadOut, vvb_best* best )
 {
-  if( !ctx || !blocks || !pattern || n < 0 || K < 1 || ( !sadOut && !best ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  return vvb_cost_pattern( ctx, FAM_SAD, orgPlane, refPlane, blocks, n, w, h, pattern, K, par, sadOut, best );
+}
+
+int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dBlocks, const vvb_best* dBest, int n )
+{
+  if( !ctx || !dBlocks || !dBest || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   if( n == 0 ) return VVB_OK;
-  void *dB, *dP, *dS = nullptr, *dO = nullptr; int rc;
-  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 3, (size_t) K * sizeof( vvb_mv ), &dP ) ) ) return rc;
-  if( sadOut && ( rc = scratch( ctx, 2, (size_t) n * K * 4, &dS ) ) ) return rc;
-  if( best && ( rc = scratch( ctx, 1, (size_t) n * sizeof( vvb_best ), &dO ) ) ) return rc;
-  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
-  CU( cudaMemcpyAsync( dP, pattern, (size_t) K * sizeof( vvb_mv ), cudaMemcpyHostToDevice, ctx->stream ) );
-  if( ( rc = vvb_sad_pattern_dev( ctx, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (const vvb_mv*) dP, K, par, (uint32_t*) dS, (vvb_best*) dO ) ) ) return rc;
-  if( sadOut ) CU( cudaMemcpyAsync( sadOut, dS, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
-  if( best ) CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( cudaSetDevice( ctx->device ) );
+  blocks_set_start_kernel<<<std::min( ( n + 255 ) / 256, ctx->numSMs * 8 ), 256, 0, ctx->stream>>>( dBlocks, dBest, n );
+  CHECK_LAUNCH( "blocks_set_start_kernel" );
   return VVB_OK;
 }
 
@@ -625,6 +678,27 @@ int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlan
   residual_from_planes_kernel<<<grid, 256, 0, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[predPlane], dBlocks, n, par->w, par->h, (int16_t*) dR );
   CHECK_LAUNCH( "residual_from_planes_kernel" );
   return vvb_fwd_trquant_dev( ctx, par, (const int16_t*) dR, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+}
+
+int vvb_fwd_trquant_planes( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, int predPlane, const vvb_block* blocks, int n,
+                            int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, uint8_t* needRdoq )
+{
+  if( !ctx || !par || !blocks || !q || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t area = (size_t) par->w * par->h;
+  void *dB, *dC = nullptr, *dQ, *dM; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * area * 2, &dQ ) ) || ( rc = scratch( ctx, 3, (size_t) n * 12, &dM ) ) ) return rc;
+  if( coef && ( rc = scratch( ctx, 2, (size_t) n * area * 4, &dC ) ) ) return rc;
+  int32_t* dSum = (int32_t*) dM; int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_fwd_trquant_planes_dev( ctx, par, orgPlane, predPlane, (const vvb_block*) dB, n, (int32_t*) dC, (int16_t*) dQ, dSum, dLast, dNr ) ) ) return rc;
+  CU( cudaMemcpyAsync( q, dQ, (size_t) n * area * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( coef )     CU( cudaMemcpyAsync( coef, dC, (size_t) n * area * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( absSum )   CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( lastPos )  CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
 }
 
 // ---- MCTF ----------------------------------------------------------------------------------------------------------

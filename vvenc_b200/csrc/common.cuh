@@ -42,7 +42,7 @@ template<int G> __device__ __forceinline__ unsigned gmask()
   if( G == 32 ) return 0xffffffffu;
   unsigned lane;
   asm( "mov.u32 %0, %%laneid;" : "=r"( lane ) );
-  return ( ( 1u << G ) - 1u ) << ( lane & ~( G - 1 ) );
+  return ( 0xffffffffu >> ( 32 - G ) ) << ( lane & ~( G - 1 ) );
 }
 template<int G> __device__ __forceinline__ uint32_t group_sum_u32( uint32_t v )
 {

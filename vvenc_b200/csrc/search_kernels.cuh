@@ -176,9 +176,9 @@ __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constan
 // fixed pattern around a start vector; one CTA per block, G-lane groups take candidates round-robin
 // ---------------------------------------------------------------------------------------------------------------
 template<int G>
-__global__ void __launch_bounds__( 128 ) sad_pattern_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
-                                                             const vvb_block* __restrict__ blocks, int w, int h, const vvb_mv* __restrict__ pattern, int K,
-                                                             const __grid_constant__ MePar par, uint32_t* __restrict__ sadOut, vvb_best* __restrict__ bestOut )
+__global__ void __launch_bounds__( 128 ) cost_pattern_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+                                                              const vvb_block* __restrict__ blocks, int w, int h, int fam, const vvb_mv* __restrict__ pattern, int K,
+                                                              const __grid_constant__ MePar par, uint32_t* __restrict__ sadOut, vvb_best* __restrict__ bestOut )
 {
   __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
   for( int i = threadIdx.x; i < VVB_MVCOST_ENTRIES; i += blockDim.x ) sMv[i] = par.tab.cost[i];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__( 128 ) sad_pattern_kernel( const __grid_consta
     if( inside )        // uniform per group
     {
       const int16_t* cur = refPlane.origin + (ptrdiff_t)( blk.y + my ) * refPlane.stride + blk.x + mx;
-      sad = group_sad<G>( org, orgPlane.stride, cur, refPlane.stride, w, h, par.subShift, lg );
+      sad = (uint32_t) group_dist<G>( fam, org, orgPlane.stride, cur, refPlane.stride, w, h, par.subShift, lg );
       const unsigned long long c = (unsigned long long) sad + mv_cost( par, sMv, mx, my, blk.pred_hor, blk.pred_ver );
       if( better( c, (uint32_t) k, bestCost, bestOrder ) ) { bestCost = c; bestOrder = (uint32_t) k; bestSad = sad; }
     }
@@ -217,6 +217,15 @@ __global__ void __launch_bounds__( 128 ) sad_pattern_kernel( const __grid_consta
     if( bestOrder == 0xffffffffu ) { b.dx = 0; b.dy = 0; b.sad = 0xffffffffu; b.cost = ~0ull; }
     else { const vvb_mv pm = pattern[bestOrder]; b.dx = (int16_t)( blk.start_x + pm.dx ); b.dy = (int16_t)( blk.start_y + pm.dy ); b.sad = bestSad; b.cost = bestCost; }
     bestOut[blockIdx.x] = b;
+  }
+}
+
+// chains device-resident stages: the best vector of a search becomes the start / prediction offset of the next stage
+__global__ void blocks_set_start_kernel( vvb_block* __restrict__ blocks, const vvb_best* __restrict__ best, int n )
+{
+  for( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+  {
+    blocks[i].start_x = best[i].dx; blocks[i].start_y = best[i].dy;
   }
 }
 

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_consta
     const int tu = base + team;
     const bool live = tu < n;
     __syncthreads();                                           // previous iteration's smem fully consumed; matrices visible
-    if( tt < 8 ) myRed[tt] = 0;
+    for( int i = tt; i < 8; i += T ) myRed[i] = 0;
     // ---- load residual (compact [h][w]) as 32-bit words
     if( live )
     {
