@@ -384,7 +384,7 @@ def main():
             pel_diffs += nb * nx * nx * n * n
         # ALU ceiling for the packed-SAD instruction mix
         ctas, iters = 148 * 8, 4096
-        t_probe = time_launch(lambda: chk(lib.vvb_alu_probe_dev(eng.h, ctas, iters)), reps=5)
+        t_probe = time_launch(lambda: chk(lib.vvb_alu_probe_dev(eng.h, ctas, iters, 1)), reps=5)
         alu_peak = ctas * 256 * iters * 16 / (t_probe * 1e-3)
         ach = comp_bytes / (t_search * 1e-3) / 1e9
         roofline = {'kernel': 'sad_search_kernel (4 launches per step: 8x8..64x64)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
@@ -392,7 +392,7 @@ def main():
                     'note': 'dense +-32 search re-uses every reference pel up to 4225x from shared memory: integer-ALU bound by construction (SURVEY 8d W2); '
                             'bytes = compulsory 2N^2 + 2(N+2R)^2 + 16 per block; see "alu" for the binding roof',
                     'alu': {'achieved': pel_diffs / (t_search * 1e-3) / 1e12, 'peak': alu_peak / 1e12, 'unit': 'Tpel-diff/s', 'frac': pel_diffs / (t_search * 1e-3) / alu_peak,
-                            'peak_source': 'alu_probe_kernel: same 2xVIMNMX.S16x2 + 2xIDP.2A mix on register operands, measured in this run'},
+                            'peak_source': 'alu_probe_kernel mode 1: the same VIMNMX.S16x2 + IDP.2A per pel pair on register operands, measured in this run'},
                     'share_of_step': t_search / ms_step}
         extra['kernel_ms'] = kt
         # HBM-streaming evidence: candidate-pool SAD / SATD, 16x16, pool >> L2 (2wh + 2wh/K + 8 bytes per candidate)
@@ -402,6 +402,7 @@ def main():
             pos = np.zeros(nb, dtype=V.POS_DT); pos['x'] = blocks_np[n]['x']; pos['y'] = blocks_np[n]['y']
             d_pos = dev(pos); d_out = torch.empty(nb * Kp, dtype=torch.int32, device='cuda')
             sweep = {}
+            chk(lib.vvb_pool_hint(eng.h, 1))
             for fam, name in ((V.DF_SAD, 'sad'), (V.DF_HAD, 'satd'), (V.DF_SSE, 'sse')):
                 t = time_launch(lambda fam=fam: chk(lib.vvb_dist_pool_dev(eng.h, fam, 0, P_(d_pos.data_ptr()), nb, n, n, Kp, P_(pool.data_ptr()), 0, P_(d_out.data_ptr()))), reps=5)
                 byt = nb * Kp * (2 * n * n + 2 * n * n / Kp + 8)

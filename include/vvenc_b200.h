@@ -50,7 +50,7 @@ void*       vvb_stream     ( vvb_ctx* ctx );                /* cudaStream_t of t
 int         vvb_launch_count( const vvb_ctx* ctx, uint64_t* kernels_launched );   /* kernels this context has launched so far */
 
 /* measurement aid (bench.py): issue-rate probe of the packed-SAD instruction mix; no reference counterpart */
-int         vvb_alu_probe_dev( vvb_ctx* ctx, int grid_ctas, int iters );
+int         vvb_alu_probe_dev( vvb_ctx* ctx, int grid_ctas, int iters, int mode /* 0: max-min SAD mix, 1: min-only mix of the dense search */ );
 
 /* ---- pictures ("planes") ---------------------------------------------------------------------------------
  * int16 sample planes (Pel, CommonLib/TypeDef.h:181) with a margin on all sides, like the encoder's padded
@@ -94,6 +94,8 @@ int vvb_dist_pool    ( vvb_ctx* ctx, int dfunc, int org_plane, const vvb_pos* bl
                        const int16_t* pool, int sub_shift, uint32_t* cost_out /* n_blocks*K */ );
 int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int org_plane, const vvb_pos* dev_blocks, int n_blocks, int w, int h, int K,
                        const int16_t* dev_pool, int sub_shift, uint32_t* dev_cost_out );
+/* promise for the _dev variant: every block x in the device-resident lists is a multiple of 8 pels (enables 16-byte streaming loads) */
+int vvb_pool_hint    ( vvb_ctx* ctx, int blocks_x_aligned_to_8 );
 
 /* ---- motion-search regimes (EncoderLib/InterSearch.cpp) ----------------------------------------------------
  * MV rate: cost += Distortion( sqrt(lambda) * bits ), bits = EG((x<<cost_scale) - pred_hor >> imv_shift) + EG(y...)

@@ -46,7 +46,7 @@ SYMBOLS = {
     'vvb_synchronize': (c_i, [c_p]),
     'vvb_stream': (c_p, [c_p]),
     'vvb_launch_count': (c_i, [c_p, ctypes.POINTER(ctypes.c_uint64)]),
-    'vvb_alu_probe_dev': (c_i, [c_p, c_i, c_i]),
+    'vvb_alu_probe_dev': (c_i, [c_p, c_i, c_i, c_i]),
     'vvb_plane_upload': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),
     'vvb_plane_bind_dev': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),
     'vvb_plane_free': (c_i, [c_p, c_i]),
@@ -58,6 +58,7 @@ SYMBOLS = {
     'vvb_fix_wsse_block': (ctypes.c_uint64, [c_p, c_p, c_i, c_p, c_i, c_i, c_i, ctypes.c_uint32, ctypes.POINTER(c_i)]),
     'vvb_dist_pool': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     'vvb_dist_pool_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'vvb_pool_hint': (c_i, [c_p, c_i]),
     'vvb_sad_search': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, ctypes.POINTER(vvb_me_par), c_p, c_i, c_p]),
     'vvb_sad_search_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_p, c_i, c_p]),
     'vvb_sad_pattern': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),

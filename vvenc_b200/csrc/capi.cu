@@ -144,6 +144,7 @@ __global__ void fix_wsse_kernel( const int16_t* org, int so, const int16_t* cur,
 
 // Issue-rate probe for the packed-SAD instruction mix (2 x VIMNMX.S16x2 + 2 x IDP.2A per pel pair) on register operands:
 // the measured ceiling the dense search kernel is compared against (bench.py "alu" roofline).
+template<int MODE>
 __global__ void __launch_bounds__( 256 ) alu_probe_kernel( int iters, uint32_t seed, uint32_t* out )
 {
   uint32_t a[8], b[8]; int acc[8];
@@ -152,7 +153,23 @@ __global__ void __launch_bounds__( 256 ) alu_probe_kernel( int iters, uint32_t s
   for( int it = 0; it < iters; it++ )
   {
 #pragma unroll
-    for( int i = 0; i < 8; i++ ) { acc[i] = sad2_acc( a[i], b[i], acc[i] ); a[i] += 0x00010001u; }
+    for( int i = 0; i < 8; i++ )
+    {
+      // exactly the 4 instructions of one packed SAD step; feeding max/min back keeps the loop body from being hoisted
+      if( MODE == 0 )      // list / pattern kernels: |a-b| = max - min
+      {
+        const uint32_t mx = __vmaxs2( a[i], b[i] ), mn = __vmins2( a[i], b[i] );
+        acc[i] = __dp2a_lo( (int) mx, 0x00000101, acc[i] );
+        acc[i] = __dp2a_lo( (int) mn, (int) 0x0000ffffu, acc[i] );
+        a[i] = mx; b[i] = mn;
+      }
+      else                 // dense search: only sum min(a,b) is per-candidate work
+      {
+        const uint32_t mn = __vmins2( a[i], b[i] );
+        acc[i] = __dp2a_lo( (int) mn, (int) 0x0000ffffu, acc[i] );
+        a[i] = b[i]; b[i] = mn;
+      }
+    }
   }
   int s = 0;
 #pragma unroll
@@ -233,13 +250,14 @@ void* vvb_stream( vvb_ctx* ctx ) { return ctx ? (void*) ctx->stream : nullptr; }
 int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) return VVB_ERR_ARG; *k = ctx->launches; return VVB_OK; }
 
 // launches the ALU probe: grid_ctas CTAs x 256 threads x iters iterations x 8 packed SADs (16 pel differences) each
-int vvb_alu_probe_dev( vvb_ctx* ctx, int gridCtas, int iters )
+int vvb_alu_probe_dev( vvb_ctx* ctx, int gridCtas, int iters, int mode )
 {
   if( !ctx || gridCtas < 1 || iters < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   CU( cudaSetDevice( ctx->device ) );
   void* d; int rc;
   if( ( rc = scratch( ctx, 1, 64, &d ) ) ) return rc;
-  alu_probe_kernel<<<gridCtas, 256, 0, ctx->stream>>>( iters, 12345u, (uint32_t*) d );
+  if( mode == 0 ) alu_probe_kernel<0><<<gridCtas, 256, 0, ctx->stream>>>( iters, 12345u, (uint32_t*) d );
+  else            alu_probe_kernel<1><<<gridCtas, 256, 0, ctx->stream>>>( iters, 12345u, (uint32_t*) d );
   CHECK_LAUNCH( "alu_probe_kernel" );
   return VVB_OK;
 }
@@ -248,7 +266,7 @@ int vvb_alu_probe_dev( vvb_ctx* ctx, int gridCtas, int iters )
 int vvb_plane_free( vvb_ctx* ctx, int id )
 {
   if( !ctx || id < 0 || id >= VVB_MAX_PLANES - 2 ) return fail( ctx, VVB_ERR_ARG, "plane id out of range" );
-  if( ctx->owned[id] ) { cudaStreamSynchronize( ctx->stream ); cudaFree( ctx->owned[id] ); ctx->owned[id] = nullptr; }
+  if( ctx->owned[id] ) { cudaStreamSynchronize( ctx->stream ); cudaFree( ctx->owned[id] ); ctx->owned[id] = nullptr; ctx->ownedBytes[id] = 0; }
   ctx->planes.p[id] = Plane{};
   return VVB_OK;
 }
@@ -258,13 +276,17 @@ int vvb_plane_upload( vvb_ctx* ctx, int id, const int16_t* origin, int stride, i
   if( !ctx || !origin || id < 0 || id >= VVB_MAX_PLANES - 2 || width <= 0 || height <= 0 || margin < 0 || stride < width + 2 * margin )
     return fail( ctx, VVB_ERR_ARG, "bad plane arguments" );
   CU( cudaSetDevice( ctx->device ) );
-  vvb_plane_free( ctx, id );
   const int dw = width + 2 * margin, dh = height + 2 * margin;
   const int dstride = ( dw + 7 ) & ~7;                                 // rows 16-byte aligned
-  void* d = nullptr;
-  CU( cudaMalloc( &d, (size_t) dstride * dh * sizeof( int16_t ) + 256 ) );
+  const size_t bytes = (size_t) dstride * dh * sizeof( int16_t ) + 256;
+  void* d = ctx->owned[id];
+  if( !d || ctx->ownedBytes[id] < bytes )                              // a new picture of the same geometry re-uses the allocation
+  {
+    vvb_plane_free( ctx, id );
+    CU( cudaMalloc( &d, bytes ) );
+    ctx->ownedBytes[id] = bytes;
+  }
   const int16_t* src = origin - (ptrdiff_t) margin * stride - margin;
-  // margin rounded so that sample (0,0) keeps 16-byte alignment when margin % 8 == 0
   CU( cudaMemcpy2DAsync( d, (size_t) dstride * 2, src, (size_t) stride * 2, (size_t) dw * 2, dh, cudaMemcpyHostToDevice, ctx->stream ) );
   ctx->owned[id] = d;
   Plane p; p.origin = reinterpret_cast<int16_t*>( d ) + (size_t) margin * dstride + margin; p.stride = dstride; p.width = width; p.height = height; p.margin = margin; p.bitDepth = bitDepth;
@@ -416,6 +438,15 @@ uint64_t vvb_fix_wsse_block( vvb_ctx* ctx, const int16_t* org, int orgStride, co
   return result;
 }
 
+// _dev callers state whether every block x position in their (device-resident) lists is a multiple of 8 pels; only then the
+// 16-byte streaming kernels are used (default: not assumed).
+int vvb_pool_hint( vvb_ctx* ctx, int blocksXAlignedTo8 )
+{
+  if( !ctx ) return VVB_ERR_ARG;
+  ctx->poolBlocksAligned = blocksXAlignedTo8 != 0;
+  return VVB_OK;
+}
+
 // ---- candidate pool ----------------------------------------------------------------------------------------------
 int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* dBlocks, int nBlocks, int w, int h, int K, const int16_t* dPool, int subShift, uint32_t* dOut )
 {
@@ -425,15 +456,54 @@ int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* dBl
   if( rc ) return rc;
   if( nBlocks == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const int G = pick_group( dfunc, w, h );
   const long long total = (long long) nBlocks * K;
-  const long long threads = total * G;
-  const int block = 256;
-  const int grid = (int) std::min<long long>( ( threads + block - 1 ) / block, (long long) ctx->numSMs * 32 );
   const Plane& op = ctx->planes.p[orgPlane];
+  // fast streaming paths need 16-byte aligned rows of the original (block x on a multiple of 8 is checked on the device side by
+  // construction of the batch: callers with unaligned block positions get the generic kernel via the alignment test below)
+  const bool planeAligned = ( ( (uintptr_t) op.origin & 15 ) == 0 ) && ( ( op.stride & 7 ) == 0 ) && ( ( (uintptr_t) dPool & 15 ) == 0 );
+  const bool posAligned = ctx->poolBlocksAligned;     // set by the host entry point after inspecting the positions; _dev callers promise it via vvb_pool_hint
+  bool launched = false;
+  if( planeAligned && posAligned && w >= 8 && ( dfunc == FAM_SAD || dfunc == FAM_SSE ) )
+  {
+    const int rows = h >> ( dfunc == FAM_SAD ? subShift : 0 );
+    const int chunks = rows * ( w >> 3 );
+    int G = 4; while( G < 32 && chunks / G > 4 ) G <<= 1;             // aim at L = 4 chunks (64 bytes) per lane per pass
+    const long long wantGroups = (long long) ctx->numSMs * 2048 / G * 2;
+    int kSplit = 1; while( (long long) nBlocks * kSplit < wantGroups && kSplit < K ) kSplit <<= 1;
+    if( kSplit > K ) kSplit = K;
+    const long long threads = (long long) nBlocks * kSplit * G;
+    const int grid = (int) std::min<long long>( ( threads + 255 ) / 256, (long long) ctx->numSMs * 32 );
+    const int ss = dfunc == FAM_SAD ? subShift : 0;
+#define LAUNCH_SP( GG, SS ) sad_pool_stream_kernel<GG, 4, SS><<<grid, 256, 0, ctx->stream>>>( op, dBlocks, nBlocks, w, h, K, kSplit, ss, dPool, dOut )
+    if( dfunc == FAM_SAD ) { switch( G ) { case 4: LAUNCH_SP( 4, false ); break; case 8: LAUNCH_SP( 8, false ); break; case 16: LAUNCH_SP( 16, false ); break; default: LAUNCH_SP( 32, false ); break; } }
+    else                   { switch( G ) { case 4: LAUNCH_SP( 4, true ); break; case 8: LAUNCH_SP( 8, true ); break; case 16: LAUNCH_SP( 16, true ); break; default: LAUNCH_SP( 32, true ); break; } }
+#undef LAUNCH_SP
+    launched = true;
+  }
+  else if( planeAligned && posAligned && ( dfunc == FAM_HAD || dfunc == FAM_HAD_2SAD ) && ( w & 7 ) == 0 && ( h & 7 ) == 0 &&
+           !( w > h && ( w & 15 ) == 0 ) && !( w < h && ( h & 15 ) == 0 ) )
+  {
+    // tile dispatch lands on 8x8 (RdCost.cpp:1836-1905 with the rectangular 16x8 / 8x16 cases excluded above)
+    const int T = ( w >> 3 ) * ( h >> 3 );
+    const int LPC = T >= 32 ? 32 : T;
+    const long long threads = total * LPC;
+    const int grid = (int) std::min<long long>( ( threads + 127 ) / 128, (long long) ctx->numSMs * 32 );
+    const int two = dfunc == FAM_HAD_2SAD ? 1 : 0;
+#define LAUNCH_HP( LL ) had8_pool_stream_kernel<LL><<<grid, 128, 0, ctx->stream>>>( op, dBlocks, nBlocks, w, h, K, two, dPool, dOut )
+    switch( LPC ) { case 1: LAUNCH_HP( 1 ); break; case 2: LAUNCH_HP( 2 ); break; case 4: LAUNCH_HP( 4 ); break; case 8: LAUNCH_HP( 8 ); break; case 16: LAUNCH_HP( 16 ); break; default: LAUNCH_HP( 32 ); break; }
+#undef LAUNCH_HP
+    launched = true;
+  }
+  if( !launched )
+  {
+    const int G = pick_group( dfunc, w, h );
+    const long long threads = total * G;
+    const int block = 256;
+    const int grid = (int) std::min<long long>( ( threads + block - 1 ) / block, (long long) ctx->numSMs * 32 );
 #define LAUNCH_POOL( GG ) dist_pool_kernel<GG><<<grid, block, 0, ctx->stream>>>( op, dBlocks, nBlocks, w, h, K, dfunc, subShift, dPool, dOut )
-  switch( G ) { case 4: LAUNCH_POOL( 4 ); break; case 8: LAUNCH_POOL( 8 ); break; case 16: LAUNCH_POOL( 16 ); break; default: LAUNCH_POOL( 32 ); break; }
+    switch( G ) { case 4: LAUNCH_POOL( 4 ); break; case 8: LAUNCH_POOL( 8 ); break; case 16: LAUNCH_POOL( 16 ); break; default: LAUNCH_POOL( 32 ); break; }
 #undef LAUNCH_POOL
+  }
   CHECK_LAUNCH( "dist_pool_kernel" );
   return VVB_OK;
 }
@@ -445,6 +515,9 @@ int vvb_dist_pool( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* blocks,
   void *dB, *dP, *dO; int rc;
   const size_t total = (size_t) nBlocks * K;
   if( ( rc = scratch( ctx, 0, (size_t) nBlocks * sizeof( vvb_pos ), &dB ) ) || ( rc = scratch( ctx, 2, total * w * h * 2, &dP ) ) || ( rc = scratch( ctx, 1, total * 4, &dO ) ) ) return rc;
+  bool aligned = true;
+  for( int i = 0; i < nBlocks && aligned; i++ ) aligned = ( blocks[i].x & 7 ) == 0;
+  ctx->poolBlocksAligned = aligned;
   CU( cudaMemcpyAsync( dB, blocks, (size_t) nBlocks * sizeof( vvb_pos ), cudaMemcpyHostToDevice, ctx->stream ) );
   CU( cudaMemcpyAsync( dP, pool, total * w * h * 2, cudaMemcpyHostToDevice, ctx->stream ) );
   if( ( rc = vvb_dist_pool_dev( ctx, dfunc, orgPlane, (const vvb_pos*) dB, nBlocks, w, h, K, (const int16_t*) dP, subShift, (uint32_t*) dO ) ) ) return rc;
@@ -474,14 +547,18 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
   if( mp.subShift && ( h & ( ( 1 << mp.subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const int nStrips = ( maxNx + SS_STRIP - 1 ) / SS_STRIP;
-  const int ws = w + nStrips * SS_STRIP + 8, winH = h + maxNy - 1;
-  const size_t smem = ( (size_t) winH * ws + (size_t) w * h ) * sizeof( int16_t ) + 16;
+  const SearchSmem L = search_smem( w, h, maxNx, maxNy );
+  const size_t smem = (size_t) L.total + 16;
   if( smem > 220 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search window does not fit shared memory (reduce the range)" );
-  // block size: enough threads for the (ny x strips) items, rounded to warps, capped at 256
-  const int items = maxNy * nStrips;
-  int bd = 256;
-  if( items < 256 ) bd = std::max( 32, ( items + 31 ) & ~31 );
+  // block size: the multiple of 32 in 64..256 that wastes the fewest thread slots on the (ny x strips) work items; ties -> larger
+  const int items = maxNy * ( ( maxNx + SS_STRIP - 1 ) / SS_STRIP );
+  int bd = 256; double bestEff = -1.0;
+  for( int cand = 64; cand <= 256; cand += 32 )
+  {
+    const int rounds = ( items + cand - 1 ) / cand;
+    const double eff = (double) items / ( (double) rounds * cand );
+    if( eff >= bestEff - 1e-9 && ( w * h >= 1024 ? cand >= 128 : true ) ) { bestEff = std::max( bestEff, eff ); bd = cand; }
+  }
   sad_search_kernel<<<n, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, w, h, mp, dTables, tableStride, dBest );
   CHECK_LAUNCH( "sad_search_kernel" );
   return VVB_OK;

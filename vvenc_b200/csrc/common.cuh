@@ -78,9 +78,11 @@ struct vvb_ctx
   cudaStream_t   stream   = nullptr;
   vvb::PlaneTable planes  {};
   void*          owned[VVB_MAX_PLANES] = {};
+  size_t         ownedBytes[VVB_MAX_PLANES] = {};
   bool           bound[VVB_MAX_PLANES] = {};
   std::string    err;
   uint64_t       launches = 0;
+  bool           poolBlocksAligned = false;   // see vvb_pool_hint
   int            numSMs   = 148;
   // device-side constant data
   int8_t*        d_trTable   = nullptr;     // all transform matrices (vvc_tables.h)

@@ -331,4 +331,160 @@ __global__ void __launch_bounds__( 256 ) dist_pool_kernel( const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// streaming fast paths for uniform candidate pools (HBM bound): many independent 16-byte loads in flight per lane,
+// no shared memory, the original block is re-read through L1.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream( const uint4* p )
+{
+  uint4 r;
+  asm volatile( "ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( r.x ), "=r"( r.y ), "=r"( r.z ), "=r"( r.w ) : "l"( p ) );
+  return r;
+}
+
+// SAD / SSE over a pool: G lanes per candidate, L = chunks (8 pels) per lane per pass, candidates of one block are walked by the same
+// group so that the original chunks stay in registers.  Requires w >= 8 (chunks never straddle rows) and 16-byte aligned original rows.
+template<int G, int L, bool SSE>
+__global__ void __launch_bounds__( 256 ) sad_pool_stream_kernel( const __grid_constant__ Plane orgPlane, const vvb_pos* __restrict__ blocks, int nBlocks,
+                                                                 int w, int h, int K, int kSplit, int subShift, const int16_t* __restrict__ pool,
+                                                                 uint32_t* __restrict__ out )
+{
+  const int lg = threadIdx.x & ( G - 1 );
+  const long long groupsPerGrid = ( (long long) gridDim.x * blockDim.x ) / G;
+  const long long jobs = (long long) nBlocks * kSplit;                 // job = (block, slice of its K candidates)
+  const int cpr = w >> 3;                                              // chunks per row
+  const int rows = h >> subShift;
+  const int chunks = rows * cpr;                                       // visited chunks per candidate
+  const int passes = ( chunks + G * L - 1 ) / ( G * L );
+  const int kPer = ( K + kSplit - 1 ) / kSplit;
+  const unsigned mk = gmask<G>();
+  for( long long job = ( (long long) blockIdx.x * blockDim.x + threadIdx.x ) / G; job < jobs; job += groupsPerGrid )
+  {
+    const int b = (int)( job / kSplit ), ks = (int)( job - (long long) b * kSplit );
+    const int k0 = ks * kPer, k1 = min( K, k0 + kPer );
+    const vvb_pos p = blocks[b];
+    const int16_t* org = orgPlane.origin + (ptrdiff_t) p.y * orgPlane.stride + p.x;
+    for( int k = k0; k < k1; k++ )
+    {
+      const uint4* cur = reinterpret_cast<const uint4*>( pool + ( (size_t) b * K + k ) * w * h );
+      int acc = 0; unsigned long long acc64 = 0;
+      for( int ps = 0; ps < passes; ps++ )
+      {
+        uint4 c[L], o[L];
+#pragma unroll
+        for( int i = 0; i < L; i++ )
+        {
+          const int ch = ( ps * L + i ) * G + lg;
+          if( ch < chunks )
+          {
+            const int r = ch / cpr, cc = ch - r * cpr, y = r << subShift;
+            c[i] = ld_stream( cur + y * cpr + cc );
+            o[i] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc );
+          }
+          else { c[i] = make_uint4( 0, 0, 0, 0 ); o[i] = c[i]; }
+        }
+#pragma unroll
+        for( int i = 0; i < L; i++ )
+        {
+          if( !SSE )
+          {
+            acc = sad2_acc( o[i].x, c[i].x, acc ); acc = sad2_acc( o[i].y, c[i].y, acc );
+            acc = sad2_acc( o[i].z, c[i].z, acc ); acc = sad2_acc( o[i].w, c[i].w, acc );
+          }
+          else
+          {
+            const uint32_t ow[4] = { o[i].x, o[i].y, o[i].z, o[i].w }, cw[4] = { c[i].x, c[i].y, c[i].z, c[i].w };
+#pragma unroll
+            for( int j = 0; j < 4; j++ )
+            {
+              const int d0 = lo16( ow[j] ) - lo16( cw[j] ), d1 = hi16( ow[j] ) - hi16( cw[j] );
+              acc64 += (unsigned long long)( (unsigned) ( d0 * d0 ) ) + (unsigned long long)( (unsigned) ( d1 * d1 ) );
+            }
+          }
+        }
+      }
+      if( !SSE )
+      {
+        uint32_t v = (uint32_t) acc;
+#pragma unroll
+        for( int m = G >> 1; m > 0; m >>= 1 ) v += __shfl_xor_sync( mk, v, m );
+        if( lg == 0 ) out[(size_t) b * K + k] = v << subShift;
+      }
+      else
+      {
+#pragma unroll
+        for( int m = G >> 1; m > 0; m >>= 1 ) acc64 += __shfl_xor_sync( mk, acc64, m );
+        if( lg == 0 ) out[(size_t) b * K + k] = (uint32_t) acc64;
+      }
+    }
+  }
+}
+
+// SATD with 8x8 tiles (every block whose dispatch lands on xCalcHADs8x8, RdCost.cpp:1894-1905): ONE LANE PER TILE, the whole 8x8
+// Hadamard in registers (no shuffles); LPC = min(tiles, 32) lanes per candidate.  Also serves HAD_2SAD (min(SATD, 2 SAD)).
+template<int LPC>
+__global__ void __launch_bounds__( 128 ) had8_pool_stream_kernel( const __grid_constant__ Plane orgPlane, const vvb_pos* __restrict__ blocks, int nBlocks,
+                                                                  int w, int h, int K, int with2Sad, const int16_t* __restrict__ pool, uint32_t* __restrict__ out )
+{
+  const int lg = threadIdx.x & ( LPC - 1 );
+  const long long groupsPerGrid = ( (long long) gridDim.x * blockDim.x ) / LPC;
+  const long long total = (long long) nBlocks * K;
+  const int tilesX = w >> 3, T = tilesX * ( h >> 3 );
+  const unsigned mk = gmask<LPC>();
+  for( long long ci = ( (long long) blockIdx.x * blockDim.x + threadIdx.x ) / LPC; ci < total; ci += groupsPerGrid )
+  {
+    const int b = (int)( ci / K );
+    const vvb_pos p = blocks[b];
+    const int16_t* org = orgPlane.origin + (ptrdiff_t) p.y * orgPlane.stride + p.x;
+    const int16_t* cur = pool + (size_t) ci * w * h;
+    uint32_t hadSum = 0, sadSum = 0;
+    for( int t = lg; t < T; t += LPC )
+    {
+      const int ty = t / tilesX, tx = t - ty * tilesX;
+      uint4 c[8], o[8];
+#pragma unroll
+      for( int r = 0; r < 8; r++ ) c[r] = ld_stream( reinterpret_cast<const uint4*>( cur + ( ty * 8 + r ) * w + tx * 8 ) );
+#pragma unroll
+      for( int r = 0; r < 8; r++ ) o[r] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t)( ty * 8 + r ) * orgPlane.stride + tx * 8 ) );
+      int d[64];
+#pragma unroll
+      for( int r = 0; r < 8; r++ )
+      {
+        d[8*r+0] = lo16( o[r].x ) - lo16( c[r].x ); d[8*r+1] = hi16( o[r].x ) - hi16( c[r].x );
+        d[8*r+2] = lo16( o[r].y ) - lo16( c[r].y ); d[8*r+3] = hi16( o[r].y ) - hi16( c[r].y );
+        d[8*r+4] = lo16( o[r].z ) - lo16( c[r].z ); d[8*r+5] = hi16( o[r].z ) - hi16( c[r].z );
+        d[8*r+6] = lo16( o[r].w ) - lo16( c[r].w ); d[8*r+7] = hi16( o[r].w ) - hi16( c[r].w );
+      }
+      if( with2Sad )
+      {
+#pragma unroll
+        for( int i = 0; i < 64; i++ ) sadSum += (uint32_t) abs( d[i] );
+      }
+      // 2-D Walsh-Hadamard: the index bits 0..5 are butterflied one after another (order-free for sum|.| and for the DC term)
+#pragma unroll
+      for( int bit = 0; bit < 6; bit++ )
+      {
+#pragma unroll
+        for( int i = 0; i < 64; i++ )
+        {
+          if( !( i & ( 1 << bit ) ) )
+          {
+            const int a = d[i], bb = d[i | ( 1 << bit )];
+            d[i] = a + bb; d[i | ( 1 << bit )] = a - bb;
+          }
+        }
+      }
+      uint32_t s = 0;
+#pragma unroll
+      for( int i = 0; i < 64; i++ ) s += (uint32_t) abs( d[i] );
+      const uint32_t dc = (uint32_t) abs( d[0] );
+      s = s - dc + ( dc >> 2 );                        // RdCost.cpp:1316-1318
+      hadSum += ( s + 2 ) >> 2;                        // :1319
+    }
+#pragma unroll
+    for( int m = LPC >> 1; m > 0; m >>= 1 ) { hadSum += __shfl_xor_sync( mk, hadSum, m ); sadSum += __shfl_xor_sync( mk, sadSum, m ); }
+    if( lg == 0 ) out[ci] = with2Sad ? min( hadSum, 2u * sadSum ) : hadSum;
+  }
+}
+
 } // namespace vvb

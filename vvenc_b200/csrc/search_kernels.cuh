@@ -35,67 +35,138 @@ __device__ __forceinline__ bool better( unsigned long long c, uint32_t o, unsign
 #define SS_STRIP 8          // candidates per strip (consecutive dx)
 #define SS_XCHUNK 16        // original pels consumed per inner step
 
-// smem layout: win[(h + ny - 1)][ws] int16 (ws even, >= w + nxPad), org[h][w]
+// smem layout: win[winH][ws] int16 | org[h][w] int16 | box[winH][nxp] uint32 | bitsX[nxp], bitsY[ny] uint8 (packed in uint32 words)
+//
+// SAD via  sum|a-b| = sum a + sum b - 2 sum min(a,b):
+//   sum a           : once per block
+//   sum b (box sum) : for every candidate from row-sliding sums of the staged window (O(window) work, shared by all candidates)
+//   sum min(a,b)    : the only per-(candidate, pel) work: VIMNMX.S16x2 + IDP.2A per pel PAIR, i.e. one instruction per pel difference
+// All three are exact integers, so the result is bit-identical to the direct sum.
+struct SearchSmem { int ws, winH, nxp, offOrg, offBox, offBits, total; };
+
+__host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny )
+{
+  SearchSmem s;
+  const int nStrips = ( nx + SS_STRIP - 1 ) / SS_STRIP;
+  s.nxp  = nStrips * SS_STRIP;
+  s.ws   = w + s.nxp + 8;
+  s.winH = h + ny - 1;
+  s.offOrg  = s.winH * s.ws * 2;                       // bytes
+  s.offBox  = s.offOrg + w * h * 2;
+  s.offBits = s.offBox + s.winH * s.nxp * 4;
+  s.total   = s.offBits + ( ( s.nxp + ny + 15 ) & ~15 ) * 4;
+  return s;
+}
+
 __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                             const vvb_block* __restrict__ blocks, int w, int h, const __grid_constant__ MePar par,
                                                             uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut )
 {
   extern __shared__ __align__( 16 ) unsigned char smemRaw[];
   __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
-  for( int i = threadIdx.x; i < VVB_MVCOST_ENTRIES; i += blockDim.x ) sMv[i] = par.tab.cost[i];
+  __shared__ int sSumA;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nWarps = nthr >> 5;
+  for( int i = tid; i < VVB_MVCOST_ENTRIES; i += nthr ) sMv[i] = par.tab.cost[i];
+  if( tid == 0 ) sSumA = 0;
   const vvb_block blk = blocks[blockIdx.x];
   const int nx = blk.right - blk.left + 1, ny = blk.bottom - blk.top + 1;
   const int nStrips = ( nx + SS_STRIP - 1 ) / SS_STRIP;
-  const int winW = w + nStrips * SS_STRIP;                 // multiple of 8 pels beyond w: every strip can read w + 8 pels (+1 word slack below)
-  const int ws = winW + 8;                                  // row pitch in pels (even, keeps 16-byte alignment of rows)
-  const int winH = h + ny - 1;
-  int16_t* win  = reinterpret_cast<int16_t*>( smemRaw );
-  int16_t* orgS = win + (size_t) winH * ws;
+  const SearchSmem L = search_smem( w, h, nx, ny );
+  const int ws = L.ws, winH = L.winH, nxp = L.nxp;
+  int16_t*  win   = reinterpret_cast<int16_t*>( smemRaw );
+  int16_t*  orgS  = reinterpret_cast<int16_t*>( smemRaw + L.offOrg );
+  uint32_t* box   = reinterpret_cast<uint32_t*>( smemRaw + L.offBox );      // [winH][nxp]: row sums first, then (in place) box sums for rows < ny
+  int*      bitsX = reinterpret_cast<int*>( smemRaw + L.offBits );          // [nxp]
+  int*      bitsY = bitsX + nxp;                                            // [ny]
+  const int step = 1 << par.subShift;
 
-  // ---- stage window (origin = block position + (left, top)) and original block
+  // ---- stage window (origin = block position + (left, top)) and original block; one window row per warp pass
   {
     const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
     const int validW = w + nx - 1;
-    for( int i = threadIdx.x; i < winH * ws; i += blockDim.x )
+    for( int r = warp; r < winH; r += nWarps )
     {
-      const int r = i / ws, c = i - r * ws;
-      win[i] = c < validW ? __ldg( src + (ptrdiff_t) r * refPlane.stride + c ) : (int16_t) 0;
+      const int16_t* srow = src + (ptrdiff_t) r * refPlane.stride;
+      int16_t* drow = win + r * ws;
+      for( int c = lane; c < ws; c += 32 ) drow[c] = c < validW ? __ldg( srow + c ) : (int16_t) 0;
     }
     const int16_t* so = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
-    for( int i = threadIdx.x; i < w * h; i += blockDim.x )
+    int sumA = 0;
+    for( int i = tid; i < w * h; i += nthr )
     {
       const int r = i / w, c = i - r * w;
-      orgS[i] = __ldg( so + (ptrdiff_t) r * orgPlane.stride + c );
+      const int16_t v = __ldg( so + (ptrdiff_t) r * orgPlane.stride + c );
+      orgS[i] = v;
+      if( ( r & ( step - 1 ) ) == 0 ) sumA += v;
+    }
+#pragma unroll
+    for( int m = 16; m > 0; m >>= 1 ) sumA += __shfl_xor_sync( 0xffffffffu, sumA, m );
+    __syncthreads();                                   // sSumA initialised, window visible
+    if( lane == 0 && sumA ) atomicAdd( &sSumA, sumA );
+    // MV-rate bit counts per column / row of the window (RdCost.h:183-203)
+    for( int i = tid; i < nxp; i += nthr ) bitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - blk.pred_hor ) >> par.imvShift );
+    for( int i = tid; i < ny;  i += nthr ) bitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - blk.pred_ver ) >> par.imvShift );
+  }
+  // ---- row sums Hs[r][cx] = sum_{x<w} win[r][cx+x]: one task = (row, strip of 8 cx)
+  for( int t = tid; t < winH * nStrips; t += nthr )
+  {
+    const int r = t / nStrips, st = t - r * nStrips;
+    const int16_t* row = win + r * ws + st * SS_STRIP;
+    int s = 0;
+    for( int x = 0; x < w; x++ ) s += row[x];
+    uint32_t* dst = box + r * nxp + st * SS_STRIP;
+    dst[0] = (uint32_t) s;
+#pragma unroll
+    for( int k = 1; k < SS_STRIP; k++ ) { s += row[w + k - 1] - row[k - 1]; dst[k] = (uint32_t) s; }
+  }
+  __syncthreads();
+  // ---- box sums in place: B[cy][cx] = sum_{k < h/step} Hs[cy + k*step][cx]; rows of one phase (cy mod step) only depend on that phase
+  {
+    const int m = h >> par.subShift;
+    for( int t = tid; t < nxp * step; t += nthr )
+    {
+      const int cx = t % nxp, p = t / nxp;
+      if( p < ny )
+      {
+        int cur = 0;
+        for( int k = 0; k < m; k++ ) cur += (int) box[( p + k * step ) * nxp + cx];
+        int prevTop = (int) box[p * nxp + cx];
+        box[p * nxp + cx] = (uint32_t) cur;
+        for( int cy = p + step; cy < ny; cy += step )
+        {
+          cur += (int) box[( cy + ( m - 1 ) * step ) * nxp + cx] - prevTop;
+          prevTop = (int) box[cy * nxp + cx];
+          box[cy * nxp + cx] = (uint32_t) cur;
+        }
+      }
     }
   }
   __syncthreads();
+  const int sumA = sSumA;
 
-  const int step = 1 << par.subShift;
   unsigned long long bestCost = ~0ull; uint32_t bestOrder = 0xffffffffu, bestSad = 0;
-
   const int items = ny * nStrips;
-  for( int it = threadIdx.x; it < items; it += blockDim.x )
+  for( int it = tid; it < items; it += nthr )
   {
     const int cy = it / nStrips, st = it - cy * nStrips;
     const int cx0 = st * SS_STRIP;
-    int acc[SS_STRIP];
+    int acc[SS_STRIP];                                 // = - sum min(org, ref)
 #pragma unroll
     for( int k = 0; k < SS_STRIP; k++ ) acc[k] = 0;
 
     for( int y = 0; y < h; y += step )
     {
       const uint32_t* orow = reinterpret_cast<const uint32_t*>( orgS + y * w );
-      const uint32_t* rrow = reinterpret_cast<const uint32_t*>( win + ( cy + y ) * ws + cx0 );   // cx0 multiple of 8 -> 16-byte aligned
+      const uint32_t* rrow = reinterpret_cast<const uint32_t*>( win + ( cy + y ) * ws + cx0 );   // cx0 multiple of 8 -> 16-byte aligned when ws % 8 == 0
       if( w >= SS_XCHUNK )
       {
         for( int x = 0; x < w; x += SS_XCHUNK )
         {
-          uint32_t o[SS_XCHUNK / 2], r[SS_XCHUNK / 2 + SS_STRIP / 2 + 1];
+          uint32_t o[SS_XCHUNK / 2], r[SS_XCHUNK / 2 + SS_STRIP / 2];
 #pragma unroll
           for( int i = 0; i < SS_XCHUNK / 2; i += 4 ) *reinterpret_cast<uint4*>( &o[i] ) = *reinterpret_cast<const uint4*>( orow + x / 2 + i );
 #pragma unroll
           for( int i = 0; i < SS_XCHUNK / 2 + SS_STRIP / 2; i += 4 ) *reinterpret_cast<uint4*>( &r[i] ) = *reinterpret_cast<const uint4*>( rrow + x / 2 + i );
-          r[SS_XCHUNK / 2 + SS_STRIP / 2] = rrow[x / 2 + SS_XCHUNK / 2 + SS_STRIP / 2];
 #pragma unroll
           for( int k = 0; k < SS_STRIP; k++ )
           {
@@ -103,18 +174,18 @@ __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constan
             for( int i = 0; i < SS_XCHUNK / 2; i++ )
             {
               const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
-              acc[k] = sad2_acc( o[i], rv, acc[k] );
+              acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
             }
           }
         }
       }
       else
       {
-        // w = 4 or 8 (2 or 4 words of original per row); w == 2 handled as a single word
+        // w = 4 or 8: 2 or 4 words of original per row
         const int nw = w >> 1;
-        uint32_t r[4 + SS_STRIP / 2 + 1];
+        uint32_t r[4 + SS_STRIP / 2];
 #pragma unroll
-        for( int i = 0; i < 4 + SS_STRIP / 2 + 1; i++ ) r[i] = ( i < nw + SS_STRIP / 2 + 1 ) ? rrow[i] : 0u;
+        for( int i = 0; i < 4 + SS_STRIP / 2; i++ ) r[i] = ( i < nw + SS_STRIP / 2 ) ? rrow[i] : 0u;
 #pragma unroll
         for( int i = 0; i < 4; i++ )
         {
@@ -125,24 +196,26 @@ __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constan
             for( int k = 0; k < SS_STRIP; k++ )
             {
               const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
-              acc[k] = sad2_acc( ov, rv, acc[k] );
+              acc[k] = __dp2a_lo( (int) __vmins2( ov, rv ), (int) 0x0000ffffu, acc[k] );
             }
           }
         }
       }
     }
 
-    const int dy = blk.top + cy;
+    const int by = bitsY[cy];
+    const uint32_t* brow = box + cy * nxp + cx0;
 #pragma unroll
     for( int k = 0; k < SS_STRIP; k++ )
     {
       const int cx = cx0 + k;
       if( cx < nx )
       {
-        const uint32_t sad = (uint32_t) acc[k] << par.subShift;
+        const uint32_t sad = (uint32_t)( sumA + (int) brow[k] + 2 * acc[k] ) << par.subShift;
         const uint32_t order = (uint32_t)( cy * nx + cx );
         if( sadTables ) sadTables[(size_t) blockIdx.x * tableStride + order] = sad;
-        const unsigned long long c = (unsigned long long) sad + mv_cost( par, sMv, blk.left + cx, dy, blk.pred_hor, blk.pred_ver );
+        const uint32_t bits = (uint32_t)( bitsX[cx] + by );
+        const unsigned long long c = (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1];
         if( better( c, order, bestCost, bestOrder ) ) { bestCost = c; bestOrder = order; bestSad = sad; }
       }
     }
@@ -158,10 +231,9 @@ __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constan
     const uint32_t oo = __shfl_xor_sync( 0xffffffffu, bestOrder, m ), os = __shfl_xor_sync( 0xffffffffu, bestSad, m );
     if( better( oc, oo, bestCost, bestOrder ) ) { bestCost = oc; bestOrder = oo; bestSad = os; }
   }
-  const int warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-  if( ( threadIdx.x & 31 ) == 0 ) { sCost[warp] = bestCost; sOrder[warp] = bestOrder; sSad[warp] = bestSad; }
+  if( lane == 0 ) { sCost[warp] = bestCost; sOrder[warp] = bestOrder; sSad[warp] = bestSad; }
   __syncthreads();
-  if( threadIdx.x == 0 )
+  if( tid == 0 )
   {
     for( int i = 1; i < nWarps; i++ )
       if( better( sCost[i], sOrder[i], bestCost, bestOrder ) ) { bestCost = sCost[i]; bestOrder = sOrder[i]; bestSad = sSad[i]; }
