@@ -215,6 +215,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget', type=float, default=12.0)
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true', help='profiling runs: no CPU baseline leg')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
     u = units_per_step()
@@ -475,7 +476,7 @@ def main():
         extra['e2e_matches_resident'] = bool(np.array_equal(bv['cost'][:64], dv['cost'][:64])) if (2 + ke - 1) % N_PICTURE_SETS == (max(3, args.warmup) + args.steps - 1) % N_PICTURE_SETS else None
 
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_arm(args.cpu_budget)
 
     if rank == 0:

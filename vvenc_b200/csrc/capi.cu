@@ -553,11 +553,11 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
   // block size: the multiple of 32 in 64..256 that wastes the fewest thread slots on the (ny x strips) work items; ties -> larger
   const int items = maxNy * ( ( maxNx + SS_STRIP - 1 ) / SS_STRIP );
   int bd = 256; double bestEff = -1.0;
-  for( int cand = 64; cand <= 256; cand += 32 )
+  for( int cand = 64; cand <= 384; cand += 32 )
   {
     const int rounds = ( items + cand - 1 ) / cand;
     const double eff = (double) items / ( (double) rounds * cand );
-    if( eff >= bestEff - 1e-9 && ( w * h >= 1024 ? cand >= 128 : true ) ) { bestEff = std::max( bestEff, eff ); bd = cand; }
+    if( eff >= bestEff - 1e-9 && ( w * h >= 1024 ? cand >= 128 : cand <= 256 ) ) { bestEff = std::max( bestEff, eff ); bd = cand; }
   }
   sad_search_kernel<<<n, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, w, h, mp, dTables, tableStride, dBest );
   CHECK_LAUNCH( "sad_search_kernel" );

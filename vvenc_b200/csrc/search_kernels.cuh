@@ -58,7 +58,7 @@ __host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny 
   return s;
 }
 
-__global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+__global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                             const vvb_block* __restrict__ blocks, int w, int h, const __grid_constant__ MePar par,
                                                             uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut )
 {
@@ -84,11 +84,51 @@ __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constan
   {
     const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
     const int validW = w + nx - 1;
-    for( int r = warp; r < winH; r += nWarps )
+    // 32-bit words when the window start is even (plane rows are even-pitched), 16 independent loads in flight per thread:
+    // the staging loop is latency bound otherwise (one L2 round trip per iteration).
+    const bool even = ( ( (uintptr_t) src & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
+    if( even )
     {
-      const int16_t* srow = src + (ptrdiff_t) r * refPlane.stride;
-      int16_t* drow = win + r * ws;
-      for( int c = lane; c < ws; c += 32 ) drow[c] = c < validW ? __ldg( srow + c ) : (int16_t) 0;
+      const int wpr = ws >> 1, total = winH * wpr, validWords = ( validW + 1 ) >> 1;
+      uint32_t* win32 = reinterpret_cast<uint32_t*>( win );
+      for( int i0 = tid; i0 < total; i0 += nthr * 16 )
+      {
+        uint32_t v[16];
+#pragma unroll
+        for( int u = 0; u < 16; u++ )
+        {
+          const int i = i0 + u * nthr;
+          v[u] = 0u;
+          if( i < total )
+          {
+            const int r = i / wpr, c = i - r * wpr;
+            if( c < validWords ) v[u] = __ldg( reinterpret_cast<const uint32_t*>( src + (ptrdiff_t) r * refPlane.stride ) + c );
+          }
+        }
+#pragma unroll
+        for( int u = 0; u < 16; u++ ) { const int i = i0 + u * nthr; if( i < total ) win32[i] = v[u]; }
+      }
+    }
+    else
+    {
+      const int total = winH * ws;
+      for( int i0 = tid; i0 < total; i0 += nthr * 16 )
+      {
+        int16_t v[16];
+#pragma unroll
+        for( int u = 0; u < 16; u++ )
+        {
+          const int i = i0 + u * nthr;
+          v[u] = 0;
+          if( i < total )
+          {
+            const int r = i / ws, c = i - r * ws;
+            if( c < validW ) v[u] = __ldg( src + (ptrdiff_t) r * refPlane.stride + c );
+          }
+        }
+#pragma unroll
+        for( int u = 0; u < 16; u++ ) { const int i = i0 + u * nthr; if( i < total ) win[i] = v[u]; }
+      }
     }
     const int16_t* so = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
     int sumA = 0;
@@ -222,8 +262,8 @@ __global__ void __launch_bounds__( 256 ) sad_search_kernel( const __grid_constan
   }
 
   // ---- block argmin (cost, raster order)
-  __shared__ unsigned long long sCost[8];
-  __shared__ uint32_t sOrder[8], sSad[8];
+  __shared__ unsigned long long sCost[12];
+  __shared__ uint32_t sOrder[12], sSad[12];
 #pragma unroll
   for( int m = 16; m > 0; m >>= 1 )
   {
