@@ -412,6 +412,23 @@ def main():
             del pool
         except Exception as ex:     # the sweep is evidence, not part of the metric
             extra['hbm_sweep_16x16_pool'] = {'error': str(ex)}
+        # fixed diamond-search candidate set (SURVEY 8d W3 -> W1 byte formula): TZ point pattern, range 64, around the zero vector
+        try:
+            from vvenc_b200 import candidates as cand
+            tz = cand.tz_diamond_pattern(64)
+            d_tz = dev(tz); Kt = len(tz); dia = {}
+            for n in (8, 16, 32, 64):
+                nb = len(blocks_np[n])
+                bb = blocks_np[n].copy(); bb['left'] = -64; bb['right'] = 64; bb['top'] = -64; bb['bottom'] = 64
+                d_bb = dev(bb); d_s = torch.empty(nb * Kt, dtype=torch.int32, device='cuda'); d_b = torch.empty(nb * 16, dtype=torch.uint8, device='cuda')
+                t = time_launch(lambda: chk(lib.vvb_sad_pattern_dev(eng.h, 0, 1, P_(d_bb.data_ptr()), nb, n, n, P_(d_tz.data_ptr()), Kt, ctypes.byref(me),
+                                                                    P_(d_s.data_ptr()), P_(d_b.data_ptr()))), reps=5)
+                byt = nb * Kt * (2 * n * n + 2 * n * n / Kt + 8)
+                dia[str(n)] = {'ms': t, 'cand_per_s': nb * Kt / (t * 1e-3), 'GBps_w1_formula': byt / (t * 1e-3) / 1e9, 'frac_hbm_w1_formula': byt / (t * 1e-3) / 1e9 / hbm_peak}
+            extra['diamond_set_sad'] = {'points': Kt, 'range': 64, 'note': 'candidates overlap in the L2-resident reference plane: the W1 byte formula counts every candidate block '
+                                        'as fresh bytes, so fractions above 1.0 mean L2 hits, not missing work (DRAM traffic in profiles/)', **dia}
+        except Exception as ex:
+            extra['diamond_set_sad'] = {'error': str(ex)}
 
     # ------------------------------------------------------------------------------------------- end-to-end through the host-buffer C ABI
     e2e = None

@@ -9,6 +9,7 @@
 #include "dist_kernels.cuh"
 #include "search_kernels.cuh"
 #include "trquant_kernels.cuh"
+#include "trquant_tc_kernels.cuh"
 #include "mctf_affine_kernels.cuh"
 #include "vvc_tables.h"
 
@@ -218,6 +219,9 @@ int vvb_create( vvb_ctx** out, int device )
   }
   cudaFuncSetAttribute( sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+  cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   *out = ctx;
   return VVB_OK;
 }
@@ -248,6 +252,14 @@ int vvb_synchronize( vvb_ctx* ctx )
 void* vvb_stream( vvb_ctx* ctx ) { return ctx ? (void*) ctx->stream : nullptr; }
 
 int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) return VVB_ERR_ARG; *k = ctx->launches; return VVB_OK; }
+
+// selects the transform engine for square 16/32/64 TUs: 1 = tcgen05 tensor cores (default), 0 = IDP.2A CUDA-core kernel
+int vvb_set_tensor_transform( vvb_ctx* ctx, int enable )
+{
+  if( !ctx ) return VVB_ERR_ARG;
+  ctx->tensorTransform = enable != 0;
+  return VVB_OK;
+}
 
 // launches the ALU probe: grid_ctas CTAs x 256 threads x iters iterations x 8 packed SADs (16 pel differences) each
 int vvb_alu_probe_dev( vvb_ctx* ctx, int gridCtas, int iters, int mode )
@@ -709,6 +721,18 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
+  if( ctx->tensorTransform && p.w == p.h && ( p.w == 16 || p.w == 32 || p.w == 64 ) )
+  {
+    // tcgen05 path: 128 stacked rows (128/N TUs) per tile, persistent CTAs
+    const int tpt = 128 / p.w;
+    const int tiles = ( n + tpt - 1 ) / tpt;
+    const int grid = std::min( tiles, ctx->numSMs * 3 );
+    if( p.w == 16 )      fwd_trquant_tc_kernel<16><<<grid, 128, trquant_tc_smem<16>(), ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+    else if( p.w == 32 ) fwd_trquant_tc_kernel<32><<<grid, 128, trquant_tc_smem<32>(), ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+    else                 fwd_trquant_tc_kernel<64><<<grid, 128, trquant_tc_smem<64>(), ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+    CHECK_LAUNCH( "fwd_trquant_tc_kernel" );
+    return VVB_OK;
+  }
   const int nTeams = 128 / p.team;
   const TeamSmem ts = team_smem( p );
   const size_t smem = ( (size_t)( p.w >> 2 ) * p.keepW + (size_t)( p.h >> 2 ) * p.keepH + (size_t) nTeams * ts.total ) * 4;

@@ -83,6 +83,7 @@ struct vvb_ctx
   std::string    err;
   uint64_t       launches = 0;
   bool           poolBlocksAligned = false;   // see vvb_pool_hint
+  bool           tensorTransform = true;      // see vvb_set_tensor_transform
   int            numSMs   = 148;
   // device-side constant data
   int8_t*        d_trTable   = nullptr;     // all transform matrices (vvc_tables.h)
