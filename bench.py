@@ -55,8 +55,9 @@ def synth_picture_pair(seed, w=W, h=H, margin=MARGIN):
 
 
 def block_grid(n, w=W, h=H):
-    xs, ys = np.meshgrid(np.arange(0, w - n + 1, n), np.arange(0, h - n + 1, n))
-    return xs.ravel().astype(np.int32), ys.ravel().astype(np.int32)
+    # quad-tree z-order, as the encoder's partitioner visits the blocks of one depth
+    from vvenc_b200.candidates import quad_order_grid
+    return quad_order_grid(n, w, h)
 
 
 def units_per_step():
@@ -262,7 +263,7 @@ def main():
     pat_np = np.zeros(len(refine_pattern()), dtype=V.MV_DT)
     pat_np['dx'] = [p[0] for p in refine_pattern()]; pat_np['dy'] = [p[1] for p in refine_pattern()]
     KP = len(pat_np)
-    me = eng.me_par(LAMBDA, 2, 0, 0)
+    me = eng.me_par(LAMBDA, 2, 0, 0, 1)      # quad_order: the block lists below are in z-order
     nx = 2 * SEARCH_RANGE + 1
 
     def dev(a):

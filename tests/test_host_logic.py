@@ -27,3 +27,12 @@ def test_window_clip():
     assert cand.full_search_window(0, 0, 32, 3840, 2160, 0, 0, 16, 16, 80) == (-32, 32, -32, 32)
     l, r, t, b = cand.full_search_window(0, 0, 128, 3840, 2160, 3824, 0, 16, 16, 80)
     assert r == 80 and l == -128 and t == -80
+
+
+def test_quad_order_grid_is_a_permutation_of_the_raster_grid():
+    for (b, w, h) in ((8, 64, 48), (16, 3840, 2160), (64, 3840, 2160), (32, 96, 96)):
+        xs, ys = cand.quad_order_grid(b, w, h)
+        want = set((x, y) for y in range(0, h - b + 1, b) for x in range(0, w - b + 1, b))
+        assert len(xs) == len(want) and set(zip(xs.tolist(), ys.tolist())) == want
+        # leading entries come in proper quads
+        assert (xs[1], ys[1]) == (xs[0] + b, ys[0]) and (xs[2], ys[2]) == (xs[0], ys[0] + b) and (xs[3], ys[3]) == (xs[0] + b, ys[0] + b)

@@ -53,3 +53,21 @@ def full_search_window(pred_x, pred_y, search_range, pic_w, pic_h, x, y, w, h, m
     top = max(pred_y - search_range, -margin - y)
     bottom = min(pred_y + search_range, pic_h + margin - h - y)
     return left, right, top, bottom
+
+
+def quad_order_grid(block, pic_w, pic_h):
+    """Top-left positions of the block x block grid in quad-tree z-order: (x,y),(x+b,y),(x,y+b),(x+b,y+b) per 2x2 group, the way the encoder's
+    partitioner visits them; an odd last block row / column is appended afterwards.  The dense search evaluates each quad on a shared window."""
+    nbx, nby = pic_w // block, pic_h // block
+    xs, ys = [], []
+    for qy in range(0, nby - 1, 2):
+        for qx in range(0, nbx - 1, 2):
+            for (dx, dy) in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                xs.append((qx + dx) * block); ys.append((qy + dy) * block)
+    if nbx % 2:
+        for by in range(nby - nby % 2):
+            xs.append((nbx - 1) * block); ys.append(by * block)
+    if nby % 2:
+        for bx in range(nbx):
+            xs.append(bx * block); ys.append((nby - 1) * block)
+    return np.array(xs, dtype=np.int32), np.array(ys, dtype=np.int32)

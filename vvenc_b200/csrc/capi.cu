@@ -550,28 +550,36 @@ static int checkSearchShape( vvb_ctx* ctx, int orgPlane, int refPlane, int w, in
 
 // host-known maximum window (nx, ny) variant used by both public entry points
 static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_me_par* par,
-                            int maxNx, int maxNy, uint32_t* dTables, int tableStride, vvb_best* dBest )
+                            int maxNx, int maxNy, int quad, uint32_t* dTables, int tableStride, vvb_best* dBest )
 {
   int rc = checkSearchShape( ctx, orgPlane, refPlane, w, h );
   if( rc ) return rc;
   MePar mp;
   if( ( rc = makeMePar( ctx, par, mp ) ) ) return rc;
   if( mp.subShift && ( h & ( ( 1 << mp.subShift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
+  if( maxNx * maxNy > 65536 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search window above 65536 positions" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const SearchSmem L = search_smem( w, h, maxNx, maxNy );
+  // z-order quads share one staged window; fall back to one block per CTA when the quad window does not fit
+  int nb = ( quad && w >= 8 && n >= 4 ) ? 2 : 1;
+  SearchSmem L = search_smem( w, h, maxNx, maxNy, nb, nb );
+  if( nb == 2 && (size_t) L.total + 16 > 100 * 1024 ) { nb = 1; L = search_smem( w, h, maxNx, maxNy, 1, 1 ); }
   const size_t smem = (size_t) L.total + 16;
   if( smem > 220 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search window does not fit shared memory (reduce the range)" );
-  // block size: the multiple of 32 in 64..256 that wastes the fewest thread slots on the (ny x strips) work items; ties -> larger
-  const int items = maxNy * ( ( maxNx + SS_STRIP - 1 ) / SS_STRIP );
-  int bd = 256; double bestEff = -1.0;
+  // block size: the multiple of 32 in 64..384 that wastes the fewest thread slots on the (members x ny x strips) work items; ties -> larger
+  const int items = nb * nb * maxNy * ( ( maxNx + SS_STRIP - 1 ) / SS_STRIP );
+  int bd = 256; double bestScore = -1.0;
   for( int cand = 64; cand <= 384; cand += 32 )
   {
     const int rounds = ( items + cand - 1 ) / cand;
     const double eff = (double) items / ( (double) rounds * cand );
-    if( eff >= bestEff - 1e-9 && ( w * h >= 1024 ? cand >= 128 : cand <= 256 ) ) { bestEff = std::max( bestEff, eff ); bd = cand; }
+    const int ctasPerSM = (int) std::min<size_t>( std::min<size_t>( 32, ( 227 * 1024 ) / ( smem + 1024 ) ), 2048 / cand );
+    const double occ = std::min( 1.0, ( ctasPerSM * cand / 32 ) / 24.0 );          // >= 24 resident warps hide the LDS latency
+    const double score = eff * ( 0.5 + 0.5 * occ );
+    if( score >= bestScore - 1e-9 ) { bestScore = std::max( bestScore, score ); bd = cand; }
   }
-  sad_search_kernel<<<n, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, w, h, mp, dTables, tableStride, dBest );
+  const int grid = nb == 2 ? ( n + 3 ) / 4 : n;
+  sad_search_kernel<<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, dTables, tableStride, dBest );
   CHECK_LAUNCH( "sad_search_kernel" );
   return VVB_OK;
 }
@@ -582,8 +590,8 @@ extern "C" {
 int vvb_sad_search_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_me_par* par,
                         int maxNx, int maxNy, uint32_t* dTables, int tableStride, vvb_best* dBest )
 {
-  if( !ctx || !dBlocks || !dBest || n < 0 || maxNx < 1 || maxNy < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
-  return sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks, n, w, h, par, maxNx, maxNy, dTables, tableStride, dBest );
+  if( !ctx || !dBlocks || !dBest || !par || n < 0 || maxNx < 1 || maxNy < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  return sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks, n, w, h, par, maxNx, maxNy, par->quad_order, dTables, tableStride, dBest );
 }
 
 int vvb_sad_search( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_me_par* par,
@@ -603,7 +611,7 @@ int vvb_sad_search( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* b
   if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * sizeof( vvb_best ), &dO ) ) ) return rc;
   if( tables && ( rc = scratch( ctx, 2, (size_t) n * tableStride * 4, &dT ) ) ) return rc;
   CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
-  if( ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, par, maxNx, maxNy, (uint32_t*) dT, tableStride, (vvb_best*) dO ) ) ) return rc;
+  if( ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, par, maxNx, maxNy, 1 /* quads are verified per CTA */, (uint32_t*) dT, tableStride, (vvb_best*) dO ) ) ) return rc;
   CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
   if( tables ) CU( cudaMemcpyAsync( tables, dT, (size_t) n * tableStride * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( cudaStreamSynchronize( ctx->stream ) );

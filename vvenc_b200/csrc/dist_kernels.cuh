@@ -352,21 +352,33 @@ __global__ void __launch_bounds__( 256 ) sad_pool_stream_kernel( const __grid_co
   const int lg = threadIdx.x & ( G - 1 );
   const long long groupsPerGrid = ( (long long) gridDim.x * blockDim.x ) / G;
   const long long jobs = (long long) nBlocks * kSplit;                 // job = (block, slice of its K candidates)
-  const int cpr = w >> 3;                                              // chunks per row
+  const int cpr = w >> 3, lcpr = ilog2_dev( cpr );                    // chunks per row (power of two)
   const int rows = h >> subShift;
   const int chunks = rows * cpr;                                       // visited chunks per candidate
   const int passes = ( chunks + G * L - 1 ) / ( G * L );
   const int kPer = ( K + kSplit - 1 ) / kSplit;
   const unsigned mk = gmask<G>();
+  const int area8 = ( w * h ) >> 3;                                    // uint4 units per candidate
   for( long long job = ( (long long) blockIdx.x * blockDim.x + threadIdx.x ) / G; job < jobs; job += groupsPerGrid )
   {
     const int b = (int)( job / kSplit ), ks = (int)( job - (long long) b * kSplit );
     const int k0 = ks * kPer, k1 = min( K, k0 + kPer );
     const vvb_pos p = blocks[b];
     const int16_t* org = orgPlane.origin + (ptrdiff_t) p.y * orgPlane.stride + p.x;
+    // per-lane chunk coordinates of the first pass; with a single pass the original chunks are loaded once per block
+    int offC[L]; uint4 o0[L]; bool ok[L];
+#pragma unroll
+    for( int i = 0; i < L; i++ )
+    {
+      const int ch = i * G + lg;
+      ok[i] = ch < chunks;
+      const int r = ch >> lcpr, cc = ch & ( cpr - 1 ), y = r << subShift;
+      offC[i] = y * cpr + cc;
+      o0[i] = ok[i] ? __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc ) : make_uint4( 0, 0, 0, 0 );
+    }
     for( int k = k0; k < k1; k++ )
     {
-      const uint4* cur = reinterpret_cast<const uint4*>( pool + ( (size_t) b * K + k ) * w * h );
+      const uint4* cur = reinterpret_cast<const uint4*>( pool ) + ( (size_t) b * K + k ) * area8;
       int acc = 0; unsigned long long acc64 = 0;
       for( int ps = 0; ps < passes; ps++ )
       {
@@ -374,14 +386,22 @@ __global__ void __launch_bounds__( 256 ) sad_pool_stream_kernel( const __grid_co
 #pragma unroll
         for( int i = 0; i < L; i++ )
         {
-          const int ch = ( ps * L + i ) * G + lg;
-          if( ch < chunks )
+          if( ps == 0 )
           {
-            const int r = ch / cpr, cc = ch - r * cpr, y = r << subShift;
-            c[i] = ld_stream( cur + y * cpr + cc );
-            o[i] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc );
+            c[i] = ok[i] ? ld_stream( cur + offC[i] ) : make_uint4( 0, 0, 0, 0 );
+            o[i] = o0[i];
           }
-          else { c[i] = make_uint4( 0, 0, 0, 0 ); o[i] = c[i]; }
+          else
+          {
+            const int ch = ( ps * L + i ) * G + lg;
+            if( ch < chunks )
+            {
+              const int r = ch >> lcpr, cc = ch & ( cpr - 1 ), y = r << subShift;
+              c[i] = ld_stream( cur + y * cpr + cc );
+              o[i] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc );
+            }
+            else { c[i] = make_uint4( 0, 0, 0, 0 ); o[i] = c[i]; }
+          }
         }
 #pragma unroll
         for( int i = 0; i < L; i++ )

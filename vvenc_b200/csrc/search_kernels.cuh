@@ -35,183 +35,261 @@ __device__ __forceinline__ bool better( unsigned long long c, uint32_t o, unsign
 #define SS_STRIP 8          // candidates per strip (consecutive dx)
 #define SS_XCHUNK 16        // original pels consumed per inner step
 
-// smem layout: win[winH][ws] int16 | org[h][w] int16 | box[winH][nxp] uint32 | bitsX[nxp], bitsY[ny] uint8 (packed in uint32 words)
+// One CTA evaluates a MACRO block of nbx x nby adjacent blocks (1x1, or a z-order quad 2x2 whose members share range and
+// predictor -- the encoder's quad-tree order): the staged window, the row sums and the column sums are shared by the members.
+//
+// smem layout: win[winH][ws] int16 | org[MH][MW] int16 | V[winH][nxpV] uint32 | bitsX[nxp], bitsY[ny] | per-member sumA / best keys
 //
 // SAD via  sum|a-b| = sum a + sum b - 2 sum min(a,b):
-//   sum a           : once per block
-//   sum b (box sum) : for every candidate from row-sliding sums of the staged window (O(window) work, shared by all candidates)
+//   sum a           : once per member block
+//   sum b (box sum) : V[cy'][cx'] = sum over a w x h box of the staged window, from row-sliding sums + in-place column sums
+//                     (O(window) work, shared by all candidates and all members: member (bx,by) reads V[cy + by*h][cx + bx*w])
 //   sum min(a,b)    : the only per-(candidate, pel) work: VIMNMX.S16x2 + IDP.2A per pel PAIR, i.e. one instruction per pel difference
 // All three are exact integers, so the result is bit-identical to the direct sum.
-struct SearchSmem { int ws, winH, nxp, offOrg, offBox, offBits, total; };
+struct SearchSmem { int ws, winH, nxp, nStrips, nxpV, nStripsV, vRows, offOrg, offV, offBits, offMisc, total; };
 
-__host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny )
+__host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny, int nbx, int nby )
 {
   SearchSmem s;
-  const int nStrips = ( nx + SS_STRIP - 1 ) / SS_STRIP;
-  s.nxp  = nStrips * SS_STRIP;
-  s.ws   = w + s.nxp + 8;
-  s.winH = h + ny - 1;
-  s.offOrg  = s.winH * s.ws * 2;                       // bytes
-  s.offBox  = s.offOrg + w * h * 2;
-  s.offBits = s.offBox + s.winH * s.nxp * 4;
-  s.total   = s.offBits + ( ( s.nxp + ny + 15 ) & ~15 ) * 4;
+  s.nStrips  = ( nx + SS_STRIP - 1 ) / SS_STRIP;
+  s.nxp      = s.nStrips * SS_STRIP;
+  s.nStripsV = ( nx + ( nbx - 1 ) * w + SS_STRIP - 1 ) / SS_STRIP;
+  s.nxpV     = s.nStripsV * SS_STRIP;
+  s.ws       = ( nbx * w + s.nxp + 8 + 7 ) & ~7;         // row pitch in pels, multiple of 8 -> every row 16-byte aligned
+  s.winH     = nby * h + ny - 1;
+  s.vRows    = ny + ( nby - 1 ) * h;
+  s.offOrg   = s.winH * s.ws * 2;                          // bytes
+  s.offV     = s.offOrg + nbx * w * nby * h * 2;
+  s.offBits  = s.offV + s.winH * s.nxpV * 4;
+  s.offMisc  = s.offBits + ( ( s.nxp + ny + 3 ) & ~3 ) * 4;
+  s.total    = s.offMisc + 64;
   return s;
 }
 
+__device__ __forceinline__ int fast_div( int i, float inv ) { return __float2int_rz( ( (float) i + 0.5f ) * inv ); }   // exact for i < 2^20, small divisors
+
 __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
-                                                            const vvb_block* __restrict__ blocks, int w, int h, const __grid_constant__ MePar par,
+                                                            const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int quadMode,
+                                                            const __grid_constant__ MePar par,
                                                             uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut )
 {
   extern __shared__ __align__( 16 ) unsigned char smemRaw[];
   __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
-  __shared__ int sSumA;
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nWarps = nthr >> 5;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   for( int i = tid; i < VVB_MVCOST_ENTRIES; i += nthr ) sMv[i] = par.tab.cost[i];
-  if( tid == 0 ) sSumA = 0;
-  const vvb_block blk = blocks[blockIdx.x];
-  const int nx = blk.right - blk.left + 1, ny = blk.bottom - blk.top + 1;
-  const int nStrips = ( nx + SS_STRIP - 1 ) / SS_STRIP;
-  const SearchSmem L = search_smem( w, h, nx, ny );
-  const int ws = L.ws, winH = L.winH, nxp = L.nxp;
-  int16_t*  win   = reinterpret_cast<int16_t*>( smemRaw );
-  int16_t*  orgS  = reinterpret_cast<int16_t*>( smemRaw + L.offOrg );
-  uint32_t* box   = reinterpret_cast<uint32_t*>( smemRaw + L.offBox );      // [winH][nxp]: row sums first, then (in place) box sums for rows < ny
-  int*      bitsX = reinterpret_cast<int*>( smemRaw + L.offBits );          // [nxp]
-  int*      bitsY = bitsX + nxp;                                            // [ny]
   const int step = 1 << par.subShift;
 
-  // ---- stage window (origin = block position + (left, top)) and original block; one window row per warp pass
+  // ---- which blocks does this CTA own, and are they a proper quad?
+  const int first = quadMode ? blockIdx.x * 4 : blockIdx.x;
+  const int owned = quadMode ? min( 4, nBlocks - first ) : 1;
+  const vvb_block b0 = blocks[first];
+  bool isQuad = false;
+  if( quadMode && owned == 4 && w >= 8 )
   {
-    const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
-    const int validW = w + nx - 1;
-    // 32-bit words when the window start is even (plane rows are even-pitched), 16 independent loads in flight per thread:
-    // the staging loop is latency bound otherwise (one L2 round trip per iteration).
-    const bool even = ( ( (uintptr_t) src & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
-    if( even )
-    {
-      const int wpr = ws >> 1, total = winH * wpr, validWords = ( validW + 1 ) >> 1;
-      uint32_t* win32 = reinterpret_cast<uint32_t*>( win );
-      for( int i0 = tid; i0 < total; i0 += nthr * 16 )
-      {
-        uint32_t v[16];
+    const vvb_block b1 = blocks[first + 1], b2 = blocks[first + 2], b3 = blocks[first + 3];
+    isQuad = b1.x == b0.x + w && b1.y == b0.y && b2.x == b0.x && b2.y == b0.y + h && b3.x == b0.x + w && b3.y == b0.y + h;
+    const vvb_block* q[3] = { &b1, &b2, &b3 };
 #pragma unroll
-        for( int u = 0; u < 16; u++ )
+    for( int i = 0; i < 3; i++ )
+      isQuad = isQuad && q[i]->left == b0.left && q[i]->right == b0.right && q[i]->top == b0.top && q[i]->bottom == b0.bottom &&
+               q[i]->pred_hor == b0.pred_hor && q[i]->pred_ver == b0.pred_ver;
+  }
+  const int nSub = isQuad ? 1 : owned;
+
+  for( int sub = 0; sub < nSub; sub++ )
+  {
+    const vvb_block blk = isQuad ? b0 : blocks[first + sub];
+    const int nbx = isQuad ? 2 : 1, nby = isQuad ? 2 : 1, nMem = nbx * nby;
+    const int nx = blk.right - blk.left + 1, ny = blk.bottom - blk.top + 1;
+    const SearchSmem L = search_smem( w, h, nx, ny, nbx, nby );
+    const int ws = L.ws, winH = L.winH, nxp = L.nxp, nStrips = L.nStrips, nxpV = L.nxpV;
+    const int MW = nbx * w, MH = nby * h;
+    int16_t*  win   = reinterpret_cast<int16_t*>( smemRaw );
+    int16_t*  orgS  = reinterpret_cast<int16_t*>( smemRaw + L.offOrg );          // [MH][MW]
+    uint32_t* V     = reinterpret_cast<uint32_t*>( smemRaw + L.offV );            // [winH][nxpV]
+    int*      bitsX = reinterpret_cast<int*>( smemRaw + L.offBits );              // [nxp]
+    int*      bitsY = bitsX + nxp;                                                // [ny]
+    int*      sSumA = reinterpret_cast<int*>( smemRaw + L.offMisc );              // [4]
+    unsigned long long* sKey = reinterpret_cast<unsigned long long*>( smemRaw + L.offMisc + 16 );   // [4] (cost << 16 | raster order)
+
+    __syncthreads();                                      // previous sub-iteration fully consumed
+    if( tid < 4 ) { sSumA[tid] = 0; sKey[tid] = ~0ull; }
+
+    // ---- stage the window: 32-bit words when the start is even, 16 loads in flight per thread (latency bound otherwise)
+    {
+      const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
+      const int validW = MW + nx - 1;
+      const bool even = ( ( (uintptr_t) src & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
+      if( even )
+      {
+        const int wpr = ws >> 1, total = winH * wpr, validWords = ( validW + 1 ) >> 1;
+        const float inv = 1.0f / (float) wpr;
+        uint32_t* win32 = reinterpret_cast<uint32_t*>( win );
+        for( int i0 = tid; i0 < total; i0 += nthr * 16 )
         {
-          const int i = i0 + u * nthr;
-          v[u] = 0u;
-          if( i < total )
+          uint32_t v[16];
+#pragma unroll
+          for( int u = 0; u < 16; u++ )
           {
-            const int r = i / wpr, c = i - r * wpr;
-            if( c < validWords ) v[u] = __ldg( reinterpret_cast<const uint32_t*>( src + (ptrdiff_t) r * refPlane.stride ) + c );
+            const int i = i0 + u * nthr;
+            v[u] = 0u;
+            if( i < total )
+            {
+              const int r = fast_div( i, inv ), c = i - r * wpr;
+              if( c < validWords ) v[u] = __ldg( reinterpret_cast<const uint32_t*>( src + (ptrdiff_t) r * refPlane.stride ) + c );
+            }
+          }
+#pragma unroll
+          for( int u = 0; u < 16; u++ ) { const int i = i0 + u * nthr; if( i < total ) win32[i] = v[u]; }
+        }
+      }
+      else
+      {
+        const int total = winH * ws;
+        const float inv = 1.0f / (float) ws;
+        for( int i0 = tid; i0 < total; i0 += nthr * 16 )
+        {
+          int16_t v[16];
+#pragma unroll
+          for( int u = 0; u < 16; u++ )
+          {
+            const int i = i0 + u * nthr;
+            v[u] = 0;
+            if( i < total )
+            {
+              const int r = fast_div( i, inv ), c = i - r * ws;
+              if( c < validW ) v[u] = __ldg( src + (ptrdiff_t) r * refPlane.stride + c );
+            }
+          }
+#pragma unroll
+          for( int u = 0; u < 16; u++ ) { const int i = i0 + u * nthr; if( i < total ) win[i] = v[u]; }
+        }
+      }
+      // original macro block (MW is a power of two or twice one -> shifts) and per-member sum a
+      const int16_t* so = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
+      const int lMW = ilog2_dev( MW );
+      int sumA[4] = { 0, 0, 0, 0 };
+      for( int i = tid; i < MW * MH; i += nthr )
+      {
+        const int r = i >> lMW, c = i & ( MW - 1 );
+        const int16_t v = __ldg( so + (ptrdiff_t) r * orgPlane.stride + c );
+        orgS[i] = v;
+        const int ry = r >= h ? r - h : r;                 // row inside the member
+        if( ( ry & ( step - 1 ) ) == 0 ) sumA[( r >= h ? 2 : 0 ) + ( c >= w ? 1 : 0 )] += v;
+      }
+      __syncthreads();                                     // sSumA / sKey initialised, window visible
+#pragma unroll
+      for( int m4 = 0; m4 < 4; m4++ )
+      {
+        int v = sumA[m4];
+#pragma unroll
+        for( int m = 16; m > 0; m >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, m );
+        if( lane == 0 && v ) atomicAdd( &sSumA[m4], v );
+      }
+      // MV-rate bit counts per column / row of the window (RdCost.h:183-203)
+      for( int i = tid; i < nxp; i += nthr ) bitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - blk.pred_hor ) >> par.imvShift );
+      for( int i = tid; i < ny;  i += nthr ) bitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - blk.pred_ver ) >> par.imvShift );
+    }
+    // ---- row sums Hs[r][cx'] = sum_{x<w} win[r][cx'+x]: one task = (row, strip of 8 cx')
+    {
+      const int nTasks = winH * L.nStripsV;
+      const float inv = 1.0f / (float) L.nStripsV;
+      for( int t = tid; t < nTasks; t += nthr )
+      {
+        const int r = fast_div( t, inv ), st = t - r * L.nStripsV;
+        const int16_t* row = win + r * ws + st * SS_STRIP;
+        int s = 0;
+        for( int x = 0; x < w; x++ ) s += row[x];
+        uint32_t* dst = V + r * nxpV + st * SS_STRIP;
+        dst[0] = (uint32_t) s;
+#pragma unroll
+        for( int k = 1; k < SS_STRIP; k++ ) { s += row[w + k - 1] - row[k - 1]; dst[k] = (uint32_t) s; }
+      }
+    }
+    __syncthreads();
+    // ---- column sums in place: V[cy'][cx'] = sum_{k < h/step} Hs[cy' + k*step][cx']; rows of one phase (cy' mod step) only depend on that phase
+    {
+      const int m = h >> par.subShift;
+      for( int t = tid; t < nxpV * step; t += nthr )
+      {
+        const int cx = t % nxpV, p = t / nxpV;
+        if( p < L.vRows )
+        {
+          int cur = 0;
+          for( int k = 0; k < m; k++ ) cur += (int) V[( p + k * step ) * nxpV + cx];
+          int prevTop = (int) V[p * nxpV + cx];
+          V[p * nxpV + cx] = (uint32_t) cur;
+          for( int cy = p + step; cy < L.vRows; cy += step )
+          {
+            cur += (int) V[( cy + ( m - 1 ) * step ) * nxpV + cx] - prevTop;
+            prevTop = (int) V[cy * nxpV + cx];
+            V[cy * nxpV + cx] = (uint32_t) cur;
           }
         }
-#pragma unroll
-        for( int u = 0; u < 16; u++ ) { const int i = i0 + u * nthr; if( i < total ) win32[i] = v[u]; }
       }
     }
-    else
-    {
-      const int total = winH * ws;
-      for( int i0 = tid; i0 < total; i0 += nthr * 16 )
-      {
-        int16_t v[16];
-#pragma unroll
-        for( int u = 0; u < 16; u++ )
-        {
-          const int i = i0 + u * nthr;
-          v[u] = 0;
-          if( i < total )
-          {
-            const int r = i / ws, c = i - r * ws;
-            if( c < validW ) v[u] = __ldg( src + (ptrdiff_t) r * refPlane.stride + c );
-          }
-        }
-#pragma unroll
-        for( int u = 0; u < 16; u++ ) { const int i = i0 + u * nthr; if( i < total ) win[i] = v[u]; }
-      }
-    }
-    const int16_t* so = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
-    int sumA = 0;
-    for( int i = tid; i < w * h; i += nthr )
-    {
-      const int r = i / w, c = i - r * w;
-      const int16_t v = __ldg( so + (ptrdiff_t) r * orgPlane.stride + c );
-      orgS[i] = v;
-      if( ( r & ( step - 1 ) ) == 0 ) sumA += v;
-    }
-#pragma unroll
-    for( int m = 16; m > 0; m >>= 1 ) sumA += __shfl_xor_sync( 0xffffffffu, sumA, m );
-    __syncthreads();                                   // sSumA initialised, window visible
-    if( lane == 0 && sumA ) atomicAdd( &sSumA, sumA );
-    // MV-rate bit counts per column / row of the window (RdCost.h:183-203)
-    for( int i = tid; i < nxp; i += nthr ) bitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - blk.pred_hor ) >> par.imvShift );
-    for( int i = tid; i < ny;  i += nthr ) bitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - blk.pred_ver ) >> par.imvShift );
-  }
-  // ---- row sums Hs[r][cx] = sum_{x<w} win[r][cx+x]: one task = (row, strip of 8 cx)
-  for( int t = tid; t < winH * nStrips; t += nthr )
-  {
-    const int r = t / nStrips, st = t - r * nStrips;
-    const int16_t* row = win + r * ws + st * SS_STRIP;
-    int s = 0;
-    for( int x = 0; x < w; x++ ) s += row[x];
-    uint32_t* dst = box + r * nxp + st * SS_STRIP;
-    dst[0] = (uint32_t) s;
-#pragma unroll
-    for( int k = 1; k < SS_STRIP; k++ ) { s += row[w + k - 1] - row[k - 1]; dst[k] = (uint32_t) s; }
-  }
-  __syncthreads();
-  // ---- box sums in place: B[cy][cx] = sum_{k < h/step} Hs[cy + k*step][cx]; rows of one phase (cy mod step) only depend on that phase
-  {
-    const int m = h >> par.subShift;
-    for( int t = tid; t < nxp * step; t += nthr )
-    {
-      const int cx = t % nxp, p = t / nxp;
-      if( p < ny )
-      {
-        int cur = 0;
-        for( int k = 0; k < m; k++ ) cur += (int) box[( p + k * step ) * nxp + cx];
-        int prevTop = (int) box[p * nxp + cx];
-        box[p * nxp + cx] = (uint32_t) cur;
-        for( int cy = p + step; cy < ny; cy += step )
-        {
-          cur += (int) box[( cy + ( m - 1 ) * step ) * nxp + cx] - prevTop;
-          prevTop = (int) box[cy * nxp + cx];
-          box[cy * nxp + cx] = (uint32_t) cur;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const int sumA = sSumA;
+    __syncthreads();
 
-  unsigned long long bestCost = ~0ull; uint32_t bestOrder = 0xffffffffu, bestSad = 0;
-  const int items = ny * nStrips;
-  for( int it = tid; it < items; it += nthr )
-  {
-    const int cy = it / nStrips, st = it - cy * nStrips;
-    const int cx0 = st * SS_STRIP;
-    int acc[SS_STRIP];                                 // = - sum min(org, ref)
-#pragma unroll
-    for( int k = 0; k < SS_STRIP; k++ ) acc[k] = 0;
-
-    for( int y = 0; y < h; y += step )
+    // ---- candidates: item = (member, cy, strip of 8 cx); a thread walks items in increasing order, so members are visited in order
+    const int perMem = ny * nStrips, items = nMem * perMem;
+    const float invPer = 1.0f / (float) perMem, invStr = 1.0f / (float) nStrips;
+    unsigned long long bestKey = ~0ull; int curMem = -1;
+    for( int it = tid; it < items; it += nthr )
     {
-      const uint32_t* orow = reinterpret_cast<const uint32_t*>( orgS + y * w );
-      const uint32_t* rrow = reinterpret_cast<const uint32_t*>( win + ( cy + y ) * ws + cx0 );   // cx0 multiple of 8 -> 16-byte aligned when ws % 8 == 0
+      const int mem = fast_div( it, invPer ), loc = it - mem * perMem;
+      const int cy = fast_div( loc, invStr ), st = loc - cy * nStrips;
+      const int bx = mem & ( nbx - 1 ), by = mem >> ( nbx - 1 );
+      const int cx0 = st * SS_STRIP;
+      if( mem != curMem )
+      {
+        if( curMem >= 0 && bestKey != ~0ull ) atomicMin( &sKey[curMem], bestKey );
+        curMem = mem; bestKey = ~0ull;
+      }
+      int acc[SS_STRIP];                                 // = - sum min(org, ref)
+#pragma unroll
+      for( int k = 0; k < SS_STRIP; k++ ) acc[k] = 0;
+
+      const int16_t* obase = orgS + ( by * h ) * MW + bx * w;
+      const int16_t* rbase = win + ( by * h + cy ) * ws + bx * w + cx0;       // 16-byte aligned: ws % 8 == 0, bx*w % 8 == 0, cx0 % 8 == 0
       if( w >= SS_XCHUNK )
       {
-        for( int x = 0; x < w; x += SS_XCHUNK )
+        for( int y = 0; y < h; y += step )
         {
-          uint32_t o[SS_XCHUNK / 2], r[SS_XCHUNK / 2 + SS_STRIP / 2];
+          const uint32_t* orow = reinterpret_cast<const uint32_t*>( obase + y * MW );
+          const uint32_t* rrow = reinterpret_cast<const uint32_t*>( rbase + y * ws );
+          for( int x = 0; x < w; x += SS_XCHUNK )
+          {
+            uint32_t o[SS_XCHUNK / 2], r[SS_XCHUNK / 2 + SS_STRIP / 2];
 #pragma unroll
-          for( int i = 0; i < SS_XCHUNK / 2; i += 4 ) *reinterpret_cast<uint4*>( &o[i] ) = *reinterpret_cast<const uint4*>( orow + x / 2 + i );
+            for( int i = 0; i < SS_XCHUNK / 2; i += 4 ) *reinterpret_cast<uint4*>( &o[i] ) = *reinterpret_cast<const uint4*>( orow + x / 2 + i );
 #pragma unroll
-          for( int i = 0; i < SS_XCHUNK / 2 + SS_STRIP / 2; i += 4 ) *reinterpret_cast<uint4*>( &r[i] ) = *reinterpret_cast<const uint4*>( rrow + x / 2 + i );
+            for( int i = 0; i < SS_XCHUNK / 2 + SS_STRIP / 2; i += 4 ) *reinterpret_cast<uint4*>( &r[i] ) = *reinterpret_cast<const uint4*>( rrow + x / 2 + i );
+#pragma unroll
+            for( int k = 0; k < SS_STRIP; k++ )
+            {
+#pragma unroll
+              for( int i = 0; i < SS_XCHUNK / 2; i++ )
+              {
+                const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
+                acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
+              }
+            }
+          }
+        }
+      }
+      else if( w == 8 )
+      {
+        for( int y = 0; y < h; y += step )
+        {
+          uint32_t o[4], r[8];
+          *reinterpret_cast<uint4*>( &o[0] ) = *reinterpret_cast<const uint4*>( obase + y * MW );
+          *reinterpret_cast<uint4*>( &r[0] ) = *reinterpret_cast<const uint4*>( rbase + y * ws );
+          *reinterpret_cast<uint4*>( &r[4] ) = *reinterpret_cast<const uint4*>( rbase + y * ws + 8 );
 #pragma unroll
           for( int k = 0; k < SS_STRIP; k++ )
           {
 #pragma unroll
-            for( int i = 0; i < SS_XCHUNK / 2; i++ )
+            for( int i = 0; i < 4; i++ )
             {
               const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
               acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
@@ -219,68 +297,61 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
           }
         }
       }
-      else
+      else      // w == 4 (single-block mode only)
       {
-        // w = 4 or 8: 2 or 4 words of original per row
-        const int nw = w >> 1;
-        uint32_t r[4 + SS_STRIP / 2];
-#pragma unroll
-        for( int i = 0; i < 4 + SS_STRIP / 2; i++ ) r[i] = ( i < nw + SS_STRIP / 2 ) ? rrow[i] : 0u;
-#pragma unroll
-        for( int i = 0; i < 4; i++ )
+        for( int y = 0; y < h; y += step )
         {
-          if( i < nw )
-          {
-            const uint32_t ov = orow[i];
+          uint32_t o[2], r[8];
+          *reinterpret_cast<uint2*>( &o[0] ) = *reinterpret_cast<const uint2*>( obase + y * MW );
+          *reinterpret_cast<uint4*>( &r[0] ) = *reinterpret_cast<const uint4*>( rbase + y * ws );
+          *reinterpret_cast<uint4*>( &r[4] ) = *reinterpret_cast<const uint4*>( rbase + y * ws + 8 );
 #pragma unroll
-            for( int k = 0; k < SS_STRIP; k++ )
+          for( int k = 0; k < SS_STRIP; k++ )
+          {
+#pragma unroll
+            for( int i = 0; i < 2; i++ )
             {
               const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
-              acc[k] = __dp2a_lo( (int) __vmins2( ov, rv ), (int) 0x0000ffffu, acc[k] );
+              acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
             }
           }
         }
       }
-    }
 
-    const int by = bitsY[cy];
-    const uint32_t* brow = box + cy * nxp + cx0;
+      const int byBits = bitsY[cy];
+      const int sumA = sSumA[( by << 1 ) | bx];
+      const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
+      const int gblk = first + ( isQuad ? mem : sub );
 #pragma unroll
-    for( int k = 0; k < SS_STRIP; k++ )
-    {
-      const int cx = cx0 + k;
-      if( cx < nx )
+      for( int k = 0; k < SS_STRIP; k++ )
       {
-        const uint32_t sad = (uint32_t)( sumA + (int) brow[k] + 2 * acc[k] ) << par.subShift;
-        const uint32_t order = (uint32_t)( cy * nx + cx );
-        if( sadTables ) sadTables[(size_t) blockIdx.x * tableStride + order] = sad;
-        const uint32_t bits = (uint32_t)( bitsX[cx] + by );
-        const unsigned long long c = (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1];
-        if( better( c, order, bestCost, bestOrder ) ) { bestCost = c; bestOrder = order; bestSad = sad; }
+        const int cx = cx0 + k;
+        if( cx < nx )
+        {
+          const uint32_t sad = (uint32_t)( sumA + (int) vrow[k] + 2 * acc[k] ) << par.subShift;
+          const uint32_t order = (uint32_t)( cy * nx + cx );
+          if( sadTables ) sadTables[(size_t) gblk * tableStride + order] = sad;
+          const uint32_t bits = (uint32_t)( bitsX[cx] + byBits );
+          const unsigned long long c = (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1];
+          const unsigned long long key = ( c << 16 ) | order;          // lexicographic (cost, raster order): first strictly smaller wins
+          bestKey = key < bestKey ? key : bestKey;
+        }
       }
     }
-  }
-
-  // ---- block argmin (cost, raster order)
-  __shared__ unsigned long long sCost[12];
-  __shared__ uint32_t sOrder[12], sSad[12];
-#pragma unroll
-  for( int m = 16; m > 0; m >>= 1 )
-  {
-    const unsigned long long oc = __shfl_xor_sync( 0xffffffffu, bestCost, m );
-    const uint32_t oo = __shfl_xor_sync( 0xffffffffu, bestOrder, m ), os = __shfl_xor_sync( 0xffffffffu, bestSad, m );
-    if( better( oc, oo, bestCost, bestOrder ) ) { bestCost = oc; bestOrder = oo; bestSad = os; }
-  }
-  if( lane == 0 ) { sCost[warp] = bestCost; sOrder[warp] = bestOrder; sSad[warp] = bestSad; }
-  __syncthreads();
-  if( tid == 0 )
-  {
-    for( int i = 1; i < nWarps; i++ )
-      if( better( sCost[i], sOrder[i], bestCost, bestOrder ) ) { bestCost = sCost[i]; bestOrder = sOrder[i]; bestSad = sSad[i]; }
-    vvb_best b;
-    const int cy = bestOrder / nx, cx = bestOrder - cy * nx;
-    b.dx = (int16_t)( blk.left + cx ); b.dy = (int16_t)( blk.top + cy ); b.sad = bestSad; b.cost = bestCost;
-    bestOut[blockIdx.x] = b;
+    if( curMem >= 0 && bestKey != ~0ull ) atomicMin( &sKey[curMem], bestKey );
+    __syncthreads();
+    if( tid < nMem )
+    {
+      const unsigned long long key = sKey[tid];
+      const uint32_t order = (uint32_t)( key & 0xffffu );
+      const unsigned long long cost = key >> 16;
+      const int cy = order / nx, cx = order - cy * nx;
+      const uint32_t bits = (uint32_t)( bitsX[cx] + bitsY[cy] );
+      vvb_best b;
+      b.dx = (int16_t)( blk.left + cx ); b.dy = (int16_t)( blk.top + cy ); b.cost = cost;
+      b.sad = (uint32_t)( cost - sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] );
+      bestOut[first + ( isQuad ? tid : sub )] = b;
+    }
   }
 }
 
