@@ -486,9 +486,12 @@ int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* dBl
     const long long threads = (long long) nBlocks * kSplit * G;
     const int grid = (int) std::min<long long>( ( threads + 255 ) / 256, (long long) ctx->numSMs * 32 );
     const int ss = dfunc == FAM_SAD ? subShift : 0;
-#define LAUNCH_SP( GG, SS ) sad_pool_stream_kernel<GG, 4, SS><<<grid, 256, 0, ctx->stream>>>( op, dBlocks, nBlocks, w, h, K, kSplit, ss, dPool, dOut )
+    const bool single = chunks <= G * 4;
+#define LAUNCH_SP2( GG, SS, SG ) sad_pool_stream_kernel<GG, 4, SS, SG><<<grid, 256, 0, ctx->stream>>>( op, dBlocks, nBlocks, w, h, K, kSplit, ss, dPool, dOut )
+#define LAUNCH_SP( GG, SS ) do { if( single ) LAUNCH_SP2( GG, SS, true ); else LAUNCH_SP2( GG, SS, false ); } while( 0 )
     if( dfunc == FAM_SAD ) { switch( G ) { case 4: LAUNCH_SP( 4, false ); break; case 8: LAUNCH_SP( 8, false ); break; case 16: LAUNCH_SP( 16, false ); break; default: LAUNCH_SP( 32, false ); break; } }
     else                   { switch( G ) { case 4: LAUNCH_SP( 4, true ); break; case 8: LAUNCH_SP( 8, true ); break; case 16: LAUNCH_SP( 16, true ); break; default: LAUNCH_SP( 32, true ); break; } }
+#undef LAUNCH_SP2
 #undef LAUNCH_SP
     launched = true;
   }

@@ -342,12 +342,32 @@ __device__ __forceinline__ uint4 ld_stream( const uint4* p )
   return r;
 }
 
-// SAD / SSE over a pool: G lanes per candidate, L = chunks (8 pels) per lane per pass, candidates of one block are walked by the same
-// group so that the original chunks stay in registers.  Requires w >= 8 (chunks never straddle rows) and 16-byte aligned original rows.
-template<int G, int L, bool SSE>
-__global__ void __launch_bounds__( 256 ) sad_pool_stream_kernel( const __grid_constant__ Plane orgPlane, const vvb_pos* __restrict__ blocks, int nBlocks,
-                                                                 int w, int h, int K, int kSplit, int subShift, const int16_t* __restrict__ pool,
-                                                                 uint32_t* __restrict__ out )
+// SAD / SSE over a pool: G lanes per candidate, L = chunks (8 pels = 16 bytes) per lane per pass; the candidates of one block are walked
+// by the same group.  SINGLE (chunks <= G*L, the common case): the original chunks are loaded once per block and stay in registers, the
+// loop body is 4 independent streaming loads followed by arithmetic -- no branches between the loads.
+// Requires w >= 8 (chunks never straddle rows) and 16-byte aligned original rows.
+template<bool SSE> __device__ __forceinline__ void chunk_acc( const uint4& o, const uint4& c, int& acc, unsigned long long& acc64 )
+{
+  if( !SSE )
+  {
+    acc = sad2_acc( o.x, c.x, acc ); acc = sad2_acc( o.y, c.y, acc ); acc = sad2_acc( o.z, c.z, acc ); acc = sad2_acc( o.w, c.w, acc );
+  }
+  else
+  {
+    const uint32_t ow[4] = { o.x, o.y, o.z, o.w }, cw[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+    for( int j = 0; j < 4; j++ )
+    {
+      const int d0 = lo16( ow[j] ) - lo16( cw[j] ), d1 = hi16( ow[j] ) - hi16( cw[j] );
+      acc64 += (unsigned long long)( (unsigned) ( d0 * d0 ) ) + (unsigned long long)( (unsigned) ( d1 * d1 ) );
+    }
+  }
+}
+
+template<int G, int L, bool SSE, bool SINGLE>
+__global__ void __launch_bounds__( 256, 3 ) sad_pool_stream_kernel( const __grid_constant__ Plane orgPlane, const vvb_pos* __restrict__ blocks, int nBlocks,
+                                                                    int w, int h, int K, int kSplit, int subShift, const int16_t* __restrict__ pool,
+                                                                    uint32_t* __restrict__ out )
 {
   const int lg = threadIdx.x & ( G - 1 );
   const long long groupsPerGrid = ( (long long) gridDim.x * blockDim.x ) / G;
@@ -355,7 +375,6 @@ __global__ void __launch_bounds__( 256 ) sad_pool_stream_kernel( const __grid_co
   const int cpr = w >> 3, lcpr = ilog2_dev( cpr );                    // chunks per row (power of two)
   const int rows = h >> subShift;
   const int chunks = rows * cpr;                                       // visited chunks per candidate
-  const int passes = ( chunks + G * L - 1 ) / ( G * L );
   const int kPer = ( K + kSplit - 1 ) / kSplit;
   const unsigned mk = gmask<G>();
   const int area8 = ( w * h ) >> 3;                                    // uint4 units per candidate
@@ -365,76 +384,75 @@ __global__ void __launch_bounds__( 256 ) sad_pool_stream_kernel( const __grid_co
     const int k0 = ks * kPer, k1 = min( K, k0 + kPer );
     const vvb_pos p = blocks[b];
     const int16_t* org = orgPlane.origin + (ptrdiff_t) p.y * orgPlane.stride + p.x;
-    // per-lane chunk coordinates of the first pass; with a single pass the original chunks are loaded once per block
-    int offC[L]; uint4 o0[L]; bool ok[L];
-#pragma unroll
-    for( int i = 0; i < L; i++ )
+    if( SINGLE )
     {
-      const int ch = i * G + lg;
-      ok[i] = ch < chunks;
-      const int r = ch >> lcpr, cc = ch & ( cpr - 1 ), y = r << subShift;
-      offC[i] = y * cpr + cc;
-      o0[i] = ok[i] ? __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc ) : make_uint4( 0, 0, 0, 0 );
+      int offC[L]; uint4 o0[L];
+#pragma unroll
+      for( int i = 0; i < L; i++ )
+      {
+        const int ch = min( i * G + lg, chunks - 1 );                  // lanes past the end redo the last chunk with a zeroed original
+        const int r = ch >> lcpr, cc = ch & ( cpr - 1 ), y = r << subShift;
+        offC[i] = y * cpr + cc;
+        o0[i] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc );
+      }
+      const uint4* cur = reinterpret_cast<const uint4*>( pool ) + ( (size_t) b * K + k0 ) * area8;
+      for( int k = k0; k < k1; k++, cur += area8 )
+      {
+        uint4 c[L];
+#pragma unroll
+        for( int i = 0; i < L; i++ ) c[i] = ld_stream( cur + offC[i] );
+        int acc = 0; unsigned long long acc64 = 0;
+#pragma unroll
+        for( int i = 0; i < L; i++ ) if( i * G + lg < chunks ) chunk_acc<SSE>( o0[i], c[i], acc, acc64 );
+        if( !SSE )
+        {
+          uint32_t v = (uint32_t) acc;
+#pragma unroll
+          for( int m = G >> 1; m > 0; m >>= 1 ) v += __shfl_xor_sync( mk, v, m );
+          if( lg == 0 ) out[(size_t) b * K + k] = v << subShift;
+        }
+        else
+        {
+#pragma unroll
+          for( int m = G >> 1; m > 0; m >>= 1 ) acc64 += __shfl_xor_sync( mk, acc64, m );
+          if( lg == 0 ) out[(size_t) b * K + k] = (uint32_t) acc64;
+        }
+      }
     }
-    for( int k = k0; k < k1; k++ )
+    else
     {
-      const uint4* cur = reinterpret_cast<const uint4*>( pool ) + ( (size_t) b * K + k ) * area8;
-      int acc = 0; unsigned long long acc64 = 0;
-      for( int ps = 0; ps < passes; ps++ )
+      const int passes = ( chunks + G * L - 1 ) / ( G * L );
+      for( int k = k0; k < k1; k++ )
       {
-        uint4 c[L], o[L];
-#pragma unroll
-        for( int i = 0; i < L; i++ )
+        const uint4* cur = reinterpret_cast<const uint4*>( pool ) + ( (size_t) b * K + k ) * area8;
+        int acc = 0; unsigned long long acc64 = 0;
+        for( int ps = 0; ps < passes; ps++ )
         {
-          if( ps == 0 )
-          {
-            c[i] = ok[i] ? ld_stream( cur + offC[i] ) : make_uint4( 0, 0, 0, 0 );
-            o[i] = o0[i];
-          }
-          else
-          {
-            const int ch = ( ps * L + i ) * G + lg;
-            if( ch < chunks )
-            {
-              const int r = ch >> lcpr, cc = ch & ( cpr - 1 ), y = r << subShift;
-              c[i] = ld_stream( cur + y * cpr + cc );
-              o[i] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc );
-            }
-            else { c[i] = make_uint4( 0, 0, 0, 0 ); o[i] = c[i]; }
-          }
-        }
+          uint4 c[L], o[L];
 #pragma unroll
-        for( int i = 0; i < L; i++ )
+          for( int i = 0; i < L; i++ )
+          {
+            const int ch = min( ( ps * L + i ) * G + lg, chunks - 1 );
+            const int r = ch >> lcpr, cc = ch & ( cpr - 1 ), y = r << subShift;
+            c[i] = ld_stream( cur + y * cpr + cc );
+            o[i] = __ldg( reinterpret_cast<const uint4*>( org + (ptrdiff_t) y * orgPlane.stride ) + cc );
+          }
+#pragma unroll
+          for( int i = 0; i < L; i++ ) if( ( ps * L + i ) * G + lg < chunks ) chunk_acc<SSE>( o[i], c[i], acc, acc64 );
+        }
+        if( !SSE )
         {
-          if( !SSE )
-          {
-            acc = sad2_acc( o[i].x, c[i].x, acc ); acc = sad2_acc( o[i].y, c[i].y, acc );
-            acc = sad2_acc( o[i].z, c[i].z, acc ); acc = sad2_acc( o[i].w, c[i].w, acc );
-          }
-          else
-          {
-            const uint32_t ow[4] = { o[i].x, o[i].y, o[i].z, o[i].w }, cw[4] = { c[i].x, c[i].y, c[i].z, c[i].w };
+          uint32_t v = (uint32_t) acc;
 #pragma unroll
-            for( int j = 0; j < 4; j++ )
-            {
-              const int d0 = lo16( ow[j] ) - lo16( cw[j] ), d1 = hi16( ow[j] ) - hi16( cw[j] );
-              acc64 += (unsigned long long)( (unsigned) ( d0 * d0 ) ) + (unsigned long long)( (unsigned) ( d1 * d1 ) );
-            }
-          }
+          for( int m = G >> 1; m > 0; m >>= 1 ) v += __shfl_xor_sync( mk, v, m );
+          if( lg == 0 ) out[(size_t) b * K + k] = v << subShift;
         }
-      }
-      if( !SSE )
-      {
-        uint32_t v = (uint32_t) acc;
+        else
+        {
 #pragma unroll
-        for( int m = G >> 1; m > 0; m >>= 1 ) v += __shfl_xor_sync( mk, v, m );
-        if( lg == 0 ) out[(size_t) b * K + k] = v << subShift;
-      }
-      else
-      {
-#pragma unroll
-        for( int m = G >> 1; m > 0; m >>= 1 ) acc64 += __shfl_xor_sync( mk, acc64, m );
-        if( lg == 0 ) out[(size_t) b * K + k] = (uint32_t) acc64;
+          for( int m = G >> 1; m > 0; m >>= 1 ) acc64 += __shfl_xor_sync( mk, acc64, m );
+          if( lg == 0 ) out[(size_t) b * K + k] = (uint32_t) acc64;
+        }
       }
     }
   }
