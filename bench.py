@@ -263,7 +263,7 @@ def main():
     pat_np = np.zeros(len(refine_pattern()), dtype=V.MV_DT)
     pat_np['dx'] = [p[0] for p in refine_pattern()]; pat_np['dy'] = [p[1] for p in refine_pattern()]
     KP = len(pat_np)
-    me = eng.me_par(LAMBDA, 2, 0, 0, 1)      # quad_order: the block lists below are in z-order
+    me = eng.me_par(LAMBDA, 2, 0, 0, 1, 2)   # quad_order: the block lists below are in z-order; pattern_radius 2: the refinement ring
     nx = 2 * SEARCH_RANGE + 1
 
     def dev(a):

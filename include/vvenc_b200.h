@@ -112,7 +112,8 @@ typedef struct { int16_t dx, dy; uint32_t sad; uint64_t cost; } vvb_best;   /* 1
 
 /* quad_order (dense search, _dev only): the block list is in quad-tree z-order (x,y),(x+w,y),(x,y+h),(x+w,y+h); quads whose members share
  * range and predictor are evaluated by one CTA on a shared window (verified per quad on the device, results identical either way) */
-typedef struct { double lambda; int32_t cost_scale, imv_shift, sub_shift, quad_order; } vvb_me_par;
+/* pattern_radius (pattern regime, _dev only; the host-buffer calls derive it): max |dx|,|dy| of the pattern, 0 = unknown */
+typedef struct { double lambda; int32_t cost_scale, imv_shift, sub_shift, quad_order, pattern_radius, pad; } vvb_me_par;
 
 /* Dense full search = InterSearch::xPatternSearch (InterSearch.cpp:2209-2251): every (dx,dy) in
  * [left..right]x[top..bottom], raster order, first strictly smaller total cost wins.  Optional SAD table

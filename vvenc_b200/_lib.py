@@ -18,7 +18,7 @@ class vvb_cand(ctypes.Structure):
 
 
 class vvb_me_par(ctypes.Structure):
-    _fields_ = [('lam', ctypes.c_double), ('cost_scale', ctypes.c_int32), ('imv_shift', ctypes.c_int32), ('sub_shift', ctypes.c_int32), ('quad_order', ctypes.c_int32)]
+    _fields_ = [('lam', ctypes.c_double), ('cost_scale', ctypes.c_int32), ('imv_shift', ctypes.c_int32), ('sub_shift', ctypes.c_int32), ('quad_order', ctypes.c_int32), ('pattern_radius', ctypes.c_int32), ('pad', ctypes.c_int32)]
 
 
 class vvb_tu_par(ctypes.Structure):

@@ -130,8 +130,8 @@ class CostEngine:
 
     # ---- motion search
     @staticmethod
-    def me_par(lam, cost_scale=2, imv_shift=0, sub_shift=0, quad_order=0):
-        return L.vvb_me_par(float(lam), cost_scale, imv_shift, sub_shift, quad_order)
+    def me_par(lam, cost_scale=2, imv_shift=0, sub_shift=0, quad_order=0, pattern_radius=0):
+        return L.vvb_me_par(float(lam), cost_scale, imv_shift, sub_shift, quad_order, pattern_radius, 0)
 
     def sad_search(self, org_plane, ref_plane, blocks, w, h, par, want_tables=False):
         blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)

@@ -219,6 +219,7 @@ int vvb_create( vvb_ctx** out, int device )
   }
   cudaFuncSetAttribute( sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+  cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -633,8 +634,27 @@ int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, c
   if( ( rc = checkDistShape( ctx, dfunc, w, h, mp.subShift ) ) ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const int G = dfunc == FAM_SAD ? pick_group( FAM_SAD, w, h >> mp.subShift ) : pick_group( dfunc, w, h );
   const Plane &op = ctx->planes.p[orgPlane], &rp = ctx->planes.p[refPlane];
+  // small-radius Hadamard refinement on 8x8 tiles: staged region + register Hadamard (one lane per candidate tile)
+  const int R = par->pattern_radius;
+  if( dfunc == FAM_HAD && R > 0 && R <= 8 && K <= 1024 && ( w & 7 ) == 0 && ( h & 7 ) == 0 && !( w > h && ( w & 15 ) == 0 ) && !( w < h && ( h & 15 ) == 0 ) )
+  {
+    const HadPatSmem L = had_pat_smem( w, h, R, K );
+    const int T = ( w >> 3 ) * ( h >> 3 );
+    int bpc = std::max( 1, std::min( 8, 128 / std::max( 1, K * T ) ) );
+    while( bpc > 1 && (size_t) bpc * L.slotWords * 4 > 40 * 1024 ) bpc--;
+    const size_t smem = (size_t) bpc * L.slotWords * 4;
+    if( smem <= 96 * 1024 )
+    {
+      const int work = bpc * K * T;
+      const int bd = std::min( 256, std::max( 64, ( work + 31 ) & ~31 ) );
+      const int grid = ( n + bpc - 1 ) / bpc;
+      had8_pattern_kernel<<<grid, bd, smem, ctx->stream>>>( op, rp, dBlocks, n, w, h, R, bpc, dPattern, K, mp, dCost, dBest );
+      CHECK_LAUNCH( "had8_pattern_kernel" );
+      return VVB_OK;
+    }
+  }
+  const int G = dfunc == FAM_SAD ? pick_group( FAM_SAD, w, h >> mp.subShift ) : pick_group( dfunc, w, h );
 #define LAUNCH_PAT( GG ) cost_pattern_kernel<GG><<<n, 128, 0, ctx->stream>>>( op, rp, dBlocks, w, h, dfunc, dPattern, K, mp, dCost, dBest )
   switch( G ) { case 4: LAUNCH_PAT( 4 ); break; case 8: LAUNCH_PAT( 8 ); break; case 16: LAUNCH_PAT( 16 ); break; default: LAUNCH_PAT( 32 ); break; }
 #undef LAUNCH_PAT
@@ -653,7 +673,10 @@ int vvb_cost_pattern( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const
   if( best && ( rc = scratch( ctx, 1, (size_t) n * sizeof( vvb_best ), &dO ) ) ) return rc;
   CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
   CU( cudaMemcpyAsync( dP, pattern, (size_t) K * sizeof( vvb_mv ), cudaMemcpyHostToDevice, ctx->stream ) );
-  if( ( rc = vvb_cost_pattern_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (const vvb_mv*) dP, K, par, (uint32_t*) dS, (vvb_best*) dO ) ) ) return rc;
+  vvb_me_par hp = *par;                                   // the host sees the pattern: its radius selects the staged Hadamard kernel
+  hp.pattern_radius = 0;
+  for( int i = 0; i < K; i++ ) hp.pattern_radius = std::max( hp.pattern_radius, std::max( std::abs( (int) pattern[i].dx ), std::abs( (int) pattern[i].dy ) ) );
+  if( ( rc = vvb_cost_pattern_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (const vvb_mv*) dP, K, &hp, (uint32_t*) dS, (vvb_best*) dO ) ) ) return rc;
   if( costOut ) CU( cudaMemcpyAsync( costOut, dS, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( best ) CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( cudaStreamSynchronize( ctx->stream ) );

@@ -403,6 +403,163 @@ __global__ void __launch_bounds__( 128 ) cost_pattern_kernel( const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Hadamard refinement over a SMALL pattern (radius R <= 8) for shapes whose SATD dispatch lands on 8x8 tiles:
+// the (w+2R) x (h+2R) reference region around the start vector and the original block are staged once per block,
+// then ONE LANE PER (candidate, 8x8 tile) does the whole 64-point Hadamard in registers.  BPC blocks share a CTA.
+// ---------------------------------------------------------------------------------------------------------------
+struct HadPatSmem { int pitch, rows, slotWords; };
+__host__ __device__ inline HadPatSmem had_pat_smem( int w, int h, int R, int K )
+{
+  HadPatSmem s;
+  s.pitch = ( w + 2 * R + 2 + 7 ) & ~7;                    // pels per staged reference row (multiple of 8)
+  s.rows  = h + 2 * R;
+  s.slotWords = ( w * h ) / 2 + ( s.rows * s.pitch ) / 2 + ( ( K + 3 ) & ~3 ) + 4;    // org | ref | cost[K] | key(2)+pad
+  return s;
+}
+
+__global__ void __launch_bounds__( 256 ) had8_pattern_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+                                                              const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int R, int BPC,
+                                                              const vvb_mv* __restrict__ pattern, int K, const __grid_constant__ MePar par,
+                                                              uint32_t* __restrict__ costOut, vvb_best* __restrict__ bestOut )
+{
+  extern __shared__ __align__( 16 ) uint32_t smemHp[];
+  __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for( int i = tid; i < VVB_MVCOST_ENTRIES; i += nthr ) sMv[i] = par.tab.cost[i];
+  const HadPatSmem L = had_pat_smem( w, h, R, K );
+  const int tilesX = w >> 3, T = tilesX * ( h >> 3 );
+  const int orgWords = ( w * h ) >> 1, refWords = ( L.rows * L.pitch ) >> 1, wpr = L.pitch >> 1;
+  const int firstBlk = blockIdx.x * BPC;
+  const int nSlot = min( BPC, nBlocks - firstBlk );
+
+  // ---- stage BPC blocks: original (32-bit words, 16-byte aligned rows in smem) and the reference region from an even x
+  for( int j = 0; j < nSlot; j++ )
+  {
+    uint32_t* slot = smemHp + j * L.slotWords;
+    const vvb_block blk = blocks[firstBlk + j];
+    const int16_t* so = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
+    const bool oEven = ( ( (uintptr_t) so & 3 ) == 0 ) && ( ( orgPlane.stride & 1 ) == 0 );
+    const int lw2 = ilog2_dev( w ) - 1;
+    for( int i = tid; i < orgWords; i += nthr )
+    {
+      const int r = i >> lw2, c = i & ( ( w >> 1 ) - 1 );
+      const int16_t* p = so + (ptrdiff_t) r * orgPlane.stride + 2 * c;
+      slot[i] = oEven ? __ldg( reinterpret_cast<const uint32_t*>( p ) ) : ( (uint32_t)(uint16_t) __ldg( p ) | ( (uint32_t)(uint16_t) __ldg( p + 1 ) << 16 ) );
+    }
+    const int gx0 = blk.x + blk.start_x - R, gy0 = blk.y + blk.start_y - R;
+    const int ax0 = gx0 & ~1;
+    const int16_t* sr = refPlane.origin + (ptrdiff_t) gy0 * refPlane.stride + ax0;
+    const bool rEven = ( ( (uintptr_t) sr & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
+    uint32_t* refS = slot + orgWords;
+    const float inv = 1.0f / (float) wpr;
+    for( int i = tid; i < refWords; i += nthr )
+    {
+      const int r = fast_div( i, inv ), c = i - r * wpr;
+      const int16_t* p = sr + (ptrdiff_t) r * refPlane.stride + 2 * c;
+      uint32_t v = 0;
+      if( 2 * c < w + 2 * R + 2 ) v = rEven ? __ldg( reinterpret_cast<const uint32_t*>( p ) ) : ( (uint32_t)(uint16_t) __ldg( p ) | ( (uint32_t)(uint16_t) __ldg( p + 1 ) << 16 ) );
+      refS[i] = v;
+    }
+    uint32_t* costS = refS + refWords;
+    for( int i = tid; i < K; i += nthr ) costS[i] = 0u;
+    if( tid == 0 ) { costS[( ( K + 3 ) & ~3 )] = 0xffffffffu; costS[( ( K + 3 ) & ~3 ) + 1] = 0xffffffffu; }
+  }
+  __syncthreads();
+
+  // ---- one lane per (slot, candidate, tile)
+  const int perSlot = K * T, items = nSlot * perSlot;
+  const float invPer = 1.0f / (float) perSlot, invT = 1.0f / (float) T, invTx = 1.0f / (float) tilesX;
+  for( int it = tid; it < items; it += nthr )
+  {
+    const int j = fast_div( it, invPer ), loc = it - j * perSlot;
+    const int k = fast_div( loc, invT ), t = loc - k * T;
+    const int ty = fast_div( t, invTx ), tx = t - ty * tilesX;
+    const vvb_block blk = blocks[firstBlk + j];
+    const vvb_mv pm = pattern[k];
+    const int mx = blk.start_x + pm.dx, my = blk.start_y + pm.dy;
+    uint32_t* slot = smemHp + j * L.slotWords;
+    uint32_t* costS = slot + orgWords + refWords;
+    const bool inside = mx >= blk.left && mx <= blk.right && my >= blk.top && my <= blk.bottom && abs( (int) pm.dx ) <= R && abs( (int) pm.dy ) <= R;
+    if( !inside ) { if( t == 0 ) costS[k] = 0xffffffffu; continue; }
+    const int xoff = ( blk.x + blk.start_x - R ) & 1;
+    const int col0 = pm.dx + R + xoff + tx * 8, par1 = col0 & 1, wcol = col0 >> 1;
+    const uint32_t* refS = slot + orgWords;
+    int d[64];
+#pragma unroll
+    for( int r = 0; r < 8; r++ )
+    {
+      const uint4 o = *reinterpret_cast<const uint4*>( slot + ( ( ty * 8 + r ) * w + tx * 8 ) / 2 );
+      const uint32_t* rp = refS + ( pm.dy + R + ty * 8 + r ) * wpr + wcol;
+      uint32_t c0 = rp[0], c1 = rp[1], c2 = rp[2], c3 = rp[3];
+      if( par1 )
+      {
+        const uint32_t c4 = rp[4];
+        c0 = __funnelshift_r( c0, c1, 16 ); c1 = __funnelshift_r( c1, c2, 16 ); c2 = __funnelshift_r( c2, c3, 16 ); c3 = __funnelshift_r( c3, c4, 16 );
+      }
+      d[8*r+0] = lo16( o.x ) - lo16( c0 ); d[8*r+1] = hi16( o.x ) - hi16( c0 );
+      d[8*r+2] = lo16( o.y ) - lo16( c1 ); d[8*r+3] = hi16( o.y ) - hi16( c1 );
+      d[8*r+4] = lo16( o.z ) - lo16( c2 ); d[8*r+5] = hi16( o.z ) - hi16( c2 );
+      d[8*r+6] = lo16( o.w ) - lo16( c3 ); d[8*r+7] = hi16( o.w ) - hi16( c3 );
+    }
+#pragma unroll
+    for( int bit = 0; bit < 6; bit++ )
+    {
+#pragma unroll
+      for( int i = 0; i < 64; i++ )
+      {
+        if( !( i & ( 1 << bit ) ) )
+        {
+          const int a = d[i], bb = d[i | ( 1 << bit )];
+          d[i] = a + bb; d[i | ( 1 << bit )] = a - bb;
+        }
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for( int i = 0; i < 64; i++ ) s += (uint32_t) abs( d[i] );
+    const uint32_t dc = (uint32_t) abs( d[0] );
+    s = s - dc + ( dc >> 2 );                                  // RdCost.cpp:1316-1318
+    atomicAdd( &costS[k], ( s + 2 ) >> 2 );                    // :1319, summed over the tiles of the candidate
+  }
+  __syncthreads();
+
+  // ---- per block: cost table out, argmin with MV rate in list order
+  for( int i = tid; i < nSlot * K; i += nthr )
+  {
+    const int j = i / K, k = i - j * K;
+    uint32_t* slot = smemHp + j * L.slotWords;
+    uint32_t* costS = slot + orgWords + refWords;
+    const uint32_t c = costS[k];
+    if( costOut ) costOut[(size_t)( firstBlk + j ) * K + k] = c;
+    if( bestOut && c != 0xffffffffu )
+    {
+      const vvb_block blk = blocks[firstBlk + j];
+      const vvb_mv pm = pattern[k];
+      const unsigned long long tot = (unsigned long long) c + mv_cost( par, sMv, blk.start_x + pm.dx, blk.start_y + pm.dy, blk.pred_hor, blk.pred_ver );
+      atomicMin( reinterpret_cast<unsigned long long*>( costS + ( ( K + 3 ) & ~3 ) ), ( tot << 16 ) | (unsigned) k );
+    }
+  }
+  if( !bestOut ) return;
+  __syncthreads();
+  if( tid < nSlot )
+  {
+    uint32_t* slot = smemHp + tid * L.slotWords;
+    uint32_t* costS = slot + orgWords + refWords;
+    const unsigned long long key = *reinterpret_cast<unsigned long long*>( costS + ( ( K + 3 ) & ~3 ) );
+    vvb_best b;
+    if( key == ~0ull ) { b.dx = 0; b.dy = 0; b.sad = 0xffffffffu; b.cost = ~0ull; }
+    else
+    {
+      const int k = (int)( key & 0xffffu );
+      const vvb_block blk = blocks[firstBlk + tid];
+      const vvb_mv pm = pattern[k];
+      b.dx = (int16_t)( blk.start_x + pm.dx ); b.dy = (int16_t)( blk.start_y + pm.dy ); b.sad = costS[k]; b.cost = key >> 16;
+    }
+    bestOut[firstBlk + tid] = b;
+  }
+}
+
 // chains device-resident stages: the best vector of a search becomes the start / prediction offset of the next stage
 __global__ void blocks_set_start_kernel( vvb_block* __restrict__ blocks, const vvb_best* __restrict__ best, int n )
 {
