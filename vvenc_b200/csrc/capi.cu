@@ -218,6 +218,12 @@ int vvb_create( vvb_ctx** out, int device )
     return VVB_ERR_CUDA;
   }
   cudaFuncSetAttribute( sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  {
+    // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) == cudaSuccess && qres == cudaDriverEntryPointSuccess ) ctx->tmaEncode = fn;
+    cudaGetLastError();
+  }
   cudaFuncSetAttribute( fwd_trquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -253,6 +259,14 @@ int vvb_synchronize( vvb_ctx* ctx )
 void* vvb_stream( vvb_ctx* ctx ) { return ctx ? (void*) ctx->stream : nullptr; }
 
 int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) return VVB_ERR_ARG; *k = ctx->launches; return VVB_OK; }
+
+// window staging of the dense search: 1 = TMA (cp.async.bulk.tensor.2d, default when available), 0 = load/store loop
+int vvb_set_tma_staging( vvb_ctx* ctx, int enable )
+{
+  if( !ctx ) return VVB_ERR_ARG;
+  ctx->useTma = enable != 0;
+  return VVB_OK;
+}
 
 // selects the transform engine for square 16/32/64 TUs: 1 = tcgen05 tensor cores (default), 0 = IDP.2A CUDA-core kernel
 int vvb_set_tensor_transform( vvb_ctx* ctx, int enable )
@@ -583,7 +597,27 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
     if( score >= bestScore - 1e-9 ) { bestScore = std::max( bestScore, score ); bd = cand; }
   }
   const int grid = nb == 2 ? ( n + 3 ) / 4 : n;
-  sad_search_kernel<<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, dTables, tableStride, dBest );
+  // TMA descriptor of the padded reference plane with a (ws x winH) box; needs a 16-byte aligned buffer start and row pitch
+  CUtensorMap tmap; memset( &tmap, 0, sizeof( tmap ) );
+  TmaInfo ti; memset( &ti, 0, sizeof( ti ) );
+  const Plane& rp = ctx->planes.p[refPlane];
+  if( ctx->tmaEncode && ctx->useTma && L.ws <= 256 && L.winH <= 256 )
+  {
+    const int16_t* base = rp.origin - (ptrdiff_t) rp.margin * rp.stride - rp.margin;
+    if( ( (uintptr_t) base & 15 ) == 0 && ( rp.stride & 7 ) == 0 )
+    {
+      typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+      const cuuint64_t gdim[2] = { (cuuint64_t) rp.stride, (cuuint64_t)( rp.height + 2 * rp.margin ) };
+      const cuuint64_t gstr[1] = { (cuuint64_t) rp.stride * 2 };
+      const cuuint32_t box[2]  = { (cuuint32_t) L.ws, (cuuint32_t) L.winH };
+      const cuuint32_t estr[2] = { 1, 1 };
+      const CUresult r = ( (EncodeFn) ctx->tmaEncode )( &tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*) base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+      if( r == CUDA_SUCCESS ) { ti.enabled = 1; ti.nx = maxNx; ti.ny = maxNy; ti.quad = nb == 2 ? 1 : 0; ti.margin = rp.margin; }
+    }
+  }
+  sad_search_kernel<<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest );
   CHECK_LAUNCH( "sad_search_kernel" );
   return VVB_OK;
 }

@@ -84,6 +84,8 @@ struct vvb_ctx
   uint64_t       launches = 0;
   bool           poolBlocksAligned = false;   // see vvb_pool_hint
   bool           tensorTransform = true;      // see vvb_set_tensor_transform
+  bool           useTma = true;               // see vvb_set_tma_staging
+  void*          tmaEncode = nullptr;         // cuTensorMapEncodeTiled, resolved at vvb_create
   int            numSMs   = 148;
   // device-side constant data
   int8_t*        d_trTable   = nullptr;     // all transform matrices (vvc_tables.h)

@@ -496,7 +496,7 @@ __global__ void __launch_bounds__( 128 ) had8_pool_stream_kernel( const __grid_c
       if( with2Sad )
       {
 #pragma unroll
-        for( int i = 0; i < 64; i++ ) sadSum += (uint32_t) abs( d[i] );
+        for( int i = 0; i < 64; i++ ) sadSum = __sad( d[i], 0, sadSum );
       }
       // 2-D Walsh-Hadamard: the index bits 0..5 are butterflied one after another (order-free for sum|.| and for the DC term)
 #pragma unroll
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__( 128 ) had8_pool_stream_kernel( const __grid_c
       }
       uint32_t s = 0;
 #pragma unroll
-      for( int i = 0; i < 64; i++ ) s += (uint32_t) abs( d[i] );
+      for( int i = 0; i < 64; i++ ) s = __sad( d[i], 0, s );          // VABSDIFF: |d| + s in one instruction
       const uint32_t dc = (uint32_t) abs( d[0] );
       s = s - dc + ( dc >> 2 );                        // RdCost.cpp:1316-1318
       hadSum += ( s + 2 ) >> 2;                        // :1319

@@ -11,6 +11,7 @@
 // Both add the MV rate Distortion(sqrt(lambda)*bits) (CommonLib/RdCost.h:181-203) from a host-computed table and
 // resolve the argmin with the reference's tie-break: first strictly smaller cost in evaluation order.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder entry point is fetched at run time, libcuda is not linked)
 #include "common.cuh"
 #include "dist_kernels.cuh"
 
@@ -68,16 +69,39 @@ __host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny,
 
 __device__ __forceinline__ int fast_div( int i, float inv ) { return __float2int_rz( ( (float) i + 0.5f ) * inv ); }   // exact for i < 2^20, small divisors
 
+// TMA window staging: tmap describes the whole padded reference plane (uint16 elements), box = (ws x winH) of the launch's
+// largest window; (tmaNx, tmaNy, tmaQuad) say which window geometry the box was built for -- blocks with another geometry
+// use the load/store staging loop.  The copy is one cp.async.bulk.tensor.2d per CTA (any start alignment, zero fill outside).
+struct TmaInfo { int enabled, nx, ny, quad, margin, pad[3]; };
+
+__device__ __forceinline__ void mbar_init_s( uint32_t addr, uint32_t count ) { asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"( addr ), "r"( count ) : "memory" ); }
+__device__ __forceinline__ void mbar_expect_tx_s( uint32_t addr, uint32_t bytes ) { asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( addr ), "r"( bytes ) : "memory" ); }
+__device__ __forceinline__ void mbar_wait_s( uint32_t addr, uint32_t parity )
+{
+  uint32_t done = 0;
+  while( !done )
+    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"( done ) : "r"( addr ), "r"( parity ) : "memory" );
+}
+__device__ __forceinline__ void tma_load_2d( uint32_t smemDst, const CUtensorMap* tmap, uint32_t mbar, int x, int y )
+{
+  asm volatile( "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                :: "r"( smemDst ), "l"( (unsigned long long) tmap ), "r"( mbar ), "r"( x ), "r"( y ) : "memory" );
+}
+
 __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                             const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int quadMode,
-                                                            const __grid_constant__ MePar par,
+                                                            const __grid_constant__ MePar par, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TmaInfo tma,
                                                             uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut )
 {
-  extern __shared__ __align__( 16 ) unsigned char smemRaw[];
+  extern __shared__ __align__( 128 ) unsigned char smemRaw[];
   __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
+  __shared__ __align__( 8 ) unsigned long long sTmaBar;
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   for( int i = tid; i < VVB_MVCOST_ENTRIES; i += nthr ) sMv[i] = par.tab.cost[i];
   const int step = 1 << par.subShift;
+  const uint32_t tmaBar = (uint32_t) __cvta_generic_to_shared( &sTmaBar );
+  uint32_t tmaPhase = 0;
+  if( tma.enabled && tid == 0 ) { mbar_init_s( tmaBar, 1 ); asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" ); }
 
   // ---- which blocks does this CTA own, and are they a proper quad?
   const int first = quadMode ? blockIdx.x * 4 : blockIdx.x;
@@ -115,12 +139,22 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
     __syncthreads();                                      // previous sub-iteration fully consumed
     if( tid < 4 ) { sSumA[tid] = 0; sKey[tid] = ~0ull; }
 
-    // ---- stage the window: 32-bit words when the start is even, 16 loads in flight per thread (latency bound otherwise)
+    // ---- stage the window: TMA when the box matches this window, else 32-bit words (even start) / 16-bit, 16 loads in flight per thread
     {
       const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
       const int validW = MW + nx - 1;
       const bool even = ( ( (uintptr_t) src & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
-      if( even )
+      const bool viaTma = tma.enabled && nx == tma.nx && ny == tma.ny && ( isQuad ? 1 : 0 ) == tma.quad;
+      if( viaTma )
+      {
+        if( tid == 0 )
+        {
+          asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" );      // earlier generic accesses to the window are ordered before the async write
+          mbar_expect_tx_s( tmaBar, (uint32_t)( winH * ws * 2 ) );
+          tma_load_2d( (uint32_t) __cvta_generic_to_shared( win ), &tmap, tmaBar, blk.x + blk.left + tma.margin, blk.y + blk.top + tma.margin );
+        }
+      }
+      else if( even )
       {
         const int wpr = ws >> 1, total = winH * wpr, validWords = ( validW + 1 ) >> 1;
         const float inv = 1.0f / (float) wpr;
@@ -177,6 +211,7 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
         const int ry = r >= h ? r - h : r;                 // row inside the member
         if( ( ry & ( step - 1 ) ) == 0 ) sumA[( r >= h ? 2 : 0 ) + ( c >= w ? 1 : 0 )] += v;
       }
+      if( viaTma ) { mbar_wait_s( tmaBar, tmaPhase ); tmaPhase ^= 1; }
       __syncthreads();                                     // sSumA / sKey initialised, window visible
 #pragma unroll
       for( int m4 = 0; m4 < 4; m4++ )
@@ -517,7 +552,7 @@ __global__ void __launch_bounds__( 256 ) had8_pattern_kernel( const __grid_const
     }
     uint32_t s = 0;
 #pragma unroll
-    for( int i = 0; i < 64; i++ ) s += (uint32_t) abs( d[i] );
+    for( int i = 0; i < 64; i++ ) s = __sad( d[i], 0, s );            // VABSDIFF: |d| + s in one instruction
     const uint32_t dc = (uint32_t) abs( d[0] );
     s = s - dc + ( dc >> 2 );                                  // RdCost.cpp:1316-1318
     atomicAdd( &costS[k], ( s + 2 ) >> 2 );                    // :1319, summed over the tiles of the candidate
