@@ -84,7 +84,7 @@ struct vvb_ctx
   uint64_t       launches = 0;
   bool           poolBlocksAligned = false;   // see vvb_pool_hint
   bool           tensorTransform = true;      // see vvb_set_tensor_transform
-  bool           useTma = true;               // see vvb_set_tma_staging
+  bool           useTma = false;              // see vvb_set_tma_staging (off by default: unresolved illegal-instruction fault on the round-1 driver)
   void*          tmaEncode = nullptr;         // cuTensorMapEncodeTiled, resolved at vvb_create
   int            numSMs   = 148;
   // device-side constant data
