@@ -54,10 +54,15 @@ def synth_picture_pair(seed, w=W, h=H, margin=MARGIN):
     return np.ascontiguousarray(org), np.ascontiguousarray(ref), S
 
 
+_GRID_CACHE = {}
+
+
 def block_grid(n, w=W, h=H):
-    # quad-tree z-order, as the encoder's partitioner visits the blocks of one depth
-    from vvenc_b200.candidates import quad_order_grid
-    return quad_order_grid(n, w, h)
+    # quad-tree order of the encoder's partitioner: block j of size 2n is the parent of blocks 4j..4j+3 of size n (vvenc_b200.candidates.pyramid_lists)
+    if (w, h) not in _GRID_CACHE:
+        from vvenc_b200.candidates import pyramid_lists
+        _GRID_CACHE[(w, h)] = pyramid_lists(SIZES[0], len(SIZES), w, h)
+    return _GRID_CACHE[(w, h)][SIZES.index(n)]
 
 
 def units_per_step():
@@ -221,7 +226,7 @@ def main():
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
     u = units_per_step()
     total_units = u['sad'] + u['satd'] + u['tu']
-    config = {'workload': '2160p10_fullsearch_me_rdo', 'picture': '%dx%d 10-bit luma, 1 reference picture' % (W, H), 'block_sizes': list(SIZES),
+    config = {'workload': '2160p10_fullsearch_me_rdo', 'search': 'SAD pyramid (exact): pels visited at 8x8, 16/32/64 = sums of children; extra.direct_search has the per-size search', 'picture': '%dx%d 10-bit luma, 1 reference picture' % (W, H), 'block_sizes': list(SIZES),
               'search_range': SEARCH_RANGE, 'satd_points': len(refine_pattern()), 'tu': 'DCT-II + quant, one per block', 'qp': QP,
               'units_per_step': u, 'l2': 'inputs rotated over %d picture sets (> L2)' % N_PICTURE_SETS,
               'parallelism': 'ctu-row bands x%d' % max(1, args.gpus)}
@@ -307,12 +312,20 @@ def main():
         if rc != 0:
             raise RuntimeError('vvenc_b200: ' + lib.vvb_last_error(eng.h).decode())
 
-    def step_resident(i):
+    nlev = len(SIZES)
+    pyr_blocks = (ctypes.c_void_p * nlev)(*[d_blocks[n].data_ptr() for n in SIZES])
+    pyr_best = (ctypes.c_void_p * nlev)(*[d_best[n].data_ptr() for n in SIZES])
+    pyr_counts = (ctypes.c_int * nlev)(*[len(blocks_np[n]) for n in SIZES])
+
+    def step_resident(i, direct=False):
         s = i % N_PICTURE_SETS
         po, pr = 2 * s, 2 * s + 1
+        if not direct:       # SAD pyramid: pel work at 8x8 only, larger sizes are exact sums of their children's SADs at the same vector
+            chk(lib.vvb_sad_search_pyramid_dev(eng.h, po, pr, nlev, pyr_blocks, pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, pyr_best))
         for n in SIZES:
             nb = len(blocks_np[n])
-            chk(lib.vvb_sad_search_dev(eng.h, po, pr, P_(d_blocks[n].data_ptr()), nb, n, n, ctypes.byref(me), nx, nx, None, 0, P_(d_best[n].data_ptr())))
+            if direct:       # every size searched on its own (what InterSearch::xPatternSearch does per PU)
+                chk(lib.vvb_sad_search_dev(eng.h, po, pr, P_(d_blocks[n].data_ptr()), nb, n, n, ctypes.byref(me), nx, nx, None, 0, P_(d_best[n].data_ptr())))
             chk(lib.vvb_blocks_set_start_dev(eng.h, P_(d_blocks[n].data_ptr()), P_(d_best[n].data_ptr()), nb))
             chk(lib.vvb_cost_pattern_dev(eng.h, V.DF_HAD, po, pr, P_(d_blocks[n].data_ptr()), nb, n, n, P_(d_pat.data_ptr()), KP, ctypes.byref(me),
                                          P_(d_satd[n].data_ptr()), None))
@@ -349,6 +362,8 @@ def main():
     ms_total, launches = timed(step_resident, args.steps, max(3, args.warmup))
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
+    ms_direct, _ = timed(lambda i: step_resident(i, True), max(3, args.steps // 2), 3)
+    ms_direct /= max(3, args.steps // 2)
     value = total_units * world / (ms_step * 1e-3)
 
     # ------------------------------------------------------------------------------------------- per-kernel timing + rooflines (rank 0)
@@ -366,6 +381,15 @@ def main():
             return e0.elapsed_time(e1) / reps
         kt = {}
         comp_bytes = 0; t_search = 0.0; pel_diffs = 0
+        ctrp = [0]
+        def f_pyr():
+            s = ctrp[0] % N_PICTURE_SETS; ctrp[0] += 1
+            chk(lib.vvb_sad_search_pyramid_dev(eng.h, 2 * s, 2 * s + 1, nlev, pyr_blocks, pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, pyr_best))
+        def f_base():
+            s = ctrp[0] % N_PICTURE_SETS; ctrp[0] += 1
+            chk(lib.vvb_sad_search_dev(eng.h, 2 * s, 2 * s + 1, P_(d_blocks[SIZES[0]].data_ptr()), len(blocks_np[SIZES[0]]), SIZES[0], SIZES[0], ctypes.byref(me), nx, nx, None, 0,
+                                       P_(d_best[SIZES[0]].data_ptr())))
+        t_pyr = time_launch(f_pyr); t_base = time_launch(f_base)
         for n in SIZES:
             nb = len(blocks_np[n])
             ctr = [0]
@@ -388,15 +412,23 @@ def main():
         ctas, iters = 148 * 8, 4096
         t_probe = time_launch(lambda: chk(lib.vvb_alu_probe_dev(eng.h, ctas, iters, 1)), reps=5)
         alu_peak = ctas * 256 * iters * 16 / (t_probe * 1e-3)
-        ach = comp_bytes / (t_search * 1e-3) / 1e9
-        roofline = {'kernel': 'sad_search_kernel (4 launches per step: 8x8..64x64)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+        n0 = SIZES[0]; nb0 = len(blocks_np[n0])
+        pyr_bytes = nb0 * (2 * n0 * n0 + 2 * (n0 + 2 * SEARCH_RANGE) ** 2 + 16)            # compulsory bytes per block, base level (the only pel pass)
+        pyr_pel = nb0 * nx * nx * n0 * n0                                                     # pel differences actually evaluated by the pyramid
+        ach = pyr_bytes / (t_pyr * 1e-3) / 1e9
+        roofline = {'kernel': 'sad_search_kernel<quads + parent> + sad_table_sum_kernel (vvb_sad_search_pyramid_dev, 1 + %d launches per step)' % (nlev - 2), 'bound': 'hbm',
+                    'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
                     'note': 'dense +-32 search re-uses every reference pel up to 4225x from shared memory: integer-ALU bound by construction (SURVEY 8d W2); '
-                            'bytes = compulsory 2N^2 + 2(N+2R)^2 + 16 per block; see "alu" for the binding roof',
-                    'alu': {'achieved': pel_diffs / (t_search * 1e-3) / 1e12, 'peak': alu_peak / 1e12, 'unit': 'Tpel-diff/s', 'frac': pel_diffs / (t_search * 1e-3) / alu_peak,
-                            'peak_source': 'alu_probe_kernel mode 1: the same VIMNMX.S16x2 + IDP.2A per pel pair on register operands, measured in this run'},
-                    'share_of_step': t_search / ms_step}
+                            'bytes = compulsory 2N^2 + 2(N+2R)^2 + 16 per 8x8 block; see "alu" for the binding roof',
+                    'alu': {'achieved': pyr_pel / (t_pyr * 1e-3) / 1e12, 'peak': alu_peak / 1e12, 'unit': 'Tpel-diff/s', 'frac': pyr_pel / (t_pyr * 1e-3) / alu_peak,
+                            'peak_source': 'alu_probe_kernel mode 1: the same VIMNMX.S16x2 + IDP.2A per pel pair on register operands, measured in this run',
+                            'note': 'pel differences actually evaluated (base level); the %d larger block sizes cost 4 additions per candidate' % (nlev - 1)},
+                    'share_of_step': t_pyr / ms_step}
         extra['kernel_ms'] = kt
+        extra['pyramid_ms'] = t_pyr; extra['base_level_direct_ms'] = t_base
+        extra['direct_search'] = {'ms_per_step': ms_direct, 'value': total_units * world / (ms_direct * 1e-3), 'search_ms': t_search,
+                                  'alu_achieved_Tpel_diff_s': pel_diffs / (t_search * 1e-3) / 1e12, 'alu_frac': pel_diffs / (t_search * 1e-3) / alu_peak,
+                                  'note': 'same step with every block size searched on its own (no SAD pyramid): 4 sad_search launches'}
         # HBM-streaming evidence: candidate-pool SAD / SATD, 16x16, pool >> L2 (2wh + 2wh/K + 8 bytes per candidate)
         try:
             n = 16; Kp = 32; nb = len(blocks_np[n])
@@ -448,6 +480,8 @@ def main():
         for n in SIZES:
             h_blocks[n][:] = np.frombuffer(blocks_np[n].tobytes(), dtype=np.uint8)
         PA = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        h_pyr_blocks = (ctypes.c_void_p * nlev)(*[h_blocks[n].ctypes.data for n in SIZES])
+        h_pyr_best = (ctypes.c_void_p * nlev)(*[h_best[n].ctypes.data for n in SIZES])
         E0, E1 = 40, 41        # plane ids of the uploaded pictures
         h2d = 0; d2h = 0
         for n in SIZES:
@@ -462,9 +496,9 @@ def main():
             base = MARGIN * S + MARGIN
             chk(lib.vvb_plane_upload(eng.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
             chk(lib.vvb_plane_upload(eng.h, E1, ctypes.c_void_p(pr.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
+            chk(lib.vvb_sad_search_pyramid(eng.h, E0, E1, nlev, h_pyr_blocks, pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, h_pyr_best))
             for n in SIZES:
                 nb = len(blocks_np[n])
-                chk(lib.vvb_sad_search(eng.h, E0, E1, PA(h_blocks[n]), nb, n, n, ctypes.byref(me), None, 0, PA(h_best[n])))
                 # host logic between the calls: the best vector becomes the refinement centre / prediction offset
                 bv = h_best[n].view(V.BEST_DT); bl = h_blocks[n].view(V.BLOCK_DT)
                 bl['start_x'] = bv['dx']; bl['start_y'] = bv['dy']

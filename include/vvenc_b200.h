@@ -124,6 +124,18 @@ int vvb_sad_search    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_bl
 int vvb_sad_search_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, const vvb_me_par* par,
                         int max_nx, int max_ny, uint32_t* dev_sad_tables, int table_stride, vvb_best* dev_best_out );
 
+/* SAD pyramid over a quad-tree: level 0 holds blocks of base_w x base_w, level l blocks of (base_w << l); block p of level l+1 is the
+ * parent of blocks 4p..4p+3 of level l (z-order: (x,y),(x+s,y),(x,y+s),(x+s,y+s)); a level may carry extra blocks after its 4*count[l+1]
+ * children-of-parents.  Every block of every level gets the result InterSearch::xPatternSearch would give it over the SAME search range
+ * (nx x ny positions, identical for all blocks; each block keeps its own MV predictor): pel work happens once, at level 0, and the SAD of a
+ * larger block at a vector is the exact sum of its four children's SADs at that vector.  Parents whose children are not a proper quad or
+ * whose range differs are reported with cost = ~0. */
+int vvb_sad_search_pyramid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, int levels, const vvb_block* const* dev_blocks /* [levels] */,
+                                const int* counts /* [levels] */, int base_w, const vvb_me_par* par, int nx, int ny, vvb_best* const* dev_best_out /* [levels] */ );
+
+int vvb_sad_search_pyramid    ( vvb_ctx* ctx, int org_plane, int ref_plane, int levels, const vvb_block* const* blocks /* [levels], host */,
+                                const int* counts, int base_w, const vvb_me_par* par, int nx, int ny, vvb_best* const* best_out /* [levels], host */ );
+
 /* Fixed candidate set = the static point pattern of xTZ8PointDiamondSearch / raster scan
  * (InterSearch.cpp:557-758, 2491-2497) around (start_x,start_y): pattern[k] = (dx,dy) offsets, clipped against the
  * block's SearchRange (points outside are reported as UINT32_MAX and never win).  costs are SAD only;

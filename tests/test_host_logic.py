@@ -36,3 +36,19 @@ def test_quad_order_grid_is_a_permutation_of_the_raster_grid():
         assert len(xs) == len(want) and set(zip(xs.tolist(), ys.tolist())) == want
         # leading entries come in proper quads
         assert (xs[1], ys[1]) == (xs[0] + b, ys[0]) and (xs[2], ys[2]) == (xs[0], ys[0] + b) and (xs[3], ys[3]) == (xs[0] + b, ys[0] + b)
+
+
+def test_pyramid_lists_parent_child_relation():
+    for (base, levels, w, h) in ((8, 4, 192, 152), (8, 4, 3840, 2160), (16, 2, 96, 80)):
+        lists = cand.pyramid_lists(base, levels, w, h)
+        for l in range(levels):
+            s = base << l
+            xs, ys = lists[l]
+            want = set((x, y) for y in range(0, (h // s) * s, s) for x in range(0, (w // s) * s, s))
+            assert set(zip(xs.tolist(), ys.tolist())) == want and len(xs) == len(want)      # every level tiles the picture exactly once
+        for l in range(levels - 1):
+            cx, cy = lists[l]; px, py = lists[l + 1]; s = base << l
+            assert len(cx) >= 4 * len(px)
+            for j in range(len(px)):
+                kids = [(int(cx[4 * j + i]), int(cy[4 * j + i])) for i in range(4)]
+                assert kids == [(px[j], py[j]), (px[j] + s, py[j]), (px[j], py[j] + s), (px[j] + s, py[j] + s)]

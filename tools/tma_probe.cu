@@ -56,6 +56,7 @@ __global__ void k_lib( const __grid_constant__ CUtensorMap pm, int x, int y, int
 int main( int argc, char** argv )
 {
   const int onlyMode = argc > 1 ? atoi( argv[1] ) : -1;
+  const int variant = argc > 2 ? atoi( argv[2] ) : 0;   // 0: uint16 + L2_128B, 1: uint16 + promotion none, 2: int32 elements + promotion none
   const int S = 288, R = 224, bw = 56, bh = 36;
   std::vector<uint16_t> h( S * R ); for( int i = 0; i < S * R; i++ ) h[i] = (uint16_t)( i * 7 + 3 );
   uint16_t *d, *o; cudaMalloc( &d, S * R * 2 ); cudaMalloc( &o, bw * bh * 2 ); cudaMemcpy( d, h.data(), S * R * 2, cudaMemcpyHostToDevice );
@@ -65,22 +66,23 @@ int main( int argc, char** argv )
   typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
   CUtensorMap tm; memset( &tm, 0, sizeof( tm ) );
-  const cuuint64_t gdim[2] = { S, R }; const cuuint64_t gstr[1] = { S * 2 }; const cuuint32_t box[2] = { bw, bh }; const cuuint32_t es[2] = { 1, 1 };
-  CUresult r = ( (EncodeFn) fn )( &tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+  const cuuint64_t gdim[2] = { (cuuint64_t)( variant == 2 ? S / 2 : S ), R }; const cuuint64_t gstr[1] = { S * 2 };
+  const cuuint32_t box[2] = { (cuuint32_t)( variant == 2 ? bw / 2 : bw ), bh }; const cuuint32_t es[2] = { 1, 1 };
+  CUresult r = ( (EncodeFn) fn )( &tm, variant == 2 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, variant == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
   printf( "encode: %d\n", (int) r );
   CUtensorMap* gtm; cudaMalloc( &gtm, sizeof( tm ) ); cudaMemcpy( gtm, &tm, sizeof( tm ), cudaMemcpyHostToDevice );
   for( int mode = 0; mode < 3; mode++ )
   {
     if( onlyMode >= 0 && mode != onlyMode ) continue;
-    const int x = 33, y = 17;
+    const int x = variant == 2 ? 16 : 33, y = 17;     // variant 2: x counts int32 elements (= pel 32)
     if( mode == 2 ) k_lib<<<1, 128, bw * bh * 2 + 256>>>( tm, x, y, bw, bh, o ); else
     if( mode == 0 ) k<0><<<1, 128, bw * bh * 2 + 256>>>( tm, gtm, x, y, bw, bh, o ); else k<1><<<1, 128, bw * bh * 2 + 256>>>( tm, gtm, x, y, bw, bh, o );
     e = cudaDeviceSynchronize();
     printf( "mode %d: %s\n", mode, cudaGetErrorString( e ) );
     if( e != cudaSuccess ) return 1;
     std::vector<uint16_t> res( bw * bh ); cudaMemcpy( res.data(), o, bw * bh * 2, cudaMemcpyDeviceToHost );
-    int bad = 0; for( int r2 = 0; r2 < bh; r2++ ) for( int c = 0; c < bw; c++ ) bad += res[r2 * bw + c] != h[( y + r2 ) * S + x + c];
+    int bad = 0; for( int r2 = 0; r2 < bh; r2++ ) for( int c = 0; c < bw; c++ ) bad += res[r2 * bw + c] != h[( y + r2 ) * S + ( variant == 2 ? 2 * x : x ) + c];
     printf( "mode %d mismatches %d\n", mode, bad );
   }
   return 0;

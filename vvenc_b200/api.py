@@ -144,6 +144,20 @@ class CostEngine:
         self._chk(self.lib.vvb_sad_search(self.h, org_plane, ref_plane, _p(blocks), n, w, h, ctypes.byref(par), _p(tab), ts, _p(best)))
         return (best, tab) if want_tables else best
 
+    def sad_search_pyramid(self, org_plane, ref_plane, level_blocks, base_w, par, nx, ny):
+        """level_blocks: list of BLOCK_DT arrays (level 0 = base size).  Device-resident call wrapped with torch buffers; returns [BEST_DT array] per level."""
+        import torch
+        levels = len(level_blocks)
+        d_blk = [torch.from_numpy(np.frombuffer(np.ascontiguousarray(b, dtype=L.BLOCK_DT).tobytes(), dtype=np.uint8).copy()).cuda() for b in level_blocks]
+        d_best = [torch.empty(max(1, len(b)) * 16, dtype=torch.uint8, device='cuda') for b in level_blocks]
+        pb = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in d_blk])
+        po = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in d_best])
+        cnt = (ctypes.c_int * levels)(*[len(b) for b in level_blocks])
+        torch.cuda.synchronize()
+        self._chk(self.lib.vvb_sad_search_pyramid_dev(self.h, org_plane, ref_plane, levels, pb, cnt, base_w, ctypes.byref(par), nx, ny, po))
+        self.synchronize()
+        return [np.frombuffer(t.cpu().numpy().tobytes(), dtype=L.BEST_DT)[:len(b)].copy() for t, b in zip(d_best, level_blocks)]
+
     def sad_pattern(self, org_plane, ref_plane, blocks, w, h, pattern, par, want_sad=True, want_best=True):
         blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
         pattern = np.ascontiguousarray(pattern, dtype=L.MV_DT)

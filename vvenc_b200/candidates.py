@@ -71,3 +71,30 @@ def quad_order_grid(block, pic_w, pic_h):
         for bx in range(nbx):
             xs.append(bx * block); ys.append((nby - 1) * block)
     return np.array(xs, dtype=np.int32), np.array(ys, dtype=np.int32)
+
+
+def pyramid_lists(base, levels, pic_w, pic_h):
+    """Block lists for vvb_sad_search_pyramid: level l holds blocks of size base << l; block j of level l+1 is the parent of blocks
+    4j..4j+3 of level l (z-order).  Blocks that no larger block covers (picture size not a multiple of the larger size) are appended
+    after the children of the level above, together with their own descendants.  Returns [(xs, ys)] per level."""
+    lists = [[] for _ in range(levels)]
+
+    def emit(level, x, y):
+        lists[level].append((x, y))
+        if level > 0:
+            s = base << (level - 1)
+            for (dx, dy) in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                emit(level - 1, x + dx * s, y + dy * s)
+
+    top = base << (levels - 1)
+    for y in range(0, pic_h - top + 1, top):
+        for x in range(0, pic_w - top + 1, top):
+            emit(levels - 1, x, y)
+    for l in range(levels - 2, -1, -1):
+        s = base << l
+        wc, hc = (pic_w // (2 * s)) * 2 * s, (pic_h // (2 * s)) * 2 * s      # area covered by the level above
+        for y in range(0, (pic_h // s) * s, s):
+            for x in range(0, (pic_w // s) * s, s):
+                if x >= wc or y >= hc:
+                    emit(l, x, y)
+    return [(np.array([p[0] for p in L], dtype=np.int32), np.array([p[1] for p in L], dtype=np.int32)) for L in lists]

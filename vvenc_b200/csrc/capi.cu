@@ -217,7 +217,8 @@ int vvb_create( vvb_ctx** out, int device )
     vvb_destroy( ctx );
     return VVB_ERR_CUDA;
   }
-  cudaFuncSetAttribute( sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   {
     // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
@@ -239,7 +240,7 @@ void vvb_destroy( vvb_ctx* ctx )
   cudaSetDevice( ctx->device );
   if( ctx->stream ) cudaStreamSynchronize( ctx->stream );
   for( int i = 0; i < VVB_MAX_PLANES; i++ ) if( ctx->owned[i] ) cudaFree( ctx->owned[i] );
-  for( int i = 0; i < 6; i++ ) if( ctx->d_scratch[i] ) cudaFree( ctx->d_scratch[i] );
+  for( int i = 0; i < 8; i++ ) if( ctx->d_scratch[i] ) cudaFree( ctx->d_scratch[i] );
   if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
   if( ctx->d_scan ) cudaFree( ctx->d_scan );
   if( ctx->h_pinned ) cudaFreeHost( ctx->h_pinned );
@@ -566,9 +567,11 @@ static int checkSearchShape( vvb_ctx* ctx, int orgPlane, int refPlane, int w, in
 
 } // extern "C"
 
+struct PyramidOut { const vvb_block* parents; vvb_best* best; uint32_t* tables; int stride; };
+
 // host-known maximum window (nx, ny) variant used by both public entry points
 static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_me_par* par,
-                            int maxNx, int maxNy, int quad, uint32_t* dTables, int tableStride, vvb_best* dBest )
+                            int maxNx, int maxNy, int quad, uint32_t* dTables, int tableStride, vvb_best* dBest, const PyramidOut* pyr = nullptr )
 {
   int rc = checkSearchShape( ctx, orgPlane, refPlane, w, h );
   if( rc ) return rc;
@@ -581,7 +584,8 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
   // z-order quads share one staged window; fall back to one block per CTA when the quad window does not fit
   int nb = ( quad && w >= 8 && n >= 4 ) ? 2 : 1;
   SearchSmem L = search_smem( w, h, maxNx, maxNy, nb, nb );
-  if( nb == 2 && (size_t) L.total + 16 > 100 * 1024 ) { nb = 1; L = search_smem( w, h, maxNx, maxNy, 1, 1 ); }
+  if( nb == 2 && (size_t) L.total + 16 > 100 * 1024 && !pyr ) { nb = 1; L = search_smem( w, h, maxNx, maxNy, 1, 1 ); }
+  if( pyr && nb != 2 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "the SAD pyramid needs quads of blocks at least 8 wide" );
   const size_t smem = (size_t) L.total + 16;
   if( smem > 220 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search window does not fit shared memory (reduce the range)" );
   // block size: the multiple of 32 in 64..384 that wastes the fewest thread slots on the (members x ny x strips) work items; ties -> larger
@@ -617,12 +621,77 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
       if( r == CUDA_SUCCESS ) { ti.enabled = 1; ti.nx = maxNx; ti.ny = maxNy; ti.quad = nb == 2 ? 1 : 0; ti.margin = rp.margin; }
     }
   }
-  sad_search_kernel<<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest );
+  if( ti.enabled ) sad_search_kernel<true><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest,
+                                                                            pyr ? pyr->parents : nullptr, pyr ? pyr->best : nullptr, pyr ? pyr->tables : nullptr, pyr ? pyr->stride : 0 );
+  else             sad_search_kernel<false><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest,
+                                                                             pyr ? pyr->parents : nullptr, pyr ? pyr->best : nullptr, pyr ? pyr->tables : nullptr, pyr ? pyr->stride : 0 );
   CHECK_LAUNCH( "sad_search_kernel" );
   return VVB_OK;
 }
 
 extern "C" {
+
+// SAD pyramid (see include/vvenc_b200.h): pel work at the base level only, every higher level is the exact sum of its children's SADs
+int vvb_sad_search_pyramid_dev( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, const vvb_block* const* dBlocks, const int* counts, int baseW,
+                                const vvb_me_par* par, int nx, int ny, vvb_best* const* dBest )
+{
+  if( !ctx || !dBlocks || !counts || !dBest || !par || levels < 2 || levels > 5 || nx < 1 || ny < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  for( int l = 0; l < levels; l++ ) if( !dBlocks[l] || !dBest[l] || counts[l] < 0 ) return fail( ctx, VVB_ERR_ARG, "bad level arguments" );
+  for( int l = 0; l + 1 < levels; l++ ) if( counts[l] < 4 * counts[l + 1] ) return fail( ctx, VVB_ERR_ARG, "a level is shorter than four times the next one" );
+  if( ( baseW << ( levels - 1 ) ) > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "top level above 128" );
+  if( counts[0] == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int T = nx * ny;
+  void* tab[2] = { nullptr, nullptr };
+  int rc;
+  if( levels > 2 && ( rc = scratch( ctx, 6, (size_t) counts[1] * T * 4, &tab[1] ) ) ) return rc;
+  if( levels > 3 && ( rc = scratch( ctx, 7, (size_t) counts[2] * T * 4, &tab[0] ) ) ) return rc;
+  CU( cudaMemsetAsync( dBest[1], 0xff, (size_t) counts[1] * sizeof( vvb_best ), ctx->stream ) );   // parents of broken quads stay "invalid" (cost = ~0)
+  PyramidOut po{ dBlocks[1], dBest[1], (uint32_t*) tab[1], T };
+  ctx->launches++;                                                                                  // the memset node
+  if( counts[1] > 0 && ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks[0], 4 * counts[1], baseW, baseW, par, nx, ny, 1, nullptr, 0, dBest[0], &po ) ) ) return rc;
+  if( counts[0] > 4 * counts[1] &&      // base-level blocks without a parent
+      ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks[0] + 4 * counts[1], counts[0] - 4 * counts[1], baseW, baseW, par, nx, ny, 1, nullptr, 0, dBest[0] + 4 * counts[1] ) ) ) return rc;
+  MePar mp;
+  if( ( rc = makeMePar( ctx, par, mp ) ) ) return rc;
+  for( int l = 2; l < levels; l++ )
+  {
+    uint32_t* in  = (uint32_t*) tab[( l - 1 ) & 1];
+    uint32_t* out = l + 1 < levels ? (uint32_t*) tab[l & 1] : nullptr;
+    if( counts[l] == 0 ) continue;
+    sad_table_sum_kernel<<<counts[l], 256, 0, ctx->stream>>>( dBlocks[l], counts[l], nx, ny, mp, in, T, out, T, dBest[l] );
+    CHECK_LAUNCH( "sad_table_sum_kernel" );
+  }
+  return VVB_OK;
+}
+
+// host-buffer twin of the pyramid: block lists up, best tables down, one synchronisation
+int vvb_sad_search_pyramid( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, const vvb_block* const* blocks, const int* counts, int baseW,
+                            const vvb_me_par* par, int nx, int ny, vvb_best* const* best )
+{
+  if( !ctx || !blocks || !counts || !best || !par || levels < 2 || levels > 5 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  size_t total = 0;
+  for( int l = 0; l < levels; l++ ) { if( !blocks[l] || !best[l] || counts[l] < 0 ) return fail( ctx, VVB_ERR_ARG, "bad level arguments" ); total += (size_t) counts[l]; }
+  for( int l = 0; l < levels; l++ )
+    for( int i = 0; i < counts[l]; i++ )
+      if( blocks[l][i].right - blocks[l][i].left + 1 != nx || blocks[l][i].bottom - blocks[l][i].top + 1 != ny ) return fail( ctx, VVB_ERR_ARG, "pyramid blocks must share one nx x ny range" );
+  if( total == 0 ) return VVB_OK;
+  void *dB, *dO; int rc;
+  if( ( rc = scratch( ctx, 0, total * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 1, total * sizeof( vvb_best ), &dO ) ) ) return rc;
+  const vvb_block* pb[5]; vvb_best* po[5];
+  size_t off = 0;
+  for( int l = 0; l < levels; l++ )
+  {
+    pb[l] = (const vvb_block*) dB + off; po[l] = (vvb_best*) dO + off;
+    if( counts[l] ) CU( cudaMemcpyAsync( (void*) pb[l], blocks[l], (size_t) counts[l] * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+    off += (size_t) counts[l];
+  }
+  if( ( rc = vvb_sad_search_pyramid_dev( ctx, orgPlane, refPlane, levels, pb, counts, baseW, par, nx, ny, po ) ) ) return rc;
+  for( int l = 0; l < levels; l++ )
+    if( counts[l] ) CU( cudaMemcpyAsync( best[l], po[l], (size_t) counts[l] * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
 
 // device-resident variant: the host states the largest window (max_nx x max_ny positions) in the batch, it sizes shared memory
 int vvb_sad_search_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_me_par* par,

@@ -62,7 +62,7 @@ __host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny,
   s.offOrg   = s.winH * s.ws * 2;                          // bytes
   s.offV     = s.offOrg + nbx * w * nby * h * 2;
   s.offBits  = s.offV + s.winH * s.nxpV * 4;
-  s.offMisc  = s.offBits + ( ( s.nxp + ny + 3 ) & ~3 ) * 4;
+  s.offMisc  = s.offBits + ( ( 2 * ( s.nxp + ny ) + 3 ) & ~3 ) * 4;   // member bits + parent bits (pyramid mode)
   s.total    = s.offMisc + 64;
   return s;
 }
@@ -88,10 +88,86 @@ __device__ __forceinline__ void tma_load_2d( uint32_t smemDst, const CUtensorMap
                 :: "r"( smemDst ), "l"( (unsigned long long) tmap ), "r"( mbar ), "r"( x ), "r"( y ) : "memory" );
 }
 
+// - sum over the visited rows of min(org, ref) for a strip of 8 adjacent candidates: acc[k] = -sum min(o, r(k))
+__device__ __forceinline__ void strip_min_sums( const int16_t* __restrict__ obase, const int16_t* __restrict__ rbase, int MW, int ws, int w, int h, int step, int (&acc)[SS_STRIP] )
+{
+#pragma unroll
+  for( int k = 0; k < SS_STRIP; k++ ) acc[k] = 0;
+  if( w >= SS_XCHUNK )
+  {
+    for( int y = 0; y < h; y += step )
+    {
+      const uint32_t* orow = reinterpret_cast<const uint32_t*>( obase + y * MW );
+      const uint32_t* rrow = reinterpret_cast<const uint32_t*>( rbase + y * ws );
+      for( int x = 0; x < w; x += SS_XCHUNK )
+      {
+        uint32_t o[SS_XCHUNK / 2], r[SS_XCHUNK / 2 + SS_STRIP / 2];
+#pragma unroll
+        for( int i = 0; i < SS_XCHUNK / 2; i += 4 ) *reinterpret_cast<uint4*>( &o[i] ) = *reinterpret_cast<const uint4*>( orow + x / 2 + i );
+#pragma unroll
+        for( int i = 0; i < SS_XCHUNK / 2 + SS_STRIP / 2; i += 4 ) *reinterpret_cast<uint4*>( &r[i] ) = *reinterpret_cast<const uint4*>( rrow + x / 2 + i );
+#pragma unroll
+        for( int k = 0; k < SS_STRIP; k++ )
+        {
+#pragma unroll
+          for( int i = 0; i < SS_XCHUNK / 2; i++ )
+          {
+            const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
+            acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
+          }
+        }
+      }
+    }
+  }
+  else if( w == 8 )
+  {
+    for( int y = 0; y < h; y += step )
+    {
+      uint32_t o[4], r[8];
+      *reinterpret_cast<uint4*>( &o[0] ) = *reinterpret_cast<const uint4*>( obase + y * MW );
+      *reinterpret_cast<uint4*>( &r[0] ) = *reinterpret_cast<const uint4*>( rbase + y * ws );
+      *reinterpret_cast<uint4*>( &r[4] ) = *reinterpret_cast<const uint4*>( rbase + y * ws + 8 );
+#pragma unroll
+      for( int k = 0; k < SS_STRIP; k++ )
+      {
+#pragma unroll
+        for( int i = 0; i < 4; i++ )
+        {
+          const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
+          acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
+        }
+      }
+    }
+  }
+  else      // w == 4 (single-block mode only)
+  {
+    for( int y = 0; y < h; y += step )
+    {
+      uint32_t o[2], r[8];
+      *reinterpret_cast<uint2*>( &o[0] ) = *reinterpret_cast<const uint2*>( obase + y * MW );
+      *reinterpret_cast<uint4*>( &r[0] ) = *reinterpret_cast<const uint4*>( rbase + y * ws );
+      *reinterpret_cast<uint4*>( &r[4] ) = *reinterpret_cast<const uint4*>( rbase + y * ws + 8 );
+#pragma unroll
+      for( int k = 0; k < SS_STRIP; k++ )
+      {
+#pragma unroll
+        for( int i = 0; i < 2; i++ )
+        {
+          const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
+          acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
+        }
+      }
+    }
+  }
+}
+
+template<bool USE_TMA>
 __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                             const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int quadMode,
                                                             const __grid_constant__ MePar par, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TmaInfo tma,
-                                                            uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut )
+                                                            uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut,
+                                                            const vvb_block* __restrict__ parentBlocks, vvb_best* __restrict__ parentBest,
+                                                            uint32_t* __restrict__ parentTables, int parentStride )
 {
   extern __shared__ __align__( 128 ) unsigned char smemRaw[];
   __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
@@ -101,7 +177,7 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
   const int step = 1 << par.subShift;
   const uint32_t tmaBar = (uint32_t) __cvta_generic_to_shared( &sTmaBar );
   uint32_t tmaPhase = 0;
-  if( tma.enabled && tid == 0 ) { mbar_init_s( tmaBar, 1 ); asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" ); }
+  if( USE_TMA && tma.enabled && tid == 0 ) { mbar_init_s( tmaBar, 1 ); asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" ); }
 
   // ---- which blocks does this CTA own, and are they a proper quad?
   const int first = quadMode ? blockIdx.x * 4 : blockIdx.x;
@@ -134,17 +210,18 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
     int*      bitsX = reinterpret_cast<int*>( smemRaw + L.offBits );              // [nxp]
     int*      bitsY = bitsX + nxp;                                                // [ny]
     int*      sSumA = reinterpret_cast<int*>( smemRaw + L.offMisc );              // [4]
-    unsigned long long* sKey = reinterpret_cast<unsigned long long*>( smemRaw + L.offMisc + 16 );   // [4] (cost << 16 | raster order)
+    unsigned long long* sKey = reinterpret_cast<unsigned long long*>( smemRaw + L.offMisc + 16 );   // [5] members + parent (cost << 16 | raster order)
 
     __syncthreads();                                      // previous sub-iteration fully consumed
-    if( tid < 4 ) { sSumA[tid] = 0; sKey[tid] = ~0ull; }
+    if( tid < 4 ) sSumA[tid] = 0;
+    if( tid < 5 ) sKey[tid] = ~0ull;
 
     // ---- stage the window: TMA when the box matches this window, else 32-bit words (even start) / 16-bit, 16 loads in flight per thread
     {
       const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
       const int validW = MW + nx - 1;
       const bool even = ( ( (uintptr_t) src & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
-      const bool viaTma = tma.enabled && nx == tma.nx && ny == tma.ny && ( isQuad ? 1 : 0 ) == tma.quad;
+      const bool viaTma = USE_TMA && tma.enabled && nx == tma.nx && ny == tma.ny && ( isQuad ? 1 : 0 ) == tma.quad;
       if( viaTma )
       {
         if( tid == 0 )
@@ -265,115 +342,142 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
     }
     __syncthreads();
 
-    // ---- candidates: item = (member, cy, strip of 8 cx); a thread walks items in increasing order, so members are visited in order
-    const int perMem = ny * nStrips, items = nMem * perMem;
-    const float invPer = 1.0f / (float) perMem, invStr = 1.0f / (float) nStrips;
-    unsigned long long bestKey = ~0ull; int curMem = -1;
-    for( int it = tid; it < items; it += nthr )
+    // ---- candidates
+    const int perMem = ny * nStrips;
+    const float invStr = 1.0f / (float) nStrips;
+    const bool withParent = isQuad && parentBest != nullptr;
+    if( !withParent )
     {
-      const int mem = fast_div( it, invPer ), loc = it - mem * perMem;
-      const int cy = fast_div( loc, invStr ), st = loc - cy * nStrips;
-      const int bx = mem & ( nbx - 1 ), by = mem >> ( nbx - 1 );
-      const int cx0 = st * SS_STRIP;
-      if( mem != curMem )
+      // item = (member, cy, strip of 8 cx); a thread walks items in increasing order, so members are visited in order
+      const int items = nMem * perMem;
+      const float invPer = 1.0f / (float) perMem;
+      unsigned long long bestKey = ~0ull; int curMem = -1;
+      for( int it = tid; it < items; it += nthr )
       {
-        if( curMem >= 0 && bestKey != ~0ull ) atomicMin( &sKey[curMem], bestKey );
-        curMem = mem; bestKey = ~0ull;
-      }
-      int acc[SS_STRIP];                                 // = - sum min(org, ref)
-#pragma unroll
-      for( int k = 0; k < SS_STRIP; k++ ) acc[k] = 0;
-
-      const int16_t* obase = orgS + ( by * h ) * MW + bx * w;
-      const int16_t* rbase = win + ( by * h + cy ) * ws + bx * w + cx0;       // 16-byte aligned: ws % 8 == 0, bx*w % 8 == 0, cx0 % 8 == 0
-      if( w >= SS_XCHUNK )
-      {
-        for( int y = 0; y < h; y += step )
+        const int mem = fast_div( it, invPer ), loc = it - mem * perMem;
+        const int cy = fast_div( loc, invStr ), st = loc - cy * nStrips;
+        const int bx = mem & ( nbx - 1 ), by = mem >> ( nbx - 1 );
+        const int cx0 = st * SS_STRIP;
+        if( mem != curMem )
         {
-          const uint32_t* orow = reinterpret_cast<const uint32_t*>( obase + y * MW );
-          const uint32_t* rrow = reinterpret_cast<const uint32_t*>( rbase + y * ws );
-          for( int x = 0; x < w; x += SS_XCHUNK )
+          if( curMem >= 0 && bestKey != ~0ull ) atomicMin( &sKey[curMem], bestKey );
+          curMem = mem; bestKey = ~0ull;
+        }
+        int acc[SS_STRIP];
+        strip_min_sums( orgS + ( by * h ) * MW + bx * w, win + ( by * h + cy ) * ws + bx * w + cx0, MW, ws, w, h, step, acc );
+        const int byBits = bitsY[cy];
+        const int sumA = sSumA[( by << 1 ) | bx];
+        const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
+        const int gblk = first + ( isQuad ? mem : sub );
+#pragma unroll
+        for( int k = 0; k < SS_STRIP; k++ )
+        {
+          const int cx = cx0 + k;
+          if( cx < nx )
           {
-            uint32_t o[SS_XCHUNK / 2], r[SS_XCHUNK / 2 + SS_STRIP / 2];
-#pragma unroll
-            for( int i = 0; i < SS_XCHUNK / 2; i += 4 ) *reinterpret_cast<uint4*>( &o[i] ) = *reinterpret_cast<const uint4*>( orow + x / 2 + i );
-#pragma unroll
-            for( int i = 0; i < SS_XCHUNK / 2 + SS_STRIP / 2; i += 4 ) *reinterpret_cast<uint4*>( &r[i] ) = *reinterpret_cast<const uint4*>( rrow + x / 2 + i );
-#pragma unroll
-            for( int k = 0; k < SS_STRIP; k++ )
-            {
-#pragma unroll
-              for( int i = 0; i < SS_XCHUNK / 2; i++ )
-              {
-                const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
-                acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
-              }
-            }
+            const uint32_t sad = (uint32_t)( sumA + (int) vrow[k] + 2 * acc[k] ) << par.subShift;
+            const uint32_t order = (uint32_t)( cy * nx + cx );
+            if( sadTables ) sadTables[(size_t) gblk * tableStride + order] = sad;
+            const uint32_t bits = (uint32_t)( bitsX[cx] + byBits );
+            const unsigned long long c = (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1];
+            const unsigned long long key = ( c << 16 ) | order;          // lexicographic (cost, raster order): first strictly smaller wins
+            bestKey = key < bestKey ? key : bestKey;
           }
         }
       }
-      else if( w == 8 )
+      if( curMem >= 0 && bestKey != ~0ull ) atomicMin( &sKey[curMem], bestKey );
+    }
+    else
+    {
+      // SAD pyramid: item = (cy, strip); the thread evaluates the strip for all four members, so the parent block's SAD at the same
+      // vector -- the exact sum of its children's SADs -- costs four additions instead of a second pass over the pels.
+      const vvb_block pblk = parentBlocks[blockIdx.x];
+      const bool parentOk = pblk.left == blk.left && pblk.right == blk.right && pblk.top == blk.top && pblk.bottom == blk.bottom;
+      int* pBitsX = bitsY + ny;                           // parent MV bits (its own predictor) -- room reserved by search_smem
+      int* pBitsY = pBitsX + nxp;
+      for( int i = tid; i < nxp; i += nthr ) pBitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - pblk.pred_hor ) >> par.imvShift );
+      for( int i = tid; i < ny;  i += nthr ) pBitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - pblk.pred_ver ) >> par.imvShift );
+      __syncthreads();
+      unsigned long long key4[4] = { ~0ull, ~0ull, ~0ull, ~0ull }, keyP = ~0ull;
+      for( int it = tid; it < perMem; it += nthr )
       {
-        for( int y = 0; y < h; y += step )
+        const int cy = fast_div( it, invStr ), st = it - cy * nStrips;
+        const int cx0 = st * SS_STRIP;
+        const int byBits = bitsY[cy], pByBits = pBitsY[cy];
+        uint32_t psad[SS_STRIP];
+#pragma unroll
+        for( int k = 0; k < SS_STRIP; k++ ) psad[k] = 0;
+#pragma unroll
+        for( int mem = 0; mem < 4; mem++ )
         {
-          uint32_t o[4], r[8];
-          *reinterpret_cast<uint4*>( &o[0] ) = *reinterpret_cast<const uint4*>( obase + y * MW );
-          *reinterpret_cast<uint4*>( &r[0] ) = *reinterpret_cast<const uint4*>( rbase + y * ws );
-          *reinterpret_cast<uint4*>( &r[4] ) = *reinterpret_cast<const uint4*>( rbase + y * ws + 8 );
+          const int bx = mem & 1, by = mem >> 1;
+          int acc[SS_STRIP];
+          strip_min_sums( orgS + ( by * h ) * MW + bx * w, win + ( by * h + cy ) * ws + bx * w + cx0, MW, ws, w, h, step, acc );
+          const int sumA = sSumA[mem];
+          const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
+          unsigned long long bk = key4[mem];
 #pragma unroll
           for( int k = 0; k < SS_STRIP; k++ )
           {
-#pragma unroll
-            for( int i = 0; i < 4; i++ )
+            const int cx = cx0 + k;
+            if( cx < nx )
             {
-              const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
-              acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
+              const uint32_t sad = (uint32_t)( sumA + (int) vrow[k] + 2 * acc[k] ) << par.subShift;
+              const uint32_t order = (uint32_t)( cy * nx + cx );
+              psad[k] += sad;
+              if( sadTables ) sadTables[(size_t)( first + mem ) * tableStride + order] = sad;
+              const uint32_t bits = (uint32_t)( bitsX[cx] + byBits );
+              const unsigned long long key = ( ( (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | order;
+              bk = key < bk ? key : bk;
             }
           }
+          key4[mem] = bk;
         }
-      }
-      else      // w == 4 (single-block mode only)
-      {
-        for( int y = 0; y < h; y += step )
-        {
-          uint32_t o[2], r[8];
-          *reinterpret_cast<uint2*>( &o[0] ) = *reinterpret_cast<const uint2*>( obase + y * MW );
-          *reinterpret_cast<uint4*>( &r[0] ) = *reinterpret_cast<const uint4*>( rbase + y * ws );
-          *reinterpret_cast<uint4*>( &r[4] ) = *reinterpret_cast<const uint4*>( rbase + y * ws + 8 );
 #pragma unroll
-          for( int k = 0; k < SS_STRIP; k++ )
+        for( int k = 0; k < SS_STRIP; k++ )
+        {
+          const int cx = cx0 + k;
+          if( cx < nx )
           {
-#pragma unroll
-            for( int i = 0; i < 2; i++ )
-            {
-              const uint32_t rv = ( k & 1 ) ? __funnelshift_r( r[i + k / 2], r[i + k / 2 + 1], 16 ) : r[i + k / 2];
-              acc[k] = __dp2a_lo( (int) __vmins2( o[i], rv ), (int) 0x0000ffffu, acc[k] );
-            }
+            const uint32_t order = (uint32_t)( cy * nx + cx );
+            if( parentTables ) parentTables[(size_t) blockIdx.x * parentStride + order] = psad[k];
+            const uint32_t bits = (uint32_t)( pBitsX[cx] + pByBits );
+            const unsigned long long key = ( ( (unsigned long long) psad[k] + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | order;
+            keyP = key < keyP ? key : keyP;
           }
         }
       }
-
-      const int byBits = bitsY[cy];
-      const int sumA = sSumA[( by << 1 ) | bx];
-      const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
-      const int gblk = first + ( isQuad ? mem : sub );
+      // warp minimum first, then one atomic per warp and key
 #pragma unroll
-      for( int k = 0; k < SS_STRIP; k++ )
+      for( int m = 16; m > 0; m >>= 1 )
       {
-        const int cx = cx0 + k;
-        if( cx < nx )
+#pragma unroll
+        for( int q = 0; q < 4; q++ ) { const unsigned long long o = __shfl_xor_sync( 0xffffffffu, key4[q], m ); key4[q] = o < key4[q] ? o : key4[q]; }
+        const unsigned long long o = __shfl_xor_sync( 0xffffffffu, keyP, m ); keyP = o < keyP ? o : keyP;
+      }
+      if( lane == 0 )
+      {
+#pragma unroll
+        for( int q = 0; q < 4; q++ ) if( key4[q] != ~0ull ) atomicMin( &sKey[q], key4[q] );
+        if( keyP != ~0ull ) atomicMin( &sKey[4], keyP );
+      }
+      __syncthreads();
+      if( tid == 0 )
+      {
+        vvb_best b;
+        const unsigned long long key = sKey[4];
+        if( !parentOk || key == ~0ull ) { b.dx = 0; b.dy = 0; b.sad = 0xffffffffu; b.cost = ~0ull; }
+        else
         {
-          const uint32_t sad = (uint32_t)( sumA + (int) vrow[k] + 2 * acc[k] ) << par.subShift;
-          const uint32_t order = (uint32_t)( cy * nx + cx );
-          if( sadTables ) sadTables[(size_t) gblk * tableStride + order] = sad;
-          const uint32_t bits = (uint32_t)( bitsX[cx] + byBits );
-          const unsigned long long c = (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1];
-          const unsigned long long key = ( c << 16 ) | order;          // lexicographic (cost, raster order): first strictly smaller wins
-          bestKey = key < bestKey ? key : bestKey;
+          const uint32_t order = (uint32_t)( key & 0xffffu );
+          const int cy = order / nx, cx = order - cy * nx;
+          const uint32_t bits = (uint32_t)( pBitsX[cx] + pBitsY[cy] );
+          b.dx = (int16_t)( blk.left + cx ); b.dy = (int16_t)( blk.top + cy ); b.cost = key >> 16;
+          b.sad = (uint32_t)( b.cost - sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] );
         }
+        parentBest[blockIdx.x] = b;
       }
     }
-    if( curMem >= 0 && bestKey != ~0ull ) atomicMin( &sKey[curMem], bestKey );
     __syncthreads();
     if( tid < nMem )
     {
@@ -387,6 +491,57 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
       b.sad = (uint32_t)( cost - sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] );
       bestOut[first + ( isQuad ? tid : sub )] = b;
     }
+  }
+}
+
+// Pyramid level >= 2: the SAD table of a parent block is the sum of its four children's tables (children 4p..4p+3 of the level below);
+// argmin with the parent's own MV predictor; optional table output for the next level.  One CTA per parent.
+__global__ void __launch_bounds__( 256 ) sad_table_sum_kernel( const vvb_block* __restrict__ parents, int nParents, int nx, int ny, const __grid_constant__ MePar par,
+                                                               const uint32_t* __restrict__ childTables, int childStride, uint32_t* __restrict__ outTables, int outStride,
+                                                               vvb_best* __restrict__ bestOut )
+{
+  __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
+  __shared__ int sBitsX[512], sBitsY[512];
+  __shared__ unsigned long long sKeyP;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  const vvb_block blk = parents[blockIdx.x];
+  for( int i = tid; i < VVB_MVCOST_ENTRIES; i += nthr ) sMv[i] = par.tab.cost[i];
+  for( int i = tid; i < nx; i += nthr ) sBitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - blk.pred_hor ) >> par.imvShift );
+  for( int i = tid; i < ny; i += nthr ) sBitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - blk.pred_ver ) >> par.imvShift );
+  if( tid == 0 ) sKeyP = ~0ull;
+  __syncthreads();
+  const bool ok = ( blk.right - blk.left + 1 ) == nx && ( blk.bottom - blk.top + 1 ) == ny;
+  const uint32_t* c0 = childTables + (size_t)( 4 * blockIdx.x ) * childStride;
+  const int total = nx * ny;
+  const float inv = 1.0f / (float) nx;
+  unsigned long long best = ~0ull;
+  for( int o = tid; o < total; o += nthr )
+  {
+    const uint32_t s = __ldg( c0 + o ) + __ldg( c0 + childStride + o ) + __ldg( c0 + 2 * (size_t) childStride + o ) + __ldg( c0 + 3 * (size_t) childStride + o );
+    if( outTables ) outTables[(size_t) blockIdx.x * outStride + o] = s;
+    const int cy = fast_div( o, inv ), cx = o - cy * nx;
+    const uint32_t bits = (uint32_t)( sBitsX[cx] + sBitsY[cy] );
+    const unsigned long long key = ( ( (unsigned long long) s + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | (unsigned) o;
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for( int m = 16; m > 0; m >>= 1 ) { const unsigned long long o = __shfl_xor_sync( 0xffffffffu, best, m ); best = o < best ? o : best; }
+  if( lane == 0 && best != ~0ull ) atomicMin( &sKeyP, best );
+  __syncthreads();
+  if( tid == 0 )
+  {
+    vvb_best b;
+    const unsigned long long key = sKeyP;
+    if( !ok || key == ~0ull ) { b.dx = 0; b.dy = 0; b.sad = 0xffffffffu; b.cost = ~0ull; }
+    else
+    {
+      const uint32_t order = (uint32_t)( key & 0xffffu );
+      const int cy = order / nx, cx = order - cy * nx;
+      const uint32_t bits = (uint32_t)( sBitsX[cx] + sBitsY[cy] );
+      b.dx = (int16_t)( blk.left + cx ); b.dy = (int16_t)( blk.top + cy ); b.cost = key >> 16;
+      b.sad = (uint32_t)( b.cost - sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] );
+    }
+    bestOut[blockIdx.x] = b;
   }
 }
 
