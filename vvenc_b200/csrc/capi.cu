@@ -217,8 +217,10 @@ int vvb_create( vvb_ctx** out, int device )
     vvb_destroy( ctx );
     return VVB_ERR_CUDA;
   }
-  cudaFuncSetAttribute( sad_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
-  cudaFuncSetAttribute( sad_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   {
     // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
@@ -589,9 +591,9 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
   const size_t smem = (size_t) L.total + 16;
   if( smem > 220 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "search window does not fit shared memory (reduce the range)" );
   // block size: the multiple of 32 in 64..384 that wastes the fewest thread slots on the (members x ny x strips) work items; ties -> larger
-  const int items = nb * nb * maxNy * ( ( maxNx + SS_STRIP - 1 ) / SS_STRIP );
+  const int items = ( pyr ? 1 : nb * nb ) * maxNy * ( ( maxNx + SS_STRIP - 1 ) / SS_STRIP );      // pyramid items cover all four members
   int bd = 256; double bestScore = -1.0;
-  for( int cand = 64; cand <= 384; cand += 32 )
+  for( int cand = 64; cand <= ( pyr ? 256 : 384 ); cand += 32 )
   {
     const int rounds = ( items + cand - 1 ) / cand;
     const double eff = (double) items / ( (double) rounds * cand );
@@ -621,10 +623,11 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
       if( r == CUDA_SUCCESS ) { ti.enabled = 1; ti.nx = maxNx; ti.ny = maxNy; ti.quad = nb == 2 ? 1 : 0; ti.margin = rp.margin; }
     }
   }
-  if( ti.enabled ) sad_search_kernel<true><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest,
-                                                                            pyr ? pyr->parents : nullptr, pyr ? pyr->best : nullptr, pyr ? pyr->tables : nullptr, pyr ? pyr->stride : 0 );
-  else             sad_search_kernel<false><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest,
-                                                                             pyr ? pyr->parents : nullptr, pyr ? pyr->best : nullptr, pyr ? pyr->tables : nullptr, pyr ? pyr->stride : 0 );
+#define LAUNCH_SS( T_, P_ ) sad_search_kernel<T_, P_><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest, \
+                                                                                    pyr ? pyr->parents : nullptr, pyr ? pyr->best : nullptr, pyr ? pyr->tables : nullptr, pyr ? pyr->stride : 0 )
+  if( pyr ) { if( ti.enabled ) LAUNCH_SS( true, true ); else LAUNCH_SS( false, true ); }
+  else      { if( ti.enabled ) LAUNCH_SS( true, false ); else LAUNCH_SS( false, false ); }
+#undef LAUNCH_SS
   CHECK_LAUNCH( "sad_search_kernel" );
   return VVB_OK;
 }

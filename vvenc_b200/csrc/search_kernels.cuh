@@ -62,7 +62,7 @@ __host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny,
   s.offOrg   = s.winH * s.ws * 2;                          // bytes
   s.offV     = s.offOrg + nbx * w * nby * h * 2;
   s.offBits  = s.offV + s.winH * s.nxpV * 4;
-  s.offMisc  = s.offBits + ( ( 2 * ( s.nxp + ny ) + 3 ) & ~3 ) * 4;   // member bits + parent bits (pyramid mode)
+  s.offMisc  = s.offBits + ( ( 5 * ( s.nxp + ny ) + 3 ) & ~3 ) * 4;   // MV bits per member (4) + parent (pyramid mode)
   s.total    = s.offMisc + 64;
   return s;
 }
@@ -161,8 +161,8 @@ __device__ __forceinline__ void strip_min_sums( const int16_t* __restrict__ obas
   }
 }
 
-template<bool USE_TMA>
-__global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+template<bool USE_TMA, bool PARENT>
+__global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                             const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int quadMode,
                                                             const __grid_constant__ MePar par, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TmaInfo tma,
                                                             uint32_t* __restrict__ sadTables, int tableStride, vvb_best* __restrict__ bestOut,
@@ -191,10 +191,15 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
     const vvb_block* q[3] = { &b1, &b2, &b3 };
 #pragma unroll
     for( int i = 0; i < 3; i++ )
-      isQuad = isQuad && q[i]->left == b0.left && q[i]->right == b0.right && q[i]->top == b0.top && q[i]->bottom == b0.bottom &&
-               q[i]->pred_hor == b0.pred_hor && q[i]->pred_ver == b0.pred_ver;
+      isQuad = isQuad && q[i]->left == b0.left && q[i]->right == b0.right && q[i]->top == b0.top && q[i]->bottom == b0.bottom;   // predictors may differ
   }
   const int nSub = isQuad ? 1 : owned;
+  if( PARENT && !isQuad )
+  {
+    // pyramid launches handle proper quads only: a broken quad reports its members and its parent as invalid
+    if( tid < owned ) { vvb_best b; b.dx = 0; b.dy = 0; b.sad = 0xffffffffu; b.cost = ~0ull; bestOut[first + tid] = b; }
+    return;
+  }
 
   for( int sub = 0; sub < nSub; sub++ )
   {
@@ -207,8 +212,8 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
     int16_t*  win   = reinterpret_cast<int16_t*>( smemRaw );
     int16_t*  orgS  = reinterpret_cast<int16_t*>( smemRaw + L.offOrg );          // [MH][MW]
     uint32_t* V     = reinterpret_cast<uint32_t*>( smemRaw + L.offV );            // [winH][nxpV]
-    int*      bitsX = reinterpret_cast<int*>( smemRaw + L.offBits );              // [nxp]
-    int*      bitsY = bitsX + nxp;                                                // [ny]
+    int*      bitsAll = reinterpret_cast<int*>( smemRaw + L.offBits );            // per member m: X bits [nxp] then Y bits [ny] at m*(nxp+ny); set 4 = parent
+    const int bitsSet = nxp + ny;
     int*      sSumA = reinterpret_cast<int*>( smemRaw + L.offMisc );              // [4]
     unsigned long long* sKey = reinterpret_cast<unsigned long long*>( smemRaw + L.offMisc + 16 );   // [5] members + parent (cost << 16 | raster order)
 
@@ -298,9 +303,14 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
         for( int m = 16; m > 0; m >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, m );
         if( lane == 0 && v ) atomicAdd( &sSumA[m4], v );
       }
-      // MV-rate bit counts per column / row of the window (RdCost.h:183-203)
-      for( int i = tid; i < nxp; i += nthr ) bitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - blk.pred_hor ) >> par.imvShift );
-      for( int i = tid; i < ny;  i += nthr ) bitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - blk.pred_ver ) >> par.imvShift );
+      // MV-rate bit counts per column / row of the window (RdCost.h:183-203), one set per member (each keeps its own predictor)
+      for( int mm = 0; mm < nMem; mm++ )
+      {
+        const vvb_block mb = isQuad ? blocks[first + mm] : blk;
+        int* bx_ = bitsAll + mm * bitsSet; int* by_ = bx_ + nxp;
+        for( int i = tid; i < nxp; i += nthr ) bx_[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - mb.pred_hor ) >> par.imvShift );
+        for( int i = tid; i < ny;  i += nthr ) by_[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - mb.pred_ver ) >> par.imvShift );
+      }
     }
     // ---- row sums Hs[r][cx'] = sum_{x<w} win[r][cx'+x]: one task = (row, strip of 8 cx')
     {
@@ -345,8 +355,7 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
     // ---- candidates
     const int perMem = ny * nStrips;
     const float invStr = 1.0f / (float) nStrips;
-    const bool withParent = isQuad && parentBest != nullptr;
-    if( !withParent )
+    if( !PARENT )
     {
       // item = (member, cy, strip of 8 cx); a thread walks items in increasing order, so members are visited in order
       const int items = nMem * perMem;
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
         }
         int acc[SS_STRIP];
         strip_min_sums( orgS + ( by * h ) * MW + bx * w, win + ( by * h + cy ) * ws + bx * w + cx0, MW, ws, w, h, step, acc );
+        const int* bitsX = bitsAll + mem * bitsSet; const int* bitsY = bitsX + nxp;
         const int byBits = bitsY[cy];
         const int sumA = sSumA[( by << 1 ) | bx];
         const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
       // vector -- the exact sum of its children's SADs -- costs four additions instead of a second pass over the pels.
       const vvb_block pblk = parentBlocks[blockIdx.x];
       const bool parentOk = pblk.left == blk.left && pblk.right == blk.right && pblk.top == blk.top && pblk.bottom == blk.bottom;
-      int* pBitsX = bitsY + ny;                           // parent MV bits (its own predictor) -- room reserved by search_smem
+      int* pBitsX = bitsAll + 4 * bitsSet;                // parent MV bits (its own predictor)
       int* pBitsY = pBitsX + nxp;
       for( int i = tid; i < nxp; i += nthr ) pBitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - pblk.pred_hor ) >> par.imvShift );
       for( int i = tid; i < ny;  i += nthr ) pBitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - pblk.pred_ver ) >> par.imvShift );
@@ -403,18 +413,20 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
       {
         const int cy = fast_div( it, invStr ), st = it - cy * nStrips;
         const int cx0 = st * SS_STRIP;
-        const int byBits = bitsY[cy], pByBits = pBitsY[cy];
+        const int pByBits = pBitsY[cy];
         uint32_t psad[SS_STRIP];
 #pragma unroll
         for( int k = 0; k < SS_STRIP; k++ ) psad[k] = 0;
-#pragma unroll
-        for( int mem = 0; mem < 4; mem++ )
+#pragma unroll 1
+        for( int mem = 0; mem < 4; mem++ )       // not unrolled on purpose: one copy of the strip code, key4[] lives in local memory (2 accesses per member)
         {
           const int bx = mem & 1, by = mem >> 1;
           int acc[SS_STRIP];
           strip_min_sums( orgS + ( by * h ) * MW + bx * w, win + ( by * h + cy ) * ws + bx * w + cx0, MW, ws, w, h, step, acc );
           const int sumA = sSumA[mem];
           const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
+          const int* bitsX = bitsAll + mem * bitsSet;
+          const int byBits = bitsX[nxp + cy];
           unsigned long long bk = key4[mem];
 #pragma unroll
           for( int k = 0; k < SS_STRIP; k++ )
@@ -485,7 +497,8 @@ __global__ void __launch_bounds__( 384 ) sad_search_kernel( const __grid_constan
       const uint32_t order = (uint32_t)( key & 0xffffu );
       const unsigned long long cost = key >> 16;
       const int cy = order / nx, cx = order - cy * nx;
-      const uint32_t bits = (uint32_t)( bitsX[cx] + bitsY[cy] );
+      const int* bitsX = bitsAll + tid * bitsSet;
+      const uint32_t bits = (uint32_t)( bitsX[cx] + bitsX[nxp + cy] );
       vvb_best b;
       b.dx = (int16_t)( blk.left + cx ); b.dy = (int16_t)( blk.top + cy ); b.cost = cost;
       b.sad = (uint32_t)( cost - sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] );
