@@ -68,7 +68,7 @@ int main( int argc, char** argv )
   CUtensorMap tm; memset( &tm, 0, sizeof( tm ) );
   const cuuint64_t gdim[2] = { (cuuint64_t)( variant == 2 ? S / 2 : S ), R }; const cuuint64_t gstr[1] = { S * 2 };
   const cuuint32_t box[2] = { (cuuint32_t)( variant == 2 ? bw / 2 : bw ), bh }; const cuuint32_t es[2] = { 1, 1 };
-  CUresult r = ( (EncodeFn) fn )( &tm, variant == 2 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = ( (EncodeFn) fn )( &tm, variant == 2 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : variant == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : variant == 4 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   CU_TENSOR_MAP_SWIZZLE_NONE, variant == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
   printf( "encode: %d\n", (int) r );
   CUtensorMap* gtm; cudaMalloc( &gtm, sizeof( tm ) ); cudaMemcpy( gtm, &tm, sizeof( tm ), cudaMemcpyHostToDevice );
