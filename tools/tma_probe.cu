@@ -75,7 +75,7 @@ int main( int argc, char** argv )
   for( int mode = 0; mode < 3; mode++ )
   {
     if( onlyMode >= 0 && mode != onlyMode ) continue;
-    const int x = variant == 2 ? 16 : 33, y = 17;     // variant 2: x counts int32 elements (= pel 32)
+    const int x = argc > 3 ? atoi( argv[3] ) : ( variant == 2 ? 16 : 33 ), y = 17;     // variant 2: x counts int32 elements (= pel 32)
     if( mode == 2 ) k_lib<<<1, 128, bw * bh * 2 + 256>>>( tm, x, y, bw, bh, o ); else
     if( mode == 0 ) k<0><<<1, 128, bw * bh * 2 + 256>>>( tm, gtm, x, y, bw, bh, o ); else k<1><<<1, 128, bw * bh * 2 + 256>>>( tm, gtm, x, y, bw, bh, o );
     e = cudaDeviceSynchronize();

@@ -56,14 +56,22 @@ __host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny,
   s.nxp      = s.nStrips * SS_STRIP;
   s.nStripsV = ( nx + ( nbx - 1 ) * w + SS_STRIP - 1 ) / SS_STRIP;
   s.nxpV     = s.nStripsV * SS_STRIP;
-  s.ws       = ( nbx * w + s.nxp + 8 + 7 ) & ~7;         // row pitch in pels, multiple of 8 -> every row 16-byte aligned
   s.winH     = nby * h + ny - 1;
   s.vRows    = ny + ( nby - 1 ) * h;
-  s.offOrg   = s.winH * s.ws * 2;                          // bytes
-  s.offV     = s.offOrg + nbx * w * nby * h * 2;
-  s.offBits  = s.offV + s.winH * s.nxpV * 4;
-  s.offMisc  = s.offBits + ( ( 5 * ( s.nxp + ny ) + 3 ) & ~3 ) * 4;   // MV bits per member (4) + parent (pyramid mode)
-  s.total    = s.offMisc + 64;
+  const int need = ( nbx * w + s.nxp + 8 + 7 ) & ~7;      // row pitch in pels, multiple of 8 -> every row 16-byte aligned
+  // Threads walk (row, strip) items in order, a warp's LDS.128 therefore wraps from strip nStrips-1 of one row to strip 0 of the next:
+  // with pitch*2 == 16*nStrips (mod 128) the wrap continues in the next 16-byte bank group (conflict-free); take that pitch if it fits.
+  const int padded = need + ( ( ( 8 * s.nStrips - need ) % 64 ) + 64 ) % 64;
+  for( int attempt = 0; attempt < 2; attempt++ )
+  {
+    s.ws       = attempt == 0 ? padded : need;
+    s.offOrg   = s.winH * s.ws * 2;                        // bytes
+    s.offV     = s.offOrg + nbx * w * nby * h * 2;
+    s.offBits  = s.offV + s.winH * s.nxpV * 4;
+    s.offMisc  = s.offBits + 5 * ( s.nxp + ( ( ny + 3 ) & ~3 ) ) * 4;   // MV bits per member (4) + parent (pyramid mode), each set 16-byte aligned
+    s.total    = s.offMisc + 64;
+    if( s.total + 16 <= ( nbx * nby > 1 ? 100 * 1024 : 220 * 1024 ) && s.ws <= 256 ) break;
+  }
   return s;
 }
 
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
     int16_t*  orgS  = reinterpret_cast<int16_t*>( smemRaw + L.offOrg );          // [MH][MW]
     uint32_t* V     = reinterpret_cast<uint32_t*>( smemRaw + L.offV );            // [winH][nxpV]
     int*      bitsAll = reinterpret_cast<int*>( smemRaw + L.offBits );            // per member m: X bits [nxp] then Y bits [ny] at m*(nxp+ny); set 4 = parent
-    const int bitsSet = nxp + ny;
+    const int bitsSet = nxp + ( ( ny + 3 ) & ~3 );
     int*      sSumA = reinterpret_cast<int*>( smemRaw + L.offMisc );              // [4]
     unsigned long long* sKey = reinterpret_cast<unsigned long long*>( smemRaw + L.offMisc + 16 );   // [5] members + parent (cost << 16 | raster order)
 
@@ -377,18 +385,23 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
         const int* bitsX = bitsAll + mem * bitsSet; const int* bitsY = bitsX + nxp;
         const int byBits = bitsY[cy];
         const int sumA = sSumA[( by << 1 ) | bx];
-        const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
         const int gblk = first + ( isQuad ? mem : sub );
+        // 8 consecutive words per thread: two LDS.128 each instead of 8 bank-conflicting LDS.32
+        uint32_t vv[SS_STRIP]; int bxv[SS_STRIP];
+        *reinterpret_cast<uint4*>( &vv[0] )  = *reinterpret_cast<const uint4*>( V + ( cy + by * h ) * nxpV + bx * w + cx0 );
+        *reinterpret_cast<uint4*>( &vv[4] )  = *reinterpret_cast<const uint4*>( V + ( cy + by * h ) * nxpV + bx * w + cx0 + 4 );
+        *reinterpret_cast<int4*>( &bxv[0] )  = *reinterpret_cast<const int4*>( bitsX + cx0 );
+        *reinterpret_cast<int4*>( &bxv[4] )  = *reinterpret_cast<const int4*>( bitsX + cx0 + 4 );
 #pragma unroll
         for( int k = 0; k < SS_STRIP; k++ )
         {
           const int cx = cx0 + k;
           if( cx < nx )
           {
-            const uint32_t sad = (uint32_t)( sumA + (int) vrow[k] + 2 * acc[k] ) << par.subShift;
+            const uint32_t sad = (uint32_t)( sumA + (int) vv[k] + 2 * acc[k] ) << par.subShift;
             const uint32_t order = (uint32_t)( cy * nx + cx );
             if( sadTables ) sadTables[(size_t) gblk * tableStride + order] = sad;
-            const uint32_t bits = (uint32_t)( bitsX[cx] + byBits );
+            const uint32_t bits = (uint32_t)( bxv[k] + byBits );
             const unsigned long long c = (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1];
             const unsigned long long key = ( c << 16 ) | order;          // lexicographic (cost, raster order): first strictly smaller wins
             bestKey = key < bestKey ? key : bestKey;
@@ -424,27 +437,34 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
           int acc[SS_STRIP];
           strip_min_sums( orgS + ( by * h ) * MW + bx * w, win + ( by * h + cy ) * ws + bx * w + cx0, MW, ws, w, h, step, acc );
           const int sumA = sSumA[mem];
-          const uint32_t* vrow = V + ( cy + by * h ) * nxpV + bx * w + cx0;
           const int* bitsX = bitsAll + mem * bitsSet;
           const int byBits = bitsX[nxp + cy];
           unsigned long long bk = key4[mem];
+          uint32_t vv[SS_STRIP]; int bxv[SS_STRIP];
+          *reinterpret_cast<uint4*>( &vv[0] )  = *reinterpret_cast<const uint4*>( V + ( cy + by * h ) * nxpV + bx * w + cx0 );
+          *reinterpret_cast<uint4*>( &vv[4] )  = *reinterpret_cast<const uint4*>( V + ( cy + by * h ) * nxpV + bx * w + cx0 + 4 );
+          *reinterpret_cast<int4*>( &bxv[0] )  = *reinterpret_cast<const int4*>( bitsX + cx0 );
+          *reinterpret_cast<int4*>( &bxv[4] )  = *reinterpret_cast<const int4*>( bitsX + cx0 + 4 );
 #pragma unroll
           for( int k = 0; k < SS_STRIP; k++ )
           {
             const int cx = cx0 + k;
             if( cx < nx )
             {
-              const uint32_t sad = (uint32_t)( sumA + (int) vrow[k] + 2 * acc[k] ) << par.subShift;
+              const uint32_t sad = (uint32_t)( sumA + (int) vv[k] + 2 * acc[k] ) << par.subShift;
               const uint32_t order = (uint32_t)( cy * nx + cx );
               psad[k] += sad;
               if( sadTables ) sadTables[(size_t)( first + mem ) * tableStride + order] = sad;
-              const uint32_t bits = (uint32_t)( bitsX[cx] + byBits );
+              const uint32_t bits = (uint32_t)( bxv[k] + byBits );
               const unsigned long long key = ( ( (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | order;
               bk = key < bk ? key : bk;
             }
           }
           key4[mem] = bk;
         }
+        int pbx[SS_STRIP];
+        *reinterpret_cast<int4*>( &pbx[0] ) = *reinterpret_cast<const int4*>( pBitsX + cx0 );
+        *reinterpret_cast<int4*>( &pbx[4] ) = *reinterpret_cast<const int4*>( pBitsX + cx0 + 4 );
 #pragma unroll
         for( int k = 0; k < SS_STRIP; k++ )
         {
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
           {
             const uint32_t order = (uint32_t)( cy * nx + cx );
             if( parentTables ) parentTables[(size_t) blockIdx.x * parentStride + order] = psad[k];
-            const uint32_t bits = (uint32_t)( pBitsX[cx] + pByBits );
+            const uint32_t bits = (uint32_t)( pbx[k] + pByBits );
             const unsigned long long key = ( ( (unsigned long long) psad[k] + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | order;
             keyP = key < keyP ? key : keyP;
           }
