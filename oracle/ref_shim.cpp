@@ -51,6 +51,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <immintrin.h>
+#include <dlfcn.h>
+#include "../include/vvenc_b200.h"   // only for the drop-in demo below (types + prototypes; symbols are resolved with dlsym)
 
 #define private public
 #define protected public
@@ -76,9 +78,13 @@ using namespace vvenc;
 
 namespace {
 
+void createRd( RdCost& rc, int opt );
+
 struct RefCtx
 {
-  RdCost                 rdScalar, rdSimd;
+  RdCost                 rdScalar, rdSimd, rdB200;
+  bool                   b200Ready = false;
+  RdCost& rd( int opt ) { if( opt == 2 && !b200Ready ) { createRd( rdB200, 2 ); b200Ready = true; } return opt == 2 ? rdB200 : opt ? rdSimd : rdScalar; }
   TrQuant*               tq      = nullptr;
   MCTF*                  mctf[2] = { nullptr, nullptr };
   AffineGradientSearch*  ags[2]  = { nullptr, nullptr };
@@ -146,6 +152,84 @@ inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, co
   dp.maximumDistortionForEarlyExit = MAX_DISTORTION;
   dp.distFunc = pickFunc( rc, family, w, bitDepth );
   return dp.distFunc( dp );
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Drop-in demo (compiled for real): the reference's own RdCost function-pointer tables
+// (RdCost.h:117-121) are overwritten with trampolines into libvvenc_b200.so -- exactly what a maintainer-written
+// RdCost::_initRdCostB200() would do.  opt == 2 in the probes below selects an RdCost patched this way, so the tests can
+// drive UNMODIFIED reference call sites (DistParam + distFunc, dmvrSadX5, m_fxdWtdPredPtr, the xPatternSearch replay)
+// with the GPU library underneath and compare against the AVX2 table.
+struct B200Api
+{
+  void* handle = nullptr;
+  decltype( &vvb_create )          create = nullptr;
+  decltype( &vvb_last_error )      lastError = nullptr;
+  decltype( &vvb_dist_block )      distBlock = nullptr;
+  decltype( &vvb_sad_mask_block )  sadMask = nullptr;
+  decltype( &vvb_sad_x5_block )    sadX5 = nullptr;
+  decltype( &vvb_fix_wsse_block )  fixWsse = nullptr;
+  decltype( &vvb_launch_count )    launchCount = nullptr;
+  std::string error;
+} g_b200;
+
+thread_local vvb_ctx* t_b200ctx = nullptr;
+vvb_ctx* b200CtxOfThread()
+{
+  if( !t_b200ctx && ( !g_b200.create || g_b200.create( &t_b200ctx, 0 ) != VVB_OK ) ) THROW( "no B200 context" );
+  return t_b200ctx;
+}
+
+template<int FAM> Distortion distB200( const DistParam& dp )
+{
+  if( dp.applyWeight ) THROW( " no support" );
+  int err = 0;
+  const Distortion d = g_b200.distBlock( b200CtxOfThread(), FAM, dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride,
+                                         dp.org.width, dp.org.height, dp.bitDepth, dp.subShift, &err );
+  if( err ) THROW( g_b200.lastError( b200CtxOfThread() ) );
+  return d;
+}
+Distortion sadMaskB200( const DistParam& dp )
+{
+  int err = 0;
+  const Distortion d = g_b200.sadMask( b200CtxOfThread(), dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, dp.org.width, dp.org.height,
+                                       dp.mask, dp.maskStride, dp.stepX, dp.maskStride2, dp.subShift, &err );
+  if( err ) THROW( g_b200.lastError( b200CtxOfThread() ) );
+  return d;
+}
+void sadX5B200( const DistParam& dp, Distortion* cost, bool centre )
+{
+  uint64_t c5[5];
+  if( g_b200.sadX5( b200CtxOfThread(), dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, dp.org.width, dp.org.height, dp.subShift, centre, c5 ) ) THROW( "b200 sadX5" );
+  for( int i = 0; i < 5; i++ ) if( i != 2 || centre ) cost[i] = c5[i];
+}
+Distortion fixWsseB200( const DistParam& dp, uint32_t w )
+{
+  int err = 0;
+  const Distortion d = g_b200.fixWsse( b200CtxOfThread(), dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, dp.org.width, dp.org.height, w, &err );
+  if( err ) THROW( g_b200.lastError( b200CtxOfThread() ) );
+  return d;
+}
+
+void installB200( RdCost& rc )      // slot = base + log2(width), TypeDef.h:339-382; row [1] (>10 bit) stays scalar like RdCost.cpp:125-126
+{
+  for( int l = 1; l < 8; l++ )
+  {
+    rc.m_afpDistortFunc[0][DF_SSE      + l] = distB200<VVB_DF_SSE>;
+    rc.m_afpDistortFunc[0][DF_SAD      + l] = distB200<VVB_DF_SAD>;
+    rc.m_afpDistortFunc[0][DF_HAD      + l] = distB200<VVB_DF_HAD>;
+    rc.m_afpDistortFunc[0][DF_HAD_fast + l] = distB200<VVB_DF_HAD_FAST>;
+  }
+  rc.m_afpDistortFunc[0][DF_HAD_2SAD]      = distB200<VVB_DF_HAD_2SAD>;
+  rc.m_afpDistortFunc[0][DF_SAD_WITH_MASK] = sadMaskB200;
+  rc.m_afpDistortFuncX5[0] = sadX5B200;  rc.m_afpDistortFuncX5[1] = sadX5B200;
+  rc.m_fxdWtdPredPtr       = fixWsseB200;
+}
+
+void createRd( RdCost& rc, int opt )     // 0 scalar, 1 SIMD, 2 SIMD table patched with the B200 trampolines
+{
+  rc.create( opt != 0 );
+  if( opt == 2 ) { if( !g_b200.handle ) THROW( "refshim_install_b200 not called" ); installB200( rc ); }
 }
 
 template<class F>
@@ -231,7 +315,29 @@ int mtsIdxFor( int trHor, int trVer )   // ours: 0 DCT2, 1 DCT8, 2 DST7 (referen
 
 extern "C" {
 
-int refshim_version() { return 3; }
+int refshim_version() { return 4; }
+
+// Drop-in demo: load libvvenc_b200.so (path given by the test) and remember its entry points; opt == 2 then patches them into RdCost.
+int refshim_install_b200( const char* libPath )
+{
+  std::lock_guard<std::mutex> lk( g_mtx );
+  if( g_b200.handle ) return 0;
+  void* h = dlopen( libPath, RTLD_NOW | RTLD_LOCAL );
+  if( !h ) { g_b200.error = dlerror(); return -1; }
+#define RESOLVE( member, name ) g_b200.member = (decltype( g_b200.member )) dlsym( h, #name ); if( !g_b200.member ) { g_b200.error = "missing " #name; dlclose( h ); return -2; }
+  RESOLVE( create, vvb_create )  RESOLVE( lastError, vvb_last_error )  RESOLVE( distBlock, vvb_dist_block )  RESOLVE( sadMask, vvb_sad_mask_block )
+  RESOLVE( sadX5, vvb_sad_x5_block )  RESOLVE( fixWsse, vvb_fix_wsse_block )  RESOLVE( launchCount, vvb_launch_count )
+#undef RESOLVE
+  g_b200.handle = h;
+  return 0;
+}
+const char* refshim_b200_error() { return g_b200.error.c_str(); }
+uint64_t refshim_b200_launches()   // kernels launched by the calling thread's drop-in context (proof that the numbers came from the GPU)
+{
+  uint64_t n = 0;
+  if( t_b200ctx && g_b200.launchCount ) g_b200.launchCount( t_b200ctx, &n );
+  return n;
+}
 
 // "SCALAR" | "SSE41" | "SSE42" | "AVX" | "AVX2"; rebuilds every probe object so that the per-instance pointers
 // are re-resolved (vvenc.cpp:412 -> VVEncImpl::setSIMDExtension, vvencimpl.cpp:800-866).
@@ -248,7 +354,7 @@ uint64_t refshim_dist( int opt, int family, const int16_t* org, int orgStride, c
                        int w, int h, int bitDepth, int subShift )
 {
   RefCtx& c = ctx();
-  return callDist( opt ? c.rdSimd : c.rdScalar, family, org, orgStride, cur, curStride, w, h, bitDepth, subShift );
+  return callDist( c.rd( opt ), family, org, orgStride, cur, curStride, w, h, bitDepth, subShift );
 }
 
 // Pair list over two planes: desc[i] = { org_x, org_y, cur_x, cur_y, w, h } (plane coordinates, may be negative inside the margin).
@@ -258,7 +364,7 @@ void refshim_dist_list( int opt, int family, const int16_t* orgPlane, int orgStr
   RefCtx& c = ctx();
   parallelFor( n, nthreads, [&]( int b, int e, int )
   {
-    RdCost rc; rc.create( opt != 0 );     // one RdCost per worker, as EncSlice.cpp:142-147 does
+    RdCost rc; createRd( rc, opt );     // one RdCost per worker, as EncSlice.cpp:142-147 does
     for( int i = b; i < e; i++ )
     {
       const int32_t* d = desc + 6 * (size_t) i;
@@ -274,7 +380,7 @@ uint64_t refshim_sad_mask( int opt, const int16_t* org, int orgStride, const int
                            const int16_t* mask, int maskStride, int stepX, int maskStride2, int bitDepth, int subShift )
 {
   RefCtx& c = ctx();
-  RdCost& rc = opt ? c.rdSimd : c.rdScalar;
+  RdCost& rc = c.rd( opt );
   DistParam dp;
   dp.org.buf = org; dp.org.stride = orgStride; dp.org.width = w; dp.org.height = h;
   dp.cur.buf = cur; dp.cur.stride = curStride; dp.cur.width = w; dp.cur.height = h;
@@ -287,7 +393,7 @@ void refshim_sad_x5( int opt, const int16_t* org, int orgStride, const int16_t* 
                      int bitDepth, int subShift, int calcCentre, uint64_t* cost5 )
 {
   RefCtx& c = ctx();
-  RdCost& rc = opt ? c.rdSimd : c.rdScalar;
+  RdCost& rc = c.rd( opt );
   DistParam dp = rc.setDistParam( org, cur, orgStride, curStride, bitDepth, COMP_Y, w, h, subShift, true );   // RdCost.cpp:228
   Distortion tmp[5] = { 0, 0, 0, 0, 0 };
   dp.dmvrSadX5( dp, tmp, calcCentre != 0 );
@@ -298,7 +404,7 @@ uint64_t refshim_fix_wsse( int opt, const int16_t* org, int orgStride, const int
                            int bitDepth, uint32_t fixedWeight )
 {
   RefCtx& c = ctx();
-  RdCost& rc = opt ? c.rdSimd : c.rdScalar;
+  RdCost& rc = c.rd( opt );
   DistParam dp;
   dp.org.buf = org; dp.org.stride = orgStride; dp.org.width = w; dp.org.height = h;
   dp.cur.buf = cur; dp.cur.stride = curStride; dp.cur.width = w; dp.cur.height = h;
@@ -338,7 +444,7 @@ void refshim_full_search( int opt, const int16_t* orgPlane, int orgStride, const
   // then return a partial sum for W >= 64 (RdCostX86.h:372-410) -- same decisions, used by the timed CPU baseline only.
   parallelFor( n, nthreads, [&]( int b, int e, int )
   {
-    RdCost rc; rc.create( opt != 0 );
+    RdCost rc; createRd( rc, opt );
     BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
     rc.setLambda( lambda, bd );
     rc.selectMotionLambda();

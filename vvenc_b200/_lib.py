@@ -3,7 +3,7 @@ there is no Python or CPU fallback for any entry point."""
 import ctypes, os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libvvenc_b200.so')
+LIB_PATH = os.environ.get('VVENC_B200_LIB') or os.path.join(HERE, 'csrc', 'libvvenc_b200.so')   # override: A/B builds of the same ABI
 
 VVB_OK, VVB_ERR_ARG, VVB_ERR_UNSUPPORTED, VVB_ERR_CUDA, VVB_ERR_NOMEM = 0, -1, -2, -3, -4
 

@@ -61,7 +61,11 @@ __host__ __device__ inline SearchSmem search_smem( int w, int h, int nx, int ny,
   const int need = ( nbx * w + s.nxp + 8 + 7 ) & ~7;      // row pitch in pels, multiple of 8 -> every row 16-byte aligned
   // Threads walk (row, strip) items in order, a warp's LDS.128 therefore wraps from strip nStrips-1 of one row to strip 0 of the next:
   // with pitch*2 == 16*nStrips (mod 128) the wrap continues in the next 16-byte bank group (conflict-free); take that pitch if it fits.
+#ifdef SS_NO_PAD
+  const int padded = need;
+#else
   const int padded = need + ( ( ( 8 * s.nStrips - need ) % 64 ) + 64 ) % 64;
+#endif
   for( int attempt = 0; attempt < 2; attempt++ )
   {
     s.ws       = attempt == 0 ? padded : need;
