@@ -186,6 +186,28 @@ int vvb_fwd_trquant_planes    ( vvb_ctx* ctx, const vvb_tu_par* par, int org_pla
 int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int org_plane, int pred_plane, const vvb_block* dev_blocks, int n,
                          int32_t* dev_coef, int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos, uint8_t* dev_need_rdoq );
 
+/* ---- inverse path of the TU loop -------------------------------------------------------------------
+ * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
+ * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp}. */
+int vvb_inv_trquant    ( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* q, int n, int16_t* resi );
+int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_q, int n, int16_t* dev_resi );
+
+/* One luma TU candidate end to end in one kernel -- the loop body of IntraSearch::xIntraCodingTUBlock (IntraSearch.cpp:1328-1429) and of
+ * InterSearch::xEstimateInterResidualQT (InterSearch.cpp:3659-3714):  residual = org - pred (PelBuf::subtract), TrQuant::transformNxN,
+ * abs_sum > 0 ? TrQuant::invTransformNxN : zero residual, PelBuf::reconstruct (Buffer.cpp:719, clip to [0, 2^bitDepth - 1]), then
+ *   dist_reco = SSE(org, reco)                 (intra: IntraSearch.cpp:1429)
+ *   dist_resi = SSE(org - pred, rec. residual) (inter: InterSearch.cpp:3714)
+ *   dist_zero = SSE(0, org - pred)             (inter zero-residual alternative: InterSearch.cpp:3670)
+ * org / pred: n compact blocks [n][h][w]; q (levels) required, reco and need_rdoq nullable. */
+typedef struct { uint64_t dist_reco, dist_resi, dist_zero; int32_t abs_sum, last_pos; } vvb_tu_result;   /* 32 bytes */
+int vvb_tu_roundtrip    ( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* org, const int16_t* pred, int n,
+                          int16_t* q, int16_t* reco, vvb_tu_result* res, uint8_t* need_rdoq );
+int vvb_tu_roundtrip_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_org, const int16_t* dev_pred, int n,
+                          int16_t* dev_q, int16_t* dev_reco, vvb_tu_result* dev_res, uint8_t* dev_need_rdoq );
+/* same with org / pred taken from resident planes: TU i sits at (blocks[i].x, blocks[i].y), its prediction at (+start_x, +start_y) in pred_plane */
+int vvb_tu_roundtrip_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int org_plane, int pred_plane, const vvb_block* dev_blocks, int n,
+                          int16_t* dev_q, int16_t* dev_reco, vvb_tu_result* dev_res, uint8_t* dev_need_rdoq );
+
 /* ---- MCTF block matching (CommonLib/MCTF.cpp:122-257 via MCTF::motionErrorLuma :1099-1164) ----------------- */
 typedef struct { int32_t x, y; int32_t mvx, mvy; /* 1/16 pel */ uint16_t w, h; } vvb_mctf_cand;   /* 20 bytes */
 int vvb_mctf_error_batch    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* cands, int n, int low_res_filter /* 4-tap */, int32_t* err_out );

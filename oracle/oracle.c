@@ -411,6 +411,112 @@ int orc_transform_quant( int trHor, int trVer, const Pel* resi, int stride, int 
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * Inverse path of the TU loop: Quant::dequant (CommonLib/Quant.cpp:520-609) with DeQuantCore
+ * (:232-262), TrQuant::xIT (CommonLib/TrQuant.cpp:567-660) with _fastInverseMM / the B2..B8 butterflies which equal the
+ * matrix product (TrQuant_EMT.cpp:64-194,231-636), PelBuf::reconstruct (Buffer.cpp:719) and the SSE that follows
+ * (IntraSearch.cpp:1353-1429, InterSearch.cpp:3659-3714).  Luma, no scaling lists / LFNST / transform skip / BDPCM.
+ * ---------------------------------------------------------------------------------------------------- */
+static const int inv_quant_scales[2][6] = { { 40, 45, 51, 57, 64, 72 }, { 57, 64, 72, 80, 90, 102 } };   /* Rom.cpp:1396-1400 */
+
+static inline int32_t clip3i( int32_t lo, int32_t hi, int32_t v ) { return v < lo ? lo : ( v > hi ? hi : v ); }
+
+int orc_dequant( const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef )
+{
+  int baseQp = qp + 6 * ( bitDepth - 8 );
+  if( baseQp < 0 ) baseQp = 0;
+  if( baseQp > 63 + 6 * ( bitDepth - 8 ) ) baseQp = 63 + 6 * ( bitDepth - 8 );
+  const int per = baseQp / 6, rem = baseQp % 6;
+  const int sqrt2 = ( ilog2u( w ) + ilog2u( h ) ) & 1;
+  const int trShift = 15 - bitDepth - ( ( ilog2u( w ) + ilog2u( h ) ) >> 1 ) - sqrt2;    /* Quant.cpp:554-556 */
+  const int rightShift = 6 - ( trShift + per );                                          /* :561, IQUANT_SHIFT = 6 */
+  const int scale = inv_quant_scales[sqrt2][rem];
+  int tib = 32 + rightShift - 7; if( tib > 16 ) tib = 16;                                /* :606 targetInputBitDepth */
+  const int32_t inMax = ( 1 << ( tib - 1 ) ) - 1, inMin = -( inMax + 1 );
+  const int32_t trMax = 32767, trMin = -32768;
+  for( int n = 0; n < w * h; n++ )
+  {
+    const int32_t c = clip3i( inMin, inMax, q[n] );
+    int32_t v;
+    if( rightShift > 0 ) v = ( c * scale + ( 1 << ( rightShift - 1 ) ) ) >> rightShift;   /* :238-249 */
+    else                 v = (int32_t)( (uint32_t)( c * scale ) << ( -rightShift ) );     /* :251-261 (int32 product times 2^leftShift) */
+    coef[n] = clip3i( trMin, trMax, v );
+  }
+  return 0;
+}
+
+/* xIT: first pass over columns (vertical transform, shift 7), second over rows (shift 20 - bitDepth); both clip to 16 bit */
+int orc_inv_transform( int trHor, int trVer, const int32_t* coef, int w, int h, int bitDepth, Pel* resi, int stride )
+{
+  const int8_t* th = tr_matrix( trHor, w );
+  const int8_t* tv = tr_matrix( trVer, h );
+  if( !th || !tv ) return -1;
+  const int skipW = ( trHor != 0 && w == 32 ) ? 16 : ( w > 32 ? w - 32 : 0 );    /* TrQuant.cpp:588-589 */
+  const int skipH = ( trVer != 0 && h == 32 ) ? 16 : ( h > 32 ? h - 32 : 0 );
+  const int s1 = 7, s2 = 20 - bitDepth;                                          /* :608-609 */
+  int32_t* tmp = (int32_t*) calloc( (size_t) w * h, sizeof( int32_t ) );
+  /* pass 1 (fastInvTrans[trVer], line = w, skip lines = skipW, cutoff = h - skipH): tmp[i*h + j] = clip((sum_k coef[k*w + i] * Tv[k][j] + 64) >> 7) */
+  for( int i = 0; i < w - skipW; i++ )
+    for( int j = 0; j < h; j++ )
+    {
+      int32_t sum = 0;
+      for( int k = 0; k < h - skipH; k++ ) sum += coef[k * w + i] * tv[k * h + j];
+      tmp[i * h + j] = clip3i( -32768, 32767, ( sum + ( 1 << ( s1 - 1 ) ) ) >> s1 );
+    }
+  /* pass 2 (fastInvTrans[trHor], line = h, no skipped lines, cutoff = w - skipW): blk[i*w + j] = clip((sum_k tmp[k*h + i] * Th[k][j] + rnd) >> s2) */
+  for( int i = 0; i < h; i++ )
+    for( int j = 0; j < w; j++ )
+    {
+      int32_t sum = 0;
+      for( int k = 0; k < w - skipW; k++ ) sum += tmp[k * h + i] * th[k * w + j];
+      resi[i * stride + j] = (Pel) clip3i( -32768, 32767, ( sum + ( 1 << ( s2 - 1 ) ) ) >> s2 );
+    }
+  free( tmp );
+  return 0;
+}
+
+/* TrQuant::invTransformNxN (TrQuant.cpp:318-348) */
+int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride )
+{
+  orc_dequant( q, w, h, bitDepth, qp, coef );
+  return orc_inv_transform( trHor, trVer, coef, w, h, bitDepth, resi, stride );
+}
+
+/* PelBuf::reconstruct (Buffer.cpp:719-760): reco = ClipPel( pred + resi ) with the default clipping range [0, 2^bd - 1] */
+void orc_reconstruct( const Pel* pred, int ps, const Pel* resi, int rs, Pel* reco, int cs, int w, int h, int bitDepth )
+{
+  const int mx = ( 1 << bitDepth ) - 1;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ ) reco[y * cs + x] = (Pel) clip3i( 0, mx, pred[y * ps + x] + resi[y * rs + x] );
+}
+
+/* One TU candidate end to end, as xIntraCodingTUBlock does for luma (IntraSearch.cpp:1353-1429): residual = org - pred, transformNxN, then
+ * (absSum > 0 ? invTransformNxN : zero residual), reconstruct, SSE(org, reco).  Also returns the residual-domain distortions of the inter loop
+ * (InterSearch.cpp:3670 zero-residual SSE, :3714 SSE(orgResi, recResi)).  out4 = { dist_reco, dist_resi, dist_zero, absSum | lastPos<<32 } */
+int orc_tu_roundtrip( int trHor, int trVer, const Pel* org, int so, const Pel* pred, int ps, int w, int h, int bitDepth, int qp, int isIRAP,
+                      int16_t* q, Pel* reco, int cs, uint64_t* out4 )
+{
+  Pel* resi = (Pel*) malloc( sizeof( Pel ) * w * h );
+  Pel* rec  = (Pel*) malloc( sizeof( Pel ) * w * h );
+  Pel* zero = (Pel*) calloc( (size_t) w * h, sizeof( Pel ) );
+  int32_t* coef = (int32_t*) malloc( sizeof( int32_t ) * w * h );
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) resi[y * w + x] = (Pel)( org[y * so + x] - pred[y * ps + x] );
+  int32_t absSum = 0, lastPos = 0;
+  int rc = orc_transform_quant( trHor, trVer, resi, w, w, h, bitDepth, qp, isIRAP, coef, q, &absSum, &lastPos );
+  if( !rc )
+  {
+    if( absSum > 0 ) rc = orc_inv_transform_quant( trHor, trVer, q, w, h, bitDepth, qp, coef, rec, w );
+    else memset( rec, 0, sizeof( Pel ) * w * h );
+    orc_reconstruct( pred, ps, rec, w, reco, cs, w, h, bitDepth );
+    out4[0] = orc_sse( org, so, reco, cs, w, h );
+    out4[1] = orc_sse( resi, w, rec, w, w, h );
+    out4[2] = orc_sse( zero, w, resi, w, w, h );
+    out4[3] = (uint64_t)(uint32_t) absSum | ( (uint64_t)(uint32_t) lastPos << 32 );
+  }
+  free( resi ); free( rec ); free( zero ); free( coef );
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * MCTF block matching (CommonLib/MCTF.cpp:122-145 int, :147-203 6-tap, :205-257 4-tap); filters :72-110
  * ---------------------------------------------------------------------------------------------------- */
 static const int16_t mctf_f8[16][8] = {

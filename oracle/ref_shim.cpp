@@ -579,6 +579,84 @@ int refshim_transform_quant( int trHor, int trVer, const int16_t* resi, int stri
   return 0;
 }
 
+// Inverse path: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520) + xIT (TrQuant.cpp:567).
+// q: quantised levels [h][w] compact; coef (nullable) receives the dequantised coefficients; resi written with `stride`.
+int refshim_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, false, true, qp );
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  alignas(64) static thread_local TCoeff tmpCoef[ 64 * 64 ];
+  CoeffBuf deq( tmpCoef, w, w, h );
+  static_cast<Quant*>( c.tq->m_quant )->Quant::dequant( r.tu, deq, COMP_Y, qpp );
+  if( coef ) memcpy( coef, tmpCoef, sizeof( int32_t ) * w * h );
+  PelBuf out( resi, stride, w, h );
+  c.tq->xIT( r.tu, COMP_Y, CCoeffBuf( tmpCoef, w, w, h ), out );
+  return 0;
+}
+
+// PelBuf::reconstruct (Buffer.cpp:719) with the slice clipping range of the given bit depth.  The SIMD kernels behind g_pelBufOP use aligned
+// loads (the encoder's CU-local buffers are compact and MEMORY_ALIGN_DEF_SIZE aligned), so the probe marshals through such buffers.
+struct AlignedPel
+{
+  int16_t* p;
+  explicit AlignedPel( size_t n ) : p( (int16_t*) aligned_alloc( 64, ( n * 2 + 127 ) & ~size_t( 63 ) ) ) {}
+  ~AlignedPel() { free( p ); }
+};
+void refshim_reconstruct( const int16_t* pred, int ps, const int16_t* resi, int rs, int16_t* reco, int cs, int w, int h, int bitDepth )
+{
+  ClpRng rng; rng.bd = bitDepth;
+  AlignedPel a( (size_t) w * h ), b( (size_t) w * h ), d( (size_t) w * h );
+  for( int y = 0; y < h; y++ ) { memcpy( a.p + y * w, pred + (ptrdiff_t) y * ps, 2 * w ); memcpy( b.p + y * w, resi + (ptrdiff_t) y * rs, 2 * w ); }
+  PelBuf dst( d.p, w, w, h );
+  dst.reconstruct( CPelBuf( a.p, w, w, h ), CPelBuf( b.p, w, w, h ), rng );
+  for( int y = 0; y < h; y++ ) memcpy( reco + (ptrdiff_t) y * cs, d.p + y * w, 2 * w );
+}
+
+// One luma TU candidate end to end the way xIntraCodingTUBlock runs it (IntraSearch.cpp:1353-1429); out4 as in oracle.c orc_tu_roundtrip.
+int refshim_tu_roundtrip( int opt, int trHor, int trVer, const int16_t* org, int so, const int16_t* pred, int ps, int w, int h, int bitDepth, int qp, int isIRAP,
+                          int16_t* q, int16_t* reco, int cs, uint64_t* out4 )
+{
+  RefCtx& c = ctx();
+  const size_t n = (size_t) w * h;
+  AlignedPel ao( n ), ap( n ), resi( n ), rec( n ), zero( n ), arc( n );
+  std::vector<int32_t> coef( n + 16 );
+  int32_t* coefA = (int32_t*)( ( (uintptr_t) coef.data() + 63 ) & ~uintptr_t( 63 ) );
+  for( int y = 0; y < h; y++ ) { memcpy( ao.p + y * w, org + (ptrdiff_t) y * so, 2 * w ); memcpy( ap.p + y * w, pred + (ptrdiff_t) y * ps, 2 * w ); }
+  memset( zero.p, 0, 2 * n ); memset( rec.p, 0, 2 * n );
+  PelBuf resiBuf( resi.p, w, w, h );
+  resiBuf.subtract( CPelBuf( ao.p, w, w, h ), CPelBuf( ap.p, w, w, h ) );
+  int32_t absSum = 0, lastPos = 0;
+  if( refshim_transform_quant( trHor, trVer, resi.p, w, w, h, bitDepth, qp, isIRAP, coefA, q, &absSum, &lastPos ) ) return -1;
+  if( absSum > 0 ) refshim_inv_transform_quant( trHor, trVer, q, w, h, bitDepth, qp, nullptr, rec.p, w );
+  refshim_reconstruct( ap.p, w, rec.p, w, arc.p, w, w, h, bitDepth );
+  for( int y = 0; y < h; y++ ) memcpy( reco + (ptrdiff_t) y * cs, arc.p + y * w, 2 * w );
+  RdCost& rc = c.rd( opt );
+  out4[0] = callDist( rc, 0, ao.p, w, arc.p, w, w, h, bitDepth, 0 );
+  out4[1] = callDist( rc, 0, resi.p, w, rec.p, w, w, h, bitDepth, 0 );
+  out4[2] = callDist( rc, 0, zero.p, w, resi.p, w, w, h, bitDepth, 0 );
+  out4[3] = (uint64_t)(uint32_t) absSum | ( (uint64_t)(uint32_t) lastPos << 32 );
+  return 0;
+}
+
+void refshim_tu_roundtrip_batch( int opt, int trHor, int trVer, const int16_t* org, const int16_t* pred, int n, int w, int h, int bitDepth, int qp, int isIRAP,
+                                 int16_t* q, int16_t* reco, uint64_t* out4, int nthreads )
+{
+  ctx();
+  parallelFor( n, nthreads, [&]( int b, int e, int )
+  {
+    for( int i = b; i < e; i++ )
+    {
+      const size_t o = (size_t) i * w * h;
+      refshim_tu_roundtrip( opt, trHor, trVer, org + o, w, pred + o, w, w, h, bitDepth, qp, isIRAP, q + o, reco + o, w, out4 + 4 * (size_t) i );
+    }
+  } );
+}
+
 // Batch of equal-shape TUs laid out back to back (resi: n * h * w int16, compact), threaded; used by the CPU baseline.
 void refshim_transform_quant_batch( int trHor, int trVer, const int16_t* resi, int n, int w, int h, int bitDepth, int qp, int isIRAP,
                                     int16_t* q, int32_t* absSum, int32_t* lastPos, int nthreads )

@@ -97,6 +97,76 @@ def tq_inputs(row):
     return a.astype(np.int16)
 
 
+def itq_cases():
+    """inverse path rows: trHor, trVer, w, h, stride (of the residual written), kind, qp, bit_depth, seed
+    kind 0: sparse decaying levels (what a quantiser emits), 1: dense +-amp levels everywhere (zero-out region included: the
+    reference ignores it), 2: extreme levels (int16 limits: dequant input/output clipping), 3: DC only, 4: all zero"""
+    rows = []
+    seed = 15000
+    rs = np.random.RandomState(1234)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            for (th, tv) in ((0, 0), (2, 2), (1, 2), (2, 1), (1, 1)):
+                if (th or tv) and (w > 32 or h > 32):
+                    continue
+                for kind in (0, 1, 2):
+                    bd = 8 if seed % 5 == 0 else 10
+                    qp = int(rs.randint(0, 64)) if kind else int(rs.randint(12, 48))
+                    rows.append([th, tv, w, h, w + int(rs.randint(0, 6)), kind, qp, bd, seed])
+                    seed += 1
+            rows.append([0, 0, w, h, w, 3, int(rs.randint(0, 64)), 10, seed]); seed += 1
+    rows.append([0, 0, 16, 16, 16, 4, 30, 10, seed])
+    return np.array(rows, dtype=np.int32)
+
+
+def itq_inputs(row):
+    th, tv, w, h, st, kind, qp, bd, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    q = np.zeros((h, w), dtype=np.int64)
+    if kind == 0:
+        yy, xx = np.mgrid[0:h, 0:w]
+        mag = 60.0 / (1.0 + 0.9 * (xx + yy))
+        q = np.rint(rs.standard_normal((h, w)) * mag).astype(np.int64)
+        q[rs.rand(h, w) < 0.35] = 0
+    elif kind == 1:
+        amp = int(rs.choice([1, 7, 300, 4000]))
+        q = rs.randint(-amp, amp + 1, size=(h, w))
+    elif kind == 2:
+        q = rs.choice(np.array([-32768, -32767, -20000, -1, 0, 1, 12345, 32767]), size=(h, w))
+    elif kind == 3:
+        q[0, 0] = int(rs.randint(-2000, 2000))
+    return np.ascontiguousarray(q.astype(np.int16))
+
+
+def rt_cases():
+    """TU round-trip rows: trHor, trVer, w, h, org_stride, pred_stride, amp, qp, isIRAP, bit_depth, seed"""
+    rows = []
+    seed = 17000
+    rs = np.random.RandomState(4321)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            for (th, tv) in ((0, 0), (2, 2), (1, 2)):
+                if (th or tv) and (w > 32 or h > 32):
+                    continue
+                for amp in (1023, 60, 3):
+                    bd = 8 if seed % 7 == 0 else 10
+                    rows.append([th, tv, w, h, w + int(rs.randint(0, 9)), w + int(rs.randint(0, 9)), min(amp, (1 << bd) - 1),
+                                 int(rs.randint(10, 50)), int(rs.randint(0, 2)), bd, seed])
+                    seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def rt_inputs(row):
+    th, tv, w, h, so, ps, amp, qp, irap, bd, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    mx = (1 << bd) - 1
+    org = rs.randint(0, mx + 1, size=(h, so))
+    base = org[:, :w] if amp < mx else rs.randint(0, mx + 1, size=(h, w))
+    pred = np.zeros((h, ps), dtype=np.int64)
+    pred[:, :w] = np.clip(base + rs.randint(-amp, amp + 1, size=(h, w)), 0, mx)
+    return np.ascontiguousarray(org.astype(np.int16)), np.ascontiguousarray(pred.astype(np.int16))
+
+
 def mctf_cases():
     """rows: w, h, mvx, mvy (1/16 pel), tap4, bit_depth, seed"""
     rows = []

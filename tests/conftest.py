@@ -13,3 +13,9 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v1.npz'))
+
+
+@pytest.fixture(scope="session")
+def golden_tu():
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v2_tu.npz'))

@@ -25,6 +25,18 @@ class OracleImpl:
     def need_rdoq(self, coef, w, h, bd, qp, dq):
         return int(self.L.orc_need_rdoq(P(coef), w, h, bd, qp, dq))
 
+    def inv_transform_quant(self, th, tv, q, w, h, bd, qp, stride):
+        """-> (dequantised coefficients int32 [h][w], residual int16 [h][w])"""
+        coef = np.zeros((h, w), dtype=np.int32); resi = np.zeros((h, stride), dtype=np.int16)
+        assert self.L.orc_inv_transform_quant(th, tv, P(q), w, h, bd, qp, P(coef), P(resi), stride) == 0
+        return coef, np.ascontiguousarray(resi[:, :w])
+
+    def tu_roundtrip(self, th, tv, org, so, pred, ps, w, h, bd, qp, irap):
+        """-> (levels [h][w], reco [h][w], [dist_reco, dist_resi, dist_zero, abs_sum, last_pos])"""
+        q = np.zeros((h, w), dtype=np.int16); reco = np.zeros((h, w), dtype=np.int16); o4 = np.zeros(4, dtype=np.uint64)
+        assert self.L.orc_tu_roundtrip(th, tv, P(org), so, P(pred), ps, w, h, bd, qp, irap, P(q), P(reco), w, P(o4)) == 0
+        return q, reco, [int(o4[0]), int(o4[1]), int(o4[2]), int(o4[3]) & 0xffffffff, np.int32(np.uint32(int(o4[3]) >> 32)).item()]
+
     def mctf_err(self, tap4, org, so, buf, sb, x, y, mvx, mvy, w, h, bd):
         desc = np.array([[x, y, mvx, mvy, w, h]], dtype=np.int32); out = np.zeros(1, dtype=np.int32)
         self.L.orc_mctf_err_list(tap4, PO(org, -(y * so + x)), so, P(buf), sb, P(desc), 1, bd, P(out))
@@ -78,6 +90,18 @@ class RefImpl(OracleImpl):
     def need_rdoq(self, coef, w, h, bd, qp, dq):
         self._simd()
         return int(self.L.refshim_need_rdoq(P(coef), w, h, bd, qp, dq))
+
+    def inv_transform_quant(self, th, tv, q, w, h, bd, qp, stride):
+        self._simd()
+        coef = np.zeros((h, w), dtype=np.int32); resi = np.zeros((h, stride), dtype=np.int16)
+        assert self.L.refshim_inv_transform_quant(th, tv, P(q), w, h, bd, qp, P(coef), P(resi), stride) == 0
+        return coef, np.ascontiguousarray(resi[:, :w])
+
+    def tu_roundtrip(self, th, tv, org, so, pred, ps, w, h, bd, qp, irap):
+        self._simd()
+        q = np.zeros((h, w), dtype=np.int16); reco = np.zeros((h, w), dtype=np.int16); o4 = np.zeros(4, dtype=np.uint64)
+        assert self.L.refshim_tu_roundtrip(self.opt, th, tv, P(org), so, P(pred), ps, w, h, bd, qp, irap, P(q), P(reco), w, P(o4)) == 0
+        return q, reco, [int(o4[0]), int(o4[1]), int(o4[2]), int(o4[3]) & 0xffffffff, np.int32(np.uint32(int(o4[3]) >> 32)).item()]
 
     def mctf_err(self, tap4, org, so, buf, sb, x, y, mvx, mvy, w, h, bd):
         desc = np.array([[x, y, mvx, mvy, w, h]], dtype=np.int32); out = np.zeros(1, dtype=np.int32)
@@ -136,6 +160,31 @@ def run_tq(impl, rows, coef, q, meta):
     return bad
 
 
+def run_itq(impl, rows, coef, resi):
+    """inverse path: dequantised coefficients (where the implementation exposes them) and the residual"""
+    bad = []; off = 0
+    for row in rows:
+        th, tv, w, h, st, kind, qp, bd, seed = [int(v) for v in row]
+        q = C.itq_inputs(row)
+        c, r = impl.inv_transform_quant(th, tv, q, w, h, bd, qp, st)
+        ec = coef[off:off + w * h].reshape(h, w); er = resi[off:off + w * h].reshape(h, w); off += w * h
+        if not ((c is None or np.array_equal(c, ec)) and np.array_equal(r, er)):
+            bad.append(('itq', row.tolist(), c is None or bool(np.array_equal(c, ec)), bool(np.array_equal(r, er))))
+    return bad
+
+
+def run_rt(impl, rows, q, reco, meta):
+    bad = []; off = 0
+    for i, row in enumerate(rows):
+        th, tv, w, h, so, ps, amp, qp, irap, bd, seed = [int(v) for v in row]
+        org, pred = C.rt_inputs(row)
+        gq, gr, gm = impl.tu_roundtrip(th, tv, org, so, pred, ps, w, h, bd, qp, irap)
+        eq = q[off:off + w * h].reshape(h, w); er = reco[off:off + w * h].reshape(h, w); off += w * h
+        if not (np.array_equal(gq, eq) and np.array_equal(gr, er) and [int(v) for v in gm] == [int(v) for v in meta[i]]):
+            bad.append(('rt', row.tolist(), bool(np.array_equal(gq, eq)), bool(np.array_equal(gr, er)), gm, meta[i].tolist()))
+    return bad
+
+
 def run_mctf(impl, rows, expect):
     bad = []
     m = C.MCTF_MARGIN
@@ -180,6 +229,16 @@ class GpuImpl:
         par = self.eng.tu_par(w, h, th, tv, bd, qp, bool(irap), bool(dq))
         r = self.eng.fwd_trquant(par, np.ascontiguousarray(resi[:, :w]).reshape(1, h, w))
         return r['coef'][0], r['q'][0], int(r['abs_sum'][0]), int(r['last_pos'][0]), int(r['need_rdoq'][0])
+
+    def inv_transform_quant(self, th, tv, q, w, h, bd, qp, stride):
+        par = self.eng.tu_par(w, h, th, tv, bd, qp, False, False)
+        return None, self.eng.inv_trquant(par, q.reshape(1, h, w))[0]
+
+    def tu_roundtrip(self, th, tv, org, so, pred, ps, w, h, bd, qp, irap):
+        par = self.eng.tu_par(w, h, th, tv, bd, qp, bool(irap), False)
+        r = self.eng.tu_roundtrip(par, np.ascontiguousarray(org[:, :w]).reshape(1, h, w), np.ascontiguousarray(pred[:, :w]).reshape(1, h, w))
+        x = r['res'][0]
+        return r['q'][0], r['reco'][0], [int(x['dist_reco']), int(x['dist_resi']), int(x['dist_zero']), int(x['abs_sum']), int(x['last_pos'])]
 
     def mctf_err(self, tap4, org, so, buf, sb, x, y, mvx, mvy, w, h, bd):
         m = min(x, y)

@@ -34,7 +34,8 @@ def test_reference_rdcost_table_patched_with_b200(patched, golden):
     before = int(L.refshim_b200_launches())
     assert impls.run_dist(patched, golden['dist_rows'], golden['dist_expect']) == []
     launched = int(L.refshim_b200_launches()) - before
-    rows10 = sum(1 for r in golden['dist_rows'] if int(r[8]) <= 10)       # >10-bit cases use table row [1], which stays scalar (RdCost.cpp:125-126)
+    # slots patched: base + log2(w) for w >= 2 (like initRdCostX86, the w == 1 slot keeps the scalar kernel); >10-bit uses table row [1] (RdCost.cpp:125-126)
+    rows10 = sum(1 for r in golden['dist_rows'] if int(r[8]) <= 10 and int(r[1]) >= 2)
     assert launched >= rows10 > 0, (launched, rows10)
 
 

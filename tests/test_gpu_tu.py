@@ -1,0 +1,127 @@
+"""GPU parity (-m gpu) of the inverse TU path and the fused TU round trip, through the C ABI:
+golden vectors from the unmodified reference, oracle comparison on seeded batches (compact pools and resident planes),
+and algebraic properties at full picture size."""
+import numpy as np
+import pytest
+import cases as C
+import impls
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return impls.GpuImpl(0)
+
+
+def test_gpu_inverse_path_golden(gpu, golden_tu):
+    assert impls.run_itq(gpu, golden_tu['itq_rows'], golden_tu['itq_coef'], golden_tu['itq_resi']) == []
+
+
+def test_gpu_tu_roundtrip_golden(gpu, golden_tu):
+    assert impls.run_rt(gpu, golden_tu['rt_rows'], golden_tu['rt_q'], golden_tu['rt_reco'], golden_tu['rt_meta']) == []
+
+
+SHAPES = ((4, 4, 0, 0), (8, 8, 2, 2), (16, 16, 0, 0), (16, 16, 2, 1), (32, 32, 1, 2), (32, 32, 0, 0), (64, 64, 0, 0), (4, 16, 2, 1), (64, 8, 0, 0),
+          (16, 64, 0, 0), (32, 4, 2, 2), (8, 32, 0, 0), (64, 32, 0, 0))
+
+
+def test_gpu_inverse_batch_vs_oracle(gpu):
+    O = impls.OracleImpl()
+    rs = np.random.RandomState(808)
+    for (w, h, th, tv) in SHAPES:
+        n = 67 if w * h < 4096 else 35                       # not a multiple of the teams per CTA: tail teams idle
+        amp = np.array([32767, 3000, 60, 3])[rs.randint(0, 4, n)]
+        q = (rs.randint(-1000, 1001, size=(n, h, w)) * amp[:, None, None] // 1000).astype(np.int16)
+        q[rs.rand(n, h, w) < 0.6] = 0
+        q[0] = 32767; q[1] = -32768; q[2] = 0
+        for bd, qp in ((10, int(rs.randint(0, 64))), (8, int(rs.randint(0, 64))), (12, int(rs.randint(-20, 64)))):
+            par = gpu.eng.tu_par(w, h, th, tv, bd, qp, False, False)
+            r = gpu.eng.inv_trquant(par, q)
+            for i in range(n):
+                _, e = O.inv_transform_quant(th, tv, np.ascontiguousarray(q[i]), w, h, bd, qp, w)
+                assert np.array_equal(r[i], e), (w, h, th, tv, bd, qp, i)
+
+
+def _pool(rs, n, w, h, bd=10):
+    mx = (1 << bd) - 1
+    org = rs.randint(0, mx + 1, size=(n, h, w))
+    amp = np.array([mx, 300, 40, 6, 0])[rs.randint(0, 5, n)]
+    noise = rs.randint(-1000, 1001, size=(n, h, w)) * amp[:, None, None] // 1000
+    pred = np.clip(org + noise, 0, mx)
+    pred[0] = mx - org[0]                                     # large residuals of both signs
+    return org.astype(np.int16), pred.astype(np.int16)
+
+
+def test_gpu_tu_roundtrip_batch_vs_oracle(gpu):
+    O = impls.OracleImpl()
+    rs = np.random.RandomState(909)
+    for (w, h, th, tv) in SHAPES:
+        n = 67 if w * h < 4096 else 35
+        for bd in (10, 8):
+            org, pred = _pool(rs, n, w, h, bd)
+            qp = int(rs.randint(8, 52)); irap = int(rs.randint(0, 2))
+            par = gpu.eng.tu_par(w, h, th, tv, bd, qp, bool(irap), False)
+            r = gpu.eng.tu_roundtrip(par, org, pred)
+            zeros = 0
+            for i in range(n):
+                q, reco, m = O.tu_roundtrip(th, tv, np.ascontiguousarray(org[i]), w, np.ascontiguousarray(pred[i]), w, w, h, bd, qp, irap)
+                x = r['res'][i]
+                got = [int(x['dist_reco']), int(x['dist_resi']), int(x['dist_zero']), int(x['abs_sum']), int(x['last_pos'])]
+                assert np.array_equal(r['q'][i], q) and np.array_equal(r['reco'][i], reco) and got == m, (w, h, th, tv, bd, qp, i, got, m)
+                zeros += m[3] == 0
+            assert 0 < zeros < n, (w, h, zeros)               # both branches (inverse / zero residual) are exercised
+
+
+def test_gpu_tu_roundtrip_planes_vs_pool(gpu):
+    """plane-addressed variant == pool variant on the same pels (odd prediction displacements included)"""
+    rs = np.random.RandomState(1001)
+    W, H, m = 256, 128, 16
+    S = W + 2 * m
+    base = rs.randint(0, 1024, size=(H + 2 * m, S)).astype(np.int16)
+    pred_pl = np.clip(base.astype(np.int32) + rs.randint(-30, 31, size=base.shape), 0, 1023).astype(np.int16)
+    gpu.eng.upload_plane(0, base, W, H, m, 10)
+    gpu.eng.upload_plane(1, pred_pl, W, H, m, 10)
+    for (w, h, th, tv) in ((8, 8, 0, 0), (16, 16, 2, 2), (32, 32, 0, 0), (64, 64, 0, 0), (16, 4, 1, 2)):
+        xs = np.arange(0, W - w + 1, w); ys = np.arange(0, H - h + 1, h)
+        B = np.zeros(len(xs) * len(ys), dtype=gpu.V.BLOCK_DT)
+        k = 0
+        for y in ys:
+            for x in xs:
+                B[k] = (x, y, 0, 0, 0, 0, 0, 0, int(rs.randint(-5, 6)), int(rs.randint(-5, 6))); k += 1
+        par = gpu.eng.tu_par(w, h, th, tv, 10, 30, False, False)
+        a = gpu.eng.tu_roundtrip_planes(par, 0, 1, B)
+        org = np.stack([base[m + b['y']:m + b['y'] + h, m + b['x']:m + b['x'] + w] for b in B])
+        pred = np.stack([pred_pl[m + b['y'] + b['start_y']:m + b['y'] + b['start_y'] + h, m + b['x'] + b['start_x']:m + b['x'] + b['start_x'] + w] for b in B])
+        b_ = gpu.eng.tu_roundtrip(par, org, pred)
+        assert np.array_equal(a['q'], b_['q']) and np.array_equal(a['reco'], b_['reco']) and np.array_equal(a['res'], b_['res']), (w, h)
+
+
+def test_gpu_tu_roundtrip_properties_full_size(gpu):
+    """3840x2160 worth of 16x16 TUs: (1) pred == org -> all-zero levels, reco == org, all distortions 0;
+    (2) fused levels == vvb_fwd_trquant levels and fused reco == clip(pred + vvb_inv_trquant(levels)) -- the fused kernel agrees with the
+    separately tested pieces on 32400 TUs; (3) dist_zero == sum (org-pred)^2 computed in numpy."""
+    rs = np.random.RandomState(2002)
+    w = h = 16; n = (3840 // w) * (2160 // h)
+    org = rs.randint(0, 1024, size=(n, h, w)).astype(np.int16)
+    par = gpu.eng.tu_par(w, h, 0, 0, 10, 27, False, False)
+    r = gpu.eng.tu_roundtrip(par, org, org)
+    assert not r['q'].any() and np.array_equal(r['reco'], org)
+    assert not r['res']['dist_reco'].any() and not r['res']['dist_resi'].any() and not r['res']['dist_zero'].any() and not r['res']['abs_sum'].any()
+    pred = np.clip(org.astype(np.int32) + rs.randint(-50, 51, size=org.shape), 0, 1023).astype(np.int16)
+    r = gpu.eng.tu_roundtrip(par, org, pred)
+    resi = (org.astype(np.int32) - pred).astype(np.int16)
+    f = gpu.eng.fwd_trquant(par, resi, want_coef=False)
+    assert np.array_equal(f['q'], r['q']) and np.array_equal(f['abs_sum'], r['res']['abs_sum']) and np.array_equal(f['last_pos'], r['res']['last_pos'])
+    rec = gpu.eng.inv_trquant(par, r['q']).astype(np.int32)
+    rec[r['res']['abs_sum'] == 0] = 0
+    reco = np.clip(pred.astype(np.int32) + rec, 0, 1023)
+    assert np.array_equal(reco.astype(np.int16), r['reco'])
+    d = org.astype(np.int64) - pred
+    assert np.array_equal((d * d).sum(axis=(1, 2)).astype(np.uint64), r['res']['dist_zero'])
+    e = org.astype(np.int64) - reco
+    assert np.array_equal((e * e).sum(axis=(1, 2)).astype(np.uint64), r['res']['dist_reco'])
+    g = d - rec
+    assert np.array_equal((g * g).sum(axis=(1, 2)).astype(np.uint64), r['res']['dist_resi'])

@@ -42,3 +42,16 @@ def test_oracle_mv_rate_golden(golden):
         a = [int(v) for v in row]
         assert O.mv_bits(*a) == int(golden['mv_bits'][i])
         assert O.mv_cost(57.25 + i, *a) == int(golden['mv_cost'][i])
+
+
+def test_tu_case_tables_match_fixture(golden_tu):
+    assert np.array_equal(golden_tu['itq_rows'], C.itq_cases())
+    assert np.array_equal(golden_tu['rt_rows'], C.rt_cases())
+
+
+def test_oracle_inverse_path_golden(golden_tu):
+    assert impls.run_itq(impls.OracleImpl(), golden_tu['itq_rows'], golden_tu['itq_coef'], golden_tu['itq_resi']) == []
+
+
+def test_oracle_tu_roundtrip_golden(golden_tu):
+    assert impls.run_rt(impls.OracleImpl(), golden_tu['rt_rows'], golden_tu['rt_q'], golden_tu['rt_reco'], golden_tu['rt_meta']) == []

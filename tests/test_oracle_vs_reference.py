@@ -114,3 +114,37 @@ def test_tables_match_reference():
             a = np.zeros(1024, dtype=np.int32); b = np.zeros(1024, dtype=np.int32)
             from _libs import oracle
             assert R.refshim_scan_order(w, h, P(a)) == oracle().orc_scan_order(w, h, P(b)) and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_inverse_path_sweep(opt):
+    """dequant + inverse transform (TrQuant::invTransformNxN), random levels over the full QP range, 8/10/12 bit"""
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    rs = np.random.RandomState(177 + opt)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            for (th, tv) in ((0, 0), (2, 2), (1, 2), (2, 1), (1, 1)):
+                if (th or tv) and (w > 32 or h > 32): continue
+                for bd in (8, 10, 12):
+                    amp = int(rs.choice([32767, 2000, 40, 2])); qp = int(rs.randint(-6 * (bd - 8), 64)); st = w + int(rs.randint(0, 9))
+                    q = rs.randint(-amp - 1, amp + 1, size=(h, w)).astype(np.int16)
+                    q[rs.rand(h, w) < 0.5] = 0
+                    a = O.inv_transform_quant(th, tv, q, w, h, bd, qp, st); b = R.inv_transform_quant(th, tv, q, w, h, bd, qp, st)
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (th, tv, w, h, bd, qp)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_tu_roundtrip_sweep(opt):
+    """residual -> transformNxN -> invTransformNxN -> reconstruct -> SSE, as xIntraCodingTUBlock chains them"""
+    O = impls.OracleImpl(); R = impls.RefImpl(opt)
+    rs = np.random.RandomState(277 + opt)
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            for (th, tv) in ((0, 0), (2, 2), (2, 1)):
+                if (th or tv) and (w > 32 or h > 32): continue
+                amp = int(rs.choice([400, 60, 8])); qp = int(rs.randint(4, 56)); irap = int(rs.randint(0, 2)); so = w + int(rs.randint(0, 9)); ps = w + int(rs.randint(0, 9))
+                org = rs.randint(0, 1024, size=(h, so)).astype(np.int16)
+                pred = np.zeros((h, ps), dtype=np.int16)
+                pred[:, :w] = np.clip(org[:, :w] + rs.randint(-amp, amp + 1, size=(h, w)), 0, 1023)
+                a = O.tu_roundtrip(th, tv, org, so, pred, ps, w, h, 10, qp, irap); b = R.tu_roundtrip(th, tv, org, so, pred, ps, w, h, 10, qp, irap)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2], (th, tv, w, h, qp, irap, a[2], b[2])

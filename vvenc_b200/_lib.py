@@ -35,6 +35,7 @@ BLOCK_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('left', '<i2'), ('right', '<i2
                      ('pred_hor', '<i2'), ('pred_ver', '<i2'), ('start_x', '<i2'), ('start_y', '<i2')])
 BEST_DT = np.dtype([('dx', '<i2'), ('dy', '<i2'), ('sad', '<u4'), ('cost', '<u8')])
 MV_DT = np.dtype([('dx', '<i2'), ('dy', '<i2')])
+TU_RESULT_DT = np.dtype([('dist_reco', '<u8'), ('dist_resi', '<u8'), ('dist_zero', '<u8'), ('abs_sum', '<i4'), ('last_pos', '<i4')])
 MCTF_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('mvx', '<i4'), ('mvy', '<i4'), ('w', '<u2'), ('h', '<u2')])
 assert CAND_DT.itemsize == 32 and BLOCK_DT.itemsize == 24 and BEST_DT.itemsize == 16 and MCTF_DT.itemsize == 20
 
@@ -74,6 +75,11 @@ SYMBOLS = {
     'vvb_set_tensor_transform': (c_i, [c_p, c_i]),
     'vvb_fwd_trquant_planes': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
+    'vvb_inv_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
+    'vvb_tu_roundtrip': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
+    'vvb_tu_roundtrip_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
+    'vvb_tu_roundtrip_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
     'vvb_mctf_error_batch': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_mctf_error_batch_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_affine_sobel': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i]),

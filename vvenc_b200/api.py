@@ -208,6 +208,43 @@ class CostEngine:
         self._chk(self.lib.vvb_fwd_trquant_planes(self.h, ctypes.byref(par), org_plane, pred_plane, _p(blocks), n, _p(coef), _p(q), _p(s), _p(lp), _p(nr)))
         return dict(coef=coef, q=q, abs_sum=s, last_pos=lp, need_rdoq=nr)
 
+    # ---- inverse path / fused TU round trip
+    def inv_trquant(self, par, q):
+        """TrQuant::invTransformNxN for n compact level blocks q [n][h][w] -> residual int16 [n][h][w]"""
+        q = np.ascontiguousarray(q, dtype=np.int16)
+        n = q.shape[0]
+        resi = np.zeros((n, par.h, par.w), dtype=np.int16)
+        self._chk(self.lib.vvb_inv_trquant(self.h, ctypes.byref(par), _p(q), n, _p(resi)))
+        return resi
+
+    def tu_roundtrip(self, par, org, pred, want_reco=True):
+        """org, pred: int16 [n][h][w] compact.  residual -> transformNxN -> invTransformNxN -> reconstruct -> SSE in one kernel.
+        Returns dict(q, reco, res (TU_RESULT_DT: dist_reco, dist_resi, dist_zero, abs_sum, last_pos), need_rdoq)."""
+        org = np.ascontiguousarray(org, dtype=np.int16); pred = np.ascontiguousarray(pred, dtype=np.int16)
+        n = org.shape[0]
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        reco = np.zeros((n, par.h, par.w), dtype=np.int16) if want_reco else None
+        res = np.zeros(n, dtype=L.TU_RESULT_DT); nr = np.zeros(n, dtype=np.uint8)
+        self._chk(self.lib.vvb_tu_roundtrip(self.h, ctypes.byref(par), _p(org), _p(pred), n, _p(q), _p(reco), _p(res), _p(nr)))
+        return dict(q=q, reco=reco, res=res, need_rdoq=nr)
+
+    def tu_roundtrip_planes(self, par, org_plane, pred_plane, blocks, want_reco=True):
+        """same round trip with org / pred taken from resident planes (blocks: BLOCK_DT, prediction displaced by start_x/start_y).
+        Device-resident entry point wrapped with torch buffers."""
+        import torch
+        blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
+        n = len(blocks); area = par.w * par.h
+        d_blk = torch.from_numpy(np.frombuffer(blocks.tobytes(), dtype=np.uint8).copy()).cuda()
+        d_q = torch.empty(n * area, dtype=torch.int16, device='cuda')
+        d_reco = torch.empty(n * area, dtype=torch.int16, device='cuda') if want_reco else None
+        d_res = torch.empty(n * 32, dtype=torch.uint8, device='cuda'); d_nr = torch.empty(n, dtype=torch.uint8, device='cuda')
+        torch.cuda.synchronize()
+        self._chk(self.lib.vvb_tu_roundtrip_planes_dev(self.h, ctypes.byref(par), org_plane, pred_plane, d_blk.data_ptr(), n, d_q.data_ptr(),
+                                                       d_reco.data_ptr() if want_reco else None, d_res.data_ptr(), d_nr.data_ptr()))
+        self.synchronize()
+        return dict(q=d_q.cpu().numpy().reshape(n, par.h, par.w), reco=d_reco.cpu().numpy().reshape(n, par.h, par.w) if want_reco else None,
+                    res=np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=L.TU_RESULT_DT).copy(), need_rdoq=d_nr.cpu().numpy())
+
     # ---- MCTF
     def mctf_error_batch(self, org_plane, ref_plane, cands, low_res_filter=False):
         cands = np.ascontiguousarray(cands, dtype=L.MCTF_DT)

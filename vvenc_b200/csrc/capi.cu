@@ -10,6 +10,7 @@
 #include "search_kernels.cuh"
 #include "trquant_kernels.cuh"
 #include "trquant_tc_kernels.cuh"
+#include "itrquant_kernels.cuh"
 #include "mctf_affine_kernels.cuh"
 #include "vvc_tables.h"
 
@@ -850,6 +851,20 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
   p.useThres = thres / ( p.scale << 2 );                                                 // Quant.cpp:180
   int t = ( w * h ) / 4;
   p.team = std::max( 4, std::min( 128, t ) );
+  {                                                                                      // Quant::dequant, Quant.cpp:554-607
+    int baseQp = in->qp + 6 * ( in->bit_depth - 8 );
+    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) );
+    const int per = baseQp / 6, rem = baseQp % 6;
+    const int sqrt2 = ( p.lw + p.lh ) & 1;
+    const int trShift = 15 - in->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;
+    static const int invScales[2][6] = { { 40, 45, 51, 57, 64, 72 }, { 57, 64, 72, 80, 90, 102 } };   // g_invQuantScales, Rom.cpp:1396-1400
+    p.dqScale = invScales[sqrt2][rem];
+    p.dqShift = 6 - ( trShift + per );                                                   // IQUANT_SHIFT = 6 (CommonDef.h:370)
+    const int tib = std::min( 16, 32 + p.dqShift - 7 );                                  // targetInputBitDepth, Quant.cpp:606
+    p.dqInMax = ( 1 << ( tib - 1 ) ) - 1;
+    p.s2Inv   = 20 - in->bit_depth;                                                      // TrQuant.cpp:609
+    p.pelMax  = ( 1 << in->bit_depth ) - 1;
+  }
   return VVB_OK;
 }
 
@@ -937,6 +952,108 @@ int vvb_fwd_trquant_planes( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, i
   if( coef )     CU( cudaMemcpyAsync( coef, dC, (size_t) n * area * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( absSum )   CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( lastPos )  CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+// ---- inverse path + fused TU round trip ------------------------------------------------------------------------------
+static int teamGrid( vvb_ctx* ctx, int n, int nTeams, size_t smem )
+{
+  const int ctasNeeded = ( n + nTeams - 1 ) / nTeams;
+  const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 16, ( 200 * 1024 ) / ( smem + 1024 ) ) );
+  return std::min( ctasNeeded, ctx->numSMs * perSM );
+}
+
+int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ, int n, int16_t* dResi )
+{
+  if( !ctx || !dQ || !dResi || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  TuPar p;
+  int rc = makeTuPar( ctx, par, p );
+  if( rc ) return rc;
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int nTeams = 128 / p.team;
+  const size_t smem = inv_trquant_smem( p, nTeams );
+  inv_trquant_kernel<<<teamGrid( ctx, n, nTeams, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, dQ, n, dResi );
+  CHECK_LAUNCH( "inv_trquant_kernel" );
+  return VVB_OK;
+}
+
+int vvb_inv_trquant( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* q, int n, int16_t* resi )
+{
+  if( !ctx || !par || !q || !resi || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t bytes = (size_t) n * par->w * par->h * 2;
+  void *dQ, *dR; int rc;
+  if( ( rc = scratch( ctx, 0, bytes, &dQ ) ) || ( rc = scratch( ctx, 1, bytes, &dR ) ) ) return rc;
+  CU( cudaMemcpyAsync( dQ, q, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_inv_trquant_dev( ctx, par, (const int16_t*) dQ, n, (int16_t*) dR ) ) ) return rc;
+  CU( cudaMemcpyAsync( resi, dR, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  return VVB_OK;
+}
+
+static_assert( sizeof( vvb_tu_result ) == sizeof( TuResult ) && sizeof( TuResult ) == 32, "vvb_tu_result layout" );
+
+static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, int predPlane, const vvb_block* dBlocks, const int16_t* dOrg, const int16_t* dPred,
+                              int n, int16_t* dQ, int16_t* dReco, vvb_tu_result* dRes, uint8_t* dNeedRdoq )
+{
+  TuPar p;
+  int rc = makeTuPar( ctx, par, p );
+  if( rc ) return rc;
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int nTeams = 128 / p.team;
+  const size_t smem = tu_roundtrip_smem( p, nTeams );
+  const int grid = teamGrid( ctx, n, nTeams, smem );
+  if( dBlocks )
+  {
+    static bool attr = false;
+    if( !attr ) { cudaFuncSetAttribute( tu_roundtrip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 ); attr = true; }
+    tu_roundtrip_kernel<true><<<grid, 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, ctx->planes.p[orgPlane], ctx->planes.p[predPlane], dBlocks,
+                                                                 nullptr, nullptr, n, dQ, dReco, (TuResult*) dRes, dNeedRdoq );
+  }
+  else
+  {
+    static bool attr = false;
+    if( !attr ) { cudaFuncSetAttribute( tu_roundtrip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 ); attr = true; }
+    tu_roundtrip_kernel<false><<<grid, 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, Plane{}, Plane{}, nullptr, dOrg, dPred, n, dQ, dReco, (TuResult*) dRes, dNeedRdoq );
+  }
+  CHECK_LAUNCH( "tu_roundtrip_kernel" );
+  return VVB_OK;
+}
+
+int vvb_tu_roundtrip_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dOrg, const int16_t* dPred, int n, int16_t* dQ, int16_t* dReco, vvb_tu_result* dRes, uint8_t* dNeedRdoq )
+{
+  if( !ctx || !dOrg || !dPred || !dQ || !dRes || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  return tuRoundtripLaunch( ctx, par, -1, -1, nullptr, dOrg, dPred, n, dQ, dReco, dRes, dNeedRdoq );
+}
+
+int vvb_tu_roundtrip_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, int predPlane, const vvb_block* dBlocks, int n,
+                                 int16_t* dQ, int16_t* dReco, vvb_tu_result* dRes, uint8_t* dNeedRdoq )
+{
+  if( !ctx || !dBlocks || !dQ || !dRes || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, predPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  return tuRoundtripLaunch( ctx, par, orgPlane, predPlane, dBlocks, nullptr, nullptr, n, dQ, dReco, dRes, dNeedRdoq );
+}
+
+int vvb_tu_roundtrip( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* org, const int16_t* pred, int n, int16_t* q, int16_t* reco, vvb_tu_result* res, uint8_t* needRdoq )
+{
+  if( !ctx || !par || !org || !pred || !q || !res || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t bytes = (size_t) n * par->w * par->h * 2;
+  void *dO, *dP, *dQ, *dR = nullptr, *dM; int rc;
+  if( ( rc = scratch( ctx, 0, bytes, &dO ) ) || ( rc = scratch( ctx, 1, bytes, &dP ) ) || ( rc = scratch( ctx, 2, bytes, &dQ ) ) ||
+      ( rc = scratch( ctx, 3, (size_t) n * ( sizeof( vvb_tu_result ) + 1 ), &dM ) ) ) return rc;
+  if( reco && ( rc = scratch( ctx, 4, bytes, &dR ) ) ) return rc;
+  uint8_t* dNr = (uint8_t*) dM + (size_t) n * sizeof( vvb_tu_result );
+  CU( cudaMemcpyAsync( dO, org, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  CU( cudaMemcpyAsync( dP, pred, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_tu_roundtrip_dev( ctx, par, (const int16_t*) dO, (const int16_t*) dP, n, (int16_t*) dQ, (int16_t*) dR, (vvb_tu_result*) dM, dNr ) ) ) return rc;
+  CU( cudaMemcpyAsync( q, dQ, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( reco )     CU( cudaMemcpyAsync( reco, dR, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( cudaMemcpyAsync( res, dM, (size_t) n * sizeof( vvb_tu_result ), cudaMemcpyDeviceToHost, ctx->stream ) );
   if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( cudaStreamSynchronize( ctx->stream ) );
   return VVB_OK;

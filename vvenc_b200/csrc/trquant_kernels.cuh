@@ -29,12 +29,16 @@ struct TuPar
   int scanOff;               // offset (entries) of this shape's raster->scanpos table
   int regionW, regionH;      // min(32,w), min(32,h)
   int team;                  // threads per TU
+  int dqScale, dqShift;      // g_invQuantScales entry, rightShift of Quant::dequant (may be <= 0)   (Quant.cpp:554-561,601)
+  int dqInMax;               // input clipping bound (Quant.cpp:606-607)
+  int s2Inv;                 // second inverse shift 20 - bitDepth (TrQuant.cpp:609); the first is 7
+  int pelMax;                // (1 << bitDepth) - 1, reconstruction clipping (Buffer.cpp:719)
 };
 
 // shared-memory carve-up per team (all in 32-bit words)
 struct TeamSmem { int resiWords, tmpWords, coefWords, total; };
 
-static inline TeamSmem team_smem( const TuPar& p )
+__host__ __device__ inline TeamSmem team_smem( const TuPar& p )
 {
   TeamSmem s;
   s.resiWords = ( p.w * p.h ) / 2;                       // int16 residual, later reused for the int16 levels
@@ -55,43 +59,41 @@ __device__ __forceinline__ void stage_matrix( uint32_t* dst, const int8_t* __res
   }
 }
 
-__global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
-                                                             const int16_t* __restrict__ resi, int n,
-                                                             int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
-                                                             int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
+// Views into one team's shared memory.
+struct TeamView
 {
-  extern __shared__ __align__( 16 ) uint32_t smem[];
-  const int T = par.team, nTeams = blockDim.x / T;
-  const int team = threadIdx.x / T, tt = threadIdx.x - team * T;
+  uint32_t* resi;     // int16 residual [h][w] as words; holds the int16 levels after team_forward
+  uint32_t* tmp;      // stage-1 output [keepW][h] (int32)
+  int32_t*  coef;     // int32 coefficients of the scanned region [regionH][regionW]
+  int*      red;      // [0] ovf, [1] lastNZ, [2] cgLo, [3] cgHi, [4] absSum, [5] lastQ+1, [6] rdoq
+};
+
+__device__ __forceinline__ TeamView team_view( const TuPar& par, uint32_t* teamBase, int team )
+{
+  const int resiWords = ( par.w * par.h ) >> 1, tmpWords = par.keepW * par.h, coefWords = par.regionW * par.regionH;
+  TeamView v;
+  v.resi = teamBase + team * ( resiWords + tmpWords + coefWords + 8 );
+  v.tmp  = v.resi + resiWords;
+  v.coef = reinterpret_cast<int32_t*>( v.tmp + tmpWords );
+  v.red  = reinterpret_cast<int*>( v.coef + coefWords );
+  return v;
+}
+
+// Forward transform + quantiser of one TU by one team.  `load( i )` returns residual word i (two int16, row-major compact).
+// Contains __syncthreads(): every thread of the CTA must call it, `live` masks the work.  On return (all threads synchronised)
+// v.resi holds the levels, v.coef the coefficients, v.red[4] absSum, v.red[5] lastQ+1, v.red[6] the RDOQ flag; returns the final scan pos.
+template<class LOAD>
+__device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* MtH, const uint32_t* MtV, const TeamView& v, const int32_t* __restrict__ scanTab,
+                                             int tt, int T, bool live, LOAD load )
+{
   const int w = par.w, h = par.h;
-
-  // ---- matrices, shared by all teams of the CTA
-  uint32_t* MtH = smem;                                        // [w/4][keepW]
-  uint32_t* MtV = MtH + ( w >> 2 ) * par.keepW;                // [h/4][keepH]
-  uint32_t* teamBase = MtV + ( h >> 2 ) * par.keepH;
-  stage_matrix( MtH, trTable, par.offH, w, par.keepW, threadIdx.x, blockDim.x );
-  stage_matrix( MtV, trTable, par.offV, h, par.keepH, threadIdx.x, blockDim.x );
-
-  const int resiWords = ( w * h ) >> 1, tmpWords = par.keepW * h, coefWords = par.regionW * par.regionH;
-  uint32_t* myResi = teamBase + team * ( resiWords + tmpWords + coefWords + 8 );
-  uint32_t* myTmp  = myResi + resiWords;
-  int32_t*  myCoef = reinterpret_cast<int32_t*>( myTmp + tmpWords );
-  int*      myRed  = reinterpret_cast<int*>( myCoef + coefWords );     // [0] ovf, [1] lastNZ, [2] cgLo, [3] cgHi, [4] absSum, [5] lastQ, [6] rdoq
-
-  for( int base = blockIdx.x * nTeams; base < n; base += gridDim.x * nTeams )
-  {
-    const int tu = base + team;
-    const bool live = tu < n;
+  const int resiWords = ( w * h ) >> 1, coefWords = par.regionW * par.regionH;
+  uint32_t* myResi = v.resi; uint32_t* myTmp = v.tmp; int32_t* myCoef = v.coef; int* myRed = v.red;
     __syncthreads();                                           // previous iteration's smem fully consumed; matrices visible
     for( int i = tt; i < 8; i += T ) myRed[i] = 0;
-    // ---- load residual (compact [h][w]) as 32-bit words
     if( live )
-    {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>( resi + (size_t) tu * w * h );
-      for( int i = tt; i < resiWords; i += T ) myResi[i] = __ldg( src + i );
-    }
+      for( int i = tt; i < resiWords; i += T ) myResi[i] = load( i );
     __syncthreads();
-
     // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < h, j < keepW
     {
       const int jGroups = par.keepW >> 2, items = h * jGroups;
@@ -244,27 +246,64 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_consta
       if( lastQ >= 0 ) atomicMax( &myRed[5], lastQ + 1 );     // stored +1 so that 0 means "none"
     }
     __syncthreads();
-    if( live )
+  return pos;
+}
+
+// results of team_forward -> global memory (q compact [h][w]; optional coefficients and per-TU scalars)
+__device__ __forceinline__ void team_forward_store( const TuPar& par, const TeamView& v, int pos, int tu, int tt, int T, bool live,
+                                                    int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
+                                                    int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
+{
+  const int w = par.w, h = par.h, resiWords = ( w * h ) >> 1;
+  const uint32_t* myResi = v.resi; const int32_t* myCoef = v.coef; const int* myRed = v.red;
+  if( live )
+  {
+    uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * w * h );
+    for( int i = tt; i < resiWords; i += T ) dst[i] = myResi[i];
+    if( coefOut )
     {
-      uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * w * h );
-      for( int i = tt; i < resiWords; i += T ) dst[i] = myResi[i];
-      if( coefOut )
+      int32_t* cd = coefOut + (size_t) tu * w * h;
+      for( int i = tt; i < w * h; i += T )
       {
-        int32_t* cd = coefOut + (size_t) tu * w * h;
-        for( int i = tt; i < w * h; i += T )
-        {
-          const int y = i / w, x = i - y * w;
-          cd[i] = ( x < par.regionW && y < par.regionH ) ? myCoef[y * par.regionW + x] : 0;
-        }
-      }
-      if( tt == 0 )
-      {
-        const int sum = myRed[4];
-        if( absSumOut )   absSumOut[tu]   = sum;
-        if( lastPosOut )  lastPosOut[tu]  = sum ? myRed[5] - 1 : pos;      // Quant.cpp:806-816, :830
-        if( needRdoqOut ) needRdoqOut[tu] = (uint8_t) myRed[6];
+        const int y = i / w, x = i - y * w;
+        cd[i] = ( x < par.regionW && y < par.regionH ) ? myCoef[y * par.regionW + x] : 0;
       }
     }
+    if( tt == 0 )
+    {
+      const int sum = myRed[4];
+      if( absSumOut )   absSumOut[tu]   = sum;
+      if( lastPosOut )  lastPosOut[tu]  = sum ? myRed[5] - 1 : pos;      // Quant.cpp:806-816, :830
+      if( needRdoqOut ) needRdoqOut[tu] = (uint8_t) myRed[6];
+    }
+  }
+}
+
+__global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
+                                                             const int16_t* __restrict__ resi, int n,
+                                                             int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
+                                                             int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
+{
+  extern __shared__ __align__( 16 ) uint32_t smem[];
+  const int T = par.team, nTeams = blockDim.x / T;
+  const int team = threadIdx.x / T, tt = threadIdx.x - team * T;
+  const int w = par.w, h = par.h;
+
+  // ---- matrices, shared by all teams of the CTA
+  uint32_t* MtH = smem;                                        // [w/4][keepW]
+  uint32_t* MtV = MtH + ( w >> 2 ) * par.keepW;                // [h/4][keepH]
+  uint32_t* teamBase = MtV + ( h >> 2 ) * par.keepH;
+  stage_matrix( MtH, trTable, par.offH, w, par.keepW, threadIdx.x, blockDim.x );
+  stage_matrix( MtV, trTable, par.offV, h, par.keepH, threadIdx.x, blockDim.x );
+  const TeamView v = team_view( par, teamBase, team );
+
+  for( int base = blockIdx.x * nTeams; base < n; base += gridDim.x * nTeams )
+  {
+    const int tu = base + team;
+    const bool live = tu < n;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>( resi + (size_t)( live ? tu : 0 ) * w * h );
+    const int pos = team_forward( par, MtH, MtV, v, scanTab, tt, T, live, [&]( int i ) { return __ldg( src + i ); } );
+    team_forward_store( par, v, pos, tu, tt, T, live, coefOut, qOut, absSumOut, lastPosOut, needRdoqOut );
   }
 }
 
