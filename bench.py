@@ -445,6 +445,26 @@ def main():
             del pool
         except Exception as ex:     # the sweep is evidence, not part of the metric
             extra['hbm_sweep_16x16_pool'] = {'error': str(ex)}
+        # TU round trip (residual -> transform -> quant -> dequant -> inverse -> reconstruct -> SSE in one kernel) over candidate pools >> L2;
+        # algorithmic bytes per TU = 2wh (org) + 2wh (pred) + 2wh (levels out) + 2wh (reco out) + 32 (result record)
+        try:
+            rt = {}
+            for n in SIZES:
+                ntu = (512 << 20) // (8 * n * n)                                   # 4 x 128 MB of pel data per launch
+                d_o = torch.randint(0, 1024, (ntu * n * n,), dtype=torch.int16, device='cuda')
+                d_p = (d_o + torch.randint(-24, 25, (ntu * n * n,), dtype=torch.int16, device='cuda')).clamp_(0, 1023)
+                d_lv = torch.empty(ntu * n * n, dtype=torch.int16, device='cuda'); d_rc = torch.empty(ntu * n * n, dtype=torch.int16, device='cuda')
+                d_rs = torch.empty(ntu * 32, dtype=torch.uint8, device='cuda')
+                torch.cuda.synchronize()
+                t = time_launch(lambda: chk(lib.vvb_tu_roundtrip_dev(eng.h, ctypes.byref(tu_par[n]), P_(d_o.data_ptr()), P_(d_p.data_ptr()), ntu, P_(d_lv.data_ptr()),
+                                                                     P_(d_rc.data_ptr()), P_(d_rs.data_ptr()), None)), reps=3)
+                byt = ntu * (8 * n * n + 32)
+                nz = int((torch.frombuffer(bytearray(d_rs.cpu().numpy().tobytes()), dtype=torch.int32).view(-1, 8)[:, 6] > 0).sum())
+                rt[str(n)] = {'ms': t, 'tus': ntu, 'tu_per_s': ntu / (t * 1e-3), 'GBps': byt / (t * 1e-3) / 1e9, 'frac_hbm': byt / (t * 1e-3) / 1e9 / hbm_peak, 'nonzero_tus': nz}
+                del d_o, d_p, d_lv, d_rc, d_rs
+            extra['tu_roundtrip_pool'] = rt
+        except Exception as ex:
+            extra['tu_roundtrip_pool'] = {'error': str(ex)}
         # fixed diamond-search candidate set (SURVEY 8d W3 -> W1 byte formula): TZ point pattern, range 64, around the zero vector
         try:
             from vvenc_b200 import candidates as cand
@@ -466,22 +486,30 @@ def main():
     # ------------------------------------------------------------------------------------------- end-to-end through the host-buffer C ABI
     e2e = None
     if not args.skip_e2e:
+        # Two contexts (as two encoder workers would own, EncSlice.cpp:142-147) in asynchronous mode alternate steps: the downloads of step i
+        # overlap the upload and search of step i+1.  Every step still uploads its own pictures and downloads all of its results inside the timed region.
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
         h_planes = []
         for (org, ref, S) in host_sets:
             po = pin(org.shape, torch.int16); pr = pin(ref.shape, torch.int16); po[:] = org; pr[:] = ref
             h_planes.append((po, pr, S))
-        h_blocks = {n: pin((len(blocks_np[n]) * 24,), torch.uint8) for n in SIZES}
-        h_best = {n: pin((len(blocks_np[n]) * 16,), torch.uint8) for n in SIZES}
-        h_satd = {n: pin((len(blocks_np[n]) * KP,), torch.int32) for n in SIZES}
-        h_q = {n: pin((len(blocks_np[n]) * n * n,), torch.int16) for n in SIZES}
-        h_sum = {n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES}; h_last = {n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES}
-        h_nr = {n: pin((len(blocks_np[n]),), torch.uint8) for n in SIZES}
-        for n in SIZES:
-            h_blocks[n][:] = np.frombuffer(blocks_np[n].tobytes(), dtype=np.uint8)
+        NCTX = 2
+        engs = [eng, V.CostEngine(local)]
+        for e in engs:
+            e.set_async(True)
         PA = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        h_pyr_blocks = (ctypes.c_void_p * nlev)(*[h_blocks[n].ctypes.data for n in SIZES])
-        h_pyr_best = (ctypes.c_void_p * nlev)(*[h_best[n].ctypes.data for n in SIZES])
+        hb = []
+        for c in range(NCTX):
+            d = dict(blocks={n: pin((len(blocks_np[n]) * 24,), torch.uint8) for n in SIZES}, best={n: pin((len(blocks_np[n]) * 16,), torch.uint8) for n in SIZES},
+                     satd={n: pin((len(blocks_np[n]) * KP,), torch.int32) for n in SIZES}, q={n: pin((len(blocks_np[n]) * n * n,), torch.int16) for n in SIZES},
+                     sum={n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES}, last={n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES},
+                     nr={n: pin((len(blocks_np[n]),), torch.uint8) for n in SIZES})
+            for n in SIZES:
+                d['blocks'][n][:] = np.frombuffer(blocks_np[n].tobytes(), dtype=np.uint8)
+            d['pyr_blocks'] = (ctypes.c_void_p * nlev)(*[d['blocks'][n].ctypes.data for n in SIZES])
+            d['pyr_best'] = (ctypes.c_void_p * nlev)(*[d['best'][n].ctypes.data for n in SIZES])
+            hb.append(d)
+        h_pat = pin((KP * 4,), torch.uint8); h_pat[:] = np.frombuffer(pat_np.tobytes(), dtype=np.uint8)
         E0, E1 = 40, 41        # plane ids of the uploaded pictures
         h2d = 0; d2h = 0
         for n in SIZES:
@@ -492,28 +520,38 @@ def main():
         h2d += 2 * (H + 2 * MARGIN) * S0 * 2
 
         def step_e2e(i):
+            c = i % NCTX
+            e = engs[c]; d = hb[c]
+            chk(lib.vvb_synchronize(e.h))                      # results of this context's previous step are complete (consumed by the encoder here)
             po, pr, S = h_planes[i % N_PICTURE_SETS]
             base = MARGIN * S + MARGIN
-            chk(lib.vvb_plane_upload(eng.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
-            chk(lib.vvb_plane_upload(eng.h, E1, ctypes.c_void_p(pr.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
-            chk(lib.vvb_sad_search_pyramid(eng.h, E0, E1, nlev, h_pyr_blocks, pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, h_pyr_best))
+            chk(lib.vvb_plane_upload(e.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
+            chk(lib.vvb_plane_upload(e.h, E1, ctypes.c_void_p(pr.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
+            chk(lib.vvb_sad_search_pyramid(e.h, E0, E1, nlev, d['pyr_blocks'], pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, d['pyr_best']))
+            chk(lib.vvb_synchronize(e.h))                      # the host needs the vectors now
             for n in SIZES:
                 nb = len(blocks_np[n])
                 # host logic between the calls: the best vector becomes the refinement centre / prediction offset
-                bv = h_best[n].view(V.BEST_DT); bl = h_blocks[n].view(V.BLOCK_DT)
+                bv = d['best'][n].view(V.BEST_DT); bl = d['blocks'][n].view(V.BLOCK_DT)
                 bl['start_x'] = bv['dx']; bl['start_y'] = bv['dy']
-                chk(lib.vvb_cost_pattern(eng.h, V.DF_HAD, E0, E1, PA(h_blocks[n]), nb, n, n, PA(pat_np), KP, ctypes.byref(me), PA(h_satd[n]), None))
-                chk(lib.vvb_fwd_trquant_planes(eng.h, ctypes.byref(tu_par[n]), E0, E1, PA(h_blocks[n]), nb, None, PA(h_q[n]), PA(h_sum[n]), PA(h_last[n]), PA(h_nr[n])))
+                chk(lib.vvb_cost_pattern(e.h, V.DF_HAD, E0, E1, PA(d['blocks'][n]), nb, n, n, PA(h_pat), KP, ctypes.byref(me), PA(d['satd'][n]), None))
+                chk(lib.vvb_fwd_trquant_planes(e.h, ctypes.byref(tu_par[n]), E0, E1, PA(d['blocks'][n]), nb, None, PA(d['q'][n]), PA(d['sum'][n]), PA(d['last'][n]), PA(d['nr'][n])))
 
-        ke = max(3, min(args.steps, 10))
-        for i in range(2):
+        def drain():
+            for e in engs:
+                chk(lib.vvb_synchronize(e.h))
+
+        ke = max(4, min(args.steps, 10))
+        for i in range(NCTX + 1):
             step_e2e(i)
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(ke):
-            step_e2e(2 + i)
+            step_e2e(NCTX + 1 + i)
+        drain()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / ke
         t = torch.tensor([dt], dtype=torch.float64, device='cuda')
@@ -521,11 +559,18 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {'value': total_units * world / dt, 'unit': 'candidate-blocks/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'ms_per_step': dt * 1e3, 'steps': ke, 'timing': 'host wall clock around synchronous C-ABI calls (each call ends with a stream sync), max over ranks'}
+               'ms_per_step': dt * 1e3, 'steps': ke, 'contexts': NCTX,
+               'timing': 'host wall clock over %d steps issued through the host-buffer C ABI from pinned memory; %d contexts in asynchronous mode alternate steps so that the '
+                         'downloads of one step overlap the upload + search of the next; all contexts drained inside the timed region; max over ranks' % (ke, NCTX)}
+        last = NCTX + ke                                       # index of the last step issued
+        h_best = hb[last % NCTX]['best']
+        for e in engs:
+            e.set_async(False)
+        engs[1].close()
         # parity spot-check of what came back (device-resident and host paths must agree bit for bit)
         bv = h_best[16].view(V.BEST_DT)
         dv = np.frombuffer(d_best[16].cpu().numpy().tobytes(), dtype=V.BEST_DT)
-        extra['e2e_matches_resident'] = bool(np.array_equal(bv['cost'][:64], dv['cost'][:64])) if (2 + ke - 1) % N_PICTURE_SETS == (max(3, args.warmup) + args.steps - 1) % N_PICTURE_SETS else None
+        extra['e2e_matches_resident'] = bool(np.array_equal(bv['cost'][:64], dv['cost'][:64])) if last % N_PICTURE_SETS == (max(3, args.warmup) + args.steps - 1) % N_PICTURE_SETS else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:

@@ -47,7 +47,13 @@ void        vvb_destroy    ( vvb_ctx* ctx );
 const char* vvb_last_error ( const vvb_ctx* ctx );
 int         vvb_synchronize( vvb_ctx* ctx );
 void*       vvb_stream     ( vvb_ctx* ctx );                /* cudaStream_t of the context, for event timing / interop */
-int         vvb_launch_count( const vvb_ctx* ctx, uint64_t* kernels_launched );   /* kernels this context has launched so far */
+int         vvb_launch_count( const vvb_ctx* ctx, uint64_t* kernels_launched );
+/* Asynchronous mode (default off).  When on, the host-buffer entry points below (batch / search / pattern / trquant / roundtrip / plane upload)
+ * only ENQUEUE their copies and kernels on the context's stream and return; vvb_synchronize() is the completion point.  Host input buffers
+ * stay borrowed and host output buffers undefined until then; use page-locked host memory, otherwise the copies degrade to blocking ones.
+ * Work of one context stays ordered; independent contexts (one per worker, EncSlice.cpp:142-147) overlap each other's copies and kernels.
+ * The *_block helpers that return a value always block. */
+int         vvb_set_async  ( vvb_ctx* ctx, int enable );   /* kernels this context has launched so far */
 
 /* measurement aid (bench.py): issue-rate probe of the packed-SAD instruction mix; no reference counterpart */
 int         vvb_alu_probe_dev( vvb_ctx* ctx, int grid_ctas, int iters, int mode /* 0: max-min SAD mix, 1: min-only mix of the dense search */ );

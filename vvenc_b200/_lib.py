@@ -46,6 +46,7 @@ SYMBOLS = {
     'vvb_last_error': (ctypes.c_char_p, [c_p]),
     'vvb_synchronize': (c_i, [c_p]),
     'vvb_stream': (c_p, [c_p]),
+    'vvb_set_async': (c_i, [c_p, c_i]),
     'vvb_launch_count': (c_i, [c_p, ctypes.POINTER(ctypes.c_uint64)]),
     'vvb_alu_probe_dev': (c_i, [c_p, c_i, c_i, c_i]),
     'vvb_plane_upload': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i]),

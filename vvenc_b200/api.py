@@ -64,6 +64,10 @@ class CostEngine:
     def synchronize(self):
         self._chk(self.lib.vvb_synchronize(self.h))
 
+    def set_async(self, enable=True):
+        """host-buffer calls only enqueue; synchronize() completes them (buffers should be page-locked)"""
+        self._chk(self.lib.vvb_set_async(self.h, int(enable)))
+
     @property
     def stream(self):
         return self.lib.vvb_stream(self.h)

@@ -262,6 +262,11 @@ int vvb_synchronize( vvb_ctx* ctx )
 
 void* vvb_stream( vvb_ctx* ctx ) { return ctx ? (void*) ctx->stream : nullptr; }
 
+// End of a host-buffer entry point: blocking mode waits for the stream (results are in the caller's buffers on return); in asynchronous mode the
+// call only enqueues (copies included) and vvb_synchronize() is the completion point.
+static inline cudaError_t endCall( vvb_ctx* ctx ) { return ctx->async ? cudaSuccess : cudaStreamSynchronize( ctx->stream ); }
+int vvb_set_async( vvb_ctx* ctx, int enable ) { if( !ctx ) return VVB_ERR_ARG; ctx->async = enable != 0; return VVB_OK; }
+
 int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) return VVB_ERR_ARG; *k = ctx->launches; return VVB_OK; }
 
 // window staging of the dense search: 1 = TMA (cp.async.bulk.tensor.2d, default when available), 0 = load/store loop
@@ -322,7 +327,7 @@ int vvb_plane_upload( vvb_ctx* ctx, int id, const int16_t* origin, int stride, i
   ctx->owned[id] = d;
   Plane p; p.origin = reinterpret_cast<int16_t*>( d ) + (size_t) margin * dstride + margin; p.stride = dstride; p.width = width; p.height = height; p.margin = margin; p.bitDepth = bitDepth;
   ctx->planes.p[id] = p;
-  CU( cudaStreamSynchronize( ctx->stream ) );                          // the host buffer is only borrowed for the call
+  CU( endCall( ctx ) );                          // the host buffer is only borrowed for the call
   return VVB_OK;
 }
 
@@ -365,7 +370,7 @@ int vvb_dist_batch( vvb_ctx* ctx, const vvb_cand* cands, int n, uint64_t* out )
   CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
   if( ( rc = vvb_dist_batch_dev( ctx, (const vvb_cand*) dC, n, (uint64_t*) dO ) ) ) return rc;
   CU( cudaMemcpyAsync( out, dO, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -442,7 +447,7 @@ int vvb_sad_x5_block( vvb_ctx* ctx, const int16_t* org, int orgStride, const int
   CHECK_LAUNCH( "sad_x5_kernel" );
   uint64_t tmp[5];
   CU( cudaMemcpyAsync( tmp, dOut, 40, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   for( int i = 0; i < 5; i++ ) if( i != 2 || calcCentre ) cost5[i] = tmp[i];
   return VVB_OK;
 }
@@ -556,7 +561,7 @@ int vvb_dist_pool( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* blocks,
   CU( cudaMemcpyAsync( dP, pool, total * w * h * 2, cudaMemcpyHostToDevice, ctx->stream ) );
   if( ( rc = vvb_dist_pool_dev( ctx, dfunc, orgPlane, (const vvb_pos*) dB, nBlocks, w, h, K, (const int16_t*) dP, subShift, (uint32_t*) dO ) ) ) return rc;
   CU( cudaMemcpyAsync( out, dO, total * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -693,7 +698,7 @@ int vvb_sad_search_pyramid( vvb_ctx* ctx, int orgPlane, int refPlane, int levels
   if( ( rc = vvb_sad_search_pyramid_dev( ctx, orgPlane, refPlane, levels, pb, counts, baseW, par, nx, ny, po ) ) ) return rc;
   for( int l = 0; l < levels; l++ )
     if( counts[l] ) CU( cudaMemcpyAsync( best[l], po[l], (size_t) counts[l] * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -725,7 +730,7 @@ int vvb_sad_search( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* b
   if( ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, par, maxNx, maxNy, 1 /* quads are verified per CTA */, (uint32_t*) dT, tableStride, (vvb_best*) dO ) ) ) return rc;
   CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
   if( tables ) CU( cudaMemcpyAsync( tables, dT, (size_t) n * tableStride * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -786,7 +791,7 @@ int vvb_cost_pattern( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const
   if( ( rc = vvb_cost_pattern_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (const vvb_mv*) dP, K, &hp, (uint32_t*) dS, (vvb_best*) dO ) ) ) return rc;
   if( costOut ) CU( cudaMemcpyAsync( costOut, dS, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( best ) CU( cudaMemcpyAsync( best, dO, (size_t) n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -915,7 +920,7 @@ int vvb_fwd_trquant( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* resi, i
   if( absSum )   CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( lastPos )  CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -953,7 +958,7 @@ int vvb_fwd_trquant_planes( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, i
   if( absSum )   CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( lastPos )  CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -990,7 +995,7 @@ int vvb_inv_trquant( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* q, int 
   CU( cudaMemcpyAsync( dQ, q, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
   if( ( rc = vvb_inv_trquant_dev( ctx, par, (const int16_t*) dQ, n, (int16_t*) dR ) ) ) return rc;
   CU( cudaMemcpyAsync( resi, dR, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -1055,7 +1060,7 @@ int vvb_tu_roundtrip( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* org, c
   if( reco )     CU( cudaMemcpyAsync( reco, dR, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( cudaMemcpyAsync( res, dM, (size_t) n * sizeof( vvb_tu_result ), cudaMemcpyDeviceToHost, ctx->stream ) );
   if( needRdoq ) CU( cudaMemcpyAsync( needRdoq, dNr, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -1084,7 +1089,7 @@ int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mc
   CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_mctf_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
   if( ( rc = vvb_mctf_error_batch_dev( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, (int32_t*) dE ) ) ) return rc;
   CU( cudaMemcpyAsync( err, dE, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -1099,7 +1104,7 @@ int vvb_affine_sobel( vvb_ctx* ctx, int vertical, const int16_t* pred, int predS
   sobel_kernel<<<( w * h + 255 ) / 256, 256, 0, ctx->stream>>>( dP, w, (int16_t*) dD, w, w, h, vertical );
   CHECK_LAUNCH( "sobel_kernel" );
   CU( cudaMemcpy2DAsync( deriv, (size_t) derivStride * 2, dD, (size_t) w * 2, (size_t) w * 2, h, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 
@@ -1118,7 +1123,7 @@ int vvb_affine_equal_coeff( vvb_ctx* ctx, int sixParam, const int16_t* resi, int
   CHECK_LAUNCH( "equal_coeff_kernel" );
   int64_t tmp[49];
   CU( cudaMemcpyAsync( tmp, dE, 49 * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( cudaStreamSynchronize( ctx->stream ) );
+  CU( endCall( ctx ) );
   for( int i = 0; i < 49; i++ ) eq[i] += tmp[i];
   return VVB_OK;
 }
