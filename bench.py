@@ -452,7 +452,7 @@ def main():
             for n in SIZES:
                 ntu = (512 << 20) // (8 * n * n)                                   # 4 x 128 MB of pel data per launch
                 d_o = torch.randint(0, 1024, (ntu * n * n,), dtype=torch.int16, device='cuda')
-                d_p = (d_o + torch.randint(-24, 25, (ntu * n * n,), dtype=torch.int16, device='cuda')).clamp_(0, 1023)
+                d_p = (d_o + torch.randint(-200, 201, (ntu * n * n,), dtype=torch.int16, device='cuda')).clamp_(0, 1023)
                 d_lv = torch.empty(ntu * n * n, dtype=torch.int16, device='cuda'); d_rc = torch.empty(ntu * n * n, dtype=torch.int16, device='cuda')
                 d_rs = torch.empty(ntu * 32, dtype=torch.uint8, device='cuda')
                 torch.cuda.synchronize()

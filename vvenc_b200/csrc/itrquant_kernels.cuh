@@ -268,11 +268,20 @@ __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_const
       const int xGroups = w >> 2, items = h * xGroups;
       for( int it = tt; it < items; it += T ) { const int y = it / xGroups; account( y, ( it - y * xGroups ) << 2, 0, 0, 0, 0 ); }
     }
-    if( live )
+    // team reduction: shuffles inside the warp (teams of 4..16 lanes are aligned lane groups), then one shared atomic per warp and value
     {
-      if( dReco ) atomicAdd( &acc[0], dReco );
-      if( dResi ) atomicAdd( &acc[1], dResi );
-      if( dZero ) atomicAdd( &acc[2], dZero );
+      const int span = T < 32 ? T : 32;
+      for( int off = span >> 1; off > 0; off >>= 1 )
+      {
+        dReco += __shfl_xor_sync( 0xffffffffu, dReco, off );
+        dResi += __shfl_xor_sync( 0xffffffffu, dResi, off );
+        dZero += __shfl_xor_sync( 0xffffffffu, dZero, off );
+      }
+      if( live && ( tt & ( span - 1 ) ) == 0 )
+      {
+        if( T <= 32 ) { acc[0] = dReco; acc[1] = dResi; acc[2] = dZero; }
+        else { atomicAdd( &acc[0], dReco ); atomicAdd( &acc[1], dResi ); atomicAdd( &acc[2], dZero ); }
+      }
     }
     __syncthreads();
     if( live && tt == 0 )
