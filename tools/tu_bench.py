@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Component timing of the TU kernels on pools larger than L2: forward (tcgen05 / IDP.2A), inverse, fused round trip.
-usage: python tools/tu_bench.py [noise_amp]   (GPU box)"""
+usage: python tools/tu_bench.py [noise_amp [WxH ...]]   (GPU box)"""
 import ctypes, sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,6 +28,8 @@ def tl(fn, reps=3):
 
 
 shapes = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (32, 8), (64, 16)]
+if len(sys.argv) > 2:
+    shapes = [tuple(int(v) for v in a.split('x')) for a in sys.argv[2:]]
 for (w, h) in shapes:
     ntu = (256 << 20) // (8 * w * h)
     par = eng.tu_par(w, h, 0, 0, 10, 32, False, False)

@@ -870,6 +870,14 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
     p.s2Inv   = 20 - in->bit_depth;                                                      // TrQuant.cpp:609
     p.pelMax  = ( 1 << in->bit_depth ) - 1;
   }
+  p.lKeepW = ilog2h( p.keepW ); p.lKeepH = ilog2h( p.keepH ); p.lRegW = ilog2h( p.regionW );
+  p.q32 = p.qbits <= 30 ? 1 : 0;
+  p.add32 = (unsigned)( p.add & 0xffffffffll );
+  {
+    const long long num = ( 1ll << p.qbitsRdoq ) - p.addRdoq;                         // > 0: addRdoq = 171 << (qbits-9) < 2^(qbits-1)
+    const long long thr = ( num + p.scaleRdoq - 1 ) / p.scaleRdoq;
+    p.rdoqThr = thr > 0xffffffffll ? 0xffffffffu : (unsigned) thr;
+  }
   return VVB_OK;
 }
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* 
     const int sc = par.dqScale, sh = par.dqShift, inMax = par.dqInMax, inMin = -inMax - 1;
     for( int it = tt; it < pairs; it += T )
     {
-      const int kp = it / keepW, i = it - kp * keepW;
+      const int kp = it >> par.lKeepW, i = it & ( keepW - 1 );
       int c0 = max( inMin, min( inMax, (int) qS[( 2 * kp ) * w + i] ) );
       int c1 = max( inMin, min( inMax, (int) qS[( 2 * kp + 1 ) * w + i] ) );
       if( sh > 0 ) { const int add = 1 << ( sh - 1 ); c0 = ( c0 * sc + add ) >> sh; c1 = ( c1 * sc + add ) >> sh; }
@@ -64,17 +64,17 @@ __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* 
   //      stored transposed and packed: tT[j][i/2] = ( tmp[i][j], tmp[i+1][j] )
   if( active )
   {
-    const int jGroups = h >> 2, items = ( keepW >> 1 ) * jGroups, Q = keepH >> 2, pitchT = keepW >> 1;
+    const int lJG = par.lh - 2, items = ( keepW >> 1 ) << lJG, Q = keepH >> 2, pitchT = keepW >> 1;
     for( int it = tt; it < items; it += T )
     {
-      const int ip = it / jGroups, j0 = ( it - ip * jGroups ) << 2;
+      const int ip = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
       int a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
       const uint2* ca = reinterpret_cast<const uint2*>( cT + ( 2 * ip ) * pitchC );
       const uint2* cb = reinterpret_cast<const uint2*>( cT + ( 2 * ip + 1 ) * pitchC );
       for( int q = 0; q < Q; q++ )
       {
         const uint2 va = ca[q], vb = cb[q];
-        const uint4 m = *reinterpret_cast<const uint4*>( MvI + q * h + j0 );
+        const uint4 m = *reinterpret_cast<const uint4*>( MvI + ( q << par.lh ) + j0 );
         a0 = __dp2a_lo( (int) va.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) va.y, (int) m.x, a0 );
         a1 = __dp2a_lo( (int) va.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) va.y, (int) m.y, a1 );
         a2 = __dp2a_lo( (int) va.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) va.y, (int) m.z, a2 );
@@ -96,17 +96,17 @@ __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* 
   // ---- pass 2 (horizontal, shift 20 - bitDepth): resi[y][x] = clip16( ( sum_{k<keepW} tmp[k][y] * Th[k][x] + rnd ) >> s2 )
   if( active )
   {
-    const int xGroups = w >> 2, items = h * xGroups, Q = keepW >> 2, pitchT = keepW >> 1;
+    const int lXG = par.lw - 2, items = h << lXG, Q = keepW >> 2, pitchT = keepW >> 1;
     const int s2 = par.s2Inv, r2 = 1 << ( s2 - 1 );
     for( int it = tt; it < items; it += T )
     {
-      const int y = it / xGroups, x0 = ( it - y * xGroups ) << 2;
+      const int y = it >> lXG, x0 = ( it & ( ( 1 << lXG ) - 1 ) ) << 2;
       int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const uint2* tr = reinterpret_cast<const uint2*>( tT + y * pitchT );
       for( int q = 0; q < Q; q++ )
       {
         const uint2 tv = tr[q];
-        const uint4 m = *reinterpret_cast<const uint4*>( MhI + q * w + x0 );
+        const uint4 m = *reinterpret_cast<const uint4*>( MhI + ( q << par.lw ) + x0 );
         a0 = __dp2a_lo( (int) tv.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) tv.y, (int) m.x, a0 );
         a1 = __dp2a_lo( (int) tv.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) tv.y, (int) m.y, a1 );
         a2 = __dp2a_lo( (int) tv.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) tv.y, (int) m.z, a2 );
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__( 128 ) inv_trquant_kernel( const __grid_consta
                     uint2 o;
                     o.x = ( (uint32_t) r0 & 0xffffu ) | ( (uint32_t) r1 << 16 );
                     o.y = ( (uint32_t) r2 & 0xffffu ) | ( (uint32_t) r3 << 16 );
-                    *reinterpret_cast<uint2*>( dst + y * w + x0 ) = o;
+                    *reinterpret_cast<uint2*>( dst + ( y << par.lw ) + x0 ) = o;
                   } );
   }
 }
@@ -219,10 +219,14 @@ __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_const
     }
     const int pos = team_forward( par, MtH, MtV, v, scanTab, tt, T, live, [&]( int i )
     {
-      const int y = i / hw, x = ( i - y * hw ) << 1;
+      const int y = i >> ( par.lw - 1 ), x = ( i & ( hw - 1 ) ) << 1;
       const int16_t* o = oBase + (ptrdiff_t) y * so + x; const int16_t* p = pBase + (ptrdiff_t) y * sp + x;
-      const int d0 = (int) __ldg( o ) - (int) __ldg( p ), d1 = (int) __ldg( o + 1 ) - (int) __ldg( p + 1 );
-      return ( (uint32_t) d0 & 0xffffu ) | ( (uint32_t) d1 << 16 );
+      if( PLANES )
+      {
+        const int d0 = (int) __ldg( o ) - (int) __ldg( p ), d1 = (int) __ldg( o + 1 ) - (int) __ldg( p + 1 );
+        return ( (uint32_t) d0 & 0xffffu ) | ( (uint32_t) d1 << 16 );
+      }
+      return __vsub2( __ldg( reinterpret_cast<const uint32_t*>( o ) ), __ldg( reinterpret_cast<const uint32_t*>( p ) ) );   // compact pools: words are aligned
     } );
     const int absSum = v.red[4];
     if( live )
@@ -240,11 +244,22 @@ __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_const
     {
       const int16_t* o = oBase + (ptrdiff_t) y * so + x0; const int16_t* p = pBase + (ptrdiff_t) y * sp + x0;
       const int r[4] = { r0, r1, r2, r3 };
-      int rc[4];
+      int rc[4], ovs[4], pvs[4];
+      if( !PLANES || ( ( ( reinterpret_cast<uintptr_t>( o ) | reinterpret_cast<uintptr_t>( p ) ) & 7 ) == 0 ) )
+      {
+        const uint2 ow = __ldg( reinterpret_cast<const uint2*>( o ) ), pw = __ldg( reinterpret_cast<const uint2*>( p ) );
+        ovs[0] = lo16( ow.x ); ovs[1] = hi16( ow.x ); ovs[2] = lo16( ow.y ); ovs[3] = hi16( ow.y );
+        pvs[0] = lo16( pw.x ); pvs[1] = hi16( pw.x ); pvs[2] = lo16( pw.y ); pvs[3] = hi16( pw.y );
+      }
+      else
+      {
+#pragma unroll
+        for( int c = 0; c < 4; c++ ) { ovs[c] = __ldg( o + c ); pvs[c] = __ldg( p + c ); }
+      }
 #pragma unroll
       for( int c = 0; c < 4; c++ )
       {
-        const int ov = __ldg( o + c ), pv = __ldg( p + c );
+        const int ov = ovs[c], pv = pvs[c];
         rc[c] = max( 0, min( pelMax, pv + r[c] ) );
         const int dz = ov - pv;                 // original residual
         const long long dr = (long long) dz - r[c];
@@ -258,15 +273,15 @@ __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_const
         uint2 ov2;
         ov2.x = ( (uint32_t) rc[0] & 0xffffu ) | ( (uint32_t) rc[1] << 16 );
         ov2.y = ( (uint32_t) rc[2] & 0xffffu ) | ( (uint32_t) rc[3] << 16 );
-        *reinterpret_cast<uint2*>( rBase + y * w + x0 ) = ov2;
+        *reinterpret_cast<uint2*>( rBase + ( y << par.lw ) + x0 ) = ov2;
       }
     };
     // inverse scratch aliases the forward tmp / coef areas (both dead once the levels are in v.resi)
     team_inverse( par, MvI, MhI, reinterpret_cast<const int16_t*>( v.resi ), v.tmp, v.tmp + par.keepW * inv_ct_pitch( par ), tt, T, active, account );
     if( live && !active )                       // quantised to zero: residual 0 (IntraSearch.cpp:1366-1369 piResi.fill(0))
     {
-      const int xGroups = w >> 2, items = h * xGroups;
-      for( int it = tt; it < items; it += T ) { const int y = it / xGroups; account( y, ( it - y * xGroups ) << 2, 0, 0, 0, 0 ); }
+      const int lXG = par.lw - 2, items = h << lXG;
+      for( int it = tt; it < items; it += T ) account( it >> lXG, ( it & ( ( 1 << lXG ) - 1 ) ) << 2, 0, 0, 0, 0 );
     }
     // team reduction: shuffles inside the warp (teams of 4..16 lanes are aligned lane groups), then one shared atomic per warp and value
     {

@@ -33,6 +33,10 @@ struct TuPar
   int dqInMax;               // input clipping bound (Quant.cpp:606-607)
   int s2Inv;                 // second inverse shift 20 - bitDepth (TrQuant.cpp:609); the first is 7
   int pelMax;                // (1 << bitDepth) - 1, reconstruction clipping (Buffer.cpp:719)
+  int lKeepW, lKeepH, lRegW; // log2 of keepW, keepH, regionW (all powers of two: every index split is a shift)
+  int q32;                   // qbits <= 30: (|c| * scale + add) fits 32 bit for |c| < 2^16 (always true for residuals inside the bit depth)
+  unsigned add32;            // low 32 bits of add (valid when q32)
+  unsigned rdoqThr;          // smallest |c| with ((|c| * scaleRdoq + addRdoq) >> qbitsRdoq) != 0  (needRdoqCore as one compare)
 };
 
 // shared-memory carve-up per team (all in 32-bit words)
@@ -82,6 +86,110 @@ __device__ __forceinline__ TeamView team_view( const TuPar& par, uint32_t* teamB
 // Forward transform + quantiser of one TU by one team.  `load( i )` returns residual word i (two int16, row-major compact).
 // Contains __syncthreads(): every thread of the CTA must call it, `live` masks the work.  On return (all threads synchronised)
 // v.resi holds the levels, v.coef the coefficients, v.red[4] absSum, v.red[5] lastQ+1, v.red[6] the RDOQ flag; returns the final scan pos.
+// lanes of the calling thread's team inside its warp (teams of 4..16 threads are aligned lane groups; larger teams span whole warps)
+__device__ __forceinline__ unsigned team_lane_mask( int T )
+{
+  const unsigned lane = threadIdx.x & 31u;
+  return T >= 32 ? 0xffffffffu : ( ( ( 1u << T ) - 1u ) << ( lane & ~(unsigned)( T - 1 ) ) );
+}
+
+// Plain quantiser of one TU by its team (Quant.cpp:132-230 QuantCore, :735-833 wrapper; needRdoqCore :264-278).
+// coef: int32 [regionH][regionW] in shared memory; qWords: the level block int16 [h][w] (as words) in shared memory; inv: raster -> scan position.
+// Every thread works on quads of 4 raster-consecutive coefficients (LDS.128 + one LDG.128 of scan positions); reductions are redux.sync inside
+// the warp plus one shared atomic per warp for multi-warp teams.  Contains __syncthreads(); ends synchronised with red[4] = absSum,
+// red[5] = last non-zero level's scan position + 1, red[6] = RDOQ flag; returns the final scan position (Quant.cpp:182-208).
+__device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* coef, uint32_t* qWords, int* red, const int32_t* __restrict__ inv,
+                                              int tt, int T, bool live )
+{
+  const unsigned tmask = team_lane_mask( T );
+  const bool multi = T > 32;
+  const int nQuads = live ? ( par.regionW * par.regionH ) >> 2 : 0;
+  const int4* c4 = reinterpret_cast<const int4*>( coef );
+  const int4* s4 = reinterpret_cast<const int4*>( inv );
+  // ---- pass 1: last non-zero scan position, coefficient groups holding a value above the threshold, RDOQ pre-check
+  int lastNZ = 0; unsigned cgLo = 0, cgHi = 0, rd = 0;
+  for( int qi = tt; qi < nQuads; qi += T )
+  {
+    const int4 c = c4[qi];
+    if( c.x | c.y | c.z | c.w )
+    {
+      const int4 sp = __ldg( s4 + qi );
+#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); lastNZ = max( lastNZ, sv ); rd |= (unsigned) ac >= par.rdoqThr; \
+        if( ac > par.useThres ) { const int cg = ( sv ) >> 4; if( cg < 32 ) cgLo |= 1u << cg; else cgHi |= 1u << ( cg - 32 ); } }
+      VVB_Q1( c.x, sp.x ) VVB_Q1( c.y, sp.y ) VVB_Q1( c.z, sp.z ) VVB_Q1( c.w, sp.w )
+#undef VVB_Q1
+    }
+  }
+  lastNZ = __reduce_max_sync( tmask, lastNZ );
+  cgLo   = __reduce_or_sync( tmask, cgLo );
+  cgHi   = __reduce_or_sync( tmask, cgHi );
+  rd     = __reduce_or_sync( tmask, rd );
+  if( multi )
+  {
+    if( ( threadIdx.x & 31 ) == 0 )
+    {
+      if( lastNZ ) atomicMax( &red[1], lastNZ );
+      if( cgLo ) atomicOr( reinterpret_cast<unsigned*>( &red[2] ), cgLo );
+      if( cgHi ) atomicOr( reinterpret_cast<unsigned*>( &red[3] ), cgHi );
+      if( rd ) atomicOr( &red[6], 1 );
+    }
+    __syncthreads();
+    lastNZ = red[1]; cgLo = (unsigned) red[2]; cgHi = (unsigned) red[3];
+  }
+  else if( tt == 0 ) red[6] = (int) rd;
+  // ---- final scan position after trailing-CG trimming (Quant.cpp:182-208)
+  int pos = lastNZ;
+  {
+    const int initCg = pos >> 4;
+    if( initCg >= 1 )
+    {
+      const unsigned long long mask = ( (unsigned long long) cgHi << 32 ) | cgLo;
+      const unsigned long long m = mask & ( initCg >= 63 ? ~0ull : ( ( 1ull << ( initCg + 1 ) ) - 1ull ) ) & ~1ull;   // CGs 1..initCg
+      if( m == 0 ) pos = 15;
+      else { const int g = 63 - __clzll( (long long) m ); if( g != initCg ) pos = g * 16 + 15; }
+    }
+  }
+  // ---- quantise (Quant.cpp:211-227): levels of the scanned region, zeros elsewhere
+  const int w = par.w;
+  if( live && ( w > par.regionW || par.h > par.regionH ) )
+    for( int i = tt; i < ( w * par.h ) >> 1; i += T )
+    {
+      const int y = i >> ( par.lw - 1 ), x = ( i & ( ( w >> 1 ) - 1 ) ) << 1;
+      if( x >= par.regionW || y >= par.regionH ) qWords[i] = 0u;
+    }
+  int sum = 0, lastQ = 0;                                   // lastQ holds scan position + 1
+  for( int qi = tt; qi < nQuads; qi += T )
+  {
+    const int4 c = c4[qi];
+    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if( c.x | c.y | c.z | c.w )
+    {
+      const int4 sp = __ldg( s4 + qi );
+#define VVB_Q2( cv, sv, vv ) if( ( cv ) && ( sv ) <= pos ) { \
+        const unsigned ac = (unsigned) abs( cv ); \
+        const int mag = ( par.q32 && ac < 65536u ) ? (int)( ( ac * (unsigned) par.scale + par.add32 ) >> par.qbits ) \
+                                                   : (int)( ( (long long) ac * par.scale + par.add ) >> par.qbits ); \
+        sum += mag; vv = min( 32767, mag ); if( ( cv ) < 0 ) vv = max( -32768, -mag ); if( vv ) lastQ = max( lastQ, ( sv ) + 1 ); }
+      VVB_Q2( c.x, sp.x, v0 ) VVB_Q2( c.y, sp.y, v1 ) VVB_Q2( c.z, sp.z, v2 ) VVB_Q2( c.w, sp.w, v3 )
+#undef VVB_Q2
+    }
+    const int idx = qi << 2, y = idx >> par.lRegW, x = idx & ( par.regionW - 1 );
+    uint2 o;
+    o.x = ( (uint32_t) v0 & 0xffffu ) | ( (uint32_t) v1 << 16 );
+    o.y = ( (uint32_t) v2 & 0xffffu ) | ( (uint32_t) v3 << 16 );
+    *reinterpret_cast<uint2*>( qWords + ( ( y * w + x ) >> 1 ) ) = o;
+  }
+  sum   = __reduce_add_sync( tmask, sum );
+  lastQ = __reduce_max_sync( tmask, lastQ );
+  if( multi )
+  {
+    if( ( threadIdx.x & 31 ) == 0 ) { if( sum ) atomicAdd( &red[4], sum ); if( lastQ ) atomicMax( &red[5], lastQ ); }
+  }
+  else if( tt == 0 ) { red[4] = sum; red[5] = lastQ; }
+  __syncthreads();
+  return pos;
+}
+
 template<class LOAD>
 __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* MtH, const uint32_t* MtV, const TeamView& v, const int32_t* __restrict__ scanTab,
                                              int tt, int T, bool live, LOAD load )
@@ -89,164 +197,93 @@ __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* M
   const int w = par.w, h = par.h;
   const int resiWords = ( w * h ) >> 1, coefWords = par.regionW * par.regionH;
   uint32_t* myResi = v.resi; uint32_t* myTmp = v.tmp; int32_t* myCoef = v.coef; int* myRed = v.red;
-    __syncthreads();                                           // previous iteration's smem fully consumed; matrices visible
-    for( int i = tt; i < 8; i += T ) myRed[i] = 0;
-    if( live )
-      for( int i = tt; i < resiWords; i += T ) myResi[i] = load( i );
-    __syncthreads();
-    // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < h, j < keepW
+  __syncthreads();                                           // previous iteration's smem fully consumed; matrices visible
+  for( int i = tt; i < 8; i += T ) myRed[i] = 0;
+  if( live )
+    for( int i = tt; i < resiWords; i += T ) myResi[i] = load( i );
+  __syncthreads();
+  // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < h, j < keepW
+  {
+    const int lJG = par.lKeepW - 2, items = h << lJG;
+    const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0;
+    const int Q = w >> 2;
+    int ovf = 0;
+    int32_t* t = reinterpret_cast<int32_t*>( myTmp );
+    for( int it = tt; live && it < items; it += T )
     {
-      const int jGroups = par.keepW >> 2, items = h * jGroups;
-      const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0;
-      const int Q = w >> 2;
-      int ovf = 0;
-      // pass A: compute and detect int16 overflow; results parked in registers for the common 1-item-per-thread case would
-      // complicate the code, so outputs go to smem as int32 first and are repacked in place when they fit.
-      for( int it = tt; live && it < items; it += T )
+      const int i = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const uint2* rrow = reinterpret_cast<const uint2*>( myResi + ( i << ( par.lw - 1 ) ) );
+      const uint32_t* mcol = MtH + j0;
+      for( int q = 0; q < Q; q++ )
       {
-        const int i = it / jGroups, j0 = ( it - i * jGroups ) << 2;
-        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        const uint2* rrow = reinterpret_cast<const uint2*>( myResi + i * ( w >> 1 ) );
+        const uint2 rv = rrow[q];
+        const uint4 m = *reinterpret_cast<const uint4*>( mcol + ( q << par.lKeepW ) );
+        a0 = __dp2a_lo( (int) rv.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) rv.y, (int) m.x, a0 );
+        a1 = __dp2a_lo( (int) rv.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) rv.y, (int) m.y, a1 );
+        a2 = __dp2a_lo( (int) rv.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) rv.y, (int) m.z, a2 );
+        a3 = __dp2a_lo( (int) rv.x, (int) m.w, a3 ); a3 = __dp2a_hi( (int) rv.y, (int) m.w, a3 );
+      }
+      a0 = ( a0 + r1 ) >> par.s1; a1 = ( a1 + r1 ) >> par.s1; a2 = ( a2 + r1 ) >> par.s1; a3 = ( a3 + r1 ) >> par.s1;
+      ovf |= ( a0 != (short) a0 ) | ( a1 != (short) a1 ) | ( a2 != (short) a2 ) | ( a3 != (short) a3 );
+      int32_t* td = t + ( j0 << par.lh ) + i;
+      td[0] = a0; td[h] = a1; td[2 * h] = a2; td[3 * h] = a3;
+    }
+    if( ovf ) atomicOr( &myRed[0], 1 );
+  }
+  __syncthreads();
+  // ---- stage 2: coef[j][i] = ( sum_k tmp[i][k] * Tv[j][k] + r2 ) >> s2   for i < keepW, j < keepH
+  {
+    const int lJG = par.lKeepH - 2, items = par.keepW << lJG;
+    const int r2 = 1 << ( par.s2 - 1 );
+    const int Q = h >> 2;
+    const bool wide = myRed[0] != 0;
+    const int32_t* t32 = reinterpret_cast<const int32_t*>( myTmp );
+    for( int it = tt; live && it < items; it += T )
+    {
+      const int i = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const int4* trow = reinterpret_cast<const int4*>( t32 + ( i << par.lh ) );
+      const uint32_t* mcol = MtV + j0;
+      if( !wide )
+      {
         for( int q = 0; q < Q; q++ )
         {
-          const uint2 rv = rrow[q];
-          const uint4 m = *reinterpret_cast<const uint4*>( MtH + q * par.keepW + j0 );
-          a0 = __dp2a_lo( (int) rv.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) rv.y, (int) m.x, a0 );
-          a1 = __dp2a_lo( (int) rv.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) rv.y, (int) m.y, a1 );
-          a2 = __dp2a_lo( (int) rv.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) rv.y, (int) m.z, a2 );
-          a3 = __dp2a_lo( (int) rv.x, (int) m.w, a3 ); a3 = __dp2a_hi( (int) rv.y, (int) m.w, a3 );
+          const int4 tv = trow[q];
+          const uint32_t p0 = __byte_perm( (uint32_t) tv.x, (uint32_t) tv.y, 0x5410 );
+          const uint32_t p1 = __byte_perm( (uint32_t) tv.z, (uint32_t) tv.w, 0x5410 );
+          const uint4 m = *reinterpret_cast<const uint4*>( mcol + ( q << par.lKeepH ) );
+          a0 = __dp2a_lo( (int) p0, (int) m.x, a0 ); a0 = __dp2a_hi( (int) p1, (int) m.x, a0 );
+          a1 = __dp2a_lo( (int) p0, (int) m.y, a1 ); a1 = __dp2a_hi( (int) p1, (int) m.y, a1 );
+          a2 = __dp2a_lo( (int) p0, (int) m.z, a2 ); a2 = __dp2a_hi( (int) p1, (int) m.z, a2 );
+          a3 = __dp2a_lo( (int) p0, (int) m.w, a3 ); a3 = __dp2a_hi( (int) p1, (int) m.w, a3 );
         }
-        a0 = ( a0 + r1 ) >> par.s1; a1 = ( a1 + r1 ) >> par.s1; a2 = ( a2 + r1 ) >> par.s1; a3 = ( a3 + r1 ) >> par.s1;
-        ovf |= ( a0 != (short) a0 ) | ( a1 != (short) a1 ) | ( a2 != (short) a2 ) | ( a3 != (short) a3 );
-        int32_t* t = reinterpret_cast<int32_t*>( myTmp );
-        t[( j0 + 0 ) * h + i] = a0; t[( j0 + 1 ) * h + i] = a1; t[( j0 + 2 ) * h + i] = a2; t[( j0 + 3 ) * h + i] = a3;
       }
-      if( ovf ) atomicOr( &myRed[0], 1 );
-    }
-    __syncthreads();
-
-    // ---- stage 2: coef[j][i] = ( sum_k tmp[i][k] * Tv[j][k] + r2 ) >> s2   for i < keepW, j < keepH
-    {
-      const int jGroups = par.keepH >> 2, items = par.keepW * jGroups;
-      const int r2 = 1 << ( par.s2 - 1 );
-      const int Q = h >> 2;
-      const bool wide = myRed[0] != 0;
-      const int32_t* t32 = reinterpret_cast<const int32_t*>( myTmp );
-      for( int it = tt; live && it < items; it += T )
+      else
       {
-        const int i = it / jGroups, j0 = ( it - i * jGroups ) << 2;
-        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        const int4* trow = reinterpret_cast<const int4*>( t32 + i * h );
-        if( !wide )
+        for( int q = 0; q < Q; q++ )
         {
-          for( int q = 0; q < Q; q++ )
-          {
-            const int4 tv = trow[q];
-            const uint32_t p0 = ( (uint32_t) tv.x & 0xffffu ) | ( (uint32_t) tv.y << 16 );
-            const uint32_t p1 = ( (uint32_t) tv.z & 0xffffu ) | ( (uint32_t) tv.w << 16 );
-            const uint4 m = *reinterpret_cast<const uint4*>( MtV + q * par.keepH + j0 );
-            a0 = __dp2a_lo( (int) p0, (int) m.x, a0 ); a0 = __dp2a_hi( (int) p1, (int) m.x, a0 );
-            a1 = __dp2a_lo( (int) p0, (int) m.y, a1 ); a1 = __dp2a_hi( (int) p1, (int) m.y, a1 );
-            a2 = __dp2a_lo( (int) p0, (int) m.z, a2 ); a2 = __dp2a_hi( (int) p1, (int) m.z, a2 );
-            a3 = __dp2a_lo( (int) p0, (int) m.w, a3 ); a3 = __dp2a_hi( (int) p1, (int) m.w, a3 );
-          }
-        }
-        else
-        {
-          for( int q = 0; q < Q; q++ )
-          {
-            const int4 tv = trow[q];
-            const uint4 m = *reinterpret_cast<const uint4*>( MtV + q * par.keepH + j0 );
+          const int4 tv = trow[q];
+          const uint4 m = *reinterpret_cast<const uint4*>( mcol + ( q << par.lKeepH ) );
 #define VVB_MAC4( acc, mw ) acc += tv.x * (int)(signed char)( (mw) & 0xff ) + tv.y * (int)(signed char)( ( (mw) >> 8 ) & 0xff ) + tv.z * (int)(signed char)( ( (mw) >> 16 ) & 0xff ) + tv.w * (int)(signed char)( (mw) >> 24 )
-            VVB_MAC4( a0, m.x ); VVB_MAC4( a1, m.y ); VVB_MAC4( a2, m.z ); VVB_MAC4( a3, m.w );
+          VVB_MAC4( a0, m.x ); VVB_MAC4( a1, m.y ); VVB_MAC4( a2, m.z ); VVB_MAC4( a3, m.w );
 #undef VVB_MAC4
-          }
         }
-        a0 = ( a0 + r2 ) >> par.s2; a1 = ( a1 + r2 ) >> par.s2; a2 = ( a2 + r2 ) >> par.s2; a3 = ( a3 + r2 ) >> par.s2;
-        myCoef[( j0 + 0 ) * par.regionW + i] = a0; myCoef[( j0 + 1 ) * par.regionW + i] = a1;
-        myCoef[( j0 + 2 ) * par.regionW + i] = a2; myCoef[( j0 + 3 ) * par.regionW + i] = a3;
       }
-      // rows/columns of the scanned region that were zeroed out (MTS 32 -> 16)
-      if( live && ( par.keepW < par.regionW || par.keepH < par.regionH ) )
-        for( int i = tt; i < coefWords; i += T )
-        {
-          const int y = i / par.regionW, x = i - y * par.regionW;
-          if( x >= par.keepW || y >= par.keepH ) myCoef[i] = 0;
-        }
+      a0 = ( a0 + r2 ) >> par.s2; a1 = ( a1 + r2 ) >> par.s2; a2 = ( a2 + r2 ) >> par.s2; a3 = ( a3 + r2 ) >> par.s2;
+      int32_t* cd = myCoef + ( j0 << par.lRegW ) + i;
+      cd[0] = a0; cd[par.regionW] = a1; cd[2 * par.regionW] = a2; cd[3 * par.regionW] = a3;
     }
-    __syncthreads();
-
-    // ---- quantiser pass 1: last non-zero scan position, coefficient groups holding a value above the threshold, RDOQ pre-check
-    const int32_t* inv = scanTab + par.scanOff;                // raster (y*regionW + x) -> scan position
-    if( live )
-    {
-      int lastNZ = 0; uint32_t cgLo = 0, cgHi = 0; int rd = 0;
+    // rows/columns of the scanned region that were zeroed out (MTS 32 -> 16)
+    if( live && ( par.keepW < par.regionW || par.keepH < par.regionH ) )
       for( int i = tt; i < coefWords; i += T )
       {
-        const int c = myCoef[i];
-        const int ac = abs( c );
-        if( c )
-        {
-          const int sp = __ldg( inv + i );
-          lastNZ = max( lastNZ, sp );
-          if( ac > par.useThres ) { const int cg = sp >> 4; if( cg < 32 ) cgLo |= 1u << cg; else cgHi |= 1u << ( cg - 32 ); }
-          if( (int)( ( (long long) ac * par.scaleRdoq + par.addRdoq ) >> par.qbitsRdoq ) != 0 ) rd = 1;
-        }
+        const int y = i >> par.lRegW, x = i & ( par.regionW - 1 );
+        if( x >= par.keepW || y >= par.keepH ) myCoef[i] = 0;
       }
-      if( lastNZ ) atomicMax( &myRed[1], lastNZ );
-      if( cgLo ) atomicOr( reinterpret_cast<unsigned*>( &myRed[2] ), cgLo );
-      if( cgHi ) atomicOr( reinterpret_cast<unsigned*>( &myRed[3] ), cgHi );
-      if( rd ) atomicOr( &myRed[6], 1 );
-    }
-    __syncthreads();
-
-    // ---- final scan position after trailing-CG trimming (Quant.cpp:182-208)
-    int pos = myRed[1];
-    {
-      const int initCg = pos >> 4;
-      if( initCg >= 1 )
-      {
-        const unsigned long long mask = ( (unsigned long long)(unsigned) myRed[3] << 32 ) | (unsigned) myRed[2];
-        const unsigned long long m = mask & ( initCg >= 63 ? ~0ull : ( ( 1ull << ( initCg + 1 ) ) - 1ull ) ) & ~1ull;   // CGs 1..initCg
-        if( m == 0 ) pos = 15;
-        else { const int g = 63 - __clzll( (long long) m ); if( g != initCg ) pos = g * 16 + 15; }
-      }
-    }
-
-    // ---- quantise (Quant.cpp:211-227), write int16 levels into the residual buffer (reused), optional coef output
-    int16_t* qS = reinterpret_cast<int16_t*>( myResi );
-    if( live )
-    {
-      for( int i = tt; i < resiWords; i += T ) myResi[i] = 0u;
-    }
-    __syncthreads();
-    if( live )
-    {
-      int sum = 0, lastQ = -1;
-      for( int i = tt; i < coefWords; i += T )
-      {
-        const int c = myCoef[i];
-        if( c )
-        {
-          const int sp = __ldg( inv + i );
-          if( sp <= pos )
-          {
-            const long long t = (long long) abs( c ) * par.scale;
-            const int mag = (int)( ( t + par.add ) >> par.qbits );
-            sum += mag;
-            int v = c < 0 ? -mag : mag;
-            v = max( -32768, min( 32767, v ) );
-            const int y = i / par.regionW, x = i - y * par.regionW;
-            qS[y * w + x] = (int16_t) v;
-            if( v ) lastQ = max( lastQ, sp );
-          }
-        }
-      }
-      if( sum ) atomicAdd( &myRed[4], sum );
-      if( lastQ >= 0 ) atomicMax( &myRed[5], lastQ + 1 );     // stored +1 so that 0 means "none"
-    }
-    __syncthreads();
-  return pos;
+  }
+  __syncthreads();
+  return team_quantise( par, myCoef, myResi, myRed, scanTab + par.scanOff, tt, T, live );
 }
 
 // results of team_forward -> global memory (q compact [h][w]; optional coefficients and per-TU scalars)
@@ -265,8 +302,8 @@ __device__ __forceinline__ void team_forward_store( const TuPar& par, const Team
       int32_t* cd = coefOut + (size_t) tu * w * h;
       for( int i = tt; i < w * h; i += T )
       {
-        const int y = i / w, x = i - y * w;
-        cd[i] = ( x < par.regionW && y < par.regionH ) ? myCoef[y * par.regionW + x] : 0;
+        const int y = i >> par.lw, x = i & ( w - 1 );
+        cd[i] = ( x < par.regionW && y < par.regionH ) ? myCoef[( y << par.lRegW ) + x] : 0;
       }
     }
     if( tt == 0 )

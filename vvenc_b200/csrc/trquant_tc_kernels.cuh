@@ -292,71 +292,13 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_tc_kernel( const __grid_con
     tc_fence_before();
     __syncthreads();
 
-    // ---- quantiser (identical arithmetic to fwd_trquant_kernel): team of N threads per TU
+    // ---- quantiser: the same device function as the CUDA-core kernel, team of N threads per TU
     {
       const int tt = rowInTu, T = N;
       int32_t*  myCoef = sCoef + tuInTile * REGION;
       int*      myRed  = sRed + tuInTile * 8;
       uint32_t* myQ    = sQ + tuInTile * ( N * N / 2 );
-      if( live )
-      {
-        int lastNZ = 0; uint32_t cgLo = 0, cgHi = 0; int rd = 0;
-        for( int i = tt; i < REGION; i += T )
-        {
-          const int c = myCoef[i];
-          if( c )
-          {
-            const int ac = abs( c ), sp = __ldg( inv + i );
-            lastNZ = max( lastNZ, sp );
-            if( ac > par.useThres ) { const int cg = sp >> 4; if( cg < 32 ) cgLo |= 1u << cg; else cgHi |= 1u << ( cg - 32 ); }
-            if( (int)( ( (long long) ac * par.scaleRdoq + par.addRdoq ) >> par.qbitsRdoq ) != 0 ) rd = 1;
-          }
-        }
-        if( lastNZ ) atomicMax( &myRed[1], lastNZ );
-        if( cgLo ) atomicOr( reinterpret_cast<unsigned*>( &myRed[2] ), cgLo );
-        if( cgHi ) atomicOr( reinterpret_cast<unsigned*>( &myRed[3] ), cgHi );
-        if( rd ) atomicOr( &myRed[6], 1 );
-        for( int i = tt; i < N * N / 2; i += T ) myQ[i] = 0u;
-      }
-      __syncthreads();
-      int pos = myRed[1];
-      {
-        const int initCg = pos >> 4;
-        if( initCg >= 1 )
-        {
-          const unsigned long long mask = ( (unsigned long long)(unsigned) myRed[3] << 32 ) | (unsigned) myRed[2];
-          const unsigned long long m = mask & ( initCg >= 63 ? ~0ull : ( ( 1ull << ( initCg + 1 ) ) - 1ull ) ) & ~1ull;
-          if( m == 0 ) pos = 15;
-          else { const int g = 63 - __clzll( (long long) m ); if( g != initCg ) pos = g * 16 + 15; }
-        }
-      }
-      int16_t* qS = reinterpret_cast<int16_t*>( myQ );
-      if( live )
-      {
-        int sum = 0, lastQ = -1;
-        for( int i = tt; i < REGION; i += T )
-        {
-          const int c = myCoef[i];
-          if( c )
-          {
-            const int sp = __ldg( inv + i );
-            if( sp <= pos )
-            {
-              const long long t = (long long) abs( c ) * par.scale;
-              const int mag = (int)( ( t + par.add ) >> par.qbits );
-              sum += mag;
-              int v = c < 0 ? -mag : mag;
-              v = max( -32768, min( 32767, v ) );
-              const int y = i / KEEP, x = i - y * KEEP;
-              qS[y * N + x] = (int16_t) v;
-              if( v ) lastQ = max( lastQ, sp );
-            }
-          }
-        }
-        if( sum ) atomicAdd( &myRed[4], sum );
-        if( lastQ >= 0 ) atomicMax( &myRed[5], lastQ + 1 );
-      }
-      __syncthreads();
+      const int pos = team_quantise( par, myCoef, myQ, myRed, inv, tt, T, live );
       if( live )
       {
         uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * N * N );
