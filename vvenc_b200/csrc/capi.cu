@@ -228,7 +228,6 @@ int vvb_create( vvb_ctx** out, int device )
     if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) == cudaSuccess && qres == cudaDriverEntryPointSuccess ) ctx->tmaEncode = fn;
     cudaGetLastError();
   }
-  cudaFuncSetAttribute( fwd_trquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -818,6 +817,13 @@ int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dBlocks, const vvb_best* 
 }
 
 // ---- transform + quantise ----------------------------------------------------------------------------------------
+static int teamGrid( vvb_ctx* ctx, int n, int nTeams, size_t smem )
+{
+  const int ctasNeeded = ( n + nTeams - 1 ) / nTeams;
+  const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 16, ( 200 * 1024 ) / ( smem + 1024 ) ) );
+  return std::min( ctasNeeded, ctx->numSMs * perSM );
+}
+
 static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
 {
   if( !in ) return fail( ctx, VVB_ERR_ARG, "null tu_par" );
@@ -901,13 +907,10 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
     CHECK_LAUNCH( "fwd_trquant_tc_kernel" );
     return VVB_OK;
   }
-  const int nTeams = 128 / p.team;
-  const TeamSmem ts = team_smem( p );
-  const size_t smem = ( (size_t)( p.w >> 2 ) * p.keepW + (size_t)( p.h >> 2 ) * p.keepH + (size_t) nTeams * ts.total ) * 4;
-  const int ctasNeeded = ( n + nTeams - 1 ) / nTeams;
-  const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 16, ( 200 * 1024 ) / ( smem + 1024 ) ) );
-  const int grid = std::min( ctasNeeded, ctx->numSMs * perSM );
-  fwd_trquant_kernel<<<grid, 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
+#define VVB_FWD_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = (size_t)( S::MAT_WORDS + S::NTEAMS * S::TEAM_WORDS ) * 4; \
+    fwd_trquant_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+  VVB_TU_DISPATCH( p.lw, p.lh, VVB_FWD_CALL )
+#undef VVB_FWD_CALL
   CHECK_LAUNCH( "fwd_trquant_kernel" );
   return VVB_OK;
 }
@@ -971,13 +974,6 @@ int vvb_fwd_trquant_planes( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, i
 }
 
 // ---- inverse path + fused TU round trip ------------------------------------------------------------------------------
-static int teamGrid( vvb_ctx* ctx, int n, int nTeams, size_t smem )
-{
-  const int ctasNeeded = ( n + nTeams - 1 ) / nTeams;
-  const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 16, ( 200 * 1024 ) / ( smem + 1024 ) ) );
-  return std::min( ctasNeeded, ctx->numSMs * perSM );
-}
-
 int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ, int n, int16_t* dResi )
 {
   if( !ctx || !dQ || !dResi || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
@@ -986,9 +982,10 @@ int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ,
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const int nTeams = 128 / p.team;
-  const size_t smem = inv_trquant_smem( p, nTeams );
-  inv_trquant_kernel<<<teamGrid( ctx, n, nTeams, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, dQ, n, dResi );
+#define VVB_INV_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = inv_trquant_smem<LWv, LHv>(); \
+    inv_trquant_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, dQ, n, dResi ); }
+  VVB_TU_DISPATCH( p.lw, p.lh, VVB_INV_CALL )
+#undef VVB_INV_CALL
   CHECK_LAUNCH( "inv_trquant_kernel" );
   return VVB_OK;
 }
@@ -1017,22 +1014,12 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const int nTeams = 128 / p.team;
-  const size_t smem = tu_roundtrip_smem( p, nTeams );
-  const int grid = teamGrid( ctx, n, nTeams, smem );
-  if( dBlocks )
-  {
-    static bool attr = false;
-    if( !attr ) { cudaFuncSetAttribute( tu_roundtrip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 ); attr = true; }
-    tu_roundtrip_kernel<true><<<grid, 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, ctx->planes.p[orgPlane], ctx->planes.p[predPlane], dBlocks,
-                                                                 nullptr, nullptr, n, dQ, dReco, (TuResult*) dRes, dNeedRdoq );
-  }
-  else
-  {
-    static bool attr = false;
-    if( !attr ) { cudaFuncSetAttribute( tu_roundtrip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 ); attr = true; }
-    tu_roundtrip_kernel<false><<<grid, 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, Plane{}, Plane{}, nullptr, dOrg, dPred, n, dQ, dReco, (TuResult*) dRes, dNeedRdoq );
-  }
+  const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
+#define VVB_RT_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
+    tu_roundtrip_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
+                                                                                              dQ, dReco, (TuResult*) dRes, dNeedRdoq ); }
+  VVB_TU_DISPATCH( p.lw, p.lh, VVB_RT_CALL )
+#undef VVB_RT_CALL
   CHECK_LAUNCH( "tu_roundtrip_kernel" );
   return VVB_OK;
 }

@@ -39,90 +39,114 @@ struct TuPar
   unsigned rdoqThr;          // smallest |c| with ((|c| * scaleRdoq + addRdoq) >> qbitsRdoq) != 0  (needRdoqCore as one compare)
 };
 
-// shared-memory carve-up per team (all in 32-bit words)
+// Compile-time geometry of one TU shape (W = 2^LW, H = 2^LH).  The kernels are instantiated per shape so that every loop has a constant trip
+// count and every index split is a shift; only the number of kept outputs of a 32-wide / 32-high MTS dimension (16 instead of 32) stays a run-time value.
+template<int LW, int LH> struct TuShape
+{
+  static constexpr int W = 1 << LW, H = 1 << LH;
+  static constexpr int T  = ( W * H / 4 > 128 ) ? 128 : ( W * H / 4 < 4 ? 4 : W * H / 4 );   // threads per TU
+  static constexpr int RW = W > 32 ? 32 : W, RH = H > 32 ? 32 : H;                            // scanned region = upper bound of the kept outputs
+  static constexpr int LRW = LW > 5 ? 5 : LW, LRH = LH > 5 ? 5 : LH;
+  static constexpr int RESI_WORDS = W * H / 2;         // int16 residual, later the int16 levels
+  static constexpr int TMP_WORDS  = RW * H;            // int32 stage-1 output [keepW][H]
+  static constexpr int COEF_WORDS = RW * RH;           // int32 coefficients of the scanned region
+  static constexpr int TEAM_WORDS = RESI_WORDS + TMP_WORDS + COEF_WORDS + 8;
+  static constexpr int MAT_WORDS  = ( W / 4 ) * RW + ( H / 4 ) * RH;                          // forward matrices MtH [W/4][RW], MtV [H/4][RH]
+  static constexpr int NTEAMS = 128 / T;
+  __host__ __device__ static constexpr int cdiv( int a, int b ) { return ( a + b - 1 ) / b; }
+};
+
+// shared-memory carve-up per team (all in 32-bit words) -- the run-time mirror of TuShape for the host
 struct TeamSmem { int resiWords, tmpWords, coefWords, total; };
 
 __host__ __device__ inline TeamSmem team_smem( const TuPar& p )
 {
   TeamSmem s;
-  s.resiWords = ( p.w * p.h ) / 2;                       // int16 residual, later reused for the int16 levels
-  s.tmpWords  = p.keepW * p.h;                           // int32 or packed int16 stage-1 output [keepW][h]
-  s.coefWords = p.regionW * p.regionH;                   // int32 coefficients of the scanned region
+  s.resiWords = ( p.w * p.h ) / 2;
+  s.tmpWords  = p.regionW * p.h;
+  s.coefWords = p.regionW * p.regionH;
   s.total     = s.resiWords + s.tmpWords + s.coefWords + 8;
   return s;
 }
 
-// Matrix staging: Mt[q][j] (32-bit word) = bytes T[j][4q..4q+3]; j fastest so that a thread's 4 consecutive j are one LDS.128
-__device__ __forceinline__ void stage_matrix( uint32_t* dst, const int8_t* __restrict__ table, int off, int N, int keep, int tid, int nthr )
+// Matrix staging: Mt[q][j] (32-bit word) = bytes T[j][4q..4q+3], row pitch `pitch` words; j fastest so that a thread's 4 consecutive j are one LDS.128
+__device__ __forceinline__ void stage_matrix( uint32_t* dst, const int8_t* __restrict__ table, int off, int N, int keep, int pitch, int tid, int nthr )
 {
   const int Q = N >> 2;
-  for( int i = tid; i < Q * keep; i += nthr )
+  for( int i = tid; i < Q * pitch; i += nthr )
   {
-    const int q = i / keep, j = i - q * keep;
-    dst[i] = *reinterpret_cast<const uint32_t*>( table + off + j * N + 4 * q );
+    const int q = i / pitch, j = i - q * pitch;
+    dst[i] = j < keep ? *reinterpret_cast<const uint32_t*>( table + off + j * N + 4 * q ) : 0u;
   }
 }
 
 // Views into one team's shared memory.
 struct TeamView
 {
-  uint32_t* resi;     // int16 residual [h][w] as words; holds the int16 levels after team_forward
-  uint32_t* tmp;      // stage-1 output [keepW][h] (int32)
-  int32_t*  coef;     // int32 coefficients of the scanned region [regionH][regionW]
+  uint32_t* resi;     // int16 residual [H][W] as words; holds the int16 levels after team_forward
+  uint32_t* tmp;      // stage-1 output [keepW][H] (int32)
+  int32_t*  coef;     // int32 coefficients of the scanned region [RH][RW]
   int*      red;      // [0] ovf, [1] lastNZ, [2] cgLo, [3] cgHi, [4] absSum, [5] lastQ+1, [6] rdoq
 };
 
-__device__ __forceinline__ TeamView team_view( const TuPar& par, uint32_t* teamBase, int team )
+template<class S> __device__ __forceinline__ TeamView team_view( uint32_t* teamBase, int team )
 {
-  const int resiWords = ( par.w * par.h ) >> 1, tmpWords = par.keepW * par.h, coefWords = par.regionW * par.regionH;
   TeamView v;
-  v.resi = teamBase + team * ( resiWords + tmpWords + coefWords + 8 );
-  v.tmp  = v.resi + resiWords;
-  v.coef = reinterpret_cast<int32_t*>( v.tmp + tmpWords );
-  v.red  = reinterpret_cast<int*>( v.coef + coefWords );
+  v.resi = teamBase + team * S::TEAM_WORDS;
+  v.tmp  = v.resi + S::RESI_WORDS;
+  v.coef = reinterpret_cast<int32_t*>( v.tmp + S::TMP_WORDS );
+  v.red  = reinterpret_cast<int*>( v.coef + S::COEF_WORDS );
   return v;
 }
 
-// Forward transform + quantiser of one TU by one team.  `load( i )` returns residual word i (two int16, row-major compact).
-// Contains __syncthreads(): every thread of the CTA must call it, `live` masks the work.  On return (all threads synchronised)
-// v.resi holds the levels, v.coef the coefficients, v.red[4] absSum, v.red[5] lastQ+1, v.red[6] the RDOQ flag; returns the final scan pos.
 // lanes of the calling thread's team inside its warp (teams of 4..16 threads are aligned lane groups; larger teams span whole warps)
-__device__ __forceinline__ unsigned team_lane_mask( int T )
+template<int T> __device__ __forceinline__ unsigned team_lane_mask()
 {
+  if( T >= 32 ) return 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
-  return T >= 32 ? 0xffffffffu : ( ( ( 1u << T ) - 1u ) << ( lane & ~(unsigned)( T - 1 ) ) );
+  return ( ( 1u << ( T & 31 ) ) - 1u ) << ( lane & ~(unsigned)( T - 1 ) );
 }
 
-// Plain quantiser of one TU by its team (Quant.cpp:132-230 QuantCore, :735-833 wrapper; needRdoqCore :264-278).
-// coef: int32 [regionH][regionW] in shared memory; qWords: the level block int16 [h][w] (as words) in shared memory; inv: raster -> scan position.
+// Plain quantiser of one TU by its team of T threads (Quant.cpp:132-230 QuantCore, :735-833 wrapper; needRdoqCore :264-278).
+// coef: int32 [RH][RW] in shared memory; qWords: the level block int16 [H][W] (as words) in shared memory; inv: raster -> scan position.
 // Every thread works on quads of 4 raster-consecutive coefficients (LDS.128 + one LDG.128 of scan positions); reductions are redux.sync inside
 // the warp plus one shared atomic per warp for multi-warp teams.  Contains __syncthreads(); ends synchronised with red[4] = absSum,
 // red[5] = last non-zero level's scan position + 1, red[6] = RDOQ flag; returns the final scan position (Quant.cpp:182-208).
-__device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* coef, uint32_t* qWords, int* red, const int32_t* __restrict__ inv,
-                                              int tt, int T, bool live )
+template<int LW, int LH, int T>
+__device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* coef, uint32_t* qWords, int* red, const int32_t* __restrict__ inv, int tt, bool live )
 {
-  const unsigned tmask = team_lane_mask( T );
-  const bool multi = T > 32;
-  const int nQuads = live ? ( par.regionW * par.regionH ) >> 2 : 0;
+  using S = TuShape<LW, LH>;
+  constexpr int NQUADS = S::RW * S::RH / 4, ITERS = S::cdiv( NQUADS, T );
+  constexpr bool CACHE = ITERS <= 4;                        // keep the quads and their scan positions in registers between the two passes
+  const unsigned tmask = team_lane_mask<T>();
+  constexpr bool multi = T > 32;
   const int4* c4 = reinterpret_cast<const int4*>( coef );
   const int4* s4 = reinterpret_cast<const int4*>( inv );
+  const int useThres = par.useThres; const unsigned rdoqThr = par.rdoqThr;
   // ---- pass 1: last non-zero scan position, coefficient groups holding a value above the threshold, RDOQ pre-check
   int lastNZ = 0; unsigned cgLo = 0, cgHi = 0, rd = 0;
-  for( int qi = tt; qi < nQuads; qi += T )
+  int4 cq[CACHE ? ITERS : 1], sq[CACHE ? ITERS : 1];
+#pragma unroll
+  for( int kk = 0; kk < ITERS; kk++ )
   {
-    const int4 c = c4[qi];
-    if( c.x | c.y | c.z | c.w )
+    const int qi = tt + kk * T, k = CACHE ? kk : 0;
+    cq[k] = make_int4( 0, 0, 0, 0 ); sq[k] = make_int4( 0, 0, 0, 0 );
+    if( live && ( NQUADS % T == 0 || qi < NQUADS ) )
     {
-      const int4 sp = __ldg( s4 + qi );
-#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); lastNZ = max( lastNZ, sv ); rd |= (unsigned) ac >= par.rdoqThr; \
-        if( ac > par.useThres ) { const int cg = ( sv ) >> 4; if( cg < 32 ) cgLo |= 1u << cg; else cgHi |= 1u << ( cg - 32 ); } }
-      VVB_Q1( c.x, sp.x ) VVB_Q1( c.y, sp.y ) VVB_Q1( c.z, sp.z ) VVB_Q1( c.w, sp.w )
+      cq[k] = c4[qi];
+      if( cq[k].x | cq[k].y | cq[k].z | cq[k].w )
+      {
+        sq[k] = __ldg( s4 + qi );
+#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); lastNZ = max( lastNZ, sv ); rd |= (unsigned) ac >= rdoqThr; \
+          if( ac > useThres ) { const int cg = ( sv ) >> 4; if( NQUADS <= 128 || cg < 32 ) cgLo |= 1u << ( cg & 31 ); else cgHi |= 1u << ( cg - 32 ); } }
+        VVB_Q1( cq[k].x, sq[k].x ) VVB_Q1( cq[k].y, sq[k].y ) VVB_Q1( cq[k].z, sq[k].z ) VVB_Q1( cq[k].w, sq[k].w )
 #undef VVB_Q1
+      }
     }
   }
   lastNZ = __reduce_max_sync( tmask, lastNZ );
   cgLo   = __reduce_or_sync( tmask, cgLo );
-  cgHi   = __reduce_or_sync( tmask, cgHi );
+  if( NQUADS > 128 ) cgHi = __reduce_or_sync( tmask, cgHi );
   rd     = __reduce_or_sync( tmask, rd );
   if( multi )
   {
@@ -150,34 +174,38 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
     }
   }
   // ---- quantise (Quant.cpp:211-227): levels of the scanned region, zeros elsewhere
-  const int w = par.w;
-  if( live && ( w > par.regionW || par.h > par.regionH ) )
-    for( int i = tt; i < ( w * par.h ) >> 1; i += T )
-    {
-      const int y = i >> ( par.lw - 1 ), x = ( i & ( ( w >> 1 ) - 1 ) ) << 1;
-      if( x >= par.regionW || y >= par.regionH ) qWords[i] = 0u;
-    }
-  int sum = 0, lastQ = 0;                                   // lastQ holds scan position + 1
-  for( int qi = tt; qi < nQuads; qi += T )
+  if( S::W > S::RW || S::H > S::RH )
   {
-    const int4 c = c4[qi];
-    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    if( c.x | c.y | c.z | c.w )
+#pragma unroll
+    for( int k = 0; k < S::cdiv( S::RESI_WORDS, T ); k++ )
     {
-      const int4 sp = __ldg( s4 + qi );
+      const int i = tt + k * T;
+      const int y = i >> ( LW - 1 ), x = ( i & ( S::W / 2 - 1 ) ) << 1;
+      if( live && i < S::RESI_WORDS && ( x >= S::RW || y >= S::RH ) ) qWords[i] = 0u;
+    }
+  }
+  int sum = 0, lastQ = 0;                                   // lastQ holds scan position + 1
+  const int qbits = par.qbits; const unsigned scale = (unsigned) par.scale, add32 = par.add32; const bool q32 = par.q32 != 0;
+#pragma unroll
+  for( int kk = 0; kk < ITERS; kk++ )
+  {
+    const int qi = tt + kk * T, k = CACHE ? kk : 0;
+    if( live && ( NQUADS % T == 0 || qi < NQUADS ) )
+    {
+      if( !CACHE ) { cq[0] = c4[qi]; sq[0] = ( cq[0].x | cq[0].y | cq[0].z | cq[0].w ) ? __ldg( s4 + qi ) : make_int4( 0, 0, 0, 0 ); }
+      int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
 #define VVB_Q2( cv, sv, vv ) if( ( cv ) && ( sv ) <= pos ) { \
         const unsigned ac = (unsigned) abs( cv ); \
-        const int mag = ( par.q32 && ac < 65536u ) ? (int)( ( ac * (unsigned) par.scale + par.add32 ) >> par.qbits ) \
-                                                   : (int)( ( (long long) ac * par.scale + par.add ) >> par.qbits ); \
+        const int mag = ( q32 && ac < 65536u ) ? (int)( ( ac * scale + add32 ) >> qbits ) : (int)( ( (long long) ac * par.scale + par.add ) >> qbits ); \
         sum += mag; vv = min( 32767, mag ); if( ( cv ) < 0 ) vv = max( -32768, -mag ); if( vv ) lastQ = max( lastQ, ( sv ) + 1 ); }
-      VVB_Q2( c.x, sp.x, v0 ) VVB_Q2( c.y, sp.y, v1 ) VVB_Q2( c.z, sp.z, v2 ) VVB_Q2( c.w, sp.w, v3 )
+      VVB_Q2( cq[k].x, sq[k].x, v0 ) VVB_Q2( cq[k].y, sq[k].y, v1 ) VVB_Q2( cq[k].z, sq[k].z, v2 ) VVB_Q2( cq[k].w, sq[k].w, v3 )
 #undef VVB_Q2
+      const int idx = qi << 2, y = idx >> S::LRW, x = idx & ( S::RW - 1 );
+      uint2 o;
+      o.x = ( (uint32_t) v0 & 0xffffu ) | ( (uint32_t) v1 << 16 );
+      o.y = ( (uint32_t) v2 & 0xffffu ) | ( (uint32_t) v3 << 16 );
+      *reinterpret_cast<uint2*>( qWords + ( ( ( y << LW ) + x ) >> 1 ) ) = o;
     }
-    const int idx = qi << 2, y = idx >> par.lRegW, x = idx & ( par.regionW - 1 );
-    uint2 o;
-    o.x = ( (uint32_t) v0 & 0xffffu ) | ( (uint32_t) v1 << 16 );
-    o.y = ( (uint32_t) v2 & 0xffffu ) | ( (uint32_t) v3 << 16 );
-    *reinterpret_cast<uint2*>( qWords + ( ( y * w + x ) >> 1 ) ) = o;
   }
   sum   = __reduce_add_sync( tmask, sum );
   lastQ = __reduce_max_sync( tmask, lastQ );
@@ -190,159 +218,181 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
   return pos;
 }
 
-template<class LOAD>
+// Forward transform + quantiser of one TU by one team.  `load( i )` returns residual word i (two int16, row-major compact).
+// Contains __syncthreads(): every thread of the CTA must call it, `live` masks the work.  On return (all threads synchronised)
+// v.resi holds the levels, v.coef the coefficients, v.red[4] absSum, v.red[5] lastQ+1, v.red[6] the RDOQ flag; returns the final scan pos.
+template<int LW, int LH, class LOAD>
 __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* MtH, const uint32_t* MtV, const TeamView& v, const int32_t* __restrict__ scanTab,
-                                             int tt, int T, bool live, LOAD load )
+                                             int tt, bool live, LOAD load )
 {
-  const int w = par.w, h = par.h;
-  const int resiWords = ( w * h ) >> 1, coefWords = par.regionW * par.regionH;
-  uint32_t* myResi = v.resi; uint32_t* myTmp = v.tmp; int32_t* myCoef = v.coef; int* myRed = v.red;
+  using S = TuShape<LW, LH>;
+  constexpr int W = S::W, H = S::H, T = S::T, RW = S::RW, RH = S::RH;
+  const int keepW = LW == 5 ? par.keepW : RW, keepH = LH == 5 ? par.keepH : RH;     // 16 for an MTS dimension of 32 (TrQuant.cpp:496-497)
+  uint32_t* myResi = v.resi; int32_t* myTmp = reinterpret_cast<int32_t*>( v.tmp ); int32_t* myCoef = v.coef; int* myRed = v.red;
   __syncthreads();                                           // previous iteration's smem fully consumed; matrices visible
-  for( int i = tt; i < 8; i += T ) myRed[i] = 0;
-  if( live )
-    for( int i = tt; i < resiWords; i += T ) myResi[i] = load( i );
+  if( tt < 8 ) myRed[tt] = 0;
+  if( T < 8 && tt < 4 ) myRed[tt + 4] = 0;
+#pragma unroll
+  for( int k = 0; k < S::RESI_WORDS / T; k++ ) { const int i = tt + k * T; if( live ) myResi[i] = load( i ); }
   __syncthreads();
-  // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < h, j < keepW
+  // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < H, j < keepW ; item = (row i, 4 outputs j0..j0+3)
   {
-    const int lJG = par.lKeepW - 2, items = h << lJG;
-    const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0;
-    const int Q = w >> 2;
+    const int s1 = par.s1, r1 = s1 > 0 ? 1 << ( s1 - 1 ) : 0;
+    const int lJG = ( LW == 5 ? par.lKeepW : S::LRW ) - 2, items = H << lJG;
     int ovf = 0;
-    int32_t* t = reinterpret_cast<int32_t*>( myTmp );
-    for( int it = tt; live && it < items; it += T )
+#pragma unroll
+    for( int k = 0; k < S::cdiv( H * RW / 4, T ); k++ )
     {
-      const int i = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
-      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      const uint2* rrow = reinterpret_cast<const uint2*>( myResi + ( i << ( par.lw - 1 ) ) );
-      const uint32_t* mcol = MtH + j0;
-      for( int q = 0; q < Q; q++ )
+      const int it = tt + k * T;
+      if( live && it < items )
       {
-        const uint2 rv = rrow[q];
-        const uint4 m = *reinterpret_cast<const uint4*>( mcol + ( q << par.lKeepW ) );
-        a0 = __dp2a_lo( (int) rv.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) rv.y, (int) m.x, a0 );
-        a1 = __dp2a_lo( (int) rv.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) rv.y, (int) m.y, a1 );
-        a2 = __dp2a_lo( (int) rv.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) rv.y, (int) m.z, a2 );
-        a3 = __dp2a_lo( (int) rv.x, (int) m.w, a3 ); a3 = __dp2a_hi( (int) rv.y, (int) m.w, a3 );
+        const int i = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const uint2* rrow = reinterpret_cast<const uint2*>( myResi + i * ( W / 2 ) );
+        const uint32_t* mcol = MtH + j0;
+#pragma unroll
+        for( int q = 0; q < W / 4; q++ )
+        {
+          const uint2 rv = rrow[q];
+          const uint4 m = *reinterpret_cast<const uint4*>( mcol + q * RW );
+          a0 = __dp2a_lo( (int) rv.x, (int) m.x, a0 ); a0 = __dp2a_hi( (int) rv.y, (int) m.x, a0 );
+          a1 = __dp2a_lo( (int) rv.x, (int) m.y, a1 ); a1 = __dp2a_hi( (int) rv.y, (int) m.y, a1 );
+          a2 = __dp2a_lo( (int) rv.x, (int) m.z, a2 ); a2 = __dp2a_hi( (int) rv.y, (int) m.z, a2 );
+          a3 = __dp2a_lo( (int) rv.x, (int) m.w, a3 ); a3 = __dp2a_hi( (int) rv.y, (int) m.w, a3 );
+        }
+        a0 = ( a0 + r1 ) >> s1; a1 = ( a1 + r1 ) >> s1; a2 = ( a2 + r1 ) >> s1; a3 = ( a3 + r1 ) >> s1;
+        ovf |= ( a0 != (short) a0 ) | ( a1 != (short) a1 ) | ( a2 != (short) a2 ) | ( a3 != (short) a3 );
+        int32_t* td = myTmp + j0 * H + i;
+        td[0] = a0; td[H] = a1; td[2 * H] = a2; td[3 * H] = a3;
       }
-      a0 = ( a0 + r1 ) >> par.s1; a1 = ( a1 + r1 ) >> par.s1; a2 = ( a2 + r1 ) >> par.s1; a3 = ( a3 + r1 ) >> par.s1;
-      ovf |= ( a0 != (short) a0 ) | ( a1 != (short) a1 ) | ( a2 != (short) a2 ) | ( a3 != (short) a3 );
-      int32_t* td = t + ( j0 << par.lh ) + i;
-      td[0] = a0; td[h] = a1; td[2 * h] = a2; td[3 * h] = a3;
     }
     if( ovf ) atomicOr( &myRed[0], 1 );
   }
   __syncthreads();
   // ---- stage 2: coef[j][i] = ( sum_k tmp[i][k] * Tv[j][k] + r2 ) >> s2   for i < keepW, j < keepH
   {
-    const int lJG = par.lKeepH - 2, items = par.keepW << lJG;
-    const int r2 = 1 << ( par.s2 - 1 );
-    const int Q = h >> 2;
+    const int s2 = par.s2, r2 = 1 << ( s2 - 1 );
+    const int lJG = ( LH == 5 ? par.lKeepH : S::LRH ) - 2, items = keepW << lJG;
     const bool wide = myRed[0] != 0;
-    const int32_t* t32 = reinterpret_cast<const int32_t*>( myTmp );
-    for( int it = tt; live && it < items; it += T )
+#pragma unroll
+    for( int k = 0; k < S::cdiv( RW * RH / 4, T ); k++ )
     {
-      const int i = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
-      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      const int4* trow = reinterpret_cast<const int4*>( t32 + ( i << par.lh ) );
-      const uint32_t* mcol = MtV + j0;
-      if( !wide )
+      const int it = tt + k * T;
+      if( live && it < items )
       {
-        for( int q = 0; q < Q; q++ )
+        const int i = it >> lJG, j0 = ( it & ( ( 1 << lJG ) - 1 ) ) << 2;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const int4* trow = reinterpret_cast<const int4*>( myTmp + i * H );
+        const uint32_t* mcol = MtV + j0;
+        if( !wide )
         {
-          const int4 tv = trow[q];
-          const uint32_t p0 = __byte_perm( (uint32_t) tv.x, (uint32_t) tv.y, 0x5410 );
-          const uint32_t p1 = __byte_perm( (uint32_t) tv.z, (uint32_t) tv.w, 0x5410 );
-          const uint4 m = *reinterpret_cast<const uint4*>( mcol + ( q << par.lKeepH ) );
-          a0 = __dp2a_lo( (int) p0, (int) m.x, a0 ); a0 = __dp2a_hi( (int) p1, (int) m.x, a0 );
-          a1 = __dp2a_lo( (int) p0, (int) m.y, a1 ); a1 = __dp2a_hi( (int) p1, (int) m.y, a1 );
-          a2 = __dp2a_lo( (int) p0, (int) m.z, a2 ); a2 = __dp2a_hi( (int) p1, (int) m.z, a2 );
-          a3 = __dp2a_lo( (int) p0, (int) m.w, a3 ); a3 = __dp2a_hi( (int) p1, (int) m.w, a3 );
+#pragma unroll
+          for( int q = 0; q < H / 4; q++ )
+          {
+            const int4 tv = trow[q];
+            const uint32_t p0 = __byte_perm( (uint32_t) tv.x, (uint32_t) tv.y, 0x5410 );
+            const uint32_t p1 = __byte_perm( (uint32_t) tv.z, (uint32_t) tv.w, 0x5410 );
+            const uint4 m = *reinterpret_cast<const uint4*>( mcol + q * RH );
+            a0 = __dp2a_lo( (int) p0, (int) m.x, a0 ); a0 = __dp2a_hi( (int) p1, (int) m.x, a0 );
+            a1 = __dp2a_lo( (int) p0, (int) m.y, a1 ); a1 = __dp2a_hi( (int) p1, (int) m.y, a1 );
+            a2 = __dp2a_lo( (int) p0, (int) m.z, a2 ); a2 = __dp2a_hi( (int) p1, (int) m.z, a2 );
+            a3 = __dp2a_lo( (int) p0, (int) m.w, a3 ); a3 = __dp2a_hi( (int) p1, (int) m.w, a3 );
+          }
         }
-      }
-      else
-      {
-        for( int q = 0; q < Q; q++ )
+        else
         {
-          const int4 tv = trow[q];
-          const uint4 m = *reinterpret_cast<const uint4*>( mcol + ( q << par.lKeepH ) );
+          for( int q = 0; q < H / 4; q++ )
+          {
+            const int4 tv = trow[q];
+            const uint4 m = *reinterpret_cast<const uint4*>( mcol + q * RH );
 #define VVB_MAC4( acc, mw ) acc += tv.x * (int)(signed char)( (mw) & 0xff ) + tv.y * (int)(signed char)( ( (mw) >> 8 ) & 0xff ) + tv.z * (int)(signed char)( ( (mw) >> 16 ) & 0xff ) + tv.w * (int)(signed char)( (mw) >> 24 )
-          VVB_MAC4( a0, m.x ); VVB_MAC4( a1, m.y ); VVB_MAC4( a2, m.z ); VVB_MAC4( a3, m.w );
+            VVB_MAC4( a0, m.x ); VVB_MAC4( a1, m.y ); VVB_MAC4( a2, m.z ); VVB_MAC4( a3, m.w );
 #undef VVB_MAC4
+          }
         }
+        a0 = ( a0 + r2 ) >> s2; a1 = ( a1 + r2 ) >> s2; a2 = ( a2 + r2 ) >> s2; a3 = ( a3 + r2 ) >> s2;
+        int32_t* cd = myCoef + j0 * RW + i;
+        cd[0] = a0; cd[RW] = a1; cd[2 * RW] = a2; cd[3 * RW] = a3;
       }
-      a0 = ( a0 + r2 ) >> par.s2; a1 = ( a1 + r2 ) >> par.s2; a2 = ( a2 + r2 ) >> par.s2; a3 = ( a3 + r2 ) >> par.s2;
-      int32_t* cd = myCoef + ( j0 << par.lRegW ) + i;
-      cd[0] = a0; cd[par.regionW] = a1; cd[2 * par.regionW] = a2; cd[3 * par.regionW] = a3;
     }
     // rows/columns of the scanned region that were zeroed out (MTS 32 -> 16)
-    if( live && ( par.keepW < par.regionW || par.keepH < par.regionH ) )
-      for( int i = tt; i < coefWords; i += T )
+    if( ( LW == 5 || LH == 5 ) && live && ( keepW < RW || keepH < RH ) )
+      for( int i = tt; i < S::COEF_WORDS; i += T )
       {
-        const int y = i >> par.lRegW, x = i & ( par.regionW - 1 );
-        if( x >= par.keepW || y >= par.keepH ) myCoef[i] = 0;
+        const int y = i >> S::LRW, x = i & ( RW - 1 );
+        if( x >= keepW || y >= keepH ) myCoef[i] = 0;
       }
   }
   __syncthreads();
-  return team_quantise( par, myCoef, myResi, myRed, scanTab + par.scanOff, tt, T, live );
+  return team_quantise<LW, LH, T>( par, myCoef, myResi, myRed, scanTab + par.scanOff, tt, live );
 }
 
-// results of team_forward -> global memory (q compact [h][w]; optional coefficients and per-TU scalars)
-__device__ __forceinline__ void team_forward_store( const TuPar& par, const TeamView& v, int pos, int tu, int tt, int T, bool live,
+// results of team_forward -> global memory (q compact [H][W]; optional coefficients and per-TU scalars)
+template<int LW, int LH>
+__device__ __forceinline__ void team_forward_store( const TeamView& v, int pos, int tu, int tt, bool live,
                                                     int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
                                                     int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
 {
-  const int w = par.w, h = par.h, resiWords = ( w * h ) >> 1;
-  const uint32_t* myResi = v.resi; const int32_t* myCoef = v.coef; const int* myRed = v.red;
+  using S = TuShape<LW, LH>;
+  constexpr int W = S::W, H = S::H, T = S::T;
   if( live )
   {
-    uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * w * h );
-    for( int i = tt; i < resiWords; i += T ) dst[i] = myResi[i];
+    uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * W * H );
+#pragma unroll
+    for( int k = 0; k < S::RESI_WORDS / T; k++ ) dst[tt + k * T] = v.resi[tt + k * T];
     if( coefOut )
     {
-      int32_t* cd = coefOut + (size_t) tu * w * h;
-      for( int i = tt; i < w * h; i += T )
+      int32_t* cd = coefOut + (size_t) tu * W * H;
+      for( int i = tt; i < W * H; i += T )
       {
-        const int y = i >> par.lw, x = i & ( w - 1 );
-        cd[i] = ( x < par.regionW && y < par.regionH ) ? myCoef[( y << par.lRegW ) + x] : 0;
+        const int y = i >> LW, x = i & ( W - 1 );
+        cd[i] = ( x < S::RW && y < S::RH ) ? v.coef[( y << S::LRW ) + x] : 0;
       }
     }
     if( tt == 0 )
     {
-      const int sum = myRed[4];
+      const int sum = v.red[4];
       if( absSumOut )   absSumOut[tu]   = sum;
-      if( lastPosOut )  lastPosOut[tu]  = sum ? myRed[5] - 1 : pos;      // Quant.cpp:806-816, :830
-      if( needRdoqOut ) needRdoqOut[tu] = (uint8_t) myRed[6];
+      if( lastPosOut )  lastPosOut[tu]  = sum ? v.red[5] - 1 : pos;      // Quant.cpp:806-816, :830
+      if( needRdoqOut ) needRdoqOut[tu] = (uint8_t) v.red[6];
     }
   }
 }
 
+template<int LW, int LH>
 __global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
                                                              const int16_t* __restrict__ resi, int n,
                                                              int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
                                                              int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
 {
+  using S = TuShape<LW, LH>;
   extern __shared__ __align__( 16 ) uint32_t smem[];
-  const int T = par.team, nTeams = blockDim.x / T;
-  const int team = threadIdx.x / T, tt = threadIdx.x - team * T;
-  const int w = par.w, h = par.h;
-
+  constexpr int T = S::T, NTEAMS = S::NTEAMS;
+  const int team = threadIdx.x / T, tt = threadIdx.x % T;
   // ---- matrices, shared by all teams of the CTA
-  uint32_t* MtH = smem;                                        // [w/4][keepW]
-  uint32_t* MtV = MtH + ( w >> 2 ) * par.keepW;                // [h/4][keepH]
-  uint32_t* teamBase = MtV + ( h >> 2 ) * par.keepH;
-  stage_matrix( MtH, trTable, par.offH, w, par.keepW, threadIdx.x, blockDim.x );
-  stage_matrix( MtV, trTable, par.offV, h, par.keepH, threadIdx.x, blockDim.x );
-  const TeamView v = team_view( par, teamBase, team );
+  uint32_t* MtH = smem;                                        // [W/4][RW]
+  uint32_t* MtV = MtH + ( S::W / 4 ) * S::RW;                  // [H/4][RH]
+  uint32_t* teamBase = smem + S::MAT_WORDS;
+  stage_matrix( MtH, trTable, par.offH, S::W, par.keepW, S::RW, threadIdx.x, blockDim.x );
+  stage_matrix( MtV, trTable, par.offV, S::H, par.keepH, S::RH, threadIdx.x, blockDim.x );
+  const TeamView v = team_view<S>( teamBase, team );
 
-  for( int base = blockIdx.x * nTeams; base < n; base += gridDim.x * nTeams )
+  for( int base = blockIdx.x * NTEAMS; base < n; base += gridDim.x * NTEAMS )
   {
     const int tu = base + team;
     const bool live = tu < n;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>( resi + (size_t)( live ? tu : 0 ) * w * h );
-    const int pos = team_forward( par, MtH, MtV, v, scanTab, tt, T, live, [&]( int i ) { return __ldg( src + i ); } );
-    team_forward_store( par, v, pos, tu, tt, T, live, coefOut, qOut, absSumOut, lastPosOut, needRdoqOut );
+    const uint32_t* src = reinterpret_cast<const uint32_t*>( resi + (size_t)( live ? tu : 0 ) * S::W * S::H );
+    const int pos = team_forward<LW, LH>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i ) { return __ldg( src + i ); } );
+    team_forward_store<LW, LH>( v, pos, tu, tt, live, coefOut, qOut, absSumOut, lastPosOut, needRdoqOut );
   }
 }
+
+// host-side dispatch over the 25 TU shapes: CALL( LW, LH ) is expanded with constant arguments
+#define VVB_TU_DISPATCH_LH( LWv, lh, CALL ) \
+  switch( lh ) { case 2: CALL( LWv, 2 ); break; case 3: CALL( LWv, 3 ); break; case 4: CALL( LWv, 4 ); break; case 5: CALL( LWv, 5 ); break; default: CALL( LWv, 6 ); break; }
+#define VVB_TU_DISPATCH( lw, lh, CALL ) \
+  switch( lw ) { case 2: VVB_TU_DISPATCH_LH( 2, lh, CALL ) break; case 3: VVB_TU_DISPATCH_LH( 3, lh, CALL ) break; case 4: VVB_TU_DISPATCH_LH( 4, lh, CALL ) break; \
+                 case 5: VVB_TU_DISPATCH_LH( 5, lh, CALL ) break; default: VVB_TU_DISPATCH_LH( 6, lh, CALL ) break; }
 
 // residual = org(x,y) - pred(x + start_x, y + start_y), written compactly so that fwd_trquant_kernel can consume it
 __global__ void residual_from_planes_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane,

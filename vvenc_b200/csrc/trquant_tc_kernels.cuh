@@ -294,11 +294,11 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_tc_kernel( const __grid_con
 
     // ---- quantiser: the same device function as the CUDA-core kernel, team of N threads per TU
     {
-      const int tt = rowInTu, T = N;
+      const int tt = rowInTu; constexpr int T = N;
       int32_t*  myCoef = sCoef + tuInTile * REGION;
       int*      myRed  = sRed + tuInTile * 8;
       uint32_t* myQ    = sQ + tuInTile * ( N * N / 2 );
-      const int pos = team_quantise( par, myCoef, myQ, myRed, inv, tt, T, live );
+      const int pos = team_quantise<( N == 16 ? 4 : N == 32 ? 5 : 6 ), ( N == 16 ? 4 : N == 32 ? 5 : 6 ), N>( par, myCoef, myQ, myRed, inv, tt, live );
       if( live )
       {
         uint32_t* dst = reinterpret_cast<uint32_t*>( qOut + (size_t) tu * N * N );
