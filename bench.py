@@ -465,6 +465,46 @@ def main():
             extra['tu_roundtrip_pool'] = rt
         except Exception as ex:
             extra['tu_roundtrip_pool'] = {'error': str(ex)}
+        # W4 at scale: forward transform + quantiser alone and the inverse path alone over the same kind of pools
+        #   fwd bytes per TU = 2wh (Pel in) + 2wh (TCoeffSig out) + 9 ; inv bytes per TU = 2wh + 2wh
+        try:
+            tq = {}
+            for n in SIZES:
+                ntu = (256 << 20) // (4 * n * n)
+                d_r = torch.randint(-200, 201, (ntu * n * n,), dtype=torch.int16, device='cuda')
+                d_lv = torch.empty(ntu * n * n, dtype=torch.int16, device='cuda'); d_rc = torch.empty(ntu * n * n, dtype=torch.int16, device='cuda')
+                d_s = torch.empty(ntu, dtype=torch.int32, device='cuda'); d_l = torch.empty(ntu, dtype=torch.int32, device='cuda'); d_n = torch.empty(ntu, dtype=torch.uint8, device='cuda')
+                torch.cuda.synchronize()
+                tf = time_launch(lambda: chk(lib.vvb_fwd_trquant_dev(eng.h, ctypes.byref(tu_par[n]), P_(d_r.data_ptr()), ntu, None, P_(d_lv.data_ptr()), P_(d_s.data_ptr()),
+                                                                     P_(d_l.data_ptr()), P_(d_n.data_ptr()))), reps=3)
+                ti = time_launch(lambda: chk(lib.vvb_inv_trquant_dev(eng.h, ctypes.byref(tu_par[n]), P_(d_lv.data_ptr()), ntu, P_(d_rc.data_ptr()))), reps=3)
+                bf = ntu * (4 * n * n + 9); bi = ntu * 4 * n * n
+                tq[str(n)] = {'tus': ntu, 'fwd_ms': tf, 'fwd_GBps': bf / (tf * 1e-3) / 1e9, 'fwd_frac_hbm': bf / (tf * 1e-3) / 1e9 / hbm_peak, 'fwd_tu_per_s': ntu / (tf * 1e-3),
+                              'inv_ms': ti, 'inv_GBps': bi / (ti * 1e-3) / 1e9, 'inv_frac_hbm': bi / (ti * 1e-3) / 1e9 / hbm_peak}
+                del d_r, d_lv, d_rc
+            extra['trquant_pool'] = tq
+        except Exception as ex:
+            extra['trquant_pool'] = {'error': str(ex)}
+        # W5: MCTF block matching, final-level shape -- every 16x16 block of the picture against one neighbour frame, 49 quarter-step
+        # candidates (7x7 around the integer vector, 6-tap 1/16-pel filters) as MCTF::estimateLumaLn's doubleRes refinement evaluates (MCTF.cpp:1245-1287)
+        try:
+            B = 16
+            xs = np.arange(0, W - B + 1, B); ys = np.arange(0, H - B + 1, B)
+            gx, gy = np.meshgrid(xs, ys)
+            off = np.array([(dx, dy) for dy in range(-12, 13, 4) for dx in range(-12, 13, 4)], dtype=np.int32)
+            nbk = gx.size; K5 = len(off)
+            c5 = np.zeros(nbk * K5, dtype=V.MCTF_DT)
+            c5['x'] = np.repeat(gx.reshape(-1), K5); c5['y'] = np.repeat(gy.reshape(-1), K5)
+            c5['mvx'] = np.tile(off[:, 0], nbk) + 16 * 2; c5['mvy'] = np.tile(off[:, 1], nbk) - 16
+            c5['w'] = B; c5['h'] = B
+            d_c5 = dev(c5); d_e5 = torch.empty(nbk * K5, dtype=torch.int32, device='cuda')
+            t5 = time_launch(lambda: chk(lib.vvb_mctf_error_batch_dev(eng.h, 0, 1, P_(d_c5.data_ptr()), nbk * K5, 0, P_(d_e5.data_ptr()))), reps=5)
+            byt = nbk * (2 * B * B + 2 * (B + 2 * 1 + 6) ** 2 + 16)
+            extra['mctf_match_16x16'] = {'blocks': int(nbk), 'candidates_per_block': K5, 'ms': t5, 'cand_per_s': nbk * K5 / (t5 * 1e-3), 'block_refs_per_s': nbk / (t5 * 1e-3),
+                                         'GBps_w5_formula': byt / (t5 * 1e-3) / 1e9, 'frac_hbm_w5_formula': byt / (t5 * 1e-3) / 1e9 / hbm_peak,
+                                         'note': 'fractional candidates: separable 6-tap filtering per candidate (ALU-bound by construction, SURVEY 8d W5)'}
+        except Exception as ex:
+            extra['mctf_match_16x16'] = {'error': str(ex)}
         # fixed diamond-search candidate set (SURVEY 8d W3 -> W1 byte formula): TZ point pattern, range 64, around the zero vector
         try:
             from vvenc_b200 import candidates as cand
@@ -567,10 +607,16 @@ def main():
         for e in engs:
             e.set_async(False)
         engs[1].close()
-        # parity spot-check of what came back (device-resident and host paths must agree bit for bit)
-        bv = h_best[16].view(V.BEST_DT)
-        dv = np.frombuffer(d_best[16].cpu().numpy().tobytes(), dtype=V.BEST_DT)
-        extra['e2e_matches_resident'] = bool(np.array_equal(bv['cost'][:64], dv['cost'][:64])) if last % N_PICTURE_SETS == (max(3, args.warmup) + args.steps - 1) % N_PICTURE_SETS else None
+        # parity check of what came back: replay the last e2e step (same picture set) on the device-resident path and compare every best vector / cost
+        # and every TU's level sum bit for bit
+        step_resident(last)
+        eng.synchronize(); torch.cuda.synchronize()
+        hl = hb[last % NCTX]
+        ok = True
+        for n in SIZES:
+            ok = ok and np.array_equal(np.frombuffer(d_best[n].cpu().numpy().tobytes(), dtype=np.uint8), hl['best'][n])
+            ok = ok and np.array_equal(d_sum[n].cpu().numpy(), hl['sum'][n]) and np.array_equal(d_q[n].cpu().numpy().reshape(-1), hl['q'][n])
+        extra['e2e_matches_resident'] = bool(ok)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:

@@ -44,7 +44,7 @@ for (w, h) in shapes:
         eng.set_tensor_transform(tens)
         res['fwd_tc%d' % tens] = tl(lambda: chk(lib.vvb_fwd_trquant_dev(eng.h, ctypes.byref(par), P_(d_r.data_ptr()), ntu, None, P_(d_q.data_ptr()), P_(d_sum.data_ptr()),
                                                                      P_(d_last.data_ptr()), P_(d_nr.data_ptr()))))
-    eng.set_tensor_transform(1)
+    eng.set_tensor_transform(2)
     res['inv'] = tl(lambda: chk(lib.vvb_inv_trquant_dev(eng.h, ctypes.byref(par), P_(d_q.data_ptr()), ntu, P_(d_rc.data_ptr()))))
     res['roundtrip'] = tl(lambda: chk(lib.vvb_tu_roundtrip_dev(eng.h, ctypes.byref(par), P_(d_o.data_ptr()), P_(d_p.data_ptr()), ntu, P_(d_q.data_ptr()), P_(d_rc.data_ptr()),
                                                                P_(d_rs.data_ptr()), None)))

@@ -280,7 +280,7 @@ int vvb_set_tma_staging( vvb_ctx* ctx, int enable )
 int vvb_set_tensor_transform( vvb_ctx* ctx, int enable )
 {
   if( !ctx ) return VVB_ERR_ARG;
-  ctx->tensorTransform = enable != 0;
+  ctx->tensorTransform = enable;
   return VVB_OK;
 }
 
@@ -895,7 +895,7 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  if( ctx->tensorTransform && p.w == p.h && ( p.w == 16 || p.w == 32 || p.w == 64 ) )
+  if( p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) ) )
   {
     // tcgen05 path: 128 stacked rows (128/N TUs) per tile, persistent CTAs
     const int tpt = 128 / p.w;

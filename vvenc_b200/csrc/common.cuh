@@ -83,7 +83,7 @@ struct vvb_ctx
   std::string    err;
   uint64_t       launches = 0;
   bool           poolBlocksAligned = false;   // see vvb_pool_hint
-  bool           tensorTransform = true;      // see vvb_set_tensor_transform
+  int            tensorTransform = 2;         // see vvb_set_tensor_transform: 0 off, 1 all square 16/32/64 TUs, 2 where measured faster (64x64)
   bool           useTma = false;              // see vvb_set_tma_staging (off by default: unresolved illegal-instruction fault on the round-1 driver)
   void*          tmaEncode = nullptr;         // cuTensorMapEncodeTiled, resolved at vvb_create
   int            numSMs   = 148;
