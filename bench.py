@@ -498,6 +498,7 @@ def main():
             c5['mvx'] = np.tile(off[:, 0], nbk) + 16 * 2; c5['mvy'] = np.tile(off[:, 1], nbk) - 16
             c5['w'] = B; c5['h'] = B
             d_c5 = dev(c5); d_e5 = torch.empty(nbk * K5, dtype=torch.int32, device='cuda')
+            chk(lib.vvb_mctf_hint(eng.h, B))
             t5 = time_launch(lambda: chk(lib.vvb_mctf_error_batch_dev(eng.h, 0, 1, P_(d_c5.data_ptr()), nbk * K5, 0, P_(d_e5.data_ptr()))), reps=5)
             byt = nbk * (2 * B * B + 2 * (B + 2 * 1 + 6) ** 2 + 16)
             extra['mctf_match_16x16'] = {'blocks': int(nbk), 'candidates_per_block': K5, 'ms': t5, 'cand_per_s': nbk * K5 / (t5 * 1e-3), 'block_refs_per_s': nbk / (t5 * 1e-3),

@@ -219,6 +219,9 @@ int vvb_tu_roundtrip_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int org_pl
 typedef struct { int32_t x, y; int32_t mvx, mvy; /* 1/16 pel */ uint16_t w, h; } vvb_mctf_cand;   /* 20 bytes */
 int vvb_mctf_error_batch    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* cands, int n, int low_res_filter /* 4-tap */, int32_t* err_out );
 int vvb_mctf_error_batch_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* dev_cands, int n, int low_res_filter, int32_t* dev_err_out );
+/* promise for the _dev variant: no candidate in the device-resident lists is wider or taller than max_block_dim (8..64, default 64; sizes the per-warp
+ * shared-memory window -- MCTF uses 8/16/32, vvencCfg.cpp:1495).  A candidate that breaks the promise gets error -1. */
+int vvb_mctf_hint( vvb_ctx* ctx, int max_block_dim );
 
 /* ---- affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190) ---------------------------------- */
 int vvb_affine_sobel      ( vvb_ctx* ctx, int vertical, const int16_t* pred, int pred_stride, int16_t* deriv, int deriv_stride, int w, int h );

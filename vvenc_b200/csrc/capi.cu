@@ -229,6 +229,7 @@ int vvb_create( vvb_ctx** out, int device )
     cudaGetLastError();
   }
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1060,16 +1061,32 @@ int vvb_tu_roundtrip( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* org, c
 }
 
 // ---- MCTF ----------------------------------------------------------------------------------------------------------
+static int mctfLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dCands, int n, int lowRes, int maxDim, int32_t* dErr )
+{
+  CU( cudaSetDevice( ctx->device ) );
+  maxDim = std::max( 8, std::min( 64, ( maxDim + 7 ) & ~7 ) );
+  const MctfSmem L = mctf_smem( maxDim );
+  const size_t smem = (size_t) MCTF_WARPS * L.warpWords * 4;
+  const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 12, ( 220 * 1024 ) / ( smem + 1024 ) ) );
+  const int grid = std::min( ( n + MCTF_WARPS - 1 ) / MCTF_WARPS, ctx->numSMs * perSM );
+  mctf_error_packed_kernel<<<grid, MCTF_WARPS * 32, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dCands, n, lowRes ? 1 : 0, maxDim, dErr );
+  CHECK_LAUNCH( "mctf_error_packed_kernel" );
+  return VVB_OK;
+}
+
+int vvb_mctf_hint( vvb_ctx* ctx, int maxBlockDim )
+{
+  if( !ctx || maxBlockDim < 8 || maxBlockDim > 64 ) return fail( ctx, VVB_ERR_ARG, "MCTF block dimension hint must be 8..64" );
+  ctx->mctfMaxDim = maxBlockDim;
+  return VVB_OK;
+}
+
 int vvb_mctf_error_batch_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dCands, int n, int lowRes, int32_t* dErr )
 {
   if( !ctx || !dCands || !dErr || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
   if( n == 0 ) return VVB_OK;
-  CU( cudaSetDevice( ctx->device ) );
-  const int grid = std::min( ( n + MCTF_WARPS - 1 ) / MCTF_WARPS, ctx->numSMs * 8 );
-  mctf_error_kernel<<<grid, MCTF_WARPS * 32, 0, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dCands, n, lowRes ? 1 : 0, dErr );
-  CHECK_LAUNCH( "mctf_error_kernel" );
-  return VVB_OK;
+  return mctfLaunch( ctx, orgPlane, refPlane, dCands, n, lowRes, ctx->mctfMaxDim, dErr );
 }
 
 int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* cands, int n, int lowRes, int32_t* err )
@@ -1082,7 +1099,10 @@ int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mc
   void *dC, *dE; int rc;
   if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_mctf_cand ), &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * 4, &dE ) ) ) return rc;
   CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_mctf_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
-  if( ( rc = vvb_mctf_error_batch_dev( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, (int32_t*) dE ) ) ) return rc;
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  int maxDim = 8;
+  for( int i = 0; i < n; i++ ) maxDim = std::max( maxDim, (int) std::max( cands[i].w, cands[i].h ) );
+  if( ( rc = mctfLaunch( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, maxDim, (int32_t*) dE ) ) ) return rc;
   CU( cudaMemcpyAsync( err, dE, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( endCall( ctx ) );
   return VVB_OK;

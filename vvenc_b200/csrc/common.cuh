@@ -91,6 +91,7 @@ struct vvb_ctx
   int8_t*        d_trTable   = nullptr;     // all transform matrices (vvc_tables.h)
   int32_t*       d_scan      = nullptr;     // scan tables for all (log2w, log2h) in 2..6, 1024 entries each
   // grow-only scratch arenas (device + pinned host) used by the host-buffer entry points
+  int            mctfMaxDim = 64;      // largest MCTF block dimension in device-resident candidate lists (vvb_mctf_hint)
   bool           async = false;        // host-buffer calls enqueue only; vvb_synchronize() completes them (vvb_set_async)
   void*          d_scratch[8] = {};
   size_t         d_scratchSize[8] = {};
