@@ -501,6 +501,14 @@ def main():
             chk(lib.vvb_mctf_hint(eng.h, B))
             t5 = time_launch(lambda: chk(lib.vvb_mctf_error_batch_dev(eng.h, 0, 1, P_(d_c5.data_ptr()), nbk * K5, 0, P_(d_e5.data_ptr()))), reps=5)
             byt = nbk * (2 * B * B + 2 * (B + 2 * 1 + 6) ** 2 + 16)
+            # the same 49 vectors through the grid-search entry point (window staged once per block, horizontal pass shared per column of the grid)
+            b5 = np.zeros(nbk, dtype=V.MCTF_DT)
+            b5['x'] = gx.reshape(-1); b5['y'] = gy.reshape(-1); b5['mvx'] = 32; b5['mvy'] = -16; b5['w'] = B; b5['h'] = B
+            d_b5 = dev(b5); d_g5 = torch.empty(nbk * K5, dtype=torch.int32, device='cuda')
+            tg = time_launch(lambda: chk(lib.vvb_mctf_search_grid_dev(eng.h, 0, 1, P_(d_b5.data_ptr()), nbk, 4, 3, 0, P_(d_g5.data_ptr()))), reps=5)
+            same = bool(torch.equal(d_g5.view(nbk, K5), d_e5.view(nbk, K5)))
+            extra['mctf_grid_16x16'] = {'blocks': int(nbk), 'step': 4, 'radius': 3, 'ms': tg, 'cand_per_s': nbk * K5 / (tg * 1e-3), 'block_refs_per_s': nbk / (tg * 1e-3),
+                                        'GBps_w5_formula': byt / (tg * 1e-3) / 1e9, 'frac_hbm_w5_formula': byt / (tg * 1e-3) / 1e9 / hbm_peak, 'equals_candidate_list': same}
             extra['mctf_match_16x16'] = {'blocks': int(nbk), 'candidates_per_block': K5, 'ms': t5, 'cand_per_s': nbk * K5 / (t5 * 1e-3), 'block_refs_per_s': nbk / (t5 * 1e-3),
                                          'GBps_w5_formula': byt / (t5 * 1e-3) / 1e9, 'frac_hbm_w5_formula': byt / (t5 * 1e-3) / 1e9 / hbm_peak,
                                          'note': 'fractional candidates: separable 6-tap filtering per candidate (ALU-bound by construction, SURVEY 8d W5)'}

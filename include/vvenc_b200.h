@@ -223,6 +223,13 @@ int vvb_mctf_error_batch_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const 
  * shared-memory window -- MCTF uses 8/16/32, vvencCfg.cpp:1495).  A candidate that breaks the promise gets error -1. */
 int vvb_mctf_hint( vvb_ctx* ctx, int max_block_dim );
 
+/* Grid search of MCTF::estimateLumaLn (MCTF.cpp:1218-1287): for every block (x, y, w, h) all (2*radius+1)^2 vectors  (mvx, mvy) + (i - radius, j - radius) * step,
+ * step in 1/16 pel (16 = the integer grid with range 5/8, then 4, 2, 1 for the doubleRes refinements).  err_out[n][j][i] = motionErrorLuma of that vector
+ * (no early exit).  One CTA per block: the window is staged once and the horizontally filtered rows are shared by the candidates of a column.
+ * The `error < best.error` chain, the predictor candidates and the final error scaling (:1308-1321) replay on the host from these tables. */
+int vvb_mctf_search_grid    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* blocks, int n, int step, int radius, int low_res_filter, int32_t* err_out );
+int vvb_mctf_search_grid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* dev_blocks, int n, int step, int radius, int low_res_filter, int32_t* dev_err_out );
+
 /* ---- affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190) ---------------------------------- */
 int vvb_affine_sobel      ( vvb_ctx* ctx, int vertical, const int16_t* pred, int pred_stride, int16_t* deriv, int deriv_stride, int w, int h );
 int vvb_affine_equal_coeff( vvb_ctx* ctx, int six_param, const int16_t* resi, int resi_stride, const int16_t* deriv_x, const int16_t* deriv_y,

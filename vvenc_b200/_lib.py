@@ -82,6 +82,8 @@ SYMBOLS = {
     'vvb_tu_roundtrip_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
     'vvb_tu_roundtrip_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
     'vvb_mctf_error_batch': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'vvb_mctf_search_grid': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p]),
+    'vvb_mctf_search_grid_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p]),
     'vvb_mctf_hint': (c_i, [c_p, c_i]),
     'vvb_mctf_error_batch_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_affine_sobel': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i]),

@@ -256,6 +256,14 @@ class CostEngine:
         self._chk(self.lib.vvb_mctf_error_batch(self.h, org_plane, ref_plane, _p(cands), len(cands), int(low_res_filter), _p(out)))
         return out
 
+    def mctf_search_grid(self, org_plane, ref_plane, blocks, step, radius, low_res_filter=False):
+        """blocks: MCTF_DT (x, y, centre mvx/mvy in 1/16 pel, w, h) -> errors int32 [n][2r+1 (dy)][2r+1 (dx)] of centre + (i-r, j-r)*step"""
+        blocks = np.ascontiguousarray(blocks, dtype=L.MCTF_DT)
+        k1 = 2 * radius + 1
+        out = np.zeros((len(blocks), k1, k1), dtype=np.int32)
+        self._chk(self.lib.vvb_mctf_search_grid(self.h, org_plane, ref_plane, _p(blocks), len(blocks), step, radius, int(low_res_filter), _p(out)))
+        return out
+
     # ---- affine
     def affine_sobel(self, vertical, pred, pred_stride, deriv_stride, w, h):
         d = np.zeros((h, deriv_stride), dtype=np.int16)

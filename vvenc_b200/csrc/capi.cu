@@ -230,6 +230,7 @@ int vvb_create( vvb_ctx** out, int device )
   }
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1104,6 +1105,57 @@ int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mc
   for( int i = 0; i < n; i++ ) maxDim = std::max( maxDim, (int) std::max( cands[i].w, cands[i].h ) );
   if( ( rc = mctfLaunch( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, maxDim, (int32_t*) dE ) ) ) return rc;
   CU( cudaMemcpyAsync( err, dE, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// MCTF grid search: all (2r+1)^2 candidates around each block's centre vector in one CTA (estimateLumaLn loops, MCTF.cpp:1218-1287)
+static int mctfGridLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dBlocks, int n, int step, int radius, int lowRes, int maxDim, int32_t* dErr )
+{
+  CU( cudaSetDevice( ctx->device ) );
+  maxDim = std::max( 8, std::min( 64, ( maxDim + 7 ) & ~7 ) );
+  const MctfGridSmem L = mctf_grid_smem( maxDim, step, radius );
+  const size_t smem = (size_t) L.total * 4;
+  if( smem > 200 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF grid too large for shared memory" );
+  const int threads = std::max( 32, std::min( 256, ( ( maxDim / 2 ) * maxDim + 31 ) & ~31 ) );
+  mctf_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, step, radius, lowRes ? 1 : 0, maxDim, dErr );
+  CHECK_LAUNCH( "mctf_grid_kernel" );
+  return VVB_OK;
+}
+
+static int mctfGridArgs( vvb_ctx* ctx, int orgPlane, int refPlane, int n, int step, int radius )
+{
+  if( n < 0 || step < 1 || step > 16 || radius < 0 || radius > 8 ) return fail( ctx, VVB_ERR_ARG, "MCTF grid: step 1..16 (1/16 pel), radius 0..8 steps" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  return VVB_OK;
+}
+
+int vvb_mctf_search_grid_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dBlocks, int n, int step, int radius, int lowRes, int32_t* dErr )
+{
+  if( !ctx || !dBlocks || !dErr ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  int rc = mctfGridArgs( ctx, orgPlane, refPlane, n, step, radius );
+  if( rc || n == 0 ) return rc;
+  return mctfGridLaunch( ctx, orgPlane, refPlane, dBlocks, n, step, radius, lowRes, ctx->mctfMaxDim, dErr );
+}
+
+int vvb_mctf_search_grid( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* blocks, int n, int step, int radius, int lowRes, int32_t* err )
+{
+  if( !ctx || !blocks || !err ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  int rc = mctfGridArgs( ctx, orgPlane, refPlane, n, step, radius );
+  if( rc || n == 0 ) return rc;
+  int maxDim = 8;
+  for( int i = 0; i < n; i++ )
+  {
+    if( blocks[i].w < 8 || blocks[i].h < 8 || blocks[i].w > 64 || blocks[i].h > 64 || ( blocks[i].w & 7 ) || ( blocks[i].h & 7 ) )
+      return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF blocks are multiples of 8 up to 64 (MCTF.cpp:1113-1118)" );
+    maxDim = std::max( maxDim, (int) std::max( blocks[i].w, blocks[i].h ) );
+  }
+  const size_t K = (size_t)( 2 * radius + 1 ) * ( 2 * radius + 1 );
+  void *dB, *dE;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_mctf_cand ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * K * 4, &dE ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_mctf_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = mctfGridLaunch( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dB, n, step, radius, lowRes, maxDim, (int32_t*) dE ) ) ) return rc;
+  CU( cudaMemcpyAsync( err, dE, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( endCall( ctx ) );
   return VVB_OK;
 }

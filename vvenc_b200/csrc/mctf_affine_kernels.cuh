@@ -209,6 +209,145 @@ __global__ void __launch_bounds__( MCTF_WARPS * 32 ) mctf_error_packed_kernel( c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Grid search: all (2r+1)^2 candidates  centre + (i - r, j - r) * step  (1/16 pel) of one block in one CTA -- the loops of
+// MCTF::estimateLumaLn (CommonLib/MCTF.cpp:1218-1287: integer grid step 16 range 5/8, then 7x7 step 4, 3x3 step 2, 3x3 step 1).
+// The source window is staged once per block; for every distinct horizontal vector the horizontally filtered rows are computed once
+// (packed as row pairs) and shared by the 2r+1 candidates above it; a thread owns output positions (row pair, column), so the original
+// pels are read once and each candidate's error is reduced with one REDUX + one shared atomic per warp.  Same arithmetic as
+// mctf_error_packed_kernel (IDP.2A, int32 sums, clip after each pass): results equal motionErrorLuma for every candidate.
+struct MctfGridSmem { int winPitch, winWords, hWords, orgWords, errWords, total; };
+__host__ __device__ inline MctfGridSmem mctf_grid_smem( int maxDim, int step, int radius )
+{
+  const int span = ( ( 2 * radius * step + 15 ) >> 4 ) + 1;      // upper bound of (max - min) integer displacement
+  const int K1 = 2 * radius + 1;
+  MctfGridSmem m;
+  const int rows = ( maxDim + 6 + span + 1 ) & ~1;
+  m.winPitch = ( maxDim + 5 + span + 2 + 1 ) >> 1;
+  m.winWords = rows * m.winPitch;
+  m.hWords   = 2 * ( rows >> 1 ) * maxDim;                       // two buffers of row pairs x w
+  m.orgWords = ( maxDim >> 1 ) * maxDim;
+  m.errWords = ( K1 * K1 + 1 ) & ~1;
+  m.total    = m.winWords + m.hWords + m.orgWords + m.errWords;
+  return m;
+}
+
+__global__ void __launch_bounds__( 256 ) mctf_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+                                                           const vvb_mctf_cand* __restrict__ blocks, int n, int step, int radius, int tap4, int maxDim,
+                                                           int32_t* __restrict__ out )
+{
+  extern __shared__ __align__( 16 ) uint32_t sGrid[];
+  const MctfGridSmem L = mctf_grid_smem( maxDim, step, radius );
+  uint32_t* win  = sGrid;
+  uint32_t* hbuf = win + L.winWords;
+  uint32_t* orgP = hbuf + L.hWords;
+  int*      sErr = reinterpret_cast<int*>( orgP + L.orgWords );
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int K1 = 2 * radius + 1, K = K1 * K1;
+  const int maxv = ( 1 << refPlane.bitDepth ) - 1;
+  const int PW = L.winPitch;
+
+  for( int b = blockIdx.x; b < n; b += gridDim.x )
+  {
+    const vvb_mctf_cand blk = blocks[b];
+    const int w = blk.w, h = blk.h;
+    if( w > maxDim || h > maxDim || ( ( w | h ) & 1 ) ) { for( int k = tid; k < K; k += T ) out[(size_t) b * K + k] = -1; continue; }
+    const int hw = w >> 1, hh = h >> 1;
+    const float invHw = 1.0f / (float) hw, invW = 1.0f / (float) w;
+    const int dxMin = ( blk.mvx - radius * step ) >> 4, dyMin = ( blk.mvy - radius * step ) >> 4;
+    const int dxMax = ( blk.mvx + radius * step ) >> 4, dyMax = ( blk.mvy + radius * step ) >> 4;
+    const int rowsP = ( h + 6 + ( dyMax - dyMin ) + 1 ) & ~1;
+    // ---- stage the window (rows y+dyMin-2 .., pels from the even pel at or below x+dxMin-2), the original block as row pairs, clear the errors
+    const int16_t* src0 = refPlane.origin + (ptrdiff_t)( blk.y + dyMin - 2 ) * refPlane.stride + blk.x + dxMin - 2;
+    const int o = (int)( ( reinterpret_cast<uintptr_t>( src0 ) >> 1 ) & 1 );
+    const uint32_t* srcW = reinterpret_cast<const uint32_t*>( src0 - o );
+    const int nW = ( w + 5 + ( dxMax - dxMin ) + o + 1 ) >> 1;
+    const float invNw = 1.0f / (float) nW;
+    const int strideW = refPlane.stride >> 1;
+    __syncthreads();
+    for( int i = tid; i < rowsP * nW; i += T )
+    {
+      const int r = mctf_div( i, invNw ), k = i - r * nW;
+      win[r * PW + k] = __ldg( srcW + (ptrdiff_t) r * strideW + k );
+    }
+    {
+      const int16_t* org = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
+      for( int i = tid; i < hh * w; i += T )
+      {
+        const int yp = mctf_div( i, invW ), x = i - yp * w;
+        const int16_t* op = org + (ptrdiff_t)( 2 * yp ) * orgPlane.stride + x;
+        orgP[i] = (uint32_t)(uint16_t) __ldg( op ) | ( (uint32_t)(uint16_t) __ldg( op + orgPlane.stride ) << 16 );
+      }
+    }
+    for( int k = tid; k < K; k += T ) sErr[k] = 0;
+    __syncthreads();
+#define VVB_B4( a, b, c_, d ) ( (uint32_t)( (a) & 255 ) | ( (uint32_t)( (b) & 255 ) << 8 ) | ( (uint32_t)( (c_) & 255 ) << 16 ) | ( (uint32_t)( (d) & 255 ) << 24 ) )
+#define VVB_E( a, b, c_, FA, FB ) __dp2a_lo( (int)(c_), FB, __dp2a_hi( (int)(b), FA, __dp2a_lo( (int)(a), FA, 0 ) ) )
+#define VVB_O( a, b, c_, d, GA, GB ) __dp2a_hi( (int)(d), GB, __dp2a_lo( (int)(c_), GB, __dp2a_hi( (int)(b), GA, __dp2a_lo( (int)(a), GA, 0 ) ) ) )
+#define VVB_RC( v ) max( min( ( (v) + 32 ) >> 6, maxv ), 0 )
+#define VVB_TAPS( f, ph ) { _Pragma( "unroll" ) for( int t = 0; t < 6; t++ ) f[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[ph][t - 1] : 0 ) : c_mctfF8[ph][t + 1]; }
+    for( int i = 0; i < K1; i++ )
+    {
+      const int mvx = blk.mvx + ( i - radius ) * step;
+      const int e = ( mvx >> 4 ) - dxMin + o, eo = e & 1, ew = e >> 1;      // pel offset of this vector inside the window rows
+      int f[6];
+      VVB_TAPS( f, mvx & 15 )
+      const int xFA = (int) VVB_B4( f[0], f[1], f[2], f[3] ), xFB = (int) VVB_B4( f[4], f[5], 0, 0 );
+      const int xGA = (int) VVB_B4( 0, f[0], f[1], f[2] ),    xGB = (int) VVB_B4( f[3], f[4], f[5], 0 );
+      uint32_t* H = hbuf + ( i & 1 ) * ( L.hWords >> 1 );
+      // ---- horizontal pass for this mvx: item = (row pair, column pair)
+      for( int it = tid; it < ( rowsP >> 1 ) * hw; it += T )
+      {
+        const int rp = mctf_div( it, invHw ), cp = it - rp * hw;
+        const uint32_t* ra = win + ( 2 * rp ) * PW + cp + ew;
+        const uint32_t* rb = ra + PW;
+        const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
+        int ha0, ha1, hb0, hb1;
+        if( eo == 0 ) { ha0 = VVB_E( a0, a1, a2, xFA, xFB ); ha1 = VVB_O( a0, a1, a2, a3, xGA, xGB ); hb0 = VVB_E( b0, b1, b2, xFA, xFB ); hb1 = VVB_O( b0, b1, b2, b3, xGA, xGB ); }
+        else          { ha0 = VVB_O( a0, a1, a2, a3, xGA, xGB ); ha1 = VVB_E( a1, a2, a3, xFA, xFB ); hb0 = VVB_O( b0, b1, b2, b3, xGA, xGB ); hb1 = VVB_E( b1, b2, b3, xFA, xFB ); }
+        ha0 = VVB_RC( ha0 ); ha1 = VVB_RC( ha1 ); hb0 = VVB_RC( hb0 ); hb1 = VVB_RC( hb1 );
+        uint2 pk;
+        pk.x = (uint32_t) ha0 | ( (uint32_t) hb0 << 16 );
+        pk.y = (uint32_t) ha1 | ( (uint32_t) hb1 << 16 );
+        *reinterpret_cast<uint2*>( H + rp * w + 2 * cp ) = pk;
+      }
+      __syncthreads();               // H(i) complete; H(i-1) readers finished before anyone writes H(i+1) (they passed this barrier)
+      // ---- vertical pass + SSE for the 2r+1 candidates sharing this mvx
+      for( int j = 0; j < K1; j++ )
+      {
+        const int mvy = blk.mvy + ( j - radius ) * step;
+        const int q0 = ( mvy >> 4 ) - dyMin;                                 // first filtered row of output row 0
+        VVB_TAPS( f, mvy & 15 )
+        const int yFA = (int) VVB_B4( f[0], f[1], f[2], f[3] ), yFB = (int) VVB_B4( f[4], f[5], 0, 0 );
+        const int yGA = (int) VVB_B4( 0, f[0], f[1], f[2] ),    yGB = (int) VVB_B4( f[3], f[4], f[5], 0 );
+        int err = 0;
+        for( int p = tid; p < hh * w; p += T )
+        {
+          const int yp = mctf_div( p, invW ), x = p - yp * w;
+          const int q = q0 + 2 * yp;
+          const uint32_t* tp = H + ( q >> 1 ) * w + x;
+          const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
+          int v0, v1;
+          if( ( q & 1 ) == 0 ) { v0 = VVB_E( p0, p1, p2, yFA, yFB ); v1 = VVB_O( p0, p1, p2, p3, yGA, yGB ); }
+          else                 { v0 = VVB_O( p0, p1, p2, p3, yGA, yGB ); v1 = VVB_E( p1, p2, p3, yFA, yFB ); }
+          const uint32_t ow = orgP[p];
+          const int d0 = VVB_RC( v0 ) - (int)( ow & 0xffffu ), d1 = VVB_RC( v1 ) - (int)( ow >> 16 );
+          err += d0 * d0 + d1 * d1;
+        }
+        err = __reduce_add_sync( 0xffffffffu, err );
+        if( ( tid & 31 ) == 0 && err ) atomicAdd( &sErr[j * K1 + i], err );
+      }
+    }
+#undef VVB_B4
+#undef VVB_E
+#undef VVB_O
+#undef VVB_RC
+#undef VVB_TAPS
+    __syncthreads();
+    for( int k = tid; k < K; k += T ) out[(size_t) b * K + k] = sErr[k];
+  }
+}
+
 // ---- affine: Sobel on a w x h prediction block with border replication (AffineGradientSearch.cpp:84-147)
 __global__ void sobel_kernel( const int16_t* __restrict__ pred, int ps, int16_t* __restrict__ deriv, int ds, int w, int h, int vertical )
 {
