@@ -261,6 +261,8 @@ def main():
     import vvenc_b200 as V
     import vvenc_b200._lib as L
     eng = V.CostEngine(local)
+    if os.environ.get('VVB_TMA', '') == '1':            # A/B switch: stage the search windows with cp.async.bulk.tensor where they are 16-byte aligned
+        eng.set_tma_staging(1)
     lib = eng.lib
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', local))
     hbm_peak, peak_src = measured_peaks()

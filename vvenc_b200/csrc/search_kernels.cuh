@@ -238,7 +238,9 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
       const int16_t* src = refPlane.origin + (ptrdiff_t)( blk.y + blk.top ) * refPlane.stride + blk.x + blk.left;
       const int validW = MW + nx - 1;
       const bool even = ( ( (uintptr_t) src & 3 ) == 0 ) && ( ( refPlane.stride & 1 ) == 0 );
-      const bool viaTma = USE_TMA && tma.enabled && nx == tma.nx && ny == tma.ny && ( isQuad ? 1 : 0 ) == tma.quad;
+      // cp.async.bulk.tensor with 16-bit elements needs the innermost start coordinate on a 16-byte boundary (multiple of 8 pels; measured with
+      // tools/tma_probe.cu: any other start raises an illegal-instruction fault) -- windows that start elsewhere take the manual path below
+      const bool viaTma = USE_TMA && tma.enabled && nx == tma.nx && ny == tma.ny && ( isQuad ? 1 : 0 ) == tma.quad && ( ( ( blk.x + blk.left + tma.margin ) & 7 ) == 0 );
       if( viaTma )
       {
         if( tid == 0 )
