@@ -152,8 +152,9 @@ int vvb_sad_pattern    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_b
 int vvb_sad_pattern_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, const vvb_mv* dev_pattern, int K,
                          const vvb_me_par* par, uint32_t* dev_sad_out, vvb_best* dev_best_out );
 
-/* Dense-search window staging: 1 = TMA (cp.async.bulk.tensor.2d, needs cuTensorMapEncodeTiled and a 16-byte aligned reference plane buffer),
- * 0 = load/store loop (DEFAULT in round 1: the TMA copy still faults on the test driver).  Results are identical. */
+/* Dense-search window staging: 1 = TMA (cp.async.bulk.tensor.2d; needs cuTensorMapEncodeTiled and a 16-byte aligned reference plane buffer) for every
+ * window whose first column sits on a 16-byte boundary (8 pels), the load/store loop for the others; 0 = load/store loop only;
+ * 2 (default) = TMA where it is measured faster (blocks up to 8 pels wide, i.e. the base level of the SAD pyramid).  Results are identical. */
 int vvb_set_tma_staging( vvb_ctx* ctx, int enable );
 
 /* Same candidate pattern with any distortion family (e.g. Hadamard integer refinement, InterSearch.cpp:2582,2630 and

@@ -274,7 +274,7 @@ int vvb_launch_count( const vvb_ctx* ctx, uint64_t* k ) { if( !ctx || !k ) retur
 int vvb_set_tma_staging( vvb_ctx* ctx, int enable )
 {
   if( !ctx ) return VVB_ERR_ARG;
-  ctx->useTma = enable != 0;
+  ctx->useTma = enable;
   return VVB_OK;
 }
 
@@ -614,7 +614,7 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
   CUtensorMap tmap; memset( &tmap, 0, sizeof( tmap ) );
   TmaInfo ti; memset( &ti, 0, sizeof( ti ) );
   const Plane& rp = ctx->planes.p[refPlane];
-  if( ctx->tmaEncode && ctx->useTma && L.ws <= 256 && L.winH <= 256 )
+  if( ctx->tmaEncode && ( ctx->useTma == 1 || ( ctx->useTma == 2 && w <= 8 ) ) && L.ws <= 256 && L.winH <= 256 )
   {
     const int16_t* base = rp.origin - (ptrdiff_t) rp.margin * rp.stride - rp.margin;
     if( ( (uintptr_t) base & 15 ) == 0 && ( rp.stride & 7 ) == 0 )

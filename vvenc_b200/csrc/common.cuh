@@ -84,7 +84,7 @@ struct vvb_ctx
   uint64_t       launches = 0;
   bool           poolBlocksAligned = false;   // see vvb_pool_hint
   int            tensorTransform = 2;         // see vvb_set_tensor_transform: 0 off, 1 all square 16/32/64 TUs, 2 where measured faster (64x64)
-  bool           useTma = false;              // see vvb_set_tma_staging (off by default: unresolved illegal-instruction fault on the round-1 driver)
+  int            useTma = 2;                  // see vvb_set_tma_staging: 0 off, 1 on, 2 (default) on where measured faster (blocks up to 8 wide)
   void*          tmaEncode = nullptr;         // cuTensorMapEncodeTiled, resolved at vvb_create
   int            numSMs   = 148;
   // device-side constant data
