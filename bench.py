@@ -551,15 +551,16 @@ def main():
     # ------------------------------------------------------------------------------------------- end-to-end through the host-buffer C ABI
     e2e = None
     if not args.skip_e2e:
-        # Two contexts (as two encoder workers would own, EncSlice.cpp:142-147) in asynchronous mode alternate steps: the downloads of step i
-        # overlap the upload and search of step i+1.  Every step still uploads its own pictures and downloads all of its results inside the timed region.
+        # Three contexts (as three encoder workers would own, EncSlice.cpp:142-147) in asynchronous mode take the steps in turn: while step i searches,
+        # the pictures of step i+1 upload and the results of step i-1 download.  Every step still uploads its own pictures and downloads all of its
+        # results inside the timed region.
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
         h_planes = []
         for (org, ref, S) in host_sets:
             po = pin(org.shape, torch.int16); pr = pin(ref.shape, torch.int16); po[:] = org; pr[:] = ref
             h_planes.append((po, pr, S))
-        NCTX = 2
-        engs = [eng, V.CostEngine(local)]
+        NCTX = 3
+        engs = [eng] + [V.CostEngine(local) for _ in range(NCTX - 1)]
         for e in engs:
             e.set_async(True)
         PA = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -584,15 +585,22 @@ def main():
         S0 = host_sets[0][2]
         h2d += 2 * (H + 2 * MARGIN) * S0 * 2
 
-        def step_e2e(i):
+        def e2e_upload(i):
             c = i % NCTX
-            e = engs[c]; d = hb[c]
+            e = engs[c]
             chk(lib.vvb_synchronize(e.h))                      # results of this context's previous step are complete (consumed by the encoder here)
             po, pr, S = h_planes[i % N_PICTURE_SETS]
             base = MARGIN * S + MARGIN
             chk(lib.vvb_plane_upload(e.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
             chk(lib.vvb_plane_upload(e.h, E1, ctypes.c_void_p(pr.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
-            chk(lib.vvb_sad_search_pyramid(e.h, E0, E1, nlev, d['pyr_blocks'], pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, d['pyr_best']))
+
+        def e2e_search(i):
+            c = i % NCTX
+            chk(lib.vvb_sad_search_pyramid(engs[c].h, E0, E1, nlev, hb[c]['pyr_blocks'], pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, hb[c]['pyr_best']))
+
+        def e2e_tail(i):
+            c = i % NCTX
+            e = engs[c]; d = hb[c]
             chk(lib.vvb_synchronize(e.h))                      # the host needs the vectors now
             for n in SIZES:
                 nb = len(blocks_np[n])
@@ -602,21 +610,24 @@ def main():
                 chk(lib.vvb_cost_pattern(e.h, V.DF_HAD, E0, E1, PA(d['blocks'][n]), nb, n, n, PA(h_pat), KP, ctypes.byref(me), PA(d['satd'][n]), None))
                 chk(lib.vvb_fwd_trquant_planes(e.h, ctypes.byref(tu_par[n]), E0, E1, PA(d['blocks'][n]), nb, None, PA(d['q'][n]), PA(d['sum'][n]), PA(d['last'][n]), PA(d['nr'][n])))
 
-        def drain():
+        def run_e2e(first, count):
+            # software pipeline over the contexts: the pictures of step i+1 go up while step i searches, the results of step i-1 come down meanwhile
+            e2e_upload(first)
+            for i in range(first, first + count):
+                e2e_search(i)
+                if i + 1 < first + count:
+                    e2e_upload(i + 1)
+                e2e_tail(i)
             for e in engs:
                 chk(lib.vvb_synchronize(e.h))
 
         ke = max(4, min(args.steps, 10))
-        for i in range(NCTX + 1):
-            step_e2e(i)
-        drain()
+        run_e2e(0, NCTX + 1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for i in range(ke):
-            step_e2e(NCTX + 1 + i)
-        drain()
+        run_e2e(NCTX + 1, ke)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / ke
         t = torch.tensor([dt], dtype=torch.float64, device='cuda')
@@ -625,13 +636,15 @@ def main():
         dt = float(t.item())
         e2e = {'value': total_units * world / dt, 'unit': 'candidate-blocks/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'ms_per_step': dt * 1e3, 'steps': ke, 'contexts': NCTX,
-               'timing': 'host wall clock over %d steps issued through the host-buffer C ABI from pinned memory; %d contexts in asynchronous mode alternate steps so that the '
-                         'downloads of one step overlap the upload + search of the next; all contexts drained inside the timed region; max over ranks' % (ke, NCTX)}
+               'timing': 'host wall clock over %d steps issued through the host-buffer C ABI from pinned memory; %d contexts in asynchronous mode take the steps in turn: '
+                         'the pictures of step i+1 are uploaded while step i searches and the results of step i-1 download; every upload and download of the %d steps and the '
+                         'final drain are inside the timed region; max over ranks' % (ke, NCTX, ke)}
         last = NCTX + ke                                       # index of the last step issued
         h_best = hb[last % NCTX]['best']
         for e in engs:
             e.set_async(False)
-        engs[1].close()
+        for e in engs[1:]:
+            e.close()
         # parity check of what came back: replay the last e2e step (same picture set) on the device-resident path and compare every best vector / cost
         # and every TU's level sum bit for bit
         step_resident(last)
