@@ -551,15 +551,15 @@ def main():
     # ------------------------------------------------------------------------------------------- end-to-end through the host-buffer C ABI
     e2e = None
     if not args.skip_e2e:
-        # Three contexts (as three encoder workers would own, EncSlice.cpp:142-147) in asynchronous mode take the steps in turn: while step i searches,
-        # the pictures of step i+1 upload and the results of step i-1 download.  Every step still uploads its own pictures and downloads all of its
-        # results inside the timed region.
+        # Three contexts, each driven by its own host thread (as three encoder workers would, EncSlice.cpp:142-147), take the steps in turn; the GPU overlaps
+        # one worker's uploads / downloads with the other workers' kernels.  Every step still uploads its own pictures and downloads all of its results
+        # inside the timed region.
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
         h_planes = []
         for (org, ref, S) in host_sets:
             po = pin(org.shape, torch.int16); pr = pin(ref.shape, torch.int16); po[:] = org; pr[:] = ref
             h_planes.append((po, pr, S))
-        NCTX = 3
+        NCTX = int(os.environ.get('VVB_E2E_CTX', '4'))
         engs = [eng] + [V.CostEngine(local) for _ in range(NCTX - 1)]
         for e in engs:
             e.set_async(True)
@@ -588,7 +588,6 @@ def main():
         def e2e_upload(i):
             c = i % NCTX
             e = engs[c]
-            chk(lib.vvb_synchronize(e.h))                      # results of this context's previous step are complete (consumed by the encoder here)
             po, pr, S = h_planes[i % N_PICTURE_SETS]
             base = MARGIN * S + MARGIN
             chk(lib.vvb_plane_upload(e.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, H, MARGIN, BITDEPTH))
@@ -611,18 +610,34 @@ def main():
                 chk(lib.vvb_fwd_trquant_planes(e.h, ctypes.byref(tu_par[n]), E0, E1, PA(d['blocks'][n]), nb, None, PA(d['q'][n]), PA(d['sum'][n]), PA(d['last'][n]), PA(d['nr'][n])))
 
         def run_e2e(first, count):
-            # software pipeline over the contexts: the pictures of step i+1 go up while step i searches, the results of step i-1 come down meanwhile
-            e2e_upload(first)
-            for i in range(first, first + count):
-                e2e_search(i)
-                if i + 1 < first + count:
-                    e2e_upload(i + 1)
-                e2e_tail(i)
-            for e in engs:
-                chk(lib.vvb_synchronize(e.h))
+            # one host thread per context, as one encoder worker per context would run (EncSlice.cpp:142-147; ctypes releases the GIL inside the library):
+            # worker c takes the steps first+c, first+c+NCTX, ... and runs each of them upload -> search -> wait for the vectors -> refinement + TU coding ->
+            # wait for the downloads; the GPU overlaps one worker's copies with the other workers' kernels
+            errs = []
+            skip = os.environ.get('VVB_E2E_SKIP', '')          # diagnostic switches only (upload / tail); the reported e2e never sets them
+            def worker(c):
+                try:
+                    pc = time.perf_counter
+                    for i in range(first + c, first + count, NCTX):
+                        t = pc()
+                        if 'upload' not in skip or i < NCTX: e2e_upload(i)
+                        e2e_search(i); host_ms['upload_search_enqueue'] += pc() - t
+                        t = pc()
+                        if 'tail' not in skip: e2e_tail(i)
+                        host_ms['wait_vectors_and_tail_enqueue'] += pc() - t
+                        t = pc(); chk(lib.vvb_synchronize(engs[i % NCTX].h)); host_ms['wait_downloads'] += pc() - t
+                except Exception as ex:
+                    errs.append(ex)
+            th = [threading.Thread(target=worker, args=(c,)) for c in range(NCTX)]
+            for t_ in th: t_.start()
+            for t_ in th: t_.join()
+            if errs:
+                raise errs[0]
 
-        ke = max(4, min(args.steps, 10))
+        host_ms = {k: 0.0 for k in ('upload_search_enqueue', 'wait_vectors_and_tail_enqueue', 'wait_downloads')}
+        ke = max(6, min(args.steps, 12)) // NCTX * NCTX
         run_e2e(0, NCTX + 1)
+        host_ms = {k: 0.0 for k in host_ms}
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -635,16 +650,37 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {'value': total_units * world / dt, 'unit': 'candidate-blocks/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'ms_per_step': dt * 1e3, 'steps': ke, 'contexts': NCTX,
-               'timing': 'host wall clock over %d steps issued through the host-buffer C ABI from pinned memory; %d contexts in asynchronous mode take the steps in turn: '
-                         'the pictures of step i+1 are uploaded while step i searches and the results of step i-1 download; every upload and download of the %d steps and the '
-                         'final drain are inside the timed region; max over ranks' % (ke, NCTX, ke)}
+               'ms_per_step': dt * 1e3, 'steps': ke, 'contexts': NCTX, 'worker_ms_per_step': {k: v * 1e3 / ke for k, v in host_ms.items()},
+               'timing': 'host wall clock over %d steps issued through the host-buffer C ABI from pinned memory by %d worker threads, one context each (asynchronous mode, '
+                         'explicit waits for the vectors and for the downloads); every upload and download of the %d steps is inside the timed region; max over ranks' % (ke, NCTX, ke)}
         last = NCTX + ke                                       # index of the last step issued
         h_best = hb[last % NCTX]['best']
         for e in engs:
             e.set_async(False)
         for e in engs[1:]:
             e.close()
+        # raw PCIe copy rates of this box (pinned, 64 MB, each direction alone and both together): the floor under any host-buffer path
+        try:
+            hp = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(); hp2 = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+            dp = torch.empty(64 << 20, dtype=torch.uint8, device='cuda'); dp2 = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+            s1 = torch.cuda.Stream(); s2 = torch.cuda.Stream()
+            def rate(fn, nbytes):
+                fn(); torch.cuda.synchronize()
+                t_ = time.perf_counter()
+                for _ in range(4): fn()
+                torch.cuda.synchronize()
+                return nbytes * 4 / (time.perf_counter() - t_) / 1e9
+            def f_h2d():
+                with torch.cuda.stream(s1): dp.copy_(hp, non_blocking=True)
+            def f_d2h():
+                with torch.cuda.stream(s2): hp2.copy_(dp2, non_blocking=True)
+            def f_both():
+                f_h2d(); f_d2h()
+            extra['pcie_GBps'] = {'h2d': rate(f_h2d, 64 << 20), 'd2h': rate(f_d2h, 64 << 20), 'both_directions_sum': rate(f_both, 128 << 20)}
+            extra['pcie_GBps']['e2e_floor_ms_per_step'] = max(h2d, d2h) / 1e6 / min(extra['pcie_GBps']['h2d'], extra['pcie_GBps']['d2h'])
+            del hp, hp2, dp, dp2
+        except Exception as ex:
+            extra['pcie_GBps'] = {'error': str(ex)}
         # parity check of what came back: replay the last e2e step (same picture set) on the device-resident path and compare every best vector / cost
         # and every TU's level sum bit for bit
         step_resident(last)
