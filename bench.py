@@ -530,6 +530,28 @@ def main():
                                          'note': 'fractional candidates: separable 6-tap filtering per candidate (ALU-bound by construction, SURVEY 8d W5)'}
         except Exception as ex:
             extra['mctf_match_16x16'] = {'error': str(ex)}
+        # MCTF apply stage: the whole 3840x2160 luma picture filtered against 8 neighbour pictures, unit 16 (xFinalizeBlkLine per block)
+        try:
+            from vvenc_b200 import _lib as VL
+            B = 16; nrefs = 8
+            nbk = (W // B) * (H // B)
+            rs_ = np.random.RandomState(5)
+            mv = np.zeros((nrefs, nbk), dtype=V.MCTF_MV_DT)
+            mv['x'] = rs_.randint(-40, 41, size=(nrefs, nbk)); mv['y'] = rs_.randint(-40, 41, size=(nrefs, nbk))
+            mv['error'] = rs_.randint(5, 150, size=(nrefs, nbk)); mv['rmsme'] = rs_.randint(0, 30, size=(nrefs, nbk))
+            d_mv = dev(mv)
+            apar = VL.vvb_mctf_apply_par()
+            apar.num_refs = nrefs; apar.block_size = B; apar.low_res_filter = 0; apar.planar_correction = 1; apar.weight_scaling = 0.4; apar.sigma_sq = 9 * (128.0 + 3.0 / 256.0 * 32 ** 3)
+            for i_, (pl, st) in enumerate(zip([1, 3, 5, 7, 2, 4, 6, 1], [0.85, 0.57, 0.41, 0.33, 0.30, 0.20, 0.18, 0.15])):
+                apar.ref_plane[i_] = pl; apar.ref_strength[i_] = st
+            d_flt = torch.empty(W * H, dtype=torch.int16, device='cuda')
+            ta = time_launch(lambda: chk(lib.vvb_mctf_apply_dev(eng.h, 0, ctypes.byref(apar), P_(d_mv.data_ptr()), P_(d_flt.data_ptr()), W)), reps=5)
+            byt = nbk * (nrefs * (2 * (B + 5) ** 2 + 16) + 4 * B * B)
+            extra['mctf_apply_2160p'] = {'blocks': int(nbk), 'refs': nrefs, 'unit': B, 'ms': ta, 'pels_per_s': W * H / (ta * 1e-3), 'block_refs_per_s': nbk * nrefs / (ta * 1e-3),
+                                         'GBps': byt / (ta * 1e-3) / 1e9, 'frac_hbm': byt / (ta * 1e-3) / 1e9 / hbm_peak,
+                                         'bytes_formula': 'per block: refs * (2 (B+5)^2 window + 16 vector) + 2 B^2 original + 2 B^2 filtered'}
+        except Exception as ex:
+            extra['mctf_apply_2160p'] = {'error': str(ex)}
         # fixed diamond-search candidate set (SURVEY 8d W3 -> W1 byte formula): TZ point pattern, range 64, around the zero vector
         try:
             from vvenc_b200 import candidates as cand

@@ -231,6 +231,20 @@ int vvb_mctf_hint( vvb_ctx* ctx, int max_block_dim );
 int vvb_mctf_search_grid    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* blocks, int n, int step, int radius, int low_res_filter, int32_t* err_out );
 int vvb_mctf_search_grid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* dev_blocks, int n, int step, int radius, int low_res_filter, int32_t* dev_err_out );
 
+/* ---- MCTF apply stage: the per-block body of MCTF::xFinalizeBlkLine (MCTF.cpp:1437-1483) for the luma plane, fused:
+ * per reference picture applyFrac (m_applyFrac, :259-357) at the block's vector, applyPlanarCorrection (:372-420) when rmsme > 0 and
+ * planar_correction (the caller passes m_QP <= 32) and the block is square <= 32, then applyBlock (:422-518: noise estimate, weights, bilateral
+ * blend with fastExp).  mvs[r][block] in raster order of block_size x block_size units; out is the filtered luma plane (newOrgPic).
+ * Float results equal the reference's scalar and AVX2 kernels bit for bit. */
+typedef struct { int32_t x, y; int32_t error; uint16_t rmsme, pad; } vvb_mctf_mv;                       /* 16 bytes; MotionVector (MCTF.h:72-82), 1/16 pel */
+typedef struct { int32_t num_refs, block_size, low_res_filter /* 4-tap */, planar_correction; double weight_scaling /* overallStrength * 0.4 */, sigma_sq;
+                 double ref_strength[8]; int32_t ref_plane[8]; } vvb_mctf_apply_par;
+int vvb_mctf_apply    ( vvb_ctx* ctx, int org_plane, const vvb_mctf_apply_par* par, const vvb_mctf_mv* mvs, int16_t* out, int out_stride );
+int vvb_mctf_apply_dev( vvb_ctx* ctx, int org_plane, const vvb_mctf_apply_par* par, const vvb_mctf_mv* dev_mvs, int16_t* dev_out, int out_stride );
+/* MCTF::m_calcVar (calcVarCore, MCTF.cpp:520-546) for a list of blocks (x, y, w, h of vvb_mctf_cand; vectors ignored) */
+int vvb_mctf_calc_var    ( vvb_ctx* ctx, int plane, const vvb_mctf_cand* blocks, int n, double* var_out );
+int vvb_mctf_calc_var_dev( vvb_ctx* ctx, int plane, const vvb_mctf_cand* dev_blocks, int n, double* dev_var_out );
+
 /* ---- affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190) ---------------------------------- */
 int vvb_affine_sobel      ( vvb_ctx* ctx, int vertical, const int16_t* pred, int pred_stride, int16_t* deriv, int deriv_stride, int w, int h );
 int vvb_affine_equal_coeff( vvb_ctx* ctx, int six_param, const int16_t* resi, int resi_stride, const int16_t* deriv_x, const int16_t* deriv_y,

@@ -590,6 +590,163 @@ void orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPla
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * MCTF apply stage: applyFrac8Core_6Tap / _4Tap (CommonLib/MCTF.cpp:259-357), applyPlanarCorrectionCore
+ * (:372-420), applyBlockCore (:422-518), calcVarCore (:520-546) and the per-block body of MCTF::xFinalizeBlkLine (:1437-1483).
+ * Float arithmetic follows the C++ expression types of the reference literally (float *= double rounds through double, etc.).
+ * ---------------------------------------------------------------------------------------------------- */
+void orc_mctf_apply_frac( int tap4, const Pel* org, int so, Pel* dst, int ds, int w, int h, int fx, int fy, int bitDepth )
+{
+  const int maxv = ( 1 << bitDepth ) - 1;
+  const int taps = tap4 ? 4 : 6, first = tap4 ? 0 : 1, back = tap4 ? 1 : 2;
+  const int16_t* xf = tap4 ? mctf_f4[fx] : mctf_f8[fx];
+  const int16_t* yf = tap4 ? mctf_f4[fy] : mctf_f8[fy];
+  Pel* tmp = (Pel*) malloc( sizeof( Pel ) * ( h + taps ) * w );
+  for( int r = 0; r < h + taps - 1; r++ )                 /* source rows y - back .. y + h + taps - 2 - back */
+    for( int x = 0; x < w; x++ )
+    {
+      const Pel* p = org + ( r - back ) * so + x - back;
+      int sum = 0;
+      for( int t = 0; t < taps; t++ ) sum += xf[first + t] * p[t];
+      tmp[r * w + x] = (Pel)( ( sum + 32 ) >> 6 );        /* no clipping after the first pass (:284, :344) */
+    }
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      int sum = 0;
+      for( int t = 0; t < taps; t++ ) sum += yf[first + t] * tmp[( y + t ) * w + x];
+      sum = ( sum + 32 ) >> 6;
+      dst[y * ds + x] = (Pel)( sum < 0 ? 0 : ( sum > maxv ? maxv : sum ) );
+    }
+  free( tmp );
+}
+
+void orc_mctf_planar_correction( const Pel* ref, int rs, Pel* dst, int ds, int w, int h, int bitDepth, unsigned motionError )
+{
+  static const int32_t xSzm[6] = { 0, 1, 20, 336, 5440, 87296 };                 /* MCTF.cpp:369 */
+  const int32_t blockSize = w * h, log2Width = ilog2u( w ), maxPel = ( 1 << bitDepth ) - 1;
+  const uint32_t me2 = motionError * motionError;
+  const int32_t mWeight = (int32_t)( me2 < 512u ? me2 : 512u );
+  const int32_t xSum = ( blockSize * ( w - 1 ) ) >> 1;
+  int32_t x1yzm = 0, x2yzm = 0, ySum = 0;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ ) { const int32_t z = dst[y * ds + x] - ref[y * rs + x]; x1yzm += x * z; x2yzm += y * z; ySum += z; }
+  const int64_t denom = (int64_t) blockSize * xSzm[log2Width];
+  int64_t numer = (int64_t) mWeight * ( (int64_t) x1yzm * blockSize - (int64_t) xSum * ySum );
+  int32_t b1 = (int32_t)( ( numer < 0 ? numer - ( denom >> 1 ) : numer + ( denom >> 1 ) ) / denom );
+  b1 = b1 < -32768 ? -32768 : ( b1 > 32767 ? 32767 : b1 );
+  numer = (int64_t) mWeight * ( (int64_t) x2yzm * blockSize - (int64_t) xSum * ySum );
+  int32_t b2 = (int32_t)( ( numer < 0 ? numer - ( denom >> 1 ) : numer + ( denom >> 1 ) ) / denom );
+  b2 = b2 > 32767 ? 32767 : ( b2 < -32768 ? -32768 : b2 );
+  const int32_t b0 = ( mWeight * ySum - ( b1 + b2 ) * xSum + ( blockSize >> 1 ) ) >> ( log2Width << 1 );
+  if( b0 == 0 && b1 == 0 && b2 == 0 ) return;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      const int32_t p = ( b0 + b1 * x + b2 * y + 256 ) >> 9;
+      const int32_t z = dst[y * ds + x] - p;
+      dst[y * ds + x] = (Pel)( z < 0 ? 0 : ( z > maxPel ? maxPel : z ) );
+    }
+}
+
+static float orc_fast_exp( float n, float d )
+{
+  float x = 1.0f + n / ( d * 1024 );
+  x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x;
+  return x;
+}
+
+/* corrected: numRefs compact w*h blocks back to back */
+void orc_mctf_apply_block( const Pel* src, int ss, Pel* dst, int ds, int w, int h, int bitDepth, const Pel* corrected, int numRefs,
+                           const int32_t* verror, const double* refStrengths, double weightScaling, double sigmaSq )
+{
+  const int maxv = ( 1 << bitDepth ) - 1;
+  int vnoise[16]; float vsw[16], vww[16];
+  int minError = 0x7fffffff;
+  for( int i = 0; i < numRefs; i++ )
+  {
+    int64_t variance = 0, diffsum = 0;
+    const Pel* ref = corrected + (size_t) i * w * h;
+    for( int y = 0; y < h; y++ )
+      for( int x = 0; x < w; x++ )
+      {
+        const int diff = src[y * ss + x] - ref[y * w + x];
+        variance += diff * diff;
+        if( x != w - 1 ) { const int dR = src[y * ss + x + 1] - ref[y * w + x + 1]; diffsum += ( dR - diff ) * ( dR - diff ); }
+        if( y != h - 1 ) { const int dD = src[( y + 1 ) * ss + x] - ref[( y + 1 ) * w + x]; diffsum += ( dD - diff ) * ( dD - diff ); }
+      }
+    variance *= (int64_t) 1 << ( 2 * ( 10 - bitDepth ) );
+    diffsum  *= (int64_t) 1 << ( 2 * ( 10 - bitDepth ) );
+    const int cntV = w * h, cntD = 2 * cntV - w - h;
+    vnoise[i] = (int) round( ( 15.0 * cntD / cntV * variance + 5.0 ) / ( diffsum + 5.0 ) );
+    if( verror[i] < minError ) minError = verror[i];
+  }
+  for( int i = 0; i < numRefs; i++ )
+  {
+    const int error = verror[i], noise = vnoise[i];
+    float ww = 1, sw = 1;
+    ww *= ( noise < 25 ) ? 1.0 : 0.6;
+    sw *= ( noise < 25 ) ? 1.0 : 0.8;
+    ww *= ( error < 50 ) ? 1.2 : ( ( error > 100 ) ? 0.6 : 1.0 );
+    sw *= ( error < 50 ) ? 1.0 : 0.8;
+    ww *= ( ( minError + 1.0 ) / ( error + 1.0 ) );
+    vww[i] = ww * weightScaling * refStrengths[i];
+    vsw[i] = sw * 2 * sigmaSq;
+  }
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      const Pel orgVal = src[y * ss + x];
+      float temporalWeightSum = 1.0;
+      float newVal = (float) orgVal;
+      for( int i = 0; i < numRefs; i++ )
+      {
+        const int refVal = corrected[(size_t) i * w * h + y * w + x];
+        const int diff = refVal - orgVal;
+        const float diffSq = diff * diff;
+        float weight = vww[i] * orc_fast_exp( -diffSq, vsw[i] );
+        newVal += weight * refVal;
+        temporalWeightSum += weight;
+      }
+      newVal /= temporalWeightSum;
+      Pel sampleVal = (Pel)( newVal + 0.5 );
+      sampleVal = sampleVal < 0 ? 0 : ( sampleVal > maxv ? maxv : sampleVal );
+      dst[y * ds + x] = sampleVal;
+    }
+}
+
+double orc_mctf_calc_var( const Pel* org, int so, int w, int h )
+{
+  int avg = 0;
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) avg += org[y * so + x];
+  avg <<= 4;
+  avg = avg / ( w * h );
+  int64_t variance = 0;
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) { const int pix = org[y * so + x] << 4; variance += ( pix - avg ) * ( pix - avg ); }
+  return variance / 256.0;
+}
+
+/* Body of MCTF::xFinalizeBlkLine for one luma block (MCTF.cpp:1437-1483): per reference applyFrac (+ planar correction), then applyBlock.
+ * refs[i]: pointer to sample (0,0) of reference picture i (same stride rs); mv[i] = { x, y, error, rmsme } in 1/16 pel. */
+void orc_mctf_finalize_block( const Pel* orgPlane, int so, const Pel* const* refs, int rs, int numRefs, const int32_t* mv4, int bx, int by, int w, int h,
+                              int bitDepth, int tap4, int planarEnabled, const double* refStrengths, double weightScaling, double sigmaSq, Pel* dstPlane, int ds )
+{
+  Pel* corrected = (Pel*) malloc( sizeof( Pel ) * numRefs * w * h );
+  int32_t verror[16];
+  for( int i = 0; i < numRefs; i++ )
+  {
+    const int32_t* mv = mv4 + 4 * i;
+    const Pel* src = refs[i] + (ptrdiff_t)( by + ( mv[1] >> 4 ) ) * rs + bx + ( mv[0] >> 4 );
+    Pel* dst = corrected + (size_t) i * w * h;
+    orc_mctf_apply_frac( tap4, src, rs, dst, w, w, h, mv[0] & 15, mv[1] & 15, bitDepth );
+    if( mv[3] > 0 && planarEnabled && w == h && w <= 32 )
+      orc_mctf_planar_correction( orgPlane + (ptrdiff_t) by * so + bx, so, dst, w, w, h, bitDepth, (unsigned) mv[3] );
+    verror[i] = mv[2];
+  }
+  orc_mctf_apply_block( orgPlane + (ptrdiff_t) by * so + bx, so, dstPlane + (ptrdiff_t) by * ds + bx, ds, w, h, bitDepth, corrected, numRefs, verror, refStrengths, weightScaling, sigmaSq );
+  free( corrected );
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * Affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190)
  * ---------------------------------------------------------------------------------------------------- */
 void orc_sobel( int vertical, const Pel* p, int ps, Pel* d, int ds, int w, int h )

@@ -728,6 +728,72 @@ void refshim_mctf_err_list( int opt, int tap4, const int16_t* orgPlane, int orgS
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// MCTF apply stage (MCTF.h:168-170 function pointers; callers MCTF.cpp:1437-1483)
+void refshim_mctf_apply_frac( int opt, int tap4, const int16_t* org, int orgStride, int16_t* dst, int dstStride, int w, int h, int fx, int fy, int bitDepth )
+{
+  RefCtx& c = ctx();
+  const int16_t* xf = tap4 ? MCTF::m_interpolationFilter4[fx] : MCTF::m_interpolationFilter8[fx];
+  const int16_t* yf = tap4 ? MCTF::m_interpolationFilter4[fy] : MCTF::m_interpolationFilter8[fy];
+  c.mctf[opt?1:0]->m_applyFrac[CH_L][tap4?1:0]( org, orgStride, dst, dstStride, w, h, xf, yf, bitDepth );
+}
+
+void refshim_mctf_planar_correction( int opt, const int16_t* ref, int refStride, int16_t* dst, int dstStride, int w, int h, int bitDepth, unsigned motionError )
+{
+  RefCtx& c = ctx();
+  ClpRng rng; rng.bd = bitDepth;
+  c.mctf[opt?1:0]->m_applyPlanarCorrection( ref, refStride, dst, dstStride, w, h, rng, (uint16_t) motionError );
+}
+
+// src / dst: whole planes (origin pointers) with the block at (bx, by); corrected: numRefs compact w*h blocks back to back
+void refshim_mctf_apply_block( int opt, const int16_t* srcPlane, int srcStride, int16_t* dstPlane, int dstStride, int planeW, int planeH, int bx, int by, int w, int h, int bitDepth,
+                               const int16_t* corrected, int numRefs, const int32_t* verror, const double* refStrengths, double weightScaling, double sigmaSq )
+{
+  RefCtx& c = ctx();
+  ClpRng rng; rng.bd = bitDepth;
+  const Pel* cp[2 * VVENC_MCTF_RANGE] = { nullptr, };
+  for( int i = 0; i < numRefs; i++ ) cp[i] = corrected + (size_t) i * w * h;
+  CPelBuf src( srcPlane, srcStride, planeW, planeH );
+  PelBuf  dst( dstPlane, dstStride, planeW, planeH );
+  c.mctf[opt?1:0]->m_applyBlock( src, dst, CompArea( COMP_Y, CHROMA_400, Area( bx, by, w, h ) ), rng, cp, numRefs, verror, refStrengths, weightScaling, sigmaSq );
+}
+
+double refshim_mctf_calc_var( int opt, const int16_t* org, int orgStride, int w, int h )
+{
+  RefCtx& c = ctx();
+  return c.mctf[opt?1:0]->m_calcVar( org, orgStride, w, h );
+}
+
+// Replay of the per-block body of MCTF::xFinalizeBlkLine for luma (MCTF.cpp:1437-1483; that member needs a whole encoder configuration, so its 40 lines
+// are replayed here on top of the reference's function pointers).  mv4[i] = { x, y, error, rmsme }.
+void refshim_mctf_finalize_block( int opt, const int16_t* orgPlane, int orgStride, const int16_t* const* refs, int refStride, int numRefs, const int32_t* mv4,
+                                  int planeW, int planeH, int bx, int by, int w, int h, int bitDepth, int tap4, int planarEnabled, const double* refStrengths,
+                                  double weightScaling, double sigmaSq, int16_t* dstPlane, int dstStride )
+{
+  RefCtx& c = ctx();
+  MCTF* m = c.mctf[opt?1:0];
+  ClpRng rng; rng.bd = bitDepth;
+  std::vector<Pel> dstBufs( (size_t) numRefs * w * h + 64 );
+  const Pel* cp[2 * VVENC_MCTF_RANGE] = { nullptr, };
+  int verror[2 * VVENC_MCTF_RANGE] = { 0, };
+  for( int i = 0; i < numRefs; i++ )
+  {
+    const int32_t* mv = mv4 + 4 * i;
+    Pel* dst = dstBufs.data() + (size_t) i * w * h;
+    cp[i] = dst;
+    const Pel* src = refs[i] + (ptrdiff_t)( by + ( mv[1] >> 4 ) ) * refStride + bx + ( mv[0] >> 4 );
+    const int16_t* xf = tap4 ? MCTF::m_interpolationFilter4[mv[0] & 0xf] : MCTF::m_interpolationFilter8[mv[0] & 0xf];
+    const int16_t* yf = tap4 ? MCTF::m_interpolationFilter4[mv[1] & 0xf] : MCTF::m_interpolationFilter8[mv[1] & 0xf];
+    m->m_applyFrac[CH_L][tap4?1:0]( src, refStride, dst, w, w, h, xf, yf, bitDepth );
+    if( mv[3] > 0 && planarEnabled && w == h && w <= 32 )
+      m->m_applyPlanarCorrection( orgPlane + (ptrdiff_t) by * orgStride + bx, orgStride, dst, w, w, h, rng, (uint16_t) mv[3] );
+    verror[i] = mv[2];
+  }
+  CPelBuf src( orgPlane, orgStride, planeW, planeH );
+  PelBuf  dst( dstPlane, dstStride, planeW, planeH );
+  m->m_applyBlock( src, dst, CompArea( COMP_Y, CHROMA_400, Area( bx, by, w, h ) ), rng, cp, numRefs, verror, refStrengths, weightScaling, sigmaSq );
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Affine gradient helpers (AffineGradientSearch.h:67-69)
 void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )
 {

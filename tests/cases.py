@@ -237,3 +237,34 @@ def search_case(seed=777, W=192, H=128, margin=48):
             blks.append([x, y, bw, bh, -r, r, -r, r, int(rs.randint(-60, 60)), int(rs.randint(-60, 60))])
     return dict(org=np.ascontiguousarray(org), ref=np.ascontiguousarray(ref), stride=S, margin=margin, W=W, H=H,
                 blk=np.array(blks, dtype=np.int32), lam=57.25, cost_scale=2, imv_shift=0)
+
+
+def mctf_apply_case(seed, W=96, H=64, margin=24, num_refs=4, bs=16, bit_depth=10):
+    """one small picture + num_refs neighbour pictures (noisy, shifted copies) and per-block motion vectors with error / rmsme, for the MCTF
+    apply stage (xFinalizeBlkLine).  Returns dict(org, refs[list], stride, margin, W, H, mvs[num_refs][blocks][4], strengths, ws, sigma)"""
+    rs = np.random.RandomState(seed)
+    mx = (1 << bit_depth) - 1
+    S = W + 2 * margin
+    base = rs.randint(0, mx + 1, size=(H + 2 * margin + 8, S + 8))
+    sm = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4
+    org = np.ascontiguousarray(sm[4:4 + H + 2 * margin, 4:4 + S].astype(np.int16))
+    refs = []
+    for r in range(num_refs):
+        sh = (int(rs.randint(-2, 3)), int(rs.randint(-2, 3)))
+        amp = [3, 12, 60, mx][r % 4]
+        ref = np.clip(sm[4 + sh[0]:4 + sh[0] + H + 2 * margin, 4 + sh[1]:4 + sh[1] + S] + rs.randint(-amp, amp + 1, size=org.shape), 0, mx).astype(np.int16)
+        refs.append(np.ascontiguousarray(ref))
+    nb = ((W + bs - 1) // bs) * ((H + bs - 1) // bs)
+    mvs = np.zeros((num_refs, nb, 4), dtype=np.int32)
+    mvs[..., 0] = rs.randint(-16 * 6, 16 * 6 + 1, size=(num_refs, nb)); mvs[..., 1] = rs.randint(-16 * 6, 16 * 6 + 1, size=(num_refs, nb))
+    mvs[..., 2] = rs.choice([3, 20, 49, 50, 75, 100, 101, 400], size=(num_refs, nb))
+    mvs[..., 3] = rs.choice([0, 1, 5, 22, 23, 60], size=(num_refs, nb))
+    mvs[0, 0, :2] = 0
+    strengths = np.array([0.85, 0.57, 0.41, 0.33, 0.30, 0.20, 0.18, 0.15][:num_refs], dtype=np.float64)
+    return dict(org=org, refs=refs, stride=S, margin=margin, W=W, H=H, mvs=mvs, strengths=strengths, ws=0.4 * float(rs.choice([0.5, 1.0, 1.5])),
+                sigma=float(rs.choice([9 * (128.0 + 3.0 / 256.0 * q * q * q) for q in (22, 32, 42)])) / (1.0 if bit_depth == 10 else 16.0), bs=bs, bd=bit_depth,
+                num_refs=num_refs)
+
+
+MCTF_APPLY_CASES = ((31, 96, 64, 4, 16, 10, 0, 1), (32, 64, 48, 8, 8, 10, 0, 1), (33, 128, 64, 6, 32, 10, 0, 1), (34, 96, 40, 3, 16, 8, 0, 1),
+                    (35, 96, 64, 5, 16, 10, 1, 1), (36, 72, 56, 2, 16, 10, 0, 0))      # seed, W, H, refs, bs, bit depth, tap4, planar

@@ -19,3 +19,9 @@ def golden():
 def golden_tu():
     import numpy as np
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v2_tu.npz'))
+
+
+@pytest.fixture(scope="session")
+def golden_mctf_apply():
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v3_mctf_apply.npz'))

@@ -185,6 +185,27 @@ def run_rt(impl, rows, q, reco, meta):
     return bad
 
 
+def mctf_apply_expected(L, prefix, case, tap4, planar, opt=None):
+    """filtered picture [H][W] through the oracle (prefix 'orc') or the reference probe (prefix 'refshim', opt = 0/1), block by block"""
+    S = case['stride']; m = case['margin']; W = case['W']; H = case['H']; bs = case['bs']; base = m * S + m
+    out = np.zeros((H, W), dtype=np.int16)
+    n = case['num_refs']
+    ptrs = (ctypes.c_void_p * n)(*[r.ctypes.data + base * 2 for r in case['refs']])
+    bxn = (W + bs - 1) // bs
+    for by in range(0, H, bs):
+        for bx in range(0, W, bs):
+            b = (by // bs) * bxn + bx // bs
+            w = min(bs, W - bx); h = min(bs, H - by)
+            mv4 = np.ascontiguousarray(case['mvs'][:, b, :])
+            if prefix == 'orc':
+                L.orc_mctf_finalize_block(PO(case['org'], base), S, ptrs, S, n, P(mv4), bx, by, w, h, case['bd'], tap4, planar, P(case['strengths']),
+                                          ctypes.c_double(case['ws']), ctypes.c_double(case['sigma']), P(out), W)
+            else:
+                L.refshim_mctf_finalize_block(opt, PO(case['org'], base), S, ptrs, S, n, P(mv4), W, H, bx, by, w, h, case['bd'], tap4, planar, P(case['strengths']),
+                                              ctypes.c_double(case['ws']), ctypes.c_double(case['sigma']), P(out), W)
+    return out
+
+
 def run_mctf(impl, rows, expect):
     bad = []
     m = C.MCTF_MARGIN

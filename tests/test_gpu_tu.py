@@ -125,3 +125,32 @@ def test_gpu_tu_roundtrip_properties_full_size(gpu):
     assert np.array_equal((e * e).sum(axis=(1, 2)).astype(np.uint64), r['res']['dist_reco'])
     g = d - rec
     assert np.array_equal((g * g).sum(axis=(1, 2)).astype(np.uint64), r['res']['dist_resi'])
+
+
+# ------------------------------------------------------------------------------------------ MCTF apply stage
+def test_gpu_mctf_apply_golden(gpu, golden_mctf_apply):
+    """xFinalizeBlkLine for whole small pictures: motion compensation with the 6/4-tap filters, planar correction, bilateral blend -- equal to the
+    reference's output (float arithmetic included), 8 and 10 bit, unit sizes 8/16/32, 2..8 references, clipped edge blocks"""
+    O = impls.OracleImpl()
+    for k, (seed, W, H, refs, bs, bd, tap4, planar) in enumerate(C.MCTF_APPLY_CASES):
+        case = C.mctf_apply_case(seed, W, H, 24, refs, bs, bd)
+        m = case['margin']
+        gpu.eng.upload_plane(0, case['org'], W, H, m, bd)
+        for r in range(refs):
+            gpu.eng.upload_plane(1 + r, case['refs'][r], W, H, m, bd)
+        mv = np.zeros(case['mvs'].shape[:2], dtype=gpu.V.MCTF_MV_DT)
+        mv['x'] = case['mvs'][..., 0]; mv['y'] = case['mvs'][..., 1]; mv['error'] = case['mvs'][..., 2]; mv['rmsme'] = case['mvs'][..., 3]
+        got = gpu.eng.mctf_apply(0, list(range(1, 1 + refs)), mv, bs, case['strengths'], case['ws'], case['sigma'], W, H, planar=bool(planar), low_res_filter=bool(tap4))
+        exp = golden_mctf_apply['apply_%d' % k]
+        assert np.array_equal(got, exp), (seed, int(np.abs(got.astype(int) - exp).max()), np.argwhere(got != exp)[:4])
+        assert np.array_equal(impls.mctf_apply_expected(O.L, 'orc', case, tap4, planar), exp)
+
+
+def test_gpu_mctf_calc_var_golden(gpu, golden_mctf_apply):
+    plane = golden_mctf_apply['var_plane']
+    H, W = plane.shape
+    gpu.eng.upload_plane(0, np.ascontiguousarray(plane), W, H, 0, 10)
+    blocks = np.zeros(len(golden_mctf_apply['var_blocks']), dtype=gpu.V.MCTF_DT)
+    b = golden_mctf_apply['var_blocks']
+    blocks['x'] = b[:, 0]; blocks['y'] = b[:, 1]; blocks['w'] = b[:, 2]; blocks['h'] = b[:, 3]
+    assert np.array_equal(gpu.eng.mctf_calc_var(0, blocks), golden_mctf_apply['var_expect'])

@@ -55,3 +55,16 @@ def test_oracle_inverse_path_golden(golden_tu):
 
 def test_oracle_tu_roundtrip_golden(golden_tu):
     assert impls.run_rt(impls.OracleImpl(), golden_tu['rt_rows'], golden_tu['rt_q'], golden_tu['rt_reco'], golden_tu['rt_meta']) == []
+
+
+def test_oracle_mctf_apply_golden(golden_mctf_apply):
+    import ctypes
+    from _libs import oracle, P
+    O = oracle(); O.orc_mctf_calc_var.restype = ctypes.c_double
+    for k, (seed, W, H, refs, bs, bd, tap4, planar) in enumerate(C.MCTF_APPLY_CASES):
+        case = C.mctf_apply_case(seed, W, H, 24, refs, bs, bd)
+        assert np.array_equal(impls.mctf_apply_expected(O, 'orc', case, tap4, planar), golden_mctf_apply['apply_%d' % k]), seed
+    plane = golden_mctf_apply['var_plane']
+    for (x, y, w, h), e in zip(golden_mctf_apply['var_blocks'], golden_mctf_apply['var_expect']):
+        blk = np.ascontiguousarray(plane[y:y + h, x:x + w])
+        assert O.orc_mctf_calc_var(P(blk), int(w), int(w), int(h)) == e

@@ -148,3 +148,31 @@ def test_tu_roundtrip_sweep(opt):
                 pred[:, :w] = np.clip(org[:, :w] + rs.randint(-amp, amp + 1, size=(h, w)), 0, 1023)
                 a = O.tu_roundtrip(th, tv, org, so, pred, ps, w, h, 10, qp, irap); b = R.tu_roundtrip(th, tv, org, so, pred, ps, w, h, 10, qp, irap)
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2], (th, tv, w, h, qp, irap, a[2], b[2])
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_mctf_apply_stage(opt):
+    """applyFrac + applyPlanarCorrection + applyBlock chained per block as xFinalizeBlkLine does: oracle == reference (float results included)"""
+    from _libs import oracle, refshim
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    for (seed, W, H, refs, bs, bd, tap4, planar) in C.MCTF_APPLY_CASES:
+        case = C.mctf_apply_case(seed, W, H, 24, refs, bs, bd)
+        a = impls.mctf_apply_expected(O, 'orc', case, tap4, planar)
+        b = impls.mctf_apply_expected(R, 'refshim', case, tap4, planar, opt)
+        assert np.array_equal(a, b), (seed, np.abs(a.astype(int) - b).max())
+        assert np.any(a != case['org'][24:24 + H, 24:24 + W])           # the filter does something
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_mctf_calc_var(opt):
+    import ctypes
+    from _libs import oracle, refshim, P
+    O = oracle(); R = refshim()
+    O.orc_mctf_calc_var.restype = ctypes.c_double; R.refshim_mctf_calc_var.restype = ctypes.c_double
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(88)
+    for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 8)):
+        for bd in (8, 10):
+            org = C.aligned((h, w + 16), np.int16); org[:] = rs.randint(0, 1 << bd, size=(h, w + 16))
+            assert O.orc_mctf_calc_var(P(org), w + 16, w, h) == R.refshim_mctf_calc_var(opt, P(org), w + 16, w, h), (w, h, bd)

@@ -17,6 +17,11 @@ class vvb_cand(ctypes.Structure):
                 ('w', ctypes.c_uint16), ('h', ctypes.c_uint16), ('dfunc', ctypes.c_uint8), ('sub_shift', ctypes.c_uint8), ('pad', ctypes.c_uint8 * 2)]
 
 
+class vvb_mctf_apply_par(ctypes.Structure):
+    _fields_ = [('num_refs', ctypes.c_int32), ('block_size', ctypes.c_int32), ('low_res_filter', ctypes.c_int32), ('planar_correction', ctypes.c_int32),
+                ('weight_scaling', ctypes.c_double), ('sigma_sq', ctypes.c_double), ('ref_strength', ctypes.c_double * 8), ('ref_plane', ctypes.c_int32 * 8)]
+
+
 class vvb_me_par(ctypes.Structure):
     _fields_ = [('lam', ctypes.c_double), ('cost_scale', ctypes.c_int32), ('imv_shift', ctypes.c_int32), ('sub_shift', ctypes.c_int32), ('quad_order', ctypes.c_int32), ('pattern_radius', ctypes.c_int32), ('pad', ctypes.c_int32)]
 
@@ -36,6 +41,7 @@ BLOCK_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('left', '<i2'), ('right', '<i2
 BEST_DT = np.dtype([('dx', '<i2'), ('dy', '<i2'), ('sad', '<u4'), ('cost', '<u8')])
 MV_DT = np.dtype([('dx', '<i2'), ('dy', '<i2')])
 TU_RESULT_DT = np.dtype([('dist_reco', '<u8'), ('dist_resi', '<u8'), ('dist_zero', '<u8'), ('abs_sum', '<i4'), ('last_pos', '<i4')])
+MCTF_MV_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('error', '<i4'), ('rmsme', '<u2'), ('pad', '<u2')])
 MCTF_DT = np.dtype([('x', '<i4'), ('y', '<i4'), ('mvx', '<i4'), ('mvy', '<i4'), ('w', '<u2'), ('h', '<u2')])
 assert CAND_DT.itemsize == 32 and BLOCK_DT.itemsize == 24 and BEST_DT.itemsize == 16 and MCTF_DT.itemsize == 20
 
@@ -84,6 +90,10 @@ SYMBOLS = {
     'vvb_mctf_error_batch': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_mctf_search_grid': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p]),
     'vvb_mctf_search_grid_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p]),
+    'vvb_mctf_apply': (c_i, [c_p, c_i, ctypes.POINTER(vvb_mctf_apply_par), c_p, c_p, c_i]),
+    'vvb_mctf_apply_dev': (c_i, [c_p, c_i, ctypes.POINTER(vvb_mctf_apply_par), c_p, c_p, c_i]),
+    'vvb_mctf_calc_var': (c_i, [c_p, c_i, c_p, c_i, c_p]),
+    'vvb_mctf_calc_var_dev': (c_i, [c_p, c_i, c_p, c_i, c_p]),
     'vvb_mctf_hint': (c_i, [c_p, c_i]),
     'vvb_mctf_error_batch_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_affine_sobel': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i]),

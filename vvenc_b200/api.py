@@ -264,6 +264,24 @@ class CostEngine:
         self._chk(self.lib.vvb_mctf_search_grid(self.h, org_plane, ref_plane, _p(blocks), len(blocks), step, radius, int(low_res_filter), _p(out)))
         return out
 
+    def mctf_apply(self, org_plane, ref_planes, mvs, block_size, ref_strengths, weight_scaling, sigma_sq, width, height, planar=True, low_res_filter=False):
+        """xFinalizeBlkLine for the luma plane: mvs MCTF_MV_DT [num_refs][blocks]; returns the filtered picture int16 [height][width]"""
+        par = L.vvb_mctf_apply_par()
+        par.num_refs = len(ref_planes); par.block_size = block_size; par.low_res_filter = int(low_res_filter); par.planar_correction = int(planar)
+        par.weight_scaling = weight_scaling; par.sigma_sq = sigma_sq
+        for i, (pl, st) in enumerate(zip(ref_planes, ref_strengths)):
+            par.ref_plane[i] = pl; par.ref_strength[i] = st
+        mvs = np.ascontiguousarray(mvs, dtype=L.MCTF_MV_DT)
+        out = np.zeros((height, width), dtype=np.int16)
+        self._chk(self.lib.vvb_mctf_apply(self.h, org_plane, ctypes.byref(par), _p(mvs), _p(out), width))
+        return out
+
+    def mctf_calc_var(self, plane, blocks):
+        blocks = np.ascontiguousarray(blocks, dtype=L.MCTF_DT)
+        out = np.zeros(len(blocks), dtype=np.float64)
+        self._chk(self.lib.vvb_mctf_calc_var(self.h, plane, _p(blocks), len(blocks), _p(out)))
+        return out
+
     # ---- affine
     def affine_sobel(self, vertical, pred, pred_stride, deriv_stride, w, h):
         d = np.zeros((h, deriv_stride), dtype=np.int16)

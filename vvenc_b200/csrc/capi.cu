@@ -231,6 +231,7 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+  cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1105,6 +1106,89 @@ int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mc
   for( int i = 0; i < n; i++ ) maxDim = std::max( maxDim, (int) std::max( cands[i].w, cands[i].h ) );
   if( ( rc = mctfLaunch( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, maxDim, (int32_t*) dE ) ) ) return rc;
   CU( cudaMemcpyAsync( err, dE, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// ---- MCTF apply stage (xFinalizeBlkLine body per block) ---------------------------------------------------------------------
+static_assert( sizeof( vvb_mctf_mv ) == 16, "vvb_mctf_mv layout" );
+
+static int mctfApplyPar( vvb_ctx* ctx, int orgPlane, const vvb_mctf_apply_par* in, MctfApplyPar& p, int& nBlocks )
+{
+  if( !in ) return fail( ctx, VVB_ERR_ARG, "null apply parameters" );
+  if( !validPlane( ctx, orgPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( in->num_refs < 1 || in->num_refs > 8 ) return fail( ctx, VVB_ERR_ARG, "1..8 reference pictures (2 * VVENC_MCTF_RANGE, MCTF.cpp:430)" );
+  if( in->block_size != 8 && in->block_size != 16 && in->block_size != 32 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF unit size 8, 16 or 32" );
+  const Plane& o = ctx->planes.p[orgPlane];
+  if( ( o.width & 7 ) || ( o.height & 7 ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "picture dimensions must be multiples of 8" );
+  if( o.bitDepth > 10 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF supports up to 10 bit (MCTF.cpp:1313 CHECKD)" );
+  memset( &p, 0, sizeof( p ) );
+  p.numRefs = in->num_refs; p.blockSize = in->block_size; p.tap4 = in->low_res_filter ? 1 : 0; p.planar = in->planar_correction ? 1 : 0;
+  p.width = o.width; p.height = o.height; p.blocksX = ( o.width + in->block_size - 1 ) / in->block_size; p.bitDepth = o.bitDepth; p.orgPlane = orgPlane;
+  p.weightScaling = in->weight_scaling; p.sigmaSq = in->sigma_sq;
+  for( int i = 0; i < in->num_refs; i++ )
+  {
+    if( !validPlane( ctx, in->ref_plane[i] ) ) return fail( ctx, VVB_ERR_ARG, "unknown reference plane" );
+    p.refPlane[i] = in->ref_plane[i]; p.refStrength[i] = in->ref_strength[i];
+  }
+  nBlocks = p.blocksX * ( ( o.height + in->block_size - 1 ) / in->block_size );
+  return VVB_OK;
+}
+
+int vvb_mctf_apply_dev( vvb_ctx* ctx, int orgPlane, const vvb_mctf_apply_par* par, const vvb_mctf_mv* dMvs, int16_t* dOut, int outStride )
+{
+  if( !ctx || !dMvs || !dOut ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  MctfApplyPar p; int nBlocks = 0;
+  int rc = mctfApplyPar( ctx, orgPlane, par, p, nBlocks );
+  if( rc ) return rc;
+  if( outStride < p.width ) return fail( ctx, VVB_ERR_ARG, "output stride below the picture width" );
+  p.outStride = outStride;
+  CU( cudaSetDevice( ctx->device ) );
+  const MctfApplySmem L = mctf_apply_smem( p.blockSize, p.numRefs );
+  const size_t smem = (size_t) L.total * 4;
+  const int threads = std::max( 32, std::min( 256, ( ( p.blockSize / 2 ) * p.blockSize + 31 ) & ~31 ) );
+  mctf_apply_kernel<<<std::min( nBlocks, ctx->numSMs * 16 ), threads, smem, ctx->stream>>>( ctx->planes, p, (const int4*) dMvs, nBlocks, dOut );
+  CHECK_LAUNCH( "mctf_apply_kernel" );
+  return VVB_OK;
+}
+
+int vvb_mctf_apply( vvb_ctx* ctx, int orgPlane, const vvb_mctf_apply_par* par, const vvb_mctf_mv* mvs, int16_t* out, int outStride )
+{
+  if( !ctx || !mvs || !out ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  MctfApplyPar p; int nBlocks = 0;
+  int rc = mctfApplyPar( ctx, orgPlane, par, p, nBlocks );
+  if( rc ) return rc;
+  if( outStride < p.width ) return fail( ctx, VVB_ERR_ARG, "output stride below the picture width" );
+  void *dM, *dO;
+  const size_t mvBytes = (size_t) p.numRefs * nBlocks * sizeof( vvb_mctf_mv ), outBytes = (size_t) p.width * p.height * 2;
+  if( ( rc = scratch( ctx, 0, mvBytes, &dM ) ) || ( rc = scratch( ctx, 1, outBytes, &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dM, mvs, mvBytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_mctf_apply_dev( ctx, orgPlane, par, (const vvb_mctf_mv*) dM, (int16_t*) dO, p.width ) ) ) return rc;
+  CU( cudaMemcpy2DAsync( out, (size_t) outStride * 2, dO, (size_t) p.width * 2, (size_t) p.width * 2, p.height, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+int vvb_mctf_calc_var_dev( vvb_ctx* ctx, int plane, const vvb_mctf_cand* dBlocks, int n, double* dVar )
+{
+  if( !ctx || !dBlocks || !dVar || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, plane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  mctf_calc_var_kernel<<<( n + 3 ) / 4, 128, 0, ctx->stream>>>( ctx->planes.p[plane], dBlocks, n, dVar );
+  CHECK_LAUNCH( "mctf_calc_var_kernel" );
+  return VVB_OK;
+}
+
+int vvb_mctf_calc_var( vvb_ctx* ctx, int plane, const vvb_mctf_cand* blocks, int n, double* var )
+{
+  if( !ctx || !blocks || !var || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  void *dB, *dV; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_mctf_cand ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * 8, &dV ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_mctf_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_mctf_calc_var_dev( ctx, plane, (const vvb_mctf_cand*) dB, n, (double*) dV ) ) ) return rc;
+  CU( cudaMemcpyAsync( var, dV, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( endCall( ctx ) );
   return VVB_OK;
 }

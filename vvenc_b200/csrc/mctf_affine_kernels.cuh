@@ -348,6 +348,266 @@ __global__ void __launch_bounds__( 256 ) mctf_grid_kernel( const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// MCTF apply stage: the per-block body of MCTF::xFinalizeBlkLine (CommonLib/MCTF.cpp:1437-1483) for luma, one CTA per block:
+//   for every reference picture: applyFrac8Core_6Tap / _4Tap (:259-357, first pass unclipped, second pass clipped) at the block's motion vector,
+//   applyPlanarCorrectionCore (:372-420) when rmsme > 0, QP <= 32, square block <= 32; then applyBlockCore (:422-518): noise estimate per
+//   reference, weights, per-pel bilateral blend with fastExp (:359-367).  Integer parts are exact; the float parts follow the C++ expression
+//   types of the reference literally (float *= double goes through double, `newVal + 0.5` is a double add) and the library is built with
+//   --fmad=false, so results equal the scalar and the AVX2 reference bit for bit.
+struct MctfApplyPar
+{
+  int    numRefs, blockSize, tap4, planar, width, height, blocksX, bitDepth, orgPlane, outStride;
+  int    refPlane[8];
+  double weightScaling, sigmaSq, refStrength[8];
+};
+struct MctfApplySmem { int winPitch, winWords, hWords, corrWords, orgWords, total; };
+__host__ __device__ inline MctfApplySmem mctf_apply_smem( int bs, int numRefs )
+{
+  MctfApplySmem m;
+  m.winPitch  = bs / 2 + 4;
+  m.winWords  = ( bs + 6 ) * m.winPitch;
+  m.hWords    = ( ( bs + 6 ) / 2 ) * bs;
+  m.corrWords = numRefs * bs * bs / 2;
+  m.orgWords  = bs * bs / 2;
+  m.total     = m.winWords + m.hWords + m.corrWords + m.orgWords + 64 + 8 * 6;      // + weights + 64-bit accumulators
+  return m;
+}
+
+__device__ __forceinline__ float mctf_fast_exp( float n, float d )
+{
+  float x = 1.0f + n / ( d * 1024 );
+  x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; x *= x;
+  return x;
+}
+
+__global__ void __launch_bounds__( 256 ) mctf_apply_kernel( const __grid_constant__ PlaneTable planes, const __grid_constant__ MctfApplyPar par,
+                                                            const int4* __restrict__ mvs, int nBlocks, int16_t* __restrict__ out )
+{
+  extern __shared__ __align__( 16 ) uint32_t sApply[];
+  const int bs = par.blockSize;
+  const MctfApplySmem L = mctf_apply_smem( bs, par.numRefs );
+  uint32_t* win  = sApply;
+  uint32_t* hbuf = win + L.winWords;
+  int16_t*  corr = reinterpret_cast<int16_t*>( hbuf + L.hWords );                   // [numRefs][h][w]
+  int16_t*  orgB = reinterpret_cast<int16_t*>( hbuf + L.hWords + L.corrWords );     // [h][w]
+  float*    sW   = reinterpret_cast<float*>( hbuf + L.hWords + L.corrWords + L.orgWords );   // vww[8], vsw[8]
+  int*      sI   = reinterpret_cast<int*>( sW + 16 );                                // [0..2] planar sums, [8..15] vnoise
+  unsigned long long* sAcc = reinterpret_cast<unsigned long long*>( sW + 64 );      // [0] variance, [1] diffsum
+  const int tid = threadIdx.x, T = blockDim.x;
+  const Plane orgPlane = planes.p[par.orgPlane];
+  const int maxv = ( 1 << par.bitDepth ) - 1;
+  const int PW = L.winPitch;
+  const int tap4 = par.tap4;
+
+  for( int b = blockIdx.x; b < nBlocks; b += gridDim.x )
+  {
+    const int bxI = b % par.blocksX, byI = b / par.blocksX;
+    const int bx = bxI * bs, by = byI * bs;
+    const int w = min( bs, par.width - bx ), h = min( bs, par.height - by );
+    const int hw = w >> 1, hh = h >> 1;
+    const float invHw = 1.0f / (float) hw, invW = 1.0f / (float) w;
+    __syncthreads();
+    for( int i = tid; i < h * w; i += T )
+    {
+      const int y = mctf_div( i, invW ), x = i - y * w;
+      orgB[i] = __ldg( orgPlane.origin + (ptrdiff_t)( by + y ) * orgPlane.stride + bx + x );
+    }
+#define VVB_B4( a, b_, c_, d ) ( (uint32_t)( (a) & 255 ) | ( (uint32_t)( (b_) & 255 ) << 8 ) | ( (uint32_t)( (c_) & 255 ) << 16 ) | ( (uint32_t)( (d) & 255 ) << 24 ) )
+#define VVB_E( a, b_, c_, FA, FB ) __dp2a_lo( (int)(c_), FB, __dp2a_hi( (int)(b_), FA, __dp2a_lo( (int)(a), FA, 0 ) ) )
+#define VVB_O( a, b_, c_, d, GA, GB ) __dp2a_hi( (int)(d), GB, __dp2a_lo( (int)(c_), GB, __dp2a_hi( (int)(b_), GA, __dp2a_lo( (int)(a), GA, 0 ) ) ) )
+#define VVB_R( v ) ( ( (v) + 32 ) >> 6 )
+#define VVB_TAPS( f, ph ) { _Pragma( "unroll" ) for( int t = 0; t < 6; t++ ) f[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[ph][t - 1] : 0 ) : c_mctfF8[ph][t + 1]; }
+    for( int r = 0; r < par.numRefs; r++ )
+    {
+      const Plane refPlane = planes.p[par.refPlane[r]];
+      const int4 mv = __ldg( mvs + (size_t) r * nBlocks + b );                        // x, y, error, rmsme
+      int16_t* cr = corr + r * h * w;
+      // ---- window: rows by+yInt-2 .., pels from the even pel at or below bx+xInt-2
+      const int16_t* src0 = refPlane.origin + (ptrdiff_t)( by + ( mv.y >> 4 ) - 2 ) * refPlane.stride + bx + ( mv.x >> 4 ) - 2;
+      const int o = (int)( ( reinterpret_cast<uintptr_t>( src0 ) >> 1 ) & 1 );
+      const uint32_t* srcW = reinterpret_cast<const uint32_t*>( src0 - o );
+      const int nW = ( w + 5 + o + 1 ) >> 1, rowsP = ( h + 6 ) & ~1;
+      const float invNw = 1.0f / (float) nW;
+      const int strideW = refPlane.stride >> 1;
+      __syncthreads();                                   // previous reference's readers of win / hbuf are done
+      for( int i = tid; i < rowsP * nW; i += T )
+      {
+        const int rr = mctf_div( i, invNw ), k = i - rr * nW;
+        win[rr * PW + k] = __ldg( srcW + (ptrdiff_t) rr * strideW + k );
+      }
+      if( tid < 3 ) sI[tid] = 0;
+      if( tid < 2 ) sAcc[tid] = 0ull;
+      __syncthreads();
+      int f[6];
+      VVB_TAPS( f, mv.x & 15 )
+      const int xFA = (int) VVB_B4( f[0], f[1], f[2], f[3] ), xFB = (int) VVB_B4( f[4], f[5], 0, 0 );
+      const int xGA = (int) VVB_B4( 0, f[0], f[1], f[2] ),    xGB = (int) VVB_B4( f[3], f[4], f[5], 0 );
+      for( int it = tid; it < ( rowsP >> 1 ) * hw; it += T )
+      {
+        const int rp = mctf_div( it, invHw ), cp = it - rp * hw;
+        const uint32_t* ra = win + ( 2 * rp ) * PW + cp;
+        const uint32_t* rb = ra + PW;
+        const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
+        int ha0, ha1, hb0, hb1;
+        if( o == 0 ) { ha0 = VVB_E( a0, a1, a2, xFA, xFB ); ha1 = VVB_O( a0, a1, a2, a3, xGA, xGB ); hb0 = VVB_E( b0, b1, b2, xFA, xFB ); hb1 = VVB_O( b0, b1, b2, b3, xGA, xGB ); }
+        else         { ha0 = VVB_O( a0, a1, a2, a3, xGA, xGB ); ha1 = VVB_E( a1, a2, a3, xFA, xFB ); hb0 = VVB_O( b0, b1, b2, b3, xGA, xGB ); hb1 = VVB_E( b1, b2, b3, xFA, xFB ); }
+        uint2 pk;                                        // first pass is NOT clipped (MCTF.cpp:284): signed 16-bit halves
+        pk.x = ( (uint32_t) VVB_R( ha0 ) & 0xffffu ) | ( (uint32_t) VVB_R( hb0 ) << 16 );
+        pk.y = ( (uint32_t) VVB_R( ha1 ) & 0xffffu ) | ( (uint32_t) VVB_R( hb1 ) << 16 );
+        *reinterpret_cast<uint2*>( hbuf + rp * w + 2 * cp ) = pk;
+      }
+      __syncthreads();
+      VVB_TAPS( f, mv.y & 15 )
+      const int yFA = (int) VVB_B4( f[0], f[1], f[2], f[3] ), yFB = (int) VVB_B4( f[4], f[5], 0, 0 );
+      const int yGA = (int) VVB_B4( 0, f[0], f[1], f[2] ),    yGB = (int) VVB_B4( f[3], f[4], f[5], 0 );
+      const bool doPlanar = ( mv.w & 0xffff ) > 0 && par.planar && w == h && w <= 32;
+      int s1 = 0, s2 = 0, s0 = 0;
+      for( int p = tid; p < hh * w; p += T )
+      {
+        const int yp = mctf_div( p, invW ), x = p - yp * w;
+        const uint32_t* tp = hbuf + yp * w + x;
+        const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
+        const int v0 = max( min( VVB_R( VVB_E( p0, p1, p2, yFA, yFB ) ), maxv ), 0 ), v1 = max( min( VVB_R( VVB_O( p0, p1, p2, p3, yGA, yGB ) ), maxv ), 0 );
+        cr[( 2 * yp ) * w + x] = (int16_t) v0; cr[( 2 * yp + 1 ) * w + x] = (int16_t) v1;
+        if( doPlanar )
+        {
+          const int z0 = v0 - orgB[( 2 * yp ) * w + x], z1 = v1 - orgB[( 2 * yp + 1 ) * w + x];
+          s1 += x * ( z0 + z1 ); s2 += ( 2 * yp ) * z0 + ( 2 * yp + 1 ) * z1; s0 += z0 + z1;
+        }
+      }
+      if( doPlanar )
+      {
+        s1 = __reduce_add_sync( 0xffffffffu, s1 ); s2 = __reduce_add_sync( 0xffffffffu, s2 ); s0 = __reduce_add_sync( 0xffffffffu, s0 );
+        if( ( tid & 31 ) == 0 ) { atomicAdd( &sI[0], s1 ); atomicAdd( &sI[1], s2 ); atomicAdd( &sI[2], s0 ); }
+      }
+      __syncthreads();
+      if( doPlanar )                                     // applyPlanarCorrectionCore, fixed-point plane fit (MCTF.cpp:395-418)
+      {
+        const int xSzm[6] = { 0, 1, 20, 336, 5440, 87296 };
+        const int blockSize = w * h, log2W = 31 - __clz( w );
+        const unsigned me = (unsigned)( mv.w & 0xffff );
+        const int mWeight = (int) min( 512u, me * me );
+        const int xSum = ( blockSize * ( w - 1 ) ) >> 1;
+        const int x1yzm = sI[0], x2yzm = sI[1], ySum = sI[2];
+        const long long denom = (long long) blockSize * xSzm[log2W];
+        long long numer = (long long) mWeight * ( (long long) x1yzm * blockSize - (long long) xSum * ySum );
+        int b1 = (int)( ( numer < 0 ? numer - ( denom >> 1 ) : numer + ( denom >> 1 ) ) / denom );
+        b1 = max( -32768, min( 32767, b1 ) );
+        numer = (long long) mWeight * ( (long long) x2yzm * blockSize - (long long) xSum * ySum );
+        int b2 = (int)( ( numer < 0 ? numer - ( denom >> 1 ) : numer + ( denom >> 1 ) ) / denom );
+        b2 = max( -32768, min( 32767, b2 ) );
+        const int b0 = ( mWeight * ySum - ( b1 + b2 ) * xSum + ( blockSize >> 1 ) ) >> ( log2W << 1 );
+        if( b0 | b1 | b2 )
+          for( int i = tid; i < h * w; i += T )
+          {
+            const int y = mctf_div( i, invW ), x = i - y * w;
+            const int pc = ( b0 + b1 * x + b2 * y + 256 ) >> 9;
+            cr[i] = (int16_t) max( 0, min( maxv, (int) cr[i] - pc ) );
+          }
+        __syncthreads();
+      }
+      // ---- noise estimate of applyBlockCore (MCTF.cpp:442-472): variance and first-difference energy of (org - corrected)
+      {
+        unsigned long long var = 0, dsum = 0;
+        for( int i = tid; i < h * w; i += T )
+        {
+          const int y = mctf_div( i, invW ), x = i - y * w;
+          const int diff = (int) orgB[i] - (int) cr[i];
+          var += (unsigned)( diff * diff );
+          if( x != w - 1 ) { const int dR = (int) orgB[i + 1] - (int) cr[i + 1]; dsum += (unsigned)( ( dR - diff ) * ( dR - diff ) ); }
+          if( y != h - 1 ) { const int dD = (int) orgB[i + w] - (int) cr[i + w]; dsum += (unsigned)( ( dD - diff ) * ( dD - diff ) ); }
+        }
+#pragma unroll
+        for( int m = 16; m > 0; m >>= 1 ) { var += __shfl_xor_sync( 0xffffffffu, var, m ); dsum += __shfl_xor_sync( 0xffffffffu, dsum, m ); }
+        if( ( tid & 31 ) == 0 ) { atomicAdd( &sAcc[0], var ); atomicAdd( &sAcc[1], dsum ); }
+        __syncthreads();
+        if( tid == 0 )
+        {
+          long long variance = (long long) sAcc[0], diffsum = (long long) sAcc[1];
+          variance *= 1ll << ( 2 * ( 10 - par.bitDepth ) );
+          diffsum  *= 1ll << ( 2 * ( 10 - par.bitDepth ) );
+          const int cntV = w * h, cntD = 2 * cntV - w - h;
+          sI[8 + r] = (int) round( ( 15.0 * cntD / cntV * (double) variance + 5.0 ) / ( (double) diffsum + 5.0 ) );
+          sI[16 + r] = mv.z;                             // verror
+        }
+      }
+    }
+    __syncthreads();
+    if( tid == 0 )                                       // weights (MCTF.cpp:474-489)
+    {
+      int minError = 0x7fffffff;
+      for( int r = 0; r < par.numRefs; r++ ) minError = min( minError, sI[16 + r] );
+      for( int r = 0; r < par.numRefs; r++ )
+      {
+        const int error = sI[16 + r], noise = sI[8 + r];
+        float ww = 1, sw = 1;
+        ww = (float)( (double) ww * ( ( noise < 25 ) ? 1.0 : 0.6 ) );
+        sw = (float)( (double) sw * ( ( noise < 25 ) ? 1.0 : 0.8 ) );
+        ww = (float)( (double) ww * ( ( error < 50 ) ? 1.2 : ( ( error > 100 ) ? 0.6 : 1.0 ) ) );
+        sw = (float)( (double) sw * ( ( error < 50 ) ? 1.0 : 0.8 ) );
+        ww = (float)( (double) ww * ( ( minError + 1.0 ) / ( error + 1.0 ) ) );
+        sW[r]     = (float)( (double) ww * par.weightScaling * par.refStrength[r] );
+        sW[8 + r] = (float)( (double)( sw * 2 ) * par.sigmaSq );
+      }
+    }
+    __syncthreads();
+    // ---- per-pel blend (MCTF.cpp:491-517)
+    for( int i = tid; i < h * w; i += T )
+    {
+      const int y = mctf_div( i, invW ), x = i - y * w;
+      const int orgVal = orgB[i];
+      float temporalWeightSum = 1.0f;
+      float newVal = (float) orgVal;
+      for( int r = 0; r < par.numRefs; r++ )
+      {
+        const int refVal = corr[r * h * w + i];
+        const int diff = refVal - orgVal;
+        const float diffSq = (float)( diff * diff );
+        const float weight = sW[r] * mctf_fast_exp( -diffSq, sW[8 + r] );
+        newVal += weight * (float) refVal;
+        temporalWeightSum += weight;
+      }
+      newVal /= temporalWeightSum;
+      int sampleVal = (int)(short)(int)( (double) newVal + 0.5 );
+      sampleVal = max( 0, min( maxv, sampleVal ) );
+      out[(size_t)( by + y ) * par.outStride + bx + x] = (int16_t) sampleVal;
+    }
+#undef VVB_B4
+#undef VVB_E
+#undef VVB_O
+#undef VVB_R
+#undef VVB_TAPS
+  }
+}
+
+// calcVarCore (MCTF.cpp:520-546): 16 * variance of a block in 1/256 units, double result
+__global__ void mctf_calc_var_kernel( const __grid_constant__ Plane plane, const vvb_mctf_cand* __restrict__ blocks, int n, double* __restrict__ out )
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * ( blockDim.x >> 5 ) + warp;
+  if( b >= n ) return;
+  const vvb_mctf_cand c = blocks[b];
+  const int w = c.w, h = c.h;
+  const int16_t* org = plane.origin + (ptrdiff_t) c.y * plane.stride + c.x;
+  const float invW = 1.0f / (float) w;
+  int avg = 0;
+  for( int i = lane; i < w * h; i += 32 ) { const int y = mctf_div( i, invW ), x = i - y * w; avg += __ldg( org + (ptrdiff_t) y * plane.stride + x ); }
+  avg = __reduce_add_sync( 0xffffffffu, avg );
+  avg <<= 4;
+  avg = avg / ( w * h );
+  long long var = 0;
+  for( int i = lane; i < w * h; i += 32 )
+  {
+    const int y = mctf_div( i, invW ), x = i - y * w;
+    const int pix = (int) __ldg( org + (ptrdiff_t) y * plane.stride + x ) << 4;
+    var += (long long)( ( pix - avg ) * ( pix - avg ) );
+  }
+#pragma unroll
+  for( int m = 16; m > 0; m >>= 1 ) var += __shfl_xor_sync( 0xffffffffu, var, m );
+  if( lane == 0 ) out[b] = (double) var / 256.0;
+}
+
 // ---- affine: Sobel on a w x h prediction block with border replication (AffineGradientSearch.cpp:84-147)
 __global__ void sobel_kernel( const int16_t* __restrict__ pred, int ps, int16_t* __restrict__ deriv, int ds, int w, int h, int vertical )
 {
