@@ -65,7 +65,7 @@ int checkDistShape( vvb_ctx* ctx, int fam, int w, int h, int subShift )
 int makeMePar( vvb_ctx* ctx, const vvb_me_par* in, MePar& out )
 {
   if( !in ) return fail( ctx, VVB_ERR_ARG, "null me_par" );
-  out.costScale = in->cost_scale; out.imvShift = in->imv_shift; out.subShift = in->sub_shift;
+  out.costScale = in->cost_scale; out.imvShift = in->imv_shift; out.subShift = in->sub_shift; out.orderBits = 0;
   const double motionLambda = std::sqrt( in->lambda );                 // RdCost.cpp:77
   for( int b = 0; b < VVB_MVCOST_ENTRIES; b++ )
   {
@@ -222,6 +222,8 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( sad_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   cudaFuncSetAttribute( sad_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   cudaFuncSetAttribute( sad_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
+  cudaFuncSetAttribute( sad_search_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024 );
   {
     // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
@@ -631,11 +633,22 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
       if( r == CUDA_SUCCESS ) { ti.enabled = 1; ti.nx = maxNx; ti.ny = maxNy; ti.quad = nb == 2 ? 1 : 0; ti.margin = rp.margin; }
     }
   }
-#define LAUNCH_SS( T_, P_ ) sad_search_kernel<T_, P_><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest, \
+#define LAUNCH_SS( T_, P_ ) LAUNCH_SS3( T_, P_, false )
+#define LAUNCH_SS3( T_, P_, K_ ) sad_search_kernel<T_, P_, K_><<<grid, bd, smem, ctx->stream>>>( ctx->planes.p[orgPlane], rp, dBlocks, n, w, h, nb == 2 ? 1 : 0, mp, tmap, ti, dTables, tableStride, dBest, \
                                                                                     pyr ? pyr->parents : nullptr, pyr ? pyr->best : nullptr, pyr ? pyr->tables : nullptr, pyr ? pyr->stride : 0 )
-  if( pyr ) { if( ti.enabled ) LAUNCH_SS( true, true ); else LAUNCH_SS( false, true ); }
+  // 32-bit argmin keys in the pyramid base kernel when the largest possible parent cost (4 members' SAD + MV cost) leaves room for the raster order
+  bool key32 = false;
+  if( pyr )
+  {
+    int ob = 1; while( ( 1 << ob ) < maxNx * maxNy ) ob++;
+    const unsigned long long maxCost = 4ull * w * h * ( ( 1ull << rp.bitDepth ) - 1 ) + mp.tab.cost[VVB_MVCOST_ENTRIES - 1];
+    if( ob <= 16 && maxCost < ( 1ull << ( 32 - ob ) ) - 1 ) { key32 = true; mp.orderBits = ob; }
+  }
+  if( pyr && key32 ) { if( ti.enabled ) LAUNCH_SS3( true, true, true ); else LAUNCH_SS3( false, true, true ); }
+  else if( pyr ) { if( ti.enabled ) LAUNCH_SS( true, true ); else LAUNCH_SS( false, true ); }
   else      { if( ti.enabled ) LAUNCH_SS( true, false ); else LAUNCH_SS( false, false ); }
 #undef LAUNCH_SS
+#undef LAUNCH_SS3
   CHECK_LAUNCH( "sad_search_kernel" );
   return VVB_OK;
 }

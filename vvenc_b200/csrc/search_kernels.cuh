@@ -17,7 +17,7 @@
 
 namespace vvb {
 
-struct MePar { int costScale, imvShift, subShift; MvCostTable tab; };
+struct MePar { int costScale, imvShift, subShift, orderBits; MvCostTable tab; };   // orderBits: width of the raster-order field of 32-bit argmin keys (KEY32 kernels)
 
 // tab: shared-memory copy of MePar::tab (dynamic indexing of the parameter bank would serialise per distinct address)
 __device__ __forceinline__ uint32_t mv_cost( const MePar& p, const uint32_t* tab, int x, int y, int predHor, int predVer )
@@ -173,7 +173,10 @@ __device__ __forceinline__ void strip_min_sums( const int16_t* __restrict__ obas
   }
 }
 
-template<bool USE_TMA, bool PARENT>
+template<bool K32> struct KeyType { typedef unsigned long long type; };
+template<> struct KeyType<true> { typedef uint32_t type; };
+
+template<bool USE_TMA, bool PARENT, bool KEY32 = false>
 __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_search_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                             const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int quadMode,
                                                             const __grid_constant__ MePar par, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TmaInfo tma,
@@ -427,7 +430,12 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
       for( int i = tid; i < nxp; i += nthr ) pBitsX[i] = (int) eg_bits( ( ( blk.left + i ) * ( 1 << par.costScale ) - pblk.pred_hor ) >> par.imvShift );
       for( int i = tid; i < ny;  i += nthr ) pBitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - pblk.pred_ver ) >> par.imvShift );
       __syncthreads();
-      unsigned long long key4[4] = { ~0ull, ~0ull, ~0ull, ~0ull }, keyP = ~0ull;
+      // argmin keys (cost << ob | raster order): 64 bit with a 16-bit order field in general; KEY32 instantiations are launched when the host has
+      // verified that every possible cost of the batch fits 32 - ob bits (half the epilogue arithmetic, REDUX instead of shuffle trees)
+      typedef typename KeyType<KEY32>::type KT;
+      const int ob = KEY32 ? par.orderBits : 16;
+      const KT KMAX = ~(KT) 0;
+      KT key4[4] = { KMAX, KMAX, KMAX, KMAX }, keyP = KMAX;
       for( int it = tid; it < perMem; it += nthr )
       {
         const int cy = fast_div( it, invStr ), st = it - cy * nStrips;
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
           const int sumA = sSumA[mem];
           const int* bitsX = bitsAll + mem * bitsSet;
           const int byBits = bitsX[nxp + cy];
-          unsigned long long bk = key4[mem];
+          KT bk = key4[mem];
           uint32_t vv[SS_STRIP]; int bxv[SS_STRIP];
           *reinterpret_cast<uint4*>( &vv[0] )  = *reinterpret_cast<const uint4*>( V + ( cy + by * h ) * nxpV + bx * w + cx0 );
           *reinterpret_cast<uint4*>( &vv[4] )  = *reinterpret_cast<const uint4*>( V + ( cy + by * h ) * nxpV + bx * w + cx0 + 4 );
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
               psad[k] += sad;
               if( sadTables ) sadTables[(size_t)( first + mem ) * tableStride + order] = sad;
               const uint32_t bits = (uint32_t)( bxv[k] + byBits );
-              const unsigned long long key = ( ( (unsigned long long) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | order;
+              const KT key = ( ( (KT) sad + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << ob ) | order;
               bk = key < bk ? key : bk;
             }
           }
@@ -480,24 +488,37 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
             const uint32_t order = (uint32_t)( cy * nx + cx );
             if( parentTables ) parentTables[(size_t) blockIdx.x * parentStride + order] = psad[k];
             const uint32_t bits = (uint32_t)( pbx[k] + pByBits );
-            const unsigned long long key = ( ( (unsigned long long) psad[k] + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << 16 ) | order;
+            const KT key = ( ( (KT) psad[k] + sMv[bits < VVB_MVCOST_ENTRIES ? bits : VVB_MVCOST_ENTRIES - 1] ) << ob ) | order;
             keyP = key < keyP ? key : keyP;
           }
         }
       }
       // warp minimum first, then one atomic per warp and key
-#pragma unroll
-      for( int m = 16; m > 0; m >>= 1 )
+      unsigned long long k64[5];
+      if( KEY32 )
       {
 #pragma unroll
-        for( int q = 0; q < 4; q++ ) { const unsigned long long o = __shfl_xor_sync( 0xffffffffu, key4[q], m ); key4[q] = o < key4[q] ? o : key4[q]; }
-        const unsigned long long o = __shfl_xor_sync( 0xffffffffu, keyP, m ); keyP = o < keyP ? o : keyP;
+        for( int q = 0; q < 5; q++ )
+        {
+          const uint32_t k = __reduce_min_sync( 0xffffffffu, (uint32_t)( q < 4 ? key4[q] : keyP ) );
+          k64[q] = k == 0xffffffffu ? ~0ull : ( ( (unsigned long long)( k >> ob ) << 16 ) | ( k & ( ( 1u << ob ) - 1u ) ) );
+        }
+      }
+      else
+      {
+#pragma unroll
+        for( int q = 0; q < 5; q++ ) k64[q] = (unsigned long long)( q < 4 ? key4[q] : keyP );
+#pragma unroll
+        for( int m = 16; m > 0; m >>= 1 )
+        {
+#pragma unroll
+          for( int q = 0; q < 5; q++ ) { const unsigned long long o = __shfl_xor_sync( 0xffffffffu, k64[q], m ); k64[q] = o < k64[q] ? o : k64[q]; }
+        }
       }
       if( lane == 0 )
       {
 #pragma unroll
-        for( int q = 0; q < 4; q++ ) if( key4[q] != ~0ull ) atomicMin( &sKey[q], key4[q] );
-        if( keyP != ~0ull ) atomicMin( &sKey[4], keyP );
+        for( int q = 0; q < 5; q++ ) if( k64[q] != ~0ull ) atomicMin( &sKey[q], k64[q] );
       }
       __syncthreads();
       if( tid == 0 )
