@@ -231,6 +231,16 @@ int vvb_mctf_hint( vvb_ctx* ctx, int max_block_dim );
 int vvb_mctf_search_grid    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* blocks, int n, int step, int radius, int low_res_filter, int32_t* err_out );
 int vvb_mctf_search_grid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* dev_blocks, int n, int step, int radius, int low_res_filter, int32_t* dev_err_out );
 
+/* ---- fractional-pel refinement feeding SATD -------------------------------------------------------------------------------
+ * For every block (x, y; integer vector start_x/start_y) the distortion dfunc (VVB_DF_SAD, or VVB_DF_HAD on square blocks) between the original and
+ * the filtered block at every quarter-pel offset (i, j), i, j = -3..3: cost_out[n][j+3][i+3] -- every position InterSearch::xPatternRefinement
+ * (InterSearch.cpp:760-972) can visit in its half-pel round and in its quarter-pel round around the best half-pel position.  The filtered blocks are
+ * produced exactly as there: InterpolationFilter::filterHor(frac_x, isLast=false) then filterVer(frac_y, isFirst=false, isLast=true) with the 8-tap
+ * luma filter (InterpolationFilter.cpp:357-455, reduceTap = 0, no alternative half-pel filter).  The MV rate and the two-round selection
+ * (incl. the m_fastSubPel skip tables) replay on the host from the table. */
+int vvb_frac_cost_grid    ( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, uint32_t* cost_out );
+int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, uint32_t* dev_cost_out );
+
 /* ---- MCTF apply stage: the per-block body of MCTF::xFinalizeBlkLine (MCTF.cpp:1437-1483) for the luma plane, fused:
  * per reference picture applyFrac (m_applyFrac, :259-357) at the block's vector, applyPlanarCorrection (:372-420) when rmsme > 0 and
  * planar_correction (the caller passes m_QP <= 32) and the block is square <= 32, then applyBlock (:422-518: noise estimate, weights, bilateral

@@ -747,6 +747,63 @@ void orc_mctf_finalize_block( const Pel* orgPlane, int so, const Pel* const* ref
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * Fractional-pel refinement feeding SATD: the filtered blocks InterSearch::xPatternRefinement evaluates
+ * (EncoderLib/InterSearch.cpp:760-972; xExtDIFUpSamplingH/Q :2912,2973) are always produced by TWO passes of the 8-tap luma filter:
+ * InterpolationFilter::filterHor(frac_x, isLast = false) then filterVer(frac_y, isFirst = false, isLast = true)
+ * (CommonLib/InterpolationFilter.cpp:357-455 filter<N,...>, :258-340 filterCopy for frac 0, which equals the filter with the
+ * tap 64).  Quarter-pel phases of m_lumaFilter (:85-104 rows 0, 4, 8, 12); reduceTap = 0, no alternative half-pel filter.
+ * ---------------------------------------------------------------------------------------------------- */
+static const int8_t luma_qpel[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+
+/* src points at the integer position of the block; fx, fy in quarter pels (0..3) */
+void orc_if_two_pass( const Pel* src, int ss, int w, int h, int fx, int fy, int bitDepth, Pel* dst, int ds )
+{
+  const int headRoom = 14 - bitDepth > 2 ? 14 - bitDepth : 2;
+  const int shift1 = 6 - headRoom, offset1 = -( 8192 << shift1 );
+  const int shift2 = 6 + headRoom, offset2 = ( 1 << ( shift2 - 1 ) ) + ( 8192 << 6 );
+  const int maxv = ( 1 << bitDepth ) - 1;
+  int16_t* tmp = (int16_t*) malloc( sizeof( int16_t ) * ( h + 7 ) * w );
+  for( int r = 0; r < h + 7; r++ )
+    for( int x = 0; x < w; x++ )
+    {
+      const Pel* p = src + ( r - 3 ) * ss + x - 3;
+      int sum = 0;
+      for( int t = 0; t < 8; t++ ) sum += luma_qpel[fx][t] * p[t];
+      tmp[r * w + x] = (int16_t)( ( sum + offset1 ) >> shift1 );
+    }
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      int sum = 0;
+      for( int t = 0; t < 8; t++ ) sum += luma_qpel[fy][t] * tmp[( y + t ) * w + x];
+      const int v = ( sum + offset2 ) >> shift2;
+      dst[y * ds + x] = (Pel)( v < 0 ? 0 : ( v > maxv ? maxv : v ) );
+    }
+  free( tmp );
+}
+
+/* Distortion table of all quarter-pel offsets (i, j) in -3..3 around the integer vector: out[b][j+3][i+3].
+ * blk[b] = { x, y, w, h, mvx, mvy } (integer pel vector); family 1 = SAD, 2 = HAD (xGetHADs). */
+void orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, uint32_t* out )
+{
+  Pel* pred = (Pel*) malloc( sizeof( Pel ) * 64 * 64 );
+  for( int b = 0; b < n; b++ )
+  {
+    const int32_t* d = blk + 6 * (size_t) b;
+    const int w = d[2], h = d[3];
+    const Pel* org = orgPlane + (ptrdiff_t) d[1] * so + d[0];
+    for( int j = -3; j <= 3; j++ )
+      for( int i = -3; i <= 3; i++ )
+      {
+        const Pel* src = refPlane + (ptrdiff_t)( d[1] + d[5] + ( j >> 2 ) ) * sr + d[0] + d[4] + ( i >> 2 );
+        orc_if_two_pass( src, sr, w, h, i & 3, j & 3, bitDepth, pred, w );
+        out[( (size_t) b * 7 + ( j + 3 ) ) * 7 + ( i + 3 )] = (uint32_t) orc_dist( family, org, so, pred, w, w, h, 0 );
+      }
+  }
+  free( pred );
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * Affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190)
  * ---------------------------------------------------------------------------------------------------- */
 void orc_sobel( int vertical, const Pel* p, int ps, Pel* d, int ds, int w, int h )

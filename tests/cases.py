@@ -268,3 +268,28 @@ def mctf_apply_case(seed, W=96, H=64, margin=24, num_refs=4, bs=16, bit_depth=10
 
 MCTF_APPLY_CASES = ((31, 96, 64, 4, 16, 10, 0, 1), (32, 64, 48, 8, 8, 10, 0, 1), (33, 128, 64, 6, 32, 10, 0, 1), (34, 96, 40, 3, 16, 8, 0, 1),
                     (35, 96, 64, 5, 16, 10, 1, 1), (36, 72, 56, 2, 16, 10, 0, 0))      # seed, W, H, refs, bs, bit depth, tap4, planar
+
+
+def frac_case(seed=4242, W=160, H=96, margin=24, bit_depth=10):
+    """picture pair + block lists for the fractional-pel refinement grid: list of (family, w, h, blocks[n][6] = x, y, w, h, mvx, mvy)"""
+    rs = np.random.RandomState(seed)
+    mx = (1 << bit_depth) - 1
+    S = W + 2 * margin
+    base = rs.randint(0, mx + 1, size=(H + 2 * margin + 8, S + 8))
+    sm = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4
+    org = np.ascontiguousarray(sm[4:4 + H + 2 * margin, 4:4 + S].astype(np.int16))
+    ref = np.ascontiguousarray(np.clip(sm[4 + 1:4 + 1 + H + 2 * margin, 4 - 2:4 - 2 + S] + rs.randint(-9, 10, size=org.shape), 0, mx).astype(np.int16))
+    if seed % 2:                       # extreme content: full-range checkerboard noise in a corner exercises the intermediate range
+        ref[margin:margin + 40, margin:margin + 40] = np.where(rs.randint(0, 2, size=(40, 40)) > 0, mx, 0)
+    lists = []
+    for (fam, w, h) in ((1, 8, 8), (2, 8, 8), (1, 16, 16), (2, 16, 16), (2, 32, 32), (2, 64, 64), (1, 16, 8), (1, 32, 16), (1, 8, 32), (1, 64, 64)):
+        n = 6 if w * h <= 256 else 3
+        b = np.zeros((n, 6), dtype=np.int32)
+        for k in range(n):
+            b[k] = (int(rs.randint(0, W - w + 1)), int(rs.randint(0, H - h + 1)), w, h, int(rs.randint(-9, 10)), int(rs.randint(-9, 10)))
+        b[0, :2] = 0
+        lists.append((fam, w, h, b))
+    return dict(org=org, ref=ref, stride=S, margin=margin, W=W, H=H, bd=bit_depth, lists=lists)
+
+
+FRAC_CASES = ((4242, 10), (4243, 10), (4244, 8))

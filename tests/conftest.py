@@ -25,3 +25,9 @@ def golden_tu():
 def golden_mctf_apply():
     import numpy as np
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v3_mctf_apply.npz'))
+
+
+@pytest.fixture(scope="session")
+def golden_frac():
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v4_frac.npz'))

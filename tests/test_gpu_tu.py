@@ -154,3 +154,37 @@ def test_gpu_mctf_calc_var_golden(gpu, golden_mctf_apply):
     b = golden_mctf_apply['var_blocks']
     blocks['x'] = b[:, 0]; blocks['y'] = b[:, 1]; blocks['w'] = b[:, 2]; blocks['h'] = b[:, 3]
     assert np.array_equal(gpu.eng.mctf_calc_var(0, blocks), golden_mctf_apply['var_expect'])
+
+
+# ------------------------------------------------------------------------------------------ fractional-pel refinement grid
+def test_gpu_frac_cost_grid_golden(gpu, golden_frac):
+    """every quarter-pel offset (-3..3)^2 around integer vectors of mixed alignment: two-pass 8-tap interpolation + SAD / SATD equal to the
+    reference's filterHor/filterVer + distFunc results (8 and 10 bit, blocks 8..64, extreme content)"""
+    for ci, (seed, bd) in enumerate(C.FRAC_CASES):
+        case = C.frac_case(seed, bit_depth=bd)
+        gpu.eng.upload_plane(0, case['org'], case['W'], case['H'], case['margin'], bd)
+        gpu.eng.upload_plane(1, case['ref'], case['W'], case['H'], case['margin'], bd)
+        for li, (fam, w, h, b) in enumerate(case['lists']):
+            blk = np.zeros(len(b), dtype=gpu.V.BLOCK_DT)
+            blk['x'] = b[:, 0]; blk['y'] = b[:, 1]; blk['start_x'] = b[:, 4]; blk['start_y'] = b[:, 5]
+            got = gpu.eng.frac_cost_grid(gpu.V.DF_SAD if fam == 1 else gpu.V.DF_HAD, 0, 1, blk, w, h)
+            exp = golden_frac['c%d_l%d' % (ci, li)]
+            assert np.array_equal(got, exp), (seed, fam, w, h, np.argwhere(got != exp)[:5], got[got != exp][:4], exp[got != exp][:4])
+
+
+def test_gpu_frac_grid_centre_equals_integer_distortion(gpu):
+    """property at full picture size: the centre entry of the table (offset 0,0: both passes with the single tap 64) is the integer-pel SAD / SATD"""
+    rs = np.random.RandomState(77)
+    W, H, m = 3840, 2160, 16
+    S = W + 2 * m
+    org = rs.randint(0, 1024, size=(H + 2 * m, S)).astype(np.int16)
+    ref = np.clip(org.astype(np.int32) + rs.randint(-20, 21, size=org.shape), 0, 1023).astype(np.int16)
+    gpu.eng.upload_plane(0, org, W, H, m, 10); gpu.eng.upload_plane(1, ref, W, H, m, 10)
+    xs, ys = np.meshgrid(np.arange(0, W, 16), np.arange(0, H, 16))
+    blk = np.zeros(xs.size, dtype=gpu.V.BLOCK_DT)
+    blk['x'] = xs.ravel(); blk['y'] = ys.ravel(); blk['start_x'] = rs.randint(-3, 4, size=xs.size); blk['start_y'] = rs.randint(-3, 4, size=xs.size)
+    blk['left'] = -8; blk['right'] = 8; blk['top'] = -8; blk['bottom'] = 8
+    t = gpu.eng.frac_cost_grid(gpu.V.DF_HAD, 0, 1, blk, 16, 16)
+    pat = np.zeros(1, dtype=gpu.V.MV_DT)
+    cost, _ = gpu.eng.cost_pattern(gpu.V.DF_HAD, 0, 1, blk, 16, 16, pat, gpu.eng.me_par(0.0), want_best=False)
+    assert np.array_equal(t[:, 3, 3], cost[:, 0])

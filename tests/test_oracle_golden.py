@@ -68,3 +68,16 @@ def test_oracle_mctf_apply_golden(golden_mctf_apply):
     for (x, y, w, h), e in zip(golden_mctf_apply['var_blocks'], golden_mctf_apply['var_expect']):
         blk = np.ascontiguousarray(plane[y:y + h, x:x + w])
         assert O.orc_mctf_calc_var(P(blk), int(w), int(w), int(h)) == e
+
+
+def test_oracle_frac_grid_golden(golden_frac):
+    """two-pass 8-tap luma interpolation at every quarter-pel offset + SAD / SATD (xPatternRefinement's filtered blocks)"""
+    from _libs import oracle, P, PO
+    O = oracle()
+    for ci, (seed, bd) in enumerate(C.FRAC_CASES):
+        case = C.frac_case(seed, bit_depth=bd)
+        S = case['stride']; base = case['margin'] * S + case['margin']
+        for li, (fam, w, h, b) in enumerate(case['lists']):
+            t = np.zeros((len(b), 7, 7), dtype=np.uint32)
+            O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), len(b), fam, bd, P(t))
+            assert np.array_equal(t, golden_frac['c%d_l%d' % (ci, li)]), (seed, fam, w, h)

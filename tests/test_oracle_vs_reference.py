@@ -176,3 +176,25 @@ def test_mctf_calc_var(opt):
         for bd in (8, 10):
             org = C.aligned((h, w + 16), np.int16); org[:] = rs.randint(0, 1 << bd, size=(h, w + 16))
             assert O.orc_mctf_calc_var(P(org), w + 16, w, h) == R.refshim_mctf_calc_var(opt, P(org), w + 16, w, h), (w, h, bd)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_two_pass_interpolation(opt):
+    """filterHor(isLast=false) + filterVer(isFirst=false, isLast=true), every quarter-pel phase pair, 8 and 10 bit, extreme content included"""
+    from _libs import oracle, refshim, P, PO
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(11 + opt)
+    for bd in (8, 10):
+        mx = (1 << bd) - 1
+        for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (64, 32)):
+            S = w + 32
+            src = rs.randint(0, mx + 1, size=(h + 24, S)).astype(np.int16)
+            if (w, h) == (8, 8):
+                src[:] = np.where(rs.randint(0, 2, size=src.shape) > 0, mx, 0)
+            for fx in range(4):
+                for fy in range(4):
+                    d1 = np.zeros((h, w), np.int16); d2 = np.zeros((h, w), np.int16)
+                    O.orc_if_two_pass(PO(src, 8 * S + 12), S, w, h, fx, fy, bd, P(d1), w)
+                    R.refshim_if_two_pass(opt, PO(src, 8 * S + 12), S, w, h, fx, fy, bd, P(d2), w)
+                    assert np.array_equal(d1, d2), (bd, w, h, fx, fy)

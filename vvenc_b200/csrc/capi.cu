@@ -12,6 +12,7 @@
 #include "trquant_tc_kernels.cuh"
 #include "itrquant_kernels.cuh"
 #include "mctf_affine_kernels.cuh"
+#include "frac_kernels.cuh"
 #include "vvc_tables.h"
 
 using namespace vvb;
@@ -1119,6 +1120,47 @@ int vvb_mctf_error_batch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mc
   for( int i = 0; i < n; i++ ) maxDim = std::max( maxDim, (int) std::max( cands[i].w, cands[i].h ) );
   if( ( rc = mctfLaunch( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dC, n, lowRes, maxDim, (int32_t*) dE ) ) ) return rc;
   CU( cudaMemcpyAsync( err, dE, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// ---- fractional-pel refinement grid (xPatternRefinement's filtered blocks + distFunc) -----------------------------------------------
+static int fracGridArgs( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, int n, int w, int h )
+{
+  if( n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: SAD or HAD" );
+  if( w < 8 || h < 8 || w > 64 || h > 64 || ( w & 7 ) || ( h & 7 ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: block sizes 8..64 in multiples of 8" );
+  if( dfunc == VVB_DF_HAD && ( w != h || !isPow2( w ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: HAD on square blocks only (8x8 Hadamard tiles, RdCost.cpp:1818-1938)" );
+  if( ctx->planes.p[refPlane].bitDepth > 12 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth above 12" );
+  return VVB_OK;
+}
+
+int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, uint32_t* dCost )
+{
+  if( !ctx || !dBlocks || !dCost ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  int rc = fracGridArgs( ctx, dfunc, orgPlane, refPlane, n, w, h );
+  if( rc || n == 0 ) return rc;
+  CU( cudaSetDevice( ctx->device ) );
+  const FracSmem L = frac_smem( w, h );
+  const int jobs = 7 * ( w / 8 ) * ( h / 8 );
+  const int threads = std::max( 32, std::min( 128, ( jobs + 31 ) & ~31 ) );
+  frac_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, (size_t) L.total * 4, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h,
+                                                                                                  dfunc == VVB_DF_HAD ? 2 : 1, dCost );
+  CHECK_LAUNCH( "frac_grid_kernel" );
+  return VVB_OK;
+}
+
+int vvb_frac_cost_grid( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, uint32_t* cost )
+{
+  if( !ctx || !blocks || !cost ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  int rc = fracGridArgs( ctx, dfunc, orgPlane, refPlane, n, w, h );
+  if( rc || n == 0 ) return rc;
+  void *dB, *dC;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * 49 * 4, &dC ) ) ) return rc;
+  CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_frac_cost_grid_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (uint32_t*) dC ) ) ) return rc;
+  CU( cudaMemcpyAsync( cost, dC, (size_t) n * 49 * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( endCall( ctx ) );
   return VVB_OK;
 }

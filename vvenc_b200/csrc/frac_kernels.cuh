@@ -1,0 +1,198 @@
+// frac_kernels.cuh -- fractional-pel refinement feeding SATD.
+//
+// frac_grid_kernel: for every block and its integer vector, the distortion (SAD or 8x8-tiled SATD) of all 49 quarter-pel offsets (-3..3)^2 -- every
+// position InterSearch::xPatternRefinement (EncoderLib/InterSearch.cpp:760-972) can visit in its half-pel round (+-2) and its quarter-pel round
+// around the best half-pel position (+-1 more).  The filtered blocks are produced as the reference produces them (xPatternRefinement :790-850,
+// xExtDIFUpSamplingH/Q :2912-3040): TWO passes of the 8-tap luma filter for every position, InterpolationFilter::filterHor( frac_x, isLast = false )
+// then filterVer( frac_y, isFirst = false, isLast = true ) (CommonLib/InterpolationFilter.cpp:357-455; phase 0 is filterCopy :258-340, identical to
+// the filter with the single tap 64), 14-bit signed intermediates, clip after the second pass.  reduceTap = 0, no alternative half-pel filter.
+//
+// One CTA per block.  The window (h + 8 rows) is staged once; for each of the 7 horizontal offsets the horizontally filtered rows are computed once
+// (packed as row pairs, IDP.2A) and shared by the 7 vertical offsets; a lane owns one (vertical offset, 8x8 tile): it runs the vertical filter for its
+// tile (IDP.2A on row pairs), forms the 64 differences in registers and either sums |d| or runs the 64-point 2-D Hadamard there (as had8_pattern_kernel).
+#pragma once
+#include "common.cuh"
+
+namespace vvb {
+
+__device__ __constant__ signed char c_lumaQpel[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+
+struct FracSmem { int winPitch, winWords, hWords, orgWords, total; };
+__host__ __device__ inline FracSmem frac_smem( int w, int h )
+{
+  FracSmem m;
+  m.winPitch = w / 2 + 6;                       // w + 8 pels + alignment + one word of slack for the zero-weighted tap
+  m.winWords = ( h + 8 ) * m.winPitch;
+  m.hWords   = 2 * ( ( h + 8 ) / 2 ) * w;       // two buffers of row pairs x w
+  m.orgWords = h * w / 2;
+  m.total    = m.winWords + m.hWords + m.orgWords + 52;
+  return m;
+}
+
+__device__ __forceinline__ int frac_div( int i, float inv ) { return __float2int_rz( ( (float) i + 0.5f ) * inv ); }
+
+#define VVB_FB4( a, b, c_, d ) ( (int)( (uint32_t)( (a) & 255 ) | ( (uint32_t)( (b) & 255 ) << 8 ) | ( (uint32_t)( (c_) & 255 ) << 16 ) | ( (uint32_t)( (d) & 255 ) << 24 ) ) )
+// 8 taps over pel pairs: E = first pel in the low half of w0 (4 IDP.2A), O = first pel in the high half of w0 (5 IDP.2A, zero-weighted ends)
+#define VVB_E8( w0, w1, w2, w3, FA, FB ) __dp2a_hi( (int)(w3), FB, __dp2a_lo( (int)(w2), FB, __dp2a_hi( (int)(w1), FA, __dp2a_lo( (int)(w0), FA, 0 ) ) ) )
+#define VVB_O8( w0, w1, w2, w3, w4, GA, GB, GC ) __dp2a_lo( (int)(w4), GC, __dp2a_hi( (int)(w3), GB, __dp2a_lo( (int)(w2), GB, __dp2a_hi( (int)(w1), GA, __dp2a_lo( (int)(w0), GA, 0 ) ) ) ) )
+
+struct FracTaps { int FA, FB, GA, GB, GC; };
+__device__ __forceinline__ FracTaps frac_taps( int phase )
+{
+  int f[8];
+#pragma unroll
+  for( int t = 0; t < 8; t++ ) f[t] = c_lumaQpel[phase][t];
+  FracTaps T;
+  T.FA = VVB_FB4( f[0], f[1], f[2], f[3] ); T.FB = VVB_FB4( f[4], f[5], f[6], f[7] );
+  T.GA = VVB_FB4( 0, f[0], f[1], f[2] );    T.GB = VVB_FB4( f[3], f[4], f[5], f[6] ); T.GC = VVB_FB4( f[7], 0, 0, 0 );
+  return T;
+}
+
+// family: 1 = SAD, 2 = HAD (8x8 tiles: square blocks 8..64)
+__global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+                                                           const vvb_block* __restrict__ blocks, int n, int w, int h, int family, uint32_t* __restrict__ out )
+{
+  extern __shared__ __align__( 16 ) uint32_t sFrac[];
+  const FracSmem L = frac_smem( w, h );
+  uint32_t* win  = sFrac;
+  uint32_t* hbuf = win + L.winWords;
+  uint32_t* orgS = hbuf + L.hWords;                 // [h][w/2] words, rows 16-byte aligned (w multiple of 8)
+  uint32_t* sOut = orgS + L.orgWords;               // [49]
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int PW = L.winPitch, hw = w >> 1, rowsP = h + 8, tilesX = w >> 3, nTiles = tilesX * ( h >> 3 );
+  const int bd = refPlane.bitDepth, maxv = ( 1 << bd ) - 1;
+  const int headRoom = 14 - bd;                      // bit depths 8..12
+  const int shift1 = 6 - headRoom, offset1 = -( 8192 << shift1 );
+  const int shift2 = 6 + headRoom, offset2 = ( 1 << ( shift2 - 1 ) ) + ( 8192 << 6 );
+  const float invHw = 1.0f / (float) hw, invNt = 1.0f / (float) nTiles, invTx = 1.0f / (float) tilesX;
+
+  for( int b = blockIdx.x; b < n; b += gridDim.x )
+  {
+    const vvb_block blk = blocks[b];
+    // ---- window: rows y+my-4 .. y+my+h+3, pels from the even pel at or below x+mx-4; original block; clear the table
+    const int16_t* src0 = refPlane.origin + (ptrdiff_t)( blk.y + blk.start_y - 4 ) * refPlane.stride + blk.x + blk.start_x - 4;
+    const int o = (int)( ( reinterpret_cast<uintptr_t>( src0 ) >> 1 ) & 1 );
+    const uint32_t* srcW = reinterpret_cast<const uint32_t*>( src0 - o );
+    const int nW = ( w + 8 + o + 1 ) >> 1;
+    const float invNw = 1.0f / (float) nW;
+    const int strideW = refPlane.stride >> 1;
+    __syncthreads();
+    for( int i = tid; i < rowsP * nW; i += T )
+    {
+      const int r = frac_div( i, invNw ), k = i - r * nW;
+      win[r * PW + k] = __ldg( srcW + (ptrdiff_t) r * strideW + k );
+    }
+    {
+      const int16_t* org = orgPlane.origin + (ptrdiff_t) blk.y * orgPlane.stride + blk.x;
+      for( int i = tid; i < h * hw; i += T )
+      {
+        const int y = frac_div( i, invHw ), c = i - y * hw;
+        const int16_t* p = org + (ptrdiff_t) y * orgPlane.stride + 2 * c;
+        orgS[i] = (uint32_t)(uint16_t) __ldg( p ) | ( (uint32_t)(uint16_t) __ldg( p + 1 ) << 16 );
+      }
+    }
+    if( tid < 49 ) sOut[tid] = 0u;
+    __syncthreads();
+    for( int i = 0; i < 7; i++ )
+    {
+      const int qx = i - 3;
+      const int e = ( qx >> 2 ) + 1 + o, eo = e & 1, ew = e >> 1;
+      const FracTaps X = frac_taps( qx & 3 );
+      uint32_t* H = hbuf + ( i & 1 ) * ( L.hWords >> 1 );
+      // ---- horizontal pass (filterHor, isLast = false): item = (row pair, column pair), results packed as row pairs
+      for( int it = tid; it < ( rowsP >> 1 ) * hw; it += T )
+      {
+        const int rp = frac_div( it, invHw ), cp = it - rp * hw;
+        const uint32_t* ra = win + ( 2 * rp ) * PW + cp + ew;
+        const uint32_t* rb = ra + PW;
+        const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], a4 = ra[4], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3], b4 = rb[4];
+        int ha0, ha1, hb0, hb1;
+        if( eo == 0 )
+        {
+          ha0 = VVB_E8( a0, a1, a2, a3, X.FA, X.FB ); ha1 = VVB_O8( a0, a1, a2, a3, a4, X.GA, X.GB, X.GC );
+          hb0 = VVB_E8( b0, b1, b2, b3, X.FA, X.FB ); hb1 = VVB_O8( b0, b1, b2, b3, b4, X.GA, X.GB, X.GC );
+        }
+        else
+        {
+          ha0 = VVB_O8( a0, a1, a2, a3, a4, X.GA, X.GB, X.GC ); ha1 = VVB_E8( a1, a2, a3, a4, X.FA, X.FB );
+          hb0 = VVB_O8( b0, b1, b2, b3, b4, X.GA, X.GB, X.GC ); hb1 = VVB_E8( b1, b2, b3, b4, X.FA, X.FB );
+        }
+        ha0 = ( ha0 + offset1 ) >> shift1; ha1 = ( ha1 + offset1 ) >> shift1; hb0 = ( hb0 + offset1 ) >> shift1; hb1 = ( hb1 + offset1 ) >> shift1;
+        uint2 pk;
+        pk.x = ( (uint32_t) ha0 & 0xffffu ) | ( (uint32_t) hb0 << 16 );
+        pk.y = ( (uint32_t) ha1 & 0xffffu ) | ( (uint32_t) hb1 << 16 );
+        *reinterpret_cast<uint2*>( H + rp * w + 2 * cp ) = pk;
+      }
+      __syncthreads();               // H(i) complete; readers of H(i-1) are past this barrier before H(i+1) is written
+      // ---- vertical pass (filterVer, isFirst = false, isLast = true) + distortion: lane = (vertical offset j, 8x8 tile)
+      for( int job = tid; job < 7 * nTiles; job += T )
+      {
+        const int j = frac_div( job, invNt ), t = job - j * nTiles;
+        const int ty = frac_div( t, invTx ), tx = t - ty * tilesX;
+        const int qy = j - 3;
+        const FracTaps Y = frac_taps( qy & 3 );
+        const int q = ( qy >> 2 ) + 1 + ty * 8;                                 // first filtered row of the tile's first output row
+        const uint32_t* hp = H + ( q >> 1 ) * w + tx * 8;
+        const bool odd = ( q & 1 ) != 0;
+        int d[64];
+#pragma unroll
+        for( int c = 0; c < 8; c++ )
+        {
+          uint32_t P[8];
+#pragma unroll
+          for( int k = 0; k < 8; k++ ) P[k] = hp[k * w + c];
+#pragma unroll
+          for( int m = 0; m < 4; m++ )
+          {
+            int v0, v1;
+            if( !odd ) { v0 = VVB_E8( P[m], P[m + 1], P[m + 2], P[m + 3], Y.FA, Y.FB ); v1 = VVB_O8( P[m], P[m + 1], P[m + 2], P[m + 3], P[m + 4], Y.GA, Y.GB, Y.GC ); }
+            else       { v0 = VVB_O8( P[m], P[m + 1], P[m + 2], P[m + 3], P[m + 4], Y.GA, Y.GB, Y.GC ); v1 = VVB_E8( P[m + 1], P[m + 2], P[m + 3], P[m + 4], Y.FA, Y.FB ); }
+            d[8 * ( 2 * m ) + c]     = max( min( ( v0 + offset2 ) >> shift2, maxv ), 0 );
+            d[8 * ( 2 * m + 1 ) + c] = max( min( ( v1 + offset2 ) >> shift2, maxv ), 0 );
+          }
+        }
+#pragma unroll
+        for( int r = 0; r < 8; r++ )
+        {
+          const uint4 ow = *reinterpret_cast<const uint4*>( orgS + ( ( ty * 8 + r ) * w + tx * 8 ) / 2 );
+          d[8*r+0] = lo16( ow.x ) - d[8*r+0]; d[8*r+1] = hi16( ow.x ) - d[8*r+1];
+          d[8*r+2] = lo16( ow.y ) - d[8*r+2]; d[8*r+3] = hi16( ow.y ) - d[8*r+3];
+          d[8*r+4] = lo16( ow.z ) - d[8*r+4]; d[8*r+5] = hi16( ow.z ) - d[8*r+5];
+          d[8*r+6] = lo16( ow.w ) - d[8*r+6]; d[8*r+7] = hi16( ow.w ) - d[8*r+7];
+        }
+        uint32_t s = 0;
+        if( family == 2 )
+        {
+#pragma unroll
+          for( int bit = 0; bit < 6; bit++ )
+          {
+#pragma unroll
+            for( int k = 0; k < 64; k++ )
+            {
+              if( !( k & ( 1 << bit ) ) ) { const int a = d[k], bb = d[k | ( 1 << bit )]; d[k] = a + bb; d[k | ( 1 << bit )] = a - bb; }
+            }
+          }
+#pragma unroll
+          for( int k = 0; k < 64; k++ ) s = __sad( d[k], 0, s );
+          const uint32_t dc = (uint32_t) abs( d[0] );
+          s = s - dc + ( dc >> 2 );                                  // RdCost.cpp:1316-1318
+          s = ( s + 2 ) >> 2;                                        // :1319
+        }
+        else
+        {
+#pragma unroll
+          for( int k = 0; k < 64; k++ ) s = __sad( d[k], 0, s );
+        }
+        atomicAdd( &sOut[j * 7 + i], s );
+      }
+    }
+    __syncthreads();
+    if( tid < 49 ) out[(size_t) b * 49 + tid] = sOut[tid];
+  }
+}
+
+#undef VVB_FB4
+#undef VVB_E8
+#undef VVB_O8
+
+} // namespace vvb
