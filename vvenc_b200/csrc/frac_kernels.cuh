@@ -91,7 +91,7 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
         orgS[i] = (uint32_t)(uint16_t) __ldg( p ) | ( (uint32_t)(uint16_t) __ldg( p + 1 ) << 16 );
       }
     }
-    if( tid < 49 ) sOut[tid] = 0u;
+    for( int k = tid; k < 49; k += T ) sOut[k] = 0u;
     __syncthreads();
     for( int i = 0; i < 7; i++ )
     {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
       }
     }
     __syncthreads();
-    if( tid < 49 ) out[(size_t) b * 49 + tid] = sOut[tid];
+    for( int k = tid; k < 49; k += T ) out[(size_t) b * 49 + k] = sOut[k];
   }
 }
 
