@@ -530,6 +530,19 @@ def main():
                                          'note': 'fractional candidates: separable 6-tap filtering per candidate (ALU-bound by construction, SURVEY 8d W5)'}
         except Exception as ex:
             extra['mctf_match_16x16'] = {'error': str(ex)}
+        # fractional-pel refinement grid: every 16x16 block of the picture, SATD at all 49 quarter-pel offsets around the best integer vector
+        try:
+            fr = {}
+            for n in (8, 16, 32):
+                nb = len(blocks_np[n])
+                d_ft = torch.empty(nb * 49, dtype=torch.int32, device='cuda')
+                tf_ = time_launch(lambda: chk(lib.vvb_frac_cost_grid_dev(eng.h, V.DF_HAD, 0, 1, P_(d_blocks[n].data_ptr()), nb, n, n, P_(d_ft.data_ptr()))), reps=5)
+                byt = nb * (2 * n * n + 2 * (n + 8) ** 2 + 49 * 4)
+                fr[str(n)] = {'blocks': nb, 'ms': tf_, 'cand_per_s': nb * 49 / (tf_ * 1e-3), 'GBps': byt / (tf_ * 1e-3) / 1e9, 'frac_hbm': byt / (tf_ * 1e-3) / 1e9 / hbm_peak}
+            fr['bytes_formula'] = 'per block: 2 N^2 original + 2 (N+8)^2 window + 196 table; ALU-bound by construction (two 8-tap passes + 8x8 Hadamard per candidate)'
+            extra['frac_satd_grid'] = fr
+        except Exception as ex:
+            extra['frac_satd_grid'] = {'error': str(ex)}
         # MCTF apply stage: the whole 3840x2160 luma picture filtered against 8 neighbour pictures, unit 16 (xFinalizeBlkLine per block)
         try:
             from vvenc_b200 import _lib as VL
