@@ -536,7 +536,7 @@ def main():
             for n in (8, 16, 32):
                 nb = len(blocks_np[n])
                 d_ft = torch.empty(nb * 49, dtype=torch.int32, device='cuda')
-                tf_ = time_launch(lambda: chk(lib.vvb_frac_cost_grid_dev(eng.h, V.DF_HAD, 0, 1, P_(d_blocks[n].data_ptr()), nb, n, n, P_(d_ft.data_ptr()))), reps=5)
+                tf_ = time_launch(lambda: chk(lib.vvb_frac_cost_grid_dev(eng.h, V.DF_HAD, 0, 1, P_(d_blocks[n].data_ptr()), nb, n, n, 2, 0, P_(d_ft.data_ptr()))), reps=5)
                 byt = nb * (2 * n * n + 2 * (n + 8) ** 2 + 49 * 4)
                 fr[str(n)] = {'blocks': nb, 'ms': tf_, 'cand_per_s': nb * 49 / (tf_ * 1e-3), 'GBps': byt / (tf_ * 1e-3) / 1e9, 'frac_hbm': byt / (tf_ * 1e-3) / 1e9 / hbm_peak}
             fr['bytes_formula'] = 'per block: 2 N^2 original + 2 (N+8)^2 window + 196 table; ALU-bound by construction (two 8-tap passes + 8x8 Hadamard per candidate)'

@@ -236,10 +236,11 @@ int vvb_mctf_search_grid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const 
  * the filtered block at every quarter-pel offset (i, j), i, j = -3..3: cost_out[n][j+3][i+3] -- every position InterSearch::xPatternRefinement
  * (InterSearch.cpp:760-972) can visit in its half-pel round and in its quarter-pel round around the best half-pel position.  The filtered blocks are
  * produced exactly as there: InterpolationFilter::filterHor(frac_x, isLast=false) then filterVer(frac_y, isFirst=false, isLast=true) with the 8-tap
- * luma filter (InterpolationFilter.cpp:357-455, reduceTap = 0, no alternative half-pel filter).  The MV rate and the two-round selection
- * (incl. the m_fastSubPel skip tables) replay on the host from the table. */
-int vvb_frac_cost_grid    ( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, uint32_t* cost_out );
-int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, uint32_t* dev_cost_out );
+ * luma filter family of InterpolationFilter.cpp:557-600: reduce_tap = m_meReduceTap (0: 8-tap m_lumaFilter, 1: 6-tap m_lumaFilter4x4, 2: 4-tap
+ * m_chromaFilter[frac<<1], the value every preset sets), alt_hpel = useAltHpelIf (half-pel phase from m_lumaAltHpelIFilter).  The MV rate and the
+ * two-round selection (incl. the m_fastSubPel skip tables) replay on the host from the table. */
+int vvb_frac_cost_grid    ( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, int reduce_tap, int alt_hpel, uint32_t* cost_out );
+int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, int reduce_tap, int alt_hpel, uint32_t* dev_cost_out );
 
 /* ---- MCTF apply stage: the per-block body of MCTF::xFinalizeBlkLine (MCTF.cpp:1437-1483) for the luma plane, fused:
  * per reference picture applyFrac (m_applyFrac, :259-357) at the block's vector, applyPlanarCorrection (:372-420) when rmsme > 0 and

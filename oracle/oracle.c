@@ -751,13 +751,25 @@ void orc_mctf_finalize_block( const Pel* orgPlane, int so, const Pel* const* ref
  * (EncoderLib/InterSearch.cpp:760-972; xExtDIFUpSamplingH/Q :2912,2973) are always produced by TWO passes of the 8-tap luma filter:
  * InterpolationFilter::filterHor(frac_x, isLast = false) then filterVer(frac_y, isFirst = false, isLast = true)
  * (CommonLib/InterpolationFilter.cpp:357-455 filter<N,...>, :258-340 filterCopy for frac 0, which equals the filter with the
- * tap 64).  Quarter-pel phases of m_lumaFilter (:85-104 rows 0, 4, 8, 12); reduceTap = 0, no alternative half-pel filter.
+ * tap 64).  Quarter-pel phases; the filter set follows m_meReduceTap (0: 8-tap m_lumaFilter, 1: 6-tap m_lumaFilter4x4, 2: 4-tap m_chromaFilter[frac<<1],
+ * InterpolationFilter.cpp:557-600) and useAltHpelIf replaces the half-pel phase by m_lumaAltHpelIFilter.
  * ---------------------------------------------------------------------------------------------------- */
-static const int8_t luma_qpel[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+/* quarter-pel phases as 8-tap rows over pels x-3 .. x+4: [reduceTap][phase][tap]
+ *   0: m_lumaFilter rows 0,4,8,12 (8 taps)   1: m_lumaFilter4x4 rows 4,8,12 used as 6 taps (:64-83, filter<6> skips entry 0)
+ *   2: m_chromaFilter rows 8,16,24 (4 taps over x-1 .. x+2, :107-142; what every preset's ReduceFilterME = 2 selects)
+ * alt: m_lumaAltHpelIFilter as 6 taps (:106), replaces the half-pel phase when useAltHpelIf */
+static const int8_t luma_qpel_sets[3][4][8] = {
+  { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } },
+  { { 0, 0, 0, 64, 0, 0, 0, 0 }, {  0, 3, -10, 58, 17, -5, 1, 0 }, {  0, 3, -11, 40, 40, -11, 3,  0 }, { 0, 1, -5, 17, 58, -10, 3,  0 } },
+  { { 0, 0, 0, 64, 0, 0, 0, 0 }, {  0, 0,  -4, 54, 16, -2, 0, 0 }, {  0, 0,  -4, 36, 36,  -4, 0,  0 }, { 0, 0, -2, 16, 54,  -4, 0,  0 } } };
+static const int8_t luma_alt_hpel[8] = { 0, 3, 9, 20, 20, 9, 3, 0 };
+static const int8_t* qpel_taps( int reduceTap, int altHpel, int phase ) { return ( altHpel && phase == 2 ) ? luma_alt_hpel : luma_qpel_sets[reduceTap][phase]; }
 
 /* src points at the integer position of the block; fx, fy in quarter pels (0..3) */
-void orc_if_two_pass( const Pel* src, int ss, int w, int h, int fx, int fy, int bitDepth, Pel* dst, int ds )
+void orc_if_two_pass( const Pel* src, int ss, int w, int h, int fx, int fy, int bitDepth, int reduceTap, int altHpel, Pel* dst, int ds )
 {
+  const int8_t* cx = qpel_taps( reduceTap, altHpel, fx );
+  const int8_t* cy = qpel_taps( reduceTap, altHpel, fy );
   const int headRoom = 14 - bitDepth > 2 ? 14 - bitDepth : 2;
   const int shift1 = 6 - headRoom, offset1 = -( 8192 << shift1 );
   const int shift2 = 6 + headRoom, offset2 = ( 1 << ( shift2 - 1 ) ) + ( 8192 << 6 );
@@ -768,14 +780,14 @@ void orc_if_two_pass( const Pel* src, int ss, int w, int h, int fx, int fy, int 
     {
       const Pel* p = src + ( r - 3 ) * ss + x - 3;
       int sum = 0;
-      for( int t = 0; t < 8; t++ ) sum += luma_qpel[fx][t] * p[t];
+      for( int t = 0; t < 8; t++ ) sum += cx[t] * p[t];
       tmp[r * w + x] = (int16_t)( ( sum + offset1 ) >> shift1 );
     }
   for( int y = 0; y < h; y++ )
     for( int x = 0; x < w; x++ )
     {
       int sum = 0;
-      for( int t = 0; t < 8; t++ ) sum += luma_qpel[fy][t] * tmp[( y + t ) * w + x];
+      for( int t = 0; t < 8; t++ ) sum += cy[t] * tmp[( y + t ) * w + x];
       const int v = ( sum + offset2 ) >> shift2;
       dst[y * ds + x] = (Pel)( v < 0 ? 0 : ( v > maxv ? maxv : v ) );
     }
@@ -784,7 +796,7 @@ void orc_if_two_pass( const Pel* src, int ss, int w, int h, int fx, int fy, int 
 
 /* Distortion table of all quarter-pel offsets (i, j) in -3..3 around the integer vector: out[b][j+3][i+3].
  * blk[b] = { x, y, w, h, mvx, mvy } (integer pel vector); family 1 = SAD, 2 = HAD (xGetHADs). */
-void orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, uint32_t* out )
+void orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel, uint32_t* out )
 {
   Pel* pred = (Pel*) malloc( sizeof( Pel ) * 64 * 64 );
   for( int b = 0; b < n; b++ )
@@ -796,7 +808,7 @@ void orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int s
       for( int i = -3; i <= 3; i++ )
       {
         const Pel* src = refPlane + (ptrdiff_t)( d[1] + d[5] + ( j >> 2 ) ) * sr + d[0] + d[4] + ( i >> 2 );
-        orc_if_two_pass( src, sr, w, h, i & 3, j & 3, bitDepth, pred, w );
+        orc_if_two_pass( src, sr, w, h, i & 3, j & 3, bitDepth, reduceTap, altHpel, pred, w );
         out[( (size_t) b * 7 + ( j + 3 ) ) * 7 + ( i + 3 )] = (uint32_t) orc_dist( family, org, so, pred, w, w, h, 0 );
       }
   }

@@ -798,7 +798,7 @@ void refshim_mctf_finalize_block( int opt, const int16_t* orgPlane, int orgStrid
 // Fractional-pel refinement: the two filter calls behind every filtered block of InterSearch::xPatternRefinement / xExtDIFUpSamplingH/Q
 // (InterSearch.cpp:790-850, 2912-3040): filterHor( frac_x, isLast = false ) over h + 7 rows, then filterVer( frac_y, isFirst = false, isLast = true ).
 // src points at the integer position of the block; fx, fy in quarter pels.
-void refshim_if_two_pass( int opt, const int16_t* src, int srcStride, int w, int h, int fx, int fy, int bitDepth, int16_t* dst, int dstStride )
+void refshim_if_two_pass( int opt, const int16_t* src, int srcStride, int w, int h, int fx, int fy, int bitDepth, int reduceTap, int altHpel, int16_t* dst, int dstStride )
 {
   static InterpolationFilter* ifs[2] = { nullptr, nullptr };
   {
@@ -812,13 +812,13 @@ void refshim_if_two_pass( int opt, const int16_t* src, int srcStride, int w, int
   Pel* tmp = (Pel*)( ( (uintptr_t) tmpStore.data() + 63 ) & ~uintptr_t( 63 ) );
   std::vector<Pel> outStore( (size_t) h * ts + 64 );
   Pel* outp = (Pel*)( ( (uintptr_t) outStore.data() + 63 ) & ~uintptr_t( 63 ) );
-  f.filterHor( COMP_Y, src - 3 * srcStride, srcStride, tmp, ts, w, h + 7, fx << 2, false, CHROMA_400, rng, false, 0, 0 );
-  f.filterVer( COMP_Y, tmp + 3 * ts, ts, outp, ts, w, h, fy << 2, false, true, CHROMA_400, rng, false, 0, 0 );
+  f.filterHor( COMP_Y, src - 3 * srcStride, srcStride, tmp, ts, w, h + 7, fx << 2, false, CHROMA_400, rng, altHpel != 0, 0, reduceTap );
+  f.filterVer( COMP_Y, tmp + 3 * ts, ts, outp, ts, w, h, fy << 2, false, true, CHROMA_400, rng, altHpel != 0, 0, reduceTap );
   for( int y = 0; y < h; y++ ) memcpy( dst + (ptrdiff_t) y * dstStride, outp + (ptrdiff_t) y * ts, sizeof( Pel ) * w );
 }
 
 // blk[b] = { x, y, w, h, mvx, mvy } ; out[b][j+3][i+3] = distFunc( org, filtered block at quarter-pel offset (i, j) ), family 1 SAD / 2 HAD
-void refshim_frac_cost_grid( int opt, const int16_t* orgPlane, int so, const int16_t* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, uint32_t* out )
+void refshim_frac_cost_grid( int opt, const int16_t* orgPlane, int so, const int16_t* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel, uint32_t* out )
 {
   RefCtx& c = ctx();
   RdCost& rc = c.rd( opt );
@@ -832,7 +832,7 @@ void refshim_frac_cost_grid( int opt, const int16_t* orgPlane, int so, const int
       for( int i = -3; i <= 3; i++ )
       {
         const int16_t* src = refPlane + (ptrdiff_t)( d[1] + d[5] + ( j >> 2 ) ) * sr + d[0] + d[4] + ( i >> 2 );
-        refshim_if_two_pass( opt, src, sr, w, h, i & 3, j & 3, bitDepth, pred.p, w );
+        refshim_if_two_pass( opt, src, sr, w, h, i & 3, j & 3, bitDepth, reduceTap, altHpel, pred.p, w );
         out[( (size_t) b * 7 + ( j + 3 ) ) * 7 + ( i + 3 )] = (uint32_t) callDist( rc, family, org.p, w, pred.p, w, w, h, bitDepth, 0 );
       }
   }

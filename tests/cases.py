@@ -293,3 +293,8 @@ def frac_case(seed=4242, W=160, H=96, margin=24, bit_depth=10):
 
 
 FRAC_CASES = ((4242, 10), (4243, 10), (4244, 8))
+
+
+def frac_filter_of(list_index):
+    """(reduce_tap, alt_hpel) used for block list `list_index` of a frac_case: cycles through the filter sets (ReduceFilterME 2 first: what the presets use)"""
+    return ((2, 0), (2, 0), (0, 0), (1, 0), (2, 1), (0, 1), (2, 0), (1, 1), (0, 0), (2, 0))[list_index % 10]

@@ -16,11 +16,12 @@ def main():
         case = C.frac_case(seed, bit_depth=bd)
         S = case['stride']; base = case['margin'] * S + case['margin']
         for li, (fam, w, h, b) in enumerate(case['lists']):
+            rt, alt = C.frac_filter_of(li)
             res = []
             for opt, simd in ((0, b'SCALAR'), (1, b'AVX2')):
                 R.refshim_set_simd(simd)
                 t = np.zeros((len(b), 7, 7), dtype=np.uint32)
-                R.refshim_frac_cost_grid(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), len(b), fam, bd, P(t))
+                R.refshim_frac_cost_grid(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), len(b), fam, bd, rt, alt, P(t))
                 res.append(t)
             assert np.array_equal(res[0], res[1]), ('scalar != AVX2', seed, fam, w, h)
             out['c%d_l%d' % (ci, li)] = res[1]

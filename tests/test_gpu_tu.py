@@ -167,7 +167,8 @@ def test_gpu_frac_cost_grid_golden(gpu, golden_frac):
         for li, (fam, w, h, b) in enumerate(case['lists']):
             blk = np.zeros(len(b), dtype=gpu.V.BLOCK_DT)
             blk['x'] = b[:, 0]; blk['y'] = b[:, 1]; blk['start_x'] = b[:, 4]; blk['start_y'] = b[:, 5]
-            got = gpu.eng.frac_cost_grid(gpu.V.DF_SAD if fam == 1 else gpu.V.DF_HAD, 0, 1, blk, w, h)
+            rt, alt = C.frac_filter_of(li)
+            got = gpu.eng.frac_cost_grid(gpu.V.DF_SAD if fam == 1 else gpu.V.DF_HAD, 0, 1, blk, w, h, rt, alt)
             exp = golden_frac['c%d_l%d' % (ci, li)]
             assert np.array_equal(got, exp), (seed, fam, w, h, np.argwhere(got != exp)[:5], got[got != exp][:4], exp[got != exp][:4])
 
@@ -184,7 +185,7 @@ def test_gpu_frac_grid_centre_equals_integer_distortion(gpu):
     blk = np.zeros(xs.size, dtype=gpu.V.BLOCK_DT)
     blk['x'] = xs.ravel(); blk['y'] = ys.ravel(); blk['start_x'] = rs.randint(-3, 4, size=xs.size); blk['start_y'] = rs.randint(-3, 4, size=xs.size)
     blk['left'] = -8; blk['right'] = 8; blk['top'] = -8; blk['bottom'] = 8
-    t = gpu.eng.frac_cost_grid(gpu.V.DF_HAD, 0, 1, blk, 16, 16)
+    t = gpu.eng.frac_cost_grid(gpu.V.DF_HAD, 0, 1, blk, 16, 16, 2, False)
     pat = np.zeros(1, dtype=gpu.V.MV_DT)
     cost, _ = gpu.eng.cost_pattern(gpu.V.DF_HAD, 0, 1, blk, 16, 16, pat, gpu.eng.me_par(0.0), want_best=False)
     assert np.array_equal(t[:, 3, 3], cost[:, 0])

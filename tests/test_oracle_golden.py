@@ -79,5 +79,6 @@ def test_oracle_frac_grid_golden(golden_frac):
         S = case['stride']; base = case['margin'] * S + case['margin']
         for li, (fam, w, h, b) in enumerate(case['lists']):
             t = np.zeros((len(b), 7, 7), dtype=np.uint32)
-            O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), len(b), fam, bd, P(t))
+            rt, alt = C.frac_filter_of(li)
+            O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), len(b), fam, bd, rt, alt, P(t))
             assert np.array_equal(t, golden_frac['c%d_l%d' % (ci, li)]), (seed, fam, w, h)

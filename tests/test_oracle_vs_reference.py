@@ -180,7 +180,8 @@ def test_mctf_calc_var(opt):
 
 @pytest.mark.parametrize("opt", [0, 1])
 def test_two_pass_interpolation(opt):
-    """filterHor(isLast=false) + filterVer(isFirst=false, isLast=true), every quarter-pel phase pair, 8 and 10 bit, extreme content included"""
+    """filterHor(isLast=false) + filterVer(isFirst=false, isLast=true), every quarter-pel phase pair, the 8/6/4-tap ME filter sets and the
+    alternative half-pel filter, 8 and 10 bit, extreme content included"""
     from _libs import oracle, refshim, P, PO
     O = oracle(); R = refshim()
     R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
@@ -192,9 +193,10 @@ def test_two_pass_interpolation(opt):
             src = rs.randint(0, mx + 1, size=(h + 24, S)).astype(np.int16)
             if (w, h) == (8, 8):
                 src[:] = np.where(rs.randint(0, 2, size=src.shape) > 0, mx, 0)
-            for fx in range(4):
-                for fy in range(4):
-                    d1 = np.zeros((h, w), np.int16); d2 = np.zeros((h, w), np.int16)
-                    O.orc_if_two_pass(PO(src, 8 * S + 12), S, w, h, fx, fy, bd, P(d1), w)
-                    R.refshim_if_two_pass(opt, PO(src, 8 * S + 12), S, w, h, fx, fy, bd, P(d2), w)
-                    assert np.array_equal(d1, d2), (bd, w, h, fx, fy)
+            for (rt, alt) in ((0, 0), (1, 0), (2, 0), (0, 1), (2, 1)):
+                for fx in range(4):
+                    for fy in range(4):
+                        d1 = np.zeros((h, w), np.int16); d2 = np.zeros((h, w), np.int16)
+                        O.orc_if_two_pass(PO(src, 8 * S + 12), S, w, h, fx, fy, bd, rt, alt, P(d1), w)
+                        R.refshim_if_two_pass(opt, PO(src, 8 * S + 12), S, w, h, fx, fy, bd, rt, alt, P(d2), w)
+                        assert np.array_equal(d1, d2), (bd, w, h, rt, alt, fx, fy)

@@ -90,8 +90,8 @@ SYMBOLS = {
     'vvb_mctf_error_batch': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     'vvb_mctf_search_grid': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p]),
     'vvb_mctf_search_grid_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p]),
-    'vvb_frac_cost_grid': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p]),
-    'vvb_frac_cost_grid_dev': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p]),
+    'vvb_frac_cost_grid': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    'vvb_frac_cost_grid_dev': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     'vvb_mctf_apply': (c_i, [c_p, c_i, ctypes.POINTER(vvb_mctf_apply_par), c_p, c_p, c_i]),
     'vvb_mctf_apply_dev': (c_i, [c_p, c_i, ctypes.POINTER(vvb_mctf_apply_par), c_p, c_p, c_i]),
     'vvb_mctf_calc_var': (c_i, [c_p, c_i, c_p, c_i, c_p]),

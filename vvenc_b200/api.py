@@ -212,12 +212,12 @@ class CostEngine:
         self._chk(self.lib.vvb_fwd_trquant_planes(self.h, ctypes.byref(par), org_plane, pred_plane, _p(blocks), n, _p(coef), _p(q), _p(s), _p(lp), _p(nr)))
         return dict(coef=coef, q=q, abs_sum=s, last_pos=lp, need_rdoq=nr)
 
-    def frac_cost_grid(self, dfunc, org_plane, ref_plane, blocks, w, h):
+    def frac_cost_grid(self, dfunc, org_plane, ref_plane, blocks, w, h, reduce_tap=2, alt_hpel=False):
         """distortion of the filtered block at every quarter-pel offset (-3..3)^2 around each block's integer vector (start_x, start_y):
         uint32 [n][7 (dy)][7 (dx)] -- the positions of InterSearch::xPatternRefinement"""
         blocks = np.ascontiguousarray(blocks, dtype=L.BLOCK_DT)
         out = np.zeros((len(blocks), 7, 7), dtype=np.uint32)
-        self._chk(self.lib.vvb_frac_cost_grid(self.h, dfunc, org_plane, ref_plane, _p(blocks), len(blocks), w, h, _p(out)))
+        self._chk(self.lib.vvb_frac_cost_grid(self.h, dfunc, org_plane, ref_plane, _p(blocks), len(blocks), w, h, int(reduce_tap), int(alt_hpel), _p(out)))
         return out
 
     # ---- inverse path / fused TU round trip

@@ -1136,22 +1136,25 @@ static int fracGridArgs( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, in
   return VVB_OK;
 }
 
-int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, uint32_t* dCost )
+int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, int reduceTap, int altHpel, uint32_t* dCost )
 {
   if( !ctx || !dBlocks || !dCost ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   int rc = fracGridArgs( ctx, dfunc, orgPlane, refPlane, n, w, h );
-  if( rc || n == 0 ) return rc;
+  if( rc ) return rc;
+  if( reduceTap < 0 || reduceTap > 2 ) return fail( ctx, VVB_ERR_ARG, "reduce_tap is 0, 1 or 2 (ReduceFilterME, vvencCfg.cpp:2058)" );
+  if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   const FracSmem L = frac_smem( w, h );
+  const FracFilter flt = frac_filter( reduceTap, altHpel );
   const int jobs = 7 * ( w / 8 ) * ( h / 8 );
   const int threads = std::max( 32, std::min( 128, ( jobs + 31 ) & ~31 ) );
   frac_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, (size_t) L.total * 4, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h,
-                                                                                                  dfunc == VVB_DF_HAD ? 2 : 1, dCost );
+                                                                                                  dfunc == VVB_DF_HAD ? 2 : 1, flt, dCost );
   CHECK_LAUNCH( "frac_grid_kernel" );
   return VVB_OK;
 }
 
-int vvb_frac_cost_grid( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, uint32_t* cost )
+int vvb_frac_cost_grid( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, int reduceTap, int altHpel, uint32_t* cost )
 {
   if( !ctx || !blocks || !cost ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   int rc = fracGridArgs( ctx, dfunc, orgPlane, refPlane, n, w, h );
@@ -1159,7 +1162,7 @@ int vvb_frac_cost_grid( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, con
   void *dB, *dC;
   if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 1, (size_t) n * 49 * 4, &dC ) ) ) return rc;
   CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
-  if( ( rc = vvb_frac_cost_grid_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, (uint32_t*) dC ) ) ) return rc;
+  if( ( rc = vvb_frac_cost_grid_dev( ctx, dfunc, orgPlane, refPlane, (const vvb_block*) dB, n, w, h, reduceTap, altHpel, (uint32_t*) dC ) ) ) return rc;
   CU( cudaMemcpyAsync( cost, dC, (size_t) n * 49 * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( endCall( ctx ) );
   return VVB_OK;

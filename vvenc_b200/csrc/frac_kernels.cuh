@@ -5,7 +5,7 @@
 // around the best half-pel position (+-1 more).  The filtered blocks are produced as the reference produces them (xPatternRefinement :790-850,
 // xExtDIFUpSamplingH/Q :2912-3040): TWO passes of the 8-tap luma filter for every position, InterpolationFilter::filterHor( frac_x, isLast = false )
 // then filterVer( frac_y, isFirst = false, isLast = true ) (CommonLib/InterpolationFilter.cpp:357-455; phase 0 is filterCopy :258-340, identical to
-// the filter with the single tap 64), 14-bit signed intermediates, clip after the second pass.  reduceTap = 0, no alternative half-pel filter.
+// the filter with the single tap 64), 14-bit signed intermediates, clip after the second pass.  The filter set follows m_meReduceTap / useAltHpelIf.
 //
 // One CTA per block.  The window (h + 8 rows) is staged once; for each of the 7 horizontal offsets the horizontally filtered rows are computed once
 // (packed as row pairs, IDP.2A) and shared by the 7 vertical offsets; a lane owns one (vertical offset, 8x8 tile): it runs the vertical filter for its
@@ -15,7 +15,21 @@
 
 namespace vvb {
 
-__device__ __constant__ signed char c_lumaQpel[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+// Quarter-pel phases as 8-tap rows over pels x-3 .. x+4, chosen by the host (frac_filter): m_meReduceTap 0 -> m_lumaFilter rows 0,4,8,12;
+// 1 -> m_lumaFilter4x4 rows as 6 taps; 2 -> m_chromaFilter rows 8,16,24 as 4 taps (InterpolationFilter.cpp:64-142, 557-600; every preset's
+// ReduceFilterME = 2); useAltHpelIf replaces the half-pel phase by m_lumaAltHpelIFilter.  Shorter filters are zero-padded: same pels, same sums.
+struct FracFilter { signed char c[4][8]; };
+static inline FracFilter frac_filter( int reduceTap, int altHpel )
+{
+  static const signed char sets[3][4][8] = {
+    { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } },
+    { { 0, 0, 0, 64, 0, 0, 0, 0 }, {  0, 3, -10, 58, 17, -5, 1, 0 }, {  0, 3, -11, 40, 40, -11, 3,  0 }, { 0, 1, -5, 17, 58, -10, 3,  0 } },
+    { { 0, 0, 0, 64, 0, 0, 0, 0 }, {  0, 0,  -4, 54, 16, -2, 0, 0 }, {  0, 0,  -4, 36, 36,  -4, 0,  0 }, { 0, 0, -2, 16, 54,  -4, 0,  0 } } };
+  static const signed char alt[8] = { 0, 3, 9, 20, 20, 9, 3, 0 };
+  FracFilter f;
+  for( int p = 0; p < 4; p++ ) for( int t = 0; t < 8; t++ ) f.c[p][t] = ( altHpel && p == 2 ) ? alt[t] : sets[reduceTap][p][t];
+  return f;
+}
 
 struct FracSmem { int winPitch, winWords, hWords, orgWords, total; };
 __host__ __device__ inline FracSmem frac_smem( int w, int h )
@@ -37,11 +51,11 @@ __device__ __forceinline__ int frac_div( int i, float inv ) { return __float2int
 #define VVB_O8( w0, w1, w2, w3, w4, GA, GB, GC ) __dp2a_lo( (int)(w4), GC, __dp2a_hi( (int)(w3), GB, __dp2a_lo( (int)(w2), GB, __dp2a_hi( (int)(w1), GA, __dp2a_lo( (int)(w0), GA, 0 ) ) ) ) )
 
 struct FracTaps { int FA, FB, GA, GB, GC; };
-__device__ __forceinline__ FracTaps frac_taps( int phase )
+__device__ __forceinline__ FracTaps frac_taps( const FracFilter& flt, int phase )
 {
   int f[8];
 #pragma unroll
-  for( int t = 0; t < 8; t++ ) f[t] = c_lumaQpel[phase][t];
+  for( int t = 0; t < 8; t++ ) f[t] = flt.c[phase][t];
   FracTaps T;
   T.FA = VVB_FB4( f[0], f[1], f[2], f[3] ); T.FB = VVB_FB4( f[4], f[5], f[6], f[7] );
   T.GA = VVB_FB4( 0, f[0], f[1], f[2] );    T.GB = VVB_FB4( f[3], f[4], f[5], f[6] ); T.GC = VVB_FB4( f[7], 0, 0, 0 );
@@ -50,7 +64,8 @@ __device__ __forceinline__ FracTaps frac_taps( int phase )
 
 // family: 1 = SAD, 2 = HAD (8x8 tiles: square blocks 8..64)
 __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
-                                                           const vvb_block* __restrict__ blocks, int n, int w, int h, int family, uint32_t* __restrict__ out )
+                                                           const vvb_block* __restrict__ blocks, int n, int w, int h, int family, const __grid_constant__ FracFilter flt,
+                                                           uint32_t* __restrict__ out )
 {
   extern __shared__ __align__( 16 ) uint32_t sFrac[];
   const FracSmem L = frac_smem( w, h );
@@ -97,7 +112,7 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
     {
       const int qx = i - 3;
       const int e = ( qx >> 2 ) + 1 + o, eo = e & 1, ew = e >> 1;
-      const FracTaps X = frac_taps( qx & 3 );
+      const FracTaps X = frac_taps( flt, qx & 3 );
       uint32_t* H = hbuf + ( i & 1 ) * ( L.hWords >> 1 );
       // ---- horizontal pass (filterHor, isLast = false): item = (row pair, column pair), results packed as row pairs
       for( int it = tid; it < ( rowsP >> 1 ) * hw; it += T )
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
         const int j = frac_div( job, invNt ), t = job - j * nTiles;
         const int ty = frac_div( t, invTx ), tx = t - ty * tilesX;
         const int qy = j - 3;
-        const FracTaps Y = frac_taps( qy & 3 );
+        const FracTaps Y = frac_taps( flt, qy & 3 );
         const int q = ( qy >> 2 ) + 1 + ty * 8;                                 // first filtered row of the tile's first output row
         const uint32_t* hp = H + ( q >> 1 ) * w + tx * 8;
         const bool odd = ( q & 1 ) != 0;
