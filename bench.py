@@ -649,17 +649,12 @@ def main():
             # worker c takes the steps first+c, first+c+NCTX, ... and runs each of them upload -> search -> wait for the vectors -> refinement + TU coding ->
             # wait for the downloads; the GPU overlaps one worker's copies with the other workers' kernels
             errs = []
-            skip = os.environ.get('VVB_E2E_SKIP', '')          # diagnostic switches only (upload / tail); the reported e2e never sets them
             def worker(c):
                 try:
                     pc = time.perf_counter
                     for i in range(first + c, first + count, NCTX):
-                        t = pc()
-                        if 'upload' not in skip or i < NCTX: e2e_upload(i)
-                        e2e_search(i); host_ms['upload_search_enqueue'] += pc() - t
-                        t = pc()
-                        if 'tail' not in skip: e2e_tail(i)
-                        host_ms['wait_vectors_and_tail_enqueue'] += pc() - t
+                        t = pc(); e2e_upload(i); e2e_search(i); host_ms['upload_search_enqueue'] += pc() - t
+                        t = pc(); e2e_tail(i); host_ms['wait_vectors_and_tail_enqueue'] += pc() - t
                         t = pc(); chk(lib.vvb_synchronize(engs[i % NCTX].h)); host_ms['wait_downloads'] += pc() - t
                 except Exception as ex:
                     errs.append(ex)

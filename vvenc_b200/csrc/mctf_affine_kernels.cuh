@@ -18,74 +18,10 @@ __device__ __constant__ short c_mctfF4[16][4] = {
   {-4,36,36,-4},{-4,30,42,-4},{-4,28,46,-6},{-2,20,52,-6},{-2,16,54,-4},{-2,14,56,-4},{-2,10,58,-2},{0,4,62,-2} };
 
 #define MCTF_WARPS 4
-#define MCTF_TMP_PITCH 64
-
-// one warp per candidate; int32 error exactly as the reference (no early exit: besterror = INT_MAX, vvenc_unit_test.cpp:1552)
-__global__ void __launch_bounds__( MCTF_WARPS * 32 ) mctf_error_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
-                                                                        const vvb_mctf_cand* __restrict__ cands, int n, int tap4, int32_t* __restrict__ out )
-{
-  __shared__ short sTmp[MCTF_WARPS][( 64 + 6 ) * MCTF_TMP_PITCH];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warpsPerGrid = gridDim.x * MCTF_WARPS;
-  const int maxv = ( 1 << refPlane.bitDepth ) - 1;
-  for( int ci = blockIdx.x * MCTF_WARPS + warp; ci < n; ci += warpsPerGrid )
-  {
-    const vvb_mctf_cand c = cands[ci];
-    const int w = c.w, h = c.h;
-    int dx = c.mvx, dy = c.mvy;
-    const int fx = dx & 15, fy = dy & 15;
-    const int16_t* org = orgPlane.origin + (ptrdiff_t) c.y * orgPlane.stride + c.x;
-    int err = 0;
-    if( ( fx | fy ) == 0 )
-    {
-      dx /= 16; dy /= 16;                                  // MCTF.cpp:1121-1122 (C division, truncating)
-      const int16_t* buf = refPlane.origin + (ptrdiff_t)( c.y + dy ) * refPlane.stride + c.x + dx;
-      for( int i = lane; i < w * h; i += 32 )
-      {
-        const int y = i / w, x = i - y * w;
-        const int d = (int) __ldg( org + (ptrdiff_t) y * orgPlane.stride + x ) - (int) __ldg( buf + (ptrdiff_t) y * refPlane.stride + x );
-        err += d * d;
-      }
-    }
-    else
-    {
-      dx >>= 4; dy >>= 4;                                  // MCTF.cpp:1136-1137 / :1151-1152 (arithmetic shift)
-      const int16_t* buf = refPlane.origin + (ptrdiff_t)( c.y + dy ) * refPlane.stride + c.x + dx;
-      const int taps = tap4 ? 4 : 6, first = tap4 ? 0 : 1, back = tap4 ? 1 : 2;
-      const short* xf = tap4 ? c_mctfF4[fx] : c_mctfF8[fx];
-      const short* yf = tap4 ? c_mctfF4[fy] : c_mctfF8[fy];
-      short* tmp = sTmp[warp];
-      const int rows = h + taps - 1;
-      __syncwarp();
-      for( int i = lane; i < rows * w; i += 32 )
-      {
-        const int r = i / w, x = i - r * w;
-        const int16_t* p = buf + (ptrdiff_t)( r - back ) * refPlane.stride + x - back;
-        int sum = 0;
-        for( int t = 0; t < taps; t++ ) sum += xf[first + t] * (int) __ldg( p + t );
-        sum = ( sum + 32 ) >> 6;
-        tmp[r * MCTF_TMP_PITCH + x] = (short) min( max( sum, 0 ), maxv );
-      }
-      __syncwarp();
-      for( int i = lane; i < w * h; i += 32 )
-      {
-        const int y = i / w, x = i - y * w;
-        int sum = 0;
-        for( int t = 0; t < taps; t++ ) sum += yf[first + t] * (int) tmp[( y + t ) * MCTF_TMP_PITCH + x];
-        sum = ( sum + 32 ) >> 6;
-        sum = min( max( sum, 0 ), maxv );
-        const int d = sum - (int) __ldg( org + (ptrdiff_t) y * orgPlane.stride + x );
-        err += d * d;
-      }
-    }
-#pragma unroll
-    for( int m = 16; m > 0; m >>= 1 ) err += __shfl_xor_sync( 0xffffffffu, err, m );
-    if( lane == 0 ) out[ci] = err;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// Packed version: one warp per candidate, the source region and the horizontally filtered rows live in the warp's slice of shared
+// mctf_error_packed_kernel: one warp per candidate (int32 error exactly as the reference, no early exit: besterror = INT_MAX as in
+// vvenc_unit_test.cpp:1552); the source region and the horizontally filtered rows live in the warp's slice of shared
 // memory, both filter passes run on IDP.2A.  Pel pairs are packed along x for the horizontal pass and along y (row pairs) for the
 // vertical pass; a 6-tap output whose first pel sits in the low half of a word takes 3 IDP.2A ("E"), one that starts in the high half
 // takes 4 with zero-padded taps ("O").  The 4-tap filters are embedded as (0, t0, t1, t2, t3, 0): same pels, same sums.
