@@ -235,6 +235,7 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
   cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( frac_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1146,7 +1147,7 @@ int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane,
   CU( cudaSetDevice( ctx->device ) );
   const FracSmem L = frac_smem( w, h );
   const FracFilter flt = frac_filter( reduceTap, altHpel );
-  const int jobs = 7 * ( w / 8 ) * ( h / 8 );
+  const int jobs = L.G * 7 * ( w / 8 ) * ( h / 8 );                                   // (horizontal offsets per pass) x vertical offsets x tiles
   const int threads = std::max( 32, std::min( 128, ( jobs + 31 ) & ~31 ) );
   frac_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, (size_t) L.total * 4, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h,
                                                                                                   dfunc == VVB_DF_HAD ? 2 : 1, flt, dCost );

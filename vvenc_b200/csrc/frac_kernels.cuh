@@ -7,8 +7,8 @@
 // then filterVer( frac_y, isFirst = false, isLast = true ) (CommonLib/InterpolationFilter.cpp:357-455; phase 0 is filterCopy :258-340, identical to
 // the filter with the single tap 64), 14-bit signed intermediates, clip after the second pass.  The filter set follows m_meReduceTap / useAltHpelIf.
 //
-// One CTA per block.  The window (h + 8 rows) is staged once; for each of the 7 horizontal offsets the horizontally filtered rows are computed once
-// (packed as row pairs, IDP.2A) and shared by the 7 vertical offsets; a lane owns one (vertical offset, 8x8 tile): it runs the vertical filter for its
+// One CTA per block.  The window (h + 8 rows) is staged once; the horizontally filtered rows of up to 7 horizontal offsets at a time (as many as fit
+// 40 KB of shared memory) are computed once (packed as row pairs, IDP.2A) and shared by the 7 vertical offsets; a lane owns one (vertical offset, 8x8 tile): it runs the vertical filter for its
 // tile (IDP.2A on row pairs), forms the 64 differences in registers and either sums |d| or runs the 64-point 2-D Hadamard there (as had8_pattern_kernel).
 #pragma once
 #include "common.cuh"
@@ -31,15 +31,17 @@ static inline FracFilter frac_filter( int reduceTap, int altHpel )
   return f;
 }
 
-struct FracSmem { int winPitch, winWords, hWords, orgWords, total; };
+struct FracSmem { int winPitch, winWords, colWords, G, hWords, orgWords, total; };
 __host__ __device__ inline FracSmem frac_smem( int w, int h )
 {
   FracSmem m;
   m.winPitch = w / 2 + 6;                       // w + 8 pels + alignment + one word of slack for the zero-weighted tap
   m.winWords = ( h + 8 ) * m.winPitch;
-  m.hWords   = 2 * ( ( h + 8 ) / 2 ) * w;       // two buffers of row pairs x w
+  m.colWords = ( ( h + 8 ) / 2 ) * w;           // horizontally filtered rows of one horizontal offset: row pairs x w
+  m.G        = 10240 / m.colWords < 1 ? 1 : ( 10240 / m.colWords > 7 ? 7 : 10240 / m.colWords );   // offsets per pass: up to 40 KB of filtered rows
+  m.hWords   = m.G * m.colWords;
   m.orgWords = h * w / 2;
-  m.total    = m.winWords + m.hWords + m.orgWords + 52;
+  m.total    = m.winWords + m.hWords + m.orgWords + 52 + 40;     // + table + packed taps of the 4 phases
   return m;
 }
 
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
   uint32_t* hbuf = win + L.winWords;
   uint32_t* orgS = hbuf + L.hWords;                 // [h][w/2] words, rows 16-byte aligned (w multiple of 8)
   uint32_t* sOut = orgS + L.orgWords;               // [49]
+  FracTaps* sTaps = reinterpret_cast<FracTaps*>( sOut + 52 );   // packed taps of the 4 phases (same for both passes)
   const int tid = threadIdx.x, T = blockDim.x;
   const int PW = L.winPitch, hw = w >> 1, rowsP = h + 8, tilesX = w >> 3, nTiles = tilesX * ( h >> 3 );
   const int bd = refPlane.bitDepth, maxv = ( 1 << bd ) - 1;
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
   const int shift1 = 6 - headRoom, offset1 = -( 8192 << shift1 );
   const int shift2 = 6 + headRoom, offset2 = ( 1 << ( shift2 - 1 ) ) + ( 8192 << 6 );
   const float invHw = 1.0f / (float) hw, invNt = 1.0f / (float) nTiles, invTx = 1.0f / (float) tilesX;
+  if( threadIdx.x < 4 ) sTaps[threadIdx.x] = frac_taps( flt, threadIdx.x );
 
   for( int b = blockIdx.x; b < n; b += gridDim.x )
   {
@@ -108,16 +112,19 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
     }
     for( int k = tid; k < 49; k += T ) sOut[k] = 0u;
     __syncthreads();
-    for( int i = 0; i < 7; i++ )
+    const int perCol = ( rowsP >> 1 ) * hw, jobsPerCol = 7 * nTiles;
+    const float invPerCol = 1.0f / (float) perCol, invJobs = 1.0f / (float) jobsPerCol;
+    for( int i0 = 0; i0 < 7; i0 += L.G )
     {
-      const int qx = i - 3;
-      const int e = ( qx >> 2 ) + 1 + o, eo = e & 1, ew = e >> 1;
-      const FracTaps X = frac_taps( flt, qx & 3 );
-      uint32_t* H = hbuf + ( i & 1 ) * ( L.hWords >> 1 );
-      // ---- horizontal pass (filterHor, isLast = false): item = (row pair, column pair), results packed as row pairs
-      for( int it = tid; it < ( rowsP >> 1 ) * hw; it += T )
+      const int gcount = min( L.G, 7 - i0 );
+      // ---- horizontal pass (filterHor, isLast = false) for gcount horizontal offsets: item = (offset, row pair, column pair), results packed as row pairs
+      for( int it = tid; it < gcount * perCol; it += T )
       {
-        const int rp = frac_div( it, invHw ), cp = it - rp * hw;
+        const int g = frac_div( it, invPerCol ), rem = it - g * perCol;
+        const int rp = frac_div( rem, invHw ), cp = rem - rp * hw;
+        const int qx = i0 + g - 3;
+        const int e = ( qx >> 2 ) + 1 + o, eo = e & 1, ew = e >> 1;
+        const FracTaps X = sTaps[qx & 3];
         const uint32_t* ra = win + ( 2 * rp ) * PW + cp + ew;
         const uint32_t* rb = ra + PW;
         const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], a4 = ra[4], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3], b4 = rb[4];
@@ -136,18 +143,20 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
         uint2 pk;
         pk.x = ( (uint32_t) ha0 & 0xffffu ) | ( (uint32_t) hb0 << 16 );
         pk.y = ( (uint32_t) ha1 & 0xffffu ) | ( (uint32_t) hb1 << 16 );
-        *reinterpret_cast<uint2*>( H + rp * w + 2 * cp ) = pk;
+        *reinterpret_cast<uint2*>( hbuf + g * L.colWords + rp * w + 2 * cp ) = pk;
       }
-      __syncthreads();               // H(i) complete; readers of H(i-1) are past this barrier before H(i+1) is written
-      // ---- vertical pass (filterVer, isFirst = false, isLast = true) + distortion: lane = (vertical offset j, 8x8 tile)
-      for( int job = tid; job < 7 * nTiles; job += T )
+      __syncthreads();
+      // ---- vertical pass (filterVer, isFirst = false, isLast = true) + distortion: lane = (horizontal offset, vertical offset j, 8x8 tile)
+      for( int job = tid; job < gcount * jobsPerCol; job += T )
       {
-        const int j = frac_div( job, invNt ), t = job - j * nTiles;
+        const int g = frac_div( job, invJobs ), jr = job - g * jobsPerCol;
+        const int i = i0 + g;
+        const int j = frac_div( jr, invNt ), t = jr - j * nTiles;
         const int ty = frac_div( t, invTx ), tx = t - ty * tilesX;
         const int qy = j - 3;
-        const FracTaps Y = frac_taps( flt, qy & 3 );
+        const FracTaps Y = sTaps[qy & 3];
         const int q = ( qy >> 2 ) + 1 + ty * 8;                                 // first filtered row of the tile's first output row
-        const uint32_t* hp = H + ( q >> 1 ) * w + tx * 8;
+        const uint32_t* hp = hbuf + g * L.colWords + ( q >> 1 ) * w + tx * 8;
         const bool odd = ( q & 1 ) != 0;
         int d[64];
 #pragma unroll
@@ -200,8 +209,8 @@ __global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant
         }
         atomicAdd( &sOut[j * 7 + i], s );
       }
+      __syncthreads();               // the filtered rows are consumed before the next group of offsets overwrites them
     }
-    __syncthreads();
     for( int k = tid; k < 49; k += T ) out[(size_t) b * 49 + k] = sOut[k];
   }
 }
