@@ -149,10 +149,10 @@ __global__ void __launch_bounds__( MCTF_WARPS * 32 ) mctf_error_packed_kernel( c
 // Grid search: all (2r+1)^2 candidates  centre + (i - r, j - r) * step  (1/16 pel) of one block in one CTA -- the loops of
 // MCTF::estimateLumaLn (CommonLib/MCTF.cpp:1218-1287: integer grid step 16 range 5/8, then 7x7 step 4, 3x3 step 2, 3x3 step 1).
 // The source window is staged once per block; for every distinct horizontal vector the horizontally filtered rows are computed once
-// (packed as row pairs) and shared by the 2r+1 candidates above it; a thread owns output positions (row pair, column), so the original
+// (packed as row pairs; as many grid columns per pass as fit 40 KB of shared memory) and shared by the 2r+1 candidates above it; a thread owns output positions (row pair, column), so the original
 // pels are read once and each candidate's error is reduced with one REDUX + one shared atomic per warp.  Same arithmetic as
 // mctf_error_packed_kernel (IDP.2A, int32 sums, clip after each pass): results equal motionErrorLuma for every candidate.
-struct MctfGridSmem { int winPitch, winWords, hWords, orgWords, errWords, total; };
+struct MctfGridSmem { int winPitch, winWords, colWords, G, hWords, orgWords, errWords, tapOff, tapWords, total; };
 __host__ __device__ inline MctfGridSmem mctf_grid_smem( int maxDim, int step, int radius )
 {
   const int span = ( ( 2 * radius * step + 15 ) >> 4 ) + 1;      // upper bound of (max - min) integer displacement
@@ -161,10 +161,14 @@ __host__ __device__ inline MctfGridSmem mctf_grid_smem( int maxDim, int step, in
   const int rows = ( maxDim + 6 + span + 1 ) & ~1;
   m.winPitch = ( maxDim + 5 + span + 2 + 1 ) >> 1;
   m.winWords = rows * m.winPitch;
-  m.hWords   = 2 * ( rows >> 1 ) * maxDim;                       // two buffers of row pairs x w
+  m.colWords = ( rows >> 1 ) * maxDim;                           // filtered rows of one horizontal vector: row pairs x w
+  m.G        = 10240 / m.colWords < 1 ? 1 : ( 10240 / m.colWords > K1 ? K1 : 10240 / m.colWords );   // grid columns per pass (up to 40 KB)
+  m.hWords   = m.G * m.colWords;
   m.orgWords = ( maxDim >> 1 ) * maxDim;
   m.errWords = ( K1 * K1 + 1 ) & ~1;
-  m.total    = m.winWords + m.hWords + m.orgWords + m.errWords;
+  m.tapWords = 8 * K1;                                           // packed taps per grid column (x) and row (y)
+  m.tapOff   = ( m.winWords + m.hWords + m.orgWords + m.errWords + 3 ) & ~3;   // int4 entries: 16-byte aligned
+  m.total    = m.tapOff + m.tapWords;
   return m;
 }
 
@@ -178,6 +182,7 @@ __global__ void __launch_bounds__( 256 ) mctf_grid_kernel( const __grid_constant
   uint32_t* hbuf = win + L.winWords;
   uint32_t* orgP = hbuf + L.hWords;
   int*      sErr = reinterpret_cast<int*>( orgP + L.orgWords );
+  int4*     sTap = reinterpret_cast<int4*>( sGrid + L.tapOff );           // [2 * K1]: x columns, then y rows
   const int tid = threadIdx.x, T = blockDim.x;
   const int K1 = 2 * radius + 1, K = K1 * K1;
   const int maxv = ( 1 << refPlane.bitDepth ) - 1;
@@ -222,19 +227,29 @@ __global__ void __launch_bounds__( 256 ) mctf_grid_kernel( const __grid_constant
 #define VVB_O( a, b, c_, d, GA, GB ) __dp2a_hi( (int)(d), GB, __dp2a_lo( (int)(c_), GB, __dp2a_hi( (int)(b), GA, __dp2a_lo( (int)(a), GA, 0 ) ) ) )
 #define VVB_RC( v ) max( min( ( (v) + 32 ) >> 6, maxv ), 0 )
 #define VVB_TAPS( f, ph ) { _Pragma( "unroll" ) for( int t = 0; t < 6; t++ ) f[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[ph][t - 1] : 0 ) : c_mctfF8[ph][t + 1]; }
-    for( int i = 0; i < K1; i++ )
+    // packed taps of every grid column / row (phase = vector & 15)
+    for( int k = tid; k < 2 * K1; k += T )
     {
-      const int mvx = blk.mvx + ( i - radius ) * step;
-      const int e = ( mvx >> 4 ) - dxMin + o, eo = e & 1, ew = e >> 1;      // pel offset of this vector inside the window rows
+      const int mv = ( k < K1 ? blk.mvx : blk.mvy ) + ( ( k < K1 ? k : k - K1 ) - radius ) * step;
       int f[6];
-      VVB_TAPS( f, mvx & 15 )
-      const int xFA = (int) VVB_B4( f[0], f[1], f[2], f[3] ), xFB = (int) VVB_B4( f[4], f[5], 0, 0 );
-      const int xGA = (int) VVB_B4( 0, f[0], f[1], f[2] ),    xGB = (int) VVB_B4( f[3], f[4], f[5], 0 );
-      uint32_t* H = hbuf + ( i & 1 ) * ( L.hWords >> 1 );
-      // ---- horizontal pass for this mvx: item = (row pair, column pair)
-      for( int it = tid; it < ( rowsP >> 1 ) * hw; it += T )
+      VVB_TAPS( f, mv & 15 )
+      sTap[k] = make_int4( (int) VVB_B4( f[0], f[1], f[2], f[3] ), (int) VVB_B4( f[4], f[5], 0, 0 ), (int) VVB_B4( 0, f[0], f[1], f[2] ), (int) VVB_B4( f[3], f[4], f[5], 0 ) );
+    }
+    __syncthreads();
+    const int perCol = ( rowsP >> 1 ) * hw;
+    const float invPerCol = 1.0f / (float) perCol;
+    for( int i0 = 0; i0 < K1; i0 += L.G )
+    {
+      const int gcount = min( L.G, K1 - i0 );
+      // ---- horizontal pass for gcount grid columns: item = (column, row pair, column pair)
+      for( int it = tid; it < gcount * perCol; it += T )
       {
-        const int rp = mctf_div( it, invHw ), cp = it - rp * hw;
+        const int g = mctf_div( it, invPerCol ), rem = it - g * perCol;
+        const int rp = mctf_div( rem, invHw ), cp = rem - rp * hw;
+        const int mvx = blk.mvx + ( i0 + g - radius ) * step;
+        const int e = ( mvx >> 4 ) - dxMin + o, eo = e & 1, ew = e >> 1;      // pel offset of this vector inside the window rows
+        const int4 tx = sTap[i0 + g];
+        const int xFA = tx.x, xFB = tx.y, xGA = tx.z, xGB = tx.w;
         const uint32_t* ra = win + ( 2 * rp ) * PW + cp + ew;
         const uint32_t* rb = ra + PW;
         const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
@@ -245,34 +260,38 @@ __global__ void __launch_bounds__( 256 ) mctf_grid_kernel( const __grid_constant
         uint2 pk;
         pk.x = (uint32_t) ha0 | ( (uint32_t) hb0 << 16 );
         pk.y = (uint32_t) ha1 | ( (uint32_t) hb1 << 16 );
-        *reinterpret_cast<uint2*>( H + rp * w + 2 * cp ) = pk;
+        *reinterpret_cast<uint2*>( hbuf + g * L.colWords + rp * w + 2 * cp ) = pk;
       }
-      __syncthreads();               // H(i) complete; H(i-1) readers finished before anyone writes H(i+1) (they passed this barrier)
-      // ---- vertical pass + SSE for the 2r+1 candidates sharing this mvx
-      for( int j = 0; j < K1; j++ )
+      __syncthreads();
+      // ---- vertical pass + SSE for the gcount * (2r+1) candidates of these columns; a thread keeps its output positions
+      for( int g = 0; g < gcount; g++ )
       {
-        const int mvy = blk.mvy + ( j - radius ) * step;
-        const int q0 = ( mvy >> 4 ) - dyMin;                                 // first filtered row of output row 0
-        VVB_TAPS( f, mvy & 15 )
-        const int yFA = (int) VVB_B4( f[0], f[1], f[2], f[3] ), yFB = (int) VVB_B4( f[4], f[5], 0, 0 );
-        const int yGA = (int) VVB_B4( 0, f[0], f[1], f[2] ),    yGB = (int) VVB_B4( f[3], f[4], f[5], 0 );
-        int err = 0;
-        for( int p = tid; p < hh * w; p += T )
+        const uint32_t* H = hbuf + g * L.colWords;
+        for( int j = 0; j < K1; j++ )
         {
-          const int yp = mctf_div( p, invW ), x = p - yp * w;
-          const int q = q0 + 2 * yp;
-          const uint32_t* tp = H + ( q >> 1 ) * w + x;
-          const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
-          int v0, v1;
-          if( ( q & 1 ) == 0 ) { v0 = VVB_E( p0, p1, p2, yFA, yFB ); v1 = VVB_O( p0, p1, p2, p3, yGA, yGB ); }
-          else                 { v0 = VVB_O( p0, p1, p2, p3, yGA, yGB ); v1 = VVB_E( p1, p2, p3, yFA, yFB ); }
-          const uint32_t ow = orgP[p];
-          const int d0 = VVB_RC( v0 ) - (int)( ow & 0xffffu ), d1 = VVB_RC( v1 ) - (int)( ow >> 16 );
-          err += d0 * d0 + d1 * d1;
+          const int mvy = blk.mvy + ( j - radius ) * step;
+          const int q0 = ( mvy >> 4 ) - dyMin;                                 // first filtered row of output row 0
+          const int4 ty = sTap[K1 + j];
+          const int yFA = ty.x, yFB = ty.y, yGA = ty.z, yGB = ty.w;
+          int err = 0;
+          for( int p = tid; p < hh * w; p += T )
+          {
+            const int yp = mctf_div( p, invW ), x = p - yp * w;
+            const int q = q0 + 2 * yp;
+            const uint32_t* tp = H + ( q >> 1 ) * w + x;
+            const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
+            int v0, v1;
+            if( ( q & 1 ) == 0 ) { v0 = VVB_E( p0, p1, p2, yFA, yFB ); v1 = VVB_O( p0, p1, p2, p3, yGA, yGB ); }
+            else                 { v0 = VVB_O( p0, p1, p2, p3, yGA, yGB ); v1 = VVB_E( p1, p2, p3, yFA, yFB ); }
+            const uint32_t ow = orgP[p];
+            const int d0 = VVB_RC( v0 ) - (int)( ow & 0xffffu ), d1 = VVB_RC( v1 ) - (int)( ow >> 16 );
+            err += d0 * d0 + d1 * d1;
+          }
+          err = __reduce_add_sync( 0xffffffffu, err );
+          if( ( tid & 31 ) == 0 && err ) atomicAdd( &sErr[j * K1 + i0 + g], err );
         }
-        err = __reduce_add_sync( 0xffffffffu, err );
-        if( ( tid & 31 ) == 0 && err ) atomicAdd( &sErr[j * K1 + i], err );
       }
+      __syncthreads();               // the filtered rows are consumed before the next group of columns overwrites them
     }
 #undef VVB_B4
 #undef VVB_E
