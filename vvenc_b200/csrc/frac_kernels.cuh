@@ -65,7 +65,7 @@ __device__ __forceinline__ FracTaps frac_taps( const FracFilter& flt, int phase 
 }
 
 // family: 1 = SAD, 2 = HAD (8x8 tiles: square blocks 8..64)
-__global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+__global__ void __launch_bounds__( 256 ) frac_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                            const vvb_block* __restrict__ blocks, int n, int w, int h, int family, const __grid_constant__ FracFilter flt,
                                                            uint32_t* __restrict__ out )
 {
