@@ -1148,12 +1148,7 @@ int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane,
   const FracSmem L = frac_smem( w, h );
   const FracFilter flt = frac_filter( reduceTap, altHpel );
   const int jobs = L.G * 7 * ( w / 8 ) * ( h / 8 );                                   // (horizontal offsets per pass) x vertical offsets x tiles
-  int threads = 32; double bestEff = 0.0;                                               // thread count that wastes the fewest lanes on the (offset, tile) jobs
-  for( int cand = 32; cand <= 256; cand += 32 )
-  {
-    const double eff = (double) jobs / ( (double)( ( jobs + cand - 1 ) / cand ) * cand );
-    if( eff >= bestEff - 1e-9 ) { bestEff = std::max( bestEff, eff ); threads = cand; }
-  }
+  const int threads = std::max( 32, std::min( 128, ( jobs + 31 ) & ~31 ) );
   frac_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, (size_t) L.total * 4, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h,
                                                                                                   dfunc == VVB_DF_HAD ? 2 : 1, flt, dCost );
   CHECK_LAUNCH( "frac_grid_kernel" );

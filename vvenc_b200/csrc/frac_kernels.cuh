@@ -7,8 +7,8 @@
 // then filterVer( frac_y, isFirst = false, isLast = true ) (CommonLib/InterpolationFilter.cpp:357-455; phase 0 is filterCopy :258-340, identical to
 // the filter with the single tap 64), 14-bit signed intermediates, clip after the second pass.  The filter set follows m_meReduceTap / useAltHpelIf.
 //
-// One CTA per block.  The window (h + 8 rows) is staged once; the horizontally filtered rows of up to 7 horizontal offsets at a time (as many as fit
-// 40 KB of shared memory) are computed once (packed as row pairs, IDP.2A) and shared by the 7 vertical offsets; a lane owns one (vertical offset, 8x8 tile): it runs the vertical filter for its
+// One CTA per block.  The window (h + 8 rows) is staged once; the horizontally filtered rows of one horizontal offset at a time (all seven at once for
+// 8x8 blocks) are computed once (packed as row pairs, IDP.2A) and shared by the 7 vertical offsets; a lane owns one (vertical offset, 8x8 tile): it runs the vertical filter for its
 // tile (IDP.2A on row pairs), forms the 64 differences in registers and either sums |d| or runs the 64-point 2-D Hadamard there (as had8_pattern_kernel).
 #pragma once
 #include "common.cuh"
@@ -38,7 +38,7 @@ __host__ __device__ inline FracSmem frac_smem( int w, int h )
   m.winPitch = w / 2 + 6;                       // w + 8 pels + alignment + one word of slack for the zero-weighted tap
   m.winWords = ( h + 8 ) * m.winPitch;
   m.colWords = ( ( h + 8 ) / 2 ) * w;           // horizontally filtered rows of one horizontal offset: row pairs x w
-  m.G        = 10240 / m.colWords < 1 ? 1 : ( 10240 / m.colWords > 7 ? 7 : 10240 / m.colWords );   // offsets per pass: up to 40 KB of filtered rows
+  m.G        = w * h <= 64 ? 7 : 1;             // horizontal offsets per pass: all seven for 8x8 blocks (lane utilisation), one otherwise (measured faster)
   m.hWords   = m.G * m.colWords;
   m.orgWords = h * w / 2;
   m.total    = m.winWords + m.hWords + m.orgWords + 52 + 40;     // + table + packed taps of the 4 phases
@@ -65,7 +65,7 @@ __device__ __forceinline__ FracTaps frac_taps( const FracFilter& flt, int phase 
 }
 
 // family: 1 = SAD, 2 = HAD (8x8 tiles: square blocks 8..64)
-__global__ void __launch_bounds__( 256 ) frac_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+__global__ void __launch_bounds__( 128 ) frac_grid_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                            const vvb_block* __restrict__ blocks, int n, int w, int h, int family, const __grid_constant__ FracFilter flt,
                                                            uint32_t* __restrict__ out )
 {
