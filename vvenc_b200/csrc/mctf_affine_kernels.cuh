@@ -264,6 +264,36 @@ __global__ void __launch_bounds__( 256 ) mctf_grid_kernel( const __grid_constant
       }
       __syncthreads();
       // ---- vertical pass + SSE for the gcount * (2r+1) candidates of these columns; a thread keeps its output positions
+      if( hh * w <= T )                // one position per thread (blocks up to 16x16): decode it and fetch the original pels once
+      {
+        const bool act = tid < hh * w;
+        const int yp = mctf_div( tid, invW ), x = tid - yp * w;
+        const uint32_t ow = act ? orgP[tid] : 0u;
+        const int o0 = (int)( ow & 0xffffu ), o1 = (int)( ow >> 16 );
+        const uint32_t* hx = hbuf + x;
+        for( int g = 0; g < gcount; g++, hx += L.colWords )
+        {
+          for( int j = 0; j < K1; j++ )
+          {
+            const int q = ( ( blk.mvy + ( j - radius ) * step ) >> 4 ) - dyMin + 2 * yp;
+            const int4 ty = sTap[K1 + j];
+            int err = 0;
+            if( act )
+            {
+              const uint32_t* tp = hx + ( q >> 1 ) * w;
+              const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
+              int v0, v1;
+              if( ( q & 1 ) == 0 ) { v0 = VVB_E( p0, p1, p2, ty.x, ty.y ); v1 = VVB_O( p0, p1, p2, p3, ty.z, ty.w ); }
+              else                 { v0 = VVB_O( p0, p1, p2, p3, ty.z, ty.w ); v1 = VVB_E( p1, p2, p3, ty.x, ty.y ); }
+              const int d0 = VVB_RC( v0 ) - o0, d1 = VVB_RC( v1 ) - o1;
+              err = d0 * d0 + d1 * d1;
+            }
+            err = __reduce_add_sync( 0xffffffffu, err );
+            if( ( tid & 31 ) == 0 && err ) atomicAdd( &sErr[j * K1 + i0 + g], err );
+          }
+        }
+      }
+      else
       for( int g = 0; g < gcount; g++ )
       {
         const uint32_t* H = hbuf + g * L.colWords;
