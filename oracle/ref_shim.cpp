@@ -51,8 +51,6 @@
 #include <cstdarg>
 #include <cstdio>
 #include <immintrin.h>
-#include <dlfcn.h>
-#include "../include/vvenc_b200.h"   // only for the drop-in demo below (types + prototypes; symbols are resolved with dlsym)
 
 #define private public
 #define protected public
@@ -161,71 +159,7 @@ inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, co
 // RdCost::_initRdCostB200() would do.  opt == 2 in the probes below selects an RdCost patched this way, so the tests can
 // drive UNMODIFIED reference call sites (DistParam + distFunc, dmvrSadX5, m_fxdWtdPredPtr, the xPatternSearch replay)
 // with the GPU library underneath and compare against the AVX2 table.
-struct B200Api
-{
-  void* handle = nullptr;
-  decltype( &vvb_create )          create = nullptr;
-  decltype( &vvb_last_error )      lastError = nullptr;
-  decltype( &vvb_dist_block )      distBlock = nullptr;
-  decltype( &vvb_sad_mask_block )  sadMask = nullptr;
-  decltype( &vvb_sad_x5_block )    sadX5 = nullptr;
-  decltype( &vvb_fix_wsse_block )  fixWsse = nullptr;
-  decltype( &vvb_launch_count )    launchCount = nullptr;
-  std::string error;
-} g_b200;
-
-thread_local vvb_ctx* t_b200ctx = nullptr;
-vvb_ctx* b200CtxOfThread()
-{
-  if( !t_b200ctx && ( !g_b200.create || g_b200.create( &t_b200ctx, 0 ) != VVB_OK ) ) THROW( "no B200 context" );
-  return t_b200ctx;
-}
-
-template<int FAM> Distortion distB200( const DistParam& dp )
-{
-  if( dp.applyWeight ) THROW( " no support" );
-  int err = 0;
-  const Distortion d = g_b200.distBlock( b200CtxOfThread(), FAM, dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride,
-                                         dp.org.width, dp.org.height, dp.bitDepth, dp.subShift, &err );
-  if( err ) THROW( g_b200.lastError( b200CtxOfThread() ) );
-  return d;
-}
-Distortion sadMaskB200( const DistParam& dp )
-{
-  int err = 0;
-  const Distortion d = g_b200.sadMask( b200CtxOfThread(), dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, dp.org.width, dp.org.height,
-                                       dp.mask, dp.maskStride, dp.stepX, dp.maskStride2, dp.subShift, &err );
-  if( err ) THROW( g_b200.lastError( b200CtxOfThread() ) );
-  return d;
-}
-void sadX5B200( const DistParam& dp, Distortion* cost, bool centre )
-{
-  uint64_t c5[5];
-  if( g_b200.sadX5( b200CtxOfThread(), dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, dp.org.width, dp.org.height, dp.subShift, centre, c5 ) ) THROW( "b200 sadX5" );
-  for( int i = 0; i < 5; i++ ) if( i != 2 || centre ) cost[i] = c5[i];
-}
-Distortion fixWsseB200( const DistParam& dp, uint32_t w )
-{
-  int err = 0;
-  const Distortion d = g_b200.fixWsse( b200CtxOfThread(), dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, dp.org.width, dp.org.height, w, &err );
-  if( err ) THROW( g_b200.lastError( b200CtxOfThread() ) );
-  return d;
-}
-
-void installB200( RdCost& rc )      // slot = base + log2(width), TypeDef.h:339-382; row [1] (>10 bit) stays scalar like RdCost.cpp:125-126
-{
-  for( int l = 1; l < 8; l++ )
-  {
-    rc.m_afpDistortFunc[0][DF_SSE      + l] = distB200<VVB_DF_SSE>;
-    rc.m_afpDistortFunc[0][DF_SAD      + l] = distB200<VVB_DF_SAD>;
-    rc.m_afpDistortFunc[0][DF_HAD      + l] = distB200<VVB_DF_HAD>;
-    rc.m_afpDistortFunc[0][DF_HAD_fast + l] = distB200<VVB_DF_HAD_FAST>;
-  }
-  rc.m_afpDistortFunc[0][DF_HAD_2SAD]      = distB200<VVB_DF_HAD_2SAD>;
-  rc.m_afpDistortFunc[0][DF_SAD_WITH_MASK] = sadMaskB200;
-  rc.m_afpDistortFuncX5[0] = sadX5B200;  rc.m_afpDistortFuncX5[1] = sadX5B200;
-  rc.m_fxdWtdPredPtr       = fixWsseB200;
-}
+#include "../integration/RdCostB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
 
 void createRd( RdCost& rc, int opt )     // 0 scalar, 1 SIMD, 2 SIMD table patched with the B200 trampolines
 {
@@ -322,15 +256,7 @@ int refshim_version() { return 4; }
 int refshim_install_b200( const char* libPath )
 {
   std::lock_guard<std::mutex> lk( g_mtx );
-  if( g_b200.handle ) return 0;
-  void* h = dlopen( libPath, RTLD_NOW | RTLD_LOCAL );
-  if( !h ) { g_b200.error = dlerror(); return -1; }
-#define RESOLVE( member, name ) g_b200.member = (decltype( g_b200.member )) dlsym( h, #name ); if( !g_b200.member ) { g_b200.error = "missing " #name; dlclose( h ); return -2; }
-  RESOLVE( create, vvb_create )  RESOLVE( lastError, vvb_last_error )  RESOLVE( distBlock, vvb_dist_block )  RESOLVE( sadMask, vvb_sad_mask_block )
-  RESOLVE( sadX5, vvb_sad_x5_block )  RESOLVE( fixWsse, vvb_fix_wsse_block )  RESOLVE( launchCount, vvb_launch_count )
-#undef RESOLVE
-  g_b200.handle = h;
-  return 0;
+  return b200Load( libPath );
 }
 const char* refshim_b200_error() { return g_b200.error.c_str(); }
 uint64_t refshim_b200_launches()   // kernels launched by the calling thread's drop-in context (proof that the numbers came from the GPU)
