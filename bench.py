@@ -121,6 +121,26 @@ class ClockSampler:
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def ncu_dram_traffic(kernel_substr, profile='profiles/r01_v8_ncu_step_kernels.txt'):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first capture whose kernel name contains `kernel_substr`, from the committed
+    `ncu --set full` summary; None when the file or the kernel is not there"""
+    try:
+        unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        for blk in open(os.path.join(os.path.dirname(os.path.abspath(__file__)), profile)).read().split('-' * 100):
+            name = [l for l in blk.split('\n') if l.startswith('Kernel Name')]
+            if not name or kernel_substr not in name[0]:
+                continue
+            tot = 0.0; seen = 0
+            for l in blk.split('\n'):
+                if l.startswith('dram__bytes_read.sum') or l.startswith('dram__bytes_write.sum'):
+                    f = l.split()
+                    tot += float(f[1].replace(',', '')) * unit[f[2]]; seen += 1
+            return tot if seen == 2 else None
+    except Exception:
+        return None
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -433,7 +453,8 @@ def main():
         pyr_pel = nb0 * nx * nx * n0 * n0                                                     # pel differences actually evaluated by the pyramid
         ach = pyr_bytes / (t_pyr * 1e-3) / 1e9
         roofline = {'kernel': 'sad_search_kernel<quads + parent> + sad_table_sum_kernel (vvb_sad_search_pyramid_dev, 1 + %d launches per step)' % (nlev - 2), 'bound': 'hbm',
-                    'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                    'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': ncu_dram_traffic('sad_search_kernel<1, 1, 1>'),
+                    'traffic_source': 'bytes per launch of sad_search_kernel<1,1,1> (DRAM read + write; the writes are the 16x16 parent cost tables) from profiles/r01_v8_ncu_step_kernels.txt', 'peak_source': peak_src,
                     'note': 'dense +-32 search re-uses every reference pel up to 4225x from shared memory: integer-ALU bound by construction (SURVEY 8d W2); '
                             'bytes = compulsory 2N^2 + 2(N+2R)^2 + 16 per 8x8 block; see "alu" for the binding roof',
                     'alu': {'achieved': pyr_pel / (t_pyr * 1e-3) / 1e12, 'peak': alu_peak / 1e12, 'unit': 'Tpel-diff/s', 'frac': pyr_pel / (t_pyr * 1e-3) / alu_peak,
