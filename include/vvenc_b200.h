@@ -61,7 +61,9 @@ int         vvb_alu_probe_dev( vvb_ctx* ctx, int grid_ctas, int iters, int mode 
 /* ---- pictures ("planes") ---------------------------------------------------------------------------------
  * int16 sample planes (Pel, CommonLib/TypeDef.h:181) with a margin on all sides, like the encoder's padded
  * reference pictures (CommonLib/Picture.cpp:461-501).  `origin` points at sample (0,0); rows -margin..height+margin-1
- * and columns -margin..width+margin-1 must be readable.  Uploaded once per picture, referenced by id afterwards. */
+ * and columns -margin..width+margin-1 must be readable.  Uploaded once per picture, referenced by id afterwards.
+ * Kernels do not clamp addresses: as in the encoder (Picture::extendPicBorder, MCTF_PADDING = 128) the margin has to cover the largest displacement
+ * plus the filter reach -- search range for vvb_sad_search*, |vector| + 4 pels for vvb_frac_cost_grid, |vector|/16 + 4 pels for the MCTF calls. */
 int vvb_plane_upload  ( vvb_ctx* ctx, int plane_id, const int16_t* origin, int stride, int width, int height, int margin, int bit_depth );
 int vvb_plane_bind_dev( vvb_ctx* ctx, int plane_id, const int16_t* dev_origin, int stride, int width, int height, int margin, int bit_depth );
 int vvb_plane_free    ( vvb_ctx* ctx, int plane_id );
