@@ -765,6 +765,42 @@ void refshim_frac_cost_grid( int opt, const int16_t* orgPlane, int so, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The reference's OWN MCTF motion search for one pyramid level: MCTF::motionEstimationLuma (MCTF.cpp:1329-1397) -> estimateLumaLn (:1166-1327),
+// run on caller-provided pictures (sample (0,0) pointers into padded buffers).  prev (nullable): motion field of the coarser level
+// [prevH][prevW] x { x, y }.  out: [blocksY][blocksX] x { x, y, error, rmsme } ; overlapOut (nullable): doubles.
+// Only members the search reads are set (private members are reachable through the probe's `#define private public`).
+void refshim_mctf_estimate_level( int opt, const int16_t* org, int orgStride, const int16_t* buf, int bufStride, int width, int height, int bitDepth,
+                                  int blockSize, const int32_t* prev, int prevW, int prevH, int factor, int doubleRes, int lowResFilter, int unitSize,
+                                  int32_t* out, double* overlapOut )
+{
+  RefCtx& c = ctx();
+  MCTF* m = c.mctf[opt?1:0];
+  static VVEncCfg cfg;
+  cfg.m_internalBitDepth[CH_L] = bitDepth; cfg.m_internalBitDepth[CH_C] = bitDepth;
+  m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_searchPttrn = 0; m->m_mctfUnitSize = unitSize; m->m_lowResFltSearch = lowResFilter != 0;
+  PelStorage orig, buffer;
+  orig.createFromBuf( PelUnitBuf( CHROMA_400, PelBuf( const_cast<Pel*>( org ), orgStride, width, height ) ) );
+  buffer.createFromBuf( PelUnitBuf( CHROMA_400, PelBuf( const_cast<Pel*>( buf ), bufStride, width, height ) ) );
+  const int bxN = width / blockSize, byN = height / blockSize;                       // MCTF.cpp:688: Array2D<MotionVector>( width / blockSize, height / blockSize )
+  Array2D<MotionVector> mvs( bxN, byN );
+  Array2D<MotionVector> previous;
+  if( prev )
+  {
+    previous.allocate( prevW, prevH );
+    for( int y = 0; y < prevH; y++ ) for( int x = 0; x < prevW; x++ ) { MotionVector& v = previous.get( x, y ); v.x = prev[2 * ( y * prevW + x )]; v.y = prev[2 * ( y * prevW + x ) + 1]; }
+  }
+  m->motionEstimationLuma( mvs, orig, buffer, blockSize, prev ? &previous : nullptr, factor, doubleRes != 0 );
+  for( int y = 0; y < byN; y++ )
+    for( int x = 0; x < bxN; x++ )
+    {
+      const MotionVector& v = mvs.get( x, y );
+      int32_t* o = out + 4 * ( y * bxN + x );
+      o[0] = v.x; o[1] = v.y; o[2] = v.error; o[3] = v.rmsme;
+      if( overlapOut ) overlapOut[y * bxN + x] = v.overlap;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Affine gradient helpers (AffineGradientSearch.h:67-69)
 void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )
 {
