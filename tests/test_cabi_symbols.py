@@ -45,3 +45,15 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dp, f), errors='ignore').read()
                 assert 'liboracle' not in txt and 'refshim' not in txt and 'oracle/' not in txt.replace('oracle/vvc_tables.h', ''), f
+
+
+def test_reference_side_binding_resolves_only_declared_symbols():
+    """integration/RdCostB200.h binds the library with dlsym: every name it asks for must be declared in the C ABI header (and hence exported)"""
+    txt = open(os.path.join(ROOT, 'integration', 'RdCostB200.h')).read()
+    asked = sorted(set(re.findall(r'VVB_RESOLVE\(\s*\w+\s*,\s*(vvb_[a-z0-9_]+)\s*\)', txt)))
+    assert len(asked) >= 6
+    declared = set(_declared())
+    assert [n for n in asked if n not in declared] == []
+    # the trampolines cover every slot family the x86 back end overwrites (RdCostX86.h:3376-3425)
+    for slot in ('DF_SSE', 'DF_SAD', 'DF_HAD', 'DF_HAD_fast', 'DF_HAD_2SAD', 'DF_SAD_WITH_MASK', 'm_afpDistortFuncX5', 'm_fxdWtdPredPtr'):
+        assert slot in txt, slot
