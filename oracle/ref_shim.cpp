@@ -800,6 +800,55 @@ void refshim_mctf_estimate_level( int opt, const int16_t* org, int orgStride, co
     }
 }
 
+// The whole MCTF motion search of one neighbour picture, as MCTF::motionEstimationMCTF chains it (MCTF.cpp:666-724): subsampleLuma pyramids (:1072-1097,
+// reference code, incl. its border extension) and four or five motionEstimationLuma levels.  org / ref: compact width x height pictures; the probe pads
+// them by MCTF_PADDING with border replication as Picture buffers are.  out: [hInBlks][wInBlks] x { x, y, error, rmsme }.
+void refshim_mctf_estimate_pyramid( int opt, const int16_t* org, const int16_t* ref, int width, int height, int bitDepth, int unitSize, int addLevel, int32_t* out )
+{
+  RefCtx& c = ctx();
+  MCTF* m = c.mctf[opt?1:0];
+  static VVEncCfg cfg;
+  cfg.m_internalBitDepth[CH_L] = bitDepth; cfg.m_internalBitDepth[CH_C] = bitDepth;
+  m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_searchPttrn = 0; m->m_mctfUnitSize = unitSize; m->m_lowResFltSearch = false;
+  const int pad = MCTF_PADDING;
+  auto load = [&]( PelStorage& ps, const int16_t* src )
+  {
+    ps.create( CHROMA_400, Area( 0, 0, width, height ), 0, pad );
+    PelBuf b = ps.Y();
+    for( int y = 0; y < height; y++ ) memcpy( b.buf + (ptrdiff_t) y * b.stride, src + (size_t) y * width, sizeof( Pel ) * width );
+    ps.extendBorderPel( pad, pad );
+  };
+  PelStorage origBuf, refBuf, o2, o4, o8, r2, r4, r8;
+  load( origBuf, org ); load( refBuf, ref );
+  m->subsampleLuma( origBuf, o2 ); m->subsampleLuma( o2, o4 );
+  m->subsampleLuma( refBuf, r2 );  m->subsampleLuma( r2, r4 );
+  Array2D<MotionVector> mv_0( width / ( unitSize * 8 ) + 1, height / ( unitSize * 8 ) + 1 );
+  Array2D<MotionVector> mv_1( width / ( unitSize * 4 ) + 1, height / ( unitSize * 4 ) + 1 );
+  Array2D<MotionVector> mv_2( width / ( unitSize * 2 ) + 1, height / ( unitSize * 2 ) + 1 );
+  if( addLevel )
+  {
+    Array2D<MotionVector> mv_m( width / ( unitSize * 16 ) + 1, height / ( unitSize * 16 ) + 1 );
+    m->subsampleLuma( o4, o8 ); m->subsampleLuma( r4, r8 );
+    m->motionEstimationLuma( mv_m, o8, r8, 2 * unitSize );
+    m->motionEstimationLuma( mv_0, o4, r4, 2 * unitSize, &mv_m, 2 );
+  }
+  else m->motionEstimationLuma( mv_0, o4, r4, 2 * unitSize );
+  m->motionEstimationLuma( mv_1, o2, r2, 2 * unitSize, &mv_0, 2 );
+  m->motionEstimationLuma( mv_2, origBuf, refBuf, 2 * unitSize, &mv_1, 2 );
+  const int wInBlks = ( width + unitSize - 1 ) / unitSize, hInBlks = ( height + unitSize - 1 ) / unitSize;
+  Array2D<MotionVector> mvs( wInBlks, hInBlks );
+  m->motionEstimationLuma( mvs, origBuf, refBuf, unitSize, &mv_2, 1, true );
+  for( int y = 0; y < hInBlks; y++ )
+    for( int x = 0; x < wInBlks; x++ )
+    {
+      const MotionVector& v = mvs.get( x, y );
+      int32_t* o = out + 4 * ( y * wInBlks + x );
+      o[0] = v.x; o[1] = v.y; o[2] = v.error; o[3] = v.rmsme;
+    }
+  origBuf.destroy(); refBuf.destroy(); o2.destroy(); o4.destroy(); r2.destroy(); r4.destroy();
+  if( addLevel ) { o8.destroy(); r8.destroy(); }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Affine gradient helpers (AffineGradientSearch.h:67-69)
 void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )

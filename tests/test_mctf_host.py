@@ -119,3 +119,33 @@ def test_engine_provider_path_equals_oracle_provider():
     d = MH.estimate_level(eng, W, H, 8, prev, 1, True, 10, 8)
     for k in c:
         assert np.array_equal(c[k], d[k]), k
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("add_level", [0, 1])
+def test_pyramid_replay_equals_reference(add_level):
+    """the whole motion search of one neighbour picture (MCTF::motionEstimationMCTF: 2x2-averaged pyramids + 4 or 5 chained levels) on a picture whose
+    size is not a multiple of the coarse block sizes: the final field equals the reference's, vectors, scaled errors and rmsme"""
+    rs = np.random.RandomState(21 + add_level)
+    W, H = 208, 136
+    base = rs.randint(0, 1024, size=(H + 16, W + 16))
+    sm = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4
+    org = np.ascontiguousarray(sm[8:8 + H, 8:8 + W].astype(np.int16))
+    a = sm[8 + 3:8 + 3 + H, 8 - 5:8 - 5 + W]; b = sm[8 + 3:8 + 3 + H, 8 - 4:8 - 4 + W]
+    ref = np.ascontiguousarray(np.clip((a + b + 1) // 2 + rs.randint(-5, 6, size=org.shape), 0, 1023).astype(np.int16))
+    R = refshim(); R.refshim_set_simd(b'AVX2')
+    u = 8
+    wb, hb = (W + u - 1) // u, (H + u - 1) // u
+    exp = np.zeros((hb, wb, 4), dtype=np.int32)
+    R.refshim_mctf_estimate_pyramid(1, P(org), P(ref), W, H, 10, u, add_level, P(exp))
+
+    def make_provider(o, r):
+        pad = 128
+        po, pr = MH.pad_edge(o, pad), MH.pad_edge(r, pad)
+        return OracleProvider(po, pr, po.shape[1], pad)
+
+    got = MH.estimate_pyramid(make_provider, org, ref, u, bool(add_level))
+    assert got['x'].shape == (hb, wb)
+    assert np.array_equal(got['x'], exp[..., 0]) and np.array_equal(got['y'], exp[..., 1])
+    assert np.array_equal(got['error'], exp[..., 2]) and np.array_equal(got['rmsme'].astype(np.int32), exp[..., 3])
+    assert (got['x'] != 0).any() and ((got['x'] & 15).any() or (got['y'] & 15).any())

@@ -68,7 +68,7 @@ def estimate_level(provider, width, height, block_size, previous=None, factor=2,
     """One level of the MCTF motion search for the whole picture.  previous: None or (prev_x, prev_y) int arrays [prevH][prevW] of the coarser level.
     Returns dict(x, y, error, rmsme, overlap) with arrays [blocksY][blocksX] (vectors in 1/16 pel) -- MotionVector fields of MCTF.h:72-82."""
     bs = block_size
-    bxn, byn = width // bs, height // bs
+    bxn, byn = len(range(0, width - 7, bs)), len(range(0, height - 7, bs))       # `blockX + 8 <= origWidth` (:1174, :1388): partial blocks of >= 8 pels count
     gx, gy = np.meshgrid(np.arange(bxn) * bs, np.arange(byn) * bs)
     n = bxn * byn
     X = gx.reshape(-1).astype(np.int32); Y = gy.reshape(-1).astype(np.int32)
@@ -151,3 +151,44 @@ def estimate_level(provider, width, height, block_size, previous=None, factor=2,
         overlap = wh / float(unit_size * unit_size)
     shp = (byn, bxn)
     return dict(x=best_x.reshape(shp), y=best_y.reshape(shp), error=err_out.astype(np.int32).reshape(shp), rmsme=rmsme.reshape(shp), overlap=overlap.reshape(shp))
+
+
+def subsample_luma(pic):
+    """MCTF::subsampleLuma (MCTF.cpp:1072-1097): 2x2 average with rounding; pic is the unpadded picture [H][W]"""
+    h, w = pic.shape[0] // 2, pic.shape[1] // 2
+    p = pic[:2 * h, :2 * w].astype(np.int32)
+    return ((p[0::2, 0::2] + p[1::2, 0::2] + p[0::2, 1::2] + p[1::2, 1::2] + 2) >> 2).astype(np.int16)
+
+
+def pad_edge(pic, pad=128):
+    """border replication as PelStorage::extendBorderPel (MCTF_PADDING = 128, CommonDef.h:520)"""
+    return np.ascontiguousarray(np.pad(pic, pad, mode='edge'))
+
+
+def estimate_pyramid(make_provider, org, ref, unit_size=16, add_level=False, bit_depth=10):
+    """MCTF::motionEstimationMCTF (MCTF.cpp:666-724) for one neighbour picture: subsampled pyramids and four (five with add_level) chained levels.
+    org / ref: unpadded pictures [H][W]; make_provider(org_pic, ref_pic) returns a provider for that pair of level pictures (it pads / uploads them).
+    The motion-field arrays of the intermediate levels are sized as the reference sizes them (width / (unit * k) + 1): entries no block writes keep the
+    default vector (0, 0).  Returns the final field dict of estimate_level with [ceil(H/unit)][ceil(W/unit)] entries."""
+    H, W = org.shape
+    o = [org]; r = [ref]
+    for _ in range(3 if add_level else 2):
+        o.append(subsample_luma(o[-1])); r.append(subsample_luma(r[-1]))
+
+    def level(lv, bs, prev, factor, double_res, out_w, out_h):
+        h, w = o[lv].shape
+        f = estimate_level(make_provider(o[lv], r[lv]), w, h, bs, prev, factor, double_res, bit_depth, unit_size)
+        fx = np.zeros((out_h, out_w), dtype=np.int32); fy = np.zeros((out_h, out_w), dtype=np.int32)
+        fh, fw = min(out_h, f['x'].shape[0]), min(out_w, f['x'].shape[1])
+        fx[:fh, :fw] = f['x'][:fh, :fw]; fy[:fh, :fw] = f['y'][:fh, :fw]
+        return f, (fx, fy)
+
+    u = unit_size
+    prev = None
+    if add_level:
+        _, prev = level(3, 2 * u, None, 2, False, W // (u * 16) + 1, H // (u * 16) + 1)
+    _, prev = level(2, 2 * u, prev, 2, False, W // (u * 8) + 1, H // (u * 8) + 1)
+    _, prev = level(1, 2 * u, prev, 2, False, W // (u * 4) + 1, H // (u * 4) + 1)
+    _, prev = level(0, 2 * u, prev, 2, False, W // (u * 2) + 1, H // (u * 2) + 1)
+    final, _ = level(0, u, prev, 1, True, (W + u - 1) // u, (H + u - 1) // u)
+    return final
