@@ -68,6 +68,7 @@
 #include "CommonLib/MCTF.h"
 #include "CommonLib/AffineGradientSearch.h"
 #include "CommonLib/InterpolationFilter.h"
+#include "EncoderLib/InterSearch.h"
 #include "CommonLib/Rom.h"
 #include "CommonLib/Contexts.h"
 #undef private
@@ -847,6 +848,45 @@ void refshim_mctf_estimate_pyramid( int opt, const int16_t* org, const int16_t* 
     }
   origBuf.destroy(); refBuf.destroy(); o2.destroy(); o4.destroy(); r2.destroy(); r4.destroy();
   if( addLevel ) { o8.destroy(); r8.destroy(); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The reference's OWN full search: InterSearch::xPatternSearch (InterSearch.cpp:2209-2251) called as a member on a default-constructed InterSearch whose
+// only live members are the ones the function reads (m_pcRdCost, m_cDistParam, m_lumaClpRng).  Same block list / output layout as refshim_full_search;
+// subShiftMode is passed through RdCost::setDistParam's own rule (RdCost.cpp:187-200): 0 -> no sub-sampling, 2 -> every second row when h > 8.
+void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
+                                    const int32_t* blk, int n, int bitDepth, int subShiftMode, double lambda, int costScale, int imvShift, int32_t* out )
+{
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t* b = blk + 10 * (size_t) i;
+    RdCost rc; createRd( rc, opt );
+    BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
+    rc.setLambda( lambda, bd );
+    rc.selectMotionLambda();
+    rc.setCostScale( costScale );
+    rc.setPredictor( Mv( b[8], b[9] ) );
+    static thread_local InterSearch* isp = new InterSearch;          // large object: heap, one per thread, never initialised beyond the three members read
+    InterSearch& is = *isp;
+    is.m_pcRdCost = &rc;
+    is.m_lumaClpRng.bd = bitDepth;
+    const int w = b[2], h = b[3];
+    AlignedPel org( (size_t) w * h );                                   // the pattern key is a compact CU-local buffer in the encoder
+    for( int y = 0; y < h; y++ ) memcpy( org.p + y * w, orgPlane + (ptrdiff_t)( b[1] + y ) * orgStride + b[0], 2 * w );
+    CPelBuf key( org.p, w, w, h );
+    InterSearch::TZSearchStruct st;
+    memset( &st, 0, sizeof( st ) );
+    st.pcPatternKey = &key;
+    st.piRefY = refPlane + (ptrdiff_t) b[1] * refStride + b[0];
+    st.iRefStride = refStride;
+    st.subShiftMode = subShiftMode;
+    st.imvShift = (unsigned) imvShift;
+    st.searchRange.left = b[4]; st.searchRange.right = b[5]; st.searchRange.top = b[6]; st.searchRange.bottom = b[7];
+    Mv mv; Distortion sad = 0;
+    is.xPatternSearch( st, mv, sad );
+    int32_t* o = out + 4 * (size_t) i;
+    o[0] = mv.hor; o[1] = mv.ver; o[2] = (int32_t)( st.uiBestSad & 0xffffffffu ); o[3] = (int32_t)( st.uiBestSad >> 32 );
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -200,3 +200,22 @@ def test_two_pass_interpolation(opt):
                         O.orc_if_two_pass(PO(src, 8 * S + 12), S, w, h, fx, fy, bd, rt, alt, P(d1), w)
                         R.refshim_if_two_pass(opt, PO(src, 8 * S + 12), S, w, h, fx, fy, bd, rt, alt, P(d2), w)
                         assert np.array_equal(d1, d2), (bd, w, h, rt, alt, fx, fy)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_full_search_against_the_reference_member_function(opt, golden):
+    """InterSearch::xPatternSearch itself (called as a member on an InterSearch whose only live members are the ones it reads) against the oracle's
+    replay and the golden argmins; sub-sampling through RdCost::setDistParam's own subShiftMode rule (mode 2: every second row when h > 8)"""
+    from _libs import refshim, P, PO
+    R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    O = impls.OracleImpl()
+    sc = C.search_case()
+    n = len(sc['blk']); S = sc['stride']; base = sc['margin'] * S + sc['margin']
+    for ss, mode in ((0, 0), (1, 2)):
+        out = np.zeros((n, 4), dtype=np.int32)
+        R.refshim_pattern_search_member(opt, PO(sc['org'], base), S, PO(sc['ref'], base), S, P(sc['blk']), n, 10, mode, sc['lam'], sc['cost_scale'], sc['imv_shift'], P(out))
+        same = [i for i in range(n) if ss == 0 or sc['blk'][i][3] > 8]
+        assert len(same) >= 20
+        assert np.array_equal(out[same], O.full_search(sc, ss)[same])
+        assert np.array_equal(out[same], golden['search_best_ss%d' % ss][same])
