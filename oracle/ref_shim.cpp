@@ -889,6 +889,59 @@ void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStr
   }
 }
 
+// The reference's OWN apply stage for a whole luma picture: MCTF::bilateralFilter (MCTF.cpp:1489-1556) -> xFinalizeBlkLine (:1399-1487), called as members.
+// org: compact width x height; refs[i]: compact width x height neighbour pictures (padded here by MCTF_PADDING with border replication);
+// mv4: [numRefs][hInBlks][wInBlks] x { x, y, error, rmsme }; refIndex[i] = min(5, |POC distance| - 1) selects m_refStrengths[picReordering ? 0 : 1][.].
+// strengthsOut (nullable) receives the strengths the reference used, sigmaSqOut its luma sigma^2 -- so that callers of the C ABI can be fed the same numbers.
+void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
+                                    int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply,
+                                    int16_t* out, double* strengthsOut, double* sigmaSqOut )
+{
+  RefCtx& c = ctx();
+  MCTF* m = c.mctf[opt?1:0];
+  static VVEncCfg cfg;
+  cfg.m_internalBitDepth[CH_L] = bitDepth; cfg.m_internalBitDepth[CH_C] = bitDepth;
+  cfg.m_internChromaFormat = VVENC_CHROMA_400; cfg.m_QP = qp; cfg.m_picReordering = picReordering != 0;
+  m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_mctfUnitSize = unitSize; m->m_lowResFltApply = lowResApply != 0;
+  const int pad = MCTF_PADDING;
+  auto load = [&]( PelStorage& ps, const int16_t* src, int margin )
+  {
+    ps.create( CHROMA_400, Area( 0, 0, width, height ), 0, margin );
+    PelBuf b = ps.Y();
+    for( int y = 0; y < height; y++ ) memcpy( b.buf + (ptrdiff_t) y * b.stride, src + (size_t) y * width, sizeof( Pel ) * width );
+    if( margin ) ps.extendBorderPel( margin, margin );
+  };
+  PelStorage orgPic, newOrgPic;
+  load( orgPic, org, 0 ); load( newOrgPic, org, 0 );
+  const int wInBlks = ( width + unitSize - 1 ) / unitSize, hInBlks = ( height + unitSize - 1 ) / unitSize;
+  std::deque<TemporalFilterSourcePicInfo> info( numRefs );
+  for( int i = 0; i < numRefs; i++ )
+  {
+    load( info[i].picBuffer, refs[i], pad );
+    info[i].mvs.allocate( wInBlks, hInBlks );
+    info[i].index = refIndex[i];
+    for( int y = 0; y < hInBlks; y++ )
+      for( int x = 0; x < wInBlks; x++ )
+      {
+        const int32_t* v = mv4 + 4 * ( ( (size_t) i * hInBlks + y ) * wInBlks + x );
+        MotionVector& mv = info[i].mvs.get( x, y );
+        mv.x = v[0]; mv.y = v[1]; mv.error = v[2]; mv.rmsme = (uint16_t) v[3];
+      }
+    if( strengthsOut ) strengthsOut[i] = MCTF::m_refStrengths[picReordering ? 0 : 1][refIndex[i]];
+  }
+  if( sigmaSqOut )
+  {
+    const double lumaSigmaSq = MCTF::m_sigmaMultiplier * ( 128.0 + 3.0 / 256.0 * qp * qp * qp );
+    const double w = 1024.0 / ( ( 1 << bitDepth ) );
+    *sigmaSqOut = lumaSigmaSq / ( w * w );
+  }
+  m->bilateralFilter( orgPic, info, newOrgPic, overallStrength );
+  CPelBuf r = newOrgPic.Y();
+  for( int y = 0; y < height; y++ ) memcpy( out + (size_t) y * width, r.buf + (ptrdiff_t) y * r.stride, sizeof( Pel ) * width );
+  orgPic.destroy(); newOrgPic.destroy();
+  for( int i = 0; i < numRefs; i++ ) info[i].picBuffer.destroy();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Affine gradient helpers (AffineGradientSearch.h:67-69)
 void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )

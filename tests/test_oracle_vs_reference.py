@@ -219,3 +219,39 @@ def test_full_search_against_the_reference_member_function(opt, golden):
         assert len(same) >= 20
         assert np.array_equal(out[same], O.full_search(sc, ss)[same])
         assert np.array_equal(out[same], golden['search_best_ss%d' % ss][same])
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_mctf_apply_against_the_reference_member_function(opt):
+    """MCTF::bilateralFilter -> xFinalizeBlkLine called as members on whole small pictures (unit 8 and 16, QP on both sides of the planar-correction
+    threshold, 6-tap and 4-tap apply filters, clipped edge blocks): the oracle chain fed with the same strengths / sigma gives the same picture"""
+    import ctypes
+    from _libs import oracle, refshim, P
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(303 + opt)
+    for (W, H, unit, nrefs, qp, tap4, reorder) in ((96, 64, 16, 4, 22, 0, 1), (72, 40, 8, 6, 40, 0, 1), (64, 48, 16, 2, 32, 1, 0), (48, 32, 8, 8, 27, 0, 1)):
+        base = rs.randint(0, 1024, size=(H + 8, W + 8))
+        sm = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4
+        org = np.ascontiguousarray(sm[4:4 + H, 4:4 + W].astype(np.int16))
+        refs = []
+        for a in ([3, 12, 60, 300] * 2)[:nrefs]:
+            dy = int(rs.randint(-1, 2)); dx = int(rs.randint(-1, 2))
+            refs.append(np.ascontiguousarray(np.clip(sm[4 + dy:4 + dy + H, 4 + dx:4 + dx + W] + rs.randint(-a, a + 1, size=org.shape), 0, 1023).astype(np.int16)))
+        wb, hb = (W + unit - 1) // unit, (H + unit - 1) // unit
+        mv = np.zeros((nrefs, hb * wb, 4), dtype=np.int32)
+        mv[..., 0] = rs.randint(-16 * 5, 16 * 5 + 1, size=(nrefs, hb * wb)); mv[..., 1] = rs.randint(-16 * 5, 16 * 5 + 1, size=(nrefs, hb * wb))
+        mv[..., 2] = rs.choice([3, 20, 49, 50, 75, 100, 101, 400], size=(nrefs, hb * wb)); mv[..., 3] = rs.choice([0, 1, 5, 22, 60], size=(nrefs, hb * wb))
+        idx = np.array([i % 6 for i in range(nrefs)], dtype=np.int32)
+        ptrs = (ctypes.c_void_p * nrefs)(*[r.ctypes.data for r in refs])
+        got = np.zeros((H, W), dtype=np.int16); strg = np.zeros(nrefs, dtype=np.float64); sig = ctypes.c_double()
+        overall = 0.95
+        R.refshim_mctf_bilateral_filter(opt, P(org), ptrs, nrefs, P(np.ascontiguousarray(mv)), P(idx), W, H, 10, unit, qp, ctypes.c_double(overall), reorder, tap4,
+                                        P(got), P(strg), ctypes.byref(sig))
+        assert sig.value == 9.0 * (128.0 + 3.0 / 256.0 * qp * qp * qp)                      # 10 bit: bitDepthDiffWeighting = 1
+        pad = 128
+        case = dict(org=np.ascontiguousarray(np.pad(org, pad, mode='edge')), refs=[np.ascontiguousarray(np.pad(r, pad, mode='edge')) for r in refs],
+                    stride=W + 2 * pad, margin=pad, W=W, H=H, mvs=mv, strengths=strg, ws=overall * 0.4, sigma=sig.value, bs=unit, bd=10, num_refs=nrefs)
+        exp = impls.mctf_apply_expected(O, 'orc', case, tap4, 1 if qp <= 32 else 0)
+        assert np.array_equal(got, exp), (W, H, unit, nrefs, qp, int(np.abs(got.astype(int) - exp).max()))
+        assert np.any(got != org)
