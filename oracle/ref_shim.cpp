@@ -942,6 +942,52 @@ void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* 
   for( int i = 0; i < numRefs; i++ ) info[i].picBuffer.destroy();
 }
 
+// The reference's OWN fractional refinement: InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2683-2725) called as a member -- xExtDIFUpSamplingH, the half-pel
+// round of xPatternRefinement, xExtDIFUpSamplingQ and the quarter-pel round (m_fastSubPel = 0: all nine positions of both rounds are evaluated).
+// blk[i] = { x, y, w, h, mvx, mvy (integer vector), predHor, predVer } ; out[i] = { halfX, halfY, qterX, qterY, costLo, costHi } with the offsets the member
+// returns in rcMvHalf / rcMvQter.  Only the members the call tree reads are initialised (InterPredInterpolation::init allocates the filtered-block buffers).
+void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
+                                 int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int32_t* out )
+{
+  static thread_local InterSearch* isp = nullptr;
+  static thread_local int inited = -1;
+  static VVEncCfg cfg;
+  if( !isp ) isp = new InterSearch;
+  InterSearch& is = *isp;
+  if( inited != ( opt ? 1 : 0 ) ) { if( inited >= 0 ) is.InterPredInterpolation::destroy(); is.InterPredInterpolation::init( opt != 0 ); inited = opt ? 1 : 0; }
+  cfg.m_fastSubPel = 0; cfg.m_meReduceTap = reduceTap; cfg.m_bUseHADME = useHad != 0; cfg.m_fastHad = false;
+  is.m_pcEncCfg = &cfg;
+  is.m_lumaClpRng.bd = bitDepth;
+  is.m_currChromaFormat = CHROMA_400;
+  static CodingUnit dummyCu;
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t* b = blk + 8 * (size_t) i;
+    RdCost rc; createRd( rc, opt );
+    BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
+    rc.setLambda( lambda, bd );
+    rc.selectMotionLambda();
+    rc.setPredictor( Mv( b[6], b[7] ) );
+    is.m_pcRdCost = &rc;
+    const int w = b[2], h = b[3];
+    AlignedPel org( (size_t) w * h );
+    for( int y = 0; y < h; y++ ) memcpy( org.p + y * w, orgPlane + (ptrdiff_t)( b[1] + y ) * orgStride + b[0], 2 * w );
+    CPelBuf key( org.p, w, w, h );
+    InterSearch::TZSearchStruct st;
+    memset( &st, 0, sizeof( st ) );
+    st.pcPatternKey = &key;
+    st.piRefY = refPlane + (ptrdiff_t) b[1] * refStride + b[0];
+    st.iRefStride = refStride;
+    st.imvShift = altHpel ? IMV_HPEL : IMV_OFF;                        // the alternative half-pel filter belongs to AMVR half-pel mode: no quarter-pel round (:2712)
+    st.useAltHpelIf = altHpel != 0;
+    Mv mvInt( b[4], b[5] ), mvHalf, mvQter;
+    Distortion cost = 0;
+    is.xPatternSearchFracDIF( dummyCu, REF_PIC_LIST_0, 0, st, mvInt, mvHalf, mvQter, cost );
+    int32_t* o = out + 6 * (size_t) i;
+    o[0] = mvHalf.hor; o[1] = mvHalf.ver; o[2] = mvQter.hor; o[3] = mvQter.ver; o[4] = (int32_t)( cost & 0xffffffffu ); o[5] = (int32_t)( cost >> 32 );
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Affine gradient helpers (AffineGradientSearch.h:67-69)
 void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )

@@ -255,3 +255,44 @@ def test_mctf_apply_against_the_reference_member_function(opt):
         exp = impls.mctf_apply_expected(O, 'orc', case, tap4, 1 if qp <= 32 else 0)
         assert np.array_equal(got, exp), (W, H, unit, nrefs, qp, int(np.abs(got.astype(int) - exp).max()))
         assert np.any(got != org)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_fractional_refinement_against_the_reference_member_function(opt):
+    """InterSearch::xPatternSearchFracDIF itself (xExtDIFUpSamplingH/Q + both rounds of xPatternRefinement, m_fastSubPel = 0) against the replay of the two
+    rounds on the oracle's 7x7 quarter-pel table: the chosen half / quarter offsets and the final cost agree -- for the 8-, 6- and 4-tap ME filter sets,
+    SATD and SAD, and vectors of both parities.  This pins (a) that every filtered block of the encoder is the two-pass interpolation the table holds and
+    (b) the host-side selection in vvenc_b200.candidates.subpel_refinement."""
+    import ctypes
+    from _libs import oracle, refshim, P, PO
+    from vvenc_b200 import candidates as cand
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    R.refshim_frac_search_member.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    O.orc_mv_cost.restype = ctypes.c_uint64
+    case = C.frac_case(5151 + opt)
+    S = case['stride']; base = case['margin'] * S + case['margin']
+    rs = np.random.RandomState(17)
+    lam = 57.25
+    checked = 0
+    for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64)):
+        n = 5
+        blk = np.zeros((n, 8), dtype=np.int32)
+        for k in range(n):
+            blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
+                      int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
+        for (rt, had, alt) in ((2, 1, 0), (0, 1, 0), (1, 1, 0), (2, 0, 0), (2, 1, 1)):
+            out = np.zeros((n, 6), dtype=np.int32)
+            R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, rt, had, alt, P(out))
+            tab = np.zeros((n, 7, 7), dtype=np.uint32)
+            b6 = np.ascontiguousarray(blk[:, :6])
+            O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(b6), n, 2 if had else 1, 10, rt, alt, P(tab))
+            for k in range(n):
+                ph, pv = int(blk[k, 6]), int(blk[k, 7])
+                half, quarter, cost = cand.subpel_refinement(tab[k], (int(blk[k, 4]), int(blk[k, 5])), lambda x, y, cs: int(O.orc_mv_cost(lam, x, y, ph, pv, cs, 0)),
+                                                             quarter_round=not alt)
+                got_cost = (int(out[k, 4]) & 0xffffffff) | (int(out[k, 5]) << 32)
+                assert (half, quarter, cost) == ((int(out[k, 0]), int(out[k, 1])), (int(out[k, 2]), int(out[k, 3])), got_cost), (w, h, rt, had, alt, k, half, quarter, cost, out[k])
+                checked += 1
+    assert checked == 100

@@ -98,3 +98,32 @@ def pyramid_lists(base, levels, pic_w, pic_h):
                 if x >= wc or y >= hc:
                     emit(l, x, y)
     return [(np.array([p[0] for p in L], dtype=np.int32), np.array([p[1] for p in L], dtype=np.int32)) for L in lists]
+
+
+# ---- fractional refinement control (InterSearch::xPatternSearchFracDIF, EncoderLib/InterSearch.cpp:2683-2725, with m_fastSubPel = 0) --------------
+# visiting order of the two rounds of xPatternRefinement (:67-91): offsets in half-pel / quarter-pel units
+REFINE_HALF = ((0, 0), (0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (1, -1), (-1, 1), (1, 1))
+REFINE_QUARTER = ((0, 0), (0, -1), (0, 1), (-1, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (1, 1))
+
+
+def subpel_refinement(table, mv_int, mv_cost, quarter_round=True):
+    """Replays the half-pel and the quarter-pel round on the 7x7 distortion table of vvb_frac_cost_grid (table[j+3][i+3], quarter-pel offsets) for one
+    block.  mv_int: integer vector (x, y); mv_cost(x, y, cost_scale) -> rate of the vector in the units of that round (cost scale 1: half pel, 0: quarter
+    pel; RdCost::getCostOfVectorWithPredictor).  Every round starts from MAX_DISTORTION and takes the first strictly smaller cost in visiting order.
+    quarter_round=False stops after the half-pel round (AMVR half-pel mode, the only mode that uses the alternative half-pel filter, :2712).
+    Returns (half_offset, quarter_offset, cost): the offsets rcMvHalf / rcMvQter of the reference and the final cost."""
+    best = None; half = (0, 0)
+    bx, by = mv_int[0] << 1, mv_int[1] << 1                    # rcMvHalf base = rcMvInt << 1
+    for (dx, dy) in REFINE_HALF:
+        c = int(table[2 * dy + 3][2 * dx + 3]) + mv_cost(bx + dx, by + dy, 1)
+        if best is None or c < best:
+            best = c; half = (dx, dy)
+    if not quarter_round:
+        return half, (0, 0), best
+    qbx, qby = (bx + half[0]) << 1, (by + half[1]) << 1       # rcMvQter base = ((rcMvInt << 1) + rcMvHalf) << 1
+    best = None; quarter = (0, 0)
+    for (dx, dy) in REFINE_QUARTER:
+        c = int(table[2 * half[1] + dy + 3][2 * half[0] + dx + 3]) + mv_cost(qbx + dx, qby + dy, 0)
+        if best is None or c < best:
+            best = c; quarter = (dx, dy)
+    return half, quarter, best
