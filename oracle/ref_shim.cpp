@@ -804,13 +804,14 @@ void refshim_mctf_estimate_level( int opt, const int16_t* org, int orgStride, co
 // The whole MCTF motion search of one neighbour picture, as MCTF::motionEstimationMCTF chains it (MCTF.cpp:666-724): subsampleLuma pyramids (:1072-1097,
 // reference code, incl. its border extension) and four or five motionEstimationLuma levels.  org / ref: compact width x height pictures; the probe pads
 // them by MCTF_PADDING with border replication as Picture buffers are.  out: [hInBlks][wInBlks] x { x, y, error, rmsme }.
-void refshim_mctf_estimate_pyramid( int opt, const int16_t* org, const int16_t* ref, int width, int height, int bitDepth, int unitSize, int addLevel, int32_t* out )
+void refshim_mctf_estimate_pyramid( int opt, const int16_t* org, const int16_t* ref, int width, int height, int bitDepth, int unitSize, int addLevel,
+                                    int searchPattern, int lowResFilter, int32_t* out )
 {
   RefCtx& c = ctx();
   MCTF* m = c.mctf[opt?1:0];
   static VVEncCfg cfg;
   cfg.m_internalBitDepth[CH_L] = bitDepth; cfg.m_internalBitDepth[CH_C] = bitDepth;
-  m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_searchPttrn = 0; m->m_mctfUnitSize = unitSize; m->m_lowResFltSearch = false;
+  m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_searchPttrn = searchPattern; m->m_mctfUnitSize = unitSize; m->m_lowResFltSearch = lowResFilter != 0;
   const int pad = MCTF_PADDING;
   auto load = [&]( PelStorage& ps, const int16_t* src )
   {

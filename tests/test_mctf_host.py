@@ -122,10 +122,11 @@ def test_engine_provider_path_equals_oracle_provider():
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("add_level", [0, 1])
-def test_pyramid_replay_equals_reference(add_level):
+@pytest.mark.parametrize("add_level,pattern,tap4", [(0, 0, 0), (1, 0, 0), (0, 1, 1), (1, 2, 1), (0, 2, 0)])
+def test_pyramid_replay_equals_reference(add_level, pattern, tap4):
     """the whole motion search of one neighbour picture (MCTF::motionEstimationMCTF: 2x2-averaged pyramids + 4 or 5 chained levels) on a picture whose
-    size is not a multiple of the coarse block sizes: the final field equals the reference's, vectors, scaled errors and rmsme"""
+    size is not a multiple of the coarse block sizes, for the three search patterns (MCTFSpeed 0 / 1-2 / 3-4) and both filter sets: the final field equals
+    the reference's, vectors, scaled errors and rmsme"""
     rs = np.random.RandomState(21 + add_level)
     W, H = 208, 136
     base = rs.randint(0, 1024, size=(H + 16, W + 16))
@@ -137,14 +138,14 @@ def test_pyramid_replay_equals_reference(add_level):
     u = 8
     wb, hb = (W + u - 1) // u, (H + u - 1) // u
     exp = np.zeros((hb, wb, 4), dtype=np.int32)
-    R.refshim_mctf_estimate_pyramid(1, P(org), P(ref), W, H, 10, u, add_level, P(exp))
+    R.refshim_mctf_estimate_pyramid(1, P(org), P(ref), W, H, 10, u, add_level, pattern, tap4, P(exp))
 
     def make_provider(o, r):
         pad = 128
         po, pr = MH.pad_edge(o, pad), MH.pad_edge(r, pad)
-        return OracleProvider(po, pr, po.shape[1], pad)
+        return OracleProvider(po, pr, po.shape[1], pad, 10, tap4)
 
-    got = MH.estimate_pyramid(make_provider, org, ref, u, bool(add_level))
+    got = MH.estimate_pyramid(make_provider, org, ref, u, bool(add_level), 10, pattern)
     assert got['x'].shape == (hb, wb)
     assert np.array_equal(got['x'], exp[..., 0]) and np.array_equal(got['y'], exp[..., 1])
     assert np.array_equal(got['error'], exp[..., 2]) and np.array_equal(got['rmsme'].astype(np.int32), exp[..., 3])

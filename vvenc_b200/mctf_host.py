@@ -2,7 +2,7 @@
 
 MCTF::estimateLumaLn (CommonLib/MCTF.cpp:1166-1327) decides with `error < best.error` chains over a few candidate sets; the errors themselves are what
 the GPU library returns in bulk (vvb_mctf_search_grid: whole search grids per block, vvb_mctf_error_batch: explicit candidates, vvb_mctf_calc_var).
-`estimate_level` reproduces one pyramid level (MCTF::motionEstimationLuma, :1329-1397) for search pattern 0:
+`estimate_level` reproduces one pyramid level (MCTF::motionEstimationLuma, :1329-1397) for the three search patterns (MCTFSpeed 0 / 1-2 / 3-4, :598-599):
 
   stage A  predictors: the 3x3 neighbourhood of the coarser level's field (scaled by `factor`) and the zero vector            (:1191-1214)
   stage B  integer grid around trunc(best / 16): range 8 without a coarser level, 5 with one, none when doubleRes              (:1216-1228)
@@ -49,22 +49,37 @@ def _trunc_div16(v):
     return np.where(v >= 0, v // 16, -((-v) // 16)).astype(np.int32)
 
 
-def _take_first_min(best_x, best_y, best_e, sel, tab, cx, cy, step, radius, skip_centre):
-    """loop order of the reference: y outer, x inner, strictly smaller wins; updates best_* in place for the blocks `sel`"""
-    k1 = 2 * radius + 1
-    for j in range(k1):
-        for i in range(k1):
-            if skip_centre and i == radius and j == radius:
+def _offset_table(provider, cands, cx, cy, offs):
+    """errors of the vectors (cx + ox, cy + oy) for ox, oy in the equally spaced offset list `offs` (1/16 pel), through one grid call: the grid entry point takes
+    centre +- k * step with step <= 16, so wider or centre-less sets ({-6,-2,2,6}, step 32) are read out of the smallest covering lattice"""
+    offs = list(offs)
+    if len(offs) == 1:
+        c = cands.copy(); c['mvx'] = cx + offs[0]; c['mvy'] = cy + offs[0]
+        return provider.errors(c).astype(np.int64).reshape(-1, 1, 1)
+    d = offs[1] - offs[0]
+    step = d
+    while step > 16:
+        step //= 2
+    radius = -(-(offs[-1] - offs[0]) // (2 * step))
+    shift = offs[0] + radius * step
+    c = cands.copy(); c['mvx'] = cx + shift; c['mvy'] = cy + shift
+    tab = provider.grid(c, step, radius).astype(np.int64)
+    idx = [(o - offs[0]) // step for o in offs]
+    return tab[:, idx, :][:, :, idx]
+
+
+def _take_first_min_offsets(best_x, best_y, best_e, tab, cx, cy, offs, skip_zero):
+    """loop order of the reference: y outer, x inner, strictly smaller wins"""
+    for j, oy in enumerate(offs):
+        for i, ox in enumerate(offs):
+            if skip_zero and ox == 0 and oy == 0:
                 continue
             e = tab[:, j, i]
-            better = e < best_e[sel]
-            idx = sel[better]
-            best_e[idx] = e[better]
-            best_x[idx] = cx[better] + (i - radius) * step
-            best_y[idx] = cy[better] + (j - radius) * step
+            better = e < best_e
+            best_e[better] = e[better]; best_x[better] = cx[better] + ox; best_y[better] = cy[better] + oy
 
 
-def estimate_level(provider, width, height, block_size, previous=None, factor=2, double_res=False, bit_depth=10, unit_size=16):
+def estimate_level(provider, width, height, block_size, previous=None, factor=2, double_res=False, bit_depth=10, unit_size=16, search_pattern=0):
     """One level of the MCTF motion search for the whole picture.  previous: None or (prev_x, prev_y) int arrays [prevH][prevW] of the coarser level.
     Returns dict(x, y, error, rmsme, overlap) with arrays [blocksY][blocksX] (vectors in 1/16 pel) -- MotionVector fields of MCTF.h:72-82."""
     bs = block_size
@@ -84,7 +99,7 @@ def estimate_level(provider, width, height, block_size, previous=None, factor=2,
     # ---- stage A: predictors of the coarser level (3x3 neighbourhood, raster order) and the zero vector
     search_range = 8
     if previous is not None:
-        search_range = 0 if double_res else 5
+        search_range = 0 if double_res else (3 if search_pattern == 2 else 5)
         px, py = previous
         ph, pw = px.shape
         for dy in (-1, 0, 1):
@@ -102,21 +117,20 @@ def estimate_level(provider, width, height, block_size, previous=None, factor=2,
         e = provider.errors(cands_of(allb, 0, 0)).astype(np.int64)
         better = e < best_e
         best_e[better] = e[better]; best_x[better] = 0; best_y[better] = 0
-    # ---- stage B: integer grid around trunc(prevBest / 16)
+    # ---- stage B: integer grid around trunc(prevBest / 16); search pattern 2 visits every second position of the first level (:1217)
     cx = _trunc_div16(best_x) * 16; cy = _trunc_div16(best_y) * 16
-    if search_range > 0:
-        tab = provider.grid(cands_of(allb, cx, cy), 16, search_range)
-        _take_first_min(best_x, best_y, best_e, allb, tab.astype(np.int64), cx, cy, 16, search_range, False)
-    else:                                                   # range 0: the single vector trunc(prevBest / 16) * 16 is still evaluated (:1218-1228)
-        e = provider.errors(cands_of(allb, cx, cy)).astype(np.int64)
-        better = e < best_e
-        best_e[better] = e[better]; best_x[better] = cx[better]; best_y[better] = cy[better]
-    # ---- stage C: sub-pel refinement around the running best
+    d = 2 if (previous is None and search_pattern == 2) else 1
+    offs = [16 * v for v in range(-search_range, search_range + 1, d)]
+    tab = _offset_table(provider, cands_of(allb, 0, 0), cx, cy, offs)
+    _take_first_min_offsets(best_x, best_y, best_e, tab, cx, cy, offs, False)
+    # ---- stage C: sub-pel refinement around the running best (:1229-1287): +-12 step 4 (pattern 0), +-6 step 4 (1) or step 6 (2); then +-2 step 2; then +-1
     if double_res:
-        for (step, radius) in ((4, 3), (2, 1), (1, 1)):
+        rng = 12 if search_pattern == 0 else 6
+        d1 = 6 if search_pattern == 2 else 4
+        for offs in (list(range(-rng, rng + 1, d1)), [-2, 0, 2], [-1, 0, 1]):
             cx = best_x.copy(); cy = best_y.copy()
-            tab = provider.grid(cands_of(allb, cx, cy), step, radius)
-            _take_first_min(best_x, best_y, best_e, allb, tab.astype(np.int64), cx, cy, step, radius, True)
+            tab = _offset_table(provider, cands_of(allb, 0, 0), cx, cy, offs)
+            _take_first_min_offsets(best_x, best_y, best_e, tab, cx, cy, offs, True)
     # ---- stage D: final vectors of the upper and the left neighbour, along anti-diagonals
     bxi = (X // bs); byi = (Y // bs)
     for wave in range(1, bxn + byn - 1):
@@ -165,7 +179,7 @@ def pad_edge(pic, pad=128):
     return np.ascontiguousarray(np.pad(pic, pad, mode='edge'))
 
 
-def estimate_pyramid(make_provider, org, ref, unit_size=16, add_level=False, bit_depth=10):
+def estimate_pyramid(make_provider, org, ref, unit_size=16, add_level=False, bit_depth=10, search_pattern=0):
     """MCTF::motionEstimationMCTF (MCTF.cpp:666-724) for one neighbour picture: subsampled pyramids and four (five with add_level) chained levels.
     org / ref: unpadded pictures [H][W]; make_provider(org_pic, ref_pic) returns a provider for that pair of level pictures (it pads / uploads them).
     The motion-field arrays of the intermediate levels are sized as the reference sizes them (width / (unit * k) + 1): entries no block writes keep the
@@ -177,7 +191,7 @@ def estimate_pyramid(make_provider, org, ref, unit_size=16, add_level=False, bit
 
     def level(lv, bs, prev, factor, double_res, out_w, out_h):
         h, w = o[lv].shape
-        f = estimate_level(make_provider(o[lv], r[lv]), w, h, bs, prev, factor, double_res, bit_depth, unit_size)
+        f = estimate_level(make_provider(o[lv], r[lv]), w, h, bs, prev, factor, double_res, bit_depth, unit_size, search_pattern)
         fx = np.zeros((out_h, out_w), dtype=np.int32); fy = np.zeros((out_h, out_w), dtype=np.int32)
         fh, fw = min(out_h, f['x'].shape[0]), min(out_w, f['x'].shape[1])
         fx[:fh, :fw] = f['x'][:fh, :fw]; fy[:fh, :fw] = f['y'][:fh, :fw]
