@@ -944,11 +944,12 @@ void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* 
 }
 
 // The reference's OWN fractional refinement: InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2683-2725) called as a member -- xExtDIFUpSamplingH, the half-pel
-// round of xPatternRefinement, xExtDIFUpSamplingQ and the quarter-pel round (m_fastSubPel = 0: all nine positions of both rounds are evaluated).
+// round of xPatternRefinement, xExtDIFUpSamplingQ and the quarter-pel round (fastSubPel 0: all nine positions of both rounds; 1: the preset heuristics, where
+// xPatternRefinement filters the half-pel blocks itself and skips positions by s_skipQpelPosition).
 // blk[i] = { x, y, w, h, mvx, mvy (integer vector), predHor, predVer } ; out[i] = { halfX, halfY, qterX, qterY, costLo, costHi } with the offsets the member
 // returns in rcMvHalf / rcMvQter.  Only the members the call tree reads are initialised (InterPredInterpolation::init allocates the filtered-block buffers).
 void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
-                                 int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int32_t* out )
+                                 int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int fastSubPel, int32_t* out )
 {
   static thread_local InterSearch* isp = nullptr;
   static thread_local int inited = -1;
@@ -956,7 +957,7 @@ void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride
   if( !isp ) isp = new InterSearch;
   InterSearch& is = *isp;
   if( inited != ( opt ? 1 : 0 ) ) { if( inited >= 0 ) is.InterPredInterpolation::destroy(); is.InterPredInterpolation::init( opt != 0 ); inited = opt ? 1 : 0; }
-  cfg.m_fastSubPel = 0; cfg.m_meReduceTap = reduceTap; cfg.m_bUseHADME = useHad != 0; cfg.m_fastHad = false;
+  cfg.m_fastSubPel = fastSubPel; cfg.m_meReduceTap = reduceTap; cfg.m_bUseHADME = useHad != 0; cfg.m_fastHad = false;
   is.m_pcEncCfg = &cfg;
   is.m_lumaClpRng.bd = bitDepth;
   is.m_currChromaFormat = CHROMA_400;

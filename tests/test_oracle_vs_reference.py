@@ -269,7 +269,7 @@ def test_fractional_refinement_against_the_reference_member_function(opt):
     O = oracle(); R = refshim()
     R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
     R.refshim_frac_search_member.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
-                                             ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+                                             ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     O.orc_mv_cost.restype = ctypes.c_uint64
     case = C.frac_case(5151 + opt)
     S = case['stride']; base = case['margin'] * S + case['margin']
@@ -284,7 +284,7 @@ def test_fractional_refinement_against_the_reference_member_function(opt):
                       int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
         for (rt, had, alt) in ((2, 1, 0), (0, 1, 0), (1, 1, 0), (2, 0, 0), (2, 1, 1)):
             out = np.zeros((n, 6), dtype=np.int32)
-            R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, rt, had, alt, P(out))
+            R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, rt, had, alt, 0, P(out))
             tab = np.zeros((n, 7, 7), dtype=np.uint32)
             b6 = np.ascontiguousarray(blk[:, :6])
             O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(b6), n, 2 if had else 1, 10, rt, alt, P(tab))
@@ -296,3 +296,26 @@ def test_fractional_refinement_against_the_reference_member_function(opt):
                 assert (half, quarter, cost) == ((int(out[k, 0]), int(out[k, 1])), (int(out[k, 2]), int(out[k, 3])), got_cost), (w, h, rt, had, alt, k, half, quarter, cost, out[k])
                 checked += 1
     assert checked == 100
+    # the preset control (m_fastSubPel = 1): positions are skipped by the encoder's own heuristics, but whatever position it ends on, its cost must be the
+    # table entry of that position plus the vector rate -- the half-pel blocks filtered inside xPatternRefinement and the partial xExtDIFUpSamplingQ planes
+    # are the same two-pass interpolations
+    for (w, h) in ((8, 8), (16, 16), (32, 32)):
+        n = 8
+        blk = np.zeros((n, 8), dtype=np.int32)
+        for k in range(n):
+            blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
+                      int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
+        out = np.zeros((n, 6), dtype=np.int32)
+        R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, 2, 1, 0, 1, P(out))
+        tab = np.zeros((n, 7, 7), dtype=np.uint32)
+        O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk[:, :6])), n, 2, 10, 2, 0, P(tab))
+        for k in range(n):
+            ph, pv = int(blk[k, 6]), int(blk[k, 7]); mx, my = int(blk[k, 4]), int(blk[k, 5])
+            hx, hy, qx, qy = [int(v) for v in out[k, :4]]
+            got_cost = (int(out[k, 4]) & 0xffffffff) | (int(out[k, 5]) << 32)
+            c_half = int(tab[k][2 * hy + 3][2 * hx + 3]) + int(O.orc_mv_cost(lam, 2 * mx + hx, 2 * my + hy, ph, pv, 1, 0))
+            ok = got_cost == c_half
+            if abs(qx) <= 1 and abs(qy) <= 1:
+                c_q = int(tab[k][2 * hy + qy + 3][2 * hx + qx + 3]) + int(O.orc_mv_cost(lam, 2 * (2 * mx + hx) + qx, 2 * (2 * my + hy) + qy, ph, pv, 0, 0))
+                ok = ok or got_cost == c_q
+            assert ok, (w, h, k, out[k], c_half)
