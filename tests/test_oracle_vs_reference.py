@@ -186,7 +186,7 @@ def test_two_pass_interpolation(opt):
     O = oracle(); R = refshim()
     R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
     rs = np.random.RandomState(11 + opt)
-    for bd in (8, 10):
+    for bd in (8, 10, 12):
         mx = (1 << bd) - 1
         for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (64, 32)):
             S = w + 32
