@@ -232,6 +232,97 @@ def cpu_arm(sample_budget_s=12.0, threads=None, quiet=False):
             'cpu_s_per_step': t_step, 'legs': legs}
 
 
+def cpu_rows(threads=None, budget_s=1.5):
+    """the reference's own AVX2 code on the host cores for the rows of SURVEY section 8 outside the headline step (TU round trip, MCTF block
+    matching grid, fractional SATD grid, MCTF apply): a bounded sample each, same units as the matching extra.* GPU entries.  Needs oracle/_ref."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _libs import have_ref, refshim, P, PO
+    if not have_ref():
+        return {'unavailable': 'oracle/_ref not built'}
+    R = refshim()
+    threads = threads or (os.cpu_count() or 1)
+    w, h = 1280, 720
+    org, ref, S = synth_picture_pair(4321, w, h, MARGIN)
+    base = MARGIN * S + MARGIN
+    rs = np.random.RandomState(77)
+    rows = {'cores': threads, 'kind': 'reference', 'picture': '%dx%d sample of the same synthetic content' % (w, h)}
+
+    def sized(run, n0, cap):
+        """calibrate on n0 units, then one run sized to the budget"""
+        t = run(n0)
+        n = int(min(cap, max(n0, n0 * budget_s / max(t, 1e-6))))
+        t = run(n)
+        reps = int(min(50, max(1, budget_s / max(t, 1e-6))))                      # sample capped by the picture: repeat it until the budget is used
+        return n, sum(run(n) for _ in range(reps)) / reps
+
+    # TU round trip (TrQuant::transformNxN + Quant::quant + dequant + invTransformNxN + reconstruct + SSE), DCT-II, QP of the step
+    tu = {}
+    for n in SIZES:
+        cap = (64 << 20) // (4 * n * n)
+        o = rs.randint(0, 1024, size=cap * n * n).astype(np.int16)
+        pr = np.clip(o + rs.randint(-200, 201, size=o.size), 0, 1023).astype(np.int16)
+        q = np.zeros(cap * n * n, dtype=np.int16); rc = np.zeros(cap * n * n, dtype=np.int16); o4 = np.zeros(cap * 4, dtype=np.uint64)
+        def run(cnt):
+            t0 = time.perf_counter()
+            R.refshim_tu_roundtrip_batch(1, 0, 0, P(o), P(pr), cnt, n, n, BITDEPTH, QP, 0, P(q), P(rc), P(o4), threads)
+            return time.perf_counter() - t0
+        cnt, t = sized(run, 16 * threads, cap)
+        tu[str(n)] = {'tus': cnt, 's': t, 'tu_per_s': cnt / t}
+    rows['tu_roundtrip'] = tu
+
+    # MCTF block matching (motionErrorLumaFrac6/Int8): every 16x16 block, the 49 quarter-step vectors of the doubleRes refinement
+    B = 16
+    gx, gy = np.meshgrid(np.arange(0, w - B + 1, B), np.arange(0, h - B + 1, B))
+    off = np.array([(dx, dy) for dy in range(-12, 13, 4) for dx in range(-12, 13, 4)], dtype=np.int32)
+    nbk = gx.size; K = len(off)
+    desc = np.zeros((nbk * K, 6), dtype=np.int32)
+    desc[:, 0] = np.repeat(gx.reshape(-1), K); desc[:, 1] = np.repeat(gy.reshape(-1), K)
+    desc[:, 2] = np.tile(off[:, 0], nbk) + 32; desc[:, 3] = np.tile(off[:, 1], nbk) - 16; desc[:, 4] = B; desc[:, 5] = B
+    err = np.zeros(nbk * K, dtype=np.int32)
+    def run(cnt):
+        t0 = time.perf_counter()
+        R.refshim_mctf_err_list(1, 0, PO(org, base), S, PO(ref, base), S, P(desc), cnt, BITDEPTH, P(err), threads)
+        return time.perf_counter() - t0
+    cnt, t = sized(run, K * 4 * threads, nbk * K)
+    rows['mctf_match_16x16'] = {'candidates': cnt, 's': t, 'cand_per_s': cnt / t, 'block_refs_per_s': cnt / K / t}
+
+    # fractional SATD grid (InterpolationFilter two-pass + HAD): 49 quarter-pel offsets per block
+    fr = {}
+    for n in (8, 16, 32):
+        xs, ys = block_grid(n, w, h)
+        blk = np.zeros((len(xs), 6), dtype=np.int32)
+        blk[:, 0] = xs; blk[:, 1] = ys; blk[:, 2] = n; blk[:, 3] = n; blk[:, 4] = rs.randint(-8, 9, size=len(xs)); blk[:, 5] = rs.randint(-8, 9, size=len(xs))
+        out = np.zeros(len(xs) * 49, dtype=np.uint32)
+        def run(cnt):
+            t0 = time.perf_counter()
+            R.refshim_frac_cost_grid_mt(1, PO(org, base), S, PO(ref, base), S, P(blk), cnt, 2, BITDEPTH, 2, 0, P(out), threads)
+            return time.perf_counter() - t0
+        cnt, t = sized(run, min(len(xs), 2 * threads), len(xs))
+        fr[str(n)] = {'blocks': cnt, 's': t, 'cand_per_s': cnt * 49 / t}
+    rows['frac_satd_grid'] = fr
+
+    # MCTF apply stage (xFinalizeBlkLine: applyFrac + planar correction + applyBlock), 8 neighbour pictures, unit 16
+    nrefs = 8
+    planes = [np.ascontiguousarray(np.roll(ref, (i + 1, 2 * i - 5), axis=(0, 1))) for i in range(nrefs)]
+    ptrs = (ctypes.c_void_p * nrefs)(*[ctypes.cast(PO(p_, base), ctypes.c_void_p).value for p_ in planes])
+    bxN, byN = w // B, h // B
+    mv4 = np.zeros((nrefs, bxN * byN, 4), dtype=np.int32)
+    mv4[:, :, 0] = rs.randint(-40, 41, size=(nrefs, bxN * byN)); mv4[:, :, 1] = rs.randint(-40, 41, size=(nrefs, bxN * byN))
+    mv4[:, :, 2] = rs.randint(5, 150, size=(nrefs, bxN * byN)); mv4[:, :, 3] = rs.randint(0, 30, size=(nrefs, bxN * byN))
+    stg = (ctypes.c_double * nrefs)(0.85, 0.57, 0.41, 0.33, 0.30, 0.20, 0.18, 0.15)
+    dst = np.zeros((h, w), dtype=np.int16)
+    R.refshim_mctf_finalize_picture.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+                                                ctypes.c_int, ctypes.c_int]
+    def run(_):
+        t0 = time.perf_counter()
+        R.refshim_mctf_finalize_picture(1, PO(org, base), S, ptrs, S, nrefs, P(mv4), w, h, B, BITDEPTH, 0, 1, stg, 0.4, 9 * (128.0 + 3.0 / 256.0 * 32 ** 3), P(dst), w, threads)
+        return time.perf_counter() - t0
+    _, t = sized(run, 1, 1)
+    rows['mctf_apply'] = {'pels': w * h, 'refs': nrefs, 'unit': B, 's': t, 'pels_per_s': w * h / t, 'block_refs_per_s': bxN * byN * nrefs / t}
+    return rows
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -746,6 +837,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_arm(args.cpu_budget)
+        try:
+            extra['cpu_rows'] = cpu_rows()
+        except Exception as ex:
+            extra['cpu_rows'] = {'error': str(ex)}
 
     if rank == 0:
         line = {'metric': 'candidate-blocks/s (SAD+SATD+DCT-quant) on 2160p10', 'value': value, 'unit': 'candidate-blocks/s', 'n_gpus': world,

@@ -741,15 +741,27 @@ void refshim_if_two_pass( int opt, const int16_t* src, int srcStride, int w, int
   Pel* outp = (Pel*)( ( (uintptr_t) outStore.data() + 63 ) & ~uintptr_t( 63 ) );
   f.filterHor( COMP_Y, src - 3 * srcStride, srcStride, tmp, ts, w, h + 7, fx << 2, false, CHROMA_400, rng, altHpel != 0, 0, reduceTap );
   f.filterVer( COMP_Y, tmp + 3 * ts, ts, outp, ts, w, h, fy << 2, false, true, CHROMA_400, rng, altHpel != 0, 0, reduceTap );
-  for( int y = 0; y < h; y++ ) memcpy( dst + (ptrdiff_t) y * dstStride, outp + (ptrdiff_t) y * ts, sizeof( Pel ) * w );
+  if( dst ) for( int y = 0; y < h; y++ ) memcpy( dst + (ptrdiff_t) y * dstStride, outp + (ptrdiff_t) y * ts, sizeof( Pel ) * w );
 }
 
 // blk[b] = { x, y, w, h, mvx, mvy } ; out[b][j+3][i+3] = distFunc( org, filtered block at quarter-pel offset (i, j) ), family 1 SAD / 2 HAD
+void refshim_frac_cost_grid_mt( int opt, const int16_t* orgPlane, int so, const int16_t* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel,
+                                uint32_t* out, int nthreads );
 void refshim_frac_cost_grid( int opt, const int16_t* orgPlane, int so, const int16_t* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel, uint32_t* out )
 {
-  RefCtx& c = ctx();
-  RdCost& rc = c.rd( opt );
-  for( int b = 0; b < n; b++ )
+  refshim_frac_cost_grid_mt( opt, orgPlane, so, refPlane, sr, blk, n, family, bitDepth, reduceTap, altHpel, out, 1 );
+}
+
+// threaded form for the CPU baseline of the row (one RdCost per worker, blocks split statically)
+void refshim_frac_cost_grid_mt( int opt, const int16_t* orgPlane, int so, const int16_t* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel,
+                                uint32_t* out, int nthreads )
+{
+  ctx();
+  refshim_if_two_pass( opt, refPlane, sr, 8, 8, 0, 0, bitDepth, reduceTap, altHpel, nullptr, 0 );   // creates the shared InterpolationFilter before the workers start
+  parallelFor( n, nthreads, [&]( int b0, int b1, int )
+  {
+  RdCost rc; createRd( rc, opt );
+  for( int b = b0; b < b1; b++ )
   {
     const int32_t* d = blk + 6 * (size_t) b;
     const int w = d[2], h = d[3];
@@ -763,6 +775,7 @@ void refshim_frac_cost_grid( int opt, const int16_t* orgPlane, int so, const int
         out[( (size_t) b * 7 + ( j + 3 ) ) * 7 + ( i + 3 )] = (uint32_t) callDist( rc, family, org.p, w, pred.p, w, w, h, bitDepth, 0 );
       }
   }
+  } );
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -988,6 +1001,28 @@ void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride
     int32_t* o = out + 6 * (size_t) i;
     o[0] = mvHalf.hor; o[1] = mvHalf.ver; o[2] = mvQter.hor; o[3] = mvQter.ver; o[4] = (int32_t)( cost & 0xffffffffu ); o[5] = (int32_t)( cost >> 32 );
   }
+}
+
+// whole-picture, threaded form of refshim_mctf_finalize_block for the CPU baseline of the apply row: block rows are split over the workers
+// (mv4: [numRefs][blocksY * blocksX][4]); planes are sample-(0,0) pointers into padded buffers
+void refshim_mctf_finalize_picture( int opt, const int16_t* orgPlane, int orgStride, const int16_t* const* refs, int refStride, int numRefs, const int32_t* mv4,
+                                    int width, int height, int blockSize, int bitDepth, int tap4, int planarEnabled, const double* refStrengths,
+                                    double weightScaling, double sigmaSq, int16_t* dstPlane, int dstStride, int nthreads )
+{
+  ctx();
+  const int bxN = ( width + blockSize - 1 ) / blockSize, byN = ( height + blockSize - 1 ) / blockSize;
+  parallelFor( byN, nthreads, [&]( int r0, int r1, int )
+  {
+    std::vector<int32_t> mv( (size_t) 4 * numRefs );
+    for( int by = r0; by < r1; by++ )
+      for( int bx = 0; bx < bxN; bx++ )
+      {
+        for( int i = 0; i < numRefs; i++ ) memcpy( &mv[4 * i], mv4 + 4 * ( (size_t) i * bxN * byN + (size_t) by * bxN + bx ), 16 );
+        const int x = bx * blockSize, y = by * blockSize;
+        refshim_mctf_finalize_block( opt, orgPlane, orgStride, refs, refStride, numRefs, mv.data(), width, height, x, y, std::min( blockSize, width - x ), std::min( blockSize, height - y ),
+                                     bitDepth, tap4, planarEnabled, refStrengths, weightScaling, sigmaSq, dstPlane, dstStride );
+      }
+  } );
 }
 
 // ---------------------------------------------------------------------------------------------------------
