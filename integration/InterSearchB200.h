@@ -1,0 +1,194 @@
+// integration/InterSearchB200.h -- reference-side binding of libvvenc_b200.so for the motion-search loops of EncoderLib/InterSearch.cpp.
+//
+// Companion of RdCostB200.h (which patches the per-call function-pointer tables): here whole loops of the reference are handed to one batched call and
+// their selection logic is replayed on the returned numbers:
+//
+//   xPatternSearchB200         <->  InterSearch::xPatternSearch        (InterSearch.cpp:2209-2251)   one vvb_sad_search
+//   xPatternSearchFracDIFB200  <->  InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2677-2725)   one vvb_frac_cost_grid + the two xPatternRefinement rounds
+//                                                                      (:760-972, m_fastSubPel == 0) as table look-ups
+//   B200RowSearch                   the production shape: all PUs of a CTU row against resident pictures, one launch per block size
+//
+// The member-shaped functions take the InterSearch object and the TZSearchStruct the reference already fills (piRefY, iRefStride, pcPatternKey, searchRange,
+// imvShift, subShiftMode, useAltHpelIf) and read the predictor / lambda / cost scale from its RdCost exactly as the members do, so a maintainer can
+// swap the call inside xMotionEstimation (:2441-2497) without touching the callers.  They upload the pattern key and the reference window per call:
+// that is the correctness-first form (it is what tests compare with the members themselves); B200RowSearch is the form that performs.
+//
+// Include after RdCostB200.h, EncoderLib/InterSearch.h and CommonLib/RdCost.h.  Private members are used (m_pcRdCost, m_pcEncCfg, m_lumaClpRng):
+// inside the encoder these would be member functions of InterSearch; oracle/ref_shim.cpp compiles this file against the unmodified reference.
+#pragma once
+#include <cmath>
+#include <vector>
+#include "RdCostB200.h"
+
+struct B200SearchApi
+{
+  bool bound = false;
+  decltype( &vvb_plane_upload )    planeUpload = nullptr;
+  decltype( &vvb_sad_search )      sadSearch = nullptr;
+  decltype( &vvb_frac_cost_grid )  fracCostGrid = nullptr;
+} ;
+static B200SearchApi g_b200s;
+
+// binds the search entry points of the library RdCostB200.h has opened; returns 0, -1 (library not loaded) or -2 (symbol missing)
+inline int b200LoadSearch( const char* libPath )
+{
+  if( g_b200s.bound ) return 0;
+  int rc = b200Load( libPath );
+  if( rc ) return rc;
+  void* h = g_b200.handle;
+#define VVB_RESOLVE( member, name ) g_b200s.member = (decltype( g_b200s.member )) dlsym( h, #name ); if( !g_b200s.member ) { g_b200.error = "missing " #name; return -2; }
+  VVB_RESOLVE( planeUpload, vvb_plane_upload )  VVB_RESOLVE( sadSearch, vvb_sad_search )  VVB_RESOLVE( fracCostGrid, vvb_frac_cost_grid )
+#undef VVB_RESOLVE
+  g_b200s.bound = true;
+  return 0;
+}
+
+inline void b200Check( int rc ) { if( rc != VVB_OK ) THROW( g_b200.lastError( b200CtxOfThread() ) ); }
+
+// vvb_me_par of an RdCost in its current state: the library derives the motion lambda as sqrt( lambda ) like RdCost::setLambda (RdCost.cpp:73-78)
+inline vvb_me_par b200MePar( RdCost& rc, int costScale, unsigned imvShift, int subShift )
+{
+  if( rc.m_motionLambda != std::sqrt( rc.m_dLambda ) ) THROW( "motion lambda is not sqrt( lambda ): call selectMotionLambda() after setLambda()" );
+  vvb_me_par me = {};
+  me.lambda = rc.m_dLambda; me.cost_scale = costScale; me.imv_shift = (int) imvShift; me.sub_shift = subShift;
+  return me;
+}
+
+// plane ids the per-call forms use for their uploads
+enum { B200_PLANE_KEY = 14, B200_PLANE_WINDOW = 15 };
+
+// uploads the pattern key (margin 0) and the reference window around piRefY (margin `reach` on every side: the reference pictures are padded, Picture.cpp:461-501)
+inline void b200UploadKeyAndWindow( const CPelBuf& key, const Pel* piRefY, int refStride, int reach, int bitDepth )
+{
+  vvb_ctx* ctx = b200CtxOfThread();
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_KEY, key.buf, key.stride, key.width, key.height, 0, bitDepth ) );
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_WINDOW, piRefY, refStride, key.width, key.height, reach, bitDepth ) );
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------------
+// InterSearch::xPatternSearch (InterSearch.cpp:2209-2251): full search over cStruct.searchRange, raster order, first strictly smaller SAD + MV cost wins
+inline void xPatternSearchB200( InterSearch& is, InterSearch::TZSearchStruct& cStruct, Mv& rcMv, Distortion& ruiSAD )
+{
+  RdCost& rc = *is.m_pcRdCost;
+  const CPelBuf& key = *cStruct.pcPatternKey;
+  const InterSearch::SearchRange& sr = cStruct.searchRange;
+  int subShift = 0;                                                                       // RdCost::setDistParam (RdCost.cpp:187-200)
+  if( cStruct.subShiftMode == 1 && key.height > 8 && key.width <= 128 ) subShift = 1;
+  if( cStruct.subShiftMode == 2 && key.height > 8 ) subShift = 1;
+  const int reach = std::max( std::max( -sr.left, sr.right ), std::max( -sr.top, sr.bottom ) );
+  b200UploadKeyAndWindow( key, cStruct.piRefY, cStruct.iRefStride, std::max( reach, 0 ), is.m_lumaClpRng.bd );
+
+  vvb_block blk = {};
+  blk.left = (int16_t) sr.left; blk.right = (int16_t) sr.right; blk.top = (int16_t) sr.top; blk.bottom = (int16_t) sr.bottom;
+  blk.pred_hor = (int16_t) rc.m_mvPredictor.hor; blk.pred_ver = (int16_t) rc.m_mvPredictor.ver;
+  if( blk.pred_hor != rc.m_mvPredictor.hor || blk.pred_ver != rc.m_mvPredictor.ver ) THROW( "predictor outside the 16-bit range of vvb_block" );
+  const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, cStruct.imvShift, subShift );
+  vvb_best best = {};
+  b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, nullptr, 0, &best ) );
+
+  rcMv.set( best.dx, best.dy );
+  cStruct.uiBestSad = best.cost;                                                          // :2248
+  ruiSAD = best.cost - rc.getCostOfVectorWithPredictor( best.dx, best.dy, cStruct.imvShift );
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------------
+// InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2677-2725) for m_fastSubPel == 0: the interpolation of xExtDIFUpSamplingH / Q and the distortion
+// calls of xPatternRefinement come back as one 7x7 table t[j+3][i+3] (quarter-pel offset (i, j) from rcMvInt); the two rounds are replayed on it.
+inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStruct& cStruct, const Mv& rcMvInt, Mv& rcMvHalf, Mv& rcMvQter, Distortion& ruiCost )
+{
+  const VVEncCfg& cfg = *is.m_pcEncCfg;
+  if( cfg.m_fastSubPel != 0 ) THROW( "the table replay covers m_fastSubPel == 0" );
+  if( cfg.m_bUseHADME && cfg.m_fastHad ) THROW( "DF_HAD_fast is not offered by vvb_frac_cost_grid" );
+  RdCost& rc = *is.m_pcRdCost;
+  const CPelBuf& key = *cStruct.pcPatternKey;
+  const int reach = std::max( std::abs( rcMvInt.hor ), std::abs( rcMvInt.ver ) ) + 5;        // integer vector + one pel of refinement + 4 pels of filter
+  b200UploadKeyAndWindow( key, cStruct.piRefY, cStruct.iRefStride, reach, is.m_lumaClpRng.bd );
+
+  vvb_block blk = {};
+  blk.start_x = (int16_t) rcMvInt.hor; blk.start_y = (int16_t) rcMvInt.ver;
+  uint32_t t[7][7];
+  b200Check( g_b200s.fracCostGrid( b200CtxOfThread(), cfg.m_bUseHADME ? VVB_DF_HAD : VVB_DF_SAD, B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height,
+                                   cfg.m_meReduceTap, cStruct.useAltHpelIf ? 1 : 0, &t[0][0] ) );
+
+  // one round of xPatternRefinement (:800-960): nine candidates in the order of s_acMvRefineH / s_acMvRefineQ, first strictly smaller cost wins
+  static const int8_t orderH[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 }, { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } };
+  static const int8_t orderQ[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, -1 }, { 1, -1 }, { -1, 0 }, { 1, 0 }, { -1, 1 }, { 1, 1 } };
+  auto round = [&]( const int8_t ( *order )[2], int iFrac, const Mv& baseRefMv, Mv& rcMvFrac ) -> Distortion
+  {
+    Distortion best = MAX_DISTORTION; int dir = 0;
+    for( int i = 0; i < 9; i++ )
+    {
+      const int hor = ( order[i][0] + baseRefMv.hor ) * iFrac, ver = ( order[i][1] + baseRefMv.ver ) * iFrac;      // quarter-pel offset from rcMvInt (:820-823)
+      Distortion d = t[ver + 3][hor + 3];
+      d += rc.getCostOfVectorWithPredictor( order[i][0] + rcMvFrac.hor, order[i][1] + rcMvFrac.ver, 0 );           // :935 (imvShift 0 inside the refinement)
+      if( d < best ) { best = d; dir = i; }
+    }
+    rcMvFrac.set( order[dir][0], order[dir][1] );
+    return best;
+  };
+
+  rc.setCostScale( 1 );                                                                       // :2697
+  rcMvHalf = rcMvInt; rcMvHalf <<= 1;
+  ruiCost = round( orderH, 2, Mv( 0, 0 ), rcMvHalf );
+  if( cStruct.imvShift == IMV_OFF )                                                           // :2712
+  {
+    rc.setCostScale( 0 );
+    Mv baseRefMv = rcMvHalf; baseRefMv <<= 1;
+    rcMvQter = rcMvInt; rcMvQter <<= 1; rcMvQter += rcMvHalf; rcMvQter <<= 1;
+    ruiCost = round( orderQ, 1, baseRefMv, rcMvQter );
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------------
+// Production shape: the pictures are uploaded once, the PUs of a CTU row are queued with the search range and predictor the
+// reference computed for them (xSetSearchRange :2178-2206, setPredictor), and run() issues one vvb_sad_search per block size.  Results equal
+// xPatternSearch per PU, including the raster tie-break.
+class B200RowSearch
+{
+public:
+  struct Result { Mv mv; Distortion sad; Distortion cost; };
+
+  void setPictures( const CPelBuf& org, const CPelBuf& ref, int margin, int bitDepth )
+  {
+    b200Check( g_b200s.planeUpload( b200CtxOfThread(), 0, org.buf, org.stride, org.width, org.height, 0, bitDepth ) );
+    b200Check( g_b200s.planeUpload( b200CtxOfThread(), 1, ref.buf, ref.stride, ref.width, ref.height, margin, bitDepth ) );
+  }
+  // returns the index under which results() reports this PU
+  int add( int x, int y, int w, int h, const InterSearch::SearchRange& sr, const Mv& predictor )
+  {
+    Group* g = nullptr;
+    for( auto& c : m_groups ) if( c.w == w && c.h == h ) g = &c;
+    if( !g ) { m_groups.push_back( Group() ); g = &m_groups.back(); g->w = w; g->h = h; }
+    vvb_block b = {};
+    b.x = x; b.y = y; b.left = (int16_t) sr.left; b.right = (int16_t) sr.right; b.top = (int16_t) sr.top; b.bottom = (int16_t) sr.bottom;
+    b.pred_hor = (int16_t) predictor.hor; b.pred_ver = (int16_t) predictor.ver;
+    g->blocks.push_back( b ); g->index.push_back( (int) m_results.size() );
+    m_results.push_back( Result() );
+    return (int) m_results.size() - 1;
+  }
+  void run( RdCost& rc, unsigned imvShift, int subShiftMode )
+  {
+    for( auto& g : m_groups )
+    {
+      int subShift = 0;
+      if( subShiftMode == 1 && g.h > 8 && g.w <= 128 ) subShift = 1;
+      if( subShiftMode == 2 && g.h > 8 ) subShift = 1;
+      const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, imvShift, subShift );
+      std::vector<vvb_best> best( g.blocks.size() );
+      b200Check( g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, nullptr, 0, best.data() ) );
+      for( size_t i = 0; i < best.size(); i++ )
+      {
+        Result& r = m_results[g.index[i]];
+        r.mv.set( best[i].dx, best[i].dy ); r.cost = best[i].cost; r.sad = best[i].sad;
+      }
+    }
+    m_groups.clear();
+  }
+  const std::vector<Result>& results() const { return m_results; }
+  void clear() { m_groups.clear(); m_results.clear(); }
+
+private:
+  struct Group { int w, h; std::vector<vvb_block> blocks; std::vector<int> index; };
+  std::vector<Group>  m_groups;
+  std::vector<Result> m_results;
+};

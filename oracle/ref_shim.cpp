@@ -160,7 +160,8 @@ inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, co
 // RdCost::_initRdCostB200() would do.  opt == 2 in the probes below selects an RdCost patched this way, so the tests can
 // drive UNMODIFIED reference call sites (DistParam + distFunc, dmvrSadX5, m_fxdWtdPredPtr, the xPatternSearch replay)
 // with the GPU library underneath and compare against the AVX2 table.
-#include "../integration/RdCostB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
+#include "../integration/RdCostB200.h"
+#include "../integration/InterSearchB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
 
 void createRd( RdCost& rc, int opt )     // 0 scalar, 1 SIMD, 2 SIMD table patched with the B200 trampolines
 {
@@ -868,8 +869,8 @@ void refshim_mctf_estimate_pyramid( int opt, const int16_t* org, const int16_t* 
 // The reference's OWN full search: InterSearch::xPatternSearch (InterSearch.cpp:2209-2251) called as a member on a default-constructed InterSearch whose
 // only live members are the ones the function reads (m_pcRdCost, m_cDistParam, m_lumaClpRng).  Same block list / output layout as refshim_full_search;
 // subShiftMode is passed through RdCost::setDistParam's own rule (RdCost.cpp:187-200): 0 -> no sub-sampling, 2 -> every second row when h > 8.
-void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
-                                    const int32_t* blk, int n, int bitDepth, int subShiftMode, double lambda, int costScale, int imvShift, int32_t* out )
+static void patternSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
+                                const int32_t* blk, int n, int bitDepth, int subShiftMode, double lambda, int costScale, int imvShift, int32_t* out, bool b200 )
 {
   for( int i = 0; i < n; i++ )
   {
@@ -897,10 +898,59 @@ void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStr
     st.imvShift = (unsigned) imvShift;
     st.searchRange.left = b[4]; st.searchRange.right = b[5]; st.searchRange.top = b[6]; st.searchRange.bottom = b[7];
     Mv mv; Distortion sad = 0;
-    is.xPatternSearch( st, mv, sad );
+    if( b200 ) xPatternSearchB200( is, st, mv, sad ); else is.xPatternSearch( st, mv, sad );
+    if( sad != st.uiBestSad - rc.getCostOfVectorWithPredictor( mv.hor, mv.ver, st.imvShift ) ) THROW( "ruiSAD is not the best cost minus its MV rate" );
     int32_t* o = out + 4 * (size_t) i;
     o[0] = mv.hor; o[1] = mv.ver; o[2] = (int32_t)( st.uiBestSad & 0xffffffffu ); o[3] = (int32_t)( st.uiBestSad >> 32 );
   }
+}
+void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
+                                    const int32_t* blk, int n, int bitDepth, int subShiftMode, double lambda, int costScale, int imvShift, int32_t* out )
+{
+  patternSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, blk, n, bitDepth, subShiftMode, lambda, costScale, imvShift, out, false );
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// integration/InterSearchB200.h in action: the same set-up as the member probes, the loops replaced by the batched C-ABI calls.  The library is whatever
+// refshim_install_b200_search() bound: libvvenc_b200.so on the GPU box, tests/mock (the C ABI answered by the CPU oracle) for the host-logic tests.
+int refshim_install_b200_search( const char* libPath ) { return b200LoadSearch( libPath ); }
+
+// 0 = ok; 1 = the binding threw (text through refshim_b200_error)
+int refshim_pattern_search_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride,
+                                 const int32_t* blk, int n, int bitDepth, int subShiftMode, double lambda, int costScale, int imvShift, int32_t* out )
+{
+  try { patternSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, blk, n, bitDepth, subShiftMode, lambda, costScale, imvShift, out, true ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
+  return 0;
+}
+
+// B200RowSearch: every block of the list queued against the two whole pictures, one launch per block size.  Same block list / output as above.
+int refshim_row_search_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int width, int height, int margin,
+                             const int32_t* blk, int n, int bitDepth, int subShiftMode, double lambda, int costScale, int imvShift, int32_t* out )
+{
+  try
+  {
+    RdCost rc; createRd( rc, opt );
+    BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
+    rc.setLambda( lambda, bd ); rc.selectMotionLambda(); rc.setCostScale( costScale );
+    B200RowSearch rows;
+    rows.setPictures( CPelBuf( orgPlane, orgStride, width, height ), CPelBuf( refPlane, refStride, width, height ), margin, bitDepth );
+    for( int i = 0; i < n; i++ )
+    {
+      const int32_t* b = blk + 10 * (size_t) i;
+      InterSearch::SearchRange sr; sr.left = b[4]; sr.right = b[5]; sr.top = b[6]; sr.bottom = b[7];
+      rows.add( b[0], b[1], b[2], b[3], sr, Mv( b[8], b[9] ) );
+    }
+    rows.run( rc, (unsigned) imvShift, subShiftMode );
+    for( int i = 0; i < n; i++ )
+    {
+      const B200RowSearch::Result& r = rows.results()[i];
+      int32_t* o = out + 4 * (size_t) i;
+      o[0] = r.mv.hor; o[1] = r.mv.ver; o[2] = (int32_t)( r.cost & 0xffffffffu ); o[3] = (int32_t)( r.cost >> 32 );
+    }
+  }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
+  return 0;
 }
 
 // The reference's OWN apply stage for a whole luma picture: MCTF::bilateralFilter (MCTF.cpp:1489-1556) -> xFinalizeBlkLine (:1399-1487), called as members.
@@ -961,8 +1011,8 @@ void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* 
 // xPatternRefinement filters the half-pel blocks itself and skips positions by s_skipQpelPosition).
 // blk[i] = { x, y, w, h, mvx, mvy (integer vector), predHor, predVer } ; out[i] = { halfX, halfY, qterX, qterY, costLo, costHi } with the offsets the member
 // returns in rcMvHalf / rcMvQter.  Only the members the call tree reads are initialised (InterPredInterpolation::init allocates the filtered-block buffers).
-void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
-                                 int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int fastSubPel, int32_t* out )
+static void fracSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
+                             int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int fastSubPel, int32_t* out, bool b200 )
 {
   static thread_local InterSearch* isp = nullptr;
   static thread_local int inited = -1;
@@ -997,10 +1047,22 @@ void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride
     st.useAltHpelIf = altHpel != 0;
     Mv mvInt( b[4], b[5] ), mvHalf, mvQter;
     Distortion cost = 0;
-    is.xPatternSearchFracDIF( dummyCu, REF_PIC_LIST_0, 0, st, mvInt, mvHalf, mvQter, cost );
+    if( b200 ) xPatternSearchFracDIFB200( is, st, mvInt, mvHalf, mvQter, cost ); else is.xPatternSearchFracDIF( dummyCu, REF_PIC_LIST_0, 0, st, mvInt, mvHalf, mvQter, cost );
     int32_t* o = out + 6 * (size_t) i;
     o[0] = mvHalf.hor; o[1] = mvHalf.ver; o[2] = mvQter.hor; o[3] = mvQter.ver; o[4] = (int32_t)( cost & 0xffffffffu ); o[5] = (int32_t)( cost >> 32 );
   }
+}
+void refshim_frac_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
+                                 int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int fastSubPel, int32_t* out )
+{
+  fracSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, blk, n, bitDepth, lambda, reduceTap, useHad, altHpel, fastSubPel, out, false );
+}
+int refshim_frac_search_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
+                              int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int32_t* out )
+{
+  try { fracSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, blk, n, bitDepth, lambda, reduceTap, useHad, altHpel, 0, out, true ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
+  return 0;
 }
 
 // whole-picture, threaded form of refshim_mctf_finalize_block for the CPU baseline of the apply row: block rows are split over the workers

@@ -1,0 +1,79 @@
+"""Body of tests/test_integration_host.py, run in a process of its own: the reference probe binds ONE C-ABI library per process (dlopen in
+integration/RdCostB200.h), here the oracle-backed mock, while the -m gpu drop-in tests bind libvvenc_b200.so.  Prints one JSON object."""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+import cases as C
+import impls
+from _libs import refshim, P, PO
+
+
+def main(mock_path):
+    R = refshim()
+    R.refshim_b200_error.restype = ctypes.c_char_p
+    res = {}
+    assert R.refshim_install_b200(mock_path.encode()) == 0, R.refshim_b200_error()
+    assert R.refshim_install_b200_search(mock_path.encode()) == 0, R.refshim_b200_error()
+    dbl = ctypes.c_double
+    R.refshim_pattern_search_b200.argtypes = R.refshim_pattern_search_member.argtypes
+    R.refshim_row_search_b200.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, dbl, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    fr_args = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dbl, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    R.refshim_frac_search_member.argtypes = fr_args + [ctypes.c_int, ctypes.c_void_p]
+    R.refshim_frac_search_b200.argtypes = fr_args + [ctypes.c_void_p]
+
+    # ---- RdCost tables patched with the trampolines of RdCostB200.h (opt 2) against the AVX2 table (opt 1), golden distortion rows
+    g = np.load(os.path.join(HERE, 'golden', 'golden_v1.npz'), allow_pickle=True)
+    res['dist_mismatches'] = len(impls.run_dist(impls.RefImpl(opt=2), g['dist_rows'], g['dist_expect']))
+    res['dist_rows'] = int(len(g['dist_rows']))
+
+    # ---- xPatternSearchB200 / B200RowSearch against InterSearch::xPatternSearch
+    sc = C.search_case()
+    n = len(sc['blk']); S = sc['stride']; base = sc['margin'] * S + sc['margin']
+    H = sc['org'].shape[0] - 2 * sc['margin']; W = S - 2 * sc['margin']
+    res['search'] = []
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for mode in (0, 1, 2):
+            for imv in (sc['imv_shift'], 2):
+                a = np.zeros((n, 4), dtype=np.int32); b = np.zeros((n, 4), dtype=np.int32); c = np.zeros((n, 4), dtype=np.int32)
+                args = (PO(sc['org'], base), S, PO(sc['ref'], base), S, P(sc['blk']), n, 10, mode, sc['lam'], sc['cost_scale'], imv)
+                R.refshim_pattern_search_member(opt, *args, P(a))
+                rc1 = R.refshim_pattern_search_b200(opt, *args, P(b))
+                rc2 = R.refshim_row_search_b200(opt, PO(sc['org'], base), S, PO(sc['ref'], base), S, W, H, sc['margin'], P(sc['blk']), n, 10, mode, sc['lam'], sc['cost_scale'], imv, P(c))
+                res['search'].append({'opt': opt, 'mode': mode, 'imv': imv, 'rc': [rc1, rc2], 'blocks': n, 'member_eq_b200': bool(np.array_equal(a, b)),
+                                      'member_eq_rows': bool(np.array_equal(a, c)), 'err': (R.refshim_b200_error() or b'').decode() if (rc1 or rc2) else ''})
+
+    # ---- xPatternSearchFracDIFB200 against InterSearch::xPatternSearchFracDIF (m_fastSubPel 0)
+    res['frac'] = []
+    rs = np.random.RandomState(23)
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        case = C.frac_case(6161 + opt)
+        S = case['stride']; base = case['margin'] * S + case['margin']
+        for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 32)):
+            nb = 6
+            blk = np.zeros((nb, 8), dtype=np.int32)
+            for k in range(nb):
+                blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
+                          int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
+            for (rt, had, alt) in ((2, 1, 0), (0, 1, 0), (1, 1, 0), (2, 0, 0), (0, 0, 0), (2, 1, 1)):
+                if had and w != h:
+                    continue                                                   # the grid offers SATD on square blocks
+                a = np.zeros((nb, 6), dtype=np.int32); b = np.zeros((nb, 6), dtype=np.int32)
+                args = (PO(case['org'], base), S, PO(case['ref'], base), S, P(blk), nb, 10, 57.25, rt, had, alt)
+                R.refshim_frac_search_member(opt, *args, 0, P(a))
+                rc = R.refshim_frac_search_b200(opt, *args, P(b))
+                res['frac'].append({'opt': opt, 'w': w, 'h': h, 'rt': rt, 'had': had, 'alt': alt, 'rc': rc, 'eq': bool(np.array_equal(a, b)),
+                                    'err': (R.refshim_b200_error() or b'').decode() if rc else ''})
+    print('RESULT ' + json.dumps(res))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])

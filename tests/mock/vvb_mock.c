@@ -1,0 +1,151 @@
+/* tests/mock/vvb_mock.c -- TEST INFRASTRUCTURE: the subset of the C ABI (include/vvenc_b200.h) that the reference-side bindings in integration/ call,
+ * answered by the CPU oracle (oracle/oracle.c is compiled into this library).  It lets the host logic of integration/ headers -- argument marshalling, the
+ * replay of the selection rounds on the returned tables -- run next to the reference's own member functions on a machine without a GPU
+ * (tests/test_integration_host.py).  It is never shipped, never loaded by the product package, and no `-m gpu` test or bench leg uses it. */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/vvenc_b200.h"
+
+typedef int16_t Pel;
+/* oracle entry points (oracle/oracle.c) */
+void     orc_full_search( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int subShift, double lambda, int costScale, int imvShift,
+                          int32_t* out, uint32_t* sadTables, int tableStride );
+uint64_t orc_mv_cost( double lambda, int x, int y, int predHor, int predVer, int costScale, int imvShift );
+void     orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel, uint32_t* out );
+void     orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPlane, int sb, const int32_t* desc, int n, int bitDepth, int32_t* out );
+
+#define MOCK_PLANES 64
+typedef struct { Pel* mem; Pel* origin; int stride, width, height, margin, bitDepth; } mock_plane;
+struct vvb_ctx { mock_plane pl[MOCK_PLANES]; char err[256]; uint64_t calls; };
+
+static int fail( vvb_ctx* c, int code, const char* msg ) { snprintf( c->err, sizeof( c->err ), "%s", msg ); return code; }
+
+int vvb_create( vvb_ctx** out, int device ) { (void) device; if( !out ) return VVB_ERR_ARG; *out = (vvb_ctx*) calloc( 1, sizeof( vvb_ctx ) ); return *out ? VVB_OK : VVB_ERR_NOMEM; }
+void vvb_destroy( vvb_ctx* c ) { if( !c ) return; for( int i = 0; i < MOCK_PLANES; i++ ) free( c->pl[i].mem ); free( c ); }
+const char* vvb_last_error( const vvb_ctx* c ) { return c ? c->err : "no context"; }
+int vvb_launch_count( const vvb_ctx* c, uint64_t* n ) { if( !c || !n ) return VVB_ERR_ARG; *n = c->calls; return VVB_OK; }
+
+int vvb_plane_upload( vvb_ctx* c, int id, const int16_t* origin, int stride, int width, int height, int margin, int bitDepth )
+{
+  if( !c || id < 0 || id >= MOCK_PLANES || !origin || width <= 0 || height <= 0 || margin < 0 ) return c ? fail( c, VVB_ERR_ARG, "bad plane arguments" ) : VVB_ERR_ARG;
+  mock_plane* p = &c->pl[id];
+  free( p->mem );
+  const int s = width + 2 * margin;
+  p->mem = (Pel*) malloc( sizeof( Pel ) * (size_t) s * ( height + 2 * margin ) );
+  if( !p->mem ) return fail( c, VVB_ERR_NOMEM, "plane" );
+  for( int y = -margin; y < height + margin; y++ ) memcpy( p->mem + (size_t)( y + margin ) * s, origin + (ptrdiff_t) y * stride - margin, sizeof( Pel ) * s );
+  p->origin = p->mem + (size_t) margin * s + margin; p->stride = s; p->width = width; p->height = height; p->margin = margin; p->bitDepth = bitDepth;
+  return VVB_OK;
+}
+int vvb_plane_free( vvb_ctx* c, int id ) { if( !c || id < 0 || id >= MOCK_PLANES ) return VVB_ERR_ARG; free( c->pl[id].mem ); memset( &c->pl[id], 0, sizeof( mock_plane ) ); return VVB_OK; }
+
+static mock_plane* plane( vvb_ctx* c, int id ) { return ( id >= 0 && id < MOCK_PLANES && c->pl[id].mem ) ? &c->pl[id] : NULL; }
+
+int vvb_sad_search( vvb_ctx* c, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_me_par* par, uint32_t* sadTables, int tableStride, vvb_best* bestOut )
+{
+  if( !c ) return VVB_ERR_ARG;
+  mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
+  if( !o || !r || !blocks || !par || !bestOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad search arguments" );
+  for( int i = 0; i < n; i++ )
+  {
+    const vvb_block* b = &blocks[i];
+    if( -b->left > r->margin || b->right > r->margin || -b->top > r->margin || b->bottom > r->margin ) return fail( c, VVB_ERR_ARG, "search range exceeds the plane margin" );
+    const int32_t blk[10] = { b->x, b->y, w, h, b->left, b->right, b->top, b->bottom, b->pred_hor, b->pred_ver };
+    int32_t out[4];
+    orc_full_search( o->origin, o->stride, r->origin, r->stride, blk, 1, par->sub_shift, par->lambda, par->cost_scale, par->imv_shift, out,
+                     sadTables ? sadTables + (size_t) i * tableStride : NULL, tableStride );
+    const uint64_t cost = (uint32_t) out[2] | ( (uint64_t)(uint32_t) out[3] << 32 );
+    bestOut[i].dx = (int16_t) out[0]; bestOut[i].dy = (int16_t) out[1]; bestOut[i].cost = cost;
+    bestOut[i].sad = (uint32_t)( cost - orc_mv_cost( par->lambda, out[0], out[1], b->pred_hor, b->pred_ver, par->cost_scale, par->imv_shift ) );
+  }
+  c->calls++;
+  return VVB_OK;
+}
+
+int vvb_frac_cost_grid( vvb_ctx* c, int dfunc, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, int reduceTap, int altHpel, uint32_t* costOut )
+{
+  if( !c ) return VVB_ERR_ARG;
+  mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
+  if( !o || !r || !blocks || !costOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad grid arguments" );
+  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD ) return fail( c, VVB_ERR_UNSUPPORTED, "dfunc" );
+  for( int i = 0; i < n; i++ )
+  {
+    const vvb_block* b = &blocks[i];
+    const int reach = ( abs( b->start_x ) > abs( b->start_y ) ? abs( b->start_x ) : abs( b->start_y ) ) + 5;
+    if( reach > r->margin ) return fail( c, VVB_ERR_ARG, "vector + filter reach exceeds the plane margin" );
+    const int32_t blk[6] = { b->x, b->y, w, h, b->start_x, b->start_y };
+    orc_frac_cost_grid( o->origin, o->stride, r->origin, r->stride, blk, 1, dfunc == VVB_DF_HAD ? 2 : 1, o->bitDepth, reduceTap, altHpel, costOut + (size_t) i * 49 );
+  }
+  c->calls++;
+  return VVB_OK;
+}
+
+int vvb_mctf_error_batch( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf_cand* cands, int n, int lowRes, int32_t* errOut )
+{
+  if( !c ) return VVB_ERR_ARG;
+  mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
+  if( !o || !r || !cands || !errOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad mctf arguments" );
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t d[6] = { cands[i].x, cands[i].y, cands[i].mvx, cands[i].mvy, cands[i].w, cands[i].h };
+    orc_mctf_err_list( lowRes, o->origin, o->stride, r->origin, r->stride, d, 1, o->bitDepth, errOut + i );
+  }
+  c->calls++;
+  return VVB_OK;
+}
+
+int vvb_mctf_search_grid( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf_cand* blocks, int n, int step, int radius, int lowRes, int32_t* errOut )
+{
+  if( !c ) return VVB_ERR_ARG;
+  mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
+  if( !o || !r || !blocks || !errOut || n < 0 || radius < 0 || step <= 0 ) return fail( c, VVB_ERR_ARG, "bad mctf grid arguments" );
+  const int side = 2 * radius + 1;
+  for( int i = 0; i < n; i++ )
+    for( int j = 0; j < side; j++ )
+      for( int k = 0; k < side; k++ )
+      {
+        const int32_t d[6] = { blocks[i].x, blocks[i].y, blocks[i].mvx + ( k - radius ) * step, blocks[i].mvy + ( j - radius ) * step, blocks[i].w, blocks[i].h };
+        orc_mctf_err_list( lowRes, o->origin, o->stride, r->origin, r->stride, d, 1, o->bitDepth, errOut + ( (size_t) i * side + j ) * side + k );
+      }
+  c->calls++;
+  return VVB_OK;
+}
+
+/* per-block entry points (FpDistFunc-shaped, RdCostB200.h) */
+uint64_t orc_dist( int family, const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift );
+uint64_t orc_sad_mask( const Pel* org, int so, const Pel* cur, int sc, int w, int h, const Pel* mask, int maskStride, int stepX, int maskStride2, int subShift );
+void     orc_sad_x5( const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift, int calcCentre, uint64_t* cost5 );
+uint64_t orc_fix_wsse( const Pel* org, int so, const Pel* cur, int sc, int w, int h, uint32_t weight );
+
+uint64_t vvb_dist_block( vvb_ctx* c, int dfunc, const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int bitDepth, int subShift, int* err )
+{
+  (void) bitDepth;
+  if( err ) *err = VVB_OK;
+  if( !c || !org || !cur || dfunc < 0 || dfunc > 4 ) { if( err ) *err = VVB_ERR_ARG; return 0; }
+  c->calls++;
+  return orc_dist( dfunc, org, so, cur, sc, w, h, subShift );
+}
+uint64_t vvb_sad_mask_block( vvb_ctx* c, const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, const int16_t* mask, int maskStride, int stepX, int maskStride2,
+                             int subShift, int* err )
+{
+  if( err ) *err = VVB_OK;
+  if( !c || !org || !cur || !mask ) { if( err ) *err = VVB_ERR_ARG; return 0; }
+  c->calls++;
+  return orc_sad_mask( org, so, cur, sc, w, h, mask, maskStride, stepX, maskStride2, subShift );
+}
+int vvb_sad_x5_block( vvb_ctx* c, const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int subShift, int calcCentre, uint64_t cost5[5] )
+{
+  if( !c || !org || !cur || !cost5 ) return VVB_ERR_ARG;
+  c->calls++;
+  orc_sad_x5( org, so, cur, sc, w, h, subShift, calcCentre, cost5 );
+  return VVB_OK;
+}
+uint64_t vvb_fix_wsse_block( vvb_ctx* c, const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, uint32_t weight, int* err )
+{
+  if( err ) *err = VVB_OK;
+  if( !c || !org || !cur ) { if( err ) *err = VVB_ERR_ARG; return 0; }
+  c->calls++;
+  return orc_fix_wsse( org, so, cur, sc, w, h, weight );
+}

@@ -45,13 +45,18 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dp, f), errors='ignore').read()
                 assert 'liboracle' not in txt and 'refshim' not in txt and 'oracle/' not in txt.replace('oracle/vvc_tables.h', ''), f
+                assert 'vvb_mock' not in txt, f
+    # the oracle-backed mock of the C ABI (tests/mock) is for the host-logic tests only: neither the bench nor smoke() may touch it
+    for f in ('bench.py', '__graft_entry__.py'):
+        assert 'vvb_mock' not in open(os.path.join(ROOT, f)).read(), f
 
 
 def test_reference_side_binding_resolves_only_declared_symbols():
     """integration/RdCostB200.h binds the library with dlsym: every name it asks for must be declared in the C ABI header (and hence exported)"""
     txt = open(os.path.join(ROOT, 'integration', 'RdCostB200.h')).read()
-    asked = sorted(set(re.findall(r'VVB_RESOLVE\(\s*\w+\s*,\s*(vvb_[a-z0-9_]+)\s*\)', txt)))
-    assert len(asked) >= 6
+    txt_search = open(os.path.join(ROOT, 'integration', 'InterSearchB200.h')).read()
+    asked = sorted(set(re.findall(r'VVB_RESOLVE\(\s*\w+\s*,\s*(vvb_[a-z0-9_]+)\s*\)', txt + txt_search)))
+    assert len(asked) >= 9 and 'vvb_sad_search' in asked and 'vvb_frac_cost_grid' in asked
     declared = set(_declared())
     assert [n for n in asked if n not in declared] == []
     # the trampolines cover every slot family the x86 back end overwrites (RdCostX86.h:3376-3425)

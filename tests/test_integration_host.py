@@ -1,0 +1,49 @@
+"""Host logic of the reference-side bindings in integration/ (RdCostB200.h, InterSearchB200.h), on the CPU: the bindings are compiled into the reference
+probe (oracle/_ref) and bound to tests/mock -- the C ABI answered by the oracle -- so that what is under test is the glue itself: argument marshalling
+out of DistParam / TZSearchStruct / RdCost, and the replay of the reference's selection rounds on the returned tables.  Checked against the reference's
+own code in the same process:
+
+  * RdCost tables patched by installB200() vs the AVX2 table on every golden distortion row,
+  * xPatternSearchB200 and B200RowSearch vs InterSearch::xPatternSearch (member call), all subShift modes, two AMVR shifts,
+  * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular.
+
+The same bindings run against libvvenc_b200.so in tests/test_gpu_dropin.py (-m gpu)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from _libs import have_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not have_ref(), reason='oracle/_ref not built')
+
+
+@pytest.fixture(scope='module')
+def result():
+    subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    mock = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), mock], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')]
+    assert line, out.stdout[-2000:]
+    return json.loads(line[-1][len('RESULT '):])
+
+
+def test_rdcost_tables_patched_through_the_binding(result):
+    assert result['dist_rows'] > 600 and result['dist_mismatches'] == 0
+
+
+def test_pattern_search_binding_equals_the_member(result):
+    assert len(result['search']) == 12
+    for r in result['search']:
+        assert r['rc'] == [0, 0], r
+        assert r['member_eq_b200'] and r['member_eq_rows'], r
+
+
+def test_fractional_search_binding_equals_the_member(result):
+    assert len(result['frac']) >= 50
+    for r in result['frac']:
+        assert r['rc'] == 0 and r['eq'], r
