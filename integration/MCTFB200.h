@@ -1,0 +1,217 @@
+// integration/MCTFB200.h -- reference-side binding of libvvenc_b200.so for the MCTF motion search (CommonLib/MCTF.cpp).
+//
+//   motionEstimationLumaB200  <->  MCTF::motionEstimationLuma (MCTF.cpp:1329-1397) -> estimateLumaLn (:1166-1327)
+//
+// Same arguments as the member.  The per-block `error < best.error` chains of estimateLumaLn are kept; what changes is where the errors come from:
+// motionErrorLuma (:1099-1164) is not called per candidate, the candidate sets of a whole picture go out as tables:
+//
+//   stage A  predictors of the coarser level (3x3 neighbourhood, scaled by `factor`) and the zero vector   vvb_mctf_error_batch, one call per neighbour  (:1191-1214)
+//   stage B  integer grid around trunc(best / 16), range 8 / 5 / 3 / none                                  vvb_mctf_search_grid                         (:1216-1228)
+//   stage C  doubleRes: +-12 (or +-6) step 4 (or 6), +-2 step 2, +-1 step 1 around the running best        vvb_mctf_search_grid, three calls            (:1229-1287)
+//   stage D  final vectors of the upper and left neighbour: a true dependency, followed along              vvb_mctf_error_batch per anti-diagonal       (:1288-1306)
+//            anti-diagonals (all blocks with the same bx + by at once)
+//   stage E  doubleRes: variance for the error scaling                                                     vvb_mctf_calc_var                            (:1308-1321)
+//
+// Early exits of the reference's error kernels never change a decision (a partial sum is only returned once it exceeds the best), so full sums give the
+// same field.  This is the C++ twin of vvenc_b200/mctf_host.py; tests/test_integration_host.py runs it next to the member itself.
+// Include after RdCostB200.h / InterSearchB200.h and CommonLib/MCTF.h; private members of MCTF are read (m_searchPttrn, m_mctfUnitSize, ...): inside
+// the encoder this is a member function.
+#pragma once
+#include <cmath>
+#include <vector>
+#include "InterSearchB200.h"
+
+struct B200MctfApi
+{
+  bool bound = false;
+  decltype( &vvb_mctf_error_batch )  errorBatch = nullptr;
+  decltype( &vvb_mctf_search_grid )  searchGrid = nullptr;
+  decltype( &vvb_mctf_calc_var )     calcVar = nullptr;
+} ;
+static B200MctfApi g_b200m;
+
+inline int b200LoadMctf( const char* libPath )
+{
+  if( g_b200m.bound ) return 0;
+  int rc = b200LoadSearch( libPath );
+  if( rc ) return rc;
+  void* h = g_b200.handle;
+#define VVB_RESOLVE( member, name ) g_b200m.member = (decltype( g_b200m.member )) dlsym( h, #name ); if( !g_b200m.member ) { g_b200.error = "missing " #name; return -2; }
+  VVB_RESOLVE( errorBatch, vvb_mctf_error_batch )  VVB_RESOLVE( searchGrid, vvb_mctf_search_grid )  VVB_RESOLVE( calcVar, vvb_mctf_calc_var )
+#undef VVB_RESOLVE
+  g_b200m.bound = true;
+  return 0;
+}
+
+enum { B200_PLANE_MCTF_ORG = 12, B200_PLANE_MCTF_REF = 13 };
+
+namespace b200mctf
+{
+struct Best { int x = 0, y = 0; int64_t error = INT_LEAST32_MAX; };               // MotionVector() starts at INT_LEAST32_MAX (MCTF.h:79)
+
+struct Level
+{
+  int lowRes = 0;
+  std::vector<vvb_mctf_cand> blocks;                                                // x, y, w, h of every block; vectors filled per call
+  std::vector<Best>          best;
+
+  std::vector<int32_t> errors( const std::vector<int>& sel, const std::vector<int>& mvx, const std::vector<int>& mvy ) const
+  {
+    std::vector<vvb_mctf_cand> c( sel.size() );
+    for( size_t i = 0; i < sel.size(); i++ ) { c[i] = blocks[sel[i]]; c[i].mvx = mvx[i]; c[i].mvy = mvy[i]; }
+    std::vector<int32_t> e( sel.size() );
+    if( !sel.empty() ) b200Check( g_b200m.errorBatch( b200CtxOfThread(), B200_PLANE_MCTF_ORG, B200_PLANE_MCTF_REF, c.data(), (int) c.size(), lowRes, e.data() ) );
+    return e;
+  }
+
+  // every block: candidates centre + (ox, oy) for ox, oy in the equally spaced list offs (1/16 pel), visited y outer / x inner, strictly smaller wins.
+  // The grid entry point takes centre +- k * step with step <= 16, so wider or centre-less sets (e.g. {-6, 6} or 32-pel steps) are read out of the smallest
+  // covering lattice.
+  void gridRound( const std::vector<int>& cx, const std::vector<int>& cy, const std::vector<int>& offs, bool skipZero )
+  {
+    const int n = (int) blocks.size(), m = (int) offs.size();
+    if( m == 1 )                                                                    // a single position: the candidate-list entry point
+    {
+      if( skipZero && offs[0] == 0 ) return;
+      std::vector<int> sel( n ), mvx( n ), mvy( n );
+      for( int i = 0; i < n; i++ ) { sel[i] = i; mvx[i] = cx[i] + offs[0]; mvy[i] = cy[i] + offs[0]; }
+      const std::vector<int32_t> e = errors( sel, mvx, mvy );
+      for( int i = 0; i < n; i++ ) if( e[i] < best[i].error ) { best[i].error = e[i]; best[i].x = mvx[i]; best[i].y = mvy[i]; }
+      return;
+    }
+    int step = offs[1] - offs[0];
+    while( step > 16 ) step /= 2;
+    const int span = offs[m - 1] - offs[0];
+    const int radius = ( span + 2 * step - 1 ) / ( 2 * step );
+    const int shift = offs[0] + radius * step, side = 2 * radius + 1;
+    std::vector<vvb_mctf_cand> c( blocks );
+    for( int i = 0; i < n; i++ ) { c[i].mvx = cx[i] + shift; c[i].mvy = cy[i] + shift; }
+    std::vector<int32_t> tab( (size_t) n * side * side );
+    b200Check( g_b200m.searchGrid( b200CtxOfThread(), B200_PLANE_MCTF_ORG, B200_PLANE_MCTF_REF, c.data(), n, step, radius, lowRes, tab.data() ) );
+    for( int i = 0; i < n; i++ )
+      for( int j = 0; j < m; j++ )
+        for( int k = 0; k < m; k++ )
+        {
+          if( skipZero && offs[j] == 0 && offs[k] == 0 ) continue;
+          const int64_t e = tab[( (size_t) i * side + ( offs[j] - offs[0] ) / step ) * side + ( offs[k] - offs[0] ) / step];
+          if( e < best[i].error ) { best[i].error = e; best[i].x = cx[i] + offs[k]; best[i].y = cy[i] + offs[j]; }
+        }
+  }
+};
+}   // namespace b200mctf
+
+inline void motionEstimationLumaB200( const MCTF& m, Array2D<MotionVector>& mvs, const PelStorage& orig, const PelStorage& buffer, const int blockSize,
+                                      const Array2D<MotionVector>* previous, const int factor, const bool doubleRes )
+{
+  using namespace b200mctf;
+  const CPelBuf org = orig.Y(), buf = buffer.Y();
+  const int width = org.width, height = org.height, bitDepth = m.m_encCfg->m_internalBitDepth[CH_L];
+  const int pattern = m.m_searchPttrn, mvf = m.m_motionVectorFactor;
+  vvb_ctx* ctx = b200CtxOfThread();
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_ORG, org.buf, org.stride, width, height, 0, bitDepth ) );
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_REF, buf.buf, buf.stride, width, height, MCTF_PADDING, bitDepth ) );       // picture buffers are padded (MCTF.cpp:1072-1097, Picture.cpp)
+
+  Level lv; lv.lowRes = m.m_lowResFltSearch ? 1 : 0;
+  int bxN = 0, byN = 0;
+  for( int y = 0; y + 8 <= height; y += blockSize ) byN++;                         // `blockY + 8 <= origHeight` (:1388), `blockX + 8 <= origWidth` (:1174)
+  for( int x = 0; x + 8 <= width; x += blockSize ) bxN++;
+  const int n = bxN * byN;
+  lv.blocks.resize( n ); lv.best.resize( n );
+  for( int by = 0; by < byN; by++ )
+    for( int bx = 0; bx < bxN; bx++ )
+    {
+      vvb_mctf_cand& c = lv.blocks[by * bxN + bx];
+      c.x = bx * blockSize; c.y = by * blockSize; c.mvx = c.mvy = 0;
+      c.w = (uint16_t)( std::min( blockSize, width - c.x ) & ~7 ); c.h = (uint16_t)( std::min( blockSize, height - c.y ) & ~7 );   // motionErrorLuma :1105-1106
+    }
+  std::vector<int> all( n ); for( int i = 0; i < n; i++ ) all[i] = i;
+
+  // ---- stage A
+  int range = doubleRes ? 0 : ( pattern == 2 ? 3 : 5 );
+  if( !previous ) range = 8;
+  else
+  {
+    for( int py = -1; py <= 1; py++ )
+      for( int px = -1; px <= 1; px++ )
+      {
+        std::vector<int> sel, mvx, mvy;
+        for( int i = 0; i < n; i++ )
+        {
+          const int testy = lv.blocks[i].y / ( 2 * blockSize ) + py, testx = lv.blocks[i].x / ( 2 * blockSize ) + px;
+          if( testy < 0 || testy >= (int) previous->h() || testx < 0 || testx >= (int) previous->w() ) continue;
+          const MotionVector& old = previous->get( testx, testy );
+          sel.push_back( i ); mvx.push_back( old.x * factor ); mvy.push_back( old.y * factor );
+        }
+        const std::vector<int32_t> e = lv.errors( sel, mvx, mvy );
+        for( size_t k = 0; k < sel.size(); k++ ) if( e[k] < lv.best[sel[k]].error ) { lv.best[sel[k]].error = e[k]; lv.best[sel[k]].x = mvx[k]; lv.best[sel[k]].y = mvy[k]; }
+      }
+    const std::vector<int> zero( n, 0 );
+    const std::vector<int32_t> e = lv.errors( all, zero, zero );
+    for( int i = 0; i < n; i++ ) if( e[i] < lv.best[i].error ) { lv.best[i].error = e[i]; lv.best[i].x = 0; lv.best[i].y = 0; }
+  }
+
+  // ---- stage B: integer grid around prevBest / m_motionVectorFactor (C division, truncation toward zero)
+  std::vector<int> cx( n ), cy( n ), offs;
+  {
+    const int d = ( !previous && pattern == 2 ) ? 2 : 1;
+    for( int i = 0; i < n; i++ ) { cx[i] = lv.best[i].x / mvf * mvf; cy[i] = lv.best[i].y / mvf * mvf; }
+    for( int v = -range; v <= range; v += d ) offs.push_back( v * mvf );
+    lv.gridRound( cx, cy, offs, false );
+  }
+
+  // ---- stage C
+  if( doubleRes )
+  {
+    const int doubleRange = pattern ? 6 : 12, d1 = pattern == 2 ? 6 : 4;
+    const int rounds[3][2] = { { doubleRange, d1 }, { 2, 2 }, { 1, 1 } };
+    for( const auto& r : rounds )
+    {
+      offs.clear();
+      for( int v = -r[0]; v <= r[0]; v += r[1] ) offs.push_back( v );
+      for( int i = 0; i < n; i++ ) { cx[i] = lv.best[i].x; cy[i] = lv.best[i].y; }
+      lv.gridRound( cx, cy, offs, true );
+    }
+  }
+
+  // ---- stage D: anti-diagonal wavefront over the upper / left dependency
+  for( int wave = 1; wave < bxN + byN - 1; wave++ )
+  {
+    for( int pass = 0; pass < 2; pass++ )                                          // above first, then left (:1288-1306)
+    {
+      std::vector<int> sel, mvx, mvy;
+      for( int by = std::max( 0, wave - bxN + 1 ); by <= std::min( wave, byN - 1 ); by++ )
+      {
+        const int bx = wave - by;
+        if( pass == 0 ? by == 0 : bx == 0 ) continue;
+        const int src = pass == 0 ? ( by - 1 ) * bxN + bx : by * bxN + bx - 1;
+        sel.push_back( by * bxN + bx ); mvx.push_back( lv.best[src].x ); mvy.push_back( lv.best[src].y );
+      }
+      const std::vector<int32_t> e = lv.errors( sel, mvx, mvy );
+      for( size_t k = 0; k < sel.size(); k++ ) if( e[k] < lv.best[sel[k]].error ) { lv.best[sel[k]].error = e[k]; lv.best[sel[k]].x = mvx[k]; lv.best[sel[k]].y = mvy[k]; }
+    }
+  }
+
+  // ---- stage E and write-back
+  std::vector<double> var;
+  if( doubleRes )
+  {
+    var.resize( n );
+    b200Check( g_b200m.calcVar( ctx, B200_PLANE_MCTF_ORG, lv.blocks.data(), n, var.data() ) );
+  }
+  for( int i = 0; i < n; i++ )
+  {
+    MotionVector best;
+    best.set( lv.best[i].x, lv.best[i].y, (int) lv.best[i].error );
+    if( doubleRes )
+    {
+      const int w = lv.blocks[i].w, h = lv.blocks[i].h;
+      const double bdScale = double( 1 << ( 2 * ( 10 - bitDepth ) ) );
+      const double dvar = var[i] * bdScale;
+      const double mse  = best.error * bdScale / double( w * h );
+      best.error   = (int)( 20 * ( ( best.error * bdScale + 5.0 ) / ( dvar + 5.0 ) ) + mse / 50.0 );
+      best.rmsme   = uint16_t( 0.5 + sqrt( mse ) );
+      best.overlap = ( (double) w * h ) / ( m.m_mctfUnitSize * m.m_mctfUnitSize );
+    }
+    mvs.get( i % bxN, i / bxN ) = best;
+  }
+}

@@ -161,7 +161,8 @@ inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, co
 // drive UNMODIFIED reference call sites (DistParam + distFunc, dmvrSadX5, m_fxdWtdPredPtr, the xPatternSearch replay)
 // with the GPU library underneath and compare against the AVX2 table.
 #include "../integration/RdCostB200.h"
-#include "../integration/InterSearchB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
+#include "../integration/InterSearchB200.h"
+#include "../integration/MCTFB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
 
 void createRd( RdCost& rc, int opt )     // 0 scalar, 1 SIMD, 2 SIMD table patched with the B200 trampolines
 {
@@ -813,6 +814,48 @@ void refshim_mctf_estimate_level( int opt, const int16_t* org, int orgStride, co
       o[0] = v.x; o[1] = v.y; o[2] = v.error; o[3] = v.rmsme;
       if( overlapOut ) overlapOut[y * bxN + x] = v.overlap;
     }
+}
+
+// integration/MCTFB200.h in action: the set-up of refshim_mctf_estimate_level with the search pattern exposed; useB200 != 0 runs motionEstimationLumaB200 on the
+// bound C-ABI library instead of the member.  Returns 0, or 1 when the binding threw (text through refshim_b200_error).
+int refshim_install_b200_mctf( const char* libPath ) { return b200LoadMctf( libPath ); }
+int refshim_mctf_estimate_level_b200( int opt, int useB200, const int16_t* org, int orgStride, const int16_t* buf, int bufStride, int width, int height, int bitDepth,
+                                      int blockSize, const int32_t* prev, int prevW, int prevH, int factor, int doubleRes, int lowResFilter, int unitSize, int searchPattern,
+                                      int32_t* out, double* overlapOut )
+{
+  RefCtx& c = ctx();
+  MCTF* m = c.mctf[opt?1:0];
+  static VVEncCfg cfg;
+  cfg.m_internalBitDepth[CH_L] = bitDepth; cfg.m_internalBitDepth[CH_C] = bitDepth;
+  m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_searchPttrn = searchPattern; m->m_mctfUnitSize = unitSize; m->m_lowResFltSearch = lowResFilter != 0;
+  PelStorage orig, buffer;
+  orig.createFromBuf( PelUnitBuf( CHROMA_400, PelBuf( const_cast<Pel*>( org ), orgStride, width, height ) ) );
+  buffer.createFromBuf( PelUnitBuf( CHROMA_400, PelBuf( const_cast<Pel*>( buf ), bufStride, width, height ) ) );
+  const int bxN = width / blockSize, byN = height / blockSize;
+  Array2D<MotionVector> mvs( bxN + 1, byN + 1 );                                       // room for a partial last block (>= 8 pels)
+  Array2D<MotionVector> previous;
+  if( prev )
+  {
+    previous.allocate( prevW, prevH );
+    for( int y = 0; y < prevH; y++ ) for( int x = 0; x < prevW; x++ ) { MotionVector& v = previous.get( x, y ); v.x = prev[2 * ( y * prevW + x )]; v.y = prev[2 * ( y * prevW + x ) + 1]; }
+  }
+  try
+  {
+    if( useB200 ) motionEstimationLumaB200( *m, mvs, orig, buffer, blockSize, prev ? &previous : nullptr, factor, doubleRes != 0 );
+    else          m->motionEstimationLuma( mvs, orig, buffer, blockSize, prev ? &previous : nullptr, factor, doubleRes != 0 );
+  }
+  catch( std::exception& e ) { g_b200.error = e.what(); m->m_searchPttrn = 0; return 1; }
+  m->m_searchPttrn = 0;
+  const int oxN = ( width + blockSize - 8 ) / blockSize, oyN = ( height + blockSize - 8 ) / blockSize;     // blocks with x + 8 <= width
+  for( int y = 0; y < oyN; y++ )
+    for( int x = 0; x < oxN; x++ )
+    {
+      const MotionVector& v = mvs.get( x, y );
+      int32_t* o = out + 4 * ( y * oxN + x );
+      o[0] = v.x; o[1] = v.y; o[2] = v.error; o[3] = v.rmsme;
+      if( overlapOut ) overlapOut[y * oxN + x] = doubleRes ? v.overlap : 0.0;
+    }
+  return 0;
 }
 
 // The whole MCTF motion search of one neighbour picture, as MCTF::motionEstimationMCTF chains it (MCTF.cpp:666-724): subsampleLuma pyramids (:1072-1097,

@@ -27,6 +27,8 @@ def main(mock_path):
     fr_args = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dbl, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     R.refshim_frac_search_member.argtypes = fr_args + [ctypes.c_int, ctypes.c_void_p]
     R.refshim_frac_search_b200.argtypes = fr_args + [ctypes.c_void_p]
+    R.refshim_mctf_estimate_level_b200.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 4 + \
+        [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p]
 
     # ---- RdCost tables patched with the trampolines of RdCostB200.h (opt 2) against the AVX2 table (opt 1), golden distortion rows
     g = np.load(os.path.join(HERE, 'golden', 'golden_v1.npz'), allow_pickle=True)
@@ -72,6 +74,37 @@ def main(mock_path):
                 rc = R.refshim_frac_search_b200(opt, *args, P(b))
                 res['frac'].append({'opt': opt, 'w': w, 'h': h, 'rt': rt, 'had': had, 'alt': alt, 'rc': rc, 'eq': bool(np.array_equal(a, b)),
                                     'err': (R.refshim_b200_error() or b'').decode() if rc else ''})
+    # ---- motionEstimationLumaB200 against MCTF::motionEstimationLuma: a coarse level without predecessor, a chained level, the doubleRes final level
+    assert R.refshim_install_b200_mctf(mock_path.encode()) == 0, R.refshim_b200_error()
+    from test_mctf_host import _pictures
+    res['mctf'] = []
+    m = 128                                                                        # MCTF_PADDING
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for (W, H, seed) in ((136, 104, 31), (96, 64, 32)):
+            org, ref, S = _pictures(seed + opt, W, H, m, shift=(2, -3))
+            base = m * S + m
+
+            def level(use, bs, prev, factor, dbl, low, pattern, unit=16):
+                oxn, oyn = (W + bs - 8) // bs, (H + bs - 8) // bs
+                out = np.zeros((oyn, oxn, 4), dtype=np.int32); ov = np.zeros((oyn, oxn), dtype=np.float64)
+                pv = None if prev is None else np.ascontiguousarray(prev[:, :, :2])
+                rc = R.refshim_mctf_estimate_level_b200(opt, use, PO(org, base), S, PO(ref, base), S, W, H, 10, bs, None if pv is None else P(pv), 0 if pv is None else pv.shape[1],
+                                                        0 if pv is None else pv.shape[0], factor, int(dbl), low, unit, pattern, P(out), P(ov))
+                return rc, out, ov
+
+            for pattern in (0, 1, 2):
+                for low in (0, 1):
+                    rc0, a0, _ = level(0, 32, None, 2, False, low, pattern)
+                    rc1, b0, _ = level(1, 32, None, 2, False, low, pattern)
+                    rc2, a1, _ = level(0, 16, a0, 1, False, low, pattern)
+                    rc3, b1, _ = level(1, 16, a0, 1, False, low, pattern)
+                    rc4, a2, oa = level(0, 16, a0, 1, True, low, pattern)
+                    rc5, b2, ob = level(1, 16, a0, 1, True, low, pattern)
+                    res['mctf'].append({'opt': opt, 'W': W, 'H': H, 'pattern': pattern, 'low': low, 'rc': [rc0, rc1, rc2, rc3, rc4, rc5],
+                                        'eq': [bool(np.array_equal(a0, b0)), bool(np.array_equal(a1, b1)), bool(np.array_equal(a2, b2)), bool(np.array_equal(oa, ob))],
+                                        'moving': int((a2[:, :, :2] != 0).any(axis=2).sum()), 'blocks': int(a2.shape[0] * a2.shape[1]),
+                                        'err': (R.refshim_b200_error() or b'').decode() if any([rc1, rc3, rc5]) else ''})
     print('RESULT ' + json.dumps(res))
 
 

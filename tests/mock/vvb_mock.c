@@ -113,6 +113,17 @@ int vvb_mctf_search_grid( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf
   return VVB_OK;
 }
 
+double orc_mctf_calc_var( const Pel* org, int so, int w, int h );
+int vvb_mctf_calc_var( vvb_ctx* c, int planeId, const vvb_mctf_cand* blocks, int n, double* varOut )
+{
+  if( !c ) return VVB_ERR_ARG;
+  mock_plane* o = plane( c, planeId );
+  if( !o || !blocks || !varOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad calc_var arguments" );
+  for( int i = 0; i < n; i++ ) varOut[i] = orc_mctf_calc_var( o->origin + (ptrdiff_t) blocks[i].y * o->stride + blocks[i].x, o->stride, blocks[i].w, blocks[i].h );
+  c->calls++;
+  return VVB_OK;
+}
+
 /* per-block entry points (FpDistFunc-shaped, RdCostB200.h) */
 uint64_t orc_dist( int family, const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift );
 uint64_t orc_sad_mask( const Pel* org, int so, const Pel* cur, int sc, int w, int h, const Pel* mask, int maskStride, int stepX, int maskStride2, int subShift );

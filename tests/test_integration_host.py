@@ -5,7 +5,9 @@ own code in the same process:
 
   * RdCost tables patched by installB200() vs the AVX2 table on every golden distortion row,
   * xPatternSearchB200 and B200RowSearch vs InterSearch::xPatternSearch (member call), all subShift modes, two AMVR shifts,
-  * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular.
+  * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular,
+  * motionEstimationLumaB200 vs MCTF::motionEstimationLuma (member call): first level, chained level and the doubleRes final level, search patterns 0/1/2,
+    6- and 4-tap search filters, pictures with partial border blocks.
 
 The same bindings run against libvvenc_b200.so in tests/test_gpu_dropin.py (-m gpu)."""
 import json
@@ -47,3 +49,10 @@ def test_fractional_search_binding_equals_the_member(result):
     assert len(result['frac']) >= 50
     for r in result['frac']:
         assert r['rc'] == 0 and r['eq'], r
+
+
+def test_mctf_search_binding_equals_the_member(result):
+    assert len(result['mctf']) == 24
+    for r in result['mctf']:
+        assert r['rc'] == [0] * 6 and all(r['eq']), r
+        assert r['moving'] > r['blocks'] // 2, r                 # the synthetic displacement is found: the fields are not trivially zero
