@@ -43,8 +43,6 @@ inline int b200LoadSearch( const char* libPath )
   return 0;
 }
 
-inline void b200Check( int rc ) { if( rc != VVB_OK ) THROW( g_b200.lastError( b200CtxOfThread() ) ); }
-
 // vvb_me_par of an RdCost in its current state: the library derives the motion lambda as sqrt( lambda ) like RdCost::setLambda (RdCost.cpp:73-78)
 inline vvb_me_par b200MePar( RdCost& rc, int costScale, unsigned imvShift, int subShift )
 {

@@ -48,6 +48,9 @@ inline vvb_ctx* b200CtxOfThread()
   return t_b200ctx;
 }
 
+// C-ABI status -> the reference's THROW (used by the batched bindings: InterSearchB200.h, MCTFB200.h, TrQuantB200.h)
+inline void b200Check( int rc ) { if( rc != VVB_OK ) THROW( g_b200.lastError( b200CtxOfThread() ) ); }
+
 template<int FAM> Distortion distB200( const DistParam& dp )
 {
   if( dp.applyWeight ) THROW( " no support" );

@@ -1,0 +1,87 @@
+// integration/TrQuantB200.h -- reference-side binding of libvvenc_b200.so for the transform / quantisation seam of CommonLib/TrQuant.cpp.
+//
+//   xTQuantB200          <->  the xT + xQuant pair inside TrQuant::transformNxN (TrQuant.cpp:709-733 -> xT :481-564, Quant::quant Quant.cpp:735-833)
+//   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
+//
+// for the TUs the library covers: luma, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), LFNST index 0, no transform
+// skip, no scaling lists, plain quantiser (RDOQ / dependent quantisation stay on the host and use the coefficients this call leaves in the temp buffer).
+// vvb_tu_par is derived from the TransformUnit exactly as the members derive their parameters (xSetTrTypes, QpParam, slice type), so the call sites keep
+// their arguments.  One TU per call here; the production shape batches the TU candidates of a CU (vvb_fwd_trquant with n > 1 or
+// vvb_tu_roundtrip).  Include after RdCostB200.h and CommonLib/TrQuant.h; TrQuant::xSetTrTypes is private: inside the encoder these are member functions.
+#pragma once
+#include <vector>
+#include "RdCostB200.h"
+
+struct B200TuApi
+{
+  bool bound = false;
+  decltype( &vvb_fwd_trquant )  fwdTrQuant = nullptr;
+  decltype( &vvb_inv_trquant )  invTrQuant = nullptr;
+} ;
+static B200TuApi g_b200t;
+
+inline int b200LoadTu( const char* libPath )
+{
+  if( g_b200t.bound ) return 0;
+  int rc = b200Load( libPath );
+  if( rc ) return rc;
+  void* h = g_b200.handle;
+#define VVB_RESOLVE( member, name ) g_b200t.member = (decltype( g_b200t.member )) dlsym( h, #name ); if( !g_b200t.member ) { g_b200.error = "missing " #name; return -2; }
+  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )
+#undef VVB_RESOLVE
+  g_b200t.bound = true;
+  return 0;
+}
+
+inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const ComponentID compID, const QpParam& cQP )
+{
+  if( compID != COMP_Y ) THROW( "luma TUs only" );
+  if( tu.mtsIdx[compID] == MTS_SKIP || tu.cu->bdpcmM[CH_L] ) THROW( "transform skip stays on the host" );
+  if( tu.cu->lfnstIdx ) THROW( "LFNST stays on the host" );
+  if( tu.cs->sps->scalingListEnabled ) THROW( "scaling lists stay on the host" );
+  const SPS& sps = *tu.cs->sps;
+  int trHor = DCT2, trVer = DCT2;
+  tq.xSetTrTypes( tu, compID, tu.blocks[compID].width, tu.blocks[compID].height, trHor, trVer );     // TrQuant.cpp:417-478
+  vvb_tu_par par = {};
+  par.w = tu.blocks[compID].width; par.h = tu.blocks[compID].height;
+  par.tr_hor = trHor; par.tr_ver = trVer;                                                    // enum TransType: DCT2 0, DCT8 1, DST7 2 -- the ABI's numbering
+  par.bit_depth = sps.bitDepths[CH_L];
+  par.qp = cQP.Qp( false ) - sps.qpBDOffset[CH_L];                                           // the library adds 6 * (bitDepth - 8) itself (Quant.cpp:99)
+  if( sps.qpBDOffset[CH_L] != 6 * ( par.bit_depth - 8 ) ) THROW( "unexpected qpBDOffset" );
+  par.is_irap = tu.cs->slice->isIRAP() ? 1 : 0;                                              // rounding offset 171 vs 85 (Quant.cpp:772)
+  par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;
+  return par;
+}
+
+// xT( tu, compID, resiBuf, tempCoeff, w, h ) followed by xQuant( tu, compID, tempCoeff, uiAbsSum, cQP, ctx ) with the plain quantiser:
+// tempCoeff receives the transform coefficients, tu.getCoeffs( compID ) the levels, tu.lastPos[compID] and uiAbsSum as Quant::quant sets them.
+// needRdoq (nullable) receives Quant::xNeedRDOQ of the coefficients (Quant.cpp:835-891).
+inline void xTQuantB200( TrQuant& tq, TransformUnit& tu, const ComponentID compID, const CPelBuf& resiBuf, CoeffBuf& tempCoeff, const QpParam& cQP, TCoeff& uiAbsSum,
+                         bool* needRdoq = nullptr )
+{
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
+  const int w = par.w, h = par.h;
+  std::vector<int16_t> resi( (size_t) w * h ), q( (size_t) w * h );
+  std::vector<int32_t> coef( (size_t) w * h );
+  for( int y = 0; y < h; y++ ) memcpy( &resi[(size_t) y * w], resiBuf.buf + (ptrdiff_t) y * resiBuf.stride, sizeof( int16_t ) * w );
+  int32_t absSum = 0, lastPos = -1; uint8_t nr = 0;
+  b200Check( g_b200t.fwdTrQuant( b200CtxOfThread(), &par, resi.data(), 1, coef.data(), q.data(), &absSum, &lastPos, &nr ) );
+  for( int y = 0; y < h; y++ ) memcpy( tempCoeff.buf + (ptrdiff_t) y * tempCoeff.stride, &coef[(size_t) y * w], sizeof( TCoeff ) * w );
+  CoeffSigBuf dst = tu.getCoeffs( compID );
+  for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
+  tu.lastPos[compID] = lastPos;
+  uiAbsSum = absSum;
+  if( needRdoq ) *needRdoq = nr != 0;
+}
+
+// TrQuant::invTransformNxN( tu, compID, pResi, cQP ) for the same class of TUs: levels of tu.getCoeffs( compID ) -> residual
+inline void invTransformNxNB200( TrQuant& tq, TransformUnit& tu, const ComponentID compID, PelBuf& pResi, const QpParam& cQP )
+{
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
+  const int w = par.w, h = par.h;
+  std::vector<int16_t> q( (size_t) w * h ), resi( (size_t) w * h );
+  const CCoeffSigBuf src = tu.getCoeffs( compID );
+  for( int y = 0; y < h; y++ ) memcpy( &q[(size_t) y * w], src.buf + (ptrdiff_t) y * src.stride, sizeof( TCoeffSig ) * w );
+  b200Check( g_b200t.invTrQuant( b200CtxOfThread(), &par, q.data(), 1, resi.data() ) );
+  for( int y = 0; y < h; y++ ) memcpy( pResi.buf + (ptrdiff_t) y * pResi.stride, &resi[(size_t) y * w], sizeof( Pel ) * w );
+}

@@ -162,7 +162,8 @@ inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, co
 // with the GPU library underneath and compare against the AVX2 table.
 #include "../integration/RdCostB200.h"
 #include "../integration/InterSearchB200.h"
-#include "../integration/MCTFB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
+#include "../integration/MCTFB200.h"
+#include "../integration/TrQuantB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
 
 void createRd( RdCost& rc, int opt )     // 0 scalar, 1 SIMD, 2 SIMD table patched with the B200 trampolines
 {
@@ -506,6 +507,44 @@ int refshim_transform_quant( int trHor, int trVer, const int16_t* resi, int stri
   static_cast<Quant*>( c.tq->m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
   *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  return 0;
+}
+
+// integration/TrQuantB200.h in action: the same TU rig, xT + Quant::quant replaced by xTQuantB200 / invTransformNxN by invTransformNxNB200 on the bound library.
+// Return 0, -1 (transform pair not expressible as an mtsIdx) or 1 (the binding threw; text through refshim_b200_error).
+int refshim_install_b200_tu( const char* libPath ) { return b200LoadTu( libPath ); }
+int refshim_transform_quant_b200( int trHor, int trVer, const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int depQuant,
+                                  int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, isIRAP != 0, true, qp );
+  r.slice.depQuantEnabled = depQuant != 0;
+  CPelBuf  resiBuf( resi, stride, w, h );
+  CoeffBuf dst( coef, w, w, h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  TCoeff sum = 0; bool nr = false;
+  try { xTQuantB200( *c.tq, r.tu, COMP_Y, resiBuf, dst, qpp, sum, &nr ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); r.slice.depQuantEnabled = false; return 1; }
+  r.slice.depQuantEnabled = false;
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y]; *needRdoq = nr ? 1 : 0;
+  return 0;
+}
+int refshim_inv_transform_quant_b200( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, false, true, qp );
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  PelBuf out( resi, stride, w, h );
+  try { invTransformNxNB200( *c.tq, r.tu, COMP_Y, out, qpp ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
   return 0;
 }
 

@@ -105,6 +105,39 @@ def main(mock_path):
                                         'eq': [bool(np.array_equal(a0, b0)), bool(np.array_equal(a1, b1)), bool(np.array_equal(a2, b2)), bool(np.array_equal(oa, ob))],
                                         'moving': int((a2[:, :, :2] != 0).any(axis=2).sum()), 'blocks': int(a2.shape[0] * a2.shape[1]),
                                         'err': (R.refshim_b200_error() or b'').decode() if any([rc1, rc3, rc5]) else ''})
+    # ---- xTQuantB200 / invTransformNxNB200 against TrQuant::xT + Quant::quant / Quant::dequant + xIT on the probe's TransformUnit rig: every case row of the
+    #      parity tables (all shapes, DCT-II / DST-VII / DCT-VIII pairs, 8 and 10 bit, strided residuals, both slice types, xNeedRDOQ with and without depQuant)
+    assert R.refshim_install_b200_tu(mock_path.encode()) == 0, R.refshim_b200_error()
+    I32 = ctypes.c_int32
+    bad = []; nfwd = 0
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for row in C.tq_cases()[opt::2]:
+            th, tv, w, h, st, amp, qp, irap, bd, seed = [int(v) for v in row]
+            resi = C.tq_inputs(row)
+            dq = seed & 1
+            ca = np.zeros((h, w), dtype=np.int32); qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32()
+            cb = np.zeros((h, w), dtype=np.int32); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32(); nb = I32()
+            assert R.refshim_transform_quant(th, tv, P(resi), st, w, h, bd, qp, irap, P(ca), P(qa), ctypes.byref(sa), ctypes.byref(la)) == 0
+            na = R.refshim_need_rdoq(P(ca), w, h, bd, qp, dq)
+            rc = R.refshim_transform_quant_b200(th, tv, P(resi), st, w, h, bd, qp, irap, dq, P(cb), P(qb), ctypes.byref(sb), ctypes.byref(lb), ctypes.byref(nb))
+            nfwd += 1
+            if rc or not (np.array_equal(ca, cb) and np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value and int(na) == nb.value):
+                bad.append(['fwd', opt] + [int(v) for v in row] + [rc])
+    res['tu_fwd'] = {'cases': nfwd, 'bad': bad[:5]}
+    bad = []; ninv = 0
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for row in C.itq_cases()[opt::2]:
+            th, tv, w, h, st, kind, qp, bd, seed = [int(v) for v in row]
+            q = C.itq_inputs(row)
+            ra = np.zeros((h, st), dtype=np.int16); rb = np.zeros((h, st), dtype=np.int16)
+            assert R.refshim_inv_transform_quant(th, tv, P(q), w, h, bd, qp, None, P(ra), st) == 0
+            rc = R.refshim_inv_transform_quant_b200(th, tv, P(q), w, h, bd, qp, P(rb), st)
+            ninv += 1
+            if rc or not np.array_equal(ra, rb):
+                bad.append(['inv', opt] + [int(v) for v in row] + [rc])
+    res['tu_inv'] = {'cases': ninv, 'bad': bad[:5]}
     print('RESULT ' + json.dumps(res))
 
 

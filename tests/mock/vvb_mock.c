@@ -113,6 +113,47 @@ int vvb_mctf_search_grid( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf
   return VVB_OK;
 }
 
+int orc_transform_quant( int trHor, int trVer, const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
+int orc_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant );
+int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride );
+
+int vvb_fwd_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* resi, int n, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, uint8_t* needRdoq )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !par || !resi || !q || n < 0 ) return fail( c, VVB_ERR_ARG, "bad trquant arguments" );
+  const size_t area = (size_t) par->w * par->h;
+  int32_t* tmp = (int32_t*) malloc( sizeof( int32_t ) * area );
+  if( !tmp ) return fail( c, VVB_ERR_NOMEM, "trquant" );
+  for( int i = 0; i < n; i++ )
+  {
+    int32_t s = 0, l = -1;
+    int32_t* co = coef ? coef + area * i : tmp;
+    if( orc_transform_quant( par->tr_hor, par->tr_ver, resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, co, q + area * i, &s, &l ) )
+    { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }
+    if( absSum ) absSum[i] = s;
+    if( lastPos ) lastPos[i] = l;
+    if( needRdoq ) needRdoq[i] = (uint8_t) orc_need_rdoq( co, par->w, par->h, par->bit_depth, par->qp, par->dep_quant );
+  }
+  free( tmp );
+  c->calls++;
+  return VVB_OK;
+}
+
+int vvb_inv_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* q, int n, int16_t* resi )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !par || !resi || !q || n < 0 ) return fail( c, VVB_ERR_ARG, "bad inverse arguments" );
+  const size_t area = (size_t) par->w * par->h;
+  int32_t* tmp = (int32_t*) malloc( sizeof( int32_t ) * area );
+  if( !tmp ) return fail( c, VVB_ERR_NOMEM, "inverse" );
+  for( int i = 0; i < n; i++ )
+    if( orc_inv_transform_quant( par->tr_hor, par->tr_ver, q + area * i, par->w, par->h, par->bit_depth, par->qp, tmp, resi + area * i, par->w ) )
+    { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }
+  free( tmp );
+  c->calls++;
+  return VVB_OK;
+}
+
 double orc_mctf_calc_var( const Pel* org, int so, int w, int h );
 int vvb_mctf_calc_var( vvb_ctx* c, int planeId, const vvb_mctf_cand* blocks, int n, double* varOut )
 {

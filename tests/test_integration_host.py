@@ -7,7 +7,8 @@ own code in the same process:
   * xPatternSearchB200 and B200RowSearch vs InterSearch::xPatternSearch (member call), all subShift modes, two AMVR shifts,
   * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular,
   * motionEstimationLumaB200 vs MCTF::motionEstimationLuma (member call): first level, chained level and the doubleRes final level, search patterns 0/1/2,
-    6- and 4-tap search filters, pictures with partial border blocks.
+    6- and 4-tap search filters, pictures with partial border blocks,
+  * xTQuantB200 / invTransformNxNB200 vs TrQuant::xT + Quant::quant (+ xNeedRDOQ) / Quant::dequant + xIT on a TransformUnit: every row of the parity tables.
 
 The same bindings run against libvvenc_b200.so in tests/test_gpu_dropin.py (-m gpu)."""
 import json
@@ -56,3 +57,8 @@ def test_mctf_search_binding_equals_the_member(result):
     for r in result['mctf']:
         assert r['rc'] == [0] * 6 and all(r['eq']), r
         assert r['moving'] > r['blocks'] // 2, r                 # the synthetic displacement is found: the fields are not trivially zero
+
+
+def test_transform_quant_binding_equals_the_members(result):
+    assert result['tu_fwd']['cases'] > 250 and result['tu_fwd']['bad'] == []
+    assert result['tu_inv']['cases'] > 250 and result['tu_inv']['bad'] == []
