@@ -1039,9 +1039,9 @@ int refshim_row_search_b200( int opt, const int16_t* orgPlane, int orgStride, co
 // org: compact width x height; refs[i]: compact width x height neighbour pictures (padded here by MCTF_PADDING with border replication);
 // mv4: [numRefs][hInBlks][wInBlks] x { x, y, error, rmsme }; refIndex[i] = min(5, |POC distance| - 1) selects m_refStrengths[picReordering ? 0 : 1][.].
 // strengthsOut (nullable) receives the strengths the reference used, sigmaSqOut its luma sigma^2 -- so that callers of the C ABI can be fed the same numbers.
-void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
-                                    int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply,
-                                    int16_t* out, double* strengthsOut, double* sigmaSqOut )
+static void bilateralFilterProbe( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
+                                  int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply,
+                                  int16_t* out, double* strengthsOut, double* sigmaSqOut, bool b200 )
 {
   RefCtx& c = ctx();
   MCTF* m = c.mctf[opt?1:0];
@@ -1081,11 +1081,25 @@ void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* 
     const double w = 1024.0 / ( ( 1 << bitDepth ) );
     *sigmaSqOut = lumaSigmaSq / ( w * w );
   }
-  m->bilateralFilter( orgPic, info, newOrgPic, overallStrength );
+  if( b200 ) bilateralFilterB200( *m, orgPic, info, newOrgPic, overallStrength ); else m->bilateralFilter( orgPic, info, newOrgPic, overallStrength );
   CPelBuf r = newOrgPic.Y();
   for( int y = 0; y < height; y++ ) memcpy( out + (size_t) y * width, r.buf + (ptrdiff_t) y * r.stride, sizeof( Pel ) * width );
   orgPic.destroy(); newOrgPic.destroy();
   for( int i = 0; i < numRefs; i++ ) info[i].picBuffer.destroy();
+}
+void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
+                                    int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply,
+                                    int16_t* out, double* strengthsOut, double* sigmaSqOut )
+{
+  bilateralFilterProbe( opt, org, refs, numRefs, mv4, refIndex, width, height, bitDepth, unitSize, qp, overallStrength, picReordering, lowResApply, out, strengthsOut, sigmaSqOut, false );
+}
+// the same set-up with bilateralFilterB200 (integration/MCTFB200.h) in place of the member; 0 = ok, 1 = the binding threw
+int refshim_mctf_bilateral_filter_b200( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
+                                        int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply, int16_t* out )
+{
+  try { bilateralFilterProbe( opt, org, refs, numRefs, mv4, refIndex, width, height, bitDepth, unitSize, qp, overallStrength, picReordering, lowResApply, out, nullptr, nullptr, true ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
+  return 0;
 }
 
 // The reference's OWN fractional refinement: InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2683-2725) called as a member -- xExtDIFUpSamplingH, the half-pel

@@ -105,6 +105,32 @@ def main(mock_path):
                                         'eq': [bool(np.array_equal(a0, b0)), bool(np.array_equal(a1, b1)), bool(np.array_equal(a2, b2)), bool(np.array_equal(oa, ob))],
                                         'moving': int((a2[:, :, :2] != 0).any(axis=2).sum()), 'blocks': int(a2.shape[0] * a2.shape[1]),
                                         'err': (R.refshim_b200_error() or b'').decode() if any([rc1, rc3, rc5]) else ''})
+    # ---- bilateralFilterB200 against MCTF::bilateralFilter (whole small luma pictures: unit 8 / 16, QP on both sides of the planar-correction threshold,
+    #      6- and 4-tap apply filters, 2..8 neighbour pictures, both strength rows, clipped edge blocks)
+    res['mctf_apply'] = []
+    rs = np.random.RandomState(404)
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for (W, H, unit, nrefs, qp, tap4, reorder) in ((96, 64, 16, 4, 22, 0, 1), (72, 40, 8, 6, 40, 0, 1), (64, 48, 16, 2, 32, 1, 0), (48, 32, 8, 8, 27, 0, 1), (80, 56, 32, 3, 30, 0, 0)):
+            base_ = rs.randint(0, 1024, size=(H + 8, W + 8))
+            sm = (base_ + np.roll(base_, 1, 0) + np.roll(base_, 1, 1) + np.roll(base_, (1, 1), (0, 1))) // 4
+            org = np.ascontiguousarray(sm[4:4 + H, 4:4 + W].astype(np.int16))
+            refs = []
+            for a in ([3, 12, 60, 300] * 2)[:nrefs]:
+                dy = int(rs.randint(-1, 2)); dx = int(rs.randint(-1, 2))
+                refs.append(np.ascontiguousarray(np.clip(sm[4 + dy:4 + dy + H, 4 + dx:4 + dx + W] + rs.randint(-a, a + 1, size=org.shape), 0, 1023).astype(np.int16)))
+            wb, hb = (W + unit - 1) // unit, (H + unit - 1) // unit
+            mv = np.zeros((nrefs, hb * wb, 4), dtype=np.int32)
+            mv[..., 0] = rs.randint(-80, 81, size=(nrefs, hb * wb)); mv[..., 1] = rs.randint(-80, 81, size=(nrefs, hb * wb))
+            mv[..., 2] = rs.choice([3, 20, 49, 50, 75, 100, 101, 400], size=(nrefs, hb * wb)); mv[..., 3] = rs.choice([0, 1, 5, 22, 60], size=(nrefs, hb * wb))
+            idx = np.array([i % 6 for i in range(nrefs)], dtype=np.int32)
+            ptrs = (ctypes.c_void_p * nrefs)(*[r_.ctypes.data for r_ in refs])
+            a_ = np.zeros((H, W), dtype=np.int16); b_ = np.zeros((H, W), dtype=np.int16)
+            R.refshim_mctf_bilateral_filter(opt, P(org), ptrs, nrefs, P(mv), P(idx), W, H, 10, unit, qp, ctypes.c_double(0.95), reorder, tap4, P(a_), None, None)
+            rc = R.refshim_mctf_bilateral_filter_b200(opt, P(org), ptrs, nrefs, P(mv), P(idx), W, H, 10, unit, qp, ctypes.c_double(0.95), reorder, tap4, P(b_))
+            res['mctf_apply'].append({'opt': opt, 'W': W, 'H': H, 'unit': unit, 'refs': nrefs, 'qp': qp, 'rc': rc, 'eq': bool(np.array_equal(a_, b_)),
+                                      'changed': bool(np.any(a_ != org)), 'err': (R.refshim_b200_error() or b'').decode() if rc else ''})
+
     # ---- xTQuantB200 / invTransformNxNB200 against TrQuant::xT + Quant::quant / Quant::dequant + xIT on the probe's TransformUnit rig: every case row of the
     #      parity tables (all shapes, DCT-II / DST-VII / DCT-VIII pairs, 8 and 10 bit, strided residuals, both slice types, xNeedRDOQ with and without depQuant)
     assert R.refshim_install_b200_tu(mock_path.encode()) == 0, R.refshim_b200_error()

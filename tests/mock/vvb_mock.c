@@ -165,6 +165,38 @@ int vvb_mctf_calc_var( vvb_ctx* c, int planeId, const vvb_mctf_cand* blocks, int
   return VVB_OK;
 }
 
+void orc_mctf_finalize_block( const Pel* orgPlane, int so, const Pel* const* refs, int rs, int numRefs, const int32_t* mv4, int bx, int by, int w, int h,
+                              int bitDepth, int tap4, int planarEnabled, const double* refStrengths, double weightScaling, double sigmaSq, Pel* dstPlane, int ds );
+int vvb_mctf_apply( vvb_ctx* c, int orgPlane, const vvb_mctf_apply_par* par, const vvb_mctf_mv* mvs, int16_t* out, int outStride )
+{
+  if( !c ) return VVB_ERR_ARG;
+  mock_plane* o = plane( c, orgPlane );
+  if( !o || !par || !mvs || !out || par->num_refs < 1 || par->num_refs > 8 || par->block_size < 8 ) return fail( c, VVB_ERR_ARG, "bad apply arguments" );
+  const Pel* refs[8]; int rs = 0;
+  for( int i = 0; i < par->num_refs; i++ )
+  {
+    mock_plane* r = plane( c, par->ref_plane[i] );
+    if( !r || ( i && r->stride != rs ) ) return fail( c, VVB_ERR_ARG, "reference planes missing or of different geometry" );
+    refs[i] = r->origin; rs = r->stride;
+  }
+  const int B = par->block_size, bxN = ( o->width + B - 1 ) / B, byN = ( o->height + B - 1 ) / B;
+  for( int by = 0; by < byN; by++ )
+    for( int bx = 0; bx < bxN; bx++ )
+    {
+      int32_t mv4[8 * 4];
+      for( int i = 0; i < par->num_refs; i++ )
+      {
+        const vvb_mctf_mv* v = &mvs[( (size_t) i * byN + by ) * bxN + bx];
+        mv4[4 * i] = v->x; mv4[4 * i + 1] = v->y; mv4[4 * i + 2] = v->error; mv4[4 * i + 3] = v->rmsme;
+      }
+      const int x = bx * B, y = by * B, w = o->width - x < B ? o->width - x : B, h = o->height - y < B ? o->height - y : B;
+      orc_mctf_finalize_block( o->origin, o->stride, refs, rs, par->num_refs, mv4, x, y, w, h, o->bitDepth, par->low_res_filter, par->planar_correction,
+                               par->ref_strength, par->weight_scaling, par->sigma_sq, out, outStride );
+    }
+  c->calls++;
+  return VVB_OK;
+}
+
 /* per-block entry points (FpDistFunc-shaped, RdCostB200.h) */
 uint64_t orc_dist( int family, const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift );
 uint64_t orc_sad_mask( const Pel* org, int so, const Pel* cur, int sc, int w, int h, const Pel* mask, int maskStride, int stepX, int maskStride2, int subShift );

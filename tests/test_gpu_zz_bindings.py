@@ -32,4 +32,6 @@ def test_batched_bindings_on_the_real_library():
         assert f['rc'] == 0 and f['eq'], f
     for m in r['mctf']:
         assert m['rc'] == [0] * 6 and all(m['eq']), m
+    for a in r['mctf_apply']:
+        assert a['rc'] == 0 and a['eq'], a
     assert r['tu_fwd']['bad'] == [] and r['tu_inv']['bad'] == []

@@ -8,6 +8,8 @@ own code in the same process:
   * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular,
   * motionEstimationLumaB200 vs MCTF::motionEstimationLuma (member call): first level, chained level and the doubleRes final level, search patterns 0/1/2,
     6- and 4-tap search filters, pictures with partial border blocks,
+  * bilateralFilterB200 vs MCTF::bilateralFilter (member call) on whole luma pictures: units 8/16/32, 2..8 neighbour pictures, both filter sets, QP on both
+    sides of the planar-correction threshold,
   * xTQuantB200 / invTransformNxNB200 vs TrQuant::xT + Quant::quant (+ xNeedRDOQ) / Quant::dequant + xIT on a TransformUnit: every row of the parity tables.
 
 The same bindings run against libvvenc_b200.so in tests/test_gpu_dropin.py (-m gpu)."""
@@ -62,3 +64,9 @@ def test_mctf_search_binding_equals_the_member(result):
 def test_transform_quant_binding_equals_the_members(result):
     assert result['tu_fwd']['cases'] > 250 and result['tu_fwd']['bad'] == []
     assert result['tu_inv']['cases'] > 250 and result['tu_inv']['bad'] == []
+
+
+def test_mctf_apply_binding_equals_the_member(result):
+    assert len(result['mctf_apply']) == 10
+    for r in result['mctf_apply']:
+        assert r['rc'] == 0 and r['eq'] and r['changed'], r
