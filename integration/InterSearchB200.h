@@ -6,6 +6,8 @@
 //   xPatternSearchB200         <->  InterSearch::xPatternSearch        (InterSearch.cpp:2209-2251)   one vvb_sad_search
 //   xPatternSearchFracDIFB200  <->  InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2677-2725)   one vvb_frac_cost_grid + the two xPatternRefinement rounds
 //                                                                      (:760-972, m_fastSubPel == 0) as table look-ups
+//   xTZSearchB200              <->  InterSearch::xTZSearch             (InterSearch.cpp:2297-2573)   one vvb_sad_search with its SAD table, then the UNMODIFIED
+//                                                                      member runs on that table (its SAD function-pointer slot answers by look-up)
 //   B200RowSearch                   the production shape: all PUs of a CTU row against resident pictures, one launch per block size
 //
 // The member-shaped functions take the InterSearch object and the TZSearchStruct the reference already fills (piRefY, iRefStride, pcPatternKey, searchRange,
@@ -135,6 +137,75 @@ inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStr
     rcMvQter = rcMvInt; rcMvQter <<= 1; rcMvQter += rcMvHalf; rcMvQter <<= 1;
     ruiCost = round( orderQ, 1, baseRefMv, rcMvQter );
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------------
+// InterSearch::xTZSearch (InterSearch.cpp:2297-2573).  The TZ search is a data-dependent walk (start candidates, log-spaced diamonds, raster, star refinement,
+// xTZ2PointSearch) whose every step is `SAD of one position + MV rate, keep if smaller` (xTZSearchHelp :410-438).  Instead of re-implementing the walk, the SADs
+// of the whole window it can visit are produced by ONE dense launch (vvb_sad_search with its SAD table -- pels are visited once, the headline kernel), the
+// RdCost slot the walk calls through (m_afpDistortFunc[.][DF_SAD + log2 w], selected by RdCost::setDistParam :158-200) is pointed at a table look-up for the
+// duration of the call, and the reference's own xTZSearch runs unchanged.  Positions outside the table (a start candidate far from the predictor) are answered by
+// the per-block entry point, so the result never depends on the window guess -- only the number of launches does.
+struct B200TzTable
+{
+  const Pel* piRefY = nullptr; ptrdiff_t stride = 0;
+  int left = 0, top = 0, nx = 0, ny = 0, subShift = 0;
+  std::vector<uint32_t> sad;
+  uint64_t hits = 0, misses = 0;
+};
+static thread_local B200TzTable t_b200tz;
+
+inline Distortion tzTableSadB200( const DistParam& dp )
+{
+  B200TzTable& t = t_b200tz;
+  const ptrdiff_t off = dp.cur.buf - t.piRefY;
+  // off = dy * stride + dx with left <= dx < left + nx << stride: floor division after shifting dx into [0, nx)
+  const ptrdiff_t sh = off - t.left;
+  ptrdiff_t dy = sh / t.stride; if( sh - dy * t.stride < 0 ) dy--;
+  const ptrdiff_t dx = off - dy * t.stride;
+  if( dp.subShift == t.subShift && dx >= t.left && dx < t.left + t.nx && dy >= t.top && dy < t.top + t.ny )
+  {
+    t.hits++;
+    return t.sad[(size_t)( dy - t.top ) * t.nx + ( dx - t.left )];
+  }
+  t.misses++;
+  return distB200<VVB_DF_SAD>( dp );
+}
+
+// refReach: how far (in pels, every direction) the reference picture is readable around the block -- the picture margin the encoder pads (Picture.cpp:461-501)
+inline void xTZSearchB200( InterSearch& is, const CodingUnit& cu, RefPicList refPicList, int iRefIdxPred, InterSearch::TZSearchStruct& cStruct, Mv& rcMv, Distortion& ruiSAD,
+                           const bool bExtendedSettings, const bool bFastSettings, const int refReach )
+{
+  RdCost& rc = *is.m_pcRdCost;
+  const CPelBuf& key = *cStruct.pcPatternKey;
+  const int bitDepth = is.m_lumaClpRng.bd;
+  int subShift = 0;
+  if( cStruct.subShiftMode == 1 && key.height > 8 && key.width <= 128 ) subShift = 1;
+  if( cStruct.subShiftMode == 2 && key.height > 8 ) subShift = 1;
+
+  // window guess: the range around the integer predictor and around the zero vector (the two start candidates of :2338-2346), inside the readable area
+  const int R = ( is.m_iSearchRange >> ( bFastSettings ? 1 : 0 ) ) + 1;
+  const int px = rcMv.hor >> MV_FRACTIONAL_BITS_INTERNAL, py = rcMv.ver >> MV_FRACTIONAL_BITS_INTERNAL;
+  auto clampR = [&]( int v ) { return std::max( -refReach, std::min( refReach, v ) ); };
+  const int left = clampR( std::min( px, 0 ) - R ), right = clampR( std::max( px, 0 ) + R ), top = clampR( std::min( py, 0 ) - R ), bottom = clampR( std::max( py, 0 ) + R );
+  b200UploadKeyAndWindow( key, cStruct.piRefY, cStruct.iRefStride, refReach, bitDepth );
+
+  B200TzTable& t = t_b200tz;
+  t.piRefY = cStruct.piRefY; t.stride = cStruct.iRefStride; t.left = left; t.top = top; t.nx = right - left + 1; t.ny = bottom - top + 1; t.subShift = subShift;
+  t.sad.assign( (size_t) t.nx * t.ny, 0 ); t.hits = t.misses = 0;
+  vvb_block blk = {};
+  blk.left = (int16_t) left; blk.right = (int16_t) right; blk.top = (int16_t) top; blk.bottom = (int16_t) bottom;
+  blk.pred_hor = (int16_t) rc.m_mvPredictor.hor; blk.pred_ver = (int16_t) rc.m_mvPredictor.ver;
+  const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, cStruct.imvShift, subShift );
+  vvb_best best = {};
+  b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, t.sad.data(), t.nx * t.ny, &best ) );
+
+  const int base = bitDepth > 10 ? 1 : 0, slot = DF_SAD + Log2( key.width );                 // RdCost::setDistParam :172-176
+  const FpDistFunc saved = rc.m_afpDistortFunc[base][slot];
+  rc.m_afpDistortFunc[base][slot] = tzTableSadB200;
+  try { is.xTZSearch( cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings ); }
+  catch( ... ) { rc.m_afpDistortFunc[base][slot] = saved; throw; }
+  rc.m_afpDistortFunc[base][slot] = saved;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------------------

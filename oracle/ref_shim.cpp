@@ -993,6 +993,79 @@ void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The reference's OWN TZ search: InterSearch::xTZSearch (InterSearch.cpp:2297-2573; diamond / raster / star refinement) called as a member, and the same call through
+// xTZSearchB200 (integration/InterSearchB200.h: one dense SAD table, the unmodified member walking it).  The CodingUnit carries what the member reads: position and size,
+// cs->pcv (picture and CTU size for xClipMvSearch / xSetSearchRange).  blk[i] = { x, y, w, h, predHor, predVer } with the predictor in internal (1/16 pel) units, used both
+// as RdCost predictor and as start vector like xMotionEstimation does (:2040-2043, :2104).  out[i] = { mvx, mvy, ruiSAD lo, hi, uiBestSad lo, hi, table hits, misses }.
+static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
+                          int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift,
+                          int64_t* out, bool b200 )
+{
+  static thread_local InterSearch* isp = new InterSearch;
+  static thread_local BlkUniMvInfoBuffer* uni = new BlkUniMvInfoBuffer;
+  static thread_local TuRig* rg = new TuRig;
+  static VVEncCfg cfg;
+  InterSearch& is = *isp;
+  cfg.m_ifpLines = 0; cfg.m_bIntegerET = integerET != 0; cfg.m_bFastMEAssumingSmootherMVEnabled = firstSearchStop != 0;
+  is.m_pcEncCfg = &cfg; is.m_iSearchRange = searchRange; is.m_BlkUniMvInfoBuffer = uni; is.m_lumaClpRng.bd = bitDepth;
+  TuRig& r = *rg;
+  r.setup( 8, 8, bitDepth, 0, false, false, 32 );
+  r.sps.CTUSize = ctuSize; r.sps.log2MinCodingBlockSize = 2;
+  r.pps.picWidthInLumaSamples = picW; r.pps.picHeightInLumaSamples = picH;
+  const unsigned maxQt[3] = { (unsigned) ctuSize, (unsigned) ctuSize, (unsigned) ctuSize };
+  PreCalcValues pcv( r.sps, r.pps, maxQt );
+  r.cs.pcv = &pcv;
+  int rcAll = 0;
+  for( int i = 0; i < n; i++ )
+  {
+    const int32_t* b = blk + 6 * (size_t) i;
+    const int w = b[2], h = b[3];
+    static_cast<UnitArea&>( r.cu ) = UnitArea( CHROMA_400, Area( b[0], b[1], w, h ) );
+    RdCost rc; createRd( rc, opt );
+    BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
+    rc.setLambda( lambda, bd ); rc.selectMotionLambda();
+    Mv pred( b[4], b[5] );
+    Mv predQuarter = pred; predQuarter.changePrecision( MV_PRECISION_INTERNAL, MV_PRECISION_QUARTER );
+    rc.setPredictor( predQuarter ); rc.setCostScale( 2 );
+    is.m_pcRdCost = &rc;
+    AlignedPel org( (size_t) w * h );
+    for( int y = 0; y < h; y++ ) memcpy( org.p + y * w, orgPlane + (ptrdiff_t)( b[1] + y ) * orgStride + b[0], 2 * w );
+    CPelBuf key( org.p, w, w, h );
+    InterSearch::TZSearchStruct st;
+    memset( &st, 0, sizeof( st ) );
+    st.pcPatternKey = &key;
+    st.piRefY = refPlane + (ptrdiff_t) b[1] * refStride + b[0];
+    st.iRefStride = refStride;
+    st.subShiftMode = subShiftMode; st.imvShift = (unsigned) imvShift;
+    st.uiBestSad = MAX_DISTORTION;
+    is.xSetSearchRange( r.cu, pred, searchRange, st.searchRange );                    // :2002 (xMotionEstimation)
+    Mv mv = pred; Distortion sad = 0;
+    int64_t* o = out + 8 * (size_t) i;
+    try
+    {
+      if( b200 ) { xTZSearchB200( is, r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0, refReach ); o[6] = (int64_t) t_b200tz.hits; o[7] = (int64_t) t_b200tz.misses; }
+      else       { is.xTZSearch( r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0 ); o[6] = o[7] = 0; }
+    }
+    catch( std::exception& e ) { g_b200.error = e.what(); rcAll = 1; }
+    o[0] = mv.hor; o[1] = mv.ver; o[2] = (int64_t) sad; o[3] = 0; o[4] = (int64_t) st.uiBestSad; o[5] = st.uiBestDistance;
+  }
+  r.cs.pcv = nullptr;
+  return rcAll;
+}
+int refshim_tz_search_member( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
+                              int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift, int64_t* out )
+{
+  return tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk, n, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast, integerET,
+                        firstSearchStop, imvShift, out, false );
+}
+int refshim_tz_search_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
+                            int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift, int64_t* out )
+{
+  return tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk, n, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast, integerET,
+                        firstSearchStop, imvShift, out, true );
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // integration/InterSearchB200.h in action: the same set-up as the member probes, the loops replaced by the batched C-ABI calls.  The library is whatever
 // refshim_install_b200_search() bound: libvvenc_b200.so on the GPU box, tests/mock (the C ABI answered by the CPU oracle) for the host-logic tests.
 int refshim_install_b200_search( const char* libPath ) { return b200LoadSearch( libPath ); }

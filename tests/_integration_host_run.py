@@ -52,6 +52,32 @@ def main(mock_path):
                 res['search'].append({'opt': opt, 'mode': mode, 'imv': imv, 'rc': [rc1, rc2], 'blocks': n, 'member_eq_b200': bool(np.array_equal(a, b)),
                                       'member_eq_rows': bool(np.array_equal(a, c)), 'err': (R.refshim_b200_error() or b'').decode() if (rc1 or rc2) else ''})
 
+    # ---- xTZSearchB200 against InterSearch::xTZSearch: the unmodified member walking the dense SAD table; diamond / enhanced / fast settings, integer early
+    #      termination, first-search stop, all sub-sampling modes; the last configuration shrinks the readable reach so that part of the walk leaves the table
+    tz_args = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+               ctypes.c_int, dbl] + [ctypes.c_int] * 7 + [ctypes.c_void_p]
+    R.refshim_tz_search_member.argtypes = tz_args; R.refshim_tz_search_b200.argtypes = tz_args
+    tz = C.search_case(seed=909, W=256, H=160, margin=96)
+    tS = tz['stride']; tbase = tz['margin'] * tS + tz['margin']
+    rs = np.random.RandomState(5)
+    tblk = []
+    for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (32, 16), (4, 8), (64, 32)):
+        for k in range(6):
+            tblk.append((int(rs.randint(0, 256 - w + 1)), int(rs.randint(0, 160 - h + 1)), w, h, int(rs.randint(-20 * 16, 20 * 16 + 1)), int(rs.randint(-12 * 16, 12 * 16 + 1))))
+    tblk = np.array(tblk, dtype=np.int32); tn = len(tblk)
+    res['tz'] = []
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for (ext, fast, iet, stop, mode, rng, reach) in ((0, 0, 0, 0, 0, 24, 80), (1, 0, 0, 0, 1, 24, 80), (0, 1, 0, 1, 1, 32, 80), (0, 0, 1, 1, 2, 16, 80), (1, 1, 1, 0, 0, 24, 80),
+                                                         (1, 0, 0, 0, 0, 24, 14)):
+            a = np.zeros((tn, 8), dtype=np.int64); b = np.zeros((tn, 8), dtype=np.int64)
+            args = (PO(tz['org'], tbase), tS, PO(tz['ref'], tbase), tS, 256, 160, reach, P(tblk), tn, 10, mode, 57.0, rng, 32, ext, fast, iet, stop, 0)
+            rc1 = R.refshim_tz_search_member(opt, *args, P(a))
+            rc2 = R.refshim_tz_search_b200(opt, *args, P(b))
+            res['tz'].append({'opt': opt, 'cfg': [ext, fast, iet, stop, mode, rng, reach], 'rc': [rc1, rc2], 'eq': bool(np.array_equal(a[:, :6], b[:, :6])),
+                              'hits': int(b[:, 6].sum()), 'misses': int(b[:, 7].sum()), 'moving': int((a[:, :2] != 0).any(axis=1).sum()), 'blocks': tn,
+                              'err': (R.refshim_b200_error() or b'').decode() if rc2 else ''})
+
     # ---- xPatternSearchFracDIFB200 against InterSearch::xPatternSearchFracDIF (m_fastSubPel 0)
     res['frac'] = []
     rs = np.random.RandomState(23)

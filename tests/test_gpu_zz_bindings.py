@@ -28,6 +28,8 @@ def test_batched_bindings_on_the_real_library():
     assert r['dist_mismatches'] == 0
     for s in r['search']:
         assert s['rc'] == [0, 0] and s['member_eq_b200'] and s['member_eq_rows'], s
+    for t in r['tz']:
+        assert t['rc'] == [0, 0] and t['eq'], t
     for f in r['frac']:
         assert f['rc'] == 0 and f['eq'], f
     for m in r['mctf']:
