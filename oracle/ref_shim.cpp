@@ -87,7 +87,7 @@ struct RefCtx
   RdCost& rd( int opt ) { if( opt == 2 && !b200Ready ) { createRd( rdB200, 2 ); b200Ready = true; } return opt == 2 ? rdB200 : opt ? rdSimd : rdScalar; }
   TrQuant*               tq      = nullptr;
   MCTF*                  mctf[2] = { nullptr, nullptr };
-  AffineGradientSearch*  ags[2]  = { nullptr, nullptr };
+  AffineGradientSearch*  ags[3]  = { nullptr, nullptr, nullptr };   // [2]: pointers patched by installB200( AffineGradientSearch& ), created on demand
   std::string            simd;
 };
 
@@ -163,7 +163,8 @@ inline uint64_t callDist( RdCost& rc, int family, const int16_t* org, int so, co
 #include "../integration/RdCostB200.h"
 #include "../integration/InterSearchB200.h"
 #include "../integration/MCTFB200.h"
-#include "../integration/TrQuantB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
+#include "../integration/TrQuantB200.h"
+#include "../integration/AffineGradientB200.h"   // the reference-side binding (B200Api, trampolines, installB200), compiled for real here
 
 void createRd( RdCost& rc, int opt )     // 0 scalar, 1 SIMD, 2 SIMD table patched with the B200 trampolines
 {
@@ -1258,10 +1259,18 @@ void refshim_mctf_finalize_picture( int opt, const int16_t* orgPlane, int orgStr
 
 // ---------------------------------------------------------------------------------------------------------
 // Affine gradient helpers (AffineGradientSearch.h:67-69)
+// opt == 2: an AffineGradientSearch whose pointers installB200() patched (integration/AffineGradientB200.h); needs refshim_install_b200_affine first
+int refshim_install_b200_affine( const char* libPath ) { return b200LoadAffine( libPath ); }
+static AffineGradientSearch* agsOf( RefCtx& c, int opt )
+{
+  if( opt != 2 ) return c.ags[opt?1:0];
+  if( !c.ags[2] ) { c.ags[2] = new AffineGradientSearch( false ); installB200( *c.ags[2] ); }
+  return c.ags[2];
+}
 void refshim_sobel( int opt, int vertical, const int16_t* pred, int predStride, int16_t* deriv, int derivStride, int w, int h )
 {
   RefCtx& c = ctx();
-  AffineGradientSearch* a = c.ags[opt?1:0];
+  AffineGradientSearch* a = agsOf( c, opt );
   if( vertical ) a->m_VerticalSobelFilter  ( const_cast<Pel*>( pred ), predStride, deriv, derivStride, w, h );
   else           a->m_HorizontalSobelFilter( const_cast<Pel*>( pred ), predStride, deriv, derivStride, w, h );
 }
@@ -1270,7 +1279,7 @@ void refshim_equal_coeff( int opt, int sixParam, const int16_t* resi, int resiSt
                           int w, int h, int64_t* eq /*7x7, accumulated into*/ )
 {
   RefCtx& c = ctx();
-  AffineGradientSearch* a = c.ags[opt?1:0];
+  AffineGradientSearch* a = agsOf( c, opt );
   Pel* d[2] = { const_cast<Pel*>( dx ), const_cast<Pel*>( dy ) };
   a->m_EqualCoeffComputer[sixParam?1:0]( const_cast<Pel*>( resi ), resiStride, d, derivStride, w, h, reinterpret_cast<int64_t(*)[7]>( eq ) );
 }

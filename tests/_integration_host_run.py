@@ -35,6 +35,21 @@ def main(mock_path):
     res['dist_mismatches'] = len(impls.run_dist(impls.RefImpl(opt=2), g['dist_rows'], g['dist_expect']))
     res['dist_rows'] = int(len(g['dist_rows']))
 
+    # ---- AffineGradientSearch pointers patched by installB200( AffineGradientSearch& ) (opt 2) against the AVX2 kernels (opt 1): Sobel planes and the
+    #      normal equations of every affine case row
+    assert R.refshim_install_b200_affine(mock_path.encode()) == 0, R.refshim_b200_error()
+    bad = 0; na = 0
+    A1 = impls.RefImpl(opt=1); A2 = impls.RefImpl(opt=2)
+    for row in C.affine_cases():
+        w, h, ps, ds, six, seed = [int(v) for v in row]
+        pred, resi, gx, gy = C.affine_inputs(row)
+        for vert in (0, 1):
+            bad += int(not np.array_equal(A1.sobel(vert, pred, ps, ds, w, h)[1:h - 1, 1:w - 1], A2.sobel(vert, pred, ps, ds, w, h)[1:h - 1, 1:w - 1]))
+            bad += int(not np.array_equal(A1.sobel(vert, pred, ps, ds, w, h)[:, :w], A2.sobel(vert, pred, ps, ds, w, h)[:, :w]))
+        e1 = A1.equal_coeff(six, resi, ps, gx, gy, ds, w, h); e2 = A2.equal_coeff(six, resi, ps, gx, gy, ds, w, h)
+        bad += int(not np.array_equal(e1, e2)); na += 1
+    res['affine'] = {'cases': na, 'bad': bad}
+
     # ---- xPatternSearchB200 / B200RowSearch against InterSearch::xPatternSearch
     sc = C.search_case()
     n = len(sc['blk']); S = sc['stride']; base = sc['margin'] * S + sc['margin']

@@ -197,6 +197,25 @@ int vvb_mctf_apply( vvb_ctx* c, int orgPlane, const vvb_mctf_apply_par* par, con
   return VVB_OK;
 }
 
+void orc_sobel( int vertical, const Pel* p, int ps, Pel* d, int ds, int w, int h );
+void orc_equal_coeff( int sixParam, const Pel* resi, int rs, const Pel* gx, const Pel* gy, int ds, int w, int h, int64_t* eq );
+int vvb_affine_sobel( vvb_ctx* c, int vertical, const int16_t* pred, int ps, int16_t* deriv, int ds, int w, int h )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !pred || !deriv || w < 3 || h < 3 ) return fail( c, VVB_ERR_ARG, "bad sobel arguments" );
+  orc_sobel( vertical, pred, ps, deriv, ds, w, h );
+  c->calls++;
+  return VVB_OK;
+}
+int vvb_affine_equal_coeff( vvb_ctx* c, int sixParam, const int16_t* resi, int rs, const int16_t* dx, const int16_t* dy, int ds, int w, int h, int64_t eq[49] )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !resi || !dx || !dy || !eq ) return fail( c, VVB_ERR_ARG, "bad equal_coeff arguments" );
+  orc_equal_coeff( sixParam, resi, rs, dx, dy, ds, w, h, eq );
+  c->calls++;
+  return VVB_OK;
+}
+
 /* per-block entry points (FpDistFunc-shaped, RdCostB200.h) */
 uint64_t orc_dist( int family, const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subShift );
 uint64_t orc_sad_mask( const Pel* org, int so, const Pel* cur, int sc, int w, int h, const Pel* mask, int maskStride, int stepX, int maskStride2, int subShift );

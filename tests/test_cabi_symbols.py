@@ -55,9 +55,9 @@ def test_reference_side_binding_resolves_only_declared_symbols():
     """integration/RdCostB200.h binds the library with dlsym: every name it asks for must be declared in the C ABI header (and hence exported)"""
     txt = open(os.path.join(ROOT, 'integration', 'RdCostB200.h')).read()
     txt_search = open(os.path.join(ROOT, 'integration', 'InterSearchB200.h')).read() + open(os.path.join(ROOT, 'integration', 'MCTFB200.h')).read() + \
-        open(os.path.join(ROOT, 'integration', 'TrQuantB200.h')).read()
+        open(os.path.join(ROOT, 'integration', 'TrQuantB200.h')).read() + open(os.path.join(ROOT, 'integration', 'AffineGradientB200.h')).read()
     asked = sorted(set(re.findall(r'VVB_RESOLVE\(\s*\w+\s*,\s*(vvb_[a-z0-9_]+)\s*\)', txt + txt_search)))
-    assert len(asked) >= 14 and 'vvb_fwd_trquant' in asked and 'vvb_sad_search' in asked and 'vvb_frac_cost_grid' in asked and 'vvb_mctf_search_grid' in asked
+    assert len(asked) >= 16 and 'vvb_affine_sobel' in asked and 'vvb_fwd_trquant' in asked and 'vvb_sad_search' in asked and 'vvb_frac_cost_grid' in asked and 'vvb_mctf_search_grid' in asked
     declared = set(_declared())
     assert [n for n in asked if n not in declared] == []
     # the trampolines cover every slot family the x86 back end overwrites (RdCostX86.h:3376-3425)

@@ -25,7 +25,7 @@ def test_batched_bindings_on_the_real_library():
     line = [ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')]
     assert line, out.stdout[-2000:]
     r = json.loads(line[-1][len('RESULT '):])
-    assert r['dist_mismatches'] == 0
+    assert r['dist_mismatches'] == 0 and r['affine']['bad'] == 0
     for s in r['search']:
         assert s['rc'] == [0, 0] and s['member_eq_b200'] and s['member_eq_rows'], s
     for t in r['tz']:

@@ -4,6 +4,7 @@ out of DistParam / TZSearchStruct / RdCost, and the replay of the reference's se
 own code in the same process:
 
   * RdCost tables patched by installB200() vs the AVX2 table on every golden distortion row,
+  * AffineGradientSearch pointers patched by installB200() vs the AVX2 kernels on every affine case row,
   * xPatternSearchB200 and B200RowSearch vs InterSearch::xPatternSearch (member call), all subShift modes, two AMVR shifts,
   * xTZSearchB200 vs InterSearch::xTZSearch (member call): the unmodified member walks the dense SAD table of one vvb_sad_search launch -- diamond / enhanced /
     fast settings, integer early termination, first-search stop; with a reach too small for the walk the per-block path answers the rest,
@@ -41,6 +42,7 @@ def result():
 
 def test_rdcost_tables_patched_through_the_binding(result):
     assert result['dist_rows'] > 600 and result['dist_mismatches'] == 0
+    assert result['affine']['cases'] >= 12 and result['affine']['bad'] == 0
 
 
 def test_pattern_search_binding_equals_the_member(result):
