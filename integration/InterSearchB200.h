@@ -54,6 +54,14 @@ inline vvb_me_par b200MePar( RdCost& rc, int costScale, unsigned imvShift, int s
   return me;
 }
 
+// RdCost::setDistParam's sub-sampling rule (RdCost.cpp:187-200)
+inline int b200SubShift( int subShiftMode, int w, int h )
+{
+  if( subShiftMode == 1 && h > 8 && w <= 128 ) return 1;
+  if( subShiftMode == 2 && h > 8 ) return 1;
+  return 0;
+}
+
 // plane ids the per-call forms use for their uploads
 enum { B200_PLANE_KEY = 14, B200_PLANE_WINDOW = 15 };
 
@@ -72,9 +80,7 @@ inline void xPatternSearchB200( InterSearch& is, InterSearch::TZSearchStruct& cS
   RdCost& rc = *is.m_pcRdCost;
   const CPelBuf& key = *cStruct.pcPatternKey;
   const InterSearch::SearchRange& sr = cStruct.searchRange;
-  int subShift = 0;                                                                       // RdCost::setDistParam (RdCost.cpp:187-200)
-  if( cStruct.subShiftMode == 1 && key.height > 8 && key.width <= 128 ) subShift = 1;
-  if( cStruct.subShiftMode == 2 && key.height > 8 ) subShift = 1;
+  const int subShift = b200SubShift( cStruct.subShiftMode, key.width, key.height );
   const int reach = std::max( std::max( -sr.left, sr.right ), std::max( -sr.top, sr.bottom ) );
   b200UploadKeyAndWindow( key, cStruct.piRefY, cStruct.iRefStride, std::max( reach, 0 ), is.m_lumaClpRng.bd );
 
@@ -150,7 +156,7 @@ struct B200TzTable
 {
   const Pel* piRefY = nullptr; ptrdiff_t stride = 0;
   int left = 0, top = 0, nx = 0, ny = 0, subShift = 0;
-  std::vector<uint32_t> sad;
+  const uint32_t* sad = nullptr;                                                              // [ny][nx], row-major over the window
   uint64_t hits = 0, misses = 0;
 };
 static thread_local B200TzTable t_b200tz;
@@ -172,40 +178,51 @@ inline Distortion tzTableSadB200( const DistParam& dp )
   return distB200<VVB_DF_SAD>( dp );
 }
 
+// window guess for the walk: the search range (+1 for xTZ2PointSearch) around the integer start vector and around the zero vector -- the two start candidates of
+// :2338-2346 --, kept inside the readable reach.  rcMv: the start vector in internal (1/16 pel) units, as xTZSearch receives it.
+inline void b200TzWindow( const Mv& rcMv, int searchRange, bool bFastSettings, int refReach, int& left, int& right, int& top, int& bottom )
+{
+  const int R = ( searchRange >> ( bFastSettings ? 1 : 0 ) ) + 1;
+  const int px = rcMv.hor >> MV_FRACTIONAL_BITS_INTERNAL, py = rcMv.ver >> MV_FRACTIONAL_BITS_INTERNAL;
+  auto clampR = [&]( int v ) { return std::max( -refReach, std::min( refReach, v ) ); };
+  left = clampR( std::min( px, 0 ) - R ); right = clampR( std::max( px, 0 ) + R ); top = clampR( std::min( py, 0 ) - R ); bottom = clampR( std::max( py, 0 ) + R );
+}
+
+// the unmodified member on a prepared table: the SAD slot RdCost::setDistParam will select (:172-176) answers by look-up for the duration of the call
+inline void b200TzWalk( InterSearch& is, const CodingUnit& cu, RefPicList refPicList, int iRefIdxPred, InterSearch::TZSearchStruct& cStruct, Mv& rcMv, Distortion& ruiSAD,
+                        const bool bExtendedSettings, const bool bFastSettings, const uint32_t* sad, int left, int top, int nx, int ny, int subShift )
+{
+  RdCost& rc = *is.m_pcRdCost;
+  B200TzTable& t = t_b200tz;
+  t.piRefY = cStruct.piRefY; t.stride = cStruct.iRefStride; t.left = left; t.top = top; t.nx = nx; t.ny = ny; t.subShift = subShift; t.sad = sad; t.hits = t.misses = 0;
+  const int base = is.m_lumaClpRng.bd > 10 ? 1 : 0, slot = DF_SAD + Log2( cStruct.pcPatternKey->width );
+  const FpDistFunc saved = rc.m_afpDistortFunc[base][slot];
+  rc.m_afpDistortFunc[base][slot] = tzTableSadB200;
+  try { is.xTZSearch( cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings ); }
+  catch( ... ) { rc.m_afpDistortFunc[base][slot] = saved; t.sad = nullptr; throw; }
+  rc.m_afpDistortFunc[base][slot] = saved; t.sad = nullptr;
+}
+
 // refReach: how far (in pels, every direction) the reference picture is readable around the block -- the picture margin the encoder pads (Picture.cpp:461-501)
 inline void xTZSearchB200( InterSearch& is, const CodingUnit& cu, RefPicList refPicList, int iRefIdxPred, InterSearch::TZSearchStruct& cStruct, Mv& rcMv, Distortion& ruiSAD,
                            const bool bExtendedSettings, const bool bFastSettings, const int refReach )
 {
   RdCost& rc = *is.m_pcRdCost;
   const CPelBuf& key = *cStruct.pcPatternKey;
-  const int bitDepth = is.m_lumaClpRng.bd;
-  int subShift = 0;
-  if( cStruct.subShiftMode == 1 && key.height > 8 && key.width <= 128 ) subShift = 1;
-  if( cStruct.subShiftMode == 2 && key.height > 8 ) subShift = 1;
+  const int subShift = b200SubShift( cStruct.subShiftMode, key.width, key.height );
+  int left, right, top, bottom;
+  b200TzWindow( rcMv, is.m_iSearchRange, bFastSettings, refReach, left, right, top, bottom );
+  b200UploadKeyAndWindow( key, cStruct.piRefY, cStruct.iRefStride, refReach, is.m_lumaClpRng.bd );
 
-  // window guess: the range around the integer predictor and around the zero vector (the two start candidates of :2338-2346), inside the readable area
-  const int R = ( is.m_iSearchRange >> ( bFastSettings ? 1 : 0 ) ) + 1;
-  const int px = rcMv.hor >> MV_FRACTIONAL_BITS_INTERNAL, py = rcMv.ver >> MV_FRACTIONAL_BITS_INTERNAL;
-  auto clampR = [&]( int v ) { return std::max( -refReach, std::min( refReach, v ) ); };
-  const int left = clampR( std::min( px, 0 ) - R ), right = clampR( std::max( px, 0 ) + R ), top = clampR( std::min( py, 0 ) - R ), bottom = clampR( std::max( py, 0 ) + R );
-  b200UploadKeyAndWindow( key, cStruct.piRefY, cStruct.iRefStride, refReach, bitDepth );
-
-  B200TzTable& t = t_b200tz;
-  t.piRefY = cStruct.piRefY; t.stride = cStruct.iRefStride; t.left = left; t.top = top; t.nx = right - left + 1; t.ny = bottom - top + 1; t.subShift = subShift;
-  t.sad.assign( (size_t) t.nx * t.ny, 0 ); t.hits = t.misses = 0;
+  const int nx = right - left + 1, ny = bottom - top + 1;
+  std::vector<uint32_t> sad( (size_t) nx * ny );
   vvb_block blk = {};
   blk.left = (int16_t) left; blk.right = (int16_t) right; blk.top = (int16_t) top; blk.bottom = (int16_t) bottom;
   blk.pred_hor = (int16_t) rc.m_mvPredictor.hor; blk.pred_ver = (int16_t) rc.m_mvPredictor.ver;
   const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, cStruct.imvShift, subShift );
   vvb_best best = {};
-  b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, t.sad.data(), t.nx * t.ny, &best ) );
-
-  const int base = bitDepth > 10 ? 1 : 0, slot = DF_SAD + Log2( key.width );                 // RdCost::setDistParam :172-176
-  const FpDistFunc saved = rc.m_afpDistortFunc[base][slot];
-  rc.m_afpDistortFunc[base][slot] = tzTableSadB200;
-  try { is.xTZSearch( cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings ); }
-  catch( ... ) { rc.m_afpDistortFunc[base][slot] = saved; throw; }
-  rc.m_afpDistortFunc[base][slot] = saved;
+  b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, sad.data(), nx * ny, &best ) );
+  b200TzWalk( is, cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings, sad.data(), left, top, nx, ny, subShift );
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------------------
@@ -239,9 +256,7 @@ public:
   {
     for( auto& g : m_groups )
     {
-      int subShift = 0;
-      if( subShiftMode == 1 && g.h > 8 && g.w <= 128 ) subShift = 1;
-      if( subShiftMode == 2 && g.h > 8 ) subShift = 1;
+      const int subShift = b200SubShift( subShiftMode, g.w, g.h );
       const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, imvShift, subShift );
       std::vector<vvb_best> best( g.blocks.size() );
       b200Check( g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, nullptr, 0, best.data() ) );
@@ -254,10 +269,50 @@ public:
     m_groups.clear();
   }
   const std::vector<Result>& results() const { return m_results; }
-  void clear() { m_groups.clear(); m_results.clear(); }
+  void clear() { m_groups.clear(); m_results.clear(); m_tables.clear(); }
+
+  // ---- TZ search for the row: one dense launch per block size fills every PU's SAD table, then the reference's own xTZSearch walks each table on the host.
+  // addTz queues a PU with the window b200TzWindow derives from its start vector; runTables launches; tzSearch( i, ... ) is xTZSearch for PU i (same
+  // arguments as the member: the TZSearchStruct still names the PU's pattern key and its position in the reference picture).
+  int addTz( int x, int y, int w, int h, const Mv& startMvInternal, const Mv& predictor, int searchRange, bool bFastSettings, int refReach )
+  {
+    InterSearch::SearchRange sr;
+    b200TzWindow( startMvInternal, searchRange, bFastSettings, refReach, sr.left, sr.right, sr.top, sr.bottom );
+    return add( x, y, w, h, sr, predictor );
+  }
+  void runTables( RdCost& rc, unsigned imvShift, int subShiftMode )
+  {
+    m_tables.assign( m_results.size(), Table() );
+    for( auto& g : m_groups )
+    {
+      const int subShift = b200SubShift( subShiftMode, g.w, g.h );
+      const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, imvShift, subShift );
+      int tableStride = 0;
+      for( const vvb_block& b : g.blocks ) tableStride = std::max( tableStride, ( b.right - b.left + 1 ) * ( b.bottom - b.top + 1 ) );
+      std::vector<uint32_t> tabs( (size_t) tableStride * g.blocks.size() );
+      std::vector<vvb_best> best( g.blocks.size() );
+      b200Check( g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, tabs.data(), tableStride, best.data() ) );
+      for( size_t i = 0; i < g.blocks.size(); i++ )
+      {
+        const vvb_block& b = g.blocks[i];
+        Table& t = m_tables[g.index[i]];
+        t.left = b.left; t.top = b.top; t.nx = b.right - b.left + 1; t.ny = b.bottom - b.top + 1; t.subShift = subShift;
+        t.sad.assign( tabs.begin() + (ptrdiff_t)( i * tableStride ), tabs.begin() + (ptrdiff_t)( i * tableStride + (size_t) t.nx * t.ny ) );
+      }
+    }
+    m_groups.clear();
+  }
+  void tzSearch( int i, InterSearch& is, const CodingUnit& cu, RefPicList refPicList, int iRefIdxPred, InterSearch::TZSearchStruct& cStruct, Mv& rcMv, Distortion& ruiSAD,
+                 const bool bExtendedSettings, const bool bFastSettings ) const
+  {
+    const Table& t = m_tables[i];
+    b200TzWalk( is, cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings, t.sad.data(), t.left, t.top, t.nx, t.ny, t.subShift );
+  }
 
 private:
   struct Group { int w, h; std::vector<vvb_block> blocks; std::vector<int> index; };
+  struct Table { int left = 0, top = 0, nx = 0, ny = 0, subShift = 0; std::vector<uint32_t> sad; };
   std::vector<Group>  m_groups;
   std::vector<Result> m_results;
+  std::vector<Table>  m_tables;
 };

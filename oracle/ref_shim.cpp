@@ -1000,7 +1000,7 @@ void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStr
 // as RdCost predictor and as start vector like xMotionEstimation does (:2040-2043, :2104).  out[i] = { mvx, mvy, ruiSAD lo, hi, uiBestSad lo, hi, table hits, misses }.
 static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
                           int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift,
-                          int64_t* out, bool b200 )
+                          int64_t* out, int b200 /* 0 member, 1 xTZSearchB200 per PU, 2 B200RowSearch: one launch per block size, then the walks */ )
 {
   static thread_local InterSearch* isp = new InterSearch;
   static thread_local BlkUniMvInfoBuffer* uni = new BlkUniMvInfoBuffer;
@@ -1017,6 +1017,25 @@ static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const
   PreCalcValues pcv( r.sps, r.pps, maxQt );
   r.cs.pcv = &pcv;
   int rcAll = 0;
+  B200RowSearch rows;
+  if( b200 == 2 )
+  {
+    try
+    {
+      RdCost rc; createRd( rc, opt );
+      BitDepths bd; bd.recon[CH_L] = bitDepth; bd.recon[CH_C] = bitDepth;
+      rc.setLambda( lambda, bd ); rc.selectMotionLambda(); rc.setCostScale( 2 );
+      rows.setPictures( CPelBuf( orgPlane, orgStride, picW, picH ), CPelBuf( refPlane, refStride, picW, picH ), refReach, bitDepth );
+      for( int i = 0; i < n; i++ )
+      {
+        const int32_t* b = blk + 6 * (size_t) i;
+        Mv pred( b[4], b[5] ), predQuarter = pred; predQuarter.changePrecision( MV_PRECISION_INTERNAL, MV_PRECISION_QUARTER );
+        rows.addTz( b[0], b[1], b[2], b[3], pred, predQuarter, searchRange, fast != 0, refReach );
+      }
+      rows.runTables( rc, (unsigned) imvShift, subShiftMode );
+    }
+    catch( std::exception& e ) { g_b200.error = e.what(); r.cs.pcv = nullptr; return 1; }
+  }
   for( int i = 0; i < n; i++ )
   {
     const int32_t* b = blk + 6 * (size_t) i;
@@ -1044,7 +1063,8 @@ static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const
     int64_t* o = out + 8 * (size_t) i;
     try
     {
-      if( b200 ) { xTZSearchB200( is, r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0, refReach ); o[6] = (int64_t) t_b200tz.hits; o[7] = (int64_t) t_b200tz.misses; }
+      if( b200 == 2 ) { rows.tzSearch( i, is, r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0 ); o[6] = (int64_t) t_b200tz.hits; o[7] = (int64_t) t_b200tz.misses; }
+      else if( b200 ) { xTZSearchB200( is, r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0, refReach ); o[6] = (int64_t) t_b200tz.hits; o[7] = (int64_t) t_b200tz.misses; }
       else       { is.xTZSearch( r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0 ); o[6] = o[7] = 0; }
     }
     catch( std::exception& e ) { g_b200.error = e.what(); rcAll = 1; }
@@ -1057,13 +1077,19 @@ int refshim_tz_search_member( int opt, const int16_t* orgPlane, int orgStride, c
                               int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift, int64_t* out )
 {
   return tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk, n, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast, integerET,
-                        firstSearchStop, imvShift, out, false );
+                        firstSearchStop, imvShift, out, 0 );
 }
 int refshim_tz_search_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
                             int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift, int64_t* out )
 {
   return tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk, n, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast, integerET,
-                        firstSearchStop, imvShift, out, true );
+                        firstSearchStop, imvShift, out, 1 );
+}
+int refshim_tz_search_rows_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
+                                 int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift, int64_t* out )
+{
+  return tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk, n, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast, integerET,
+                        firstSearchStop, imvShift, out, 2 );
 }
 
 // ---------------------------------------------------------------------------------------------------------

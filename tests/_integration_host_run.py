@@ -71,7 +71,7 @@ def main(mock_path):
     #      termination, first-search stop, all sub-sampling modes; the last configuration shrinks the readable reach so that part of the walk leaves the table
     tz_args = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                ctypes.c_int, dbl] + [ctypes.c_int] * 7 + [ctypes.c_void_p]
-    R.refshim_tz_search_member.argtypes = tz_args; R.refshim_tz_search_b200.argtypes = tz_args
+    R.refshim_tz_search_member.argtypes = tz_args; R.refshim_tz_search_b200.argtypes = tz_args; R.refshim_tz_search_rows_b200.argtypes = tz_args
     tz = C.search_case(seed=909, W=256, H=160, margin=96)
     tS = tz['stride']; tbase = tz['margin'] * tS + tz['margin']
     rs = np.random.RandomState(5)
@@ -89,9 +89,12 @@ def main(mock_path):
             args = (PO(tz['org'], tbase), tS, PO(tz['ref'], tbase), tS, 256, 160, reach, P(tblk), tn, 10, mode, 57.0, rng, 32, ext, fast, iet, stop, 0)
             rc1 = R.refshim_tz_search_member(opt, *args, P(a))
             rc2 = R.refshim_tz_search_b200(opt, *args, P(b))
-            res['tz'].append({'opt': opt, 'cfg': [ext, fast, iet, stop, mode, rng, reach], 'rc': [rc1, rc2], 'eq': bool(np.array_equal(a[:, :6], b[:, :6])),
+            c = np.zeros((tn, 8), dtype=np.int64)
+            rc3 = R.refshim_tz_search_rows_b200(opt, *args, P(c))                        # B200RowSearch: one launch per block size, then the same walks
+            res['tz'].append({'opt': opt, 'cfg': [ext, fast, iet, stop, mode, rng, reach], 'rc': [rc1, rc2 or rc3],
+                              'eq': bool(np.array_equal(a[:, :6], b[:, :6]) and np.array_equal(a[:, :6], c[:, :6])), 'row_hits': int(c[:, 6].sum()), 'row_misses': int(c[:, 7].sum()),
                               'hits': int(b[:, 6].sum()), 'misses': int(b[:, 7].sum()), 'moving': int((a[:, :2] != 0).any(axis=1).sum()), 'blocks': tn,
-                              'err': (R.refshim_b200_error() or b'').decode() if rc2 else ''})
+                              'err': (R.refshim_b200_error() or b'').decode() if (rc2 or rc3) else ''})
 
     # ---- xPatternSearchFracDIFB200 against InterSearch::xPatternSearchFracDIF (m_fastSubPel 0)
     res['frac'] = []

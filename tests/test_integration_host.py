@@ -7,7 +7,8 @@ own code in the same process:
   * AffineGradientSearch pointers patched by installB200() vs the AVX2 kernels on every affine case row,
   * xPatternSearchB200 and B200RowSearch vs InterSearch::xPatternSearch (member call), all subShift modes, two AMVR shifts,
   * xTZSearchB200 vs InterSearch::xTZSearch (member call): the unmodified member walks the dense SAD table of one vvb_sad_search launch -- diamond / enhanced /
-    fast settings, integer early termination, first-search stop; with a reach too small for the walk the per-block path answers the rest,
+    fast settings, integer early termination, first-search stop; with a reach too small for the walk the per-block path answers the rest; per PU and
+    per row (B200RowSearch: one launch per block size fills all tables, then the walks),
   * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular,
   * motionEstimationLumaB200 vs MCTF::motionEstimationLuma (member call): first level, chained level and the doubleRes final level, search patterns 0/1/2,
     6- and 4-tap search filters, pictures with partial border blocks,
@@ -80,6 +81,6 @@ def test_tz_search_binding_equals_the_member(result):
     assert len(result['tz']) == 12
     for r in result['tz']:
         assert r['rc'] == [0, 0] and r['eq'], r
-        assert r['moving'] > r['blocks'] // 2 and r['hits'] > 20 * r['blocks'], r
+        assert r['moving'] > r['blocks'] // 2 and r['hits'] > 20 * r['blocks'] and r['row_hits'] == r['hits'] and r['row_misses'] == r['misses'], r
     assert all(r['misses'] == 0 for r in result['tz'] if r['cfg'][6] == 80)               # the window guess covers the whole walk
     assert all(r['misses'] > 0 for r in result['tz'] if r['cfg'][6] == 14)                # ... and the fallback is exercised when it cannot
