@@ -221,8 +221,11 @@ inline void xTZSearchB200( InterSearch& is, const CodingUnit& cu, RefPicList ref
   blk.pred_hor = (int16_t) rc.m_mvPredictor.hor; blk.pred_ver = (int16_t) rc.m_mvPredictor.ver;
   const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, cStruct.imvShift, subShift );
   vvb_best best = {};
-  b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, sad.data(), nx * ny, &best ) );
-  b200TzWalk( is, cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings, sad.data(), left, top, nx, ny, subShift );
+  const int rcSearch = g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, sad.data(), nx * ny, &best );
+  if( rcSearch != VVB_OK && rcSearch != VVB_ERR_UNSUPPORTED ) b200Check( rcSearch );
+  // a window the dense kernel cannot stage (block + range beyond its shared-memory budget) leaves the table empty: every position then takes the per-block path
+  const bool haveTable = rcSearch == VVB_OK;
+  b200TzWalk( is, cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings, sad.data(), left, top, haveTable ? nx : 0, haveTable ? ny : 0, subShift );
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------------------
