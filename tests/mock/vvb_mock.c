@@ -29,7 +29,7 @@ int vvb_launch_count( const vvb_ctx* c, uint64_t* n ) { if( !c || !n ) return VV
 
 int vvb_plane_upload( vvb_ctx* c, int id, const int16_t* origin, int stride, int width, int height, int margin, int bitDepth )
 {
-  if( !c || id < 0 || id >= MOCK_PLANES || !origin || width <= 0 || height <= 0 || margin < 0 ) return c ? fail( c, VVB_ERR_ARG, "bad plane arguments" ) : VVB_ERR_ARG;
+  if( !c || id < 0 || id >= MOCK_PLANES - 2 || !origin || width <= 0 || height <= 0 || margin < 0 || stride < width + 2 * margin ) return c ? fail( c, VVB_ERR_ARG, "bad plane arguments" ) : VVB_ERR_ARG;
   mock_plane* p = &c->pl[id];
   free( p->mem );
   const int s = width + 2 * margin;
@@ -41,6 +41,8 @@ int vvb_plane_upload( vvb_ctx* c, int id, const int16_t* origin, int stride, int
 }
 int vvb_plane_free( vvb_ctx* c, int id ) { if( !c || id < 0 || id >= MOCK_PLANES ) return VVB_ERR_ARG; free( c->pl[id].mem ); memset( &c->pl[id], 0, sizeof( mock_plane ) ); return VVB_OK; }
 
+static int is_pow2( int v ) { return v > 0 && ( v & ( v - 1 ) ) == 0; }
+/* The argument checks below repeat those of vvenc_b200/csrc/capi.cu, so that a binding which passes here does not trip over a validation on the real library. */
 static mock_plane* plane( vvb_ctx* c, int id ) { return ( id >= 0 && id < MOCK_PLANES && c->pl[id].mem ) ? &c->pl[id] : NULL; }
 
 int vvb_sad_search( vvb_ctx* c, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_me_par* par, uint32_t* sadTables, int tableStride, vvb_best* bestOut )
@@ -48,10 +50,17 @@ int vvb_sad_search( vvb_ctx* c, int orgPlane, int refPlane, const vvb_block* blo
   if( !c ) return VVB_ERR_ARG;
   mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
   if( !o || !r || !blocks || !par || !bestOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad search arguments" );
+  if( !is_pow2( w ) || !is_pow2( h ) || w < 4 || h < 4 || w > 128 || h > 128 ) return fail( c, VVB_ERR_UNSUPPORTED, "search blocks are 4..128 powers of two" );
+  if( par->sub_shift && ( h & ( ( 1 << par->sub_shift ) - 1 ) ) ) return fail( c, VVB_ERR_UNSUPPORTED, "subShift needs an even height" );
   for( int i = 0; i < n; i++ )
   {
     const vvb_block* b = &blocks[i];
     if( -b->left > r->margin || b->right > r->margin || -b->top > r->margin || b->bottom > r->margin ) return fail( c, VVB_ERR_ARG, "search range exceeds the plane margin" );
+    const int nx = b->right - b->left + 1, ny = b->bottom - b->top + 1;
+    if( nx < 1 || ny < 1 ) return fail( c, VVB_ERR_ARG, "empty search range" );
+    if( sadTables && nx * ny > tableStride ) return fail( c, VVB_ERR_ARG, "table_stride smaller than the window" );
+    if( nx * ny > 65536 ) return fail( c, VVB_ERR_UNSUPPORTED, "search window above 65536 positions" );
+    if( (size_t)( w + nx ) * ( h + ny ) * 2 > 220 * 1024 ) return fail( c, VVB_ERR_UNSUPPORTED, "search window does not fit shared memory (reduce the range)" );
     const int32_t blk[10] = { b->x, b->y, w, h, b->left, b->right, b->top, b->bottom, b->pred_hor, b->pred_ver };
     int32_t out[4];
     orc_full_search( o->origin, o->stride, r->origin, r->stride, blk, 1, par->sub_shift, par->lambda, par->cost_scale, par->imv_shift, out,
@@ -69,7 +78,10 @@ int vvb_frac_cost_grid( vvb_ctx* c, int dfunc, int orgPlane, int refPlane, const
   if( !c ) return VVB_ERR_ARG;
   mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
   if( !o || !r || !blocks || !costOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad grid arguments" );
-  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD ) return fail( c, VVB_ERR_UNSUPPORTED, "dfunc" );
+  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: SAD or HAD" );
+  if( w < 8 || h < 8 || w > 64 || h > 64 || ( w & 7 ) || ( h & 7 ) ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: block sizes 8..64 in multiples of 8" );
+  if( dfunc == VVB_DF_HAD && ( w != h || !is_pow2( w ) ) ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: HAD on square blocks only" );
+  if( reduceTap < 0 || reduceTap > 2 ) return fail( c, VVB_ERR_ARG, "reduce_tap is 0, 1 or 2" );
   for( int i = 0; i < n; i++ )
   {
     const vvb_block* b = &blocks[i];
@@ -88,6 +100,8 @@ int vvb_mctf_error_batch( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf
   mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
   if( !o || !r || !cands || !errOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad mctf arguments" );
   for( int i = 0; i < n; i++ )
+    if( cands[i].w < 8 || cands[i].h < 8 || cands[i].w > 64 || cands[i].h > 64 || ( cands[i].w & 7 ) || ( cands[i].h & 7 ) ) return fail( c, VVB_ERR_UNSUPPORTED, "MCTF blocks are multiples of 8 up to 64" );
+  for( int i = 0; i < n; i++ )
   {
     const int32_t d[6] = { cands[i].x, cands[i].y, cands[i].mvx, cands[i].mvy, cands[i].w, cands[i].h };
     orc_mctf_err_list( lowRes, o->origin, o->stride, r->origin, r->stride, d, 1, o->bitDepth, errOut + i );
@@ -100,7 +114,10 @@ int vvb_mctf_search_grid( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf
 {
   if( !c ) return VVB_ERR_ARG;
   mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
-  if( !o || !r || !blocks || !errOut || n < 0 || radius < 0 || step <= 0 ) return fail( c, VVB_ERR_ARG, "bad mctf grid arguments" );
+  if( !o || !r || !blocks || !errOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad mctf grid arguments" );
+  if( step < 1 || step > 16 || radius < 0 || radius > 8 ) return fail( c, VVB_ERR_ARG, "MCTF grid: step 1..16 (1/16 pel), radius 0..8 steps" );
+  for( int i = 0; i < n; i++ )
+    if( blocks[i].w < 8 || blocks[i].h < 8 || blocks[i].w > 64 || blocks[i].h > 64 || ( blocks[i].w & 7 ) || ( blocks[i].h & 7 ) ) return fail( c, VVB_ERR_UNSUPPORTED, "MCTF blocks are multiples of 8 up to 64" );
   const int side = 2 * radius + 1;
   for( int i = 0; i < n; i++ )
     for( int j = 0; j < side; j++ )
@@ -117,10 +134,20 @@ int orc_transform_quant( int trHor, int trVer, const Pel* resi, int stride, int 
 int orc_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant );
 int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride );
 
+static int tu_par_ok( vvb_ctx* c, const vvb_tu_par* p )
+{
+  if( !is_pow2( p->w ) || !is_pow2( p->h ) || p->w < 4 || p->h < 4 || p->w > 64 || p->h > 64 ) return fail( c, VVB_ERR_UNSUPPORTED, "TU sizes are 4..64" );
+  if( p->tr_hor < 0 || p->tr_hor > 2 || p->tr_ver < 0 || p->tr_ver > 2 ) return fail( c, VVB_ERR_ARG, "unknown transform type" );
+  if( ( p->tr_hor && p->w > 32 ) || ( p->tr_ver && p->h > 32 ) ) return fail( c, VVB_ERR_UNSUPPORTED, "DST-VII/DCT-VIII exist for 4..32 only" );
+  if( p->bit_depth < 8 || p->bit_depth > 12 ) return fail( c, VVB_ERR_UNSUPPORTED, "bit depth 8..12" );
+  return VVB_OK;
+}
+
 int vvb_fwd_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* resi, int n, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, uint8_t* needRdoq )
 {
   if( !c ) return VVB_ERR_ARG;
   if( !par || !resi || !q || n < 0 ) return fail( c, VVB_ERR_ARG, "bad trquant arguments" );
+  if( tu_par_ok( c, par ) ) return VVB_ERR_UNSUPPORTED;
   const size_t area = (size_t) par->w * par->h;
   int32_t* tmp = (int32_t*) malloc( sizeof( int32_t ) * area );
   if( !tmp ) return fail( c, VVB_ERR_NOMEM, "trquant" );
@@ -143,6 +170,7 @@ int vvb_inv_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* q, int n,
 {
   if( !c ) return VVB_ERR_ARG;
   if( !par || !resi || !q || n < 0 ) return fail( c, VVB_ERR_ARG, "bad inverse arguments" );
+  if( tu_par_ok( c, par ) ) return VVB_ERR_UNSUPPORTED;
   const size_t area = (size_t) par->w * par->h;
   int32_t* tmp = (int32_t*) malloc( sizeof( int32_t ) * area );
   if( !tmp ) return fail( c, VVB_ERR_NOMEM, "inverse" );
@@ -171,7 +199,10 @@ int vvb_mctf_apply( vvb_ctx* c, int orgPlane, const vvb_mctf_apply_par* par, con
 {
   if( !c ) return VVB_ERR_ARG;
   mock_plane* o = plane( c, orgPlane );
-  if( !o || !par || !mvs || !out || par->num_refs < 1 || par->num_refs > 8 || par->block_size < 8 ) return fail( c, VVB_ERR_ARG, "bad apply arguments" );
+  if( !o || !par || !mvs || !out || par->num_refs < 1 || par->num_refs > 8 ) return fail( c, VVB_ERR_ARG, "bad apply arguments" );
+  if( par->block_size != 8 && par->block_size != 16 && par->block_size != 32 ) return fail( c, VVB_ERR_UNSUPPORTED, "MCTF unit size 8, 16 or 32" );
+  if( ( o->width & 7 ) || ( o->height & 7 ) ) return fail( c, VVB_ERR_UNSUPPORTED, "picture dimensions must be multiples of 8" );
+  if( o->bitDepth > 10 ) return fail( c, VVB_ERR_UNSUPPORTED, "MCTF supports up to 10 bit" );
   const Pel* refs[8]; int rs = 0;
   for( int i = 0; i < par->num_refs; i++ )
   {
@@ -202,7 +233,8 @@ void orc_equal_coeff( int sixParam, const Pel* resi, int rs, const Pel* gx, cons
 int vvb_affine_sobel( vvb_ctx* c, int vertical, const int16_t* pred, int ps, int16_t* deriv, int ds, int w, int h )
 {
   if( !c ) return VVB_ERR_ARG;
-  if( !pred || !deriv || w < 3 || h < 3 ) return fail( c, VVB_ERR_ARG, "bad sobel arguments" );
+  if( !pred || !deriv ) return fail( c, VVB_ERR_ARG, "null pointer" );
+  if( w < 4 || h < 4 || w > 128 || h > 128 ) return fail( c, VVB_ERR_UNSUPPORTED, "affine blocks are 4..128" );
   orc_sobel( vertical, pred, ps, deriv, ds, w, h );
   c->calls++;
   return VVB_OK;
