@@ -58,3 +58,45 @@ def test_split_covers_picture():
         b = bands.split_ctu_rows(hgt, ctu, world)
         assert b[0][0] == 0 and b[-1][1] == hgt and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
         assert all((y0 % ctu == 0) for y0, _ in b if y0 < hgt)
+
+
+MCTF_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(%(root)r, 'tests')); sys.path.insert(0, %(root)r)
+from test_mctf_host import OracleProvider, mctf_shard_case
+from vvenc_b200 import bands, mctf_host as MH
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%(port)d', rank=int(sys.argv[1]), world_size=2)
+org, refs, unit = mctf_shard_case()
+H, W = org.shape
+local = {}
+for ref in bands.split_refs(len(refs), 2)[dist.get_rank()]:
+    f = MH.estimate_pyramid(lambda o, r: OracleProvider(MH.pad_edge(o), MH.pad_edge(r), o.shape[1] + 256, 128), org, refs[ref], unit_size=unit)
+    local[ref] = np.stack([f['x'], f['y'], f['error'], f['rmsme'].astype(np.int32)], axis=-1).reshape(-1, 4)
+blocks = ((W + unit - 1) // unit) * ((H + unit - 1) // unit)
+allf = bands.all_gather_motion_fields(local, len(refs), blocks)
+if dist.get_rank() == 1:                       # any rank holds the complete set
+    np.save(sys.argv[2], allf)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_two_rank_mctf_reference_sharding_matches_single_process(tmp_path):
+    """SURVEY 8e, W5: neighbour pictures dealt over the ranks, one all-gather of the motion fields; equals the single-process search of every picture"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_mctf_host import OracleProvider, mctf_shard_case
+    from vvenc_b200 import bands, mctf_host as MH
+    port = 29850 + (os.getpid() % 100)
+    script = tmp_path / 'mctf_worker.py'
+    script.write_text(MCTF_WORKER % {'root': ROOT, 'port': port})
+    outp = str(tmp_path / 'fields.npy')
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), outp]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    got = np.load(outp)
+    org, refs, unit = mctf_shard_case()
+    assert bands.split_refs(3, 2) == [[0, 2], [1]] and bands.split_refs(8, 4) == [[0, 4], [1, 5], [2, 6], [3, 7]]
+    for i, ref in enumerate(refs):
+        f = MH.estimate_pyramid(lambda o, r: OracleProvider(MH.pad_edge(o), MH.pad_edge(r), o.shape[1] + 256, 128), org, ref, unit_size=unit)
+        exp = np.stack([f['x'], f['y'], f['error'], f['rmsme'].astype(np.int32)], axis=-1).reshape(-1, 4)
+        assert np.array_equal(got[i], exp), i
+    assert np.any(got[:, :, :2] != 0)

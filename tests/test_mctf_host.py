@@ -64,6 +64,19 @@ def _pictures(seed, W, H, m, shift=(1, -2), noise=6):
     return org, ref, S
 
 
+def mctf_shard_case():
+    """one target picture and three neighbour pictures with different displacements (tests/test_bands_gloo.py deals them over two ranks)"""
+    rs = np.random.RandomState(77)
+    W, H = 128, 96
+    base = rs.randint(0, 1024, size=(H + 16, W + 16))
+    sm = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4
+    org = np.ascontiguousarray(sm[8:8 + H, 8:8 + W].astype(np.int16))
+    refs = []
+    for (dy, dx, noise) in ((1, -2, 4), (-3, 2, 6), (2, 4, 9)):
+        refs.append(np.ascontiguousarray(np.clip(sm[8 + dy:8 + dy + H, 8 + dx:8 + dx + W] + rs.randint(-noise, noise + 1, size=org.shape), 0, 1023).astype(np.int16)))
+    return org, refs, 8
+
+
 def _reference_level(opt, org, ref, S, m, W, H, bs, prev, factor, double_res, unit):
     R = refshim()
     R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')

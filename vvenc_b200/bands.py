@@ -1,4 +1,4 @@
-"""CTU-row band sharding of the candidate batch across the GPUs of one box.
+"""Sharding of the path across the GPUs of one box: CTU-row bands for the block-cost sweeps, neighbour pictures for the MCTF search.
 
 Every block's candidates are independent of every other block once the pictures are finished, so a picture is cut
 into contiguous bands of CTU rows, one band per rank (one process per GPU); pictures are replicated, never halo-exchanged.
@@ -44,3 +44,30 @@ def all_gather_tables(local, counts=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)])
+
+
+def split_refs(num_refs, world):
+    """MCTF: the neighbour pictures of one target picture are searched independently of each other (MCTF.cpp:788-796), so they -- not block rows, which
+    depend on the row above through the upper-neighbour candidate (:1289-1306) -- are what is dealt out: rank r gets the reference indices r, r + world, ...
+    (round robin keeps the near, cheap-to-match and the far pictures evenly mixed)."""
+    return [list(range(r, num_refs, world)) for r in range(world)]
+
+
+def all_gather_motion_fields(local_fields, num_refs, blocks):
+    """local_fields: {ref index: int32 array [blocks][4] (x, y, error, rmsme)} of this rank's share (split_refs).  One all-gather of fixed-size slots;
+    returns the int32 array [num_refs][blocks][4] every rank needs for the apply stage (vvb_mctf_apply takes the fields of all neighbour pictures)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    per = (num_refs + world - 1) // world
+    mine = split_refs(num_refs, world)[dist.get_rank()]
+    slot = torch.zeros((per, blocks, 4), dtype=torch.int32)
+    for k, ref in enumerate(mine):
+        slot[k] = torch.from_numpy(np.ascontiguousarray(local_fields[ref], dtype=np.int32).reshape(blocks, 4))
+    bufs = [torch.empty_like(slot) for _ in range(world)]
+    dist.all_gather(bufs, slot)
+    out = np.zeros((num_refs, blocks, 4), dtype=np.int32)
+    for r, refs in enumerate(split_refs(num_refs, world)):
+        for k, ref in enumerate(refs):
+            out[ref] = bufs[r][k].numpy()
+    return out
