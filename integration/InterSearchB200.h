@@ -116,7 +116,7 @@ inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStr
   b200Check( g_b200s.fracCostGrid( b200CtxOfThread(), cfg.m_bUseHADME ? VVB_DF_HAD : VVB_DF_SAD, B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height,
                                    cfg.m_meReduceTap, cStruct.useAltHpelIf ? 1 : 0, &t[0][0] ) );
 
-  // one round of xPatternRefinement (:800-960): nine candidates in the order of s_acMvRefineH / s_acMvRefineQ, first strictly smaller cost wins
+  // one round of xPatternRefinement (:798-887): nine candidates in the order of s_acMvRefineH / s_acMvRefineQ, first strictly smaller cost wins
   static const int8_t orderH[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 }, { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } };
   static const int8_t orderQ[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, -1 }, { 1, -1 }, { -1, 0 }, { 1, 0 }, { -1, 1 }, { 1, 1 } };
   auto round = [&]( const int8_t ( *order )[2], int iFrac, const Mv& baseRefMv, Mv& rcMvFrac ) -> Distortion
@@ -124,9 +124,9 @@ inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStr
     Distortion best = MAX_DISTORTION; int dir = 0;
     for( int i = 0; i < 9; i++ )
     {
-      const int hor = ( order[i][0] + baseRefMv.hor ) * iFrac, ver = ( order[i][1] + baseRefMv.ver ) * iFrac;      // quarter-pel offset from rcMvInt (:820-823)
+      const int hor = ( order[i][0] + baseRefMv.hor ) * iFrac, ver = ( order[i][1] + baseRefMv.ver ) * iFrac;      // quarter-pel offset from rcMvInt (:852-856)
       Distortion d = t[ver + 3][hor + 3];
-      d += rc.getCostOfVectorWithPredictor( order[i][0] + rcMvFrac.hor, order[i][1] + rcMvFrac.ver, 0 );           // :935 (imvShift 0 inside the refinement)
+      d += rc.getCostOfVectorWithPredictor( order[i][0] + rcMvFrac.hor, order[i][1] + rcMvFrac.ver, 0 );           // :875 (imvShift 0 inside the refinement)
       if( d < best ) { best = d; dir = i; }
     }
     rcMvFrac.set( order[dir][0], order[dir][1] );
