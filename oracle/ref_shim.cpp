@@ -1005,7 +1005,7 @@ static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const
   static thread_local InterSearch* isp = new InterSearch;
   static thread_local BlkUniMvInfoBuffer* uni = new BlkUniMvInfoBuffer;
   static thread_local TuRig* rg = new TuRig;
-  static VVEncCfg cfg;
+  static thread_local VVEncCfg cfg;
   InterSearch& is = *isp;
   cfg.m_ifpLines = 0; cfg.m_bIntegerET = integerET != 0; cfg.m_bFastMEAssumingSmootherMVEnabled = firstSearchStop != 0;
   is.m_pcEncCfg = &cfg; is.m_iSearchRange = searchRange; is.m_BlkUniMvInfoBuffer = uni; is.m_lumaClpRng.bd = bitDepth;
@@ -1084,6 +1084,20 @@ int refshim_tz_search_b200( int opt, const int16_t* orgPlane, int orgStride, con
 {
   return tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk, n, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast, integerET,
                         firstSearchStop, imvShift, out, 1 );
+}
+// worker-thread form: the PU list is split over nthreads threads, each with its own InterSearch / RdCost / rig and -- through b200CtxOfThread() -- its own vvb_ctx and
+// look-up table (thread_local in the binding), as the encoder's pool workers would call it (EncSlice.cpp:142-147)
+int refshim_tz_search_b200_mt( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
+                               int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift,
+                               int64_t* out, int nthreads )
+{
+  std::atomic<int> bad( 0 );
+  parallelFor( n, nthreads, [&]( int b, int e, int )
+  {
+    if( tzSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, picW, picH, refReach, blk + 6 * (size_t) b, e - b, bitDepth, subShiftMode, lambda, searchRange, ctuSize, extended, fast,
+                       integerET, firstSearchStop, imvShift, out + 8 * (size_t) b, 1 ) ) bad++;
+  } );
+  return bad.load() ? 1 : 0;
 }
 int refshim_tz_search_rows_b200( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
                                  int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift, int64_t* out )

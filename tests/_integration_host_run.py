@@ -72,6 +72,7 @@ def main(mock_path):
     tz_args = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                ctypes.c_int, dbl] + [ctypes.c_int] * 7 + [ctypes.c_void_p]
     R.refshim_tz_search_member.argtypes = tz_args; R.refshim_tz_search_b200.argtypes = tz_args; R.refshim_tz_search_rows_b200.argtypes = tz_args
+    R.refshim_tz_search_b200_mt.argtypes = tz_args + [ctypes.c_int]
     tz = C.search_case(seed=909, W=256, H=160, margin=96)
     tS = tz['stride']; tbase = tz['margin'] * tS + tz['margin']
     rs = np.random.RandomState(5)
@@ -91,6 +92,9 @@ def main(mock_path):
             rc2 = R.refshim_tz_search_b200(opt, *args, P(b))
             c = np.zeros((tn, 8), dtype=np.int64)
             rc3 = R.refshim_tz_search_rows_b200(opt, *args, P(c))                        # B200RowSearch: one launch per block size, then the same walks
+            d = np.zeros((tn, 8), dtype=np.int64)
+            rc4 = R.refshim_tz_search_b200_mt(opt, *args, P(d), 4)                      # four worker threads, one context / table each
+            rc3 = rc3 or rc4 or int(not np.array_equal(a[:, :6], d[:, :6]))
             res['tz'].append({'opt': opt, 'cfg': [ext, fast, iet, stop, mode, rng, reach], 'rc': [rc1, rc2 or rc3],
                               'eq': bool(np.array_equal(a[:, :6], b[:, :6]) and np.array_equal(a[:, :6], c[:, :6])), 'row_hits': int(c[:, 6].sum()), 'row_misses': int(c[:, 7].sum()),
                               'hits': int(b[:, 6].sum()), 'misses': int(b[:, 7].sum()), 'moving': int((a[:, :2] != 0).any(axis=1).sum()), 'blocks': tn,

@@ -8,7 +8,7 @@ own code in the same process:
   * xPatternSearchB200 and B200RowSearch vs InterSearch::xPatternSearch (member call), all subShift modes, two AMVR shifts,
   * xTZSearchB200 vs InterSearch::xTZSearch (member call): the unmodified member walks the dense SAD table of one vvb_sad_search launch -- diamond / enhanced /
     fast settings, integer early termination, first-search stop; with a reach too small for the walk the per-block path answers the rest; per PU and
-    per row (B200RowSearch: one launch per block size fills all tables, then the walks),
+    per row (B200RowSearch: one launch per block size fills all tables, then the walks), and from four worker threads at once (a context and a table each),
   * xPatternSearchFracDIFB200 vs InterSearch::xPatternSearchFracDIF (member call), 8/6/4-tap ME filters, SATD and SAD, alt half-pel, square and rectangular,
   * motionEstimationLumaB200 vs MCTF::motionEstimationLuma (member call): first level, chained level and the doubleRes final level, search patterns 0/1/2,
     6- and 4-tap search filters, pictures with partial border blocks,
