@@ -116,6 +116,22 @@ RefCtx& ctx()
   return *g_ctx;
 }
 
+// TrQuant keeps scratch buffers (m_plTempCoeff, m_blk, m_tmp): one instance per calling thread, rebuilt when refshim_set_simd() replaced the context so that
+// the per-instance quantiser pointers are re-resolved; released at thread exit (the batch probes run on short-lived worker threads)
+TrQuant& tqOfThread()
+{
+  static thread_local std::unique_ptr<TrQuant> t;
+  static thread_local RefCtx* owner = nullptr;
+  RefCtx& c = ctx();
+  if( owner != &c )
+  {
+    t.reset( new TrQuant );
+    t->init( nullptr, 0, false, false, true, 8 );   // rdoq off, thrVal 8 (vvencCfg.cpp:971-973)
+    owner = &c;
+  }
+  return *t;
+}
+
 inline int ilog2( unsigned v ) { int r = 0; while( v > 1 ) { v >>= 1; r++; } return r; }
 
 // DFunc family (ours) -> reference table base (CommonLib/TypeDef.h:339-382)
@@ -424,7 +440,7 @@ int refshim_fwd_transform( int trHor, int trVer, const int16_t* resi, int stride
   r.setup( w, h, bitDepth, mts, false, true, 32 );
   CPelBuf  resiBuf( resi, stride, w, h );
   CoeffBuf dst( coef, w, w, h );
-  c.tq->xT( r.tu, COMP_Y, resiBuf, dst, w, h );
+  tqOfThread().xT( r.tu, COMP_Y, resiBuf, dst, w, h );
   return 0;
 }
 
@@ -469,7 +485,7 @@ int refshim_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int 
   TCoeff sum = 0;
   alignas(64) static thread_local unsigned char ctxMem[ sizeof( Ctx ) ];   // unused by the plain quantiser
   const Ctx& dummy = *reinterpret_cast<const Ctx*>( ctxMem );
-  static_cast<Quant*>( c.tq->m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
+  static_cast<Quant*>( tqOfThread().m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
   *absSum  = sum;
   *lastPos = r.tu.lastPos[COMP_Y];
@@ -485,7 +501,7 @@ int refshim_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, 
   r.slice.depQuantEnabled = depQuant != 0;
   QpParam qpp( r.tu, COMP_Y, false );
   CCoeffBuf src( coef, w, w, h );
-  return static_cast<Quant*>( c.tq->m_quant )->xNeedRDOQ( r.tu, COMP_Y, src, qpp ) ? 1 : 0;
+  return static_cast<Quant*>( tqOfThread().m_quant )->xNeedRDOQ( r.tu, COMP_Y, src, qpp ) ? 1 : 0;
 }
 
 // Whole TU: xT then Quant::quant, as TrQuant::transformNxN does for LFNST-off, non-skip TUs (TrQuant.cpp:688-736).
@@ -499,13 +515,13 @@ int refshim_transform_quant( int trHor, int trVer, const int16_t* resi, int stri
   r.setup( w, h, bitDepth, mts, isIRAP != 0, true, qp );
   CPelBuf  resiBuf( resi, stride, w, h );
   CoeffBuf dst( coef, w, w, h );
-  c.tq->xT( r.tu, COMP_Y, resiBuf, dst, w, h );
+  tqOfThread().xT( r.tu, COMP_Y, resiBuf, dst, w, h );
   QpParam qpp( r.tu, COMP_Y, false );
   CCoeffBuf src( coef, w, w, h );
   TCoeff sum = 0;
   alignas(64) static thread_local unsigned char ctxMem[ sizeof( Ctx ) ];
   const Ctx& dummy = *reinterpret_cast<const Ctx*>( ctxMem );
-  static_cast<Quant*>( c.tq->m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
+  static_cast<Quant*>( tqOfThread().m_quant )->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
   *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
   return 0;
@@ -527,7 +543,7 @@ int refshim_transform_quant_b200( int trHor, int trVer, const int16_t* resi, int
   CoeffBuf dst( coef, w, w, h );
   QpParam qpp( r.tu, COMP_Y, false );
   TCoeff sum = 0; bool nr = false;
-  try { xTQuantB200( *c.tq, r.tu, COMP_Y, resiBuf, dst, qpp, sum, &nr ); }
+  try { xTQuantB200( tqOfThread(), r.tu, COMP_Y, resiBuf, dst, qpp, sum, &nr ); }
   catch( std::exception& e ) { g_b200.error = e.what(); r.slice.depQuantEnabled = false; return 1; }
   r.slice.depQuantEnabled = false;
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
@@ -544,7 +560,7 @@ int refshim_inv_transform_quant_b200( int trHor, int trVer, const int16_t* q, in
   memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
   QpParam qpp( r.tu, COMP_Y, false );
   PelBuf out( resi, stride, w, h );
-  try { invTransformNxNB200( *c.tq, r.tu, COMP_Y, out, qpp ); }
+  try { invTransformNxNB200( tqOfThread(), r.tu, COMP_Y, out, qpp ); }
   catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
   return 0;
 }
@@ -562,10 +578,10 @@ int refshim_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, 
   QpParam qpp( r.tu, COMP_Y, false );
   alignas(64) static thread_local TCoeff tmpCoef[ 64 * 64 ];
   CoeffBuf deq( tmpCoef, w, w, h );
-  static_cast<Quant*>( c.tq->m_quant )->Quant::dequant( r.tu, deq, COMP_Y, qpp );
+  static_cast<Quant*>( tqOfThread().m_quant )->Quant::dequant( r.tu, deq, COMP_Y, qpp );
   if( coef ) memcpy( coef, tmpCoef, sizeof( int32_t ) * w * h );
   PelBuf out( resi, stride, w, h );
-  c.tq->xIT( r.tu, COMP_Y, CCoeffBuf( tmpCoef, w, w, h ), out );
+  tqOfThread().xIT( r.tu, COMP_Y, CCoeffBuf( tmpCoef, w, w, h ), out );
   return 0;
 }
 
