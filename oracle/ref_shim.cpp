@@ -116,20 +116,50 @@ RefCtx& ctx()
   return *g_ctx;
 }
 
-// TrQuant keeps scratch buffers (m_plTempCoeff, m_blk, m_tmp): one instance per calling thread, rebuilt when refshim_set_simd() replaced the context so that
-// the per-instance quantiser pointers are re-resolved; released at thread exit (the batch probes run on short-lived worker threads)
+// TrQuant keeps scratch buffers (m_plTempCoeff, m_blk, m_tmp), so every calling thread needs its own instance -- and building one costs about a millisecond
+// (quantiser tables), which would dominate the batched probes on short-lived worker threads.  Instances are therefore leased from a pool: a thread takes one on
+// first use and hands it back when it exits; the pool is dropped when refshim_set_simd() replaced the context (per-instance quantiser pointers are re-resolved).
+struct TqPool
+{
+  std::mutex            mtx;
+  std::vector<TrQuant*> idle;
+  RefCtx*               owner = nullptr;
+};
+TqPool g_tqPool;
+
+struct TqLease
+{
+  TrQuant* t = nullptr;
+  RefCtx*  owner = nullptr;
+  TrQuant& get()
+  {
+    RefCtx& c = ctx();
+    if( owner != &c )
+    {
+      release();
+      {
+        std::lock_guard<std::mutex> lk( g_tqPool.mtx );
+        if( g_tqPool.owner != &c ) { g_tqPool.idle.clear(); g_tqPool.owner = &c; }       // instances of the previous SIMD mode are leaked on purpose (tiny, rare)
+        if( !g_tqPool.idle.empty() ) { t = g_tqPool.idle.back(); g_tqPool.idle.pop_back(); }
+      }
+      if( !t ) { t = new TrQuant; t->init( nullptr, 0, false, false, true, 8 ); }        // rdoq off, thrVal 8 (vvencCfg.cpp:971-973)
+      owner = &c;
+    }
+    return *t;
+  }
+  void release()
+  {
+    if( !t ) return;
+    std::lock_guard<std::mutex> lk( g_tqPool.mtx );
+    if( g_tqPool.owner == owner ) g_tqPool.idle.push_back( t );
+    t = nullptr; owner = nullptr;
+  }
+  ~TqLease() { release(); }
+};
 TrQuant& tqOfThread()
 {
-  static thread_local std::unique_ptr<TrQuant> t;
-  static thread_local RefCtx* owner = nullptr;
-  RefCtx& c = ctx();
-  if( owner != &c )
-  {
-    t.reset( new TrQuant );
-    t->init( nullptr, 0, false, false, true, 8 );   // rdoq off, thrVal 8 (vvencCfg.cpp:971-973)
-    owner = &c;
-  }
-  return *t;
+  static thread_local TqLease lease;
+  return lease.get();
 }
 
 inline int ilog2( unsigned v ) { int r = 0; while( v > 1 ) { v >>= 1; r++; } return r; }
@@ -256,8 +286,24 @@ struct TuRig
   }
 };
 
-thread_local TuRig* t_rig = nullptr;
-TuRig& rig() { if( !t_rig ) t_rig = new TuRig; return *t_rig; }
+// the rig (CodingStructure, XUCache, ...) is expensive to build: leased from a pool like the TrQuant instances, handed back when the calling thread exits
+struct RigPool { std::mutex mtx; std::vector<TuRig*> idle; };
+RigPool g_rigPool;
+struct RigLease
+{
+  TuRig* r = nullptr;
+  TuRig& get()
+  {
+    if( !r )
+    {
+      { std::lock_guard<std::mutex> lk( g_rigPool.mtx ); if( !g_rigPool.idle.empty() ) { r = g_rigPool.idle.back(); g_rigPool.idle.pop_back(); } }
+      if( !r ) r = new TuRig;
+    }
+    return *r;
+  }
+  ~RigLease() { if( r ) { std::lock_guard<std::mutex> lk( g_rigPool.mtx ); g_rigPool.idle.push_back( r ); } }
+};
+TuRig& rig() { static thread_local RigLease lease; return lease.get(); }
 
 int mtsIdxFor( int trHor, int trVer )   // ours: 0 DCT2, 1 DCT8, 2 DST7 (reference enum TransType, TypeDef.h)
 {
