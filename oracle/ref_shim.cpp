@@ -831,17 +831,23 @@ void refshim_mctf_finalize_block( int opt, const int16_t* orgPlane, int orgStrid
 // src points at the integer position of the block; fx, fy in quarter pels.
 void refshim_if_two_pass( int opt, const int16_t* src, int srcStride, int w, int h, int fx, int fy, int bitDepth, int reduceTap, int altHpel, int16_t* dst, int dstStride )
 {
-  static InterpolationFilter* ifs[2] = { nullptr, nullptr };
+  // one InterpolationFilter per back end, built once; the fast path takes no lock (this function runs once per candidate on every worker thread of the CPU baseline)
+  static std::atomic<InterpolationFilter*> ifs[2];
+  InterpolationFilter* fp = ifs[opt?1:0].load( std::memory_order_acquire );
+  if( !fp )
   {
     std::lock_guard<std::mutex> lk( g_mtx );
-    if( !ifs[opt?1:0] ) { ifs[opt?1:0] = new InterpolationFilter; ifs[opt?1:0]->initInterpolationFilter( opt != 0 ); }
+    fp = ifs[opt?1:0].load( std::memory_order_relaxed );
+    if( !fp ) { fp = new InterpolationFilter; fp->initInterpolationFilter( opt != 0 ); ifs[opt?1:0].store( fp, std::memory_order_release ); }
   }
-  InterpolationFilter& f = *ifs[opt?1:0];
+  InterpolationFilter& f = *fp;
   ClpRng rng; rng.bd = bitDepth;
   const int ts = w + 8;
-  std::vector<Pel> tmpStore( (size_t)( h + 8 ) * ts + 64 );
+  // scratch like the encoder's preallocated m_filteredBlockTmp / m_filteredBlock (InterPrediction.cpp): per thread, grown on demand
+  static thread_local std::vector<Pel> tmpStore, outStore;
+  if( tmpStore.size() < (size_t)( h + 8 ) * ts + 64 ) tmpStore.resize( (size_t)( h + 8 ) * ts + 64 );
+  if( outStore.size() < (size_t) h * ts + 64 ) outStore.resize( (size_t) h * ts + 64 );
   Pel* tmp = (Pel*)( ( (uintptr_t) tmpStore.data() + 63 ) & ~uintptr_t( 63 ) );
-  std::vector<Pel> outStore( (size_t) h * ts + 64 );
   Pel* outp = (Pel*)( ( (uintptr_t) outStore.data() + 63 ) & ~uintptr_t( 63 ) );
   f.filterHor( COMP_Y, src - 3 * srcStride, srcStride, tmp, ts, w, h + 7, fx << 2, false, CHROMA_400, rng, altHpel != 0, 0, reduceTap );
   f.filterVer( COMP_Y, tmp + 3 * ts, ts, outp, ts, w, h, fy << 2, false, true, CHROMA_400, rng, altHpel != 0, 0, reduceTap );
