@@ -154,25 +154,30 @@ inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStr
 // the per-block entry point, so the result never depends on the window guess -- only the number of launches does.
 struct B200TzTable
 {
-  const Pel* piRefY = nullptr; ptrdiff_t stride = 0;
-  int left = 0, top = 0, nx = 0, ny = 0, subShift = 0;
+  const Pel* corner = nullptr;                                                                // address of the window's top-left position: piRefY + top * stride + left
+  uint32_t   stride = 0, nx = 0, ny = 0, span = 0;                                            // span = ny * stride
+  uint64_t   invStride = 0;                                                                   // ceil( 2^40 / stride ): off / stride without a divide (exact for off < 2^20)
+  int        subShift = 0;
   const uint32_t* sad = nullptr;                                                              // [ny][nx], row-major over the window
   uint64_t hits = 0, misses = 0;
+  void set( const Pel* piRefY, ptrdiff_t refStride, int left, int top, int nx_, int ny_, int subShift_, const uint32_t* sad_ )
+  {
+    corner = piRefY + (ptrdiff_t) top * refStride + left; stride = (uint32_t) refStride; nx = (uint32_t) nx_; ny = (uint32_t) ny_;
+    span = ( ny && (uint64_t) ny * stride < ( 1u << 20 ) ) ? ny * stride : 0;                 // a window beyond the exact range of the reciprocal is treated as empty
+    invStride = ( ( 1ull << 40 ) + stride - 1 ) / ( stride ? stride : 1 );
+    subShift = subShift_; sad = sad_; hits = misses = 0;
+  }
 };
 static thread_local B200TzTable t_b200tz;
 
 inline Distortion tzTableSadB200( const DistParam& dp )
 {
   B200TzTable& t = t_b200tz;
-  const ptrdiff_t off = dp.cur.buf - t.piRefY;
-  // off = dy * stride + dx with left <= dx < left + nx << stride: floor division after shifting dx into [0, nx)
-  const ptrdiff_t sh = off - t.left;
-  ptrdiff_t dy = sh / t.stride; if( sh - dy * t.stride < 0 ) dy--;
-  const ptrdiff_t dx = off - dy * t.stride;
-  if( dp.subShift == t.subShift && dx >= t.left && dx < t.left + t.nx && dy >= t.top && dy < t.top + t.ny )
+  const uint64_t off = (uint64_t)( dp.cur.buf - t.corner );                                   // positions before the corner wrap to huge values and miss
+  if( off < t.span && dp.subShift == t.subShift )
   {
-    t.hits++;
-    return t.sad[(size_t)( dy - t.top ) * t.nx + ( dx - t.left )];
+    const uint32_t dy = (uint32_t)( ( off * t.invStride ) >> 40 ), dx = (uint32_t) off - dy * t.stride;
+    if( dx < t.nx ) { t.hits++; return t.sad[dy * t.nx + dx]; }
   }
   t.misses++;
   return distB200<VVB_DF_SAD>( dp );
@@ -194,13 +199,13 @@ inline void b200TzWalk( InterSearch& is, const CodingUnit& cu, RefPicList refPic
 {
   RdCost& rc = *is.m_pcRdCost;
   B200TzTable& t = t_b200tz;
-  t.piRefY = cStruct.piRefY; t.stride = cStruct.iRefStride; t.left = left; t.top = top; t.nx = nx; t.ny = ny; t.subShift = subShift; t.sad = sad; t.hits = t.misses = 0;
+  t.set( cStruct.piRefY, cStruct.iRefStride, left, top, nx, ny, subShift, sad );
   const int base = is.m_lumaClpRng.bd > 10 ? 1 : 0, slot = DF_SAD + Log2( cStruct.pcPatternKey->width );
   const FpDistFunc saved = rc.m_afpDistortFunc[base][slot];
   rc.m_afpDistortFunc[base][slot] = tzTableSadB200;
   try { is.xTZSearch( cu, refPicList, iRefIdxPred, cStruct, rcMv, ruiSAD, bExtendedSettings, bFastSettings ); }
-  catch( ... ) { rc.m_afpDistortFunc[base][slot] = saved; t.sad = nullptr; throw; }
-  rc.m_afpDistortFunc[base][slot] = saved; t.sad = nullptr;
+  catch( ... ) { rc.m_afpDistortFunc[base][slot] = saved; t.sad = nullptr; t.span = 0; throw; }
+  rc.m_afpDistortFunc[base][slot] = saved; t.sad = nullptr; t.span = 0;
 }
 
 // refReach: how far (in pels, every direction) the reference picture is readable around the block -- the picture margin the encoder pads (Picture.cpp:461-501)

@@ -1066,6 +1066,10 @@ void refshim_pattern_search_member( int opt, const int16_t* orgPlane, int orgStr
 // xTZSearchB200 (integration/InterSearchB200.h: one dense SAD table, the unmodified member walking it).  The CodingUnit carries what the member reads: position and size,
 // cs->pcv (picture and CTU size for xClipMvSearch / xSetSearchRange).  blk[i] = { x, y, w, h, predHor, predVer } with the predictor in internal (1/16 pel) units, used both
 // as RdCost predictor and as start vector like xMotionEstimation does (:2040-2043, :2104).  out[i] = { mvx, mvy, ruiSAD lo, hi, uiBestSad lo, hi, table hits, misses }.
+// seconds spent inside the search calls of the last probes (member: the whole xTZSearch; per-row binding: the walks only, the tables exist already) -- read and reset
+// by refshim_tz_search_seconds(): the host-side cost that remains per PU when the SADs come from the device
+static double g_tzSearchSeconds = 0.0;
+double refshim_tz_search_seconds() { const double v = g_tzSearchSeconds; g_tzSearchSeconds = 0.0; return v; }
 static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, int picW, int picH, int refReach, const int32_t* blk, int n,
                           int bitDepth, int subShiftMode, double lambda, int searchRange, int ctuSize, int extended, int fast, int integerET, int firstSearchStop, int imvShift,
                           int64_t* out, int b200 /* 0 member, 1 xTZSearchB200 per PU, 2 B200RowSearch: one launch per block size, then the walks */ )
@@ -1129,6 +1133,7 @@ static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const
     is.xSetSearchRange( r.cu, pred, searchRange, st.searchRange );                    // :2002 (xMotionEstimation)
     Mv mv = pred; Distortion sad = 0;
     int64_t* o = out + 8 * (size_t) i;
+    const auto t0 = std::chrono::steady_clock::now();
     try
     {
       if( b200 == 2 ) { rows.tzSearch( i, is, r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0 ); o[6] = (int64_t) t_b200tz.hits; o[7] = (int64_t) t_b200tz.misses; }
@@ -1136,6 +1141,7 @@ static int tzSearchProbe( int opt, const int16_t* orgPlane, int orgStride, const
       else       { is.xTZSearch( r.cu, REF_PIC_LIST_0, 0, st, mv, sad, extended != 0, fast != 0 ); o[6] = o[7] = 0; }
     }
     catch( std::exception& e ) { g_b200.error = e.what(); rcAll = 1; }
+    g_tzSearchSeconds += std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
     o[0] = mv.hor; o[1] = mv.ver; o[2] = (int64_t) sad; o[3] = 0; o[4] = (int64_t) st.uiBestSad; o[5] = st.uiBestDistance;
   }
   r.cs.pcv = nullptr;
