@@ -28,6 +28,7 @@ struct B200SearchApi
   decltype( &vvb_plane_upload )    planeUpload = nullptr;
   decltype( &vvb_sad_search )      sadSearch = nullptr;
   decltype( &vvb_frac_cost_grid )  fracCostGrid = nullptr;
+  decltype( &vvb_set_tma_staging ) setTmaStaging = nullptr;
 } ;
 static B200SearchApi g_b200s;
 
@@ -40,6 +41,7 @@ inline int b200LoadSearch( const char* libPath )
   void* h = g_b200.handle;
 #define VVB_RESOLVE( member, name ) g_b200s.member = (decltype( g_b200s.member )) dlsym( h, #name ); if( !g_b200s.member ) { g_b200.error = "missing " #name; return -2; }
   VVB_RESOLVE( planeUpload, vvb_plane_upload )  VVB_RESOLVE( sadSearch, vvb_sad_search )  VVB_RESOLVE( fracCostGrid, vvb_frac_cost_grid )
+  VVB_RESOLVE( setTmaStaging, vvb_set_tma_staging )
 #undef VVB_RESOLVE
   g_b200s.bound = true;
   return 0;
@@ -64,6 +66,14 @@ inline int b200SubShift( int subShiftMode, int w, int h )
 
 // plane ids the per-call forms use for their uploads
 enum { B200_PLANE_KEY = 14, B200_PLANE_WINDOW = 15 };
+
+// The per-PU forms search a window that was uploaded for this one call: nothing for the TMA staging of the dense kernel to win (it pays on resident pictures, where the
+// aligned boxes of neighbouring blocks hit in L2), so they run with the load/store staging and put the context's default back afterwards.
+struct B200NoTmaScope
+{
+  B200NoTmaScope()  { g_b200s.setTmaStaging( b200CtxOfThread(), 0 ); }
+  ~B200NoTmaScope() { g_b200s.setTmaStaging( b200CtxOfThread(), 2 ); }
+};
 
 // uploads the pattern key (margin 0) and the reference window around piRefY (margin `reach` on every side: the reference pictures are padded, Picture.cpp:461-501)
 inline void b200UploadKeyAndWindow( const CPelBuf& key, const Pel* piRefY, int refStride, int reach, int bitDepth )
@@ -90,7 +100,7 @@ inline void xPatternSearchB200( InterSearch& is, InterSearch::TZSearchStruct& cS
   if( blk.pred_hor != rc.m_mvPredictor.hor || blk.pred_ver != rc.m_mvPredictor.ver ) THROW( "predictor outside the 16-bit range of vvb_block" );
   const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, cStruct.imvShift, subShift );
   vvb_best best = {};
-  b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, nullptr, 0, &best ) );
+  { B200NoTmaScope noTma; b200Check( g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, nullptr, 0, &best ) ); }
 
   rcMv.set( best.dx, best.dy );
   cStruct.uiBestSad = best.cost;                                                          // :2248
@@ -226,7 +236,8 @@ inline void xTZSearchB200( InterSearch& is, const CodingUnit& cu, RefPicList ref
   blk.pred_hor = (int16_t) rc.m_mvPredictor.hor; blk.pred_ver = (int16_t) rc.m_mvPredictor.ver;
   const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, cStruct.imvShift, subShift );
   vvb_best best = {};
-  const int rcSearch = g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, sad.data(), nx * ny, &best );
+  int rcSearch;
+  { B200NoTmaScope noTma; rcSearch = g_b200s.sadSearch( b200CtxOfThread(), B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height, &me, sad.data(), nx * ny, &best ); }
   if( rcSearch != VVB_OK && rcSearch != VVB_ERR_UNSUPPORTED ) b200Check( rcSearch );
   // a window the dense kernel cannot stage (block + range beyond its shared-memory budget) leaves the table empty: every position then takes the per-block path
   const bool haveTable = rcSearch == VVB_OK;
@@ -246,6 +257,7 @@ public:
   {
     b200Check( g_b200s.planeUpload( b200CtxOfThread(), 0, org.buf, org.stride, org.width, org.height, 0, bitDepth ) );
     b200Check( g_b200s.planeUpload( b200CtxOfThread(), 1, ref.buf, ref.stride, ref.width, ref.height, margin, bitDepth ) );
+    m_margin = margin;
   }
   // returns the index under which results() reports this PU
   int add( int x, int y, int w, int h, const InterSearch::SearchRange& sr, const Mv& predictor )
@@ -267,7 +279,11 @@ public:
       const int subShift = b200SubShift( subShiftMode, g.w, g.h );
       const vvb_me_par me = b200MePar( rc, rc.m_iCostScale, imvShift, subShift );
       std::vector<vvb_best> best( g.blocks.size() );
-      b200Check( g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, nullptr, 0, best.data() ) );
+      const bool tma = boxesInside( g.blocks );
+      if( !tma ) g_b200s.setTmaStaging( b200CtxOfThread(), 0 );
+      const int rcS = g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, nullptr, 0, best.data() );
+      if( !tma ) g_b200s.setTmaStaging( b200CtxOfThread(), 2 );
+      b200Check( rcS );
       for( size_t i = 0; i < best.size(); i++ )
       {
         Result& r = m_results[g.index[i]];
@@ -275,6 +291,12 @@ public:
       }
     }
     m_groups.clear();
+  }
+  // the TMA boxes of the dense kernel are whole windows rounded up to 8 pels: keep them inside the uploaded margin, else stage with loads
+  bool boxesInside( const std::vector<vvb_block>& blocks ) const
+  {
+    for( const vvb_block& b : blocks ) if( std::max( std::max( -b.left, (int) b.right ), std::max( -b.top, (int) b.bottom ) ) + 8 > m_margin ) return false;
+    return true;
   }
   const std::vector<Result>& results() const { return m_results; }
   void clear() { m_groups.clear(); m_results.clear(); m_tables.clear(); }
@@ -299,7 +321,11 @@ public:
       for( const vvb_block& b : g.blocks ) tableStride = std::max( tableStride, ( b.right - b.left + 1 ) * ( b.bottom - b.top + 1 ) );
       std::vector<uint32_t> tabs( (size_t) tableStride * g.blocks.size() );
       std::vector<vvb_best> best( g.blocks.size() );
-      b200Check( g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, tabs.data(), tableStride, best.data() ) );
+      const bool tma = boxesInside( g.blocks );
+      if( !tma ) g_b200s.setTmaStaging( b200CtxOfThread(), 0 );
+      const int rcS = g_b200s.sadSearch( b200CtxOfThread(), 0, 1, g.blocks.data(), (int) g.blocks.size(), g.w, g.h, &me, tabs.data(), tableStride, best.data() );
+      if( !tma ) g_b200s.setTmaStaging( b200CtxOfThread(), 2 );
+      b200Check( rcS );
       for( size_t i = 0; i < g.blocks.size(); i++ )
       {
         const vvb_block& b = g.blocks[i];
@@ -323,4 +349,5 @@ private:
   std::vector<Group>  m_groups;
   std::vector<Result> m_results;
   std::vector<Table>  m_tables;
+  int                 m_margin = 0;
 };

@@ -27,6 +27,8 @@ void vvb_destroy( vvb_ctx* c ) { if( !c ) return; for( int i = 0; i < MOCK_PLANE
 const char* vvb_last_error( const vvb_ctx* c ) { return c ? c->err : "no context"; }
 int vvb_launch_count( const vvb_ctx* c, uint64_t* n ) { if( !c || !n ) return VVB_ERR_ARG; *n = c->calls; return VVB_OK; }
 
+int vvb_set_tma_staging( vvb_ctx* c, int enable ) { if( !c || enable < 0 || enable > 2 ) return VVB_ERR_ARG; return VVB_OK; }   /* staging choice of the real kernel: nothing to do here */
+
 int vvb_plane_upload( vvb_ctx* c, int id, const int16_t* origin, int stride, int width, int height, int margin, int bitDepth )
 {
   if( !c || id < 0 || id >= MOCK_PLANES - 2 || !origin || width <= 0 || height <= 0 || margin < 0 || stride < width + 2 * margin ) return c ? fail( c, VVB_ERR_ARG, "bad plane arguments" ) : VVB_ERR_ARG;
