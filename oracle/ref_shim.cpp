@@ -1304,7 +1304,7 @@ static void fracSearchProbe( int opt, const int16_t* orgPlane, int orgStride, co
   if( !isp ) isp = new InterSearch;
   InterSearch& is = *isp;
   if( inited != ( opt ? 1 : 0 ) ) { if( inited >= 0 ) is.InterPredInterpolation::destroy(); is.InterPredInterpolation::init( opt != 0 ); inited = opt ? 1 : 0; }
-  cfg.m_fastSubPel = fastSubPel; cfg.m_meReduceTap = reduceTap; cfg.m_bUseHADME = useHad != 0; cfg.m_fastHad = false;
+  cfg.m_fastSubPel = fastSubPel; cfg.m_meReduceTap = reduceTap; cfg.m_bUseHADME = useHad != 0; cfg.m_fastHad = useHad == 2;   // useHad: 0 SAD, 1 SATD, 2 fast SATD (DF_HAD_fast, 16x16_fast tiles on square multiples of 32)
   is.m_pcEncCfg = &cfg;
   is.m_lumaClpRng.bd = bitDepth;
   is.m_currChromaFormat = CHROMA_400;

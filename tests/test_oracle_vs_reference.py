@@ -296,6 +296,42 @@ def test_fractional_refinement_against_the_reference_member_function(opt):
                 assert (half, quarter, cost) == ((int(out[k, 0]), int(out[k, 1])), (int(out[k, 2]), int(out[k, 3])), got_cost), (w, h, rt, had, alt, k, half, quarter, cost, out[k])
                 checked += 1
     assert checked == 100
+    # rectangular PUs: SATD built from the 16x8 / 8x16 / 8x4 / 4x8 tiles (RdCost.cpp:1840-1905, fp64 normalisation) -- not offered by vvb_frac_cost_grid yet, the
+    # oracle's table already equals what the member sees
+    for (w, h) in ((16, 8), (8, 16), (32, 16), (16, 32), (8, 4), (4, 8)):
+        n = 4
+        blk = np.zeros((n, 8), dtype=np.int32)
+        for k in range(n):
+            blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
+                      int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
+        out = np.zeros((n, 6), dtype=np.int32)
+        R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, 2, 1, 0, 0, P(out))
+        tab = np.zeros((n, 7, 7), dtype=np.uint32)
+        O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk[:, :6])), n, 2, 10, 2, 0, P(tab))
+        for k in range(n):
+            ph, pv = int(blk[k, 6]), int(blk[k, 7])
+            half, quarter, cost = cand.subpel_refinement(tab[k], (int(blk[k, 4]), int(blk[k, 5])), lambda x, y, cs: int(O.orc_mv_cost(lam, x, y, ph, pv, cs, 0)))
+            got_cost = (int(out[k, 4]) & 0xffffffff) | (int(out[k, 5]) << 32)
+            assert (half, quarter, cost) == ((int(out[k, 0]), int(out[k, 1])), (int(out[k, 2]), int(out[k, 3])), got_cost), ('rect', w, h, k)
+    # m_fastHad (the faster / fast presets): xPatternRefinement asks for DF_HAD_fast -- the 16x16_fast tiles on square blocks that are multiples of 32, the plain
+    # tiles elsewhere (RdCost.cpp:1818-1938).  The same replay on the oracle's table of that family gives the member's offsets and cost.
+    for (w, h) in ((16, 16), (32, 32), (64, 64)):
+        n = 5
+        blk = np.zeros((n, 8), dtype=np.int32)
+        for k in range(n):
+            blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
+                      int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
+        out = np.zeros((n, 6), dtype=np.int32)
+        R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, 2, 2, 0, 0, P(out))
+        tab = np.zeros((n, 7, 7), dtype=np.uint32); plain = np.zeros((n, 7, 7), dtype=np.uint32)
+        O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk[:, :6])), n, 3, 10, 2, 0, P(tab))
+        O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk[:, :6])), n, 2, 10, 2, 0, P(plain))
+        assert np.array_equal(tab, plain) == (w < 32)                      # the fast tiles only exist from 32x32 upwards
+        for k in range(n):
+            ph, pv = int(blk[k, 6]), int(blk[k, 7])
+            half, quarter, cost = cand.subpel_refinement(tab[k], (int(blk[k, 4]), int(blk[k, 5])), lambda x, y, cs: int(O.orc_mv_cost(lam, x, y, ph, pv, cs, 0)))
+            got_cost = (int(out[k, 4]) & 0xffffffff) | (int(out[k, 5]) << 32)
+            assert (half, quarter, cost) == ((int(out[k, 0]), int(out[k, 1])), (int(out[k, 2]), int(out[k, 3])), got_cost), ('fastHad', w, h, k)
     # the preset control (m_fastSubPel = 1): positions are skipped by the encoder's own heuristics, but whatever position it ends on, its cost must be the
     # table entry of that position plus the vector rate -- the half-pel blocks filtered inside xPatternRefinement and the partial xExtDIFUpSamplingQ planes
     # are the same two-pass interpolations
