@@ -298,7 +298,7 @@ def test_fractional_refinement_against_the_reference_member_function(opt):
     assert checked == 100
     # rectangular PUs: SATD built from the 16x8 / 8x16 / 8x4 / 4x8 tiles (RdCost.cpp:1840-1905, fp64 normalisation) -- not offered by vvb_frac_cost_grid yet, the
     # oracle's table already equals what the member sees
-    for (w, h) in ((16, 8), (8, 16), (32, 16), (16, 32), (8, 4), (4, 8)):
+    for (w, h) in ((16, 8), (8, 16), (32, 16), (16, 32), (8, 4), (4, 8), (4, 4), (64, 32)):
         n = 4
         blk = np.zeros((n, 8), dtype=np.int32)
         for k in range(n):
