@@ -1,7 +1,7 @@
 // integration/MCTFB200.h -- reference-side binding of libvvenc_b200.so for the MCTF motion search (CommonLib/MCTF.cpp).
 //
 //   motionEstimationLumaB200  <->  MCTF::motionEstimationLuma (MCTF.cpp:1329-1397) -> estimateLumaLn (:1166-1327)
-//   bilateralFilterB200       <->  MCTF::bilateralFilter (MCTF.cpp:1489-1556) -> xFinalizeBlkLine (:1399-1487), luma plane: one vvb_mctf_apply per picture
+//   bilateralFilterB200       <->  MCTF::bilateralFilter (MCTF.cpp:1489-1556) -> xFinalizeBlkLine (:1399-1487): one vvb_mctf_apply per picture and component
 //
 // Same arguments as the member.  The per-block `error < best.error` chains of estimateLumaLn are kept; what changes is where the errors come from:
 // motionErrorLuma (:1099-1164) is not called per candidate, the candidate sets of a whole picture go out as tables:
@@ -219,45 +219,57 @@ inline void motionEstimationLumaB200( const MCTF& m, Array2D<MotionVector>& mvs,
   }
 }
 
-// MCTF::bilateralFilter for the luma plane: the parameters xFinalizeBlkLine derives per block (filter set, planar-correction switch, reference strengths,
-// weight scaling, sigma^2) are derived once, the motion fields of all neighbour pictures go out with one call and newOrgPic.Y() comes back whole.
+// MCTF::bilateralFilter: the parameters xFinalizeBlkLine derives per block (filter set, planar-correction switch, reference strengths, weight scaling, sigma^2) are
+// derived once per component, the motion fields of all neighbour pictures go out with one call per component and the filtered plane comes back whole.
+// Chroma (4:2:0 / 4:2:2 / 4:4:4) runs through the same entry point: units shrink by the sub-sampling, and because xFinalizeBlkLine uses the vector as
+// dx = mv.x >> csx (phase dx & 15, integer part mv.x >> (4 + csx), :1450-1453) the vectors are handed over pre-shifted.
 enum { B200_PLANE_MCTF_SRC0 = 20 };
 inline void bilateralFilterB200( const MCTF& m, const PelStorage& orgPic, std::deque<TemporalFilterSourcePicInfo>& srcFrameInfo, PelStorage& newOrgPic, double overallStrength )
 {
   const int numRefs = (int) srcFrameInfo.size();
   if( numRefs < 1 || numRefs > 8 ) THROW( "vvb_mctf_apply takes 1..8 neighbour pictures" );
   const VVEncCfg& cfg = *m.m_encCfg;
-  const int bitDepth = cfg.m_internalBitDepth[CH_L], unit = m.m_mctfUnitSize;
-  const CPelBuf org = orgPic.Y();
-  const int width = org.width, height = org.height;
-  vvb_ctx* ctx = b200CtxOfThread();
-  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_ORG, org.buf, org.stride, width, height, 0, bitDepth ) );
-
-  vvb_mctf_apply_par par = {};
-  par.num_refs = numRefs; par.block_size = unit;
-  par.low_res_filter = m.m_lowResFltApply ? 1 : 0;                                             // m_interpolationFilter4 instead of ..8 (:1459)
-  par.planar_correction = cfg.m_QP <= 32 ? 1 : 0;                                              // :1474 (the rmsme / shape conditions are per block, inside)
-  par.weight_scaling = overallStrength * 0.4;                                                  // :1417, luma
-  const double lumaSigmaSq = m.m_sigmaMultiplier * ( 128.0 + 3.0 / 256.0 * cfg.m_QP * cfg.m_QP * cfg.m_QP );     // :1491
-  const double bitDepthDiffWeighting = 1024.0 / ( ( ( 1 << bitDepth ) - 1 ) + 1 );
-  par.sigma_sq = lumaSigmaSq / ( bitDepthDiffWeighting * bitDepthDiffWeighting );              // :1500
+  const ChromaFormat chFmt = cfg.m_internChromaFormat == VVENC_CHROMA_400 ? CHROMA_400 : cfg.m_internChromaFormat == VVENC_CHROMA_420 ? CHROMA_420
+                           : cfg.m_internChromaFormat == VVENC_CHROMA_422 ? CHROMA_422 : CHROMA_444;
+  const int unit = m.m_mctfUnitSize;
   const int refStrengthRow = cfg.m_picReordering ? 0 : 1;                                      // :1405
-  const int bxN = ( width + unit - 1 ) / unit, byN = ( height + unit - 1 ) / unit;
+  const int bxN = ( orgPic.Y().width + unit - 1 ) / unit, byN = ( orgPic.Y().height + unit - 1 ) / unit;
+  const double lumaSigmaSq = m.m_sigmaMultiplier * ( 128.0 + 3.0 / 256.0 * cfg.m_QP * cfg.m_QP * cfg.m_QP ), chromaSigmaSq = 30 * 30;       // :1491-1492
+  vvb_ctx* ctx = b200CtxOfThread();
   std::vector<vvb_mctf_mv> mvs( (size_t) numRefs * bxN * byN );
-  for( int i = 0; i < numRefs; i++ )
+
+  for( int c = 0; c < (int) getNumberValidComponents( chFmt ); c++ )
   {
-    const CPelBuf src = srcFrameInfo[i].picBuffer.Y();
-    b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_SRC0 + i, src.buf, src.stride, width, height, MCTF_PADDING, bitDepth ) );
-    par.ref_plane[i] = B200_PLANE_MCTF_SRC0 + i;
-    par.ref_strength[i] = m.m_refStrengths[refStrengthRow][srcFrameInfo[i].index];            // :1480
-    for( int by = 0; by < byN; by++ )
-      for( int bx = 0; bx < bxN; bx++ )
-      {
-        const MotionVector& v = srcFrameInfo[i].mvs.get( bx, by );
-        vvb_mctf_mv& o = mvs[( (size_t) i * byN + by ) * bxN + bx];
-        o.x = v.x; o.y = v.y; o.error = v.error; o.rmsme = v.rmsme; o.pad = 0;
-      }
+    const ComponentID compID = ComponentID( c );
+    const ChannelType ch = toChannelType( compID );
+    const int csx = getComponentScaleX( compID, chFmt ), csy = getComponentScaleY( compID, chFmt );
+    if( csx != csy ) THROW( "vvb_mctf_apply takes square units: 4:2:2 chroma stays on the host" );
+    const int bitDepth = cfg.m_internalBitDepth[ch];
+    const CPelBuf org = orgPic.bufs[c];
+    b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_ORG, org.buf, org.stride, org.width, org.height, 0, bitDepth ) );
+
+    vvb_mctf_apply_par par = {};
+    par.num_refs = numRefs; par.block_size = unit >> csx;                                      // blkSizeX / blkSizeY (:1420-1421)
+    par.low_res_filter = m.m_lowResFltApply ? 1 : 0;                                           // m_interpolationFilter4 instead of ..8 (:1459)
+    par.planar_correction = cfg.m_QP <= 32 ? 1 : 0;                                            // :1474 (the rmsme / shape conditions are per block, inside)
+    par.weight_scaling = overallStrength * ( isChroma( compID ) ? m.m_chromaFactor : 0.4 );    // :1417
+    const double bitDepthDiffWeighting = 1024.0 / ( ( ( 1 << bitDepth ) - 1 ) + 1 );
+    par.sigma_sq = ( isChroma( ch ) ? chromaSigmaSq : lumaSigmaSq ) / ( bitDepthDiffWeighting * bitDepthDiffWeighting );     // :1500
+    for( int i = 0; i < numRefs; i++ )
+    {
+      const CPelBuf src = srcFrameInfo[i].picBuffer.bufs[c];
+      b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_SRC0 + i, src.buf, src.stride, org.width, org.height, MCTF_PADDING >> csx, bitDepth ) );
+      par.ref_plane[i] = B200_PLANE_MCTF_SRC0 + i;
+      par.ref_strength[i] = m.m_refStrengths[refStrengthRow][srcFrameInfo[i].index];          // :1480
+      for( int by = 0; by < byN; by++ )
+        for( int bx = 0; bx < bxN; bx++ )
+        {
+          const MotionVector& v = srcFrameInfo[i].mvs.get( bx, by );
+          vvb_mctf_mv& o = mvs[( (size_t) i * byN + by ) * bxN + bx];
+          o.x = v.x >> csx; o.y = v.y >> csy; o.error = v.error; o.rmsme = v.rmsme; o.pad = 0;
+        }
+    }
+    PelBuf dst = newOrgPic.bufs[c];
+    b200Check( g_b200m.apply( ctx, B200_PLANE_MCTF_ORG, &par, mvs.data(), dst.buf, dst.stride ) );
   }
-  PelBuf dst = newOrgPic.Y();
-  b200Check( g_b200m.apply( ctx, B200_PLANE_MCTF_ORG, &par, mvs.data(), dst.buf, dst.stride ) );
 }

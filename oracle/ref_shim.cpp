@@ -1227,23 +1227,30 @@ int refshim_row_search_b200( int opt, const int16_t* orgPlane, int orgStride, co
 // org: compact width x height; refs[i]: compact width x height neighbour pictures (padded here by MCTF_PADDING with border replication);
 // mv4: [numRefs][hInBlks][wInBlks] x { x, y, error, rmsme }; refIndex[i] = min(5, |POC distance| - 1) selects m_refStrengths[picReordering ? 0 : 1][.].
 // strengthsOut (nullable) receives the strengths the reference used, sigmaSqOut its luma sigma^2 -- so that callers of the C ABI can be fed the same numbers.
+// org / refs[i] / out: compact planes; with chroma420 the buffers are I420 (Y width x height, then Cb and Cr, (width/2) x (height/2) each) and all components are filtered
 static void bilateralFilterProbe( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
                                   int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply,
-                                  int16_t* out, double* strengthsOut, double* sigmaSqOut, bool b200 )
+                                  int16_t* out, double* strengthsOut, double* sigmaSqOut, bool b200, int chroma420 = 0 )
 {
   RefCtx& c = ctx();
   MCTF* m = c.mctf[opt?1:0];
   static VVEncCfg cfg;
+  const ChromaFormat chFmt = chroma420 ? CHROMA_420 : CHROMA_400;
   cfg.m_internalBitDepth[CH_L] = bitDepth; cfg.m_internalBitDepth[CH_C] = bitDepth;
-  cfg.m_internChromaFormat = VVENC_CHROMA_400; cfg.m_QP = qp; cfg.m_picReordering = picReordering != 0;
+  cfg.m_internChromaFormat = chroma420 ? VVENC_CHROMA_420 : VVENC_CHROMA_400; cfg.m_QP = qp; cfg.m_picReordering = picReordering != 0;
   m->m_encCfg = &cfg; m->m_threadPool = nullptr; m->m_mctfUnitSize = unitSize; m->m_lowResFltApply = lowResApply != 0;
   const int pad = MCTF_PADDING;
+  const int nComp = chroma420 ? 3 : 1;
   auto load = [&]( PelStorage& ps, const int16_t* src, int margin )
   {
-    ps.create( CHROMA_400, Area( 0, 0, width, height ), 0, margin );
-    PelBuf b = ps.Y();
-    for( int y = 0; y < height; y++ ) memcpy( b.buf + (ptrdiff_t) y * b.stride, src + (size_t) y * width, sizeof( Pel ) * width );
-    if( margin ) ps.extendBorderPel( margin, margin );
+    ps.create( chFmt, Area( 0, 0, width, height ), 0, margin );
+    for( int comp = 0; comp < nComp; comp++ )
+    {
+      PelBuf b = ps.bufs[comp];
+      for( int y = 0; y < (int) b.height; y++ ) memcpy( b.buf + (ptrdiff_t) y * b.stride, src + (size_t) y * b.width, sizeof( Pel ) * b.width );
+      src += (size_t) b.width * b.height;
+    }
+    if( margin ) ps.extendBorderPel( margin, true );
   };
   PelStorage orgPic, newOrgPic;
   load( orgPic, org, 0 ); load( newOrgPic, org, 0 );
@@ -1270,8 +1277,12 @@ static void bilateralFilterProbe( int opt, const int16_t* org, const int16_t* co
     *sigmaSqOut = lumaSigmaSq / ( w * w );
   }
   if( b200 ) bilateralFilterB200( *m, orgPic, info, newOrgPic, overallStrength ); else m->bilateralFilter( orgPic, info, newOrgPic, overallStrength );
-  CPelBuf r = newOrgPic.Y();
-  for( int y = 0; y < height; y++ ) memcpy( out + (size_t) y * width, r.buf + (ptrdiff_t) y * r.stride, sizeof( Pel ) * width );
+  for( int comp = 0; comp < nComp; comp++ )
+  {
+    CPelBuf r = newOrgPic.bufs[comp];
+    for( int y = 0; y < (int) r.height; y++ ) memcpy( out + (size_t) y * r.width, r.buf + (ptrdiff_t) y * r.stride, sizeof( Pel ) * r.width );
+    out += (size_t) r.width * r.height;
+  }
   orgPic.destroy(); newOrgPic.destroy();
   for( int i = 0; i < numRefs; i++ ) info[i].picBuffer.destroy();
 }
@@ -1280,6 +1291,14 @@ void refshim_mctf_bilateral_filter( int opt, const int16_t* org, const int16_t* 
                                     int16_t* out, double* strengthsOut, double* sigmaSqOut )
 {
   bilateralFilterProbe( opt, org, refs, numRefs, mv4, refIndex, width, height, bitDepth, unitSize, qp, overallStrength, picReordering, lowResApply, out, strengthsOut, sigmaSqOut, false );
+}
+// 4:2:0 form: I420 buffers, all three components filtered (chroma: half-size units, vectors scaled by the sub-sampling, MCTF.cpp:1417-1455); useB200 selects the binding
+int refshim_mctf_bilateral_filter420( int opt, int useB200, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,
+                                      int width, int height, int bitDepth, int unitSize, int qp, double overallStrength, int picReordering, int lowResApply, int16_t* out )
+{
+  try { bilateralFilterProbe( opt, org, refs, numRefs, mv4, refIndex, width, height, bitDepth, unitSize, qp, overallStrength, picReordering, lowResApply, out, nullptr, nullptr, useB200 != 0, 1 ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
+  return 0;
 }
 // the same set-up with bilateralFilterB200 (integration/MCTFB200.h) in place of the member; 0 = ok, 1 = the binding threw
 int refshim_mctf_bilateral_filter_b200( int opt, const int16_t* org, const int16_t* const* refs, int numRefs, const int32_t* mv4, const int32_t* refIndex,

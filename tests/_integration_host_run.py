@@ -179,6 +179,36 @@ def main(mock_path):
             res['mctf_apply'].append({'opt': opt, 'W': W, 'H': H, 'unit': unit, 'refs': nrefs, 'qp': qp, 'rc': rc, 'eq': bool(np.array_equal(a_, b_)),
                                       'changed': bool(np.any(a_ != org)), 'err': (R.refshim_b200_error() or b'').decode() if rc else ''})
 
+    # ---- the same on 4:2:0 pictures: all three components (chroma: half-size units, vectors scaled by the sub-sampling, its own weight and sigma)
+    R.refshim_mctf_bilateral_filter420.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + \
+        [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    res['mctf_apply420'] = []
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for (W, H, unit, nrefs, qp, tap4) in ((96, 64, 16, 4, 22, 0), (128, 96, 16, 3, 40, 1), (64, 64, 32, 2, 30, 0), (80, 48, 16, 8, 32, 0)):
+            def i420(seed_shift, noise):
+                planes = []
+                for (pw, ph) in ((W, H), (W // 2, H // 2), (W // 2, H // 2)):
+                    b0 = rs.randint(0, 1024, size=(ph + 8, pw + 8))
+                    sm_ = (b0 + np.roll(b0, 1, 0) + np.roll(b0, 1, 1) + np.roll(b0, (1, 1), (0, 1))) // 4
+                    planes.append(np.clip(sm_[4:4 + ph, 4:4 + pw] + rs.randint(-noise, noise + 1, size=(ph, pw)), 0, 1023).astype(np.int16).reshape(-1))
+                return np.ascontiguousarray(np.concatenate(planes))
+            org = i420(0, 0)
+            refs = [np.ascontiguousarray(np.clip(org.astype(np.int32) + rs.randint(-a, a + 1, size=org.shape), 0, 1023).astype(np.int16)) for a in ([3, 12, 60, 300] * 2)[:nrefs]]
+            wb, hb = (W + unit - 1) // unit, (H + unit - 1) // unit
+            mv = np.zeros((nrefs, hb * wb, 4), dtype=np.int32)
+            mv[..., 0] = rs.randint(-80, 81, size=(nrefs, hb * wb)); mv[..., 1] = rs.randint(-80, 81, size=(nrefs, hb * wb))
+            mv[..., 2] = rs.choice([3, 20, 49, 50, 75, 100, 101, 400], size=(nrefs, hb * wb)); mv[..., 3] = rs.choice([0, 1, 5, 22, 60], size=(nrefs, hb * wb))
+            idx = np.array([i % 6 for i in range(nrefs)], dtype=np.int32)
+            ptrs = (ctypes.c_void_p * nrefs)(*[r_.ctypes.data for r_ in refs])
+            a_ = np.zeros_like(org); b_ = np.zeros_like(org)
+            rc1 = R.refshim_mctf_bilateral_filter420(opt, 0, P(org), ptrs, nrefs, P(mv), P(idx), W, H, 10, unit, qp, 0.95, 1, tap4, P(a_))
+            rc2 = R.refshim_mctf_bilateral_filter420(opt, 1, P(org), ptrs, nrefs, P(mv), P(idx), W, H, 10, unit, qp, 0.95, 1, tap4, P(b_))
+            ny = W * H
+            res['mctf_apply420'].append({'opt': opt, 'W': W, 'H': H, 'unit': unit, 'refs': nrefs, 'qp': qp, 'rc': [rc1, rc2], 'eq_luma': bool(np.array_equal(a_[:ny], b_[:ny])),
+                                         'eq_chroma': bool(np.array_equal(a_[ny:], b_[ny:])), 'chroma_changed': bool(np.any(a_[ny:] != org[ny:])),
+                                         'err': (R.refshim_b200_error() or b'').decode() if (rc1 or rc2) else ''})
+
     # ---- xTQuantB200 / invTransformNxNB200 against TrQuant::xT + Quant::quant / Quant::dequant + xIT on the probe's TransformUnit rig: every case row of the
     #      parity tables (all shapes, DCT-II / DST-VII / DCT-VIII pairs, 8 and 10 bit, strided residuals, both slice types, xNeedRDOQ with and without depQuant)
     assert R.refshim_install_b200_tu(mock_path.encode()) == 0, R.refshim_b200_error()

@@ -36,4 +36,6 @@ def test_batched_bindings_on_the_real_library():
         assert m['rc'] == [0] * 6 and all(m['eq']), m
     for a in r['mctf_apply']:
         assert a['rc'] == 0 and a['eq'], a
+    for a in r['mctf_apply420']:
+        assert a['rc'] == [0, 0] and a['eq_luma'] and a['eq_chroma'], a
     assert r['tu_fwd']['bad'] == [] and r['tu_inv']['bad'] == []

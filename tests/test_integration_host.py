@@ -13,7 +13,7 @@ own code in the same process:
   * motionEstimationLumaB200 vs MCTF::motionEstimationLuma (member call): first level, chained level and the doubleRes final level, search patterns 0/1/2,
     6- and 4-tap search filters, pictures with partial border blocks,
   * bilateralFilterB200 vs MCTF::bilateralFilter (member call) on whole luma pictures: units 8/16/32, 2..8 neighbour pictures, both filter sets, QP on both
-    sides of the planar-correction threshold,
+    sides of the planar-correction threshold; and on 4:2:0 pictures, all three components (chroma through the same entry point: half-size units, vectors pre-shifted),
   * xTQuantB200 / invTransformNxNB200 vs TrQuant::xT + Quant::quant (+ xNeedRDOQ) / Quant::dequant + xIT on a TransformUnit: every row of the parity tables.
 
 The same bindings run against libvvenc_b200.so in tests/test_gpu_dropin.py (-m gpu)."""
@@ -75,6 +75,9 @@ def test_mctf_apply_binding_equals_the_member(result):
     assert len(result['mctf_apply']) == 10
     for r in result['mctf_apply']:
         assert r['rc'] == 0 and r['eq'] and r['changed'], r
+    assert len(result['mctf_apply420']) == 8
+    for r in result['mctf_apply420']:
+        assert r['rc'] == [0, 0] and r['eq_luma'] and r['eq_chroma'] and r['chroma_changed'], r
 
 
 def test_tz_search_binding_equals_the_member(result):
