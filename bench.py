@@ -839,6 +839,23 @@ def main():
         cpu = cpu_arm(args.cpu_budget)
         try:
             extra['cpu_rows'] = cpu_rows()
+            cr = extra['cpu_rows']; sp = {}
+            # GPU (resident) rate over the reference's all-threads rate, same unit per row; informational -- the headline ratio is e2e over the --impl reference arm
+            for n in SIZES:
+                g = extra.get('tu_roundtrip_pool', {}).get(str(n), {}).get('tu_per_s'); c = cr.get('tu_roundtrip', {}).get(str(n), {}).get('tu_per_s')
+                if g and c:
+                    sp['tu_roundtrip_%d' % n] = g / c
+            g = extra.get('mctf_grid_16x16', {}).get('cand_per_s'); c = cr.get('mctf_match_16x16', {}).get('cand_per_s')
+            if g and c:
+                sp['mctf_grid_16x16'] = g / c
+            for n in (8, 16, 32):
+                g = extra.get('frac_satd_grid', {}).get(str(n), {}).get('cand_per_s'); c = cr.get('frac_satd_grid', {}).get(str(n), {}).get('cand_per_s')
+                if g and c:
+                    sp['frac_satd_grid_%d' % n] = g / c
+            g = extra.get('mctf_apply_2160p', {}).get('pels_per_s'); c = cr.get('mctf_apply', {}).get('pels_per_s')
+            if g and c:
+                sp['mctf_apply'] = g / c
+            extra['row_speedup_vs_cpu'] = sp
         except Exception as ex:
             extra['cpu_rows'] = {'error': str(ex)}
 
