@@ -144,6 +144,10 @@ int vvb_sad_search_pyramid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, int 
 int vvb_sad_search_pyramid    ( vvb_ctx* ctx, int org_plane, int ref_plane, int levels, const vvb_block* const* blocks /* [levels], host */,
                                 const int* counts, int base_w, const vvb_me_par* par, int nx, int ny, vvb_best* const* best_out /* [levels], host */ );
 
+/* Engine of vvb_sad_search_pyramid*: 1 (default) = one CTA per root block keeps every level on the SM (8x8 base blocks, no row sub-sampling, up to four
+ * levels, window within shared memory; other cases use engine 0 automatically), 0 = one CTA per quad + cost-table sums through device memory.  Results are identical. */
+int vvb_set_pyramid_engine( vvb_ctx* ctx, int engine );
+
 /* Fixed candidate set = the static point pattern of xTZ8PointDiamondSearch / raster scan
  * (InterSearch.cpp:557-758, 2491-2497) around (start_x,start_y): pattern[k] = (dx,dy) offsets, clipped against the
  * block's SearchRange (points outside are reported as UINT32_MAX and never win).  costs are SAD only;

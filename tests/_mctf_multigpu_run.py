@@ -1,0 +1,119 @@
+"""torchrun worker (one rank per GPU, NCCL): BASELINE configs[3] -- MCTF of one target picture against 8 neighbour pictures, the neighbour pictures dealt over
+the ranks (bands.split_refs), every rank searches its pictures on its GPU (mctf_host.estimate_pyramid over vvb_mctf_search_grid / vvb_mctf_error_batch /
+vvb_mctf_calc_var), ONE all-gather of the motion fields (bands.all_gather_motion_fields), then every rank runs the apply stage (vvb_mctf_apply) with all fields.
+Rank 0 repeats everything alone and requires identical fields and an identical filtered picture; for the first neighbour picture the field must also equal the
+reference's own MCTF::motionEstimationMCTF where oracle/_ref is present.   usage: torchrun --nproc-per-node N tests/_mctf_multigpu_run.py W H [out.json]"""
+import json, os, sys, time
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import vvenc_b200 as V
+from vvenc_b200 import bands, mctf_host as MH
+
+
+def pictures(W, H, nrefs=8, seed=2024):
+    rs = np.random.RandomState(seed)
+    base = rs.randint(0, 1024, size=(H // 4 + 8, W // 4 + 8)).astype(np.float32)
+    up = np.kron(base, np.ones((4, 4), dtype=np.float32))
+    sm = (up[:-4, :-4] + up[4:, :-4] + up[:-4, 4:] + up[4:, 4:] + 2 * up[2:-2, 2:-2]) / 6.0 + rs.randint(-20, 21, size=(up.shape[0] - 4, up.shape[1] - 4))
+    sm = np.clip(sm, 0, 1023)
+    org = np.ascontiguousarray(sm[8:8 + H, 8:8 + W].astype(np.int16))
+    refs = []
+    for i in range(nrefs):
+        dy, dx = (i % 3) - 1 + (i // 4), 2 - (i % 5)
+        a = sm[8 + dy:8 + dy + H, 8 + dx:8 + dx + W]; b = sm[8 + dy:8 + dy + H, 8 + dx + (i & 1):8 + dx + (i & 1) + W]
+        refs.append(np.ascontiguousarray(np.clip((a + b + 1) // 2 + rs.randint(-3 - i, 4 + i, size=org.shape), 0, 1023).astype(np.int16)))
+    return org, refs
+
+
+class Searcher:
+    """one CostEngine; level pictures are padded (MCTF_PADDING = 128) and uploaded per provider, as MCTF::motionEstimationMCTF sees them"""
+
+    def __init__(self, device):
+        self.eng = V.CostEngine(device)
+
+    def make_provider(self, o, r):
+        pad = 128
+        po, pr = MH.pad_edge(o, pad), MH.pad_edge(r, pad)
+        self.eng.upload_plane(30, po, o.shape[1], o.shape[0], pad); self.eng.upload_plane(31, pr, r.shape[1], r.shape[0], pad)
+        return MH.EngineProvider(self.eng, 30, 31)
+
+    def field(self, org, ref, unit, add_level):
+        f = MH.estimate_pyramid(self.make_provider, org, ref, unit_size=unit, add_level=add_level)
+        return np.stack([f['x'], f['y'], f['error'], f['rmsme'].astype(np.int32)], axis=-1).reshape(-1, 4)
+
+    def apply(self, org, refs, fields, unit):
+        H, W = org.shape
+        pad = 128
+        self.eng.upload_plane(32, MH.pad_edge(org, pad), W, H, pad)
+        for i, r in enumerate(refs):
+            self.eng.upload_plane(33 + i, MH.pad_edge(r, pad), W, H, pad)
+        mvs = np.zeros((len(refs), fields.shape[1]), dtype=V.MCTF_MV_DT)
+        mvs['x'] = fields[:, :, 0]; mvs['y'] = fields[:, :, 1]; mvs['error'] = fields[:, :, 2]; mvs['rmsme'] = fields[:, :, 3]
+        strengths = [0.85, 0.57, 0.41, 0.33, 0.30, 0.20, 0.18, 0.15][:len(refs)]
+        return self.eng.mctf_apply(32, [33 + i for i in range(len(refs))], mvs, unit, strengths, 0.4, 9 * (128.0 + 3.0 / 256.0 * 32 ** 3), W, H)
+
+
+def main():
+    W, H = int(sys.argv[1]), int(sys.argv[2])
+    outp = sys.argv[3] if len(sys.argv) > 3 else None
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nrefs = 8
+    unit = 8 if min(W, H) < 720 else 16                  # vvencCfg.cpp:1495
+    add_level = W >= 1920                                  # MCTF.cpp:768
+    org, refs = pictures(W, H, nrefs)
+    S = Searcher(local)
+    blocks = ((W + unit - 1) // unit) * ((H + unit - 1) // unit)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mine = {ref: S.field(org, refs[ref], unit, add_level) for ref in bands.split_refs(nrefs, world)[rank]}
+    t_search = time.perf_counter() - t0
+    fields = bands.all_gather_motion_fields(mine, nrefs, blocks, torch.device('cuda', local))
+    t1 = time.perf_counter()
+    filtered = S.apply(org, refs, fields, unit)
+    t_apply = time.perf_counter() - t1
+    tt = torch.tensor([t_search, t_apply], dtype=torch.float64, device='cuda')
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    # every rank must hold the same filtered picture
+    chk = torch.from_numpy(filtered.astype(np.int32)).cuda().sum().reshape(1)
+    all_chk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(all_chk, chk)
+    res = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        single = np.stack([S.field(org, refs[i], unit, add_level) for i in range(nrefs)])
+        t_single = time.perf_counter() - t0
+        filt1 = S.apply(org, refs, single, unit)
+        res = {'picture': '%dx%d' % (W, H), 'refs': nrefs, 'n_gpus': world, 'unit': unit, 'levels': 5 if add_level else 4,
+               'fields_equal_single_gpu': bool(np.array_equal(fields, single)), 'filtered_equal_single_gpu': bool(np.array_equal(filtered, filt1)),
+               'filtered_equal_on_all_ranks': len(set(int(c.item()) for c in all_chk)) == 1,
+               'nonzero_vectors': int((fields[:, :, :2] != 0).any(axis=2).sum()), 'fractional_vectors': int(((fields[:, :, :2] & 15) != 0).any(axis=2).sum()),
+               'search_s_sharded_max_over_ranks': float(tt[0].item()), 'search_s_single_gpu': t_single, 'apply_s': float(tt[1].item()),
+               'block_refs_per_s_sharded': blocks * nrefs / float(tt[0].item())}
+        try:
+            from _libs import have_ref, refshim, P
+            if have_ref() and W * H <= 1000 * 600:
+                R = refshim(); R.refshim_set_simd(b'AVX2')
+                wb, hb = (W + unit - 1) // unit, (H + unit - 1) // unit
+                exp = np.zeros((hb, wb, 4), dtype=np.int32)
+                R.refshim_mctf_estimate_pyramid(1, P(org), P(refs[0]), W, H, 10, unit, int(add_level), 0, 0, P(exp))
+                res['field0_equals_reference_motionEstimationMCTF'] = bool(np.array_equal(fields[0], exp.reshape(-1, 4)))
+        except Exception as ex:
+            res['reference_check_error'] = repr(ex)
+        print('RESULT ' + json.dumps(res))
+        if outp:
+            json.dump(res, open(outp, 'w'))
+    dist.barrier(); dist.destroy_process_group()
+    S.eng.close()
+    if rank == 0 and not (res['fields_equal_single_gpu'] and res['filtered_equal_single_gpu'] and res['filtered_equal_on_all_ranks'] and res.get('field0_equals_reference_motionEstimationMCTF', True)):
+        sys.exit(3)
+
+
+if __name__ == '__main__':
+    main()

@@ -2,8 +2,7 @@
 libvvenc_b200.so and run next to the reference's own member functions -- the comparison tests/test_integration_host.py makes on the CPU with the oracle-backed
 mock, with the kernels answering instead.  Runs in a process of its own (the probe binds one library per process) and last in the suite.
 
-Written after round 1's GPU budget was spent: its first hardware run is the round-end run, hence xfail(strict=False) -- an XPASS in the log is the
-validation, a failure does not mask the parity suite before it."""
+First ran on hardware at the end of round 1 (XPASS in GPUTEST_r01.json); the xfail guard is gone since."""
 import json
 import os
 import subprocess
@@ -17,7 +16,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason='oracle/_ref not built')]
 
 
-@pytest.mark.xfail(strict=False, reason='first hardware run of the batched bindings happens at round end (GPU budget of round 1 was spent when they were written)')
 def test_batched_bindings_on_the_real_library():
     import vvenc_b200._lib as VL
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), VL.LIB_PATH], capture_output=True, text=True, timeout=400)

@@ -72,6 +72,7 @@ SYMBOLS = {
     'vvb_sad_search_pyramid': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_p]),
     'vvb_sad_search_pyramid_dev': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_p]),
     'vvb_set_tma_staging': (c_i, [c_p, c_i]),
+    'vvb_set_pyramid_engine': (c_i, [c_p, c_i]),
     'vvb_sad_pattern': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
     'vvb_sad_pattern_dev': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),
     'vvb_cost_pattern': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_p, c_p]),

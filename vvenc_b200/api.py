@@ -189,6 +189,9 @@ class CostEngine:
     def set_tma_staging(self, enable):
         self._chk(self.lib.vvb_set_tma_staging(self.h, int(enable)))
 
+    def set_pyramid_engine(self, engine):
+        self._chk(self.lib.vvb_set_pyramid_engine(self.h, int(engine)))
+
     def set_tensor_transform(self, enable):
         self._chk(self.lib.vvb_set_tensor_transform(self.h, int(enable)))
 

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "dist_kernels.cuh"
 #include "search_kernels.cuh"
+#include "pyramid_kernels.cuh"
 #include "trquant_kernels.cuh"
 #include "trquant_tc_kernels.cuh"
 #include "itrquant_kernels.cuh"
@@ -231,6 +232,9 @@ int vvb_create( vvb_ctx** out, int device )
     if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) == cudaSuccess && qres == cudaDriverEntryPointSuccess ) ctx->tmaEncode = fn;
     cudaGetLastError();
   }
+  cudaFuncSetAttribute( sad_pyramid8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
+  cudaFuncSetAttribute( sad_pyramid8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
+  cudaFuncSetAttribute( sad_pyramid8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
@@ -280,6 +284,14 @@ int vvb_set_tma_staging( vvb_ctx* ctx, int enable )
 {
   if( !ctx ) return VVB_ERR_ARG;
   ctx->useTma = enable;
+  return VVB_OK;
+}
+
+// SAD pyramid engine: 1 (default) = all levels inside one CTA per root block (pyramid_kernels.cuh) where it applies, 0 = per-quad kernel + table sums
+int vvb_set_pyramid_engine( vvb_ctx* ctx, int engine )
+{
+  if( !ctx ) return VVB_ERR_ARG;
+  ctx->pyramidEngine = engine;
   return VVB_OK;
 }
 
@@ -453,7 +465,7 @@ int vvb_sad_x5_block( vvb_ctx* ctx, const int16_t* org, int orgStride, const int
   CHECK_LAUNCH( "sad_x5_kernel" );
   uint64_t tmp[5];
   CU( cudaMemcpyAsync( tmp, dOut, 40, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( endCall( ctx ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );         // tmp is consumed right below: always wait, asynchronous mode or not
   for( int i = 0; i < 5; i++ ) if( i != 2 || calcCentre ) cost5[i] = tmp[i];
   return VVB_OK;
 }
@@ -525,8 +537,7 @@ int vvb_dist_pool_dev( vvb_ctx* ctx, int dfunc, int orgPlane, const vvb_pos* dBl
 #undef LAUNCH_SP
     launched = true;
   }
-  else if( planeAligned && posAligned && ( dfunc == FAM_HAD || dfunc == FAM_HAD_2SAD ) && ( w & 7 ) == 0 && ( h & 7 ) == 0 &&
-           !( w > h && ( w & 15 ) == 0 ) && !( w < h && ( h & 15 ) == 0 ) )
+  else if( planeAligned && posAligned && ( dfunc == FAM_HAD || dfunc == FAM_HAD_2SAD ) && ( w & 7 ) == 0 && isPow2( h ) && h >= 8 && w == h )
   {
     // tile dispatch lands on 8x8 (RdCost.cpp:1836-1905 with the rectangular 16x8 / 8x16 cases excluded above)
     const int T = ( w >> 3 ) * ( h >> 3 );
@@ -655,6 +666,38 @@ static int sadSearchLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_
   return VVB_OK;
 }
 
+// In-CTA pyramid (pyramid_kernels.cuh): usable for 8x8 base blocks, no row sub-sampling, up to four levels, 32-bit keys at the 8x8 / 16x16 levels
+template<int LV>
+static int pyramidV2LaunchLevel( vvb_ctx* ctx, int orgPlane, int refPlane, const PyrLevels& lv, int rootFirst, int nRoots, int nx, int ny, const MePar& mp )
+{
+  const PyrSmem L = pyr_smem<LV>( nx, ny );
+  const int NQ = ( 1 << ( 2 * ( LV - 1 ) ) ) / 4;
+  const int items = NQ * ( ( ny + 1 ) / 2 ) * L.nStrips;
+  int bd = 256; double bestEff = -1.0;
+  for( int cand = 128; cand <= PYR_MAX_THREADS; cand += 32 )          // fewest idle thread slots over the rounds; ties -> more threads
+  {
+    const int rounds = ( items + cand - 1 ) / cand;
+    const double eff = (double) items / ( (double) rounds * cand ) * ( cand >= 384 || cand * 2 > items ? 1.0 : 0.9 );
+    if( eff >= bestEff - 1e-9 ) { bestEff = std::max( bestEff, eff ); bd = cand; }
+  }
+  sad_pyramid8_kernel<LV><<<nRoots, bd, (size_t) L.total, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], lv, rootFirst, nx, ny, mp, 1u, 8u );
+  CHECK_LAUNCH( "sad_pyramid8_kernel" );
+  return VVB_OK;
+}
+
+static bool pyramidV2Usable( const vvb_ctx* ctx, int refPlane, int levels, int baseW, const vvb_me_par* par, int nx, int ny, MePar& mp )
+{
+  if( ctx->pyramidEngine != 1 || baseW != 8 || par->sub_shift != 0 || levels < 2 || levels > 4 ) return false;
+  int ob = 1; while( ( 1 << ob ) < nx * ny ) ob++;
+  const Plane& rp = ctx->planes.p[refPlane];
+  const unsigned long long maxCost16 = 4ull * 64 * ( ( 1ull << rp.bitDepth ) - 1 ) + mp.tab.cost[VVB_MVCOST_ENTRIES - 1];
+  if( ob > 16 || maxCost16 >= ( 1ull << ( 32 - ob ) ) || maxCost16 >= PYR_NEVER / 4 ) return false;
+  const int total = levels == 4 ? pyr_smem<4>( nx, ny ).total : ( levels == 3 ? pyr_smem<3>( nx, ny ).total : pyr_smem<2>( nx, ny ).total );
+  if( total > 227 * 1024 ) return false;
+  mp.orderBits = ob;
+  return true;
+}
+
 extern "C" {
 
 // SAD pyramid (see include/vvenc_b200.h): pel work at the base level only, every higher level is the exact sum of its children's SADs
@@ -665,16 +708,38 @@ int vvb_sad_search_pyramid_dev( vvb_ctx* ctx, int orgPlane, int refPlane, int le
   for( int l = 0; l < levels; l++ ) if( !dBlocks[l] || !dBest[l] || counts[l] < 0 ) return fail( ctx, VVB_ERR_ARG, "bad level arguments" );
   for( int l = 0; l + 1 < levels; l++ ) if( counts[l] < 4 * counts[l + 1] ) return fail( ctx, VVB_ERR_ARG, "a level is shorter than four times the next one" );
   if( ( baseW << ( levels - 1 ) ) > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "top level above 128" );
+  if( nx > 512 || ny > 512 || (long long) nx * ny > 65536 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "pyramid search range above 512 positions per axis / 65536 positions" );
   if( counts[0] == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   const int T = nx * ny;
   void* tab[2] = { nullptr, nullptr };
   int rc;
+  {
+    MePar mp2;
+    if( ( rc = makeMePar( ctx, par, mp2 ) ) ) return rc;
+    if( ( rc = checkSearchShape( ctx, orgPlane, refPlane, baseW, baseW ) ) ) return rc;
+    if( pyramidV2Usable( ctx, refPlane, levels, baseW, par, nx, ny, mp2 ) )
+    {
+      PyrLevels lv; memset( &lv, 0, sizeof( lv ) );
+      for( int l = 0; l < levels; l++ ) { lv.blocks[l] = dBlocks[l]; lv.best[l] = dBest[l]; }
+      for( int Ltop = levels - 1; Ltop >= 1; Ltop-- )                                   // roots of this level: the blocks no larger block covers
+      {
+        const int first = Ltop == levels - 1 ? 0 : 4 * counts[Ltop + 1], nRoots = counts[Ltop] - first;
+        if( nRoots <= 0 ) continue;
+        if( Ltop == 3 )      rc = pyramidV2LaunchLevel<4>( ctx, orgPlane, refPlane, lv, first, nRoots, nx, ny, mp2 );
+        else if( Ltop == 2 ) rc = pyramidV2LaunchLevel<3>( ctx, orgPlane, refPlane, lv, first, nRoots, nx, ny, mp2 );
+        else                 rc = pyramidV2LaunchLevel<2>( ctx, orgPlane, refPlane, lv, first, nRoots, nx, ny, mp2 );
+        if( rc ) return rc;
+      }
+      if( counts[0] > 4 * counts[1] &&      // base-level blocks without a parent
+          ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks[0] + 4 * counts[1], counts[0] - 4 * counts[1], baseW, baseW, par, nx, ny, 1, nullptr, 0, dBest[0] + 4 * counts[1] ) ) ) return rc;
+      return VVB_OK;
+    }
+  }
   if( levels > 2 && ( rc = scratch( ctx, 6, (size_t) counts[1] * T * 4, &tab[1] ) ) ) return rc;
   if( levels > 3 && ( rc = scratch( ctx, 7, (size_t) counts[2] * T * 4, &tab[0] ) ) ) return rc;
   CU( cudaMemsetAsync( dBest[1], 0xff, (size_t) counts[1] * sizeof( vvb_best ), ctx->stream ) );   // parents of broken quads stay "invalid" (cost = ~0)
   PyramidOut po{ dBlocks[1], dBest[1], (uint32_t*) tab[1], T };
-  ctx->launches++;                                                                                  // the memset node
   if( counts[1] > 0 && ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks[0], 4 * counts[1], baseW, baseW, par, nx, ny, 1, nullptr, 0, dBest[0], &po ) ) ) return rc;
   if( counts[0] > 4 * counts[1] &&      // base-level blocks without a parent
       ( rc = sadSearchLaunch( ctx, orgPlane, refPlane, dBlocks[0] + 4 * counts[1], counts[0] - 4 * counts[1], baseW, baseW, par, nx, ny, 1, nullptr, 0, dBest[0] + 4 * counts[1] ) ) ) return rc;
@@ -685,7 +750,7 @@ int vvb_sad_search_pyramid_dev( vvb_ctx* ctx, int orgPlane, int refPlane, int le
     uint32_t* in  = (uint32_t*) tab[( l - 1 ) & 1];
     uint32_t* out = l + 1 < levels ? (uint32_t*) tab[l & 1] : nullptr;
     if( counts[l] == 0 ) continue;
-    sad_table_sum_kernel<<<counts[l], 256, 0, ctx->stream>>>( dBlocks[l], counts[l], nx, ny, mp, in, T, out, T, dBest[l] );
+    sad_table_sum_kernel<<<counts[l], 256, 0, ctx->stream>>>( dBlocks[l], counts[l], nx, ny, mp, in, T, dBest[l - 1], out, T, dBest[l] );
     CHECK_LAUNCH( "sad_table_sum_kernel" );
   }
   return VVB_OK;
@@ -754,7 +819,7 @@ int vvb_sad_search( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_block* b
 int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* dBlocks, int n, int w, int h, const vvb_mv* dPattern, int K,
                           const vvb_me_par* par, uint32_t* dCost, vvb_best* dBest )
 {
-  if( !ctx || !dBlocks || !dPattern || n < 0 || K < 1 || ( !dCost && !dBest ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !ctx || !dBlocks || !dPattern || !par || n < 0 || K < 1 || ( !dCost && !dBest ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   int rc = checkSearchShape( ctx, orgPlane, refPlane, w, h );
   if( rc ) return rc;
   MePar mp;
@@ -766,7 +831,7 @@ int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, c
   const Plane &op = ctx->planes.p[orgPlane], &rp = ctx->planes.p[refPlane];
   // small-radius Hadamard refinement on 8x8 tiles: staged region + register Hadamard (one lane per candidate tile)
   const int R = par->pattern_radius;
-  if( dfunc == FAM_HAD && R > 0 && R <= 8 && K <= 1024 && ( w & 7 ) == 0 && ( h & 7 ) == 0 && !( w > h && ( w & 15 ) == 0 ) && !( w < h && ( h & 15 ) == 0 ) )
+  if( dfunc == FAM_HAD && R > 0 && R <= 8 && K <= 1024 && ( w & 7 ) == 0 && w == h && isPow2( h ) )     // square power-of-two blocks: the dispatch lands on 8x8 tiles (RdCost.cpp:1836-1905)
   {
     const HadPatSmem L = had_pat_smem( w, h, R, K );
     const int T = ( w >> 3 ) * ( h >> 3 );
@@ -794,7 +859,7 @@ int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, c
 int vvb_cost_pattern( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, const vvb_block* blocks, int n, int w, int h, const vvb_mv* pattern, int K,
                       const vvb_me_par* par, uint32_t* costOut, vvb_best* best )
 {
-  if( !ctx || !blocks || !pattern || n < 0 || K < 1 || ( !costOut && !best ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !ctx || !blocks || !pattern || !par || n < 0 || K < 1 || ( !costOut && !best ) ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   if( n == 0 ) return VVB_OK;
   void *dB, *dP, *dS = nullptr, *dO = nullptr; int rc;
   if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_block ), &dB ) ) || ( rc = scratch( ctx, 3, (size_t) K * sizeof( vvb_mv ), &dP ) ) ) return rc;
@@ -861,10 +926,10 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
   p.offH = vvc_tr_offset_host[p.trHor][p.lw]; p.offV = vvc_tr_offset_host[p.trVer][p.lh];
   p.regionW = std::min( 32, w ); p.regionH = std::min( 32, h );
   p.scanOff = ( ( p.lw - 2 ) * 5 + ( p.lh - 2 ) ) * 1024;
-  auto qpar = [&]( int qp, int addNum, int& scale, int& qbits, long long& add )
+  auto qpar = [&]( int qp, int plusOne, int addNum, int& scale, int& qbits, long long& add )
   {
     int baseQp = qp + 6 * ( in->bit_depth - 8 );                                         // Quant.cpp:99
-    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) );         // Quant.cpp:113
+    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) ) + plusOne; // Quant.cpp:113; the dependent-quantisation pre-check adds 1 AFTER the clip (Quant.cpp:853)
     const int per = baseQp / 6, rem = baseQp % 6;
     const int sqrt2 = ( p.lw + p.lh ) & 1;                                               // UnitTools.cpp:3616-3621
     const int trShift = 15 - in->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;           // Quant.h:69-72, Quant.cpp:767
@@ -872,8 +937,8 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
     qbits = 14 + per + trShift;                                                          // Quant.cpp:769
     add   = (long long) addNum << ( qbits - 9 );                                         // Quant.cpp:772 / :879
   };
-  qpar( in->qp, in->is_irap ? 171 : 85, p.scale, p.qbits, p.add );
-  qpar( in->dep_quant ? in->qp + 1 : in->qp, 171, p.scaleRdoq, p.qbitsRdoq, p.addRdoq );   // Quant.cpp:852-855, :879
+  qpar( in->qp, 0, in->is_irap ? 171 : 85, p.scale, p.qbits, p.add );
+  qpar( in->qp, in->dep_quant ? 1 : 0, 171, p.scaleRdoq, p.qbitsRdoq, p.addRdoq );         // Quant.cpp:852-855, :879
   if( p.qbits < 9 || p.qbitsRdoq < 9 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "quantiser shift below 9" );
   const int thrVal = 8;                                                                  // vvencCfg.cpp:971-973
   const int32_t thres = (int32_t)( (int64_t) thrVal << ( p.qbits - 1 ) );               // Quant.cpp:175-176 (TCoeff cast)
@@ -1177,9 +1242,10 @@ static int mctfApplyPar( vvb_ctx* ctx, int orgPlane, const vvb_mctf_apply_par* i
   if( !in ) return fail( ctx, VVB_ERR_ARG, "null apply parameters" );
   if( !validPlane( ctx, orgPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
   if( in->num_refs < 1 || in->num_refs > 8 ) return fail( ctx, VVB_ERR_ARG, "1..8 reference pictures (2 * VVENC_MCTF_RANGE, MCTF.cpp:430)" );
-  if( in->block_size != 8 && in->block_size != 16 && in->block_size != 32 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF unit size 8, 16 or 32" );
+  if( in->block_size != 4 && in->block_size != 8 && in->block_size != 16 && in->block_size != 32 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF unit size 4 (chroma of unit 8), 8, 16 or 32" );
   const Plane& o = ctx->planes.p[orgPlane];
-  if( ( o.width & 7 ) || ( o.height & 7 ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "picture dimensions must be multiples of 8" );
+  // trailing partial units (h = min(blkSizeY, height - by), MCTF.cpp:1427-1431) are filtered like full ones; the packed two-pass filter walks pel / row pairs
+  if( ( o.width & 1 ) || ( o.height & 1 ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "picture dimensions must be even" );
   if( o.bitDepth > 10 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF supports up to 10 bit (MCTF.cpp:1313 CHECKD)" );
   memset( &p, 0, sizeof( p ) );
   p.numRefs = in->num_refs; p.blockSize = in->block_size; p.tap4 = in->low_res_filter ? 1 : 0; p.planar = in->planar_correction ? 1 : 0;
@@ -1333,7 +1399,7 @@ int vvb_affine_equal_coeff( vvb_ctx* ctx, int sixParam, const int16_t* resi, int
   CHECK_LAUNCH( "equal_coeff_kernel" );
   int64_t tmp[49];
   CU( cudaMemcpyAsync( tmp, dE, 49 * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
-  CU( endCall( ctx ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );         // tmp is consumed right below: always wait, asynchronous mode or not
   for( int i = 0; i < 49; i++ ) eq[i] += tmp[i];
   return VVB_OK;
 }

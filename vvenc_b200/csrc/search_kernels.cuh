@@ -557,8 +557,8 @@ __global__ void __launch_bounds__( PARENT ? 256 : 384, PARENT ? 3 : 2 ) sad_sear
 // Pyramid level >= 2: the SAD table of a parent block is the sum of its four children's tables (children 4p..4p+3 of the level below);
 // argmin with the parent's own MV predictor; optional table output for the next level.  One CTA per parent.
 __global__ void __launch_bounds__( 256 ) sad_table_sum_kernel( const vvb_block* __restrict__ parents, int nParents, int nx, int ny, const __grid_constant__ MePar par,
-                                                               const uint32_t* __restrict__ childTables, int childStride, uint32_t* __restrict__ outTables, int outStride,
-                                                               vvb_best* __restrict__ bestOut )
+                                                               const uint32_t* __restrict__ childTables, int childStride, const vvb_best* __restrict__ childBest,
+                                                               uint32_t* __restrict__ outTables, int outStride, vvb_best* __restrict__ bestOut )
 {
   __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
   __shared__ int sBitsX[512], sBitsY[512];
@@ -570,7 +570,10 @@ __global__ void __launch_bounds__( 256 ) sad_table_sum_kernel( const vvb_block* 
   for( int i = tid; i < ny; i += nthr ) sBitsY[i] = (int) eg_bits( ( ( blk.top  + i ) * ( 1 << par.costScale ) - blk.pred_ver ) >> par.imvShift );
   if( tid == 0 ) sKeyP = ~0ull;
   __syncthreads();
-  const bool ok = ( blk.right - blk.left + 1 ) == nx && ( blk.bottom - blk.top + 1 ) == ny;
+  // a child reported invalid (broken quad below: its table row was never written) makes this parent invalid as well
+  bool ok = ( blk.right - blk.left + 1 ) == nx && ( blk.bottom - blk.top + 1 ) == ny;
+#pragma unroll
+  for( int c = 0; c < 4; c++ ) ok = ok && childBest[4 * (size_t) blockIdx.x + c].cost != ~0ull;
   const uint32_t* c0 = childTables + (size_t)( 4 * blockIdx.x ) * childStride;
   const int total = nx * ny;
   const float inv = 1.0f / (float) nx;
