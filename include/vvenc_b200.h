@@ -238,13 +238,15 @@ int vvb_mctf_search_grid    ( vvb_ctx* ctx, int org_plane, int ref_plane, const 
 int vvb_mctf_search_grid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_cand* dev_blocks, int n, int step, int radius, int low_res_filter, int32_t* dev_err_out );
 
 /* ---- fractional-pel refinement feeding SATD -------------------------------------------------------------------------------
- * For every block (x, y; integer vector start_x/start_y) the distortion dfunc (VVB_DF_SAD, or VVB_DF_HAD on square blocks) between the original and
+ * For every block (x, y; integer vector start_x/start_y; PU sides 4..64, powers of two, square or rectangular) the distortion dfunc -- VVB_DF_SAD, VVB_DF_HAD or
+ * VVB_DF_HAD_FAST, i.e. what setDistParam( ..., m_bUseHADME ? ( m_fastHad ? 2 : 1 ) : 0 ) selects (InterSearch.cpp:775), with the tile rules of xGetHADs -- between the original and
  * the filtered block at every quarter-pel offset (i, j), i, j = -3..3: cost_out[n][j+3][i+3] -- every position InterSearch::xPatternRefinement
  * (InterSearch.cpp:760-972) can visit in its half-pel round and in its quarter-pel round around the best half-pel position.  The filtered blocks are
  * produced exactly as there: InterpolationFilter::filterHor(frac_x, isLast=false) then filterVer(frac_y, isFirst=false, isLast=true) with the 8-tap
  * luma filter family of InterpolationFilter.cpp:557-600: reduce_tap = m_meReduceTap (0: 8-tap m_lumaFilter, 1: 6-tap m_lumaFilter4x4, 2: 4-tap
  * m_chromaFilter[frac<<1], the value every preset sets), alt_hpel = useAltHpelIf (half-pel phase from m_lumaAltHpelIFilter).  The MV rate and the
- * two-round selection (incl. the m_fastSubPel skip tables) replay on the host from the table. */
+ * two-round selection replay on the host from the table: m_fastSubPel = 0 and 1 (early stops, pattern id, skip table) in integration/InterSearchB200.h
+ * (xPatternSearchFracDIFB200) and vvenc_b200/candidates.py (subpel_refinement, subpel_refinement_fast); m_fastSubPel = 2 has no fractional search. */
 int vvb_frac_cost_grid    ( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* blocks, int n, int w, int h, int reduce_tap, int alt_hpel, uint32_t* cost_out );
 int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane, const vvb_block* dev_blocks, int n, int w, int h, int reduce_tap, int alt_hpel, uint32_t* dev_cost_out );
 

@@ -108,13 +108,18 @@ inline void xPatternSearchB200( InterSearch& is, InterSearch::TZSearchStruct& cS
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------------------
-// InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2677-2725) for m_fastSubPel == 0: the interpolation of xExtDIFUpSamplingH / Q and the distortion
-// calls of xPatternRefinement come back as one 7x7 table t[j+3][i+3] (quarter-pel offset (i, j) from rcMvInt); the two rounds are replayed on it.
+// InterSearch::xPatternSearchFracDIF (InterSearch.cpp:2677-2725): the interpolation of xExtDIFUpSamplingH / Q (and, for m_fastSubPel == 1, the half-pel blocks
+// xPatternRefinement filters itself, :812-848) and every distortion call of xPatternRefinement come back as ONE 7x7 table t[j+3][i+3] (quarter-pel offset (i, j)
+// from rcMvInt; vvb_frac_cost_grid: SAD, SATD or fast SATD, square and rectangular PUs); the two rounds are replayed on it.
+//   m_fastSubPel == 0 (slower): both rounds visit all nine positions, each round starts from MAX_DISTORTION.
+//   m_fastSubPel == 1 (fast ... slow): the half-pel round stops early (:808-811) and classifies the cost surface into a pattern id (:886-969); the quarter-pel round
+//     visits only what s_skipQpelPosition allows for that pattern (:93-137 -- file-static in the reference, restated here as one 9-bit mask per pattern, bit i =
+//     position i skipped) and keeps the half-pel best as its threshold (:769); pattern 0 ends the search after the half-pel round (:2710) with rcMvQter untouched.
+//   m_fastSubPel == 2 (faster): xMotionEstimation does not call the function (:2113).
 inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStruct& cStruct, const Mv& rcMvInt, Mv& rcMvHalf, Mv& rcMvQter, Distortion& ruiCost )
 {
   const VVEncCfg& cfg = *is.m_pcEncCfg;
-  if( cfg.m_fastSubPel != 0 ) THROW( "the table replay covers m_fastSubPel == 0" );
-  if( cfg.m_bUseHADME && cfg.m_fastHad ) THROW( "DF_HAD_fast is not offered by vvb_frac_cost_grid" );
+  if( cfg.m_fastSubPel != 0 && cfg.m_fastSubPel != 1 ) THROW( "m_fastSubPel == 2 never reaches the fractional search (InterSearch.cpp:2113)" );
   RdCost& rc = *is.m_pcRdCost;
   const CPelBuf& key = *cStruct.pcPatternKey;
   const int reach = std::max( std::abs( rcMvInt.hor ), std::abs( rcMvInt.ver ) ) + 5;        // integer vector + one pel of refinement + 4 pels of filter
@@ -123,30 +128,64 @@ inline void xPatternSearchFracDIFB200( InterSearch& is, InterSearch::TZSearchStr
   vvb_block blk = {};
   blk.start_x = (int16_t) rcMvInt.hor; blk.start_y = (int16_t) rcMvInt.ver;
   uint32_t t[7][7];
-  b200Check( g_b200s.fracCostGrid( b200CtxOfThread(), cfg.m_bUseHADME ? VVB_DF_HAD : VVB_DF_SAD, B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height,
+  const int dfunc = cfg.m_bUseHADME ? ( cfg.m_fastHad ? VVB_DF_HAD_FAST : VVB_DF_HAD ) : VVB_DF_SAD;     // setDistParam( ..., m_bUseHADME ? ( m_fastHad ? 2 : 1 ) : 0 ), :775
+  b200Check( g_b200s.fracCostGrid( b200CtxOfThread(), dfunc, B200_PLANE_KEY, B200_PLANE_WINDOW, &blk, 1, key.width, key.height,
                                    cfg.m_meReduceTap, cStruct.useAltHpelIf ? 1 : 0, &t[0][0] ) );
 
-  // one round of xPatternRefinement (:798-887): nine candidates in the order of s_acMvRefineH / s_acMvRefineQ, first strictly smaller cost wins
-  static const int8_t orderH[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 }, { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } };
-  static const int8_t orderQ[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, -1 }, { 1, -1 }, { -1, 0 }, { 1, 0 }, { -1, 1 }, { 1, 1 } };
+  static const int8_t orderH[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 }, { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } };     // s_acMvRefineH
+  static const int8_t orderQ[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, -1 }, { 1, -1 }, { -1, 0 }, { 1, 0 }, { -1, 1 }, { 1, 1 } };     // s_acMvRefineQ
+  static const uint16_t skipMask[42] = { 510, 479, 447, 509, 469, 429, 507, 347, 187, 123, 479, 347, 447, 187, 485, 479, 469, 447, 429, 175, 509, 429, 507, 187, 343, 509, 469,
+                                         507, 347, 447, 507, 187, 479, 507, 347, 447, 509, 429, 479, 509, 469, 0 };
+  const bool fast = cfg.m_fastSubPel == 1;
+  Distortion uiDistBest = MAX_DISTORTION;
+  int patternId = 41;
+  // one round of xPatternRefinement (:760-972)
   auto round = [&]( const int8_t ( *order )[2], int iFrac, const Mv& baseRefMv, Mv& rcMvFrac ) -> Distortion
   {
-    Distortion best = MAX_DISTORTION; int dir = 0;
-    for( int i = 0; i < 9; i++ )
+    if( !fast ) uiDistBest = MAX_DISTORTION;                                                                         // :769
+    uint32_t dir = 0;
+    Distortion distH[9] = { uiDistBest, uiDistBest, uiDistBest, uiDistBest, uiDistBest, uiDistBest, uiDistBest, uiDistBest, uiDistBest };
+    for( uint32_t i = 0; i < 9; i++ )
     {
+      if( fast )
+      {
+        if( ( skipMask[patternId] >> i ) & 1 ) continue;                                                             // :802
+        if( iFrac == 2 && ( ( i == 5 && dir == 0 ) || ( i == 7 && dir == 1 ) || ( i == 8 && ( dir == 1 || dir == 3 || dir == 5 ) ) ) ) break;   // :808-811
+      }
       const int hor = ( order[i][0] + baseRefMv.hor ) * iFrac, ver = ( order[i][1] + baseRefMv.ver ) * iFrac;      // quarter-pel offset from rcMvInt (:852-856)
       Distortion d = t[ver + 3][hor + 3];
       d += rc.getCostOfVectorWithPredictor( order[i][0] + rcMvFrac.hor, order[i][1] + rcMvFrac.ver, 0 );           // :875 (imvShift 0 inside the refinement)
-      if( d < best ) { best = d; dir = i; }
+      distH[i] = d;
+      if( d < uiDistBest ) { uiDistBest = d; dir = i; }
     }
     rcMvFrac.set( order[dir][0], order[dir][1] );
-    return best;
+    if( fast && iFrac == 2 )                                                                                          // :886-969, Distortion arithmetic wraps as there
+    {
+      const Distortion TH = 17, TL = 15; const int shift = 4;
+      auto ratio = [&]( int a, int b, int hi, int lo ) { distH[a] <<= shift; return distH[a] > TH * distH[b] ? hi : ( distH[a] < TL * distH[b] ? lo : 0 ); };
+      auto slope = [&]( int a, int c, int b ) { return distH[a] - distH[c] > distH[c] - distH[b]; };
+      switch( dir )
+      {
+      case 0: patternId += ratio( 3, 4, 2, 1 ); patternId += ratio( 1, 2, 6, 3 ); break;
+      case 1: patternId += ratio( 5, 6, 4, 2 ); patternId += slope( 2, 0, 1 ) ? 1 : 0; patternId += ( 41 == patternId ? 0 : 8 );  break;
+      case 2: patternId += ratio( 7, 8, 4, 2 ); patternId += slope( 1, 0, 2 ) ? 1 : 0; patternId += ( 41 == patternId ? 0 : 13 ); break;
+      case 3: patternId += slope( 4, 0, 3 ) ? 1 : 0; patternId += ratio( 5, 7, 4, 2 ); patternId += ( 41 == patternId ? 0 : 18 ); break;
+      case 4: patternId += slope( 3, 0, 4 ) ? 1 : 0; patternId += ratio( 6, 8, 4, 2 ); patternId += ( 41 == patternId ? 0 : 23 ); break;
+      case 5: patternId += slope( 6, 1, 5 ) ? 1 : 0; patternId += slope( 7, 3, 5 ) ? 2 : 0; patternId += ( 41 == patternId ? 0 : 28 ); break;
+      case 6: patternId += slope( 5, 1, 6 ) ? 1 : 0; patternId += slope( 8, 4, 6 ) ? 2 : 0; patternId += ( 41 == patternId ? 0 : 31 ); break;
+      case 7: patternId += slope( 8, 2, 7 ) ? 1 : 0; patternId += slope( 5, 3, 7 ) ? 2 : 0; patternId += ( 41 == patternId ? 0 : 34 ); break;
+      case 8: patternId += slope( 7, 2, 8 ) ? 1 : 0; patternId += slope( 6, 4, 8 ) ? 2 : 0; patternId += ( 41 == patternId ? 0 : 37 ); break;
+      default: break;
+      }
+    }
+    return uiDistBest;
   };
 
-  rc.setCostScale( 1 );                                                                       // :2697
+  rc.setCostScale( 1 );                                                                       // :2695
   rcMvHalf = rcMvInt; rcMvHalf <<= 1;
   ruiCost = round( orderH, 2, Mv( 0, 0 ), rcMvHalf );
-  if( cStruct.imvShift == IMV_OFF )                                                           // :2712
+  patternId -= fast ? 41 : 0;                                                                 // :2707
+  if( cStruct.imvShift == IMV_OFF && 0 != patternId )                                         // :2711
   {
     rc.setCostScale( 0 );
     Mv baseRefMv = rcMvHalf; baseRefMv <<= 1;

@@ -1368,6 +1368,15 @@ int refshim_frac_search_b200( int opt, const int16_t* orgPlane, int orgStride, c
   return 0;
 }
 
+// same with the sub-pel control of the presets exposed: fastSubPel 0 (slower) or 1 (fast ... slow); useHad 2 = DF_HAD_fast (m_fastHad)
+int refshim_frac_search_b200_ex( int opt, const int16_t* orgPlane, int orgStride, const int16_t* refPlane, int refStride, const int32_t* blk, int n,
+                                 int bitDepth, double lambda, int reduceTap, int useHad, int altHpel, int fastSubPel, int32_t* out )
+{
+  try { fracSearchProbe( opt, orgPlane, orgStride, refPlane, refStride, blk, n, bitDepth, lambda, reduceTap, useHad, altHpel, fastSubPel, out, true ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); return 1; }
+  return 0;
+}
+
 // whole-picture, threaded form of refshim_mctf_finalize_block for the CPU baseline of the apply row: block rows are split over the workers
 // (mv4: [numRefs][blocksY * blocksX][4]); planes are sample-(0,0) pointers into padded buffers
 void refshim_mctf_finalize_picture( int opt, const int16_t* orgPlane, int orgStride, const int16_t* const* refs, int refStride, int numRefs, const int32_t* mv4,

@@ -27,6 +27,7 @@ def main(mock_path):
     fr_args = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dbl, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     R.refshim_frac_search_member.argtypes = fr_args + [ctypes.c_int, ctypes.c_void_p]
     R.refshim_frac_search_b200.argtypes = fr_args + [ctypes.c_void_p]
+    R.refshim_frac_search_b200_ex.argtypes = fr_args + [ctypes.c_int, ctypes.c_void_p]
     R.refshim_mctf_estimate_level_b200.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 4 + \
         [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p]
 
@@ -100,27 +101,28 @@ def main(mock_path):
                               'hits': int(b[:, 6].sum()), 'misses': int(b[:, 7].sum()), 'moving': int((a[:, :2] != 0).any(axis=1).sum()), 'blocks': tn,
                               'err': (R.refshim_b200_error() or b'').decode() if (rc2 or rc3) else ''})
 
-    # ---- xPatternSearchFracDIFB200 against InterSearch::xPatternSearchFracDIF (m_fastSubPel 0)
+    # ---- xPatternSearchFracDIFB200 against InterSearch::xPatternSearchFracDIF (m_fastSubPel 0 and 1, SAD / SATD / fast SATD, square and rectangular PUs)
     res['frac'] = []
     rs = np.random.RandomState(23)
     for opt in (0, 1):
         R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
         case = C.frac_case(6161 + opt)
         S = case['stride']; base = case['margin'] * S + case['margin']
-        for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 32)):
+        for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 32), (32, 16), (8, 4), (4, 8), (4, 4), (64, 32)):
             nb = 6
             blk = np.zeros((nb, 8), dtype=np.int32)
             for k in range(nb):
                 blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
                           int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
-            for (rt, had, alt) in ((2, 1, 0), (0, 1, 0), (1, 1, 0), (2, 0, 0), (0, 0, 0), (2, 1, 1)):
-                if had and w != h:
-                    continue                                                   # the grid offers SATD on square blocks
-                a = np.zeros((nb, 6), dtype=np.int32); b = np.zeros((nb, 6), dtype=np.int32)
+            # (filter set, distortion: 0 SAD / 1 SATD / 2 fast SATD, alternative half-pel filter, m_fastSubPel)
+            for (rt, had, alt, fsp) in ((2, 1, 0, 0), (0, 1, 0, 0), (1, 1, 0, 0), (2, 0, 0, 0), (0, 0, 0, 0), (2, 1, 1, 0), (2, 2, 0, 0), (2, 1, 0, 1), (2, 2, 0, 1), (2, 0, 0, 1), (2, 1, 1, 1)):
+                if (w, h) == (4, 4) and rt != 2:
+                    continue                                                   # 4x4 is no inter PU size; InterpolationFilter swaps in its 4x4 filter set for the longer taps there
+                a = np.full((nb, 6), -7, dtype=np.int32); b = np.full((nb, 6), -7, dtype=np.int32)
                 args = (PO(case['org'], base), S, PO(case['ref'], base), S, P(blk), nb, 10, 57.25, rt, had, alt)
-                R.refshim_frac_search_member(opt, *args, 0, P(a))
-                rc = R.refshim_frac_search_b200(opt, *args, P(b))
-                res['frac'].append({'opt': opt, 'w': w, 'h': h, 'rt': rt, 'had': had, 'alt': alt, 'rc': rc, 'eq': bool(np.array_equal(a, b)),
+                R.refshim_frac_search_member(opt, *args, fsp, P(a))
+                rc = R.refshim_frac_search_b200_ex(opt, *args, fsp, P(b))
+                res['frac'].append({'opt': opt, 'w': w, 'h': h, 'rt': rt, 'had': had, 'alt': alt, 'fsp': fsp, 'rc': rc, 'eq': bool(np.array_equal(a, b)),
                                     'err': (R.refshim_b200_error() or b'').decode() if rc else ''})
     # ---- motionEstimationLumaB200 against MCTF::motionEstimationLuma: a coarse level without predecessor, a chained level, the doubleRes final level
     assert R.refshim_install_b200_mctf(mock_path.encode()) == 0, R.refshim_b200_error()

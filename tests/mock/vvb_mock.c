@@ -80,9 +80,8 @@ int vvb_frac_cost_grid( vvb_ctx* c, int dfunc, int orgPlane, int refPlane, const
   if( !c ) return VVB_ERR_ARG;
   mock_plane* o = plane( c, orgPlane ); mock_plane* r = plane( c, refPlane );
   if( !o || !r || !blocks || !costOut || n < 0 ) return fail( c, VVB_ERR_ARG, "bad grid arguments" );
-  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: SAD or HAD" );
-  if( w < 8 || h < 8 || w > 64 || h > 64 || ( w & 7 ) || ( h & 7 ) ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: block sizes 8..64 in multiples of 8" );
-  if( dfunc == VVB_DF_HAD && ( w != h || !is_pow2( w ) ) ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: HAD on square blocks only" );
+  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD && dfunc != VVB_DF_HAD_FAST ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: SAD, HAD or HAD_fast" );
+  if( !is_pow2( w ) || !is_pow2( h ) || w < 4 || h < 4 || w > 64 || h > 64 ) return fail( c, VVB_ERR_UNSUPPORTED, "fractional grid: PU sides 4..64, powers of two" );
   if( reduceTap < 0 || reduceTap > 2 ) return fail( c, VVB_ERR_ARG, "reduce_tap is 0, 1 or 2" );
   for( int i = 0; i < n; i++ )
   {
@@ -90,7 +89,7 @@ int vvb_frac_cost_grid( vvb_ctx* c, int dfunc, int orgPlane, int refPlane, const
     const int reach = ( abs( b->start_x ) > abs( b->start_y ) ? abs( b->start_x ) : abs( b->start_y ) ) + 5;
     if( reach > r->margin ) return fail( c, VVB_ERR_ARG, "vector + filter reach exceeds the plane margin" );
     const int32_t blk[6] = { b->x, b->y, w, h, b->start_x, b->start_y };
-    orc_frac_cost_grid( o->origin, o->stride, r->origin, r->stride, blk, 1, dfunc == VVB_DF_HAD ? 2 : 1, o->bitDepth, reduceTap, altHpel, costOut + (size_t) i * 49 );
+    orc_frac_cost_grid( o->origin, o->stride, r->origin, r->stride, blk, 1, dfunc == VVB_DF_HAD_FAST ? 3 : ( dfunc == VVB_DF_HAD ? 2 : 1 ), o->bitDepth, reduceTap, altHpel, costOut + (size_t) i * 49 );
   }
   c->calls++;
   return VVB_OK;

@@ -189,3 +189,35 @@ def test_gpu_frac_grid_centre_equals_integer_distortion(gpu):
     pat = np.zeros(1, dtype=gpu.V.MV_DT)
     cost, _ = gpu.eng.cost_pattern(gpu.V.DF_HAD, 0, 1, blk, 16, 16, pat, gpu.eng.me_par(0.0), want_best=False)
     assert np.array_equal(t[:, 3, 3], cost[:, 0])
+
+
+@pytest.mark.parametrize("bd", [10, 8])
+def test_gpu_frac_cost_grid_generic_shapes_vs_oracle(gpu, bd):
+    """the rest of xPatternRefinement's shapes (frac_grid_generic_kernel): rectangular PUs on 16x8 / 8x16 / 8x4 / 4x8 Hadamard tiles (fp64 normalisation), 4-pel sides,
+    DF_HAD_fast with its 16x16_fast tiles, SAD on all of them; every entry of the 7x7 table against the oracle (which equals the reference member, CPU suite)"""
+    from _libs import oracle, P, PO
+    O = oracle()
+    case = C.frac_case(9090 + bd, bit_depth=bd)
+    S = case['stride']; base = case['margin'] * S + case['margin']
+    gpu.eng.upload_plane(0, case['org'], case['W'], case['H'], case['margin'], bd)
+    gpu.eng.upload_plane(1, case['ref'], case['W'], case['H'], case['margin'], bd)
+    rs = np.random.RandomState(3 + bd)
+    fams = {1: gpu.V.DF_SAD, 2: gpu.V.DF_HAD, 3: gpu.V.DF_HAD_FAST}
+    shapes = [(2, 16, 8), (2, 8, 16), (2, 32, 16), (2, 16, 32), (2, 8, 4), (2, 4, 8), (2, 4, 4), (2, 64, 32), (2, 32, 64), (2, 4, 16), (2, 16, 4), (2, 64, 16), (2, 8, 64),
+              (3, 32, 32), (3, 64, 64), (3, 16, 16), (3, 8, 8), (3, 32, 16),
+              (1, 4, 8), (1, 8, 4), (1, 4, 4), (1, 64, 32), (1, 16, 64)]
+    for li, (fam, w, h) in enumerate(shapes):
+        n = 5
+        b = np.zeros((n, 6), dtype=np.int32)
+        for k in range(n):
+            b[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-9, 10)), int(rs.randint(-9, 10)))
+        b[0, :2] = 0
+        blk = np.zeros(n, dtype=gpu.V.BLOCK_DT)
+        blk['x'] = b[:, 0]; blk['y'] = b[:, 1]; blk['start_x'] = b[:, 4]; blk['start_y'] = b[:, 5]
+        rt, alt = ((2, 0), (2, 0), (0, 0), (1, 0), (2, 1))[li % 5]
+        if w * h == 16 and rt != 2:
+            rt = 2
+        got = gpu.eng.frac_cost_grid(fams[fam], 0, 1, blk, w, h, rt, alt)
+        exp = np.zeros((n, 7, 7), dtype=np.uint32)
+        O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), n, fam, bd, rt, alt, P(exp))
+        assert np.array_equal(got, exp), (bd, fam, w, h, rt, alt, np.argwhere(got != exp)[:5], got[got != exp][:4], exp[got != exp][:4])

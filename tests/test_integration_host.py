@@ -54,7 +54,7 @@ def test_pattern_search_binding_equals_the_member(result):
 
 
 def test_fractional_search_binding_equals_the_member(result):
-    assert len(result['frac']) >= 50
+    assert len(result["frac"]) >= 200 and any(r["fsp"] == 1 and r["w"] != r["h"] for r in result["frac"]) and any(r["had"] == 2 for r in result["frac"])
     for r in result['frac']:
         assert r['rc'] == 0 and r['eq'], r
 

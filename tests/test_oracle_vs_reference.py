@@ -355,3 +355,47 @@ def test_fractional_refinement_against_the_reference_member_function(opt):
                 c_q = int(tab[k][2 * hy + qy + 3][2 * hx + qx + 3]) + int(O.orc_mv_cost(lam, 2 * (2 * mx + hx) + qx, 2 * (2 * my + hy) + qy, ph, pv, 0, 0))
                 ok = ok or got_cost == c_q
             assert ok, (w, h, k, out[k], c_half)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_fast_subpel_replay_equals_the_reference_member(opt):
+    """m_fastSubPel = 1 (every preset between `fast` and `slow`): candidates.subpel_refinement_fast -- the early stops of the half-pel round, the pattern id and the
+    skip table of the quarter-pel round, the carried-over threshold -- on the oracle's 7x7 table gives the offsets and the cost of InterSearch::xPatternSearchFracDIF
+    itself, for square and rectangular PUs, SATD / fast SATD / SAD, and a lambda range that moves the decision between distortion and rate"""
+    import ctypes
+    from _libs import oracle, refshim, P, PO
+    from vvenc_b200 import candidates as cand
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    R.refshim_frac_search_member.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    O.orc_mv_cost.restype = ctypes.c_uint64
+    case = C.frac_case(7171 + opt)
+    S = case['stride']; base = case['margin'] * S + case['margin']
+    rs = np.random.RandomState(29)
+    checked = 0; quarter_rounds = 0; early = 0; dirs = set()
+    for (w, h, had) in ((8, 8, 1), (16, 16, 1), (32, 32, 2), (64, 64, 2), (16, 8, 1), (8, 16, 1), (32, 16, 2), (8, 4, 1), (4, 8, 1), (16, 16, 0), (64, 32, 1)):
+        for lam in (4.0, 57.25, 900.0):
+            n = 10
+            blk = np.zeros((n, 8), dtype=np.int32)
+            for k in range(n):
+                blk[k] = (int(rs.randint(0, case['W'] - w + 1)), int(rs.randint(0, case['H'] - h + 1)), w, h, int(rs.randint(-6, 7)), int(rs.randint(-6, 7)),
+                          int(rs.randint(-40, 41)), int(rs.randint(-40, 41)))
+            out = np.full((n, 6), -99, dtype=np.int32)
+            R.refshim_frac_search_member(opt, PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk)), n, 10, lam, 2, had, 0, 1, P(out))
+            tab = np.zeros((n, 7, 7), dtype=np.uint32)
+            O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(blk[:, :6])), n, 3 if had == 2 else (2 if had else 1), 10, 2, 0, P(tab))
+            for k in range(n):
+                ph, pv = int(blk[k, 6]), int(blk[k, 7])
+                half, quarter, cost = cand.subpel_refinement_fast(tab[k], (int(blk[k, 4]), int(blk[k, 5])), lambda x, y, cs: int(O.orc_mv_cost(lam, x, y, ph, pv, cs, 0)))
+                got_cost = (int(out[k, 4]) & 0xffffffff) | (int(out[k, 5]) << 32)
+                assert half == (int(out[k, 0]), int(out[k, 1])) and cost == got_cost, (w, h, had, lam, k, half, quarter, cost, out[k])
+                if quarter is None:
+                    assert (int(out[k, 2]), int(out[k, 3])) == (0, 0), (w, h, k, out[k])        # the probe passes a zero rcMvQter; the member leaves it alone
+                    early += 1
+                else:
+                    assert quarter == (int(out[k, 2]), int(out[k, 3])), (w, h, had, lam, k, quarter, out[k])
+                    quarter_rounds += 1
+                dirs.add(half)
+                checked += 1
+    assert checked == 330 and quarter_rounds > 100 and len(dirs) >= 5, (checked, quarter_rounds, early, dirs)

@@ -127,3 +127,80 @@ def subpel_refinement(table, mv_int, mv_cost, quarter_round=True):
         if best is None or c < best:
             best = c; quarter = (dx, dy)
     return half, quarter, best
+
+
+# ---- m_fastSubPel = 1 (presets fast ... slow: vvencCfg.cpp:2718-2944): xPatternRefinement visits a subset of the nine positions -------------------------
+# The half-pel round stops early (InterSearch.cpp:808-811) and classifies the cost surface into a pattern id (:886-969); the quarter-pel round then only
+# visits the positions that pattern allows (s_skipQpelPosition, :93-137; below as one 9-bit mask per pattern, bit i = position i is skipped) and keeps the
+# half-pel round's best cost as its starting threshold (:769).  Every visited position is still the two-pass interpolation of the 7x7 table.
+SKIP_QPEL_MASK = (510, 479, 447, 509, 469, 429, 507, 347, 187, 123, 479, 347, 447, 187, 485, 479, 469, 447, 429, 175, 509, 429, 507, 187, 343, 509, 469, 507, 347,
+                  447, 507, 187, 479, 507, 347, 447, 509, 429, 479, 509, 469, 0)
+_U64 = (1 << 64) - 1
+MAX_DISTORTION = _U64                 # std::numeric_limits<Distortion>::max(), CommonDef.h:202
+
+
+def _pattern_id_after_half_round(dist_h, best_dir, pattern_id):
+    """the switch of InterSearch.cpp:886-969 in uint64 wrap-around arithmetic (Distortion is uint64_t; positions not visited hold MAX_DISTORTION)"""
+    TH, TL, SH = 17, 15, 4
+    d = list(dist_h)
+
+    def ratio(a, b, hi, lo):          # distH[a] <<= shift; > TH * distH[b] ? hi : ( < TL * distH[b] ? lo : 0 )
+        d[a] = (d[a] << SH) & _U64
+        return hi if d[a] > ((TH * d[b]) & _U64) else (lo if d[a] < ((TL * d[b]) & _U64) else 0)
+
+    def slope(a, c, b):               # distH[a] - distH[c] > distH[c] - distH[b]
+        return ((d[a] - d[c]) & _U64) > ((d[c] - d[b]) & _U64)
+
+    p = pattern_id
+    if best_dir == 0:
+        p += ratio(3, 4, 2, 1)
+        p += ratio(1, 2, 6, 3)
+    elif best_dir == 1:
+        p += ratio(5, 6, 4, 2); p += 1 if slope(2, 0, 1) else 0; p += 0 if p == 41 else 8
+    elif best_dir == 2:
+        p += ratio(7, 8, 4, 2); p += 1 if slope(1, 0, 2) else 0; p += 0 if p == 41 else 13
+    elif best_dir == 3:
+        p += 1 if slope(4, 0, 3) else 0; p += ratio(5, 7, 4, 2); p += 0 if p == 41 else 18
+    elif best_dir == 4:
+        p += 1 if slope(3, 0, 4) else 0; p += ratio(6, 8, 4, 2); p += 0 if p == 41 else 23
+    elif best_dir == 5:
+        p += 1 if slope(6, 1, 5) else 0; p += 2 if slope(7, 3, 5) else 0; p += 0 if p == 41 else 28
+    elif best_dir == 6:
+        p += 1 if slope(5, 1, 6) else 0; p += 2 if slope(8, 4, 6) else 0; p += 0 if p == 41 else 31
+    elif best_dir == 7:
+        p += 1 if slope(8, 2, 7) else 0; p += 2 if slope(5, 3, 7) else 0; p += 0 if p == 41 else 34
+    elif best_dir == 8:
+        p += 1 if slope(7, 2, 8) else 0; p += 2 if slope(6, 4, 8) else 0; p += 0 if p == 41 else 37
+    return p
+
+
+def subpel_refinement_fast(table, mv_int, mv_cost, quarter_round=True):
+    """InterSearch::xPatternSearchFracDIF with m_fastSubPel = 1 replayed on the 7x7 table of vvb_frac_cost_grid.  Same arguments as subpel_refinement.
+    Returns (half_offset, quarter_offset or None, cost): quarter_offset is None when the quarter-pel round does not run (pattern id 0 or AMVR half-pel mode) --
+    the reference then leaves rcMvQter untouched."""
+    bx, by = mv_int[0] << 1, mv_int[1] << 1
+    best = MAX_DISTORTION; best_dir = 0
+    dist_h = [MAX_DISTORTION] * 9
+    pattern = 41
+    for i, (dx, dy) in enumerate(REFINE_HALF):
+        if (SKIP_QPEL_MASK[pattern] >> i) & 1:
+            continue
+        if (i == 5 and best_dir == 0) or (i == 7 and best_dir == 1) or (i == 8 and best_dir in (1, 3, 5)):
+            break
+        c = int(table[2 * dy + 3][2 * dx + 3]) + mv_cost(bx + dx, by + dy, 1)
+        dist_h[i] = c
+        if c < best:
+            best = c; best_dir = i
+    half = REFINE_HALF[best_dir]
+    pattern = _pattern_id_after_half_round(dist_h, best_dir, pattern) - 41
+    if not quarter_round or pattern == 0:
+        return half, None, best
+    qbx, qby = (bx + half[0]) << 1, (by + half[1]) << 1
+    best_dir = 0
+    for i, (dx, dy) in enumerate(REFINE_QUARTER):
+        if (SKIP_QPEL_MASK[pattern] >> i) & 1:
+            continue
+        c = int(table[2 * half[1] + dy + 3][2 * half[0] + dx + 3]) + mv_cost(qbx + dx, qby + dy, 0)
+        if c < best:                  # the threshold is the half-pel round's best (:769), cost scales differ on purpose
+            best = c; best_dir = i
+    return half, REFINE_QUARTER[best_dir], best

@@ -2,6 +2,7 @@
 // There is deliberately no CPU fallback anywhere in this file: without a usable CUDA device every entry point fails.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 #include <new>
@@ -240,6 +241,7 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
   cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( frac_grid_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -680,6 +682,8 @@ static int pyramidV2LaunchLevel( vvb_ctx* ctx, int orgPlane, int refPlane, const
     const double eff = (double) items / ( (double) rounds * cand ) * ( cand >= 384 || cand * 2 > items ? 1.0 : 0.9 );
     if( eff >= bestEff - 1e-9 ) { bestEff = std::max( bestEff, eff ); bd = cand; }
   }
+  static const int forced = []{ const char* e = getenv( "VVB_PYR_THREADS" ); return e ? atoi( e ) : 0; }();     // tuning aid: fixed CTA size
+  if( forced >= 64 && forced <= PYR_MAX_THREADS && ( forced & 31 ) == 0 ) bd = forced;
   sad_pyramid8_kernel<LV><<<nRoots, bd, (size_t) L.total, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], lv, rootFirst, nx, ny, mp, 1u, 8u );
   CHECK_LAUNCH( "sad_pyramid8_kernel" );
   return VVB_OK;
@@ -1195,9 +1199,8 @@ static int fracGridArgs( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, in
 {
   if( n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
   if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
-  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: SAD or HAD" );
-  if( w < 8 || h < 8 || w > 64 || h > 64 || ( w & 7 ) || ( h & 7 ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: block sizes 8..64 in multiples of 8" );
-  if( dfunc == VVB_DF_HAD && ( w != h || !isPow2( w ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: HAD on square blocks only (8x8 Hadamard tiles, RdCost.cpp:1818-1938)" );
+  if( dfunc != VVB_DF_SAD && dfunc != VVB_DF_HAD && dfunc != VVB_DF_HAD_FAST ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: SAD, HAD or HAD_fast" );
+  if( !isPow2( w ) || !isPow2( h ) || w < 4 || h < 4 || w > 64 || h > 64 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: PU sides 4..64, powers of two" );
   if( ctx->planes.p[refPlane].bitDepth > 12 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth above 12" );
   return VVB_OK;
 }
@@ -1210,12 +1213,24 @@ int vvb_frac_cost_grid_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane,
   if( reduceTap < 0 || reduceTap > 2 ) return fail( ctx, VVB_ERR_ARG, "reduce_tap is 0, 1 or 2 (ReduceFilterME, vvencCfg.cpp:2058)" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  const FracSmem L = frac_smem( w, h );
   const FracFilter flt = frac_filter( reduceTap, altHpel );
+  // square blocks of 8 and more whose SATD lands on 8x8 tiles (and their SAD) take the register-tile kernel; every other shape of xPatternRefinement -- rectangular
+  // PUs, 4-pel sides, DF_HAD_fast on multiples of 32 -- the generic one
+  const bool fast16 = dfunc == VVB_DF_HAD_FAST && w == h && ( w & 31 ) == 0;
+  if( w != h || w < 8 || fast16 )
+  {
+    const FracGenSmem G = frac_gen_smem( w, h );
+    if( (size_t) G.total * 4 > 100 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "fractional grid: block too large for shared memory" );
+    frac_grid_generic_kernel<<<std::min( n, ctx->numSMs * 16 ), 128, (size_t) G.total * 4, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h,
+                                                                                                       dfunc == VVB_DF_SAD ? 1 : ( fast16 ? 3 : 2 ), flt, dCost );
+    CHECK_LAUNCH( "frac_grid_generic_kernel" );
+    return VVB_OK;
+  }
+  const FracSmem L = frac_smem( w, h );
   const int jobs = L.G * 7 * ( w / 8 ) * ( h / 8 );                                   // (horizontal offsets per pass) x vertical offsets x tiles
   const int threads = std::max( 32, std::min( 128, ( jobs + 31 ) & ~31 ) );
   frac_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, (size_t) L.total * 4, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, w, h,
-                                                                                                  dfunc == VVB_DF_HAD ? 2 : 1, flt, dCost );
+                                                                                                  dfunc == VVB_DF_SAD ? 1 : 2, flt, dCost );
   CHECK_LAUNCH( "frac_grid_kernel" );
   return VVB_OK;
 }

@@ -32,7 +32,7 @@ struct PyrLevels { const vvb_block* blocks[4]; vvb_best* best[4]; };
 struct PyrSmem
 {
   int nStrips, nxp, nyp, bStride, ws, winH, winWords, vRows, vPitch, nT, tStride;
-  int offWin1, offV, offOrg, offBits, offPred, offSumA, offKey32, offKey64, offMv8, offMvRaw, offT, total;   // bytes
+  int offWin0, offWin1, offV, offOrg, offBits, offPred, offSumA, offKey32, offKey64, offMv8, offMvRaw, offT, total;   // bytes
 };
 
 template<int LV>
@@ -55,17 +55,19 @@ __host__ __device__ inline PyrSmem pyr_smem( int nx, int ny )
   s.vPitch  = R - 8 + s.nxp;
   s.nT      = LV == 4 ? 4 : ( LV == 3 ? 1 : 0 );
   s.tStride = ny * s.nxp;
-  int o = s.winWords * 4;
+  // fixed-size tables first: their shared-memory addresses are then link-time constants (the rate look-up becomes LDS [reg + imm])
+  int o = 0;
+  s.offMv8  = o;   o += 8 * PYR_MVN * 4;
+  s.offMvRaw = o;  o += VVB_MVCOST_ENTRIES * 4;
+  s.offKey64 = o;  o += 8 * 8;
+  s.offKey32 = o;  o += ( ( NB0 + NB0 / 4 ) * 4 + 15 ) & ~15;
+  s.offSumA = o;   o += ( NB0 * 4 + 15 ) & ~15;
+  s.offPred = o;   o += ( NBLK * 8 + 15 ) & ~15;
+  s.offWin0 = o;   o += s.winWords * 4;
   s.offWin1 = o;   o += s.winWords * 4;
   s.offV    = o;   o += ( ( s.vRows * s.vPitch * 2 ) + 15 ) & ~15;
   s.offOrg  = o;   o += R * R * 2;
   s.offBits = o;   o += NBLK * s.bStride;
-  s.offPred = o;   o += NBLK * 8;
-  s.offSumA = o;   o += NB0 * 4;
-  s.offKey32 = o;  o += ( ( NB0 + NB0 / 4 ) * 4 + 7 ) & ~7;
-  s.offKey64 = o;  o += 8 * 8;
-  s.offMv8  = o;   o += 8 * PYR_MVN * 4;
-  s.offMvRaw = o;  o += VVB_MVCOST_ENTRIES * 4;
   s.offT    = ( o + 15 ) & ~15;
   const int tBytes = s.nT * s.tStride * 4, hsBytes = s.winH * s.vPitch * 2;      // the row-sum scratch of the prologue lives where the tables go later
   s.total   = s.offT + ( tBytes > hsBytes ? tBytes : hsBytes ) + 16;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
   constexpr int OFF1 = NB0, OFF2 = NB0 + NQ, OFF3 = NB0 + NQ + NQ / 4;
   extern __shared__ __align__( 128 ) unsigned char smemRaw[];
   const PyrSmem L = pyr_smem<LV>( nx, ny );
-  uint32_t* win0w = reinterpret_cast<uint32_t*>( smemRaw );
+  uint32_t* win0w = reinterpret_cast<uint32_t*>( smemRaw + L.offWin0 );
   uint32_t* win1w = reinterpret_cast<uint32_t*>( smemRaw + L.offWin1 );
   uint16_t* V     = reinterpret_cast<uint16_t*>( smemRaw + L.offV );
   int16_t*  orgS  = reinterpret_cast<int16_t*>( smemRaw + L.offOrg );
@@ -283,8 +285,12 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
 
   // ---- candidates: item = (quad of four 8x8 members, pair of candidate rows, strip of 8 vectors)
   {
-    const int nPairs = ( ny + 1 ) >> 1, perQ = nPairs * nStrips, items = NQ * perQ;
-    const float invPerQ = 1.0f / (float) perQ, invStr = 1.0f / (float) nStrips;
+    // Lane mapping.  A quarter warp's LDS.128 is one wavefront when its 8 lanes read 8 consecutive 16-byte chunks: main items are groups of 8 adjacent strips
+    // of one row pair (it = ((q * nPairs + pr) * nMain + st), st fastest); the strips left over when the range is not a multiple of 64 vectors follow as
+    // tail items with the row pair as the fast index.
+    const int nPairs = ( ny + 1 ) >> 1, nMain = nStrips & ~7, nTail = nStrips - nMain;
+    const int perQm = nPairs * nMain, itemsMain = NQ * perQm, perQt = nPairs * nTail, items = itemsMain + NQ * perQt;
+    const float invPerQm = 1.0f / (float) max( 1, perQm ), invMain = 1.0f / (float) max( 1, nMain ), invPerQt = 1.0f / (float) max( 1, perQt ), invPairs = 1.0f / (float) nPairs;
     const uint32_t* org32 = reinterpret_cast<const uint32_t*>( orgS );
     for( int base = 0; base < items; base += nthr )
     {
@@ -292,8 +298,9 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
       const bool active = it < items;
       const unsigned mask = __ballot_sync( 0xffffffffu, active );
       if( !active ) continue;
-      const int q = fast_div( it, invPerQ ), rem = it - q * perQ;
-      const int pr = fast_div( rem, invStr ), st = rem - pr * nStrips;
+      int q, pr, st;
+      if( it < itemsMain ) { q = fast_div( it, invPerQm ); const int rem = it - q * perQm; pr = fast_div( rem, invMain ); st = rem - pr * nMain; }
+      else { const int i2 = it - itemsMain; q = fast_div( i2, invPerQt ); const int rem = i2 - q * perQt; const int ts = fast_div( rem, invPairs ); pr = rem - ts * nPairs; st = nMain + ts; }
       const int cy = 2 * pr, cx0 = 8 * st;
       const bool validB = cy + 1 < ny;
       const int lead = __ffs( mask ) - 1;
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
       {
         const unsigned char* bb = bitsS + ( OFF1 + q ) * L.bStride;
         const uint2 bw = *reinterpret_cast<const uint2*>( bb + cx0 );
-        uint32_t* trow = LV >= 3 ? T + ( LV == 4 ? ( q >> 2 ) : 0 ) * L.tStride + cy * nxp + cx0 : nullptr;
+        uint32_t* trow = LV >= 3 ? T + ( LV == 4 ? ( q >> 2 ) : 0 ) * L.tStride + cy * nxp + st : nullptr;      // table layout [cy][slot k][strip]: a warp's atomics spread over the banks
         uint32_t key = 0xffffffffu;
 #pragma unroll
         for( int rowB = 0; rowB < 2; rowB++ )
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
             const uint32_t idx4 = __dp4a( k < 4 ? bw.x : bw.y, 4u << ( 8 * ( k & 3 ) ), by4 );
             const uint32_t mvk  = *reinterpret_cast<const uint32_t*>( sMv8 + k * ( PYR_MVN * 4 ) + idx4 );
             bk = min( bk, ps * eight + mvk );
-            if( LV >= 3 ) atomicAdd( trow + rowB * nxp + k, ps );
+            if( LV >= 3 ) atomicAdd( trow + rowB * nxp + k * nStrips, ps );
           }
           key = min( key, ( ( bk >> 3 ) << ob ) + (uint32_t)( ( cy + rowB ) * nx + cx0 ) + ( bk & 7u ) );
         }
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
       for( int o = tid; o < nx * ny; o += nthr )
       {
         const int cy = fast_div( o, invNx ), cx = o - cy * nx;
-        const int ti = cy * nxp + cx;
+        const int ti = cy * nxp + ( cx & 7 ) * nStrips + ( cx >> 3 );
         uint32_t s;
         if( isRoot64 ) s = T[ti] + T[L.tStride + ti] + T[2 * L.tStride + ti] + T[3 * L.tStride + ti];
         else           s = T[j * L.tStride + ti];
