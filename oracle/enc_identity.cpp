@@ -1,0 +1,158 @@
+/*
+ * oracle/enc_identity.cpp -- TEST INFRASTRUCTURE, not product code.
+ *
+ * The reference's own pass criterion for a SIMD back end is whole-encoder bitstream identity (`--SIMD=SCALAR` vs default must give identical .vvc files,
+ * cmake/modules/vvencTests.cmake:52-53).  This program applies the same criterion to the B200 back end: it drives the UNMODIFIED reference encoder
+ * (oracle/_ref/libvvenc_ref.a, compiled in place from /root/reference by oracle/Makefile.ref) through its public C API (vvenc_encoder_create / open / encode)
+ * twice-compatible: once as built (AVX2 tables), once with `installB200()` of integration/RdCostB200.h and integration/AffineGradientB200.h applied to every
+ * RdCost / AffineGradientSearch instance the encoder creates, so that every xGetSAD / xGetSSE / xGetHADs / HAD_2SAD / mask-SAD / SADx5 / weighted-SSE call and
+ * the affine gradient helpers run on the GPU through libvvenc_b200.so (one call per block: the verification shape, not the production shape).
+ *
+ * How the tables get installed without touching the reference sources: the library calls RdCost::initRdCostX86() at the end of RdCost::create()
+ * (CommonLib/RdCost.cpp:137) and AffineGradientSearch::initAffineGradientSearchX86() in its constructor (AffineGradientSearch.cpp:75); both live in another
+ * object file (x86/InitX86.cpp), so the linker's --wrap redirects those two calls to the functions below, which run the original selection and then -- when
+ * asked to -- the 10-line `_initRdCostB200()` a maintainer would add.
+ *
+ * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables]
+ * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1>`
+ */
+#include <cstdint>
+#include <cstring>
+#include <cstdlib>
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include <array>
+#include <deque>
+#include <list>
+#include <map>
+#include <set>
+#include <string>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <atomic>
+#include <algorithm>
+#include <functional>
+#include <condition_variable>
+#include <chrono>
+#include <bitset>
+#include <limits>
+#include <numeric>
+#include <unordered_map>
+#include <future>
+#include <cassert>
+#include <cstdarg>
+#include <immintrin.h>
+
+#define private public
+#define protected public
+#include "vvenc/vvenc.h"
+#include "vvenc/vvencCfg.h"
+#include "CommonLib/CommonDef.h"
+#include "CommonLib/Unit.h"
+#include "CommonLib/RdCost.h"
+#include "CommonLib/AffineGradientSearch.h"
+#undef private
+#undef protected
+
+using namespace vvenc;
+#include "../integration/RdCostB200.h"
+#include "../integration/AffineGradientB200.h"
+
+static bool               g_useB200 = false;
+static std::atomic<long>  g_rdCostInstalls{ 0 }, g_affineInstalls{ 0 };
+
+extern "C" void __real__ZN5vvenc6RdCost13initRdCostX86Ev( RdCost* );
+extern "C" void __wrap__ZN5vvenc6RdCost13initRdCostX86Ev( RdCost* self )
+{
+  __real__ZN5vvenc6RdCost13initRdCostX86Ev( self );           // the x86 selection, as the library does it
+  if( g_useB200 ) { installB200( *self ); g_rdCostInstalls++; }
+}
+extern "C" void __real__ZN5vvenc20AffineGradientSearch27initAffineGradientSearchX86Ev( AffineGradientSearch* );
+extern "C" void __wrap__ZN5vvenc20AffineGradientSearch27initAffineGradientSearchX86Ev( AffineGradientSearch* self )
+{
+  __real__ZN5vvenc20AffineGradientSearch27initAffineGradientSearchX86Ev( self );
+  if( g_useB200 ) { installB200( *self ); g_affineInstalls++; }
+}
+
+// call counters: thunks between the binding's function pointers and the library (the binding itself stays as a maintainer would ship it)
+static std::atomic<unsigned long long> g_distCalls{ 0 }, g_otherCalls{ 0 };
+static decltype( &vvb_dist_block ) g_realDist = nullptr;
+static uint64_t countingDist( vvb_ctx* c, int f, const int16_t* o, int so, const int16_t* u, int su, int w, int h, int bd, int ss, int* e ) { g_distCalls++; return g_realDist( c, f, o, so, u, su, w, h, bd, ss, e ); }
+static decltype( &vvb_sad_x5_block ) g_realX5 = nullptr;
+static int countingX5( vvb_ctx* c, const int16_t* o, int so, const int16_t* u, int su, int w, int h, int ss, int cc, uint64_t* out ) { g_otherCalls++; return g_realX5( c, o, so, u, su, w, h, ss, cc, out ); }
+
+static void quietLog( void*, int, const char*, va_list ) {}
+
+int main( int argc, char** argv )
+{
+  if( argc < 8 ) { fprintf( stderr, "usage: %s in.yuv w h frames preset qp out.vvc [libvvenc_b200.so]\n", argv[0] ); return 2; }
+  const char* inPath = argv[1];
+  const int w = atoi( argv[2] ), h = atoi( argv[3] ), frames = atoi( argv[4] ), preset = atoi( argv[5] ), qp = atoi( argv[6] );
+  const char* outPath = argv[7];
+  if( argc > 8 )
+  {
+    if( b200Load( argv[8] ) || b200LoadAffine( argv[8] ) ) { fprintf( stderr, "cannot bind %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
+    g_useB200 = true;
+    g_realDist = g_b200.distBlock; g_b200.distBlock = countingDist;
+    g_realX5 = g_b200.sadX5; g_b200.sadX5 = countingX5;
+  }
+  vvenc_config cfg;
+  vvenc_init_default( &cfg, w, h, 30, 0, qp, (vvencPresetMode) preset );
+  cfg.m_numThreads = 1;                       // one worker: one vvb_ctx; the result of the reference does not depend on the thread count
+  cfg.m_inputBitDepth[0] = 8; cfg.m_internalBitDepth[0] = 10;
+  cfg.m_verbosity = VVENC_SILENT;
+  vvenc_set_msg_callback( &cfg, nullptr, quietLog );
+  vvencEncoder* enc = vvenc_encoder_create();
+  if( !enc ) return 4;
+  int rc = vvenc_encoder_open( enc, &cfg );
+  if( rc ) { fprintf( stderr, "vvenc_encoder_open: %d %s\n", rc, vvenc_get_last_error( enc ) ); return 5; }
+
+  FILE* fi = fopen( inPath, "rb" );
+  if( !fi ) { fprintf( stderr, "cannot read %s\n", inPath ); return 6; }
+  std::vector<uint8_t> out;
+  vvencYUVBuffer* yuv = vvenc_YUVBuffer_alloc();
+  vvenc_YUVBuffer_alloc_buffer( yuv, VVENC_CHROMA_420, w, h );
+  vvencAccessUnit* au = vvenc_accessUnit_alloc();
+  vvenc_accessUnit_alloc_payload( au, 2 * w * h + 65536 );
+  std::vector<uint8_t> raw( (size_t) w * h * 3 / 2 );
+  bool done = false;
+  int fed = 0;
+  try
+  {
+    while( !done )
+    {
+      vvencYUVBuffer* in = nullptr;
+      if( fed < frames )
+      {
+        if( fread( raw.data(), 1, raw.size(), fi ) != raw.size() ) { fprintf( stderr, "short read at frame %d\n", fed ); return 7; }
+        const uint8_t* p = raw.data();
+        for( int c = 0; c < 3; c++ )
+        {
+          vvencYUVPlane& pl = yuv->planes[c];
+          for( int y = 0; y < pl.height; y++ )
+            for( int x = 0; x < pl.width; x++ ) pl.ptr[y * pl.stride + x] = *p++;
+        }
+        yuv->sequenceNumber = fed; yuv->cts = fed; yuv->ctsValid = true;
+        in = yuv; fed++;
+      }
+      rc = vvenc_encode( enc, in, au, &done );
+      if( rc ) { fprintf( stderr, "vvenc_encode: %d %s\n", rc, vvenc_get_last_error( enc ) ); return 8; }
+      if( au->payloadUsedSize > 0 ) out.insert( out.end(), au->payload, au->payload + au->payloadUsedSize );
+    }
+  }
+  catch( std::exception& e ) { fprintf( stderr, "exception: %s\n", e.what() ); return 9; }
+  fclose( fi );
+  vvenc_encoder_close( enc );
+  FILE* fo = fopen( outPath, "wb" );
+  if( fo ) { fwrite( out.data(), 1, out.size(), fo ); fclose( fo ); }
+  uint64_t hsh = 1469598103934665603ull;
+  for( uint8_t b : out ) { hsh ^= b; hsh *= 1099511628211ull; }
+  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld\n", fed, out.size(), (unsigned long long) hsh,
+          g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load() );
+  return 0;
+}

@@ -1,0 +1,54 @@
+"""Whole-encoder bitstream identity, the reference's own criterion for a back end (cmake/modules/vvencTests.cmake:52-53: --SIMD=SCALAR vs default must give the
+same .vvc).  oracle/_ref/enc_identity drives the UNMODIFIED reference encoder through its public API; with a library path it installs integration/RdCostB200.h's
+and AffineGradientB200.h's tables in every RdCost / AffineGradientSearch the encoder creates (linker --wrap of the two x86 init calls, no source change).
+
+  CPU (here)  : the tables call the oracle-backed mock of the C ABI -> pins the binding + the oracle's arithmetic against the AVX2 encoder, bitstream for bitstream
+  GPU (-m gpu): the tables call libvvenc_b200.so, one launch per xGetSAD / xGetSSE / xGetHADs call -> the CUDA kernels under the real encoder control flow"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')
+MOCK = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
+pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason='oracle/_ref/enc_identity not built (needs /root/reference at build time)')
+
+
+def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600):
+    out = str(tmp_path / ('b200.vvc' if lib else 'avx2.vvc'))
+    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
+    line = [l for l in r.stdout.splitlines() if l.startswith('ENC ')][-1]
+    kv = dict(f.split('=') for f in line.split()[1:])
+    return open(out, 'rb').read(), kv
+
+
+def _identity(tmp_path, W, H, F, preset, qp, lib, timeout=600):
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout)
+    assert int(kb['rdcost_installs']) >= 1 and int(kb['dist_calls']) > 1000 and int(ka['dist_calls']) == 0
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (80, 44, 4, 2, 37), (176, 144, 3, 1, 32)])
+def test_bitstream_identity_with_b200_tables_on_the_oracle(tmp_path, W, H, F, preset, qp):
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity(tmp_path, W, H, F, preset, qp, MOCK)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (80, 44, 3, 2, 37), (416, 240, 8, 0, 37)])
+def test_bitstream_identity_with_b200_tables_on_the_gpu(tmp_path, W, H, F, preset, qp):
+    """(416, 240, 8 frames, faster, QP 37) is BASELINE configs[0]"""
+    import vvenc_b200._lib as VL
+    kb = _identity(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
+    print('encoder identity on the GPU:', W, H, F, preset, kb)
