@@ -174,7 +174,9 @@ int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dev_blocks, const vvb_bes
 
 /* ---- forward transform + quantise (TrQuant::transformNxN for LFNST-off, non-skip luma TUs; ---------------
  * CommonLib/TrQuant.cpp:688-736 -> xT :481-564 -> Quant::quant CommonLib/Quant.cpp:735-833 -> QuantCore :132-230,
- * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types. */
+ * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types.
+ * deltaU (Quant.cpp:221), whose only consumer is the sign-bit hiding of the same call, stays on the device: with sign_hiding set the returned levels are the
+ * ones Quant::quant leaves after xSignBitHidingHDQ (abs_sum stays QuantCore's sum, as uiAbsSum does; last_pos follows the hiding step). */
 typedef struct
 {
   int32_t w, h;                /* TU size, each in {4,8,16,32,64}                               */
@@ -183,6 +185,8 @@ typedef struct
   int32_t qp;                  /* CU QP (cu.qp); +6*(bit_depth-8) applied inside (Quant.cpp:99)   */
   int32_t is_irap;             /* slice->isIRAP(): rounding offset 171 vs 85 (Quant.cpp:772)      */
   int32_t dep_quant;           /* for need_rdoq only: slice->depQuantEnabled (Quant.cpp:852-855)  */
+  int32_t sign_hiding;         /* slice->signDataHidingEnabled: the levels pass through Quant::xSignBitHidingHDQ (Quant.cpp:817-826, 377-518) */
+  int32_t reserved[3];         /* zero */
 } vvb_tu_par;
 
 /* resi: n compact residual blocks [n][h][w] (Pel); outputs (each nullable except q):

@@ -4,7 +4,7 @@
 //   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
 //
 // for the TUs the library covers: luma, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), LFNST index 0, no transform
-// skip, no scaling lists, plain quantiser (RDOQ / dependent quantisation stay on the host and use the coefficients this call leaves in the temp buffer).
+// skip, no scaling lists, plain quantiser incl. its sign-bit hiding (RDOQ / dependent quantisation stay on the host and use the coefficients this call leaves in the temp buffer).
 // vvb_tu_par is derived from the TransformUnit exactly as the members derive their parameters (xSetTrTypes, QpParam, slice type), so the call sites keep
 // their arguments.  One TU per call here; the production shape batches the TU candidates of a CU (vvb_fwd_trquant with n > 1 or
 // vvb_tu_roundtrip).  Include after RdCostB200.h and CommonLib/TrQuant.h; TrQuant::xSetTrTypes is private: inside the encoder these are member functions.
@@ -50,6 +50,7 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
   if( sps.qpBDOffset[CH_L] != 6 * ( par.bit_depth - 8 ) ) THROW( "unexpected qpBDOffset" );
   par.is_irap = tu.cs->slice->isIRAP() ? 1 : 0;                                              // rounding offset 171 vs 85 (Quant.cpp:772)
   par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;
+  par.sign_hiding = tu.cs->slice->signDataHidingEnabled ? 1 : 0;                            // Quant::quant: CoeffCodingContext( ..., signDataHidingEnabled ), xSignBitHidingHDQ (Quant.cpp:748, 817-826)
   return par;
 }
 

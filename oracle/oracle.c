@@ -335,12 +335,13 @@ int orc_scan_order( int w, int h, int32_t* idx )
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct { int scale, qbits; int64_t add; } QuantPar;
 
-static QuantPar quant_par( int w, int h, int bitDepth, int qp, int addNum )
+static QuantPar quant_par_ex( int w, int h, int bitDepth, int qp, int addNum, int plusOne )
 {
   QuantPar p;
   int baseQp = qp + 6 * ( bitDepth - 8 );
   if( baseQp < 0 ) baseQp = 0;
   if( baseQp > 63 + 6 * ( bitDepth - 8 ) ) baseQp = 63 + 6 * ( bitDepth - 8 );
+  baseQp += plusOne;                                                                    /* Quant.cpp:853: cQP.Qp( false ) + 1, after QpParam's clip (:113) */
   const int per = baseQp / 6, rem = baseQp % 6;
   const int sqrt2 = ( ilog2u( w ) + ilog2u( h ) ) & 1;                                  /* UnitTools.cpp:3616 */
   const int trShift = 15 - bitDepth - ( ( ilog2u( w ) + ilog2u( h ) ) >> 1 ) - sqrt2;   /* Quant.h:69-72 */
@@ -349,8 +350,75 @@ static QuantPar quant_par( int w, int h, int bitDepth, int qp, int addNum )
   p.add   = (int64_t) addNum << ( p.qbits - 9 );
   return p;
 }
+static QuantPar quant_par( int w, int h, int bitDepth, int qp, int addNum ) { return quant_par_ex( w, h, bitDepth, qp, addNum, 0 ); }
 
+/* Sign-bit hiding of the plain quantiser: Quant::xSignBitHidingHDQ (CommonLib/Quant.cpp:377-518), run by Quant::quant when the slice enables sign data
+ * hiding and absSum >= 2 (:817-826).  Per coefficient group (from the one holding the last level down to the first): if the distance between the first and the
+ * last non-zero level is at least SBH_THRESHOLD = 4 (CommonDef.h:272) and the parity of the level sum differs from the sign of the first non-zero level, the level
+ * whose change costs least -- judged by deltaU, the quantisation remainder QuantCore leaves (:221) -- is moved by one.  deltaU is recomputed here from the
+ * coefficient (same formula); only positions QuantCore quantised are visited. */
+static int32_t sbh_delta_u( int32_t c, const QuantPar* p )
+{
+  const int64_t t = (int64_t) iabs( c ) * p->scale;
+  const int32_t mag = (int32_t)( ( t + p->add ) >> p->qbits );
+  return (int32_t)( ( t - ( (int64_t) mag << p->qbits ) ) >> ( p->qbits - 8 ) );
+}
+static void sign_bit_hiding( int16_t* q, const int32_t* coef, const int32_t* scan, const QuantPar* p, int* lastScanPos )
+{
+  const int32_t cmax = 32767, cmin = -32768;                       /* entropyCoding limits for maxLog2TrDynamicRange = 15 */
+  int lastCG = -1;
+  for( int subSet = *lastScanPos >> 4; subSet >= 0; subSet-- )
+  {
+    const int subPos = subSet << 4;
+    int firstNZ = 16, lastNZ = -1, absSum = 0, n;
+    for( n = 15; n >= 0; n-- ) if( q[scan[n + subPos]] ) { lastNZ = n; break; }
+    for( n = 0; n < 16; n++ )  if( q[scan[n + subPos]] ) { firstNZ = n; break; }
+    for( n = firstNZ; n <= lastNZ; n++ ) absSum += q[scan[n + subPos]];
+    if( lastNZ >= 0 && lastCG == -1 ) lastCG = 1;
+    if( lastNZ - firstNZ >= 4 )
+    {
+      const uint32_t signbit = q[scan[subPos + firstNZ]] > 0 ? 0 : 1;
+      if( signbit != ( (uint32_t) absSum & 1u ) )
+      {
+        int32_t curCost = INT32_MAX, minCostInc = INT32_MAX;
+        int minPos = -1, finalChange = 0, curChange = 0, minScanPos = -1;
+        for( n = ( lastCG == 1 ? lastNZ : 15 ); n >= 0; --n )
+        {
+          const int blkPos = scan[n + subPos];
+          const int32_t dU = sbh_delta_u( coef[blkPos], p );
+          if( q[blkPos] != 0 )
+          {
+            if( dU > 0 ) { curCost = -dU; curChange = 1; }
+            else if( n == firstNZ && iabs( q[blkPos] ) == 1 ) curCost = INT32_MAX;
+            else { curCost = dU; curChange = -1; }
+          }
+          else if( n < firstNZ )
+          {
+            const uint32_t thisSign = coef[blkPos] >= 0 ? 0 : 1;
+            if( thisSign != signbit ) curCost = INT32_MAX;
+            else { curCost = -dU; curChange = 1; }
+          }
+          else { curCost = -dU; curChange = 1; }
+          if( curCost < minCostInc ) { minCostInc = curCost; finalChange = curChange; minPos = blkPos; minScanPos = n + subPos; }
+        }
+        if( q[minPos] == cmax || q[minPos] == cmin ) finalChange = -1;
+        if( coef[minPos] >= 0 ) q[minPos] = (int16_t)( q[minPos] + finalChange ); else q[minPos] = (int16_t)( q[minPos] - finalChange );
+        if( minScanPos == *lastScanPos && q[minPos] == 0 )
+          for( ; *lastScanPos >= 0 && q[scan[*lastScanPos]] == 0; ( *lastScanPos )-- );
+        else if( minScanPos > *lastScanPos && q[minPos] != 0 ) *lastScanPos = minPos;     /* sic: block position, as the reference writes it (:508) */
+      }
+    }
+    if( lastCG == 1 ) lastCG = 0;
+  }
+}
+
+int orc_quant_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int orc_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  return orc_quant_ex( coef, w, h, bitDepth, qp, isIRAP, 0, q, absSum, lastPos );
+}
+
+int orc_quant_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int16_t* q, int32_t* absSum, int32_t* lastPos )
 {
   const QuantPar p = quant_par( w, h, bitDepth, qp, isIRAP ? 171 : 85 );               /* Quant.cpp:772 */
   int32_t scan[1024];
@@ -386,6 +454,7 @@ int orc_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIR
   int last = pos;
   if( sum )                                                                            /* Quant.cpp:806-816 */
     for( int sp = pos; sp >= 0; sp-- ) if( q[scan[sp]] ) { last = sp; break; }
+  if( sum >= 2 && signHiding ) sign_bit_hiding( q, coef, scan, &p, &last );            /* Quant.cpp:817-826 */
   *absSum = sum; *lastPos = last;
   return 0;
 }
@@ -393,7 +462,7 @@ int orc_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIR
 /* needRdoqCore (CommonLib/Quant.cpp:264-278) through Quant::xNeedRDOQ (:835-891), luma */
 int orc_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant )
 {
-  const QuantPar p = quant_par( w, h, bitDepth, depQuant ? qp + 1 : qp, 171 );
+  const QuantPar p = quant_par_ex( w, h, bitDepth, qp, 171, depQuant ? 1 : 0 );
   const int n = w * ( h < 32 ? h : 32 );
   for( int i = 0; i < n; i++ )
   {
@@ -408,6 +477,13 @@ int orc_transform_quant( int trHor, int trVer, const Pel* resi, int stride, int 
 {
   if( orc_fwd_transform( trHor, trVer, resi, stride, w, h, bitDepth, coef ) ) return -1;
   return orc_quant( coef, w, h, bitDepth, qp, isIRAP, q, absSum, lastPos );
+}
+/* same with slice->signDataHidingEnabled (Quant.cpp:748) */
+int orc_transform_quant_ex( int trHor, int trVer, const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding,
+                            int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( orc_fwd_transform( trHor, trVer, resi, stride, w, h, bitDepth, coef ) ) return -1;
+  return orc_quant_ex( coef, w, h, bitDepth, qp, isIRAP, signHiding, q, absSum, lastPos );
 }
 
 /* ------------------------------------------------------------------------------------------------------
@@ -492,8 +568,15 @@ void orc_reconstruct( const Pel* pred, int ps, const Pel* resi, int rs, Pel* rec
 /* One TU candidate end to end, as xIntraCodingTUBlock does for luma (IntraSearch.cpp:1353-1429): residual = org - pred, transformNxN, then
  * (absSum > 0 ? invTransformNxN : zero residual), reconstruct, SSE(org, reco).  Also returns the residual-domain distortions of the inter loop
  * (InterSearch.cpp:3670 zero-residual SSE, :3714 SSE(orgResi, recResi)).  out4 = { dist_reco, dist_resi, dist_zero, absSum | lastPos<<32 } */
+int orc_tu_roundtrip_ex( int trHor, int trVer, const Pel* org, int so, const Pel* pred, int ps, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding,
+                         int16_t* q, Pel* reco, int cs, uint64_t* out4 );
 int orc_tu_roundtrip( int trHor, int trVer, const Pel* org, int so, const Pel* pred, int ps, int w, int h, int bitDepth, int qp, int isIRAP,
                       int16_t* q, Pel* reco, int cs, uint64_t* out4 )
+{
+  return orc_tu_roundtrip_ex( trHor, trVer, org, so, pred, ps, w, h, bitDepth, qp, isIRAP, 0, q, reco, cs, out4 );
+}
+int orc_tu_roundtrip_ex( int trHor, int trVer, const Pel* org, int so, const Pel* pred, int ps, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding,
+                         int16_t* q, Pel* reco, int cs, uint64_t* out4 )
 {
   Pel* resi = (Pel*) malloc( sizeof( Pel ) * w * h );
   Pel* rec  = (Pel*) malloc( sizeof( Pel ) * w * h );
@@ -501,7 +584,7 @@ int orc_tu_roundtrip( int trHor, int trVer, const Pel* org, int so, const Pel* p
   int32_t* coef = (int32_t*) malloc( sizeof( int32_t ) * w * h );
   for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) resi[y * w + x] = (Pel)( org[y * so + x] - pred[y * ps + x] );
   int32_t absSum = 0, lastPos = 0;
-  int rc = orc_transform_quant( trHor, trVer, resi, w, w, h, bitDepth, qp, isIRAP, coef, q, &absSum, &lastPos );
+  int rc = orc_transform_quant_ex( trHor, trVer, resi, w, w, h, bitDepth, qp, isIRAP, signHiding, coef, q, &absSum, &lastPos );
   if( !rc )
   {
     if( absSum > 0 ) rc = orc_inv_transform_quant( trHor, trVer, q, w, h, bitDepth, qp, coef, rec, w );

@@ -233,6 +233,7 @@ void parallelFor( int n, int nthreads, F&& f )
   for( auto& t : th ) t.join();
 }
 
+static thread_local bool t_rigSignHiding = false;     // slice->signDataHidingEnabled of the next TuRig::setup (refshim_*_sdh entries)
 // A minimal TU that satisfies everything TrQuant::xT / Quant::quant / Quant::xNeedRDOQ dereference.
 struct TuRig
 {
@@ -262,7 +263,7 @@ struct TuRig
     slice.sps = &sps; slice.pps = &pps;
     slice.sliceType = intraSlice ? VVENC_I_SLICE : VVENC_B_SLICE;
     slice.nalUnitType = intraSlice ? VVENC_NAL_UNIT_CODED_SLICE_IDR_W_RADL : VVENC_NAL_UNIT_CODED_SLICE_TRAIL;
-    slice.signDataHidingEnabled = false;
+    slice.signDataHidingEnabled = t_rigSignHiding;
     slice.depQuantEnabled = false;
     slice.tsResidualCodingDisabled = false;
     cs.sps = &sps; cs.pps = &pps; cs.slice = &slice;
@@ -573,6 +574,16 @@ int refshim_transform_quant( int trHor, int trVer, const int16_t* resi, int stri
   return 0;
 }
 
+// same with slice->signDataHidingEnabled selectable: Quant::quant then runs xSignBitHidingHDQ (Quant.cpp:817-826, 377-518)
+int refshim_transform_quant_sdh( int trHor, int trVer, const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding,
+                                 int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  t_rigSignHiding = signHiding != 0;
+  const int rc = refshim_transform_quant( trHor, trVer, resi, stride, w, h, bitDepth, qp, isIRAP, coef, q, absSum, lastPos );
+  t_rigSignHiding = false;
+  return rc;
+}
+
 // integration/TrQuantB200.h in action: the same TU rig, xT + Quant::quant replaced by xTQuantB200 / invTransformNxN by invTransformNxNB200 on the bound library.
 // Return 0, -1 (transform pair not expressible as an mtsIdx) or 1 (the binding threw; text through refshim_b200_error).
 int refshim_install_b200_tu( const char* libPath ) { return b200LoadTu( libPath ); }
@@ -595,6 +606,14 @@ int refshim_transform_quant_b200( int trHor, int trVer, const int16_t* resi, int
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
   *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y]; *needRdoq = nr ? 1 : 0;
   return 0;
+}
+int refshim_transform_quant_b200_sdh( int trHor, int trVer, const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int depQuant, int signHiding,
+                                      int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq )
+{
+  t_rigSignHiding = signHiding != 0;
+  const int rc = refshim_transform_quant_b200( trHor, trVer, resi, stride, w, h, bitDepth, qp, isIRAP, depQuant, coef, q, absSum, lastPos, needRdoq );
+  t_rigSignHiding = false;
+  return rc;
 }
 int refshim_inv_transform_quant_b200( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int16_t* resi, int stride )
 {

@@ -231,6 +231,23 @@ def main(mock_path):
             if rc or not (np.array_equal(ca, cb) and np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value and int(na) == nb.value):
                 bad.append(['fwd', opt] + [int(v) for v in row] + [rc])
     res['tu_fwd'] = {'cases': nfwd, 'bad': bad[:5]}
+    # the same pair with slice->signDataHidingEnabled: Quant::quant ends in xSignBitHidingHDQ, the library hides on the device (vvb_tu_par.sign_hiding)
+    bad = []; nsdh = 0; hid = 0
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for row in C.tq_cases()[1 - opt::2]:
+            th, tv, w, h, st, amp, qp, irap, bd, seed = [int(v) for v in row]
+            resi = C.tq_inputs(row)
+            ca = np.zeros((h, w), dtype=np.int32); qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32()
+            cb = np.zeros((h, w), dtype=np.int32); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32(); nb = I32()
+            q0 = np.zeros((h, w), dtype=np.int16)
+            assert R.refshim_transform_quant(th, tv, P(resi), st, w, h, bd, qp, irap, P(ca), P(q0), ctypes.byref(sa), ctypes.byref(la)) == 0
+            assert R.refshim_transform_quant_sdh(th, tv, P(resi), st, w, h, bd, qp, irap, 1, P(ca), P(qa), ctypes.byref(sa), ctypes.byref(la)) == 0
+            rc = R.refshim_transform_quant_b200_sdh(th, tv, P(resi), st, w, h, bd, qp, irap, 0, 1, P(cb), P(qb), ctypes.byref(sb), ctypes.byref(lb), ctypes.byref(nb))
+            nsdh += 1; hid += int(not np.array_equal(q0, qa))
+            if rc or not (np.array_equal(ca, cb) and np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
+                bad.append(['sdh', opt] + [int(v) for v in row] + [rc])
+    res['tu_fwd_sdh'] = {'cases': nsdh, 'levels_changed_by_hiding': hid, 'bad': bad[:5]}
     bad = []; ninv = 0
     for opt in (0, 1):
         R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')

@@ -221,3 +221,39 @@ def test_gpu_frac_cost_grid_generic_shapes_vs_oracle(gpu, bd):
         exp = np.zeros((n, 7, 7), dtype=np.uint32)
         O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), n, fam, bd, rt, alt, P(exp))
         assert np.array_equal(got, exp), (bd, fam, w, h, rt, alt, np.argwhere(got != exp)[:5], got[got != exp][:4], exp[got != exp][:4])
+
+
+@pytest.mark.parametrize("tensor", [1, 0])
+def test_gpu_sign_bit_hiding_vs_oracle(gpu, tensor):
+    """vvb_tu_par.sign_hiding: the levels leave the device as Quant::quant leaves them after xSignBitHidingHDQ (Quant.cpp:377-518) -- forward call (both transform
+    engines) and the fused TU round trip (the hidden levels are the ones dequantised); every TU against the oracle, which equals the reference (CPU suite)"""
+    import ctypes
+    from _libs import oracle, P
+    O = oracle()
+    rs = np.random.RandomState(909)
+    gpu.eng.set_tensor_transform(tensor)
+    changed = 0
+    try:
+        for (w, h, th, tv) in ((4, 4, 0, 0), (8, 8, 2, 2), (16, 16, 0, 0), (16, 16, 2, 1), (32, 32, 1, 2), (32, 32, 0, 0), (64, 64, 0, 0), (4, 16, 2, 1), (64, 8, 0, 0), (16, 64, 0, 0), (32, 4, 2, 2), (8, 32, 0, 0)):
+            n = 48 if w * h < 4096 else 20
+            amp = np.array([1023, 300, 40, 8])[rs.randint(0, 4, n)]
+            resi = (rs.randint(-1000, 1001, size=(n, h, w)) * amp[:, None, None] // 1000).astype(np.int16)
+            qp = int(rs.randint(14, 46)); irap = int(rs.randint(0, 2))
+            par = gpu.eng.tu_par(w, h, th, tv, 10, qp, bool(irap), False, True)
+            r = gpu.eng.fwd_trquant(par, resi)
+            plain = gpu.eng.fwd_trquant(gpu.eng.tu_par(w, h, th, tv, 10, qp, bool(irap), False, False), resi)
+            for i in range(n):
+                coef = np.zeros((h, w), dtype=np.int32); q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); lp = ctypes.c_int32()
+                assert O.orc_transform_quant_ex(th, tv, P(np.ascontiguousarray(resi[i])), w, w, h, 10, qp, irap, 1, P(coef), P(q), ctypes.byref(s), ctypes.byref(lp)) == 0
+                assert np.array_equal(r['q'][i], q) and int(r['abs_sum'][i]) == s.value and int(r['last_pos'][i]) == lp.value, (w, h, th, tv, i, qp, int((r['q'][i] != q).sum()))
+                changed += int(not np.array_equal(plain['q'][i], q))
+            # fused round trip with hiding
+            org = rs.randint(0, 1024, size=(8, h, w)).astype(np.int16); pred = np.clip(org + rs.randint(-120, 121, size=org.shape), 0, 1023).astype(np.int16)
+            rt = gpu.eng.tu_roundtrip(par, org, pred)
+            for i in range(8):
+                q2 = np.zeros((h, w), dtype=np.int16); rc2 = np.zeros((h, w), dtype=np.int16); o4 = np.zeros(4, dtype=np.uint64)
+                O.orc_tu_roundtrip_ex(th, tv, P(np.ascontiguousarray(org[i])), w, P(np.ascontiguousarray(pred[i])), w, w, h, 10, qp, irap, 1, P(q2), P(rc2), w, P(o4))
+                assert np.array_equal(rt['q'][i], q2) and np.array_equal(rt['reco'][i], rc2) and int(rt['res'][i]['dist_reco']) == int(o4[0]), (w, h, i)
+    finally:
+        gpu.eng.set_tensor_transform(2)
+    assert changed > 60

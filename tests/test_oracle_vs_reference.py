@@ -399,3 +399,32 @@ def test_fast_subpel_replay_equals_the_reference_member(opt):
                 dirs.add(half)
                 checked += 1
     assert checked == 330 and quarter_rounds > 100 and len(dirs) >= 5, (checked, quarter_rounds, early, dirs)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_sign_bit_hiding_against_the_reference(opt):
+    """Quant::quant with slice->signDataHidingEnabled (the RDOQ = 2 presets run the plain quantiser next to sign hiding, vvencCfg.cpp:2675-2677): xSignBitHidingHDQ
+    (Quant.cpp:377-518) on top of QuantCore -- levels, absSum and lastPos of the oracle equal the reference for every TU shape, transform pair, QP and slice type,
+    and hiding changes levels in a good share of the cases"""
+    import ctypes
+    from _libs import oracle, refshim, P
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rows = C.tq_cases()
+    changed = 0; moved_last = 0; n = 0
+    for row in rows[::2] if opt else rows:
+        th, tv, w, h, st, amp, qp, irap, bd, seed = [int(v) for v in row]
+        resi = C.tq_inputs(row)
+        for sh in (1,):
+            coefR = np.zeros((h, w), dtype=np.int32); qR = np.zeros((h, w), dtype=np.int16); sR = ctypes.c_int32(); lR = ctypes.c_int32()
+            rc = R.refshim_transform_quant_sdh(th, tv, P(resi), st, w, h, bd, qp, irap, sh, P(coefR), P(qR), ctypes.byref(sR), ctypes.byref(lR))
+            if rc:
+                continue
+            coefO = np.zeros((h, w), dtype=np.int32); qO = np.zeros((h, w), dtype=np.int16); sO = ctypes.c_int32(); lO = ctypes.c_int32()
+            assert O.orc_transform_quant_ex(th, tv, P(resi), st, w, h, bd, qp, irap, sh, P(coefO), P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+            assert np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, (row, int((qO != qR).sum()), sO.value, sR.value, lO.value, lR.value)
+            q0 = np.zeros((h, w), dtype=np.int16); s0 = ctypes.c_int32(); l0 = ctypes.c_int32()
+            O.orc_transform_quant_ex(th, tv, P(resi), st, w, h, bd, qp, irap, 0, P(coefO), P(q0), ctypes.byref(s0), ctypes.byref(l0))
+            changed += int(not np.array_equal(q0, qO)); moved_last += int(l0.value != lO.value); n += 1
+            assert s0.value == sO.value                                # uiAbsSum is QuantCore's sum, hiding does not update it
+    assert n > 100 and changed > n // 4, (n, changed, moved_last)

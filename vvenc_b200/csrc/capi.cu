@@ -82,7 +82,7 @@ int makeMePar( vvb_ctx* ctx, const vvb_me_par* in, MePar& out )
 void buildScanTables( std::vector<int32_t>& inv )
 {
   // grouped 4x4 up-right diagonal scan (Rom.cpp:1098-1136, 1236-1284); inv[shape][y*regionW + x] = scan position
-  inv.assign( 25 * 1024, 0 );
+  inv.assign( 2 * 25 * 1024, 0 );                 // second half: scan position -> raster index inside the scanned region (sign-bit hiding walks groups in scan order)
   auto diag = []( int bw, int bh, std::vector<int>& xs, std::vector<int>& ys )
   {
     xs.resize( bw * bh ); ys.resize( bw * bh );
@@ -104,7 +104,10 @@ void buildScanTables( std::vector<int32_t>& inv )
       int32_t* t = inv.data() + ( ( lw - 2 ) * 5 + ( lh - 2 ) ) * 1024;
       for( int g = 0; g < ( rw >> 2 ) * ( rh >> 2 ); g++ )
         for( int c = 0; c < 16; c++ )
+        {
           t[( gy[g] * 4 + cy[c] ) * rw + gx[g] * 4 + cx[c]] = g * 16 + c;
+          t[25 * 1024 + g * 16 + c] = ( gy[g] * 4 + cy[c] ) * rw + gx[g] * 4 + cx[c];
+        }
     }
 }
 
@@ -675,12 +678,18 @@ static int pyramidV2LaunchLevel( vvb_ctx* ctx, int orgPlane, int refPlane, const
   const PyrSmem L = pyr_smem<LV>( nx, ny );
   const int NQ = ( 1 << ( 2 * ( LV - 1 ) ) ) / 4;
   const int items = NQ * ( ( ny + 1 ) / 2 ) * L.nStrips;
-  int bd = 256; double bestEff = -1.0;
-  for( int cand = 128; cand <= PYR_MAX_THREADS; cand += 32 )          // fewest idle thread slots over the rounds; ties -> more threads
+  // CTA size: one CTA per SM, so resident warps = CTA warps; measured on the 64x64 roots of the bench (4752 items): 640 threads 2.01 ms, 608 2.04, 512 2.02,
+  // 480 2.09, 448 2.26 -- more warps win over fewer idle slots in the last round.  Small roots / ranges: fewest idle thread slots, ties -> more threads.
+  int bd = PYR_MAX_THREADS;
+  if( items < 4 * PYR_MAX_THREADS )
   {
-    const int rounds = ( items + cand - 1 ) / cand;
-    const double eff = (double) items / ( (double) rounds * cand ) * ( cand >= 384 || cand * 2 > items ? 1.0 : 0.9 );
-    if( eff >= bestEff - 1e-9 ) { bestEff = std::max( bestEff, eff ); bd = cand; }
+    double bestEff = -1.0;
+    for( int cand = 128; cand <= PYR_MAX_THREADS; cand += 32 )
+    {
+      const int rounds = ( items + cand - 1 ) / cand;
+      const double eff = (double) items / ( (double) rounds * cand );
+      if( eff >= bestEff - 1e-9 ) { bestEff = std::max( bestEff, eff ); bd = cand; }
+    }
   }
   static const int forced = []{ const char* e = getenv( "VVB_PYR_THREADS" ); return e ? atoi( e ) : 0; }();     // tuning aid: fixed CTA size
   if( forced >= 64 && forced <= PYR_MAX_THREADS && ( forced & 31 ) == 0 ) bd = forced;
@@ -964,6 +973,7 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
     p.pelMax  = ( 1 << in->bit_depth ) - 1;
   }
   p.lKeepW = ilog2h( p.keepW ); p.lKeepH = ilog2h( p.keepH ); p.lRegW = ilog2h( p.regionW );
+  p.signHiding = in->sign_hiding ? 1 : 0;
   p.q32 = p.qbits <= 30 ? 1 : 0;
   p.add32 = (unsigned)( p.add & 0xffffffffll );
   {

@@ -36,6 +36,7 @@ struct TuPar
   int lKeepW, lKeepH, lRegW; // log2 of keepW, keepH, regionW (all powers of two: every index split is a shift)
   int q32;                   // qbits <= 30: (|c| * scale + add) fits 32 bit for |c| < 2^16 (always true for residuals inside the bit depth)
   unsigned add32;            // low 32 bits of add (valid when q32)
+  int signHiding;            // slice->signDataHidingEnabled: Quant::quant runs xSignBitHidingHDQ after QuantCore (Quant.cpp:817-826)
   unsigned rdoqThr;          // smallest |c| with ((|c| * scaleRdoq + addRdoq) >> qbitsRdoq) != 0  (needRdoqCore as one compare)
 };
 
@@ -105,6 +106,76 @@ template<int T> __device__ __forceinline__ unsigned team_lane_mask()
   if( T >= 32 ) return 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   return ( ( 1u << ( T & 31 ) ) - 1u ) << ( lane & ~(unsigned)( T - 1 ) );
+}
+
+#define VVB_SCAN_TABLE_ENTRIES ( 25 * 1024 )     // raster -> scan position tables of the 25 shapes; the scan position -> raster tables follow them
+
+// Sign-bit hiding of one coefficient group by one thread: Quant::xSignBitHidingHDQ (CommonLib/Quant.cpp:377-518) for the group `cg` of a TU whose levels
+// QuantCore has just produced.  Groups are independent of each other: the only state the reference carries from group to group is `lastCG` (1 exactly for
+// the group that holds the last level) and lastScanPos, which can only move inside that group (a group is only touched when its first and last level are
+// at least SBH_THRESHOLD = 4 apart, so one of them survives).  deltaU (Quant.cpp:221) is recomputed from the coefficient.  Returns the new last scan
+// position + 1 when this is the top group and its last level was zeroed, 0 otherwise.
+template<int LW, int LRW>
+__device__ __noinline__ int sbh_group( const TuPar& par, const int32_t* coef, int16_t* q16, const int32_t* __restrict__ fwd, int cg, int lastScanPos )
+{
+  constexpr int RWM = ( 1 << LRW ) - 1;
+  const int subPos = cg << 4;
+  const bool top = cg == ( lastScanPos >> 4 );
+  int pos[16]; int lev[16];
+#pragma unroll
+  for( int n = 0; n < 16; n++ ) { const int p = __ldg( fwd + subPos + n ); pos[n] = p; lev[n] = q16[( ( p >> LRW ) << LW ) + ( p & RWM )]; }
+  int firstNZ = 16, lastNZ = -1, absSum = 0;
+#pragma unroll
+  for( int n = 15; n >= 0; n-- ) if( lev[n] && lastNZ < 0 ) lastNZ = n;
+#pragma unroll
+  for( int n = 0; n < 16; n++ ) if( lev[n] && firstNZ == 16 ) firstNZ = n;
+#pragma unroll
+  for( int n = 0; n < 16; n++ ) if( n >= firstNZ && n <= lastNZ ) absSum += lev[n];
+  if( lastNZ - firstNZ < 4 ) return 0;                                        // SBH_THRESHOLD, CommonDef.h:272
+  int firstLev = 0;
+#pragma unroll
+  for( int n = 0; n < 16; n++ ) if( n == firstNZ ) firstLev = lev[n];
+  const unsigned signbit = firstLev > 0 ? 0u : 1u;
+  if( signbit == ( (unsigned) absSum & 1u ) ) return 0;
+  int curCost = 0x7fffffff, minCostInc = 0x7fffffff, minN = -1, finalChange = 0, curChange = 0;
+  const int nStart = top ? lastNZ : 15;
+#pragma unroll
+  for( int n = 15; n >= 0; n-- )
+  {
+    if( n > nStart ) continue;
+    const int c = coef[pos[n]];
+    const long long t = (long long) abs( c ) * par.scale;
+    const int mag = (int)( ( t + par.add ) >> par.qbits );
+    const int dU = (int)( ( t - ( (long long) mag << par.qbits ) ) >> ( par.qbits - 8 ) );
+    if( lev[n] != 0 )
+    {
+      if( dU > 0 ) { curCost = -dU; curChange = 1; }
+      else if( n == firstNZ && abs( lev[n] ) == 1 ) curCost = 0x7fffffff;
+      else { curCost = dU; curChange = -1; }
+    }
+    else if( n < firstNZ )
+    {
+      const unsigned thisSign = c >= 0 ? 0u : 1u;
+      if( thisSign != signbit ) curCost = 0x7fffffff;
+      else { curCost = -dU; curChange = 1; }
+    }
+    else { curCost = -dU; curChange = 1; }
+    if( curCost < minCostInc ) { minCostInc = curCost; finalChange = curChange; minN = n; }
+  }
+  int minLev = 0, minPos = 0;
+#pragma unroll
+  for( int n = 0; n < 16; n++ ) if( n == minN ) { minLev = lev[n]; minPos = pos[n]; }
+  if( minLev == 32767 || minLev == -32768 ) finalChange = -1;
+  minLev = coef[minPos] >= 0 ? minLev + finalChange : minLev - finalChange;
+  q16[( ( minPos >> LRW ) << LW ) + ( minPos & RWM )] = (int16_t) minLev;
+  if( top && subPos + minN == lastScanPos && minLev == 0 )
+  {
+    int nl = -1;
+#pragma unroll
+    for( int n = 0; n < 16; n++ ) if( n < minN && lev[n] ) nl = n;           // the next level below inside the group (one exists: the first level survives)
+    return subPos + nl + 1;
+  }
+  return 0;
 }
 
 // Plain quantiser of one TU by its team of T threads (Quant.cpp:132-230 QuantCore, :735-833 wrapper; needRdoqCore :264-278).
@@ -215,6 +286,21 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
   }
   else if( tt == 0 ) { red[4] = sum; red[5] = lastQ; }
   __syncthreads();
+  if( par.signHiding )                                       // uniform over the CTA
+  {
+    const int absSum = red[4], lastScanPos = red[5] - 1;     // scan position of the last level (Quant.cpp:806-816)
+    __syncthreads();                                         // everybody has read red[5] before the top group's thread may rewrite it
+    if( live && absSum >= 2 && lastScanPos >= 0 )
+    {
+      int16_t* q16 = reinterpret_cast<int16_t*>( qWords );
+      for( int cg = tt; cg <= ( lastScanPos >> 4 ); cg += T )
+      {
+        const int nl = sbh_group<LW, S::LRW>( par, coef, q16, inv + VVB_SCAN_TABLE_ENTRIES, cg, lastScanPos );
+        if( nl ) red[5] = nl;
+      }
+    }
+    __syncthreads();
+  }
   return pos;
 }
 
