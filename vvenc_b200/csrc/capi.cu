@@ -1039,7 +1039,24 @@ int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlan
   if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, predPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  void* dR; int rc;
+  int rc;
+  {
+    // CUDA-core engine: the residual is formed while the TU is loaded (one launch, no compact residual buffer); the tcgen05 engine keeps the staging kernel
+    TuPar p;
+    if( ( rc = makeTuPar( ctx, par, p ) ) ) return rc;
+    const bool tensor = p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) );
+    if( !tensor )
+    {
+      const Plane &po = ctx->planes.p[orgPlane], &pp = ctx->planes.p[predPlane];
+#define VVB_FWDP_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = (size_t)( S::MAT_WORDS + S::NTEAMS * S::TEAM_WORDS ) * 4; \
+      fwd_trquant_planes_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+      VVB_TU_DISPATCH( p.lw, p.lh, VVB_FWDP_CALL )
+#undef VVB_FWDP_CALL
+      CHECK_LAUNCH( "fwd_trquant_planes_kernel" );
+      return VVB_OK;
+    }
+  }
+  void* dR;
   const size_t area = (size_t) par->w * par->h;
   if( ( rc = scratch( ctx, 5, (size_t) n * area * 2, &dR ) ) ) return rc;
   const long long total = (long long) n * area;

@@ -473,6 +473,47 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_consta
   }
 }
 
+// same with the residual formed at load time: TU i sits at (blocks[i].x, blocks[i].y) of orgPlane, its prediction at (+start_x, +start_y) of predPlane
+// (PelBuf::subtract, IntraSearch.cpp:1328) -- no compact residual buffer, no extra launch
+template<int LW, int LH>
+__global__ void __launch_bounds__( 128 ) fwd_trquant_planes_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
+                                                                    const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane,
+                                                                    const vvb_block* __restrict__ blocks, int n,
+                                                                    int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
+                                                                    int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
+{
+  using S = TuShape<LW, LH>;
+  extern __shared__ __align__( 16 ) uint32_t smem[];
+  constexpr int T = S::T, NTEAMS = S::NTEAMS, W = S::W;
+  const int team = threadIdx.x / T, tt = threadIdx.x % T;
+  uint32_t* MtH = smem;
+  uint32_t* MtV = MtH + ( S::W / 4 ) * S::RW;
+  uint32_t* teamBase = smem + S::MAT_WORDS;
+  stage_matrix( MtH, trTable, par.offH, S::W, par.keepW, S::RW, threadIdx.x, blockDim.x );
+  stage_matrix( MtV, trTable, par.offV, S::H, par.keepH, S::RH, threadIdx.x, blockDim.x );
+  const TeamView v = team_view<S>( teamBase, team );
+  const int so = orgPlane.stride, sp = predPlane.stride;
+
+  for( int base = blockIdx.x * NTEAMS; base < n; base += gridDim.x * NTEAMS )
+  {
+    const int tu = base + team;
+    const bool live = tu < n;
+    const vvb_block blk = blocks[live ? tu : 0];
+    const int16_t* oBase = orgPlane.origin + (ptrdiff_t) blk.y * so + blk.x;
+    const int16_t* pBase = predPlane.origin + (ptrdiff_t)( blk.y + blk.start_y ) * sp + blk.x + blk.start_x;
+    const bool al4 = ( ( ( reinterpret_cast<uintptr_t>( oBase ) | reinterpret_cast<uintptr_t>( pBase ) ) & 3 ) | ( ( so | sp ) & 1 ) ) == 0;   // word loads allowed
+    const int pos = team_forward<LW, LH>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i )
+    {
+      const int y = i >> ( LW - 1 ), x = ( i & ( W / 2 - 1 ) ) << 1;
+      const int16_t* o = oBase + (ptrdiff_t) y * so + x; const int16_t* p = pBase + (ptrdiff_t) y * sp + x;
+      if( al4 ) return __vsub2( __ldg( reinterpret_cast<const uint32_t*>( o ) ), __ldg( reinterpret_cast<const uint32_t*>( p ) ) );
+      const int d0 = (int) __ldg( o ) - (int) __ldg( p ), d1 = (int) __ldg( o + 1 ) - (int) __ldg( p + 1 );
+      return ( (uint32_t) d0 & 0xffffu ) | ( (uint32_t) d1 << 16 );
+    } );
+    team_forward_store<LW, LH>( v, pos, tu, tt, live, coefOut, qOut, absSumOut, lastPosOut, needRdoqOut );
+  }
+}
+
 // host-side dispatch over the 25 TU shapes: CALL( LW, LH ) is expanded with constant arguments
 #define VVB_TU_DISPATCH_LH( LWv, lh, CALL ) \
   switch( lh ) { case 2: CALL( LWv, 2 ); break; case 3: CALL( LWv, 3 ); break; case 4: CALL( LWv, 4 ); break; case 5: CALL( LWv, 5 ); break; default: CALL( LWv, 6 ); break; }
