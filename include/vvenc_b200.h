@@ -175,6 +175,9 @@ int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dev_blocks, const vvb_bes
 /* ---- forward transform + quantise (TrQuant::transformNxN for LFNST-off, non-skip luma TUs; ---------------
  * CommonLib/TrQuant.cpp:688-736 -> xT :481-564 -> Quant::quant CommonLib/Quant.cpp:735-833 -> QuantCore :132-230,
  * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types.
+ * With lfnst_idx set (DCT-II only) the forward calls restate transformNxN's LFNST branch: transform zero-out to the top-left 4x4 / 8x8, the 16x16 / 16x48 int8
+ * kernel, quantisation of coefficient group 0; `coef` returns the buffer xFwdLfnst leaves.  The inverse LFNST is not offered yet (vvb_inv_trquant /
+ * vvb_tu_roundtrip return VVB_ERR_UNSUPPORTED for lfnst_idx != 0).
  * deltaU (Quant.cpp:221), whose only consumer is the sign-bit hiding of the same call, stays on the device: with sign_hiding set the returned levels are the
  * ones Quant::quant leaves after xSignBitHidingHDQ (abs_sum stays QuantCore's sum, as uiAbsSum does; last_pos follows the hiding step). */
 typedef struct
@@ -186,7 +189,9 @@ typedef struct
   int32_t is_irap;             /* slice->isIRAP(): rounding offset 171 vs 85 (Quant.cpp:772)      */
   int32_t dep_quant;           /* for need_rdoq only: slice->depQuantEnabled (Quant.cpp:852-855)  */
   int32_t sign_hiding;         /* slice->signDataHidingEnabled: the levels pass through Quant::xSignBitHidingHDQ (Quant.cpp:817-826, 377-518) */
-  int32_t reserved[3];         /* zero */
+  int32_t lfnst_idx;           /* cu.lfnstIdx of an intra CU: 0 off, 1 / 2 = TrQuant::xFwdLfnst between the transform and the quantiser (TrQuant.cpp:942-1048) */
+  int32_t lfnst_set;           /* g_lfnstLut[ xGetLFNSTIntraMode( intra mode ) ], 0..3 (Rom.cpp:95, TrQuant.cpp:806-828)                                     */
+  int32_t lfnst_transpose;     /* xGetTransposeFlag of that mode (TrQuant.cpp:831-835)                                                                           */
 } vvb_tu_par;
 
 /* resi: n compact residual blocks [n][h][w] (Pel); outputs (each nullable except q):

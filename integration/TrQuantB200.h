@@ -3,7 +3,7 @@
 //   xTQuantB200          <->  the xT + xQuant pair inside TrQuant::transformNxN (TrQuant.cpp:709-733 -> xT :481-564, Quant::quant Quant.cpp:735-833)
 //   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
 //
-// for the TUs the library covers: luma, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), LFNST index 0, no transform
+// for the TUs the library covers: luma, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), LFNST on the forward side, no transform
 // skip, no scaling lists, plain quantiser incl. its sign-bit hiding (RDOQ / dependent quantisation stay on the host and use the coefficients this call leaves in the temp buffer).
 // vvb_tu_par is derived from the TransformUnit exactly as the members derive their parameters (xSetTrTypes, QpParam, slice type), so the call sites keep
 // their arguments.  One TU per call here; the production shape batches the TU candidates of a CU (vvb_fwd_trquant with n > 1 or
@@ -33,11 +33,10 @@ inline int b200LoadTu( const char* libPath )
   return 0;
 }
 
-inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const ComponentID compID, const QpParam& cQP )
+inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const ComponentID compID, const QpParam& cQP, bool forward = true )
 {
   if( compID != COMP_Y ) THROW( "luma TUs only" );
   if( tu.mtsIdx[compID] == MTS_SKIP || tu.cu->bdpcmM[CH_L] ) THROW( "transform skip stays on the host" );
-  if( tu.cu->lfnstIdx ) THROW( "LFNST stays on the host" );
   if( tu.cs->sps->scalingListEnabled ) THROW( "scaling lists stay on the host" );
   const SPS& sps = *tu.cs->sps;
   int trHor = DCT2, trVer = DCT2;
@@ -50,6 +49,15 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
   if( sps.qpBDOffset[CH_L] != 6 * ( par.bit_depth - 8 ) ) THROW( "unexpected qpBDOffset" );
   par.is_irap = tu.cs->slice->isIRAP() ? 1 : 0;                                              // rounding offset 171 vs 85 (Quant.cpp:772)
   par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;
+  if( tu.cu->lfnstIdx && forward )                                                           // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048): kernel set and transposition from the intra mode
+  {
+    if( !tu.cs->sps->LFNST || trHor != DCT2 || trVer != DCT2 ) THROW( "LFNST index on a TU the library does not cover" );
+    uint32_t intraMode = CU::getFinalIntraMode( *tu.cu, CH_L );
+    if( CU::isMIP( *tu.cu, CH_L ) ) intraMode = PLANAR_IDX;
+    intraMode = tq.xGetLFNSTIntraMode( tu.cu->ispMode ? tu.cu->blocks[compID] : tu.blocks[compID], intraMode );
+    par.lfnst_idx = tu.cu->lfnstIdx; par.lfnst_set = g_lfnstLut[intraMode]; par.lfnst_transpose = tq.xGetTransposeFlag( intraMode ) ? 1 : 0;
+  }
+  else if( tu.cu->lfnstIdx ) THROW( "the inverse LFNST stays on the host" );
   par.sign_hiding = tu.cs->slice->signDataHidingEnabled ? 1 : 0;                            // Quant::quant: CoeffCodingContext( ..., signDataHidingEnabled ), xSignBitHidingHDQ (Quant.cpp:748, 817-826)
   return par;
 }
@@ -78,7 +86,7 @@ inline void xTQuantB200( TrQuant& tq, TransformUnit& tu, const ComponentID compI
 // TrQuant::invTransformNxN( tu, compID, pResi, cQP ) for the same class of TUs: levels of tu.getCoeffs( compID ) -> residual
 inline void invTransformNxNB200( TrQuant& tq, TransformUnit& tu, const ComponentID compID, PelBuf& pResi, const QpParam& cQP )
 {
-  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP, false );
   const int w = par.w, h = par.h;
   std::vector<int16_t> q( (size_t) w * h ), resi( (size_t) w * h );
   const CCoeffSigBuf src = tu.getCoeffs( compID );

@@ -14,6 +14,7 @@
 #include <string.h>
 #include <math.h>
 #include "vvc_tables.h"
+#include "vvc_lfnst_tables.h"
 
 typedef int16_t Pel;
 
@@ -455,6 +456,84 @@ int orc_quant_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int i
   if( sum )                                                                            /* Quant.cpp:806-816 */
     for( int sp = pos; sp >= 0; sp-- ) if( q[scan[sp]] ) { last = sp; break; }
   if( sum >= 2 && signHiding ) sign_bit_hiding( q, coef, scan, &p, &last );            /* Quant.cpp:817-826 */
+  *absSum = sum; *lastPos = last;
+  return 0;
+}
+
+
+/* ------------------------------------------------------------------------------------------------------
+ * LFNST, forward: TrQuant::xFwdLfnst (CommonLib/TrQuant.cpp:942-1048) with xFwdLfnstNxNCore (:166-187) between TrQuant::xT and the quantiser.
+ * The primary transform keeps only the top-left 4x4 (a 4-pel side) or 8x8 region when the CU carries an LFNST index (:499-511); its first 16 resp. 48
+ * coefficients (rows of 8 then rows of 4, or the transposed walk) go through a 16x16 / 16x48 int8 kernel chosen by (set = g_lfnstLut[intra mode], index),
+ * (sum + 64) >> 7, only the first 8 (4x4 and 8x8 TUs) or 16 outputs are kept, and the outputs land on the first scan positions of the top-left region
+ * (g_coefTopLeftDiagScan8x8 / the TU's grouped scan).  The quantiser then only looks at coefficient group 0 (Quant.cpp:151-158).
+ * set (0..3), index (1..2) and transpose come from the host: they follow from the intra mode through the reference's own xGetLFNSTIntraMode / g_lfnstLut /
+ * xGetTransposeFlag.
+ * ---------------------------------------------------------------------------------------------------- */
+void orc_fwd_lfnst( int32_t* coef, int w, int h, int set, int lfnstIdx, int transpose )
+{
+  const int whge3 = w >= 8 && h >= 8, sb = whge3 ? 8 : 4, nIn = whge3 ? 48 : 16;
+  const int zeroOut = ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ? 8 : 16;
+  const int8_t* mat = (const int8_t*) vvc_lfnst_words + ( whge3 ? ( set * 2 + ( lfnstIdx - 1 ) ) * 16 * 48 : VVC_LFNST_4X4_OFFSET + ( set * 2 + ( lfnstIdx - 1 ) ) * 16 * 16 );
+  int32_t in[48], out[48];
+  for( int i = 0; i < nIn; i++ )
+  {
+    int a, b;                                  /* a: index along the walk's fast axis, b: slow axis */
+    if( sb == 4 ) { b = i >> 2; a = i & 3; }
+    else if( i < 32 ) { b = i >> 3; a = i & 7; }
+    else { b = 4 + ( ( i - 32 ) >> 2 ); a = ( i - 32 ) & 3; }
+    const int x = transpose ? b : a, y = transpose ? a : b;           /* :973-1019 */
+    in[i] = coef[y * w + x];
+  }
+  for( int j = 0; j < nIn; j++ )
+  {
+    if( j < zeroOut )
+    {
+      int32_t sum = 0;
+      for( int i = 0; i < nIn; i++ ) sum += in[i] * mat[j * nIn + i];
+      out[j] = ( sum + 64 ) >> 7;
+    }
+    else out[j] = 0;                            /* :185 memset */
+  }
+  /* forward spectral rearrangement (:1037-1046): grouped 4x4 diagonal scan of the top-left region, groups (0,0), (0,1), (1,0) */
+  int gx[4], gy[4], cx[16], cy[16];
+  diag_scan( 2, 2, gx, gy ); diag_scan( 4, 4, cx, cy );
+  for( int j = 0; j < nIn; j++ )
+  {
+    const int g = j >> 4, c = j & 15;
+    coef[( gy[g] * 4 + cy[c] ) * w + gx[g] * 4 + cx[c]] = out[j];
+  }
+}
+
+/* TrQuant::transformNxN for a luma TU of an intra CU with cu.lfnstIdx = lfnstIdx (1..2): xT with the LFNST zero-out, xFwdLfnst, Quant::quant (plain quantiser,
+ * optional sign-bit hiding) and xNeedRDOQ on the same coefficients.  Transform types are DCT-II (LFNST and MTS exclude each other, IntraSearch). */
+int orc_transform_quant_lfnst( const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int set, int lfnstIdx, int transpose,
+                               int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( orc_fwd_transform( 0, 0, resi, stride, w, h, bitDepth, coef ) ) return -1;
+  const int keep = ( w >= 8 && h >= 8 ) ? 8 : 4;                                       /* TrQuant.cpp:499-511 */
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) if( x >= keep || y >= keep ) coef[y * w + x] = 0;
+  orc_fwd_lfnst( coef, w, h, set, lfnstIdx, transpose );
+  const QuantPar p = quant_par( w, h, bitDepth, qp, isIRAP ? 171 : 85 );
+  int32_t scan[1024];
+  orc_scan_order( w, h, scan );
+  int pos = ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ? 7 : 15;                 /* Quant.cpp:151-158: one coefficient group, 8 positions for 4x4 / 8x8 */
+  for( ; pos > 0; pos-- ) if( coef[scan[pos]] ) break;
+  memset( q, 0, sizeof( int16_t ) * w * h );
+  int32_t sum = 0;
+  for( int cp = 0; cp <= pos; cp++ )
+  {
+    const int32_t c = coef[scan[cp]];
+    const int64_t t = (int64_t) iabs( c ) * p.scale;
+    const int32_t mag = (int32_t)( ( t + p.add ) >> p.qbits );
+    sum += mag;
+    int32_t v = c < 0 ? -mag : mag;
+    if( v < -32768 ) v = -32768; if( v > 32767 ) v = 32767;
+    q[scan[cp]] = (int16_t) v;
+  }
+  int last = pos;
+  if( sum ) for( int sp = pos; sp >= 0; sp-- ) if( q[scan[sp]] ) { last = sp; break; }
+  if( sum >= 2 && signHiding ) sign_bit_hiding( q, coef, scan, &p, &last );
   *absSum = sum; *lastPos = last;
   return 0;
 }

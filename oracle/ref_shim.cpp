@@ -584,6 +584,81 @@ int refshim_transform_quant_sdh( int trHor, int trVer, const int16_t* resi, int 
   return rc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// LFNST: TrQuant::transformNxN's own sequence for a luma TU of an intra CU with cu.lfnstIdx = lfnstIdx -- xT (zero-out of :499-511), xFwdLfnst (:942-1048,
+// through m_fwdLfnstNxN), Quant::quant -- on the TU rig.  xFwdLfnst looks the CU up through the coding structure, so the rig's CodingStructure gets a
+// one-CU map for the call.  outSetTranspose[0] = g_lfnstLut[ xGetLFNSTIntraMode( intraMode ) ], [1] = xGetTransposeFlag: what the B200 binding passes down.
+int refshim_transform_quant_lfnst( const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int intraMode, int lfnstIdx,
+                                   int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq, int32_t* outSetTranspose )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  t_rigSignHiding = signHiding != 0;
+  r.setup( w, h, bitDepth, 0, isIRAP != 0, true, qp );
+  t_rigSignHiding = false;
+  r.sps.LFNST = true;
+  r.slice.sliceType = VVENC_B_SLICE;          // CU::isSepTree would consult cs.pcv (absent on the rig) for an I slice; the rounding offset follows isIRAP() = the NAL unit type
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx;
+  r.cu.intraDir[CH_L] = (uint8_t) intraMode; r.cu.intraDir[CH_C] = DM_CHROMA_IDX;
+  r.cu.mipFlag = false; r.cu.ispMode = 0; r.cu.chromaFormat = CHROMA_400;
+  // one-CU lookup map for CodingStructure::getCU (CodingStructure.cpp:140-156)
+  static thread_local std::vector<CodingUnit*> cuMap;
+  r.cs.area = UnitArea( CHROMA_400, Area( 0, 0, w, h ) );
+  r.cs.parent = nullptr;
+  r.cs.unitScale[COMP_Y] = UnitScale( MIN_CU_LOG2, MIN_CU_LOG2 );
+  cuMap.assign( (size_t)( ( w >> MIN_CU_LOG2 ) + 1 ) * ( ( h >> MIN_CU_LOG2 ) + 1 ), &r.cu );
+  r.cs.m_cuPtr[CH_L] = cuMap.data();
+  TrQuant& tq = tqOfThread();
+  CPelBuf  resiBuf( resi, stride, w, h );
+  CoeffBuf tmp( tq.m_plTempCoeff, w, w, h );
+  tq.xT( r.tu, COMP_Y, resiBuf, tmp, w, h );
+  tq.xFwdLfnst( r.tu, COMP_Y, false );
+  for( int y = 0; y < h; y++ ) memcpy( coef + (size_t) y * w, tq.m_plTempCoeff + (size_t) y * w, sizeof( TCoeff ) * w );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  alignas(64) static thread_local unsigned char ctxMem[ sizeof( Ctx ) ];
+  const Ctx& dummy = *reinterpret_cast<const Ctx*>( ctxMem );
+  Quant* qu = static_cast<Quant*>( tq.m_quant );
+  qu->Quant::quant( r.tu, COMP_Y, src, sum, qpp, dummy );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  if( needRdoq ) *needRdoq = qu->xNeedRDOQ( r.tu, COMP_Y, src, qpp ) ? 1 : 0;
+  const uint32_t m = tq.xGetLFNSTIntraMode( r.tu.blocks[COMP_Y], (uint32_t) intraMode );
+  outSetTranspose[0] = g_lfnstLut[m]; outSetTranspose[1] = tq.xGetTransposeFlag( m ) ? 1 : 0;
+  r.cs.m_cuPtr[CH_L] = nullptr;
+  r.cu.lfnstIdx = 0; r.sps.LFNST = false;
+  return 0;
+}
+// the same TU through integration/TrQuantB200.h (xTQuantB200 derives kernel set / transposition from the CU like xFwdLfnst does); returns 1 when the binding threw
+int refshim_transform_quant_lfnst_b200( const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int intraMode, int lfnstIdx,
+                                        int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  t_rigSignHiding = signHiding != 0;
+  r.setup( w, h, bitDepth, 0, isIRAP != 0, true, qp );
+  t_rigSignHiding = false;
+  r.sps.LFNST = true;
+  r.slice.sliceType = VVENC_B_SLICE;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx;
+  r.cu.intraDir[CH_L] = (uint8_t) intraMode; r.cu.intraDir[CH_C] = DM_CHROMA_IDX;
+  r.cu.mipFlag = false; r.cu.ispMode = 0; r.cu.chromaFormat = CHROMA_400;
+  CPelBuf  resiBuf( resi, stride, w, h );
+  CoeffBuf dst( coef, w, w, h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  TCoeff sum = 0; bool nr = false;
+  int rc = 0;
+  try { xTQuantB200( tqOfThread(), r.tu, COMP_Y, resiBuf, dst, qpp, sum, &nr ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.cu.lfnstIdx = 0; r.sps.LFNST = false;
+  if( rc ) return rc;
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y]; *needRdoq = nr ? 1 : 0;
+  return 0;
+}
+
 // integration/TrQuantB200.h in action: the same TU rig, xT + Quant::quant replaced by xTQuantB200 / invTransformNxN by invTransformNxNB200 on the bound library.
 // Return 0, -1 (transform pair not expressible as an mtsIdx) or 1 (the binding threw; text through refshim_b200_error).
 int refshim_install_b200_tu( const char* libPath ) { return b200LoadTu( libPath ); }

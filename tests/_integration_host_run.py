@@ -248,6 +248,24 @@ def main(mock_path):
             if rc or not (np.array_equal(ca, cb) and np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
                 bad.append(['sdh', opt] + [int(v) for v in row] + [rc])
     res['tu_fwd_sdh'] = {'cases': nsdh, 'levels_changed_by_hiding': hid, 'bad': bad[:5]}
+    # intra TUs with an LFNST index: xT (LFNST zero-out) + xFwdLfnst + Quant::quant against xTQuantB200 with vvb_tu_par.lfnst_*
+    bad = []; nlf = 0
+    rs2 = np.random.RandomState(77)
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for (w, h) in ((4, 4), (8, 8), (4, 8), (16, 4), (16, 16), (8, 32), (32, 32), (64, 64), (64, 16)):
+            for mode in (0, 1, 2, 18, 34, 35, 50, 66):
+                for idx in (1, 2):
+                    amp = int(rs2.choice([1023, 200, 30])); qp = int(rs2.randint(18, 46)); irap = int(rs2.randint(0, 2)); sh = int(rs2.randint(0, 2))
+                    resi = rs2.randint(-amp, amp + 1, size=(h, w)).astype(np.int16)
+                    ca = np.zeros((h, w), dtype=np.int32); qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32(); na = I32(); st2 = np.zeros(2, dtype=np.int32)
+                    cb = np.zeros((h, w), dtype=np.int32); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32(); nb = I32()
+                    assert R.refshim_transform_quant_lfnst(P(resi), w, w, h, 10, qp, irap, sh, mode, idx, P(ca), P(qa), ctypes.byref(sa), ctypes.byref(la), ctypes.byref(na), P(st2)) == 0
+                    rc = R.refshim_transform_quant_lfnst_b200(P(resi), w, w, h, 10, qp, irap, sh, mode, idx, P(cb), P(qb), ctypes.byref(sb), ctypes.byref(lb), ctypes.byref(nb))
+                    nlf += 1
+                    if rc or not (np.array_equal(ca, cb) and np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value and na.value == nb.value):
+                        bad.append(['lfnst', opt, w, h, mode, idx, qp, irap, sh, rc])
+    res['tu_fwd_lfnst'] = {'cases': nlf, 'bad': bad[:5]}
     bad = []; ninv = 0
     for opt in (0, 1):
         R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')

@@ -131,6 +131,7 @@ int vvb_mctf_search_grid( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf
   return VVB_OK;
 }
 
+int orc_transform_quant_lfnst( const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int set, int lfnstIdx, int transpose, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int orc_transform_quant_ex( int trHor, int trVer, const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int orc_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant );
 int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride );
@@ -156,8 +157,10 @@ int vvb_fwd_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* resi, int
   {
     int32_t s = 0, l = -1;
     int32_t* co = coef ? coef + area * i : tmp;
-    if( orc_transform_quant_ex( par->tr_hor, par->tr_ver, resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, par->sign_hiding, co, q + area * i, &s, &l ) )
-    { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }
+    const int rc = par->lfnst_idx
+      ? orc_transform_quant_lfnst( resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, par->sign_hiding, par->lfnst_set, par->lfnst_idx, par->lfnst_transpose, co, q + area * i, &s, &l )
+      : orc_transform_quant_ex( par->tr_hor, par->tr_ver, resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, par->sign_hiding, co, q + area * i, &s, &l );
+    if( rc ) { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }
     if( absSum ) absSum[i] = s;
     if( lastPos ) lastPos[i] = l;
     if( needRdoq ) needRdoq[i] = (uint8_t) orc_need_rdoq( co, par->w, par->h, par->bit_depth, par->qp, par->dep_quant );

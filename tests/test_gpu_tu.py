@@ -257,3 +257,30 @@ def test_gpu_sign_bit_hiding_vs_oracle(gpu, tensor):
     finally:
         gpu.eng.set_tensor_transform(2)
     assert changed > 60
+
+
+def test_gpu_lfnst_forward_vs_oracle(gpu):
+    """vvb_tu_par.lfnst_*: transform zero-out + LFNST kernel + quantiser on coefficient group 0 (TrQuant::xFwdLfnst, TrQuant.cpp:942-1048) for every TU shape that can
+    carry LFNST, all kernel sets, both indices, transposed and not, with and without sign hiding; coefficients, levels, absSum, lastPos and the RDOQ flag equal
+    the oracle (= the reference, CPU suite); the inverse side refuses LFNST"""
+    import ctypes
+    import vvenc_b200 as V
+    from _libs import oracle, P
+    O = oracle()
+    rs = np.random.RandomState(4321)
+    for (w, h) in ((4, 4), (8, 8), (4, 8), (8, 4), (16, 16), (4, 16), (16, 4), (8, 16), (32, 32), (32, 8), (64, 64), (16, 64), (64, 4)):
+        for (st, idx, tr) in ((0, 1, 0), (1, 2, 0), (2, 1, 1), (3, 2, 1), (1, 1, 1), (3, 1, 0)):
+            n = 24
+            amp = np.array([1023, 300, 40])[rs.randint(0, 3, n)]
+            resi = (rs.randint(-1000, 1001, size=(n, h, w)) * amp[:, None, None] // 1000).astype(np.int16)
+            qp = int(rs.randint(16, 46)); irap = int(rs.randint(0, 2)); sh = int(rs.randint(0, 2)); dq = int(rs.randint(0, 2))
+            par = gpu.eng.tu_par(w, h, V.DCT2, V.DCT2, 10, qp, bool(irap), bool(dq), bool(sh), idx, st, bool(tr))
+            r = gpu.eng.fwd_trquant(par, resi)
+            for i in range(n):
+                coef = np.zeros((h, w), dtype=np.int32); q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); lp = ctypes.c_int32()
+                assert O.orc_transform_quant_lfnst(P(np.ascontiguousarray(resi[i])), w, w, h, 10, qp, irap, sh, st, idx, tr, P(coef), P(q), ctypes.byref(s), ctypes.byref(lp)) == 0
+                assert np.array_equal(r['coef'][i], coef), (w, h, st, idx, tr, i, np.argwhere(r['coef'][i] != coef)[:4])
+                assert np.array_equal(r['q'][i], q) and int(r['abs_sum'][i]) == s.value and int(r['last_pos'][i]) == lp.value, (w, h, st, idx, tr, i, qp, sh)
+                assert int(r['need_rdoq'][i]) == O.orc_need_rdoq(P(coef), w, h, 10, qp, dq), (w, h, i)
+    with pytest.raises(V.VvbError):
+        gpu.eng.inv_trquant(gpu.eng.tu_par(8, 8, V.DCT2, V.DCT2, 10, 30, False, False, False, 1, 0, False), np.zeros((1, 8, 8), dtype=np.int16))

@@ -428,3 +428,32 @@ def test_sign_bit_hiding_against_the_reference(opt):
             changed += int(not np.array_equal(q0, qO)); moved_last += int(l0.value != lO.value); n += 1
             assert s0.value == sO.value                                # uiAbsSum is QuantCore's sum, hiding does not update it
     assert n > 100 and changed > n // 4, (n, changed, moved_last)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_lfnst_forward_against_the_reference(opt):
+    """TrQuant::transformNxN for intra TUs with an LFNST index (xT with the LFNST zero-out, xFwdLfnst, plain quantiser on coefficient group 0, xNeedRDOQ): the
+    oracle's restatement gives the reference's coefficients, levels, absSum, lastPos and RDOQ flag for every TU shape that can carry LFNST, both indices, intra
+    modes of all four kernel sets with and without transposition, wide-angle remapping on rectangular TUs, with and without sign-bit hiding"""
+    import ctypes
+    from _libs import oracle, refshim, P
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(31 + opt)
+    sets = set(); n = 0
+    for (w, h) in ((4, 4), (8, 8), (4, 8), (8, 4), (16, 16), (4, 16), (16, 4), (8, 16), (32, 32), (32, 8), (64, 64), (16, 64)):
+        for mode in (0, 1, 2, 10, 18, 23, 34, 35, 44, 50, 58, 66):
+            for idx in (1, 2):
+                amp = int(rs.choice([1023, 200, 30]))
+                qp = int(rs.randint(18, 46)); irap = int(rs.randint(0, 2)); sh = int(rs.randint(0, 2))
+                resi = rs.randint(-amp, amp + 1, size=(h, w)).astype(np.int16)
+                cR = np.zeros((h, w), dtype=np.int32); qR = np.zeros((h, w), dtype=np.int16); sR = ctypes.c_int32(); lR = ctypes.c_int32(); nR = ctypes.c_int32()
+                st = np.zeros(2, dtype=np.int32)
+                assert R.refshim_transform_quant_lfnst(P(resi), w, w, h, 10, qp, irap, sh, mode, idx, P(cR), P(qR), ctypes.byref(sR), ctypes.byref(lR), ctypes.byref(nR), P(st)) == 0
+                cO = np.zeros((h, w), dtype=np.int32); qO = np.zeros((h, w), dtype=np.int16); sO = ctypes.c_int32(); lO = ctypes.c_int32()
+                assert O.orc_transform_quant_lfnst(P(resi), w, w, h, 10, qp, irap, sh, int(st[0]), idx, int(st[1]), P(cO), P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+                assert np.array_equal(cO, cR), (w, h, mode, idx, st, np.argwhere(cO != cR)[:4])
+                assert np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, (w, h, mode, idx, qp, sh)
+                assert O.orc_need_rdoq(P(cO), w, h, 10, qp, 0) == nR.value
+                sets.add((int(st[0]), int(st[1]))); n += 1
+    assert n == 288 and len(sets) >= 6, (n, sets)

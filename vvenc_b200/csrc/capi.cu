@@ -16,6 +16,7 @@
 #include "mctf_affine_kernels.cuh"
 #include "frac_kernels.cuh"
 #include "vvc_tables.h"
+#include "vvc_lfnst_tables.h"
 
 using namespace vvb;
 
@@ -236,6 +237,11 @@ int vvb_create( vvb_ctx** out, int device )
     if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) == cudaSuccess && qres == cudaDriverEntryPointSuccess ) ctx->tmaEncode = fn;
     cudaGetLastError();
   }
+  if( cudaMalloc( &ctx->d_lfnst, VVC_LFNST_BYTES ) != cudaSuccess || cudaMemcpy( ctx->d_lfnst, vvc_lfnst_words, VVC_LFNST_BYTES, cudaMemcpyHostToDevice ) != cudaSuccess )
+  {
+    vvb_destroy( ctx );
+    return VVB_ERR_CUDA;
+  }
   cudaFuncSetAttribute( sad_pyramid8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
   cudaFuncSetAttribute( sad_pyramid8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
   cudaFuncSetAttribute( sad_pyramid8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
@@ -261,6 +267,7 @@ void vvb_destroy( vvb_ctx* ctx )
   for( int i = 0; i < 8; i++ ) if( ctx->d_scratch[i] ) cudaFree( ctx->d_scratch[i] );
   if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
   if( ctx->d_scan ) cudaFree( ctx->d_scan );
+  if( ctx->d_lfnst ) cudaFree( ctx->d_lfnst );
   if( ctx->h_pinned ) cudaFreeHost( ctx->h_pinned );
   if( ctx->stream ) cudaStreamDestroy( ctx->stream );
   delete ctx;
@@ -974,6 +981,17 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
   }
   p.lKeepW = ilog2h( p.keepW ); p.lKeepH = ilog2h( p.keepH ); p.lRegW = ilog2h( p.regionW );
   p.signHiding = in->sign_hiding ? 1 : 0;
+  p.lfnstIdx = 0; p.lfnstTranspose = 0; p.lfnstMat = nullptr; p.lfnstMaxScan = 0x7fffffff;
+  if( in->lfnst_idx )
+  {
+    // TrQuant::xFwdLfnst applies to intra CUs, whose luma TUs use DCT-II when an LFNST index is set (MTS and LFNST exclude each other)
+    if( in->lfnst_idx < 0 || in->lfnst_idx > 2 || in->lfnst_set < 0 || in->lfnst_set > 3 ) return fail( ctx, VVB_ERR_ARG, "lfnst_idx 0..2, lfnst_set 0..3" );
+    if( in->tr_hor != 0 || in->tr_ver != 0 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "LFNST goes with DCT-II" );
+    const bool whge3 = w >= 8 && h >= 8;
+    p.lfnstIdx = in->lfnst_idx; p.lfnstTranspose = in->lfnst_transpose ? 1 : 0;
+    p.lfnstMat = ctx->d_lfnst + ( whge3 ? ( in->lfnst_set * 2 + in->lfnst_idx - 1 ) * 16 * 48 : VVC_LFNST_4X4_OFFSET + ( in->lfnst_set * 2 + in->lfnst_idx - 1 ) * 16 * 16 );
+    p.lfnstMaxScan = ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ? 7 : 15;                   // Quant.cpp:151-158
+  }
   p.q32 = p.qbits <= 30 ? 1 : 0;
   p.add32 = (unsigned)( p.add & 0xffffffffll );
   {
@@ -992,7 +1010,7 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  if( p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) ) )
+  if( !p.lfnstIdx && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) ) )
   {
     // tcgen05 path: 128 stacked rows (128/N TUs) per tile, persistent CTAs
     const int tpt = 128 / p.w;
@@ -1044,7 +1062,7 @@ int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlan
     // CUDA-core engine: the residual is formed while the TU is loaded (one launch, no compact residual buffer); the tcgen05 engine keeps the staging kernel
     TuPar p;
     if( ( rc = makeTuPar( ctx, par, p ) ) ) return rc;
-    const bool tensor = p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) );
+    const bool tensor = !p.lfnstIdx && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) );
     if( !tensor )
     {
       const Plane &po = ctx->planes.p[orgPlane], &pp = ctx->planes.p[predPlane];
@@ -1094,6 +1112,7 @@ int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ,
   TuPar p;
   int rc = makeTuPar( ctx, par, p );
   if( rc ) return rc;
+  if( p.lfnstIdx ) return fail( ctx, VVB_ERR_UNSUPPORTED, "the inverse LFNST (TrQuant::xInvLfnst) is not on the device yet" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
 #define VVB_INV_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = inv_trquant_smem<LWv, LHv>(); \
@@ -1126,6 +1145,7 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
   TuPar p;
   int rc = makeTuPar( ctx, par, p );
   if( rc ) return rc;
+  if( p.lfnstIdx ) return fail( ctx, VVB_ERR_UNSUPPORTED, "the inverse LFNST (TrQuant::xInvLfnst) is not on the device yet" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};

@@ -90,6 +90,7 @@ struct vvb_ctx
   int            numSMs   = 148;
   // device-side constant data
   int8_t*        d_trTable   = nullptr;     // all transform matrices (vvc_tables.h)
+  int8_t*        d_lfnst     = nullptr;     // LFNST forward kernels (vvc_lfnst_tables.h)
   int32_t*       d_scan      = nullptr;     // scan tables for all (log2w, log2h) in 2..6, 1024 entries each
   // grow-only scratch arenas (device + pinned host) used by the host-buffer entry points
   int            mctfMaxDim = 64;      // largest MCTF block dimension in device-resident candidate lists (vvb_mctf_hint)

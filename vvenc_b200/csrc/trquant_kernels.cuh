@@ -36,6 +36,9 @@ struct TuPar
   int lKeepW, lKeepH, lRegW; // log2 of keepW, keepH, regionW (all powers of two: every index split is a shift)
   int q32;                   // qbits <= 30: (|c| * scale + add) fits 32 bit for |c| < 2^16 (always true for residuals inside the bit depth)
   unsigned add32;            // low 32 bits of add (valid when q32)
+  int lfnstIdx, lfnstTranspose;   // cu.lfnstIdx (0 = off) and xGetTransposeFlag of the intra mode; the kernel matrix [outputs][inputs] (int8) of (set, index):
+  const int8_t* lfnstMat;
+  int lfnstMaxScan;          // last scan position the quantiser may look at: 7 (4x4 / 8x8 TUs) or 15 with LFNST (Quant.cpp:151-158), INT_MAX without
   int signHiding;            // slice->signDataHidingEnabled: Quant::quant runs xSignBitHidingHDQ after QuantCore (Quant.cpp:817-826)
   unsigned rdoqThr;          // smallest |c| with ((|c| * scaleRdoq + addRdoq) >> qbitsRdoq) != 0  (needRdoqCore as one compare)
 };
@@ -193,7 +196,7 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
   constexpr bool multi = T > 32;
   const int4* c4 = reinterpret_cast<const int4*>( coef );
   const int4* s4 = reinterpret_cast<const int4*>( inv );
-  const int useThres = par.useThres; const unsigned rdoqThr = par.rdoqThr;
+  const int useThres = par.useThres, maxScan = par.lfnstMaxScan; const unsigned rdoqThr = par.rdoqThr;
   // ---- pass 1: last non-zero scan position, coefficient groups holding a value above the threshold, RDOQ pre-check
   int lastNZ = 0; unsigned cgLo = 0, cgHi = 0, rd = 0;
   int4 cq[CACHE ? ITERS : 1], sq[CACHE ? ITERS : 1];
@@ -208,8 +211,8 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
       if( cq[k].x | cq[k].y | cq[k].z | cq[k].w )
       {
         sq[k] = __ldg( s4 + qi );
-#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); lastNZ = max( lastNZ, sv ); rd |= (unsigned) ac >= rdoqThr; \
-          if( ac > useThres ) { const int cg = ( sv ) >> 4; if( NQUADS <= 128 || cg < 32 ) cgLo |= 1u << ( cg & 31 ); else cgHi |= 1u << ( cg - 32 ); } }
+#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); rd |= (unsigned) ac >= rdoqThr; if( ( sv ) <= maxScan ) { lastNZ = max( lastNZ, sv ); \
+          if( ac > useThres ) { const int cg = ( sv ) >> 4; if( NQUADS <= 128 || cg < 32 ) cgLo |= 1u << ( cg & 31 ); else cgHi |= 1u << ( cg - 32 ); } } }
         VVB_Q1( cq[k].x, sq[k].x ) VVB_Q1( cq[k].y, sq[k].y ) VVB_Q1( cq[k].z, sq[k].z ) VVB_Q1( cq[k].w, sq[k].w )
 #undef VVB_Q1
       }
@@ -410,6 +413,48 @@ __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* M
       }
   }
   __syncthreads();
+  if( par.lfnstIdx )                                         // uniform over the CTA: TrQuant::xFwdLfnst (TrQuant.cpp:942-1048) between xT and the quantiser
+  {
+    constexpr int KEEP = ( LW >= 3 && LH >= 3 ) ? 8 : 4, NIN = KEEP == 8 ? 48 : 16;
+    constexpr int ZOUT = ( ( W == 4 && H == 4 ) || ( W == 8 && H == 8 ) ) ? 8 : 16;
+    // the primary transform keeps the top-left KEEP x KEEP outputs only (TrQuant.cpp:499-511)
+    if( live )
+      for( int i = tt; i < S::COEF_WORDS; i += T )
+      {
+        const int y = i >> S::LRW, x = i & ( RW - 1 );
+        if( x >= KEEP || y >= KEEP ) myCoef[i] = 0;
+      }
+    __syncthreads();
+    int32_t* lfOut = myTmp;                                  // the stage-1 buffer is free now
+    if( live )
+      for( int j = tt; j < ZOUT; j += T )
+      {
+        const int8_t* m = par.lfnstMat + j * NIN;
+        int sum = 0;
+#pragma unroll 4
+        for( int i = 0; i < NIN; i++ )
+        {
+          int a, b;                                          // walk of :973-1019: rows of 8 then rows of 4 (sub-block 8), rows of 4 (sub-block 4); transposed: columns
+          if( KEEP == 4 ) { b = i >> 2; a = i & 3; }
+          else if( i < 32 ) { b = i >> 3; a = i & 7; }
+          else { b = 4 + ( ( i - 32 ) >> 2 ); a = ( i - 32 ) & 3; }
+          const int x = par.lfnstTranspose ? b : a, y = par.lfnstTranspose ? a : b;
+          sum += myCoef[( y << S::LRW ) + x] * (int) __ldg( m + i );
+        }
+        lfOut[j] = ( sum + 64 ) >> 7;                        // xFwdLfnstNxNCore, :166-187
+      }
+    __syncthreads();
+    if( live )
+    {
+      const int32_t* fwd8 = scanTab + VVB_SCAN_TABLE_ENTRIES + 6 * 1024;     // grouped 4x4 diagonal scan of an 8x8 region (= g_coefTopLeftDiagScan8x8 without the TU pitch)
+      for( int j = tt; j < NIN; j += T )
+      {
+        const int p = __ldg( fwd8 + j );
+        myCoef[( ( p >> 3 ) << S::LRW ) + ( p & 7 )] = j < ZOUT ? lfOut[j] : 0;
+      }
+    }
+    __syncthreads();
+  }
   return team_quantise<LW, LH, T>( par, myCoef, myResi, myRed, scanTab + par.scanOff, tt, live );
 }
 
