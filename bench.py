@@ -1030,7 +1030,7 @@ def main():
         h2d = 0; d2h = 0
         for n in SIZES:
             nb = len(blocks_np[n])
-            h2d += 3 * nb * 24 + KP * 4
+            h2d += nb * 24 + KP * 4
             d2h += nb * 16 + nb * KP * 4 + nb * n * n * 2 + nb * 9
         S0 = host_sets[0][2]
         h2d += 2 * (h_planes[0][3] + 2 * MARGIN) * S0 * 2
@@ -1043,36 +1043,34 @@ def main():
             chk(lib.vvb_plane_upload(e.h, E0, ctypes.c_void_p(po.ctypes.data + base * 2), S, W, hbr, MARGIN, BITDEPTH))
             chk(lib.vvb_plane_upload(e.h, E1, ctypes.c_void_p(pr.ctypes.data + base * 2), S, W, hbr, MARGIN, BITDEPTH))
 
-        def e2e_search(i):
-            c = i % NCTX
-            chk(lib.vvb_sad_search_pyramid(engs[c].h, E0, E1, nlev, hb[c]['pyr_blocks'], pyr_counts, SIZES[0], ctypes.byref(me), nx, nx, hb[c]['pyr_best']))
+        import vvenc_b200._lib as VL
+        ios = []
+        for c in range(NCTX):
+            arr = (VL.vvb_level_io * nlev)()
+            for l, n in enumerate(SIZES):
+                d = hb[c]
+                arr[l].blocks = d['blocks'][n].ctypes.data; arr[l].count = len(blocks_np[n]); arr[l].best = d['best'][n].ctypes.data
+                arr[l].refine_cost = d['satd'][n].ctypes.data; arr[l].q = d['q'][n].ctypes.data
+                arr[l].abs_sum = d['sum'][n].ctypes.data; arr[l].last_pos = d['last'][n].ctypes.data; arr[l].need_rdoq = d['nr'][n].ctypes.data
+                arr[l].tu = tu_par[n]
+            ios.append(arr)
 
-        def e2e_tail(i):
+        def e2e_chain(i):
+            # one call: block lists up, search -> start = best (on the device) -> SATD ring -> TU, every result down; nothing returns to the host in between
             c = i % NCTX
-            e = engs[c]; d = hb[c]
-            chk(lib.vvb_synchronize(e.h))                      # the host needs the vectors now
-            for n in SIZES:
-                nb = len(blocks_np[n])
-                if nb == 0:
-                    continue
-                # host logic between the calls: the best vector becomes the refinement centre / prediction offset
-                bv = d['best'][n].view(V.BEST_DT); bl = d['blocks'][n].view(V.BLOCK_DT)
-                bl['start_x'] = bv['dx']; bl['start_y'] = bv['dy']
-                chk(lib.vvb_cost_pattern(e.h, V.DF_HAD, E0, E1, PA(d['blocks'][n]), nb, n, n, PA(h_pat), KP, ctypes.byref(me), PA(d['satd'][n]), None))
-                chk(lib.vvb_fwd_trquant_planes(e.h, ctypes.byref(tu_par[n]), E0, E1, PA(d['blocks'][n]), nb, None, PA(d['q'][n]), PA(d['sum'][n]), PA(d['last'][n]), PA(d['nr'][n])))
+            chk(lib.vvb_search_refine_tu(engs[c].h, E0, E1, nlev, ios[c], SIZES[0], ctypes.byref(me), nx, nx, V.DF_HAD, PA(h_pat), KP))
 
         def run_e2e(first, count):
             # one host thread per context, as one encoder worker per context would run (EncSlice.cpp:142-147; ctypes releases the GIL inside the library):
-            # worker c takes the pictures first+c, first+c+NCTX, ... and runs each of them upload -> search -> wait for the vectors -> refinement + TU coding ->
-            # wait for the downloads; the GPU overlaps one worker's copies with the other workers' kernels
+            # worker c takes the pictures first+c, first+c+NCTX, ... and runs each of them upload -> chained search / refinement / TU call -> wait for the
+            # downloads; the GPU overlaps one worker's copies with the other workers' kernels
             errs = []
             def worker(c):
                 try:
                     pc = time.perf_counter
                     for i in range(first + c, first + count, NCTX):
-                        t = pc(); e2e_upload(i); e2e_search(i); host_ms['upload_search_enqueue'] += pc() - t
-                        t = pc(); e2e_tail(i); host_ms['wait_vectors_and_tail_enqueue'] += pc() - t
-                        t = pc(); chk(lib.vvb_synchronize(engs[i % NCTX].h)); host_ms['wait_downloads'] += pc() - t
+                        t = pc(); e2e_upload(i); e2e_chain(i); host_ms['upload_and_enqueue'] += pc() - t
+                        t = pc(); chk(lib.vvb_synchronize(engs[i % NCTX].h)); host_ms['wait_results'] += pc() - t
                 except Exception as ex:
                     errs.append(ex)
             th = [threading.Thread(target=worker, args=(c,)) for c in range(NCTX)]
@@ -1081,7 +1079,7 @@ def main():
             if errs:
                 raise errs[0]
 
-        host_ms = {k: 0.0 for k in ('upload_search_enqueue', 'wait_vectors_and_tail_enqueue', 'wait_downloads')}
+        host_ms = {k: 0.0 for k in ('upload_and_enqueue', 'wait_results')}
         ke_steps = max(2, min(args.steps, 5))
         ke = ke_steps * PPS // NCTX * NCTX                   # pictures inside the timed region
         run_e2e(0, 2 * NCTX)
@@ -1100,8 +1098,8 @@ def main():
         e2e = {'value': units_picture_all / dt, 'unit': 'candidate-blocks/s', 'h2d_bytes_per_step': int(h2d) * PPS, 'd2h_bytes_per_step': int(d2h) * PPS,
                'h2d_bytes_per_picture': int(h2d), 'd2h_bytes_per_picture': int(d2h), 'ms_per_step': dt * 1e3 * PPS, 'ms_per_picture': dt * 1e3,
                'steps': ke / PPS, 'pictures': ke, 'contexts': NCTX, 'worker_ms_per_picture': {k: v * 1e3 / ke for k, v in host_ms.items()},
-               'timing': 'host wall clock over %d pictures (%.1f steps) issued through the host-buffer C ABI from pinned memory by %d worker threads, one context each '
-                         '(asynchronous mode, explicit waits for the vectors and for the downloads); every upload and download is inside the timed region; max over ranks' % (ke, ke / PPS, NCTX)}
+               'timing': 'host wall clock over %d pictures (%.1f steps) issued through the host-buffer C ABI (vvb_plane_upload x2 + vvb_search_refine_tu per picture) from pinned memory '
+                         'by %d worker threads, one asynchronous context each; every upload and download is inside the timed region; max over ranks' % (ke, ke / PPS, NCTX)}
         last = 2 * NCTX + ke - 1                               # index of the last picture issued
         for e in engs:
             e.set_async(False)

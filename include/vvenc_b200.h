@@ -209,6 +209,25 @@ int vvb_fwd_trquant_planes    ( vvb_ctx* ctx, const vvb_tu_par* par, int org_pla
 int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int org_plane, int pred_plane, const vvb_block* dev_blocks, int n,
                          int32_t* dev_coef, int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos, uint8_t* dev_need_rdoq );
 
+/* ---- one call for the whole per-picture chain (host buffers; the production shape of "batch the per-CTU candidate evaluations into CUDA launches") -------------
+ * For a quad-tree of block lists (as vvb_sad_search_pyramid: level 0 = base_w, block p of level l+1 is the parent of blocks 4p..4p+3 of level l):
+ *   1. dense search of every block (vvb_sad_search_pyramid)                                   -> best[l]
+ *   2. blocks[l][i].start = best vector (on the device), distortion `refine_dfunc` over the fixed pattern around it (vvb_cost_pattern) -> refine_cost[l][i][K]
+ *   3. residual org - pred(best vector), forward transform + quantiser (vvb_fwd_trquant_planes) -> q[l], abs_sum[l], last_pos[l], need_rdoq[l]
+ * Nothing returns to the host between the stages; in asynchronous mode the call only enqueues (one upload, the launches, the downloads).  Results are those of
+ * the three calls made one after the other with the host patching start_x / start_y in between.  Nullable outputs: refine_cost, q (with abs_sum...), need_rdoq. */
+typedef struct
+{
+  const vvb_block* blocks; int32_t count;        /* in: block list of the level (start_x / start_y ignored)                        */
+  vvb_best*  best;                               /* out [count]                                                                    */
+  uint32_t*  refine_cost;                        /* out [count][K], nullable                                                       */
+  int16_t*   q;                                  /* out [count][h][w] levels, nullable (then no transform stage for this level)    */
+  int32_t*   abs_sum; int32_t* last_pos; uint8_t* need_rdoq;   /* out [count], each nullable                                       */
+  vvb_tu_par tu;                                 /* TU parameters of the level (w = h = base_w << l)                               */
+} vvb_level_io;
+int vvb_search_refine_tu( vvb_ctx* ctx, int org_plane, int ref_plane, int levels, const vvb_level_io* io, int base_w, const vvb_me_par* me, int nx, int ny,
+                          int refine_dfunc, const vvb_mv* pattern, int K );
+
 /* ---- inverse path of the TU loop -------------------------------------------------------------------
  * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
  * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp}. */

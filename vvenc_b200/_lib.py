@@ -31,6 +31,11 @@ class vvb_tu_par(ctypes.Structure):
                 ('qp', ctypes.c_int32), ('is_irap', ctypes.c_int32), ('dep_quant', ctypes.c_int32), ('sign_hiding', ctypes.c_int32), ('lfnst_idx', ctypes.c_int32), ('lfnst_set', ctypes.c_int32), ('lfnst_transpose', ctypes.c_int32)]
 
 
+class vvb_level_io(ctypes.Structure):
+    _fields_ = [('blocks', ctypes.c_void_p), ('count', ctypes.c_int32), ('best', ctypes.c_void_p), ('refine_cost', ctypes.c_void_p), ('q', ctypes.c_void_p),
+                ('abs_sum', ctypes.c_void_p), ('last_pos', ctypes.c_void_p), ('need_rdoq', ctypes.c_void_p), ('tu', vvb_tu_par)]
+
+
 # numpy dtypes mirroring the packed C structs
 import numpy as np
 CAND_DT = np.dtype([('org_plane', '<i4'), ('org_x', '<i4'), ('org_y', '<i4'), ('cur_plane', '<i4'), ('cur_x', '<i4'), ('cur_y', '<i4'),
@@ -81,6 +86,7 @@ SYMBOLS = {
     'vvb_fwd_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_set_tensor_transform': (c_i, [c_p, c_i]),
+    'vvb_search_refine_tu': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_i, c_p, c_i]),
     'vvb_fwd_trquant_planes': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),

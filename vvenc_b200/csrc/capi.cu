@@ -1105,6 +1105,75 @@ int vvb_fwd_trquant_planes( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, i
   return VVB_OK;
 }
 
+
+// Whole per-picture chain in one call (include/vvenc_b200.h): search -> start = best -> pattern distortion -> TU, chained on the device
+int vvb_search_refine_tu( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, const vvb_level_io* io, int baseW, const vvb_me_par* me, int nx, int ny,
+                          int refineDfunc, const vvb_mv* pattern, int K )
+{
+  if( !ctx || !io || !me || levels < 2 || levels > 5 || nx < 1 || ny < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  bool anyRefine = false;
+  for( int l = 0; l < levels; l++ )
+  {
+    if( io[l].count < 0 || ( io[l].count && ( !io[l].blocks || !io[l].best ) ) ) return fail( ctx, VVB_ERR_ARG, "bad level arguments" );
+    anyRefine = anyRefine || io[l].refine_cost;
+  }
+  if( anyRefine && ( !pattern || K < 1 ) ) return fail( ctx, VVB_ERR_ARG, "refinement needs a pattern" );
+  // one arena: per level blocks | best | refine cost | q | abs_sum, last_pos, need_rdoq ; then the pattern
+  size_t offB[5], offO[5], offC[5], offQ[5], offM[5], total = 0;
+  auto take = [&]( size_t bytes ) { const size_t o = total; total += ( bytes + 255 ) & ~(size_t) 255; return o; };
+  for( int l = 0; l < levels; l++ )
+  {
+    const size_t n = (size_t) io[l].count, side = (size_t) baseW << l;
+    offB[l] = take( n * sizeof( vvb_block ) ); offO[l] = take( n * sizeof( vvb_best ) );
+    offC[l] = take( io[l].refine_cost ? n * K * 4 : 0 ); offQ[l] = take( io[l].q ? n * side * side * 2 : 0 ); offM[l] = take( io[l].q ? n * 12 : 0 );
+  }
+  const size_t offP = take( anyRefine ? (size_t) K * sizeof( vvb_mv ) : 0 );
+  void* arena; int rc;
+  if( ( rc = scratch( ctx, 4, total, &arena ) ) ) return rc;
+  uint8_t* A = (uint8_t*) arena;
+  const vvb_block* pb[5]; vvb_best* po[5]; int counts[5];
+  for( int l = 0; l < levels; l++ )
+  {
+    pb[l] = (const vvb_block*)( A + offB[l] ); po[l] = (vvb_best*)( A + offO[l] ); counts[l] = io[l].count;
+    if( counts[l] ) CU( cudaMemcpyAsync( A + offB[l], io[l].blocks, (size_t) counts[l] * sizeof( vvb_block ), cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  if( anyRefine ) CU( cudaMemcpyAsync( A + offP, pattern, (size_t) K * sizeof( vvb_mv ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_sad_search_pyramid_dev( ctx, orgPlane, refPlane, levels, pb, counts, baseW, me, nx, ny, po ) ) ) return rc;
+  vvb_me_par hp = *me;
+  hp.pattern_radius = 0;
+  for( int i = 0; anyRefine && i < K; i++ ) hp.pattern_radius = std::max( hp.pattern_radius, std::max( std::abs( (int) pattern[i].dx ), std::abs( (int) pattern[i].dy ) ) );
+  for( int l = 0; l < levels; l++ )
+  {
+    const int n = counts[l], side = baseW << l;
+    if( !n ) continue;
+    vvb_block* dB = (vvb_block*)( A + offB[l] );
+    if( ( rc = vvb_blocks_set_start_dev( ctx, dB, po[l], n ) ) ) return rc;
+    if( io[l].refine_cost && ( rc = vvb_cost_pattern_dev( ctx, refineDfunc, orgPlane, refPlane, dB, n, side, side, (const vvb_mv*)( A + offP ), K, &hp, (uint32_t*)( A + offC[l] ), nullptr ) ) ) return rc;
+    if( io[l].q )
+    {
+      int32_t* dSum = (int32_t*)( A + offM[l] ); int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
+      if( ( rc = vvb_fwd_trquant_planes_dev( ctx, &io[l].tu, orgPlane, refPlane, dB, n, nullptr, (int16_t*)( A + offQ[l] ), dSum, dLast, dNr ) ) ) return rc;
+    }
+  }
+  for( int l = 0; l < levels; l++ )
+  {
+    const size_t n = (size_t) counts[l], side = (size_t) baseW << l;
+    if( !n ) continue;
+    CU( cudaMemcpyAsync( io[l].best, A + offO[l], n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( io[l].refine_cost ) CU( cudaMemcpyAsync( io[l].refine_cost, A + offC[l], n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( io[l].q )
+    {
+      int32_t* dSum = (int32_t*)( A + offM[l] ); int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
+      CU( cudaMemcpyAsync( io[l].q, A + offQ[l], n * side * side * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+      if( io[l].abs_sum )   CU( cudaMemcpyAsync( io[l].abs_sum, dSum, n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      if( io[l].last_pos )  CU( cudaMemcpyAsync( io[l].last_pos, dLast, n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      if( io[l].need_rdoq ) CU( cudaMemcpyAsync( io[l].need_rdoq, dNr, n, cudaMemcpyDeviceToHost, ctx->stream ) );
+    }
+  }
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
 // ---- inverse path + fused TU round trip ------------------------------------------------------------------------------
 int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ, int n, int16_t* dResi )
 {
