@@ -288,7 +288,8 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
     // Lane mapping.  A quarter warp's LDS.128 is one wavefront when its 8 lanes read 8 consecutive 16-byte chunks: main items are groups of 8 adjacent strips
     // of one row pair (it = ((q * nPairs + pr) * nMain + st), st fastest); the strips left over when the range is not a multiple of 64 vectors follow as
     // tail items with the row pair as the fast index.
-    const int nPairs = ( ny + 1 ) >> 1, nMain = nStrips & ~7, nTail = nStrips - nMain;
+    const int nFull = nx >> 3, nCols = nx & 7;                // full strips of 8 vectors; the nx % 8 columns left of them are column items (below)
+    const int nPairs = ( ny + 1 ) >> 1, nMain = nFull & ~7, nTail = nFull - nMain;
     const int perQm = nPairs * nMain, itemsMain = NQ * perQm, perQt = nPairs * nTail, items = itemsMain + NQ * perQt;
     const float invPerQm = 1.0f / (float) max( 1, perQm ), invMain = 1.0f / (float) max( 1, nMain ), invPerQt = 1.0f / (float) max( 1, perQt ), invPairs = 1.0f / (float) nPairs;
     const uint32_t* org32 = reinterpret_cast<const uint32_t*>( orgS );
@@ -390,6 +391,105 @@ __global__ void __launch_bounds__( PYR_MAX_THREADS, 1 ) sad_pyramid8_kernel( con
         }
         if( uni ) { key = __reduce_min_sync( mask, key ); if( lane == lead ) atomicMin( &sKey32[OFF1 + q], key ); }
         else atomicMin( &sKey32[OFF1 + q], key );
+      }
+    }
+
+    // ---- the nx % 8 rightmost columns (one column for every +-R range): item = (quad, column, group of 8 vertically adjacent vectors).  A strip item would
+    // spend a full strip of work on them (11 % of the kernel for 65 columns); here the thread keeps the member's eight original rows in registers and walks
+    // the 15 window rows its 8 vectors touch: window row r meets original row r - c for vector c.
+    if( nCols )
+    {
+      const int nV = ( ny + 7 ) >> 3, perQc = nCols * nV, itemsC = NQ * perQc;
+      const float invPerQc = 1.0f / (float) perQc, invNv = 1.0f / (float) nV;
+      for( int base = 0; base < itemsC; base += nthr )
+      {
+        const int it = base + tid;
+        const bool active = it < itemsC;
+        const unsigned mask = __ballot_sync( 0xffffffffu, active );
+        if( !active ) continue;
+        const int q = fast_div( it, invPerQc ), rem = it - q * perQc;
+        const int ci = fast_div( rem, invNv ), g = rem - ci * nV;
+        const int cx = 8 * nFull + ci, cy0 = 8 * g;
+        const int lead = __ffs( mask ) - 1;
+        const bool uni = __all_sync( mask, q == __shfl_sync( mask, q, lead ) );
+        const int qx = pyr_compact( q ), qy = pyr_compact( q >> 1 );
+        const uint32_t* wsrc = ( cx & 1 ) ? win1w : win0w;      // odd columns read the one-pel-shifted copy
+        const int cw = cx >> 1;                                 // word offset of the column inside a window row
+        uint32_t ps[8];
+#pragma unroll
+        for( int c = 0; c < 8; c++ ) ps[c] = 0u;
+#pragma unroll 1
+        for( int m = 0; m < 4; m++ )
+        {
+          const int bx8 = 2 * qx + ( m & 1 ), by8 = 2 * qy + ( m >> 1 ), b0 = 4 * q + m;
+          const int sumA = sSumA[b0];
+          uint32_t o[8][4];
+#pragma unroll
+          for( int y = 0; y < 8; y++ )
+          {
+            const uint4 ov = *reinterpret_cast<const uint4*>( org32 + ( by8 * 8 + y ) * ( R / 2 ) + bx8 * 4 );
+            o[y][0] = ov.x; o[y][1] = ov.y; o[y][2] = ov.z; o[y][3] = ov.w;
+          }
+          int acc[8];
+#pragma unroll
+          for( int c = 0; c < 8; c++ ) acc[c] = sumA;
+          const uint32_t* wp = wsrc + ( by8 * 8 + cy0 ) * wsw + bx8 * 4 + cw;
+#pragma unroll
+          for( int r = 0; r < 15; r++ )
+          {
+            uint32_t w[4];
+            if( ( cw & 3 ) == 0 ) { const uint4 wv = *reinterpret_cast<const uint4*>( wp + r * wsw ); w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w; }
+            else { w[0] = wp[r * wsw]; w[1] = wp[r * wsw + 1]; w[2] = wp[r * wsw + 2]; w[3] = wp[r * wsw + 3]; }
+#pragma unroll
+            for( int c = 0; c < 8; c++ )
+            {
+              if( r - c >= 0 && r - c < 8 )
+              {
+#pragma unroll
+                for( int i = 0; i < 4; i++ ) acc[c] = __dp2a_lo( (int) __vmins2( o[r - c][i], w[i] ), (int) 0x0000fefeu, acc[c] );
+              }
+            }
+          }
+          const unsigned char* bb = bitsS + b0 * L.bStride;
+          const uint32_t bx4 = 4u * bb[cx];
+          const uint2 byw = *reinterpret_cast<const uint2*>( bb + nxp + cy0 );
+          const uint16_t* vcol = V + ( by8 * 8 + cy0 ) * L.vPitch + bx8 * 8 + cx;
+          uint32_t bk = 0xffffffffu;
+#pragma unroll
+          for( int c = 0; c < 8; c++ )
+          {
+            const uint32_t idx4 = __dp4a( c < 4 ? byw.x : byw.y, 1u << ( 8 * ( c & 3 ) ), bx4 );              // row bits are stored times 4
+            const uint32_t mvk  = *reinterpret_cast<const uint32_t*>( sMv8 + c * ( PYR_MVN * 4 ) + idx4 );
+            const uint32_t sad  = (uint32_t)( (int) vcol[c * L.vPitch] + acc[c] );
+            ps[c] += sad;
+            const uint32_t key = cy0 + c < ny ? sad * eight + mvk : 0xffffffffu;
+            bk = min( bk, key );
+          }
+          uint32_t key = ( ( bk >> 3 ) << ob ) + (uint32_t)( ( cy0 + (int)( bk & 7u ) ) * nx + cx );
+          if( uni ) { key = __reduce_min_sync( mask, key ); if( lane == lead ) atomicMin( &sKey32[b0], key ); }
+          else atomicMin( &sKey32[b0], key );
+        }
+        {
+          const unsigned char* bb = bitsS + ( OFF1 + q ) * L.bStride;
+          const uint32_t bx4 = 4u * bb[cx];
+          const uint2 byw = *reinterpret_cast<const uint2*>( bb + nxp + cy0 );
+          uint32_t* tcol = LV >= 3 ? T + ( LV == 4 ? ( q >> 2 ) : 0 ) * L.tStride + cy0 * nxp + ( cx & 7 ) * nStrips + ( cx >> 3 ) : nullptr;
+          uint32_t bk = 0xffffffffu;
+#pragma unroll
+          for( int c = 0; c < 8; c++ )
+          {
+            const uint32_t idx4 = __dp4a( c < 4 ? byw.x : byw.y, 1u << ( 8 * ( c & 3 ) ), bx4 );
+            const uint32_t mvk  = *reinterpret_cast<const uint32_t*>( sMv8 + c * ( PYR_MVN * 4 ) + idx4 );
+            if( cy0 + c < ny )
+            {
+              bk = min( bk, ps[c] * eight + mvk );
+              if( LV >= 3 ) atomicAdd( tcol + c * nxp, ps[c] );
+            }
+          }
+          uint32_t key = ( ( bk >> 3 ) << ob ) + (uint32_t)( ( cy0 + (int)( bk & 7u ) ) * nx + cx );
+          if( uni ) { key = __reduce_min_sync( mask, key ); if( lane == lead ) atomicMin( &sKey32[OFF1 + q], key ); }
+          else atomicMin( &sKey32[OFF1 + q], key );
+        }
       }
     }
   }
