@@ -228,6 +228,30 @@ typedef struct
 int vvb_search_refine_tu( vvb_ctx* ctx, int org_plane, int ref_plane, int levels, const vvb_level_io* io, int base_w, const vvb_me_par* me, int nx, int ny,
                           int refine_dfunc, const vvb_mv* pattern, int K );
 
+/* ---- dependent quantisation: DepQuant::quant -> xQuantDQ (CommonLib/DepQuant.cpp:1462-1490, 1129-1264) for luma TUs without scaling lists --------
+ * The 4-state trellis over the scan positions of each TU (xDecide / xDecideAndUpdate :1266-1414, the rate-distortion checks :697-888, the state updates
+ * :907-1110, CommonCtx::update :473-531) runs on the device, one TU per thread, all TUs of the call sharing shape, QP, lambda and the rate tables.
+ * What the caller supplies is what depends on the encoder's entropy-coding state at that point of the CTU:
+ *   vvb_dq_rates -- the tables RateEstimator::initCtx (:344-471) derives from the CABAC contexts (public accessors of DQIntern::RateEstimator, DepQuant.h:161-170):
+ *                   last_bits_x/y[pos] (xSetLastCoeffOffset; lastOffset( scan ) = x + y part), sig_sbb_bits[ctx][bin] (sigSbbFracBits), sig_bits[set][ctx][bin]
+ *                   (m_sigFracBits; state k reads set max( k - 1, 0 )), gtx_bits[ctx][0..5] (gtxFracBits).
+ *   vvb_dq_par   -- lambda (Quant::m_dLambda), dq_thr_val (Quant::init thrVal, 8), zero_out = the condition of :1155 evaluated by the caller
+ *                   ( mtsIdx > MTS_SKIP || ( sps.MTS && cu.sbtInfo && w <= 32 && h <= 32 ) ): coefficients beyond 16 of a 32-sided TU are skipped.
+ *                   scalar_members: the reference's scalar and x86 state updates differ for levels above 127 (update1State adds uint8_t( level ) to the template sum,
+ *                   DepQuant.cpp:956-966; DepQuantX86.h:86-93, 163-166 adds the level capped to 126 / 127).  0 (default) follows the x86 members the encoder
+ *                   installs on this platform, 1 the scalar ones of --SIMD=SCALAR.  Below 128 they agree.
+ * The quantiser constants of Quantizer::initQuantBlock (:533-572) are derived inside from (w, h, bit_depth, qp, lambda) in the same double-precision steps.
+ * par->lfnst_idx > 0 restricts the first tested position to 7 / 15 (:1164-1167).  need_rdoq (nullable, [n]): TUs with need_rdoq[i] == 0 return all-zero levels and
+ * last_pos -1 (picture->useSelectiveRdoq, :1464-1468).  coef: [n][h][w] TCoeff as vvb_fwd_trquant returns them; q: [n][h][w] levels; abs_sum, last_pos nullable. */
+typedef struct { int32_t last_bits_x[32], last_bits_y[32], sig_sbb_bits[2][2], sig_bits[3][12][2], gtx_bits[21][6]; } vvb_dq_rates;   /* 1064 bytes */
+typedef struct { double lambda; int32_t dq_thr_val, zero_out, scalar_members, pad; } vvb_dq_par;
+int vvb_dep_quant    ( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq, const vvb_dq_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n,
+                       int16_t* q, int32_t* abs_sum, int32_t* last_pos );
+int vvb_dep_quant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq, const vvb_dq_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n,
+                       int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos );
+/* the constants the call derives (no device needed): out = qShift, maxQIdx, thresLast, distShift, qAdd, qScale, distAdd, distStepAdd, distOrgFact (Quantizer, DepQuant.h:220-231) */
+int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_t out[9] );
+
 /* ---- inverse path of the TU loop -------------------------------------------------------------------
  * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
  * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp}. */

@@ -2,6 +2,7 @@
 //
 //   xTQuantB200          <->  the xT + xQuant pair inside TrQuant::transformNxN (TrQuant.cpp:709-733 -> xT :481-564, Quant::quant Quant.cpp:735-833)
 //   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
+//   xQuantDQB200         <->  DepQuant::xQuantDQ (DepQuant.cpp:1129-1264), the trellis DepQuant::quant runs for non-skip TUs of a slice with depQuantEnabled
 //
 // for the TUs the library covers: luma, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), LFNST on the forward side, no transform
 // skip, no scaling lists, plain quantiser incl. its sign-bit hiding (RDOQ / dependent quantisation stay on the host and use the coefficients this call leaves in the temp buffer).
@@ -17,6 +18,7 @@ struct B200TuApi
   bool bound = false;
   decltype( &vvb_fwd_trquant )  fwdTrQuant = nullptr;
   decltype( &vvb_inv_trquant )  invTrQuant = nullptr;
+  decltype( &vvb_dep_quant )    depQuant   = nullptr;
 } ;
 static B200TuApi g_b200t;
 
@@ -27,7 +29,7 @@ inline int b200LoadTu( const char* libPath )
   if( rc ) return rc;
   void* h = g_b200.handle;
 #define VVB_RESOLVE( member, name ) g_b200t.member = (decltype( g_b200t.member )) dlsym( h, #name ); if( !g_b200t.member ) { g_b200.error = "missing " #name; return -2; }
-  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )
+  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )
 #undef VVB_RESOLVE
   g_b200t.bound = true;
   return 0;
@@ -93,4 +95,42 @@ inline void invTransformNxNB200( TrQuant& tq, TransformUnit& tu, const Component
   for( int y = 0; y < h; y++ ) memcpy( &q[(size_t) y * w], src.buf + (ptrdiff_t) y * src.stride, sizeof( TCoeffSig ) * w );
   b200Check( g_b200t.invTrQuant( b200CtxOfThread(), &par, q.data(), 1, resi.data() ) );
   for( int y = 0; y < h; y++ ) memcpy( pResi.buf + (ptrdiff_t) y * pResi.stride, &resi[(size_t) y * w], sizeof( Pel ) * w );
+}
+
+// DepQuant::xQuantDQ( tu, srcCoeff, compID, cQP, lambda, ctx, absSum, false, nullptr ) with the trellis on the device.  What stays here is what depends on the
+// encoder's entropy-coding state: RateEstimator::initCtx (the member DepQuant inherits) turns the CABAC contexts into the rate tables, which travel as
+// vvb_dq_rates.  Inside the encoder this is a member of DepQuant (RateEstimator is a private base); `dq` is that object.  Scaling lists stay on the host.
+#include "CommonLib/DepQuant.h"
+inline void xQuantDQB200( DepQuant& dq, TrQuant& tq, TransformUnit& tu, const CCoeffBuf& srcCoeff, const ComponentID compID, const QpParam& cQP, const double lambda, const Ctx& ctx, TCoeff& absSum )
+{
+  vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
+  const int w = par.w, h = par.h;
+  const DQIntern::TUParameters& tuPars = *dq.m_scansRom->getTUPars( tu.blocks[compID], compID );
+  DQIntern::RateEstimator& re = (DQIntern::RateEstimator&) dq;
+  re.initCtx( tuPars, tu, compID, ctx.getFracBitsAcess() );                                   // DepQuant.cpp:1199 (done before the first-position test here: the tables are inputs of the call)
+  vvb_dq_rates rates;
+  // lastOffset( scanIdx ) = m_lastBitsX[x] + m_lastBitsY[y] (DepQuant.h:167-170): split along the first row / first column, the constant part goes to x
+  const int rw = std::min( w, 32 ), rh = std::min( h, 32 );
+  std::vector<int> scanOf( (size_t) w * h, -1 );
+  for( unsigned i = 0; i < tuPars.m_numCoeff; i++ ) scanOf[tuPars.m_scanId2BlkPos[i].idx] = (int) i;
+  memset( &rates, 0, sizeof( rates ) );
+  const int32_t corner = re.lastOffset( scanOf[0] );
+  for( int x = 0; x < rw; x++ ) rates.last_bits_x[x] = re.lastOffset( scanOf[x] );
+  for( int y = 0; y < rh; y++ ) rates.last_bits_y[y] = re.lastOffset( scanOf[(size_t) y * w] ) - corner;
+  for( int i = 0; i < 2; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_sbb_bits[i][b] = re.sigSbbFracBits()[i].intBits[b];
+  for( int st = 0; st < 3; st++ ) for( int i = 0; i < 12; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_bits[st][i][b] = re.sigFlagBits( st + 1 )[i].intBits[b];   // sigFlagBits( k ) = set max( k - 1, 0 )
+  for( int i = 0; i < 21; i++ ) for( int b = 0; b < 6; b++ ) rates.gtx_bits[i][b] = re.gtxFracBits()[i].bits[b];
+  vvb_dq_par dp = {};
+  dp.lambda = lambda; dp.dq_thr_val = dq.m_quant.m_DqThrVal;
+  dp.zero_out = ( tu.mtsIdx[compID] > MTS_SKIP || ( tu.cs->sps->MTS && tu.cu->sbtInfo != 0 && h <= 32 && w <= 32 ) ) ? 1 : 0;     // DepQuant.cpp:1155
+  par.lfnst_idx = ( tu.cu->lfnstIdx > 0 && tu.mtsIdx[compID] != MTS_SKIP ) ? tu.cu->lfnstIdx : 0;                                // :1164
+  std::vector<int32_t> coef( (size_t) w * h );
+  std::vector<int16_t> q( (size_t) w * h );
+  for( int y = 0; y < h; y++ ) memcpy( &coef[(size_t) y * w], srcCoeff.buf + (ptrdiff_t) y * srcCoeff.stride, sizeof( TCoeff ) * w );
+  int32_t sum = 0, lastPos = -1;
+  b200Check( g_b200t.depQuant( b200CtxOfThread(), &par, &dp, &rates, coef.data(), nullptr, 1, q.data(), &sum, &lastPos ) );
+  CoeffSigBuf dst = tu.getCoeffs( compID );
+  for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
+  tu.lastPos[compID] = lastPos;
+  absSum = sum;
 }

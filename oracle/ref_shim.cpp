@@ -659,6 +659,115 @@ int refshim_transform_quant_lfnst_b200( const int16_t* resi, int stride, int w, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dependent quantisation: DepQuant::xQuantDQ (DepQuant.cpp:1129-1264) -- what DepQuant::quant (:1462-1490) calls for a non-skip TU of a slice with
+// depQuantEnabled, scaling lists off -- on the TU rig, with a CABAC context set initialised the way a slice start does it (Ctx::init( qp, initId )).
+// enableOpt selects the members the DepQuant constructor installs: 0 = scalar (DQIntern::checkAllRdCosts, updateStates, ...), 1 = initDepQuantX86's.
+// ratesOut: the RateEstimator tables initCtx left, in vvb_dq_rates layout (266 int32); quantOut: the 9 Quantizer constants.
+int refshim_dep_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal, int enableOpt,
+                       int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* ratesOut, int64_t* quantOut )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mtsIdx, false, intraCu != 0, qp );
+  r.slice.depQuantEnabled = true;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx; r.cu.sbtInfo = (uint8_t) sbtInfo;
+  static thread_local std::unique_ptr<DepQuant> dqs[2];
+  std::unique_ptr<DepQuant>& dq = dqs[enableOpt ? 1 : 0];
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, enableOpt != 0 ) );
+  dq->init( 0, false, dqThrVal );
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  dq->xQuantDQ( r.tu, src, COMP_Y, qpp, lambda, *cabac, sum, false, nullptr );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  if( ratesOut )
+  {
+    // the estimator is only initialised when a first position was found (:1192-1199): run it here in any case so that callers always get the tables
+    const DQIntern::TUParameters& tuPars = *dq->m_scansRom->getTUPars( r.tu.blocks[COMP_Y], COMP_Y );
+    ( (DQIntern::RateEstimator&) *dq ).initCtx( tuPars, r.tu, COMP_Y, cabac->getFracBitsAcess() );
+    const DQIntern::RateEstimator& re = (const DQIntern::RateEstimator&) *dq;      // private base: only a C-style cast reaches it
+    int32_t* o = ratesOut;
+    for( int i = 0; i < 32; i++ ) *o++ = re.m_lastBitsX[i];
+    for( int i = 0; i < 32; i++ ) *o++ = re.m_lastBitsY[i];
+    for( int i = 0; i < 2; i++ ) for( int b = 0; b < 2; b++ ) *o++ = re.m_sigSbbFracBits[i].intBits[b];
+    for( int s = 0; s < 3; s++ ) for( int i = 0; i < 12; i++ ) for( int b = 0; b < 2; b++ ) *o++ = re.m_sigFracBits[s][i].intBits[b];
+    for( int i = 0; i < 21; i++ ) for( int b = 0; b < 6; b++ ) *o++ = re.m_gtxFracBits[i].bits[b];
+  }
+  if( quantOut )
+  {
+    dq->m_quant.initQuantBlock( r.tu, COMP_Y, qpp, lambda );
+    const DQIntern::Quantizer& z = dq->m_quant;
+    quantOut[0] = z.m_QShift; quantOut[1] = z.m_maxQIdx; quantOut[2] = z.m_thresLast; quantOut[3] = z.m_DistShift; quantOut[4] = z.m_QAdd; quantOut[5] = z.m_QScale;
+    quantOut[6] = z.m_DistAdd; quantOut[7] = z.m_DistStepAdd; quantOut[8] = z.m_DistOrgFact;
+  }
+  r.cu.lfnstIdx = 0; r.cu.sbtInfo = 0; r.slice.depQuantEnabled = false;
+  return 0;
+}
+
+// the same TU through integration/TrQuantB200.h (xQuantDQB200: rate tables from the CABAC state here, trellis in the bound library); returns 1 when the binding threw
+int refshim_dep_quant_b200( const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal,
+                            int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mtsIdx, false, intraCu != 0, qp );
+  r.slice.depQuantEnabled = true;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx; r.cu.sbtInfo = (uint8_t) sbtInfo;
+  if( lfnstIdx ) { r.sps.LFNST = true; r.cu.intraDir[CH_L] = PLANAR_IDX; r.cu.intraDir[CH_C] = DM_CHROMA_IDX; r.cu.mipFlag = false; r.cu.ispMode = 0; r.cu.chromaFormat = CHROMA_400; }
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 0, false, dqThrVal );
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  int rc = 0;
+  try { xQuantDQB200( *dq, tqOfThread(), r.tu, src, COMP_Y, qpp, lambda, *cabac, sum ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.cu.lfnstIdx = 0; r.cu.sbtInfo = 0; r.slice.depQuantEnabled = false; r.sps.LFNST = false;
+  if( rc ) return rc;
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  return 0;
+}
+
+// scan geometry of DQIntern::Rom for one luma shape, repacked into the 24- / 16-byte records of vvenc_b200/csrc/depquant_core.h (DqScanInfo, DqNbOut);
+// fields the reference leaves unset (nextSbbRight / nextSbbBelow off group starts, everything "next" at scan position 0) are reported as 0
+int refshim_dep_quant_tables( int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut )
+{
+  ctx();
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, false ) );
+  const CompArea area( COMP_Y, CHROMA_400, Area( 0, 0, w, h ) );
+  const DQIntern::TUParameters& tp = *dq->m_scansRom->getTUPars( area, COMP_Y );
+  const int nc = (int) tp.m_numCoeff;
+  for( int i = 0; i < nc; i++ )
+  {
+    const DQIntern::ScanInfo& s = tp.m_scanInfo[i];
+    uint8_t* o = scanInfoOut + 24 * i;
+    memset( o, 0, 24 );
+    const bool first = s.insidePos == 0 && i > 0;
+    int16_t v16[4] = { s.rasterPos, s.sbbPos, (int16_t)( first ? s.nextSbbRight : 0 ), (int16_t)( first ? s.nextSbbBelow : 0 ) };
+    memcpy( o, v16, 8 );
+    int8_t v8[7] = { s.insidePos, (int8_t)( i ? s.nextInsidePos : 0 ), (int8_t) s.spt, s.posX, s.posY, (int8_t)( i ? s.sigCtxOffsetNext : 0 ), (int8_t)( i ? s.gtxCtxOffsetNext : 0 ) };
+    memcpy( o + 8, v8, 7 );
+    const DQIntern::NbInfoSbb& nb = tp.m_scanId2NbInfoSbb[i];
+    o[15] = nb.numInv;
+    for( int k = 0; k < 5; k++ ) o[16 + k] = k < nb.numInv ? nb.invInPos[k] : 0;
+    const DQIntern::NbInfoOut& no = tp.m_scanId2NbInfoOut[i];
+    uint16_t w16[8] = { no.maxDist, no.num, no.outPos[0], no.outPos[1], no.outPos[2], no.outPos[3], no.outPos[4], 0 };
+    memcpy( nbOutOut + 16 * i, w16, 16 );
+  }
+  return nc;
+}
+
 // integration/TrQuantB200.h in action: the same TU rig, xT + Quant::quant replaced by xTQuantB200 / invTransformNxN by invTransformNxNB200 on the bound library.
 // Return 0, -1 (transform pair not expressible as an mtsIdx) or 1 (the binding threw; text through refshim_b200_error).
 int refshim_install_b200_tu( const char* libPath ) { return b200LoadTu( libPath ); }

@@ -279,6 +279,19 @@ def main(mock_path):
             if rc or not np.array_equal(ra, rb):
                 bad.append(['inv', opt] + [int(v) for v in row] + [rc])
     res['tu_inv'] = {'cases': ninv, 'bad': bad[:5]}
+    # DepQuant::xQuantDQ against xQuantDQB200 (rate tables from the rig's CABAC contexts through the public RateEstimator accessors, trellis in the bound library)
+    bad = []; ndq = 0; nz = 0
+    R.refshim_set_simd(b'AVX2')
+    for row in C.dq_cases():
+        w, h, bd, qp, lam1000, scale, decay10, mts, lf, sbt, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_inputs(row)
+        qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32(); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32()
+        assert R.refshim_dep_quant(P(coef), w, h, bd, qp, mts, intra, lf, sbt, lam1000 / 1000.0, 8, 1, qp, init_id, P(qa), ctypes.byref(sa), ctypes.byref(la), None, None) == 0
+        rc = R.refshim_dep_quant_b200(P(coef), w, h, bd, qp, mts, intra, lf, sbt, lam1000 / 1000.0, 8, qp, init_id, P(qb), ctypes.byref(sb), ctypes.byref(lb))
+        ndq += 1; nz += int(la.value >= 0)
+        if rc or not (np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
+            bad.append(['dq'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+    res['dep_quant'] = {'cases': ndq, 'non_empty': nz, 'bad': bad[:5]}
     print('RESULT ' + json.dumps(res))
 
 

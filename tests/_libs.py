@@ -37,6 +37,23 @@ def oracle():
     return _oracle
 
 
+_dqoracle = None
+
+
+def dq_oracle():
+    """oracle/_build/libdqoracle.so: the dependent-quantisation restatement (vvenc_b200/csrc/depquant_core.h) compiled for the CPU"""
+    global _dqoracle
+    if _dqoracle is None:
+        so = os.path.join(ROOT, 'oracle', '_build', 'libdqoracle.so')
+        if not os.path.exists(so):
+            subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle')])
+        L = ctypes.CDLL(so)
+        L.orc_dep_quant.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_dep_quant_constants.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+        _dqoracle = L
+    return _dqoracle
+
+
 _ref = None
 
 
@@ -62,6 +79,8 @@ def refshim():
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.refshim_pattern_search_member.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.refshim_dep_quant.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
+        L.refshim_dep_quant_b200.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_set_simd(b'AVX2')
         _ref = L
     return _ref

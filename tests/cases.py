@@ -298,3 +298,48 @@ FRAC_CASES = ((4242, 10), (4243, 10), (4244, 8))
 def frac_filter_of(list_index):
     """(reduce_tap, alt_hpel) used for block list `list_index` of a frac_case: cycles through the filter sets (ReduceFilterME 2 first: what the presets use)"""
     return ((2, 0), (2, 0), (0, 0), (1, 0), (2, 1), (0, 1), (2, 0), (1, 1), (0, 0), (2, 0))[list_index % 10]
+
+
+# ---- dependent quantisation (DepQuant::xQuantDQ) ------------------------------------------------------------------------------------------------------------
+def dq_cases():
+    """rows: w, h, bit_depth, qp, lambda * 1000, scale, decay * 10, mtsIdx (0 or 2..5), lfnstIdx, sbtInfo, intraCu, ctxInitId, seed
+    The CABAC contexts are initialised for slice QP = qp and init type ctxInitId, as a slice start does."""
+    rows = []
+    rs = np.random.RandomState(4711)
+    seed = 9000
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 16), (32, 8), (16, 64), (64, 32), (32, 16), (4, 32), (64, 4), (16, 8)]:
+        for k in range(14):
+            bd = 8 if k % 5 == 4 else 10
+            qp = int(rs.choice([17, 22, 27, 32, 37, 42, 51]))
+            lam = float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0]))
+            scale = int(rs.choice([5, 20, 60, 200, 600, 2000, 30000]))
+            decay = int(rs.choice([1, 5, 10, 15]))
+            mts = int(rs.choice([0, 0, 2, 3, 5])) if (w <= 32 and h <= 32) else 0
+            lf = int(rs.choice([0, 0, 0, 1, 2])) if mts == 0 else 0
+            sbt = int(rs.choice([0, 0, 0, 1])) if (mts == 0 and lf == 0) else 0
+            intra = 1 if lf else (0 if sbt else int(rs.randint(2)))
+            rows.append([w, h, bd, qp, int(lam * 1000), scale, decay, mts, lf, sbt, intra, k % 3, seed])
+            seed += 1
+    # levels above 127 (large coefficients, low QP, flat spectrum): here the reference's scalar and x86 state updates part ways
+    for (w, h) in [(16, 16), (32, 32), (64, 64), (32, 16), (8, 8)]:
+        for (qp, lam) in ((27, 1500.0), (22, 4000.0), (17, 800.0), (27, 4000.0)):
+            rows.append([w, h, 10, qp, int(lam * 1000), 30000, 1, 0, 0, 0, seed & 1, seed % 3, seed])
+            seed += 1
+    return np.array(rows, dtype=np.int64)
+
+
+def dq_inputs(row):
+    w, h, bd, qp, lam1000, scale, decay10, mts, lf, sbt, intra, init_id, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    coef = rs.laplace(0, scale, size=(h, w)) * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** (decay10 / 10.0))
+    coef = np.clip(coef, -32768, 32767).astype(np.int32)
+    if w > 32:
+        coef[:, 32:] = 0          # what the transform's zero-out leaves
+    if h > 32:
+        coef[32:, :] = 0
+    return coef
+
+
+def dq_zero_out(row):
+    w, h, mts, sbt = int(row[0]), int(row[1]), int(row[7]), int(row[9])
+    return 1 if (mts > 1 or (sbt and w <= 32 and h <= 32)) else 0       # DepQuant.cpp:1155

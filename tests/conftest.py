@@ -31,3 +31,9 @@ def golden_mctf_apply():
 def golden_frac():
     import numpy as np
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v4_frac.npz'))
+
+
+@pytest.fixture(scope="session")
+def golden_depquant():
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v5_depquant.npz'))

@@ -14,6 +14,8 @@ void     orc_full_search( const Pel* orgPlane, int so, const Pel* refPlane, int 
                           int32_t* out, uint32_t* sadTables, int tableStride );
 uint64_t orc_mv_cost( double lambda, int x, int y, int predHor, int predVer, int costScale, int imvShift );
 void     orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel, uint32_t* out );
+int      orc_dep_quant( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int zeroOut, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
+                        int16_t* q, int32_t* absSum, int32_t* lastPos );   /* oracle/depquant_oracle.cpp */
 void     orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPlane, int sb, const int32_t* desc, int n, int bitDepth, int32_t* out );
 
 #define MOCK_PLANES 64
@@ -287,4 +289,23 @@ uint64_t vvb_fix_wsse_block( vvb_ctx* c, const int16_t* org, int so, const int16
   if( !c || !org || !cur ) { if( err ) *err = VVB_ERR_ARG; return 0; }
   c->calls++;
   return orc_fix_wsse( org, so, cur, sc, w, h, weight );
+}
+
+int vvb_dep_quant( vvb_ctx* c, const vvb_tu_par* par, const vvb_dq_par* dq, const vvb_dq_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n,
+                   int16_t* q, int32_t* abs_sum, int32_t* last_pos )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !par || !dq || !rates || !coef || !q || n < 0 || !( dq->lambda > 0.0 ) ) return fail( c, VVB_ERR_ARG, "bad dependent quantisation arguments" );
+  const size_t area = (size_t) par->w * par->h;
+  for( int i = 0; i < n; i++ )
+  {
+    int32_t s = 0, l = -1;
+    if( need_rdoq && !need_rdoq[i] ) memset( q + i * area, 0, sizeof( int16_t ) * area );
+    else if( orc_dep_quant( par->w, par->h, par->bit_depth, par->qp, dq->lambda, dq->dq_thr_val, dq->zero_out, par->lfnst_idx > 0, dq->scalar_members, (const int32_t*) rates,
+                            coef + i * area, 1, q + i * area, &s, &l ) ) return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
+    if( abs_sum ) abs_sum[i] = s;
+    if( last_pos ) last_pos[i] = l;
+  }
+  c->calls++;
+  return VVB_OK;
 }

@@ -284,3 +284,57 @@ def test_gpu_lfnst_forward_vs_oracle(gpu):
                 assert int(r['need_rdoq'][i]) == O.orc_need_rdoq(P(coef), w, h, 10, qp, dq), (w, h, i)
     with pytest.raises(V.VvbError):
         gpu.eng.inv_trquant(gpu.eng.tu_par(8, 8, V.DCT2, V.DCT2, 10, 30, False, False, False, 1, 0, False), np.zeros((1, 8, 8), dtype=np.int16))
+
+
+def test_gpu_dep_quant_golden(gpu, golden_depquant):
+    """DepQuant::xQuantDQ on the device against what the reference produced (tests/golden/golden_v5_depquant.npz): every row of cases.dq_cases(), scalar and x86
+    member semantics, the Quantizer constants derived inside the library against the reference's"""
+    import ctypes
+    import vvenc_b200._lib as L
+    g = golden_depquant
+    rows = C.dq_cases()
+    assert np.array_equal(rows, g['cases'])
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, scale, decay10, mts, lf, sbt, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_inputs(row)[None]
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, lfnst_idx=lf)
+        rates = gpu.eng.dq_rates(g['rates'][i])
+        dq = L.vvb_dq_par(lam1000 / 1000.0, 8, C.dq_zero_out(row), 0, 0)
+        k = np.zeros(9, dtype=np.int64)
+        assert gpu.eng.lib.vvb_dep_quant_constants(ctypes.byref(par), ctypes.byref(dq), k.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(k, g['consts'][i]), i
+        for scalar in (1, 0):
+            r = gpu.eng.dep_quant(par, rates, coef, lam1000 / 1000.0, 8, C.dq_zero_out(row), scalar_members=bool(scalar))
+            name = 'q_x86_%d' % i
+            want = g['q_scalar_%d' % i] if (scalar or name not in g) else g[name]
+            assert np.array_equal(r['q'][0], want), (i, scalar, [int(v) for v in row])
+            assert (int(r['abs_sum'][0]), int(r['last_pos'][0])) == tuple(int(v) for v in g['meta'][i, 0 if scalar else 1]), (i, scalar)
+        nonzero += int(r['last_pos'][0] >= 0)
+    assert nonzero > 100
+
+
+def test_gpu_dep_quant_batches_vs_oracle(gpu, golden_depquant):
+    """a picture's worth of TUs per launch (more TUs than resident threads for the small shapes: the threads stride over the list and reuse their arena slot),
+    the need_rdoq mask of useSelectiveRdoq, against the CPU build of the restatement on the same inputs; rate tables of a reference CABAC state"""
+    import ctypes
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_depquant
+    rs = np.random.RandomState(77)
+    for (w, h, n, qp, lam, zo, lf) in ((4, 4, 90000, 32, 57.3, 0, 0), (8, 8, 30000, 27, 30.0, 0, 1), (16, 16, 6000, 37, 120.0, 0, 0), (32, 32, 1500, 32, 57.3, 1, 0),
+                                       (64, 64, 300, 22, 11.7, 0, 0), (32, 8, 3000, 42, 800.0, 0, 0), (16, 64, 500, 32, 30.0, 0, 2)):
+        scale = rs.choice([3, 10, 40, 150, 600, 2500], size=(n, 1, 1))
+        coef = rs.laplace(0, 1.0, size=(n, h, w)) * scale * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** 0.7)
+        coef = np.clip(coef, -32768, 32767).astype(np.int32)
+        coef[:, :, 32:] = 0; coef[:, 32:, :] = 0
+        rates_flat = np.ascontiguousarray(g['rates'][int(rs.randint(len(g['rates'])))])
+        mask = (rs.randint(0, 8, size=n) > 0).astype(np.uint8)
+        par = gpu.eng.tu_par(w, h, 0, 0, 10, qp, lfnst_idx=lf)
+        r = gpu.eng.dep_quant(par, gpu.eng.dq_rates(rates_flat), coef, lam, 8, zo, need_rdoq=mask)
+        q = np.zeros((n, h, w), dtype=np.int16); s = np.zeros(n, dtype=np.int32); l = np.zeros(n, dtype=np.int32)
+        assert O.orc_dep_quant(w, h, 10, qp, lam, 8, zo, 1 if lf else 0, 0, P(rates_flat), P(coef), n, P(q), P(s), P(l)) == 0
+        q[mask == 0] = 0; s[mask == 0] = 0; l[mask == 0] = -1
+        assert np.array_equal(r['q'], q), (w, h, int((r['q'] != q).any(axis=(1, 2)).sum()))
+        assert np.array_equal(r['abs_sum'], s) and np.array_equal(r['last_pos'], l), (w, h)
+        assert (l >= 0).sum() > n // 4, (w, h, int((l >= 0).sum()))

@@ -82,3 +82,31 @@ def test_oracle_frac_grid_golden(golden_frac):
             rt, alt = C.frac_filter_of(li)
             O.orc_frac_cost_grid(PO(case['org'], base), S, PO(case['ref'], base), S, P(np.ascontiguousarray(b)), len(b), fam, bd, rt, alt, P(t))
             assert np.array_equal(t, golden_frac['c%d_l%d' % (ci, li)]), (seed, fam, w, h)
+
+
+def test_oracle_dep_quant_golden(golden_depquant):
+    """DepQuant::xQuantDQ: the trellis restatement against levels / absSum / lastPos the reference produced (scalar and x86 members), rate tables from the
+    reference's CABAC contexts; the Quantizer constants of initQuantBlock (double arithmetic) against the reference's"""
+    import ctypes
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_depquant
+    rows = C.dq_cases()
+    assert np.array_equal(rows, g['cases'])
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, scale, decay10, mts, lf, sbt, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_inputs(row)
+        k = np.zeros(9, dtype=np.int64)
+        assert O.orc_dep_quant_constants(w, h, bd, qp, lam1000 / 1000.0, 8, P(k)) == 0
+        assert np.array_equal(k, g['consts'][i]), (i, k, g['consts'][i])
+        rates = np.ascontiguousarray(g['rates'][i])
+        for scalar in (1, 0):
+            q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); l = ctypes.c_int32()
+            assert O.orc_dep_quant(w, h, bd, qp, lam1000 / 1000.0, 8, C.dq_zero_out(row), lf, scalar, P(rates), P(coef), 1, P(q), ctypes.byref(s), ctypes.byref(l)) == 0
+            name = 'q_x86_%d' % i
+            want = g['q_scalar_%d' % i] if (scalar or name not in g) else g[name]
+            assert np.array_equal(q, want), (i, scalar)
+            assert (s.value, l.value) == tuple(int(v) for v in g['meta'][i, 0 if scalar else 1]), (i, scalar)
+        nonzero += int(l.value >= 0)
+    assert nonzero > 100

@@ -457,3 +457,55 @@ def test_lfnst_forward_against_the_reference(opt):
                 assert O.orc_need_rdoq(P(cO), w, h, 10, qp, 0) == nR.value
                 sets.add((int(st[0]), int(st[1]))); n += 1
     assert n == 288 and len(sets) >= 6, (n, sets)
+
+
+def test_dep_quant_scan_tables_equal_the_reference_rom():
+    """ScanInfo / NbInfoSbb / NbInfoOut of DQIntern::Rom (DepQuant.cpp:75-342) for all 25 luma shapes: the tables the library uploads are the reference's"""
+    import ctypes
+    from _libs import dq_oracle, refshim, P
+    O = dq_oracle(); R = refshim()
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            nc = min(w, 32) * min(h, 32)
+            a = np.zeros(nc * 24, np.uint8); b = np.zeros(nc * 16, np.uint8); c = np.zeros(nc * 24, np.uint8); d = np.zeros(nc * 16, np.uint8)
+            assert R.refshim_dep_quant_tables(w, h, P(a), P(b)) == nc and O.orc_dep_quant_tables(w, h, P(c), P(d)) == nc
+            assert np.array_equal(a, c) and np.array_equal(b, d), (w, h)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_dep_quant_against_the_reference_member(opt):
+    """DepQuant::xQuantDQ on the probe's TU rig (CABAC contexts initialised for the slice QP) against the restatement fed with the rate tables the reference's
+    RateEstimator derived: levels, absSum, lastPos for every TU shape class, 8 / 10 bit, QP 17..51, explicit MTS and SBT zero-out, LFNST position limit, intra and
+    inter CUs; opt 0 = the scalar members (checkAllRdCosts, updateStates, ... of DepQuant.cpp), 1 = what initDepQuantX86 installs.  Also the Quantizer constants."""
+    import ctypes
+    from _libs import dq_oracle, refshim, P
+    O = dq_oracle(); R = refshim()
+    rs = np.random.RandomState(500 + opt)
+    n = 0; nonzero = 0; big = 0
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 16), (32, 8), (16, 64), (64, 32), (32, 16), (4, 32), (64, 4), (8, 16), (16, 4)]:
+        for bd in (10, 8):
+            for qp in (17, 22, 27, 32, 37, 42, 51):
+                for trial in range(5):
+                    lam = float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0]))
+                    scale = float(rs.choice([5, 20, 60, 200, 600, 2000, 30000]))
+                    dec = float(rs.choice([0.1, 0.5, 1.0, 1.5]))
+                    coef = rs.laplace(0, scale, size=(h, w)) * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** dec)
+                    coef = np.clip(coef, -32768, 32767).astype(np.int32)
+                    if w > 32: coef[:, 32:] = 0
+                    if h > 32: coef[32:, :] = 0
+                    mts = int(rs.choice([0, 0, 2, 3, 5])) if (w <= 32 and h <= 32) else 0
+                    lf = int(rs.choice([0, 0, 0, 1, 2])) if mts == 0 else 0
+                    sbt = int(rs.choice([0, 0, 0, 1])) if (mts == 0 and lf == 0) else 0
+                    intra = 1 if lf else (0 if sbt else int(rs.randint(2)))
+                    zo = 1 if (mts > 1 or (sbt and w <= 32 and h <= 32)) else 0
+                    thr = int(rs.choice([8, 8, 4, 16]))
+                    qR = np.zeros((h, w), np.int16); sR = ctypes.c_int32(); lR = ctypes.c_int32(); rates = np.zeros(266, np.int32); kR = np.zeros(9, np.int64)
+                    assert R.refshim_dep_quant(P(coef), w, h, bd, qp, mts, intra, lf, sbt, lam, thr, opt, int(rs.randint(17, 52)), trial % 3, P(qR), ctypes.byref(sR), ctypes.byref(lR),
+                                               P(rates), P(kR)) == 0
+                    kO = np.zeros(9, np.int64)
+                    assert O.orc_dep_quant_constants(w, h, bd, qp, lam, thr, P(kO)) == 0 and np.array_equal(kO, kR), (w, h, bd, qp, lam, kO, kR)
+                    qO = np.zeros((h, w), np.int16); sO = ctypes.c_int32(); lO = ctypes.c_int32()
+                    assert O.orc_dep_quant(w, h, bd, qp, lam, thr, zo, lf, 1 - opt, P(rates), P(coef), 1, P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+                    assert np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, (w, h, bd, qp, lam, scale, mts, lf, sbt, int((qO != qR).sum()))
+                    n += 1; nonzero += int(lR.value >= 0); big += int(np.abs(qR).max() > 127)
+    assert n == 1050 and nonzero > 500 and big > 10, (n, nonzero, big)

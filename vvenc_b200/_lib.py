@@ -31,6 +31,15 @@ class vvb_tu_par(ctypes.Structure):
                 ('qp', ctypes.c_int32), ('is_irap', ctypes.c_int32), ('dep_quant', ctypes.c_int32), ('sign_hiding', ctypes.c_int32), ('lfnst_idx', ctypes.c_int32), ('lfnst_set', ctypes.c_int32), ('lfnst_transpose', ctypes.c_int32)]
 
 
+class vvb_dq_rates(ctypes.Structure):
+    _fields_ = [('last_bits_x', ctypes.c_int32 * 32), ('last_bits_y', ctypes.c_int32 * 32), ('sig_sbb_bits', ctypes.c_int32 * 4), ('sig_bits', ctypes.c_int32 * 72),
+                ('gtx_bits', ctypes.c_int32 * 126)]
+
+
+class vvb_dq_par(ctypes.Structure):
+    _fields_ = [('lam', ctypes.c_double), ('dq_thr_val', ctypes.c_int32), ('zero_out', ctypes.c_int32), ('scalar_members', ctypes.c_int32), ('pad', ctypes.c_int32)]
+
+
 class vvb_level_io(ctypes.Structure):
     _fields_ = [('blocks', ctypes.c_void_p), ('count', ctypes.c_int32), ('best', ctypes.c_void_p), ('refine_cost', ctypes.c_void_p), ('q', ctypes.c_void_p),
                 ('abs_sum', ctypes.c_void_p), ('last_pos', ctypes.c_void_p), ('need_rdoq', ctypes.c_void_p), ('tu', vvb_tu_par)]
@@ -89,6 +98,9 @@ SYMBOLS = {
     'vvb_search_refine_tu': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_i, c_p, c_i]),
     'vvb_fwd_trquant_planes': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_dep_quant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
+    'vvb_dep_quant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
+    'vvb_dep_quant_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), c_p]),
     'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_inv_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_tu_roundtrip': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_p, c_i, c_p, c_p, c_p, c_p]),

@@ -223,6 +223,28 @@ class CostEngine:
         self._chk(self.lib.vvb_frac_cost_grid(self.h, dfunc, org_plane, ref_plane, _p(blocks), len(blocks), w, h, int(reduce_tap), int(alt_hpel), _p(out)))
         return out
 
+    # ---- dependent quantisation
+    @staticmethod
+    def dq_rates(flat):
+        """vvb_dq_rates from 266 int32 in declaration order (last_bits_x[32], last_bits_y[32], sig_sbb_bits[2][2], sig_bits[3][12][2], gtx_bits[21][6])"""
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        assert flat.size == 266
+        r = L.vvb_dq_rates()
+        ctypes.memmove(ctypes.byref(r), flat.ctypes.data, 266 * 4)
+        return r
+
+    def dep_quant(self, par, rates, coef, lam, dq_thr_val=8, zero_out=False, scalar_members=False, need_rdoq=None):
+        """DepQuant::quant for n TUs of one shape: coef int32 [n][h][w] (as fwd_trquant returns them) -> dict(q, abs_sum, last_pos).
+        rates: vvb_dq_rates (RateEstimator tables of the caller's CABAC state), lam: Quant::m_dLambda."""
+        coef = np.ascontiguousarray(coef, dtype=np.int32)
+        n = coef.shape[0]
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        s = np.zeros(n, dtype=np.int32); lp = np.zeros(n, dtype=np.int32)
+        dq = L.vvb_dq_par(float(lam), int(dq_thr_val), int(zero_out), int(scalar_members), 0)
+        nr = None if need_rdoq is None else np.ascontiguousarray(need_rdoq, dtype=np.uint8)
+        self._chk(self.lib.vvb_dep_quant(self.h, ctypes.byref(par), ctypes.byref(dq), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s), _p(lp)))
+        return dict(q=q, abs_sum=s, last_pos=lp)
+
     # ---- inverse path / fused TU round trip
     def inv_trquant(self, par, q):
         """TrQuant::invTransformNxN for n compact level blocks q [n][h][w] -> residual int16 [n][h][w]"""

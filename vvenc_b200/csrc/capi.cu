@@ -15,6 +15,8 @@
 #include "itrquant_kernels.cuh"
 #include "mctf_affine_kernels.cuh"
 #include "frac_kernels.cuh"
+#include "depquant_kernels.cuh"
+#include "depquant_host.h"
 #include "vvc_tables.h"
 #include "vvc_lfnst_tables.h"
 
@@ -268,6 +270,9 @@ void vvb_destroy( vvb_ctx* ctx )
   if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
   if( ctx->d_scan ) cudaFree( ctx->d_scan );
   if( ctx->d_lfnst ) cudaFree( ctx->d_lfnst );
+  if( ctx->d_dqScan ) cudaFree( ctx->d_dqScan );
+  if( ctx->d_dqNb ) cudaFree( ctx->d_dqNb );
+  delete[] static_cast<vvbdq::DqShapeTables*>( ctx->dqShapes );
   if( ctx->h_pinned ) cudaFreeHost( ctx->h_pinned );
   if( ctx->stream ) cudaStreamDestroy( ctx->stream );
   delete ctx;
@@ -1171,6 +1176,91 @@ int vvb_search_refine_tu( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, 
     }
   }
   CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// ---- dependent quantisation --------------------------------------------------------------------------------------------------------------------
+namespace {
+int dqTables( vvb_ctx* ctx )
+{
+  if( ctx->dqShapes ) return VVB_OK;
+  std::vector<vvbdq::DqScanInfo> si; std::vector<vvbdq::DqNbOut> nb;
+  vvbdq::DqShapeTables* shapes = new vvbdq::DqShapeTables[25];
+  vvbdq::dq_build_tables( si, nb, shapes );
+  if( cudaMalloc( &ctx->d_dqScan, si.size() * sizeof( vvbdq::DqScanInfo ) ) != cudaSuccess || cudaMalloc( &ctx->d_dqNb, nb.size() * sizeof( vvbdq::DqNbOut ) ) != cudaSuccess ||
+      cudaMemcpy( ctx->d_dqScan, si.data(), si.size() * sizeof( vvbdq::DqScanInfo ), cudaMemcpyHostToDevice ) != cudaSuccess ||
+      cudaMemcpy( ctx->d_dqNb, nb.data(), nb.size() * sizeof( vvbdq::DqNbOut ), cudaMemcpyHostToDevice ) != cudaSuccess )
+  {
+    delete[] shapes;
+    if( ctx->d_dqScan ) { cudaFree( ctx->d_dqScan ); ctx->d_dqScan = nullptr; }
+    if( ctx->d_dqNb ) { cudaFree( ctx->d_dqNb ); ctx->d_dqNb = nullptr; }
+    return fail( ctx, VVB_ERR_CUDA, "dependent quantisation tables", cudaGetLastError() );
+  }
+  ctx->dqShapes = shapes;
+  return VVB_OK;
+}
+} // namespace
+
+int vvb_dep_quant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq, const vvb_dq_rates* rates, const int32_t* dCoef, const uint8_t* dNeedRdoq, int n,
+                       int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos )
+{
+  if( !ctx || !par || !dq || !rates || !dCoef || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  const int shapeIdx = vvbdq::dq_shape_index( par->w, par->h );
+  if( shapeIdx < 0 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "TU sides must be 4, 8, 16, 32 or 64" );
+  if( par->bit_depth != 8 && par->bit_depth != 10 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth 8 or 10" );
+  if( !( dq->lambda > 0.0 ) ) return fail( ctx, VVB_ERR_ARG, "lambda must be greater than 0 (DepQuant.cpp:535)" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  int rc;
+  if( ( rc = dqTables( ctx ) ) ) return rc;
+  const vvbdq::DqShapeTables& st = static_cast<vvbdq::DqShapeTables*>( ctx->dqShapes )[shapeIdx];
+  DqLaunch L;
+  L.shape.width = st.width; L.shape.height = st.height; L.shape.numCoeff = st.numCoeff; L.shape.numSbb = st.numSbb;
+  L.shape.scanInfo = static_cast<vvbdq::DqScanInfo*>( ctx->d_dqScan ) + st.offset;
+  L.shape.nbOut    = static_cast<vvbdq::DqNbOut*>( ctx->d_dqNb ) + st.offset;
+  L.quant = vvbdq::dq_init_quant( par->w, par->h, par->bit_depth, par->qp + 6 * ( par->bit_depth - 8 ), dq->lambda, dq->dq_thr_val );
+  L.zeroOutMts = dq->zero_out; L.lfnst = par->lfnst_idx > 0; L.capSum = dq->scalar_members ? 0 : 1;
+  L.ctxBytes  = (uint32_t)( ( 8 * ( st.numSbb + st.numCoeff ) + 15 ) & ~15 );
+  L.slotBytes = (uint32_t)( ( L.ctxBytes + (size_t) st.numCoeff * 2 * sizeof( vvbdq::DqTrellis ) + 15 ) & ~(size_t) 15 );
+  // one thread per TU up to a few resident waves; beyond that the threads stride over the TU list and reuse their arena slot
+  const int maxBlocks = ctx->numSMs * 8;
+  const int blocks = std::min( ( n + VVB_DQ_THREADS - 1 ) / VVB_DQ_THREADS, maxBlocks );
+  void* arena;
+  if( ( rc = scratch( ctx, 5, (size_t) blocks * VVB_DQ_THREADS * L.slotBytes, &arena ) ) ) return rc;
+  vvbdq::DqRates r;
+  static_assert( sizeof( vvbdq::DqRates ) == sizeof( vvb_dq_rates ), "vvb_dq_rates mirrors DqRates" );
+  memcpy( &r, rates, sizeof( r ) );
+  dep_quant_kernel<<<blocks, VVB_DQ_THREADS, 0, ctx->stream>>>( L, r, dCoef, dNeedRdoq, n, dQ, dAbsSum, dLastPos, (uint8_t*) arena );
+  CHECK_LAUNCH( "dep_quant_kernel" );
+  return VVB_OK;
+}
+
+int vvb_dep_quant( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq, const vvb_dq_rates* rates, const int32_t* coef, const uint8_t* needRdoq, int n,
+                   int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( !ctx || !par || !coef || !q || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t area = (size_t) par->w * par->h;
+  void *dC, *dQ, *dM; int rc;
+  if( ( rc = scratch( ctx, 2, (size_t) n * area * 4, &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * area * 2, &dQ ) ) || ( rc = scratch( ctx, 3, (size_t) n * 12, &dM ) ) ) return rc;
+  int32_t* dSum = (int32_t*) dM; int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
+  CU( cudaMemcpyAsync( dC, coef, (size_t) n * area * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( needRdoq ) CU( cudaMemcpyAsync( dNr, needRdoq, (size_t) n, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_dep_quant_dev( ctx, par, dq, rates, (const int32_t*) dC, needRdoq ? dNr : nullptr, n, (int16_t*) dQ, dSum, dLast ) ) ) return rc;
+  CU( cudaMemcpyAsync( q, dQ, (size_t) n * area * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( absSum )  CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( lastPos ) CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// Quantizer::initQuantBlock as the device call derives it (for bindings / tests that want to inspect the constants): out[9] = qShift, maxQIdx, thresLast, distShift,
+// qAdd, qScale, distAdd, distStepAdd, distOrgFact
+int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_t out[9] )
+{
+  if( !par || !dq || !out || vvbdq::dq_shape_index( par->w, par->h ) < 0 || !( dq->lambda > 0.0 ) ) return VVB_ERR_ARG;
+  const vvbdq::DqQuant q = vvbdq::dq_init_quant( par->w, par->h, par->bit_depth, par->qp + 6 * ( par->bit_depth - 8 ), dq->lambda, dq->dq_thr_val );
+  out[0] = q.qShift; out[1] = q.maxQIdx; out[2] = q.thresLast; out[3] = q.distShift; out[4] = q.qAdd; out[5] = q.qScale; out[6] = q.distAdd; out[7] = q.distStepAdd; out[8] = q.distOrgFact;
   return VVB_OK;
 }
 

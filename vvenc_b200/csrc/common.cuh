@@ -92,6 +92,9 @@ struct vvb_ctx
   int8_t*        d_trTable   = nullptr;     // all transform matrices (vvc_tables.h)
   int8_t*        d_lfnst     = nullptr;     // LFNST forward kernels (vvc_lfnst_tables.h)
   int32_t*       d_scan      = nullptr;     // scan tables for all (log2w, log2h) in 2..6, 1024 entries each
+  void*          d_dqScan    = nullptr;     // dependent quantisation: ScanInfo / NbInfoOut tables of the 25 shapes (built at the first vvb_dep_quant call)
+  void*          d_dqNb      = nullptr;
+  void*          dqShapes    = nullptr;     // host: vvbdq::DqShapeTables[25]
   // grow-only scratch arenas (device + pinned host) used by the host-buffer entry points
   int            mctfMaxDim = 64;      // largest MCTF block dimension in device-resident candidate lists (vvb_mctf_hint)
   bool           async = false;        // host-buffer calls enqueue only; vvb_synchronize() completes them (vvb_set_async)
