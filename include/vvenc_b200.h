@@ -95,6 +95,20 @@ int      vvb_sad_x5_block  ( vvb_ctx* ctx, const int16_t* org, int org_stride, c
 uint64_t vvb_fix_wsse_block( vvb_ctx* ctx, const int16_t* org, int org_stride, const int16_t* cur, int cur_stride, int w, int h,
                              uint32_t fixed_weight, int* err );
 
+/* Descriptor-list forms of the three: the blocks sit in resident planes, one launch per list.
+ * a7 GEO: the weight masks (g_globalGeoEncSADmask, Rom.cpp) are uploaded once with vvb_mask_upload; mask_offset is the sample the reference's mask pointer starts at
+ *    (it may walk backwards from there with step_x = -1), mask_stride / mask_stride2 / step_x as DistParam carries them (RdCost.h:95-98).
+ * a8 DMVR: cost5[i][k] = SAD( org + k, cur - k ) >> 1 for k = 0..4 (all five are written; the reference skips k = 2 unless asked for it).
+ * a9: weights[i] = the fixed-point chroma weight of fixWeightedSSE. */
+typedef struct { vvb_cand c; int32_t mask_offset, mask_stride, mask_stride2, step_x; } vvb_mask_cand;      /* 48 bytes; c.dfunc ignored */
+int vvb_mask_upload       ( vvb_ctx* ctx, const int16_t* mask, int count );
+int vvb_sad_mask_batch    ( vvb_ctx* ctx, const vvb_mask_cand* cands, int n, uint64_t* cost_out );
+int vvb_sad_mask_batch_dev( vvb_ctx* ctx, const vvb_mask_cand* dev_cands, int n, uint64_t* dev_cost_out );
+int vvb_sad_x5_batch      ( vvb_ctx* ctx, const vvb_cand* cands, int n, uint64_t* cost5_out /* [n][5] */ );
+int vvb_sad_x5_batch_dev  ( vvb_ctx* ctx, const vvb_cand* dev_cands, int n, uint64_t* dev_cost5_out );
+int vvb_fix_wsse_batch    ( vvb_ctx* ctx, const vvb_cand* cands, const uint32_t* weights, int n, uint64_t* cost_out );
+int vvb_fix_wsse_batch_dev( vvb_ctx* ctx, const vvb_cand* dev_cands, const uint32_t* dev_weights, int n, uint64_t* dev_cost_out );
+
 /* ---- candidate-pool regime (RDO style): K candidate predictions per original block, each with its own
  * compact w x h buffer: pool[(b*K + k)*w*h ...].  One cost per (block, candidate); HBM streaming. ---------- */
 typedef struct { int32_t x, y; } vvb_pos;
@@ -320,6 +334,13 @@ int vvb_mctf_calc_var_dev( vvb_ctx* ctx, int plane, const vvb_mctf_cand* dev_blo
 int vvb_affine_sobel      ( vvb_ctx* ctx, int vertical, const int16_t* pred, int pred_stride, int16_t* deriv, int deriv_stride, int w, int h );
 int vvb_affine_equal_coeff( vvb_ctx* ctx, int six_param, const int16_t* resi, int resi_stride, const int16_t* deriv_x, const int16_t* deriv_y,
                             int deriv_stride, int w, int h, int64_t eq_out[49] /* accumulated into, row stride 7 */ );
+
+/* a16, batched: for n blocks of one shape (pred, resi compact [n][h][w]) the horizontal and vertical Sobel of the prediction and the normal-equation sums of
+ * xEqualCoeffComputer in one launch -- the per-iteration body of the affine motion estimation (InterSearch.cpp:5373-5387).  eq_out [n][49] (row stride 7, rows 1..np,
+ * written, not accumulated); deriv_x / deriv_y [n][h][w] nullable. */
+int vvb_affine_eq_batch    ( vvb_ctx* ctx, int six_param, const int16_t* pred, const int16_t* resi, int n, int w, int h, int16_t* deriv_x, int16_t* deriv_y, int64_t* eq_out );
+int vvb_affine_eq_batch_dev( vvb_ctx* ctx, int six_param, const int16_t* dev_pred, const int16_t* dev_resi, int n, int w, int h, int16_t* dev_deriv_x, int16_t* dev_deriv_y,
+                             int64_t* dev_eq_out );
 
 #ifdef __cplusplus
 }

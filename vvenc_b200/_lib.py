@@ -47,6 +47,9 @@ class vvb_level_io(ctypes.Structure):
 
 # numpy dtypes mirroring the packed C structs
 import numpy as np
+MASK_CAND_DT = np.dtype([('org_plane', '<i4'), ('org_x', '<i4'), ('org_y', '<i4'), ('cur_plane', '<i4'), ('cur_x', '<i4'), ('cur_y', '<i4'),
+                         ('w', '<u2'), ('h', '<u2'), ('dfunc', 'u1'), ('sub_shift', 'u1'), ('pad', 'u1', (2,)),
+                         ('mask_offset', '<i4'), ('mask_stride', '<i4'), ('mask_stride2', '<i4'), ('step_x', '<i4')])
 CAND_DT = np.dtype([('org_plane', '<i4'), ('org_x', '<i4'), ('org_y', '<i4'), ('cur_plane', '<i4'), ('cur_x', '<i4'), ('cur_y', '<i4'),
                     ('w', '<u2'), ('h', '<u2'), ('dfunc', 'u1'), ('sub_shift', 'u1'), ('pad', 'u1', (2,))])
 POS_DT = np.dtype([('x', '<i4'), ('y', '<i4')])
@@ -98,6 +101,15 @@ SYMBOLS = {
     'vvb_search_refine_tu': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_i, c_p, c_i]),
     'vvb_fwd_trquant_planes': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_mask_upload': (c_i, [c_p, c_p, c_i]),
+    'vvb_sad_mask_batch': (c_i, [c_p, c_p, c_i, c_p]),
+    'vvb_sad_mask_batch_dev': (c_i, [c_p, c_p, c_i, c_p]),
+    'vvb_sad_x5_batch': (c_i, [c_p, c_p, c_i, c_p]),
+    'vvb_sad_x5_batch_dev': (c_i, [c_p, c_p, c_i, c_p]),
+    'vvb_fix_wsse_batch': (c_i, [c_p, c_p, c_p, c_i, c_p]),
+    'vvb_fix_wsse_batch_dev': (c_i, [c_p, c_p, c_p, c_i, c_p]),
+    'vvb_affine_eq_batch': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'vvb_affine_eq_batch_dev': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'vvb_dep_quant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
     'vvb_dep_quant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
     'vvb_dep_quant_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), c_p]),

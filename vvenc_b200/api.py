@@ -124,6 +124,38 @@ class CostEngine:
         self._chk(err.value)
         return int(v)
 
+    # ---- descriptor-list forms of the mask SAD (GEO), the five-position SAD (DMVR) and the weighted SSE; blocks in resident planes
+    def mask_upload(self, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.int16)
+        self._chk(self.lib.vvb_mask_upload(self.h, _p(mask), mask.size))
+
+    def sad_mask_batch(self, cands):
+        cands = np.ascontiguousarray(cands, dtype=L.MASK_CAND_DT)
+        out = np.zeros(len(cands), dtype=np.uint64)
+        self._chk(self.lib.vvb_sad_mask_batch(self.h, _p(cands), len(cands), _p(out)))
+        return out
+
+    def sad_x5_batch(self, cands):
+        cands = np.ascontiguousarray(cands, dtype=L.CAND_DT)
+        out = np.zeros((len(cands), 5), dtype=np.uint64)
+        self._chk(self.lib.vvb_sad_x5_batch(self.h, _p(cands), len(cands), _p(out)))
+        return out
+
+    def fix_wsse_batch(self, cands, weights):
+        cands = np.ascontiguousarray(cands, dtype=L.CAND_DT); weights = np.ascontiguousarray(weights, dtype=np.uint32)
+        out = np.zeros(len(cands), dtype=np.uint64)
+        self._chk(self.lib.vvb_fix_wsse_batch(self.h, _p(cands), _p(weights), len(cands), _p(out)))
+        return out
+
+    def affine_eq_batch(self, six_param, pred, resi, want_derivs=False):
+        """pred, resi: int16 [n][h][w] -> eq int64 [n][7][7] (rows 1..np filled) and, on request, the two Sobel planes [n][h][w]"""
+        pred = np.ascontiguousarray(pred, dtype=np.int16); resi = np.ascontiguousarray(resi, dtype=np.int16)
+        n, h, w = pred.shape
+        eq = np.zeros((n, 7, 7), dtype=np.int64)
+        gx = np.zeros_like(pred) if want_derivs else None; gy = np.zeros_like(pred) if want_derivs else None
+        self._chk(self.lib.vvb_affine_eq_batch(self.h, int(six_param), _p(pred), _p(resi), n, w, h, _p(gx), _p(gy), _p(eq)))
+        return (eq, gx, gy) if want_derivs else eq
+
     def dist_pool(self, dfunc, org_plane, blocks, w, h, K, pool, sub_shift=0):
         blocks = np.ascontiguousarray(blocks, dtype=L.POS_DT)
         pool = np.ascontiguousarray(pool, dtype=np.int16)

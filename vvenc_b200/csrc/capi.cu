@@ -16,6 +16,7 @@
 #include "mctf_affine_kernels.cuh"
 #include "frac_kernels.cuh"
 #include "depquant_kernels.cuh"
+#include "batch_kernels.cuh"
 #include "depquant_host.h"
 #include "vvc_tables.h"
 #include "vvc_lfnst_tables.h"
@@ -247,6 +248,8 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( sad_pyramid8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
   cudaFuncSetAttribute( sad_pyramid8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
   cudaFuncSetAttribute( sad_pyramid8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 );
+  cudaFuncSetAttribute( affine_eq_batch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( affine_eq_batch_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
@@ -270,6 +273,7 @@ void vvb_destroy( vvb_ctx* ctx )
   if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
   if( ctx->d_scan ) cudaFree( ctx->d_scan );
   if( ctx->d_lfnst ) cudaFree( ctx->d_lfnst );
+  if( ctx->d_mask ) cudaFree( ctx->d_mask );
   if( ctx->d_dqScan ) cudaFree( ctx->d_dqScan );
   if( ctx->d_dqNb ) cudaFree( ctx->d_dqNb );
   delete[] static_cast<vvbdq::DqShapeTables*>( ctx->dqShapes );
@@ -507,6 +511,117 @@ uint64_t vvb_fix_wsse_block( vvb_ctx* ctx, const int16_t* org, int orgStride, co
   } while( 0 );
   if( err ) *err = rc;
   return result;
+}
+
+// ---- descriptor-list forms of the mask SAD, the five-position SAD and the weighted SSE -----------------------------------------------------------------------------
+namespace {
+int checkCandPlanes( vvb_ctx* ctx, const vvb_cand* c, int n )      // host lists only
+{
+  for( int i = 0; i < n; i++ )
+    if( !validPlane( ctx, c[i].org_plane ) || !validPlane( ctx, c[i].cur_plane ) || c[i].w < 1 || c[i].h < 1 || c[i].w > 128 || c[i].h > 128 ) return fail( ctx, VVB_ERR_ARG, "bad descriptor" );
+  return VVB_OK;
+}
+}
+
+int vvb_mask_upload( vvb_ctx* ctx, const int16_t* mask, int count )
+{
+  if( !ctx || !mask || count < 1 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  CU( cudaSetDevice( ctx->device ) );
+  CU( cudaStreamSynchronize( ctx->stream ) );
+  if( ctx->d_mask ) { cudaFree( ctx->d_mask ); ctx->d_mask = nullptr; ctx->maskCount = 0; }
+  CU( cudaMalloc( &ctx->d_mask, (size_t) count * 2 ) );
+  CU( cudaMemcpy( ctx->d_mask, mask, (size_t) count * 2, cudaMemcpyHostToDevice ) );
+  ctx->maskCount = count;
+  return VVB_OK;
+}
+
+int vvb_sad_mask_batch_dev( vvb_ctx* ctx, const vvb_mask_cand* dCands, int n, uint64_t* dOut )
+{
+  if( !ctx || !dCands || !dOut || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !ctx->d_mask ) return fail( ctx, VVB_ERR_ARG, "no mask table (vvb_mask_upload)" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  sad_mask_batch_kernel<<<( n + VVB_BATCH_WARPS - 1 ) / VVB_BATCH_WARPS, VVB_BATCH_WARPS * 32, 0, ctx->stream>>>( ctx->planes, dCands, n, ctx->d_mask, (unsigned long long*) dOut );
+  CHECK_LAUNCH( "sad_mask_batch_kernel" );
+  return VVB_OK;
+}
+
+int vvb_sad_mask_batch( vvb_ctx* ctx, const vvb_mask_cand* cands, int n, uint64_t* out )
+{
+  if( !ctx || !cands || !out || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  for( int i = 0; i < n; i++ )
+  {
+    const vvb_mask_cand& d = cands[i];
+    int rc = checkCandPlanes( ctx, &d.c, 1 );
+    if( rc ) return rc;
+    if( ( d.step_x != 1 && d.step_x != -1 ) || ( d.c.h & ( ( 1 << d.c.sub_shift ) - 1 ) ) ) return fail( ctx, VVB_ERR_ARG, "bad mask descriptor" );
+    // every mask sample the walk touches must lie inside the uploaded table
+    const long long rows = d.c.h >> d.c.sub_shift, rowAdv = (long long) d.c.w * d.step_x + (long long) d.mask_stride * ( 1 << d.c.sub_shift ) + d.mask_stride2;
+    const long long a = d.mask_offset, b = a + ( rows - 1 ) * rowAdv, lo = std::min( a, b ) + ( d.step_x < 0 ? -( d.c.w - 1 ) : 0 ), hi = std::max( a, b ) + ( d.step_x > 0 ? d.c.w - 1 : 0 );
+    if( lo < 0 || hi >= ctx->maskCount ) return fail( ctx, VVB_ERR_ARG, "mask walk leaves the uploaded table" );
+  }
+  void *dC, *dO; int rc;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_mask_cand ), &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * 8, &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_mask_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_sad_mask_batch_dev( ctx, (const vvb_mask_cand*) dC, n, (uint64_t*) dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( out, dO, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+int vvb_sad_x5_batch_dev( vvb_ctx* ctx, const vvb_cand* dCands, int n, uint64_t* dOut5 )
+{
+  if( !ctx || !dCands || !dOut5 || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  sad_x5_batch_kernel<<<( n + VVB_BATCH_WARPS - 1 ) / VVB_BATCH_WARPS, VVB_BATCH_WARPS * 32, 0, ctx->stream>>>( ctx->planes, dCands, n, (unsigned long long*) dOut5 );
+  CHECK_LAUNCH( "sad_x5_batch_kernel" );
+  return VVB_OK;
+}
+
+int vvb_sad_x5_batch( vvb_ctx* ctx, const vvb_cand* cands, int n, uint64_t* out5 )
+{
+  if( !ctx || !cands || !out5 || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  int rc = checkCandPlanes( ctx, cands, n );
+  if( rc ) return rc;
+  for( int i = 0; i < n; i++ )
+    if( ( cands[i].w != 8 && cands[i].w != 16 ) || ( cands[i].h & ( ( 1 << cands[i].sub_shift ) - 1 ) ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "SADX5 is defined for widths 8 and 16 (RdCost.cpp:131-132)" );
+  void *dC, *dO;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_cand ), &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * 40, &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_sad_x5_batch_dev( ctx, (const vvb_cand*) dC, n, (uint64_t*) dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( out5, dO, (size_t) n * 40, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+int vvb_fix_wsse_batch_dev( vvb_ctx* ctx, const vvb_cand* dCands, const uint32_t* dWeights, int n, uint64_t* dOut )
+{
+  if( !ctx || !dCands || !dWeights || !dOut || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  fix_wsse_batch_kernel<<<( n + VVB_BATCH_WARPS - 1 ) / VVB_BATCH_WARPS, VVB_BATCH_WARPS * 32, 0, ctx->stream>>>( ctx->planes, dCands, dWeights, n, (unsigned long long*) dOut );
+  CHECK_LAUNCH( "fix_wsse_batch_kernel" );
+  return VVB_OK;
+}
+
+int vvb_fix_wsse_batch( vvb_ctx* ctx, const vvb_cand* cands, const uint32_t* weights, int n, uint64_t* out )
+{
+  if( !ctx || !cands || !weights || !out || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  int rc = checkCandPlanes( ctx, cands, n );
+  if( rc ) return rc;
+  for( int i = 0; i < n; i++ ) if( ( cands[i].w & 1 ) && cands[i].w != 1 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "width must be even or 1 (RdCost.cpp:1966)" );
+  void *dC, *dW, *dO;
+  if( ( rc = scratch( ctx, 0, (size_t) n * sizeof( vvb_cand ), &dC ) ) || ( rc = scratch( ctx, 2, (size_t) n * 4, &dW ) ) || ( rc = scratch( ctx, 1, (size_t) n * 8, &dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( dC, cands, (size_t) n * sizeof( vvb_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
+  CU( cudaMemcpyAsync( dW, weights, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_fix_wsse_batch_dev( ctx, (const vvb_cand*) dC, (const uint32_t*) dW, n, (uint64_t*) dO ) ) ) return rc;
+  CU( cudaMemcpyAsync( out, dO, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
 }
 
 // _dev callers state whether every block x position in their (device-resident) lists is a multiple of 8 pels; only then the
@@ -1622,6 +1737,38 @@ int vvb_affine_equal_coeff( vvb_ctx* ctx, int sixParam, const int16_t* resi, int
   CU( cudaMemcpyAsync( tmp, dE, 49 * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( cudaStreamSynchronize( ctx->stream ) );         // tmp is consumed right below: always wait, asynchronous mode or not
   for( int i = 0; i < 49; i++ ) eq[i] += tmp[i];
+  return VVB_OK;
+}
+
+int vvb_affine_eq_batch_dev( vvb_ctx* ctx, int sixParam, const int16_t* dPred, const int16_t* dResi, int n, int w, int h, int16_t* dDerivX, int16_t* dDerivY, int64_t* dEq )
+{
+  if( !ctx || !dPred || !dResi || !dEq || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( w < 4 || h < 4 || w > 128 || h > 128 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "affine blocks are 4..128" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const size_t smem = (size_t) w * h * 6;
+  if( sixParam ) affine_eq_batch_kernel<6><<<n, 128, smem, ctx->stream>>>( dPred, dResi, w, h, dDerivX, dDerivY, (long long*) dEq );
+  else           affine_eq_batch_kernel<4><<<n, 128, smem, ctx->stream>>>( dPred, dResi, w, h, dDerivX, dDerivY, (long long*) dEq );
+  CHECK_LAUNCH( "affine_eq_batch_kernel" );
+  return VVB_OK;
+}
+
+int vvb_affine_eq_batch( vvb_ctx* ctx, int sixParam, const int16_t* pred, const int16_t* resi, int n, int w, int h, int16_t* derivX, int16_t* derivY, int64_t* eq )
+{
+  if( !ctx || !pred || !resi || !eq || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t bytes = (size_t) n * w * h * 2;
+  void *dP, *dR, *dX = nullptr, *dY = nullptr, *dE; int rc;
+  if( ( rc = scratch( ctx, 0, bytes, &dP ) ) || ( rc = scratch( ctx, 1, bytes, &dR ) ) || ( rc = scratch( ctx, 2, (size_t) n * 49 * 8, &dE ) ) ) return rc;
+  if( derivX && ( rc = scratch( ctx, 3, bytes, &dX ) ) ) return rc;
+  if( derivY && ( rc = scratch( ctx, 4, bytes, &dY ) ) ) return rc;
+  CU( cudaMemcpyAsync( dP, pred, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  CU( cudaMemcpyAsync( dR, resi, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_affine_eq_batch_dev( ctx, sixParam, (const int16_t*) dP, (const int16_t*) dR, n, w, h, (int16_t*) dX, (int16_t*) dY, (int64_t*) dE ) ) ) return rc;
+  CU( cudaMemcpyAsync( eq, dE, (size_t) n * 49 * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( derivX ) CU( cudaMemcpyAsync( derivX, dX, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( derivY ) CU( cudaMemcpyAsync( derivY, dY, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
   return VVB_OK;
 }
 

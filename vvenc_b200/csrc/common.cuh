@@ -95,6 +95,8 @@ struct vvb_ctx
   void*          d_dqScan    = nullptr;     // dependent quantisation: ScanInfo / NbInfoOut tables of the 25 shapes (built at the first vvb_dep_quant call)
   void*          d_dqNb      = nullptr;
   void*          dqShapes    = nullptr;     // host: vvbdq::DqShapeTables[25]
+  int16_t*       d_mask      = nullptr;     // GEO weight masks (vvb_mask_upload)
+  int            maskCount   = 0;
   // grow-only scratch arenas (device + pinned host) used by the host-buffer entry points
   int            mctfMaxDim = 64;      // largest MCTF block dimension in device-resident candidate lists (vvb_mctf_hint)
   bool           async = false;        // host-buffer calls enqueue only; vvb_synchronize() completes them (vvb_set_async)
