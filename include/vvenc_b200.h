@@ -330,6 +330,23 @@ int vvb_mctf_apply_dev( vvb_ctx* ctx, int org_plane, const vvb_mctf_apply_par* p
 int vvb_mctf_calc_var    ( vvb_ctx* ctx, int plane, const vvb_mctf_cand* blocks, int n, double* var_out );
 int vvb_mctf_calc_var_dev( vvb_ctx* ctx, int plane, const vvb_mctf_cand* dev_blocks, int n, double* dev_var_out );
 
+/* MCTF motion search with the control on the device (MCTF::motionEstimationLuma, MCTF.cpp:1329-1397 -> estimateLumaLn :1166-1327).  One call runs a whole
+ * level for the whole picture: predictor candidates from the coarser level's field, the integer grid, the three sub-pel grids of the final level, the
+ * `error < best.error` chains in the reference's loop order, the candidates of the block above and the block to the left (one warp per block row that waits for
+ * the row above -- the prevLineX scheme of :1176, 1357-1386) and the final error scaling; the host sees no number in between.  The field is an array of
+ * out_w x out_h vvb_mctf_mv in raster order (entries no block writes keep the default vector 0, 0, as the reference's field arrays do); it is what
+ * vvb_mctf_apply_dev takes.  prev: field of the coarser level (prev_w x prev_h), null for the first level.  factor: m_motionVectorFactor scale between levels.
+ * search_pattern: 0 / 1 / 2 as MCTFSpeed 0 / 1-2 / 3-4 select (:598-599).  Block sizes: multiples of 8 up to 64. */
+typedef struct { int32_t block_size, factor, double_res, search_pattern, low_res_filter, prev_w, prev_h, out_w, out_h; } vvb_mctf_level_par;
+int vvb_mctf_estimate_level    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_level_par* par, const vvb_mctf_mv* prev, vvb_mctf_mv* field_out );
+int vvb_mctf_estimate_level_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_level_par* par, const vvb_mctf_mv* dev_prev, vvb_mctf_mv* dev_field_out );
+/* MCTF::motionEstimationMCTF (MCTF.cpp:666-724) for one neighbour picture: MCTF::subsampleLuma twice (three times with add_level) into context-owned planes with
+ * 128 pels of border replication, then the levels 2u / 2u / 2u (/ 2u) / u chained through device-resident fields.  field_out: ceil(W / unit) x ceil(H / unit)
+ * entries.  Both planes need a margin that covers the vectors (MCTF_PADDING = 128). */
+typedef struct { int32_t unit_size, add_level, search_pattern, low_res_filter; } vvb_mctf_pyr_par;
+int vvb_mctf_estimate_pyramid    ( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_pyr_par* par, vvb_mctf_mv* field_out );
+int vvb_mctf_estimate_pyramid_dev( vvb_ctx* ctx, int org_plane, int ref_plane, const vvb_mctf_pyr_par* par, vvb_mctf_mv* dev_field_out );
+
 /* ---- affine gradient helpers (CommonLib/AffineGradientSearch.cpp:84-190) ---------------------------------- */
 int vvb_affine_sobel      ( vvb_ctx* ctx, int vertical, const int16_t* pred, int pred_stride, int16_t* deriv, int deriv_stride, int w, int h );
 int vvb_affine_equal_coeff( vvb_ctx* ctx, int six_param, const int16_t* resi, int resi_stride, const int16_t* deriv_x, const int16_t* deriv_y,

@@ -31,6 +31,14 @@ class vvb_tu_par(ctypes.Structure):
                 ('qp', ctypes.c_int32), ('is_irap', ctypes.c_int32), ('dep_quant', ctypes.c_int32), ('sign_hiding', ctypes.c_int32), ('lfnst_idx', ctypes.c_int32), ('lfnst_set', ctypes.c_int32), ('lfnst_transpose', ctypes.c_int32)]
 
 
+class vvb_mctf_level_par(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ('block_size', 'factor', 'double_res', 'search_pattern', 'low_res_filter', 'prev_w', 'prev_h', 'out_w', 'out_h')]
+
+
+class vvb_mctf_pyr_par(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ('unit_size', 'add_level', 'search_pattern', 'low_res_filter')]
+
+
 class vvb_dq_rates(ctypes.Structure):
     _fields_ = [('last_bits_x', ctypes.c_int32 * 32), ('last_bits_y', ctypes.c_int32 * 32), ('sig_sbb_bits', ctypes.c_int32 * 4), ('sig_bits', ctypes.c_int32 * 72),
                 ('gtx_bits', ctypes.c_int32 * 126)]
@@ -101,6 +109,10 @@ SYMBOLS = {
     'vvb_search_refine_tu': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, ctypes.POINTER(vvb_me_par), c_i, c_i, c_i, c_p, c_i]),
     'vvb_fwd_trquant_planes': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'vvb_fwd_trquant_planes_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'vvb_mctf_estimate_level': (c_i, [c_p, c_i, c_i, ctypes.POINTER(vvb_mctf_level_par), c_p, c_p]),
+    'vvb_mctf_estimate_level_dev': (c_i, [c_p, c_i, c_i, ctypes.POINTER(vvb_mctf_level_par), c_p, c_p]),
+    'vvb_mctf_estimate_pyramid': (c_i, [c_p, c_i, c_i, ctypes.POINTER(vvb_mctf_pyr_par), c_p]),
+    'vvb_mctf_estimate_pyramid_dev': (c_i, [c_p, c_i, c_i, ctypes.POINTER(vvb_mctf_pyr_par), c_p]),
     'vvb_mask_upload': (c_i, [c_p, c_p, c_i]),
     'vvb_sad_mask_batch': (c_i, [c_p, c_p, c_i, c_p]),
     'vvb_sad_mask_batch_dev': (c_i, [c_p, c_p, c_i, c_p]),

@@ -348,6 +348,26 @@ class CostEngine:
         return out
 
     # ---- affine
+    def mctf_estimate_level(self, org_plane, ref_plane, width, height, block_size, prev=None, factor=2, double_res=False, search_pattern=0, low_res_filter=False, out_shape=None):
+        """MCTF::motionEstimationLuma for the whole picture with the control on the device.  prev: None or a MCTF_MV_DT array [prevH][prevW] (field of the coarser
+        level).  Returns a MCTF_MV_DT array [out_h][out_w] (default: one entry per block)."""
+        bxn, byn = (width - 8) // block_size + 1, (height - 8) // block_size + 1
+        oh, ow = out_shape if out_shape is not None else (byn, bxn)
+        out = np.zeros((oh, ow), dtype=L.MCTF_MV_DT)
+        if prev is not None:
+            prev = np.ascontiguousarray(prev, dtype=L.MCTF_MV_DT)
+        par = L.vvb_mctf_level_par(block_size, factor, int(double_res), search_pattern, int(low_res_filter), 0 if prev is None else prev.shape[1], 0 if prev is None else prev.shape[0], ow, oh)
+        self._chk(self.lib.vvb_mctf_estimate_level(self.h, org_plane, ref_plane, ctypes.byref(par), _p(prev), _p(out)))
+        return out
+
+    def mctf_estimate_pyramid(self, org_plane, ref_plane, width, height, unit_size=16, add_level=False, search_pattern=0, low_res_filter=False):
+        """MCTF::motionEstimationMCTF for one neighbour picture, everything on the device (subsampling, 4 / 5 chained levels).  Planes: margin >= 128.
+        Returns a MCTF_MV_DT array [ceil(H / unit)][ceil(W / unit)] -- the input of mctf_apply."""
+        out = np.zeros(((height + unit_size - 1) // unit_size, (width + unit_size - 1) // unit_size), dtype=L.MCTF_MV_DT)
+        par = L.vvb_mctf_pyr_par(unit_size, int(add_level), search_pattern, int(low_res_filter))
+        self._chk(self.lib.vvb_mctf_estimate_pyramid(self.h, org_plane, ref_plane, ctypes.byref(par), _p(out)))
+        return out
+
     def affine_sobel(self, vertical, pred, pred_stride, deriv_stride, w, h):
         d = np.zeros((h, deriv_stride), dtype=np.int16)
         self._chk(self.lib.vvb_affine_sobel(self.h, int(vertical), _p(pred), pred_stride, _p(d), deriv_stride, w, h))

@@ -17,6 +17,7 @@
 #include "frac_kernels.cuh"
 #include "depquant_kernels.cuh"
 #include "batch_kernels.cuh"
+#include "mctf_control_kernels.cuh"
 #include "depquant_host.h"
 #include "vvc_tables.h"
 #include "vvc_lfnst_tables.h"
@@ -253,6 +254,7 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( had8_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+  cudaFuncSetAttribute( mctf_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1468,7 +1470,12 @@ int vvb_tu_roundtrip( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* org, c
 }
 
 // ---- MCTF ----------------------------------------------------------------------------------------------------------
+static int mctfLaunchP( vvb_ctx* ctx, const Plane& po, const Plane& pr, const vvb_mctf_cand* dCands, int n, int lowRes, int maxDim, int32_t* dErr );
 static int mctfLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dCands, int n, int lowRes, int maxDim, int32_t* dErr )
+{
+  return mctfLaunchP( ctx, ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dCands, n, lowRes, maxDim, dErr );
+}
+static int mctfLaunchP( vvb_ctx* ctx, const Plane& po, const Plane& pr, const vvb_mctf_cand* dCands, int n, int lowRes, int maxDim, int32_t* dErr )
 {
   CU( cudaSetDevice( ctx->device ) );
   maxDim = std::max( 8, std::min( 64, ( maxDim + 7 ) & ~7 ) );
@@ -1476,7 +1483,7 @@ static int mctfLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_
   const size_t smem = (size_t) MCTF_WARPS * L.warpWords * 4;
   const int perSM = (int) std::max<size_t>( 1, std::min<size_t>( 12, ( 220 * 1024 ) / ( smem + 1024 ) ) );
   const int grid = std::min( ( n + MCTF_WARPS - 1 ) / MCTF_WARPS, ctx->numSMs * perSM );
-  mctf_error_packed_kernel<<<grid, MCTF_WARPS * 32, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dCands, n, lowRes ? 1 : 0, maxDim, dErr );
+  mctf_error_packed_kernel<<<grid, MCTF_WARPS * 32, smem, ctx->stream>>>( po, pr, dCands, n, lowRes ? 1 : 0, maxDim, dErr );
   CHECK_LAUNCH( "mctf_error_packed_kernel" );
   return VVB_OK;
 }
@@ -1655,7 +1662,12 @@ int vvb_mctf_calc_var( vvb_ctx* ctx, int plane, const vvb_mctf_cand* blocks, int
 }
 
 // MCTF grid search: all (2r+1)^2 candidates around each block's centre vector in one CTA (estimateLumaLn loops, MCTF.cpp:1218-1287)
+static int mctfGridLaunchP( vvb_ctx* ctx, const Plane& po, const Plane& pr, const vvb_mctf_cand* dBlocks, int n, int step, int radius, int lowRes, int maxDim, int32_t* dErr );
 static int mctfGridLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_cand* dBlocks, int n, int step, int radius, int lowRes, int maxDim, int32_t* dErr )
+{
+  return mctfGridLaunchP( ctx, ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, step, radius, lowRes, maxDim, dErr );
+}
+static int mctfGridLaunchP( vvb_ctx* ctx, const Plane& po, const Plane& pr, const vvb_mctf_cand* dBlocks, int n, int step, int radius, int lowRes, int maxDim, int32_t* dErr )
 {
   CU( cudaSetDevice( ctx->device ) );
   maxDim = std::max( 8, std::min( 64, ( maxDim + 7 ) & ~7 ) );
@@ -1663,7 +1675,7 @@ static int mctfGridLaunch( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_m
   const size_t smem = (size_t) L.total * 4;
   if( smem > 200 * 1024 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "MCTF grid too large for shared memory" );
   const int threads = std::max( 32, std::min( 256, ( ( maxDim / 2 ) * maxDim + 31 ) & ~31 ) );
-  mctf_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, smem, ctx->stream>>>( ctx->planes.p[orgPlane], ctx->planes.p[refPlane], dBlocks, n, step, radius, lowRes ? 1 : 0, maxDim, dErr );
+  mctf_grid_kernel<<<std::min( n, ctx->numSMs * 32 ), threads, smem, ctx->stream>>>( po, pr, dBlocks, n, step, radius, lowRes ? 1 : 0, maxDim, dErr );
   CHECK_LAUNCH( "mctf_grid_kernel" );
   return VVB_OK;
 }
@@ -1701,6 +1713,203 @@ int vvb_mctf_search_grid( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mc
   CU( cudaMemcpyAsync( dB, blocks, (size_t) n * sizeof( vvb_mctf_cand ), cudaMemcpyHostToDevice, ctx->stream ) );
   if( ( rc = mctfGridLaunch( ctx, orgPlane, refPlane, (const vvb_mctf_cand*) dB, n, step, radius, lowRes, maxDim, (int32_t*) dE ) ) ) return rc;
   CU( cudaMemcpyAsync( err, dE, (size_t) n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// ---- MCTF motion search with the control on the device (MCTF::motionEstimationMCTF, MCTF.cpp:666-724 -> motionEstimationLuma :1329-1397) ---------------------------
+namespace {
+struct MctfArena { MctfBest* best; int2* centre; vvb_mctf_cand* cands; int32_t* err; double* var; int* progress; };
+
+size_t mctfArenaBytes( int n, int byn )
+{
+  return ( (size_t) n * sizeof( MctfBest ) + 255 ) / 256 * 256 + ( (size_t) n * 8 + 255 ) / 256 * 256 + ( (size_t) n * 10 * sizeof( vvb_mctf_cand ) + 255 ) / 256 * 256 +
+         ( (size_t) n * 289 * 4 + 255 ) / 256 * 256 + ( (size_t) n * 8 + 255 ) / 256 * 256 + ( (size_t)( byn + 2 ) * 4 + 255 ) / 256 * 256;
+}
+MctfArena mctfCarve( uint8_t* p, int n, int byn )
+{
+  MctfArena a;
+  auto take = [&]( size_t bytes ) { uint8_t* r = p; p += ( bytes + 255 ) / 256 * 256; return r; };
+  a.best = (MctfBest*) take( (size_t) n * sizeof( MctfBest ) ); a.centre = (int2*) take( (size_t) n * 8 ); a.cands = (vvb_mctf_cand*) take( (size_t) n * 10 * sizeof( vvb_mctf_cand ) );
+  a.err = (int32_t*) take( (size_t) n * 289 * 4 ); a.var = (double*) take( (size_t) n * 8 ); a.progress = (int*) take( (size_t)( byn + 2 ) * 4 );
+  return a;
+}
+
+// offsets off0 + k * delta (k < count) -> the smallest lattice the grid kernel can evaluate that contains them (step <= 16): vvenc_b200/mctf_host.py _offset_table
+struct MctfOffs { int off0, delta, count, step, radius, shift; };
+MctfOffs mctfOffsets( int first, int last, int delta )
+{
+  MctfOffs o; o.off0 = first; o.delta = delta; o.count = ( last - first ) / delta + 1;
+  if( o.count == 1 ) { o.delta = 16; o.step = 16; o.radius = 0; o.shift = first; return o; }
+  o.step = delta;
+  while( o.step > 16 ) o.step /= 2;
+  o.radius = ( ( last - first ) + 2 * o.step - 1 ) / ( 2 * o.step );
+  o.shift = first + o.radius * o.step;
+  return o;
+}
+
+// one level for the whole picture; every stage is enqueued on the context stream, nothing returns to the host
+int mctfLevel( vvb_ctx* ctx, const Plane& po, const Plane& pr, int width, int height, int bs, const vvb_mctf_mv* dPrev, int prevW, int prevH, int factor, bool doubleRes,
+               int bitDepth, int searchPattern, int lowRes, vvb_mctf_mv* dOut, int outW, int outH, uint8_t* arenaMem )
+{
+  MctfGeom g;
+  g.width = width; g.height = height; g.bs = bs;
+  g.bxn = width >= 8 ? ( width - 8 ) / bs + 1 : 0; g.byn = height >= 8 ? ( height - 8 ) / bs + 1 : 0; g.n = g.bxn * g.byn;
+  g.prevW = dPrev ? prevW : 0; g.prevH = dPrev ? prevH : 0; g.factor = factor; g.outW = outW; g.outH = outH;
+  CU( cudaMemsetAsync( dOut, 0, (size_t) outW * outH * sizeof( vvb_mctf_mv ), ctx->stream ) );
+  if( g.n == 0 ) return VVB_OK;
+  const MctfArena a = mctfCarve( arenaMem, g.n, g.byn );
+  const int T = 128, nb = ( g.n + T - 1 ) / T;
+  int rc;
+  mctf_init_kernel<<<( std::max( g.n, g.byn + 1 ) + T - 1 ) / T, T, 0, ctx->stream>>>( g, a.best, a.progress );
+  CHECK_LAUNCH( "mctf_init_kernel" );
+  int searchRange = 8;
+  if( dPrev )
+  {
+    searchRange = doubleRes ? 0 : ( searchPattern == 2 ? 3 : 5 );
+    mctf_pred_cands_kernel<<<( g.n * 10 + T - 1 ) / T, T, 0, ctx->stream>>>( g, dPrev, a.cands );
+    CHECK_LAUNCH( "mctf_pred_cands_kernel" );
+    if( ( rc = mctfLaunchP( ctx, po, pr, a.cands, g.n * 10, lowRes, bs, a.err ) ) ) return rc;
+    mctf_select_list_kernel<<<nb, T, 0, ctx->stream>>>( g, a.cands, a.err, a.best );
+    CHECK_LAUNCH( "mctf_select_list_kernel" );
+  }
+  auto gridStage = [&]( const MctfOffs& o, int truncInt, int skipZero ) -> int
+  {
+    mctf_centre_kernel<<<nb, T, 0, ctx->stream>>>( g, a.best, truncInt, o.shift, a.centre, a.cands );
+    CHECK_LAUNCH( "mctf_centre_kernel" );
+    int r = mctfGridLaunchP( ctx, po, pr, a.cands, g.n, o.step, o.radius, lowRes, bs, a.err );
+    if( r ) return r;
+    mctf_select_grid_kernel<<<nb, T, 0, ctx->stream>>>( g, a.err, 2 * o.radius + 1, o.off0, o.delta, o.count, o.step, skipZero, a.centre, a.best );
+    CHECK_LAUNCH( "mctf_select_grid_kernel" );
+    return VVB_OK;
+  };
+  const int d = ( !dPrev && searchPattern == 2 ) ? 2 : 1;                                                     // :1217
+  if( ( rc = gridStage( mctfOffsets( -16 * searchRange, -16 * searchRange + 16 * d * ( 2 * searchRange / d ), 16 * d ), 1, 0 ) ) ) return rc;
+  if( doubleRes )
+  {
+    const int rng = searchPattern == 0 ? 12 : 6, d1 = searchPattern == 2 ? 6 : 4;
+    if( ( rc = gridStage( mctfOffsets( -rng, -rng + d1 * ( 2 * rng / d1 ), d1 ), 0, 1 ) ) ) return rc;
+    if( ( rc = gridStage( mctfOffsets( -2, 2, 2 ), 0, 1 ) ) ) return rc;
+    if( ( rc = gridStage( mctfOffsets( -1, 1, 1 ), 0, 1 ) ) ) return rc;
+  }
+  {
+    const int maxDim = std::max( 8, std::min( 64, ( bs + 7 ) & ~7 ) );
+    const MctfSmem L = mctf_smem( maxDim );
+    mctf_wave_kernel<<<g.byn, 32, (size_t) L.warpWords * 4, ctx->stream>>>( po, pr, g, lowRes ? 1 : 0, maxDim, a.best, a.progress );
+    CHECK_LAUNCH( "mctf_wave_kernel" );
+  }
+  if( doubleRes )
+  {
+    mctf_centre_kernel<<<nb, T, 0, ctx->stream>>>( g, a.best, 0, 0, a.centre, a.cands );                      // the block list (x, y, w, h) for calcVar
+    CHECK_LAUNCH( "mctf_centre_kernel" );
+    mctf_calc_var_kernel<<<( g.n + 3 ) / 4, 128, 0, ctx->stream>>>( po, a.cands, g.n, a.var );
+    CHECK_LAUNCH( "mctf_calc_var_kernel" );
+  }
+  mctf_final_kernel<<<nb, T, 0, ctx->stream>>>( g, a.best, a.var, doubleRes ? 1 : 0, bitDepth, dOut );
+  CHECK_LAUNCH( "mctf_final_kernel" );
+  return VVB_OK;
+}
+} // namespace
+
+int vvb_mctf_estimate_level_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_level_par* lp, const vvb_mctf_mv* dPrev, vvb_mctf_mv* dOut )
+{
+  if( !ctx || !lp || !dOut ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( ( lp->block_size != 8 && lp->block_size != 16 && lp->block_size != 32 && lp->block_size != 64 ) || lp->search_pattern < 0 || lp->search_pattern > 2 || lp->out_w < 1 || lp->out_h < 1 )
+    return fail( ctx, VVB_ERR_ARG, "bad level parameters" );
+  const Plane& po = ctx->planes.p[orgPlane];
+  CU( cudaSetDevice( ctx->device ) );
+  const int bxn = ( po.width - 8 ) / lp->block_size + 1, byn = ( po.height - 8 ) / lp->block_size + 1;
+  void* arena; int rc;
+  if( ( rc = scratch( ctx, 6, mctfArenaBytes( std::max( 1, bxn * byn ), byn ), &arena ) ) ) return rc;
+  return mctfLevel( ctx, po, ctx->planes.p[refPlane], po.width, po.height, lp->block_size, dPrev, lp->prev_w, lp->prev_h, lp->factor, lp->double_res != 0, po.bitDepth,
+                    lp->search_pattern, lp->low_res_filter, dOut, lp->out_w, lp->out_h, (uint8_t*) arena );
+}
+
+int vvb_mctf_estimate_level( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_level_par* lp, const vvb_mctf_mv* prev, vvb_mctf_mv* out )
+{
+  if( !ctx || !lp || !out ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  void *dPrev = nullptr, *dOut; int rc;
+  const size_t outBytes = (size_t) lp->out_w * lp->out_h * sizeof( vvb_mctf_mv );
+  if( ( rc = scratch( ctx, 1, outBytes, &dOut ) ) ) return rc;
+  if( prev )
+  {
+    if( ( rc = scratch( ctx, 0, (size_t) lp->prev_w * lp->prev_h * sizeof( vvb_mctf_mv ), &dPrev ) ) ) return rc;
+    CU( cudaMemcpyAsync( dPrev, prev, (size_t) lp->prev_w * lp->prev_h * sizeof( vvb_mctf_mv ), cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  if( ( rc = vvb_mctf_estimate_level_dev( ctx, orgPlane, refPlane, lp, (const vvb_mctf_mv*) dPrev, (vvb_mctf_mv*) dOut ) ) ) return rc;
+  CU( cudaMemcpyAsync( out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// whole pyramid of one neighbour picture: the subsampled pictures (MCTF::subsampleLuma, border replication 128) are produced into context-owned memory, the four
+// (five with add_level) levels chain through device-resident fields; the final field has ceil(W / unit) x ceil(H / unit) entries
+int vvb_mctf_estimate_pyramid_dev( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_pyr_par* pp, vvb_mctf_mv* dOut )
+{
+  if( !ctx || !pp || !dOut ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) || !validPlane( ctx, refPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  if( ( pp->unit_size != 8 && pp->unit_size != 16 && pp->unit_size != 32 ) || pp->search_pattern < 0 || pp->search_pattern > 2 ) return fail( ctx, VVB_ERR_ARG, "bad pyramid parameters" );
+  CU( cudaSetDevice( ctx->device ) );
+  const Plane po0 = ctx->planes.p[orgPlane], pr0 = ctx->planes.p[refPlane];
+  const int W = po0.width, H = po0.height, u = pp->unit_size, nSub = pp->add_level ? 3 : 2, margin = 128;
+  if( pr0.width != W || pr0.height != H ) return fail( ctx, VVB_ERR_ARG, "picture sizes differ" );
+  // subsampled planes
+  Plane po[4], pr[4]; po[0] = po0; pr[0] = pr0;
+  size_t planeBytes[4] = { 0, 0, 0, 0 }, total = 0;
+  int lw[4] = { W, 0, 0, 0 }, lh[4] = { H, 0, 0, 0 }, strideOf[4] = { 0, 0, 0, 0 };
+  for( int l = 1; l <= nSub; l++ )
+  {
+    lw[l] = lw[l - 1] / 2; lh[l] = lh[l - 1] / 2;
+    if( lw[l] < 8 || lh[l] < 8 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "picture too small for the MCTF pyramid" );
+    strideOf[l] = ( lw[l] + 2 * margin + 7 ) & ~7;
+    planeBytes[l] = ( (size_t) strideOf[l] * ( lh[l] + 2 * margin ) * 2 + 255 ) / 256 * 256;
+    total += 2 * planeBytes[l];
+  }
+  // intermediate fields (sized as the reference sizes them: width / (unit * k) + 1)
+  const int fw[4] = { W / ( u * 2 ) + 1, W / ( u * 4 ) + 1, W / ( u * 8 ) + 1, W / ( u * 16 ) + 1 }, fh[4] = { H / ( u * 2 ) + 1, H / ( u * 4 ) + 1, H / ( u * 8 ) + 1, H / ( u * 16 ) + 1 };
+  size_t fieldOff[4], fieldBytes = 0;
+  for( int k = 0; k < 4; k++ ) { fieldOff[k] = fieldBytes; fieldBytes += ( (size_t) fw[k] * fh[k] * sizeof( vvb_mctf_mv ) + 255 ) / 256 * 256; }
+  const int nFinal = ( ( W - 8 ) / u + 1 ) * ( ( H - 8 ) / u + 1 );
+  void *dPlanes, *arena; int rc;
+  if( ( rc = scratch( ctx, 7, total + fieldBytes + 256, &dPlanes ) ) || ( rc = scratch( ctx, 6, mctfArenaBytes( std::max( 1, nFinal ), ( H - 8 ) / u + 1 ), &arena ) ) ) return rc;
+  uint8_t* mem = (uint8_t*) dPlanes;
+  for( int l = 1; l <= nSub; l++ )
+    for( int which = 0; which < 2; which++ )
+    {
+      Plane& dst = which ? pr[l] : po[l];
+      const Plane& src = which ? pr[l - 1] : po[l - 1];
+      int16_t* base = (int16_t*) mem; mem += planeBytes[l];
+      dst.origin = base + (size_t) margin * strideOf[l] + margin; dst.stride = strideOf[l]; dst.width = lw[l]; dst.height = lh[l]; dst.margin = margin; dst.bitDepth = src.bitDepth;
+      dim3 blk( 32, 8 ), grd( ( lw[l] + 2 * margin + 31 ) / 32, ( lh[l] + 2 * margin + 7 ) / 8 );
+      mctf_subsample_kernel<<<grd, blk, 0, ctx->stream>>>( src, const_cast<int16_t*>( dst.origin ), dst.stride, lw[l], lh[l], margin );
+      CHECK_LAUNCH( "mctf_subsample_kernel" );
+    }
+  vvb_mctf_mv* field[4];
+  for( int k = 0; k < 4; k++ ) field[k] = (vvb_mctf_mv*)( mem + fieldOff[k] );
+  const vvb_mctf_mv* prev = nullptr; int prevW = 0, prevH = 0;
+  const int bd = po0.bitDepth, sp = pp->search_pattern, low = pp->low_res_filter;
+  if( pp->add_level )
+  {
+    if( ( rc = mctfLevel( ctx, po[3], pr[3], lw[3], lh[3], 2 * u, nullptr, 0, 0, 2, false, bd, sp, low, field[3], fw[3], fh[3], (uint8_t*) arena ) ) ) return rc;
+    prev = field[3]; prevW = fw[3]; prevH = fh[3];
+  }
+  if( ( rc = mctfLevel( ctx, po[2], pr[2], lw[2], lh[2], 2 * u, prev, prevW, prevH, 2, false, bd, sp, low, field[2], fw[2], fh[2], (uint8_t*) arena ) ) ) return rc;
+  if( ( rc = mctfLevel( ctx, po[1], pr[1], lw[1], lh[1], 2 * u, field[2], fw[2], fh[2], 2, false, bd, sp, low, field[1], fw[1], fh[1], (uint8_t*) arena ) ) ) return rc;
+  if( ( rc = mctfLevel( ctx, po[0], pr[0], W, H, 2 * u, field[1], fw[1], fh[1], 2, false, bd, sp, low, field[0], fw[0], fh[0], (uint8_t*) arena ) ) ) return rc;
+  return mctfLevel( ctx, po[0], pr[0], W, H, u, field[0], fw[0], fh[0], 1, true, bd, sp, low, dOut, ( W + u - 1 ) / u, ( H + u - 1 ) / u, (uint8_t*) arena );
+}
+
+int vvb_mctf_estimate_pyramid( vvb_ctx* ctx, int orgPlane, int refPlane, const vvb_mctf_pyr_par* pp, vvb_mctf_mv* out )
+{
+  if( !ctx || !pp || !out ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !validPlane( ctx, orgPlane ) ) return fail( ctx, VVB_ERR_ARG, "unknown plane" );
+  const Plane& po = ctx->planes.p[orgPlane];
+  const size_t bytes = (size_t)( ( po.width + pp->unit_size - 1 ) / std::max( 1, pp->unit_size ) ) * ( ( po.height + pp->unit_size - 1 ) / std::max( 1, pp->unit_size ) ) * sizeof( vvb_mctf_mv );
+  void* dOut; int rc;
+  if( ( rc = scratch( ctx, 1, bytes, &dOut ) ) ) return rc;
+  if( ( rc = vvb_mctf_estimate_pyramid_dev( ctx, orgPlane, refPlane, pp, (vvb_mctf_mv*) dOut ) ) ) return rc;
+  CU( cudaMemcpyAsync( out, dOut, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
   CU( endCall( ctx ) );
   return VVB_OK;
 }

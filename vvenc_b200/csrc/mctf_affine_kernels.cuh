@@ -39,6 +39,101 @@ __host__ __device__ inline MctfSmem mctf_smem( int maxDim )
 
 __device__ __forceinline__ int mctf_div( int i, float inv ) { return __float2int_rz( ( (float) i + 0.5f ) * inv ); }   // exact for i < 2^20, divisors <= 64
 
+// motionErrorLuma of one candidate by one warp (no early exit); region / t2: the warp's slices of shared memory (mctf_smem); every lane returns the error
+__device__ __forceinline__ int mctf_warp_error( const Plane& orgPlane, const Plane& refPlane, const vvb_mctf_cand& c, int tap4, const MctfSmem& L, uint32_t* region, uint32_t* t2, int lane )
+{
+  const int PW = L.regionPitch;
+  const int maxv = ( 1 << refPlane.bitDepth ) - 1;
+  const int w = c.w, h = c.h;
+  int dx = c.mvx, dy = c.mvy;
+  const int fx = dx & 15, fy = dy & 15;
+  const int16_t* org = orgPlane.origin + (ptrdiff_t) c.y * orgPlane.stride + c.x;
+  const int hw = w >> 1;
+  const float invHw = 1.0f / (float) hw, invW = 1.0f / (float) w;
+  int err = 0;
+  if( ( fx | fy ) == 0 )
+  {
+    dx /= 16; dy /= 16;                                  // MCTF.cpp:1121-1122 (C division, truncating)
+    const int16_t* buf = refPlane.origin + (ptrdiff_t)( c.y + dy ) * refPlane.stride + c.x + dx;
+    for( int i = lane; i < w * h; i += 32 )
+    {
+      const int y = mctf_div( i, invW ), x = i - y * w;
+      const int d = (int) __ldg( org + (ptrdiff_t) y * orgPlane.stride + x ) - (int) __ldg( buf + (ptrdiff_t) y * refPlane.stride + x );
+      err += d * d;
+    }
+  }
+  else
+  {
+    dx >>= 4; dy >>= 4;                                  // MCTF.cpp:1136-1137 / :1151-1152 (arithmetic shift)
+    // taps as 6-tap filters f[0..5] over pels x-2 .. x+3 (rows y-2 .. y+3)
+    int fxv[6], fyv[6];
+#pragma unroll
+    for( int t = 0; t < 6; t++ )
+    {
+      fxv[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[fx][t - 1] : 0 ) : c_mctfF8[fx][t + 1];
+      fyv[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[fy][t - 1] : 0 ) : c_mctfF8[fy][t + 1];
+    }
+#define VVB_B4( a, b, c_, d ) ( (uint32_t)( (a) & 255 ) | ( (uint32_t)( (b) & 255 ) << 8 ) | ( (uint32_t)( (c_) & 255 ) << 16 ) | ( (uint32_t)( (d) & 255 ) << 24 ) )
+    const int xFA = (int) VVB_B4( fxv[0], fxv[1], fxv[2], fxv[3] ), xFB = (int) VVB_B4( fxv[4], fxv[5], 0, 0 );
+    const int xGA = (int) VVB_B4( 0, fxv[0], fxv[1], fxv[2] ),      xGB = (int) VVB_B4( fxv[3], fxv[4], fxv[5], 0 );
+    const int yFA = (int) VVB_B4( fyv[0], fyv[1], fyv[2], fyv[3] ), yFB = (int) VVB_B4( fyv[4], fyv[5], 0, 0 );
+    const int yGA = (int) VVB_B4( 0, fyv[0], fyv[1], fyv[2] ),      yGB = (int) VVB_B4( fyv[3], fyv[4], fyv[5], 0 );
+#undef VVB_B4
+#define VVB_E( a, b, c_, FA, FB ) __dp2a_lo( (int)(c_), FB, __dp2a_hi( (int)(b), FA, __dp2a_lo( (int)(a), FA, 0 ) ) )
+#define VVB_O( a, b, c_, d, GA, GB ) __dp2a_hi( (int)(d), GB, __dp2a_lo( (int)(c_), GB, __dp2a_hi( (int)(b), GA, __dp2a_lo( (int)(a), GA, 0 ) ) ) )
+#define VVB_RC( v ) max( min( ( (v) + 32 ) >> 6, maxv ), 0 )
+    // ---- stage the source region: rows y-2 .. y+h+3 (the last one only pairs up the row count), pels from the even pel at or below x-2
+    const int16_t* src0 = refPlane.origin + (ptrdiff_t)( c.y + dy - 2 ) * refPlane.stride + c.x + dx - 2;
+    const int o = (int)( ( reinterpret_cast<uintptr_t>( src0 ) >> 1 ) & 1 );            // plane rows are 16-byte aligned: same parity on every row
+    const uint32_t* srcW = reinterpret_cast<const uint32_t*>( src0 - o );
+    const int nW = ( w + 5 + o + 1 ) >> 1, rowsP = ( h + 6 ) & ~1;                      // words per row, rows rounded up to pairs
+    const float invNw = 1.0f / (float) nW;
+    const int strideW = refPlane.stride >> 1;
+    __syncwarp();
+    for( int i = lane; i < rowsP * nW; i += 32 )
+    {
+      const int r = mctf_div( i, invNw ), k = i - r * nW;
+      region[r * PW + k] = __ldg( srcW + (ptrdiff_t) r * strideW + k );
+    }
+    __syncwarp();
+    // ---- horizontal pass: item = (row pair rp, column pair cp) -> t2[rp][x], t2[rp][x+1] = packed ( row 2rp, row 2rp+1 )
+    const int nRp = rowsP >> 1;
+    for( int i = lane; i < nRp * hw; i += 32 )
+    {
+      const int rp = mctf_div( i, invHw ), cp = i - rp * hw;
+      const uint32_t* ra = region + ( 2 * rp ) * PW + cp;
+      const uint32_t* rb = ra + PW;
+      const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
+      int ha0, ha1, hb0, hb1;
+      if( o == 0 ) { ha0 = VVB_E( a0, a1, a2, xFA, xFB ); ha1 = VVB_O( a0, a1, a2, a3, xGA, xGB ); hb0 = VVB_E( b0, b1, b2, xFA, xFB ); hb1 = VVB_O( b0, b1, b2, b3, xGA, xGB ); }
+      else         { ha0 = VVB_O( a0, a1, a2, a3, xGA, xGB ); ha1 = VVB_E( a1, a2, a3, xFA, xFB ); hb0 = VVB_O( b0, b1, b2, b3, xGA, xGB ); hb1 = VVB_E( b1, b2, b3, xFA, xFB ); }
+      ha0 = VVB_RC( ha0 ); ha1 = VVB_RC( ha1 ); hb0 = VVB_RC( hb0 ); hb1 = VVB_RC( hb1 );
+      uint2 pk;
+      pk.x = (uint32_t) ha0 | ( (uint32_t) hb0 << 16 );
+      pk.y = (uint32_t) ha1 | ( (uint32_t) hb1 << 16 );
+      *reinterpret_cast<uint2*>( t2 + rp * w + 2 * cp ) = pk;
+    }
+    __syncwarp();
+    // ---- vertical pass + SSE: item = (output row pair yp, column x): rows 2yp (E on pairs yp..yp+2) and 2yp+1 (O on pairs yp..yp+3)
+    for( int i = lane; i < ( h >> 1 ) * w; i += 32 )
+    {
+      const int yp = mctf_div( i, invW ), x = i - yp * w;
+      const uint32_t* tp = t2 + yp * w + x;
+      const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
+      const int v0 = VVB_RC( VVB_E( p0, p1, p2, yFA, yFB ) ), v1 = VVB_RC( VVB_O( p0, p1, p2, p3, yGA, yGB ) );
+      const int16_t* op = org + (ptrdiff_t)( 2 * yp ) * orgPlane.stride + x;
+      const int d0 = v0 - (int) __ldg( op ), d1 = v1 - (int) __ldg( op + orgPlane.stride );
+      err += d0 * d0 + d1 * d1;
+    }
+#undef VVB_E
+#undef VVB_O
+#undef VVB_RC
+  }
+#pragma unroll
+  for( int m = 16; m > 0; m >>= 1 ) err += __shfl_xor_sync( 0xffffffffu, err, m );
+  return err;
+}
+
 __global__ void __launch_bounds__( MCTF_WARPS * 32 ) mctf_error_packed_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                                                const vvb_mctf_cand* __restrict__ cands, int n, int tap4, int maxDim, int32_t* __restrict__ out )
 {
@@ -47,100 +142,12 @@ __global__ void __launch_bounds__( MCTF_WARPS * 32 ) mctf_error_packed_kernel( c
   const MctfSmem L = mctf_smem( maxDim );
   uint32_t* region = sMctf + warp * L.warpWords;
   uint32_t* t2     = region + L.regionWords;
-  const int PW = L.regionPitch;
   const int warpsPerGrid = gridDim.x * MCTF_WARPS;
-  const int maxv = ( 1 << refPlane.bitDepth ) - 1;
   for( int ci = blockIdx.x * MCTF_WARPS + warp; ci < n; ci += warpsPerGrid )
   {
     const vvb_mctf_cand c = cands[ci];
-    const int w = c.w, h = c.h;
-    if( w > maxDim || h > maxDim || ( ( w | h ) & 1 ) ) { if( lane == 0 ) out[ci] = -1; continue; }     // outside the promised geometry
-    int dx = c.mvx, dy = c.mvy;
-    const int fx = dx & 15, fy = dy & 15;
-    const int16_t* org = orgPlane.origin + (ptrdiff_t) c.y * orgPlane.stride + c.x;
-    const int hw = w >> 1;
-    const float invHw = 1.0f / (float) hw, invW = 1.0f / (float) w;
-    int err = 0;
-    if( ( fx | fy ) == 0 )
-    {
-      dx /= 16; dy /= 16;                                  // MCTF.cpp:1121-1122 (C division, truncating)
-      const int16_t* buf = refPlane.origin + (ptrdiff_t)( c.y + dy ) * refPlane.stride + c.x + dx;
-      for( int i = lane; i < w * h; i += 32 )
-      {
-        const int y = mctf_div( i, invW ), x = i - y * w;
-        const int d = (int) __ldg( org + (ptrdiff_t) y * orgPlane.stride + x ) - (int) __ldg( buf + (ptrdiff_t) y * refPlane.stride + x );
-        err += d * d;
-      }
-    }
-    else
-    {
-      dx >>= 4; dy >>= 4;                                  // MCTF.cpp:1136-1137 / :1151-1152 (arithmetic shift)
-      // taps as 6-tap filters f[0..5] over pels x-2 .. x+3 (rows y-2 .. y+3)
-      int fxv[6], fyv[6];
-#pragma unroll
-      for( int t = 0; t < 6; t++ )
-      {
-        fxv[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[fx][t - 1] : 0 ) : c_mctfF8[fx][t + 1];
-        fyv[t] = tap4 ? ( t >= 1 && t <= 4 ? c_mctfF4[fy][t - 1] : 0 ) : c_mctfF8[fy][t + 1];
-      }
-#define VVB_B4( a, b, c_, d ) ( (uint32_t)( (a) & 255 ) | ( (uint32_t)( (b) & 255 ) << 8 ) | ( (uint32_t)( (c_) & 255 ) << 16 ) | ( (uint32_t)( (d) & 255 ) << 24 ) )
-      const int xFA = (int) VVB_B4( fxv[0], fxv[1], fxv[2], fxv[3] ), xFB = (int) VVB_B4( fxv[4], fxv[5], 0, 0 );
-      const int xGA = (int) VVB_B4( 0, fxv[0], fxv[1], fxv[2] ),      xGB = (int) VVB_B4( fxv[3], fxv[4], fxv[5], 0 );
-      const int yFA = (int) VVB_B4( fyv[0], fyv[1], fyv[2], fyv[3] ), yFB = (int) VVB_B4( fyv[4], fyv[5], 0, 0 );
-      const int yGA = (int) VVB_B4( 0, fyv[0], fyv[1], fyv[2] ),      yGB = (int) VVB_B4( fyv[3], fyv[4], fyv[5], 0 );
-#undef VVB_B4
-#define VVB_E( a, b, c_, FA, FB ) __dp2a_lo( (int)(c_), FB, __dp2a_hi( (int)(b), FA, __dp2a_lo( (int)(a), FA, 0 ) ) )
-#define VVB_O( a, b, c_, d, GA, GB ) __dp2a_hi( (int)(d), GB, __dp2a_lo( (int)(c_), GB, __dp2a_hi( (int)(b), GA, __dp2a_lo( (int)(a), GA, 0 ) ) ) )
-#define VVB_RC( v ) max( min( ( (v) + 32 ) >> 6, maxv ), 0 )
-      // ---- stage the source region: rows y-2 .. y+h+3 (the last one only pairs up the row count), pels from the even pel at or below x-2
-      const int16_t* src0 = refPlane.origin + (ptrdiff_t)( c.y + dy - 2 ) * refPlane.stride + c.x + dx - 2;
-      const int o = (int)( ( reinterpret_cast<uintptr_t>( src0 ) >> 1 ) & 1 );            // plane rows are 16-byte aligned: same parity on every row
-      const uint32_t* srcW = reinterpret_cast<const uint32_t*>( src0 - o );
-      const int nW = ( w + 5 + o + 1 ) >> 1, rowsP = ( h + 6 ) & ~1;                      // words per row, rows rounded up to pairs
-      const float invNw = 1.0f / (float) nW;
-      const int strideW = refPlane.stride >> 1;
-      __syncwarp();
-      for( int i = lane; i < rowsP * nW; i += 32 )
-      {
-        const int r = mctf_div( i, invNw ), k = i - r * nW;
-        region[r * PW + k] = __ldg( srcW + (ptrdiff_t) r * strideW + k );
-      }
-      __syncwarp();
-      // ---- horizontal pass: item = (row pair rp, column pair cp) -> t2[rp][x], t2[rp][x+1] = packed ( row 2rp, row 2rp+1 )
-      const int nRp = rowsP >> 1;
-      for( int i = lane; i < nRp * hw; i += 32 )
-      {
-        const int rp = mctf_div( i, invHw ), cp = i - rp * hw;
-        const uint32_t* ra = region + ( 2 * rp ) * PW + cp;
-        const uint32_t* rb = ra + PW;
-        const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
-        int ha0, ha1, hb0, hb1;
-        if( o == 0 ) { ha0 = VVB_E( a0, a1, a2, xFA, xFB ); ha1 = VVB_O( a0, a1, a2, a3, xGA, xGB ); hb0 = VVB_E( b0, b1, b2, xFA, xFB ); hb1 = VVB_O( b0, b1, b2, b3, xGA, xGB ); }
-        else         { ha0 = VVB_O( a0, a1, a2, a3, xGA, xGB ); ha1 = VVB_E( a1, a2, a3, xFA, xFB ); hb0 = VVB_O( b0, b1, b2, b3, xGA, xGB ); hb1 = VVB_E( b1, b2, b3, xFA, xFB ); }
-        ha0 = VVB_RC( ha0 ); ha1 = VVB_RC( ha1 ); hb0 = VVB_RC( hb0 ); hb1 = VVB_RC( hb1 );
-        uint2 pk;
-        pk.x = (uint32_t) ha0 | ( (uint32_t) hb0 << 16 );
-        pk.y = (uint32_t) ha1 | ( (uint32_t) hb1 << 16 );
-        *reinterpret_cast<uint2*>( t2 + rp * w + 2 * cp ) = pk;
-      }
-      __syncwarp();
-      // ---- vertical pass + SSE: item = (output row pair yp, column x): rows 2yp (E on pairs yp..yp+2) and 2yp+1 (O on pairs yp..yp+3)
-      for( int i = lane; i < ( h >> 1 ) * w; i += 32 )
-      {
-        const int yp = mctf_div( i, invW ), x = i - yp * w;
-        const uint32_t* tp = t2 + yp * w + x;
-        const uint32_t p0 = tp[0], p1 = tp[w], p2 = tp[2 * w], p3 = tp[3 * w];
-        const int v0 = VVB_RC( VVB_E( p0, p1, p2, yFA, yFB ) ), v1 = VVB_RC( VVB_O( p0, p1, p2, p3, yGA, yGB ) );
-        const int16_t* op = org + (ptrdiff_t)( 2 * yp ) * orgPlane.stride + x;
-        const int d0 = v0 - (int) __ldg( op ), d1 = v1 - (int) __ldg( op + orgPlane.stride );
-        err += d0 * d0 + d1 * d1;
-      }
-#undef VVB_E
-#undef VVB_O
-#undef VVB_RC
-    }
-#pragma unroll
-    for( int m = 16; m > 0; m >>= 1 ) err += __shfl_xor_sync( 0xffffffffu, err, m );
+    if( c.w > maxDim || c.h > maxDim || ( ( c.w | c.h ) & 1 ) ) { if( lane == 0 ) out[ci] = -1; continue; }     // outside the promised geometry
+    const int err = mctf_warp_error( orgPlane, refPlane, c, tap4, L, region, t2, lane );
     if( lane == 0 ) out[ci] = err;
   }
 }
