@@ -263,6 +263,8 @@ int vvb_dep_quant    ( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq
                        int16_t* q, int32_t* abs_sum, int32_t* last_pos );
 int vvb_dep_quant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq, const vvb_dq_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n,
                        int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos );
+/* kernel shape of the trellis: 1 (default) = four lanes per TU, one per trellis state, eight TUs per warp in lock step; 0 = one thread per TU.  Same results. */
+int vvb_set_depquant_engine( vvb_ctx* ctx, int engine );
 /* the constants the call derives (no device needed): out = qShift, maxQIdx, thresLast, distShift, qAdd, qScale, distAdd, distStepAdd, distOrgFact (Quantizer, DepQuant.h:220-231) */
 int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_t out[9] );
 

@@ -286,12 +286,14 @@ def test_gpu_lfnst_forward_vs_oracle(gpu):
         gpu.eng.inv_trquant(gpu.eng.tu_par(8, 8, V.DCT2, V.DCT2, 10, 30, False, False, False, 1, 0, False), np.zeros((1, 8, 8), dtype=np.int16))
 
 
-def test_gpu_dep_quant_golden(gpu, golden_depquant):
+@pytest.mark.parametrize("engine", [1, 0])
+def test_gpu_dep_quant_golden(gpu, golden_depquant, engine):
     """DepQuant::xQuantDQ on the device against what the reference produced (tests/golden/golden_v5_depquant.npz): every row of cases.dq_cases(), scalar and x86
     member semantics, the Quantizer constants derived inside the library against the reference's"""
     import ctypes
     import vvenc_b200._lib as L
     g = golden_depquant
+    gpu.eng.set_depquant_engine(engine)           # 1: four lanes per TU, 0: one thread per TU
     rows = C.dq_cases()
     assert np.array_equal(rows, g['cases'])
     nonzero = 0
@@ -311,16 +313,19 @@ def test_gpu_dep_quant_golden(gpu, golden_depquant):
             assert np.array_equal(r['q'][0], want), (i, scalar, [int(v) for v in row])
             assert (int(r['abs_sum'][0]), int(r['last_pos'][0])) == tuple(int(v) for v in g['meta'][i, 0 if scalar else 1]), (i, scalar)
         nonzero += int(r['last_pos'][0] >= 0)
+    gpu.eng.set_depquant_engine(1)
     assert nonzero > 100
 
 
-def test_gpu_dep_quant_batches_vs_oracle(gpu, golden_depquant):
+@pytest.mark.parametrize("engine", [1, 0])
+def test_gpu_dep_quant_batches_vs_oracle(gpu, golden_depquant, engine):
     """a picture's worth of TUs per launch (more TUs than resident threads for the small shapes: the threads stride over the list and reuse their arena slot),
     the need_rdoq mask of useSelectiveRdoq, against the CPU build of the restatement on the same inputs; rate tables of a reference CABAC state"""
     import ctypes
     from _libs import dq_oracle, P
     O = dq_oracle()
     g = golden_depquant
+    gpu.eng.set_depquant_engine(engine)
     rs = np.random.RandomState(77)
     for (w, h, n, qp, lam, zo, lf) in ((4, 4, 90000, 32, 57.3, 0, 0), (8, 8, 30000, 27, 30.0, 0, 1), (16, 16, 6000, 37, 120.0, 0, 0), (32, 32, 1500, 32, 57.3, 1, 0),
                                        (64, 64, 300, 22, 11.7, 0, 0), (32, 8, 3000, 42, 800.0, 0, 0), (16, 64, 500, 32, 30.0, 0, 2)):
@@ -338,3 +343,4 @@ def test_gpu_dep_quant_batches_vs_oracle(gpu, golden_depquant):
         assert np.array_equal(r['q'], q), (w, h, int((r['q'] != q).any(axis=(1, 2)).sum()))
         assert np.array_equal(r['abs_sum'], s) and np.array_equal(r['last_pos'], l), (w, h)
         assert (l >= 0).sum() > n // 4, (w, h, int((l >= 0).sum()))
+    gpu.eng.set_depquant_engine(1)

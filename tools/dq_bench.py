@@ -14,6 +14,7 @@ def main():
     from _libs import have_ref, refshim, dq_oracle, P
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     eng = V.CostEngine(0)
+    eng.set_depquant_engine(int(os.environ.get('VVB_DQ_ENGINE', '1')))
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', 0))
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v5_depquant.npz'))
     rates_flat = np.ascontiguousarray(g['rates'][3])

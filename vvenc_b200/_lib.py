@@ -124,6 +124,7 @@ SYMBOLS = {
     'vvb_affine_eq_batch_dev': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'vvb_dep_quant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
     'vvb_dep_quant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
+    'vvb_set_depquant_engine': (c_i, [c_p, c_i]),
     'vvb_dep_quant_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), c_p]),
     'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_inv_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),

@@ -256,6 +256,9 @@ class CostEngine:
         return out
 
     # ---- dependent quantisation
+    def set_depquant_engine(self, engine):
+        self._chk(self.lib.vvb_set_depquant_engine(self.h, int(engine)))
+
     @staticmethod
     def dq_rates(flat):
         """vvb_dq_rates from 266 int32 in declaration order (last_bits_x[32], last_bits_y[32], sig_sbb_bits[2][2], sig_bits[3][12][2], gtx_bits[21][6])"""

@@ -1339,16 +1339,33 @@ int vvb_dep_quant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq
   L.zeroOutMts = dq->zero_out; L.lfnst = par->lfnst_idx > 0; L.capSum = dq->scalar_members ? 0 : 1;
   L.ctxBytes  = (uint32_t)( ( 8 * ( st.numSbb + st.numCoeff ) + 15 ) & ~15 );
   L.slotBytes = (uint32_t)( ( L.ctxBytes + (size_t) st.numCoeff * 2 * sizeof( vvbdq::DqTrellis ) + 15 ) & ~(size_t) 15 );
-  // one thread per TU up to a few resident waves; beyond that the threads stride over the TU list and reuse their arena slot
-  const int maxBlocks = ctx->numSMs * 8;
-  const int blocks = std::min( ( n + VVB_DQ_THREADS - 1 ) / VVB_DQ_THREADS, maxBlocks );
-  void* arena;
-  if( ( rc = scratch( ctx, 5, (size_t) blocks * VVB_DQ_THREADS * L.slotBytes, &arena ) ) ) return rc;
   vvbdq::DqRates r;
   static_assert( sizeof( vvbdq::DqRates ) == sizeof( vvb_dq_rates ), "vvb_dq_rates mirrors DqRates" );
   memcpy( &r, rates, sizeof( r ) );
+  void* arena;
+  if( ctx->dqEngine == 1 )
+  {
+    // four lanes per TU, 32 TUs per CTA; beyond a few resident waves the quads stride over the TU list and reuse their arena slot
+    const int perCta = VVB_DQQ_THREADS / 4;
+    const int blocks = std::min( ( n + perCta - 1 ) / perCta, ctx->numSMs * 16 );
+    if( ( rc = scratch( ctx, 5, (size_t) blocks * perCta * L.slotBytes, &arena ) ) ) return rc;
+    dep_quant_quad_kernel<<<blocks, VVB_DQQ_THREADS, 0, ctx->stream>>>( L, r, dCoef, dNeedRdoq, n, dQ, dAbsSum, dLastPos, (uint8_t*) arena );
+    CHECK_LAUNCH( "dep_quant_quad_kernel" );
+    return VVB_OK;
+  }
+  // one thread per TU up to a few resident waves; beyond that the threads stride over the TU list and reuse their arena slot
+  const int maxBlocks = ctx->numSMs * 8;
+  const int blocks = std::min( ( n + VVB_DQ_THREADS - 1 ) / VVB_DQ_THREADS, maxBlocks );
+  if( ( rc = scratch( ctx, 5, (size_t) blocks * VVB_DQ_THREADS * L.slotBytes, &arena ) ) ) return rc;
   dep_quant_kernel<<<blocks, VVB_DQ_THREADS, 0, ctx->stream>>>( L, r, dCoef, dNeedRdoq, n, dQ, dAbsSum, dLastPos, (uint8_t*) arena );
   CHECK_LAUNCH( "dep_quant_kernel" );
+  return VVB_OK;
+}
+
+int vvb_set_depquant_engine( vvb_ctx* ctx, int engine )
+{
+  if( !ctx || engine < 0 || engine > 1 ) return VVB_ERR_ARG;
+  ctx->dqEngine = engine;
   return VVB_OK;
 }
 
