@@ -380,6 +380,20 @@ def cpu_rows(threads=None, budget_s=1.5):
     cnt, t = sized(run, K * 4 * threads, nbk * K)
     rows['mctf_match_16x16'] = {'candidates': cnt, 's': t, 'cand_per_s': cnt / t, 'block_refs_per_s': cnt / K / t}
 
+    # MCTF motion search of one neighbour picture (motionEstimationMCTF: pyramids + 4 levels of motionEstimationLuma), the reference's members on ONE thread
+    # (the probe drives one MCTF object; inside the encoder the block lines of a level are spread over the thread pool): a 960x544 crop, scaled by area
+    try:
+        cw, ch = min(960, w), min(544, h)
+        co = np.ascontiguousarray(org[MARGIN:MARGIN + ch, MARGIN:MARGIN + cw]); cr_ = np.ascontiguousarray(ref[MARGIN:MARGIN + ch, MARGIN:MARGIN + cw])
+        expf = np.zeros(((ch + 15) // 16, (cw + 15) // 16, 4), dtype=np.int32)
+        t0 = time.perf_counter()
+        R.refshim_mctf_estimate_pyramid(1, P(co), P(cr_), cw, ch, BITDEPTH, 16, 0, 0, 0, P(expf))
+        dt = time.perf_counter() - t0
+        rows['mctf_motion_estimation'] = {'sample': '%dx%d crop, unit 16, 4 levels, AVX2 members' % (cw, ch), 'threads': 1, 's': dt, 'pels_per_s_per_thread': cw * ch / dt,
+                                          'pels_per_s_if_all_threads_scaled': cw * ch / dt * threads}
+    except Exception as ex:
+        rows['mctf_motion_estimation'] = {'error': str(ex)}
+
     # fractional SATD grid (InterpolationFilter two-pass + HAD): 49 quarter-pel offsets per block
     fr = {}
     for n in (8, 16, 32):
@@ -960,6 +974,27 @@ def main():
             del d_flt
         except Exception as ex:
             extra['mctf_apply_2160p'] = {'error': str(ex)}
+        # MCTF motion search (BASELINE configs[3] shape): motionEstimationMCTF of one 2160p neighbour picture with the control on the device --
+        # subsampled pyramids, 5 chained levels, selection chains and the upper / left neighbour wavefront without the host seeing a number
+        try:
+            from vvenc_b200 import _lib as VL
+            o_, r_, S_ = host_sets[0]
+            pad = 128
+            po = np.ascontiguousarray(np.pad(o_[MARGIN:MARGIN + H, MARGIN:MARGIN + W], pad, mode='edge')); pr_ = np.ascontiguousarray(np.pad(r_[MARGIN:MARGIN + H, MARGIN:MARGIN + W], pad, mode='edge'))
+            eng.upload_plane(60, po, W, H, pad); eng.upload_plane(61, pr_, W, H, pad)
+            fh_, fw_ = (H + 15) // 16, (W + 15) // 16
+            d_field = torch.zeros(fh_ * fw_ * 4, dtype=torch.int32, device='cuda')
+            ppar = VL.vvb_mctf_pyr_par(16, 1, 0, 0)
+            l0 = eng.launches
+            tm = time_launch(lambda: chk(lib.vvb_mctf_estimate_pyramid_dev(eng.h, 60, 61, ctypes.byref(ppar), P_(d_field.data_ptr()))), reps=4)
+            nl = (eng.launches - l0) // 5
+            fld = d_field.cpu().numpy().reshape(fh_, fw_, 4)
+            extra['mctf_motion_estimation_2160p'] = {'unit': 16, 'levels': 5, 'ms_per_neighbour_picture': tm, 'launches_per_neighbour_picture': int(nl), 'blocks': int(fh_ * fw_),
+                                                     'block_refs_per_s': fh_ * fw_ / (tm * 1e-3), 'pels_per_s': W * H / (tm * 1e-3),
+                                                     'nonzero_vectors': int(((fld[..., 0] != 0) | (fld[..., 1] != 0)).sum()), 'fractional_vectors': int((((fld[..., 0] | fld[..., 1]) & 15) != 0).sum())}
+            eng.free_plane(60); eng.free_plane(61); del d_field
+        except Exception as ex:
+            extra['mctf_motion_estimation_2160p'] = {'error': str(ex)}
         # fixed diamond-search candidate set (SURVEY 8d W3 -> W1 byte formula): TZ point pattern, range 64, around the zero vector
         try:
             from vvenc_b200 import candidates as cand
@@ -1160,6 +1195,9 @@ def main():
             g = extra.get('mctf_apply_2160p', {}).get('pels_per_s'); c = cr.get('mctf_apply', {}).get('pels_per_s')
             if g and c:
                 sp['mctf_apply'] = g / c
+            g = extra.get('mctf_motion_estimation_2160p', {}).get('pels_per_s'); c = cr.get('mctf_motion_estimation', {}).get('pels_per_s_if_all_threads_scaled')
+            if g and c:
+                sp['mctf_motion_estimation_vs_all_threads_scaled'] = g / c
             extra['row_speedup_vs_cpu'] = sp
         except Exception as ex:
             extra['cpu_rows'] = {'error': str(ex)}

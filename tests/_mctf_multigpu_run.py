@@ -41,8 +41,17 @@ class Searcher:
         self.eng.upload_plane(30, po, o.shape[1], o.shape[0], pad); self.eng.upload_plane(31, pr, r.shape[1], r.shape[0], pad)
         return MH.EngineProvider(self.eng, 30, 31)
 
-    def field(self, org, ref, unit, add_level):
+    def field_host_replay(self, org, ref, unit, add_level):
+        """round-1 path: selection replayed on the host from downloaded error tables"""
         f = MH.estimate_pyramid(self.make_provider, org, ref, unit_size=unit, add_level=add_level)
+        return np.stack([f['x'], f['y'], f['error'], f['rmsme'].astype(np.int32)], axis=-1).reshape(-1, 4)
+
+    def field(self, org, ref, unit, add_level):
+        """the whole motion search of one neighbour picture with the control on the device (vvb_mctf_estimate_pyramid)"""
+        pad = 128
+        H, W = org.shape
+        self.eng.upload_plane(30, MH.pad_edge(org, pad), W, H, pad); self.eng.upload_plane(31, MH.pad_edge(ref, pad), W, H, pad)
+        f = self.eng.mctf_estimate_pyramid(30, 31, W, H, unit, add_level)
         return np.stack([f['x'], f['y'], f['error'], f['rmsme'].astype(np.int32)], axis=-1).reshape(-1, 4)
 
     def apply(self, org, refs, fields, unit):
@@ -91,12 +100,17 @@ def main():
         single = np.stack([S.field(org, refs[i], unit, add_level) for i in range(nrefs)])
         t_single = time.perf_counter() - t0
         filt1 = S.apply(org, refs, single, unit)
+        t0 = time.perf_counter()
+        replay0 = S.field_host_replay(org, refs[0], unit, add_level)
+        t_replay = time.perf_counter() - t0
         res = {'picture': '%dx%d' % (W, H), 'refs': nrefs, 'n_gpus': world, 'unit': unit, 'levels': 5 if add_level else 4,
                'fields_equal_single_gpu': bool(np.array_equal(fields, single)), 'filtered_equal_single_gpu': bool(np.array_equal(filtered, filt1)),
                'filtered_equal_on_all_ranks': len(set(int(c.item()) for c in all_chk)) == 1,
                'nonzero_vectors': int((fields[:, :, :2] != 0).any(axis=2).sum()), 'fractional_vectors': int(((fields[:, :, :2] & 15) != 0).any(axis=2).sum()),
                'search_s_sharded_max_over_ranks': float(tt[0].item()), 'search_s_single_gpu': t_single, 'apply_s': float(tt[1].item()),
-               'block_refs_per_s_sharded': blocks * nrefs / float(tt[0].item())}
+               'block_refs_per_s_sharded': blocks * nrefs / float(tt[0].item()),
+               'device_control_equals_host_replay_ref0': bool(np.array_equal(single[0], replay0)), 'host_replay_s_one_neighbour_picture': t_replay,
+               'note': 'search_s_* are wall-clock around upload of the padded pictures + device-controlled search + field download per neighbour picture'}
         try:
             from _libs import have_ref, refshim, P
             if have_ref() and W * H <= 1000 * 600:
@@ -112,7 +126,7 @@ def main():
             json.dump(res, open(outp, 'w'))
     dist.barrier(); dist.destroy_process_group()
     S.eng.close()
-    if rank == 0 and not (res['fields_equal_single_gpu'] and res['filtered_equal_single_gpu'] and res['filtered_equal_on_all_ranks'] and res.get('field0_equals_reference_motionEstimationMCTF', True)):
+    if rank == 0 and not (res['fields_equal_single_gpu'] and res['filtered_equal_single_gpu'] and res['filtered_equal_on_all_ranks'] and res['device_control_equals_host_replay_ref0'] and res.get('field0_equals_reference_motionEstimationMCTF', True)):
         sys.exit(3)
 
 
