@@ -255,6 +255,7 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( mctf_error_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
   cudaFuncSetAttribute( mctf_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+  cudaFuncSetAttribute( mctf_int_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1794,8 +1795,19 @@ int mctfLevel( vvb_ctx* ctx, const Plane& po, const Plane& pr, int width, int he
   {
     mctf_centre_kernel<<<nb, T, 0, ctx->stream>>>( g, a.best, truncInt, o.shift, a.centre, a.cands );
     CHECK_LAUNCH( "mctf_centre_kernel" );
-    int r = mctfGridLaunchP( ctx, po, pr, a.cands, g.n, o.step, o.radius, lowRes, bs, a.err );
-    if( r ) return r;
+    if( truncInt && o.step == 16 && ( o.shift & 15 ) == 0 )
+    {
+      // stage B: every candidate sits on the integer grid -> the SSE-only grid kernel
+      const int maxDim = std::max( 8, std::min( 64, ( bs + 7 ) & ~7 ) );
+      const MctfIntSmem LI = mctf_int_smem( maxDim, o.radius );
+      mctf_int_grid_kernel<<<std::min( g.n, ctx->numSMs * 16 ), 128, (size_t) LI.total * 4, ctx->stream>>>( po, pr, a.cands, g.n, o.radius, maxDim, a.err );
+      CHECK_LAUNCH( "mctf_int_grid_kernel" );
+    }
+    else
+    {
+      int r = mctfGridLaunchP( ctx, po, pr, a.cands, g.n, o.step, o.radius, lowRes, bs, a.err );
+      if( r ) return r;
+    }
     mctf_select_grid_kernel<<<nb, T, 0, ctx->stream>>>( g, a.err, 2 * o.radius + 1, o.off0, o.delta, o.count, o.step, skipZero, a.centre, a.best );
     CHECK_LAUNCH( "mctf_select_grid_kernel" );
     return VVB_OK;
@@ -1812,7 +1824,7 @@ int mctfLevel( vvb_ctx* ctx, const Plane& po, const Plane& pr, int width, int he
   {
     const int maxDim = std::max( 8, std::min( 64, ( bs + 7 ) & ~7 ) );
     const MctfSmem L = mctf_smem( maxDim );
-    mctf_wave_kernel<<<g.byn, 32, (size_t) L.warpWords * 4, ctx->stream>>>( po, pr, g, lowRes ? 1 : 0, maxDim, a.best, a.progress );
+    mctf_wave_kernel<<<g.byn, MCTF_WAVE_WARPS * 32, (size_t) MCTF_WAVE_WARPS * L.warpWords * 4, ctx->stream>>>( po, pr, g, lowRes ? 1 : 0, maxDim, a.best, a.progress );
     CHECK_LAUNCH( "mctf_wave_kernel" );
   }
   if( doubleRes )
