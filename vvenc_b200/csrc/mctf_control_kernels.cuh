@@ -252,12 +252,27 @@ __global__ void __launch_bounds__( 128 ) mctf_int_grid_kernel( const __grid_cons
       const uint32_t* plane = ( i0 & 1 ) ? sP1 : sP0;
       const int pw = i0 >> 1;
       unsigned lo = 0, hi = 0;
-      for( int t = lane; t < h * hw; t += 32 )
+      if( ( hw & ( hw - 1 ) ) == 0 && hw <= 32 )
       {
-        const int y = t / hw, p = t - y * hw;
-        const unsigned o = sOrg[t], r = plane[( y + j ) * L.pitch + pw + p];
-        lo = __dp2a_lo( o, r, lo ); hi = __dp2a_hi( o, r, hi );
+        // w in {8, 16, 32, 64}: a lane keeps its column pair and walks down the rows (32 / hw rows per step) -- no index division in the loop
+        const int p = lane & ( hw - 1 ), y0 = lane / hw, rowsPerStep = 32 / hw;
+        const uint32_t* rp = plane + ( y0 + j ) * L.pitch + pw + p;
+        const uint32_t* op = sOrg + lane;
+        const int rstep = rowsPerStep * L.pitch;
+#pragma unroll 4
+        for( int y = y0; y < h; y += rowsPerStep, rp += rstep, op += 32 )
+        {
+          const unsigned o = *op, r = *rp;
+          lo = __dp2a_lo( o, r, lo ); hi = __dp2a_hi( o, r, hi );
+        }
       }
+      else
+        for( int t = lane; t < h * hw; t += 32 )
+        {
+          const int y = t / hw, p = t - y * hw;
+          const unsigned o = sOrg[t], r = plane[( y + j ) * L.pitch + pw + p];
+          lo = __dp2a_lo( o, r, lo ); hi = __dp2a_hi( o, r, hi );
+        }
       unsigned long long cross = (unsigned long long) lo + 256ull * hi;
       for( int m = 16; m > 0; m >>= 1 ) cross += __shfl_xor_sync( 0xffffffffu, cross, m );
       if( lane == 0 ) out[(size_t) b * K1 * K1 + c] = (int32_t)(long long)( ooAll + (unsigned long long) sV[j * L.sqPitch + i0] - 2ull * cross );
