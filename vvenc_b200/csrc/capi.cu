@@ -1145,8 +1145,10 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
     CHECK_LAUNCH( "fwd_trquant_tc_kernel" );
     return VVB_OK;
   }
+  const bool ext = p.lfnstIdx != 0 || p.signHiding != 0;        // the plain instantiation carries neither the LFNST stage nor the sign-bit hiding pass
 #define VVB_FWD_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = (size_t)( S::MAT_WORDS + S::NTEAMS * S::TEAM_WORDS ) * 4; \
-    fwd_trquant_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+    if( ext ) fwd_trquant_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
+    else      fwd_trquant_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
   VVB_TU_DISPATCH( p.lw, p.lh, VVB_FWD_CALL )
 #undef VVB_FWD_CALL
   CHECK_LAUNCH( "fwd_trquant_kernel" );
@@ -1189,8 +1191,10 @@ int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlan
     if( !tensor )
     {
       const Plane &po = ctx->planes.p[orgPlane], &pp = ctx->planes.p[predPlane];
+      const bool ext = p.lfnstIdx != 0 || p.signHiding != 0;
 #define VVB_FWDP_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = (size_t)( S::MAT_WORDS + S::NTEAMS * S::TEAM_WORDS ) * 4; \
-      fwd_trquant_planes_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+      if( ext ) fwd_trquant_planes_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
+      else      fwd_trquant_planes_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
       VVB_TU_DISPATCH( p.lw, p.lh, VVB_FWDP_CALL )
 #undef VVB_FWDP_CALL
       CHECK_LAUNCH( "fwd_trquant_planes_kernel" );
@@ -1443,8 +1447,11 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
+  const bool ext = p.signHiding != 0;
 #define VVB_RT_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
-    tu_roundtrip_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
+    if( ext ) tu_roundtrip_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
+                                                                                              dQ, dReco, (TuResult*) dRes, dNeedRdoq ); \
+    else      tu_roundtrip_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
                                                                                               dQ, dReco, (TuResult*) dRes, dNeedRdoq ); }
   VVB_TU_DISPATCH( p.lw, p.lh, VVB_RT_CALL )
 #undef VVB_RT_CALL

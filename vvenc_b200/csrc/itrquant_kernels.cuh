@@ -205,7 +205,7 @@ template<int LW, int LH> static inline size_t tu_roundtrip_smem()
   return (size_t)( S::MAT_WORDS + I::MAT_WORDS + S::NTEAMS * ( S::TEAM_WORDS + 8 ) ) * 4;
 }
 
-template<int LW, int LH>
+template<int LW, int LH, bool EXT>
 __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
                                                               const int planes, const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane,
                                                               const vvb_block* __restrict__ blocks, const int16_t* __restrict__ orgPool, const int16_t* __restrict__ predPool, int n,
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_const
     }
     const bool al4 = ( ( ( reinterpret_cast<uintptr_t>( oBase ) | reinterpret_cast<uintptr_t>( pBase ) ) & 3 ) | ( ( so | sp ) & 1 ) ) == 0;   // word loads allowed
     const bool al8 = ( ( ( reinterpret_cast<uintptr_t>( oBase ) | reinterpret_cast<uintptr_t>( pBase ) ) & 7 ) | ( ( so | sp ) & 3 ) ) == 0;   // 4-pel loads allowed
-    const int pos = team_forward<LW, LH>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i )
+    const int pos = team_forward<LW, LH, EXT>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i )
     {
       const int y = i >> ( LW - 1 ), x = ( i & ( W / 2 - 1 ) ) << 1;
       const int16_t* o = oBase + (ptrdiff_t) y * so + x; const int16_t* p = pBase + (ptrdiff_t) y * sp + x;

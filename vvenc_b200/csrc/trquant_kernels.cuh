@@ -186,7 +186,8 @@ __device__ __noinline__ int sbh_group( const TuPar& par, const int32_t* coef, in
 // Every thread works on quads of 4 raster-consecutive coefficients (LDS.128 + one LDG.128 of scan positions); reductions are redux.sync inside
 // the warp plus one shared atomic per warp for multi-warp teams.  Contains __syncthreads(); ends synchronised with red[4] = absSum,
 // red[5] = last non-zero level's scan position + 1, red[6] = RDOQ flag; returns the final scan position (Quant.cpp:182-208).
-template<int LW, int LH, int T>
+// EXT: the instantiation that carries the LFNST position limit and the sign-bit hiding pass; the plain one (EXT = false) is the round-1 code path untouched
+template<int LW, int LH, int T, bool EXT = true>
 __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* coef, uint32_t* qWords, int* red, const int32_t* __restrict__ inv, int tt, bool live )
 {
   using S = TuShape<LW, LH>;
@@ -196,7 +197,7 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
   constexpr bool multi = T > 32;
   const int4* c4 = reinterpret_cast<const int4*>( coef );
   const int4* s4 = reinterpret_cast<const int4*>( inv );
-  const int useThres = par.useThres, maxScan = par.lfnstMaxScan; const unsigned rdoqThr = par.rdoqThr;
+  const int useThres = par.useThres, maxScan = EXT ? par.lfnstMaxScan : 0x7fffffff; const unsigned rdoqThr = par.rdoqThr;
   // ---- pass 1: last non-zero scan position, coefficient groups holding a value above the threshold, RDOQ pre-check
   int lastNZ = 0; unsigned cgLo = 0, cgHi = 0, rd = 0;
   int4 cq[CACHE ? ITERS : 1], sq[CACHE ? ITERS : 1];
@@ -211,7 +212,7 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
       if( cq[k].x | cq[k].y | cq[k].z | cq[k].w )
       {
         sq[k] = __ldg( s4 + qi );
-#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); rd |= (unsigned) ac >= rdoqThr; if( ( sv ) <= maxScan ) { lastNZ = max( lastNZ, sv ); \
+#define VVB_Q1( cv, sv ) if( cv ) { const int ac = abs( cv ); rd |= (unsigned) ac >= rdoqThr; if( !EXT || ( sv ) <= maxScan ) { lastNZ = max( lastNZ, sv ); \
           if( ac > useThres ) { const int cg = ( sv ) >> 4; if( NQUADS <= 128 || cg < 32 ) cgLo |= 1u << ( cg & 31 ); else cgHi |= 1u << ( cg - 32 ); } } }
         VVB_Q1( cq[k].x, sq[k].x ) VVB_Q1( cq[k].y, sq[k].y ) VVB_Q1( cq[k].z, sq[k].z ) VVB_Q1( cq[k].w, sq[k].w )
 #undef VVB_Q1
@@ -289,7 +290,7 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
   }
   else if( tt == 0 ) { red[4] = sum; red[5] = lastQ; }
   __syncthreads();
-  if( par.signHiding )                                       // uniform over the CTA
+  if( EXT && par.signHiding )                                // uniform over the CTA
   {
     const int absSum = red[4], lastScanPos = red[5] - 1;     // scan position of the last level (Quant.cpp:806-816)
     __syncthreads();                                         // everybody has read red[5] before the top group's thread may rewrite it
@@ -310,7 +311,7 @@ __device__ __forceinline__ int team_quantise( const TuPar& par, const int32_t* c
 // Forward transform + quantiser of one TU by one team.  `load( i )` returns residual word i (two int16, row-major compact).
 // Contains __syncthreads(): every thread of the CTA must call it, `live` masks the work.  On return (all threads synchronised)
 // v.resi holds the levels, v.coef the coefficients, v.red[4] absSum, v.red[5] lastQ+1, v.red[6] the RDOQ flag; returns the final scan pos.
-template<int LW, int LH, class LOAD>
+template<int LW, int LH, bool EXT, class LOAD>
 __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* MtH, const uint32_t* MtV, const TeamView& v, const int32_t* __restrict__ scanTab,
                                              int tt, bool live, LOAD load )
 {
@@ -413,7 +414,7 @@ __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* M
       }
   }
   __syncthreads();
-  if( par.lfnstIdx )                                         // uniform over the CTA: TrQuant::xFwdLfnst (TrQuant.cpp:942-1048) between xT and the quantiser
+  if( EXT && par.lfnstIdx )                                  // uniform over the CTA: TrQuant::xFwdLfnst (TrQuant.cpp:942-1048) between xT and the quantiser
   {
     constexpr int KEEP = ( LW >= 3 && LH >= 3 ) ? 8 : 4, NIN = KEEP == 8 ? 48 : 16;
     constexpr int ZOUT = ( ( W == 4 && H == 4 ) || ( W == 8 && H == 8 ) ) ? 8 : 16;
@@ -455,7 +456,7 @@ __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* M
     }
     __syncthreads();
   }
-  return team_quantise<LW, LH, T>( par, myCoef, myResi, myRed, scanTab + par.scanOff, tt, live );
+  return team_quantise<LW, LH, T, EXT>( par, myCoef, myResi, myRed, scanTab + par.scanOff, tt, live );
 }
 
 // results of team_forward -> global memory (q compact [H][W]; optional coefficients and per-TU scalars)
@@ -490,7 +491,7 @@ __device__ __forceinline__ void team_forward_store( const TeamView& v, int pos, 
   }
 }
 
-template<int LW, int LH>
+template<int LW, int LH, bool EXT>
 __global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
                                                              const int16_t* __restrict__ resi, int n,
                                                              int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
@@ -513,14 +514,14 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_kernel( const __grid_consta
     const int tu = base + team;
     const bool live = tu < n;
     const uint32_t* src = reinterpret_cast<const uint32_t*>( resi + (size_t)( live ? tu : 0 ) * S::W * S::H );
-    const int pos = team_forward<LW, LH>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i ) { return __ldg( src + i ); } );
+    const int pos = team_forward<LW, LH, EXT>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i ) { return __ldg( src + i ); } );
     team_forward_store<LW, LH>( v, pos, tu, tt, live, coefOut, qOut, absSumOut, lastPosOut, needRdoqOut );
   }
 }
 
 // same with the residual formed at load time: TU i sits at (blocks[i].x, blocks[i].y) of orgPlane, its prediction at (+start_x, +start_y) of predPlane
 // (PelBuf::subtract, IntraSearch.cpp:1328) -- no compact residual buffer, no extra launch
-template<int LW, int LH>
+template<int LW, int LH, bool EXT>
 __global__ void __launch_bounds__( 128 ) fwd_trquant_planes_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
                                                                     const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane,
                                                                     const vvb_block* __restrict__ blocks, int n,
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__( 128 ) fwd_trquant_planes_kernel( const __grid
     const int16_t* oBase = orgPlane.origin + (ptrdiff_t) blk.y * so + blk.x;
     const int16_t* pBase = predPlane.origin + (ptrdiff_t)( blk.y + blk.start_y ) * sp + blk.x + blk.start_x;
     const bool al4 = ( ( ( reinterpret_cast<uintptr_t>( oBase ) | reinterpret_cast<uintptr_t>( pBase ) ) & 3 ) | ( ( so | sp ) & 1 ) ) == 0;   // word loads allowed
-    const int pos = team_forward<LW, LH>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i )
+    const int pos = team_forward<LW, LH, EXT>( par, MtH, MtV, v, scanTab, tt, live, [&]( int i )
     {
       const int y = i >> ( LW - 1 ), x = ( i & ( W / 2 - 1 ) ) << 1;
       const int16_t* o = oBase + (ptrdiff_t) y * so + x; const int16_t* p = pBase + (ptrdiff_t) y * sp + x;
