@@ -976,8 +976,21 @@ int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, c
   const int R = par->pattern_radius;
   if( dfunc == FAM_HAD && R > 0 && R <= 8 && K <= 1024 && ( w & 7 ) == 0 && w == h && isPow2( h ) )     // square power-of-two blocks: the dispatch lands on 8x8 tiles (RdCost.cpp:1836-1905)
   {
-    const HadPatSmem L = had_pat_smem( w, h, R, K );
     const int T = ( w >> 3 ) * ( h >> 3 );
+    static const int hadEngine = getenv( "VVB_HAD_ENGINE" ) ? atoi( getenv( "VVB_HAD_ENGINE" ) ) : 1;     // A/B switch: 0 = the staged round-1 kernel
+    if( hadEngine == 1 && K <= 4096 )
+    {
+      // no staging: persistent CTAs, candidates read through L1, difference + first butterfly stage on IDP.2A
+      const int bpc = std::max( 1, std::min( 32, 512 / std::max( 1, K * T ) ) );
+      const HadDirSmem LD = had_dir_smem( K, bpc );
+      const int work = bpc * K * T;
+      const int bd = std::min( 256, std::max( 64, ( work + 31 ) & ~31 ) );
+      const int groups = ( n + bpc - 1 ) / bpc;
+      had8_direct_kernel<<<std::min( groups, ctx->numSMs * 8 ), bd, (size_t) LD.total * 4, ctx->stream>>>( op, rp, dBlocks, n, w, h, bpc, dPattern, K, mp, dCost, dBest );
+      CHECK_LAUNCH( "had8_direct_kernel" );
+      return VVB_OK;
+    }
+    const HadPatSmem L = had_pat_smem( w, h, R, K );
     int bpc = std::max( 1, std::min( 8, 128 / std::max( 1, K * T ) ) );
     while( bpc > 1 && (size_t) bpc * L.slotWords * 4 > 40 * 1024 ) bpc--;
     const size_t smem = (size_t) bpc * L.slotWords * 4;

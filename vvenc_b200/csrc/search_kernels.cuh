@@ -813,6 +813,144 @@ __global__ void __launch_bounds__( 256 ) had8_pattern_kernel( const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// had8_direct_kernel (round 2): the same refinement without staging.  Persistent CTAs walk groups of BPC blocks; a lane owns a (block, candidate, 8x8 tile)
+// and reads its 8 original rows (LDG.128) and 8 reference rows (5 aligned words, funnel-shifted for odd columns) straight from the L1/L2-resident planes --
+// the K candidates of a block overlap almost completely, so the reads hit L1.  The difference and the first butterfly stage come out of the packed words
+// together: (o0 - c0) + (o1 - c1) = dp2a( o, (1,1) ) + dp2a( c, (-1,-1) ), (o0 - c0) - (o1 - c1) = dp2a( o, (1,-1) ) + dp2a( c, (-1,1) ) -- four IDP.2A per
+// pel pair instead of four unpacks, two subtractions and two butterfly operations.  Pattern, MV-rate table and the group's block descriptors sit in shared
+// memory; the item -> (block, candidate, tile) split is computed once per thread.  Needs blocks whose x is a multiple of 8 and 16-byte aligned plane rows for
+// the vector loads of the original (checked per block, scalar loads otherwise).
+struct HadDirSmem { int costOff, keyOff, blkOff, patOff, total; };
+__host__ __device__ inline HadDirSmem had_dir_smem( int K, int BPC )
+{
+  HadDirSmem s;
+  s.costOff = 0; s.keyOff = ( BPC * K + 1 ) & ~1; s.blkOff = s.keyOff + 2 * BPC; s.patOff = s.blkOff + 6 * BPC; s.total = s.patOff + K;
+  return s;
+}
+
+__global__ void __launch_bounds__( 256 ) had8_direct_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
+                                                             const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int BPC,
+                                                             const vvb_mv* __restrict__ pattern, int K, const __grid_constant__ MePar par,
+                                                             uint32_t* __restrict__ costOut, vvb_best* __restrict__ bestOut )
+{
+  extern __shared__ __align__( 16 ) uint32_t smemHd[];
+  __shared__ uint32_t sMv[VVB_MVCOST_ENTRIES];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const HadDirSmem L = had_dir_smem( K, BPC );
+  uint32_t* sCost = smemHd + L.costOff;
+  unsigned long long* sKey = reinterpret_cast<unsigned long long*>( smemHd + L.keyOff );
+  vvb_block* sBlk = reinterpret_cast<vvb_block*>( smemHd + L.blkOff );
+  vvb_mv* sPat = reinterpret_cast<vvb_mv*>( smemHd + L.patOff );
+  for( int i = tid; i < VVB_MVCOST_ENTRIES; i += nthr ) sMv[i] = par.tab.cost[i];
+  for( int i = tid; i < K; i += nthr ) sPat[i] = pattern[i];
+  const int tilesX = w >> 3, T = tilesX * ( h >> 3 ), perSlot = K * T;
+  const int nGroups = ( nBlocks + BPC - 1 ) / BPC;
+  const float invPer = 1.0f / (float) perSlot, invT = 1.0f / (float) T, invTx = 1.0f / (float) tilesX;
+  for( int g = blockIdx.x; g < nGroups; g += gridDim.x )
+  {
+    const int firstBlk = g * BPC, nSlot = min( BPC, nBlocks - firstBlk );
+    __syncthreads();                                            // the previous group's epilogue is done with the shared tables
+    for( int i = tid; i < nSlot * 6; i += nthr ) reinterpret_cast<uint32_t*>( sBlk )[i] = __ldg( reinterpret_cast<const uint32_t*>( blocks + firstBlk ) + i );
+    for( int i = tid; i < nSlot * K; i += nthr ) sCost[i] = 0u;
+    if( tid < nSlot ) sKey[tid] = ~0ull;
+    __syncthreads();
+    for( int it = tid; it < nSlot * perSlot; it += nthr )
+    {
+      const int j = fast_div( it, invPer ), loc = it - j * perSlot;
+      const int k = fast_div( loc, invT ), t = loc - k * T;
+      const int ty = fast_div( t, invTx ), tx = t - ty * tilesX;
+      const vvb_block blk = sBlk[j];
+      const vvb_mv pm = sPat[k];
+      const int mx = blk.start_x + pm.dx, my = blk.start_y + pm.dy;
+      if( !( mx >= blk.left && mx <= blk.right && my >= blk.top && my <= blk.bottom ) ) { if( t == 0 ) sCost[j * K + k] = 0xffffffffu; continue; }
+      const int16_t* op = orgPlane.origin + (ptrdiff_t)( blk.y + ty * 8 ) * orgPlane.stride + blk.x + tx * 8;
+      const int16_t* rp = refPlane.origin + (ptrdiff_t)( blk.y + my + ty * 8 ) * refPlane.stride + blk.x + mx + tx * 8;
+      const bool oVec = ( ( (uintptr_t) op & 15 ) == 0 ) && ( ( orgPlane.stride & 7 ) == 0 );
+      const int odd = (int)( ( (uintptr_t) rp >> 1 ) & 1 );      // plane rows keep the parity (even strides)
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>( rp - odd );
+      const int rStrideW = refPlane.stride >> 1;
+      int d[64];
+#pragma unroll
+      for( int r = 0; r < 8; r++ )
+      {
+        uint4 o;
+        if( oVec ) o = __ldg( reinterpret_cast<const uint4*>( op + (ptrdiff_t) r * orgPlane.stride ) );
+        else
+        {
+          const int16_t* q = op + (ptrdiff_t) r * orgPlane.stride;
+          o.x = (uint32_t)(uint16_t) __ldg( q ) | ( (uint32_t)(uint16_t) __ldg( q + 1 ) << 16 ); o.y = (uint32_t)(uint16_t) __ldg( q + 2 ) | ( (uint32_t)(uint16_t) __ldg( q + 3 ) << 16 );
+          o.z = (uint32_t)(uint16_t) __ldg( q + 4 ) | ( (uint32_t)(uint16_t) __ldg( q + 5 ) << 16 ); o.w = (uint32_t)(uint16_t) __ldg( q + 6 ) | ( (uint32_t)(uint16_t) __ldg( q + 7 ) << 16 );
+        }
+        const uint32_t* rr = rw + (ptrdiff_t) r * rStrideW;
+        uint32_t c0 = __ldg( rr ), c1 = __ldg( rr + 1 ), c2 = __ldg( rr + 2 ), c3 = __ldg( rr + 3 );
+        if( odd )
+        {
+          const uint32_t c4 = __ldg( rr + 4 );
+          c0 = __funnelshift_r( c0, c1, 16 ); c1 = __funnelshift_r( c1, c2, 16 ); c2 = __funnelshift_r( c2, c3, 16 ); c3 = __funnelshift_r( c3, c4, 16 );
+        }
+        // difference + first butterfly stage (pairs along x) on IDP.2A
+#define VVB_S1( ow, cw, i0 ) d[8 * r + i0]     = __dp2a_lo( (int)( cw ), (int) 0x0000ffff, __dp2a_lo( (int)( ow ), (int) 0x00000101, 0 ) ); \
+                             d[8 * r + i0 + 1] = __dp2a_lo( (int)( cw ), (int) 0x000001ff, __dp2a_lo( (int)( ow ), (int) 0x0000ff01, 0 ) );
+        VVB_S1( o.x, c0, 0 ) VVB_S1( o.y, c1, 2 ) VVB_S1( o.z, c2, 4 ) VVB_S1( o.w, c3, 6 )
+#undef VVB_S1
+      }
+#pragma unroll
+      for( int bit = 1; bit < 6; bit++ )
+      {
+#pragma unroll
+        for( int i = 0; i < 64; i++ )
+        {
+          if( !( i & ( 1 << bit ) ) )
+          {
+            const int a = d[i], bb = d[i | ( 1 << bit )];
+            d[i] = a + bb; d[i | ( 1 << bit )] = a - bb;
+          }
+        }
+      }
+      uint32_t sacc = 0;
+#pragma unroll
+      for( int i = 0; i < 64; i++ ) sacc = __sad( d[i], 0, sacc );
+      const uint32_t dc = (uint32_t) abs( d[0] );
+      sacc = sacc - dc + ( dc >> 2 );                            // RdCost.cpp:1316-1318
+      const uint32_t tileCost = ( sacc + 2 ) >> 2;               // :1319
+      if( T == 1 ) sCost[j * K + k] = tileCost; else atomicAdd( &sCost[j * K + k], tileCost );
+    }
+    __syncthreads();
+    for( int i = tid; i < nSlot * K; i += nthr )
+    {
+      const int j = i / K, k = i - j * K;
+      const uint32_t c = sCost[i];
+      if( costOut ) costOut[(size_t)( firstBlk + j ) * K + k] = c;
+      if( bestOut && c != 0xffffffffu )
+      {
+        const vvb_block blk = sBlk[j];
+        const vvb_mv pm = sPat[k];
+        const unsigned long long tot = (unsigned long long) c + mv_cost( par, sMv, blk.start_x + pm.dx, blk.start_y + pm.dy, blk.pred_hor, blk.pred_ver );
+        atomicMin( &sKey[j], ( tot << 16 ) | (unsigned) k );
+      }
+    }
+    if( bestOut )
+    {
+      __syncthreads();
+      if( tid < nSlot )
+      {
+        const unsigned long long key = sKey[tid];
+        vvb_best b;
+        if( key == ~0ull ) { b.dx = 0; b.dy = 0; b.sad = 0xffffffffu; b.cost = ~0ull; }
+        else
+        {
+          const int k = (int)( key & 0xffffu );
+          const vvb_block blk = sBlk[tid];
+          const vvb_mv pm = sPat[k];
+          b.dx = (int16_t)( blk.start_x + pm.dx ); b.dy = (int16_t)( blk.start_y + pm.dy ); b.sad = sCost[tid * K + k]; b.cost = key >> 16;
+        }
+        bestOut[firstBlk + tid] = b;
+      }
+    }
+  }
+}
+
 // chains device-resident stages: the best vector of a search becomes the start / prediction offset of the next stage
 __global__ void blocks_set_start_kernel( vvb_block* __restrict__ blocks, const vvb_best* __restrict__ best, int n )
 {
