@@ -1053,7 +1053,7 @@ def main():
             d = dict(blocks={n: pin((len(blocks_np[n]) * 24,), torch.uint8) for n in SIZES}, best={n: pin((len(blocks_np[n]) * 16,), torch.uint8) for n in SIZES},
                      satd={n: pin((len(blocks_np[n]) * KP,), torch.int32) for n in SIZES}, q={n: pin((len(blocks_np[n]) * n * n,), torch.int16) for n in SIZES},
                      sum={n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES}, last={n: pin((len(blocks_np[n]),), torch.int32) for n in SIZES},
-                     nr={n: pin((len(blocks_np[n]),), torch.uint8) for n in SIZES})
+                     nr={n: pin((len(blocks_np[n]),), torch.uint8) for n in SIZES}, off={n: pin((len(blocks_np[n]) + 1,), torch.int32) for n in SIZES})
             for n in SIZES:
                 bl = blocks_np[n].copy(); bl['y'] -= y0b                              # the uploaded plane starts at the band's first row
                 d['blocks'][n][:] = np.frombuffer(bl.tobytes(), dtype=np.uint8)
@@ -1062,11 +1062,12 @@ def main():
             hb.append(d)
         h_pat = pin((KP * 4,), torch.uint8); h_pat[:] = np.frombuffer(pat_np.tobytes(), dtype=np.uint8)
         E0, E1 = 40, 41        # plane ids of the uploaded pictures
+        PACKED = os.environ.get('VVB_E2E_PACKED', '1') == '1'    # levels come back trimmed to lastPos, written by the device straight into the pinned buffer
         h2d = 0; d2h = 0
         for n in SIZES:
             nb = len(blocks_np[n])
             h2d += nb * 24 + KP * 4
-            d2h += nb * 16 + nb * KP * 4 + nb * n * n * 2 + nb * 9
+            d2h += nb * 16 + nb * KP * 4 + nb * 9 + ((nb + 1) * 4 if PACKED else nb * n * n * 2)      # + the packed levels themselves, counted after the run
         S0 = host_sets[0][2]
         h2d += 2 * (h_planes[0][3] + 2 * MARGIN) * S0 * 2
 
@@ -1085,7 +1086,11 @@ def main():
             for l, n in enumerate(SIZES):
                 d = hb[c]
                 arr[l].blocks = d['blocks'][n].ctypes.data; arr[l].count = len(blocks_np[n]); arr[l].best = d['best'][n].ctypes.data
-                arr[l].refine_cost = d['satd'][n].ctypes.data; arr[l].q = d['q'][n].ctypes.data
+                arr[l].refine_cost = d['satd'][n].ctypes.data
+                if PACKED:
+                    arr[l].packed_q = d['q'][n].ctypes.data; arr[l].packed_offsets = d['off'][n].ctypes.data
+                else:
+                    arr[l].q = d['q'][n].ctypes.data
                 arr[l].abs_sum = d['sum'][n].ctypes.data; arr[l].last_pos = d['last'][n].ctypes.data; arr[l].need_rdoq = d['nr'][n].ctypes.data
                 arr[l].tu = tu_par[n]
             ios.append(arr)
@@ -1136,6 +1141,12 @@ def main():
                'timing': 'host wall clock over %d pictures (%.1f steps) issued through the host-buffer C ABI (vvb_plane_upload x2 + vvb_search_refine_tu per picture) from pinned memory '
                          'by %d worker threads, one asynchronous context each; every upload and download is inside the timed region; max over ranks' % (ke, ke / PPS, NCTX)}
         last = 2 * NCTX + ke - 1                               # index of the last picture issued
+        if PACKED:
+            packed_bytes = sum(int(hb[last % NCTX]['off'][n][len(blocks_np[n])]) * 2 for n in SIZES)
+            d2h += packed_bytes
+            e2e['d2h_bytes_per_picture'] = int(d2h); e2e['d2h_bytes_per_step'] = int(d2h) * PPS
+            e2e['levels'] = {'form': 'trimmed to lastPos, scan order, written by the device into the pinned buffer (vvb_level_io.packed_q)', 'bytes_per_picture': packed_bytes,
+                             'untrimmed_bytes_per_picture': sum(len(blocks_np[n]) * n * n * 2 for n in SIZES)}
         for e in engs:
             e.set_async(False)
         for e in engs[1:]:
@@ -1171,7 +1182,19 @@ def main():
         for n in SIZES:
             nb = len(blocks_np[n])
             ok = ok and np.array_equal(np.frombuffer(d_best[n][:nb * 16].cpu().numpy().tobytes(), dtype=np.uint8), hl['best'][n])
-            ok = ok and np.array_equal(d_sum[n][:nb].cpu().numpy(), hl['sum'][n]) and np.array_equal(d_q[n][:nb * n * n].cpu().numpy().reshape(-1), hl['q'][n])
+            ok = ok and np.array_equal(d_sum[n][:nb].cpu().numpy(), hl['sum'][n])
+            if PACKED:
+                so = np.zeros(min(n, 32) ** 2, dtype=np.int32)
+                chk(lib.vvb_scan_order(n, n, so.ctypes.data_as(ctypes.c_void_p)))
+                off = hl['off'][n].astype(np.int64); lens = np.maximum(hl['last'][n].astype(np.int64) + 1, 0)
+                ok = ok and np.array_equal(np.diff(off), lens)
+                tot = int(off[nb])
+                full = np.zeros((nb, n * n), dtype=np.int16)
+                tu_idx = np.repeat(np.arange(nb), lens); pos = np.arange(tot) - np.repeat(off[:nb], lens)
+                full[tu_idx, so[pos]] = hl['q'][n][:tot]
+                ok = ok and np.array_equal(d_q[n][:nb * n * n].cpu().numpy().reshape(nb, n * n), full)
+            else:
+                ok = ok and np.array_equal(d_q[n][:nb * n * n].cpu().numpy().reshape(-1), hl['q'][n])
         extra['e2e_matches_resident'] = bool(ok)
 
     cpu = None

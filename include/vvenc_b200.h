@@ -238,9 +238,17 @@ typedef struct
   int16_t*   q;                                  /* out [count][h][w] levels, nullable (then no transform stage for this level)    */
   int32_t*   abs_sum; int32_t* last_pos; uint8_t* need_rdoq;   /* out [count], each nullable                                       */
   vvb_tu_par tu;                                 /* TU parameters of the level (w = h = base_w << l)                               */
+  int16_t*   packed_q;                           /* out, nullable: the levels of TU i at scan positions 0 .. last_pos[i], in scan order, TU after TU (capacity count * h * w);
+                                                    with it packed_offsets [count + 1] (entry i = first level of TU i, entry count = total) and last_pos are required.  When the
+                                                    buffer is page-locked (device-visible under UVA) the device writes it directly and only the used part crosses PCIe */
+  uint32_t*  packed_offsets;
 } vvb_level_io;
 int vvb_search_refine_tu( vvb_ctx* ctx, int org_plane, int ref_plane, int levels, const vvb_level_io* io, int base_w, const vvb_me_par* me, int nx, int ny,
                           int refine_dfunc, const vvb_mv* pattern, int K );
+/* the trimming on its own: out_packed (device-visible) receives the levels up to last_pos of every TU in scan order, dev_offsets [n + 1] their positions;
+ * vvb_scan_order gives scan position -> raster index (row pitch w) for unpacking (grouped 4x4 diagonal scan, Rom.cpp:1098-1136; min(w,32) * min(h,32) entries) */
+int vvb_pack_levels_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_q, const int32_t* dev_last_pos, int n, int16_t* out_packed, uint32_t* dev_offsets );
+int vvb_scan_order( int w, int h, int32_t* out );
 
 /* ---- dependent quantisation: DepQuant::quant -> xQuantDQ (CommonLib/DepQuant.cpp:1462-1490, 1129-1264) for luma TUs without scaling lists --------
  * The 4-state trellis over the scan positions of each TU (xDecide / xDecideAndUpdate :1266-1414, the rate-distortion checks :697-888, the state updates

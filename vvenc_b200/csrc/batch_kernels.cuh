@@ -134,4 +134,26 @@ __global__ void __launch_bounds__( 128 ) affine_eq_batch_kernel( const int16_t* 
   for( int i = threadIdx.x; i < 49; i += blockDim.x ) eq[(size_t) blockIdx.x * 49 + i] = (long long) sEq[i];
 }
 
+// ---- levels trimmed to the last significant scan position (round 2, e2e): TU i contributes the levels at scan positions 0 .. lastPos[i], in scan order
+__global__ void pack_sizes_kernel( const int32_t* __restrict__ lastPos, int n, uint32_t* __restrict__ sizes )
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i <= n ) sizes[i] = i < n ? (uint32_t) max( lastPos[i] + 1, 0 ) : 0u;
+}
+// warp per TU; fwd: scan position -> raster index inside the scanned region (row pitch 1 << lrw); q: compact [n][h][w]; out may be mapped host memory
+__global__ void __launch_bounds__( 128 ) pack_levels_kernel( const int16_t* __restrict__ q, const int32_t* __restrict__ lastPos, const uint32_t* __restrict__ offsets,
+                                                             const int32_t* __restrict__ fwd, int w, int area, int lrw, int n, int16_t* __restrict__ out )
+{
+  const int tu = blockIdx.x * 4 + ( threadIdx.x >> 5 ), lane = threadIdx.x & 31;
+  if( tu >= n ) return;
+  const int last = lastPos[tu];
+  const uint32_t off = offsets[tu];
+  const int16_t* qt = q + (size_t) tu * area;
+  for( int s = lane; s <= last; s += 32 )
+  {
+    const int p = __ldg( fwd + s );
+    out[off + s] = qt[( p >> lrw ) * w + ( p & ( ( 1 << lrw ) - 1 ) )];
+  }
+}
+
 } // namespace vvb

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <new>
 #include "common.cuh"
+#include <cub/device/device_scan.cuh>
 #include "dist_kernels.cuh"
 #include "search_kernels.cuh"
 #include "pyramid_kernels.cuh"
@@ -1247,6 +1248,41 @@ int vvb_fwd_trquant_planes( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane, i
 
 
 // Whole per-picture chain in one call (include/vvenc_b200.h): search -> start = best -> pattern distortion -> TU, chained on the device
+// ---- levels trimmed to lastPos, in scan order (the e2e download) --------------------------------------------------------------------------------------------
+int vvb_pack_levels_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ, const int32_t* dLastPos, int n, int16_t* outPacked, uint32_t* dOffsets )
+{
+  if( !ctx || !par || !dQ || !dLastPos || !outPacked || !dOffsets || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( !isPow2( par->w ) || !isPow2( par->h ) || par->w < 4 || par->h < 4 || par->w > 64 || par->h > 64 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "TU sizes are 4..64" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  const int lw = ilog2h( par->w ), lh = ilog2h( par->h ), lrw = std::min( lw, 5 );
+  const int32_t* fwd = ctx->d_scan + 25 * 1024 + ( ( lw - 2 ) * 5 + ( lh - 2 ) ) * 1024;
+  void *dSizes, *dTmp; int rc;
+  size_t tmpBytes = 0;
+  cub::DeviceScan::ExclusiveSum( nullptr, tmpBytes, (uint32_t*) nullptr, (uint32_t*) nullptr, n + 1, ctx->stream );
+  if( ( rc = scratch( ctx, 5, (size_t)( n + 1 ) * 4 + 256 + tmpBytes, &dSizes ) ) ) return rc;
+  dTmp = (uint8_t*) dSizes + ( ( (size_t)( n + 1 ) * 4 + 255 ) & ~(size_t) 255 );
+  pack_sizes_kernel<<<( n + 1 + 255 ) / 256, 256, 0, ctx->stream>>>( dLastPos, n, (uint32_t*) dSizes );
+  CHECK_LAUNCH( "pack_sizes_kernel" );
+  CU( cub::DeviceScan::ExclusiveSum( dTmp, tmpBytes, (uint32_t*) dSizes, dOffsets, n + 1, ctx->stream ) );
+  ctx->launches++;
+  pack_levels_kernel<<<( n + 3 ) / 4, 128, 0, ctx->stream>>>( dQ, dLastPos, dOffsets, fwd, par->w, par->w * par->h, lrw, n, outPacked );
+  CHECK_LAUNCH( "pack_levels_kernel" );
+  return VVB_OK;
+}
+
+// scan position -> raster index (row pitch w) of the grouped 4x4 diagonal scan of a w x h TU (min(w,32) * min(h,32) entries): what unpacks vvb_pack_levels output
+int vvb_scan_order( int w, int h, int32_t* out )
+{
+  if( !out || !isPow2( w ) || !isPow2( h ) || w < 4 || h < 4 || w > 64 || h > 64 ) return VVB_ERR_ARG;
+  std::vector<int32_t> inv;
+  buildScanTables( inv );
+  const int lw = ilog2h( w ), lh = ilog2h( h ), rw = std::min( w, 32 ), rh = std::min( h, 32 );
+  const int32_t* t = inv.data() + 25 * 1024 + ( ( lw - 2 ) * 5 + ( lh - 2 ) ) * 1024;
+  for( int s = 0; s < rw * rh; s++ ) out[s] = ( t[s] / rw ) * w + ( t[s] % rw );
+  return VVB_OK;
+}
+
 int vvb_search_refine_tu( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, const vvb_level_io* io, int baseW, const vvb_me_par* me, int nx, int ny,
                           int refineDfunc, const vvb_mv* pattern, int K )
 {
@@ -1259,13 +1295,24 @@ int vvb_search_refine_tu( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, 
   }
   if( anyRefine && ( !pattern || K < 1 ) ) return fail( ctx, VVB_ERR_ARG, "refinement needs a pattern" );
   // one arena: per level blocks | best | refine cost | q | abs_sum, last_pos, need_rdoq ; then the pattern
-  size_t offB[5], offO[5], offC[5], offQ[5], offM[5], total = 0;
+  size_t offB[5], offO[5], offC[5], offQ[5], offM[5], offK[5], offF[5], total = 0;
+  int16_t* packDst[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };        // device-visible destination of the packed levels (mapped host memory, or a device staging area)
   auto take = [&]( size_t bytes ) { const size_t o = total; total += ( bytes + 255 ) & ~(size_t) 255; return o; };
   for( int l = 0; l < levels; l++ )
   {
     const size_t n = (size_t) io[l].count, side = (size_t) baseW << l;
     offB[l] = take( n * sizeof( vvb_block ) ); offO[l] = take( n * sizeof( vvb_best ) );
-    offC[l] = take( io[l].refine_cost ? n * K * 4 : 0 ); offQ[l] = take( io[l].q ? n * side * side * 2 : 0 ); offM[l] = take( io[l].q ? n * 12 : 0 );
+    const bool tuStage = io[l].q || io[l].packed_q;
+    if( io[l].packed_q && ( !io[l].packed_offsets || !io[l].last_pos ) ) return fail( ctx, VVB_ERR_ARG, "packed levels need packed_offsets and last_pos" );
+    offC[l] = take( io[l].refine_cost ? n * K * 4 : 0 ); offQ[l] = take( tuStage ? n * side * side * 2 : 0 ); offM[l] = take( tuStage ? n * 12 : 0 );
+    offK[l] = take( io[l].packed_q ? ( n + 1 ) * 4 : 0 ); offF[l] = 0;
+    if( io[l].packed_q && n )
+    {
+      // pinned host memory is visible to the device under UVA: the pack kernel then writes the trimmed levels straight into the caller's buffer (no size has to come back first)
+      cudaPointerAttributes at;
+      if( cudaPointerGetAttributes( &at, io[l].packed_q ) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer ) packDst[l] = (int16_t*) at.devicePointer;
+      else { cudaGetLastError(); offF[l] = take( n * side * side * 2 ); }
+    }
   }
   const size_t offP = take( anyRefine ? (size_t) K * sizeof( vvb_mv ) : 0 );
   void* arena; int rc;
@@ -1289,10 +1336,15 @@ int vvb_search_refine_tu( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, 
     vvb_block* dB = (vvb_block*)( A + offB[l] );
     if( ( rc = vvb_blocks_set_start_dev( ctx, dB, po[l], n ) ) ) return rc;
     if( io[l].refine_cost && ( rc = vvb_cost_pattern_dev( ctx, refineDfunc, orgPlane, refPlane, dB, n, side, side, (const vvb_mv*)( A + offP ), K, &hp, (uint32_t*)( A + offC[l] ), nullptr ) ) ) return rc;
-    if( io[l].q )
+    if( io[l].q || io[l].packed_q )
     {
       int32_t* dSum = (int32_t*)( A + offM[l] ); int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
       if( ( rc = vvb_fwd_trquant_planes_dev( ctx, &io[l].tu, orgPlane, refPlane, dB, n, nullptr, (int16_t*)( A + offQ[l] ), dSum, dLast, dNr ) ) ) return rc;
+      if( io[l].packed_q )
+      {
+        if( !packDst[l] ) packDst[l] = (int16_t*)( A + offF[l] );
+        if( ( rc = vvb_pack_levels_dev( ctx, &io[l].tu, (const int16_t*)( A + offQ[l] ), dLast, n, packDst[l], (uint32_t*)( A + offK[l] ) ) ) ) return rc;
+      }
     }
   }
   for( int l = 0; l < levels; l++ )
@@ -1301,10 +1353,20 @@ int vvb_search_refine_tu( vvb_ctx* ctx, int orgPlane, int refPlane, int levels, 
     if( !n ) continue;
     CU( cudaMemcpyAsync( io[l].best, A + offO[l], n * sizeof( vvb_best ), cudaMemcpyDeviceToHost, ctx->stream ) );
     if( io[l].refine_cost ) CU( cudaMemcpyAsync( io[l].refine_cost, A + offC[l], n * K * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
-    if( io[l].q )
+    if( io[l].q || io[l].packed_q )
     {
       int32_t* dSum = (int32_t*)( A + offM[l] ); int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
-      CU( cudaMemcpyAsync( io[l].q, A + offQ[l], n * side * side * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+      if( io[l].q ) CU( cudaMemcpyAsync( io[l].q, A + offQ[l], n * side * side * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+      if( io[l].packed_q )
+      {
+        CU( cudaMemcpyAsync( io[l].packed_offsets, A + offK[l], ( n + 1 ) * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+        if( offF[l] )
+        {
+          // pageable destination: the size has to come back before the exact copy can be issued
+          CU( cudaStreamSynchronize( ctx->stream ) );
+          CU( cudaMemcpyAsync( io[l].packed_q, A + offF[l], (size_t) io[l].packed_offsets[n] * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+        }
+      }
       if( io[l].abs_sum )   CU( cudaMemcpyAsync( io[l].abs_sum, dSum, n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
       if( io[l].last_pos )  CU( cudaMemcpyAsync( io[l].last_pos, dLast, n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
       if( io[l].need_rdoq ) CU( cudaMemcpyAsync( io[l].need_rdoq, dNr, n, cudaMemcpyDeviceToHost, ctx->stream ) );
