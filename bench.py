@@ -152,7 +152,7 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_dram_traffic(kernel_substr, profiles=('profiles/r02_ncu_step_kernels.txt', 'profiles/r01_v8_ncu_step_kernels.txt')):
+def ncu_dram_traffic(kernel_substr, profiles=('profiles/r02p_ncu_step_kernels.txt', 'profiles/r02_ncu_step_kernels.txt', 'profiles/r01_v8_ncu_step_kernels.txt')):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first capture whose kernel name contains `kernel_substr`, from the committed
     `ncu --set full` summaries; (None, None) when no file holds the kernel"""
     unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
