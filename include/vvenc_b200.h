@@ -186,7 +186,7 @@ int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int org_plane, int ref_plane,
 /* device-side chaining: blocks[i].start = best[i].(dx,dy) (start of a refinement pattern / offset of the prediction block) */
 int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dev_blocks, const vvb_best* dev_best, int n );
 
-/* ---- forward transform + quantise (TrQuant::transformNxN for LFNST-off, non-skip luma TUs; ---------------
+/* ---- forward transform + quantise (TrQuant::transformNxN; luma and chroma TUs with sides 4..64, transform skip included; ---------------
  * CommonLib/TrQuant.cpp:688-736 -> xT :481-564 -> Quant::quant CommonLib/Quant.cpp:735-833 -> QuantCore :132-230,
  * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types.
  * With lfnst_idx set (DCT-II only) the forward calls restate transformNxN's LFNST branch: transform zero-out to the top-left 4x4 / 8x8, the 16x16 / 16x48 int8
@@ -206,6 +206,11 @@ typedef struct
   int32_t lfnst_idx;           /* cu.lfnstIdx of an intra CU: 0 off, 1 / 2 = TrQuant::xFwdLfnst between the transform and the quantiser (TrQuant.cpp:942-1048) */
   int32_t lfnst_set;           /* g_lfnstLut[ xGetLFNSTIntraMode( intra mode ) ], 0..3 (Rom.cpp:95, TrQuant.cpp:806-828)                                     */
   int32_t lfnst_transpose;     /* xGetTransposeFlag of that mode (TrQuant.cpp:831-835)                                                                           */
+  int32_t transform_skip;      /* tu.mtsIdx == MTS_SKIP (sides up to 32): xTransformSkip / xITransformSkip instead of the transforms (TrQuant.cpp:1050, 659), quantiser and
+                                  dequantiser without the transform shift at max( QP, 4 + 6 * input_bit_depth_delta ) (Quant.cpp:117-124, 772, 561); tr_hor / tr_ver ignored */
+  int32_t input_bit_depth_delta; /* sps.internalMinusInputBitDepth (transform skip only)                                                                               */
+  int32_t is_chroma;           /* the TU belongs to a chroma component: `qp` is then the mapped chroma QP minus qpBdOffset (the mapping of QpParam, Quant.cpp:96-101, is
+                                  host work) and Quant::xNeedRDOQ rounds with 256 instead of 171 (Quant.cpp:877).  Everything else is the luma arithmetic              */
 } vvb_tu_par;
 
 /* resi: n compact residual blocks [n][h][w] (Pel); outputs (each nullable except q):

@@ -4,8 +4,9 @@
 //   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
 //   xQuantDQB200         <->  DepQuant::xQuantDQ (DepQuant.cpp:1129-1264), the trellis DepQuant::quant runs for non-skip TUs of a slice with depQuantEnabled
 //
-// for the TUs the library covers: luma, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), LFNST on the forward side, no transform
-// skip, no scaling lists, plain quantiser incl. its sign-bit hiding (RDOQ / dependent quantisation stay on the host and use the coefficients this call leaves in the temp buffer).
+// for the TUs the library covers: luma and chroma components, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), transform skip,
+// LFNST on the forward side (luma), no scaling lists / BDPCM / joint Cb-Cr, plain quantiser incl. its sign-bit hiding (RDOQ stays on the host and uses the coefficients
+// this call leaves in the temp buffer; dependent quantisation: xQuantDQB200 below).
 // vvb_tu_par is derived from the TransformUnit exactly as the members derive their parameters (xSetTrTypes, QpParam, slice type), so the call sites keep
 // their arguments.  One TU per call here; the production shape batches the TU candidates of a CU (vvb_fwd_trquant with n > 1 or
 // vvb_tu_roundtrip).  Include after RdCostB200.h and CommonLib/TrQuant.h; TrQuant::xSetTrTypes is private: inside the encoder these are member functions.
@@ -37,29 +38,35 @@ inline int b200LoadTu( const char* libPath )
 
 inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const ComponentID compID, const QpParam& cQP, bool forward = true )
 {
-  if( compID != COMP_Y ) THROW( "luma TUs only" );
-  if( tu.mtsIdx[compID] == MTS_SKIP || tu.cu->bdpcmM[CH_L] ) THROW( "transform skip stays on the host" );
+  const ChannelType chType = toChannelType( compID );
+  if( tu.cu->bdpcmM[chType] ) THROW( "BDPCM stays on the host" );
   if( tu.cs->sps->scalingListEnabled ) THROW( "scaling lists stay on the host" );
+  if( isChroma( compID ) && ( tu.jointCbCr || tu.cu->colorTransform ) ) THROW( "joint Cb-Cr / ACT residuals stay on the host" );
   const SPS& sps = *tu.cs->sps;
+  const bool skip = tu.mtsIdx[compID] == MTS_SKIP;
   int trHor = DCT2, trVer = DCT2;
-  tq.xSetTrTypes( tu, compID, tu.blocks[compID].width, tu.blocks[compID].height, trHor, trVer );     // TrQuant.cpp:417-478
+  if( !skip ) tq.xSetTrTypes( tu, compID, tu.blocks[compID].width, tu.blocks[compID].height, trHor, trVer );     // TrQuant.cpp:417-478
   vvb_tu_par par = {};
   par.w = tu.blocks[compID].width; par.h = tu.blocks[compID].height;
   par.tr_hor = trHor; par.tr_ver = trVer;                                                    // enum TransType: DCT2 0, DCT8 1, DST7 2 -- the ABI's numbering
-  par.bit_depth = sps.bitDepths[CH_L];
-  par.qp = cQP.Qp( false ) - sps.qpBDOffset[CH_L];                                           // the library adds 6 * (bitDepth - 8) itself (Quant.cpp:99)
-  if( sps.qpBDOffset[CH_L] != 6 * ( par.bit_depth - 8 ) ) THROW( "unexpected qpBDOffset" );
+  par.bit_depth = sps.bitDepths[chType];
+  // cQP.Qp( false ) is QpParam's base QP -- for chroma already mapped through the chroma QP table and offsets (Quant.cpp:96-113); the library re-adds 6 * (bitDepth - 8)
+  par.qp = cQP.Qp( false ) - sps.qpBDOffset[chType];
+  if( sps.qpBDOffset[chType] != 6 * ( par.bit_depth - 8 ) ) THROW( "unexpected qpBDOffset" );
+  par.is_chroma = isChroma( compID ) ? 1 : 0;                                               // Quant::xNeedRDOQ rounds with 256 for chroma (Quant.cpp:877)
+  par.transform_skip = skip ? 1 : 0;                                                        // xTransformSkip / xITransformSkip, QP floor 4 + 6 * internalMinusInputBitDepth (Quant.cpp:117-124)
+  par.input_bit_depth_delta = sps.internalMinusInputBitDepth[chType];
   par.is_irap = tu.cs->slice->isIRAP() ? 1 : 0;                                              // rounding offset 171 vs 85 (Quant.cpp:772)
   par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;
-  if( tu.cu->lfnstIdx && forward )                                                           // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048): kernel set and transposition from the intra mode
+  if( tu.cu->lfnstIdx && forward && isLuma( compID ) && !skip )                                                           // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048): kernel set and transposition from the intra mode
   {
-    if( !tu.cs->sps->LFNST || trHor != DCT2 || trVer != DCT2 ) THROW( "LFNST index on a TU the library does not cover" );
+    if( !tu.cs->sps->LFNST || trHor != DCT2 || trVer != DCT2 || skip || isChroma( compID ) ) THROW( "LFNST index on a TU the library does not cover" );
     uint32_t intraMode = CU::getFinalIntraMode( *tu.cu, CH_L );
     if( CU::isMIP( *tu.cu, CH_L ) ) intraMode = PLANAR_IDX;
     intraMode = tq.xGetLFNSTIntraMode( tu.cu->ispMode ? tu.cu->blocks[compID] : tu.blocks[compID], intraMode );
     par.lfnst_idx = tu.cu->lfnstIdx; par.lfnst_set = g_lfnstLut[intraMode]; par.lfnst_transpose = tq.xGetTransposeFlag( intraMode ) ? 1 : 0;
   }
-  else if( tu.cu->lfnstIdx ) THROW( "the inverse LFNST stays on the host" );
+  else if( tu.cu->lfnstIdx && isLuma( compID ) && !skip ) THROW( "the inverse LFNST stays on the host" );
   par.sign_hiding = tu.cs->slice->signDataHidingEnabled ? 1 : 0;                            // Quant::quant: CoeffCodingContext( ..., signDataHidingEnabled ), xSignBitHidingHDQ (Quant.cpp:748, 817-826)
   return par;
 }

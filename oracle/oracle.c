@@ -419,9 +419,8 @@ int orc_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIR
   return orc_quant_ex( coef, w, h, bitDepth, qp, isIRAP, 0, q, absSum, lastPos );
 }
 
-int orc_quant_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int16_t* q, int32_t* absSum, int32_t* lastPos )
+static int quant_core( const int32_t* coef, int w, int h, QuantPar p, int signHiding, int16_t* q, int32_t* absSum, int32_t* lastPos )
 {
-  const QuantPar p = quant_par( w, h, bitDepth, qp, isIRAP ? 171 : 85 );               /* Quant.cpp:772 */
   int32_t scan[1024];
   const int nScan = orc_scan_order( w, h, scan );
   int pos = nScan - 1;
@@ -457,6 +456,67 @@ int orc_quant_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int i
     for( int sp = pos; sp >= 0; sp-- ) if( q[scan[sp]] ) { last = sp; break; }
   if( sum >= 2 && signHiding ) sign_bit_hiding( q, coef, scan, &p, &last );            /* Quant.cpp:817-826 */
   *absSum = sum; *lastPos = last;
+  return 0;
+}
+
+int orc_quant_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  return quant_core( coef, w, h, quant_par( w, h, bitDepth, qp, isIRAP ? 171 : 85 ), signHiding, q, absSum, lastPos );               /* Quant.cpp:772 */
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Transform skip (tu.mtsIdx == MTS_SKIP): TrQuant::xTransformSkip copies the residual into the coefficient buffer (TrQuant.cpp:1050-1064), Quant::quant runs with
+ * cQP.per / rem( true ) -- the QP raised to 4 + 6 * internalMinusInputBitDepth (Quant.cpp:117-124) --, no transform shift in iQBits (:772) and the first row of
+ * g_quantScales (TU::needsSqrt2Scale is false for skipped transforms); Quant::dequant drops the transform shift likewise (:561) and xITransformSkip casts the
+ * dequantised coefficient to Pel (:659-675).  xNeedRDOQ keeps the transform shift in its own iQBits even for skipped transforms (:868-873) and uses 256 instead of
+ * 171 for chroma components (:877).  inputDelta = sps.internalMinusInputBitDepth.
+ * ---------------------------------------------------------------------------------------------------- */
+static int ts_base_qp( int bitDepth, int qp, int inputDelta )
+{
+  int baseQp = qp + 6 * ( bitDepth - 8 );
+  if( baseQp < 0 ) baseQp = 0;
+  if( baseQp > 63 + 6 * ( bitDepth - 8 ) ) baseQp = 63 + 6 * ( bitDepth - 8 );
+  const int minTs = 4 + 6 * inputDelta;
+  return baseQp > minTs ? baseQp : minTs;
+}
+int orc_quant_ts( const int32_t* coef, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int inputDelta, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  const int baseQp = ts_base_qp( bitDepth, qp, inputDelta );
+  QuantPar p;
+  p.scale = vvc_quant_scales_host[0][baseQp % 6];
+  p.qbits = 14 + baseQp / 6;
+  p.add   = (int64_t)( isIRAP ? 171 : 85 ) << ( p.qbits - 9 );
+  return quant_core( coef, w, h, p, signHiding, q, absSum, lastPos );
+}
+int orc_transform_quant_ts( const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int inputDelta,
+                            int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( w > 32 || h > 32 ) return -1;                                                    /* log2MaxTransformSkipBlockSize <= 5 */
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) coef[y * w + x] = resi[y * stride + x];
+  return orc_quant_ts( coef, w, h, bitDepth, qp, isIRAP, signHiding, inputDelta, q, absSum, lastPos );
+}
+/* Quant::xNeedRDOQ in full: depQuant only counts for non-skipped transforms; chroma components use 256 */
+int orc_need_rdoq_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant, int transformSkip, int inputDelta, int chroma )
+{
+  int baseQp;
+  if( transformSkip ) baseQp = ts_base_qp( bitDepth, qp, inputDelta );
+  else
+  {
+    baseQp = qp + 6 * ( bitDepth - 8 );
+    if( baseQp < 0 ) baseQp = 0;
+    if( baseQp > 63 + 6 * ( bitDepth - 8 ) ) baseQp = 63 + 6 * ( bitDepth - 8 );
+    if( depQuant ) baseQp += 1;
+  }
+  const int sqrt2 = transformSkip ? 0 : ( ( ilog2u( w ) + ilog2u( h ) ) & 1 );
+  const int trShift = 15 - bitDepth - ( ( ilog2u( w ) + ilog2u( h ) ) >> 1 ) - sqrt2;
+  const int scale = vvc_quant_scales_host[sqrt2][baseQp % 6], qbits = 14 + baseQp / 6 + trShift;
+  const int64_t add = (int64_t)( chroma ? 256 : 171 ) << ( qbits - 9 );
+  const int n = w * ( h < 32 ? h : 32 );
+  for( int i = 0; i < n; i++ )
+  {
+    const int64_t t = (int64_t) iabs( coef[i] ) * scale;
+    if( (int32_t)( ( t + add ) >> qbits ) != 0 ) return 1;
+  }
   return 0;
 }
 
@@ -634,6 +694,27 @@ int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int 
 {
   orc_dequant( q, w, h, bitDepth, qp, coef );
   return orc_inv_transform( trHor, trVer, coef, w, h, bitDepth, resi, stride );
+}
+
+/* the same for a skipped transform: dequant without the transform shift, residual = Pel( coefficient ) */
+int orc_inv_transform_quant_ts( const int16_t* q, int w, int h, int bitDepth, int qp, int inputDelta, int32_t* coef, Pel* resi, int stride )
+{
+  const int baseQp = ts_base_qp( bitDepth, qp, inputDelta );
+  const int per = baseQp / 6, rem = baseQp % 6;
+  const int rightShift = 6 - per;                                                        /* Quant.cpp:561 with isTransformSkip */
+  const int scale = inv_quant_scales[0][rem];
+  int tib = 32 + rightShift - 7; if( tib > 16 ) tib = 16;
+  const int32_t inMax = ( 1 << ( tib - 1 ) ) - 1, inMin = -( inMax + 1 );
+  for( int n = 0; n < w * h; n++ )
+  {
+    const int32_t c = clip3i( inMin, inMax, q[n] );
+    int32_t v;
+    if( rightShift > 0 ) v = ( c * scale + ( 1 << ( rightShift - 1 ) ) ) >> rightShift;
+    else                 v = (int32_t)( (uint32_t)( c * scale ) << ( -rightShift ) );
+    coef[n] = clip3i( -32768, 32767, v );
+  }
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) resi[y * stride + x] = (Pel) coef[y * w + x];
+  return 0;
 }
 
 /* PelBuf::reconstruct (Buffer.cpp:719-760): reco = ClipPel( pred + resi ) with the default clipping range [0, 2^bd - 1] */

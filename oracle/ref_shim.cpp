@@ -250,7 +250,7 @@ struct TuRig
 
   TuRig() : cs( xuCache, &csMutex ) {}
 
-  void setup( int w, int h, int bitDepth, int mtsIdx, bool intraSlice, bool intraCu, int qp )
+  void setup( int w, int h, int bitDepth, int mtsIdx, bool intraSlice, bool intraCu, int qp, ChromaFormat fmt = CHROMA_400 )
   {
     sps.bitDepths.recon[CH_L] = bitDepth;
     sps.bitDepths.recon[CH_C] = bitDepth;
@@ -259,7 +259,7 @@ struct TuRig
     sps.internalMinusInputBitDepth[CH_L] = 0;
     sps.internalMinusInputBitDepth[CH_C] = 0;
     sps.MTS = true; sps.MTSIntra = true; sps.MTSInter = true; sps.LFNST = false;
-    sps.chromaFormatIdc = CHROMA_400;
+    sps.chromaFormatIdc = fmt;
     slice.sps = &sps; slice.pps = &pps;
     slice.sliceType = intraSlice ? VVENC_I_SLICE : VVENC_B_SLICE;
     slice.nalUnitType = intraSlice ? VVENC_NAL_UNIT_CODED_SLICE_IDR_W_RADL : VVENC_NAL_UNIT_CODED_SLICE_TRAIL;
@@ -268,7 +268,7 @@ struct TuRig
     slice.tsResidualCodingDisabled = false;
     cs.sps = &sps; cs.pps = &pps; cs.slice = &slice;
 
-    const UnitArea ua( CHROMA_400, Area( 0, 0, w, h ) );
+    const UnitArea ua( fmt, Area( 0, 0, w, h ) );
     static_cast<UnitArea&>( cu ) = ua;
     cu.cs = &cs; cu.slice = &slice; cu.chType = CH_L;
     cu.predMode = intraCu ? MODE_INTRA : MODE_INTER;
@@ -549,6 +549,60 @@ int refshim_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, 
   QpParam qpp( r.tu, COMP_Y, false );
   CCoeffBuf src( coef, w, w, h );
   return static_cast<Quant*>( tqOfThread().m_quant )->xNeedRDOQ( r.tu, COMP_Y, src, qpp ) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Transform skip and chroma components.  comp = 0 luma, 1 Cb: the rig is then built in 4:4:4 (three blocks of the TU's size) and the QpParam of the luma
+// component stands in for the chroma one (its QP is whatever the caller passes -- the chroma QP mapping is host work on both sides), so that Quant::quant /
+// xNeedRDOQ / dequant run with compID = COMP_Cb: the only arithmetic that differs is xNeedRDOQ's rounding constant (Quant.cpp:877).
+// transformSkip: tu.mtsIdx = MTS_SKIP -> xTransformSkip (TrQuant.cpp:1050), cQP.per / rem( true ) with sps.internalMinusInputBitDepth = inputDelta.
+int refshim_transform_quant_ts( const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int depQuant, int transformSkip, int inputDelta, int comp,
+                                int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  t_rigSignHiding = signHiding != 0;
+  r.setup( w, h, bitDepth, MTS_DCT2_DCT2, isIRAP != 0, true, qp, comp ? CHROMA_444 : CHROMA_400 );
+  t_rigSignHiding = false;
+  r.slice.depQuantEnabled = depQuant != 0;
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta; r.sps.internalMinusInputBitDepth[CH_C] = inputDelta;
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.tu.mtsIdx[COMP_Y] = transformSkip ? MTS_SKIP : MTS_DCT2_DCT2;          // the QpParam below is built for luma
+  r.tu.mtsIdx[compID] = transformSkip ? MTS_SKIP : MTS_DCT2_DCT2;
+  QpParam qpp( r.tu, COMP_Y, false );
+  TrQuant& tq = tqOfThread();
+  CPelBuf resiBuf( resi, stride, w, h );
+  if( transformSkip ) tq.xTransformSkip( r.tu, compID, resiBuf, coef );
+  else { CoeffBuf dst( coef, w, w, h ); tq.xT( r.tu, compID, resiBuf, dst, w, h ); }
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  alignas(64) static thread_local unsigned char ctxMem[ sizeof( Ctx ) ];
+  const Ctx& dummy = *reinterpret_cast<const Ctx*>( ctxMem );
+  Quant* qu = static_cast<Quant*>( tq.m_quant );
+  qu->Quant::quant( r.tu, compID, src, sum, qpp, dummy );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[compID];
+  if( needRdoq ) *needRdoq = qu->xNeedRDOQ( r.tu, compID, src, qpp ) ? 1 : 0;
+  r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0; r.slice.depQuantEnabled = false;
+  return 0;
+}
+// TrQuant::invTransformNxN for a skipped transform: Quant::dequant + xITransformSkip
+int refshim_inv_transform_quant_ts( const int16_t* q, int w, int h, int bitDepth, int qp, int inputDelta, int32_t* coef, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, MTS_SKIP, false, true, qp );
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta;
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  alignas(64) static thread_local TCoeff tmpCoef[ 64 * 64 ];
+  CoeffBuf deq( tmpCoef, w, w, h );
+  static_cast<Quant*>( tqOfThread().m_quant )->Quant::dequant( r.tu, deq, COMP_Y, qpp );
+  if( coef ) memcpy( coef, tmpCoef, sizeof( int32_t ) * w * h );
+  PelBuf out( resi, stride, w, h );
+  tqOfThread().xITransformSkip( CCoeffBuf( tmpCoef, w, w, h ), out, r.tu, COMP_Y );
+  r.sps.internalMinusInputBitDepth[CH_L] = 0;
+  return 0;
 }
 
 // Whole TU: xT then Quant::quant, as TrQuant::transformNxN does for LFNST-off, non-skip TUs (TrQuant.cpp:688-736).

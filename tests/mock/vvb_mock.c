@@ -159,13 +159,15 @@ int vvb_fwd_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* resi, int
   {
     int32_t s = 0, l = -1;
     int32_t* co = coef ? coef + area * i : tmp;
-    const int rc = par->lfnst_idx
+    const int rc = par->transform_skip
+      ? orc_transform_quant_ts( resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, par->sign_hiding, par->input_bit_depth_delta, co, q + area * i, &s, &l )
+      : par->lfnst_idx
       ? orc_transform_quant_lfnst( resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, par->sign_hiding, par->lfnst_set, par->lfnst_idx, par->lfnst_transpose, co, q + area * i, &s, &l )
       : orc_transform_quant_ex( par->tr_hor, par->tr_ver, resi + area * i, par->w, par->w, par->h, par->bit_depth, par->qp, par->is_irap, par->sign_hiding, co, q + area * i, &s, &l );
     if( rc ) { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }
     if( absSum ) absSum[i] = s;
     if( lastPos ) lastPos[i] = l;
-    if( needRdoq ) needRdoq[i] = (uint8_t) orc_need_rdoq( co, par->w, par->h, par->bit_depth, par->qp, par->dep_quant );
+    if( needRdoq ) needRdoq[i] = (uint8_t) orc_need_rdoq_ex( co, par->w, par->h, par->bit_depth, par->qp, par->dep_quant, par->transform_skip, par->input_bit_depth_delta, par->is_chroma );
   }
   free( tmp );
   c->calls++;
@@ -181,7 +183,8 @@ int vvb_inv_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* q, int n,
   int32_t* tmp = (int32_t*) malloc( sizeof( int32_t ) * area );
   if( !tmp ) return fail( c, VVB_ERR_NOMEM, "inverse" );
   for( int i = 0; i < n; i++ )
-    if( orc_inv_transform_quant( par->tr_hor, par->tr_ver, q + area * i, par->w, par->h, par->bit_depth, par->qp, tmp, resi + area * i, par->w ) )
+    if( par->transform_skip ? orc_inv_transform_quant_ts( q + area * i, par->w, par->h, par->bit_depth, par->qp, par->input_bit_depth_delta, tmp, resi + area * i, par->w )
+                            : orc_inv_transform_quant( par->tr_hor, par->tr_ver, q + area * i, par->w, par->h, par->bit_depth, par->qp, tmp, resi + area * i, par->w ) )
     { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }
   free( tmp );
   c->calls++;

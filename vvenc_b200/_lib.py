@@ -28,7 +28,8 @@ class vvb_me_par(ctypes.Structure):
 
 class vvb_tu_par(ctypes.Structure):
     _fields_ = [('w', ctypes.c_int32), ('h', ctypes.c_int32), ('tr_hor', ctypes.c_int32), ('tr_ver', ctypes.c_int32), ('bit_depth', ctypes.c_int32),
-                ('qp', ctypes.c_int32), ('is_irap', ctypes.c_int32), ('dep_quant', ctypes.c_int32), ('sign_hiding', ctypes.c_int32), ('lfnst_idx', ctypes.c_int32), ('lfnst_set', ctypes.c_int32), ('lfnst_transpose', ctypes.c_int32)]
+                ('qp', ctypes.c_int32), ('is_irap', ctypes.c_int32), ('dep_quant', ctypes.c_int32), ('sign_hiding', ctypes.c_int32), ('lfnst_idx', ctypes.c_int32), ('lfnst_set', ctypes.c_int32), ('lfnst_transpose', ctypes.c_int32),
+                ('transform_skip', ctypes.c_int32), ('input_bit_depth_delta', ctypes.c_int32), ('is_chroma', ctypes.c_int32)]
 
 
 class vvb_mctf_level_par(ctypes.Structure):

@@ -215,8 +215,10 @@ class CostEngine:
 
     # ---- transform + quantise
     @staticmethod
-    def tu_par(w, h, tr_hor=DCT2, tr_ver=DCT2, bit_depth=10, qp=32, is_irap=False, dep_quant=False, sign_hiding=False, lfnst_idx=0, lfnst_set=0, lfnst_transpose=False):
-        return L.vvb_tu_par(w, h, tr_hor, tr_ver, bit_depth, qp, int(is_irap), int(dep_quant), int(sign_hiding), int(lfnst_idx), int(lfnst_set), int(lfnst_transpose))
+    def tu_par(w, h, tr_hor=DCT2, tr_ver=DCT2, bit_depth=10, qp=32, is_irap=False, dep_quant=False, sign_hiding=False, lfnst_idx=0, lfnst_set=0, lfnst_transpose=False,
+               transform_skip=False, input_bit_depth_delta=0, is_chroma=False):
+        return L.vvb_tu_par(w, h, tr_hor, tr_ver, bit_depth, qp, int(is_irap), int(dep_quant), int(sign_hiding), int(lfnst_idx), int(lfnst_set), int(lfnst_transpose),
+                            int(transform_skip), int(input_bit_depth_delta), int(is_chroma))
 
     def set_tma_staging(self, enable):
         self._chk(self.lib.vvb_set_tma_staging(self.h, int(enable)))

@@ -1083,19 +1083,39 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
   p.offH = vvc_tr_offset_host[p.trHor][p.lw]; p.offV = vvc_tr_offset_host[p.trVer][p.lh];
   p.regionW = std::min( 32, w ); p.regionH = std::min( 32, h );
   p.scanOff = ( ( p.lw - 2 ) * 5 + ( p.lh - 2 ) ) * 1024;
-  auto qpar = [&]( int qp, int plusOne, int addNum, int& scale, int& qbits, long long& add )
+  p.ts = in->transform_skip ? 1 : 0;
+  if( p.ts )
   {
-    int baseQp = qp + 6 * ( in->bit_depth - 8 );                                         // Quant.cpp:99
-    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) ) + plusOne; // Quant.cpp:113; the dependent-quantisation pre-check adds 1 AFTER the clip (Quant.cpp:853)
-    const int per = baseQp / 6, rem = baseQp % 6;
-    const int sqrt2 = ( p.lw + p.lh ) & 1;                                               // UnitTools.cpp:3616-3621
-    const int trShift = 15 - in->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;           // Quant.h:69-72, Quant.cpp:767
-    scale = vvc_quant_scales_host[sqrt2][rem];
-    qbits = 14 + per + trShift;                                                          // Quant.cpp:769
-    add   = (long long) addNum << ( qbits - 9 );                                         // Quant.cpp:772 / :879
+    if( w > 32 || h > 32 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "transform skip exists up to 32 x 32 (log2MaxTransformSkipBlockSize)" );
+    if( in->lfnst_idx ) return fail( ctx, VVB_ERR_UNSUPPORTED, "LFNST does not apply to skipped transforms" );
+    if( in->input_bit_depth_delta < 0 || in->input_bit_depth_delta > 8 ) return fail( ctx, VVB_ERR_ARG, "input_bit_depth_delta 0..8" );
+    p.keepW = w; p.keepH = h;
+  }
+  // QpParam (Quant.cpp:89-124): Qps[0] = clip( qp + qpBdOffset ), Qps[1] = max( Qps[0], 4 + 6 * internalMinusInputBitDepth ) for skipped transforms
+  auto baseQpOf = [&]( bool tsQp )
+  {
+    int baseQp = in->qp + 6 * ( in->bit_depth - 8 );                                     // Quant.cpp:99
+    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) );           // Quant.cpp:113
+    if( tsQp ) baseQp = std::max( baseQp, 4 + 6 * in->input_bit_depth_delta );
+    return baseQp;
   };
-  qpar( in->qp, 0, in->is_irap ? 171 : 85, p.scale, p.qbits, p.add );
-  qpar( in->qp, in->dep_quant ? 1 : 0, 171, p.scaleRdoq, p.qbitsRdoq, p.addRdoq );         // Quant.cpp:852-855, :879
+  const int sqrt2 = p.ts ? 0 : ( ( p.lw + p.lh ) & 1 );                                   // TU::needsSqrt2Scale, UnitTools.cpp:3616-3621
+  const int trShift = 15 - in->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;              // Quant.h:69-72, Quant.cpp:767
+  {
+    const int baseQp = baseQpOf( p.ts != 0 ), per = baseQp / 6, rem = baseQp % 6;
+    p.scale = vvc_quant_scales_host[sqrt2][rem];
+    p.qbits = 14 + per + ( p.ts ? 0 : trShift );                                          // Quant.cpp:772
+    p.add   = (long long)( in->is_irap ? 171 : 85 ) << ( p.qbits - 9 );                   // :774
+  }
+  {
+    // Quant::xNeedRDOQ (:852-879): the dependent-quantisation pre-check adds 1 AFTER the clip and only for non-skipped transforms; the transform shift stays in
+    // its iQBits even for skipped transforms; chroma components round with 256
+    const bool isDq = in->dep_quant && !p.ts;
+    const int baseQp = isDq ? baseQpOf( false ) + 1 : baseQpOf( p.ts != 0 ), per = baseQp / 6, rem = baseQp % 6;
+    p.scaleRdoq = vvc_quant_scales_host[sqrt2][rem];
+    p.qbitsRdoq = 14 + per + trShift;
+    p.addRdoq   = (long long)( in->is_chroma ? 256 : 171 ) << ( p.qbitsRdoq - 9 );
+  }
   if( p.qbits < 9 || p.qbitsRdoq < 9 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "quantiser shift below 9" );
   const int thrVal = 8;                                                                  // vvencCfg.cpp:971-973
   const int32_t thres = (int32_t)( (int64_t) thrVal << ( p.qbits - 1 ) );               // Quant.cpp:175-176 (TCoeff cast)
@@ -1103,14 +1123,10 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
   int t = ( w * h ) / 4;
   p.team = std::max( 4, std::min( 128, t ) );
   {                                                                                      // Quant::dequant, Quant.cpp:554-607
-    int baseQp = in->qp + 6 * ( in->bit_depth - 8 );
-    baseQp = std::max( 0, std::min( 63 + 6 * ( in->bit_depth - 8 ), baseQp ) );
-    const int per = baseQp / 6, rem = baseQp % 6;
-    const int sqrt2 = ( p.lw + p.lh ) & 1;
-    const int trShift = 15 - in->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;
+    const int baseQp = baseQpOf( p.ts != 0 ), per = baseQp / 6, rem = baseQp % 6;
     static const int invScales[2][6] = { { 40, 45, 51, 57, 64, 72 }, { 57, 64, 72, 80, 90, 102 } };   // g_invQuantScales, Rom.cpp:1396-1400
     p.dqScale = invScales[sqrt2][rem];
-    p.dqShift = 6 - ( trShift + per );                                                   // IQUANT_SHIFT = 6 (CommonDef.h:370)
+    p.dqShift = 6 - ( ( p.ts ? 0 : trShift ) + per );                                    // IQUANT_SHIFT = 6 (CommonDef.h:370); :561
     const int tib = std::min( 16, 32 + p.dqShift - 7 );                                  // targetInputBitDepth, Quant.cpp:606
     p.dqInMax = ( 1 << ( tib - 1 ) ) - 1;
     p.s2Inv   = 20 - in->bit_depth;                                                      // TrQuant.cpp:609
@@ -1147,7 +1163,7 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
-  if( !p.lfnstIdx && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) ) )
+  if( !p.lfnstIdx && !p.ts && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) ) )
   {
     // tcgen05 path: 128 stacked rows (128/N TUs) per tile, persistent CTAs
     const int tpt = 128 / p.w;
@@ -1159,7 +1175,7 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
     CHECK_LAUNCH( "fwd_trquant_tc_kernel" );
     return VVB_OK;
   }
-  const bool ext = p.lfnstIdx != 0 || p.signHiding != 0;        // the plain instantiation carries neither the LFNST stage nor the sign-bit hiding pass
+  const bool ext = p.lfnstIdx != 0 || p.signHiding != 0 || p.ts != 0;        // the plain instantiation carries neither the LFNST stage, the sign-bit hiding pass nor transform skip
 #define VVB_FWD_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = (size_t)( S::MAT_WORDS + S::NTEAMS * S::TEAM_WORDS ) * 4; \
     if( ext ) fwd_trquant_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
     else      fwd_trquant_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
@@ -1201,11 +1217,11 @@ int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlan
     // CUDA-core engine: the residual is formed while the TU is loaded (one launch, no compact residual buffer); the tcgen05 engine keeps the staging kernel
     TuPar p;
     if( ( rc = makeTuPar( ctx, par, p ) ) ) return rc;
-    const bool tensor = !p.lfnstIdx && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) );
+    const bool tensor = !p.lfnstIdx && !p.ts && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) );
     if( !tensor )
     {
       const Plane &po = ctx->planes.p[orgPlane], &pp = ctx->planes.p[predPlane];
-      const bool ext = p.lfnstIdx != 0 || p.signHiding != 0;
+      const bool ext = p.lfnstIdx != 0 || p.signHiding != 0 || p.ts != 0;
 #define VVB_FWDP_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = (size_t)( S::MAT_WORDS + S::NTEAMS * S::TEAM_WORDS ) * 4; \
       if( ext ) fwd_trquant_planes_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
       else      fwd_trquant_planes_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
@@ -1522,7 +1538,7 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
-  const bool ext = p.signHiding != 0;
+  const bool ext = p.signHiding != 0 || p.ts != 0;
 #define VVB_RT_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
     if( ext ) tu_roundtrip_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
                                                                                               dQ, dReco, (TuResult*) dRes, dNeedRdoq ); \

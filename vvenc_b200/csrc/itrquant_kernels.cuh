@@ -55,6 +55,25 @@ __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* 
   constexpr int W = S::W, H = S::H, T = S::T, RW = S::RW, RH = S::RH;
   const int lKW = LW == 5 ? par.lKeepW : S::LRW, lKH = LH == 5 ? par.lKeepH : S::LRH;
   const int keepW = 1 << lKW, keepH = 1 << lKH;
+  if( par.ts )                                              // uniform over the launch: Quant::dequant without the transform shift + TrQuant::xITransformSkip (TrQuant.cpp:659-675)
+  {
+    const int sc = par.dqScale, sh = par.dqShift, inMax = par.dqInMax, inMin = -inMax - 1;
+    const int add = sh > 0 ? 1 << ( sh - 1 ) : 0;
+    for( int it = tt; active && it < H * W / 4; it += T )
+    {
+      const int y = it >> ( LW - 2 ), x0 = ( it & ( W / 4 - 1 ) ) << 2;
+      int r[4];
+#pragma unroll
+      for( int k = 0; k < 4; k++ )
+      {
+        int c = max( inMin, min( inMax, (int) qS[y * W + x0 + k] ) );
+        c = sh > 0 ? ( c * sc + add ) >> sh : (int)( (unsigned)( c * sc ) << ( -sh ) );
+        r[k] = clip16( c );
+      }
+      out( y, x0, r[0], r[1], r[2], r[3] );
+    }
+    return;
+  }
   // ---- dequant (DeQuantCore, Quant.cpp:232-262) + transpose: cT[i][k/2] = ( coef[k][i], coef[k+1][i] )
   {
     const int pairs = keepW << ( lKH - 1 );

@@ -40,6 +40,7 @@ struct TuPar
   const int8_t* lfnstMat;
   int lfnstMaxScan;          // last scan position the quantiser may look at: 7 (4x4 / 8x8 TUs) or 15 with LFNST (Quant.cpp:151-158), INT_MAX without
   int signHiding;            // slice->signDataHidingEnabled: Quant::quant runs xSignBitHidingHDQ after QuantCore (Quant.cpp:817-826)
+  int ts;                    // transform skip: coefficients = residual (xTransformSkip), residual = dequantised coefficient (xITransformSkip)
   unsigned rdoqThr;          // smallest |c| with ((|c| * scaleRdoq + addRdoq) >> qbitsRdoq) != 0  (needRdoqCore as one compare)
 };
 
@@ -325,7 +326,19 @@ __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* M
 #pragma unroll
   for( int k = 0; k < S::RESI_WORDS / T; k++ ) { const int i = tt + k * T; if( live ) myResi[i] = load( i ); }
   __syncthreads();
+  const bool ts = EXT && par.ts != 0;                         // uniform over the launch
+  if( ts )
+  {
+    // TrQuant::xTransformSkip (TrQuant.cpp:1050-1064): the residual is the coefficient block (sides <= 32: the scanned region is the whole TU)
+    if( live )
+      for( int i = tt; i < S::COEF_WORDS; i += T )
+      {
+        const uint32_t wv = myResi[i >> 1];
+        myCoef[i] = ( i & 1 ) ? hi16( wv ) : lo16( wv );
+      }
+  }
   // ---- stage 1: tmp[j][i] = ( sum_k resi[i][k] * Th[j][k] + r1 ) >> s1   for i < H, j < keepW ; item = (row i, 4 outputs j0..j0+3)
+  if( !ts )
   {
     const int s1 = par.s1, r1 = s1 > 0 ? 1 << ( s1 - 1 ) : 0;
     const int lJG = ( LW == 5 ? par.lKeepW : S::LRW ) - 2, items = H << lJG;
@@ -360,6 +373,7 @@ __device__ __forceinline__ int team_forward( const TuPar& par, const uint32_t* M
   }
   __syncthreads();
   // ---- stage 2: coef[j][i] = ( sum_k tmp[i][k] * Tv[j][k] + r2 ) >> s2   for i < keepW, j < keepH
+  if( !ts )
   {
     const int s2 = par.s2, r2 = 1 << ( s2 - 1 );
     const int lJG = ( LH == 5 ? par.lKeepH : S::LRH ) - 2, items = keepW << lJG;
