@@ -586,6 +586,49 @@ int refshim_transform_quant_ts( const int16_t* resi, int stride, int w, int h, i
   r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0; r.slice.depQuantEnabled = false;
   return 0;
 }
+// the same TU through integration/TrQuantB200.h (xTQuantB200 with compID / MTS_SKIP: vvb_tu_par.transform_skip, input_bit_depth_delta, is_chroma); 1 = the binding threw
+int refshim_transform_quant_ts_b200( const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int depQuant, int transformSkip, int inputDelta, int comp,
+                                     int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  t_rigSignHiding = signHiding != 0;
+  r.setup( w, h, bitDepth, MTS_DCT2_DCT2, isIRAP != 0, true, qp, comp ? CHROMA_444 : CHROMA_400 );
+  t_rigSignHiding = false;
+  r.slice.depQuantEnabled = depQuant != 0;
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta; r.sps.internalMinusInputBitDepth[CH_C] = inputDelta;
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.tu.mtsIdx[COMP_Y] = transformSkip ? MTS_SKIP : MTS_DCT2_DCT2;
+  r.tu.mtsIdx[compID] = transformSkip ? MTS_SKIP : MTS_DCT2_DCT2;
+  QpParam qpp( r.tu, COMP_Y, false );
+  CPelBuf resiBuf( resi, stride, w, h );
+  CoeffBuf dst( coef, w, w, h );
+  TCoeff sum = 0; bool nr = false;
+  int rc = 0;
+  try { xTQuantB200( tqOfThread(), r.tu, compID, resiBuf, dst, qpp, sum, &nr ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0; r.slice.depQuantEnabled = false;
+  if( rc ) return rc;
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[compID]; *needRdoq = nr ? 1 : 0;
+  return 0;
+}
+int refshim_inv_transform_quant_ts_b200( const int16_t* q, int w, int h, int bitDepth, int qp, int inputDelta, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, MTS_SKIP, false, true, qp );
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta;
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  PelBuf out( resi, stride, w, h );
+  int rc = 0;
+  try { invTransformNxNB200( tqOfThread(), r.tu, COMP_Y, out, qpp ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.sps.internalMinusInputBitDepth[CH_L] = 0;
+  return rc;
+}
+
 // TrQuant::invTransformNxN for a skipped transform: Quant::dequant + xITransformSkip
 int refshim_inv_transform_quant_ts( const int16_t* q, int w, int h, int bitDepth, int qp, int inputDelta, int32_t* coef, int16_t* resi, int stride )
 {

@@ -279,6 +279,27 @@ def main(mock_path):
             if rc or not np.array_equal(ra, rb):
                 bad.append(['inv', opt] + [int(v) for v in row] + [rc])
     res['tu_inv'] = {'cases': ninv, 'bad': bad[:5]}
+    # transform skip and chroma components through xTQuantB200 / invTransformNxNB200 (vvb_tu_par.transform_skip, input_bit_depth_delta, is_chroma)
+    bad = []; nts = 0; ninv = 0
+    R.refshim_set_simd(b'AVX2')
+    for row in C.ts_cases():
+        w, h, st, bd, amp, qp, irap, sh, dq, ts, delta, comp, seed = [int(v) for v in row]
+        resi = C.ts_inputs(row)
+        ca = np.zeros((h, w), dtype=np.int32); qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32(); na = I32()
+        cb = np.zeros((h, w), dtype=np.int32); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32(); nb = I32()
+        assert R.refshim_transform_quant_ts(P(resi), st, w, h, bd, qp, irap, sh, dq, ts, delta, comp, P(ca), P(qa), ctypes.byref(sa), ctypes.byref(la), ctypes.byref(na)) == 0
+        rc = R.refshim_transform_quant_ts_b200(P(resi), st, w, h, bd, qp, irap, sh, dq, ts, delta, comp, P(cb), P(qb), ctypes.byref(sb), ctypes.byref(lb), ctypes.byref(nb))
+        nts += 1
+        if rc or not (np.array_equal(ca, cb) and np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value and na.value == nb.value):
+            bad.append(['ts'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+        if ts and sa.value > 0 and comp == 0:
+            ra = np.zeros((h, st), dtype=np.int16); rb = np.zeros((h, st), dtype=np.int16)
+            assert R.refshim_inv_transform_quant_ts(P(qa), w, h, bd, qp, delta, None, P(ra), st) == 0
+            rc = R.refshim_inv_transform_quant_ts_b200(P(qa), w, h, bd, qp, delta, P(rb), st)
+            ninv += 1
+            if rc or not np.array_equal(ra[:, :w], rb[:, :w]):
+                bad.append(['ts_inv'] + [int(v) for v in row] + [rc])
+    res['tu_ts_chroma'] = {'cases': nts, 'inverse_cases': ninv, 'bad': bad[:5]}
     # DepQuant::xQuantDQ against xQuantDQB200 (rate tables from the rig's CABAC contexts through the public RateEstimator accessors, trellis in the bound library)
     bad = []; ndq = 0; nz = 0
     R.refshim_set_simd(b'AVX2')

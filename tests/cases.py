@@ -343,3 +343,26 @@ def dq_inputs(row):
 def dq_zero_out(row):
     w, h, mts, sbt = int(row[0]), int(row[1]), int(row[7]), int(row[9])
     return 1 if (mts > 1 or (sbt and w <= 32 and h <= 32)) else 0       # DepQuant.cpp:1155
+
+
+# ---- transform skip / chroma components (TrQuant::xTransformSkip, Quant::quant with cQP.per / rem( true ), xNeedRDOQ's chroma constant) -------------------------
+def ts_cases():
+    """rows: w, h, stride, bit_depth, amp, qp, isIRAP, signHiding, depQuant, transformSkip, inputDelta, comp (0 luma, 1 Cb), seed"""
+    rows = []
+    rs = np.random.RandomState(2024)
+    seed = 12000
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (4, 8), (16, 4), (32, 8), (8, 32), (16, 32), (64, 64), (64, 16)]:
+        for bd in (8, 10):
+            for k in range(10):
+                ts = 1 if (k % 2 == 0 and w <= 32 and h <= 32) else 0
+                amp = int(rs.choice([3, 12, 60, 300, (1 << bd) - 1]))
+                rows.append([w, h, w + int(rs.randint(0, 5)), bd, amp, int(rs.randint(-6 * (bd - 8), 64)), int(rs.randint(2)), int(rs.randint(2)), int(rs.randint(2)), ts,
+                             int(rs.choice([0, 0, 2])) if bd == 10 else 0, int(rs.randint(2)), seed])
+                seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def ts_inputs(row):
+    w, h, st, bd, amp = [int(v) for v in row[:5]]
+    rs = np.random.RandomState(int(row[12]))
+    return rs.randint(-amp, amp + 1, size=(h, st)).astype(np.int16)

@@ -136,6 +136,9 @@ int vvb_mctf_search_grid( vvb_ctx* c, int orgPlane, int refPlane, const vvb_mctf
 int orc_transform_quant_lfnst( const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int set, int lfnstIdx, int transpose, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int orc_transform_quant_ex( int trHor, int trVer, const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int orc_need_rdoq( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant );
+int orc_need_rdoq_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, int depQuant, int transformSkip, int inputDelta, int chroma );
+int orc_transform_quant_ts( const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int inputDelta, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
+int orc_inv_transform_quant_ts( const int16_t* q, int w, int h, int bitDepth, int qp, int inputDelta, int32_t* coef, Pel* resi, int stride );
 int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride );
 
 static int tu_par_ok( vvb_ctx* c, const vvb_tu_par* p )

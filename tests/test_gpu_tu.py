@@ -344,3 +344,50 @@ def test_gpu_dep_quant_batches_vs_oracle(gpu, golden_depquant, engine):
         assert np.array_equal(r['abs_sum'], s) and np.array_equal(r['last_pos'], l), (w, h)
         assert (l >= 0).sum() > n // 4, (w, h, int((l >= 0).sum()))
     gpu.eng.set_depquant_engine(1)
+
+
+def test_gpu_transform_skip_and_chroma_vs_oracle(gpu):
+    """vvb_tu_par.transform_skip / input_bit_depth_delta / is_chroma: forward (xTransformSkip + quantiser at the transform-skip QP, xNeedRDOQ with its chroma constant),
+    inverse (dequant without the transform shift + xITransformSkip) and the fused round trip against the oracle restatements that tests/test_oracle_vs_reference.py pins
+    to the reference members; batches per case row so that the EXT instantiations run with full CTAs"""
+    import ctypes
+    from _libs import oracle, P
+    O = oracle()
+    I32 = ctypes.c_int32
+    nfwd = 0; ninv = 0; nrt = 0
+    for row in C.ts_cases():
+        w, h, st, bd, amp, qp, irap, sh, dq, ts, delta, comp, seed = [int(v) for v in row]
+        rs = np.random.RandomState(seed)
+        n = 40
+        resi = rs.randint(-amp, amp + 1, size=(n, h, w)).astype(np.int16)
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, bool(irap), bool(dq), bool(sh), transform_skip=bool(ts), input_bit_depth_delta=delta, is_chroma=bool(comp))
+        r = gpu.eng.fwd_trquant(par, resi)
+        for i in range(n):
+            cO = np.zeros((h, w), np.int32); qO = np.zeros((h, w), np.int16); sO = I32(); lO = I32()
+            if ts:
+                assert O.orc_transform_quant_ts(P(resi[i]), w, w, h, bd, qp, irap, sh, delta, P(cO), P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+            else:
+                assert O.orc_transform_quant_ex(0, 0, P(resi[i]), w, w, h, bd, qp, irap, sh, P(cO), P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+            assert np.array_equal(r['coef'][i], cO) and np.array_equal(r['q'][i], qO), ([int(v) for v in row], i)
+            assert int(r['abs_sum'][i]) == sO.value and int(r['last_pos'][i]) == lO.value, ([int(v) for v in row], i)
+            assert int(r['need_rdoq'][i]) == O.orc_need_rdoq_ex(P(cO), w, h, bd, qp, dq, ts, delta, comp), ([int(v) for v in row], i)
+        nfwd += n
+        if ts:
+            got = gpu.eng.inv_trquant(par, r['q'])
+            for i in range(0, n, 5):
+                dO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
+                assert O.orc_inv_transform_quant_ts(P(np.ascontiguousarray(r['q'][i])), w, h, bd, qp, delta, P(dO), P(rO), w) == 0
+                assert np.array_equal(got[i], rO), ([int(v) for v in row], i)
+                ninv += 1
+            # fused round trip: residual = org - pred -> skip "transform" -> quant -> dequant -> reconstruct; the levels must equal the separate forward call and
+            # the reconstruction pred + residual' clipped to the bit depth
+            org = rs.randint(0, 1 << bd, size=(n, h, w)).astype(np.int16)
+            pred = np.clip(org.astype(np.int32) - resi, 0, (1 << bd) - 1).astype(np.int16)
+            rr = gpu.eng.tu_roundtrip(par, org, pred)
+            f2 = gpu.eng.fwd_trquant(par, (org.astype(np.int32) - pred).astype(np.int16))
+            assert np.array_equal(rr['q'], f2['q'])
+            rec_resi = gpu.eng.inv_trquant(par, f2['q'])
+            exp = np.clip(pred.astype(np.int32) + np.where((f2['abs_sum'] > 0)[:, None, None], rec_resi.astype(np.int32), 0), 0, (1 << bd) - 1).astype(np.int16)
+            assert np.array_equal(rr['reco'], exp), [int(v) for v in row]
+            nrt += n
+    assert nfwd == 220 * 40 and ninv > 300 and nrt > 2000, (nfwd, ninv, nrt)

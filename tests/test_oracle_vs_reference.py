@@ -509,3 +509,37 @@ def test_dep_quant_against_the_reference_member(opt):
                     assert np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, (w, h, bd, qp, lam, scale, mts, lf, sbt, int((qO != qR).sum()))
                     n += 1; nonzero += int(lR.value >= 0); big += int(np.abs(qR).max() > 127)
     assert n == 1050 and nonzero > 500 and big > 10, (n, nonzero, big)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_transform_skip_and_chroma_against_the_reference(opt):
+    """TrQuant::xTransformSkip + Quant::quant with the transform-skip QP (floor 4 + 6 * internalMinusInputBitDepth, no transform shift), Quant::xNeedRDOQ in full
+    (dependent-quantisation QP only for non-skipped transforms, the transform shift it keeps for skipped ones, 256 for chroma components), Quant::dequant +
+    xITransformSkip: the oracle's restatements against the members on the probe's rig (luma, and Cb on a 4:4:4 rig), with and without sign-bit hiding"""
+    import ctypes
+    from _libs import oracle, refshim, P
+    import cases as C
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    I32 = ctypes.c_int32
+    n = 0; nts = 0; ninv = 0
+    for row in C.ts_cases():
+        w, h, st, bd, amp, qp, irap, sh, dq, ts, delta, comp, seed = [int(v) for v in row]
+        resi = C.ts_inputs(row)
+        cR = np.zeros((h, w), np.int32); qR = np.zeros((h, w), np.int16); sR = I32(); lR = I32(); nR = I32()
+        assert R.refshim_transform_quant_ts(P(resi), st, w, h, bd, qp, irap, sh, dq, ts, delta, comp, P(cR), P(qR), ctypes.byref(sR), ctypes.byref(lR), ctypes.byref(nR)) == 0
+        cO = np.zeros((h, w), np.int32); qO = np.zeros((h, w), np.int16); sO = I32(); lO = I32()
+        if ts:
+            assert O.orc_transform_quant_ts(P(resi), st, w, h, bd, qp, irap, sh, delta, P(cO), P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+        else:
+            assert O.orc_transform_quant_ex(0, 0, P(resi), st, w, h, bd, qp, irap, sh, P(cO), P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+        assert np.array_equal(cO, cR) and np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, [int(v) for v in row]
+        assert O.orc_need_rdoq_ex(P(cO), w, h, bd, qp, dq, ts, delta, comp) == nR.value, [int(v) for v in row]
+        n += 1; nts += ts
+        if ts and sR.value > 0:
+            rR = np.zeros((h, st), np.int16); rO = np.zeros((h, st), np.int16); dR = np.zeros((h, w), np.int32); dO = np.zeros((h, w), np.int32)
+            assert R.refshim_inv_transform_quant_ts(P(qR), w, h, bd, qp, delta, P(dR), P(rR), st) == 0
+            assert O.orc_inv_transform_quant_ts(P(qR), w, h, bd, qp, delta, P(dO), P(rO), st) == 0
+            assert np.array_equal(dR, dO) and np.array_equal(rR[:, :w], rO[:, :w]), [int(v) for v in row]
+            ninv += 1
+    assert n == 220 and nts >= 80 and ninv > 40, (n, nts, ninv)
