@@ -255,7 +255,8 @@ int vvb_search_refine_tu( vvb_ctx* ctx, int org_plane, int ref_plane, int levels
 int vvb_pack_levels_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_q, const int32_t* dev_last_pos, int n, int16_t* out_packed, uint32_t* dev_offsets );
 int vvb_scan_order( int w, int h, int32_t* out );
 
-/* ---- dependent quantisation: DepQuant::quant -> xQuantDQ (CommonLib/DepQuant.cpp:1462-1490, 1129-1264) for luma TUs without scaling lists --------
+/* ---- dependent quantisation: DepQuant::quant -> xQuantDQ (CommonLib/DepQuant.cpp:1462-1490, 1129-1264), luma and chroma TUs (par->is_chroma
+ * selects the chroma context offsets of the scan tables; qp and the rate tables are then the chroma ones), without scaling lists --------
  * The 4-state trellis over the scan positions of each TU (xDecide / xDecideAndUpdate :1266-1414, the rate-distortion checks :697-888, the state updates
  * :907-1110, CommonCtx::update :473-531) runs on the device, one TU per thread, all TUs of the call sharing shape, QP, lambda and the rate tables.
  * What the caller supplies is what depends on the encoder's entropy-coding state at that point of the CTU:

@@ -129,7 +129,7 @@ inline void xQuantDQB200( DepQuant& dq, TrQuant& tq, TransformUnit& tu, const CC
   for( int i = 0; i < 21; i++ ) for( int b = 0; b < 6; b++ ) rates.gtx_bits[i][b] = re.gtxFracBits()[i].bits[b];
   vvb_dq_par dp = {};
   dp.lambda = lambda; dp.dq_thr_val = dq.m_quant.m_DqThrVal;
-  dp.zero_out = ( tu.mtsIdx[compID] > MTS_SKIP || ( tu.cs->sps->MTS && tu.cu->sbtInfo != 0 && h <= 32 && w <= 32 ) ) ? 1 : 0;     // DepQuant.cpp:1155
+  dp.zero_out = ( ( tu.mtsIdx[compID] > MTS_SKIP || ( tu.cs->sps->MTS && tu.cu->sbtInfo != 0 && h <= 32 && w <= 32 ) ) && compID == COMP_Y ) ? 1 : 0;     // DepQuant.cpp:1155
   par.lfnst_idx = ( tu.cu->lfnstIdx > 0 && tu.mtsIdx[compID] != MTS_SKIP ) ? tu.cu->lfnstIdx : 0;                                // :1164
   std::vector<int32_t> coef( (size_t) w * h );
   std::vector<int16_t> q( (size_t) w * h );

@@ -16,19 +16,19 @@
 using namespace vvbdq;
 
 namespace {
-struct Tables { std::vector<DqScanInfo> si; std::vector<DqNbOut> nb; DqShapeTables shapes[25]; Tables() { dq_build_tables( si, nb, shapes ); } };
-const Tables& tables() { static Tables t; return t; }
+struct Tables { std::vector<DqScanInfo> si; std::vector<DqNbOut> nb; DqShapeTables shapes[25]; explicit Tables( bool chroma ) { dq_build_tables( si, nb, shapes, chroma ); } };
+const Tables& tables( int chroma = 0 ) { static Tables l( false ), c( true ); return chroma ? c : l; }
 }
 
 extern "C" {
 
 // rates: the 266 int32 of vvb_dq_rates; coef [n][h][w]; q [n][h][w]; absSum / lastPos [n]
-int orc_dep_quant( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int zeroOut, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
-                   int16_t* q, int32_t* absSum, int32_t* lastPos )
+static int dep_quant_any( int chroma, int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int zeroOut, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
+                          int16_t* q, int32_t* absSum, int32_t* lastPos )
 {
   const int idx = dq_shape_index( w, h );
   if( idx < 0 ) return -1;
-  const Tables& t = tables();
+  const Tables& t = tables( chroma );
   DqShape sh; sh.width = w; sh.height = h; sh.numCoeff = t.shapes[idx].numCoeff; sh.numSbb = t.shapes[idx].numSbb;
   sh.scanInfo = t.si.data() + t.shapes[idx].offset; sh.nbOut = t.nb.data() + t.shapes[idx].offset;
   const DqQuant qu = dq_init_quant( w, h, bitDepth, qp + 6 * ( bitDepth - 8 ), lambda, dqThrVal );
@@ -41,6 +41,18 @@ int orc_dep_quant( int w, int h, int bitDepth, int qp, double lambda, int dqThrV
   return 0;
 }
 
+int orc_dep_quant( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int zeroOut, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
+                   int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  return dep_quant_any( 0, w, h, bitDepth, qp, lambda, dqThrVal, zeroOut, lfnst, scalarMembers, rates, coef, n, q, absSum, lastPos );
+}
+// chroma component: the chroma context offsets in the scan tables; qp is the mapped chroma QP minus qpBdOffset, rates come from the chroma context sets
+int orc_dep_quant_chroma( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
+                          int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  return dep_quant_any( 1, w, h, bitDepth, qp, lambda, dqThrVal, 0, lfnst, scalarMembers, rates, coef, n, q, absSum, lastPos );
+}
+
 int orc_dep_quant_constants( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int64_t out[9] )
 {
   if( dq_shape_index( w, h ) < 0 ) return -1;
@@ -50,11 +62,13 @@ int orc_dep_quant_constants( int w, int h, int bitDepth, int qp, double lambda, 
 }
 
 // scan geometry of one shape, for table-level pins: scanInfo as 24-byte records, nbOut as 16-byte records
-int orc_dep_quant_tables( int w, int h, void* scanInfoOut, void* nbOutOut )
+int orc_dep_quant_tables_ex( int chroma, int w, int h, void* scanInfoOut, void* nbOutOut );
+int orc_dep_quant_tables( int w, int h, void* scanInfoOut, void* nbOutOut ) { return orc_dep_quant_tables_ex( 0, w, h, scanInfoOut, nbOutOut ); }
+int orc_dep_quant_tables_ex( int chroma, int w, int h, void* scanInfoOut, void* nbOutOut )
 {
   const int idx = dq_shape_index( w, h );
   if( idx < 0 ) return -1;
-  const Tables& t = tables();
+  const Tables& t = tables( chroma );
   const int nc = t.shapes[idx].numCoeff;
   if( scanInfoOut ) memcpy( scanInfoOut, t.si.data() + t.shapes[idx].offset, sizeof( DqScanInfo ) * nc );
   if( nbOutOut ) memcpy( nbOutOut, t.nb.data() + t.shapes[idx].offset, sizeof( DqNbOut ) * nc );

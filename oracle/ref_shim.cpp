@@ -761,12 +761,22 @@ int refshim_transform_quant_lfnst_b200( const int16_t* resi, int stride, int w, 
 // depQuantEnabled, scaling lists off -- on the TU rig, with a CABAC context set initialised the way a slice start does it (Ctx::init( qp, initId )).
 // enableOpt selects the members the DepQuant constructor installs: 0 = scalar (DQIntern::checkAllRdCosts, updateStates, ...), 1 = initDepQuantX86's.
 // ratesOut: the RateEstimator tables initCtx left, in vvb_dq_rates layout (266 int32); quantOut: the 9 Quantizer constants.
+int refshim_dep_quant_comp( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal, int enableOpt,
+                            int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* ratesOut, int64_t* quantOut );
 int refshim_dep_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal, int enableOpt,
                        int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* ratesOut, int64_t* quantOut )
 {
+  return refshim_dep_quant_comp( 0, coef, w, h, bitDepth, qp, mtsIdx, intraCu, lfnstIdx, sbtInfo, lambda, dqThrVal, enableOpt, ctxQp, ctxInitId, q, absSum, lastPos, ratesOut, quantOut );
+}
+// comp = 1: the Cb component of a 4:4:4 rig (the QpParam of the luma component stands in: the chroma QP mapping is host work on both sides)
+int refshim_dep_quant_comp( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal, int enableOpt,
+                            int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* ratesOut, int64_t* quantOut )
+{
   RefCtx& c = ctx();
   TuRig& r = rig();
-  r.setup( w, h, bitDepth, mtsIdx, false, intraCu != 0, qp );
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.setup( w, h, bitDepth, mtsIdx, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  if( comp ) r.tu.mtsIdx[COMP_Cb] = 0;
   r.slice.depQuantEnabled = true;
   r.cu.lfnstIdx = (uint8_t) lfnstIdx; r.cu.sbtInfo = (uint8_t) sbtInfo;
   static thread_local std::unique_ptr<DepQuant> dqs[2];
@@ -779,14 +789,14 @@ int refshim_dep_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, 
   QpParam qpp( r.tu, COMP_Y, false );
   CCoeffBuf src( coef, w, w, h );
   TCoeff sum = 0;
-  dq->xQuantDQ( r.tu, src, COMP_Y, qpp, lambda, *cabac, sum, false, nullptr );
+  dq->xQuantDQ( r.tu, src, compID, qpp, lambda, *cabac, sum, false, nullptr );
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
-  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  *absSum = sum; *lastPos = r.tu.lastPos[compID];
   if( ratesOut )
   {
     // the estimator is only initialised when a first position was found (:1192-1199): run it here in any case so that callers always get the tables
-    const DQIntern::TUParameters& tuPars = *dq->m_scansRom->getTUPars( r.tu.blocks[COMP_Y], COMP_Y );
-    ( (DQIntern::RateEstimator&) *dq ).initCtx( tuPars, r.tu, COMP_Y, cabac->getFracBitsAcess() );
+    const DQIntern::TUParameters& tuPars = *dq->m_scansRom->getTUPars( r.tu.blocks[compID], compID );
+    ( (DQIntern::RateEstimator&) *dq ).initCtx( tuPars, r.tu, compID, cabac->getFracBitsAcess() );
     const DQIntern::RateEstimator& re = (const DQIntern::RateEstimator&) *dq;      // private base: only a C-style cast reaches it
     int32_t* o = ratesOut;
     for( int i = 0; i < 32; i++ ) *o++ = re.m_lastBitsX[i];
@@ -797,7 +807,7 @@ int refshim_dep_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, 
   }
   if( quantOut )
   {
-    dq->m_quant.initQuantBlock( r.tu, COMP_Y, qpp, lambda );
+    dq->m_quant.initQuantBlock( r.tu, compID, qpp, lambda );
     const DQIntern::Quantizer& z = dq->m_quant;
     quantOut[0] = z.m_QShift; quantOut[1] = z.m_maxQIdx; quantOut[2] = z.m_thresLast; quantOut[3] = z.m_DistShift; quantOut[4] = z.m_QAdd; quantOut[5] = z.m_QScale;
     quantOut[6] = z.m_DistAdd; quantOut[7] = z.m_DistStepAdd; quantOut[8] = z.m_DistOrgFact;
@@ -807,12 +817,21 @@ int refshim_dep_quant( const int32_t* coef, int w, int h, int bitDepth, int qp, 
 }
 
 // the same TU through integration/TrQuantB200.h (xQuantDQB200: rate tables from the CABAC state here, trellis in the bound library); returns 1 when the binding threw
+int refshim_dep_quant_b200_comp( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal,
+                                 int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int refshim_dep_quant_b200( const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal,
                             int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos )
 {
+  return refshim_dep_quant_b200_comp( 0, coef, w, h, bitDepth, qp, mtsIdx, intraCu, lfnstIdx, sbtInfo, lambda, dqThrVal, ctxQp, ctxInitId, q, absSum, lastPos );
+}
+int refshim_dep_quant_b200_comp( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int mtsIdx, int intraCu, int lfnstIdx, int sbtInfo, double lambda, int dqThrVal,
+                                 int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
   RefCtx& c = ctx();
   TuRig& r = rig();
-  r.setup( w, h, bitDepth, mtsIdx, false, intraCu != 0, qp );
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.setup( w, h, bitDepth, mtsIdx, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  if( comp ) r.tu.mtsIdx[COMP_Cb] = 0;
   r.slice.depQuantEnabled = true;
   r.cu.lfnstIdx = (uint8_t) lfnstIdx; r.cu.sbtInfo = (uint8_t) sbtInfo;
   if( lfnstIdx ) { r.sps.LFNST = true; r.cu.intraDir[CH_L] = PLANAR_IDX; r.cu.intraDir[CH_C] = DM_CHROMA_IDX; r.cu.mipFlag = false; r.cu.ispMode = 0; r.cu.chromaFormat = CHROMA_400; }
@@ -826,24 +845,26 @@ int refshim_dep_quant_b200( const int32_t* coef, int w, int h, int bitDepth, int
   CCoeffBuf src( coef, w, w, h );
   TCoeff sum = 0;
   int rc = 0;
-  try { xQuantDQB200( *dq, tqOfThread(), r.tu, src, COMP_Y, qpp, lambda, *cabac, sum ); }
+  try { xQuantDQB200( *dq, tqOfThread(), r.tu, src, compID, qpp, lambda, *cabac, sum ); }
   catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
   r.cu.lfnstIdx = 0; r.cu.sbtInfo = 0; r.slice.depQuantEnabled = false; r.sps.LFNST = false;
   if( rc ) return rc;
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
-  *absSum = sum; *lastPos = r.tu.lastPos[COMP_Y];
+  *absSum = sum; *lastPos = r.tu.lastPos[compID];
   return 0;
 }
 
 // scan geometry of DQIntern::Rom for one luma shape, repacked into the 24- / 16-byte records of vvenc_b200/csrc/depquant_core.h (DqScanInfo, DqNbOut);
 // fields the reference leaves unset (nextSbbRight / nextSbbBelow off group starts, everything "next" at scan position 0) are reported as 0
-int refshim_dep_quant_tables( int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut )
+int refshim_dep_quant_tables_ex( int chroma, int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut );
+int refshim_dep_quant_tables( int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut ) { return refshim_dep_quant_tables_ex( 0, w, h, scanInfoOut, nbOutOut ); }
+int refshim_dep_quant_tables_ex( int chroma, int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut )
 {
   ctx();
   static thread_local std::unique_ptr<DepQuant> dq;
   if( !dq ) dq.reset( new DepQuant( nullptr, true, false, false ) );
-  const CompArea area( COMP_Y, CHROMA_400, Area( 0, 0, w, h ) );
-  const DQIntern::TUParameters& tp = *dq->m_scansRom->getTUPars( area, COMP_Y );
+  const CompArea area( chroma ? COMP_Cb : COMP_Y, chroma ? CHROMA_444 : CHROMA_400, Area( 0, 0, w, h ) );
+  const DQIntern::TUParameters& tp = *dq->m_scansRom->getTUPars( area, chroma ? COMP_Cb : COMP_Y );
   const int nc = (int) tp.m_numCoeff;
   for( int i = 0; i < nc; i++ )
   {

@@ -313,6 +313,17 @@ def main(mock_path):
         if rc or not (np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
             bad.append(['dq'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
     res['dep_quant'] = {'cases': ndq, 'non_empty': nz, 'bad': bad[:5]}
+    bad = []; ndc = 0
+    for row in C.dq_chroma_cases():
+        w, h, bd, qp, lam1000, scale, decay10, lf, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_chroma_inputs(row)
+        qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32(); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32()
+        assert R.refshim_dep_quant_comp(1, P(coef), w, h, bd, qp, 0, intra, lf, 0, lam1000 / 1000.0, 8, 1, qp, init_id, P(qa), ctypes.byref(sa), ctypes.byref(la), None, None) == 0
+        rc = R.refshim_dep_quant_b200_comp(1, P(coef), w, h, bd, qp, 0, intra, lf, 0, lam1000 / 1000.0, 8, qp, init_id, P(qb), ctypes.byref(sb), ctypes.byref(lb))
+        ndc += 1
+        if rc or not (np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
+            bad.append(['dq_chroma'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+    res['dep_quant_chroma'] = {'cases': ndc, 'bad': bad[:5]}
     print('RESULT ' + json.dumps(res))
 
 

@@ -49,6 +49,7 @@ def dq_oracle():
             subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle')])
         L = ctypes.CDLL(so)
         L.orc_dep_quant.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_dep_quant_chroma.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_dep_quant_constants.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
         _dqoracle = L
     return _dqoracle
@@ -80,6 +81,8 @@ def refshim():
         L.refshim_pattern_search_member.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.refshim_dep_quant.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
+        L.refshim_dep_quant_comp.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
+        L.refshim_dep_quant_b200_comp.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_dep_quant_b200.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_set_simd(b'AVX2')
         _ref = L

@@ -366,3 +366,29 @@ def ts_inputs(row):
     w, h, st, bd, amp = [int(v) for v in row[:5]]
     rs = np.random.RandomState(int(row[12]))
     return rs.randint(-amp, amp + 1, size=(h, st)).astype(np.int16)
+
+
+def dq_chroma_cases():
+    """chroma components: rows w, h, bit_depth, qp, lambda * 1000, scale, decay * 10, lfnstIdx (0), intraCu, ctxInitId, seed"""
+    rows = []
+    rs = np.random.RandomState(815)
+    seed = 15000
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (32, 8), (16, 32), (64, 64)]:
+        for k in range(8):
+            bd = 8 if k % 4 == 3 else 10
+            rows.append([w, h, bd, int(rs.choice([17, 27, 37, 47])), int(float(rs.choice([3.0, 11.7, 57.3, 800.0])) * 1000), int(rs.choice([5, 20, 200, 2000, 30000])),
+                         int(rs.choice([1, 5, 10])), 0, int(rs.randint(2)), k % 3, seed])
+            seed += 1
+    return np.array(rows, dtype=np.int64)
+
+
+def dq_chroma_inputs(row):
+    w, h, bd, qp, lam1000, scale, decay10 = [int(v) for v in row[:7]]
+    rs = np.random.RandomState(int(row[10]))
+    coef = rs.laplace(0, scale, size=(h, w)) * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** (decay10 / 10.0))
+    coef = np.clip(coef, -32768, 32767).astype(np.int32)
+    if w > 32:
+        coef[:, 32:] = 0
+    if h > 32:
+        coef[32:, :] = 0
+    return coef

@@ -31,6 +31,22 @@ def main():
         if not np.array_equal(lv[0], lv[1]):
             out['q_x86_%d' % i] = lv[1]; differ += 1
     out['rates'] = rates; out['consts'] = consts; out['meta'] = meta
+    # chroma components (Cb of a 4:4:4 rig): the chroma context sets and context offsets
+    R.refshim_dep_quant_comp.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
+    crow = C.dq_chroma_cases()
+    crates = np.zeros((len(crow), 266), dtype=np.int32); cmeta = np.zeros((len(crow), 2), dtype=np.int32)
+    for i, row in enumerate(crow):
+        w, h, bd, qp, lam1000, scale, decay10, lf, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_chroma_inputs(row)
+        lv = []
+        for opt in (0, 1):
+            q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); l = ctypes.c_int32()
+            assert R.refshim_dep_quant_comp(1, P(coef), w, h, bd, qp, 0, intra, lf, 0, lam1000 / 1000.0, 8, opt, qp, init_id, P(q), ctypes.byref(s), ctypes.byref(l), P(crates[i]), None) == 0
+            lv.append(q)
+        cmeta[i] = (s.value, l.value); out['cq_%d' % i] = lv[1]            # the x86 members (what the library follows by default)
+        if not np.array_equal(lv[0], lv[1]):
+            out['cq_scalar_%d' % i] = lv[0]
+    out['chroma_cases'] = crow; out['chroma_rates'] = crates; out['chroma_meta'] = cmeta
     path = os.path.join(HERE, 'golden_v5_depquant.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, len(rows), 'cases,', differ, 'with scalar != x86 members,', int((meta[:, 0, 1] >= 0).sum()), 'non-empty,', os.path.getsize(path), 'bytes')

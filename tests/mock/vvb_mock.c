@@ -16,6 +16,8 @@ uint64_t orc_mv_cost( double lambda, int x, int y, int predHor, int predVer, int
 void     orc_frac_cost_grid( const Pel* orgPlane, int so, const Pel* refPlane, int sr, const int32_t* blk, int n, int family, int bitDepth, int reduceTap, int altHpel, uint32_t* out );
 int      orc_dep_quant( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int zeroOut, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
                         int16_t* q, int32_t* absSum, int32_t* lastPos );   /* oracle/depquant_oracle.cpp */
+int      orc_dep_quant_chroma( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
+                               int16_t* q, int32_t* absSum, int32_t* lastPos );
 void     orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPlane, int sb, const int32_t* desc, int n, int bitDepth, int32_t* out );
 
 #define MOCK_PLANES 64
@@ -307,8 +309,10 @@ int vvb_dep_quant( vvb_ctx* c, const vvb_tu_par* par, const vvb_dq_par* dq, cons
   {
     int32_t s = 0, l = -1;
     if( need_rdoq && !need_rdoq[i] ) memset( q + i * area, 0, sizeof( int16_t ) * area );
-    else if( orc_dep_quant( par->w, par->h, par->bit_depth, par->qp, dq->lambda, dq->dq_thr_val, dq->zero_out, par->lfnst_idx > 0, dq->scalar_members, (const int32_t*) rates,
-                            coef + i * area, 1, q + i * area, &s, &l ) ) return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
+    else if( par->is_chroma ? orc_dep_quant_chroma( par->w, par->h, par->bit_depth, par->qp, dq->lambda, dq->dq_thr_val, par->lfnst_idx > 0, dq->scalar_members, (const int32_t*) rates,
+                                                    coef + i * area, 1, q + i * area, &s, &l )
+                            : orc_dep_quant( par->w, par->h, par->bit_depth, par->qp, dq->lambda, dq->dq_thr_val, dq->zero_out, par->lfnst_idx > 0, dq->scalar_members, (const int32_t*) rates,
+                                             coef + i * area, 1, q + i * area, &s, &l ) ) return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
     if( abs_sum ) abs_sum[i] = s;
     if( last_pos ) last_pos[i] = l;
   }

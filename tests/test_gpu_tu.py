@@ -391,3 +391,20 @@ def test_gpu_transform_skip_and_chroma_vs_oracle(gpu):
             assert np.array_equal(rr['reco'], exp), [int(v) for v in row]
             nrt += n
     assert nfwd == 220 * 40 and ninv > 300 and nrt > 2000, (nfwd, ninv, nrt)
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+def test_gpu_dep_quant_chroma_golden(gpu, golden_depquant, engine):
+    """vvb_dep_quant with vvb_tu_par.is_chroma: the chroma scan-table set on the device against the levels the reference produced for Cb components"""
+    g = golden_depquant
+    gpu.eng.set_depquant_engine(engine)
+    rows = C.dq_chroma_cases()
+    assert np.array_equal(rows, g['chroma_cases'])
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, scale, decay10, lf, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_chroma_inputs(row)[None]
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, lfnst_idx=lf, is_chroma=True)
+        r = gpu.eng.dep_quant(par, gpu.eng.dq_rates(g['chroma_rates'][i]), coef, lam1000 / 1000.0, 8, False)
+        assert np.array_equal(r['q'][0], g['cq_%d' % i]), (i, [int(v) for v in row])
+        assert (int(r['abs_sum'][0]), int(r['last_pos'][0])) == tuple(int(v) for v in g['chroma_meta'][i]), i
+    gpu.eng.set_depquant_engine(1)

@@ -110,3 +110,26 @@ def test_oracle_dep_quant_golden(golden_depquant):
             assert (s.value, l.value) == tuple(int(v) for v in g['meta'][i, 0 if scalar else 1]), (i, scalar)
         nonzero += int(l.value >= 0)
     assert nonzero > 100
+
+
+def test_oracle_dep_quant_chroma_golden(golden_depquant):
+    """chroma components: context offsets of the chroma branch of xSetScanInfo, rate tables of the chroma context sets"""
+    import ctypes
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_depquant
+    rows = C.dq_chroma_cases()
+    assert np.array_equal(rows, g['chroma_cases'])
+    nz = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, scale, decay10, lf, intra, init_id, seed = [int(v) for v in row]
+        coef = C.dq_chroma_inputs(row)
+        rates = np.ascontiguousarray(g['chroma_rates'][i])
+        for scalar in (0, 1):
+            q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); l = ctypes.c_int32()
+            assert O.orc_dep_quant_chroma(w, h, bd, qp, lam1000 / 1000.0, 8, lf, scalar, P(rates), P(coef), 1, P(q), ctypes.byref(s), ctypes.byref(l)) == 0
+            name = 'cq_scalar_%d' % i
+            want = g[name] if (scalar and name in g) else g['cq_%d' % i]
+            assert np.array_equal(q, want), (i, scalar)
+        nz += int(l.value >= 0)
+    assert nz > 30

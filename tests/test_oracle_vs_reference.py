@@ -543,3 +543,34 @@ def test_transform_skip_and_chroma_against_the_reference(opt):
             assert np.array_equal(dR, dO) and np.array_equal(rR[:, :w], rO[:, :w]), [int(v) for v in row]
             ninv += 1
     assert n == 220 and nts >= 80 and ninv > 40, (n, nts, ninv)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_dep_quant_chroma_against_the_reference_member(opt):
+    """DepQuant::xQuantDQ on the Cb component of a 4:4:4 rig: chroma scan tables (compared with the reference's Rom entry by entry) and chroma rate tables"""
+    import ctypes
+    from _libs import dq_oracle, refshim, P
+    O = dq_oracle(); R = refshim()
+    for w in (4, 8, 16, 32, 64):
+        for h in (4, 8, 16, 32, 64):
+            nc = min(w, 32) * min(h, 32)
+            a = np.zeros(nc * 24, np.uint8); b = np.zeros(nc * 16, np.uint8); c = np.zeros(nc * 24, np.uint8); d = np.zeros(nc * 16, np.uint8)
+            assert R.refshim_dep_quant_tables_ex(1, w, h, P(a), P(b)) == nc and O.orc_dep_quant_tables_ex(1, w, h, P(c), P(d)) == nc
+            assert np.array_equal(a, c) and np.array_equal(b, d), (w, h)
+    rs = np.random.RandomState(700 + opt); n = 0; nz = 0
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (32, 8), (16, 32), (64, 64), (16, 4)]:
+        for bd in (10, 8):
+            for qp in (17, 27, 37, 47):
+                for trial in range(5):
+                    lam = float(rs.choice([3.0, 11.7, 57.3, 800.0])); scale = float(rs.choice([5, 20, 200, 2000, 30000])); dec = float(rs.choice([0.1, 0.5, 1.0]))
+                    coef = rs.laplace(0, scale, size=(h, w)) * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** dec)
+                    coef = np.clip(coef, -32768, 32767).astype(np.int32)
+                    if w > 32: coef[:, 32:] = 0
+                    if h > 32: coef[32:, :] = 0
+                    q = np.zeros((h, w), np.int16); s = ctypes.c_int32(); l = ctypes.c_int32(); rates = np.zeros(266, np.int32)
+                    assert R.refshim_dep_quant_comp(1, P(coef), w, h, bd, qp, 0, int(rs.randint(2)), 0, 0, lam, 8, opt, int(rs.randint(17, 52)), trial % 3, P(q), ctypes.byref(s), ctypes.byref(l), P(rates), None) == 0
+                    q2 = np.zeros((h, w), np.int16); s2 = ctypes.c_int32(); l2 = ctypes.c_int32()
+                    assert O.orc_dep_quant_chroma(w, h, bd, qp, lam, 8, 0, 1 - opt, P(rates), P(coef), 1, P(q2), ctypes.byref(s2), ctypes.byref(l2)) == 0
+                    assert np.array_equal(q, q2) and s.value == s2.value and l.value == l2.value, (w, h, bd, qp, lam, scale)
+                    n += 1; nz += int(l.value >= 0)
+    assert n == 400 and nz > 150, (n, nz)

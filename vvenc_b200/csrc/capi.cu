@@ -1397,9 +1397,13 @@ namespace {
 int dqTables( vvb_ctx* ctx )
 {
   if( ctx->dqShapes ) return VVB_OK;
-  std::vector<vvbdq::DqScanInfo> si; std::vector<vvbdq::DqNbOut> nb;
-  vvbdq::DqShapeTables* shapes = new vvbdq::DqShapeTables[25];
-  vvbdq::dq_build_tables( si, nb, shapes );
+  // two table sets: luma, then chroma (the context offsets of the next position differ per channel type, DepQuant.cpp:321-330)
+  std::vector<vvbdq::DqScanInfo> si, siC; std::vector<vvbdq::DqNbOut> nb, nbC;
+  vvbdq::DqShapeTables* shapes = new vvbdq::DqShapeTables[50];
+  vvbdq::dq_build_tables( si, nb, shapes, false );
+  vvbdq::dq_build_tables( siC, nbC, shapes + 25, true );
+  for( int i = 0; i < 25; i++ ) shapes[25 + i].offset += si.size();
+  si.insert( si.end(), siC.begin(), siC.end() ); nb.insert( nb.end(), nbC.begin(), nbC.end() );
   if( cudaMalloc( &ctx->d_dqScan, si.size() * sizeof( vvbdq::DqScanInfo ) ) != cudaSuccess || cudaMalloc( &ctx->d_dqNb, nb.size() * sizeof( vvbdq::DqNbOut ) ) != cudaSuccess ||
       cudaMemcpy( ctx->d_dqScan, si.data(), si.size() * sizeof( vvbdq::DqScanInfo ), cudaMemcpyHostToDevice ) != cudaSuccess ||
       cudaMemcpy( ctx->d_dqNb, nb.data(), nb.size() * sizeof( vvbdq::DqNbOut ), cudaMemcpyHostToDevice ) != cudaSuccess )
@@ -1426,13 +1430,13 @@ int vvb_dep_quant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq
   CU( cudaSetDevice( ctx->device ) );
   int rc;
   if( ( rc = dqTables( ctx ) ) ) return rc;
-  const vvbdq::DqShapeTables& st = static_cast<vvbdq::DqShapeTables*>( ctx->dqShapes )[shapeIdx];
+  const vvbdq::DqShapeTables& st = static_cast<vvbdq::DqShapeTables*>( ctx->dqShapes )[shapeIdx + ( par->is_chroma ? 25 : 0 )];
   DqLaunch L;
   L.shape.width = st.width; L.shape.height = st.height; L.shape.numCoeff = st.numCoeff; L.shape.numSbb = st.numSbb;
   L.shape.scanInfo = static_cast<vvbdq::DqScanInfo*>( ctx->d_dqScan ) + st.offset;
   L.shape.nbOut    = static_cast<vvbdq::DqNbOut*>( ctx->d_dqNb ) + st.offset;
   L.quant = vvbdq::dq_init_quant( par->w, par->h, par->bit_depth, par->qp + 6 * ( par->bit_depth - 8 ), dq->lambda, dq->dq_thr_val );
-  L.zeroOutMts = dq->zero_out; L.lfnst = par->lfnst_idx > 0; L.capSum = dq->scalar_members ? 0 : 1;
+  L.zeroOutMts = par->is_chroma ? 0 : dq->zero_out; L.lfnst = par->lfnst_idx > 0;      // the zero-out of :1155 is a luma rule L.capSum = dq->scalar_members ? 0 : 1;
   L.ctxBytes  = (uint32_t)( ( 8 * ( st.numSbb + st.numCoeff ) + 15 ) & ~15 );
   L.slotBytes = (uint32_t)( ( L.ctxBytes + (size_t) st.numCoeff * 2 * sizeof( vvbdq::DqTrellis ) + 15 ) & ~(size_t) 15 );
   vvbdq::DqRates r;

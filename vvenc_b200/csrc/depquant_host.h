@@ -33,8 +33,9 @@ inline void dq_diag( int bw, int bh, std::vector<int>& xs, std::vector<int>& ys 
   }
 }
 
-// all 25 luma shapes (sides 4..64); scanInfo / nbOut are concatenated, shapes[] says where each one starts
-inline void dq_build_tables( std::vector<DqScanInfo>& scanInfo, std::vector<DqNbOut>& nbOut, DqShapeTables shapes[25] )
+// all 25 shapes (sides 4..64) of one channel type; scanInfo / nbOut are concatenated, shapes[] says where each one starts.  chroma: the context offsets of
+// xSetScanInfo's CH_C branch (:326-330) -- the only thing in the tables that depends on the channel type
+inline void dq_build_tables( std::vector<DqScanInfo>& scanInfo, std::vector<DqNbOut>& nbOut, DqShapeTables shapes[25], bool chroma = false )
 {
   scanInfo.clear(); nbOut.clear();
   std::vector<int> cx, cy, gx, gy;
@@ -92,7 +93,7 @@ inline void dq_build_tables( std::vector<DqScanInfo>& scanInfo, std::vector<DqNb
         for( int k = 0; k < no[id].num; k++ ) no[id].outPos[k] = (uint16_t)( no[id].outPos[k] - begSbb );
         no[id].maxDist = (uint16_t)( no[id].maxDist - id );
       }
-      for( int id = 0; id < numCoeff; id++ )                                  // xSetScanInfo (:302-342), luma
+      for( int id = 0; id < numCoeff; id++ )                                  // xSetScanInfo (:302-342)
       {
         DqScanInfo& t = si[id];
         t.rasterPos = (int16_t) raster[id];
@@ -105,8 +106,16 @@ inline void dq_build_tables( std::vector<DqScanInfo>& scanInfo, std::vector<DqNb
         if( id )
         {
           const int nx = id - 1, diag = px[nx] + py[nx];
-          t.sigCtxOffsetNext = (int8_t)( diag < 2 ? 8 : diag < 5 ? 4 : 0 );
-          t.gtxCtxOffsetNext = (int8_t)( diag < 1 ? 16 : diag < 3 ? 11 : diag < 10 ? 6 : 1 );
+          if( !chroma )
+          {
+            t.sigCtxOffsetNext = (int8_t)( diag < 2 ? 8 : diag < 5 ? 4 : 0 );
+            t.gtxCtxOffsetNext = (int8_t)( diag < 1 ? 16 : diag < 3 ? 11 : diag < 10 ? 6 : 1 );
+          }
+          else
+          {
+            t.sigCtxOffsetNext = (int8_t)( diag < 2 ? 4 : 0 );
+            t.gtxCtxOffsetNext = (int8_t)( diag < 1 ? 6 : 1 );
+          }
           t.nextInsidePos = (int8_t)( nx & 15 );
           if( t.insidePos == 0 )
           {
