@@ -1431,12 +1431,13 @@ int vvb_dep_quant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_dq_par* dq
   int rc;
   if( ( rc = dqTables( ctx ) ) ) return rc;
   const vvbdq::DqShapeTables& st = static_cast<vvbdq::DqShapeTables*>( ctx->dqShapes )[shapeIdx + ( par->is_chroma ? 25 : 0 )];
-  DqLaunch L;
+  DqLaunch L = {};
   L.shape.width = st.width; L.shape.height = st.height; L.shape.numCoeff = st.numCoeff; L.shape.numSbb = st.numSbb;
   L.shape.scanInfo = static_cast<vvbdq::DqScanInfo*>( ctx->d_dqScan ) + st.offset;
   L.shape.nbOut    = static_cast<vvbdq::DqNbOut*>( ctx->d_dqNb ) + st.offset;
   L.quant = vvbdq::dq_init_quant( par->w, par->h, par->bit_depth, par->qp + 6 * ( par->bit_depth - 8 ), dq->lambda, dq->dq_thr_val );
-  L.zeroOutMts = par->is_chroma ? 0 : dq->zero_out; L.lfnst = par->lfnst_idx > 0;      // the zero-out of :1155 is a luma rule L.capSum = dq->scalar_members ? 0 : 1;
+  L.zeroOutMts = par->is_chroma ? 0 : dq->zero_out;      // the zero-out of :1155 is a luma rule
+  L.lfnst = par->lfnst_idx > 0; L.capSum = dq->scalar_members ? 0 : 1;
   L.ctxBytes  = (uint32_t)( ( 8 * ( st.numSbb + st.numCoeff ) + 15 ) & ~15 );
   L.slotBytes = (uint32_t)( ( L.ctxBytes + (size_t) st.numCoeff * 2 * sizeof( vvbdq::DqTrellis ) + 15 ) & ~(size_t) 15 );
   vvbdq::DqRates r;
