@@ -1986,6 +1986,7 @@ int vvb_mctf_estimate_pyramid_dev( vvb_ctx* ctx, int orgPlane, int refPlane, con
   const Plane po0 = ctx->planes.p[orgPlane], pr0 = ctx->planes.p[refPlane];
   const int W = po0.width, H = po0.height, u = pp->unit_size, nSub = pp->add_level ? 3 : 2, margin = 128;
   if( pr0.width != W || pr0.height != H ) return fail( ctx, VVB_ERR_ARG, "picture sizes differ" );
+  if( po0.margin < 128 || pr0.margin < 128 ) return fail( ctx, VVB_ERR_ARG, "the MCTF search needs planes with a margin of at least 128 pels (MCTF_PADDING): vectors reach that far" );
   // subsampled planes
   Plane po[4], pr[4]; po[0] = po0; pr[0] = pr0;
   size_t planeBytes[4] = { 0, 0, 0, 0 }, total = 0;
