@@ -13,8 +13,16 @@
  * object file (x86/InitX86.cpp), so the linker's --wrap redirects those two calls to the functions below, which run the original selection and then -- when
  * asked to -- the 10-line `_initRdCostB200()` a maintainer would add.
  *
- * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables]
- * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1>`
+ * With a ninth argument `tu` the transform / quantisation seam is routed through the library as well: TrQuant::transformNxN and TrQuant::invTransformNxN are
+ * called from other object files (IntraSearch.cpp, InterSearch.cpp, EncCu.cpp), so --wrap hands them to the functions below, which keep the members' structure
+ * (TrQuant.cpp:688-736, 318-348) and replace
+ *   xT / xTransformSkip (+ xFwdLfnst for luma)        by xTQuantB200      (integration/TrQuantB200.h -> vvb_fwd_trquant: the coefficients it leaves are what xQuant then reads),
+ *   DepQuant::xQuantDQ (slices with depQuantEnabled)   by xQuantDQB200     (rate tables from the live CABAC contexts -> vvb_dep_quant: the 4-state trellis on the device),
+ *   Quant::dequant + xIT / xITransformSkip             by invTransformNxNB200 (slices without dependent quantisation and TUs without LFNST; the rest stays with the member),
+ * RDOQ (QuantRDOQ2) and everything the bindings THROW for (BDPCM, joint Cb-Cr, scaling lists) stay with the reference members.
+ *
+ * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu]
+ * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_inv=<n> tu_ref=<n>`
  */
 #include <cstdint>
 #include <cstring>
@@ -56,12 +64,22 @@
 #include "CommonLib/Unit.h"
 #include "CommonLib/RdCost.h"
 #include "CommonLib/AffineGradientSearch.h"
+#include "CommonLib/UnitTools.h"
+#include "CommonLib/Slice.h"
+#include "CommonLib/Picture.h"
+#include "CommonLib/CodingStructure.h"
+#include "CommonLib/TrQuant.h"
+#include "CommonLib/Quant.h"
+#include "CommonLib/DepQuant.h"
+#include "CommonLib/Rom.h"
+#include "CommonLib/Contexts.h"
 #undef private
 #undef protected
 
 using namespace vvenc;
 #include "../integration/RdCostB200.h"
 #include "../integration/AffineGradientB200.h"
+#include "../integration/TrQuantB200.h"
 
 static bool               g_useB200 = false;
 static std::atomic<long>  g_rdCostInstalls{ 0 }, g_affineInstalls{ 0 };
@@ -86,6 +104,71 @@ static uint64_t countingDist( vvb_ctx* c, int f, const int16_t* o, int so, const
 static decltype( &vvb_sad_x5_block ) g_realX5 = nullptr;
 static int countingX5( vvb_ctx* c, const int16_t* o, int so, const int16_t* u, int su, int w, int h, int ss, int cc, uint64_t* out ) { g_otherCalls++; return g_realX5( c, o, so, u, su, w, h, ss, cc, out ); }
 
+// ---- the transform / quantisation seam -------------------------------------------------------------------------------------------------------------------------
+static bool g_useTu = false;
+static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuInv{ 0 }, g_tuRef{ 0 };
+
+extern "C" void __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant*, TransformUnit&, ComponentID, const QpParam&, TCoeff&, const Ctx&, bool );
+extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant* self, TransformUnit& tu, ComponentID compID, const QpParam& cQP,
+                                                                                                                         TCoeff& uiAbsSum, const Ctx& ctx, bool loadTr )
+{
+  const ChannelType chType = toChannelType( compID );
+  const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0;
+  // what stays with the member: stored MTS coefficients, BDPCM, LFNST on chroma / ISP CUs (the binding derives the kernel set for plain luma TUs), empty TUs
+  if( !g_useTu || loadTr || tu.noResidual || tu.cu->bdpcmM[chType] || ( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) || tu.cs->sps->scalingListEnabled )
+  {
+    g_tuRef++;
+    __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( self, tu, compID, cQP, uiAbsSum, ctx, loadTr );
+    return;
+  }
+  const CompArea& rect = tu.blocks[compID];
+  const CPelBuf resiBuf = tu.cs->getResiBuf( rect );
+  uiAbsSum = 0;
+  CoeffBuf tempCoeff( self->m_plTempCoeff, rect );
+  try
+  {
+    TCoeff plainSum = 0;
+    xTQuantB200( *self, tu, compID, resiBuf, tempCoeff, cQP, plainSum );              // xT / xTransformSkip (+ xFwdLfnst): tempCoeff as the member leaves it
+    g_tuFwd++;
+  }
+  catch( std::exception& )                                                             // a TU the binding does not cover (joint Cb-Cr, ...): the member
+  {
+    g_tuRef++;
+    __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( self, tu, compID, cQP, uiAbsSum, ctx, loadTr );
+    return;
+  }
+  // xQuant (TrQuant.cpp:730 -> DepQuant::quant, DepQuant.cpp:1462-1490)
+  DepQuant* dq = dynamic_cast<DepQuant*>( self->m_quant );
+  const bool selectiveSkip = dq && tu.cs->picture->useSelectiveRdoq && !dq->xNeedRDOQ( tu, compID, tempCoeff, cQP );
+  if( dq && !selectiveSkip && tu.cs->slice->depQuantEnabled && tu.mtsIdx[compID] != MTS_SKIP )
+  {
+    uiAbsSum = 0;
+    xQuantDQB200( *dq, *self, tu, tempCoeff, compID, cQP, dq->m_dLambda, ctx, uiAbsSum );
+    g_tuDq++;
+  }
+  else
+  {
+    uiAbsSum = 0;
+    self->xQuant( tu, compID, tempCoeff, uiAbsSum, cQP, ctx );
+  }
+  TU::setCbfAtDepth( tu, compID, tu.depth, uiAbsSum > 0 );
+}
+
+extern "C" void __real__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS_11ComponentIDERNS_7AreaBufIsEERKNS_7QpParamE( TrQuant*, TransformUnit&, ComponentID, PelBuf&, const QpParam& );
+extern "C" void __wrap__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS_11ComponentIDERNS_7AreaBufIsEERKNS_7QpParamE( TrQuant* self, TransformUnit& tu, ComponentID compID, PelBuf& pResi, const QpParam& cQP )
+{
+  const ChannelType chType = toChannelType( compID );
+  const bool dqDequant = tu.cs->slice->depQuantEnabled && tu.mtsIdx[compID] != MTS_SKIP;          // DepQuant::dequant walks its state machine (DepQuant.cpp:574-629): the member
+  const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0 && tu.mtsIdx[compID] != MTS_SKIP && ( CU::isSepTree( *tu.cu ) ? true : isLuma( compID ) );
+  if( g_useTu && !dqDequant && !lfnstHere && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )
+  {
+    try { invTransformNxNB200( *self, tu, compID, pResi, cQP ); g_tuInv++; return; }
+    catch( std::exception& ) {}
+  }
+  g_tuRef++;
+  __real__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS_11ComponentIDERNS_7AreaBufIsEERKNS_7QpParamE( self, tu, compID, pResi, cQP );
+}
+
 static void quietLog( void*, int, const char*, va_list ) {}
 
 int main( int argc, char** argv )
@@ -97,6 +180,11 @@ int main( int argc, char** argv )
   if( argc > 8 )
   {
     if( b200Load( argv[8] ) || b200LoadAffine( argv[8] ) ) { fprintf( stderr, "cannot bind %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
+    if( argc > 9 && !strcmp( argv[9], "tu" ) )
+    {
+      if( b200LoadTu( argv[8] ) ) { fprintf( stderr, "cannot bind the TU entry points of %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
+      g_useTu = true;
+    }
     g_useB200 = true;
     g_realDist = g_b200.distBlock; g_b200.distBlock = countingDist;
     g_realX5 = g_b200.sadX5; g_b200.sadX5 = countingX5;
@@ -152,7 +240,8 @@ int main( int argc, char** argv )
   if( fo ) { fwrite( out.data(), 1, out.size(), fo ); fclose( fo ); }
   uint64_t hsh = 1469598103934665603ull;
   for( uint8_t b : out ) { hsh ^= b; hsh *= 1099511628211ull; }
-  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld\n", fed, out.size(), (unsigned long long) hsh,
-          g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load() );
+  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_inv=%llu tu_ref=%llu\n", fed, out.size(),
+          (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuInv.load(),
+          g_tuRef.load() );
   return 0;
 }

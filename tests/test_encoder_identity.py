@@ -16,14 +16,32 @@ MOCK = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
 pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason='oracle/_ref/enc_identity not built (needs /root/reference at build time)')
 
 
-def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600):
+def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False):
     out = str(tmp_path / ('b200.vvc' if lib else 'avx2.vvc'))
-    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else [])
+    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + (['tu'] if tu else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
     line = [l for l in r.stdout.splitlines() if l.startswith('ENC ')][-1]
     kv = dict(f.split('=') for f in line.split()[1:])
     return open(out, 'rb').read(), kv
+
+
+def _identity_tu(tmp_path, W, H, F, preset, qp, lib, want_dq, timeout=900):
+    """the same with TrQuant::transformNxN / invTransformNxN routed through the library (forward transforms, transform skip, LFNST, the DepQuant trellis with rate
+    tables from the live CABAC contexts, the inverse path where the plain dequantiser applies)"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout, tu=True)
+    assert int(kb['tu_fwd']) > 1000 and int(ka['tu_fwd']) == 0
+    if want_dq:
+        assert int(kb['tu_dq']) > 1000, kb                 # the preset enables dependent quantisation: the trellis ran in the library
+    else:
+        assert int(kb['tu_inv']) > 500, kb                 # plain dequantiser: the inverse path ran in the library
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
 
 
 def _identity(tmp_path, W, H, F, preset, qp, lib, timeout=600):
@@ -43,6 +61,20 @@ def test_bitstream_identity_with_b200_tables_on_the_oracle(tmp_path, W, H, F, pr
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity(tmp_path, W, H, F, preset, qp, MOCK)
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp,dq", [(80, 44, 4, 0, 37, False), (80, 44, 3, 2, 37, True), (176, 144, 2, 1, 32, True)])
+def test_bitstream_identity_with_the_tu_seam_on_the_oracle(tmp_path, W, H, F, preset, qp, dq):
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity_tu(tmp_path, W, H, F, preset, qp, MOCK, dq)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,F,preset,qp,dq", [(80, 44, 4, 0, 37, False), (80, 44, 3, 2, 37, True), (176, 144, 2, 1, 32, True)])
+def test_bitstream_identity_with_the_tu_seam_on_the_gpu(tmp_path, W, H, F, preset, qp, dq):
+    kb = _identity_tu(tmp_path, W, H, F, preset, qp, LIB, dq, timeout=1500)
+    print('encoder identity with the TU seam on the GPU:', W, H, F, preset, kb)
 
 
 @pytest.mark.gpu
