@@ -73,7 +73,8 @@ def test_bitstream_identity_with_the_tu_seam_on_the_oracle(tmp_path, W, H, F, pr
 @pytest.mark.gpu
 @pytest.mark.parametrize("W,H,F,preset,qp,dq", [(80, 44, 4, 0, 37, False), (80, 44, 3, 2, 37, True), (176, 144, 2, 1, 32, True)])
 def test_bitstream_identity_with_the_tu_seam_on_the_gpu(tmp_path, W, H, F, preset, qp, dq):
-    kb = _identity_tu(tmp_path, W, H, F, preset, qp, LIB, dq, timeout=1500)
+    import vvenc_b200._lib as VL
+    kb = _identity_tu(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, dq, timeout=1500)
     print('encoder identity with the TU seam on the GPU:', W, H, F, preset, kb)
 
 
