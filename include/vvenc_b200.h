@@ -201,7 +201,8 @@ typedef struct
   int32_t bit_depth;           /* 8 or 10                                                         */
   int32_t qp;                  /* CU QP (cu.qp); +6*(bit_depth-8) applied inside (Quant.cpp:99)   */
   int32_t is_irap;             /* slice->isIRAP(): rounding offset 171 vs 85 (Quant.cpp:772)      */
-  int32_t dep_quant;           /* for need_rdoq only: slice->depQuantEnabled (Quant.cpp:852-855)  */
+  int32_t dep_quant;           /* slice->depQuantEnabled: the QP of need_rdoq (Quant.cpp:852-855); vvb_inv_trquant then dequantises as DepQuant::dequant does
+                                  (state machine + qIdx at QP + 1, DepQuant.cpp:574-629).  The forward calls and the round trip keep the plain quantiser pair */
   int32_t sign_hiding;         /* slice->signDataHidingEnabled: the levels pass through Quant::xSignBitHidingHDQ (Quant.cpp:817-826, 377-518) */
   int32_t lfnst_idx;           /* cu.lfnstIdx of an intra CU: 0 off, 1 / 2 = TrQuant::xFwdLfnst between the transform and the quantiser (TrQuant.cpp:942-1048) */
   int32_t lfnst_set;           /* g_lfnstLut[ xGetLFNSTIntraMode( intra mode ) ], 0..3 (Rom.cpp:95, TrQuant.cpp:806-828)                                     */
@@ -284,7 +285,8 @@ int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_
 
 /* ---- inverse path of the TU loop -------------------------------------------------------------------
  * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
- * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp}. */
+ * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp,transform_skip,...}; with par->dep_quant
+ * (and no transform skip) the dequantiser is DepQuant::dequant's. */
 int vvb_inv_trquant    ( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* q, int n, int16_t* resi );
 int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dev_q, int n, int16_t* dev_resi );
 

@@ -57,7 +57,7 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
   par.transform_skip = skip ? 1 : 0;                                                        // xTransformSkip / xITransformSkip, QP floor 4 + 6 * internalMinusInputBitDepth (Quant.cpp:117-124)
   par.input_bit_depth_delta = sps.internalMinusInputBitDepth[chType];
   par.is_irap = tu.cs->slice->isIRAP() ? 1 : 0;                                              // rounding offset 171 vs 85 (Quant.cpp:772)
-  par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;
+  par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;                                     // xNeedRDOQ's QP; invTransformNxNB200 then dequantises as DepQuant::dequant does
   if( tu.cu->lfnstIdx && forward && isLuma( compID ) && !skip )                                                           // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048): kernel set and transposition from the intra mode
   {
     if( !tu.cs->sps->LFNST || trHor != DCT2 || trVer != DCT2 || skip || isChroma( compID ) ) THROW( "LFNST index on a TU the library does not cover" );

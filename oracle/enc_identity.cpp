@@ -18,7 +18,7 @@
  * (TrQuant.cpp:688-736, 318-348) and replace
  *   xT / xTransformSkip (+ xFwdLfnst for luma)        by xTQuantB200      (integration/TrQuantB200.h -> vvb_fwd_trquant: the coefficients it leaves are what xQuant then reads),
  *   DepQuant::xQuantDQ (slices with depQuantEnabled)   by xQuantDQB200     (rate tables from the live CABAC contexts -> vvb_dep_quant: the 4-state trellis on the device),
- *   Quant::dequant + xIT / xITransformSkip             by invTransformNxNB200 (slices without dependent quantisation and TUs without LFNST; the rest stays with the member),
+ *   Quant::dequant / DepQuant::dequant + xIT / xITransformSkip  by invTransformNxNB200 (TUs without LFNST; the rest stays with the member),
  * RDOQ (QuantRDOQ2) and everything the bindings THROW for (BDPCM, joint Cb-Cr, scaling lists) stay with the reference members.
  *
  * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu]
@@ -158,9 +158,8 @@ extern "C" void __real__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS
 extern "C" void __wrap__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS_11ComponentIDERNS_7AreaBufIsEERKNS_7QpParamE( TrQuant* self, TransformUnit& tu, ComponentID compID, PelBuf& pResi, const QpParam& cQP )
 {
   const ChannelType chType = toChannelType( compID );
-  const bool dqDequant = tu.cs->slice->depQuantEnabled && tu.mtsIdx[compID] != MTS_SKIP;          // DepQuant::dequant walks its state machine (DepQuant.cpp:574-629): the member
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0 && tu.mtsIdx[compID] != MTS_SKIP && ( CU::isSepTree( *tu.cu ) ? true : isLuma( compID ) );
-  if( g_useTu && !dqDequant && !lfnstHere && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )
+  if( g_useTu && !lfnstHere && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )       // plain and DepQuant dequantiser alike (vvb_tu_par.dep_quant)
   {
     try { invTransformNxNB200( *self, tu, compID, pResi, cQP ); g_tuInv++; return; }
     catch( std::exception& ) {}

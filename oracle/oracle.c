@@ -659,6 +659,46 @@ int orc_dequant( const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* 
   return 0;
 }
 
+int orc_inv_transform( int trHor, int trVer, const int32_t* coef, int w, int h, int bitDepth, Pel* resi, int stride );
+/* Dequantiser of dependent quantisation: DQIntern::Quantizer::dequantBlock (CommonLib/DepQuant.cpp:574-629), what DepQuant::dequant runs for non-skipped transforms of
+ * a slice with depQuantEnabled.  Walks the scan from the last significant position down with the 4-state machine (state' = (32040 >> ((state << 2) + ((level & 1) << 1))) & 3);
+ * a level reconstructs from qIdx = 2 * level -+ (state >> 1) at QP + 1.  Positions above the last significant one hold zero levels, which keep state 0, so the walk may
+ * start at the end of the scan.  No scaling lists. */
+int orc_dequant_dq( const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef )
+{
+  int baseQp = qp + 6 * ( bitDepth - 8 );
+  if( baseQp < 0 ) baseQp = 0;
+  if( baseQp > 63 + 6 * ( bitDepth - 8 ) ) baseQp = 63 + 6 * ( bitDepth - 8 );
+  const int qpDQ = baseQp + 1, per = qpDQ / 6, rem = qpDQ - 6 * per;
+  const int sqrt2 = ( ilog2u( w ) + ilog2u( h ) ) & 1;
+  const int trShift = 15 - bitDepth - ( ( ilog2u( w ) + ilog2u( h ) ) >> 1 ) - sqrt2;
+  const int shift = 6 + 1 - per - trShift;                                               /* :607 */
+  int32_t scale = inv_quant_scales[sqrt2][rem];
+  const int32_t add = shift < 0 ? 0 : ( ( 1 << shift ) >> 1 );
+  if( shift < 0 ) scale <<= -shift;                                                      /* :619-622: applied once, at the last position, and kept */
+  int32_t scan[1024];
+  const int nScan = orc_scan_order( w, h, scan );
+  memset( coef, 0, sizeof( int32_t ) * w * h );
+  int state = 0;
+  for( int sp = nScan - 1; sp >= 0; sp-- )
+  {
+    const int32_t level = q[scan[sp]];
+    if( level )
+    {
+      const int32_t qIdx = 2 * level + ( level > 0 ? -( state >> 1 ) : ( state >> 1 ) );
+      const int64_t nom = ( (int64_t) qIdx * scale + add ) >> ( shift < 0 ? 0 : shift );
+      coef[scan[sp]] = (int32_t)( nom < -32768 ? -32768 : ( nom > 32767 ? 32767 : nom ) );
+    }
+    state = ( 32040 >> ( ( state << 2 ) + ( ( level & 1 ) << 1 ) ) ) & 3;
+  }
+  return 0;
+}
+int orc_inv_transform_quant_dq( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride )
+{
+  orc_dequant_dq( q, w, h, bitDepth, qp, coef );
+  return orc_inv_transform( trHor, trVer, coef, w, h, bitDepth, resi, stride );
+}
+
 /* xIT: first pass over columns (vertical transform, shift 7), second over rows (shift 20 - bitDepth); both clip to 16 bit */
 int orc_inv_transform( int trHor, int trVer, const int32_t* coef, int w, int h, int bitDepth, Pel* resi, int stride )
 {

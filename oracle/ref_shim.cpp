@@ -952,6 +952,49 @@ int refshim_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, 
   return 0;
 }
 
+// TrQuant::invTransformNxN of a slice with depQuantEnabled: DepQuant::dequant -> Quantizer::dequantBlock (DepQuant.cpp:1492-1514, 574-629) + xIT.  lastPos: tu.lastPos of the
+// TU (the scan position of the last significant level), which dequantBlock starts from.
+int refshim_inv_transform_quant_dq( int trHor, int trVer, const int16_t* q, int lastPos, int w, int h, int bitDepth, int qp, int32_t* coef, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, false, true, qp );
+  r.slice.depQuantEnabled = true;
+  r.tu.lastPos[COMP_Y] = lastPos;
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  alignas(64) static thread_local TCoeff tmpCoef[ 64 * 64 ];
+  CoeffBuf deq( tmpCoef, w, w, h );
+  tqOfThread().m_quant->dequant( r.tu, deq, COMP_Y, qpp );            // virtual: DepQuant::dequant
+  if( coef ) memcpy( coef, tmpCoef, sizeof( int32_t ) * w * h );
+  PelBuf out( resi, stride, w, h );
+  tqOfThread().xIT( r.tu, COMP_Y, CCoeffBuf( tmpCoef, w, w, h ), out );
+  r.slice.depQuantEnabled = false;
+  return 0;
+}
+
+// the same through integration/TrQuantB200.h (invTransformNxNB200 with par.dep_quant = slice->depQuantEnabled)
+int refshim_inv_transform_quant_dq_b200( int trHor, int trVer, const int16_t* q, int lastPos, int w, int h, int bitDepth, int qp, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  const int mts = mtsIdxFor( trHor, trVer );
+  if( mts < 0 ) return -1;
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, mts, false, true, qp );
+  r.slice.depQuantEnabled = true;
+  r.tu.lastPos[COMP_Y] = lastPos;
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  PelBuf out( resi, stride, w, h );
+  int rc = 0;
+  try { invTransformNxNB200( tqOfThread(), r.tu, COMP_Y, out, qpp ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.slice.depQuantEnabled = false;
+  return rc;
+}
+
 // PelBuf::reconstruct (Buffer.cpp:719) with the slice clipping range of the given bit depth.  The SIMD kernels behind g_pelBufOP use aligned
 // loads (the encoder's CU-local buffers are compact and MEMORY_ALIGN_DEF_SIZE aligned), so the probe marshals through such buffers.
 struct AlignedPel

@@ -300,6 +300,20 @@ def main(mock_path):
             if rc or not np.array_equal(ra[:, :w], rb[:, :w]):
                 bad.append(['ts_inv'] + [int(v) for v in row] + [rc])
     res['tu_ts_chroma'] = {'cases': nts, 'inverse_cases': ninv, 'bad': bad[:5]}
+    # DepQuant::dequant + xIT against invTransformNxNB200 with par.dep_quant
+    bad = []; ndd = 0
+    from _libs import oracle as _orc
+    for row in C.dqd_cases():
+        th, tv, w, h, bd, qp, amp, seed = [int(v) for v in row]
+        so = np.zeros(1024, np.int32); _orc().orc_scan_order(w, h, P(so))
+        q, last = C.dqd_inputs(row, so)
+        ra = np.zeros((h, w), dtype=np.int16); rb = np.zeros((h, w), dtype=np.int16)
+        assert R.refshim_inv_transform_quant_dq(th, tv, P(q), last, w, h, bd, qp, None, P(ra), w) == 0
+        rc = R.refshim_inv_transform_quant_dq_b200(th, tv, P(q), last, w, h, bd, qp, P(rb), w)
+        ndd += 1
+        if rc or not np.array_equal(ra, rb):
+            bad.append(['dqd'] + [int(v) for v in row] + [rc])
+    res['tu_inv_dq'] = {'cases': ndd, 'bad': bad[:5]}
     # DepQuant::xQuantDQ against xQuantDQB200 (rate tables from the rig's CABAC contexts through the public RateEstimator accessors, trellis in the bound library)
     bad = []; ndq = 0; nz = 0
     R.refshim_set_simd(b'AVX2')

@@ -392,3 +392,35 @@ def dq_chroma_inputs(row):
     if h > 32:
         coef[32:, :] = 0
     return coef
+
+
+def dqd_cases():
+    """DepQuant dequantiser + inverse transform: rows trHor, trVer, w, h, bit_depth, qp, amp, seed"""
+    rows = []
+    rs = np.random.RandomState(606)
+    seed = 17000
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 16), (32, 8), (16, 64), (64, 32)]:
+        for (th, tv) in ((0, 0), (2, 2), (1, 2)):
+            if (th or tv) and (w > 32 or h > 32):
+                continue
+            for bd in (8, 10):
+                for k in range(4):
+                    rows.append([th, tv, w, h, bd, int(rs.randint(-6 * (bd - 8), 64)), int(rs.choice([1, 2, 5, 40, 600, 16000])), seed])
+                    seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def dqd_inputs(row, scan):
+    """levels with a random last significant scan position; scan: scan position -> raster index (row pitch w)"""
+    th, tv, w, h, bd, qp, amp, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    ns = min(w, 32) * min(h, 32)
+    last = int(rs.randint(0, ns))
+    vals = rs.randint(-amp, amp + 1, size=last + 1).astype(np.int16)
+    if rs.randint(3) == 0:
+        vals[rs.randint(0, 2, size=last + 1) > 0] = 0
+    if vals[-1] == 0:
+        vals[-1] = 1
+    q = np.zeros((h, w), dtype=np.int16)
+    q.reshape(-1)[scan[:last + 1]] = vals
+    return q, last

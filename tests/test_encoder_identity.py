@@ -38,8 +38,7 @@ def _identity_tu(tmp_path, W, H, F, preset, qp, lib, want_dq, timeout=900):
     assert int(kb['tu_fwd']) > 1000 and int(ka['tu_fwd']) == 0
     if want_dq:
         assert int(kb['tu_dq']) > 1000, kb                 # the preset enables dependent quantisation: the trellis ran in the library
-    else:
-        assert int(kb['tu_inv']) > 500, kb                 # plain dequantiser: the inverse path ran in the library
+    assert int(kb['tu_inv']) > 500, kb                     # the inverse path (plain or DepQuant dequantiser) ran in the library
     assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
     return kb
 

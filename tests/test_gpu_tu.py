@@ -408,3 +408,24 @@ def test_gpu_dep_quant_chroma_golden(gpu, golden_depquant, engine):
         assert np.array_equal(r['q'][0], g['cq_%d' % i]), (i, [int(v) for v in row])
         assert (int(r['abs_sum'][0]), int(r['last_pos'][0])) == tuple(int(v) for v in g['chroma_meta'][i]), i
     gpu.eng.set_depquant_engine(1)
+
+
+def test_gpu_dep_quant_dequantiser_vs_oracle(gpu):
+    """vvb_inv_trquant with vvb_tu_par.dep_quant: DepQuant::dequant's state machine (levels -> qIdx by one warp per TU with a shuffle scan of the state maps) + the
+    inverse transform, batches of TUs with random last positions, against the oracle restatement pinned to the reference member"""
+    from _libs import oracle, P
+    O = oracle()
+    for row in C.dqd_cases():
+        th, tv, w, h, bd, qp, amp, seed = [int(v) for v in row]
+        so = np.zeros(1024, np.int32); O.orc_scan_order(w, h, P(so))
+        n = 24
+        qs = np.zeros((n, h, w), dtype=np.int16)
+        for i in range(n):
+            r2 = row.copy(); r2[7] = seed * 31 + i
+            qs[i], _ = C.dqd_inputs(r2, so)
+        par = gpu.eng.tu_par(w, h, th, tv, bd, qp, False, True)
+        got = gpu.eng.inv_trquant(par, qs)
+        for i in range(n):
+            cO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
+            assert O.orc_inv_transform_quant_dq(th, tv, P(np.ascontiguousarray(qs[i])), w, h, bd, qp, P(cO), P(rO), w) == 0
+            assert np.array_equal(got[i], rO), ([int(v) for v in row], i)

@@ -574,3 +574,23 @@ def test_dep_quant_chroma_against_the_reference_member(opt):
                     assert np.array_equal(q, q2) and s.value == s2.value and l.value == l2.value, (w, h, bd, qp, lam, scale)
                     n += 1; nz += int(l.value >= 0)
     assert n == 400 and nz > 150, (n, nz)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_dep_quant_dequantiser_against_the_reference(opt):
+    """DepQuant::dequant -> Quantizer::dequantBlock (state machine over the scan, qIdx at QP + 1) followed by TrQuant::xIT: dequantised coefficients and residual"""
+    from _libs import oracle, refshim, P
+    import cases as C
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    n = 0
+    for row in C.dqd_cases():
+        th, tv, w, h, bd, qp, amp, seed = [int(v) for v in row]
+        so = np.zeros(1024, np.int32); O.orc_scan_order(w, h, P(so))
+        q, last = C.dqd_inputs(row, so)
+        cR = np.zeros((h, w), np.int32); rR = np.zeros((h, w), np.int16); cO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
+        assert R.refshim_inv_transform_quant_dq(th, tv, P(q), last, w, h, bd, qp, P(cR), P(rR), w) == 0
+        assert O.orc_inv_transform_quant_dq(th, tv, P(q), w, h, bd, qp, P(cO), P(rO), w) == 0
+        assert np.array_equal(cR, cO) and np.array_equal(rR, rO), [int(v) for v in row]
+        n += 1
+    assert n == 168

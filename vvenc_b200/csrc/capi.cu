@@ -1509,6 +1509,23 @@ int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ,
   if( p.lfnstIdx ) return fail( ctx, VVB_ERR_UNSUPPORTED, "the inverse LFNST (TrQuant::xInvLfnst) is not on the device yet" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
+  if( par->dep_quant && !p.ts )
+  {
+    // DepQuant::dequant (DepQuant.cpp:1492-1514 -> Quantizer::dequantBlock :574-629): the state machine turns the levels into qIdx values, which the inverse kernel
+    // then dequantises with the DepQuant scale and shift at QP + 1 -- the same ( v * scale + add ) >> shift it applies to plain levels; no input clipping there
+    const int baseQp = std::max( 0, std::min( 63 + 6 * ( par->bit_depth - 8 ), par->qp + 6 * ( par->bit_depth - 8 ) ) ) + 1;
+    const int per = baseQp / 6, rem = baseQp - 6 * per, sqrt2 = ( p.lw + p.lh ) & 1;
+    const int trShift = 15 - par->bit_depth - ( ( p.lw + p.lh ) >> 1 ) - sqrt2;
+    static const int invScales[2][6] = { { 40, 45, 51, 57, 64, 72 }, { 57, 64, 72, 80, 90, 102 } };
+    p.dqScale = invScales[sqrt2][rem]; p.dqShift = 6 + 1 - per - trShift; p.dqInMax = 32767;
+    void* dIdx;
+    if( ( rc = scratch( ctx, 6, (size_t) n * p.w * p.h * 2, &dIdx ) ) ) return rc;
+    const int lrw = std::min( p.lw, 5 ), nScan = std::min( p.w, 32 ) * std::min( p.h, 32 );
+    const int32_t* fwd = ctx->d_scan + 25 * 1024 + ( ( p.lw - 2 ) * 5 + ( p.lh - 2 ) ) * 1024;
+    dq_levels_to_qidx_kernel<<<( n + 3 ) / 4, 128, 0, ctx->stream>>>( dQ, fwd, p.w, p.h, lrw, nScan, n, (int16_t*) dIdx );
+    CHECK_LAUNCH( "dq_levels_to_qidx_kernel" );
+    dQ = (const int16_t*) dIdx;
+  }
 #define VVB_INV_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = inv_trquant_smem<LWv, LHv>(); \
     inv_trquant_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, dQ, n, dResi ); }
   VVB_TU_DISPATCH( p.lw, p.lh, VVB_INV_CALL )

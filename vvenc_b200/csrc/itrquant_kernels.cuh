@@ -169,6 +169,58 @@ __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* 
   }
 }
 
+// Dequantiser of dependent quantisation (DQIntern::Quantizer::dequantBlock, DepQuant.cpp:574-629), first half: levels -> qIdx = 2 * level -+ (state >> 1), where
+// `state` is the 4-state machine driven by the parities of the levels further up the scan.  One warp per TU: a lane folds the parities of its run of scan positions
+// into a state -> state map (2 bits per state), the maps are combined across the warp in scan order (from the end of the scan down) with a shuffle scan, and each
+// lane then walks its run with the state it starts from.  The inverse kernel reads the qIdx block like a level block with the DepQuant scale and shift (same formula).
+__device__ __forceinline__ unsigned dqd_compose( unsigned a, unsigned b )      // first a, then b
+{
+  unsigned r = 0;
+#pragma unroll
+  for( int s = 0; s < 4; s++ ) r |= ( ( b >> ( 2 * ( ( a >> ( 2 * s ) ) & 3u ) ) ) & 3u ) << ( 2 * s );
+  return r;
+}
+__global__ void __launch_bounds__( 128 ) dq_levels_to_qidx_kernel( const int16_t* __restrict__ q, const int32_t* __restrict__ fwd, int w, int h, int lrw, int nScan, int n,
+                                                                   int16_t* __restrict__ out )
+{
+  const int tu = blockIdx.x * 4 + ( threadIdx.x >> 5 ), lane = threadIdx.x & 31;
+  if( tu >= n ) return;
+  const int area = w * h, rw = 1 << lrw, rh = nScan >> lrw;
+  const int16_t* qt = q + (size_t) tu * area;
+  int16_t* ot = out + (size_t) tu * area;
+  if( rw < w || rh < h )                                       // 64-sized TUs: nothing outside the scanned 32 x 32 region carries a level
+    for( int i = lane; i < area; i += 32 ) { const int y = i / w, x = i - y * w; if( x >= rw || y >= rh ) ot[i] = 0; }
+  const int run = nScan >= 32 ? nScan >> 5 : 1;                // scan positions per lane; lane 0 holds the END of the scan
+  const int hi = nScan - 1 - lane * run;                       // first (highest) position of the lane's run
+  const bool act = hi >= 0;
+  unsigned m = 0xE4u;                                          // identity map
+  for( int k = 0; act && k < run; k++ )
+  {
+    const int p = __ldg( fwd + hi - k );
+    const int level = qt[( p >> lrw ) * w + ( p & ( rw - 1 ) )];
+    m = dqd_compose( m, ( level & 1 ) ? 0x72u : 0xD8u );       // parity 1: 0->2 1->0 2->3 3->1 ; parity 0: 0->0 1->2 2->1 3->3  (the table 32040)
+  }
+  // exclusive scan of the maps over the lanes (lane 0 first)
+  unsigned inc = m;
+#pragma unroll
+  for( int d = 1; d < 32; d <<= 1 )
+  {
+    const unsigned prev = __shfl_up_sync( 0xffffffffu, inc, d );
+    if( lane >= d ) inc = dqd_compose( prev, inc );
+  }
+  unsigned exc = __shfl_up_sync( 0xffffffffu, inc, 1 );
+  if( lane == 0 ) exc = 0xE4u;
+  int state = (int)( exc & 3u );                               // the walk starts in state 0 at the end of the scan
+  for( int k = 0; act && k < run; k++ )
+  {
+    const int p = __ldg( fwd + hi - k );
+    const int idx = ( p >> lrw ) * w + ( p & ( rw - 1 ) );
+    const int level = qt[idx];
+    ot[idx] = (int16_t)( level ? 2 * level + ( level > 0 ? -( state >> 1 ) : ( state >> 1 ) ) : 0 );
+    state = ( 32040 >> ( ( state << 2 ) + ( ( level & 1 ) << 1 ) ) ) & 3;
+  }
+}
+
 template<int LW, int LH> static inline size_t inv_trquant_smem() { using S = TuShape<LW, LH>; using I = InvShape<LW, LH>; return (size_t)( I::MAT_WORDS + S::NTEAMS * ( S::RESI_WORDS + I::WORDS ) ) * 4; }
 
 template<int LW, int LH>
