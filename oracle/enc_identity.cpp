@@ -114,8 +114,8 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
 {
   const ChannelType chType = toChannelType( compID );
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0;
-  // what stays with the member: stored MTS coefficients, BDPCM, LFNST on chroma / ISP CUs (the binding derives the kernel set for plain luma TUs), empty TUs
-  if( !g_useTu || loadTr || tu.noResidual || tu.cu->bdpcmM[chType] || ( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) || tu.cs->sps->scalingListEnabled )
+  // what stays with the member: BDPCM, LFNST on chroma / ISP CUs or on stored coefficients (the binding derives the kernel set for plain luma TUs), empty TUs
+  if( !g_useTu || tu.noResidual || tu.cu->bdpcmM[chType] || ( lfnstHere && ( loadTr || !isLuma( compID ) || tu.cu->ispMode ) ) || tu.cs->sps->scalingListEnabled )
   {
     g_tuRef++;
     __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( self, tu, compID, cQP, uiAbsSum, ctx, loadTr );
@@ -124,7 +124,8 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
   const CompArea& rect = tu.blocks[compID];
   const CPelBuf resiBuf = tu.cs->getResiBuf( rect );
   uiAbsSum = 0;
-  CoeffBuf tempCoeff( self->m_plTempCoeff, rect );
+  CoeffBuf tempCoeff( loadTr ? self->m_mtsCoeffs[tu.mtsIdx[compID]] : self->m_plTempCoeff, rect );      // loadTr: checktransformsNxN has left the coefficients (TrQuant.cpp:709)
+  if( !loadTr )
   try
   {
     TCoeff plainSum = 0;
