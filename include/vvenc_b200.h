@@ -190,8 +190,9 @@ int vvb_blocks_set_start_dev( vvb_ctx* ctx, vvb_block* dev_blocks, const vvb_bes
  * CommonLib/TrQuant.cpp:688-736 -> xT :481-564 -> Quant::quant CommonLib/Quant.cpp:735-833 -> QuantCore :132-230,
  * and Quant::xNeedRDOQ :835-891 -> needRdoqCore :264-278).  All TUs of a call share shape and transform types.
  * With lfnst_idx set (DCT-II only) the forward calls restate transformNxN's LFNST branch: transform zero-out to the top-left 4x4 / 8x8, the 16x16 / 16x48 int8
- * kernel, quantisation of coefficient group 0; `coef` returns the buffer xFwdLfnst leaves.  The inverse LFNST is not offered yet (vvb_inv_trquant /
- * vvb_tu_roundtrip return VVB_ERR_UNSUPPORTED for lfnst_idx != 0).
+ * kernel, quantisation of coefficient group 0; `coef` returns the buffer xFwdLfnst leaves.  vvb_inv_trquant / vvb_tu_roundtrip restate invTransformNxN's LFNST branch
+ * (TrQuant::xInvLfnst, TrQuant.cpp:838-940: the first 16 scan positions through the transposed kernel, then xIT over the top-left 8x8 / 4x4, :590-602); the levels
+ * are expected as a bitstream carries them, zero beyond scan position 7 (4x4, 8x8) or 15.
  * deltaU (Quant.cpp:221), whose only consumer is the sign-bit hiding of the same call, stays on the device: with sign_hiding set the returned levels are the
  * ones Quant::quant leaves after xSignBitHidingHDQ (abs_sum stays QuantCore's sum, as uiAbsSum does; last_pos follows the hiding step). */
 typedef struct

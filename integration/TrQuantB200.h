@@ -58,15 +58,15 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
   par.input_bit_depth_delta = sps.internalMinusInputBitDepth[chType];
   par.is_irap = tu.cs->slice->isIRAP() ? 1 : 0;                                              // rounding offset 171 vs 85 (Quant.cpp:772)
   par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;                                     // xNeedRDOQ's QP; invTransformNxNB200 then dequantises as DepQuant::dequant does
-  if( tu.cu->lfnstIdx && forward && isLuma( compID ) && !skip )                                                           // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048): kernel set and transposition from the intra mode
+  if( tu.cu->lfnstIdx && tu.cs->sps->LFNST && !skip && ( isLuma( compID ) || CU::isSepTree( *tu.cu ) ) )         // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048) / xInvLfnst (:838-940): kernel set and transposition from the intra mode
   {
-    if( !tu.cs->sps->LFNST || trHor != DCT2 || trVer != DCT2 || skip || isChroma( compID ) ) THROW( "LFNST index on a TU the library does not cover" );
-    uint32_t intraMode = CU::getFinalIntraMode( *tu.cu, CH_L );
-    if( CU::isMIP( *tu.cu, CH_L ) ) intraMode = PLANAR_IDX;
+    if( trHor != DCT2 || trVer != DCT2 || isChroma( compID ) ) THROW( "LFNST index on a TU the library does not cover" );
+    const CodingUnit& cu = *tu.cu;                                                           // :846 / :950 look the CU up at the TU position: the CU that owns the TU
+    uint32_t intraMode = CU::getFinalIntraMode( cu, CH_L );
+    if( CU::isMIP( cu, CH_L ) ) intraMode = PLANAR_IDX;
     intraMode = tq.xGetLFNSTIntraMode( tu.cu->ispMode ? tu.cu->blocks[compID] : tu.blocks[compID], intraMode );
     par.lfnst_idx = tu.cu->lfnstIdx; par.lfnst_set = g_lfnstLut[intraMode]; par.lfnst_transpose = tq.xGetTransposeFlag( intraMode ) ? 1 : 0;
   }
-  else if( tu.cu->lfnstIdx && isLuma( compID ) && !skip ) THROW( "the inverse LFNST stays on the host" );
   par.sign_hiding = tu.cs->slice->signDataHidingEnabled ? 1 : 0;                            // Quant::quant: CoeffCodingContext( ..., signDataHidingEnabled ), xSignBitHidingHDQ (Quant.cpp:748, 817-826)
   return par;
 }

@@ -22,7 +22,7 @@
  * RDOQ (QuantRDOQ2) and everything the bindings THROW for (BDPCM, joint Cb-Cr, scaling lists) stay with the reference members.
  *
  * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu]
- * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_inv=<n> tu_ref=<n>`
+ * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
  */
 #include <cstdint>
 #include <cstring>
@@ -106,7 +106,7 @@ static int countingX5( vvb_ctx* c, const int16_t* o, int so, const int16_t* u, i
 
 // ---- the transform / quantisation seam -------------------------------------------------------------------------------------------------------------------------
 static bool g_useTu = false;
-static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuInv{ 0 }, g_tuRef{ 0 };
+static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuInv{ 0 }, g_tuInvLfnst{ 0 }, g_tuRef{ 0 };
 
 extern "C" void __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant*, TransformUnit&, ComponentID, const QpParam&, TCoeff&, const Ctx&, bool );
 extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant* self, TransformUnit& tu, ComponentID compID, const QpParam& cQP,
@@ -160,9 +160,10 @@ extern "C" void __wrap__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS
 {
   const ChannelType chType = toChannelType( compID );
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0 && tu.mtsIdx[compID] != MTS_SKIP && ( CU::isSepTree( *tu.cu ) ? true : isLuma( compID ) );
-  if( g_useTu && !lfnstHere && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )       // plain and DepQuant dequantiser alike (vvb_tu_par.dep_quant)
+  // plain and DepQuant dequantiser alike (vvb_tu_par.dep_quant); LFNST on plain luma TUs as in the forward wrapper
+  if( g_useTu && !( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )
   {
-    try { invTransformNxNB200( *self, tu, compID, pResi, cQP ); g_tuInv++; return; }
+    try { invTransformNxNB200( *self, tu, compID, pResi, cQP ); g_tuInv++; if( lfnstHere ) g_tuInvLfnst++; return; }
     catch( std::exception& ) {}
   }
   g_tuRef++;
@@ -240,8 +241,8 @@ int main( int argc, char** argv )
   if( fo ) { fwrite( out.data(), 1, out.size(), fo ); fclose( fo ); }
   uint64_t hsh = 1469598103934665603ull;
   for( uint8_t b : out ) { hsh ^= b; hsh *= 1099511628211ull; }
-  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_inv=%llu tu_ref=%llu\n", fed, out.size(),
+  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu\n", fed, out.size(),
           (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuInv.load(),
-          g_tuRef.load() );
+          g_tuInvLfnst.load(), g_tuRef.load() );
   return 0;
 }

@@ -757,6 +757,45 @@ int orc_inv_transform_quant_ts( const int16_t* q, int w, int h, int bitDepth, in
   return 0;
 }
 
+/* LFNST, inverse: TrQuant::xInvLfnst (TrQuant.cpp:838-940) with xInvLfnstNxNCore (:190-213) between the dequantiser and xIT.  The first 16 scan positions (the top-left
+ * 4x4 group in diagonal order) hold the secondary coefficients; the inverse kernel is the transpose of the forward one (g_lfnstInv* == g_lfnstFwd*^T, checked when the
+ * tables were generated), outputs are clipped to 16 bit and land on the walk the forward side read (rows of 8 then rows of 4, or transposed).  xIT then only uses the
+ * top-left 8x8 (4x4) coefficients (:590-602 skipWidth / skipHeight). */
+void orc_inv_lfnst( int32_t* coef, int w, int h, int set, int lfnstIdx, int transpose )
+{
+  const int whge3 = w >= 8 && h >= 8, sb = whge3 ? 8 : 4, nOut = whge3 ? 48 : 16;
+  const int zeroOut = ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ? 8 : 16;
+  const int8_t* mat = (const int8_t*) vvc_lfnst_words + ( whge3 ? ( set * 2 + ( lfnstIdx - 1 ) ) * 16 * 48 : VVC_LFNST_4X4_OFFSET + ( set * 2 + ( lfnstIdx - 1 ) ) * 16 * 16 );
+  int cx[16], cy[16];
+  diag_scan( 4, 4, cx, cy );
+  int32_t src[16], out[48];
+  for( int i = 0; i < 16; i++ ) src[i] = coef[cy[i] * w + cx[i]];
+  for( int j = 0; j < nOut; j++ )
+  {
+    int32_t sum = 0;
+    for( int i = 0; i < zeroOut; i++ ) sum += src[i] * mat[i * nOut + j];
+    out[j] = clip3i( -32768, 32767, ( sum + 64 ) >> 7 );
+  }
+  for( int j = 0; j < nOut; j++ )
+  {
+    int a, b;
+    if( sb == 4 ) { b = j >> 2; a = j & 3; }
+    else if( j < 32 ) { b = j >> 3; a = j & 7; }
+    else { b = 4 + ( ( j - 32 ) >> 2 ); a = ( j - 32 ) & 3; }
+    const int x = transpose ? b : a, y = transpose ? a : b;
+    coef[y * w + x] = out[j];
+  }
+}
+int orc_inv_transform_quant_lfnst( const int16_t* q, int w, int h, int bitDepth, int qp, int depQuant, int set, int lfnstIdx, int transpose, int32_t* coef, Pel* resi, int stride )
+{
+  if( depQuant ) orc_dequant_dq( q, w, h, bitDepth, qp, coef );
+  else           orc_dequant( q, w, h, bitDepth, qp, coef );
+  orc_inv_lfnst( coef, w, h, set, lfnstIdx, transpose );
+  const int keep = ( w >= 8 && h >= 8 ) ? 8 : 4;
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) if( x >= keep || y >= keep ) coef[y * w + x] = 0;
+  return orc_inv_transform( 0, 0, coef, w, h, bitDepth, resi, stride );
+}
+
 /* PelBuf::reconstruct (Buffer.cpp:719-760): reco = ClipPel( pred + resi ) with the default clipping range [0, 2^bd - 1] */
 void orc_reconstruct( const Pel* pred, int ps, const Pel* resi, int rs, Pel* reco, int cs, int w, int h, int bitDepth )
 {

@@ -728,6 +728,60 @@ int refshim_transform_quant_lfnst( const int16_t* resi, int stride, int w, int h
   r.cu.lfnstIdx = 0; r.sps.LFNST = false;
   return 0;
 }
+// TrQuant::invTransformNxN of the same kind of TU (the member itself: xDeQuant, xInvLfnst :838-940, xIT with the LFNST skip :590-602).  coefOut: the buffer xInvLfnst leaves
+int refshim_inv_transform_quant_lfnst( const int16_t* q, int w, int h, int bitDepth, int qp, int depQuant, int lastPos, int intraMode, int lfnstIdx, int32_t* coefOut, int16_t* resi, int stride,
+                                       int32_t* outSetTranspose )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, 0, false, true, qp );
+  r.slice.depQuantEnabled = depQuant != 0;
+  r.tu.lastPos[COMP_Y] = lastPos;
+  r.sps.LFNST = true;
+  r.slice.sliceType = VVENC_B_SLICE;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx;
+  r.cu.intraDir[CH_L] = (uint8_t) intraMode; r.cu.intraDir[CH_C] = DM_CHROMA_IDX;
+  r.cu.mipFlag = false; r.cu.ispMode = 0; r.cu.chromaFormat = CHROMA_400;
+  static thread_local std::vector<CodingUnit*> cuMap;
+  r.cs.area = UnitArea( CHROMA_400, Area( 0, 0, w, h ) );
+  r.cs.parent = nullptr;
+  r.cs.unitScale[COMP_Y] = UnitScale( MIN_CU_LOG2, MIN_CU_LOG2 );
+  cuMap.assign( (size_t)( ( w >> MIN_CU_LOG2 ) + 1 ) * ( ( h >> MIN_CU_LOG2 ) + 1 ), &r.cu );
+  r.cs.m_cuPtr[CH_L] = cuMap.data();
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  TrQuant& tq = tqOfThread();
+  QpParam qpp( r.tu, COMP_Y, false );
+  PelBuf out( resi, stride, w, h );
+  tq.invTransformNxN( r.tu, COMP_Y, out, qpp );
+  if( coefOut ) for( int y = 0; y < h; y++ ) memcpy( coefOut + (size_t) y * w, tq.m_plTempCoeff + (size_t) y * w, sizeof( TCoeff ) * w );
+  const uint32_t m = tq.xGetLFNSTIntraMode( r.tu.blocks[COMP_Y], (uint32_t) intraMode );
+  outSetTranspose[0] = g_lfnstLut[m]; outSetTranspose[1] = tq.xGetTransposeFlag( m ) ? 1 : 0;
+  r.cs.m_cuPtr[CH_L] = nullptr;
+  r.cu.lfnstIdx = 0; r.sps.LFNST = false; r.slice.depQuantEnabled = false;
+  return 0;
+}
+// the inverse through integration/TrQuantB200.h (invTransformNxNB200 derives kernel set / transposition from the CU); returns 1 when the binding threw
+int refshim_inv_transform_quant_lfnst_b200( const int16_t* q, int w, int h, int bitDepth, int qp, int depQuant, int lastPos, int intraMode, int lfnstIdx, int16_t* resi, int stride )
+{
+  RefCtx& c = ctx();
+  TuRig& r = rig();
+  r.setup( w, h, bitDepth, 0, false, true, qp );
+  r.slice.depQuantEnabled = depQuant != 0;
+  r.tu.lastPos[COMP_Y] = lastPos;
+  r.sps.LFNST = true;
+  r.slice.sliceType = VVENC_B_SLICE;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx;
+  r.cu.intraDir[CH_L] = (uint8_t) intraMode; r.cu.intraDir[CH_C] = DM_CHROMA_IDX;
+  r.cu.mipFlag = false; r.cu.ispMode = 0; r.cu.chromaFormat = CHROMA_400;
+  memcpy( r.qcoef.data(), q, sizeof( int16_t ) * w * h );
+  QpParam qpp( r.tu, COMP_Y, false );
+  PelBuf out( resi, stride, w, h );
+  int rc = 0;
+  try { invTransformNxNB200( tqOfThread(), r.tu, COMP_Y, out, qpp ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.cu.lfnstIdx = 0; r.sps.LFNST = false; r.slice.depQuantEnabled = false;
+  return rc;
+}
 // the same TU through integration/TrQuantB200.h (xTQuantB200 derives kernel set / transposition from the CU like xFwdLfnst does); returns 1 when the binding threw
 int refshim_transform_quant_lfnst_b200( const int16_t* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int intraMode, int lfnstIdx,
                                         int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* needRdoq )

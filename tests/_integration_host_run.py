@@ -314,6 +314,21 @@ def main(mock_path):
         if rc or not np.array_equal(ra, rb):
             bad.append(['dqd'] + [int(v) for v in row] + [rc])
     res['tu_inv_dq'] = {'cases': ndd, 'bad': bad[:5]}
+    # invTransformNxN of LFNST TUs (dequantiser, xInvLfnst, xIT) against invTransformNxNB200 with vvb_tu_par.lfnst_*
+    bad = []; nil = 0
+    for opt in (0, 1):
+        R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+        for row in C.ilf_cases()[opt::2]:
+            w, h, bd, qp, mode, idx, dq, amp, seed = [int(v) for v in row]
+            so = np.zeros(1024, np.int32); _orc().orc_scan_order(w, h, P(so))
+            q, last = C.ilf_inputs(row, so)
+            ra = np.zeros((h, w), dtype=np.int16); rb = np.zeros((h, w), dtype=np.int16); st2 = np.zeros(2, dtype=np.int32)
+            assert R.refshim_inv_transform_quant_lfnst(P(q), w, h, bd, qp, dq, last, mode, idx, None, P(ra), w, P(st2)) == 0
+            rc = R.refshim_inv_transform_quant_lfnst_b200(P(q), w, h, bd, qp, dq, last, mode, idx, P(rb), w)
+            nil += 1
+            if rc or not np.array_equal(ra, rb):
+                bad.append(['ilf'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+    res['tu_inv_lfnst'] = {'cases': nil, 'bad': bad[:5]}
     # DepQuant::xQuantDQ against xQuantDQB200 (rate tables from the rig's CABAC contexts through the public RateEstimator accessors, trellis in the bound library)
     bad = []; ndq = 0; nz = 0
     R.refshim_set_simd(b'AVX2')

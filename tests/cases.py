@@ -424,3 +424,31 @@ def dqd_inputs(row, scan):
     q = np.zeros((h, w), dtype=np.int16)
     q.reshape(-1)[scan[:last + 1]] = vals
     return q, last
+
+
+def ilf_cases():
+    """inverse LFNST (dequantiser, xInvLfnst, xIT on the top-left 8x8 / 4x4): rows w, h, bit_depth, qp, intra mode, lfnst index, dep quant, amp, seed"""
+    rows = []
+    rs = np.random.RandomState(707)
+    seed = 19000
+    for (w, h) in [(4, 4), (8, 8), (4, 8), (8, 4), (16, 16), (4, 16), (16, 4), (8, 16), (32, 32), (32, 8), (64, 64), (16, 64)]:
+        for mode in (0, 1, 2, 10, 18, 23, 34, 35, 44, 50, 58, 66):
+            for idx in (1, 2):
+                bd = int(rs.choice([8, 10]))
+                rows.append([w, h, bd, int(rs.randint(-6 * (bd - 8), 64)), mode, idx, int(rs.randint(0, 2)), int(rs.choice([2, 20, 300, 5000])), seed])
+                seed += 1
+    return np.array(rows, dtype=np.int32)
+
+
+def ilf_inputs(row, scan):
+    """levels as the bitstream of an LFNST TU can carry them: non-zero inside the first 8 (4x4, 8x8) or 16 scan positions only; returns levels, last position"""
+    w, h, bd, qp, mode, idx, dq, amp, seed = [int(v) for v in row]
+    rs = np.random.RandomState(seed)
+    npos = 8 if (w, h) in ((4, 4), (8, 8)) else 16
+    last = int(rs.randint(0, npos))
+    vals = rs.randint(-amp, amp + 1, size=last + 1).astype(np.int16)
+    if vals[-1] == 0:
+        vals[-1] = -1
+    q = np.zeros((h, w), dtype=np.int16)
+    q.reshape(-1)[scan[:last + 1]] = vals
+    return q, last

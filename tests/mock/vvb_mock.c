@@ -142,6 +142,7 @@ int orc_need_rdoq_ex( const int32_t* coef, int w, int h, int bitDepth, int qp, i
 int orc_transform_quant_ts( const Pel* resi, int stride, int w, int h, int bitDepth, int qp, int isIRAP, int signHiding, int inputDelta, int32_t* coef, int16_t* q, int32_t* absSum, int32_t* lastPos );
 int orc_inv_transform_quant_ts( const int16_t* q, int w, int h, int bitDepth, int qp, int inputDelta, int32_t* coef, Pel* resi, int stride );
 int orc_inv_transform_quant_dq( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride );
+int orc_inv_transform_quant_lfnst( const int16_t* q, int w, int h, int bitDepth, int qp, int depQuant, int set, int lfnstIdx, int transpose, int32_t* coef, Pel* resi, int stride );
 int orc_inv_transform_quant( int trHor, int trVer, const int16_t* q, int w, int h, int bitDepth, int qp, int32_t* coef, Pel* resi, int stride );
 
 static int tu_par_ok( vvb_ctx* c, const vvb_tu_par* p )
@@ -190,6 +191,7 @@ int vvb_inv_trquant( vvb_ctx* c, const vvb_tu_par* par, const int16_t* q, int n,
   if( !tmp ) return fail( c, VVB_ERR_NOMEM, "inverse" );
   for( int i = 0; i < n; i++ )
     if( par->transform_skip ? orc_inv_transform_quant_ts( q + area * i, par->w, par->h, par->bit_depth, par->qp, par->input_bit_depth_delta, tmp, resi + area * i, par->w )
+        : par->lfnst_idx    ? orc_inv_transform_quant_lfnst( q + area * i, par->w, par->h, par->bit_depth, par->qp, par->dep_quant, par->lfnst_set, par->lfnst_idx, par->lfnst_transpose, tmp, resi + area * i, par->w )
         : par->dep_quant    ? orc_inv_transform_quant_dq( par->tr_hor, par->tr_ver, q + area * i, par->w, par->h, par->bit_depth, par->qp, tmp, resi + area * i, par->w )
                             : orc_inv_transform_quant( par->tr_hor, par->tr_ver, q + area * i, par->w, par->h, par->bit_depth, par->qp, tmp, resi + area * i, par->w ) )
     { free( tmp ); return fail( c, VVB_ERR_UNSUPPORTED, "transform shape" ); }

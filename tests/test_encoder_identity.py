@@ -28,7 +28,7 @@ def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False
 
 def _identity_tu(tmp_path, W, H, F, preset, qp, lib, want_dq, timeout=900):
     """the same with TrQuant::transformNxN / invTransformNxN routed through the library (forward transforms, transform skip, LFNST, the DepQuant trellis with rate
-    tables from the live CABAC contexts, the inverse path where the plain dequantiser applies)"""
+    tables from the live CABAC contexts, the inverse path with either dequantiser and the inverse LFNST)"""
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from _clips import write_clip
     clip = str(tmp_path / 'clip.yuv')
@@ -39,6 +39,8 @@ def _identity_tu(tmp_path, W, H, F, preset, qp, lib, want_dq, timeout=900):
     if want_dq:
         assert int(kb['tu_dq']) > 1000, kb                 # the preset enables dependent quantisation: the trellis ran in the library
     assert int(kb['tu_inv']) > 500, kb                     # the inverse path (plain or DepQuant dequantiser) ran in the library
+    if want_dq:
+        assert int(kb['tu_inv_lfnst']) > 500, kb           # these presets enable LFNST: the inverse LFNST ran in the library too
     assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
     return kb
 

@@ -262,7 +262,7 @@ def test_gpu_sign_bit_hiding_vs_oracle(gpu, tensor):
 def test_gpu_lfnst_forward_vs_oracle(gpu):
     """vvb_tu_par.lfnst_*: transform zero-out + LFNST kernel + quantiser on coefficient group 0 (TrQuant::xFwdLfnst, TrQuant.cpp:942-1048) for every TU shape that can
     carry LFNST, all kernel sets, both indices, transposed and not, with and without sign hiding; coefficients, levels, absSum, lastPos and the RDOQ flag equal
-    the oracle (= the reference, CPU suite); the inverse side refuses LFNST"""
+    the oracle (= the reference, CPU suite)"""
     import ctypes
     import vvenc_b200 as V
     from _libs import oracle, P
@@ -282,8 +282,6 @@ def test_gpu_lfnst_forward_vs_oracle(gpu):
                 assert np.array_equal(r['coef'][i], coef), (w, h, st, idx, tr, i, np.argwhere(r['coef'][i] != coef)[:4])
                 assert np.array_equal(r['q'][i], q) and int(r['abs_sum'][i]) == s.value and int(r['last_pos'][i]) == lp.value, (w, h, st, idx, tr, i, qp, sh)
                 assert int(r['need_rdoq'][i]) == O.orc_need_rdoq(P(coef), w, h, 10, qp, dq), (w, h, i)
-    with pytest.raises(V.VvbError):
-        gpu.eng.inv_trquant(gpu.eng.tu_par(8, 8, V.DCT2, V.DCT2, 10, 30, False, False, False, 1, 0, False), np.zeros((1, 8, 8), dtype=np.int16))
 
 
 @pytest.mark.parametrize("engine", [1, 0])
@@ -429,3 +427,55 @@ def test_gpu_dep_quant_dequantiser_vs_oracle(gpu):
             cO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
             assert O.orc_inv_transform_quant_dq(th, tv, P(np.ascontiguousarray(qs[i])), w, h, bd, qp, P(cO), P(rO), w) == 0
             assert np.array_equal(got[i], rO), ([int(v) for v in row], i)
+
+
+def test_gpu_lfnst_inverse_and_roundtrip_vs_oracle(gpu):
+    """vvb_inv_trquant / vvb_tu_roundtrip with vvb_tu_par.lfnst_*: dequantiser (plain or DepQuant's), TrQuant::xInvLfnst on the first 16 scan positions, xIT over the
+    top-left 8x8 / 4x4, for every TU shape that can carry LFNST, all kernel sets, both indices, transposed and not, against the oracle restatement that
+    tests/test_oracle_vs_reference.py pins to the reference member; then the fused round trip of LFNST TUs (forward LFNST -> levels -> inverse LFNST -> reconstruction ->
+    distortions) against the separate calls"""
+    import ctypes
+    import vvenc_b200 as V
+    from _libs import oracle, P
+    O = oracle()
+    rs = np.random.RandomState(977)
+    ninv = 0; nrt = 0; live = 0
+    for (w, h) in ((4, 4), (8, 8), (4, 8), (8, 4), (16, 16), (4, 16), (16, 4), (8, 16), (32, 32), (32, 8), (64, 64), (16, 64), (64, 4)):
+        so = np.zeros(1024, np.int32); O.orc_scan_order(w, h, P(so))
+        for (st, idx, tr) in ((0, 1, 0), (1, 2, 0), (2, 1, 1), (3, 2, 1), (1, 1, 1), (3, 1, 0)):
+            for dq in (0, 1):
+                n = 24; bd = int(rs.choice([8, 10])); qp = int(rs.randint(-6 * (bd - 8), 64))
+                qs = np.zeros((n, h, w), dtype=np.int16)
+                for i in range(n):
+                    qs[i], _ = C.ilf_inputs(np.array([w, h, bd, qp, 0, idx, dq, int(rs.choice([2, 20, 300, 5000])), int(rs.randint(1 << 30))]), so)
+                par = gpu.eng.tu_par(w, h, V.DCT2, V.DCT2, bd, qp, False, bool(dq), False, idx, st, bool(tr))
+                got = gpu.eng.inv_trquant(par, qs)
+                for i in range(n):
+                    cO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
+                    assert O.orc_inv_transform_quant_lfnst(P(np.ascontiguousarray(qs[i])), w, h, bd, qp, dq, st, idx, tr, P(cO), P(rO), w) == 0
+                    assert np.array_equal(got[i], rO), (w, h, st, idx, tr, dq, bd, qp, i)
+                    ninv += 1
+            # fused round trip (plain quantiser)
+            n = 40; bd = 10; qp = int(rs.randint(12, 40)); irap = int(rs.randint(0, 2)); sh = int(rs.randint(0, 2))
+            org = rs.randint(0, 1 << bd, size=(n, h, w)).astype(np.int16)
+            amp = np.array([600, 120, 20])[rs.randint(0, 3, n)]
+            pred = np.clip(org.astype(np.int32) - (rs.randint(-1000, 1001, size=(n, h, w)) * amp[:, None, None] // 1000), 0, (1 << bd) - 1).astype(np.int16)
+            par = gpu.eng.tu_par(w, h, V.DCT2, V.DCT2, bd, qp, bool(irap), False, bool(sh), idx, st, bool(tr))
+            rr = gpu.eng.tu_roundtrip(par, org, pred)
+            resi = (org.astype(np.int32) - pred).astype(np.int16)
+            f2 = gpu.eng.fwd_trquant(par, resi)
+            assert np.array_equal(rr['q'], f2['q']) and np.array_equal(rr['res']['abs_sum'], f2['abs_sum']) and np.array_equal(rr['res']['last_pos'], f2['last_pos'])
+            assert np.array_equal(rr['need_rdoq'], f2['need_rdoq'])
+            rec_resi = np.where((f2['abs_sum'] > 0)[:, None, None], gpu.eng.inv_trquant(par, f2['q']).astype(np.int32), 0)
+            for i in range(0, n, 8):
+                cO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
+                assert O.orc_inv_transform_quant_lfnst(P(np.ascontiguousarray(f2['q'][i])), w, h, bd, qp, 0, st, idx, tr, P(cO), P(rO), w) == 0
+                assert np.array_equal(rec_resi[i], rO if f2['abs_sum'][i] > 0 else 0 * rO), (w, h, st, idx, tr, i)
+            exp = np.clip(pred.astype(np.int32) + rec_resi, 0, (1 << bd) - 1)
+            assert np.array_equal(rr['reco'], exp.astype(np.int16)), (w, h, st, idx, tr)
+            d = org.astype(np.int64) - exp
+            assert np.array_equal(rr['res']['dist_reco'], (d * d).sum(axis=(1, 2)).astype(np.uint64))
+            d = resi.astype(np.int64) - rec_resi
+            assert np.array_equal(rr['res']['dist_resi'], (d * d).sum(axis=(1, 2)).astype(np.uint64))
+            nrt += n; live += int((f2['abs_sum'] > 0).sum())
+    assert ninv == 13 * 6 * 2 * 24 and nrt == 13 * 6 * 40 and live > nrt // 2, (ninv, nrt, live)

@@ -39,6 +39,7 @@ def test_batched_bindings_on_the_real_library():
     assert r['tu_fwd_lfnst']['cases'] == 288 and r['tu_fwd_lfnst']['bad'] == []
     assert r['tu_ts_chroma']['cases'] == 220 and r['tu_ts_chroma']['bad'] == []
     assert r['tu_inv_dq']['cases'] == 168 and r['tu_inv_dq']['bad'] == []
+    assert r['tu_inv_lfnst']['cases'] == 288 and r['tu_inv_lfnst']['bad'] == []
     assert r['dep_quant_chroma']['cases'] == 72 and r['dep_quant_chroma']['bad'] == []
     assert r['dep_quant']['cases'] == 216 and r['dep_quant']['non_empty'] > 100 and r['dep_quant']['bad'] == []
     assert r['tu_fwd']['bad'] == [] and r['tu_inv']['bad'] == [] and r['tu_fwd_sdh']['bad'] == [] and r['tu_fwd_sdh']['levels_changed_by_hiding'] > 60

@@ -73,6 +73,7 @@ def test_transform_quant_binding_equals_the_members(result):
     assert result['tu_inv']['cases'] > 250 and result['tu_inv']['bad'] == []
     assert result['tu_ts_chroma']['cases'] == 220 and result['tu_ts_chroma']['inverse_cases'] > 20 and result['tu_ts_chroma']['bad'] == []      # transform skip, chroma components
     assert result['tu_inv_dq']['cases'] == 168 and result['tu_inv_dq']['bad'] == []      # DepQuant dequantiser
+    assert result['tu_inv_lfnst']['cases'] == 288 and result['tu_inv_lfnst']['bad'] == []   # inverse LFNST
     assert result['dep_quant_chroma']['cases'] == 72 and result['dep_quant_chroma']['bad'] == []
     assert result['dep_quant']['cases'] == 216 and result['dep_quant']['non_empty'] > 100 and result['dep_quant']['bad'] == []      # dependent quantisation (xQuantDQB200)
 

@@ -594,3 +594,28 @@ def test_dep_quant_dequantiser_against_the_reference(opt):
         assert np.array_equal(cR, cO) and np.array_equal(rR, rO), [int(v) for v in row]
         n += 1
     assert n == 168
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_lfnst_inverse_against_the_reference(opt):
+    """TrQuant::invTransformNxN for intra TUs with an LFNST index (dequantiser of either quantiser, xInvLfnst on the first 16 scan positions, xIT over the
+    top-left 8x8 / 4x4): the oracle's restatement (the inverse kernel read as the transpose of the forward one) gives the reference's residual for every TU
+    shape that can carry LFNST, both indices, intra modes of all four kernel sets with and without transposition, plain and dependent quantisation"""
+    from _libs import oracle, refshim, P
+    import cases as C
+    O = oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    n = 0; sets = set(); nz = 0
+    for row in C.ilf_cases():
+        w, h, bd, qp, mode, idx, dq, amp, seed = [int(v) for v in row]
+        so = np.zeros(1024, np.int32); O.orc_scan_order(w, h, P(so))
+        q, last = C.ilf_inputs(row, so)
+        cR = np.zeros((h, w), np.int32); rR = np.zeros((h, w), np.int16); st = np.zeros(2, np.int32)
+        assert R.refshim_inv_transform_quant_lfnst(P(q), w, h, bd, qp, dq, last, mode, idx, P(cR), P(rR), w, P(st)) == 0
+        cO = np.zeros((h, w), np.int32); rO = np.zeros((h, w), np.int16)
+        assert O.orc_inv_transform_quant_lfnst(P(q), w, h, bd, qp, dq, int(st[0]), idx, int(st[1]), P(cO), P(rO), w) == 0
+        assert np.array_equal(rR, rO), [int(v) for v in row]
+        k = 8 if (w >= 8 and h >= 8) else 4
+        assert np.array_equal(cR[:k, :k], cO[:k, :k]), [int(v) for v in row]       # what xIT reads
+        sets.add((int(st[0]), int(st[1]))); n += 1; nz += int(rR.any())
+    assert n == 288 and len(sets) >= 6 and nz > 200, (n, sets, nz)

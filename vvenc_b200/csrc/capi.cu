@@ -1506,7 +1506,6 @@ int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ,
   TuPar p;
   int rc = makeTuPar( ctx, par, p );
   if( rc ) return rc;
-  if( p.lfnstIdx ) return fail( ctx, VVB_ERR_UNSUPPORTED, "the inverse LFNST (TrQuant::xInvLfnst) is not on the device yet" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   if( par->dep_quant && !p.ts )
@@ -1527,7 +1526,8 @@ int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ,
     dQ = (const int16_t*) dIdx;
   }
 #define VVB_INV_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = inv_trquant_smem<LWv, LHv>(); \
-    inv_trquant_kernel<LWv, LHv><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, dQ, n, dResi ); }
+    if( p.lfnstIdx ) inv_trquant_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dQ, n, dResi ); \
+    else             inv_trquant_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dQ, n, dResi ); }
   VVB_TU_DISPATCH( p.lw, p.lh, VVB_INV_CALL )
 #undef VVB_INV_CALL
   CHECK_LAUNCH( "inv_trquant_kernel" );
@@ -1556,11 +1556,10 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
   TuPar p;
   int rc = makeTuPar( ctx, par, p );
   if( rc ) return rc;
-  if( p.lfnstIdx ) return fail( ctx, VVB_ERR_UNSUPPORTED, "the inverse LFNST (TrQuant::xInvLfnst) is not on the device yet" );
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
-  const bool ext = p.signHiding != 0 || p.ts != 0;
+  const bool ext = p.signHiding != 0 || p.ts != 0 || p.lfnstIdx != 0;
 #define VVB_RT_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
     if( ext ) tu_roundtrip_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
                                                                                               dQ, dReco, (TuResult*) dRes, dNeedRdoq ); \

@@ -47,9 +47,10 @@ template<int LW, int LH> struct InvShape
 // Dequantise + inverse-transform one TU by one team.  qS: int16 levels [H][W] in shared memory; cT / tT: scratch (InvShape).
 // out( y, x0, r0, r1, r2, r3 ) receives the residual of row y, columns x0..x0+3.  Contains __syncthreads(): all threads of the CTA call it;
 // `active` masks the work (a team whose TU quantised to zero, or a tail team, only walks the barriers).
-template<int LW, int LH, class OUT>
+// LFN: the instantiation that carries the inverse LFNST (TrQuant::xInvLfnst); scanTab is only read there
+template<int LW, int LH, bool LFN = false, class OUT>
 __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* MvI, const uint32_t* MhI, const int16_t* qS, uint32_t* cT, uint32_t* tT,
-                                              int tt, bool active, OUT out )
+                                              int tt, bool active, OUT out, const int32_t* __restrict__ scanTab = nullptr )
 {
   using S = TuShape<LW, LH>; using I = InvShape<LW, LH>;
   constexpr int W = S::W, H = S::H, T = S::T, RW = S::RW, RH = S::RH;
@@ -91,11 +92,60 @@ __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* 
         if( sh > 0 ) { c0 = ( c0 * sc + add ) >> sh; c1 = ( c1 * sc + add ) >> sh; }
         else         { c0 = (int)( (unsigned)( c0 * sc ) << ( -sh ) ); c1 = (int)( (unsigned)( c1 * sc ) << ( -sh ) ); }
         c0 = clip16( c0 ); c1 = clip16( c1 );
+        if( LFN && par.lfnstIdx )
+        {
+          constexpr int K = ( LW >= 3 && LH >= 3 ) ? 8 : 4;      // xIT only reads the top-left K x K coefficients of an LFNST TU (TrQuant.cpp:590-602)
+          if( i >= K || 2 * kp >= K ) { c0 = 0; c1 = 0; }
+        }
         cT[i * I::PITCH_C + kp] = ( (uint32_t) c0 & 0xffffu ) | ( (uint32_t) c1 << 16 );
       }
     }
   }
   __syncthreads();
+  if( LFN && par.lfnstIdx )                                   // uniform over the launch: TrQuant::xInvLfnst (TrQuant.cpp:838-940), xInvLfnstNxNCore (:190-213)
+  {
+    constexpr int K = ( LW >= 3 && LH >= 3 ) ? 8 : 4, NOUT = K == 8 ? 48 : 16;
+    constexpr int ZIN = ( ( W == 4 && H == 4 ) || ( W == 8 && H == 8 ) ) ? 8 : 16;
+    int16_t* c16 = reinterpret_cast<int16_t*>( cT );
+    // the secondary coefficients: the first 16 scan positions = the top-left 4x4 group in diagonal order (table of the 8x8 region: same first group)
+    const int32_t* fwd8 = scanTab + VVB_SCAN_TABLE_ENTRIES + 6 * 1024;
+    constexpr int PER = S::cdiv( NOUT, T );
+    int outv[PER];
+    if( active )
+    {
+      int src[ZIN];
+#pragma unroll
+      for( int i = 0; i < ZIN; i++ )
+      {
+        const int p = __ldg( fwd8 + i ), x = p & 7, y = p >> 3;
+        src[i] = c16[( x * I::PITCH_C + ( y >> 1 ) ) * 2 + ( y & 1 )];
+      }
+#pragma unroll
+      for( int k = 0; k < PER; k++ )
+      {
+        const int j = min( tt + k * T, NOUT - 1 );
+        int sum = 0;
+#pragma unroll
+        for( int i = 0; i < ZIN; i++ ) sum += src[i] * (int) __ldg( par.lfnstMat + i * NOUT + j );     // the inverse kernel is the transpose of the forward one
+        outv[k] = clip16( ( sum + 64 ) >> 7 );
+      }
+    }
+    __syncthreads();
+    if( active )
+#pragma unroll
+      for( int k = 0; k < PER; k++ )
+      {
+        const int j = tt + k * T;
+        if( j >= NOUT ) break;
+        int a, b;                                              // the walk of :893-936: rows of 8 then rows of 4 (sub-block 8), rows of 4 (sub-block 4); transposed: columns
+        if( K == 4 ) { b = j >> 2; a = j & 3; }
+        else if( j < 32 ) { b = j >> 3; a = j & 7; }
+        else { b = 4 + ( ( j - 32 ) >> 2 ); a = ( j - 32 ) & 3; }
+        const int x = par.lfnstTranspose ? b : a, y = par.lfnstTranspose ? a : b;
+        c16[( x * I::PITCH_C + ( y >> 1 ) ) * 2 + ( y & 1 )] = (int16_t) outv[k];
+      }
+    __syncthreads();
+  }
   // ---- pass 1 (vertical, shift 7): tmp[i][j] = clip16( ( sum_{k<keepH} coef[k][i] * Tv[k][j] + 64 ) >> 7 ), two columns i per item;
   //      stored transposed and packed: tT[j][i/2] = ( tmp[i][j], tmp[i+1][j] ).  Kept rows k >= keepH of MvI are zero and cT beyond keepH is
   //      never read past Q, so the loop runs over the kept coefficients only.
@@ -223,8 +273,8 @@ __global__ void __launch_bounds__( 128 ) dq_levels_to_qidx_kernel( const int16_t
 
 template<int LW, int LH> static inline size_t inv_trquant_smem() { using S = TuShape<LW, LH>; using I = InvShape<LW, LH>; return (size_t)( I::MAT_WORDS + S::NTEAMS * ( S::RESI_WORDS + I::WORDS ) ) * 4; }
 
-template<int LW, int LH>
-__global__ void __launch_bounds__( 128 ) inv_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable,
+template<int LW, int LH, bool LFN>
+__global__ void __launch_bounds__( 128 ) inv_trquant_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
                                                              const int16_t* __restrict__ q, int n, int16_t* __restrict__ resiOut )
 {
   using S = TuShape<LW, LH>; using I = InvShape<LW, LH>;
@@ -252,7 +302,7 @@ __global__ void __launch_bounds__( 128 ) inv_trquant_kernel( const __grid_consta
     }
     __syncthreads();
     int16_t* dst = resiOut + (size_t)( live ? tu : 0 ) * W * H;
-    team_inverse<LW, LH>( par, MvI, MhI, reinterpret_cast<const int16_t*>( myQ ), cT, tT, tt, live,
+    team_inverse<LW, LH, LFN>( par, MvI, MhI, reinterpret_cast<const int16_t*>( myQ ), cT, tT, tt, live,
                           [&]( int y, int x0, int r0, int r1, int r2, int r3 )
                           {
                             uint2 o;
@@ -374,7 +424,7 @@ __global__ void __launch_bounds__( 128 ) tu_roundtrip_kernel( const __grid_const
       }
     };
     // inverse scratch aliases the forward tmp / coef areas (both dead once the levels are in v.resi)
-    team_inverse<LW, LH>( par, MvI, MhI, reinterpret_cast<const int16_t*>( v.resi ), v.tmp, v.tmp + I::CT_WORDS, tt, active, account );
+    team_inverse<LW, LH, EXT>( par, MvI, MhI, reinterpret_cast<const int16_t*>( v.resi ), v.tmp, v.tmp + I::CT_WORDS, tt, active, account, scanTab );
     if( live && !active )                       // quantised to zero: residual 0 (IntraSearch.cpp:1366-1369 piResi.fill(0))
     {
 #pragma unroll
