@@ -50,7 +50,7 @@ template<int LW, int LH> struct InvShape
 // LFN: the instantiation that carries the inverse LFNST (TrQuant::xInvLfnst); scanTab is only read there
 template<int LW, int LH, bool LFN = false, class OUT>
 __device__ __forceinline__ void team_inverse( const TuPar& par, const uint32_t* MvI, const uint32_t* MhI, const int16_t* qS, uint32_t* cT, uint32_t* tT,
-                                              int tt, bool active, OUT out, const int32_t* __restrict__ scanTab = nullptr )
+                                              int tt, bool active, OUT out, const int32_t* __restrict__ scanTab )
 {
   using S = TuShape<LW, LH>; using I = InvShape<LW, LH>;
   constexpr int W = S::W, H = S::H, T = S::T, RW = S::RW, RH = S::RH;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__( 128 ) inv_trquant_kernel( const __grid_consta
                             o.x = ( (uint32_t) r0 & 0xffffu ) | ( (uint32_t) r1 << 16 );
                             o.y = ( (uint32_t) r2 & 0xffffu ) | ( (uint32_t) r3 << 16 );
                             *reinterpret_cast<uint2*>( dst + y * W + x0 ) = o;
-                          } );
+                          }, scanTab );
   }
 }
 
