@@ -479,3 +479,66 @@ def test_gpu_lfnst_inverse_and_roundtrip_vs_oracle(gpu):
             assert np.array_equal(rr['res']['dist_resi'], (d * d).sum(axis=(1, 2)).astype(np.uint64))
             nrt += n; live += int((f2['abs_sum'] > 0).sum())
     assert ninv == 13 * 6 * 2 * 24 and nrt == 13 * 6 * 40 and live > nrt // 2, (ninv, nrt, live)
+
+
+def test_gpu_raw_byte_tensor_engine_vs_cuda_core_engine_and_oracle(gpu):
+    """vvb_set_tensor_transform(3): the tcgen05 engine whose MMA operands are the raw bytes of the residual / the stage-1 values (trquant_tc2_kernels.cuh), square TUs
+    8..64: compact pools and residuals formed from planes (every pel alignment of org and pred), all transform pairs, 8/10/12 bit, tails that do not fill a tile,
+    int16 extremes (the full input domain is exact), with and without the coefficient output -- levels, coefficients, absSum, lastPos and the RDOQ flag equal the
+    CUDA-core engine on everything and the oracle on a sample"""
+    import vvenc_b200 as V
+    O = impls.OracleImpl()
+    rs = np.random.RandomState(8086)
+    checked = 0
+    try:
+        for (N, pairs) in ((8, ((0, 0), (2, 2), (1, 2))), (16, ((0, 0), (2, 1))), (32, ((0, 0), (1, 2), (2, 2))), (64, ((0, 0),))):
+            for (th, tv) in pairs:
+                for bd in (8, 10, 12):
+                    n = int(rs.choice([1, 3, 37, 130, 1000])) if N < 64 else int(rs.choice([1, 3, 37, 130]))
+                    lim = 1 << bd
+                    amp = np.array([lim - 1, lim // 3, 40, 5, 0])[rs.randint(0, 5, n)]
+                    resi = (rs.randint(-1000, 1001, size=(n, N, N)) * amp[:, None, None] // 1000).astype(np.int16)
+                    resi[0] = np.where((np.arange(N)[None, :] + np.arange(N)[:, None]) % 2 == 0, lim - 1, -(lim - 1))
+                    if n > 2:
+                        resi[1] = rs.randint(-32768, 32768, size=(N, N))          # any int16 input
+                        resi[2] = rs.choice([-32768, 32767], size=(N, N))
+                    qp = int(rs.randint(-6 * (bd - 8), 58)); irap = int(rs.randint(0, 2)); dq = int(rs.randint(0, 2))
+                    par = gpu.eng.tu_par(N, N, th, tv, bd, qp, bool(irap), bool(dq))
+                    gpu.eng.set_tensor_transform(0); a = gpu.eng.fwd_trquant(par, resi)
+                    gpu.eng.set_tensor_transform(3); b = gpu.eng.fwd_trquant(par, resi); c = gpu.eng.fwd_trquant(par, resi, want_coef=False)
+                    for k in ('coef', 'q', 'abs_sum', 'last_pos', 'need_rdoq'):
+                        assert np.array_equal(a[k], b[k]), (N, th, tv, bd, qp, n, k, np.argwhere(a[k] != b[k])[:4])
+                        if k != 'coef':
+                            assert np.array_equal(a[k], c[k]), (N, th, tv, bd, k)
+                    for i in (0, n - 1):
+                        if np.abs(resi[i].astype(np.int32)).max() < lim:
+                            co, q, s, lp, nr = O.transform_quant(th, tv, np.ascontiguousarray(resi[i]), N, N, N, bd, qp, irap, dq)
+                            assert np.array_equal(b['coef'][i], co) and np.array_equal(b['q'][i], q) and (int(b['abs_sum'][i]), int(b['last_pos'][i]), int(b['need_rdoq'][i])) == (s, lp, nr)
+                            checked += 1
+        # residual from planes: org and pred at every pel alignment
+        W, H, m = 320, 192, 16
+        a_, b_, S = _tc2_planes(rs, W, H, m)
+        po, pp = 0, 1
+        gpu.eng.upload_plane(po, a_, W, H, m, 10); gpu.eng.upload_plane(pp, b_, W, H, m, 10)
+        for N in (8, 16, 32, 64):
+            n = 333 if N < 64 else 45
+            blocks = np.zeros(n, dtype=gpu.V.BLOCK_DT)
+            blocks['x'] = rs.randint(0, W - N + 1, n); blocks['y'] = rs.randint(0, H - N + 1, n)
+            blocks['x'][: n // 2] &= ~7                                           # half of the TUs on the 8-pel grid the encoder uses, the rest anywhere
+            blocks['start_x'] = rs.randint(-m, m + 1, n); blocks['start_y'] = rs.randint(-m, m + 1, n)
+            par = gpu.eng.tu_par(N, N, 0, 0, 10, int(rs.randint(20, 40)), False, False)
+            gpu.eng.set_tensor_transform(0); a = gpu.eng.fwd_trquant_planes(par, po, pp, blocks, want_coef=True)
+            gpu.eng.set_tensor_transform(3); b = gpu.eng.fwd_trquant_planes(par, po, pp, blocks, want_coef=True)
+            for k in ('coef', 'q', 'abs_sum', 'last_pos', 'need_rdoq'):
+                assert np.array_equal(a[k], b[k]), (N, k, np.argwhere(a[k] != b[k])[:4])
+            assert (a['abs_sum'] > 0).sum() > n // 2
+    finally:
+        gpu.eng.set_tensor_transform(2)
+    assert checked > 30
+
+
+def _tc2_planes(rs, W, H, m, bd=10):
+    S = W + 2 * m
+    a = rs.randint(0, 1 << bd, size=(H + 2 * m, S)).astype(np.int16)
+    b = np.clip(np.roll(a, (2, -3), (0, 1)) + rs.randint(-40, 41, size=a.shape), 0, (1 << bd) - 1).astype(np.int16)
+    return np.ascontiguousarray(a), np.ascontiguousarray(b), S

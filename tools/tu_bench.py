@@ -40,7 +40,7 @@ for (w, h) in shapes:
     d_sum = torch.empty(ntu, dtype=torch.int32, device='cuda'); d_last = torch.empty_like(d_sum); d_nr = torch.empty(ntu, dtype=torch.uint8, device='cuda')
     torch.cuda.synchronize()
     res = {}
-    for tens in (1, 0):
+    for tens in (3, 1, 0):
         eng.set_tensor_transform(tens)
         res['fwd_tc%d' % tens] = tl(lambda: chk(lib.vvb_fwd_trquant_dev(eng.h, ctypes.byref(par), P_(d_r.data_ptr()), ntu, None, P_(d_q.data_ptr()), P_(d_sum.data_ptr()),
                                                                      P_(d_last.data_ptr()), P_(d_nr.data_ptr()))))

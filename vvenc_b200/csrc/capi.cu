@@ -13,6 +13,7 @@
 #include "pyramid_kernels.cuh"
 #include "trquant_kernels.cuh"
 #include "trquant_tc_kernels.cuh"
+#include "trquant_tc2_kernels.cuh"
 #include "itrquant_kernels.cuh"
 #include "mctf_affine_kernels.cuh"
 #include "frac_kernels.cuh"
@@ -260,6 +261,10 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
+#define VVB_TC2_ATTR( Nv ) cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM ); \
+                          cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM );
+  VVB_TC2_ATTR( 8 ) VVB_TC2_ATTR( 16 ) VVB_TC2_ATTR( 32 ) VVB_TC2_ATTR( 64 )
+#undef VVB_TC2_ATTR
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1155,6 +1160,24 @@ static int makeTuPar( vvb_ctx* ctx, const vvb_tu_par* in, TuPar& p )
   return VVB_OK;
 }
 
+// second tensor-core engine (trquant_tc2_kernels.cuh): square TUs 8..64 with the plain quantiser
+static bool tc2Eligible( const vvb_ctx* ctx, const TuPar& p )
+{
+  return ctx->tensorTransform == 3 && !p.lfnstIdx && !p.ts && !p.signHiding && p.w == p.h && p.w >= 8 && p.w <= 64 && p.s1 >= 0;
+}
+static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int orgPlane, int predPlane, const vvb_block* dBlocks, int n,
+                      int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
+{
+  const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
+#define VVB_TC2_CALL( Nv ) { using S = Tc2Shape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; const int grid = std::min( tiles, ctx->numSMs * 3 ); \
+    if( dBlocks ) fwd_trquant_tc2_kernel<Nv, true><<<grid, 128, S::SMEM, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, nullptr, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
+    else          fwd_trquant_tc2_kernel<Nv, false><<<grid, 128, S::SMEM, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, po, pp, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+  switch( p.w ) { case 8: VVB_TC2_CALL( 8 ) break; case 16: VVB_TC2_CALL( 16 ) break; case 32: VVB_TC2_CALL( 32 ) break; default: VVB_TC2_CALL( 64 ) break; }
+#undef VVB_TC2_CALL
+  CHECK_LAUNCH( "fwd_trquant_tc2_kernel" );
+  return VVB_OK;
+}
+
 int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dResi, int n, int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
 {
   if( !ctx || !dResi || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
@@ -1163,6 +1186,7 @@ int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dRe
   if( rc ) return rc;
   if( n == 0 ) return VVB_OK;
   CU( cudaSetDevice( ctx->device ) );
+  if( tc2Eligible( ctx, p ) ) return tc2Launch( ctx, p, dResi, 0, 0, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
   if( !p.lfnstIdx && !p.ts && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) ) )
   {
     // tcgen05 path: 128 stacked rows (128/N TUs) per tile, persistent CTAs
@@ -1217,6 +1241,7 @@ int vvb_fwd_trquant_planes_dev( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlan
     // CUDA-core engine: the residual is formed while the TU is loaded (one launch, no compact residual buffer); the tcgen05 engine keeps the staging kernel
     TuPar p;
     if( ( rc = makeTuPar( ctx, par, p ) ) ) return rc;
+    if( tc2Eligible( ctx, p ) ) return tc2Launch( ctx, p, nullptr, orgPlane, predPlane, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq );
     const bool tensor = !p.lfnstIdx && !p.ts && p.w == p.h && ( ( ctx->tensorTransform == 1 && ( p.w == 16 || p.w == 32 || p.w == 64 ) ) || ( ctx->tensorTransform == 2 && p.w == 64 ) );
     if( !tensor )
     {

@@ -1,0 +1,367 @@
+// trquant_tc2_kernels.cuh -- forward 2-D integer transform + quantiser of square TUs 8x8 .. 64x64 on the tcgen05 tensor cores, second engine.
+//
+// What changed against trquant_tc_kernels.cuh (kept as engine 1 / 2 for A/B runs): the operands of the MMAs are the RAW little-endian bytes of the
+// values, so no thread ever splits a number into planes:
+//   stage 1:  A1[row (tu, y)][2x + b] = byte b of the int16 residual r[y][x]            (a plain 16-byte copy of the residual row)
+//             B1lo[j][2x] = Th[j][x], B1lo[j][2x+1] = 0 ; B1hi[j][2x] = 0, B1hi[j][2x+1] = Th[j][x]
+//             Dlo = A1(u8) x B1lo^T , Dhi = A1(s8) x B1hi^T : sum_x r * Th[j][x] = Dlo + 256 * Dhi      (low byte unsigned, high byte signed)
+//   stage 2:  A2[row (tu, j)][4y + b] = byte b of the int32 tmp[y][j] = (stage 1 + rnd) >> s1   (one 32-bit store per value, transposed on the way)
+//             B2p[i][4y + b] = ( b == p ) ? Tv[i][y] : 0 , p = 0, 1 (A read as u8), 2 (A read as s8: |tmp| < 2^23 for every int16 residual)
+//             sum_y tmp * Tv[i][y] = D0 + 256 * D1 + 65536 * D2
+// The zero entries of the B matrices cost tensor throughput only, which this path has to spare (the kernel is bound by instruction issue).
+// All sums are int32 like the reference's TCoeff arithmetic (TrQuant_EMT.cpp:1973-2000), no value is rounded: bit exact for every int16 input.
+//
+// Tile = 128 stage-2 rows = TPT TUs (16 / 8 / 4 / 4 for 8 / 16 / 32 / 64): one CTA of 128 threads, thread = one row in every phase:
+//   A  copy residual rows (pool) or org - pred (planes) into A1            B  2 x M1 MMAs chains, commit, wait
+//   C  tcgen05.ld row of Dlo / Dhi -> tmp -> transposed int32 stores to A2  D  3 MMA chains, commit, wait
+//   E  tcgen05.ld the coefficient column (tu, j) -> QuantCore (Quant.cpp:132-230) in registers: the KEEP lanes of a TU reduce with redux.sync
+//      (last significant position, coefficient-group masks, sums), levels go out as int16 with 2*KEEP-byte row segments per warp store.
+// The quantiser restates team_quantise (trquant_kernels.cuh) for EXT = false: plain quantiser, no LFNST limit, no sign-bit hiding, no transform skip.
+#pragma once
+#include "trquant_tc_kernels.cuh"
+
+namespace vvb {
+
+// kind::i8 instruction descriptor with the A format selectable (0 = u8, 1 = s8); B is s8, D is s32, both operands K-major
+__device__ __forceinline__ uint32_t umma_idesc_i8_a( int M, int N, int aSigned )
+{
+  uint32_t d = 0;
+  d |= 2u << 4;
+  d |= (uint32_t)( aSigned ? 1u : 0u ) << 7;
+  d |= 1u << 10;
+  d |= (uint32_t)( N >> 3 ) << 17;
+  d |= (uint32_t)( M >> 4 ) << 24;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld8( uint32_t taddr, int (&v)[8] )
+{
+  asm volatile( "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"( v[0] ), "=r"( v[1] ), "=r"( v[2] ), "=r"( v[3] ), "=r"( v[4] ), "=r"( v[5] ), "=r"( v[6] ), "=r"( v[7] ) : "r"( taddr ) : "memory" );
+}
+template<int CH> __device__ __forceinline__ void tmem_ldc( uint32_t taddr, int (&v)[CH] );
+template<> __device__ __forceinline__ void tmem_ldc<8>( uint32_t taddr, int (&v)[8] )   { tmem_ld8( taddr, v ); }
+template<> __device__ __forceinline__ void tmem_ldc<16>( uint32_t taddr, int (&v)[16] ) { tmem_ld16( taddr, v ); }
+
+template<int N> struct Tc2Shape
+{
+  static constexpr int KEEP = N > 32 ? 32 : N;             // kept outputs per dimension (DCT-II zero-out at 64; MTS at 32 keeps 16: run-time, rows beyond are zero)
+  static constexpr int NMMA = KEEP < 16 ? 16 : KEEP;       // N of the MMAs (M = 128 needs a multiple of 16)
+  static constexpr int TPT  = 128 / KEEP;                  // TUs per tile: the stage-2 rows (tu, j) fill the 128 lanes
+  static constexpr int ROWS1 = TPT * N, M1 = ROWS1 / 128;  // stage-1 rows (tu, y): 128, or 256 at 64x64 (two M tiles)
+  static constexpr int K1 = 2 * N < 32 ? 32 : 2 * N, NCH1 = K1 / 16;
+  static constexpr int LBO1 = ROWS1 * 16, A1_BYTES = NCH1 * LBO1;
+  static constexpr int K2 = 4 * N, NCH2 = K2 / 16;
+  // A2: 8-row groups 160 bytes apart, K chunks one group-stride + 16 bytes apart: the transposed 32-bit stores of a warp (32 different y, or TUs x y) hit 32 banks
+  static constexpr int SBO2 = 160, LBO2 = 16 * SBO2 + 16, A2_BYTES = NCH2 * LBO2;
+  static constexpr bool ALIAS = N >= 16;                   // A2 reuses A1's bytes (A1 is dead once the stage-1 MMAs completed); 8x8 keeps its zero K padding apart
+  static constexpr int A_BYTES = ALIAS ? ( A1_BYTES > A2_BYTES ? A1_BYTES : A2_BYTES ) : A1_BYTES + A2_BYTES;
+  static constexpr int BCH = NMMA * 16;                    // K-chunk stride of the B operands
+  static constexpr int B1_BYTES = NCH1 * BCH, B2_BYTES = NCH2 * BCH;
+  static constexpr int SMEM = A_BYTES + 2 * B1_BYTES + 3 * B2_BYTES;
+  static constexpr int CH = KEEP < 16 ? 8 : 16;            // columns per tcgen05.ld
+};
+
+// 8 residuals = org - pred of one row segment as 4 packed words; pred may sit at any pel offset
+__device__ __forceinline__ uint4 tc2_resi8( const int16_t* __restrict__ o, const int16_t* __restrict__ p )
+{
+  uint32_t a[4], b[4];
+  if( ( reinterpret_cast<uintptr_t>( o ) & 15 ) == 0 ) { const uint4 v = __ldg( reinterpret_cast<const uint4*>( o ) ); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+  else if( ( reinterpret_cast<uintptr_t>( o ) & 3 ) == 0 ) { const uint32_t* w = reinterpret_cast<const uint32_t*>( o ); a[0] = __ldg( w ); a[1] = __ldg( w + 1 ); a[2] = __ldg( w + 2 ); a[3] = __ldg( w + 3 ); }
+  else
+  {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>( o + 1 );
+    const uint32_t h0 = (uint16_t) __ldg( o ), w0 = __ldg( w ), w1 = __ldg( w + 1 ), w2 = __ldg( w + 2 ), h7 = (uint16_t) __ldg( o + 7 );
+    a[0] = h0 | ( w0 << 16 ); a[1] = __funnelshift_r( w0, w1, 16 ); a[2] = __funnelshift_r( w1, w2, 16 ); a[3] = ( w2 >> 16 ) | ( h7 << 16 );
+  }
+  if( ( reinterpret_cast<uintptr_t>( p ) & 3 ) == 0 ) { const uint32_t* w = reinterpret_cast<const uint32_t*>( p ); b[0] = __ldg( w ); b[1] = __ldg( w + 1 ); b[2] = __ldg( w + 2 ); b[3] = __ldg( w + 3 ); }
+  else
+  {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>( p + 1 );
+    const uint32_t h0 = (uint16_t) __ldg( p ), w0 = __ldg( w ), w1 = __ldg( w + 1 ), w2 = __ldg( w + 2 ), h7 = (uint16_t) __ldg( p + 7 );
+    b[0] = h0 | ( w0 << 16 ); b[1] = __funnelshift_r( w0, w1, 16 ); b[2] = __funnelshift_r( w1, w2, 16 ); b[3] = ( w2 >> 16 ) | ( h7 << 16 );
+  }
+  return make_uint4( __vsub2( a[0], b[0] ), __vsub2( a[1], b[1] ), __vsub2( a[2], b[2] ), __vsub2( a[3], b[3] ) );
+}
+
+template<int N, bool PLANES>
+__global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
+                                                                    const int16_t* __restrict__ resi,
+                                                                    const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane, const vvb_block* __restrict__ blocks,
+                                                                    int n, int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
+                                                                    int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
+{
+  using S = Tc2Shape<N>;
+  constexpr int KEEP = S::KEEP, NMMA = S::NMMA, TPT = S::TPT, M1 = S::M1, CH = S::CH;
+  extern __shared__ __align__( 128 ) unsigned char smemTc2[];
+  unsigned char* sA1 = smemTc2;
+  unsigned char* sA2 = S::ALIAS ? smemTc2 : smemTc2 + S::A1_BYTES;
+  unsigned char* sB1 = smemTc2 + S::A_BYTES;                // lo, hi
+  unsigned char* sB2 = sB1 + 2 * S::B1_BYTES;               // p = 0, 1, 2
+  __shared__ __align__( 8 ) unsigned long long sMbar;
+  __shared__ uint32_t sTmemBase;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t mbar = smem_u32( &sMbar );
+  const int keepW = par.keepW, keepH = par.keepH;
+
+  // ---- one-time set-up
+  if( warp == 0 )
+  {
+    asm volatile( "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"( smem_u32( &sTmemBase ) ), "r"( (uint32_t) TC_TMEM_COLS ) : "memory" );
+    asm volatile( "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory" );
+  }
+  if( tid == 0 ) { mbar_init( mbar, 1 ); asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" ); }
+  for( int i = tid; i < S::B1_BYTES; i += 128 )             // canonical K-major: [16-byte K chunk][row][16 B]
+  {
+    const int c = i / S::BCH, j = ( i / 16 ) % NMMA, kb = c * 16 + ( i & 15 ), x = kb >> 1;
+    const unsigned char v = ( j < keepW && x < N ) ? (unsigned char) trTable[par.offH + j * N + x] : 0;
+    sB1[i] = ( kb & 1 ) ? 0 : v;
+    sB1[S::B1_BYTES + i] = ( kb & 1 ) ? v : 0;
+  }
+  for( int i = tid; i < S::B2_BYTES; i += 128 )
+  {
+    const int c = i / S::BCH, r = ( i / 16 ) % NMMA, kb = c * 16 + ( i & 15 ), y = kb >> 2, b = kb & 3;
+    const unsigned char v = r < keepH ? (unsigned char) trTable[par.offV + r * N + y] : 0;
+    sB2[i] = b == 0 ? v : 0; sB2[S::B2_BYTES + i] = b == 1 ? v : 0; sB2[2 * S::B2_BYTES + i] = b == 2 ? v : 0;
+  }
+  if( !S::ALIAS ) for( int i = tid; i < S::A1_BYTES / 16; i += 128 ) reinterpret_cast<uint4*>( sA1 )[i] = make_uint4( 0, 0, 0, 0 );    // K padding of the 8x8 rows stays zero
+  // stage-2 role of this thread: row (t2, j2) of the tile; its column of scan positions stays in registers for the whole launch
+  const int t2 = tid / KEEP, j2 = tid % KEEP;
+  int sPos[KEEP];
+  {
+    const int32_t* inv = scanTab + par.scanOff;
+#pragma unroll
+    for( int i = 0; i < KEEP; i++ ) sPos[i] = __ldg( inv + i * KEEP + j2 );
+  }
+  const unsigned tmask = KEEP >= 32 ? 0xffffffffu : ( ( 1u << ( KEEP & 31 ) ) - 1u ) << ( ( tid & 31 ) & ~( KEEP - 1 ) );
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sTmemBase;
+  uint32_t phase = 0;
+  const uint32_t idescU = umma_idesc_i8_a( 128, NMMA, 0 ), idescS = umma_idesc_i8_a( 128, NMMA, 1 );
+  const uint32_t a1Addr = smem_u32( sA1 ), a2Addr = smem_u32( sA2 ), b1Addr = smem_u32( sB1 ), b2Addr = smem_u32( sB2 );
+  const int numTiles = ( n + TPT - 1 ) / TPT;
+  const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0, r2 = 1 << ( par.s2 - 1 ), s1 = par.s1, s2 = par.s2;
+  const uint32_t laneBase = (uint32_t)( warp * 32 ) << 16;
+
+  for( int tile = blockIdx.x; tile < numTiles; tile += gridDim.x )
+  {
+    // ---- A: residual rows -> A1 (raw bytes)
+#pragma unroll
+    for( int m = 0; m < M1; m++ )
+    {
+      const int r = m * 128 + tid, tl = r / N, y = r % N, tu = tile * TPT + tl;
+      const bool live = tu < n;
+      if( PLANES )
+      {
+        const vvb_block blk = blocks[live ? tu : 0];
+        const int16_t* o = orgPlane.origin + (ptrdiff_t)( blk.y + y ) * orgPlane.stride + blk.x;
+        const int16_t* p = predPlane.origin + (ptrdiff_t)( blk.y + blk.start_y + y ) * predPlane.stride + blk.x + blk.start_x;
+#pragma unroll
+        for( int c = 0; c < N / 8; c++ )
+          *reinterpret_cast<uint4*>( sA1 + c * S::LBO1 + r * 16 ) = live ? tc2_resi8( o + 8 * c, p + 8 * c ) : make_uint4( 0, 0, 0, 0 );
+      }
+      else
+      {
+        const uint4* src = reinterpret_cast<const uint4*>( resi + ( (size_t)( live ? tu : 0 ) * N + y ) * N );
+#pragma unroll
+        for( int c = 0; c < N / 8; c++ )
+          *reinterpret_cast<uint4*>( sA1 + c * S::LBO1 + r * 16 ) = live ? __ldg( src + c ) : make_uint4( 0, 0, 0, 0 );
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- B: stage-1 MMAs
+    if( tid == 0 )
+    {
+      tc_fence_after();
+#pragma unroll
+      for( int m = 0; m < M1; m++ )
+#pragma unroll
+        for( int p = 0; p < 2; p++ )
+#pragma unroll
+          for( int ks = 0; ks < S::K1 / 32; ks++ )
+          {
+            const uint64_t da = umma_desc_kmajor( a1Addr + m * 128 * 16 + ks * 2 * S::LBO1, S::LBO1, 128 );
+            const uint64_t db = umma_desc_kmajor( b1Addr + p * S::B1_BYTES + ks * 2 * S::BCH, S::BCH, 128 );
+            umma_i8( tmem + ( m * 2 + p ) * NMMA, da, db, p ? idescS : idescU, ks > 0 ? 1u : 0u );
+          }
+      umma_commit( mbar );
+    }
+    mbar_wait( mbar, phase ); phase ^= 1;
+    tc_fence_after();
+    // ---- C: tmp = ( Dlo + 256 * Dhi + rnd ) >> s1, stored transposed as the raw int32 bytes of A2
+#pragma unroll
+    for( int m = 0; m < M1; m++ )
+    {
+      const int r = m * 128 + tid, tl = r / N, y = r % N;
+      unsigned char* dstBase = sA2 + ( y >> 2 ) * S::LBO2 + ( tl * KEEP / 8 ) * S::SBO2 + ( y & 3 ) * 4;
+#pragma unroll
+      for( int c0 = 0; c0 < KEEP; c0 += CH )
+      {
+        int lo[CH], hi[CH];
+        tmem_ldc<CH>( tmem + laneBase + ( m * 2 + 0 ) * NMMA + c0, lo );
+        tmem_ldc<CH>( tmem + laneBase + ( m * 2 + 1 ) * NMMA + c0, hi );
+        tmem_ld_wait();
+#pragma unroll
+        for( int k = 0; k < CH; k++ )
+        {
+          const int j = c0 + k;
+          const int t = ( ( hi[k] << 8 ) + lo[k] + r1 ) >> s1;
+          *reinterpret_cast<int*>( dstBase + ( j >> 3 ) * S::SBO2 + ( j & 7 ) * 16 ) = t;
+        }
+      }
+    }
+    tc_fence_before();
+    fence_async_smem();
+    __syncthreads();
+    // ---- D: stage-2 MMAs
+    if( tid == 0 )
+    {
+      tc_fence_after();
+#pragma unroll
+      for( int p = 0; p < 3; p++ )
+#pragma unroll
+        for( int ks = 0; ks < S::K2 / 32; ks++ )
+        {
+          const uint64_t da = umma_desc_kmajor( a2Addr + ks * 2 * S::LBO2, S::LBO2, S::SBO2 );
+          const uint64_t db = umma_desc_kmajor( b2Addr + p * S::B2_BYTES + ks * 2 * S::BCH, S::BCH, 128 );
+          umma_i8( tmem + p * NMMA, da, db, p == 2 ? idescS : idescU, ks > 0 ? 1u : 0u );
+        }
+      umma_commit( mbar );
+    }
+    mbar_wait( mbar, phase ); phase ^= 1;
+    tc_fence_after();
+    // ---- E: coefficient column (t2, j2): c[i] = ( D0 + 256 * D1 + 65536 * D2 + rnd ) >> s2, then QuantCore in registers
+    {
+      const int tu = tile * TPT + t2;
+      const bool live = tu < n;
+      int cf[KEEP];
+#pragma unroll
+      for( int c0 = 0; c0 < KEEP; c0 += CH )
+      {
+        int d0[CH], d1[CH], d2[CH];
+        tmem_ldc<CH>( tmem + laneBase + 0 * NMMA + c0, d0 );
+        tmem_ldc<CH>( tmem + laneBase + 1 * NMMA + c0, d1 );
+        tmem_ldc<CH>( tmem + laneBase + 2 * NMMA + c0, d2 );
+        tmem_ld_wait();
+#pragma unroll
+        for( int k = 0; k < CH; k++ ) cf[c0 + k] = ( ( d2[k] << 16 ) + ( d1[k] << 8 ) + d0[k] + r2 ) >> s2;
+      }
+      // pass 1 (Quant.cpp:160-208): last non-zero coefficient, coefficient groups above the threshold, RDOQ pre-check (largest magnitude)
+      int lastNZ = 0, amax = 0; unsigned cgLo = 0, cgHi = 0;
+      const int useThres = par.useThres;
+#pragma unroll
+      for( int g = 0; g < KEEP / 4; g++ )
+      {
+        int m4 = 0;
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+          const int i = 4 * g + k, ac = abs( cf[i] );
+          m4 = max( m4, ac );
+          if( cf[i] ) lastNZ = max( lastNZ, sPos[i] );
+        }
+        amax = max( amax, m4 );
+        if( m4 > useThres ) { const int cg = sPos[4 * g] >> 4; if( KEEP < 32 || cg < 32 ) cgLo |= 1u << ( cg & 31 ); else cgHi |= 1u << ( cg - 32 ); }
+      }
+      lastNZ = __reduce_max_sync( tmask, lastNZ );
+      cgLo   = __reduce_or_sync( tmask, cgLo );
+      if( KEEP == 32 ) cgHi = __reduce_or_sync( tmask, cgHi );
+      amax   = __reduce_max_sync( tmask, amax );
+      int pos = lastNZ;
+      {
+        const int initCg = pos >> 4;
+        if( initCg >= 1 )
+        {
+          const unsigned long long mask = ( (unsigned long long) cgHi << 32 ) | cgLo;
+          const unsigned long long mm = mask & ( initCg >= 63 ? ~0ull : ( ( 1ull << ( initCg + 1 ) ) - 1ull ) ) & ~1ull;
+          if( mm == 0 ) pos = 15;
+          else { const int gg = 63 - __clzll( (long long) mm ); if( gg != initCg ) pos = gg * 16 + 15; }
+        }
+      }
+      // pass 2 (Quant.cpp:211-227)
+      int sum = 0, lastQ = 0;
+      const int qbits = par.qbits; const unsigned scale = (unsigned) par.scale, add32 = par.add32;
+      int16_t* qd = qOut + (size_t)( live ? tu : 0 ) * N * N + j2;
+      if( par.q32 && (unsigned) amax < 65536u )
+      {
+#pragma unroll
+        for( int i = 0; i < KEEP; i++ )
+        {
+          const unsigned ac = sPos[i] <= pos ? (unsigned) abs( cf[i] ) : 0u;
+          const int mag = (int)( ( ac * scale + add32 ) >> qbits );
+          sum += mag;
+          int v = cf[i] < 0 ? -mag : mag;
+          v = max( -32768, min( 32767, v ) );
+          if( v ) lastQ = max( lastQ, sPos[i] + 1 );
+          if( live ) qd[i * N] = (int16_t) v;
+        }
+      }
+      else
+      {
+#pragma unroll
+        for( int i = 0; i < KEEP; i++ )
+        {
+          const long long ac = sPos[i] <= pos ? (long long) abs( cf[i] ) : 0ll;
+          const int mag = (int)( ( ac * par.scale + par.add ) >> qbits );
+          sum += mag;
+          int v = cf[i] < 0 ? max( -32768, -mag ) : min( 32767, mag );
+          if( v ) lastQ = max( lastQ, sPos[i] + 1 );
+          if( live ) qd[i * N] = (int16_t) v;
+        }
+      }
+      sum   = __reduce_add_sync( tmask, sum );
+      lastQ = __reduce_max_sync( tmask, lastQ );
+      if( live )
+      {
+        if( coefOut )
+        {
+          int32_t* cd = coefOut + (size_t) tu * N * N + j2;
+#pragma unroll
+          for( int i = 0; i < KEEP; i++ ) cd[i * N] = cf[i];
+        }
+        if( j2 == 0 )
+        {
+          if( absSumOut )   absSumOut[tu]   = sum;
+          if( lastPosOut )  lastPosOut[tu]  = sum ? lastQ - 1 : pos;          // Quant.cpp:806-816, :830
+          if( needRdoqOut ) needRdoqOut[tu] = (uint8_t)( (unsigned) amax >= par.rdoqThr );
+        }
+      }
+      if( N > KEEP )                                                            // 64x64: the zeroed-out three quarters of the level (and coefficient) blocks
+      {
+        // per TU: rows 0..31 columns 32..63 (4 x 16 B per row) and rows 32..63 (8 x 16 B per row) = 128 + 256 vectors; 128 threads x TPT TUs
+        for( int t = 0; t < TPT; t++ )
+        {
+          const int tz = tile * TPT + t;
+          if( tz >= n ) break;
+          uint4* qz = reinterpret_cast<uint4*>( qOut + (size_t) tz * N * N );
+          for( int v = tid; v < 384; v += 128 )
+          {
+            const int idx = v < 128 ? ( v >> 2 ) * 8 + 4 + ( v & 3 ) : 256 + ( v - 128 );
+            qz[idx] = make_uint4( 0, 0, 0, 0 );
+          }
+          if( coefOut )
+          {
+            uint4* cz = reinterpret_cast<uint4*>( coefOut + (size_t) tz * N * N );
+            for( int v = tid; v < 768; v += 128 )
+            {
+              const int idx = v < 256 ? ( v >> 3 ) * 16 + 8 + ( v & 7 ) : 512 + ( v - 256 );
+              cz[idx] = make_uint4( 0, 0, 0, 0 );
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if( warp == 0 ) asm volatile( "tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"( tmem ), "r"( (uint32_t) TC_TMEM_COLS ) : "memory" );
+}
+
+} // namespace vvb
