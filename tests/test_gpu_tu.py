@@ -255,7 +255,7 @@ def test_gpu_sign_bit_hiding_vs_oracle(gpu, tensor):
                 O.orc_tu_roundtrip_ex(th, tv, P(np.ascontiguousarray(org[i])), w, P(np.ascontiguousarray(pred[i])), w, w, h, 10, qp, irap, 1, P(q2), P(rc2), w, P(o4))
                 assert np.array_equal(rt['q'][i], q2) and np.array_equal(rt['reco'][i], rc2) and int(rt['res'][i]['dist_reco']) == int(o4[0]), (w, h, i)
     finally:
-        gpu.eng.set_tensor_transform(2)
+        gpu.eng.set_tensor_transform(3)
     assert changed > 60
 
 
@@ -533,7 +533,7 @@ def test_gpu_raw_byte_tensor_engine_vs_cuda_core_engine_and_oracle(gpu):
                 assert np.array_equal(a[k], b[k]), (N, k, np.argwhere(a[k] != b[k])[:4])
             assert (a['abs_sum'] > 0).sum() > n // 2
     finally:
-        gpu.eng.set_tensor_transform(2)
+        gpu.eng.set_tensor_transform(3)
     assert checked > 30
 
 

@@ -44,7 +44,15 @@ for (w, h) in shapes:
         eng.set_tensor_transform(tens)
         res['fwd_tc%d' % tens] = tl(lambda: chk(lib.vvb_fwd_trquant_dev(eng.h, ctypes.byref(par), P_(d_r.data_ptr()), ntu, None, P_(d_q.data_ptr()), P_(d_sum.data_ptr()),
                                                                      P_(d_last.data_ptr()), P_(d_nr.data_ptr()))))
-    eng.set_tensor_transform(2)
+    if os.environ.get('TC2_SWEEP'):
+        eng.set_tensor_transform(3)
+        for st in (1, 0):
+            for ct in (2, 3, 4, 6, 8):
+                os.environ['VVB_TC2_CTAS'] = str(ct); os.environ['VVB_TC2_STREAM'] = str(st)
+                res['fwd_s%dc%d' % (st, ct)] = tl(lambda: chk(lib.vvb_fwd_trquant_dev(eng.h, ctypes.byref(par), P_(d_r.data_ptr()), ntu, None, P_(d_q.data_ptr()), P_(d_sum.data_ptr()),
+                                                                                     P_(d_last.data_ptr()), P_(d_nr.data_ptr()))))
+        os.environ.pop('VVB_TC2_CTAS'); os.environ.pop('VVB_TC2_STREAM')
+    eng.set_tensor_transform(3)
     res['inv'] = tl(lambda: chk(lib.vvb_inv_trquant_dev(eng.h, ctypes.byref(par), P_(d_q.data_ptr()), ntu, P_(d_rc.data_ptr()))))
     res['roundtrip'] = tl(lambda: chk(lib.vvb_tu_roundtrip_dev(eng.h, ctypes.byref(par), P_(d_o.data_ptr()), P_(d_p.data_ptr()), ntu, P_(d_q.data_ptr()), P_(d_rc.data_ptr()),
                                                                P_(d_rs.data_ptr()), None)))

@@ -280,6 +280,7 @@ void vvb_destroy( vvb_ctx* ctx )
   for( int i = 0; i < VVB_MAX_PLANES; i++ ) if( ctx->owned[i] ) cudaFree( ctx->owned[i] );
   for( int i = 0; i < 8; i++ ) if( ctx->d_scratch[i] ) cudaFree( ctx->d_scratch[i] );
   if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
+  for( void*& im : ctx->tc2Image ) if( im ) { cudaFree( im ); im = nullptr; }
   if( ctx->d_scan ) cudaFree( ctx->d_scan );
   if( ctx->d_lfnst ) cudaFree( ctx->d_lfnst );
   if( ctx->d_mask ) cudaFree( ctx->d_mask );
@@ -1169,9 +1170,32 @@ static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int or
                       int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
 {
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
-#define VVB_TC2_CALL( Nv ) { using S = Tc2Shape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; const int grid = std::min( tiles, ctx->numSMs * 3 ); \
-    if( dBlocks ) fwd_trquant_tc2_kernel<Nv, true><<<grid, 128, S::SMEM, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, nullptr, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
-    else          fwd_trquant_tc2_kernel<Nv, false><<<grid, 128, S::SMEM, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dResi, po, pp, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+  // B operand images, built once per (size, horizontal type, vertical type) and kept on the device
+  const int key = ( ( p.lw - 3 ) * 3 + p.trHor ) * 3 + p.trVer;
+  if( !ctx->tc2Image[key] )
+  {
+    std::vector<unsigned char> img;
+#define VVB_TC2_IMG( Nv ) { using S = Tc2Shape<Nv>; img.resize( 2 * S::B1_BYTES + 3 * S::B2_BYTES ); tc2_build_b_image<Nv>( vvc_tr_table_host, p.offH, p.offV, p.keepW, p.keepH, img.data() ); }
+    switch( p.w ) { case 8: VVB_TC2_IMG( 8 ) break; case 16: VVB_TC2_IMG( 16 ) break; case 32: VVB_TC2_IMG( 32 ) break; default: VVB_TC2_IMG( 64 ) break; }
+#undef VVB_TC2_IMG
+    void* d = nullptr;
+    CU( cudaMalloc( &d, img.size() ) );
+    CU( cudaMemcpyAsync( d, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream ) );
+    CU( cudaStreamSynchronize( ctx->stream ) );                // img is a local
+    ctx->tc2Image[key] = d;
+  }
+  const uint4* dImg = (const uint4*) ctx->tc2Image[key];
+  const char* envC = getenv( "VVB_TC2_CTAS" ); const char* envS = getenv( "VVB_TC2_STREAM" );
+  const int capC = envC ? atoi( envC ) : 0, streamOn = envS ? atoi( envS ) : 1;
+#define VVB_TC2_CALL( Nv ) { using S = Tc2Shape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; \
+    static int perSm[2] = { 0, 0 }; int& ps = perSm[dBlocks ? 1 : 0]; \
+    if( !ps ) { cudaFuncAttributes fa = {}; \
+                if( dBlocks ) cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, true> ); else cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, false> ); \
+                const int regs = std::max( fa.numRegs, 32 ); \
+                ps = std::min( std::min( 65536 / ( regs * 128 ), ( 227 * 1024 ) / ( (int) S::SMEM + (int) fa.sharedSizeBytes + 1024 ) ), 512 / S::TMEM_COLS ); ps = std::max( std::min( ps, Nv == 8 ? 6 : 8 ), 1 ); } \
+    const int grid = std::min( tiles, ctx->numSMs * ( capC > 0 ? std::min( capC, ps ) : ps ) ); \
+    if( dBlocks ) fwd_trquant_tc2_kernel<Nv, true><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, nullptr, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
+    else          fwd_trquant_tc2_kernel<Nv, false><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, dResi, po, pp, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
   switch( p.w ) { case 8: VVB_TC2_CALL( 8 ) break; case 16: VVB_TC2_CALL( 16 ) break; case 32: VVB_TC2_CALL( 32 ) break; default: VVB_TC2_CALL( 64 ) break; }
 #undef VVB_TC2_CALL
   CHECK_LAUNCH( "fwd_trquant_tc2_kernel" );

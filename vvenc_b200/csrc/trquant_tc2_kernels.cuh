@@ -54,12 +54,15 @@ template<int N> struct Tc2Shape
   static constexpr int K2 = 4 * N, NCH2 = K2 / 16;
   // A2: 8-row groups 160 bytes apart, K chunks one group-stride + 16 bytes apart: the transposed 32-bit stores of a warp (32 different y, or TUs x y) hit 32 banks
   static constexpr int SBO2 = 160, LBO2 = 16 * SBO2 + 16, A2_BYTES = NCH2 * LBO2;
-  static constexpr bool ALIAS = N >= 16;                   // A2 reuses A1's bytes (A1 is dead once the stage-1 MMAs completed); 8x8 keeps its zero K padding apart
+  static constexpr bool ALIAS = N >= 64;                   // 64x64: A2 reuses A1's bytes (A1 is dead once the stage-1 MMAs completed).  Smaller TUs keep A1 apart so that
+                                                           // the next tile's rows can stream in (cp.async) while the rest of this tile runs; 8x8 also keeps its zero K padding
+  static constexpr int TMEM_COLS = N <= 16 ? 64 : 128;     // stage 1: 2 * M1 * NMMA columns, stage 2 (over them): 3 * NMMA
   static constexpr int A_BYTES = ALIAS ? ( A1_BYTES > A2_BYTES ? A1_BYTES : A2_BYTES ) : A1_BYTES + A2_BYTES;
   static constexpr int BCH = NMMA * 16;                    // K-chunk stride of the B operands
   static constexpr int B1_BYTES = NCH1 * BCH, B2_BYTES = NCH2 * BCH;
   static constexpr int SMEM = A_BYTES + 2 * B1_BYTES + 3 * B2_BYTES;
-  static constexpr int CH = KEEP < 16 ? 8 : 16;            // columns per tcgen05.ld
+  static constexpr int ECH = N == 8 ? 8 : 16;   // columns per tcgen05.ld in the stage-2 epilogue (three accumulators live)
+  static constexpr int CH = KEEP < 16 ? 8 : 16;            // columns per tcgen05.ld in the stage-1 epilogue
 };
 
 // 8 residuals = org - pred of one row segment as 4 packed words; pred may sit at any pel offset
@@ -84,8 +87,29 @@ __device__ __forceinline__ uint4 tc2_resi8( const int16_t* __restrict__ o, const
   return make_uint4( __vsub2( a[0], b[0] ), __vsub2( a[1], b[1] ), __vsub2( a[2], b[2] ), __vsub2( a[3], b[3] ) );
 }
 
+// Host side: the B operands of one (size, horizontal type, vertical type) in the canonical K-major layout [16-byte K chunk][row][16 B], rows >= keep zero.
+// tab: the int8 transform table, offH / offV the offsets of the two N x N matrices (row = output index).  Layout of the image: B1lo | B1hi | B2p0 | B2p1 | B2p2.
+template<int N> static void tc2_build_b_image( const int8_t* tab, int offH, int offV, int keepW, int keepH, unsigned char* out )
+{
+  using S = Tc2Shape<N>;
+  for( int i = 0; i < S::B1_BYTES; i++ )
+  {
+    const int c = i / S::BCH, j = ( i / 16 ) % S::NMMA, kb = c * 16 + ( i & 15 ), x = kb >> 1;
+    const unsigned char v = ( j < keepW && x < N ) ? (unsigned char) tab[offH + j * N + x] : 0;
+    out[i] = ( kb & 1 ) ? 0 : v;
+    out[S::B1_BYTES + i] = ( kb & 1 ) ? v : 0;
+  }
+  unsigned char* o2 = out + 2 * S::B1_BYTES;
+  for( int i = 0; i < S::B2_BYTES; i++ )
+  {
+    const int c = i / S::BCH, r = ( i / 16 ) % S::NMMA, kb = c * 16 + ( i & 15 ), y = kb >> 2, b = kb & 3;
+    const unsigned char v = r < keepH ? (unsigned char) tab[offV + r * N + y] : 0;
+    o2[i] = b == 0 ? v : 0; o2[S::B2_BYTES + i] = b == 1 ? v : 0; o2[2 * S::B2_BYTES + i] = b == 2 ? v : 0;
+  }
+}
+
 template<int N, bool PLANES>
-__global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid_constant__ TuPar par, const int8_t* __restrict__ trTable, const int32_t* __restrict__ scanTab,
+__global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel( const __grid_constant__ TuPar par, const uint4* __restrict__ bImage, int streamOn, const int32_t* __restrict__ scanTab,
                                                                     const int16_t* __restrict__ resi,
                                                                     const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane, const vvb_block* __restrict__ blocks,
                                                                     int n, int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
@@ -108,32 +132,21 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
   // ---- one-time set-up
   if( warp == 0 )
   {
-    asm volatile( "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"( smem_u32( &sTmemBase ) ), "r"( (uint32_t) TC_TMEM_COLS ) : "memory" );
+    asm volatile( "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"( smem_u32( &sTmemBase ) ), "r"( (uint32_t) S::TMEM_COLS ) : "memory" );
     asm volatile( "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory" );
   }
   if( tid == 0 ) { mbar_init( mbar, 1 ); asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" ); }
-  for( int i = tid; i < S::B1_BYTES; i += 128 )             // canonical K-major: [16-byte K chunk][row][16 B]
-  {
-    const int c = i / S::BCH, j = ( i / 16 ) % NMMA, kb = c * 16 + ( i & 15 ), x = kb >> 1;
-    const unsigned char v = ( j < keepW && x < N ) ? (unsigned char) trTable[par.offH + j * N + x] : 0;
-    sB1[i] = ( kb & 1 ) ? 0 : v;
-    sB1[S::B1_BYTES + i] = ( kb & 1 ) ? v : 0;
-  }
-  for( int i = tid; i < S::B2_BYTES; i += 128 )
-  {
-    const int c = i / S::BCH, r = ( i / 16 ) % NMMA, kb = c * 16 + ( i & 15 ), y = kb >> 2, b = kb & 3;
-    const unsigned char v = r < keepH ? (unsigned char) trTable[par.offV + r * N + y] : 0;
-    sB2[i] = b == 0 ? v : 0; sB2[S::B2_BYTES + i] = b == 1 ? v : 0; sB2[2 * S::B2_BYTES + i] = b == 2 ? v : 0;
-  }
-  if( !S::ALIAS ) for( int i = tid; i < S::A1_BYTES / 16; i += 128 ) reinterpret_cast<uint4*>( sA1 )[i] = make_uint4( 0, 0, 0, 0 );    // K padding of the 8x8 rows stays zero
-  // stage-2 role of this thread: row (t2, j2) of the tile; its column of scan positions stays in registers for the whole launch
+  // the five B operands (B1 lo, hi of the horizontal matrix; B2 p = 0, 1, 2 of the vertical one) as the host laid them out (tc2_build_b_image): a straight copy
+  for( int i = tid; i < ( 2 * S::B1_BYTES + 3 * S::B2_BYTES ) / 16; i += 128 ) reinterpret_cast<uint4*>( sB1 )[i] = __ldg( bImage + i );
+  if( N == 8 ) for( int i = tid; i < S::A1_BYTES / 16; i += 128 ) reinterpret_cast<uint4*>( sA1 )[i] = make_uint4( 0, 0, 0, 0 );    // K padding of the 8x8 rows stays zero
+  // stage-2 role of this thread: row (t2, j2) of the tile = column j2 of TU t2.  Down a column the scan position grows with the row (diagonal scan inside a
+  // coefficient group, groups in diagonal order), so "last significant position" is "highest significant row" + one table look-up; what stays in registers is the
+  // coefficient-group index (scan position >> 4) of each group of four rows
   const int t2 = tid / KEEP, j2 = tid % KEEP;
-  int sPos[KEEP];
-  {
-    const int32_t* inv = scanTab + par.scanOff;
+  const int32_t* invCol = scanTab + par.scanOff + j2;
+  int cgIdx[KEEP / 4];
 #pragma unroll
-    for( int i = 0; i < KEEP; i++ ) sPos[i] = __ldg( inv + i * KEEP + j2 );
-  }
+  for( int g = 0; g < KEEP / 4; g++ ) cgIdx[g] = __ldg( invCol + 4 * g * KEEP ) >> 4;
   const unsigned tmask = KEEP >= 32 ? 0xffffffffu : ( ( 1u << ( KEEP & 31 ) ) - 1u ) << ( ( tid & 31 ) & ~( KEEP - 1 ) );
   tc_fence_before();
   __syncthreads();
@@ -146,9 +159,12 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
   const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0, r2 = 1 << ( par.s2 - 1 ), s1 = par.s1, s2 = par.s2;
   const uint32_t laneBase = (uint32_t)( warp * 32 ) << 16;
 
-  for( int tile = blockIdx.x; tile < numTiles; tile += gridDim.x )
+  // ---- A: residual rows of one tile -> A1 (raw bytes).  Compact pools of TUs up to 32x32 stream in with cp.async (STREAM): the copy of tile k+1 is issued as soon as
+  //      the stage-1 MMAs of tile k have consumed A1 and lands while the rest of tile k runs.
+  constexpr bool STREAMC = !PLANES && !S::ALIAS;
+  const bool STREAM = STREAMC && streamOn;
+  auto load_tile = [&]( int tile )
   {
-    // ---- A: residual rows -> A1 (raw bytes)
 #pragma unroll
     for( int m = 0; m < M1; m++ )
     {
@@ -163,6 +179,14 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
         for( int c = 0; c < N / 8; c++ )
           *reinterpret_cast<uint4*>( sA1 + c * S::LBO1 + r * 16 ) = live ? tc2_resi8( o + 8 * c, p + 8 * c ) : make_uint4( 0, 0, 0, 0 );
       }
+      else if( STREAMC && STREAM )
+      {
+        const int16_t* src = resi + ( (size_t)( live ? tu : 0 ) * N + y ) * N;
+        const uint32_t bytes = live ? 16u : 0u;                                  // 0: the 16 bytes are zero-filled
+#pragma unroll
+        for( int c = 0; c < N / 8; c++ )
+          asm volatile( "cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"( a1Addr + c * S::LBO1 + r * 16 ), "l"( src + 8 * c ), "r"( bytes ) : "memory" );
+      }
       else
       {
         const uint4* src = reinterpret_cast<const uint4*>( resi + ( (size_t)( live ? tu : 0 ) * N + y ) * N );
@@ -171,6 +195,14 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
           *reinterpret_cast<uint4*>( sA1 + c * S::LBO1 + r * 16 ) = live ? __ldg( src + c ) : make_uint4( 0, 0, 0, 0 );
       }
     }
+    if( STREAM ) asm volatile( "cp.async.commit_group;" ::: "memory" );
+  };
+  if( STREAM && (int) blockIdx.x < numTiles ) load_tile( blockIdx.x );
+
+  for( int tile = blockIdx.x; tile < numTiles; tile += gridDim.x )
+  {
+    if( STREAM ) asm volatile( "cp.async.wait_group 0;" ::: "memory" );
+    else load_tile( tile );
     fence_async_smem();
     __syncthreads();
     // ---- B: stage-1 MMAs
@@ -192,6 +224,7 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
     }
     mbar_wait( mbar, phase ); phase ^= 1;
     tc_fence_after();
+    if( STREAM && tile + (int) gridDim.x < numTiles ) load_tile( tile + gridDim.x );
     // ---- C: tmp = ( Dlo + 256 * Dhi + rnd ) >> s1, stored transposed as the raw int32 bytes of A2
 #pragma unroll
     for( int m = 0; m < M1; m++ )
@@ -240,18 +273,18 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
       const bool live = tu < n;
       int cf[KEEP];
 #pragma unroll
-      for( int c0 = 0; c0 < KEEP; c0 += CH )
+      for( int c0 = 0; c0 < KEEP; c0 += S::ECH )
       {
-        int d0[CH], d1[CH], d2[CH];
-        tmem_ldc<CH>( tmem + laneBase + 0 * NMMA + c0, d0 );
-        tmem_ldc<CH>( tmem + laneBase + 1 * NMMA + c0, d1 );
-        tmem_ldc<CH>( tmem + laneBase + 2 * NMMA + c0, d2 );
+        int d0[S::ECH], d1[S::ECH], d2[S::ECH];
+        tmem_ldc<S::ECH>( tmem + laneBase + 0 * NMMA + c0, d0 );
+        tmem_ldc<S::ECH>( tmem + laneBase + 1 * NMMA + c0, d1 );
+        tmem_ldc<S::ECH>( tmem + laneBase + 2 * NMMA + c0, d2 );
         tmem_ld_wait();
 #pragma unroll
-        for( int k = 0; k < CH; k++ ) cf[c0 + k] = ( ( d2[k] << 16 ) + ( d1[k] << 8 ) + d0[k] + r2 ) >> s2;
+        for( int k = 0; k < S::ECH; k++ ) cf[c0 + k] = ( ( d2[k] << 16 ) + ( d1[k] << 8 ) + d0[k] + r2 ) >> s2;
       }
-      // pass 1 (Quant.cpp:160-208): last non-zero coefficient, coefficient groups above the threshold, RDOQ pre-check (largest magnitude)
-      int lastNZ = 0, amax = 0; unsigned cgLo = 0, cgHi = 0;
+      // pass 1 (Quant.cpp:160-208): last non-zero coefficient, highest coefficient group above the threshold, RDOQ pre-check (largest magnitude)
+      int hiNZ = -1, amax = 0, cgMax = 0;
       const int useThres = par.useThres;
 #pragma unroll
       for( int g = 0; g < KEEP / 4; g++ )
@@ -260,43 +293,52 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
 #pragma unroll
         for( int k = 0; k < 4; k++ )
         {
-          const int i = 4 * g + k, ac = abs( cf[i] );
-          m4 = max( m4, ac );
-          if( cf[i] ) lastNZ = max( lastNZ, sPos[i] );
+          const int i = 4 * g + k;
+          m4 = max( m4, abs( cf[i] ) );
+          if( cf[i] ) hiNZ = i;
         }
         amax = max( amax, m4 );
-        if( m4 > useThres ) { const int cg = sPos[4 * g] >> 4; if( KEEP < 32 || cg < 32 ) cgLo |= 1u << ( cg & 31 ); else cgHi |= 1u << ( cg - 32 ); }
+        if( m4 > useThres ) cgMax = max( cgMax, cgIdx[g] );
       }
+      int lastNZ = hiNZ >= 0 ? __ldg( invCol + hiNZ * KEEP ) : 0;
       lastNZ = __reduce_max_sync( tmask, lastNZ );
-      cgLo   = __reduce_or_sync( tmask, cgLo );
-      if( KEEP == 32 ) cgHi = __reduce_or_sync( tmask, cgHi );
+      cgMax  = __reduce_max_sync( tmask, cgMax );
       amax   = __reduce_max_sync( tmask, amax );
+      // Quant.cpp:182-208: the groups above the threshold all hold a non-zero coefficient, hence lie at or below the last one: the highest of them decides
       int pos = lastNZ;
+      if( ( lastNZ >> 4 ) >= 1 )
       {
-        const int initCg = pos >> 4;
-        if( initCg >= 1 )
-        {
-          const unsigned long long mask = ( (unsigned long long) cgHi << 32 ) | cgLo;
-          const unsigned long long mm = mask & ( initCg >= 63 ? ~0ull : ( ( 1ull << ( initCg + 1 ) ) - 1ull ) ) & ~1ull;
-          if( mm == 0 ) pos = 15;
-          else { const int gg = 63 - __clzll( (long long) mm ); if( gg != initCg ) pos = gg * 16 + 15; }
-        }
+        if( cgMax == 0 ) pos = 15;
+        else if( cgMax != ( lastNZ >> 4 ) ) pos = cgMax * 16 + 15;
+      }
+      if( live && coefOut )                                 // the transform coefficients as xT leaves them (before the trimming below)
+      {
+        int32_t* cd = coefOut + (size_t) tu * N * N + j2;
+#pragma unroll
+        for( int i = 0; i < KEEP; i++ ) cd[i * N] = cf[i];
+      }
+      if( pos != lastNZ )                                   // trimmed: whole groups beyond the final position drop out (scan position <= pos <=> group <= pos >> 4)
+      {
+        const int posCg = pos >> 4;
+#pragma unroll
+        for( int g = 0; g < KEEP / 4; g++ )
+          if( cgIdx[g] > posCg ) { cf[4 * g] = 0; cf[4 * g + 1] = 0; cf[4 * g + 2] = 0; cf[4 * g + 3] = 0; }
       }
       // pass 2 (Quant.cpp:211-227)
-      int sum = 0, lastQ = 0;
+      int sum = 0, hiQ = -1;
       const int qbits = par.qbits; const unsigned scale = (unsigned) par.scale, add32 = par.add32;
       int16_t* qd = qOut + (size_t)( live ? tu : 0 ) * N * N + j2;
-      if( par.q32 && (unsigned) amax < 65536u )
+      if( par.q32 && (unsigned) amax < 32768u && ( ( (unsigned) amax * scale + add32 ) >> qbits ) <= 32767u )
       {
+        // -(( |c| * scale + add ) >> qbits) == ( c * scale + 2^qbits - 1 - add ) >> qbits for c < 0 (arithmetic shift): one multiply-add per level, no clipping needed
+        const int addP = (int) add32, addN = (int)( ( 1u << qbits ) - 1u - add32 );
 #pragma unroll
         for( int i = 0; i < KEEP; i++ )
         {
-          const unsigned ac = sPos[i] <= pos ? (unsigned) abs( cf[i] ) : 0u;
-          const int mag = (int)( ( ac * scale + add32 ) >> qbits );
-          sum += mag;
-          int v = cf[i] < 0 ? -mag : mag;
-          v = max( -32768, min( 32767, v ) );
-          if( v ) lastQ = max( lastQ, sPos[i] + 1 );
+          const int c = cf[i];
+          const int v = ( c * (int) scale + ( c < 0 ? addN : addP ) ) >> qbits;
+          sum += abs( v );
+          if( v ) hiQ = i;
           if( live ) qd[i * N] = (int16_t) v;
         }
       }
@@ -305,24 +347,19 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
 #pragma unroll
         for( int i = 0; i < KEEP; i++ )
         {
-          const long long ac = sPos[i] <= pos ? (long long) abs( cf[i] ) : 0ll;
+          const long long ac = (long long) abs( cf[i] );
           const int mag = (int)( ( ac * par.scale + par.add ) >> qbits );
           sum += mag;
-          int v = cf[i] < 0 ? max( -32768, -mag ) : min( 32767, mag );
-          if( v ) lastQ = max( lastQ, sPos[i] + 1 );
+          const int v = cf[i] < 0 ? max( -32768, -mag ) : min( 32767, mag );
+          if( v ) hiQ = i;
           if( live ) qd[i * N] = (int16_t) v;
         }
       }
+      int lastQ = hiQ >= 0 ? __ldg( invCol + hiQ * KEEP ) + 1 : 0;
       sum   = __reduce_add_sync( tmask, sum );
       lastQ = __reduce_max_sync( tmask, lastQ );
       if( live )
       {
-        if( coefOut )
-        {
-          int32_t* cd = coefOut + (size_t) tu * N * N + j2;
-#pragma unroll
-          for( int i = 0; i < KEEP; i++ ) cd[i * N] = cf[i];
-        }
         if( j2 == 0 )
         {
           if( absSumOut )   absSumOut[tu]   = sum;
@@ -361,7 +398,7 @@ __global__ void __launch_bounds__( 128, 3 ) fwd_trquant_tc2_kernel( const __grid
 
   tc_fence_before();
   __syncthreads();
-  if( warp == 0 ) asm volatile( "tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"( tmem ), "r"( (uint32_t) TC_TMEM_COLS ) : "memory" );
+  if( warp == 0 ) asm volatile( "tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"( tmem ), "r"( (uint32_t) S::TMEM_COLS ) : "memory" );
 }
 
 } // namespace vvb
