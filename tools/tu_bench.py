@@ -46,8 +46,8 @@ for (w, h) in shapes:
                                                                      P_(d_last.data_ptr()), P_(d_nr.data_ptr()))))
     if os.environ.get('TC2_SWEEP'):
         eng.set_tensor_transform(3)
-        for st in (1, 0):
-            for ct in (2, 3, 4, 6, 8):
+        for st in (3, 1):
+            for ct in (4, 6, 8):
                 os.environ['VVB_TC2_CTAS'] = str(ct); os.environ['VVB_TC2_STREAM'] = str(st)
                 res['fwd_s%dc%d' % (st, ct)] = tl(lambda: chk(lib.vvb_fwd_trquant_dev(eng.h, ctypes.byref(par), P_(d_r.data_ptr()), ntu, None, P_(d_q.data_ptr()), P_(d_sum.data_ptr()),
                                                                                      P_(d_last.data_ptr()), P_(d_nr.data_ptr()))))

@@ -1185,8 +1185,8 @@ static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int or
     ctx->tc2Image[key] = d;
   }
   const uint4* dImg = (const uint4*) ctx->tc2Image[key];
-  const char* envC = getenv( "VVB_TC2_CTAS" ); const char* envS = getenv( "VVB_TC2_STREAM" );
-  const int capC = envC ? atoi( envC ) : 0, streamOn = envS ? atoi( envS ) : 1;
+  const char* envC = getenv( "VVB_TC2_CTAS" ); const char* envS = getenv( "VVB_TC2_STREAM" );     // tuning knobs: CTAs per SM; bit 0 cp.async streaming, bit 1 single-thread wait
+  const int capC = envC ? atoi( envC ) : 0, streamOn = envS ? atoi( envS ) : 3;
 #define VVB_TC2_CALL( Nv ) { using S = Tc2Shape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; \
     static int perSm[2] = { 0, 0 }; int& ps = perSm[dBlocks ? 1 : 0]; \
     if( !ps ) { cudaFuncAttributes fa = {}; \

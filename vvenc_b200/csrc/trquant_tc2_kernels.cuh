@@ -43,6 +43,37 @@ template<int CH> __device__ __forceinline__ void tmem_ldc( uint32_t taddr, int (
 template<> __device__ __forceinline__ void tmem_ldc<8>( uint32_t taddr, int (&v)[8] )   { tmem_ld8( taddr, v ); }
 template<> __device__ __forceinline__ void tmem_ldc<16>( uint32_t taddr, int (&v)[16] ) { tmem_ld16( taddr, v ); }
 
+__device__ __forceinline__ void mbar_wait_hint( uint32_t addr, uint32_t parity )
+{
+  uint32_t done = 0;
+  while( !done )
+  {
+    asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n" : "=r"( done ) : "r"( addr ), "r"( parity ), "r"( 100000u ) : "memory" );
+  }
+}
+
+// reductions over the KEEP lanes of one TU (aligned lane groups of 8 / 16 lanes, or the warp): xor butterflies for the partial groups so that every lane of the
+// warp executes the same shuffles whatever its group does
+template<int KEEP> __device__ __forceinline__ int team_max( int v )
+{
+  if( KEEP >= 32 ) return __reduce_max_sync( 0xffffffffu, v );
+#pragma unroll
+  for( int d = KEEP / 2; d >= 1; d >>= 1 ) v = max( v, __shfl_xor_sync( 0xffffffffu, v, d ) );
+  return v;
+}
+template<int KEEP> __device__ __forceinline__ int team_sum( int v )
+{
+  if( KEEP >= 32 ) return __reduce_add_sync( 0xffffffffu, v );
+#pragma unroll
+  for( int d = KEEP / 2; d >= 1; d >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, d );
+  return v;
+}
+
 template<int N> struct Tc2Shape
 {
   static constexpr int KEEP = N > 32 ? 32 : N;             // kept outputs per dimension (DCT-II zero-out at 64; MTS at 32 keeps 16: run-time, rows beyond are zero)
@@ -147,7 +178,6 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
   int cgIdx[KEEP / 4];
 #pragma unroll
   for( int g = 0; g < KEEP / 4; g++ ) cgIdx[g] = __ldg( invCol + 4 * g * KEEP ) >> 4;
-  const unsigned tmask = KEEP >= 32 ? 0xffffffffu : ( ( 1u << ( KEEP & 31 ) ) - 1u ) << ( ( tid & 31 ) & ~( KEEP - 1 ) );
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -158,11 +188,15 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
   const int numTiles = ( n + TPT - 1 ) / TPT;
   const int r1 = par.s1 > 0 ? 1 << ( par.s1 - 1 ) : 0, r2 = 1 << ( par.s2 - 1 ), s1 = par.s1, s2 = par.s2;
   const uint32_t laneBase = (uint32_t)( warp * 32 ) << 16;
+  // shared-memory descriptors of the four operand families; inside the loops only the start-address field (16-byte units, low word) moves
+  const uint64_t dA1 = umma_desc_kmajor( a1Addr, S::LBO1, 128 ), dB1 = umma_desc_kmajor( b1Addr, S::BCH, 128 );
+  const uint64_t dA2 = umma_desc_kmajor( a2Addr, S::LBO2, S::SBO2 ), dB2 = umma_desc_kmajor( b2Addr, S::BCH, 128 );
 
   // ---- A: residual rows of one tile -> A1 (raw bytes).  Compact pools of TUs up to 32x32 stream in with cp.async (STREAM): the copy of tile k+1 is issued as soon as
   //      the stage-1 MMAs of tile k have consumed A1 and lands while the rest of tile k runs.
   constexpr bool STREAMC = !PLANES && !S::ALIAS;
-  const bool STREAM = STREAMC && streamOn;
+  const bool STREAM = STREAMC && ( streamOn & 1 );
+  const bool singleWait = ( streamOn & 2 ) != 0;
   auto load_tile = [&]( int tile )
   {
 #pragma unroll
@@ -216,13 +250,17 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
 #pragma unroll
           for( int ks = 0; ks < S::K1 / 32; ks++ )
           {
-            const uint64_t da = umma_desc_kmajor( a1Addr + m * 128 * 16 + ks * 2 * S::LBO1, S::LBO1, 128 );
-            const uint64_t db = umma_desc_kmajor( b1Addr + p * S::B1_BYTES + ks * 2 * S::BCH, S::BCH, 128 );
+            const uint64_t da = dA1 + (uint64_t)( ( m * 128 * 16 + ks * 2 * S::LBO1 ) >> 4 );
+            const uint64_t db = dB1 + (uint64_t)( ( p * S::B1_BYTES + ks * 2 * S::BCH ) >> 4 );
             umma_i8( tmem + ( m * 2 + p ) * NMMA, da, db, p ? idescS : idescU, ks > 0 ? 1u : 0u );
           }
       umma_commit( mbar );
     }
-    mbar_wait( mbar, phase ); phase ^= 1;
+    if( singleWait ) { if( tid == 0 ) mbar_wait_hint( mbar, phase ); }   // one thread polls the MMA completion, the others sleep in the CTA barrier
+    else mbar_wait( mbar, phase );
+    phase ^= 1;
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
     if( STREAM && tile + (int) gridDim.x < numTiles ) load_tile( tile + gridDim.x );
     // ---- C: tmp = ( Dlo + 256 * Dhi + rnd ) >> s1, stored transposed as the raw int32 bytes of A2
@@ -259,13 +297,17 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
 #pragma unroll
         for( int ks = 0; ks < S::K2 / 32; ks++ )
         {
-          const uint64_t da = umma_desc_kmajor( a2Addr + ks * 2 * S::LBO2, S::LBO2, S::SBO2 );
-          const uint64_t db = umma_desc_kmajor( b2Addr + p * S::B2_BYTES + ks * 2 * S::BCH, S::BCH, 128 );
+          const uint64_t da = dA2 + (uint64_t)( ( ks * 2 * S::LBO2 ) >> 4 );
+          const uint64_t db = dB2 + (uint64_t)( ( p * S::B2_BYTES + ks * 2 * S::BCH ) >> 4 );
           umma_i8( tmem + p * NMMA, da, db, p == 2 ? idescS : idescU, ks > 0 ? 1u : 0u );
         }
       umma_commit( mbar );
     }
-    mbar_wait( mbar, phase ); phase ^= 1;
+    if( singleWait ) { if( tid == 0 ) mbar_wait_hint( mbar, phase ); }   // one thread polls the MMA completion, the others sleep in the CTA barrier
+    else mbar_wait( mbar, phase );
+    phase ^= 1;
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
     // ---- E: coefficient column (t2, j2): c[i] = ( D0 + 256 * D1 + 65536 * D2 + rnd ) >> s2, then QuantCore in registers
     {
@@ -283,46 +325,35 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
 #pragma unroll
         for( int k = 0; k < S::ECH; k++ ) cf[c0 + k] = ( ( d2[k] << 16 ) + ( d1[k] << 8 ) + d0[k] + r2 ) >> s2;
       }
-      // pass 1 (Quant.cpp:160-208): last non-zero coefficient, highest coefficient group above the threshold, RDOQ pre-check (largest magnitude)
-      int hiNZ = -1, amax = 0, cgMax = 0;
+      // pass 1 (Quant.cpp:160-208) at coefficient-group granularity: the group of the last non-zero coefficient, the highest group above the threshold, the RDOQ
+      // pre-check (largest magnitude).  The group index grows down the column, so the last assignment is the maximum.
+      int amax = 0, cgMax = 0, initCg = 0;
       const int useThres = par.useThres;
 #pragma unroll
       for( int g = 0; g < KEEP / 4; g++ )
       {
-        int m4 = 0;
-#pragma unroll
-        for( int k = 0; k < 4; k++ )
-        {
-          const int i = 4 * g + k;
-          m4 = max( m4, abs( cf[i] ) );
-          if( cf[i] ) hiNZ = i;
-        }
+        const int m4 = max( max( abs( cf[4 * g] ), abs( cf[4 * g + 1] ) ), max( abs( cf[4 * g + 2] ), abs( cf[4 * g + 3] ) ) );
         amax = max( amax, m4 );
-        if( m4 > useThres ) cgMax = max( cgMax, cgIdx[g] );
+        if( m4 ) initCg = cgIdx[g];
+        if( m4 > useThres ) cgMax = cgIdx[g];
       }
-      int lastNZ = hiNZ >= 0 ? __ldg( invCol + hiNZ * KEEP ) : 0;
-      lastNZ = __reduce_max_sync( tmask, lastNZ );
-      cgMax  = __reduce_max_sync( tmask, cgMax );
-      amax   = __reduce_max_sync( tmask, amax );
-      // Quant.cpp:182-208: the groups above the threshold all hold a non-zero coefficient, hence lie at or below the last one: the highest of them decides
-      int pos = lastNZ;
-      if( ( lastNZ >> 4 ) >= 1 )
-      {
-        if( cgMax == 0 ) pos = 15;
-        else if( cgMax != ( lastNZ >> 4 ) ) pos = cgMax * 16 + 15;
-      }
+      initCg = team_max<KEEP>( initCg );
+      cgMax  = team_max<KEEP>( cgMax );
+      amax   = team_max<KEEP>( amax );
+      // Quant.cpp:182-208: the groups above the threshold all hold a non-zero coefficient, hence lie at or below the last one: the highest of them decides.
+      // Trimmed: the final position is the end of group cgMax (15 when cgMax == 0) and whole groups beyond it drop out (scan position <= pos <=> group <= pos >> 4).
+      const bool trimmed = initCg >= 1 && cgMax != initCg;
       if( live && coefOut )                                 // the transform coefficients as xT leaves them (before the trimming below)
       {
         int32_t* cd = coefOut + (size_t) tu * N * N + j2;
 #pragma unroll
         for( int i = 0; i < KEEP; i++ ) cd[i * N] = cf[i];
       }
-      if( pos != lastNZ )                                   // trimmed: whole groups beyond the final position drop out (scan position <= pos <=> group <= pos >> 4)
+      if( trimmed )
       {
-        const int posCg = pos >> 4;
 #pragma unroll
         for( int g = 0; g < KEEP / 4; g++ )
-          if( cgIdx[g] > posCg ) { cf[4 * g] = 0; cf[4 * g + 1] = 0; cf[4 * g + 2] = 0; cf[4 * g + 3] = 0; }
+          if( cgIdx[g] > cgMax ) { cf[4 * g] = 0; cf[4 * g + 1] = 0; cf[4 * g + 2] = 0; cf[4 * g + 3] = 0; }
       }
       // pass 2 (Quant.cpp:211-227)
       int sum = 0, hiQ = -1;
@@ -356,8 +387,18 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
         }
       }
       int lastQ = hiQ >= 0 ? __ldg( invCol + hiQ * KEEP ) + 1 : 0;
-      sum   = __reduce_add_sync( tmask, sum );
-      lastQ = __reduce_max_sync( tmask, lastQ );
+      sum   = team_sum<KEEP>( sum );
+      lastQ = team_max<KEEP>( lastQ );
+      int pos = cgMax * 16 + 15;                            // the final scan position is only reported when every level is zero (Quant.cpp:830)
+      const bool exact = sum == 0 && !trimmed;              // ... and then, untrimmed, it is the exact position of the last non-zero coefficient
+      if( __any_sync( 0xffffffffu, exact ) )                // rare; the whole warp walks through so that the lane groups reduce together
+      {
+        int hiNZ = -1;
+#pragma unroll
+        for( int i = 0; i < KEEP; i++ ) if( cf[i] ) hiNZ = i;
+        const int lastNZ = team_max<KEEP>( hiNZ >= 0 ? __ldg( invCol + hiNZ * KEEP ) : 0 );
+        if( exact ) pos = lastNZ;
+      }
       if( live )
       {
         if( j2 == 0 )
