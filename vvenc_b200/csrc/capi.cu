@@ -993,7 +993,10 @@ int vvb_cost_pattern_dev( vvb_ctx* ctx, int dfunc, int orgPlane, int refPlane, c
       const int work = bpc * K * T;
       const int bd = std::min( 256, std::max( 64, ( work + 31 ) & ~31 ) );
       const int groups = ( n + bpc - 1 ) / bpc;
-      had8_direct_kernel<<<std::min( groups, ctx->numSMs * 8 ), bd, (size_t) LD.total * 4, ctx->stream>>>( op, rp, dBlocks, n, w, h, bpc, dPattern, K, mp, dCost, dBest );
+      if( op.bitDepth <= 10 && rp.bitDepth <= 10 )
+        had8_direct_kernel<true><<<std::min( groups, ctx->numSMs * 8 ), bd, (size_t) LD.total * 4, ctx->stream>>>( op, rp, dBlocks, n, w, h, bpc, dPattern, K, mp, dCost, dBest );
+      else
+        had8_direct_kernel<false><<<std::min( groups, ctx->numSMs * 8 ), bd, (size_t) LD.total * 4, ctx->stream>>>( op, rp, dBlocks, n, w, h, bpc, dPattern, K, mp, dCost, dBest );
       CHECK_LAUNCH( "had8_direct_kernel" );
       return VVB_OK;
     }

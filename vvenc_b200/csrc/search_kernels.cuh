@@ -829,6 +829,14 @@ __host__ __device__ inline HadDirSmem had_dir_smem( int K, int BPC )
   return s;
 }
 
+// dp2a with unsigned 16-bit halves against signed byte weights (the biased packed values of the PACKED path below)
+__device__ __forceinline__ int dp2a_lo_us( uint32_t a, int b, int c ) { int d; asm( "dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( c ) ); return d; }
+
+// PACKED (planes of at most 10 bits): the tile lives in 32 registers as pairs of 16-bit values biased by 0x8000.  Difference and the five butterfly stages across
+// registers are one IADD3 per register each: ( A + B - K ) and ( A - B + K ) with K = 0x80008000 keep both halves inside [0, 65535] (|value| <= 32 * 1023), so the
+// carry between the halves cancels exactly.  The sixth stage (the two halves of a word against each other, results up to 64 * 1023) and the bias removal are two
+// dp2a per word.  Half the instructions and half the registers of the scalar form, bit-exact.
+template<bool PACKED>
 __global__ void __launch_bounds__( 256 ) had8_direct_kernel( const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane refPlane,
                                                              const vvb_block* __restrict__ blocks, int nBlocks, int w, int h, int BPC,
                                                              const vvb_mv* __restrict__ pattern, int K, const __grid_constant__ MePar par,
@@ -870,6 +878,55 @@ __global__ void __launch_bounds__( 256 ) had8_direct_kernel( const __grid_consta
       const int odd = (int)( ( (uintptr_t) rp >> 1 ) & 1 );      // plane rows keep the parity (even strides)
       const uint32_t* rw = reinterpret_cast<const uint32_t*>( rp - odd );
       const int rStrideW = refPlane.stride >> 1;
+      uint32_t sacc = 0, dc;
+      if( PACKED )
+      {
+        uint32_t u[32];
+#pragma unroll
+        for( int r = 0; r < 8; r++ )
+        {
+        uint4 o;
+        if( oVec ) o = __ldg( reinterpret_cast<const uint4*>( op + (ptrdiff_t) r * orgPlane.stride ) );
+        else
+        {
+          const int16_t* q = op + (ptrdiff_t) r * orgPlane.stride;
+          o.x = (uint32_t)(uint16_t) __ldg( q ) | ( (uint32_t)(uint16_t) __ldg( q + 1 ) << 16 ); o.y = (uint32_t)(uint16_t) __ldg( q + 2 ) | ( (uint32_t)(uint16_t) __ldg( q + 3 ) << 16 );
+          o.z = (uint32_t)(uint16_t) __ldg( q + 4 ) | ( (uint32_t)(uint16_t) __ldg( q + 5 ) << 16 ); o.w = (uint32_t)(uint16_t) __ldg( q + 6 ) | ( (uint32_t)(uint16_t) __ldg( q + 7 ) << 16 );
+        }
+        const uint32_t* rr = rw + (ptrdiff_t) r * rStrideW;
+        uint32_t c0 = __ldg( rr ), c1 = __ldg( rr + 1 ), c2 = __ldg( rr + 2 ), c3 = __ldg( rr + 3 );
+        if( odd )
+        {
+          const uint32_t c4 = __ldg( rr + 4 );
+          c0 = __funnelshift_r( c0, c1, 16 ); c1 = __funnelshift_r( c1, c2, 16 ); c2 = __funnelshift_r( c2, c3, 16 ); c3 = __funnelshift_r( c3, c4, 16 );
+        }
+          u[4 * r] = o.x - c0 + 0x80008000u; u[4 * r + 1] = o.y - c1 + 0x80008000u; u[4 * r + 2] = o.z - c2 + 0x80008000u; u[4 * r + 3] = o.w - c3 + 0x80008000u;
+        }
+#pragma unroll
+        for( int bit = 0; bit < 5; bit++ )
+        {
+#pragma unroll
+          for( int i = 0; i < 32; i++ )
+          {
+            if( !( i & ( 1 << bit ) ) )
+            {
+              const uint32_t a = u[i], bb = u[i | ( 1 << bit )];
+              u[i] = a + bb - 0x80008000u; u[i | ( 1 << bit )] = a - bb + 0x80008000u;
+            }
+          }
+        }
+        int s0 = 0;
+#pragma unroll
+        for( int i = 0; i < 32; i++ )
+        {
+          const int sp = dp2a_lo_us( u[i], 0x00000101, -65536 ), sm = dp2a_lo_us( u[i], 0x0000ff01, 0 );
+          if( i == 0 ) s0 = sp;
+          sacc = __sad( sp, 0, sacc ); sacc = __sad( sm, 0, sacc );
+        }
+        dc = (uint32_t) abs( s0 );
+      }
+      else
+      {
       int d[64];
 #pragma unroll
       for( int r = 0; r < 8; r++ )
@@ -908,10 +965,10 @@ __global__ void __launch_bounds__( 256 ) had8_direct_kernel( const __grid_consta
           }
         }
       }
-      uint32_t sacc = 0;
 #pragma unroll
       for( int i = 0; i < 64; i++ ) sacc = __sad( d[i], 0, sacc );
-      const uint32_t dc = (uint32_t) abs( d[0] );
+      dc = (uint32_t) abs( d[0] );
+      }
       sacc = sacc - dc + ( dc >> 2 );                            // RdCost.cpp:1316-1318
       const uint32_t tileCost = ( sacc + 2 ) >> 2;               // :1319
       if( T == 1 ) sCost[j * K + k] = tileCost; else atomicAdd( &sCost[j * K + k], tileCost );
