@@ -261,8 +261,9 @@ int vvb_create( vvb_ctx** out, int device )
   cudaFuncSetAttribute( mctf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
   cudaFuncSetAttribute( frac_grid_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
-#define VVB_TC2_ATTR( Nv ) cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM ); \
-                          cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM );
+#define VVB_TC2_ATTR( Nv ) cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM ); \
+                          cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM ); \
+                          cudaFuncSetAttribute( fwd_trquant_tc2_kernel<Nv, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<Nv>::SMEM );
   VVB_TC2_ATTR( 8 ) VVB_TC2_ATTR( 16 ) VVB_TC2_ATTR( 32 ) VVB_TC2_ATTR( 64 )
 #undef VVB_TC2_ATTR
   cudaFuncSetAttribute( fwd_trquant_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 );
@@ -1169,8 +1170,9 @@ static bool tc2Eligible( const vvb_ctx* ctx, const TuPar& p )
 {
   return ctx->tensorTransform == 3 && !p.lfnstIdx && !p.ts && !p.signHiding && p.w == p.h && p.w >= 8 && p.w <= 64 && p.s1 >= 0;
 }
+// dResi alone: residual pool; dResi + dResi2: original and prediction pools; dBlocks: positions in the two planes
 static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int orgPlane, int predPlane, const vvb_block* dBlocks, int n,
-                      int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
+                      int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq, const int16_t* dResi2 = nullptr )
 {
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
   // B operand images, built once per (size, horizontal type, vertical type) and kept on the device
@@ -1191,14 +1193,16 @@ static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int or
   const char* envC = getenv( "VVB_TC2_CTAS" ); const char* envS = getenv( "VVB_TC2_STREAM" );     // tuning knobs: CTAs per SM; bit 0 cp.async streaming, bit 1 single-thread wait
   const int capC = envC ? atoi( envC ) : 0, streamOn = envS ? atoi( envS ) : 3;
 #define VVB_TC2_CALL( Nv ) { using S = Tc2Shape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; \
-    static int perSm[2] = { 0, 0 }; int& ps = perSm[dBlocks ? 1 : 0]; \
+    static int perSm[3] = { 0, 0, 0 }; const int mode = dBlocks ? 1 : dResi2 ? 2 : 0; int& ps = perSm[mode]; \
     if( !ps ) { cudaFuncAttributes fa = {}; \
-                if( dBlocks ) cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, true> ); else cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, false> ); \
+                if( mode == 1 ) cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, 1> ); else if( mode == 2 ) cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, 2> ); \
+                else cudaFuncGetAttributes( &fa, fwd_trquant_tc2_kernel<Nv, 0> ); \
                 const int regs = std::max( fa.numRegs, 32 ); \
                 ps = std::min( std::min( 65536 / ( regs * 128 ), ( 227 * 1024 ) / ( (int) S::SMEM + (int) fa.sharedSizeBytes + 1024 ) ), 512 / S::TMEM_COLS ); ps = std::max( std::min( ps, Nv == 8 ? 6 : 8 ), 1 ); } \
     const int grid = std::min( tiles, ctx->numSMs * ( capC > 0 ? std::min( capC, ps ) : ps ) ); \
-    if( dBlocks ) fwd_trquant_tc2_kernel<Nv, true><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, nullptr, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
-    else          fwd_trquant_tc2_kernel<Nv, false><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, dResi, po, pp, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
+    if( mode == 1 )      fwd_trquant_tc2_kernel<Nv, 1><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, nullptr, nullptr, po, pp, dBlocks, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
+    else if( mode == 2 ) fwd_trquant_tc2_kernel<Nv, 2><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, dResi, dResi2, po, pp, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); \
+    else                 fwd_trquant_tc2_kernel<Nv, 0><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, streamOn, ctx->d_scan, dResi, nullptr, po, pp, nullptr, n, dCoef, dQ, dAbsSum, dLastPos, dNeedRdoq ); }
   switch( p.w ) { case 8: VVB_TC2_CALL( 8 ) break; case 16: VVB_TC2_CALL( 16 ) break; case 32: VVB_TC2_CALL( 32 ) break; default: VVB_TC2_CALL( 64 ) break; }
 #undef VVB_TC2_CALL
   CHECK_LAUNCH( "fwd_trquant_tc2_kernel" );
@@ -1612,6 +1616,21 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
   CU( cudaSetDevice( ctx->device ) );
   const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
   const bool ext = p.signHiding != 0 || p.ts != 0 || p.lfnstIdx != 0;
+  // square 8..64 TUs with the plain quantiser: the forward half on the tensor-core engine (levels, absSum, lastPos, RDOQ flag), then the inverse half from the levels
+  if( tc2Eligible( ctx, p ) && ( dBlocks || ( ( ( (uintptr_t) dOrg | (uintptr_t) dPred ) & 15 ) == 0 ) ) )
+  {
+    void* dM;
+    if( ( rc = scratch( ctx, 7, (size_t) n * 8, &dM ) ) ) return rc;
+    int32_t* dSum = (int32_t*) dM; int32_t* dLast = dSum + n;
+    if( ( rc = tc2Launch( ctx, p, dBlocks ? nullptr : dOrg, orgPlane, predPlane, dBlocks, n, nullptr, dQ, dSum, dLast, dNeedRdoq, dBlocks ? nullptr : dPred ) ) ) return rc;
+#define VVB_RTQ_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
+      tu_roundtrip_kernel<LWv, LHv, false, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
+                                                                                              dQ, dReco, (TuResult*) dRes, dNeedRdoq, dSum, dLast ); }
+    switch( p.lw ) { case 3: VVB_RTQ_CALL( 3, 3 ) break; case 4: VVB_RTQ_CALL( 4, 4 ) break; case 5: VVB_RTQ_CALL( 5, 5 ) break; default: VVB_RTQ_CALL( 6, 6 ) break; }
+#undef VVB_RTQ_CALL
+    CHECK_LAUNCH( "tu_roundtrip_kernel (from levels)" );
+    return VVB_OK;
+  }
 #define VVB_RT_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
     if( ext ) tu_roundtrip_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
                                                                                               dQ, dReco, (TuResult*) dRes, dNeedRdoq ); \

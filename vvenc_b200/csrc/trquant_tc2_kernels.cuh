@@ -139,9 +139,10 @@ template<int N> static void tc2_build_b_image( const int8_t* tab, int offH, int 
   }
 }
 
-template<int N, bool PLANES>
+// MODE 0: compact residual pool (resi); 1: residual formed from resident planes at the block positions; 2: residual = resi[] - resi2[] of two compact pools (org, pred)
+template<int N, int MODE>
 __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel( const __grid_constant__ TuPar par, const uint4* __restrict__ bImage, int streamOn, const int32_t* __restrict__ scanTab,
-                                                                    const int16_t* __restrict__ resi,
+                                                                    const int16_t* __restrict__ resi, const int16_t* __restrict__ resi2,
                                                                     const __grid_constant__ Plane orgPlane, const __grid_constant__ Plane predPlane, const vvb_block* __restrict__ blocks,
                                                                     int n, int32_t* __restrict__ coefOut, int16_t* __restrict__ qOut, int32_t* __restrict__ absSumOut,
                                                                     int32_t* __restrict__ lastPosOut, uint8_t* __restrict__ needRdoqOut )
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
 
   // ---- A: residual rows of one tile -> A1 (raw bytes).  Compact pools of TUs up to 32x32 stream in with cp.async (STREAM): the copy of tile k+1 is issued as soon as
   //      the stage-1 MMAs of tile k have consumed A1 and lands while the rest of tile k runs.
-  constexpr bool STREAMC = !PLANES && !S::ALIAS;
+  constexpr bool PLANES = MODE == 1;
+  constexpr bool STREAMC = MODE == 0 && !S::ALIAS;
   const bool STREAM = STREAMC && ( streamOn & 1 );
   const bool singleWait = ( streamOn & 2 ) != 0;
   auto load_tile = [&]( int tile )
@@ -212,6 +214,18 @@ __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel
 #pragma unroll
         for( int c = 0; c < N / 8; c++ )
           *reinterpret_cast<uint4*>( sA1 + c * S::LBO1 + r * 16 ) = live ? tc2_resi8( o + 8 * c, p + 8 * c ) : make_uint4( 0, 0, 0, 0 );
+      }
+      else if( MODE == 2 )
+      {
+        const size_t off = ( (size_t)( live ? tu : 0 ) * N + y ) * N;
+        const uint4* so = reinterpret_cast<const uint4*>( resi + off ); const uint4* sp = reinterpret_cast<const uint4*>( resi2 + off );
+#pragma unroll
+        for( int c = 0; c < N / 8; c++ )
+        {
+          uint4 d = make_uint4( 0, 0, 0, 0 );
+          if( live ) { const uint4 a = __ldg( so + c ), b = __ldg( sp + c ); d = make_uint4( __vsub2( a.x, b.x ), __vsub2( a.y, b.y ), __vsub2( a.z, b.z ), __vsub2( a.w, b.w ) ); }
+          *reinterpret_cast<uint4*>( sA1 + c * S::LBO1 + r * 16 ) = d;
+        }
       }
       else if( STREAMC && STREAM )
       {
