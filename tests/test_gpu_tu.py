@@ -542,3 +542,53 @@ def _tc2_planes(rs, W, H, m, bd=10):
     a = rs.randint(0, 1 << bd, size=(H + 2 * m, S)).astype(np.int16)
     b = np.clip(np.roll(a, (2, -3), (0, 1)) + rs.randint(-40, 41, size=a.shape), 0, (1 << bd) - 1).astype(np.int16)
     return np.ascontiguousarray(a), np.ascontiguousarray(b), S
+
+
+def test_gpu_inverse_tensor_engine_vs_cuda_core_engine(gpu):
+    """vvb_set_tensor_transform(3) also routes vvb_inv_trquant and the second half of vvb_tu_roundtrip of square 8 / 16 / 32 TUs through the tcgen05 inverse engine
+    (itrquant_tc_kernels.cuh: dequantised coefficients and first-pass outputs as raw int16 bytes): residuals, reconstructions and the three distortions equal the
+    CUDA-core engine for every transform pair, 8 / 10 / 12 bit, plain and DepQuant dequantiser, levels up to the int16 extremes, tails that do not fill a tile, and
+    resident-plane addressing with any prediction displacement"""
+    rs = np.random.RandomState(4004)
+    try:
+        for (N, pairs) in ((8, ((0, 0), (2, 2), (1, 2))), (16, ((0, 0), (2, 1))), (32, ((0, 0), (1, 2), (2, 2)))):
+            for (th, tv) in pairs:
+                for bd in (8, 10, 12):
+                    for dq in (0, 1):
+                        n = int(rs.choice([1, 5, 37, 130, 700]))
+                        amp = np.array([32767, 2000, 60, 3, 0])[rs.randint(0, 5, n)]
+                        q = (rs.randint(-1000, 1001, size=(n, N, N)) * amp[:, None, None] // 1000).astype(np.int16)
+                        q[rs.randint(0, 3, size=q.shape) > 0] = 0
+                        if n > 2:
+                            q[1] = rs.choice([-32768, 32767], size=(N, N))
+                        qp = int(rs.randint(-6 * (bd - 8), 64))
+                        par = gpu.eng.tu_par(N, N, th, tv, bd, qp, False, bool(dq))
+                        gpu.eng.set_tensor_transform(0); a = gpu.eng.inv_trquant(par, q)
+                        gpu.eng.set_tensor_transform(3); b = gpu.eng.inv_trquant(par, q)
+                        assert np.array_equal(a, b), (N, th, tv, bd, dq, qp, n, np.argwhere(a != b)[:4])
+                    # fused round trip, pools
+                    n = int(rs.choice([3, 37, 500])); lim = 1 << bd
+                    org = rs.randint(0, lim, size=(n, N, N)).astype(np.int16)
+                    amp = np.array([lim // 2, 60, 8, 0])[rs.randint(0, 4, n)]
+                    pred = np.clip(org.astype(np.int32) - (rs.randint(-1000, 1001, size=(n, N, N)) * amp[:, None, None] // 1000), 0, lim - 1).astype(np.int16)
+                    par = gpu.eng.tu_par(N, N, th, tv, bd, int(rs.randint(0, 50)), bool(rs.randint(0, 2)), False)
+                    gpu.eng.set_tensor_transform(0); a = gpu.eng.tu_roundtrip(par, org, pred)
+                    gpu.eng.set_tensor_transform(3); b = gpu.eng.tu_roundtrip(par, org, pred); c = gpu.eng.tu_roundtrip(par, org, pred, want_reco=False)
+                    for k in ('q', 'reco', 'need_rdoq'):
+                        assert np.array_equal(a[k], b[k]), (N, th, tv, bd, k)
+                    assert np.array_equal(a['res'], b['res']) and np.array_equal(a['res'], c['res']) and np.array_equal(a['q'], c['q']), (N, th, tv, bd)
+                    assert (a['res']['abs_sum'] == 0).any() or n < 30
+        W, H, m = 320, 192, 16
+        a_, b_, S = _tc2_planes(rs, W, H, m)
+        gpu.eng.upload_plane(0, a_, W, H, m, 10); gpu.eng.upload_plane(1, b_, W, H, m, 10)
+        for N in (8, 16, 32, 64):
+            n = 301 if N < 64 else 40
+            blocks = np.zeros(n, dtype=gpu.V.BLOCK_DT)
+            blocks['x'] = rs.randint(0, W - N + 1, n); blocks['y'] = rs.randint(0, H - N + 1, n)
+            blocks['start_x'] = rs.randint(-m, m + 1, n); blocks['start_y'] = rs.randint(-m, m + 1, n)
+            par = gpu.eng.tu_par(N, N, 0, 0, 10, int(rs.randint(20, 40)), False, False)
+            gpu.eng.set_tensor_transform(0); a = gpu.eng.tu_roundtrip_planes(par, 0, 1, blocks)
+            gpu.eng.set_tensor_transform(3); b = gpu.eng.tu_roundtrip_planes(par, 0, 1, blocks)
+            assert np.array_equal(a['q'], b['q']) and np.array_equal(a['reco'], b['reco']) and np.array_equal(a['res'], b['res']) and np.array_equal(a['need_rdoq'], b['need_rdoq']), N
+    finally:
+        gpu.eng.set_tensor_transform(3)

@@ -15,6 +15,7 @@
 #include "trquant_tc_kernels.cuh"
 #include "trquant_tc2_kernels.cuh"
 #include "itrquant_kernels.cuh"
+#include "itrquant_tc_kernels.cuh"
 #include "mctf_affine_kernels.cuh"
 #include "frac_kernels.cuh"
 #include "depquant_kernels.cuh"
@@ -282,6 +283,7 @@ void vvb_destroy( vvb_ctx* ctx )
   for( int i = 0; i < 8; i++ ) if( ctx->d_scratch[i] ) cudaFree( ctx->d_scratch[i] );
   if( ctx->d_trTable ) cudaFree( ctx->d_trTable );
   for( void*& im : ctx->tc2Image ) if( im ) { cudaFree( im ); im = nullptr; }
+  for( void*& im : ctx->itcImage ) if( im ) { cudaFree( im ); im = nullptr; }
   if( ctx->d_scan ) cudaFree( ctx->d_scan );
   if( ctx->d_lfnst ) cudaFree( ctx->d_lfnst );
   if( ctx->d_mask ) cudaFree( ctx->d_mask );
@@ -1209,6 +1211,39 @@ static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int or
   return VVB_OK;
 }
 
+// inverse tensor-core engine (itrquant_tc_kernels.cuh): square 8 / 16 / 32 TUs, plain or DepQuant dequantiser parameters in p, no LFNST / transform skip
+static bool itcEligible( const vvb_ctx* ctx, const TuPar& p, const void* dQ )
+{
+  return ctx->tensorTransform == 3 && !p.lfnstIdx && !p.ts && p.w == p.h && p.w >= 8 && p.w <= 32 && ( ( (uintptr_t) dQ ) & 15 ) == 0;
+}
+// dResi != nullptr: levels -> residual.  Otherwise the second half of the TU round trip (reconstruction + distortions; dSum / dLast from the forward engine)
+static int itcLaunch( vvb_ctx* ctx, const TuPar& p, const int16_t* dQ, int n, int16_t* dResi,
+                      int orgPlane, int predPlane, const vvb_block* dBlocks, const int16_t* dOrg, const int16_t* dPred, int16_t* dReco, TuResult* dRes, const int32_t* dSum, const int32_t* dLast )
+{
+  const int key = ( ( p.lw - 3 ) * 3 + p.trHor ) * 3 + p.trVer;
+  if( !ctx->itcImage[key] )
+  {
+    std::vector<unsigned char> img;
+#define VVB_ITC_IMG( Nv ) { using S = ItcShape<Nv>; img.resize( 4 * S::B_BYTES ); itc_build_b_image<Nv>( vvc_tr_table_host, p.offH, p.offV, p.keepW, p.keepH, img.data() ); }
+    switch( p.w ) { case 8: VVB_ITC_IMG( 8 ) break; case 16: VVB_ITC_IMG( 16 ) break; default: VVB_ITC_IMG( 32 ) break; }
+#undef VVB_ITC_IMG
+    void* d = nullptr;
+    CU( cudaMalloc( &d, img.size() ) );
+    CU( cudaMemcpyAsync( d, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream ) );
+    CU( cudaStreamSynchronize( ctx->stream ) );
+    ctx->itcImage[key] = d;
+  }
+  const uint4* dImg = (const uint4*) ctx->itcImage[key];
+  const Plane po = dBlocks ? ctx->planes.p[orgPlane] : Plane{}, pp = dBlocks ? ctx->planes.p[predPlane] : Plane{};
+#define VVB_ITC_CALL( Nv ) { using S = ItcShape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; const int grid = std::min( tiles, ctx->numSMs * std::min( 6, 512 / S::TMEM_COLS ) ); \
+    if( dResi ) inv_trquant_tc_kernel<Nv, false><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, dQ, n, dResi, 0, po, pp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr ); \
+    else        inv_trquant_tc_kernel<Nv, true><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, dQ, n, nullptr, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, dReco, dRes, dSum, dLast ); }
+  switch( p.w ) { case 8: VVB_ITC_CALL( 8 ) break; case 16: VVB_ITC_CALL( 16 ) break; default: VVB_ITC_CALL( 32 ) break; }
+#undef VVB_ITC_CALL
+  CHECK_LAUNCH( "inv_trquant_tc_kernel" );
+  return VVB_OK;
+}
+
 int vvb_fwd_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dResi, int n, int32_t* dCoef, int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos, uint8_t* dNeedRdoq )
 {
   if( !ctx || !dResi || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
@@ -1581,6 +1616,7 @@ int vvb_inv_trquant_dev( vvb_ctx* ctx, const vvb_tu_par* par, const int16_t* dQ,
     CHECK_LAUNCH( "dq_levels_to_qidx_kernel" );
     dQ = (const int16_t*) dIdx;
   }
+  if( itcEligible( ctx, p, dQ ) && ( ( (uintptr_t) dResi ) & 15 ) == 0 ) return itcLaunch( ctx, p, dQ, n, dResi, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr );
 #define VVB_INV_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = inv_trquant_smem<LWv, LHv>(); \
     if( p.lfnstIdx ) inv_trquant_kernel<LWv, LHv, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dQ, n, dResi ); \
     else             inv_trquant_kernel<LWv, LHv, false><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dQ, n, dResi ); }
@@ -1623,6 +1659,8 @@ static int tuRoundtripLaunch( vvb_ctx* ctx, const vvb_tu_par* par, int orgPlane,
     if( ( rc = scratch( ctx, 7, (size_t) n * 8, &dM ) ) ) return rc;
     int32_t* dSum = (int32_t*) dM; int32_t* dLast = dSum + n;
     if( ( rc = tc2Launch( ctx, p, dBlocks ? nullptr : dOrg, orgPlane, predPlane, dBlocks, n, nullptr, dQ, dSum, dLast, dNeedRdoq, dBlocks ? nullptr : dPred ) ) ) return rc;
+    if( itcEligible( ctx, p, dQ ) && ( !dReco || ( ( (uintptr_t) dReco ) & 15 ) == 0 ) )
+      return itcLaunch( ctx, p, dQ, n, nullptr, orgPlane, predPlane, dBlocks, dOrg, dPred, dReco, (TuResult*) dRes, dSum, dLast );
 #define VVB_RTQ_CALL( LWv, LHv ) { using S = TuShape<LWv, LHv>; const size_t smem = tu_roundtrip_smem<LWv, LHv>(); \
       tu_roundtrip_kernel<LWv, LHv, false, true><<<teamGrid( ctx, n, S::NTEAMS, smem ), 128, smem, ctx->stream>>>( p, ctx->d_trTable, ctx->d_scan, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, n, \
                                                                                               dQ, dReco, (TuResult*) dRes, dNeedRdoq, dSum, dLast ); }

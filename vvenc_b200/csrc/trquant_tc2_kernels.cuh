@@ -96,47 +96,24 @@ template<int N> struct Tc2Shape
   static constexpr int CH = KEEP < 16 ? 8 : 16;            // columns per tcgen05.ld in the stage-1 epilogue
 };
 
-// 8 residuals = org - pred of one row segment as 4 packed words; pred may sit at any pel offset
-__device__ __forceinline__ uint4 tc2_resi8( const int16_t* __restrict__ o, const int16_t* __restrict__ p )
+// 8 pels of a row segment as 4 packed words, whatever the alignment of the segment (16-byte, 4-byte or odd pel)
+__device__ __forceinline__ void tc2_load8( const int16_t* __restrict__ p, uint32_t (&a)[4] )
 {
-  uint32_t a[4], b[4];
-  if( ( reinterpret_cast<uintptr_t>( o ) & 15 ) == 0 ) { const uint4 v = __ldg( reinterpret_cast<const uint4*>( o ) ); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-  else if( ( reinterpret_cast<uintptr_t>( o ) & 3 ) == 0 ) { const uint32_t* w = reinterpret_cast<const uint32_t*>( o ); a[0] = __ldg( w ); a[1] = __ldg( w + 1 ); a[2] = __ldg( w + 2 ); a[3] = __ldg( w + 3 ); }
-  else
-  {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>( o + 1 );
-    const uint32_t h0 = (uint16_t) __ldg( o ), w0 = __ldg( w ), w1 = __ldg( w + 1 ), w2 = __ldg( w + 2 ), h7 = (uint16_t) __ldg( o + 7 );
-    a[0] = h0 | ( w0 << 16 ); a[1] = __funnelshift_r( w0, w1, 16 ); a[2] = __funnelshift_r( w1, w2, 16 ); a[3] = ( w2 >> 16 ) | ( h7 << 16 );
-  }
-  if( ( reinterpret_cast<uintptr_t>( p ) & 3 ) == 0 ) { const uint32_t* w = reinterpret_cast<const uint32_t*>( p ); b[0] = __ldg( w ); b[1] = __ldg( w + 1 ); b[2] = __ldg( w + 2 ); b[3] = __ldg( w + 3 ); }
+  if( ( reinterpret_cast<uintptr_t>( p ) & 15 ) == 0 ) { const uint4 v = __ldg( reinterpret_cast<const uint4*>( p ) ); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+  else if( ( reinterpret_cast<uintptr_t>( p ) & 3 ) == 0 ) { const uint32_t* w = reinterpret_cast<const uint32_t*>( p ); a[0] = __ldg( w ); a[1] = __ldg( w + 1 ); a[2] = __ldg( w + 2 ); a[3] = __ldg( w + 3 ); }
   else
   {
     const uint32_t* w = reinterpret_cast<const uint32_t*>( p + 1 );
     const uint32_t h0 = (uint16_t) __ldg( p ), w0 = __ldg( w ), w1 = __ldg( w + 1 ), w2 = __ldg( w + 2 ), h7 = (uint16_t) __ldg( p + 7 );
-    b[0] = h0 | ( w0 << 16 ); b[1] = __funnelshift_r( w0, w1, 16 ); b[2] = __funnelshift_r( w1, w2, 16 ); b[3] = ( w2 >> 16 ) | ( h7 << 16 );
+    a[0] = h0 | ( w0 << 16 ); a[1] = __funnelshift_r( w0, w1, 16 ); a[2] = __funnelshift_r( w1, w2, 16 ); a[3] = ( w2 >> 16 ) | ( h7 << 16 );
   }
-  return make_uint4( __vsub2( a[0], b[0] ), __vsub2( a[1], b[1] ), __vsub2( a[2], b[2] ), __vsub2( a[3], b[3] ) );
 }
-
-// Host side: the B operands of one (size, horizontal type, vertical type) in the canonical K-major layout [16-byte K chunk][row][16 B], rows >= keep zero.
-// tab: the int8 transform table, offH / offV the offsets of the two N x N matrices (row = output index).  Layout of the image: B1lo | B1hi | B2p0 | B2p1 | B2p2.
-template<int N> static void tc2_build_b_image( const int8_t* tab, int offH, int offV, int keepW, int keepH, unsigned char* out )
+// 8 residuals = org - pred of one row segment as 4 packed words; pred may sit at any pel offset
+__device__ __forceinline__ uint4 tc2_resi8( const int16_t* __restrict__ o, const int16_t* __restrict__ p )
 {
-  using S = Tc2Shape<N>;
-  for( int i = 0; i < S::B1_BYTES; i++ )
-  {
-    const int c = i / S::BCH, j = ( i / 16 ) % S::NMMA, kb = c * 16 + ( i & 15 ), x = kb >> 1;
-    const unsigned char v = ( j < keepW && x < N ) ? (unsigned char) tab[offH + j * N + x] : 0;
-    out[i] = ( kb & 1 ) ? 0 : v;
-    out[S::B1_BYTES + i] = ( kb & 1 ) ? v : 0;
-  }
-  unsigned char* o2 = out + 2 * S::B1_BYTES;
-  for( int i = 0; i < S::B2_BYTES; i++ )
-  {
-    const int c = i / S::BCH, r = ( i / 16 ) % S::NMMA, kb = c * 16 + ( i & 15 ), y = kb >> 2, b = kb & 3;
-    const unsigned char v = r < keepH ? (unsigned char) tab[offV + r * N + y] : 0;
-    o2[i] = b == 0 ? v : 0; o2[S::B2_BYTES + i] = b == 1 ? v : 0; o2[2 * S::B2_BYTES + i] = b == 2 ? v : 0;
-  }
+  uint32_t a[4], b[4];
+  tc2_load8( o, a ); tc2_load8( p, b );
+  return make_uint4( __vsub2( a[0], b[0] ), __vsub2( a[1], b[1] ), __vsub2( a[2], b[2] ), __vsub2( a[3], b[3] ) );
 }
 
 // MODE 0: compact residual pool (resi); 1: residual formed from resident planes at the block positions; 2: residual = resi[] - resi2[] of two compact pools (org, pred)
