@@ -1214,7 +1214,7 @@ static int tc2Launch( vvb_ctx* ctx, const TuPar& p, const int16_t* dResi, int or
 // inverse tensor-core engine (itrquant_tc_kernels.cuh): square 8 / 16 / 32 TUs, plain or DepQuant dequantiser parameters in p, no LFNST / transform skip
 static bool itcEligible( const vvb_ctx* ctx, const TuPar& p, const void* dQ )
 {
-  return ctx->tensorTransform == 3 && !p.lfnstIdx && !p.ts && p.w == p.h && p.w >= 8 && p.w <= 32 && ( ( (uintptr_t) dQ ) & 15 ) == 0;
+  return ctx->tensorTransform == 3 && !p.lfnstIdx && !p.ts && p.w == p.h && p.w >= 8 && p.w <= 64 && ( ( (uintptr_t) dQ ) & 15 ) == 0;
 }
 // dResi != nullptr: levels -> residual.  Otherwise the second half of the TU round trip (reconstruction + distortions; dSum / dLast from the forward engine)
 static int itcLaunch( vvb_ctx* ctx, const TuPar& p, const int16_t* dQ, int n, int16_t* dResi,
@@ -1225,7 +1225,7 @@ static int itcLaunch( vvb_ctx* ctx, const TuPar& p, const int16_t* dQ, int n, in
   {
     std::vector<unsigned char> img;
 #define VVB_ITC_IMG( Nv ) { using S = ItcShape<Nv>; img.resize( 4 * S::B_BYTES ); itc_build_b_image<Nv>( vvc_tr_table_host, p.offH, p.offV, p.keepW, p.keepH, img.data() ); }
-    switch( p.w ) { case 8: VVB_ITC_IMG( 8 ) break; case 16: VVB_ITC_IMG( 16 ) break; default: VVB_ITC_IMG( 32 ) break; }
+    switch( p.w ) { case 8: VVB_ITC_IMG( 8 ) break; case 16: VVB_ITC_IMG( 16 ) break; case 32: VVB_ITC_IMG( 32 ) break; default: VVB_ITC_IMG( 64 ) break; }
 #undef VVB_ITC_IMG
     void* d = nullptr;
     CU( cudaMalloc( &d, img.size() ) );
@@ -1238,7 +1238,7 @@ static int itcLaunch( vvb_ctx* ctx, const TuPar& p, const int16_t* dQ, int n, in
 #define VVB_ITC_CALL( Nv ) { using S = ItcShape<Nv>; const int tiles = ( n + S::TPT - 1 ) / S::TPT; const int grid = std::min( tiles, ctx->numSMs * std::min( 6, 512 / S::TMEM_COLS ) ); \
     if( dResi ) inv_trquant_tc_kernel<Nv, false><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, dQ, n, dResi, 0, po, pp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr ); \
     else        inv_trquant_tc_kernel<Nv, true><<<grid, 128, S::SMEM, ctx->stream>>>( p, dImg, dQ, n, nullptr, dBlocks ? 1 : 0, po, pp, dBlocks, dOrg, dPred, dReco, dRes, dSum, dLast ); }
-  switch( p.w ) { case 8: VVB_ITC_CALL( 8 ) break; case 16: VVB_ITC_CALL( 16 ) break; default: VVB_ITC_CALL( 32 ) break; }
+  switch( p.w ) { case 8: VVB_ITC_CALL( 8 ) break; case 16: VVB_ITC_CALL( 16 ) break; case 32: VVB_ITC_CALL( 32 ) break; default: VVB_ITC_CALL( 64 ) break; }
 #undef VVB_ITC_CALL
   CHECK_LAUNCH( "inv_trquant_tc_kernel" );
   return VVB_OK;

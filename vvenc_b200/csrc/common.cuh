@@ -83,7 +83,7 @@ struct vvb_ctx
   std::string    err;
   uint64_t       launches = 0;
   bool           poolBlocksAligned = false;   // see vvb_pool_hint
-  void*          itcImage[27] = {};           // the same for the inverse tensor engine (sizes 8, 16, 32)
+  void*          itcImage[36] = {};           // the same for the inverse tensor engine
   void*          tc2Image[36] = {};           // B operand images of the raw-byte tensor engine, index ((lw - 3) * 3 + trHor) * 3 + trVer
   int            tensorTransform = 3;         // see vvb_set_tensor_transform: 0 off, 1 byte-plane engine for square 16/32/64 TUs, 2 that engine at 64x64 only, 3 raw-byte engine for square 8..64 TUs
   int            dqEngine = 1;                // see vvb_set_depquant_engine: 1 = four lanes per TU (one per trellis state), 0 = one thread per TU

@@ -116,6 +116,27 @@ __device__ __forceinline__ uint4 tc2_resi8( const int16_t* __restrict__ o, const
   return make_uint4( __vsub2( a[0], b[0] ), __vsub2( a[1], b[1] ), __vsub2( a[2], b[2] ), __vsub2( a[3], b[3] ) );
 }
 
+// Host side: the B operands of one (size, horizontal type, vertical type) in the canonical K-major layout [16-byte K chunk][row][16 B], rows >= keep zero.
+// tab: the int8 transform table, offH / offV the offsets of the two N x N matrices (row = output index).  Layout of the image: B1lo | B1hi | B2p0 | B2p1 | B2p2.
+template<int N> static void tc2_build_b_image( const int8_t* tab, int offH, int offV, int keepW, int keepH, unsigned char* out )
+{
+  using S = Tc2Shape<N>;
+  for( int i = 0; i < S::B1_BYTES; i++ )
+  {
+    const int c = i / S::BCH, j = ( i / 16 ) % S::NMMA, kb = c * 16 + ( i & 15 ), x = kb >> 1;
+    const unsigned char v = ( j < keepW && x < N ) ? (unsigned char) tab[offH + j * N + x] : 0;
+    out[i] = ( kb & 1 ) ? 0 : v;
+    out[S::B1_BYTES + i] = ( kb & 1 ) ? v : 0;
+  }
+  unsigned char* o2 = out + 2 * S::B1_BYTES;
+  for( int i = 0; i < S::B2_BYTES; i++ )
+  {
+    const int c = i / S::BCH, r = ( i / 16 ) % S::NMMA, kb = c * 16 + ( i & 15 ), y = kb >> 2, b = kb & 3;
+    const unsigned char v = r < keepH ? (unsigned char) tab[offV + r * N + y] : 0;
+    o2[i] = b == 0 ? v : 0; o2[S::B2_BYTES + i] = b == 1 ? v : 0; o2[2 * S::B2_BYTES + i] = b == 2 ? v : 0;
+  }
+}
+
 // MODE 0: compact residual pool (resi); 1: residual formed from resident planes at the block positions; 2: residual = resi[] - resi2[] of two compact pools (org, pred)
 template<int N, int MODE>
 __global__ void __launch_bounds__( 128, N >= 64 ? 3 : 4 ) fwd_trquant_tc2_kernel( const __grid_constant__ TuPar par, const uint4* __restrict__ bImage, int streamOn, const int32_t* __restrict__ scanTab,
