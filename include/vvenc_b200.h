@@ -286,6 +286,34 @@ int vvb_set_depquant_engine( vvb_ctx* ctx, int engine );
 /* the constants the call derives (no device needed): out = qShift, maxQIdx, thresLast, distShift, qAdd, qScale, distAdd, distStepAdd, distOrgFact (Quantizer, DepQuant.h:220-231) */
 int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_t out[9] );
 
+/* ---- fast rate-distortion optimised quantisation: QuantRDOQ2::quant -> xRateDistOptQuant -> xRateDistOptQuantFast<bSBH, false>
+ * (CommonLib/QuantRDOQ2.cpp:247-301, 1283-1296, 475-1281), what Quant::m_RDOQ == 2 (presets faster and fast, vvencCfg.cpp:2675, 2737) runs for every TU that is not
+ * transform skipped and what DepQuant::quant falls back to in slices without dependent quantisation (DepQuant.cpp:1486-1489).  Luma and chroma components, sides 4..64,
+ * with and without sign-bit hiding (par->sign_hiding = slice->signDataHidingEnabled), no scaling lists; transform skip (rateDistOptQuantTS) and BDPCM stay on the host.
+ * Per coefficient group, from the last scan position down: level decision between floor and ceil of |c| * scale >> qBits by distortion + lambda * bits (:697-969, bits
+ * from the context the template of already-decided neighbours selects, ContextModelling.h:158-269), group zero-out (:971-1036), last-position optimisation (:1038-1095),
+ * parity adjustment for sign-bit hiding (:1097-1167), coded-block-flag decision (:1185-1233), signs (:1251-1257).  One TU per thread, all TUs of a call sharing shape,
+ * QP, lambda and the rate tables.  The caller supplies what depends on the encoder's entropy-coding state at that point of the CTU:
+ *   vvb_rdoq_rates -- BinFracBits::intBits of the contexts the routine reads (FracBitsAccess::getFracBitsArray): sig_bits[ctxOfs] = Ctx::SigFlag[chType]( ctxOfs ),
+ *                     par_bits[o] = Ctx::ParFlag[chType]( o ), gt1_bits[o] = Ctx::GtxFlag[chType + 2]( o ), gt2_bits[o] = Ctx::GtxFlag[chType]( o ),
+ *                     sig_group_bits[i] = Ctx::SigCoeffGroup[chType]( i ); last_bits_x / last_bits_y = m_lastBitsX / m_lastBitsY[chType] as xInitLastPosBitsTab (:408-434)
+ *                     leaves them (for Cr after a coded Cb the table of the Cb call, :490); cbf_bits = the context of :1185-1226 (QtRootCbf for the luma component of an
+ *                     inter CU, QtCbf[compID]( CtxQtCbf(...) ) otherwise; zeros when the flag is inferred -- the last ISP partition after uncoded ones).
+ *   vvb_rdoq_par   -- lambda (Quant::m_dLambda), thr_val (Quant::init thrVal, 8), sbt_zero_out = the condition of TransformUnit::getTbAreaAfterCoefZeroOut
+ *                     (Unit.cpp:580: sps.MTS && cu.sbtInfo && w <= 32 && h <= 32 && luma) for the budget of context-coded bins.
+ * Uses par->{w, h, bit_depth, qp, is_chroma, sign_hiding, lfnst_idx}: lfnst_idx > 0 (the CU's index, whatever the component: :552-559) limits the scan to group 0 and,
+ * for 4x4 / 8x8, to position 7.  The error scale of xSetErrScaleCoeffNoScalingList (:203-219) is derived inside in the same double-precision steps.
+ * need_rdoq (nullable, [n]): TUs with need_rdoq[i] == 0 return all-zero levels (picture->useSelectiveRdoq, :273, 291-295).  coef: [n][h][w] TCoeff as vvb_fwd_trquant
+ * returns them; q: [n][h][w] levels; abs_sum / last_pos (nullable) as uiAbsSum / tu.lastPos are left (last_pos -1 where the routine does not write it: nothing coded). */
+typedef struct { int32_t sig_bits[12][2], par_bits[21][2], gt1_bits[21][2], gt2_bits[21][2], sig_group_bits[2][2], last_bits_x[16], last_bits_y[16], cbf_bits[2], pad[2]; } vvb_rdoq_rates;   /* 760 bytes */
+typedef struct { double lambda; int32_t thr_val, sbt_zero_out, pad[2]; } vvb_rdoq_par;
+int vvb_rdoq    ( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, const vvb_rdoq_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n,
+                  int16_t* q, int32_t* abs_sum, int32_t* last_pos );
+int vvb_rdoq_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, const vvb_rdoq_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n,
+                  int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos );
+/* the constants the call derives (no device needed): out = quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos (QuantRDOQ2.cpp:518-559, 573-583) */
+int vvb_rdoq_constants( const vvb_tu_par* par, const vvb_rdoq_par* rq, int32_t out[7] );
+
 /* ---- inverse path of the TU loop -------------------------------------------------------------------
  * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
  * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp,transform_skip,...}; with par->dep_quant

@@ -3,6 +3,7 @@
 //   xTQuantB200          <->  the xT + xQuant pair inside TrQuant::transformNxN (TrQuant.cpp:709-733 -> xT :481-564, Quant::quant Quant.cpp:735-833)
 //   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
 //   xQuantDQB200         <->  DepQuant::xQuantDQ (DepQuant.cpp:1129-1264), the trellis DepQuant::quant runs for non-skip TUs of a slice with depQuantEnabled
+//   xRateDistOptQuantB200 <-> QuantRDOQ2::xRateDistOptQuant (QuantRDOQ2.cpp:1283-1296 -> xRateDistOptQuantFast :475-1281), the fast RDOQ of m_RDOQ == 2
 //
 // for the TUs the library covers: luma and chroma components, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), transform skip,
 // LFNST on the forward side (luma), no scaling lists / BDPCM / joint Cb-Cr, plain quantiser incl. its sign-bit hiding (RDOQ stays on the host and uses the coefficients
@@ -20,6 +21,7 @@ struct B200TuApi
   decltype( &vvb_fwd_trquant )  fwdTrQuant = nullptr;
   decltype( &vvb_inv_trquant )  invTrQuant = nullptr;
   decltype( &vvb_dep_quant )    depQuant   = nullptr;
+  decltype( &vvb_rdoq )         rdoq       = nullptr;
 } ;
 static B200TuApi g_b200t;
 
@@ -30,7 +32,7 @@ inline int b200LoadTu( const char* libPath )
   if( rc ) return rc;
   void* h = g_b200.handle;
 #define VVB_RESOLVE( member, name ) g_b200t.member = (decltype( g_b200t.member )) dlsym( h, #name ); if( !g_b200t.member ) { g_b200.error = "missing " #name; return -2; }
-  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )
+  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )  VVB_RESOLVE( rdoq, vvb_rdoq )
 #undef VVB_RESOLVE
   g_b200t.bound = true;
   return 0;
@@ -140,4 +142,75 @@ inline void xQuantDQB200( DepQuant& dq, TrQuant& tq, TransformUnit& tu, const CC
   for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
   tu.lastPos[compID] = lastPos;
   absSum = sum;
+}
+
+// QuantRDOQ2::xRateDistOptQuant( tu, compID, pSrc, uiAbsSum, cQP, ctx, false ) with the level decisions on the device.  What stays here is what depends on the
+// encoder's entropy-coding state: the fractional bits of the contexts the routine reads travel as vvb_rdoq_rates.  The last-position table is the member's own
+// (xInitLastPosBitsTab, run under the member's condition so that a Cr TU after a coded Cb TU sees the table of the Cb call, QuantRDOQ2.cpp:490); the coded-block-flag
+// context is resolved as :1185-1226 resolve it.  Inside the encoder this is a member of QuantRDOQ2; `rq` is that object (the DepQuant instance TrQuant owns).
+// Transform skip (rateDistOptQuantTS), BDPCM and scaling lists stay on the host.
+#include "CommonLib/QuantRDOQ2.h"
+inline void xRateDistOptQuantB200( QuantRDOQ2& rq, TrQuant& tq, TransformUnit& tu, const ComponentID compID, const CCoeffBuf& pSrc, TCoeff& uiAbsSum, const QpParam& cQP, const Ctx& ctx )
+{
+  if( tu.mtsIdx[compID] == MTS_SKIP ) THROW( "transform-skip RDOQ stays on the host" );
+  vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
+  const int w = par.w, h = par.h;
+  const ChannelType ch = toChannelType( compID );
+  const FracBitsAccess& fb = ctx.getFracBitsAcess();
+  const bool sbh = tu.cs->slice->signDataHidingEnabled;
+  if( compID != COMP_Cr || !tu.cbf[COMP_Cb] )                                                   // :490
+  {
+    CoeffCodingContext cctx( tu, compID, sbh, false, rq.m_tplBuf );
+    rq.xInitLastPosBitsTab( cctx, w, h, ch, fb );
+  }
+  vvb_rdoq_rates rates;
+  memset( &rates, 0, sizeof( rates ) );
+  for( int i = 0; i < (int) Ctx::SigFlag[ch].size() && i < 12; i++ )     for( int b = 0; b < 2; b++ ) rates.sig_bits[i][b] = fb.getFracBitsArray( Ctx::SigFlag[ch]( i ) ).intBits[b];
+  for( int i = 0; i < (int) Ctx::ParFlag[ch].size() && i < 21; i++ )     for( int b = 0; b < 2; b++ ) rates.par_bits[i][b] = fb.getFracBitsArray( Ctx::ParFlag[ch]( i ) ).intBits[b];
+  for( int i = 0; i < (int) Ctx::GtxFlag[ch + 2].size() && i < 21; i++ ) for( int b = 0; b < 2; b++ ) rates.gt1_bits[i][b] = fb.getFracBitsArray( Ctx::GtxFlag[ch + 2]( i ) ).intBits[b];
+  for( int i = 0; i < (int) Ctx::GtxFlag[ch].size() && i < 21; i++ )     for( int b = 0; b < 2; b++ ) rates.gt2_bits[i][b] = fb.getFracBitsArray( Ctx::GtxFlag[ch]( i ) ).intBits[b];
+  for( int i = 0; i < 2; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_group_bits[i][b] = fb.getFracBitsArray( Ctx::SigCoeffGroup[ch]( i ) ).intBits[b];
+  for( int i = 0; i < LAST_SIGNIFICANT_GROUPS; i++ ) { rates.last_bits_x[i] = rq.QuantRDOQ2::m_lastBitsX[ch][i]; rates.last_bits_y[i] = rq.QuantRDOQ2::m_lastBitsY[ch][i]; }
+  if( !CU::isIntra( *tu.cu ) && isLuma( compID ) )                                              // :1185-1190
+  {
+    const BinFracBits f = fb.getFracBitsArray( Ctx::QtRootCbf() );
+    rates.cbf_bits[0] = f.intBits[0]; rates.cbf_bits[1] = f.intBits[1];
+  }
+  else                                                                                          // :1191-1226
+  {
+    bool previousCbf = tu.cbf[COMP_Cb], lastCbfIsInferred = false;
+    const bool useIntraSubPartitions = tu.cu->ispMode && isLuma( compID );
+    if( useIntraSubPartitions )
+    {
+      bool rootCbfSoFar = false;
+      const bool isLastSubPartition = CU::isISPLast( *tu.cu, tu.Y(), compID );
+      const uint32_t nTus = tu.cu->ispMode == HOR_INTRA_SUBPARTITIONS ? tu.cu->lheight() >> Log2( tu.lheight() ) : tu.cu->lwidth() >> Log2( tu.lwidth() );
+      if( isLastSubPartition )
+      {
+        TransformUnit* tuPointer = tu.cu->firstTU;
+        for( int tuIdx = 0; tuIdx < (int) nTus - 1; tuIdx++ ) { rootCbfSoFar |= TU::getCbfAtDepth( *tuPointer, COMP_Y, tu.depth ); tuPointer = tuPointer->next; }
+        if( !rootCbfSoFar ) lastCbfIsInferred = true;
+      }
+      if( !lastCbfIsInferred ) previousCbf = TU::getPrevTuCbfAtDepth( tu, compID, tu.depth );
+    }
+    if( !lastCbfIsInferred )
+    {
+      const BinFracBits f = fb.getFracBitsArray( Ctx::QtCbf[compID]( DeriveCtx::CtxQtCbf( tu.blocks[compID].compID, previousCbf, useIntraSubPartitions ) ) );
+      rates.cbf_bits[0] = f.intBits[0]; rates.cbf_bits[1] = f.intBits[1];
+    }
+  }
+  vvb_rdoq_par rp = {};
+  rp.lambda = rq.m_dLambda; rp.thr_val = rq.m_thrVal;
+  rp.sbt_zero_out = ( tu.cs->sps->MTS && tu.cu->sbtInfo != 0 && w <= 32 && h <= 32 && compID == COMP_Y ) ? 1 : 0;     // TransformUnit::getTbAreaAfterCoefZeroOut, Unit.cpp:580
+  par.lfnst_idx = tu.cu->lfnstIdx;                                                              // the routine reads the CU's index for every component (:552-559); the set / transposition fields are not used
+  par.sign_hiding = sbh ? 1 : 0;
+  std::vector<int32_t> coef( (size_t) w * h );
+  std::vector<int16_t> q( (size_t) w * h );
+  for( int y = 0; y < h; y++ ) memcpy( &coef[(size_t) y * w], pSrc.buf + (ptrdiff_t) y * pSrc.stride, sizeof( TCoeff ) * w );
+  int32_t sum = 0, lastPos = -1;
+  b200Check( g_b200t.rdoq( b200CtxOfThread(), &par, &rp, &rates, coef.data(), nullptr, 1, q.data(), &sum, &lastPos ) );
+  CoeffSigBuf dst = tu.getCoeffs( compID );
+  for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
+  if( lastPos >= 0 ) tu.lastPos[compID] = lastPos;                                              // the member writes tu.lastPos only when it codes something (:1258)
+  uiAbsSum = sum;
 }

@@ -19,10 +19,12 @@
  *   xT / xTransformSkip (+ xFwdLfnst for luma)        by xTQuantB200      (integration/TrQuantB200.h -> vvb_fwd_trquant: the coefficients it leaves are what xQuant then reads),
  *   DepQuant::xQuantDQ (slices with depQuantEnabled)   by xQuantDQB200     (rate tables from the live CABAC contexts -> vvb_dep_quant: the 4-state trellis on the device),
  *   Quant::dequant / DepQuant::dequant + xIT / xITransformSkip  by invTransformNxNB200 (TUs without LFNST; the rest stays with the member),
- * RDOQ (QuantRDOQ2) and everything the bindings THROW for (BDPCM, joint Cb-Cr, scaling lists) stay with the reference members.
+ *   QuantRDOQ2::xRateDistOptQuant (Quant::m_RDOQ == 2: presets faster / fast, and slices without dependent quantisation)  by xRateDistOptQuantB200 (fractional bits of the
+ *                                                       live CABAC contexts -> vvb_rdoq: level decisions, group zero-out, last position, sign-bit hiding on the device),
+ * transform-skip RDOQ, RDOQ of m_RDOQ == 1 and everything the bindings THROW for (BDPCM, joint Cb-Cr, scaling lists) stay with the reference members.
  *
- * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu]
- * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
+ * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu | turdoq]
+ * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_rdoq=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
  */
 #include <cstdint>
 #include <cstring>
@@ -105,8 +107,8 @@ static decltype( &vvb_sad_x5_block ) g_realX5 = nullptr;
 static int countingX5( vvb_ctx* c, const int16_t* o, int so, const int16_t* u, int su, int w, int h, int ss, int cc, uint64_t* out ) { g_otherCalls++; return g_realX5( c, o, so, u, su, w, h, ss, cc, out ); }
 
 // ---- the transform / quantisation seam -------------------------------------------------------------------------------------------------------------------------
-static bool g_useTu = false;
-static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuInv{ 0 }, g_tuInvLfnst{ 0 }, g_tuRef{ 0 };
+static bool g_useTu = false, g_useRdoq = false;      // g_useRdoq: argument `turdoq` -- the fast RDOQ of m_RDOQ == 2 through the library as well
+static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuRdoq{ 0 }, g_tuInv{ 0 }, g_tuInvLfnst{ 0 }, g_tuRef{ 0 };
 
 extern "C" void __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant*, TransformUnit&, ComponentID, const QpParam&, TCoeff&, const Ctx&, bool );
 extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant* self, TransformUnit& tu, ComponentID compID, const QpParam& cQP,
@@ -150,7 +152,14 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
   else
   {
     uiAbsSum = 0;
-    self->xQuant( tu, compID, tempCoeff, uiAbsSum, cQP, ctx );
+    // QuantRDOQ2::quant (QuantRDOQ2.cpp:247-301): m_RDOQ == 2, not transform skipped, sides above 2 -> xRateDistOptQuant, unless the selective pre-check says "all zero"
+    bool done = false;
+    if( g_useRdoq && dq && !selectiveSkip && dq->m_RDOQ == 2 && tu.mtsIdx[compID] != MTS_SKIP && rect.width > 2 && rect.height > 2 && !dq->getScalingListEnabled() )
+    {
+      try { xRateDistOptQuantB200( *dq, *self, tu, compID, tempCoeff, uiAbsSum, cQP, ctx ); g_tuRdoq++; done = true; }
+      catch( std::exception& ) { uiAbsSum = 0; }
+    }
+    if( !done ) self->xQuant( tu, compID, tempCoeff, uiAbsSum, cQP, ctx );
   }
   TU::setCbfAtDepth( tu, compID, tu.depth, uiAbsSum > 0 );
 }
@@ -181,8 +190,9 @@ int main( int argc, char** argv )
   if( argc > 8 )
   {
     if( b200Load( argv[8] ) || b200LoadAffine( argv[8] ) ) { fprintf( stderr, "cannot bind %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
-    if( argc > 9 && !strcmp( argv[9], "tu" ) )
+    if( argc > 9 && ( !strcmp( argv[9], "tu" ) || !strcmp( argv[9], "turdoq" ) ) )
     {
+      g_useRdoq = !strcmp( argv[9], "turdoq" );
       if( b200LoadTu( argv[8] ) ) { fprintf( stderr, "cannot bind the TU entry points of %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
       g_useTu = true;
     }
@@ -241,8 +251,8 @@ int main( int argc, char** argv )
   if( fo ) { fwrite( out.data(), 1, out.size(), fo ); fclose( fo ); }
   uint64_t hsh = 1469598103934665603ull;
   for( uint8_t b : out ) { hsh ^= b; hsh *= 1099511628211ull; }
-  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu\n", fed, out.size(),
-          (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuInv.load(),
+  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_rdoq=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu\n", fed, out.size(),
+          (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuRdoq.load(), g_tuInv.load(),
           g_tuInvLfnst.load(), g_tuRef.load() );
   return 0;
 }

@@ -1,0 +1,46 @@
+/*
+ * oracle/rdoq_oracle.cpp -- TEST INFRASTRUCTURE, not product code.
+ *
+ * CPU build of the RDOQ restatement (QuantRDOQ2::xRateDistOptQuantFast).  The algorithm text is vvenc_b200/csrc/rdoq_core.h (each block there cites the lines of
+ * CommonLib/QuantRDOQ2.cpp / ContextModelling.h it follows) and the constant set-up is rdoq_host.h; this file compiles both with g++ so that
+ *   - tests/test_oracle_vs_reference.py can pin the restatement against the reference's own QuantRDOQ2::xRateDistOptQuant (oracle/_ref probe) and against the
+ *     golden vectors the reference generated (tests/golden/golden_v6_rdoq.npz), here, without a GPU;
+ *   - the GPU tests compare the device kernel (the same text compiled by nvcc for sm_100a) with this build on the same inputs.
+ * The product library never loads this file.
+ */
+#include "../vvenc_b200/csrc/rdoq_core.h"
+#include "../vvenc_b200/csrc/rdoq_host.h"
+#include <vector>
+#include <cstring>
+
+using namespace vvbrq;
+
+extern "C" {
+
+// rates: the 190 int32 of vvb_rdoq_rates; coef [n][h][w]; q [n][h][w]; absSum / lastPos [n].  qp: CU QP (the bit-depth offset is added here, as the library does)
+int orc_rdoq( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int sbtZeroOut, int signHiding, double lambda, int thrVal, const int32_t* rates,
+              const int32_t* coef, int n, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( !rq_shape_ok( w, h ) ) return -1;
+  int qpInternal = qp + 6 * ( bitDepth - 8 );
+  qpInternal = qpInternal < 0 ? 0 : qpInternal > 63 + 6 * ( bitDepth - 8 ) ? 63 + 6 * ( bitDepth - 8 ) : qpInternal;
+  const RqPar p = rq_init_par( w, h, bitDepth, qpInternal, lfnst, sbtZeroOut, signHiding, isChroma, lambda, thrVal );
+  RqRates r; memcpy( &r, rates, sizeof( r ) );
+  std::vector<int32_t> scan( 1024 );
+  rq_build_scan( w, h, scan.data() );
+  for( int i = 0; i < n; i++ ) rq_quant_tu( p, r, scan.data(), coef + (size_t) i * w * h, q + (size_t) i * w * h, absSum + i, lastPos + i );
+  return 0;
+}
+
+// the constants of one call: quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos
+int orc_rdoq_constants( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int sbtZeroOut, int thrVal, int32_t out[7] )
+{
+  if( !rq_shape_ok( w, h ) ) return -1;
+  int qpInternal = qp + 6 * ( bitDepth - 8 );
+  qpInternal = qpInternal < 0 ? 0 : qpInternal > 63 + 6 * ( bitDepth - 8 ) ? 63 + 6 * ( bitDepth - 8 ) : qpInternal;
+  const RqPar p = rq_init_par( w, h, bitDepth, qpInternal, lfnst, sbtZeroOut, 0, isChroma, 1.0, thrVal );
+  out[0] = p.quantScale; out[1] = p.errScale; out[2] = p.qBits; out[3] = p.useThres; out[4] = p.remRegBins; out[5] = p.numCG; out[6] = p.firstScanPos;
+  return 0;
+}
+
+}

@@ -908,6 +908,115 @@ int refshim_dep_quant_b200_comp( int comp, const int32_t* coef, int w, int h, in
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast RDOQ: QuantRDOQ2::xRateDistOptQuant (QuantRDOQ2.cpp:1283-1296 -> xRateDistOptQuantFast<bSBH, false> :475-1281) -- what QuantRDOQ2::quant (:247-301) runs with
+// m_RDOQ == 2 for a TU that is not transform skipped -- on the TU rig, with a CABAC context set initialised the way a slice start does it.  The object is a DepQuant
+// (the class TrQuant instantiates; QuantRDOQ2 is its base) after init( 2, ., thrVal ) and setFlatScalingList (the error scales, EncCu.cpp:351).
+// ratesOut: the fractional bits the routine read, in vvb_rdoq_rates layout (190 int32); constOut: quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos.
+// cbCbf: tu.cbf[COMP_Cb] when comp == 2 (Cr reuses the last-position table of the Cb call, :490, and its coded-block-flag context depends on it).
+static void rdoqRatesOf( DepQuant& dq, const TransformUnit& tu, const ComponentID compID, const Ctx& cabac, int32_t* o )
+{
+  const ChannelType ch = toChannelType( compID );
+  const FracBitsAccess& fb = cabac.getFracBitsAcess();
+  memset( o, 0, sizeof( int32_t ) * 190 );
+  int32_t* sig = o, *par = o + 24, *gt1 = par + 42, *gt2 = gt1 + 42, *grp = gt2 + 42, *lx = grp + 4, *ly = lx + 16, *cbf = ly + 16;
+  for( int i = 0; i < (int) Ctx::SigFlag[ch].size() && i < 12; i++ ) for( int b = 0; b < 2; b++ ) sig[2 * i + b] = fb.getFracBitsArray( Ctx::SigFlag[ch]( i ) ).intBits[b];
+  for( int i = 0; i < (int) Ctx::ParFlag[ch].size() && i < 21; i++ ) for( int b = 0; b < 2; b++ ) par[2 * i + b] = fb.getFracBitsArray( Ctx::ParFlag[ch]( i ) ).intBits[b];
+  for( int i = 0; i < (int) Ctx::GtxFlag[ch + 2].size() && i < 21; i++ ) for( int b = 0; b < 2; b++ ) gt1[2 * i + b] = fb.getFracBitsArray( Ctx::GtxFlag[ch + 2]( i ) ).intBits[b];
+  for( int i = 0; i < (int) Ctx::GtxFlag[ch].size() && i < 21; i++ ) for( int b = 0; b < 2; b++ ) gt2[2 * i + b] = fb.getFracBitsArray( Ctx::GtxFlag[ch]( i ) ).intBits[b];
+  for( int i = 0; i < 2; i++ ) for( int b = 0; b < 2; b++ ) grp[2 * i + b] = fb.getFracBitsArray( Ctx::SigCoeffGroup[ch]( i ) ).intBits[b];
+  for( int i = 0; i < LAST_SIGNIFICANT_GROUPS; i++ ) { lx[i] = dq.QuantRDOQ2::m_lastBitsX[ch][i]; ly[i] = dq.QuantRDOQ2::m_lastBitsY[ch][i]; }
+  if( !CU::isIntra( *tu.cu ) && isLuma( compID ) ) { const BinFracBits f = fb.getFracBitsArray( Ctx::QtRootCbf() ); cbf[0] = f.intBits[0]; cbf[1] = f.intBits[1]; }
+  else { const BinFracBits f = fb.getFracBitsArray( Ctx::QtCbf[compID]( DeriveCtx::CtxQtCbf( compID, tu.cbf[COMP_Cb], false ) ) ); cbf[0] = f.intBits[0]; cbf[1] = f.intBits[1]; }
+}
+int refshim_rdoq( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int intraCu, int lfnstIdx, int sbtInfo, int signHiding, int cbCbf, double lambda, int thrVal,
+                  int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos, int32_t* ratesOut, int32_t* constOut )
+{
+  RefCtx& c = ctx(); (void) c;
+  TuRig& r = rig();
+  const ComponentID compID = comp == 2 ? COMP_Cr : comp ? COMP_Cb : COMP_Y;
+  t_rigSignHiding = signHiding != 0;
+  r.setup( w, h, bitDepth, 0, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  t_rigSignHiding = false;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx; r.cu.sbtInfo = (uint8_t) sbtInfo;
+  r.tu.cbf[COMP_Cb] = (uint8_t)( cbCbf ? 1 : 0 );
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 2, false, thrVal );
+  const int maxLog2TrDynamicRange[MAX_NUM_CH] = { 15, 15 };
+  dq->setFlatScalingList( maxLog2TrDynamicRange, r.sps.bitDepths );
+  dq->m_dLambda = lambda;
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  if( comp == 2 && cbCbf )
+  {
+    // the Cb call that precedes a Cr call in the encoder fills the chroma last-position table (:490): run the table set-up it would have run
+    CoeffCodingContext cctx( r.tu, COMP_Cb, signHiding != 0, false, dq->m_tplBuf );
+    dq->xInitLastPosBitsTab( cctx, w, h, CH_C, cabac->getFracBitsAcess() );
+  }
+  dq->xRateDistOptQuant( r.tu, compID, src, sum, qpp, *cabac, false );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[compID];
+  if( ratesOut ) rdoqRatesOf( *dq, r.tu, compID, *cabac, ratesOut );
+  if( constOut )
+  {
+    const int rem = qpp.rem( false ), per = qpp.per( false );
+    const bool sqrt2 = TU::needsSqrt2Scale( r.tu, compID );
+    const int trShift = getTransformShift( bitDepth, r.tu.blocks[compID].size(), 15 );
+    constOut[0] = g_quantScales[sqrt2 ? 1 : 0][rem];
+    constOut[1] = dq->xGetErrScaleCoeffNoScalingList( getScalingListType( r.cu.predMode, compID ), Log2( w ), Log2( h ), rem );
+    constOut[2] = QUANT_SHIFT + per + trShift + ( sqrt2 ? -1 : 0 );
+    const TCoeff thres = constOut[2] ? TCoeff( ( int64_t( thrVal ) << ( constOut[2] - 1 ) ) ) : TCoeff( ( int64_t( thrVal >> 1 ) << constOut[2] ) );
+    constOut[3] = thres / ( constOut[0] << 2 );
+    constOut[4] = ( r.tu.getTbAreaAfterCoefZeroOut( compID ) * MAX_TU_LEVEL_CTX_CODED_BIN_CONSTRAINT ) >> 4;
+    constOut[5] = lfnstIdx > 0 ? 1 : ( std::min<int>( JVET_C0024_ZERO_OUT_TH, w ) * std::min<int>( JVET_C0024_ZERO_OUT_TH, h ) ) >> 4;
+    constOut[6] = ( lfnstIdx > 0 && ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ) ? 7 : ( constOut[5] << 4 ) - 1;
+  }
+  r.cu.lfnstIdx = 0; r.cu.sbtInfo = 0; r.tu.cbf[COMP_Cb] = 0;
+  return 0;
+}
+
+// the same TU through integration/TrQuantB200.h (xRateDistOptQuantB200: rates from the CABAC state here, level decisions in the bound library); returns 1 when the binding threw
+int refshim_rdoq_b200( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int intraCu, int lfnstIdx, int sbtInfo, int signHiding, int cbCbf, double lambda, int thrVal,
+                       int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  RefCtx& c = ctx(); (void) c;
+  TuRig& r = rig();
+  const ComponentID compID = comp == 2 ? COMP_Cr : comp ? COMP_Cb : COMP_Y;
+  t_rigSignHiding = signHiding != 0;
+  r.setup( w, h, bitDepth, 0, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  t_rigSignHiding = false;
+  r.cu.lfnstIdx = (uint8_t) lfnstIdx; r.cu.sbtInfo = (uint8_t) sbtInfo;
+  r.tu.cbf[COMP_Cb] = (uint8_t)( cbCbf ? 1 : 0 );
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 2, false, thrVal );
+  dq->m_dLambda = lambda;
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  if( comp == 2 && cbCbf )
+  {
+    CoeffCodingContext cctx( r.tu, COMP_Cb, signHiding != 0, false, dq->m_tplBuf );
+    dq->xInitLastPosBitsTab( cctx, w, h, CH_C, cabac->getFracBitsAcess() );
+  }
+  int rc = 0;
+  try { xRateDistOptQuantB200( *dq, tqOfThread(), r.tu, compID, src, sum, qpp, *cabac ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.cu.lfnstIdx = 0; r.cu.sbtInfo = 0; r.tu.cbf[COMP_Cb] = 0;
+  if( rc ) return rc;
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum; *lastPos = r.tu.lastPos[compID];
+  return 0;
+}
+
 // scan geometry of DQIntern::Rom for one luma shape, repacked into the 24- / 16-byte records of vvenc_b200/csrc/depquant_core.h (DqScanInfo, DqNbOut);
 // fields the reference leaves unset (nextSbbRight / nextSbbBelow off group starts, everything "next" at scan position 0) are reported as 0
 int refshim_dep_quant_tables_ex( int chroma, int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut );

@@ -356,5 +356,31 @@ def main(mock_path):
     print('RESULT ' + json.dumps(res))
 
 
+def main_rdoq(lib_path):
+    """QuantRDOQ2::xRateDistOptQuant (member, AVX2 build) against xRateDistOptQuantB200 (fractional bits from the rig's CABAC contexts, the member's own last-position
+    table incl. the Cr-after-coded-Cb reuse, level decisions in the bound library): every row of cases.rdoq_cases().  A run of its own (argument `rdoq`) so that the
+    long-standing binding run keeps its exact shape."""
+    R = refshim()
+    R.refshim_b200_error.restype = ctypes.c_char_p
+    assert R.refshim_install_b200(lib_path.encode()) == 0, R.refshim_b200_error()
+    assert R.refshim_install_b200_tu(lib_path.encode()) == 0, R.refshim_b200_error()
+    R.refshim_set_simd(b'AVX2')
+    I32 = ctypes.c_int32
+    bad = []; n = 0; nz = 0; nsh = 0
+    for row in C.rdoq_cases():
+        w, h, bd, qp, lam1000, scale, decay10, comp, lf, sbt, intra, sh, cb, thr, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_inputs(row)
+        qa = np.zeros((h, w), dtype=np.int16); sa = I32(); la = I32(); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); lb = I32()
+        assert R.refshim_rdoq(comp, P(coef), w, h, bd, qp, intra, lf, sbt, sh, cb, lam1000 / 1000.0, thr, qp, init_id, P(qa), ctypes.byref(sa), ctypes.byref(la), None, None) == 0
+        rc = R.refshim_rdoq_b200(comp, P(coef), w, h, bd, qp, intra, lf, sbt, sh, cb, lam1000 / 1000.0, thr, qp, init_id, P(qb), ctypes.byref(sb), ctypes.byref(lb))
+        n += 1; nz += int(la.value >= 0); nsh += int(sh and la.value >= 0)
+        if rc or not (np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
+            bad.append(['rdoq'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+    print('RESULT ' + json.dumps({'rdoq': {'cases': n, 'non_empty': nz, 'non_empty_with_hiding': nsh, 'bad': bad[:5]}}))
+
+
 if __name__ == '__main__':
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == 'rdoq':
+        main_rdoq(sys.argv[1])
+    else:
+        main(sys.argv[1])

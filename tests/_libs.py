@@ -51,6 +51,9 @@ def dq_oracle():
         L.orc_dep_quant.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_dep_quant_chroma.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_dep_quant_constants.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+        # oracle/rdoq_oracle.cpp (vvenc_b200/csrc/rdoq_core.h compiled for the CPU) lives in the same library
+        L.orc_rdoq.argtypes = [ctypes.c_int] * 8 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_rdoq_constants.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
         _dqoracle = L
     return _dqoracle
 
@@ -84,6 +87,8 @@ def refshim():
         L.refshim_dep_quant_comp.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5
         L.refshim_dep_quant_b200_comp.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_dep_quant_b200.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+        L.refshim_rdoq.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5
+        L.refshim_rdoq_b200.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_set_simd(b'AVX2')
         _ref = L
     return _ref

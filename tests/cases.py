@@ -394,6 +394,41 @@ def dq_chroma_inputs(row):
     return coef
 
 
+# ---- fast RDOQ (QuantRDOQ2::xRateDistOptQuant, m_RDOQ == 2) -----------------------------------------------------------------------------------------------------
+def rdoq_cases():
+    """rows: w, h, bit_depth, qp, lambda * 1000, scale, decay * 10, comp (0 Y, 1 Cb, 2 Cr), lfnstIdx, sbtInfo, intraCu, signHiding, cbCbf, thrVal, ctxInitId, seed
+    The CABAC contexts are initialised for slice QP = qp and init type ctxInitId, as a slice start does."""
+    rows = []
+    rs = np.random.RandomState(2602)
+    seed = 21000
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 16), (32, 8), (16, 64), (64, 32), (32, 16), (4, 32), (64, 4), (16, 8)]:
+        for k in range(16):
+            bd = 8 if k % 5 == 4 else 10
+            qp = int(rs.choice([17, 22, 27, 32, 37, 42, 51]))
+            lam = float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0]))
+            scale = int(rs.choice([5, 20, 60, 200, 600, 2000, 30000]))
+            decay = int(rs.choice([1, 5, 10, 15]))
+            comp = int(rs.choice([0, 0, 0, 1, 2]))
+            lf = int(rs.choice([0, 0, 0, 1, 2]))
+            sbt = int(rs.choice([0, 0, 0, 1])) if (lf == 0 and comp == 0) else 0
+            intra = 1 if lf else (0 if sbt else int(rs.randint(2)))
+            rows.append([w, h, bd, qp, int(lam * 1000), scale, decay, comp, lf, sbt, intra, k & 1, int(rs.randint(2)) if comp == 2 else 0, int(rs.choice([8, 8, 4, 16])), k % 3, seed])
+            seed += 1
+    return np.array(rows, dtype=np.int64)
+
+
+def rdoq_inputs(row):
+    w, h, bd, qp, lam1000, scale, decay10 = [int(v) for v in row[:7]]
+    rs = np.random.RandomState(int(row[15]))
+    coef = rs.laplace(0, scale, size=(h, w)) * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** (decay10 / 10.0))
+    coef = np.clip(coef, -32768, 32767).astype(np.int32)
+    if w > 32:
+        coef[:, 32:] = 0          # what the transform's zero-out leaves
+    if h > 32:
+        coef[32:, :] = 0
+    return coef
+
+
 def dqd_cases():
     """DepQuant dequantiser + inverse transform: rows trHor, trVer, w, h, bit_depth, qp, amp, seed"""
     rows = []

@@ -37,3 +37,9 @@ def golden_frac():
 def golden_depquant():
     import numpy as np
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v5_depquant.npz'))
+
+
+@pytest.fixture(scope="session")
+def golden_rdoq():
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_v6_rdoq.npz'))

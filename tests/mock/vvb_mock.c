@@ -18,6 +18,8 @@ int      orc_dep_quant( int w, int h, int bitDepth, int qp, double lambda, int d
                         int16_t* q, int32_t* absSum, int32_t* lastPos );   /* oracle/depquant_oracle.cpp */
 int      orc_dep_quant_chroma( int w, int h, int bitDepth, int qp, double lambda, int dqThrVal, int lfnst, int scalarMembers, const int32_t* rates, const int32_t* coef, int n,
                                int16_t* q, int32_t* absSum, int32_t* lastPos );
+int      orc_rdoq( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int sbtZeroOut, int signHiding, double lambda, int thrVal, const int32_t* rates,
+                   const int32_t* coef, int n, int16_t* q, int32_t* absSum, int32_t* lastPos );   /* oracle/rdoq_oracle.cpp */
 void     orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPlane, int sb, const int32_t* desc, int n, int bitDepth, int32_t* out );
 
 #define MOCK_PLANES 64
@@ -317,6 +319,26 @@ int vvb_dep_quant( vvb_ctx* c, const vvb_tu_par* par, const vvb_dq_par* dq, cons
                                                     coef + i * area, 1, q + i * area, &s, &l )
                             : orc_dep_quant( par->w, par->h, par->bit_depth, par->qp, dq->lambda, dq->dq_thr_val, dq->zero_out, par->lfnst_idx > 0, dq->scalar_members, (const int32_t*) rates,
                                              coef + i * area, 1, q + i * area, &s, &l ) ) return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
+    if( abs_sum ) abs_sum[i] = s;
+    if( last_pos ) last_pos[i] = l;
+  }
+  c->calls++;
+  return VVB_OK;
+}
+
+int vvb_rdoq( vvb_ctx* c, const vvb_tu_par* par, const vvb_rdoq_par* rq, const vvb_rdoq_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n,
+              int16_t* q, int32_t* abs_sum, int32_t* last_pos )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !par || !rq || !rates || !coef || !q || n < 0 || !( rq->lambda > 0.0 ) ) return fail( c, VVB_ERR_ARG, "bad RDOQ arguments" );
+  if( par->transform_skip ) return fail( c, VVB_ERR_UNSUPPORTED, "transform-skip RDOQ stays on the host" );
+  const size_t area = (size_t) par->w * par->h;
+  for( int i = 0; i < n; i++ )
+  {
+    int32_t s = 0, l = -1;
+    if( need_rdoq && !need_rdoq[i] ) memset( q + i * area, 0, sizeof( int16_t ) * area );
+    else if( orc_rdoq( par->w, par->h, par->bit_depth, par->qp, par->is_chroma, par->lfnst_idx > 0, rq->sbt_zero_out, par->sign_hiding, rq->lambda, rq->thr_val, (const int32_t*) rates,
+                       coef + i * area, 1, q + i * area, &s, &l ) ) return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
     if( abs_sum ) abs_sum[i] = s;
     if( last_pos ) last_pos[i] = l;
   }

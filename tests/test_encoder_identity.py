@@ -16,9 +16,9 @@ MOCK = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
 pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason='oracle/_ref/enc_identity not built (needs /root/reference at build time)')
 
 
-def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False):
+def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False):
     out = str(tmp_path / ('b200.vvc' if lib else 'avx2.vvc'))
-    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + (['tu'] if tu else [])
+    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + ((['turdoq'] if rdoq else ['tu']) if tu else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
     line = [l for l in r.stdout.splitlines() if l.startswith('ENC ')][-1]
@@ -41,6 +41,20 @@ def _identity_tu(tmp_path, W, H, F, preset, qp, lib, want_dq, timeout=900):
     assert int(kb['tu_inv']) > 500, kb                     # the inverse path (plain or DepQuant dequantiser) ran in the library
     if want_dq:
         assert int(kb['tu_inv_lfnst']) > 500, kb           # these presets enable LFNST: the inverse LFNST ran in the library too
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
+
+
+def _identity_rdoq(tmp_path, W, H, F, preset, qp, lib, timeout=900):
+    """the TU seam as above plus QuantRDOQ2::xRateDistOptQuant (the fast RDOQ of the presets faster / fast) through vvb_rdoq: fractional bits of the live CABAC
+    contexts, the member's last-position table, the coded-block-flag context of the live CU -- level decisions in the library"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout, tu=True, rdoq=True)
+    assert int(kb['tu_fwd']) > 1000 and int(kb['tu_rdoq']) > 900 and int(ka['tu_rdoq']) == 0, kb
     assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
     return kb
 
@@ -69,6 +83,14 @@ def test_bitstream_identity_with_the_tu_seam_on_the_oracle(tmp_path, W, H, F, pr
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity_tu(tmp_path, W, H, F, preset, qp, MOCK, dq)
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (176, 144, 3, 0, 27)])
+def test_bitstream_identity_with_the_rdoq_seam_on_the_oracle(tmp_path, W, H, F, preset, qp):
+    """preset faster runs Quant::m_RDOQ == 2 with sign-bit hiding and selective RDOQ (vvencCfg.cpp:2675-2677): 1 000 / 7 000 TUs through xRateDistOptQuantB200"""
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity_rdoq(tmp_path, W, H, F, preset, qp, MOCK)
 
 
 @pytest.mark.gpu

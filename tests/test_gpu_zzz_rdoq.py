@@ -1,0 +1,103 @@
+"""GPU parity (-m gpu) of the fast RDOQ (QuantRDOQ2::xRateDistOptQuant, Quant::m_RDOQ == 2) through the C ABI (vvb_rdoq):
+golden vectors from the unmodified reference, picture-sized batches against the CPU build of the same restatement, the reference-side binding next to the member
+on the real library, and whole-encoder bitstream identity with the RDOQ seam routed through the GPU.  Sorted last in the suite on purpose: the entry point is the
+newest one of the library."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import cases as C
+import impls
+from _libs import have_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return impls.GpuImpl(0)          # vvb_create fails loudly without a CUDA device; no torch needed on this path
+
+
+def test_gpu_rdoq_golden(gpu, golden_rdoq):
+    """every row of cases.rdoq_cases() against what the reference produced (tests/golden/golden_v6_rdoq.npz): levels, absSum, lastPos; the constants the library
+    derives (quantiser scale / shift, error scale, thresholds, bin budget) against the reference's"""
+    import ctypes
+    import vvenc_b200._lib as L
+    g = golden_rdoq
+    rows = C.rdoq_cases()
+    assert np.array_equal(rows, g['cases'])
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, scale, decay10, comp, lf, sbt, intra, sh, cb, thr, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_inputs(row)[None]
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, sign_hiding=bool(sh), lfnst_idx=lf, is_chroma=comp > 0)
+        rq = L.vvb_rdoq_par(lam1000 / 1000.0, thr, sbt)
+        k = np.zeros(7, dtype=np.int32)
+        assert gpu.eng.lib.vvb_rdoq_constants(ctypes.byref(par), ctypes.byref(rq), k.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(k, g['consts'][i]), i
+        r = gpu.eng.rdoq(par, gpu.eng.rdoq_rates(g['rates'][i]), coef, lam1000 / 1000.0, thr, sbt)
+        assert np.array_equal(r['q'][0], g['q_%d' % i]), (i, [int(v) for v in row])
+        assert (int(r['abs_sum'][0]), int(r['last_pos'][0])) == tuple(int(v) for v in g['meta'][i]), (i, [int(v) for v in row])
+        nonzero += int(r['last_pos'][0] >= 0)
+    assert nonzero > 100
+
+
+def test_gpu_rdoq_batches_vs_oracle(gpu, golden_rdoq):
+    """a picture's worth of TUs per launch (more TUs than resident threads for the small shapes: the threads stride over the list), the need_rdoq mask of
+    useSelectiveRdoq, luma and chroma, hiding on and off, against the CPU build of the restatement on the same inputs; fractional bits of a reference CABAC state"""
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    rs = np.random.RandomState(78)
+    chroma_rows = [i for i, r in enumerate(g['cases']) if int(r[7]) > 0]
+    luma_rows = [i for i, r in enumerate(g['cases']) if int(r[7]) == 0]
+    for (w, h, n, qp, lam, sbt, lf, sh, chroma) in ((4, 4, 90000, 32, 57.3, 0, 0, 1, 0), (8, 8, 30000, 27, 30.0, 0, 1, 0, 0), (16, 16, 6000, 37, 120.0, 0, 0, 1, 0), (32, 32, 1500, 32, 57.3, 1, 0, 1, 0),
+                                                   (64, 64, 300, 22, 11.7, 0, 0, 0, 0), (32, 8, 3000, 42, 800.0, 0, 0, 1, 1), (16, 64, 500, 32, 30.0, 0, 2, 1, 0), (8, 8, 20000, 30, 40.0, 0, 0, 1, 1)):
+        scale = rs.choice([3, 10, 40, 150, 600, 2500], size=(n, 1, 1))
+        coef = rs.laplace(0, 1.0, size=(n, h, w)) * scale * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** 0.7)
+        coef = np.clip(coef, -32768, 32767).astype(np.int32)
+        coef[:, :, 32:] = 0; coef[:, 32:, :] = 0
+        pick = chroma_rows if chroma else luma_rows
+        rates_flat = np.ascontiguousarray(g['rates'][pick[int(rs.randint(len(pick)))]])
+        mask = (rs.randint(0, 8, size=n) > 0).astype(np.uint8)
+        par = gpu.eng.tu_par(w, h, 0, 0, 10, qp, sign_hiding=bool(sh), lfnst_idx=lf, is_chroma=bool(chroma))
+        r = gpu.eng.rdoq(par, gpu.eng.rdoq_rates(rates_flat), coef, lam, 8, sbt, need_rdoq=mask)
+        q = np.zeros((n, h, w), dtype=np.int16); s = np.zeros(n, dtype=np.int32); l = np.zeros(n, dtype=np.int32)
+        assert O.orc_rdoq(w, h, 10, qp, chroma, lf, sbt, sh, lam, 8, P(rates_flat), P(coef), n, P(q), P(s), P(l)) == 0
+        q[mask == 0] = 0; s[mask == 0] = 0; l[mask == 0] = -1
+        assert np.array_equal(r['q'], q), (w, h, int((r['q'] != q).any(axis=(1, 2)).sum()))
+        assert np.array_equal(r['abs_sum'], s) and np.array_equal(r['last_pos'], l), (w, h)
+        assert (l >= 0).sum() > n // 8, (w, h, int((l >= 0).sum()))
+
+
+def test_gpu_rdoq_rejects_what_stays_on_the_host(gpu, golden_rdoq):
+    import vvenc_b200 as V
+    coef = np.zeros((1, 8, 8), dtype=np.int32)
+    rates = gpu.eng.rdoq_rates(golden_rdoq['rates'][0])
+    with pytest.raises(V.VvbError):
+        gpu.eng.rdoq(gpu.eng.tu_par(8, 8, 0, 0, 10, 30, transform_skip=True), rates, coef, 30.0)          # rateDistOptQuantTS
+    with pytest.raises(V.VvbError):
+        gpu.eng.rdoq(gpu.eng.tu_par(8, 8, 0, 0, 10, 30), rates, coef, 0.0)                                  # lambda
+
+
+@pytest.mark.skipif(not have_ref(), reason='oracle/_ref not built')
+def test_rdoq_binding_on_the_real_library():
+    """xRateDistOptQuantB200 (integration/TrQuantB200.h) bound to libvvenc_b200.so next to QuantRDOQ2::xRateDistOptQuant called as a member"""
+    import vvenc_b200._lib as VL
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), VL.LIB_PATH, 'rdoq'], capture_output=True, text=True, timeout=400)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq']
+    assert r['cases'] == 224 and r['non_empty'] > 100 and r['non_empty_with_hiding'] > 40 and r['bad'] == [], r
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')), reason='oracle/_ref/enc_identity not built')
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (176, 144, 3, 0, 27)])
+def test_bitstream_identity_with_the_rdoq_seam_on_the_gpu(tmp_path, W, H, F, preset, qp):
+    import vvenc_b200._lib as VL
+    from test_encoder_identity import _identity_rdoq
+    kb = _identity_rdoq(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
+    print('encoder identity with the RDOQ seam on the GPU:', W, H, F, preset, kb)

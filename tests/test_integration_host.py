@@ -94,3 +94,13 @@ def test_tz_search_binding_equals_the_member(result):
         assert r['moving'] > r['blocks'] // 2 and r['hits'] > 20 * r['blocks'] and r['row_hits'] == r['hits'] and r['row_misses'] == r['misses'], r
     assert all(r['misses'] == 0 for r in result['tz'] if r['cfg'][6] == 80)               # the window guess covers the whole walk
     assert all(r['misses'] > 0 for r in result['tz'] if r['cfg'][6] == 14)                # ... and the fallback is exercised when it cannot
+
+
+def test_rdoq_binding_equals_the_member():
+    """xRateDistOptQuantB200 vs QuantRDOQ2::xRateDistOptQuant (member call) on the TU rig, bound to the oracle-backed mock: every row of cases.rdoq_cases()"""
+    subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    mock = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), mock, 'rdoq'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq']
+    assert r['cases'] == 224 and r['non_empty'] > 100 and r['non_empty_with_hiding'] > 40 and r['bad'] == [], r

@@ -133,3 +133,29 @@ def test_oracle_dep_quant_chroma_golden(golden_depquant):
             assert np.array_equal(q, want), (i, scalar)
         nz += int(l.value >= 0)
     assert nz > 30
+
+
+def test_oracle_rdoq_golden(golden_rdoq):
+    """QuantRDOQ2::xRateDistOptQuant (m_RDOQ == 2): the restatement (vvenc_b200/csrc/rdoq_core.h compiled for the CPU) against levels / absSum / lastPos the reference
+    produced, fractional bits from the reference's CABAC contexts; luma / Cb / Cr, sign-bit hiding on and off, LFNST scan limit, SBT bin budget; the per-call
+    constants (error scale in double arithmetic) against the reference's"""
+    import ctypes
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    rows = C.rdoq_cases()
+    assert np.array_equal(rows, g['cases'])
+    nonzero = 0; hidden = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, scale, decay10, comp, lf, sbt, intra, sh, cb, thr, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_inputs(row)
+        k = np.zeros(7, dtype=np.int32)
+        assert O.orc_rdoq_constants(w, h, bd, qp, int(comp > 0), lf, sbt, thr, P(k)) == 0
+        assert np.array_equal(k, g['consts'][i]), (i, k, g['consts'][i])
+        rates = np.ascontiguousarray(g['rates'][i])
+        q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); l = ctypes.c_int32()
+        assert O.orc_rdoq(w, h, bd, qp, int(comp > 0), lf, sbt, sh, lam1000 / 1000.0, thr, P(rates), P(coef), 1, P(q), ctypes.byref(s), ctypes.byref(l)) == 0
+        assert np.array_equal(q, g['q_%d' % i]), (i, [int(v) for v in row])
+        assert (s.value, l.value) == tuple(int(v) for v in g['meta'][i]), (i, [int(v) for v in row])
+        nonzero += int(l.value >= 0); hidden += int(sh and l.value >= 0)
+    assert nonzero > 100 and hidden > 40

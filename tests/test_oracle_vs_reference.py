@@ -512,6 +512,48 @@ def test_dep_quant_against_the_reference_member(opt):
 
 
 @pytest.mark.parametrize("opt", [0, 1])
+def test_rdoq_against_the_reference_member(opt):
+    """QuantRDOQ2::xRateDistOptQuant (what m_RDOQ == 2 runs for a TU that is not transform skipped) on the probe's TU rig against the restatement fed with the fractional
+    bits the reference read from its CABAC contexts: levels, absSum, lastPos for every TU shape class, 8 / 10 bit, QP 17..51, luma / Cb / Cr (Cr with and without a coded
+    Cb: last-position table reuse and the coded-block-flag context), sign-bit hiding, LFNST scan limit, SBT bin budget, intra and inter CUs, thrVal 4 / 8 / 16;
+    opt 0 = the scalar build of the routine's threshold pre-test, 1 = its SSE form (QuantRDOQ2.cpp:601-637).  Also the per-call constants (error scale)."""
+    import ctypes
+    from _libs import dq_oracle, refshim, P
+    O = dq_oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(700 + opt)
+    n = 0; nonzero = 0; hidden = 0; zeroed_cg = 0
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 16), (32, 8), (16, 64), (64, 32), (32, 16), (4, 32), (64, 4), (8, 16), (16, 4)]:
+        for bd in (10, 8):
+            for qp in (17, 22, 27, 32, 37, 42, 51):
+                for trial in range(5):
+                    lam = float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0]))
+                    scale = float(rs.choice([5, 20, 60, 200, 600, 2000, 30000]))
+                    dec = float(rs.choice([0.1, 0.5, 1.0, 1.5]))
+                    coef = rs.laplace(0, scale, size=(h, w)) * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** dec)
+                    coef = np.clip(coef, -32768, 32767).astype(np.int32)
+                    if w > 32: coef[:, 32:] = 0
+                    if h > 32: coef[32:, :] = 0
+                    comp = int(rs.choice([0, 0, 1, 2]))
+                    lf = int(rs.choice([0, 0, 0, 1, 2]))
+                    sbt = int(rs.choice([0, 0, 0, 1])) if (lf == 0 and comp == 0) else 0
+                    intra = 1 if lf else (0 if sbt else int(rs.randint(2)))
+                    sh = int(rs.randint(2)); cb = int(rs.randint(2)) if comp == 2 else 0
+                    thr = int(rs.choice([8, 8, 4, 16]))
+                    qR = np.zeros((h, w), np.int16); sR = ctypes.c_int32(); lR = ctypes.c_int32(); rates = np.zeros(190, np.int32); kR = np.zeros(7, np.int32)
+                    assert R.refshim_rdoq(comp, P(coef), w, h, bd, qp, intra, lf, sbt, sh, cb, lam, thr, int(rs.randint(17, 52)), trial % 3, P(qR), ctypes.byref(sR), ctypes.byref(lR),
+                                          P(rates), P(kR)) == 0
+                    kO = np.zeros(7, np.int32)
+                    assert O.orc_rdoq_constants(w, h, bd, qp, int(comp > 0), lf, sbt, thr, P(kO)) == 0 and np.array_equal(kO, kR), (w, h, bd, qp, comp, lf, sbt, kO, kR)
+                    qO = np.zeros((h, w), np.int16); sO = ctypes.c_int32(); lO = ctypes.c_int32()
+                    assert O.orc_rdoq(w, h, bd, qp, int(comp > 0), lf, sbt, sh, lam, thr, P(rates), P(coef), 1, P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
+                    assert np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, (w, h, bd, qp, comp, lf, sbt, intra, sh, cb, lam, scale, int((qO != qR).sum()))
+                    n += 1; nonzero += int(lR.value >= 0); hidden += int(sh and lR.value >= 0)
+    R.refshim_set_simd(b'AVX2')
+    assert n == 1050 and nonzero > 450 and hidden > 150, (n, nonzero, hidden)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
 def test_transform_skip_and_chroma_against_the_reference(opt):
     """TrQuant::xTransformSkip + Quant::quant with the transform-skip QP (floor 4 + 6 * internalMinusInputBitDepth, no transform shift), Quant::xNeedRDOQ in full
     (dependent-quantisation QP only for non-skipped transforms, the transform shift it keeps for skipped ones, 256 for chroma components), Quant::dequant +

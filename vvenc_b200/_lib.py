@@ -49,6 +49,15 @@ class vvb_dq_par(ctypes.Structure):
     _fields_ = [('lam', ctypes.c_double), ('dq_thr_val', ctypes.c_int32), ('zero_out', ctypes.c_int32), ('scalar_members', ctypes.c_int32), ('pad', ctypes.c_int32)]
 
 
+class vvb_rdoq_rates(ctypes.Structure):
+    _fields_ = [('sig_bits', ctypes.c_int32 * 24), ('par_bits', ctypes.c_int32 * 42), ('gt1_bits', ctypes.c_int32 * 42), ('gt2_bits', ctypes.c_int32 * 42), ('sig_group_bits', ctypes.c_int32 * 4),
+                ('last_bits_x', ctypes.c_int32 * 16), ('last_bits_y', ctypes.c_int32 * 16), ('cbf_bits', ctypes.c_int32 * 2), ('pad', ctypes.c_int32 * 2)]
+
+
+class vvb_rdoq_par(ctypes.Structure):
+    _fields_ = [('lam', ctypes.c_double), ('thr_val', ctypes.c_int32), ('sbt_zero_out', ctypes.c_int32), ('pad', ctypes.c_int32 * 2)]
+
+
 class vvb_level_io(ctypes.Structure):
     _fields_ = [('blocks', ctypes.c_void_p), ('count', ctypes.c_int32), ('best', ctypes.c_void_p), ('refine_cost', ctypes.c_void_p), ('q', ctypes.c_void_p),
                 ('abs_sum', ctypes.c_void_p), ('last_pos', ctypes.c_void_p), ('need_rdoq', ctypes.c_void_p), ('tu', vvb_tu_par), ('packed_q', ctypes.c_void_p), ('packed_offsets', ctypes.c_void_p)]
@@ -129,6 +138,9 @@ SYMBOLS = {
     'vvb_dep_quant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), ctypes.POINTER(vvb_dq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
     'vvb_set_depquant_engine': (c_i, [c_p, c_i]),
     'vvb_dep_quant_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), c_p]),
+    'vvb_rdoq': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), ctypes.POINTER(vvb_rdoq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
+    'vvb_rdoq_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), ctypes.POINTER(vvb_rdoq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
+    'vvb_rdoq_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), c_p]),
     'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_inv_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_tu_roundtrip': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_p, c_i, c_p, c_p, c_p, c_p]),

@@ -282,6 +282,28 @@ class CostEngine:
         self._chk(self.lib.vvb_dep_quant(self.h, ctypes.byref(par), ctypes.byref(dq), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s), _p(lp)))
         return dict(q=q, abs_sum=s, last_pos=lp)
 
+    @staticmethod
+    def rdoq_rates(flat):
+        """vvb_rdoq_rates from 190 int32 in declaration order (sig_bits[12][2], par_bits[21][2], gt1_bits[21][2], gt2_bits[21][2], sig_group_bits[2][2],
+        last_bits_x[16], last_bits_y[16], cbf_bits[2], pad[2])"""
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        assert flat.size == 190
+        r = L.vvb_rdoq_rates()
+        ctypes.memmove(ctypes.byref(r), flat.ctypes.data, 190 * 4)
+        return r
+
+    def rdoq(self, par, rates, coef, lam, thr_val=8, sbt_zero_out=False, need_rdoq=None):
+        """QuantRDOQ2::quant (m_RDOQ == 2) for n TUs of one shape: coef int32 [n][h][w] (as fwd_trquant returns them) -> dict(q, abs_sum, last_pos).
+        rates: vvb_rdoq_rates (fractional bits of the caller's CABAC contexts), lam: Quant::m_dLambda; par.sign_hiding / par.lfnst_idx / par.is_chroma apply."""
+        coef = np.ascontiguousarray(coef, dtype=np.int32)
+        n = coef.shape[0]
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        s = np.zeros(n, dtype=np.int32); lp = np.zeros(n, dtype=np.int32)
+        rq = L.vvb_rdoq_par(float(lam), int(thr_val), int(sbt_zero_out))
+        nr = None if need_rdoq is None else np.ascontiguousarray(need_rdoq, dtype=np.uint8)
+        self._chk(self.lib.vvb_rdoq(self.h, ctypes.byref(par), ctypes.byref(rq), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s), _p(lp)))
+        return dict(q=q, abs_sum=s, last_pos=lp)
+
     # ---- inverse path / fused TU round trip
     def inv_trquant(self, par, q):
         """TrQuant::invTransformNxN for n compact level blocks q [n][h][w] -> residual int16 [n][h][w]"""

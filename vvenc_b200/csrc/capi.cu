@@ -19,9 +19,11 @@
 #include "mctf_affine_kernels.cuh"
 #include "frac_kernels.cuh"
 #include "depquant_kernels.cuh"
+#include "rdoq_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "mctf_control_kernels.cuh"
 #include "depquant_host.h"
+#include "rdoq_host.h"
 #include "vvc_tables.h"
 #include "vvc_lfnst_tables.h"
 
@@ -1587,6 +1589,75 @@ int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_
   if( !par || !dq || !out || vvbdq::dq_shape_index( par->w, par->h ) < 0 || !( dq->lambda > 0.0 ) ) return VVB_ERR_ARG;
   const vvbdq::DqQuant q = vvbdq::dq_init_quant( par->w, par->h, par->bit_depth, par->qp + 6 * ( par->bit_depth - 8 ), dq->lambda, dq->dq_thr_val );
   out[0] = q.qShift; out[1] = q.maxQIdx; out[2] = q.thresLast; out[3] = q.distShift; out[4] = q.qAdd; out[5] = q.qScale; out[6] = q.distAdd; out[7] = q.distStepAdd; out[8] = q.distOrgFact;
+  return VVB_OK;
+}
+
+// ---- fast RDOQ: QuantRDOQ2::xRateDistOptQuantFast, one TU per thread ---------------------------------------------------------------------------
+namespace {
+int rqPar( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, vvbrq::RqPar& p )
+{
+  if( !par || !rq ) return fail( ctx, VVB_ERR_ARG, "null parameters" );
+  if( !vvbrq::rq_shape_ok( par->w, par->h ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "TU sides must be 4, 8, 16, 32 or 64" );
+  if( par->bit_depth != 8 && par->bit_depth != 10 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth 8 or 10" );
+  if( par->transform_skip ) return fail( ctx, VVB_ERR_UNSUPPORTED, "transform-skip RDOQ (rateDistOptQuantTS) stays on the host" );
+  if( !( rq->lambda > 0.0 ) ) return fail( ctx, VVB_ERR_ARG, "lambda must be greater than 0" );
+  if( rq->thr_val < 1 || rq->thr_val > 64 ) return fail( ctx, VVB_ERR_ARG, "thr_val 1..64" );
+  const int baseQp = std::max( 0, std::min( 63 + 6 * ( par->bit_depth - 8 ), par->qp + 6 * ( par->bit_depth - 8 ) ) );        // QpParam, Quant.cpp:99-113
+  p = vvbrq::rq_init_par( par->w, par->h, par->bit_depth, baseQp, par->lfnst_idx > 0, rq->sbt_zero_out, par->sign_hiding, par->is_chroma, rq->lambda, rq->thr_val );
+  if( p.qBits < 1 || p.qBits > 30 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "quantiser shift outside 1..30" );
+  return VVB_OK;
+}
+} // namespace
+
+int vvb_rdoq_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, const vvb_rdoq_rates* rates, const int32_t* dCoef, const uint8_t* dNeedRdoq, int n,
+                  int16_t* dQ, int32_t* dAbsSum, int32_t* dLastPos )
+{
+  if( !ctx || !par || !rq || !rates || !dCoef || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  RqLaunch L = {};
+  int rc = rqPar( ctx, par, rq, L.par );
+  if( rc ) return rc;
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  int lw = 0, lh = 0;
+  while( ( 1 << lw ) < par->w ) lw++;
+  while( ( 1 << lh ) < par->h ) lh++;
+  L.scan = ctx->d_scan + 25 * 1024 + ( ( lw - 2 ) * 5 + ( lh - 2 ) ) * 1024;      // scan position -> raster index inside the scanned region (buildScanTables)
+  L.numScan = std::min( 32, par->w ) * std::min( 32, par->h );
+  vvbrq::RqRates r;
+  static_assert( sizeof( vvbrq::RqRates ) == sizeof( vvb_rdoq_rates ) && sizeof( vvb_rdoq_rates ) == 760, "vvb_rdoq_rates mirrors RqRates" );
+  memcpy( &r, rates, sizeof( r ) );
+  const int blocks = std::min( ( n + VVB_RQ_THREADS - 1 ) / VVB_RQ_THREADS, ctx->numSMs * 16 );
+  rdoq_kernel<<<blocks, VVB_RQ_THREADS, 0, ctx->stream>>>( L, r, dCoef, dNeedRdoq, n, dQ, dAbsSum, dLastPos );
+  CHECK_LAUNCH( "rdoq_kernel" );
+  return VVB_OK;
+}
+
+int vvb_rdoq( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, const vvb_rdoq_rates* rates, const int32_t* coef, const uint8_t* needRdoq, int n,
+              int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( !ctx || !par || !rq || !rates || !coef || !q || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t area = (size_t) par->w * par->h;
+  void *dC, *dQ, *dM; int rc;
+  if( ( rc = scratch( ctx, 2, (size_t) n * area * 4, &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * area * 2, &dQ ) ) || ( rc = scratch( ctx, 3, (size_t) n * 12, &dM ) ) ) return rc;
+  int32_t* dSum = (int32_t*) dM; int32_t* dLast = dSum + n; uint8_t* dNr = (uint8_t*)( dLast + n );
+  CU( cudaMemcpyAsync( dC, coef, (size_t) n * area * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( needRdoq ) CU( cudaMemcpyAsync( dNr, needRdoq, (size_t) n, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_rdoq_dev( ctx, par, rq, rates, (const int32_t*) dC, needRdoq ? dNr : nullptr, n, (int16_t*) dQ, dSum, dLast ) ) ) return rc;
+  CU( cudaMemcpyAsync( q, dQ, (size_t) n * area * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( absSum )  CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( lastPos ) CU( cudaMemcpyAsync( lastPos, dLast, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
+// the per-call constants as the device call derives them (for bindings / tests): quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos
+int vvb_rdoq_constants( const vvb_tu_par* par, const vvb_rdoq_par* rq, int32_t out[7] )
+{
+  if( !par || !rq || !out || !vvbrq::rq_shape_ok( par->w, par->h ) || ( par->bit_depth != 8 && par->bit_depth != 10 ) ) return VVB_ERR_ARG;
+  const int baseQp = std::max( 0, std::min( 63 + 6 * ( par->bit_depth - 8 ), par->qp + 6 * ( par->bit_depth - 8 ) ) );
+  const vvbrq::RqPar p = vvbrq::rq_init_par( par->w, par->h, par->bit_depth, baseQp, par->lfnst_idx > 0, rq->sbt_zero_out, par->sign_hiding, par->is_chroma, rq->lambda, rq->thr_val );
+  out[0] = p.quantScale; out[1] = p.errScale; out[2] = p.qBits; out[3] = p.useThres; out[4] = p.remRegBins; out[5] = p.numCG; out[6] = p.firstScanPos;
   return VVB_OK;
 }
 

@@ -1,0 +1,83 @@
+// rdoq_host.h -- host-side set-up of the RDOQ kernel (plain C++, no CUDA): the per-call constants QuantRDOQ2::xRateDistOptQuantFast derives before its loops
+// (CommonLib/QuantRDOQ2.cpp:500-559, 573-583) and the error scale of xSetErrScaleCoeffNoScalingList (:203-219, double arithmetic in the reference's operation
+// order; build with -ffp-contract=off).
+#pragma once
+#include "rdoq_core.h"
+#include <cmath>
+
+namespace vvbrq {
+
+inline int rq_shape_ok( int w, int h )
+{
+  int lw = 0, lh = 0;
+  while( ( 1 << lw ) < w ) lw++;
+  while( ( 1 << lh ) < h ) lh++;
+  return ( 1 << lw ) == w && ( 1 << lh ) == h && lw >= 2 && lw <= 6 && lh >= 2 && lh <= 6;
+}
+
+// qpInternal = cQP.Qp( false ): clip( CU QP + qpBdOffset ) (QpParam, Quant.cpp:89-124).  lfnst = tu.cu->lfnstIdx > 0 (the routine looks at the CU's index for every
+// component, :552-559).  sbtZeroOut = the condition of TransformUnit::getTbAreaAfterCoefZeroOut (Unit.cpp:580): sps.MTS && cu.sbtInfo && w <= 32 && h <= 32 && luma.
+inline RqPar rq_init_par( int w, int h, int bitDepth, int qpInternal, int lfnst, int sbtZeroOut, int signHiding, int isChroma, double lambda, int thrVal )
+{
+  static const int quantScales[2][6] = { { 26214, 23302, 20560, 18396, 16384, 14564 }, { 18396, 16384, 14564, 13107, 11651, 10280 } };      // g_quantScales, Rom.cpp:1390-1394
+  int lw = 0, lh = 0;
+  while( ( 1 << lw ) < w ) lw++;
+  while( ( 1 << lh ) < h ) lh++;
+  const int per = qpInternal / 6, rem = qpInternal % 6;
+  const int maxLog2TrDynamicRange = 15;
+  const int transformShift = maxLog2TrDynamicRange - bitDepth - ( ( lw + lh ) >> 1 );          // getTransformShift, Quant.h:69-72
+  const bool sqrt2 = ( ( lw + lh ) & 1 ) != 0;                                                  // TU::needsSqrt2Scale (not transform skipped)
+  RqPar p;
+  p.width = w; p.height = h; p.log2W = lw;
+  p.regionW = w < 32 ? w : 32;
+  const int regionH = h < 32 ? h : 32;
+  p.numCG = lfnst ? 1 : ( p.regionW * regionH ) >> 4;                                           // :553
+  p.firstScanPos = ( p.numCG << 4 ) - 1;                                                        // :554
+  if( lfnst && ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ) p.firstScanPos = 7;           // :556-559
+  p.quantScale = quantScales[sqrt2 ? 1 : 0][rem];                                               // :518
+  p.qBits = 14 + per + transformShift + ( sqrt2 ? -1 : 0 );                                     // :522 (QUANT_SHIFT = 14)
+  {
+    // xSetErrScaleCoeffNoScalingList, :203-219 (SCALE_BITS = 15, DISTORTION_PRECISION_ADJUSTMENT = 0)
+    const double dTransShift = (double) transformShift + ( sqrt2 ? -0.5 : 0.0 );
+    double dErrScale = pow( 2.0, ( (double) RQ_SCALE_BITS / 2.0 ) );
+    dErrScale = dErrScale * pow( 2.0, ( -( dTransShift ) ) );
+    const int QStep = p.quantScale;
+    const double errScale = dErrScale / QStep / ( 1 << 0 );
+    p.errScale = (int)( errScale * (double)( 1 << RQ_ERR_SCALE_SHIFT ) );
+  }
+  int32_t thres;                                                                                // :573-583
+  if( p.qBits ) thres = (int32_t)( (int64_t) thrVal << ( p.qBits - 1 ) );
+  else          thres = (int32_t)( (int64_t)( thrVal >> 1 ) << p.qBits );
+  p.useThres = thres / ( p.quantScale << 2 );
+  int zw = p.regionW, zh = regionH;                                                             // getTbAreaAfterCoefZeroOut, Unit.cpp:574-589
+  if( sbtZeroOut && !isChroma && w <= 32 && h <= 32 ) { if( w == 32 ) zw = 16; if( h == 32 ) zh = 16; }
+  p.remRegBins = ( zw * zh * 28 ) >> 4;                                                         // MAX_TU_LEVEL_CTX_CODED_BIN_CONSTRAINT = 28, :538-539
+  p.signHiding = signHiding ? 1 : 0;
+  p.isChroma = isChroma ? 1 : 0;
+  p.pad = 0;
+  p.lambda = lambda;
+  return p;
+}
+
+// scan position -> raster index inside the scanned region (row pitch min( 32, w )): grouped 4x4 up-right diagonal scan (Rom.cpp:1098-1136, 1236-1284)
+inline void rq_build_scan( int w, int h, int32_t* out /* min(32,w) * min(32,h) */ )
+{
+  auto diag = []( int bw, int bh, int* xs, int* ys )
+  {
+    int line = 0, col = 0;
+    for( int i = 0; i < bw * bh; i++ )
+    {
+      xs[i] = col; ys[i] = line;
+      if( col == bw - 1 || line == 0 ) { line += col + 1; col = 0; if( line >= bh ) { col += line - ( bh - 1 ); line = bh - 1; } }
+      else { col++; line--; }
+    }
+  };
+  const int rw = w < 32 ? w : 32, rh = h < 32 ? h : 32;
+  int cx[16], cy[16], gx[64], gy[64];
+  diag( 4, 4, cx, cy );
+  diag( rw >> 2, rh >> 2, gx, gy );
+  for( int g = 0; g < ( rw >> 2 ) * ( rh >> 2 ); g++ )
+    for( int c = 0; c < 16; c++ ) out[g * 16 + c] = ( gy[g] * 4 + cy[c] ) * rw + gx[g] * 4 + cx[c];
+}
+
+} // namespace vvbrq

@@ -1,0 +1,47 @@
+// rdoq_kernels.cuh -- QuantRDOQ2::xRateDistOptQuantFast on the device: one thread decides the levels of one TU (rdoq_core.h holds the algorithm and the reference
+// line numbers).  Inside a TU the decisions are strictly sequential -- the context of a coefficient is a function of the levels chosen for its five already-visited
+// neighbours, the budget of context-coded bins runs along the scan, the last-position optimisation looks at running sums -- so the parallelism is across TUs: a
+// picture's worth of TUs of one shape per launch.  Rate tables and the scan order are staged in shared memory once per CTA; the level buffer a thread reads its
+// templates from is its TU's slice of the output (global memory, L1-resident for the group being worked on); the five 16-entry cost arrays of the current
+// coefficient group are thread-local.
+#pragma once
+#include "common.cuh"
+#include "rdoq_core.h"
+
+namespace vvb {
+
+struct RqLaunch
+{
+  vvbrq::RqPar   par;
+  const int32_t* scan;               // device: scan position -> raster index inside the scanned region (ctx->d_scan, second half), min(32,w) * min(32,h) entries
+  int32_t        numScan;
+};
+
+#define VVB_RQ_THREADS 64
+
+__global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_kernel( const __grid_constant__ RqLaunch L, const __grid_constant__ vvbrq::RqRates rates,
+                                                                 const int32_t* __restrict__ coef, const uint8_t* __restrict__ needRdoq, int n,
+                                                                 int16_t* __restrict__ q, int32_t* __restrict__ absSum, int32_t* __restrict__ lastPos )
+{
+  __shared__ vvbrq::RqRates sRates;
+  __shared__ int32_t sScan[1024];
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>( &rates );
+    int32_t* dst = reinterpret_cast<int32_t*>( &sRates );
+    for( int i = threadIdx.x; i < (int)( sizeof( vvbrq::RqRates ) / 4 ); i += blockDim.x ) dst[i] = src[i];
+    for( int i = threadIdx.x; i < L.numScan; i += blockDim.x ) sScan[i] = L.scan[i];
+  }
+  __syncthreads();
+  const int area = L.par.width * L.par.height;
+  for( int tu = blockIdx.x * blockDim.x + threadIdx.x; tu < n; tu += gridDim.x * blockDim.x )
+  {
+    int16_t* qt = q + (size_t) tu * area;
+    int32_t sum = 0, last = -1;
+    if( needRdoq && !needRdoq[tu] ) { for( int i = 0; i < area; i++ ) qt[i] = 0; }       // QuantRDOQ2::quant, :273, 291-295 (useSelectiveRdoq)
+    else vvbrq::rq_quant_tu( L.par, sRates, sScan, coef + (size_t) tu * area, qt, &sum, &last );
+    if( absSum ) absSum[tu] = sum;
+    if( lastPos ) lastPos[tu] = last;
+  }
+}
+
+} // namespace vvb
