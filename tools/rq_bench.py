@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Times vvb_rdoq_dev (QuantRDOQ2::xRateDistOptQuantFast on the device, one TU per thread) for a 2160p picture's worth of TUs per shape, CUDA events on the context
 stream, and the CPU side on one thread: the reference's own member (oracle/_ref, incl. the probe's per-TU rig set-up) on a bounded sample, and the port (the same
-text compiled by g++) on the whole list.  usage: python tools/rq_bench.py [reps]"""
+text compiled by g++) on the whole list.  With a second argument (e.g. 1,4,16) the device is timed on that many pictures' worth of TUs per launch as well: the
+kernel is bound by the serial chain of one TU, so the time per TU falls until the SMs are full.  usage: python tools/rq_bench.py [reps] [pictures,...] [only WxH]"""
 import ctypes, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,6 +15,8 @@ def main():
     import vvenc_b200._lib as L
     from _libs import have_ref, refshim, dq_oracle, P
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    mult = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else []
+    only = sys.argv[3] if len(sys.argv) > 3 else None
     eng = V.CostEngine(0)
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', 0))
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v6_rdoq.npz'))
@@ -23,6 +26,8 @@ def main():
     rs = np.random.RandomState(1)
     out = {}
     for (w, h) in ((8, 8), (16, 16), (32, 32), (64, 64)):
+        if only and only != '%dx%d' % (w, h):
+            continue
         n = (3840 // w) * (2160 // h)
         scale = rs.choice([3, 10, 40, 150, 600], size=(n, 1, 1))
         coef = rs.laplace(0, 1.0, size=(n, h, w)) * scale * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** 0.7)
@@ -58,6 +63,22 @@ def main():
             for i in range(m):
                 R.refshim_rdoq(0, P(coef[i]), w, h, 10, 32, 0, 0, 0, 1, 0, 57.3, 8, 32, 0, P(q), ctypes.byref(s), ctypes.byref(l), None, None)
             row['reference_ms_per_picture_1thread_incl_rig_setup'] = (time.perf_counter() - t0) / m * n * 1e3
+        for m in mult:                                   # m pictures' worth of TUs in one launch (the list repeated)
+            if m <= 1 or n * m * w * h * 6 > 6e9:
+                continue
+            dc = dcoef.repeat(m, 1, 1); dqm = torch.zeros((n * m, h, w), dtype=torch.int16, device='cuda')
+            ds = torch.zeros(n * m, dtype=torch.int32, device='cuda'); dl = torch.zeros(n * m, dtype=torch.int32, device='cuda')
+            runm = lambda: eng._chk(eng.lib.vvb_rdoq_dev(eng.h, ctypes.byref(par), ctypes.byref(rqp), ctypes.byref(rates), cp(dc), None, n * m, cp(dqm), cp(ds), cp(dl)))
+            runm(); eng.synchronize()
+            with torch.cuda.stream(ext):
+                e0.record(ext)
+                for _ in range(max(1, reps // 2)):
+                    runm()
+                e1.record(ext)
+            eng.synchronize(); torch.cuda.synchronize()
+            row['ms_per_picture_at_%d_pictures' % m] = e0.elapsed_time(e1) / max(1, reps // 2) / m
+            row['equal_at_%d_pictures' % m] = bool(torch.equal(dqm[(m - 1) * n:], dq_))
+            del dc, dqm, ds, dl
         out['%dx%d' % (w, h)] = row
     print(json.dumps(out))
 
