@@ -1012,6 +1012,42 @@ def main():
                                         'as fresh bytes, so fractions above 1.0 mean L2 hits, not missing work (DRAM traffic in profiles/)', **dia}
         except Exception as ex:
             extra['diamond_set_sad'] = {'error': str(ex)}
+        # fast RDOQ (QuantRDOQ2::xRateDistOptQuantFast, what Quant::m_RDOQ == 2 of the presets faster / fast runs): one TU per thread, bound by the serial
+        # chain of a TU, so the row holds one picture's worth of TUs per launch and sixteen; the CPU row is the same text compiled by g++ on ONE host thread
+        try:
+            from vvenc_b200 import _lib as VL
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests'))
+            from _libs import dq_oracle, P as P_np
+            g6 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests', 'golden', 'golden_v6_rdoq.npz'))
+            rates_flat = np.ascontiguousarray(g6['rates'][[i for i, r in enumerate(g6['cases']) if int(r[7]) == 0][3]])
+            rates = eng.rdoq_rates(rates_flat)
+            rsq = np.random.RandomState(1); rq_rows = {}
+            for n in (8, 16, 32, 64):
+                cnt = (W // n) * (H // n)
+                scale = rsq.choice([3, 10, 40, 150, 600], size=(cnt, 1, 1))
+                coef = rsq.laplace(0, 1.0, size=(cnt, n, n)) * scale * (1.0 / (1 + np.add.outer(np.arange(n), np.arange(n))) ** 0.7)
+                coef = np.clip(coef, -32768, 32767).astype(np.int32); coef[:, :, 32:] = 0; coef[:, 32:, :] = 0
+                par = eng.tu_par(n, n, 0, 0, BITDEPTH, QP, sign_hiding=True); rqp = VL.vvb_rdoq_par(57.3, 8, 0)
+                row = {'tus': int(cnt)}
+                for mult in (1, 16):
+                    d_c = torch.from_numpy(coef).cuda().repeat(mult, 1, 1); d_q = torch.zeros((cnt * mult, n, n), dtype=torch.int16, device='cuda')
+                    d_s = torch.zeros(cnt * mult, dtype=torch.int32, device='cuda'); d_l = torch.zeros(cnt * mult, dtype=torch.int32, device='cuda')
+                    t = time_launch(lambda: chk(lib.vvb_rdoq_dev(eng.h, ctypes.byref(par), ctypes.byref(rqp), ctypes.byref(rates), P_(d_c.data_ptr()), None, cnt * mult,
+                                                                 P_(d_q.data_ptr()), P_(d_s.data_ptr()), P_(d_l.data_ptr()))), reps=3)
+                    row['ms_per_picture' if mult == 1 else 'ms_per_picture_at_16_pictures'] = t / mult
+                    if mult == 1:
+                        q_dev = d_q.cpu().numpy(); l_dev = d_l.cpu().numpy()
+                    del d_c, d_q, d_s, d_l
+                qq = np.zeros((cnt, n, n), dtype=np.int16); ss = np.zeros(cnt, dtype=np.int32); ll = np.zeros(cnt, dtype=np.int32)
+                t0 = time.perf_counter()
+                dq_oracle().orc_rdoq(n, n, BITDEPTH, QP, 0, 0, 0, 1, 57.3, 8, P_np(rates_flat), P_np(coef), cnt, P_np(qq), P_np(ss), P_np(ll))
+                row['cpu_port_ms_per_picture_1thread'] = (time.perf_counter() - t0) * 1e3
+                row['device_equals_port'] = bool(np.array_equal(q_dev, qq) and np.array_equal(l_dev, ll))
+                row['coded_tus'] = int((ll >= 0).sum())
+                rq_rows[str(n)] = row
+            extra['rdoq_2160p'] = rq_rows
+        except Exception as ex:
+            extra['rdoq_2160p'] = {'error': str(ex)}
 
     # ------------------------------------------------------------------------------------------- BASELINE configs[4]: 4320p, strong scaling + parity
     if (world > 1 or args.strong) and not args.skip_extras:

@@ -12,7 +12,7 @@
 // kept in step with the level buffer by absVal1stPass / remAbsVal1stPass at every change) is a pure function of the level buffer, so it is read from the
 // levels directly (the form sigCtxIdAbs, ContextModelling.h:115-156, uses).
 //
-// Plain C++ without CUDA syntax outside VVB_HD: oracle/rdoq_oracle.cpp compiles the very same text for the CPU, where it is pinned against the reference's member.
+// Plain C++ without CUDA syntax outside VVB_HD: the test suite compiles the very same text for the CPU (g++), where it is pinned against the reference's member.
 #pragma once
 #include <stdint.h>
 
