@@ -85,9 +85,10 @@ def test_bitstream_identity_with_the_tu_seam_on_the_oracle(tmp_path, W, H, F, pr
     _identity_tu(tmp_path, W, H, F, preset, qp, MOCK, dq)
 
 
-@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (176, 144, 3, 0, 27)])
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (176, 144, 3, 0, 27), (416, 240, 8, 0, 37)])
 def test_bitstream_identity_with_the_rdoq_seam_on_the_oracle(tmp_path, W, H, F, preset, qp):
-    """preset faster runs Quant::m_RDOQ == 2 with sign-bit hiding and selective RDOQ (vvencCfg.cpp:2675-2677): 1 000 / 7 000 TUs through xRateDistOptQuantB200"""
+    """preset faster runs Quant::m_RDOQ == 2 with sign-bit hiding and selective RDOQ (vvencCfg.cpp:2675-2677): 1 000 / 7 000 / 16 500 TUs through xRateDistOptQuantB200;
+    (416, 240, 8 frames, faster, QP 37) is BASELINE configs[0]"""
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity_rdoq(tmp_path, W, H, F, preset, qp, MOCK)
