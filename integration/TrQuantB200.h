@@ -6,7 +6,7 @@
 //   xRateDistOptQuantB200 <-> QuantRDOQ2::xRateDistOptQuant (QuantRDOQ2.cpp:1283-1296 -> xRateDistOptQuantFast :475-1281), the fast RDOQ of m_RDOQ == 2
 //
 // for the TUs the library covers: luma and chroma components, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), transform skip,
-// LFNST on the forward side (luma), no scaling lists / BDPCM / joint Cb-Cr, plain quantiser incl. its sign-bit hiding (RDOQ stays on the host and uses the coefficients
+// LFNST (luma, and the chroma TUs of a separate tree), joint Cb-Cr TUs, no scaling lists / BDPCM / ACT, plain quantiser incl. its sign-bit hiding (transform-skip RDOQ stays on the host and uses the coefficients
 // this call leaves in the temp buffer; dependent quantisation: xQuantDQB200 below).
 // vvb_tu_par is derived from the TransformUnit exactly as the members derive their parameters (xSetTrTypes, QpParam, slice type), so the call sites keep
 // their arguments.  One TU per call here; the production shape batches the TU candidates of a CU (vvb_fwd_trquant with n > 1 or
@@ -43,7 +43,9 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
   const ChannelType chType = toChannelType( compID );
   if( tu.cu->bdpcmM[chType] ) THROW( "BDPCM stays on the host" );
   if( tu.cs->sps->scalingListEnabled ) THROW( "scaling lists stay on the host" );
-  if( isChroma( compID ) && ( tu.jointCbCr || tu.cu->colorTransform ) ) THROW( "joint Cb-Cr / ACT residuals stay on the host" );
+  // joint Cb-Cr TUs need nothing special here: the caller has already formed the joint residual (fwdTransformICT) and built cQP for the joint mode (QpParam, Quant.cpp:80-87);
+  // neither transformNxN nor the quantisers look at tu.jointCbCr.  The adaptive colour transform changes QpParam only when the caller asks for it: left to the host.
+  if( tu.cu->colorTransform ) THROW( "ACT residuals stay on the host" );
   const SPS& sps = *tu.cs->sps;
   const bool skip = tu.mtsIdx[compID] == MTS_SKIP;
   int trHor = DCT2, trVer = DCT2;
@@ -62,11 +64,12 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
   par.dep_quant = tu.cs->slice->depQuantEnabled ? 1 : 0;                                     // xNeedRDOQ's QP; invTransformNxNB200 then dequantises as DepQuant::dequant does
   if( tu.cu->lfnstIdx && tu.cs->sps->LFNST && !skip && ( isLuma( compID ) || CU::isSepTree( *tu.cu ) ) )         // TrQuant::xFwdLfnst (TrQuant.cpp:942-1048) / xInvLfnst (:838-940): kernel set and transposition from the intra mode
   {
-    if( trHor != DCT2 || trVer != DCT2 || isChroma( compID ) ) THROW( "LFNST index on a TU the library does not cover" );
+    if( trHor != DCT2 || trVer != DCT2 ) THROW( "LFNST index on a TU the library does not cover" );
     const CodingUnit& cu = *tu.cu;                                                           // :846 / :950 look the CU up at the TU position: the CU that owns the TU
-    uint32_t intraMode = CU::getFinalIntraMode( cu, CH_L );
-    if( CU::isMIP( cu, CH_L ) ) intraMode = PLANAR_IDX;
-    intraMode = tq.xGetLFNSTIntraMode( tu.cu->ispMode ? tu.cu->blocks[compID] : tu.blocks[compID], intraMode );
+    uint32_t intraMode = CU::getFinalIntraMode( cu, chType );                                // chroma TUs of a separate tree: the chroma mode, or for the cross-component modes
+    if( CU::isLMCMode( cu.intraDir[chType] ) ) intraMode = CU::getCoLocatedIntraLumaMode( cu );   // the mode of the co-located luma CU (:958-961)
+    if( CU::isMIP( cu, chType ) ) intraMode = PLANAR_IDX;
+    intraMode = tq.xGetLFNSTIntraMode( ( tu.cu->ispMode && isLuma( compID ) ) ? tu.cu->blocks[compID] : tu.blocks[compID], intraMode );
     par.lfnst_idx = tu.cu->lfnstIdx; par.lfnst_set = g_lfnstLut[intraMode]; par.lfnst_transpose = tq.xGetTransposeFlag( intraMode ) ? 1 : 0;
   }
   par.sign_hiding = tu.cs->slice->signDataHidingEnabled ? 1 : 0;                            // Quant::quant: CoeffCodingContext( ..., signDataHidingEnabled ), xSignBitHidingHDQ (Quant.cpp:748, 817-826)
@@ -86,6 +89,17 @@ inline void xTQuantB200( TrQuant& tq, TransformUnit& tu, const ComponentID compI
   for( int y = 0; y < h; y++ ) memcpy( &resi[(size_t) y * w], resiBuf.buf + (ptrdiff_t) y * resiBuf.stride, sizeof( int16_t ) * w );
   int32_t absSum = 0, lastPos = -1; uint8_t nr = 0;
   b200Check( g_b200t.fwdTrQuant( b200CtxOfThread(), &par, resi.data(), 1, coef.data(), q.data(), &absSum, &lastPos, &nr ) );
+  if( tu.cu->lfnstIdx && !par.lfnst_idx && !par.transform_skip )
+  {
+    // xT zeroes everything outside the top-left 4x4 / 8x8 whenever the CU carries an LFNST index (TrQuant.cpp:499-511) -- also for the chroma TUs of a single-tree CU, to
+    // which the LFNST itself does not apply (:948).  Zero-out only drops outputs of the separable transform, so it is applied here to the full transform the library
+    // returned; the levels of this call are not used by such callers (they quantise the coefficients afterwards), they are cleared with the coefficients
+    const int keep = ( ( w == 4 && h > 4 ) || ( w > 4 && h == 4 ) ) ? 4 : ( ( w >= 8 && h >= 8 ) ? 8 : 0 );
+    if( keep )
+      for( int y = 0; y < h; y++ )
+        for( int x = 0; x < w; x++ )
+          if( x >= keep || y >= keep ) { coef[(size_t) y * w + x] = 0; q[(size_t) y * w + x] = 0; }
+  }
   for( int y = 0; y < h; y++ ) memcpy( tempCoeff.buf + (ptrdiff_t) y * tempCoeff.stride, &coef[(size_t) y * w], sizeof( TCoeff ) * w );
   CoeffSigBuf dst = tu.getCoeffs( compID );
   for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );

@@ -21,7 +21,9 @@
  *   Quant::dequant / DepQuant::dequant + xIT / xITransformSkip  by invTransformNxNB200 (TUs without LFNST; the rest stays with the member),
  *   QuantRDOQ2::xRateDistOptQuant (Quant::m_RDOQ == 2: presets faster / fast, and slices without dependent quantisation)  by xRateDistOptQuantB200 (fractional bits of the
  *                                                       live CABAC contexts -> vvb_rdoq: level decisions, group zero-out, last position, sign-bit hiding on the device),
- * transform-skip RDOQ, RDOQ of m_RDOQ == 1 and everything the bindings THROW for (BDPCM, joint Cb-Cr, scaling lists) stay with the reference members.
+ * With `turdoq` the routing is the widest the bindings offer: LFNST also on the chroma TUs of a separate tree (kernel set from the chroma / co-located luma mode) and on ISP luma TUs,
+ * the chroma TUs of single-tree LFNST CUs (xT's zero-out applied to the full transform), joint Cb-Cr TUs (the caller has formed the joint residual and QP).
+ * Transform-skip RDOQ, RDOQ of m_RDOQ == 1, TUs with a side below 4 (thin ISP partitions, 2-wide chroma) and everything the bindings THROW for (BDPCM, ACT, scaling lists) stay with the members.
  *
  * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu | turdoq]
  * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_rdoq=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
@@ -107,7 +109,8 @@ static decltype( &vvb_sad_x5_block ) g_realX5 = nullptr;
 static int countingX5( vvb_ctx* c, const int16_t* o, int so, const int16_t* u, int su, int w, int h, int ss, int cc, uint64_t* out ) { g_otherCalls++; return g_realX5( c, o, so, u, su, w, h, ss, cc, out ); }
 
 // ---- the transform / quantisation seam -------------------------------------------------------------------------------------------------------------------------
-static bool g_useTu = false, g_useRdoq = false;      // g_useRdoq: argument `turdoq` -- the fast RDOQ of m_RDOQ == 2 through the library as well
+static bool g_useTu = false, g_useRdoq = false;      // g_useRdoq: argument `turdoq` -- the widest routing: also the fast RDOQ of m_RDOQ == 2, LFNST on the chroma TUs of a
+                                                      // separate tree and on ISP luma TUs, joint Cb-Cr TUs (`tu` keeps the narrower routing of the first hardware runs)
 static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuRdoq{ 0 }, g_tuInv{ 0 }, g_tuInvLfnst{ 0 }, g_tuRef{ 0 };
 
 extern "C" void __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant*, TransformUnit&, ComponentID, const QpParam&, TCoeff&, const Ctx&, bool );
@@ -116,8 +119,8 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
 {
   const ChannelType chType = toChannelType( compID );
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0;
-  // what stays with the member: BDPCM, LFNST on chroma / ISP CUs or on stored coefficients (the binding derives the kernel set for plain luma TUs), empty TUs
-  if( !g_useTu || tu.noResidual || tu.cu->bdpcmM[chType] || ( lfnstHere && ( loadTr || !isLuma( compID ) || tu.cu->ispMode ) ) || tu.cs->sps->scalingListEnabled )
+  // what stays with the member: BDPCM, LFNST on stored coefficients, empty TUs; with `tu` (not `turdoq`) also LFNST on chroma / ISP CUs and joint Cb-Cr TUs
+  if( !g_useTu || tu.noResidual || tu.cu->bdpcmM[chType] || ( lfnstHere && ( loadTr || ( !g_useRdoq && ( !isLuma( compID ) || tu.cu->ispMode ) ) ) ) || ( !g_useRdoq && isChroma( compID ) && tu.jointCbCr ) || tu.cs->sps->scalingListEnabled )
   {
     g_tuRef++;
     __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( self, tu, compID, cQP, uiAbsSum, ctx, loadTr );
@@ -169,8 +172,8 @@ extern "C" void __wrap__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS
 {
   const ChannelType chType = toChannelType( compID );
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0 && tu.mtsIdx[compID] != MTS_SKIP && ( CU::isSepTree( *tu.cu ) ? true : isLuma( compID ) );
-  // plain and DepQuant dequantiser alike (vvb_tu_par.dep_quant); LFNST on plain luma TUs as in the forward wrapper
-  if( g_useTu && !( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )
+  // plain and DepQuant dequantiser alike (vvb_tu_par.dep_quant); LFNST as in the forward wrapper
+  if( g_useTu && ( g_useRdoq || !( ( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) || ( isChroma( compID ) && tu.jointCbCr ) ) ) && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )
   {
     try { invTransformNxNB200( *self, tu, compID, pResi, cQP ); g_tuInv++; if( lfnstHere ) g_tuInvLfnst++; return; }
     catch( std::exception& ) {}

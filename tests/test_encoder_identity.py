@@ -59,6 +59,22 @@ def _identity_rdoq(tmp_path, W, H, F, preset, qp, lib, timeout=900):
     return kb
 
 
+def _identity_widest(tmp_path, W, H, F, preset, qp, lib, timeout=900):
+    """`turdoq` on presets with dependent quantisation and LFNST: on top of the TU seam above, LFNST on the chroma TUs of the separate tree of I-slices (kernel set from
+    the chroma mode or the co-located luma mode) and on ISP luma TUs, the chroma TUs of single-tree LFNST CUs (zero-out without the kernel), joint Cb-Cr TUs -- what
+    stays with the members is TUs with a side below 4 and little else"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout, tu=True, rdoq=True)
+    assert int(kb['tu_fwd']) > 15000 and int(kb['tu_dq']) > 15000 and int(kb['tu_inv_lfnst']) > 5000, kb
+    assert int(kb['tu_ref']) * 4 < int(kb['tu_fwd']), kb               # the narrow routing leaves more TUs to the members than it takes (tu_ref > 2 x tu_fwd)
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
+
+
 def _identity(tmp_path, W, H, F, preset, qp, lib, timeout=600):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from _clips import write_clip
@@ -92,6 +108,14 @@ def test_bitstream_identity_with_the_rdoq_seam_on_the_oracle(tmp_path, W, H, F, 
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity_rdoq(tmp_path, W, H, F, preset, qp, MOCK)
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 3, 2, 37), (176, 144, 2, 1, 32), (176, 144, 2, 3, 27)])
+def test_bitstream_identity_with_the_widest_tu_seam_on_the_oracle(tmp_path, W, H, F, preset, qp):
+    """presets medium / fast / slow: 19 000 / 57 000 / 344 000 forward TUs through the library, 3 600 / 1 600 / 68 000 left to the members"""
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity_widest(tmp_path, W, H, F, preset, qp, MOCK)
 
 
 @pytest.mark.gpu

@@ -101,3 +101,14 @@ def test_bitstream_identity_with_the_rdoq_seam_on_the_gpu(tmp_path, W, H, F, pre
     from test_encoder_identity import _identity_rdoq
     kb = _identity_rdoq(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
     print('encoder identity with the RDOQ seam on the GPU:', W, H, F, preset, kb)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')), reason='oracle/_ref/enc_identity not built')
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 3, 2, 37), (176, 144, 2, 1, 32)])
+def test_bitstream_identity_with_the_widest_tu_seam_on_the_gpu(tmp_path, W, H, F, preset, qp):
+    """the widest routing of the TU seam (LFNST on separate-tree chroma and ISP luma TUs, joint Cb-Cr TUs, single-tree chroma of LFNST CUs) with the kernels answering:
+    the same kernels as the narrower routing, fed with the chroma / ISP parameter combinations"""
+    import vvenc_b200._lib as VL
+    from test_encoder_identity import _identity_widest
+    kb = _identity_widest(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
+    print('encoder identity with the widest TU seam on the GPU:', W, H, F, preset, kb)
