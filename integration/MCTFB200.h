@@ -273,3 +273,56 @@ inline void bilateralFilterB200( const MCTF& m, const PelStorage& orgPic, std::d
     b200Check( g_b200m.apply( ctx, B200_PLANE_MCTF_ORG, &par, mvs.data(), dst.buf, dst.stride ) );
   }
 }
+
+// ---- per-call form (verification shape, like the FpDistFunc trampolines of RdCostB200.h): the MCTF error pointers answer from the library one call at a time, so that
+// the UNMODIFIED MCTF::motionEstimationLuma / estimateLumaLn control runs on top of them inside the live encoder (oracle/enc_identity.cpp ... all).
+//   m_motionErrorLumaInt8 / IntX          (MCTF.h:160-161; motionErrorLumaInt, MCTF.cpp:122-145)
+//   m_motionErrorLumaFrac8 / FracX [0|1]  (MCTF.h:163-164; motionErrorLumaFrac6 / Frac4, :147-257) -- the filter rows identify the 1/16-pel phase
+//   m_calcVar                             (MCTF.h:170; calcVarCore, :520-546)
+// Each call uploads the original block and the reference window it reads (two rows / columns before, three after: the 6-tap support) as two small planes and asks for
+// one candidate.  The full sum comes back where the member may have stopped early; a stopped sum is only ever compared with the running best it already exceeds.
+enum { B200_PLANE_MCTF_CALL_ORG = 14, B200_PLANE_MCTF_CALL_REF = 15 };
+inline int b200MctfErrorCall( const Pel* org, const ptrdiff_t origStride, const Pel* buf, const ptrdiff_t buffStride, const int w, const int h, const int fx, const int fy, const int tap4, const int bitDepth )
+{
+  vvb_ctx* ctx = b200CtxOfThread();
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_CALL_ORG, org, (int) origStride, w, h, 0, bitDepth ) );
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_CALL_REF, buf, (int) buffStride, w, h, 4, bitDepth ) );
+  vvb_mctf_cand c; c.x = 0; c.y = 0; c.mvx = fx; c.mvy = fy; c.w = (uint16_t) w; c.h = (uint16_t) h;
+  int32_t e = 0;
+  b200Check( g_b200m.errorBatch( ctx, B200_PLANE_MCTF_CALL_ORG, B200_PLANE_MCTF_CALL_REF, &c, 1, tap4, &e ) );
+  return e;
+}
+inline int b200MctfErrInt( const Pel* org, const ptrdiff_t so, const Pel* buf, const ptrdiff_t sb, const int w, const int h, const int )
+{
+  return b200MctfErrorCall( org, so, buf, sb, w, h, 0, 0, 0, 10 );               // integer position: no filter, no clipping -- the bit depth does not enter
+}
+inline int b200MctfErrFrac6( const Pel* org, const ptrdiff_t so, const Pel* buf, const ptrdiff_t sb, const int w, const int h, const int16_t* xFilter, const int16_t* yFilter, const int bitDepth, const int )
+{
+  const int fx = int( ( xFilter - &MCTF::m_interpolationFilter8[0][0] ) / 8 ), fy = int( ( yFilter - &MCTF::m_interpolationFilter8[0][0] ) / 8 );
+  if( fx < 0 || fx > 15 || fy < 0 || fy > 15 ) THROW( "filter row outside m_interpolationFilter8" );
+  return b200MctfErrorCall( org, so, buf, sb, w, h, fx, fy, 0, bitDepth );
+}
+inline int b200MctfErrFrac4( const Pel* org, const ptrdiff_t so, const Pel* buf, const ptrdiff_t sb, const int w, const int h, const int16_t* xFilter, const int16_t* yFilter, const int bitDepth, const int )
+{
+  const int fx = int( ( xFilter - &MCTF::m_interpolationFilter4[0][0] ) / 4 ), fy = int( ( yFilter - &MCTF::m_interpolationFilter4[0][0] ) / 4 );
+  if( fx < 0 || fx > 15 || fy < 0 || fy > 15 ) THROW( "filter row outside m_interpolationFilter4" );
+  return b200MctfErrorCall( org, so, buf, sb, w, h, fx, fy, 1, bitDepth );
+}
+inline double b200MctfCalcVar( const Pel* org, const ptrdiff_t so, const int w, const int h )
+{
+  vvb_ctx* ctx = b200CtxOfThread();
+  b200Check( g_b200s.planeUpload( ctx, B200_PLANE_MCTF_CALL_ORG, org, (int) so, w, h, 0, 10 ) );
+  vvb_mctf_cand c; c.x = 0; c.y = 0; c.mvx = 0; c.mvy = 0; c.w = (uint16_t) w; c.h = (uint16_t) h;
+  double v = 0.0;
+  b200Check( g_b200m.calcVar( ctx, B200_PLANE_MCTF_CALL_ORG, &c, 1, &v ) );
+  return v;
+}
+// the MCTF::_initMCTFB200() a maintainer would add next to _initMCTF_X86 (x86/MCTFX86.h:1491-1506); the apply-stage pointers keep their x86 kernels
+// (the library offers that stage per picture: bilateralFilterB200 above)
+inline void installB200( MCTF& m )
+{
+  m.m_motionErrorLumaInt8 = b200MctfErrInt;        m.m_motionErrorLumaIntX = b200MctfErrInt;
+  m.m_motionErrorLumaFrac8[0] = b200MctfErrFrac6;  m.m_motionErrorLumaFracX[0] = b200MctfErrFrac6;
+  m.m_motionErrorLumaFrac8[1] = b200MctfErrFrac4;  m.m_motionErrorLumaFracX[1] = b200MctfErrFrac4;
+  m.m_calcVar = b200MctfCalcVar;
+}

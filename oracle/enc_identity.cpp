@@ -23,9 +23,11 @@
  *                                                       live CABAC contexts -> vvb_rdoq: level decisions, group zero-out, last position, sign-bit hiding on the device),
  * With `turdoq` the routing is the widest the bindings offer: LFNST also on the chroma TUs of a separate tree (kernel set from the chroma / co-located luma mode) and on ISP luma TUs,
  * the chroma TUs of single-tree LFNST CUs (xT's zero-out applied to the full transform), joint Cb-Cr TUs (the caller has formed the joint residual and QP).
+ * With `all` additionally the block-matching errors of the MCTF pre-analysis: MCTF::initMCTF_X86 is wrapped like the RdCost one and the error pointers / m_calcVar answer from
+ * the library per call (integration/MCTFB200.h: installB200( MCTF& )), under the unmodified MCTF::motionEstimationLuma control.
  * Transform-skip RDOQ, RDOQ of m_RDOQ == 1, TUs with a side below 4 (thin ISP partitions, 2-wide chroma) and everything the bindings THROW for (BDPCM, ACT, scaling lists) stay with the members.
  *
- * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu | turdoq]
+ * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu | turdoq | all]
  * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_rdoq=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
  */
 #include <cstdint>
@@ -75,6 +77,8 @@
 #include "CommonLib/TrQuant.h"
 #include "CommonLib/Quant.h"
 #include "CommonLib/DepQuant.h"
+#include "CommonLib/MCTF.h"
+#include "EncoderLib/InterSearch.h"
 #include "CommonLib/Rom.h"
 #include "CommonLib/Contexts.h"
 #undef private
@@ -84,6 +88,7 @@ using namespace vvenc;
 #include "../integration/RdCostB200.h"
 #include "../integration/AffineGradientB200.h"
 #include "../integration/TrQuantB200.h"
+#include "../integration/MCTFB200.h"
 
 static bool               g_useB200 = false;
 static std::atomic<long>  g_rdCostInstalls{ 0 }, g_affineInstalls{ 0 };
@@ -99,6 +104,20 @@ extern "C" void __wrap__ZN5vvenc20AffineGradientSearch27initAffineGradientSearch
 {
   __real__ZN5vvenc20AffineGradientSearch27initAffineGradientSearchX86Ev( self );
   if( g_useB200 ) { installB200( *self ); g_affineInstalls++; }
+}
+
+// MCTF: the constructor calls initMCTF_X86() (MCTF.cpp:572, defined in x86/InitX86.cpp:322); with the argument `all` the error pointers and m_calcVar are then pointed at
+// the per-call trampolines of integration/MCTFB200.h, so the unmodified motion search of the pre-analysis runs on the library's block-matching errors
+static bool               g_useMctf = false;
+static std::atomic<long>  g_mctfInstalls{ 0 };
+static std::atomic<unsigned long long> g_mctfCalls{ 0 };
+static decltype( &vvb_mctf_error_batch ) g_realMctfErr = nullptr;
+static int countingMctfErr( vvb_ctx* c, int po, int pr, const vvb_mctf_cand* cd, int n, int lowRes, int32_t* e ) { g_mctfCalls++; return g_realMctfErr( c, po, pr, cd, n, lowRes, e ); }
+extern "C" void __real__ZN5vvenc4MCTF12initMCTF_X86Ev( MCTF* );
+extern "C" void __wrap__ZN5vvenc4MCTF12initMCTF_X86Ev( MCTF* self )
+{
+  __real__ZN5vvenc4MCTF12initMCTF_X86Ev( self );
+  if( g_useMctf ) { installB200( *self ); g_mctfInstalls++; }
 }
 
 // call counters: thunks between the binding's function pointers and the library (the binding itself stays as a maintainer would ship it)
@@ -193,9 +212,15 @@ int main( int argc, char** argv )
   if( argc > 8 )
   {
     if( b200Load( argv[8] ) || b200LoadAffine( argv[8] ) ) { fprintf( stderr, "cannot bind %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
-    if( argc > 9 && ( !strcmp( argv[9], "tu" ) || !strcmp( argv[9], "turdoq" ) ) )
+    if( argc > 9 && ( !strcmp( argv[9], "tu" ) || !strcmp( argv[9], "turdoq" ) || !strcmp( argv[9], "all" ) ) )
     {
-      g_useRdoq = !strcmp( argv[9], "turdoq" );
+      g_useRdoq = strcmp( argv[9], "tu" ) != 0;
+      if( !strcmp( argv[9], "all" ) )
+      {
+        if( b200LoadMctf( argv[8] ) ) { fprintf( stderr, "cannot bind the MCTF entry points of %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
+        g_useMctf = true;
+        g_realMctfErr = g_b200m.errorBatch; g_b200m.errorBatch = countingMctfErr;
+      }
       if( b200LoadTu( argv[8] ) ) { fprintf( stderr, "cannot bind the TU entry points of %s: %s\n", argv[8], g_b200.error.c_str() ); return 3; }
       g_useTu = true;
     }
@@ -254,8 +279,8 @@ int main( int argc, char** argv )
   if( fo ) { fwrite( out.data(), 1, out.size(), fo ); fclose( fo ); }
   uint64_t hsh = 1469598103934665603ull;
   for( uint8_t b : out ) { hsh ^= b; hsh *= 1099511628211ull; }
-  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_rdoq=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu\n", fed, out.size(),
+  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_rdoq=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu mctf_installs=%ld mctf_calls=%llu\n", fed, out.size(),
           (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuRdoq.load(), g_tuInv.load(),
-          g_tuInvLfnst.load(), g_tuRef.load() );
+          g_tuInvLfnst.load(), g_tuRef.load(), g_mctfInstalls.load(), g_mctfCalls.load() );
   return 0;
 }

@@ -16,9 +16,9 @@ MOCK = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
 pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason='oracle/_ref/enc_identity not built (needs /root/reference at build time)')
 
 
-def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False):
+def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False, mctf=False):
     out = str(tmp_path / ('b200.vvc' if lib else 'avx2.vvc'))
-    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + ((['turdoq'] if rdoq else ['tu']) if tu else [])
+    cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + ((['all'] if mctf else ['turdoq'] if rdoq else ['tu']) if tu else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
     line = [l for l in r.stdout.splitlines() if l.startswith('ENC ')][-1]
@@ -75,6 +75,22 @@ def _identity_widest(tmp_path, W, H, F, preset, qp, lib, timeout=900):
     return kb
 
 
+def _identity_mctf(tmp_path, W, H, F, preset, qp, lib, timeout=900):
+    """`all`: everything above plus the block-matching errors of the MCTF pre-analysis -- MCTF::initMCTF_X86 wrapped, the error pointers and m_calcVar answered per call by
+    the library (integration/MCTFB200.h: installB200( MCTF& )) under the unmodified MCTF::motionEstimationLuma control.  Nine frames, so that the temporal filter has
+    its neighbours; a perturbed error changes the bitstream (checked when the test was written), so identity pins the errors"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout, tu=True, rdoq=True, mctf=True)
+    assert int(kb['mctf_installs']) >= 1 and int(kb['mctf_calls']) > 10000 and int(ka['mctf_calls']) == 0, kb
+    assert int(kb['tu_fwd']) > 5000 and int(kb['dist_calls']) > 10000, kb
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
+
+
 def _identity(tmp_path, W, H, F, preset, qp, lib, timeout=600):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from _clips import write_clip
@@ -116,6 +132,14 @@ def test_bitstream_identity_with_the_widest_tu_seam_on_the_oracle(tmp_path, W, H
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity_widest(tmp_path, W, H, F, preset, qp, MOCK)
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 9, 2, 37), (176, 144, 9, 0, 32), (176, 144, 9, 1, 32)])
+def test_bitstream_identity_with_the_mctf_errors_on_the_oracle(tmp_path, W, H, F, preset, qp):
+    """16 700 / 44 900 / 67 300 MCTF error calls through the library next to the distortion tables and the widest TU seam"""
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity_mctf(tmp_path, W, H, F, preset, qp, MOCK)
 
 
 @pytest.mark.gpu

@@ -112,3 +112,14 @@ def test_bitstream_identity_with_the_widest_tu_seam_on_the_gpu(tmp_path, W, H, F
     from test_encoder_identity import _identity_widest
     kb = _identity_widest(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
     print('encoder identity with the widest TU seam on the GPU:', W, H, F, preset, kb)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')), reason='oracle/_ref/enc_identity not built')
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 9, 2, 37), (176, 144, 9, 0, 32)])
+def test_bitstream_identity_with_the_mctf_errors_on_the_gpu(tmp_path, W, H, F, preset, qp):
+    """the MCTF error pointers answered per call by mctf_error_packed_kernel (two small plane uploads + one candidate per call) under the unmodified motion search of the
+    pre-analysis, together with the distortion tables and the widest TU seam: the whole encoder, nine frames"""
+    import vvenc_b200._lib as VL
+    from test_encoder_identity import _identity_mctf
+    kb = _identity_mctf(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
+    print('encoder identity with the MCTF errors on the GPU:', W, H, F, preset, kb)
