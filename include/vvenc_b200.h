@@ -314,6 +314,19 @@ int vvb_rdoq_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, c
 /* the constants the call derives (no device needed): out = quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos (QuantRDOQ2.cpp:518-559, 573-583) */
 int vvb_rdoq_constants( const vvb_tu_par* par, const vvb_rdoq_par* rq, int32_t out[7] );
 
+/* Transform-skipped TUs: QuantRDOQ::rateDistOptQuantTS (CommonLib/QuantRDOQ.cpp:1124-1336; xGetCodedLevelTSPred :1578-1661, xGetICRateTS :1663-1807), what QuantRDOQ2::quant
+ * runs for a TU with mtsIdx == MTS_SKIP and no BDPCM when Quant::m_useRDOQTS is set (QuantRDOQ2.cpp:263, 275-285).  Forward scan, contexts from the left and upper neighbour,
+ * up to three candidate levels per coefficient priced in double precision (distortion = err * err * errorScale, rate = lambda * bits, summed in the member's order), group
+ * zero-out, the budget of context-coded bins ( w * h * 7 ) >> 2.  Sides 4..32 (transform skip exists up to 32 x 32); coef = the residual as TrQuant::xTransformSkip copies it
+ * (vvb_fwd_trquant with par->transform_skip returns it); uses par->{w, h, bit_depth, qp, input_bit_depth_delta}; forwardRDPCM (BDPCM) stays on the host.
+ *   vvb_rdoq_ts_rates -- BinFracBits::intBits of the transform-skip context sets: sig_bits[numPos] = Ctx::TsSigFlag, par_bits = Ctx::TsParFlag( 0 ), gtx_bits[i] = Ctx::TsGtxFlag( i ),
+ *                        lrg1_bits[numPos] = Ctx::TsLrg1Flag, sign_bits[ctx] = Ctx::TsResidualSign, sig_group_bits[sigLeft + sigAbove] = Ctx::TsSigCoeffGroup.
+ * q: [n][h][w] signed levels; abs_sum (nullable) as the member leaves uiAbsSum (tu.lastPos is not touched by the member).  need_rdoq as for vvb_rdoq. */
+typedef struct { int32_t sig_bits[3][2], par_bits[2], gtx_bits[5][2], lrg1_bits[4][2], sign_bits[6][2], sig_group_bits[3][2]; } vvb_rdoq_ts_rates;   /* 176 bytes */
+int vvb_rdoq_ts    ( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, const vvb_rdoq_ts_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n, int16_t* q, int32_t* abs_sum );
+int vvb_rdoq_ts_dev( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, const vvb_rdoq_ts_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n, int16_t* dev_q,
+                     int32_t* dev_abs_sum );
+
 /* ---- inverse path of the TU loop -------------------------------------------------------------------
  * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
  * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp,transform_skip,...}; with par->dep_quant

@@ -4,6 +4,7 @@
 //   invTransformNxNB200  <->  TrQuant::invTransformNxN (TrQuant.cpp:318-348 = Quant::dequant Quant.cpp:520-609 + xIT :567-660)
 //   xQuantDQB200         <->  DepQuant::xQuantDQ (DepQuant.cpp:1129-1264), the trellis DepQuant::quant runs for non-skip TUs of a slice with depQuantEnabled
 //   xRateDistOptQuantB200 <-> QuantRDOQ2::xRateDistOptQuant (QuantRDOQ2.cpp:1283-1296 -> xRateDistOptQuantFast :475-1281), the fast RDOQ of m_RDOQ == 2
+//   rateDistOptQuantTSB200 <-> QuantRDOQ::rateDistOptQuantTS (QuantRDOQ.cpp:1124-1336), the RDOQ of transform-skipped TUs (m_useRDOQTS)
 //
 // for the TUs the library covers: luma and chroma components, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), transform skip,
 // LFNST (luma, and the chroma TUs of a separate tree), joint Cb-Cr TUs, no scaling lists / BDPCM / ACT, plain quantiser incl. its sign-bit hiding (transform-skip RDOQ stays on the host and uses the coefficients
@@ -22,6 +23,7 @@ struct B200TuApi
   decltype( &vvb_inv_trquant )  invTrQuant = nullptr;
   decltype( &vvb_dep_quant )    depQuant   = nullptr;
   decltype( &vvb_rdoq )         rdoq       = nullptr;
+  decltype( &vvb_rdoq_ts )      rdoqTs     = nullptr;
 } ;
 static B200TuApi g_b200t;
 
@@ -32,7 +34,7 @@ inline int b200LoadTu( const char* libPath )
   if( rc ) return rc;
   void* h = g_b200.handle;
 #define VVB_RESOLVE( member, name ) g_b200t.member = (decltype( g_b200t.member )) dlsym( h, #name ); if( !g_b200t.member ) { g_b200.error = "missing " #name; return -2; }
-  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )  VVB_RESOLVE( rdoq, vvb_rdoq )
+  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )  VVB_RESOLVE( rdoq, vvb_rdoq )  VVB_RESOLVE( rdoqTs, vvb_rdoq_ts )
 #undef VVB_RESOLVE
   g_b200t.bound = true;
   return 0;
@@ -227,4 +229,29 @@ inline void xRateDistOptQuantB200( QuantRDOQ2& rq, TrQuant& tq, TransformUnit& t
   for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
   if( lastPos >= 0 ) tu.lastPos[compID] = lastPos;                                              // the member writes tu.lastPos only when it codes something (:1258)
   uiAbsSum = sum;
+}
+
+// QuantRDOQ::rateDistOptQuantTS( tu, compID, coeffs, absSum, qp, ctx ) with the level decisions on the device: the fractional bits of the six transform-skip context sets
+// travel as vvb_rdoq_ts_rates; the levels come back signed, tu.lastPos is left alone as the member leaves it.  BDPCM (forwardRDPCM) stays on the host.
+inline void rateDistOptQuantTSB200( QuantRDOQ& rq, TrQuant& tq, TransformUnit& tu, const ComponentID compID, const CCoeffBuf& coeffs, TCoeff& absSum, const QpParam& qp, const Ctx& ctx )
+{
+  if( tu.mtsIdx[compID] != MTS_SKIP ) THROW( "rateDistOptQuantTSB200 is for transform-skipped TUs" );
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, qp );                                       // THROWs for BDPCM; transform_skip and input_bit_depth_delta are set there
+  const int w = par.w, h = par.h;
+  const FracBitsAccess& fb = ctx.getFracBitsAcess();
+  vvb_rdoq_ts_rates rates;
+  for( int i = 0; i < 3; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_bits[i][b] = fb.getFracBitsArray( Ctx::TsSigFlag( i ) ).intBits[b];
+  for( int b = 0; b < 2; b++ ) rates.par_bits[b] = fb.getFracBitsArray( Ctx::TsParFlag( 0 ) ).intBits[b];
+  for( int i = 0; i < 5; i++ ) for( int b = 0; b < 2; b++ ) rates.gtx_bits[i][b] = fb.getFracBitsArray( Ctx::TsGtxFlag( i ) ).intBits[b];
+  for( int i = 0; i < 4; i++ ) for( int b = 0; b < 2; b++ ) rates.lrg1_bits[i][b] = fb.getFracBitsArray( Ctx::TsLrg1Flag( i ) ).intBits[b];
+  for( int i = 0; i < 6; i++ ) for( int b = 0; b < 2; b++ ) rates.sign_bits[i][b] = fb.getFracBitsArray( Ctx::TsResidualSign( i ) ).intBits[b];
+  for( int i = 0; i < 3; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_group_bits[i][b] = fb.getFracBitsArray( Ctx::TsSigCoeffGroup( i ) ).intBits[b];
+  std::vector<int32_t> coef( (size_t) w * h );
+  std::vector<int16_t> q( (size_t) w * h );
+  for( int y = 0; y < h; y++ ) memcpy( &coef[(size_t) y * w], coeffs.buf + (ptrdiff_t) y * coeffs.stride, sizeof( TCoeff ) * w );
+  int32_t sum = 0;
+  b200Check( g_b200t.rdoqTs( b200CtxOfThread(), &par, rq.m_dLambda, &rates, coef.data(), nullptr, 1, q.data(), &sum ) );
+  CoeffSigBuf dst = tu.getCoeffs( compID );
+  for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
+  absSum += sum;                                                                                // the member accumulates into the caller's sum (:1334)
 }

@@ -32,6 +32,33 @@ int orc_rdoq( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int s
   return 0;
 }
 
+// transform-skipped TUs (QuantRDOQ::rateDistOptQuantTS): rates = the 44 int32 of vvb_rdoq_ts_rates; qp: CU QP (luma) or mapped chroma QP minus qpBdOffset; inputDelta =
+// sps.internalMinusInputBitDepth (the QP floor of skipped transforms)
+int orc_rdoq_ts( int w, int h, int bitDepth, int qp, int inputDelta, double lambda, const int32_t* rates, const int32_t* coef, int n, int16_t* q, int32_t* absSum )
+{
+  if( !rq_ts_shape_ok( w, h ) ) return -1;
+  int qpInternal = qp + 6 * ( bitDepth - 8 );
+  qpInternal = qpInternal < 0 ? 0 : qpInternal > 63 + 6 * ( bitDepth - 8 ) ? 63 + 6 * ( bitDepth - 8 ) : qpInternal;
+  if( qpInternal < 4 + 6 * inputDelta ) qpInternal = 4 + 6 * inputDelta;
+  const RqTsPar p = rq_ts_init_par( w, h, bitDepth, qpInternal, lambda );
+  RqTsRates r; memcpy( &r, rates, sizeof( r ) );
+  std::vector<int32_t> scan( 1024 );
+  rq_build_scan( w, h, scan.data() );
+  for( int i = 0; i < n; i++ ) rq_ts_quant_tu( p, r, scan.data(), coef + (size_t) i * w * h, q + (size_t) i * w * h, absSum + i );
+  return 0;
+}
+// quantScale, qBits, maxCtxBins and the error scale (double)
+int orc_rdoq_ts_constants( int w, int h, int bitDepth, int qp, int inputDelta, int32_t outInt[3], double* errorScale )
+{
+  if( !rq_ts_shape_ok( w, h ) ) return -1;
+  int qpInternal = qp + 6 * ( bitDepth - 8 );
+  qpInternal = qpInternal < 0 ? 0 : qpInternal > 63 + 6 * ( bitDepth - 8 ) ? 63 + 6 * ( bitDepth - 8 ) : qpInternal;
+  if( qpInternal < 4 + 6 * inputDelta ) qpInternal = 4 + 6 * inputDelta;
+  const RqTsPar p = rq_ts_init_par( w, h, bitDepth, qpInternal, 1.0 );
+  outInt[0] = p.quantScale; outInt[1] = p.qBits; outInt[2] = p.maxCtxBins; *errorScale = p.errorScale;
+  return 0;
+}
+
 // the constants of one call: quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos
 int orc_rdoq_constants( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int sbtZeroOut, int thrVal, int32_t out[7] )
 {

@@ -1017,6 +1017,76 @@ int refshim_rdoq_b200( int comp, const int32_t* coef, int w, int h, int bitDepth
   return 0;
 }
 
+// Transform-skip RDOQ: QuantRDOQ::rateDistOptQuantTS (QuantRDOQ.cpp:1124-1336) on the TU rig with tu.mtsIdx = MTS_SKIP.  ratesOut: the 44 int32 of vvb_rdoq_ts_rates;
+// constOut: quantScale, qBits, maxCtxBins; errScaleOut: xGetErrScaleCoeff( ..., true ).
+static void rdoqTsRatesOf( const Ctx& cabac, int32_t* o )
+{
+  const FracBitsAccess& fb = cabac.getFracBitsAcess();
+  for( int i = 0; i < 3; i++ ) for( int b = 0; b < 2; b++ ) *o++ = fb.getFracBitsArray( Ctx::TsSigFlag( i ) ).intBits[b];
+  for( int b = 0; b < 2; b++ ) *o++ = fb.getFracBitsArray( Ctx::TsParFlag( 0 ) ).intBits[b];
+  for( int i = 0; i < 5; i++ ) for( int b = 0; b < 2; b++ ) *o++ = fb.getFracBitsArray( Ctx::TsGtxFlag( i ) ).intBits[b];
+  for( int i = 0; i < 4; i++ ) for( int b = 0; b < 2; b++ ) *o++ = fb.getFracBitsArray( Ctx::TsLrg1Flag( i ) ).intBits[b];
+  for( int i = 0; i < 6; i++ ) for( int b = 0; b < 2; b++ ) *o++ = fb.getFracBitsArray( Ctx::TsResidualSign( i ) ).intBits[b];
+  for( int i = 0; i < 3; i++ ) for( int b = 0; b < 2; b++ ) *o++ = fb.getFracBitsArray( Ctx::TsSigCoeffGroup( i ) ).intBits[b];
+}
+int refshim_rdoq_ts( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int inputDelta, int intraCu, double lambda, int ctxQp, int ctxInitId,
+                     int16_t* q, int32_t* absSum, int32_t* ratesOut, int32_t* constOut, double* errScaleOut )
+{
+  RefCtx& c = ctx(); (void) c;
+  TuRig& r = rig();
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.setup( w, h, bitDepth, MTS_SKIP, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  if( comp ) r.tu.mtsIdx[COMP_Cb] = MTS_SKIP;
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta; r.sps.internalMinusInputBitDepth[CH_C] = inputDelta;
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 2, true, 8 );
+  dq->m_dLambda = lambda;
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  dq->rateDistOptQuantTS( r.tu, compID, src, sum, qpp, *cabac );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum;
+  if( ratesOut ) rdoqTsRatesOf( *cabac, ratesOut );
+  if( constOut ) { constOut[0] = g_quantScales[0][qpp.rem( true )]; constOut[1] = QUANT_SHIFT + qpp.per( true ); constOut[2] = ( w * h * 7 ) >> 2; }
+  if( errScaleOut ) *errScaleOut = dq->QuantRDOQ::xGetErrScaleCoeff( false, w, h, qpp.rem( true ), 15, bitDepth, true );
+  r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0;
+  return 0;
+}
+
+// the same TU through integration/TrQuantB200.h (rateDistOptQuantTSB200); returns 1 when the binding threw
+int refshim_rdoq_ts_b200( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int inputDelta, int intraCu, double lambda, int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum )
+{
+  RefCtx& c = ctx(); (void) c;
+  TuRig& r = rig();
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.setup( w, h, bitDepth, MTS_SKIP, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  if( comp ) r.tu.mtsIdx[COMP_Cb] = MTS_SKIP;
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta; r.sps.internalMinusInputBitDepth[CH_C] = inputDelta;
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 2, true, 8 );
+  dq->m_dLambda = lambda;
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  int rc = 0;
+  try { rateDistOptQuantTSB200( *dq, tqOfThread(), r.tu, compID, src, sum, qpp, *cabac ); }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0;
+  if( rc ) return rc;
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum;
+  return 0;
+}
+
 // scan geometry of DQIntern::Rom for one luma shape, repacked into the 24- / 16-byte records of vvenc_b200/csrc/depquant_core.h (DqScanInfo, DqNbOut);
 // fields the reference leaves unset (nextSbbRight / nextSbbBelow off group starts, everything "next" at scan position 0) are reported as 0
 int refshim_dep_quant_tables_ex( int chroma, int w, int h, uint8_t* scanInfoOut, uint8_t* nbOutOut );

@@ -16,3 +16,23 @@ def write_clip(path, W, H, F, seed=1):
         fr.append(y.tobytes() + u.tobytes() + v.tobytes())
     with open(path, 'wb') as fh:
         fh.write(b''.join(fr))
+
+
+def write_clip_scc(path, W, H, F, seed=1):
+    """screen-content style clip (flat rectangles, thin strokes, isolated pixels, a global pan): makes transform skip win often enough to exercise its quantiser"""
+    rs = np.random.RandomState(seed)
+    base = np.full((H + 16, W + 16), 200, np.uint8)
+    for _ in range(60):
+        x, y = rs.randint(0, W), rs.randint(0, H); w, h = rs.randint(2, 24), rs.randint(1, 10)
+        base[y:y + h, x:x + w] = rs.choice([0, 30, 90, 255, 140])
+    for _ in range(400):
+        x, y = rs.randint(0, W + 8), rs.randint(0, H + 8)
+        base[y, x:x + rs.randint(1, 4)] = rs.choice([0, 255])
+    fr = []
+    for f in range(F):
+        y = base[f:f + H, 2 * f:2 * f + W].copy()
+        u = np.full((H // 2, W // 2), 128, np.uint8); u[::3, ::5] = 90
+        v = np.full((H // 2, W // 2), 128, np.uint8); v[1::4, ::3] = 170
+        fr.append(y.tobytes() + u.tobytes() + v.tobytes())
+    with open(path, 'wb') as fh:
+        fh.write(b''.join(fr))

@@ -376,7 +376,19 @@ def main_rdoq(lib_path):
         n += 1; nz += int(la.value >= 0); nsh += int(sh and la.value >= 0)
         if rc or not (np.array_equal(qa, qb) and sa.value == sb.value and la.value == lb.value):
             bad.append(['rdoq'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
-    print('RESULT ' + json.dumps({'rdoq': {'cases': n, 'non_empty': nz, 'non_empty_with_hiding': nsh, 'bad': bad[:5]}}))
+    # QuantRDOQ::rateDistOptQuantTS against rateDistOptQuantTSB200: every row of cases.rdoq_ts_cases()
+    tbad = []; tn = 0; tnz = 0
+    for row in C.rdoq_ts_cases():
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row)
+        qa = np.zeros((h, w), dtype=np.int16); sa = I32(); qb = np.zeros((h, w), dtype=np.int16); sb = I32()
+        cq = qp if qp > 16 else 27
+        assert R.refshim_rdoq_ts(comp, P(coef), w, h, bd, qp, delta, intra, lam1000 / 1000.0, cq, init_id, P(qa), ctypes.byref(sa), None, None, None) == 0
+        rc = R.refshim_rdoq_ts_b200(comp, P(coef), w, h, bd, qp, delta, intra, lam1000 / 1000.0, cq, init_id, P(qb), ctypes.byref(sb))
+        tn += 1; tnz += int(sa.value > 0)
+        if rc or not (np.array_equal(qa, qb) and sa.value == sb.value):
+            tbad.append(['rdoq_ts'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+    print('RESULT ' + json.dumps({'rdoq': {'cases': n, 'non_empty': nz, 'non_empty_with_hiding': nsh, 'bad': bad[:5]}, 'rdoq_ts': {'cases': tn, 'non_empty': tnz, 'bad': tbad[:5]}}))
 
 
 if __name__ == '__main__':

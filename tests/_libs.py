@@ -54,6 +54,8 @@ def dq_oracle():
         # oracle/rdoq_oracle.cpp (vvenc_b200/csrc/rdoq_core.h compiled for the CPU) lives in the same library
         L.orc_rdoq.argtypes = [ctypes.c_int] * 8 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_rdoq_constants.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
+        L.orc_rdoq_ts.argtypes = [ctypes.c_int] * 5 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_rdoq_ts_constants.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p]
         _dqoracle = L
     return _dqoracle
 
@@ -89,6 +91,8 @@ def refshim():
         L.refshim_dep_quant_b200.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_rdoq.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5
         L.refshim_rdoq_b200.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+        L.refshim_rdoq_ts.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5
+        L.refshim_rdoq_ts_b200.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 2
         L.refshim_set_simd(b'AVX2')
         _ref = L
     return _ref

@@ -429,6 +429,36 @@ def rdoq_inputs(row):
     return coef
 
 
+def rdoq_ts_cases():
+    """transform-skipped TUs (QuantRDOQ::rateDistOptQuantTS): rows w, h, bit_depth, qp, lambda * 1000, amp, kind (0 uniform, 1 laplace, 2 sparse), comp (0 Y, 1 Cb), intraCu, inputDelta, ctxInitId, seed"""
+    rows = []
+    rs = np.random.RandomState(3107)
+    seed = 23000
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (32, 8), (16, 32), (4, 32), (16, 4)]:
+        for k in range(14):
+            bd = 8 if k % 5 == 4 else 10
+            rows.append([w, h, bd, int(rs.choice([2, 17, 22, 27, 32, 37, 42, 51])), int(float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0])) * 1000),
+                         int(rs.choice([2, 6, 20, 60, 200, 1023])), k % 3, int(rs.randint(2)), int(rs.randint(2)), int(rs.choice([0, 0, 2])) if bd == 10 else 0, k % 3, seed])
+            seed += 1
+    return np.array(rows, dtype=np.int64)
+
+
+def rdoq_ts_inputs(row):
+    """TrQuant::xTransformSkip copies the residual unscaled (TrQuant.cpp:1050-1064), so the quantiser sees values inside the bit depth; every second row feeds values
+    scaled up by the transform shift instead, so that large levels and the exhaustion of the context-coded bins are covered as well"""
+    w, h, bd, qp, lam1000, amp, kind = [int(v) for v in row[:7]]
+    rs = np.random.RandomState(int(row[11]))
+    if kind == 0:
+        resi = rs.randint(-amp, amp + 1, size=(h, w))
+    elif kind == 1:
+        resi = rs.laplace(0, amp / 3.0 + 0.5, size=(h, w)).astype(np.int64)
+    else:
+        resi = rs.randint(-amp, amp + 1, size=(h, w)); resi[rs.rand(h, w) < 0.7] = 0
+    lim = (1 << bd) - 1
+    shift = max(0, 15 - bd - ((int(np.log2(w)) + int(np.log2(h))) >> 1)) if int(row[11]) & 1 else 0
+    return (np.clip(resi, -lim, lim) << shift).astype(np.int32)
+
+
 def dqd_cases():
     """DepQuant dequantiser + inverse transform: rows trHor, trVer, w, h, bit_depth, qp, amp, seed"""
     rows = []

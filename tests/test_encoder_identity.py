@@ -16,10 +16,13 @@ MOCK = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
 pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason='oracle/_ref/enc_identity not built (needs /root/reference at build time)')
 
 
-def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False, mctf=False):
+def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False, mctf=False, ts=False):
     out = str(tmp_path / ('b200.vvc' if lib else 'avx2.vvc'))
     cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + ((['all'] if mctf else ['turdoq'] if rdoq else ['tu']) if tu else [])
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    env = dict(os.environ)
+    if ts:
+        env['VVB_ENC_TS'] = '1'              # transform skip tried on every eligible TU (the presets leave it to the screen-content detector); both arms set it
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
     line = [l for l in r.stdout.splitlines() if l.startswith('ENC ')][-1]
     kv = dict(f.split('=') for f in line.split()[1:])
@@ -91,6 +94,20 @@ def _identity_mctf(tmp_path, W, H, F, preset, qp, lib, timeout=900):
     return kb
 
 
+def _identity_ts(tmp_path, W, H, F, preset, qp, lib, min_ts, timeout=900):
+    """screen-content style clip with transform skip enabled in both arms: the transform-skipped TUs go through xTransformSkip + rateDistOptQuantTSB200 (-> vvb_rdoq_ts)
+    and the inverse path of skipped transforms, next to everything `turdoq` routes"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip_scc
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip_scc(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp, ts=True)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout, tu=True, rdoq=True, ts=True)
+    assert int(kb['tu_rdoq_ts']) >= min_ts and int(ka['tu_rdoq_ts']) == 0 and int(kb['tu_fwd']) > 1000, kb
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
+
+
 def _identity(tmp_path, W, H, F, preset, qp, lib, timeout=600):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from _clips import write_clip
@@ -140,6 +157,14 @@ def test_bitstream_identity_with_the_mctf_errors_on_the_oracle(tmp_path, W, H, F
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity_mctf(tmp_path, W, H, F, preset, qp, MOCK)
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp,min_ts", [(80, 44, 4, 0, 32, 40), (176, 144, 3, 0, 27, 1000), (176, 144, 2, 1, 27, 3000)])
+def test_bitstream_identity_with_transform_skip_rdoq_on_the_oracle(tmp_path, W, H, F, preset, qp, min_ts):
+    """50 / 1 300 / 3 400 transform-skipped TUs through QuantRDOQ::rateDistOptQuantTS's replacement (presets faster and fast: with RDOQ 2 and with dependent quantisation)"""
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity_ts(tmp_path, W, H, F, preset, qp, MOCK, min_ts)
 
 
 @pytest.mark.gpu

@@ -123,3 +123,52 @@ def test_bitstream_identity_with_the_mctf_errors_on_the_gpu(tmp_path, W, H, F, p
     from test_encoder_identity import _identity_mctf
     kb = _identity_mctf(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, timeout=1500)
     print('encoder identity with the MCTF errors on the GPU:', W, H, F, preset, kb)
+
+
+# ---- transform-skipped TUs: QuantRDOQ::rateDistOptQuantTS (vvb_rdoq_ts).  First hardware run of this entry point is the round-end suite: the shared text is pinned on the
+#      CPU exactly like the RDOQ above, the kernel wrapper has the shape of rdoq_kernel.
+def test_gpu_rdoq_ts_golden(gpu, golden_rdoq):
+    g = golden_rdoq
+    rows = C.rdoq_ts_cases()
+    assert np.array_equal(rows, g['ts_cases'])
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row)[None]
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, transform_skip=True, input_bit_depth_delta=delta, is_chroma=comp > 0)
+        r = gpu.eng.rdoq_ts(par, gpu.eng.rdoq_ts_rates(g['ts_rates'][i]), coef, lam1000 / 1000.0)
+        assert np.array_equal(r['q'][0], g['tsq_%d' % i]) and int(r['abs_sum'][0]) == int(g['ts_abs_sum'][i]), (i, [int(v) for v in row])
+        nonzero += int(r['abs_sum'][0] > 0)
+    assert nonzero > 80
+
+
+def test_gpu_rdoq_ts_batches_vs_oracle(gpu, golden_rdoq):
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    rs = np.random.RandomState(79)
+    for (w, h, n, qp, lam, bd) in ((4, 4, 60000, 32, 57.3, 10), (8, 8, 20000, 27, 30.0, 10), (16, 16, 5000, 37, 120.0, 10), (32, 32, 1200, 22, 11.7, 10), (32, 8, 3000, 42, 800.0, 8), (4, 16, 8000, 30, 40.0, 10)):
+        amp = rs.choice([2, 6, 20, 60, 200, 1023], size=(n, 1, 1))
+        resi = (rs.laplace(0, 1.0, size=(n, h, w)) * amp / 3.0).astype(np.int64)
+        resi[rs.rand(n, h, w) < 0.4] = 0
+        lim = (1 << bd) - 1
+        shift = max(0, 15 - bd - ((int(np.log2(w)) + int(np.log2(h))) >> 1))
+        coef = np.clip(resi, -lim, lim).astype(np.int32); coef[::2] <<= shift          # unscaled as xTransformSkip leaves them, every second TU scaled up (large levels)
+        rates_flat = np.ascontiguousarray(g['ts_rates'][int(rs.randint(len(g['ts_rates'])))])
+        mask = (rs.randint(0, 8, size=n) > 0).astype(np.uint8)
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, transform_skip=True)
+        r = gpu.eng.rdoq_ts(par, gpu.eng.rdoq_ts_rates(rates_flat), coef, lam, need_rdoq=mask)
+        q = np.zeros((n, h, w), dtype=np.int16); s = np.zeros(n, dtype=np.int32)
+        assert O.orc_rdoq_ts(w, h, bd, qp, 0, lam, P(rates_flat), P(coef), n, P(q), P(s)) == 0
+        q[mask == 0] = 0; s[mask == 0] = 0
+        assert np.array_equal(r['q'], q), (w, h, int((r['q'] != q).any(axis=(1, 2)).sum()))
+        assert np.array_equal(r['abs_sum'], s) and (s > 0).sum() > n // 8, (w, h, int((s > 0).sum()))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')), reason='oracle/_ref/enc_identity not built')
+@pytest.mark.parametrize("W,H,F,preset,qp,min_ts", [(80, 44, 4, 0, 32, 40), (176, 144, 3, 0, 27, 1000)])
+def test_bitstream_identity_with_transform_skip_rdoq_on_the_gpu(tmp_path, W, H, F, preset, qp, min_ts):
+    import vvenc_b200._lib as VL
+    from test_encoder_identity import _identity_ts
+    kb = _identity_ts(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, min_ts, timeout=1500)
+    print('encoder identity with the transform-skip RDOQ on the GPU:', W, H, F, preset, kb)

@@ -102,5 +102,8 @@ def test_rdoq_binding_equals_the_member():
     mock = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), mock, 'rdoq'], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq']
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])
+    r = res['rdoq']
     assert r['cases'] == 224 and r['non_empty'] > 100 and r['non_empty_with_hiding'] > 40 and r['bad'] == [], r
+    t = res['rdoq_ts']                          # rateDistOptQuantTSB200 vs QuantRDOQ::rateDistOptQuantTS
+    assert t['cases'] == 140 and t['non_empty'] > 80 and t['bad'] == [], t

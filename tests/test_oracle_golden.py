@@ -159,3 +159,27 @@ def test_oracle_rdoq_golden(golden_rdoq):
         assert (s.value, l.value) == tuple(int(v) for v in g['meta'][i]), (i, [int(v) for v in row])
         nonzero += int(l.value >= 0); hidden += int(sh and l.value >= 0)
     assert nonzero > 100 and hidden > 40
+
+
+def test_oracle_rdoq_ts_golden(golden_rdoq):
+    """QuantRDOQ::rateDistOptQuantTS (transform-skipped TUs): the restatement against levels / absSum the reference produced, fractional bits of the transform-skip context
+    sets from the reference; the constants incl. the double-precision error scale against the reference's (equal to the last bit)"""
+    import ctypes
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    rows = C.rdoq_ts_cases()
+    assert np.array_equal(rows, g['ts_cases'])
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row)
+        k = np.zeros(3, dtype=np.int32); e = ctypes.c_double()
+        assert O.orc_rdoq_ts_constants(w, h, bd, qp, delta, P(k), ctypes.byref(e)) == 0
+        assert np.array_equal(k, g['ts_consts'][i]) and e.value == float(g['ts_err_scale'][i]), (i, k, g['ts_consts'][i])
+        rates = np.ascontiguousarray(g['ts_rates'][i])
+        q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32()
+        assert O.orc_rdoq_ts(w, h, bd, qp, delta, lam1000 / 1000.0, P(rates), P(coef), 1, P(q), ctypes.byref(s)) == 0
+        assert np.array_equal(q, g['tsq_%d' % i]) and s.value == int(g['ts_abs_sum'][i]), (i, [int(v) for v in row])
+        nonzero += int(s.value > 0)
+    assert nonzero > 80

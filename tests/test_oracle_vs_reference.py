@@ -554,6 +554,43 @@ def test_rdoq_against_the_reference_member(opt):
 
 
 @pytest.mark.parametrize("opt", [0, 1])
+def test_rdoq_ts_against_the_reference_member(opt):
+    """QuantRDOQ::rateDistOptQuantTS (transform-skipped TUs, Quant::m_useRDOQTS) on the probe's TU rig against the restatement fed with the fractional bits of the
+    transform-skip context sets the reference read: signed levels and absSum for 12 shapes up to 32 x 32, 8 / 10 bit, QP 2..51 (the QP floor of skipped transforms incl.
+    internalMinusInputBitDepth), luma and Cb, dense / laplacian / sparse residuals from 2 to full amplitude (so that the budget of context-coded bins runs out in some
+    TUs and all three rate branches are taken); costs are doubles: the comparison is exact"""
+    import ctypes
+    from _libs import dq_oracle, refshim, P
+    O = dq_oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(900 + opt)
+    n = 0; nonzero = 0; big = 0
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (32, 8), (16, 32), (32, 16), (4, 32), (8, 16), (16, 4)]:
+        for bd in (10, 8):
+            for qp in (17, 22, 27, 32, 37, 42, 51, 2):
+                for trial in range(6):
+                    lam = float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0]))
+                    amp = int(rs.choice([2, 6, 20, 60, 200, 1023]))
+                    kind = trial % 3
+                    if kind == 0: resi = rs.randint(-amp, amp + 1, size=(h, w))
+                    elif kind == 1: resi = rs.laplace(0, amp / 3.0 + 0.5, size=(h, w)).astype(np.int64)
+                    else:
+                        resi = rs.randint(-amp, amp + 1, size=(h, w)); resi[rs.rand(h, w) < 0.7] = 0
+                    coef = (np.clip(resi, -1023, 1023) << ((5 if bd == 10 else 7) if trial & 1 else 0)).astype(np.int32)     # xTransformSkip copies the residual unscaled; the shifted rows reach large levels
+                    comp = int(rs.randint(2)); intra = int(rs.randint(2)); delta = int(rs.choice([0, 0, 2])) if bd == 10 else 0
+                    qR = np.zeros((h, w), np.int16); sR = ctypes.c_int32(); rates = np.zeros(44, np.int32); kR = np.zeros(3, np.int32); eR = ctypes.c_double()
+                    assert R.refshim_rdoq_ts(comp, P(coef), w, h, bd, qp, delta, intra, lam, int(rs.randint(17, 52)), trial % 3, P(qR), ctypes.byref(sR), P(rates), P(kR), ctypes.byref(eR)) == 0
+                    kO = np.zeros(3, np.int32); eO = ctypes.c_double()
+                    assert O.orc_rdoq_ts_constants(w, h, bd, qp, delta, P(kO), ctypes.byref(eO)) == 0 and np.array_equal(kO, kR) and eO.value == eR.value, (w, h, bd, qp, delta, kO, kR)
+                    qO = np.zeros((h, w), np.int16); sO = ctypes.c_int32()
+                    assert O.orc_rdoq_ts(w, h, bd, qp, delta, lam, P(rates), P(coef), 1, P(qO), ctypes.byref(sO)) == 0
+                    assert np.array_equal(qO, qR) and sO.value == sR.value, (w, h, bd, qp, comp, intra, delta, lam, amp, kind, int((qO != qR).sum()))
+                    n += 1; nonzero += int(sR.value > 0); big += int(np.abs(qR).max() > 9)
+    R.refshim_set_simd(b'AVX2')
+    assert n == 1152 and nonzero > 600 and big > 150, (n, nonzero, big)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
 def test_transform_skip_and_chroma_against_the_reference(opt):
     """TrQuant::xTransformSkip + Quant::quant with the transform-skip QP (floor 4 + 6 * internalMinusInputBitDepth, no transform shift), Quant::xNeedRDOQ in full
     (dependent-quantisation QP only for non-skipped transforms, the transform shift it keeps for skipped ones, 256 for chroma components), Quant::dequant +

@@ -54,6 +54,11 @@ class vvb_rdoq_rates(ctypes.Structure):
                 ('last_bits_x', ctypes.c_int32 * 16), ('last_bits_y', ctypes.c_int32 * 16), ('cbf_bits', ctypes.c_int32 * 2), ('pad', ctypes.c_int32 * 2)]
 
 
+class vvb_rdoq_ts_rates(ctypes.Structure):
+    _fields_ = [('sig_bits', ctypes.c_int32 * 6), ('par_bits', ctypes.c_int32 * 2), ('gtx_bits', ctypes.c_int32 * 10), ('lrg1_bits', ctypes.c_int32 * 8), ('sign_bits', ctypes.c_int32 * 12),
+                ('sig_group_bits', ctypes.c_int32 * 6)]
+
+
 class vvb_rdoq_par(ctypes.Structure):
     _fields_ = [('lam', ctypes.c_double), ('thr_val', ctypes.c_int32), ('sbt_zero_out', ctypes.c_int32), ('pad', ctypes.c_int32 * 2)]
 
@@ -140,6 +145,8 @@ SYMBOLS = {
     'vvb_dep_quant_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_dq_par), c_p]),
     'vvb_rdoq': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), ctypes.POINTER(vvb_rdoq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
     'vvb_rdoq_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), ctypes.POINTER(vvb_rdoq_rates), c_p, c_p, c_i, c_p, c_p, c_p]),
+    'vvb_rdoq_ts': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.c_double, ctypes.POINTER(vvb_rdoq_ts_rates), c_p, c_p, c_i, c_p, c_p]),
+    'vvb_rdoq_ts_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.c_double, ctypes.POINTER(vvb_rdoq_ts_rates), c_p, c_p, c_i, c_p, c_p]),
     'vvb_rdoq_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), c_p]),
     'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_inv_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),

@@ -304,6 +304,25 @@ class CostEngine:
         self._chk(self.lib.vvb_rdoq(self.h, ctypes.byref(par), ctypes.byref(rq), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s), _p(lp)))
         return dict(q=q, abs_sum=s, last_pos=lp)
 
+    @staticmethod
+    def rdoq_ts_rates(flat):
+        """vvb_rdoq_ts_rates from 44 int32 in declaration order (sig_bits[3][2], par_bits[2], gtx_bits[5][2], lrg1_bits[4][2], sign_bits[6][2], sig_group_bits[3][2])"""
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        assert flat.size == 44
+        r = L.vvb_rdoq_ts_rates()
+        ctypes.memmove(ctypes.byref(r), flat.ctypes.data, 44 * 4)
+        return r
+
+    def rdoq_ts(self, par, rates, coef, lam, need_rdoq=None):
+        """QuantRDOQ::rateDistOptQuantTS for n transform-skipped TUs of one shape: coef int32 [n][h][w] (the residual as xTransformSkip copies it) -> dict(q, abs_sum)"""
+        coef = np.ascontiguousarray(coef, dtype=np.int32)
+        n = coef.shape[0]
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        s = np.zeros(n, dtype=np.int32)
+        nr = None if need_rdoq is None else np.ascontiguousarray(need_rdoq, dtype=np.uint8)
+        self._chk(self.lib.vvb_rdoq_ts(self.h, ctypes.byref(par), float(lam), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s)))
+        return dict(q=q, abs_sum=s)
+
     # ---- inverse path / fused TU round trip
     def inv_trquant(self, par, q):
         """TrQuant::invTransformNxN for n compact level blocks q [n][h][w] -> residual int16 [n][h][w]"""

@@ -552,4 +552,262 @@ VVB_HD void rq_quant_tu( const RqPar& P, const RqRates& R, const int32_t* scan, 
 #undef RQ_BLKPOS
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------------------------------------------
+// Transform-skip residual coding: QuantRDOQ::rateDistOptQuantTS (CommonLib/QuantRDOQ.cpp:1124-1336) with xGetCodedLevelTSPred (:1578-1661), xGetICRateTS (:1663-1807) and
+// the transform-skip members of CoeffCodingContext (ContextModelling.h:271-407, ContextModelling.cpp:130-132) -- what QuantRDOQ2::quant runs for a transform-skipped TU
+// without BDPCM (QuantRDOQ2.cpp:275-285) when Quant::m_useRDOQTS is set.  The scan runs FORWARD (group 0 first, position 0 first), the context of a position comes from its
+// left and upper neighbours, costs are doubles (distortion = err * err * errorScale, rate = lambda * bits) summed in the reference's order.  The per-position cost arrays
+// of the reference (m_pdCostCoeff, m_pdCostSig, m_pdCostCoeff0, m_pdCostCoeffGroupSig) are only ever read at the position that has just been written, so scalars stand in.
+struct RqTsRates                     // BinFracBits::intBits of the transform-skip context sets (Contexts.cpp:821-868)
+{
+  int32_t sigBits[3][2];             // Ctx::TsSigFlag( numPos ), numPos = number of non-zero left / upper neighbours
+  int32_t parBits[2];                // Ctx::TsParFlag( 0 )
+  int32_t gtxBits[5][2];             // Ctx::TsGtxFlag( cutoffVal >> 1 ): entries 1..4 are read
+  int32_t lrg1Bits[4][2];            // Ctx::TsLrg1Flag( numPos )
+  int32_t signBits[6][2];            // Ctx::TsResidualSign( signCtx )
+  int32_t sigGroupBits[3][2];        // Ctx::TsSigCoeffGroup( sigLeft + sigAbove )
+};                                   // 44 int32
+
+struct RqTsPar
+{
+  int32_t width, height, log2W;
+  int32_t quantScale;                // g_quantScales[0][ qp.rem( true ) ], :1160
+  int32_t qBits;                     // QUANT_SHIFT + qp.per( true ), :1159 (no transform shift, no sqrt(2) compensation)
+  int32_t maxCtxBins;                // ( w * h * 7 ) >> 2, :1183
+  int32_t pad[2];
+  double  errorScale;                // xGetErrScaleCoeff( false, w, h, rem, 15, bitDepth, true ), QuantRDOQ.cpp:319-329
+  double  lambda;                    // Quant::m_dLambda
+};
+
+VVB_HD int rq_golomb_bits( uint32_t symbol, uint32_t ricePar )            // the Golomb-Rice / exp-Golomb length of xGetICRateTS, in whole bits
+{
+  uint32_t length;
+  const uint32_t threshold = RQ_REMAIN_BIN_REDUCTION;
+  if( symbol < ( threshold << ricePar ) ) { length = symbol >> ricePar; return (int)( length + 1 + ricePar ); }
+  length = ricePar;
+  symbol = symbol - ( threshold << ricePar );
+  while( symbol >= ( 1u << length ) ) symbol -= ( 1u << ( length++ ) );
+  return (int)( threshold + length + 1 - ricePar + length );
+}
+
+// xGetICRateTS, :1663-1807
+VVB_HD int rq_ts_level_rate( const RqTsRates& R, uint32_t absLevel, int remRegBins, const int32_t* fbSign, const int32_t* fbGt1, int& numCtxBins, int sign, uint32_t ricePar )
+{
+  if( remRegBins < 4 )                                            // everything by-pass coded
+  {
+    int rate = absLevel ? ( 1 << RQ_SCALE_BITS ) : 0;
+    rate += rq_golomb_bits( absLevel, ricePar ) << RQ_SCALE_BITS;
+    return rate;
+  }
+  else if( remRegBins < 8 )                                       // first pass context coded, the rest by-pass
+  {
+    int rate = fbSign[sign];
+    if( absLevel ) numCtxBins++;
+    if( absLevel > 1 )
+    {
+      rate += fbGt1[1];
+      rate += R.parBits[( absLevel - 2 ) & 1];
+      numCtxBins += 2;
+      rate += rq_golomb_bits( ( absLevel - 2 ) >> 1, ricePar ) << RQ_SCALE_BITS;
+    }
+    else if( absLevel == 1 ) { rate += fbGt1[0]; numCtxBins++; }
+    else rate = 0;
+    return rate;
+  }
+  int rate = fbSign[sign];
+  if( absLevel ) numCtxBins++;
+  if( absLevel > 1 )
+  {
+    rate += fbGt1[1];
+    rate += R.parBits[( absLevel - 2 ) & 1];
+    numCtxBins += 2;
+    uint32_t cutoffVal = 2;
+    for( int i = 0; i < 4; i++ )
+    {
+      if( absLevel >= cutoffVal )
+      {
+        rate += R.gtxBits[cutoffVal >> 1][absLevel >= ( cutoffVal + 2 ) ? 1 : 0];
+        numCtxBins++;
+      }
+      cutoffVal += 2;
+    }
+    if( absLevel >= cutoffVal ) rate += rq_golomb_bits( ( absLevel - cutoffVal ) >> 1, ricePar ) << RQ_SCALE_BITS;
+  }
+  else if( absLevel == 1 ) { rate += fbGt1[0]; numCtxBins++; }
+  else rate = 0;
+  return rate;
+}
+
+// deriveModCoeff( right, below, absCoeff, 0 ), ContextModelling.h:363-386
+VVB_HD int rq_ts_mod_coeff( int rightPixel, int belowPixel, int absCoeff )
+{
+  if( absCoeff == 0 ) return 0;
+  const int pred1 = rq_max( rq_abs( belowPixel ), rq_abs( rightPixel ) );
+  if( absCoeff == pred1 ) return 1;
+  return absCoeff < pred1 ? absCoeff + 1 : absCoeff;
+}
+
+// one transform-skipped TU.  scan as for rq_quant_tu; coef [h][w]: the residual as xTransformSkip copies it; q [h][w] levels (signed, written); absSum as the reference leaves it
+VVB_HD void rq_ts_quant_tu( const RqTsPar& P, const RqTsRates& R, const int32_t* scan, const int32_t* coef, int16_t* q, int32_t* absSumOut )
+{
+  const int W = P.width, H = P.height, lw = P.log2W;
+  const int regionW = rq_min( 32, W );
+  const int lrw = ( regionW == 32 ? 5 : regionW == 16 ? 4 : regionW == 8 ? 3 : 2 );
+  const int qBits = P.qBits;
+  const int widthInGroups = W >> 2, heightInGroups = H >> 2;
+  const int sbNum = ( W * H ) >> 4;
+  const uint32_t entropyCodingMaximum = ( 1u << 15 ) - 1;
+  uint64_t sigGroupFlags = 0;
+  bool anySigCG = false;
+  int remRegBins = P.maxCtxBins;
+  int absSum = 0;
+
+  for( int i = 0; i < W * H; i++ ) q[i] = 0;                      // the caller's level buffer starts cleared (TrQuant::transformNxN works on a cleared TU, and neighbours ahead in the scan read as zero)
+
+  for( int sbId = 0; sbId < sbNum; sbId++ )
+  {
+    // initSubblock: group position, the context of its significant-group flag from the left and upper groups (ContextModelling.cpp:113-133)
+    const int cgRaster = scan[sbId << 4], cgX = ( cgRaster & ( regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int subSetPos = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
+    const int sigLeft  = cgX > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - 1 ) ) & 1 ) : 0;
+    const int sigAbove = cgY > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - widthInGroups ) ) & 1 ) : 0;
+    const int32_t* fbSigGroup = R.sigGroupBits[sigLeft + sigAbove];
+    (void) heightInGroups;
+
+    int noCoeffCoded = 0;
+    double baseCost = 0.0;
+    double d64CodedLevelandDist = 0.0, d64UncodedDist = 0.0, d64SigCost = 0.0;      // coeffGroupRDStats
+    int iNumSbbCtxBins = 0;
+
+    for( int scanPosInSB = 0; scanPosInSB <= 15; scanPosInSB++ )
+    {
+      const int scanPos = ( sbId << 4 ) + scanPosInSB;
+      const int raster = scan[scanPos], posX = raster & ( regionW - 1 ), posY = raster >> lrw;
+      const int blkPos = ( posY << lw ) + posX;
+
+      const int64_t tmpLevel = (int64_t) rq_abs( coef[blkPos] ) * P.quantScale;
+      const int64_t cap = (int64_t) INT32_MAX - ( (int64_t) 1 << ( qBits - 1 ) );
+      const int32_t levelDouble = (int32_t)( tmpLevel < cap ? tmpLevel : cap );
+
+      const uint32_t roundAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( (uint32_t)( levelDouble + ( (int32_t) 1 << ( qBits - 1 ) ) ) >> qBits ) );
+      const uint32_t minAbsLevel = roundAbsLevel > 1 ? roundAbsLevel - 1 : 1;
+      const uint32_t downAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( levelDouble >> qBits ) );
+      const uint32_t upAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( downAbsLevel + 1 ) );
+
+      uint32_t coeffLevels[3];
+      int testedLevels = 0;
+      coeffLevels[testedLevels++] = roundAbsLevel;
+      if( minAbsLevel != roundAbsLevel ) coeffLevels[testedLevels++] = minAbsLevel;
+
+      const int rightPixel = posX > 0 ? q[blkPos - 1] : 0;        // neighTS: the left and the upper neighbour (named as in the reference)
+      const int belowPixel = posY > 0 ? q[blkPos - W] : 0;
+      const int predPixel = rq_ts_mod_coeff( rightPixel, belowPixel, (int) upAbsLevel );
+      if( upAbsLevel != roundAbsLevel && upAbsLevel != minAbsLevel && predPixel == 1 ) coeffLevels[testedLevels++] = upAbsLevel;
+
+      const double dErr0 = (double) levelDouble;
+      const double costCoeff0 = dErr0 * dErr0 * P.errorScale;
+
+      // contexts from the two neighbours: significance and greater-1 count the non-zero ones, the sign context looks at their signs (ContextModelling.h:271-357)
+      const int numPos = ( rightPixel != 0 ) + ( belowPixel != 0 );
+      const int32_t* fbSig = R.sigBits[numPos];
+      const int32_t* fbGt1 = R.lrg1Bits[numPos];
+      int signCtx;
+      if( ( rightPixel == 0 && belowPixel == 0 ) || ( rightPixel * belowPixel ) < 0 ) signCtx = 0;
+      else if( rightPixel >= 0 && belowPixel >= 0 ) signCtx = 1;
+      else signCtx = 2;
+      const int32_t* fbSign = R.signBits[signCtx];
+      const int sign = coef[blkPos] < 0 ? 1 : 0;
+      const uint32_t goRiceParam = 1;
+      const bool lastCoeff = scanPosInSB == 15 && noCoeffCoded == 0;
+
+      // xGetCodedLevelTSPred, :1578-1661
+      double costCoeff, costSig = 0.0;
+      uint32_t cLevel = 0;
+      int numUsedCtxBins = 0;
+      {
+        double currCostSig = 0;
+        int numBestCtxBin = 0;
+        bool done = false;
+        if( !lastCoeff && coeffLevels[0] < 3 )
+        {
+          if( remRegBins >= 4 ) costSig = P.lambda * (double) fbSig[0];
+          else                  costSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+          costCoeff = costCoeff0 + costSig;
+          if( remRegBins >= 4 ) numUsedCtxBins++;
+          if( coeffLevels[0] == 0 ) done = true;
+        }
+        else costCoeff = 1.7e+308;                                // MAX_DOUBLE (CommonDef.h)
+        if( !done )
+        {
+          if( !lastCoeff )
+          {
+            if( remRegBins >= 4 ) currCostSig = P.lambda * (double) fbSig[1];
+            else                  currCostSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+            if( coeffLevels[0] >= 3 && remRegBins >= 4 ) numUsedCtxBins++;
+          }
+          for( int errorInd = 1; errorInd <= testedLevels; errorInd++ )
+          {
+            const int absLevel = (int) coeffLevels[errorInd - 1];
+            const double dErr = (double)( levelDouble - ( (int32_t) absLevel << qBits ) );
+            const double levelError = dErr * dErr * P.errorScale;
+            int modAbsLevel = absLevel;
+            if( remRegBins >= 4 ) modAbsLevel = rq_ts_mod_coeff( rightPixel, belowPixel, absLevel );
+            int numCtxBins = 0;
+            double dCurrCost = levelError + P.lambda * (double) rq_ts_level_rate( R, (uint32_t) modAbsLevel, remRegBins, fbSign, fbGt1, numCtxBins, sign, goRiceParam );
+            if( remRegBins >= 4 ) dCurrCost += currCostSig;
+            if( dCurrCost < costCoeff ) { cLevel = (uint32_t) absLevel; costCoeff = dCurrCost; costSig = currCostSig; numBestCtxBin = numCtxBins; }
+          }
+          numUsedCtxBins += numBestCtxBin;
+        }
+      }
+
+      remRegBins -= numUsedCtxBins;
+      iNumSbbCtxBins += numUsedCtxBins;
+      if( cLevel > 0 ) noCoeffCoded++;
+      const int level = (int) cLevel;
+      q[blkPos] = (int16_t)( ( level != 0 && coef[blkPos] < 0 ) ? -level : level );
+      baseCost   += costCoeff;
+      d64SigCost += costSig;
+      if( q[blkPos] )
+      {
+        sigGroupFlags |= cgBit;
+        d64CodedLevelandDist += costCoeff - costSig;
+        d64UncodedDist       += costCoeff0;
+      }
+    }
+
+    if( !( sigGroupFlags & cgBit ) )                              // :1271-1277
+    {
+      baseCost += P.lambda * (double) fbSigGroup[0] - d64SigCost;
+      remRegBins += iNumSbbCtxBins;
+    }
+    else if( sbId != sbNum - 1 || anySigCG )                      // :1278-1322
+    {
+      double costZeroSB = baseCost;
+      baseCost   += P.lambda * (double) fbSigGroup[1];
+      costZeroSB += P.lambda * (double) fbSigGroup[0];
+      costZeroSB += d64UncodedDist;
+      costZeroSB -= d64CodedLevelandDist;
+      costZeroSB -= d64SigCost;
+      if( costZeroSB < baseCost )
+      {
+        sigGroupFlags &= ~cgBit;
+        baseCost = costZeroSB;
+        remRegBins += iNumSbbCtxBins;
+        for( int p = 0; p <= 15; p++ )
+        {
+          const int raster = scan[( sbId << 4 ) + p];
+          q[( ( raster >> lrw ) << lw ) + ( raster & ( regionW - 1 ) )] = 0;
+        }
+      }
+      else anySigCG = true;
+    }
+  }
+
+  for( int i = 0; i < W * H; i++ ) absSum += rq_abs( q[i] );     // :1325-1335 (every position is inside the scan: transform skip exists up to 32 x 32)
+  *absSumOut = absSum;
+}
+
 } // namespace vvbrq

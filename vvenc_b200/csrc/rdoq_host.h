@@ -59,6 +59,32 @@ inline RqPar rq_init_par( int w, int h, int bitDepth, int qpInternal, int lfnst,
   return p;
 }
 
+// transform-skip variant (QuantRDOQ::rateDistOptQuantTS, QuantRDOQ.cpp:1156-1161, 1183): qpTs = cQP.Qp( true ) = max( clip( CU QP + qpBdOffset ), 4 + 6 * internalMinusInputBitDepth )
+inline int rq_ts_shape_ok( int w, int h ) { return rq_shape_ok( w, h ) && w <= 32 && h <= 32; }
+inline RqTsPar rq_ts_init_par( int w, int h, int bitDepth, int qpTs, double lambda )
+{
+  static const int quantScales[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };                // g_quantScales[0]: no sqrt(2) compensation for skipped transforms
+  int lw = 0;
+  while( ( 1 << lw ) < w ) lw++;
+  RqTsPar p;
+  p.width = w; p.height = h; p.log2W = lw;
+  p.quantScale = quantScales[qpTs % 6];
+  p.qBits = 14 + qpTs / 6;
+  p.maxCtxBins = ( w * h * 7 ) >> 2;
+  p.pad[0] = p.pad[1] = 0;
+  {
+    // xGetErrScaleCoeff( false, w, h, rem, 15, bitDepth, true ), QuantRDOQ.cpp:319-329: the transform shift is 0 for skipped transforms
+    double dErrScale = (double)( 1 << RQ_SCALE_BITS );
+    const double dTransShift = (double) 0 + 0.0;
+    dErrScale = dErrScale * pow( 2.0, ( -2.0 * dTransShift ) );
+    const int QStep = p.quantScale;
+    p.errorScale = dErrScale / QStep / QStep / ( 1 << 0 );
+  }
+  (void) bitDepth;
+  p.lambda = lambda;
+  return p;
+}
+
 // scan position -> raster index inside the scanned region (row pitch min( 32, w )): grouped 4x4 up-right diagonal scan (Rom.cpp:1098-1136, 1236-1284)
 inline void rq_build_scan( int w, int h, int32_t* out /* min(32,w) * min(32,h) */ )
 {

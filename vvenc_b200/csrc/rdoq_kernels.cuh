@@ -44,4 +44,36 @@ __global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_kernel( const __grid_co
   }
 }
 
+// transform-skip variant (rq_ts_quant_tu): the same shape -- one thread per TU, rate tables and scan order in shared memory, the level buffer is the output slice
+struct RqTsLaunch
+{
+  vvbrq::RqTsPar par;
+  const int32_t* scan;
+  int32_t        numScan;
+};
+
+__global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_ts_kernel( const __grid_constant__ RqTsLaunch L, const __grid_constant__ vvbrq::RqTsRates rates,
+                                                                    const int32_t* __restrict__ coef, const uint8_t* __restrict__ needRdoq, int n,
+                                                                    int16_t* __restrict__ q, int32_t* __restrict__ absSum )
+{
+  __shared__ vvbrq::RqTsRates sRates;
+  __shared__ int32_t sScan[1024];
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>( &rates );
+    int32_t* dst = reinterpret_cast<int32_t*>( &sRates );
+    for( int i = threadIdx.x; i < (int)( sizeof( vvbrq::RqTsRates ) / 4 ); i += blockDim.x ) dst[i] = src[i];
+    for( int i = threadIdx.x; i < L.numScan; i += blockDim.x ) sScan[i] = L.scan[i];
+  }
+  __syncthreads();
+  const int area = L.par.width * L.par.height;
+  for( int tu = blockIdx.x * blockDim.x + threadIdx.x; tu < n; tu += gridDim.x * blockDim.x )
+  {
+    int16_t* qt = q + (size_t) tu * area;
+    int32_t sum = 0;
+    if( needRdoq && !needRdoq[tu] ) { for( int i = 0; i < area; i++ ) qt[i] = 0; }
+    else vvbrq::rq_ts_quant_tu( L.par, sRates, sScan, coef + (size_t) tu * area, qt, &sum );
+    if( absSum ) absSum[tu] = sum;
+  }
+}
+
 } // namespace vvb
