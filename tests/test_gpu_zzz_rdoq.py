@@ -172,3 +172,13 @@ def test_bitstream_identity_with_transform_skip_rdoq_on_the_gpu(tmp_path, W, H, 
     from test_encoder_identity import _identity_ts
     kb = _identity_ts(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, min_ts, timeout=1500)
     print('encoder identity with the transform-skip RDOQ on the GPU:', W, H, F, preset, kb)
+
+
+@pytest.mark.skipif(not have_ref(), reason='oracle/_ref not built')
+def test_rdoq_ts_binding_on_the_real_library():
+    """rateDistOptQuantTSB200 (integration/TrQuantB200.h) bound to libvvenc_b200.so next to QuantRDOQ::rateDistOptQuantTS called as a member"""
+    import vvenc_b200._lib as VL
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), VL.LIB_PATH, 'rdoq'], capture_output=True, text=True, timeout=400)
+    assert out.returncode == 0, out.stderr[-3000:]
+    t = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq_ts']
+    assert t['cases'] == 140 and t['non_empty'] > 80 and t['bad'] == [], t
