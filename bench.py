@@ -1042,6 +1042,19 @@ def main():
                 t0 = time.perf_counter()
                 dq_oracle().orc_rdoq(n, n, BITDEPTH, QP, 0, 0, 0, 1, 57.3, 8, P_np(rates_flat), P_np(coef), cnt, P_np(qq), P_np(ss), P_np(ll))
                 row['cpu_port_ms_per_picture_1thread'] = (time.perf_counter() - t0) * 1e3
+                # ... and on all usable host CPUs (the C call releases the GIL; the TU list is cut into one chunk per thread)
+                from concurrent.futures import ThreadPoolExecutor
+                nthr, _ = host_cpus()
+                cuts = [cnt * k // nthr for k in range(nthr + 1)]
+                def port_chunk(k):
+                    a, b = cuts[k], cuts[k + 1]
+                    if b > a:
+                        dq_oracle().orc_rdoq(n, n, BITDEPTH, QP, 0, 0, 0, 1, 57.3, 8, P_np(rates_flat), P_np(coef[a:b]), b - a, P_np(qq[a:b]), P_np(ss[a:b]), P_np(ll[a:b]))
+                with ThreadPoolExecutor(nthr) as ex:
+                    t0 = time.perf_counter()
+                    list(ex.map(port_chunk, range(nthr)))
+                    row['cpu_port_ms_per_picture_all_threads'] = (time.perf_counter() - t0) * 1e3
+                row['cpu_threads'] = int(nthr)
                 row['device_equals_port'] = bool(np.array_equal(q_dev, qq) and np.array_equal(l_dev, ll))
                 row['coded_tus'] = int((ll >= 0).sum())
                 rq_rows[str(n)] = row
