@@ -289,7 +289,7 @@ int vvb_dep_quant_constants( const vvb_tu_par* par, const vvb_dq_par* dq, int64_
 /* ---- fast rate-distortion optimised quantisation: QuantRDOQ2::quant -> xRateDistOptQuant -> xRateDistOptQuantFast<bSBH, false>
  * (CommonLib/QuantRDOQ2.cpp:247-301, 1283-1296, 475-1281), what Quant::m_RDOQ == 2 (presets faster and fast, vvencCfg.cpp:2675, 2737) runs for every TU that is not
  * transform skipped and what DepQuant::quant falls back to in slices without dependent quantisation (DepQuant.cpp:1486-1489).  Luma and chroma components, sides 4..64,
- * with and without sign-bit hiding (par->sign_hiding = slice->signDataHidingEnabled), no scaling lists; transform skip (rateDistOptQuantTS) and BDPCM stay on the host.
+ * with and without sign-bit hiding (par->sign_hiding = slice->signDataHidingEnabled), no scaling lists; transform-skipped TUs: vvb_rdoq_ts below; BDPCM stays on the host.
  * Per coefficient group, from the last scan position down: level decision between floor and ceil of |c| * scale >> qBits by distortion + lambda * bits (:697-969, bits
  * from the context the template of already-decided neighbours selects, ContextModelling.h:158-269), group zero-out (:971-1036), last-position optimisation (:1038-1095),
  * parity adjustment for sign-bit hiding (:1097-1167), coded-block-flag decision (:1185-1233), signs (:1251-1257).  One TU per thread, all TUs of a call sharing shape,

@@ -7,7 +7,7 @@
 //   rateDistOptQuantTSB200 <-> QuantRDOQ::rateDistOptQuantTS (QuantRDOQ.cpp:1124-1336), the RDOQ of transform-skipped TUs (m_useRDOQTS)
 //
 // for the TUs the library covers: luma and chroma components, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), transform skip,
-// LFNST (luma, and the chroma TUs of a separate tree), joint Cb-Cr TUs, no scaling lists / BDPCM / ACT, plain quantiser incl. its sign-bit hiding (transform-skip RDOQ stays on the host and uses the coefficients
+// LFNST (luma, and the chroma TUs of a separate tree), joint Cb-Cr TUs, no scaling lists / BDPCM / ACT, plain quantiser incl. its sign-bit hiding (the RDOQ variants are separate calls below and use the coefficients
 // this call leaves in the temp buffer; dependent quantisation: xQuantDQB200 below).
 // vvb_tu_par is derived from the TransformUnit exactly as the members derive their parameters (xSetTrTypes, QpParam, slice type), so the call sites keep
 // their arguments.  One TU per call here; the production shape batches the TU candidates of a CU (vvb_fwd_trquant with n > 1 or
@@ -164,11 +164,11 @@ inline void xQuantDQB200( DepQuant& dq, TrQuant& tq, TransformUnit& tu, const CC
 // encoder's entropy-coding state: the fractional bits of the contexts the routine reads travel as vvb_rdoq_rates.  The last-position table is the member's own
 // (xInitLastPosBitsTab, run under the member's condition so that a Cr TU after a coded Cb TU sees the table of the Cb call, QuantRDOQ2.cpp:490); the coded-block-flag
 // context is resolved as :1185-1226 resolve it.  Inside the encoder this is a member of QuantRDOQ2; `rq` is that object (the DepQuant instance TrQuant owns).
-// Transform skip (rateDistOptQuantTS), BDPCM and scaling lists stay on the host.
+// Transform-skipped TUs: rateDistOptQuantTSB200 below; BDPCM and scaling lists stay on the host.
 #include "CommonLib/QuantRDOQ2.h"
 inline void xRateDistOptQuantB200( QuantRDOQ2& rq, TrQuant& tq, TransformUnit& tu, const ComponentID compID, const CCoeffBuf& pSrc, TCoeff& uiAbsSum, const QpParam& cQP, const Ctx& ctx )
 {
-  if( tu.mtsIdx[compID] == MTS_SKIP ) THROW( "transform-skip RDOQ stays on the host" );
+  if( tu.mtsIdx[compID] == MTS_SKIP ) THROW( "transform-skipped TUs go through rateDistOptQuantTSB200" );
   vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
   const int w = par.w, h = par.h;
   const ChannelType ch = toChannelType( compID );

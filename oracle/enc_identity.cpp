@@ -26,7 +26,7 @@
  * Transform-skipped TUs (environment VVB_ENC_TS=1 makes the encoder try transform skip on every eligible TU): `turdoq` / `all` route QuantRDOQ::rateDistOptQuantTS through rateDistOptQuantTSB200.
  * With `all` additionally the block-matching errors of the MCTF pre-analysis: MCTF::initMCTF_X86 is wrapped like the RdCost one and the error pointers / m_calcVar answer from
  * the library per call (integration/MCTFB200.h: installB200( MCTF& )), under the unmodified MCTF::motionEstimationLuma control.
- * Transform-skip RDOQ, RDOQ of m_RDOQ == 1, TUs with a side below 4 (thin ISP partitions, 2-wide chroma) and everything the bindings THROW for (BDPCM, ACT, scaling lists) stay with the members.
+ * RDOQ of m_RDOQ == 1 on non-skipped TUs, TUs with a side below 4 (thin ISP partitions, 2-wide chroma) and everything the bindings THROW for (BDPCM, ACT, scaling lists) stay with the members.
  *
  * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu | turdoq | all]
  * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_rdoq=<n> tu_rdoq_ts=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`

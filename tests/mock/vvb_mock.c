@@ -332,7 +332,7 @@ int vvb_rdoq( vvb_ctx* c, const vvb_tu_par* par, const vvb_rdoq_par* rq, const v
 {
   if( !c ) return VVB_ERR_ARG;
   if( !par || !rq || !rates || !coef || !q || n < 0 || !( rq->lambda > 0.0 ) ) return fail( c, VVB_ERR_ARG, "bad RDOQ arguments" );
-  if( par->transform_skip ) return fail( c, VVB_ERR_UNSUPPORTED, "transform-skip RDOQ stays on the host" );
+  if( par->transform_skip ) return fail( c, VVB_ERR_UNSUPPORTED, "transform-skipped TUs go through vvb_rdoq_ts" );
   const size_t area = (size_t) par->w * par->h;
   for( int i = 0; i < n; i++ )
   {

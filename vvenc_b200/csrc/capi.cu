@@ -1599,7 +1599,7 @@ int rqPar( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, vvbrq::R
   if( !par || !rq ) return fail( ctx, VVB_ERR_ARG, "null parameters" );
   if( !vvbrq::rq_shape_ok( par->w, par->h ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "TU sides must be 4, 8, 16, 32 or 64" );
   if( par->bit_depth != 8 && par->bit_depth != 10 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth 8 or 10" );
-  if( par->transform_skip ) return fail( ctx, VVB_ERR_UNSUPPORTED, "transform-skip RDOQ (rateDistOptQuantTS) stays on the host" );
+  if( par->transform_skip ) return fail( ctx, VVB_ERR_UNSUPPORTED, "transform-skipped TUs go through vvb_rdoq_ts" );
   if( !( rq->lambda > 0.0 ) ) return fail( ctx, VVB_ERR_ARG, "lambda must be greater than 0" );
   if( rq->thr_val < 1 || rq->thr_val > 64 ) return fail( ctx, VVB_ERR_ARG, "thr_val 1..64" );
   const int baseQp = std::max( 0, std::min( 63 + 6 * ( par->bit_depth - 8 ), par->qp + 6 * ( par->bit_depth - 8 ) ) );        // QpParam, Quant.cpp:99-113
