@@ -281,7 +281,7 @@ inline void bilateralFilterB200( const MCTF& m, const PelStorage& orgPic, std::d
 //   m_calcVar                             (MCTF.h:170; calcVarCore, :520-546)
 // Each call uploads the original block and the reference window it reads (two rows / columns before, three after: the 6-tap support) as two small planes and asks for
 // one candidate.  The full sum comes back where the member may have stopped early; a stopped sum is only ever compared with the running best it already exceeds.
-enum { B200_PLANE_MCTF_CALL_ORG = 14, B200_PLANE_MCTF_CALL_REF = 15 };
+enum { B200_PLANE_MCTF_CALL_ORG = 16, B200_PLANE_MCTF_CALL_REF = 17 };
 inline int b200MctfErrorCall( const Pel* org, const ptrdiff_t origStride, const Pel* buf, const ptrdiff_t buffStride, const int w, const int h, const int fx, const int fy, const int tap4, const int bitDepth )
 {
   vvb_ctx* ctx = b200CtxOfThread();
