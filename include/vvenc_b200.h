@@ -327,6 +327,16 @@ int vvb_rdoq_ts    ( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, const v
 int vvb_rdoq_ts_dev( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, const vvb_rdoq_ts_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n, int16_t* dev_q,
                      int32_t* dev_abs_sum );
 
+/* BDPCM TUs: QuantRDOQ::forwardRDPCM (CommonLib/QuantRDOQ.cpp:1338-1562), what QuantRDOQ2::quant runs for a transform-skipped TU whose CU carries a block-DPCM direction
+ * (dir_mode = cu.bdpcmM[chType]: 1 horizontal, 2 vertical).  As vvb_rdoq_ts, but each position quantises the residual minus the reconstructed left / upper neighbour
+ * (xDequantSample :1564-1576 of the level just chosen plus its own prediction), with the BDPCM variants of the greater-1 and sign contexts and two candidate levels.
+ * The inverse needs no entry point of its own: Quant::dequant undoes the DPCM on the levels (invResDPCM, Quant.cpp:298-340: clipped prefix sums along the direction)
+ * before the ordinary dequantiser of skipped transforms -- the binding forms the sums and calls vvb_inv_trquant with par->transform_skip. */
+int vvb_rdoq_bdpcm    ( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, int dir_mode, const vvb_rdoq_ts_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n, int16_t* q,
+                        int32_t* abs_sum );
+int vvb_rdoq_bdpcm_dev( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, int dir_mode, const vvb_rdoq_ts_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n,
+                        int16_t* dev_q, int32_t* dev_abs_sum );
+
 /* ---- inverse path of the TU loop -------------------------------------------------------------------
  * vvb_inv_trquant: TrQuant::invTransformNxN (TrQuant.cpp:318-348) = Quant::dequant (Quant.cpp:520-609, DeQuantCore :232) + TrQuant::xIT
  * (:567-660).  q: n compact level blocks [n][h][w] (TCoeffSig); resi: [n][h][w] Pel.  Uses par->{w,h,tr_hor,tr_ver,bit_depth,qp,transform_skip,...}; with par->dep_quant

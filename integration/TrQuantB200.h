@@ -5,6 +5,7 @@
 //   xQuantDQB200         <->  DepQuant::xQuantDQ (DepQuant.cpp:1129-1264), the trellis DepQuant::quant runs for non-skip TUs of a slice with depQuantEnabled
 //   xRateDistOptQuantB200 <-> QuantRDOQ2::xRateDistOptQuant (QuantRDOQ2.cpp:1283-1296 -> xRateDistOptQuantFast :475-1281), the fast RDOQ of m_RDOQ == 2
 //   rateDistOptQuantTSB200 <-> QuantRDOQ::rateDistOptQuantTS (QuantRDOQ.cpp:1124-1336), the RDOQ of transform-skipped TUs (m_useRDOQTS)
+//   forwardRDPCMB200       <-> QuantRDOQ::forwardRDPCM (QuantRDOQ.cpp:1338-1562), the quantiser of BDPCM TUs; their inverse path inside invTransformNxNB200
 //
 // for the TUs the library covers: luma and chroma components, DCT-II / DST-VII / DCT-VIII (explicit MTS and the implicit / SBT choices xSetTrTypes makes), transform skip,
 // LFNST (luma, and the chroma TUs of a separate tree), joint Cb-Cr TUs, no scaling lists / BDPCM / ACT, plain quantiser incl. its sign-bit hiding (the RDOQ variants are separate calls below and use the coefficients
@@ -24,6 +25,7 @@ struct B200TuApi
   decltype( &vvb_dep_quant )    depQuant   = nullptr;
   decltype( &vvb_rdoq )         rdoq       = nullptr;
   decltype( &vvb_rdoq_ts )      rdoqTs     = nullptr;
+  decltype( &vvb_rdoq_bdpcm )   rdoqBdpcm  = nullptr;
 } ;
 static B200TuApi g_b200t;
 
@@ -34,16 +36,16 @@ inline int b200LoadTu( const char* libPath )
   if( rc ) return rc;
   void* h = g_b200.handle;
 #define VVB_RESOLVE( member, name ) g_b200t.member = (decltype( g_b200t.member )) dlsym( h, #name ); if( !g_b200t.member ) { g_b200.error = "missing " #name; return -2; }
-  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )  VVB_RESOLVE( rdoq, vvb_rdoq )  VVB_RESOLVE( rdoqTs, vvb_rdoq_ts )
+  VVB_RESOLVE( fwdTrQuant, vvb_fwd_trquant )  VVB_RESOLVE( invTrQuant, vvb_inv_trquant )  VVB_RESOLVE( depQuant, vvb_dep_quant )  VVB_RESOLVE( rdoq, vvb_rdoq )  VVB_RESOLVE( rdoqTs, vvb_rdoq_ts )  VVB_RESOLVE( rdoqBdpcm, vvb_rdoq_bdpcm )
 #undef VVB_RESOLVE
   g_b200t.bound = true;
   return 0;
 }
 
-inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const ComponentID compID, const QpParam& cQP, bool forward = true )
+inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const ComponentID compID, const QpParam& cQP, bool forward = true, bool bdpcmOk = false )
 {
   const ChannelType chType = toChannelType( compID );
-  if( tu.cu->bdpcmM[chType] ) THROW( "BDPCM stays on the host" );
+  if( tu.cu->bdpcmM[chType] && !bdpcmOk ) THROW( "BDPCM TUs: forwardRDPCMB200 / invTransformNxNB200" );
   if( tu.cs->sps->scalingListEnabled ) THROW( "scaling lists stay on the host" );
   // joint Cb-Cr TUs need nothing special here: the caller has already formed the joint residual (fwdTransformICT) and built cQP for the joint mode (QpParam, Quant.cpp:80-87);
   // neither transformNxN nor the quantisers look at tu.jointCbCr.  The adaptive colour transform changes QpParam only when the caller asks for it: left to the host.
@@ -82,9 +84,10 @@ inline vvb_tu_par b200TuPar( TrQuant& tq, const TransformUnit& tu, const Compone
 // tempCoeff receives the transform coefficients, tu.getCoeffs( compID ) the levels, tu.lastPos[compID] and uiAbsSum as Quant::quant sets them.
 // needRdoq (nullable) receives Quant::xNeedRDOQ of the coefficients (Quant.cpp:835-891).
 inline void xTQuantB200( TrQuant& tq, TransformUnit& tu, const ComponentID compID, const CPelBuf& resiBuf, CoeffBuf& tempCoeff, const QpParam& cQP, TCoeff& uiAbsSum,
-                         bool* needRdoq = nullptr )
+                         bool* needRdoq = nullptr, bool bdpcmOk = false )
 {
-  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP );
+  // bdpcmOk: the caller quantises the coefficients itself (forwardRDPCMB200); the levels of this call carry no DPCM and are to be overwritten
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP, true, bdpcmOk );
   const int w = par.w, h = par.h;
   std::vector<int16_t> resi( (size_t) w * h ), q( (size_t) w * h );
   std::vector<int32_t> coef( (size_t) w * h );
@@ -113,11 +116,19 @@ inline void xTQuantB200( TrQuant& tq, TransformUnit& tu, const ComponentID compI
 // TrQuant::invTransformNxN( tu, compID, pResi, cQP ) for the same class of TUs: levels of tu.getCoeffs( compID ) -> residual
 inline void invTransformNxNB200( TrQuant& tq, TransformUnit& tu, const ComponentID compID, PelBuf& pResi, const QpParam& cQP )
 {
-  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP, false );
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, cQP, false, true );
   const int w = par.w, h = par.h;
   std::vector<int16_t> q( (size_t) w * h ), resi( (size_t) w * h );
   const CCoeffSigBuf src = tu.getCoeffs( compID );
   for( int y = 0; y < h; y++ ) memcpy( &q[(size_t) y * w], src.buf + (ptrdiff_t) y * src.stride, sizeof( TCoeffSig ) * w );
+  if( const int dirMode = tu.cu->bdpcmM[toChannelType( compID )] )
+  {
+    // Quant::dequant undoes the DPCM on the levels before the dequantiser of skipped transforms (invResDPCM, Quant.cpp:298-340): clipped running sums along the direction
+    if( !par.transform_skip ) THROW( "BDPCM TU without MTS_SKIP" );
+    const int lo = -( 1 << 15 ), hi = ( 1 << 15 ) - 1;
+    if( dirMode == 1 ) { for( int y = 0; y < h; y++ ) for( int x = 1; x < w; x++ ) q[(size_t) y * w + x] = (int16_t) Clip3( lo, hi, int( q[(size_t) y * w + x - 1] ) + int( q[(size_t) y * w + x] ) ); }
+    else               { for( int y = 1; y < h; y++ ) for( int x = 0; x < w; x++ ) q[(size_t) y * w + x] = (int16_t) Clip3( lo, hi, int( q[(size_t) ( y - 1 ) * w + x] ) + int( q[(size_t) y * w + x] ) ); }
+  }
   b200Check( g_b200t.invTrQuant( b200CtxOfThread(), &par, q.data(), 1, resi.data() ) );
   for( int y = 0; y < h; y++ ) memcpy( pResi.buf + (ptrdiff_t) y * pResi.stride, &resi[(size_t) y * w], sizeof( Pel ) * w );
 }
@@ -254,4 +265,30 @@ inline void rateDistOptQuantTSB200( QuantRDOQ& rq, TrQuant& tq, TransformUnit& t
   CoeffSigBuf dst = tu.getCoeffs( compID );
   for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
   absSum += sum;                                                                                // the member accumulates into the caller's sum (:1334)
+}
+
+// QuantRDOQ::forwardRDPCM( tu, compID, coeffs, absSum, qp, ctx ) for a TU whose CU carries a BDPCM direction: the same rate tables as rateDistOptQuantTSB200, the direction
+// travels as an argument, the reconstruction chain runs on the device.  coeffs must be compact (stride == width), as TrQuant's temp buffer is.
+inline void forwardRDPCMB200( QuantRDOQ& rq, TrQuant& tq, TransformUnit& tu, const ComponentID compID, const CCoeffBuf& coeffs, TCoeff& absSum, const QpParam& qp, const Ctx& ctx )
+{
+  const int dirMode = tu.cu->bdpcmM[toChannelType( compID )];
+  if( !dirMode || tu.mtsIdx[compID] != MTS_SKIP ) THROW( "forwardRDPCMB200 is for BDPCM TUs (mtsIdx == MTS_SKIP)" );
+  const vvb_tu_par par = b200TuPar( tq, tu, compID, qp, true, true );
+  const int w = par.w, h = par.h;
+  const FracBitsAccess& fb = ctx.getFracBitsAcess();
+  vvb_rdoq_ts_rates rates;
+  for( int i = 0; i < 3; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_bits[i][b] = fb.getFracBitsArray( Ctx::TsSigFlag( i ) ).intBits[b];
+  for( int b = 0; b < 2; b++ ) rates.par_bits[b] = fb.getFracBitsArray( Ctx::TsParFlag( 0 ) ).intBits[b];
+  for( int i = 0; i < 5; i++ ) for( int b = 0; b < 2; b++ ) rates.gtx_bits[i][b] = fb.getFracBitsArray( Ctx::TsGtxFlag( i ) ).intBits[b];
+  for( int i = 0; i < 4; i++ ) for( int b = 0; b < 2; b++ ) rates.lrg1_bits[i][b] = fb.getFracBitsArray( Ctx::TsLrg1Flag( i ) ).intBits[b];
+  for( int i = 0; i < 6; i++ ) for( int b = 0; b < 2; b++ ) rates.sign_bits[i][b] = fb.getFracBitsArray( Ctx::TsResidualSign( i ) ).intBits[b];
+  for( int i = 0; i < 3; i++ ) for( int b = 0; b < 2; b++ ) rates.sig_group_bits[i][b] = fb.getFracBitsArray( Ctx::TsSigCoeffGroup( i ) ).intBits[b];
+  std::vector<int32_t> coef( (size_t) w * h );
+  std::vector<int16_t> q( (size_t) w * h );
+  for( int y = 0; y < h; y++ ) memcpy( &coef[(size_t) y * w], coeffs.buf + (ptrdiff_t) y * coeffs.stride, sizeof( TCoeff ) * w );
+  int32_t sum = 0;
+  b200Check( g_b200t.rdoqBdpcm( b200CtxOfThread(), &par, rq.m_dLambda, dirMode, &rates, coef.data(), nullptr, 1, q.data(), &sum ) );
+  CoeffSigBuf dst = tu.getCoeffs( compID );
+  for( int y = 0; y < h; y++ ) memcpy( dst.buf + (ptrdiff_t) y * dst.stride, &q[(size_t) y * w], sizeof( TCoeffSig ) * w );
+  absSum += sum;
 }

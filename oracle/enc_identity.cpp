@@ -24,12 +24,14 @@
  * With `turdoq` the routing is the widest the bindings offer: LFNST also on the chroma TUs of a separate tree (kernel set from the chroma / co-located luma mode) and on ISP luma TUs,
  * the chroma TUs of single-tree LFNST CUs (xT's zero-out applied to the full transform), joint Cb-Cr TUs (the caller has formed the joint residual and QP).
  * Transform-skipped TUs (environment VVB_ENC_TS=1 makes the encoder try transform skip on every eligible TU): `turdoq` / `all` route QuantRDOQ::rateDistOptQuantTS through rateDistOptQuantTSB200.
+ * BDPCM TUs (VVB_ENC_BDPCM=1 next to VVB_ENC_TS=1): forwardRDPCMB200 (-> vvb_rdoq_bdpcm) and, on the inverse side, invTransformNxNB200 (running sums on the host + the library's inverse
+ * of skipped transforms).
  * With `all` additionally the block-matching errors of the MCTF pre-analysis: MCTF::initMCTF_X86 is wrapped like the RdCost one and the error pointers / m_calcVar answer from
  * the library per call (integration/MCTFB200.h: installB200( MCTF& )), under the unmodified MCTF::motionEstimationLuma control.
- * RDOQ of m_RDOQ == 1 on non-skipped TUs, TUs with a side below 4 (thin ISP partitions, 2-wide chroma) and everything the bindings THROW for (BDPCM, ACT, scaling lists) stay with the members.
+ * RDOQ of m_RDOQ == 1 on non-skipped TUs, TUs with a side below 4 (thin ISP partitions, 2-wide chroma) and everything the bindings THROW for (ACT, scaling lists) stay with the members.
  *
  * usage: enc_identity <in.yuv (8-bit 4:2:0)> <width> <height> <frames> <preset 0..4 (faster..slower)> <qp> <out.vvc> [path of libvvenc_b200.so -> B200 tables] [tu | turdoq | all]
- * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_rdoq=<n> tu_rdoq_ts=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
+ * prints one line: `ENC frames=<n> bytes=<n> fnv1a=<hex> dist_calls=<n> b200=<0|1> ... tu_fwd=<n> tu_dq=<n> tu_rdoq=<n> tu_rdoq_ts=<n> tu_bdpcm=<n> tu_inv=<n> tu_inv_lfnst=<n> tu_ref=<n>`
  */
 #include <cstdint>
 #include <cstring>
@@ -131,7 +133,7 @@ static int countingX5( vvb_ctx* c, const int16_t* o, int so, const int16_t* u, i
 // ---- the transform / quantisation seam -------------------------------------------------------------------------------------------------------------------------
 static bool g_useTu = false, g_useRdoq = false;      // g_useRdoq: argument `turdoq` -- the widest routing: also the fast RDOQ of m_RDOQ == 2, LFNST on the chroma TUs of a
                                                       // separate tree and on ISP luma TUs, joint Cb-Cr TUs (`tu` keeps the narrower routing of the first hardware runs)
-static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuRdoq{ 0 }, g_tuRdoqTs{ 0 }, g_tuInv{ 0 }, g_tuInvLfnst{ 0 }, g_tuRef{ 0 };
+static std::atomic<unsigned long long> g_tuFwd{ 0 }, g_tuDq{ 0 }, g_tuRdoq{ 0 }, g_tuRdoqTs{ 0 }, g_tuBdpcm{ 0 }, g_tuInv{ 0 }, g_tuInvLfnst{ 0 }, g_tuRef{ 0 };
 
 extern "C" void __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant*, TransformUnit&, ComponentID, const QpParam&, TCoeff&, const Ctx&, bool );
 extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( TrQuant* self, TransformUnit& tu, ComponentID compID, const QpParam& cQP,
@@ -140,7 +142,7 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
   const ChannelType chType = toChannelType( compID );
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0;
   // what stays with the member: BDPCM, LFNST on stored coefficients, empty TUs; with `tu` (not `turdoq`) also LFNST on chroma / ISP CUs and joint Cb-Cr TUs
-  if( !g_useTu || tu.noResidual || tu.cu->bdpcmM[chType] || ( lfnstHere && ( loadTr || ( !g_useRdoq && ( !isLuma( compID ) || tu.cu->ispMode ) ) ) ) || ( !g_useRdoq && isChroma( compID ) && tu.jointCbCr ) || tu.cs->sps->scalingListEnabled )
+  if( !g_useTu || tu.noResidual || ( tu.cu->bdpcmM[chType] && !g_useRdoq ) || ( lfnstHere && ( loadTr || ( !g_useRdoq && ( !isLuma( compID ) || tu.cu->ispMode ) ) ) ) || ( !g_useRdoq && isChroma( compID ) && tu.jointCbCr ) || tu.cs->sps->scalingListEnabled )
   {
     g_tuRef++;
     __real__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11ComponentIDERKNS_7QpParamERiRKNS_3CtxEb( self, tu, compID, cQP, uiAbsSum, ctx, loadTr );
@@ -148,13 +150,15 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
   }
   const CompArea& rect = tu.blocks[compID];
   const CPelBuf resiBuf = tu.cs->getResiBuf( rect );
+  const bool bdpcm = tu.cu->bdpcmM[chType] != 0;
+  if( bdpcm ) tu.mtsIdx[compID] = MTS_SKIP;                                            // TrQuant.cpp:703-706
   uiAbsSum = 0;
   CoeffBuf tempCoeff( loadTr ? self->m_mtsCoeffs[tu.mtsIdx[compID]] : self->m_plTempCoeff, rect );      // loadTr: checktransformsNxN has left the coefficients (TrQuant.cpp:709)
   if( !loadTr )
   try
   {
     TCoeff plainSum = 0;
-    xTQuantB200( *self, tu, compID, resiBuf, tempCoeff, cQP, plainSum );              // xT / xTransformSkip (+ xFwdLfnst): tempCoeff as the member leaves it
+    xTQuantB200( *self, tu, compID, resiBuf, tempCoeff, cQP, plainSum, nullptr, bdpcm );   // xT / xTransformSkip (+ xFwdLfnst): tempCoeff as the member leaves it
     g_tuFwd++;
   }
   catch( std::exception& )                                                             // a TU the binding does not cover (joint Cb-Cr, ...): the member
@@ -183,9 +187,14 @@ extern "C" void __wrap__ZN5vvenc7TrQuant12transformNxNERNS_13TransformUnitENS_11
       catch( std::exception& ) { uiAbsSum = 0; }
     }
     // ... and for a transform-skipped TU without BDPCM rateDistOptQuantTS when Quant::m_useRDOQTS is set (:263, 275-285)
-    if( !done && g_useRdoq && dq && !selectiveSkip && dq->m_useRDOQTS && tu.mtsIdx[compID] == MTS_SKIP && !tu.cu->bdpcmM[chType] && rect.width > 2 && rect.height > 2 )
+    if( !done && g_useRdoq && dq && !selectiveSkip && dq->m_useRDOQTS && tu.mtsIdx[compID] == MTS_SKIP && rect.width > 2 && rect.height > 2 )
     {
-      try { rateDistOptQuantTSB200( *dq, *self, tu, compID, tempCoeff, uiAbsSum, cQP, ctx ); g_tuRdoqTs++; done = true; }
+      try
+      {
+        if( bdpcm ) { forwardRDPCMB200( *dq, *self, tu, compID, tempCoeff, uiAbsSum, cQP, ctx ); g_tuBdpcm++; }
+        else        { rateDistOptQuantTSB200( *dq, *self, tu, compID, tempCoeff, uiAbsSum, cQP, ctx ); g_tuRdoqTs++; }
+        done = true;
+      }
       catch( std::exception& ) { uiAbsSum = 0; }
     }
     if( !done ) self->xQuant( tu, compID, tempCoeff, uiAbsSum, cQP, ctx );
@@ -199,7 +208,7 @@ extern "C" void __wrap__ZN5vvenc7TrQuant15invTransformNxNERNS_13TransformUnitENS
   const ChannelType chType = toChannelType( compID );
   const bool lfnstHere = tu.cs->sps->LFNST && tu.cu->lfnstIdx != 0 && tu.mtsIdx[compID] != MTS_SKIP && ( CU::isSepTree( *tu.cu ) ? true : isLuma( compID ) );
   // plain and DepQuant dequantiser alike (vvb_tu_par.dep_quant); LFNST as in the forward wrapper
-  if( g_useTu && ( g_useRdoq || !( ( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) || ( isChroma( compID ) && tu.jointCbCr ) ) ) && !tu.cu->bdpcmM[chType] && !tu.cs->sps->scalingListEnabled )
+  if( g_useTu && ( g_useRdoq || !( ( lfnstHere && ( !isLuma( compID ) || tu.cu->ispMode ) ) || ( isChroma( compID ) && tu.jointCbCr ) || tu.cu->bdpcmM[chType] ) ) && !tu.cs->sps->scalingListEnabled )
   {
     try { invTransformNxNB200( *self, tu, compID, pResi, cQP ); g_tuInv++; if( lfnstHere ) g_tuInvLfnst++; return; }
     catch( std::exception& ) {}
@@ -239,7 +248,7 @@ int main( int argc, char** argv )
   vvenc_init_default( &cfg, w, h, 30, 0, qp, (vvencPresetMode) preset );
   cfg.m_numThreads = 1;                       // one worker: one vvb_ctx; the result of the reference does not depend on the thread count
   cfg.m_inputBitDepth[0] = 8; cfg.m_internalBitDepth[0] = 10;
-  if( getenv( "VVB_ENC_TS" ) ) { cfg.m_TS = 1; cfg.m_useBDPCM = 0; }      // transform skip always tried (the presets leave it to the screen-content detector): both arms of an identity run set it
+  if( getenv( "VVB_ENC_TS" ) ) { cfg.m_TS = 1; cfg.m_useBDPCM = getenv( "VVB_ENC_BDPCM" ) ? 1 : 0; }      // transform skip always tried (the presets leave it to the screen-content detector): both arms of an identity run set it
   cfg.m_verbosity = VVENC_SILENT;
   vvenc_set_msg_callback( &cfg, nullptr, quietLog );
   vvencEncoder* enc = vvenc_encoder_create();
@@ -287,8 +296,8 @@ int main( int argc, char** argv )
   if( fo ) { fwrite( out.data(), 1, out.size(), fo ); fclose( fo ); }
   uint64_t hsh = 1469598103934665603ull;
   for( uint8_t b : out ) { hsh ^= b; hsh *= 1099511628211ull; }
-  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_rdoq=%llu tu_rdoq_ts=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu mctf_installs=%ld mctf_calls=%llu\n", fed, out.size(),
-          (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuRdoq.load(), g_tuRdoqTs.load(), g_tuInv.load(),
+  printf( "ENC frames=%d bytes=%zu fnv1a=%016llx dist_calls=%llu x5_calls=%llu b200=%d rdcost_installs=%ld affine_installs=%ld tu_fwd=%llu tu_dq=%llu tu_rdoq=%llu tu_rdoq_ts=%llu tu_bdpcm=%llu tu_inv=%llu tu_inv_lfnst=%llu tu_ref=%llu mctf_installs=%ld mctf_calls=%llu\n", fed, out.size(),
+          (unsigned long long) hsh, g_distCalls.load(), g_otherCalls.load(), g_useB200 ? 1 : 0, g_rdCostInstalls.load(), g_affineInstalls.load(), g_tuFwd.load(), g_tuDq.load(), g_tuRdoq.load(), g_tuRdoqTs.load(), g_tuBdpcm.load(), g_tuInv.load(),
           g_tuInvLfnst.load(), g_tuRef.load(), g_mctfInstalls.load(), g_mctfCalls.load() );
   return 0;
 }

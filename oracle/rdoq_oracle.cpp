@@ -47,6 +47,22 @@ int orc_rdoq_ts( int w, int h, int bitDepth, int qp, int inputDelta, double lamb
   for( int i = 0; i < n; i++ ) rq_ts_quant_tu( p, r, scan.data(), coef + (size_t) i * w * h, q + (size_t) i * w * h, absSum + i );
   return 0;
 }
+// BDPCM TUs (QuantRDOQ::forwardRDPCM): dirMode 1 horizontal, 2 vertical; everything else as orc_rdoq_ts
+int orc_rdoq_bdpcm( int w, int h, int bitDepth, int qp, int inputDelta, int dirMode, double lambda, const int32_t* rates, const int32_t* coef, int n, int16_t* q, int32_t* absSum )
+{
+  if( !rq_ts_shape_ok( w, h ) || dirMode < 1 || dirMode > 2 ) return -1;
+  int qpInternal = qp + 6 * ( bitDepth - 8 );
+  qpInternal = qpInternal < 0 ? 0 : qpInternal > 63 + 6 * ( bitDepth - 8 ) ? 63 + 6 * ( bitDepth - 8 ) : qpInternal;
+  if( qpInternal < 4 + 6 * inputDelta ) qpInternal = 4 + 6 * inputDelta;
+  const RqTsPar p = rq_ts_init_par( w, h, bitDepth, qpInternal, lambda );
+  const RqBdpcmPar b = rq_bdpcm_init_par( dirMode, qpInternal );
+  RqTsRates r; memcpy( &r, rates, sizeof( r ) );
+  std::vector<int32_t> scan( 1024 ), full( (size_t) w * h );
+  rq_build_scan( w, h, scan.data() );
+  for( int i = 0; i < n; i++ ) rq_bdpcm_quant_tu( p, b, r, scan.data(), coef + (size_t) i * w * h, q + (size_t) i * w * h, full.data(), absSum + i );
+  return 0;
+}
+
 // quantScale, qBits, maxCtxBins and the error scale (double)
 int orc_rdoq_ts_constants( int w, int h, int bitDepth, int qp, int inputDelta, int32_t outInt[3], double* errorScale )
 {

@@ -1058,6 +1058,36 @@ int refshim_rdoq_ts( int comp, const int32_t* coef, int w, int h, int bitDepth, 
   return 0;
 }
 
+// BDPCM: QuantRDOQ::forwardRDPCM (QuantRDOQ.cpp:1338-1562) on the rig with cu.bdpcmM = dirMode (1 horizontal, 2 vertical); rates as refshim_rdoq_ts
+int refshim_rdoq_bdpcm( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int inputDelta, int intraCu, int dirMode, double lambda, int ctxQp, int ctxInitId,
+                        int16_t* q, int32_t* absSum, int32_t* ratesOut )
+{
+  RefCtx& c = ctx(); (void) c;
+  TuRig& r = rig();
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.setup( w, h, bitDepth, MTS_SKIP, false, intraCu != 0, qp, comp ? CHROMA_444 : CHROMA_400 );
+  if( comp ) r.tu.mtsIdx[COMP_Cb] = MTS_SKIP;
+  r.cu.bdpcmM[comp ? CH_C : CH_L] = (uint8_t) dirMode;
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta; r.sps.internalMinusInputBitDepth[CH_C] = inputDelta;
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 2, true, 8 );
+  dq->m_dLambda = lambda;
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  dq->forwardRDPCM( r.tu, compID, src, sum, qpp, *cabac );
+  memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+  *absSum = sum;
+  if( ratesOut ) rdoqTsRatesOf( *cabac, ratesOut );
+  r.cu.bdpcmM[CH_L] = 0; r.cu.bdpcmM[CH_C] = 0;
+  r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0;
+  return 0;
+}
+
 // the same TU through integration/TrQuantB200.h (rateDistOptQuantTSB200); returns 1 when the binding threw
 int refshim_rdoq_ts_b200( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int inputDelta, int intraCu, double lambda, int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum )
 {
@@ -1085,6 +1115,51 @@ int refshim_rdoq_ts_b200( int comp, const int32_t* coef, int w, int h, int bitDe
   memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
   *absSum = sum;
   return 0;
+}
+
+// BDPCM through the bindings: forwardRDPCMB200, and (inverse != 0) Quant::dequant + xITransformSkip of the levels against invTransformNxNB200 (host running sums + the library's
+// inverse of skipped transforms); returns 1 when a binding threw
+int refshim_rdoq_bdpcm_b200( int comp, const int32_t* coef, int w, int h, int bitDepth, int qp, int inputDelta, int dirMode, double lambda, int ctxQp, int ctxInitId, int16_t* q, int32_t* absSum,
+                             int16_t* resiMember, int16_t* resiB200 )
+{
+  RefCtx& c = ctx(); (void) c;
+  TuRig& r = rig();
+  const ComponentID compID = comp ? COMP_Cb : COMP_Y;
+  r.setup( w, h, bitDepth, MTS_SKIP, false, true, qp, comp ? CHROMA_444 : CHROMA_400 );
+  if( comp ) r.tu.mtsIdx[COMP_Cb] = MTS_SKIP;
+  r.cu.bdpcmM[comp ? CH_C : CH_L] = (uint8_t) dirMode;
+  r.sps.internalMinusInputBitDepth[CH_L] = inputDelta; r.sps.internalMinusInputBitDepth[CH_C] = inputDelta;
+  static thread_local std::unique_ptr<DepQuant> dq;
+  if( !dq ) dq.reset( new DepQuant( nullptr, true, false, true ) );
+  dq->init( 2, true, 8 );
+  dq->m_dLambda = lambda;
+  static thread_local std::unique_ptr<Ctx> cabac;
+  if( !cabac ) cabac.reset( new Ctx( (const BinProbModel*) nullptr ) );
+  cabac->init( ctxQp, ctxInitId );
+  QpParam qpp( r.tu, COMP_Y, false );
+  CCoeffBuf src( coef, w, w, h );
+  TCoeff sum = 0;
+  int rc = 0;
+  try
+  {
+    forwardRDPCMB200( *dq, tqOfThread(), r.tu, compID, src, sum, qpp, *cabac );
+    memcpy( q, r.qcoef.data(), sizeof( int16_t ) * w * h );
+    *absSum = sum;
+    if( resiMember && resiB200 )
+    {
+      // inverse path of the levels just produced: the member (Quant::dequant incl. invResDPCM + xITransformSkip) against the binding
+      TrQuant& tq = tqOfThread();
+      std::vector<Pel> a( (size_t) w * h ), b( (size_t) w * h );
+      PelBuf pa( a.data(), w, w, h ), pb( b.data(), w, w, h );
+      tq.invTransformNxN( r.tu, compID, pa, qpp );
+      invTransformNxNB200( tq, r.tu, compID, pb, qpp );
+      memcpy( resiMember, a.data(), sizeof( Pel ) * w * h ); memcpy( resiB200, b.data(), sizeof( Pel ) * w * h );
+    }
+  }
+  catch( std::exception& e ) { g_b200.error = e.what(); rc = 1; }
+  r.cu.bdpcmM[CH_L] = 0; r.cu.bdpcmM[CH_C] = 0;
+  r.sps.internalMinusInputBitDepth[CH_L] = 0; r.sps.internalMinusInputBitDepth[CH_C] = 0;
+  return rc;
 }
 
 // scan geometry of DQIntern::Rom for one luma shape, repacked into the 24- / 16-byte records of vvenc_b200/csrc/depquant_core.h (DqScanInfo, DqNbOut);

@@ -388,7 +388,20 @@ def main_rdoq(lib_path):
         tn += 1; tnz += int(sa.value > 0)
         if rc or not (np.array_equal(qa, qb) and sa.value == sb.value):
             tbad.append(['rdoq_ts'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
-    print('RESULT ' + json.dumps({'rdoq': {'cases': n, 'non_empty': nz, 'non_empty_with_hiding': nsh, 'bad': bad[:5]}, 'rdoq_ts': {'cases': tn, 'non_empty': tnz, 'bad': tbad[:5]}}))
+    # QuantRDOQ::forwardRDPCM against forwardRDPCMB200, and the inverse path of the BDPCM levels (Quant::dequant incl. invResDPCM + xITransformSkip) against invTransformNxNB200
+    bbad = []; bn = 0; bnz = 0
+    for row in C.rdoq_ts_cases():
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row); dm = 1 + (seed & 1)
+        qa = np.zeros((h, w), dtype=np.int16); sa = I32(); qb = np.zeros((h, w), dtype=np.int16); sb = I32(); ra = np.zeros((h, w), dtype=np.int16); rb = np.zeros((h, w), dtype=np.int16)
+        cq = qp if qp > 16 else 27
+        assert R.refshim_rdoq_bdpcm(comp, P(coef), w, h, bd, qp, delta, 1, dm, lam1000 / 1000.0, cq, init_id, P(qa), ctypes.byref(sa), None) == 0
+        rc = R.refshim_rdoq_bdpcm_b200(comp, P(coef), w, h, bd, qp, delta, dm, lam1000 / 1000.0, cq, init_id, P(qb), ctypes.byref(sb), P(ra), P(rb))
+        bn += 1; bnz += int(sa.value > 0)
+        if rc or not (np.array_equal(qa, qb) and sa.value == sb.value and np.array_equal(ra, rb)):
+            bbad.append(['rdoq_bdpcm'] + [int(v) for v in row] + [rc, (R.refshim_b200_error() or b'').decode() if rc else ''])
+    print('RESULT ' + json.dumps({'rdoq': {'cases': n, 'non_empty': nz, 'non_empty_with_hiding': nsh, 'bad': bad[:5]}, 'rdoq_ts': {'cases': tn, 'non_empty': tnz, 'bad': tbad[:5]},
+                                  'rdoq_bdpcm': {'cases': bn, 'non_empty': bnz, 'bad': bbad[:5]}}))
 
 
 if __name__ == '__main__':

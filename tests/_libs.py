@@ -56,6 +56,7 @@ def dq_oracle():
         L.orc_rdoq_constants.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
         L.orc_rdoq_ts.argtypes = [ctypes.c_int] * 5 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_rdoq_ts_constants.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_rdoq_bdpcm.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _dqoracle = L
     return _dqoracle
 
@@ -93,6 +94,8 @@ def refshim():
         L.refshim_rdoq_b200.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_double] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.refshim_rdoq_ts.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5
         L.refshim_rdoq_ts_b200.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 2
+        L.refshim_rdoq_bdpcm.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+        L.refshim_rdoq_bdpcm_b200.argtypes = [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.refshim_set_simd(b'AVX2')
         _ref = L
     return _ref

@@ -39,10 +39,20 @@ def main():
         q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); e = ctypes.c_double()
         assert R.refshim_rdoq_ts(comp, P(coef), w, h, bd, qp, delta, intra, lam1000 / 1000.0, qp if qp > 16 else 27, init_id, P(q), ctypes.byref(s), P(trates[i]), P(tconsts[i]), ctypes.byref(e)) == 0
         tsum[i] = s.value; terr[i] = e.value; out['tsq_%d' % i] = q
+    # BDPCM TUs: QuantRDOQ::forwardRDPCM on the same rows, direction 1 + (seed & 1), intra CU
+    bsum = np.zeros(len(trow), dtype=np.int32)
+    for i, row in enumerate(trow):
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row)
+        q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32(); rt = np.zeros(44, dtype=np.int32)
+        assert R.refshim_rdoq_bdpcm(comp, P(coef), w, h, bd, qp, delta, 1, 1 + (seed & 1), lam1000 / 1000.0, qp if qp > 16 else 27, init_id, P(q), ctypes.byref(s), P(rt)) == 0
+        assert np.array_equal(rt, trates[i])
+        bsum[i] = s.value; out['bdq_%d' % i] = q
+    out['bd_abs_sum'] = bsum
     out['ts_cases'] = trow; out['ts_rates'] = trates; out['ts_consts'] = tconsts; out['ts_err_scale'] = terr; out['ts_abs_sum'] = tsum
     path = os.path.join(HERE, 'golden_v6_rdoq.npz')
     np.savez_compressed(path, **out)
-    print('wrote', path, len(rows), 'cases,', int((meta[:, 1] >= 0).sum()), 'non-empty;', len(trow), 'transform-skip cases,', int((tsum > 0).sum()), 'non-empty,', os.path.getsize(path), 'bytes')
+    print('wrote', path, len(rows), 'cases,', int((meta[:, 1] >= 0).sum()), 'non-empty;', len(trow), 'transform-skip cases,', int((tsum > 0).sum()), 'non-empty,', int((bsum > 0).sum()), 'non-empty with BDPCM,', os.path.getsize(path), 'bytes')
 
 
 if __name__ == '__main__':

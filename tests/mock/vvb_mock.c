@@ -21,6 +21,7 @@ int      orc_dep_quant_chroma( int w, int h, int bitDepth, int qp, double lambda
 int      orc_rdoq( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int sbtZeroOut, int signHiding, double lambda, int thrVal, const int32_t* rates,
                    const int32_t* coef, int n, int16_t* q, int32_t* absSum, int32_t* lastPos );   /* oracle/rdoq_oracle.cpp */
 int      orc_rdoq_ts( int w, int h, int bitDepth, int qp, int inputDelta, double lambda, const int32_t* rates, const int32_t* coef, int n, int16_t* q, int32_t* absSum );
+int      orc_rdoq_bdpcm( int w, int h, int bitDepth, int qp, int inputDelta, int dirMode, double lambda, const int32_t* rates, const int32_t* coef, int n, int16_t* q, int32_t* absSum );
 void     orc_mctf_err_list( int tap4, const Pel* orgPlane, int so, const Pel* bufPlane, int sb, const int32_t* desc, int n, int bitDepth, int32_t* out );
 
 #define MOCK_PLANES 64
@@ -357,6 +358,23 @@ int vvb_rdoq_ts( vvb_ctx* c, const vvb_tu_par* par, double lambda, const vvb_rdo
     int32_t s = 0;
     if( need_rdoq && !need_rdoq[i] ) memset( q + i * area, 0, sizeof( int16_t ) * area );
     else if( orc_rdoq_ts( par->w, par->h, par->bit_depth, par->qp, par->input_bit_depth_delta, lambda, (const int32_t*) rates, coef + i * area, 1, q + i * area, &s ) )
+      return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
+    if( abs_sum ) abs_sum[i] = s;
+  }
+  c->calls++;
+  return VVB_OK;
+}
+
+int vvb_rdoq_bdpcm( vvb_ctx* c, const vvb_tu_par* par, double lambda, int dir_mode, const vvb_rdoq_ts_rates* rates, const int32_t* coef, const uint8_t* need_rdoq, int n, int16_t* q, int32_t* abs_sum )
+{
+  if( !c ) return VVB_ERR_ARG;
+  if( !par || !rates || !coef || !q || n < 0 || !( lambda > 0.0 ) || dir_mode < 1 || dir_mode > 2 ) return fail( c, VVB_ERR_ARG, "bad BDPCM RDOQ arguments" );
+  const size_t area = (size_t) par->w * par->h;
+  for( int i = 0; i < n; i++ )
+  {
+    int32_t s = 0;
+    if( need_rdoq && !need_rdoq[i] ) memset( q + i * area, 0, sizeof( int16_t ) * area );
+    else if( orc_rdoq_bdpcm( par->w, par->h, par->bit_depth, par->qp, par->input_bit_depth_delta, dir_mode, lambda, (const int32_t*) rates, coef + i * area, 1, q + i * area, &s ) )
       return fail( c, VVB_ERR_UNSUPPORTED, "TU shape" );
     if( abs_sum ) abs_sum[i] = s;
   }

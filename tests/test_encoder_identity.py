@@ -16,12 +16,14 @@ MOCK = os.path.join(ROOT, 'tests', 'mock', '_build', 'libvvb_mock.so')
 pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason='oracle/_ref/enc_identity not built (needs /root/reference at build time)')
 
 
-def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False, mctf=False, ts=False):
+def _encode(tmp_path, clip, W, H, F, preset, qp, lib=None, timeout=600, tu=False, rdoq=False, mctf=False, ts=False, bdpcm=False):
     out = str(tmp_path / ('b200.vvc' if lib else 'avx2.vvc'))
     cmd = [BIN, clip, str(W), str(H), str(F), str(preset), str(qp), out] + ([lib] if lib else []) + ((['all'] if mctf else ['turdoq'] if rdoq else ['tu']) if tu else [])
     env = dict(os.environ)
     if ts:
         env['VVB_ENC_TS'] = '1'              # transform skip tried on every eligible TU (the presets leave it to the screen-content detector); both arms set it
+    if bdpcm:
+        env['VVB_ENC_BDPCM'] = '1'           # ... and block DPCM next to it
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
     line = [l for l in r.stdout.splitlines() if l.startswith('ENC ')][-1]
@@ -108,6 +110,20 @@ def _identity_ts(tmp_path, W, H, F, preset, qp, lib, min_ts, timeout=900):
     return kb
 
 
+def _identity_bdpcm(tmp_path, W, H, F, preset, qp, lib, min_bdpcm, timeout=900):
+    """as _identity_ts with block DPCM enabled as well: BDPCM TUs go through xTransformSkip + forwardRDPCMB200 (-> vvb_rdoq_bdpcm) and, on the inverse side, through
+    invTransformNxNB200 (the running sums of Quant::dequant on the host, then the library's inverse of skipped transforms)"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _clips import write_clip_scc
+    clip = str(tmp_path / 'clip.yuv')
+    write_clip_scc(clip, W, H, F, seed=W + F)
+    a, ka = _encode(tmp_path, clip, W, H, F, preset, qp, ts=True, bdpcm=True)
+    b, kb = _encode(tmp_path, clip, W, H, F, preset, qp, lib, timeout, tu=True, rdoq=True, ts=True, bdpcm=True)
+    assert int(kb['tu_bdpcm']) >= min_bdpcm and int(ka['tu_bdpcm']) == 0 and int(kb['tu_rdoq_ts']) > 40, kb
+    assert len(a) > 200 and a == b, (len(a), len(b), ka, kb)
+    return kb
+
+
 def _identity(tmp_path, W, H, F, preset, qp, lib, timeout=600):
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from _clips import write_clip
@@ -165,6 +181,14 @@ def test_bitstream_identity_with_transform_skip_rdoq_on_the_oracle(tmp_path, W, 
     if not os.path.exists(MOCK):
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
     _identity_ts(tmp_path, W, H, F, preset, qp, MOCK, min_ts)
+
+
+@pytest.mark.parametrize("W,H,F,preset,qp,min_bdpcm", [(80, 44, 4, 0, 32, 100), (176, 144, 3, 0, 27, 2000), (176, 144, 2, 1, 27, 6000), (176, 144, 2, 2, 32, 7000)])
+def test_bitstream_identity_with_bdpcm_on_the_oracle(tmp_path, W, H, F, preset, qp, min_bdpcm):
+    """124 / 2 700 / 8 200 / 9 400 BDPCM TUs (forward and inverse) next to 50 - 14 000 plain transform-skipped ones: presets faster, fast, medium"""
+    if not os.path.exists(MOCK):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'tests', 'mock')])
+    _identity_bdpcm(tmp_path, W, H, F, preset, qp, MOCK, min_bdpcm)
 
 
 @pytest.mark.gpu

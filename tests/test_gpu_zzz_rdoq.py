@@ -194,3 +194,61 @@ def test_rdoq_ts_binding_on_the_real_library():
     assert out.returncode == 0, out.stderr[-3000:]
     t = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq_ts']
     assert t['cases'] == 140 and t['non_empty'] > 80 and t['bad'] == [], t
+
+
+# ---- BDPCM TUs: QuantRDOQ::forwardRDPCM (vvb_rdoq_bdpcm); inverse side = host running sums + vvb_inv_trquant of skipped transforms (verified kernel)
+@first_hardware_run
+def test_gpu_rdoq_bdpcm_golden(gpu, golden_rdoq):
+    g = golden_rdoq
+    rows = C.rdoq_ts_cases()
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row)[None]
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, transform_skip=True, input_bit_depth_delta=delta, is_chroma=comp > 0)
+        r = gpu.eng.rdoq_bdpcm(par, gpu.eng.rdoq_ts_rates(g['ts_rates'][i]), coef, lam1000 / 1000.0, 1 + (seed & 1))
+        assert np.array_equal(r['q'][0], g['bdq_%d' % i]) and int(r['abs_sum'][0]) == int(g['bd_abs_sum'][i]), (i, [int(v) for v in row])
+        nonzero += int(r['abs_sum'][0] > 0)
+    assert nonzero > 70
+
+
+@first_hardware_run
+def test_gpu_rdoq_bdpcm_batches_vs_oracle(gpu, golden_rdoq):
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    rs = np.random.RandomState(80)
+    for (w, h, n, qp, lam, bd, dm) in ((4, 4, 40000, 32, 57.3, 10, 1), (8, 8, 20000, 27, 30.0, 10, 2), (16, 16, 5000, 37, 120.0, 10, 1), (32, 32, 1200, 22, 11.7, 10, 2), (32, 8, 3000, 42, 800.0, 8, 1)):
+        amp = rs.choice([2, 6, 20, 60, 200, 1023], size=(n, 1, 1))
+        resi = (rs.laplace(0, 1.0, size=(n, h, w)) * amp / 3.0).astype(np.int64)
+        resi[rs.rand(n, h, w) < 0.4] = 0
+        lim = (1 << bd) - 1
+        coef = np.clip(resi, -lim, lim).astype(np.int32)
+        rates_flat = np.ascontiguousarray(g['ts_rates'][int(rs.randint(len(g['ts_rates'])))])
+        par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, transform_skip=True)
+        r = gpu.eng.rdoq_bdpcm(par, gpu.eng.rdoq_ts_rates(rates_flat), coef, lam, dm)
+        q = np.zeros((n, h, w), dtype=np.int16); s = np.zeros(n, dtype=np.int32)
+        assert O.orc_rdoq_bdpcm(w, h, bd, qp, 0, dm, lam, P(rates_flat), P(coef), n, P(q), P(s)) == 0
+        assert np.array_equal(r['q'], q), (w, h, int((r['q'] != q).any(axis=(1, 2)).sum()))
+        assert np.array_equal(r['abs_sum'], s) and (s > 0).sum() > n // 10, (w, h, int((s > 0).sum()))
+
+
+@first_hardware_run
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')), reason='oracle/_ref/enc_identity not built')
+@pytest.mark.parametrize("W,H,F,preset,qp,min_bdpcm", [(80, 44, 4, 0, 32, 100), (176, 144, 3, 0, 27, 2000)])
+def test_bitstream_identity_with_bdpcm_on_the_gpu(tmp_path, W, H, F, preset, qp, min_bdpcm):
+    import vvenc_b200._lib as VL
+    from test_encoder_identity import _identity_bdpcm
+    kb = _identity_bdpcm(tmp_path, W, H, F, preset, qp, VL.LIB_PATH, min_bdpcm, timeout=1500)
+    print('encoder identity with BDPCM on the GPU:', W, H, F, preset, kb)
+
+
+@first_hardware_run
+@pytest.mark.skipif(not have_ref(), reason='oracle/_ref not built')
+def test_rdoq_bdpcm_binding_on_the_real_library():
+    """forwardRDPCMB200 next to QuantRDOQ::forwardRDPCM, and the inverse path of the BDPCM levels through invTransformNxNB200 next to TrQuant::invTransformNxN"""
+    import vvenc_b200._lib as VL
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_integration_host_run.py'), VL.LIB_PATH, 'rdoq'], capture_output=True, text=True, timeout=400)
+    assert out.returncode == 0, out.stderr[-3000:]
+    b = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq_bdpcm']
+    assert b['cases'] == 140 and b['non_empty'] > 70 and b['bad'] == [], b

@@ -107,3 +107,5 @@ def test_rdoq_binding_equals_the_member():
     assert r['cases'] == 224 and r['non_empty'] > 100 and r['non_empty_with_hiding'] > 40 and r['bad'] == [], r
     t = res['rdoq_ts']                          # rateDistOptQuantTSB200 vs QuantRDOQ::rateDistOptQuantTS
     assert t['cases'] == 140 and t['non_empty'] > 80 and t['bad'] == [], t
+    b = res['rdoq_bdpcm']                       # forwardRDPCMB200 vs QuantRDOQ::forwardRDPCM, and the inverse path of the BDPCM levels (invTransformNxNB200 vs the member)
+    assert b['cases'] == 140 and b['non_empty'] > 70 and b['bad'] == [], b

@@ -183,3 +183,22 @@ def test_oracle_rdoq_ts_golden(golden_rdoq):
         assert np.array_equal(q, g['tsq_%d' % i]) and s.value == int(g['ts_abs_sum'][i]), (i, [int(v) for v in row])
         nonzero += int(s.value > 0)
     assert nonzero > 80
+
+
+def test_oracle_rdoq_bdpcm_golden(golden_rdoq):
+    """QuantRDOQ::forwardRDPCM (BDPCM TUs): the restatement against the levels / absSum the reference produced on the transform-skip rows, direction 1 + (seed & 1)"""
+    import ctypes
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    rows = C.rdoq_ts_cases()
+    nonzero = 0
+    for i, row in enumerate(rows):
+        w, h, bd, qp, lam1000, amp, kind, comp, intra, delta, init_id, seed = [int(v) for v in row]
+        coef = C.rdoq_ts_inputs(row)
+        rates = np.ascontiguousarray(g['ts_rates'][i])
+        q = np.zeros((h, w), dtype=np.int16); s = ctypes.c_int32()
+        assert O.orc_rdoq_bdpcm(w, h, bd, qp, delta, 1 + (seed & 1), lam1000 / 1000.0, P(rates), P(coef), 1, P(q), ctypes.byref(s)) == 0
+        assert np.array_equal(q, g['bdq_%d' % i]) and s.value == int(g['bd_abs_sum'][i]), (i, [int(v) for v in row])
+        nonzero += int(s.value > 0)
+    assert nonzero > 70

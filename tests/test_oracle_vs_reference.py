@@ -591,6 +591,39 @@ def test_rdoq_ts_against_the_reference_member(opt):
 
 
 @pytest.mark.parametrize("opt", [0, 1])
+def test_rdoq_bdpcm_against_the_reference_member(opt):
+    """QuantRDOQ::forwardRDPCM (BDPCM TUs: horizontal and vertical direction) on the probe's TU rig against the restatement: the reconstruction chain (xDequantSample of the
+    level just chosen + its prediction), the BDPCM context variants, the member's scanPos-indexed refresh after a zeroed group; same inputs as the transform-skip test"""
+    import ctypes
+    from _libs import dq_oracle, refshim, P
+    O = dq_oracle(); R = refshim()
+    R.refshim_set_simd(b'AVX2' if opt else b'SCALAR')
+    rs = np.random.RandomState(950 + opt)
+    n = 0; nonzero = 0
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (8, 4), (4, 16), (32, 8), (16, 32), (32, 16), (4, 32), (8, 16), (16, 4)]:
+        for bd in (10, 8):
+            for qp in (17, 22, 27, 32, 37, 42, 51, 2):
+                for trial in range(6):
+                    lam = float(rs.choice([3.0, 11.7, 30.0, 57.3, 120.0, 800.0, 4000.0]))
+                    amp = int(rs.choice([2, 6, 20, 60, 200, 1023]))
+                    kind = trial % 3
+                    if kind == 0: resi = rs.randint(-amp, amp + 1, size=(h, w))
+                    elif kind == 1: resi = rs.laplace(0, amp / 3.0 + 0.5, size=(h, w)).astype(np.int64)
+                    else:
+                        resi = rs.randint(-amp, amp + 1, size=(h, w)); resi[rs.rand(h, w) < 0.7] = 0
+                    coef = (np.clip(resi, -1023, 1023) << ((5 if bd == 10 else 7) if trial & 1 else 0)).astype(np.int32)
+                    comp = int(rs.randint(2)); delta = int(rs.choice([0, 0, 2])) if bd == 10 else 0; dm = 1 + int(rs.randint(2))
+                    qR = np.zeros((h, w), np.int16); sR = ctypes.c_int32(); rates = np.zeros(44, np.int32)
+                    assert R.refshim_rdoq_bdpcm(comp, P(coef), w, h, bd, qp, delta, 1, dm, lam, int(rs.randint(17, 52)), trial % 3, P(qR), ctypes.byref(sR), P(rates)) == 0
+                    qO = np.zeros((h, w), np.int16); sO = ctypes.c_int32()
+                    assert O.orc_rdoq_bdpcm(w, h, bd, qp, delta, dm, lam, P(rates), P(coef), 1, P(qO), ctypes.byref(sO)) == 0
+                    assert np.array_equal(qO, qR) and sO.value == sR.value, (w, h, bd, qp, comp, delta, dm, lam, amp, kind, int((qO != qR).sum()))
+                    n += 1; nonzero += int(sR.value > 0)
+    R.refshim_set_simd(b'AVX2')
+    assert n == 1152 and nonzero > 700, (n, nonzero)
+
+
+@pytest.mark.parametrize("opt", [0, 1])
 def test_transform_skip_and_chroma_against_the_reference(opt):
     """TrQuant::xTransformSkip + Quant::quant with the transform-skip QP (floor 4 + 6 * internalMinusInputBitDepth, no transform shift), Quant::xNeedRDOQ in full
     (dependent-quantisation QP only for non-skipped transforms, the transform shift it keeps for skipped ones, 256 for chroma components), Quant::dequant +

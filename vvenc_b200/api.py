@@ -323,6 +323,16 @@ class CostEngine:
         self._chk(self.lib.vvb_rdoq_ts(self.h, ctypes.byref(par), float(lam), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s)))
         return dict(q=q, abs_sum=s)
 
+    def rdoq_bdpcm(self, par, rates, coef, lam, dir_mode, need_rdoq=None):
+        """QuantRDOQ::forwardRDPCM for n BDPCM TUs of one shape (dir_mode 1 horizontal, 2 vertical): coef int32 [n][h][w] (the residual) -> dict(q, abs_sum)"""
+        coef = np.ascontiguousarray(coef, dtype=np.int32)
+        n = coef.shape[0]
+        q = np.zeros((n, par.h, par.w), dtype=np.int16)
+        s = np.zeros(n, dtype=np.int32)
+        nr = None if need_rdoq is None else np.ascontiguousarray(need_rdoq, dtype=np.uint8)
+        self._chk(self.lib.vvb_rdoq_bdpcm(self.h, ctypes.byref(par), float(lam), int(dir_mode), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s)))
+        return dict(q=q, abs_sum=s)
+
     # ---- inverse path / fused TU round trip
     def inv_trquant(self, par, q):
         """TrQuant::invTransformNxN for n compact level blocks q [n][h][w] -> residual int16 [n][h][w]"""

@@ -1696,6 +1696,56 @@ int vvb_rdoq_ts( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, const vvb_r
   return VVB_OK;
 }
 
+// BDPCM TUs: QuantRDOQ::forwardRDPCM
+int vvb_rdoq_bdpcm_dev( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, int dirMode, const vvb_rdoq_ts_rates* rates, const int32_t* dCoef, const uint8_t* dNeedRdoq, int n, int16_t* dQ,
+                        int32_t* dAbsSum )
+{
+  if( !ctx || !par || !rates || !dCoef || !dQ || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( dirMode < 1 || dirMode > 2 ) return fail( ctx, VVB_ERR_ARG, "dir_mode 1 (horizontal) or 2 (vertical)" );
+  if( !vvbrq::rq_ts_shape_ok( par->w, par->h ) ) return fail( ctx, VVB_ERR_UNSUPPORTED, "BDPCM: TU sides 4, 8, 16 or 32" );
+  if( par->bit_depth != 8 && par->bit_depth != 10 ) return fail( ctx, VVB_ERR_UNSUPPORTED, "bit depth 8 or 10" );
+  if( par->input_bit_depth_delta < 0 || par->input_bit_depth_delta > 8 ) return fail( ctx, VVB_ERR_ARG, "input_bit_depth_delta 0..8" );
+  if( !( lambda > 0.0 ) ) return fail( ctx, VVB_ERR_ARG, "lambda must be greater than 0" );
+  if( n == 0 ) return VVB_OK;
+  CU( cudaSetDevice( ctx->device ) );
+  int baseQp = std::max( 0, std::min( 63 + 6 * ( par->bit_depth - 8 ), par->qp + 6 * ( par->bit_depth - 8 ) ) );
+  baseQp = std::max( baseQp, 4 + 6 * par->input_bit_depth_delta );
+  RqTsLaunch L = {};
+  L.par = vvbrq::rq_ts_init_par( par->w, par->h, par->bit_depth, baseQp, lambda );
+  const vvbrq::RqBdpcmPar B = vvbrq::rq_bdpcm_init_par( dirMode, baseQp );
+  int lw = 0, lh = 0;
+  while( ( 1 << lw ) < par->w ) lw++;
+  while( ( 1 << lh ) < par->h ) lh++;
+  L.scan = ctx->d_scan + 25 * 1024 + ( ( lw - 2 ) * 5 + ( lh - 2 ) ) * 1024;
+  L.numScan = par->w * par->h;
+  vvbrq::RqTsRates r;
+  memcpy( &r, rates, sizeof( r ) );
+  const int blocks = std::min( ( n + VVB_RQ_THREADS - 1 ) / VVB_RQ_THREADS, ctx->numSMs * 8 );
+  void* arena; int rc;
+  if( ( rc = scratch( ctx, 5, (size_t) blocks * VVB_RQ_THREADS * par->w * par->h * sizeof( int32_t ), &arena ) ) ) return rc;
+  rdoq_bdpcm_kernel<<<blocks, VVB_RQ_THREADS, 0, ctx->stream>>>( L, B, r, dCoef, dNeedRdoq, n, dQ, dAbsSum, (int32_t*) arena );
+  CHECK_LAUNCH( "rdoq_bdpcm_kernel" );
+  return VVB_OK;
+}
+
+int vvb_rdoq_bdpcm( vvb_ctx* ctx, const vvb_tu_par* par, double lambda, int dirMode, const vvb_rdoq_ts_rates* rates, const int32_t* coef, const uint8_t* needRdoq, int n, int16_t* q,
+                    int32_t* absSum )
+{
+  if( !ctx || !par || !rates || !coef || !q || n < 0 ) return fail( ctx, VVB_ERR_ARG, "bad arguments" );
+  if( n == 0 ) return VVB_OK;
+  const size_t area = (size_t) par->w * par->h;
+  void *dC, *dQ, *dM; int rc;
+  if( ( rc = scratch( ctx, 2, (size_t) n * area * 4, &dC ) ) || ( rc = scratch( ctx, 1, (size_t) n * area * 2, &dQ ) ) || ( rc = scratch( ctx, 3, (size_t) n * 8, &dM ) ) ) return rc;
+  int32_t* dSum = (int32_t*) dM; uint8_t* dNr = (uint8_t*)( dSum + n );
+  CU( cudaMemcpyAsync( dC, coef, (size_t) n * area * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( needRdoq ) CU( cudaMemcpyAsync( dNr, needRdoq, (size_t) n, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( ( rc = vvb_rdoq_bdpcm_dev( ctx, par, lambda, dirMode, rates, (const int32_t*) dC, needRdoq ? dNr : nullptr, n, (int16_t*) dQ, dSum ) ) ) return rc;
+  CU( cudaMemcpyAsync( q, dQ, (size_t) n * area * 2, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( absSum ) CU( cudaMemcpyAsync( absSum, dSum, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  CU( endCall( ctx ) );
+  return VVB_OK;
+}
+
 // the per-call constants as the device call derives them (for bindings / tests): quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos
 int vvb_rdoq_constants( const vvb_tu_par* par, const vvb_rdoq_par* rq, int32_t out[7] )
 {

@@ -810,4 +810,186 @@ VVB_HD void rq_ts_quant_tu( const RqTsPar& P, const RqTsRates& R, const int32_t*
   *absSumOut = absSum;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------------------------------------------
+// BDPCM: QuantRDOQ::forwardRDPCM (CommonLib/QuantRDOQ.cpp:1338-1562), the quantiser of a transform-skipped TU whose CU carries a block-DPCM direction (1 horizontal, 2 vertical).
+// The routine of rq_ts_quant_tu with three differences: what is quantised is the residual minus the RECONSTRUCTED left / upper neighbour (xDequantSample :1564-1576 of the level
+// just chosen plus its own prediction, kept in fullCoeff), the contexts take their BDPCM variants (greater-1: numPos 3; sign: + 3; no neighbour-based level mapping), and only
+// the rounded level and the one below are tried.  fullCoeff: w * h int32 of scratch per TU.  One quirk is kept on purpose: when a group is zeroed out, the member refreshes
+// m_fullCoeff at index scanPos instead of blkPos (:1539) -- the reconstruction other positions predict from is the one the member has.
+struct RqBdpcmPar
+{
+  int32_t dirMode;                   // tu.cu->bdpcmM[chType]: 1 horizontal, 2 vertical
+  int32_t dqScale;                   // g_invQuantScales[0][ qp.rem( true ) ], :1383
+  int32_t dqRightShift;              // IQUANT_SHIFT - qp.per( true ), :1382
+  int32_t pad;
+};
+
+VVB_HD int32_t rq_dequant_sample( int level, const RqBdpcmPar& B )          // xDequantSample, :1564-1576
+{
+  if( B.dqRightShift > 0 )
+  {
+    const int32_t qAdd = (int32_t) 1 << ( B.dqRightShift - 1 );
+    return (int32_t)( ( (int32_t) level * B.dqScale + qAdd ) >> B.dqRightShift );
+  }
+  return (int32_t)( ( (int32_t) level * B.dqScale ) * ( 1 << -B.dqRightShift ) );
+}
+
+VVB_HD void rq_bdpcm_quant_tu( const RqTsPar& P, const RqBdpcmPar& B, const RqTsRates& R, const int32_t* scan, const int32_t* coef, int16_t* q, int32_t* fullCoeff, int32_t* absSumOut )
+{
+  const int W = P.width, H = P.height, lw = P.log2W;
+  const int regionW = rq_min( 32, W );
+  const int lrw = ( regionW == 32 ? 5 : regionW == 16 ? 4 : regionW == 8 ? 3 : 2 );
+  const int qBits = P.qBits;
+  const int widthInGroups = W >> 2;
+  const int sbNum = ( W * H ) >> 4;
+  const uint32_t entropyCodingMaximum = ( 1u << 15 ) - 1;
+  const int dirMode = B.dirMode;
+  uint64_t sigGroupFlags = 0;
+  bool anySigCG = false;
+  int remRegBins = P.maxCtxBins;
+  int absSum = 0;
+
+  for( int i = 0; i < W * H; i++ ) { q[i] = 0; fullCoeff[i] = 0; }       // :1368-1370
+
+  for( int sbId = 0; sbId < sbNum; sbId++ )
+  {
+    const int cgRaster = scan[sbId << 4], cgX = ( cgRaster & ( regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int subSetPos = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
+    const int sigLeft  = cgX > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - 1 ) ) & 1 ) : 0;
+    const int sigAbove = cgY > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - widthInGroups ) ) & 1 ) : 0;
+    const int32_t* fbSigGroup = R.sigGroupBits[sigLeft + sigAbove];
+
+    int noCoeffCoded = 0;
+    double baseCost = 0.0;
+    double d64CodedLevelandDist = 0.0, d64UncodedDist = 0.0, d64SigCost = 0.0;
+    int iNumSbbCtxBins = 0;
+
+    for( int scanPosInSB = 0; scanPosInSB <= 15; scanPosInSB++ )
+    {
+      const int scanPos = ( sbId << 4 ) + scanPosInSB;
+      const int raster = scan[scanPos], posX = raster & ( regionW - 1 ), posY = raster >> lrw;
+      const int blkPos = ( posY << lw ) + posX;
+      const int posS = ( 1 == dirMode ) ? posX : posY;
+      const int posNb = ( 1 == dirMode ) ? ( posX - 1 ) + posY * W : posX + ( posY - 1 ) * W;
+      const int32_t predCoeff = ( 0 != posS ) ? fullCoeff[posNb] : 0;
+
+      const int64_t tmpLevel = (int64_t) rq_abs( coef[blkPos] - predCoeff ) * P.quantScale;
+      const int64_t cap = (int64_t) INT32_MAX - ( (int64_t) 1 << ( qBits - 1 ) );
+      const int32_t levelDouble = (int32_t)( tmpLevel < cap ? tmpLevel : cap );
+      const uint32_t roundAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( (uint32_t)( levelDouble + ( (int32_t) 1 << ( qBits - 1 ) ) ) >> qBits ) );
+      const uint32_t minAbsLevel = roundAbsLevel > 1 ? roundAbsLevel - 1 : 1;
+      uint32_t coeffLevels[3];
+      int testedLevels = 0;
+      coeffLevels[testedLevels++] = roundAbsLevel;
+      if( minAbsLevel != roundAbsLevel ) coeffLevels[testedLevels++] = minAbsLevel;
+
+      const double dErr0 = (double) levelDouble;
+      const double costCoeff0 = dErr0 * dErr0 * P.errorScale;
+
+      const int rightPixel = posX > 0 ? q[blkPos - 1] : 0;
+      const int belowPixel = posY > 0 ? q[blkPos - W] : 0;
+      const int numPos = ( rightPixel != 0 ) + ( belowPixel != 0 );
+      const int32_t* fbSig = R.sigBits[numPos];                  // sigCtxIdAbsTS has no BDPCM variant
+      const int32_t* fbGt1 = R.lrg1Bits[3];                      // lrg1CtxIdAbsTS( ., ., bdpcm ): numPos = 3
+      int signCtx;
+      if( ( rightPixel == 0 && belowPixel == 0 ) || ( rightPixel * belowPixel ) < 0 ) signCtx = 0;
+      else if( rightPixel >= 0 && belowPixel >= 0 ) signCtx = 1;
+      else signCtx = 2;
+      const int32_t* fbSign = R.signBits[signCtx + 3];           // signCtxIdAbsTS( ., ., bdpcm ): + 3
+      const int sign = coef[blkPos] - predCoeff < 0 ? 1 : 0;
+      const uint32_t goRiceParam = 1;
+      const bool lastCoeff = scanPosInSB == 15 && noCoeffCoded == 0;
+
+      double costCoeff, costSig = 0.0;
+      uint32_t cLevel = 0;
+      int numUsedCtxBins = 0;
+      {
+        double currCostSig = 0;
+        int numBestCtxBin = 0;
+        bool done = false;
+        if( !lastCoeff && coeffLevels[0] < 3 )
+        {
+          if( remRegBins >= 4 ) costSig = P.lambda * (double) fbSig[0];
+          else                  costSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+          costCoeff = costCoeff0 + costSig;
+          if( remRegBins >= 4 ) numUsedCtxBins++;
+          if( coeffLevels[0] == 0 ) done = true;
+        }
+        else costCoeff = 1.7e+308;
+        if( !done )
+        {
+          if( !lastCoeff )
+          {
+            if( remRegBins >= 4 ) currCostSig = P.lambda * (double) fbSig[1];
+            else                  currCostSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+            if( coeffLevels[0] >= 3 && remRegBins >= 4 ) numUsedCtxBins++;
+          }
+          for( int errorInd = 1; errorInd <= testedLevels; errorInd++ )
+          {
+            const int absLevel = (int) coeffLevels[errorInd - 1];
+            const double dErr = (double)( levelDouble - ( (int32_t) absLevel << qBits ) );
+            const double levelError = dErr * dErr * P.errorScale;
+            int numCtxBins = 0;                                   // deriveModCoeff( ., ., absLevel, bdpcm != 0 ) leaves the level as it is
+            double dCurrCost = levelError + P.lambda * (double) rq_ts_level_rate( R, (uint32_t) absLevel, remRegBins, fbSign, fbGt1, numCtxBins, sign, goRiceParam );
+            if( remRegBins >= 4 ) dCurrCost += currCostSig;
+            if( dCurrCost < costCoeff ) { cLevel = (uint32_t) absLevel; costCoeff = dCurrCost; costSig = currCostSig; numBestCtxBin = numCtxBins; }
+          }
+          numUsedCtxBins += numBestCtxBin;
+        }
+      }
+
+      remRegBins -= numUsedCtxBins;
+      iNumSbbCtxBins += numUsedCtxBins;
+      if( cLevel > 0 ) noCoeffCoded++;
+      q[blkPos] = (int16_t)( sign ? -(int) cLevel : (int) cLevel );
+      fullCoeff[blkPos] = rq_dequant_sample( q[blkPos], B ) + predCoeff;          // :1491-1492
+      baseCost   += costCoeff;
+      d64SigCost += costSig;
+      if( q[blkPos] )
+      {
+        sigGroupFlags |= cgBit;
+        d64CodedLevelandDist += costCoeff - costSig;
+        d64UncodedDist       += costCoeff0;
+      }
+    }
+
+    if( !( sigGroupFlags & cgBit ) )
+    {
+      baseCost += P.lambda * (double) fbSigGroup[0] - d64SigCost;
+      remRegBins += iNumSbbCtxBins;
+    }
+    else if( sbId != sbNum - 1 || anySigCG )
+    {
+      double costZeroSB = baseCost;
+      baseCost   += P.lambda * (double) fbSigGroup[1];
+      costZeroSB += P.lambda * (double) fbSigGroup[0];
+      costZeroSB += d64UncodedDist;
+      costZeroSB -= d64CodedLevelandDist;
+      costZeroSB -= d64SigCost;
+      if( costZeroSB < baseCost )
+      {
+        sigGroupFlags &= ~cgBit;
+        baseCost = costZeroSB;
+        remRegBins += iNumSbbCtxBins;
+        for( int p = 0; p <= 15; p++ )
+        {
+          const int scanPos = ( sbId << 4 ) + p;
+          const int raster = scan[scanPos], posX = raster & ( regionW - 1 ), posY = raster >> lrw;
+          const int blkPos = ( posY << lw ) + posX;
+          const int posS = ( 1 == dirMode ) ? posX : posY;
+          const int posNb = ( 1 == dirMode ) ? ( posX - 1 ) + posY * W : posX + ( posY - 1 ) * W;
+          fullCoeff[scanPos] = ( 0 != posS ) ? fullCoeff[posNb] : 0;              // the member indexes by scanPos here (:1539)
+          q[blkPos] = 0;
+        }
+      }
+      else anySigCG = true;
+    }
+  }
+
+  for( int i = 0; i < W * H; i++ ) absSum += rq_abs( q[i] );
+  *absSumOut = absSum;
+}
+
 } // namespace vvbrq

@@ -85,6 +85,15 @@ inline RqTsPar rq_ts_init_par( int w, int h, int bitDepth, int qpTs, double lamb
   return p;
 }
 
+// BDPCM (QuantRDOQ::forwardRDPCM, QuantRDOQ.cpp:1381-1383): the dequantiser of the reconstruction the next position predicts from
+inline RqBdpcmPar rq_bdpcm_init_par( int dirMode, int qpTs )
+{
+  static const int invQuantScales[6] = { 40, 45, 51, 57, 64, 72 };                               // g_invQuantScales[0], Rom.cpp:1396-1400
+  RqBdpcmPar b;
+  b.dirMode = dirMode; b.dqScale = invQuantScales[qpTs % 6]; b.dqRightShift = 6 - qpTs / 6; b.pad = 0;      // IQUANT_SHIFT = 6
+  return b;
+}
+
 // scan position -> raster index inside the scanned region (row pitch min( 32, w )): grouped 4x4 up-right diagonal scan (Rom.cpp:1098-1136, 1236-1284)
 inline void rq_build_scan( int w, int h, int32_t* out /* min(32,w) * min(32,h) */ )
 {

@@ -76,4 +76,32 @@ __global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_ts_kernel( const __grid
   }
 }
 
+// BDPCM variant (rq_bdpcm_quant_tu): the reconstruction the next position predicts from (w * h int32 per TU) lives in a global arena indexed by thread slot, like the
+// level buffers of the DepQuant kernel
+__global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_bdpcm_kernel( const __grid_constant__ RqTsLaunch L, const __grid_constant__ vvbrq::RqBdpcmPar B, const __grid_constant__ vvbrq::RqTsRates rates,
+                                                                       const int32_t* __restrict__ coef, const uint8_t* __restrict__ needRdoq, int n,
+                                                                       int16_t* __restrict__ q, int32_t* __restrict__ absSum, int32_t* __restrict__ arena )
+{
+  __shared__ vvbrq::RqTsRates sRates;
+  __shared__ int32_t sScan[1024];
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>( &rates );
+    int32_t* dst = reinterpret_cast<int32_t*>( &sRates );
+    for( int i = threadIdx.x; i < (int)( sizeof( vvbrq::RqTsRates ) / 4 ); i += blockDim.x ) dst[i] = src[i];
+    for( int i = threadIdx.x; i < L.numScan; i += blockDim.x ) sScan[i] = L.scan[i];
+  }
+  __syncthreads();
+  const int area = L.par.width * L.par.height;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t* full = arena + (size_t) slot * area;
+  for( int tu = slot; tu < n; tu += gridDim.x * blockDim.x )
+  {
+    int16_t* qt = q + (size_t) tu * area;
+    int32_t sum = 0;
+    if( needRdoq && !needRdoq[tu] ) { for( int i = 0; i < area; i++ ) qt[i] = 0; }
+    else vvbrq::rq_bdpcm_quant_tu( L.par, B, sRates, sScan, coef + (size_t) tu * area, qt, full, &sum );
+    if( absSum ) absSum[tu] = sum;
+  }
+}
+
 } // namespace vvb
