@@ -311,6 +311,9 @@ int vvb_rdoq    ( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, c
                   int16_t* q, int32_t* abs_sum, int32_t* last_pos );
 int vvb_rdoq_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, const vvb_rdoq_rates* rates, const int32_t* dev_coef, const uint8_t* dev_need_rdoq, int n,
                   int16_t* dev_q, int32_t* dev_abs_sum, int32_t* dev_last_pos );
+/* kernel of vvb_rdoq: 1 (default) = the template of a position is gathered from its five neighbours when the position is visited; 2 = the templates are accumulated in the level slots of the
+ * positions not visited yet (what the reference's m_tplBuf bookkeeping does) and lambda * bits of the frequent cases comes from per-call tables.  Same results. */
+int vvb_set_rdoq_engine( vvb_ctx* ctx, int engine );
 /* the constants the call derives (no device needed): out = quantScale, errScale, qBits, useThres, remRegBins, numCG, firstScanPos (QuantRDOQ2.cpp:518-559, 573-583) */
 int vvb_rdoq_constants( const vvb_tu_par* par, const vvb_rdoq_par* rq, int32_t out[7] );
 

@@ -32,6 +32,24 @@ int orc_rdoq( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int s
   return 0;
 }
 
+// the second engine of the same routine (accumulated templates, cost tables): same arguments, same results
+int orc_rdoq_v2( int w, int h, int bitDepth, int qp, int isChroma, int lfnst, int sbtZeroOut, int signHiding, double lambda, int thrVal, const int32_t* rates,
+                 const int32_t* coef, int n, int16_t* q, int32_t* absSum, int32_t* lastPos )
+{
+  if( !rq_shape_ok( w, h ) ) return -1;
+  int qpInternal = qp + 6 * ( bitDepth - 8 );
+  qpInternal = qpInternal < 0 ? 0 : qpInternal > 63 + 6 * ( bitDepth - 8 ) ? 63 + 6 * ( bitDepth - 8 ) : qpInternal;
+  const RqPar p = rq_init_par( w, h, bitDepth, qpInternal, lfnst, sbtZeroOut, signHiding, isChroma, lambda, thrVal );
+  RqRates r; memcpy( &r, rates, sizeof( r ) );
+  const RqCost c = rq_init_cost( p, r );
+  std::vector<int32_t> scan( 1024 );
+  rq_build_scan( w, h, scan.data() );
+  uint8_t cgIdx[64];
+  rq_build_cg_index( scan.data(), w, h, cgIdx );
+  for( int i = 0; i < n; i++ ) rq_quant_tu_v2( p, r, c, scan.data(), cgIdx, coef + (size_t) i * w * h, q + (size_t) i * w * h, absSum + i, lastPos + i );
+  return 0;
+}
+
 // transform-skipped TUs (QuantRDOQ::rateDistOptQuantTS): rates = the 44 int32 of vvb_rdoq_ts_rates; qp: CU QP (luma) or mapped chroma QP minus qpBdOffset; inputDelta =
 // sps.internalMinusInputBitDepth (the QP floor of skipped transforms)
 int orc_rdoq_ts( int w, int h, int bitDepth, int qp, int inputDelta, double lambda, const int32_t* rates, const int32_t* coef, int n, int16_t* q, int32_t* absSum )

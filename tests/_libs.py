@@ -54,6 +54,7 @@ def dq_oracle():
         # oracle/rdoq_oracle.cpp (vvenc_b200/csrc/rdoq_core.h compiled for the CPU) lives in the same library
         L.orc_rdoq.argtypes = [ctypes.c_int] * 8 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_rdoq_constants.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
+        L.orc_rdoq_v2.argtypes = L.orc_rdoq.argtypes
         L.orc_rdoq_ts.argtypes = [ctypes.c_int] * 5 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_rdoq_ts_constants.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_rdoq_bdpcm.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

@@ -381,3 +381,5 @@ int vvb_rdoq_bdpcm( vvb_ctx* c, const vvb_tu_par* par, double lambda, int dir_mo
   c->calls++;
   return VVB_OK;
 }
+
+int vvb_set_rdoq_engine( vvb_ctx* c, int engine ) { if( !c || engine < 1 || engine > 2 ) return VVB_ERR_ARG; return VVB_OK; }   /* kernel choice of the real library: nothing to do here */

@@ -252,3 +252,36 @@ def test_rdoq_bdpcm_binding_on_the_real_library():
     assert out.returncode == 0, out.stderr[-3000:]
     b = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('RESULT ')][-1][len('RESULT '):])['rdoq_bdpcm']
     assert b['cases'] == 140 and b['non_empty'] > 70 and b['bad'] == [], b
+
+
+# ---- second engine of vvb_rdoq (vvb_set_rdoq_engine 2: accumulated templates + cost tables; rq_quant_tu_v2 is pinned on the CPU against the member like the first engine)
+@first_hardware_run
+def test_gpu_rdoq_second_engine_vs_golden_and_first_engine(gpu, golden_rdoq):
+    from _libs import dq_oracle, P
+    O = dq_oracle()
+    g = golden_rdoq
+    gpu.eng.set_rdoq_engine(2)
+    try:
+        nonzero = 0
+        for i, row in enumerate(C.rdoq_cases()):
+            w, h, bd, qp, lam1000, scale, decay10, comp, lf, sbt, intra, sh, cb, thr, init_id, seed = [int(v) for v in row]
+            par = gpu.eng.tu_par(w, h, 0, 0, bd, qp, sign_hiding=bool(sh), lfnst_idx=lf, is_chroma=comp > 0)
+            r = gpu.eng.rdoq(par, gpu.eng.rdoq_rates(g['rates'][i]), C.rdoq_inputs(row)[None], lam1000 / 1000.0, thr, sbt)
+            assert np.array_equal(r['q'][0], g['q_%d' % i]) and (int(r['abs_sum'][0]), int(r['last_pos'][0])) == tuple(int(v) for v in g['meta'][i]), (i, [int(v) for v in row])
+            nonzero += int(r['last_pos'][0] >= 0)
+        assert nonzero > 100
+        rs = np.random.RandomState(81)
+        luma_rows = [i for i, r in enumerate(g['cases']) if int(r[7]) == 0]
+        for (w, h, n, qp, lam, sbt, lf, sh) in ((4, 4, 60000, 32, 57.3, 0, 0, 1), (8, 8, 30000, 27, 30.0, 0, 1, 0), (16, 16, 6000, 37, 120.0, 0, 0, 1), (32, 32, 1500, 32, 57.3, 1, 0, 1), (64, 64, 300, 22, 11.7, 0, 0, 0), (16, 64, 500, 32, 30.0, 0, 2, 1)):
+            scale = rs.choice([3, 10, 40, 150, 600, 2500], size=(n, 1, 1))
+            coef = rs.laplace(0, 1.0, size=(n, h, w)) * scale * (1.0 / (1 + np.add.outer(np.arange(h), np.arange(w))) ** 0.7)
+            coef = np.clip(coef, -32768, 32767).astype(np.int32)
+            coef[:, :, 32:] = 0; coef[:, 32:, :] = 0
+            rates_flat = np.ascontiguousarray(g['rates'][luma_rows[int(rs.randint(len(luma_rows)))]])
+            par = gpu.eng.tu_par(w, h, 0, 0, 10, qp, sign_hiding=bool(sh), lfnst_idx=lf)
+            r2 = gpu.eng.rdoq(par, gpu.eng.rdoq_rates(rates_flat), coef, lam, 8, sbt)
+            q = np.zeros((n, h, w), dtype=np.int16); s = np.zeros(n, dtype=np.int32); l = np.zeros(n, dtype=np.int32)
+            assert O.orc_rdoq(w, h, 10, qp, 0, lf, sbt, sh, lam, 8, P(rates_flat), P(coef), n, P(q), P(s), P(l)) == 0
+            assert np.array_equal(r2['q'], q) and np.array_equal(r2['abs_sum'], s) and np.array_equal(r2['last_pos'], l), (w, h, int((r2['q'] != q).any(axis=(1, 2)).sum()))
+    finally:
+        gpu.eng.set_rdoq_engine(1)

@@ -157,6 +157,9 @@ def test_oracle_rdoq_golden(golden_rdoq):
         assert O.orc_rdoq(w, h, bd, qp, int(comp > 0), lf, sbt, sh, lam1000 / 1000.0, thr, P(rates), P(coef), 1, P(q), ctypes.byref(s), ctypes.byref(l)) == 0
         assert np.array_equal(q, g['q_%d' % i]), (i, [int(v) for v in row])
         assert (s.value, l.value) == tuple(int(v) for v in g['meta'][i]), (i, [int(v) for v in row])
+        q2 = np.zeros((h, w), dtype=np.int16); s2 = ctypes.c_int32(); l2 = ctypes.c_int32()                  # second engine
+        assert O.orc_rdoq_v2(w, h, bd, qp, int(comp > 0), lf, sbt, sh, lam1000 / 1000.0, thr, P(rates), P(coef), 1, P(q2), ctypes.byref(s2), ctypes.byref(l2)) == 0
+        assert np.array_equal(q2, g['q_%d' % i]) and (s2.value, l2.value) == tuple(int(v) for v in g['meta'][i]), ('engine 2', i, [int(v) for v in row])
         nonzero += int(l.value >= 0); hidden += int(sh and l.value >= 0)
     assert nonzero > 100 and hidden > 40
 

@@ -548,6 +548,9 @@ def test_rdoq_against_the_reference_member(opt):
                     qO = np.zeros((h, w), np.int16); sO = ctypes.c_int32(); lO = ctypes.c_int32()
                     assert O.orc_rdoq(w, h, bd, qp, int(comp > 0), lf, sbt, sh, lam, thr, P(rates), P(coef), 1, P(qO), ctypes.byref(sO), ctypes.byref(lO)) == 0
                     assert np.array_equal(qO, qR) and sO.value == sR.value and lO.value == lR.value, (w, h, bd, qp, comp, lf, sbt, intra, sh, cb, lam, scale, int((qO != qR).sum()))
+                    q2 = np.zeros((h, w), np.int16); s2 = ctypes.c_int32(); l2 = ctypes.c_int32()        # the second engine (accumulated templates, cost tables)
+                    assert O.orc_rdoq_v2(w, h, bd, qp, int(comp > 0), lf, sbt, sh, lam, thr, P(rates), P(coef), 1, P(q2), ctypes.byref(s2), ctypes.byref(l2)) == 0
+                    assert np.array_equal(q2, qR) and s2.value == sR.value and l2.value == lR.value, ('engine 2', w, h, bd, qp, comp, lf, sbt, intra, sh, cb, lam, scale, int((q2 != qR).sum()))
                     n += 1; nonzero += int(lR.value >= 0); hidden += int(sh and lR.value >= 0)
     R.refshim_set_simd(b'AVX2')
     assert n == 1050 and nonzero > 450 and hidden > 150, (n, nonzero, hidden)

@@ -18,6 +18,7 @@ def main():
     mult = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else []
     only = sys.argv[3] if len(sys.argv) > 3 else None
     eng = V.CostEngine(0)
+    eng.set_rdoq_engine(int(os.environ.get('VVB_RDOQ_ENGINE', '1')))          # 2: accumulated templates + cost tables (not run on hardware yet)
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', 0))
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v6_rdoq.npz'))
     row0 = [i for i, r in enumerate(g['cases']) if int(r[7]) == 0][3]

@@ -149,6 +149,7 @@ SYMBOLS = {
     'vvb_rdoq_ts_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.c_double, ctypes.POINTER(vvb_rdoq_ts_rates), c_p, c_p, c_i, c_p, c_p]),
     'vvb_rdoq_bdpcm': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.c_double, c_i, ctypes.POINTER(vvb_rdoq_ts_rates), c_p, c_p, c_i, c_p, c_p]),
     'vvb_rdoq_bdpcm_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), ctypes.c_double, c_i, ctypes.POINTER(vvb_rdoq_ts_rates), c_p, c_p, c_i, c_p, c_p]),
+    'vvb_set_rdoq_engine': (c_i, [c_p, c_i]),
     'vvb_rdoq_constants': (c_i, [ctypes.POINTER(vvb_tu_par), ctypes.POINTER(vvb_rdoq_par), c_p]),
     'vvb_inv_trquant': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),
     'vvb_inv_trquant_dev': (c_i, [c_p, ctypes.POINTER(vvb_tu_par), c_p, c_i, c_p]),

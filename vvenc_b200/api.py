@@ -282,6 +282,10 @@ class CostEngine:
         self._chk(self.lib.vvb_dep_quant(self.h, ctypes.byref(par), ctypes.byref(dq), ctypes.byref(rates), _p(coef), _p(nr), n, _p(q), _p(s), _p(lp)))
         return dict(q=q, abs_sum=s, last_pos=lp)
 
+    def set_rdoq_engine(self, engine):
+        """1 (default): templates gathered per position; 2: accumulated templates + cost tables (same results)"""
+        self._chk(self.lib.vvb_set_rdoq_engine(self.h, int(engine)))
+
     @staticmethod
     def rdoq_rates(flat):
         """vvb_rdoq_rates from 190 int32 in declaration order (sig_bits[12][2], par_bits[21][2], gt1_bits[21][2], gt2_bits[21][2], sig_group_bits[2][2],

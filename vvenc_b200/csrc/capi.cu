@@ -1627,8 +1627,22 @@ int vvb_rdoq_dev( vvb_ctx* ctx, const vvb_tu_par* par, const vvb_rdoq_par* rq, c
   static_assert( sizeof( vvbrq::RqRates ) == sizeof( vvb_rdoq_rates ) && sizeof( vvb_rdoq_rates ) == 760, "vvb_rdoq_rates mirrors RqRates" );
   memcpy( &r, rates, sizeof( r ) );
   const int blocks = std::min( ( n + VVB_RQ_THREADS - 1 ) / VVB_RQ_THREADS, ctx->numSMs * 16 );
+  if( ctx->rdoqEngine == 2 )
+  {
+    const vvbrq::RqCost c = vvbrq::rq_init_cost( L.par, r );
+    rdoq_v2_kernel<<<blocks, VVB_RQ_THREADS, 0, ctx->stream>>>( L, r, c, dCoef, dNeedRdoq, n, dQ, dAbsSum, dLastPos );
+    CHECK_LAUNCH( "rdoq_v2_kernel" );
+    return VVB_OK;
+  }
   rdoq_kernel<<<blocks, VVB_RQ_THREADS, 0, ctx->stream>>>( L, r, dCoef, dNeedRdoq, n, dQ, dAbsSum, dLastPos );
   CHECK_LAUNCH( "rdoq_kernel" );
+  return VVB_OK;
+}
+
+int vvb_set_rdoq_engine( vvb_ctx* ctx, int engine )
+{
+  if( !ctx || engine < 1 || engine > 2 ) return VVB_ERR_ARG;
+  ctx->rdoqEngine = engine;
   return VVB_OK;
 }
 

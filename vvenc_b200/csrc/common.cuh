@@ -86,6 +86,7 @@ struct vvb_ctx
   void*          itcImage[36] = {};           // the same for the inverse tensor engine
   void*          tc2Image[36] = {};           // B operand images of the raw-byte tensor engine, index ((lw - 3) * 3 + trHor) * 3 + trVer
   int            tensorTransform = 3;         // see vvb_set_tensor_transform: 0 off, 1 byte-plane engine for square 16/32/64 TUs, 2 that engine at 64x64 only, 3 raw-byte engine for square 8..64 TUs
+  int            rdoqEngine = 1;              // see vvb_set_rdoq_engine: 1 = templates gathered per position (first engine, verified on hardware), 2 = accumulated templates + cost tables
   int            dqEngine = 1;                // see vvb_set_depquant_engine: 1 = four lanes per TU (one per trellis state), 0 = one thread per TU
   int            pyramidEngine = 1;           // see vvb_set_pyramid_engine: 1 = all pyramid levels inside one CTA per root block, 0 = per-quad kernel + table sums
   int            useTma = 2;                  // see vvb_set_tma_staging: 0 off, 1 on, 2 (default) on where measured faster (blocks up to 8 wide)

@@ -552,6 +552,453 @@ VVB_HD void rq_quant_tu( const RqPar& P, const RqRates& R, const int32_t* scan, 
 #undef RQ_BLKPOS
 }
 
+// Second engine of the same routine (vvb_set_rdoq_engine 2): identical decisions, fewer instructions per coefficient.
+//  * The template of a position is not gathered from its five neighbours when the position is visited (a quarter of the executed instructions of the first engine,
+//    profiles/r02zz_src_rdoq_kernel_32x32.txt): it is ACCUMULATED, as the reference does in m_tplBuf (absVal1stPass / remAbsVal1stPass, ContextModelling.h:180-225), in the
+//    level slot of the position itself -- a position that has not been visited yet holds no level, so its slot carries ( count << 5 | sum ) of the decided neighbours; when a
+//    level is set, changed (sign-bit hiding) or cleared (group zero-out, last-position optimisation), the five positions to the left / above that are still unvisited are
+//    updated.  A position is unvisited iff its coefficient group comes earlier in the scan than the group being worked on (cgIdx: group raster position -> group scan index).
+//  * lambda * bits of the significance flags and of the levels 1..3 with context-coded bins come from tables computed once per call (RqCost, same double product).
+struct RqCost
+{
+  int64_t sig[12][2];                // xiGetICost( sigBits[ctx][bin] )
+  int64_t lvl[21][3];                // xiGetICRateCost( 1 / 2 / 3, ... ) with remRegBins >= 4 for greater-1 / parity / greater-2 context offset ctx
+};
+#define VVB_RQ_ENC( L ) ( ( L ) ? 32 + rq_min( 4 + ( ( L ) & 1 ), ( L ) ) : 0 )
+// add `delta` to the accumulators of the unvisited dependents of (x, y): every dependent when ALL is set (the position itself is being visited: everything to its left /
+// above is still ahead), else only those in groups that come earlier in the scan than group `curCG`
+#define VVB_RQ_DEPS( q, W, x, y, delta, ALL, cgIdx, wInGroups, curCG ) { int16_t* pq_ = ( q ) + ( y ) * ( W ) + ( x ); \
+  if( ( y ) > 1 && ( ( ALL ) || cgIdx[( ( ( y ) - 2 ) >> 2 ) * ( wInGroups ) + ( ( x ) >> 2 )] < ( curCG ) ) ) pq_[-2 * ( W )] = (int16_t)( pq_[-2 * ( W )] + ( delta ) ); \
+  if( ( y ) > 0 && ( x ) > 0 && ( ( ALL ) || cgIdx[( ( ( y ) - 1 ) >> 2 ) * ( wInGroups ) + ( ( ( x ) - 1 ) >> 2 )] < ( curCG ) ) ) pq_[-( W ) - 1] = (int16_t)( pq_[-( W ) - 1] + ( delta ) ); \
+  if( ( y ) > 0 && ( ( ALL ) || cgIdx[( ( ( y ) - 1 ) >> 2 ) * ( wInGroups ) + ( ( x ) >> 2 )] < ( curCG ) ) ) pq_[-( W )] = (int16_t)( pq_[-( W )] + ( delta ) ); \
+  if( ( x ) > 1 && ( ( ALL ) || cgIdx[( ( y ) >> 2 ) * ( wInGroups ) + ( ( ( x ) - 2 ) >> 2 )] < ( curCG ) ) ) pq_[-2] = (int16_t)( pq_[-2] + ( delta ) ); \
+  if( ( x ) > 0 && ( ( ALL ) || cgIdx[( ( y ) >> 2 ) * ( wInGroups ) + ( ( ( x ) - 1 ) >> 2 )] < ( curCG ) ) ) pq_[-1] = (int16_t)( pq_[-1] + ( delta ) ); }
+VVB_HD void rq_quant_tu_v2( const RqPar& P, const RqRates& R, const RqCost& C, const int32_t* scan, const uint8_t* cgIdx, const int32_t* coef, int16_t* q, int32_t* absSumOut, int32_t* lastPosOut )
+{
+  const int W = P.width, H = P.height, lw = P.log2W;
+  const int lrw = ( P.regionW == 32 ? 5 : P.regionW == 16 ? 4 : P.regionW == 8 ? 3 : 2 );
+  const bool bSBH = P.signHiding != 0, luma = P.isChroma == 0;
+  const int iQBits = P.qBits, quantScale = P.quantScale;
+  const int iQOffset = 1 << ( iQBits - 1 );
+  const cost_t iErrScale = P.errScale;
+  const int widthInGroups = rq_min( 32, W ) >> 2, heightInGroups = rq_min( 32, H ) >> 2;
+#define RQ_BLKPOS( sp ) ( ( ( scan[sp] >> lrw ) << lw ) + ( scan[sp] & ( P.regionW - 1 ) ) )
+
+  for( int i = 0; i < W * H; i++ ) q[i] = 0;                      // :513
+
+#define RQ_LVL_COST( L, par_, gt1_, gt2_, rrb_, grz_, grp_ ) ( ( ( rrb_ ) >= 4 && (uint32_t)( L ) - 1u < 3u ) ? C.lvl[ctxOffset][(uint32_t)( L ) - 1u] : rq_level_rate_cost( P, ( L ), par_, gt1_, gt2_, rrb_, grz_, grp_ ) )
+  cost_t piCostCoeff[16], piCostSig[16], piCostCoeff0[16], piCostDeltaSBH[16];
+  int    piAddSBH[16];
+  for( int i = 0; i < 16; i++ ) { piCostCoeff[i] = 0; piCostSig[i] = 0; piCostCoeff0[i] = 0; piCostDeltaSBH[i] = 0; piAddSBH[i] = 0; }
+
+  cost_t iCodedCostBlock = 0, iUncodedCostBlock = 0;
+  int    iLastScanPos = -1, lastSubSetId = -1;
+  bool   lastOptFinished = false;
+  cost_t bestTotalCost = INT64_MAX / 2;
+  int    remRegBins = P.remRegBins;
+  uint32_t goRiceParam = 0;
+  int    uiAbsSum = 0;
+  const int iCGSize = 16, iCGSizeM1 = 15, log2CGSize = 4;
+  uint64_t sigGroupFlags = 0;                                     // m_sigCoeffGroupFlag, indexed by the raster position of the group
+  int    tmplCpDiag = -1, tmplCpSum1 = -1;                        // CoeffCodingContext::m_tmplCpDiag / m_tmplCpSum1 (persist from position to position)
+
+  int iScanPos = P.firstScanPos;
+  for( ; iScanPos > 0; iScanPos-- ) if( coef[RQ_BLKPOS( iScanPos )] ) break;        // :561-567
+
+  int subSetId = iScanPos >> log2CGSize;
+  for( ; subSetId >= 0; subSetId-- )
+  {
+    int    iNZbeforePos0 = 0, uiAbsSumCG = 0;
+    cost_t iCodedCostCG = 0, iUncodedCostCG = 0;
+    int    iScanPosinCG = iScanPos & ( iCGSize - 1 );
+
+    if( iLastScanPos < 0 && iScanPos >= 16 )                      // :599-656 (the SIMD and the scalar form test the same positions: everything above iScanPos is zero)
+    {
+      bool allSmaller = true;
+      for( int xp = iScanPosinCG, xs = iScanPos; allSmaller && xp >= 0; xp--, xs-- ) allSmaller &= rq_abs( coef[RQ_BLKPOS( xs )] ) <= P.useThres;
+      if( allSmaller ) { iScanPos -= iScanPosinCG + 1; continue; }
+    }
+
+    // group position and the context of its significant-group flag (initSubblock, ContextModelling.cpp:113-133)
+    const int cgRaster = scan[subSetId << 4], cgX = ( cgRaster & ( P.regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int subSetPos = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
+    int remRegBinsStartCG = remRegBins;
+    int sigGroupCtx = 0;
+
+    bool findLast = iLastScanPos < 0;
+    for( ;; )
+    {
+      if( findLast )                                              // findlast2, :658-686
+      {
+        for( ; iScanPosinCG >= 0; iScanPosinCG--, iScanPos-- )
+        {
+          const uint32_t maxAbsLevel = (uint32_t)( ( rq_abs( coef[RQ_BLKPOS( iScanPos )] ) * quantScale + iQOffset ) >> iQBits );
+          if( maxAbsLevel ) { iLastScanPos = iScanPos; lastSubSetId = subSetId; break; }
+        }
+        findLast = false;
+      }
+      {
+        const unsigned sigRight = ( cgX + 1 ) < widthInGroups  ? (unsigned)( ( sigGroupFlags >> ( subSetPos + 1 ) ) & 1 ) : 0u;
+        const unsigned sigLower = ( cgY + 1 ) < heightInGroups ? (unsigned)( ( sigGroupFlags >> ( subSetPos + widthInGroups ) ) & 1 ) : 0u;
+        sigGroupCtx = (int)( sigRight | sigLower );
+      }
+      remRegBinsStartCG = remRegBins;
+
+      bool again = false;
+      for( ; iScanPosinCG >= 0; iScanPosinCG--, iScanPos-- )      // :697-969
+      {
+        const int raster = scan[iScanPos], posX = raster & ( P.regionW - 1 ), posY = raster >> lrw;
+        const int uiBlkPos = ( posY << lw ) + posX;
+        const int iScaledLevel = rq_abs( coef[uiBlkPos] ) * quantScale;
+        const int iAbsLevel = ( iScaledLevel + iQOffset ) >> iQBits;
+
+        int ctxIdSig = 0;
+        if( iScanPos != iLastScanPos )                            // sigCtxIdAbsWithAcc( iScanPos, 0 ), ContextModelling.h:158-178
+        {
+          const int acc = q[uiBlkPos];                                // the accumulator the decided neighbours left in this (still unvisited) slot
+          const int numPos = acc >> 5, sumAbs = acc & 31;
+          const int diag = posX + posY;
+          ctxIdSig = rq_min( ( sumAbs + 1 ) >> 1, 3 ) + ( diag < 2 ? 4 : 0 );
+          if( luma ) ctxIdSig += diag < 5 ? 4 : 0;
+          tmplCpDiag = diag; tmplCpSum1 = sumAbs - numPos;
+        }
+        int ctxOffset = 0;                                        // ctxOffsetAbs, ContextModelling.h:227-236
+        if( tmplCpDiag != -1 )
+        {
+          ctxOffset  = rq_min( tmplCpSum1, 4 ) + 1;
+          ctxOffset += ( !tmplCpDiag ? ( luma ? 15 : 5 ) : luma ? ( tmplCpDiag < 3 ? 10 : ( tmplCpDiag < 10 ? 5 : 0 ) ) : 0 );
+        }
+        const int32_t* fbPar = R.parBits[ctxOffset];
+        const int32_t* fbGt1 = R.gt1Bits[ctxOffset];
+        const int32_t* fbGt2 = R.gt2Bits[ctxOffset];
+        uint32_t goRiceZero = 0;
+
+        if( remRegBins < 4 )                                      // :731-736
+        {
+          int sum = 0;
+#define RQ_SUM( v ) { sum += ( v ); }
+          VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_SUM )
+#undef RQ_SUM
+          const int sumAbs = rq_max( rq_min( sum, 31 ), 0 );      // templateAbsSum( ., ., 0 )
+          goRiceParam = c_rqGoRicePars[sumAbs];
+          goRiceZero  = 1u << goRiceParam;                        // g_auiGoRicePosCoeff0( 0, . ), Rom.h:137-140
+        }
+
+        piCostCoeff0[iScanPosinCG] = rq_dist( iScaledLevel, iErrScale );
+
+        uint32_t uiLevel = 0;
+        if( iAbsLevel == 0 )                                      // :748-770
+        {
+          piCostSig  [iScanPosinCG] = C.sig[ctxIdSig][0];
+          piCostCoeff[iScanPosinCG] = piCostCoeff0[iScanPosinCG] + piCostSig[iScanPosinCG];
+          if( bSBH )
+          {
+            const cost_t iErr1  = iScaledLevel - ( (int64_t) 1 << iQBits );
+            const cost_t iDist1 = rq_dist( iErr1, iErrScale );
+            const cost_t iRate1 = remRegBins < 4 ? RQ_LVL_COST( 1, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam ) -
+                                                   RQ_LVL_COST( 0, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam )
+                                                 : (cost_t) fbGt1[0];
+            const cost_t iCost1 = iDist1 + iRate1 + C.sig[ctxIdSig][1];
+            piCostDeltaSBH[iScanPosinCG] = iCost1 - piCostCoeff[iScanPosinCG];
+            piAddSBH      [iScanPosinCG] = 1;
+          }
+        }
+        else
+        {
+          const int iFloor = (int)( iScaledLevel >> iQBits );
+          const int iCeil  = iFloor + 1;
+
+          if( remRegBins >= 4 && iScanPos != iLastScanPos && iCeil >= 4 )     // :777-781
+          {
+            int sum = 0;
+#define RQ_SUM( v ) { sum += ( v ); }
+            VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_SUM )
+#undef RQ_SUM
+            goRiceParam = c_rqGoRicePars[rq_max( rq_min( sum - 5 * 4, 31 ), 0 )];
+          }
+
+          if( iScanPos == iLastScanPos )                          // last level, :783-835
+          {
+            piCostSig[iScanPosinCG] = 0;
+            cost_t iCurrCostF = piCostCoeff0[iScanPosinCG];
+            if( iFloor )
+            {
+              const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
+              iCurrCostF = rq_dist( iErrF, iErrScale ) + RQ_LVL_COST( iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+            }
+            const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
+            const cost_t iCurrCostC = rq_dist( iErrC, iErrScale ) + RQ_LVL_COST( iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+
+            if( iCurrCostC < iCurrCostF )
+            {
+              uiLevel = iCeil;
+              piCostCoeff[iScanPosinCG] = iCurrCostC;
+              if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCurrCostF - iCurrCostC; piAddSBH[iScanPosinCG] = -1; }
+            }
+            else
+            {
+              if( iFloor == 0 )                                   // the candidate last position quantises to zero: look for the next one (goto findlast2, :816-827)
+              {
+                iLastScanPos = -1; lastSubSetId = -1;
+                iScanPos--; iScanPosinCG--;
+                again = true;
+                break;
+              }
+              uiLevel = iFloor;
+              piCostCoeff[iScanPosinCG] = iCurrCostF;
+              if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCurrCostC - iCurrCostF; piAddSBH[iScanPosinCG] = 1; }
+            }
+          }
+          else
+          {
+            const cost_t iCostSig1 = C.sig[ctxIdSig][1];
+            if( iCeil < 3 )                                       // levels 0, 1, 2, :840-907
+            {
+              const cost_t iCostSig0 = C.sig[ctxIdSig][0];
+              cost_t iBestCost = piCostCoeff0[iScanPosinCG] + iCostSig0;
+              cost_t iBestCostSig = iCostSig0;
+              cost_t iCostF = iBestCost;
+              uiLevel = 0;
+              if( iFloor == 1 )
+              {
+                const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
+                iCostF = rq_dist( iErrF, iErrScale ) + iCostSig1 + RQ_LVL_COST( iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+                if( iCostF < iBestCost )
+                {
+                  uiLevel = iFloor; iBestCost = iCostF; iBestCostSig = iCostSig1;
+                  if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iBestCost - iCostF; piAddSBH[iScanPosinCG] = -1; }
+                }
+                else
+                {
+                  if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iBestCost; piAddSBH[iScanPosinCG] = 1; }
+                }
+              }
+              const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
+              const cost_t iCostC = rq_dist( iErrC, iErrScale ) + iCostSig1 + RQ_LVL_COST( iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+              if( iCostC < iBestCost )
+              {
+                uiLevel = iCeil;
+                piCostCoeff[iScanPosinCG] = iCostC;
+                piCostSig[iScanPosinCG]   = iCostSig1;
+                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iCostC; piAddSBH[iScanPosinCG] = -1; }
+              }
+              else
+              {
+                piCostCoeff[iScanPosinCG] = iBestCost;
+                piCostSig[iScanPosinCG]   = iBestCostSig;
+                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostC - iCostF; piAddSBH[iScanPosinCG] = 1; }
+              }
+            }
+            else                                                  // levels x, x + 1, :908-940
+            {
+              const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
+              const cost_t iCostF = rq_dist( iErrF, iErrScale ) + iCostSig1 + RQ_LVL_COST( iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+              const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
+              const cost_t iCostC = rq_dist( iErrC, iErrScale ) + iCostSig1 + RQ_LVL_COST( iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+              piCostSig[iScanPosinCG] = iCostSig1;
+              if( iCostC < iCostF )
+              {
+                uiLevel = iCeil;
+                piCostCoeff[iScanPosinCG] = iCostC;
+                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iCostC; piAddSBH[iScanPosinCG] = -1; }
+              }
+              else
+              {
+                uiLevel = iFloor;
+                piCostCoeff[iScanPosinCG] = iCostF;
+                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostC - iCostF; piAddSBH[iScanPosinCG] = 1; }
+              }
+            }
+          }
+          if( uiLevel )
+          {
+            uiAbsSumCG    += uiLevel;
+            iNZbeforePos0 += iScanPosinCG;
+            sigGroupFlags |= cgBit;                               // setSigGroup
+            const int enc_ = VVB_RQ_ENC( (int) uiLevel );         // absVal1stPass
+            VVB_RQ_DEPS( q, W, posX, posY, enc_, true, cgIdx, widthInGroups, subSetId )
+          }
+        }
+        q[uiBlkPos] = (int16_t) uiLevel;                          // :942; also takes the accumulator out of a slot that stays zero
+
+        if( ( ( iScanPos & iCGSizeM1 ) == 0 ) && ( iScanPos > 0 ) ) goRiceParam = 0;                      // :956-963
+        else if( remRegBins >= 4 ) remRegBins -= ( uiLevel < 2 ? (int) uiLevel : 3 ) + ( iScanPos != iLastScanPos );
+
+        iUncodedCostCG += piCostCoeff0[iScanPosinCG];
+        iCodedCostCG   += piCostCoeff[iScanPosinCG];
+      }
+      if( !again ) break;
+      findLast = true;
+    }
+
+    //================== group significance flag, :971-1036 ===================
+    cost_t iCostCoeffGroupSig = 0;
+    if( lastSubSetId >= 0 )
+    {
+      if( subSetId )
+      {
+        const cost_t iCostCoeffGroupSig0 = rq_icost( P, R.sigGroupBits[sigGroupCtx][0] );
+        if( !( sigGroupFlags & cgBit ) )
+        {
+          iCodedCostCG = iUncodedCostCG + iCostCoeffGroupSig0;
+          iCostCoeffGroupSig = iCostCoeffGroupSig0;
+        }
+        else
+        {
+          if( subSetId < lastSubSetId )
+          {
+            const cost_t iCostCoeffGroupSig1 = rq_icost( P, R.sigGroupBits[sigGroupCtx][1] );
+            iCostCoeffGroupSig = iCostCoeffGroupSig1;
+            if( !iNZbeforePos0 ) iCodedCostCG -= piCostSig[0];
+            const cost_t iUncodedCostCGTmp = iUncodedCostCG + iCostCoeffGroupSig0;
+            iCodedCostCG += iCostCoeffGroupSig1;
+            if( iUncodedCostCGTmp < iCodedCostCG )                // cheaper as an all-zero group
+            {
+              sigGroupFlags &= ~cgBit;                            // resetSigGroup
+              iCodedCostCG = iUncodedCostCGTmp;
+              iCostCoeffGroupSig = iCostCoeffGroupSig0;
+              remRegBins = remRegBinsStartCG;
+              for( int p = iCGSize - 1; p >= 0; p-- )
+              {
+                const int rs_ = scan[subSetId * iCGSize + p], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
+                const int bp_ = ( py_ << lw ) + px_;
+                if( q[bp_] ) { const int enc_ = -VVB_RQ_ENC( (int) q[bp_] ); VVB_RQ_DEPS( q, W, px_, py_, enc_, false, cgIdx, widthInGroups, subSetId ) q[bp_] = 0; }      // remAbsVal1stPass
+              }
+              uiAbsSumCG = 0;
+              if( lastSubSetId == subSetId ) { iCodedCostCG = 0; iUncodedCostCG = 0; iLastScanPos = -1; lastSubSetId = -1; }
+            }
+          }
+          else sigGroupFlags |= cgBit;
+        }
+      }
+    }
+
+    //===== last position cost, :1038-1095 =====
+    bestTotalCost += iCodedCostCG;
+    if( !lastOptFinished )
+    {
+      if( sigGroupFlags & cgBit )
+      {
+        cost_t codedCostBlockTmp = iUncodedCostBlock + iCodedCostCG - iCostCoeffGroupSig;
+        const int startPosInCG = subSetId == lastSubSetId ? iLastScanPos % iCGSize : iCGSizeM1;
+        int newAbsSumCG = uiAbsSumCG;
+        int bestLastIdxP1 = iLastScanPos + 1;
+        for( int pc = startPosInCG; pc >= 0; pc-- )
+        {
+          const int sp = ( subSetId << log2CGSize ) + pc;
+          const int raster = scan[sp], px = raster & ( P.regionW - 1 ), py = raster >> lrw;
+          const int bp = ( py << lw ) + px;
+          if( q[bp] )
+          {
+            // xiGetCostLast, :445-461
+            const uint32_t ctxX = c_rqGroupIdx[px], ctxY = c_rqGroupIdx[py];
+            uint32_t uiCost = (uint32_t) R.lastBitsX[ctxX] + (uint32_t) R.lastBitsY[ctxY];
+            if( ctxX > 3 ) uiCost += ( 1u << RQ_SCALE_BITS ) * ( ( ctxX - 2 ) >> 1 );
+            if( ctxY > 3 ) uiCost += ( 1u << RQ_SCALE_BITS ) * ( ( ctxY - 2 ) >> 1 );
+            const cost_t iCostLast = rq_icost( P, (int) uiCost );
+            const cost_t totalCost = codedCostBlockTmp + iCostLast - piCostSig[pc];
+            if( totalCost < bestTotalCost )
+            {
+              bestLastIdxP1 = sp + 1; bestTotalCost = totalCost; lastSubSetId = subSetId; uiAbsSumCG = newAbsSumCG; uiAbsSum = 0;
+            }
+            if( q[bp] > 1 ) { lastOptFinished = true; break; }
+            newAbsSumCG -= 1;
+            codedCostBlockTmp -= piCostCoeff[pc];
+            codedCostBlockTmp += piCostCoeff0[pc];
+          }
+          else codedCostBlockTmp -= piCostSig[pc];
+        }
+        for( int sp = bestLastIdxP1; sp <= iLastScanPos; sp++ )
+        {
+          const int rs_ = scan[sp], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
+          const int bp_ = ( py_ << lw ) + px_;
+          if( q[bp_] ) { const int enc_ = -VVB_RQ_ENC( (int) q[bp_] ); VVB_RQ_DEPS( q, W, px_, py_, enc_, false, cgIdx, widthInGroups, subSetId ) q[bp_] = 0; }
+        }
+        iLastScanPos = bestLastIdxP1 - 1;
+      }
+    }
+
+    //=============== sign bit hiding, :1097-1167 ================
+    if( bSBH )
+    {
+      if( uiAbsSumCG >= 2 )
+      {
+        const int iSubPos = subSetId * iCGSize;
+        int iLastNZPosInCG = -1, iFirstNZPosInCG = iCGSize;
+        for( int n = 0; n < iCGSize; n++ ) if( q[RQ_BLKPOS( n + iSubPos )] ) { iFirstNZPosInCG = n; break; }
+        if( lastSubSetId == subSetId )
+        {
+          iLastNZPosInCG = iLastScanPos % iCGSize;
+          if( q[RQ_BLKPOS( iLastScanPos )] == 1 && piAddSBH[iLastNZPosInCG] == -1 ) piCostDeltaSBH[iLastNZPosInCG] -= ( 4 << RQ_SCALE_BITS );
+        }
+        else
+        {
+          for( int n = iCGSize - 1; n >= 0; n-- ) if( q[RQ_BLKPOS( n + iSubPos )] ) { iLastNZPosInCG = n; break; }
+        }
+        if( iLastNZPosInCG - iFirstNZPosInCG >= RQ_SBH_THRESHOLD )
+        {
+          iCodedCostCG -= rq_icost( P, 1 << RQ_SCALE_BITS );
+          const bool bSign = coef[RQ_BLKPOS( iSubPos + iFirstNZPosInCG )] < 0;
+          if( (int) bSign != ( uiAbsSumCG & 0x1 ) )
+          {
+            const int iLastPosInCG = ( lastSubSetId == subSetId ) ? iLastNZPosInCG : iCGSize - 1;
+            int64_t iMinCostDelta = INT64_MAX;
+            int iMinCostPos = -1;
+            if( q[RQ_BLKPOS( iFirstNZPosInCG + iSubPos )] > 1 ) { iMinCostDelta = piCostDeltaSBH[iFirstNZPosInCG]; iMinCostPos = iFirstNZPosInCG; }
+            for( int n = 0; n < iFirstNZPosInCG; n++ )
+              if( ( coef[RQ_BLKPOS( iSubPos + n )] < 0 ) == bSign )
+                if( piCostDeltaSBH[n] < iMinCostDelta ) { iMinCostDelta = piCostDeltaSBH[n]; iMinCostPos = n; }
+            for( int n = iFirstNZPosInCG + 1; n <= iLastPosInCG; n++ )
+              if( piCostDeltaSBH[n] < iMinCostDelta ) { iMinCostDelta = piCostDeltaSBH[n]; iMinCostPos = n; }
+            const int rs_ = scan[iMinCostPos + iSubPos], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
+            const int bp = ( py_ << lw ) + px_;
+            const int encDelta_ = VVB_RQ_ENC( (int) q[bp] + piAddSBH[iMinCostPos] ) - VVB_RQ_ENC( (int) q[bp] );
+            if( encDelta_ ) VVB_RQ_DEPS( q, W, px_, py_, encDelta_, false, cgIdx, widthInGroups, subSetId )
+            q[bp] = (int16_t)( q[bp] + piAddSBH[iMinCostPos] );
+            uiAbsSumCG   += piAddSBH[iMinCostPos];
+            iCodedCostCG += iMinCostDelta;
+          }
+        }
+      }
+    }
+
+    iCodedCostBlock   += iCodedCostCG;
+    iUncodedCostBlock += iUncodedCostCG;
+    uiAbsSum += uiAbsSumCG;
+  }
+
+  iCodedCostBlock = bestTotalCost;                                // :1177
+
+  if( iLastScanPos < 0 ) { *absSumOut = uiAbsSum; *lastPosOut = -1; return; }         // :1179-1183 (uiAbsSum is 0 there)
+
+  iUncodedCostBlock += rq_icost( P, R.cbfBits[0] );               // :1185-1226 (the caller resolved which context applies; zeros when the flag is inferred)
+  iCodedCostBlock   += rq_icost( P, R.cbfBits[1] );
+
+  if( iUncodedCostBlock <= iCodedCostBlock )                      // :1228-1233
+  {
+    for( int i = 0; i < W * H; i++ ) q[i] = 0;
+    *absSumOut = 0; *lastPosOut = -1;
+    return;
+  }
+  if( bSBH && q[RQ_BLKPOS( iLastScanPos )] == 0 )                 // :1237-1249
+  {
+    int sp = iLastScanPos - 1;
+    for( ; sp >= 0; sp-- ) if( q[RQ_BLKPOS( sp )] ) break;
+    iLastScanPos = sp;
+  }
+  for( int sp = 0; sp <= iLastScanPos; sp++ )                     // signs, :1251-1257
+  {
+    const int bp = RQ_BLKPOS( sp );
+    const int level = q[bp];
+    const int iSign = coef[bp] >> 31;
+    q[bp] = (int16_t)( ( iSign ^ level ) - iSign );
+  }
+  *absSumOut = uiAbsSum; *lastPosOut = iLastScanPos;
+#undef RQ_BLKPOS
+#undef RQ_LVL_COST
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------------------------------------------------------
 // Transform-skip residual coding: QuantRDOQ::rateDistOptQuantTS (CommonLib/QuantRDOQ.cpp:1124-1336) with xGetCodedLevelTSPred (:1578-1661), xGetICRateTS (:1663-1807) and

@@ -59,6 +59,21 @@ inline RqPar rq_init_par( int w, int h, int bitDepth, int qpInternal, int lfnst,
   return p;
 }
 
+// second engine: lambda * bits tables (the products rq_icost / rq_level_rate_cost would form per coefficient) and the group raster position -> group scan index map
+inline RqCost rq_init_cost( const RqPar& p, const RqRates& r )
+{
+  RqCost c;
+  for( int i = 0; i < 12; i++ ) for( int b = 0; b < 2; b++ ) c.sig[i][b] = rq_icost( p, r.sigBits[i][b] );
+  for( int i = 0; i < 21; i++ ) for( int l = 1; l <= 3; l++ ) c.lvl[i][l - 1] = rq_level_rate_cost( p, (uint32_t) l, r.parBits[i], r.gt1Bits[i], r.gt2Bits[i], 4, 0, 0 );
+  return c;
+}
+inline void rq_build_cg_index( const int32_t* scan, int w, int h, uint8_t out[64] )
+{
+  const int rw = w < 32 ? w : 32, rh = h < 32 ? h : 32, wg = rw >> 2, n = wg * ( rh >> 2 );
+  for( int i = 0; i < 64; i++ ) out[i] = 0;
+  for( int g = 0; g < n; g++ ) { const int r = scan[g << 4], x = r % rw, y = r / rw; out[( y >> 2 ) * wg + ( x >> 2 )] = (uint8_t) g; }
+}
+
 // transform-skip variant (QuantRDOQ::rateDistOptQuantTS, QuantRDOQ.cpp:1156-1161, 1183): qpTs = cQP.Qp( true ) = max( clip( CU QP + qpBdOffset ), 4 + 6 * internalMinusInputBitDepth )
 inline int rq_ts_shape_ok( int w, int h ) { return rq_shape_ok( w, h ) && w <= 32 && h <= 32; }
 inline RqTsPar rq_ts_init_par( int w, int h, int bitDepth, int qpTs, double lambda )

@@ -44,6 +44,47 @@ __global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_kernel( const __grid_co
   }
 }
 
+// second engine (rq_quant_tu_v2): the same launch shape; the cost tables arrive as a third by-value parameter, the group index map is derived from the staged scan order
+__global__ void __launch_bounds__( VVB_RQ_THREADS ) rdoq_v2_kernel( const __grid_constant__ RqLaunch L, const __grid_constant__ vvbrq::RqRates rates, const __grid_constant__ vvbrq::RqCost cost,
+                                                                    const int32_t* __restrict__ coef, const uint8_t* __restrict__ needRdoq, int n,
+                                                                    int16_t* __restrict__ q, int32_t* __restrict__ absSum, int32_t* __restrict__ lastPos )
+{
+  __shared__ vvbrq::RqRates sRates;
+  __shared__ vvbrq::RqCost sCost;
+  __shared__ int32_t sScan[1024];
+  __shared__ uint8_t sCgIdx[64];
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>( &rates );
+    int32_t* dst = reinterpret_cast<int32_t*>( &sRates );
+    for( int i = threadIdx.x; i < (int)( sizeof( vvbrq::RqRates ) / 4 ); i += blockDim.x ) dst[i] = src[i];
+    const int32_t* srcC = reinterpret_cast<const int32_t*>( &cost );
+    int32_t* dstC = reinterpret_cast<int32_t*>( &sCost );
+    for( int i = threadIdx.x; i < (int)( sizeof( vvbrq::RqCost ) / 4 ); i += blockDim.x ) dstC[i] = srcC[i];
+    for( int i = threadIdx.x; i < L.numScan; i += blockDim.x ) sScan[i] = L.scan[i];
+    if( threadIdx.x < 64 ) sCgIdx[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  {
+    const int wg = L.par.regionW >> 2, lrw = ( L.par.regionW == 32 ? 5 : L.par.regionW == 16 ? 4 : L.par.regionW == 8 ? 3 : 2 );
+    for( int g = threadIdx.x; g < ( L.numScan >> 4 ); g += blockDim.x )
+    {
+      const int r = sScan[g << 4], x = r & ( L.par.regionW - 1 ), y = r >> lrw;
+      sCgIdx[( y >> 2 ) * wg + ( x >> 2 )] = (uint8_t) g;
+    }
+  }
+  __syncthreads();
+  const int area = L.par.width * L.par.height;
+  for( int tu = blockIdx.x * blockDim.x + threadIdx.x; tu < n; tu += gridDim.x * blockDim.x )
+  {
+    int16_t* qt = q + (size_t) tu * area;
+    int32_t sum = 0, last = -1;
+    if( needRdoq && !needRdoq[tu] ) { for( int i = 0; i < area; i++ ) qt[i] = 0; }
+    else vvbrq::rq_quant_tu_v2( L.par, sRates, sCost, sScan, sCgIdx, coef + (size_t) tu * area, qt, &sum, &last );
+    if( absSum ) absSum[tu] = sum;
+    if( lastPos ) lastPos[tu] = last;
+  }
+}
+
 // transform-skip variant (rq_ts_quant_tu): the same shape -- one thread per TU, rate tables and scan order in shared memory, the level buffer is the output slice
 struct RqTsLaunch
 {
