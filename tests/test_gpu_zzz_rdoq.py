@@ -101,7 +101,7 @@ def test_rdoq_binding_on_the_real_library():
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'enc_identity')), reason='oracle/_ref/enc_identity not built')
-@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (176, 144, 3, 0, 27), (416, 240, 8, 0, 37)])       # the last one is BASELINE configs[0]
+@pytest.mark.parametrize("W,H,F,preset,qp", [(80, 44, 4, 0, 37), (176, 144, 3, 0, 27), pytest.param(416, 240, 8, 0, 37, marks=first_hardware_run)])       # the last one is BASELINE configs[0] (added after the hardware run of the first two)
 def test_bitstream_identity_with_the_rdoq_seam_on_the_gpu(tmp_path, W, H, F, preset, qp):
     import vvenc_b200._lib as VL
     from test_encoder_identity import _identity_rdoq
