@@ -50,7 +50,7 @@ struct RqPar
   int32_t firstScanPos;              // the position the search for the first non-zero coefficient starts from, :554-559
   int32_t quantScale;                // g_quantScales[needsSqrt2][rem], :518
   int32_t errScale;                  // xGetErrScaleCoeffNoScalingList, :519
-  int32_t qBits;                     // iQBits, :522
+  int32_t qBits;                     // qShift, :522
   int32_t useThres;                  // thres / ( quantScale << 2 ), :573-583
   int32_t remRegBins;                // ( tbAreaAfterCoefZeroOut * 28 ) >> 4, :539
   int32_t signHiding;                // bSBH
@@ -74,12 +74,12 @@ VVB_HD int rq_abs( int a ) { return a < 0 ? -a : a; }
 VVB_HD cost_t rq_icost( const RqPar& P, int rate ) { return (cost_t)( P.lambda * rate ); }                   // xiGetICost, :303-306
 
 // xiGetICRateCost, :320-401
-VVB_HD cost_t rq_level_rate_cost( const RqPar& P, uint32_t absLevel, const int32_t* par, const int32_t* gt1, const int32_t* gt2, int remRegBins, uint32_t goRiceZero, uint32_t goRice )
+VVB_HD cost_t rq_level_rate_cost( const RqPar& P, uint32_t lv, const int32_t* par, const int32_t* gt1, const int32_t* gt2, int remRegBins, uint32_t riceZero, uint32_t goRice )
 {
   cost_t rate = (cost_t) 1 << RQ_SCALE_BITS;                    // xGetIEPRate: the sign bin
   if( remRegBins < 4 )
   {
-    uint32_t symbol = ( absLevel == 0 ? goRiceZero : absLevel <= goRiceZero ? absLevel - 1 : absLevel );
+    uint32_t symbol = ( lv == 0 ? riceZero : lv <= riceZero ? lv - 1 : lv );
     uint32_t length;
     const int threshold = RQ_REMAIN_BIN_REDUCTION;
     if( symbol < ( (uint32_t) threshold << goRice ) )
@@ -98,9 +98,9 @@ VVB_HD cost_t rq_level_rate_cost( const RqPar& P, uint32_t absLevel, const int32
   else
   {
     const uint32_t cthres = 4;
-    if( absLevel >= cthres )
+    if( lv >= cthres )
     {
-      uint32_t symbol = ( absLevel - cthres ) >> 1;
+      uint32_t symbol = ( lv - cthres ) >> 1;
       uint32_t length;
       const int threshold = RQ_REMAIN_BIN_REDUCTION;
       if( symbol < ( (uint32_t) threshold << goRice ) )
@@ -116,12 +116,12 @@ VVB_HD cost_t rq_level_rate_cost( const RqPar& P, uint32_t absLevel, const int32
         rate += (cost_t)( threshold + length + 1 - goRice + length ) << RQ_SCALE_BITS;
       }
       rate += gt1[1];
-      rate += par[( absLevel - 2 ) & 1];
+      rate += par[( lv - 2 ) & 1];
       rate += gt2[1];
     }
-    else if( absLevel == 1 ) { rate += gt1[0]; }
-    else if( absLevel == 2 ) { rate += gt1[1]; rate += par[0]; rate += gt2[0]; }
-    else if( absLevel == 3 ) { rate += gt1[1]; rate += par[1]; rate += gt2[0]; }
+    else if( lv == 1 ) { rate += gt1[0]; }
+    else if( lv == 2 ) { rate += gt1[1]; rate += par[0]; rate += gt2[0]; }
+    else if( lv == 3 ) { rate += gt1[1]; rate += par[1]; rate += gt2[0]; }
     else rate = 0;
   }
   return rq_icost( P, (int) rate );
@@ -145,103 +145,103 @@ VVB_HD void rq_quant_tu( const RqPar& P, const RqRates& R, const int32_t* scan, 
   const int W = P.width, H = P.height, lw = P.log2W;
   const int lrw = ( P.regionW == 32 ? 5 : P.regionW == 16 ? 4 : P.regionW == 8 ? 3 : 2 );
   const bool bSBH = P.signHiding != 0, luma = P.isChroma == 0;
-  const int iQBits = P.qBits, quantScale = P.quantScale;
-  const int iQOffset = 1 << ( iQBits - 1 );
-  const cost_t iErrScale = P.errScale;
+  const int qShift = P.qBits, quantScale = P.quantScale;
+  const int qHalf = 1 << ( qShift - 1 );
+  const cost_t errScl = P.errScale;
   const int widthInGroups = rq_min( 32, W ) >> 2, heightInGroups = rq_min( 32, H ) >> 2;
 #define RQ_BLKPOS( sp ) ( ( ( scan[sp] >> lrw ) << lw ) + ( scan[sp] & ( P.regionW - 1 ) ) )
 
   for( int i = 0; i < W * H; i++ ) q[i] = 0;                      // :513
 
-  cost_t piCostCoeff[16], piCostSig[16], piCostCoeff0[16], piCostDeltaSBH[16];
-  int    piAddSBH[16];
-  for( int i = 0; i < 16; i++ ) { piCostCoeff[i] = 0; piCostSig[i] = 0; piCostCoeff0[i] = 0; piCostDeltaSBH[i] = 0; piAddSBH[i] = 0; }
+  cost_t keepCost[16], sigCost[16], zeroCost[16], flipDelta[16];
+  int    flipStep[16];
+  for( int i = 0; i < 16; i++ ) { keepCost[i] = 0; sigCost[i] = 0; zeroCost[i] = 0; flipDelta[i] = 0; flipStep[i] = 0; }
 
-  cost_t iCodedCostBlock = 0, iUncodedCostBlock = 0;
-  int    iLastScanPos = -1, lastSubSetId = -1;
-  bool   lastOptFinished = false;
-  cost_t bestTotalCost = INT64_MAX / 2;
+  cost_t codedTu = 0, uncodedTu = 0;
+  int    lastPosNow = -1, lastGrp = -1;
+  bool   lastSearchDone = false;
+  cost_t bestTuCost = INT64_MAX / 2;
   int    remRegBins = P.remRegBins;
-  uint32_t goRiceParam = 0;
-  int    uiAbsSum = 0;
-  const int iCGSize = 16, iCGSizeM1 = 15, log2CGSize = 4;
-  uint64_t sigGroupFlags = 0;                                     // m_sigCoeffGroupFlag, indexed by the raster position of the group
-  int    tmplCpDiag = -1, tmplCpSum1 = -1;                        // CoeffCodingContext::m_tmplCpDiag / m_tmplCpSum1 (persist from position to position)
+  uint32_t rice = 0;
+  int    sumTu = 0;
+  const int grpLen = 16, grpMask = 15, lgGrpLen = 4;
+  uint64_t grpFlags = 0;                                     // m_sigCoeffGroupFlag, indexed by the raster position of the group
+  int    tplDiag = -1, tplSum1 = -1;                        // CoeffCodingContext::m_tmplCpDiag / m_tmplCpSum1 (persist from position to position)
 
-  int iScanPos = P.firstScanPos;
-  for( ; iScanPos > 0; iScanPos-- ) if( coef[RQ_BLKPOS( iScanPos )] ) break;        // :561-567
+  int spos = P.firstScanPos;
+  for( ; spos > 0; spos-- ) if( coef[RQ_BLKPOS( spos )] ) break;        // :561-567
 
-  int subSetId = iScanPos >> log2CGSize;
-  for( ; subSetId >= 0; subSetId-- )
+  int grp = spos >> lgGrpLen;
+  for( ; grp >= 0; grp-- )
   {
-    int    iNZbeforePos0 = 0, uiAbsSumCG = 0;
-    cost_t iCodedCostCG = 0, iUncodedCostCG = 0;
-    int    iScanPosinCG = iScanPos & ( iCGSize - 1 );
+    int    nzWeight = 0, sumGrp = 0;
+    cost_t codedGrp = 0, uncodedGrp = 0;
+    int    inGrp = spos & ( grpLen - 1 );
 
-    if( iLastScanPos < 0 && iScanPos >= 16 )                      // :599-656 (the SIMD and the scalar form test the same positions: everything above iScanPos is zero)
+    if( lastPosNow < 0 && spos >= 16 )                      // :599-656 (the SIMD and the scalar form test the same positions: everything above spos is zero)
     {
-      bool allSmaller = true;
-      for( int xp = iScanPosinCG, xs = iScanPos; allSmaller && xp >= 0; xp--, xs-- ) allSmaller &= rq_abs( coef[RQ_BLKPOS( xs )] ) <= P.useThres;
-      if( allSmaller ) { iScanPos -= iScanPosinCG + 1; continue; }
+      bool allBelow = true;
+      for( int xp = inGrp, xs = spos; allBelow && xp >= 0; xp--, xs-- ) allBelow &= rq_abs( coef[RQ_BLKPOS( xs )] ) <= P.useThres;
+      if( allBelow ) { spos -= inGrp + 1; continue; }
     }
 
     // group position and the context of its significant-group flag (initSubblock, ContextModelling.cpp:113-133)
-    const int cgRaster = scan[subSetId << 4], cgX = ( cgRaster & ( P.regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
-    const int subSetPos = cgY * widthInGroups + cgX;
-    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
-    int remRegBinsStartCG = remRegBins;
-    int sigGroupCtx = 0;
+    const int cgRaster = scan[grp << 4], cgX = ( cgRaster & ( P.regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int grpRaster = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << grpRaster;
+    int binsAtGrpStart = remRegBins;
+    int grpCtx = 0;
 
-    bool findLast = iLastScanPos < 0;
+    bool seekLast = lastPosNow < 0;
     for( ;; )
     {
-      if( findLast )                                              // findlast2, :658-686
+      if( seekLast )                                              // findlast2, :658-686
       {
-        for( ; iScanPosinCG >= 0; iScanPosinCG--, iScanPos-- )
+        for( ; inGrp >= 0; inGrp--, spos-- )
         {
-          const uint32_t maxAbsLevel = (uint32_t)( ( rq_abs( coef[RQ_BLKPOS( iScanPos )] ) * quantScale + iQOffset ) >> iQBits );
-          if( maxAbsLevel ) { iLastScanPos = iScanPos; lastSubSetId = subSetId; break; }
+          const uint32_t maxAbsLevel = (uint32_t)( ( rq_abs( coef[RQ_BLKPOS( spos )] ) * quantScale + qHalf ) >> qShift );
+          if( maxAbsLevel ) { lastPosNow = spos; lastGrp = grp; break; }
         }
-        findLast = false;
+        seekLast = false;
       }
       {
-        const unsigned sigRight = ( cgX + 1 ) < widthInGroups  ? (unsigned)( ( sigGroupFlags >> ( subSetPos + 1 ) ) & 1 ) : 0u;
-        const unsigned sigLower = ( cgY + 1 ) < heightInGroups ? (unsigned)( ( sigGroupFlags >> ( subSetPos + widthInGroups ) ) & 1 ) : 0u;
-        sigGroupCtx = (int)( sigRight | sigLower );
+        const unsigned sigRight = ( cgX + 1 ) < widthInGroups  ? (unsigned)( ( grpFlags >> ( grpRaster + 1 ) ) & 1 ) : 0u;
+        const unsigned sigLower = ( cgY + 1 ) < heightInGroups ? (unsigned)( ( grpFlags >> ( grpRaster + widthInGroups ) ) & 1 ) : 0u;
+        grpCtx = (int)( sigRight | sigLower );
       }
-      remRegBinsStartCG = remRegBins;
+      binsAtGrpStart = remRegBins;
 
       bool again = false;
-      for( ; iScanPosinCG >= 0; iScanPosinCG--, iScanPos-- )      // :697-969
+      for( ; inGrp >= 0; inGrp--, spos-- )      // :697-969
       {
-        const int raster = scan[iScanPos], posX = raster & ( P.regionW - 1 ), posY = raster >> lrw;
-        const int uiBlkPos = ( posY << lw ) + posX;
-        const int iScaledLevel = rq_abs( coef[uiBlkPos] ) * quantScale;
-        const int iAbsLevel = ( iScaledLevel + iQOffset ) >> iQBits;
+        const int raster = scan[spos], posX = raster & ( P.regionW - 1 ), posY = raster >> lrw;
+        const int cpos = ( posY << lw ) + posX;
+        const int scaledMag = rq_abs( coef[cpos] ) * quantScale;
+        const int roundedLvl = ( scaledMag + qHalf ) >> qShift;
 
-        int ctxIdSig = 0;
-        if( iScanPos != iLastScanPos )                            // sigCtxIdAbsWithAcc( iScanPos, 0 ), ContextModelling.h:158-178
+        int sigCtx = 0;
+        if( spos != lastPosNow )                            // sigCtxIdAbsWithAcc( iScanPos, 0 ), ContextModelling.h:158-178
         {
           int numPos = 0, sumAbs = 0;
 #define RQ_UPD( v ) { const int a_ = ( v ); sumAbs += rq_min( 4 + ( a_ & 1 ), a_ ); numPos += a_ != 0; }
           VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_UPD )
 #undef RQ_UPD
           const int diag = posX + posY;
-          ctxIdSig = rq_min( ( sumAbs + 1 ) >> 1, 3 ) + ( diag < 2 ? 4 : 0 );
-          if( luma ) ctxIdSig += diag < 5 ? 4 : 0;
-          tmplCpDiag = diag; tmplCpSum1 = sumAbs - numPos;
+          sigCtx = rq_min( ( sumAbs + 1 ) >> 1, 3 ) + ( diag < 2 ? 4 : 0 );
+          if( luma ) sigCtx += diag < 5 ? 4 : 0;
+          tplDiag = diag; tplSum1 = sumAbs - numPos;
         }
         int ctxOffset = 0;                                        // ctxOffsetAbs, ContextModelling.h:227-236
-        if( tmplCpDiag != -1 )
+        if( tplDiag != -1 )
         {
-          ctxOffset  = rq_min( tmplCpSum1, 4 ) + 1;
-          ctxOffset += ( !tmplCpDiag ? ( luma ? 15 : 5 ) : luma ? ( tmplCpDiag < 3 ? 10 : ( tmplCpDiag < 10 ? 5 : 0 ) ) : 0 );
+          ctxOffset  = rq_min( tplSum1, 4 ) + 1;
+          ctxOffset += ( !tplDiag ? ( luma ? 15 : 5 ) : luma ? ( tplDiag < 3 ? 10 : ( tplDiag < 10 ? 5 : 0 ) ) : 0 );
         }
         const int32_t* fbPar = R.parBits[ctxOffset];
         const int32_t* fbGt1 = R.gt1Bits[ctxOffset];
         const int32_t* fbGt2 = R.gt2Bits[ctxOffset];
-        const int32_t* fbSig = R.sigBits[ctxIdSig];
-        uint32_t goRiceZero = 0;
+        const int32_t* fbSig = R.sigBits[sigCtx];
+        uint32_t riceZero = 0;
 
         if( remRegBins < 4 )                                      // :731-736
         {
@@ -250,305 +250,305 @@ VVB_HD void rq_quant_tu( const RqPar& P, const RqRates& R, const int32_t* scan, 
           VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_SUM )
 #undef RQ_SUM
           const int sumAbs = rq_max( rq_min( sum, 31 ), 0 );      // templateAbsSum( ., ., 0 )
-          goRiceParam = c_rqGoRicePars[sumAbs];
-          goRiceZero  = 1u << goRiceParam;                        // g_auiGoRicePosCoeff0( 0, . ), Rom.h:137-140
+          rice = c_rqGoRicePars[sumAbs];
+          riceZero  = 1u << rice;                        // g_auiGoRicePosCoeff0( 0, . ), Rom.h:137-140
         }
 
-        piCostCoeff0[iScanPosinCG] = rq_dist( iScaledLevel, iErrScale );
+        zeroCost[inGrp] = rq_dist( scaledMag, errScl );
 
-        uint32_t uiLevel = 0;
-        if( iAbsLevel == 0 )                                      // :748-770
+        uint32_t lvlPick = 0;
+        if( roundedLvl == 0 )                                      // :748-770
         {
-          piCostSig  [iScanPosinCG] = rq_icost( P, fbSig[0] );
-          piCostCoeff[iScanPosinCG] = piCostCoeff0[iScanPosinCG] + piCostSig[iScanPosinCG];
+          sigCost  [inGrp] = rq_icost( P, fbSig[0] );
+          keepCost[inGrp] = zeroCost[inGrp] + sigCost[inGrp];
           if( bSBH )
           {
-            const cost_t iErr1  = iScaledLevel - ( (int64_t) 1 << iQBits );
-            const cost_t iDist1 = rq_dist( iErr1, iErrScale );
-            const cost_t iRate1 = remRegBins < 4 ? rq_level_rate_cost( P, 1, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam ) -
-                                                   rq_level_rate_cost( P, 0, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam )
+            const cost_t errOne  = scaledMag - ( (int64_t) 1 << qShift );
+            const cost_t distOne = rq_dist( errOne, errScl );
+            const cost_t rateOne = remRegBins < 4 ? rq_level_rate_cost( P, 1, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice ) -
+                                                   rq_level_rate_cost( P, 0, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice )
                                                  : (cost_t) fbGt1[0];
-            const cost_t iCost1 = iDist1 + iRate1 + rq_icost( P, fbSig[1] );
-            piCostDeltaSBH[iScanPosinCG] = iCost1 - piCostCoeff[iScanPosinCG];
-            piAddSBH      [iScanPosinCG] = 1;
+            const cost_t costOne = distOne + rateOne + rq_icost( P, fbSig[1] );
+            flipDelta[inGrp] = costOne - keepCost[inGrp];
+            flipStep      [inGrp] = 1;
           }
         }
         else
         {
-          const int iFloor = (int)( iScaledLevel >> iQBits );
-          const int iCeil  = iFloor + 1;
+          const int lvlDown = (int)( scaledMag >> qShift );
+          const int lvlUp  = lvlDown + 1;
 
-          if( remRegBins >= 4 && iScanPos != iLastScanPos && iCeil >= 4 )     // :777-781
+          if( remRegBins >= 4 && spos != lastPosNow && lvlUp >= 4 )     // :777-781
           {
             int sum = 0;
 #define RQ_SUM( v ) { sum += ( v ); }
             VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_SUM )
 #undef RQ_SUM
-            goRiceParam = c_rqGoRicePars[rq_max( rq_min( sum - 5 * 4, 31 ), 0 )];
+            rice = c_rqGoRicePars[rq_max( rq_min( sum - 5 * 4, 31 ), 0 )];
           }
 
-          if( iScanPos == iLastScanPos )                          // last level, :783-835
+          if( spos == lastPosNow )                          // last level, :783-835
           {
-            piCostSig[iScanPosinCG] = 0;
-            cost_t iCurrCostF = piCostCoeff0[iScanPosinCG];
-            if( iFloor )
+            sigCost[inGrp] = 0;
+            cost_t lastDown = zeroCost[inGrp];
+            if( lvlDown )
             {
-              const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
-              iCurrCostF = rq_dist( iErrF, iErrScale ) + rq_level_rate_cost( P, iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+              const cost_t errDown = scaledMag - ( lvlDown << qShift );
+              lastDown = rq_dist( errDown, errScl ) + rq_level_rate_cost( P, lvlDown, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
             }
-            const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
-            const cost_t iCurrCostC = rq_dist( iErrC, iErrScale ) + rq_level_rate_cost( P, iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+            const cost_t errUp = scaledMag - ( lvlUp << qShift );
+            const cost_t lastUp = rq_dist( errUp, errScl ) + rq_level_rate_cost( P, lvlUp, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
 
-            if( iCurrCostC < iCurrCostF )
+            if( lastUp < lastDown )
             {
-              uiLevel = iCeil;
-              piCostCoeff[iScanPosinCG] = iCurrCostC;
-              if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCurrCostF - iCurrCostC; piAddSBH[iScanPosinCG] = -1; }
+              lvlPick = lvlUp;
+              keepCost[inGrp] = lastUp;
+              if( bSBH ) { flipDelta[inGrp] = lastDown - lastUp; flipStep[inGrp] = -1; }
             }
             else
             {
-              if( iFloor == 0 )                                   // the candidate last position quantises to zero: look for the next one (goto findlast2, :816-827)
+              if( lvlDown == 0 )                                   // the candidate last position quantises to zero: look for the next one (goto findlast2, :816-827)
               {
-                iLastScanPos = -1; lastSubSetId = -1;
-                iScanPos--; iScanPosinCG--;
+                lastPosNow = -1; lastGrp = -1;
+                spos--; inGrp--;
                 again = true;
                 break;
               }
-              uiLevel = iFloor;
-              piCostCoeff[iScanPosinCG] = iCurrCostF;
-              if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCurrCostC - iCurrCostF; piAddSBH[iScanPosinCG] = 1; }
+              lvlPick = lvlDown;
+              keepCost[inGrp] = lastDown;
+              if( bSBH ) { flipDelta[inGrp] = lastUp - lastDown; flipStep[inGrp] = 1; }
             }
           }
           else
           {
-            const cost_t iCostSig1 = rq_icost( P, fbSig[1] );
-            if( iCeil < 3 )                                       // levels 0, 1, 2, :840-907
+            const cost_t sigOne = rq_icost( P, fbSig[1] );
+            if( lvlUp < 3 )                                       // levels 0, 1, 2, :840-907
             {
-              const cost_t iCostSig0 = rq_icost( P, fbSig[0] );
-              cost_t iBestCost = piCostCoeff0[iScanPosinCG] + iCostSig0;
-              cost_t iBestCostSig = iCostSig0;
-              cost_t iCostF = iBestCost;
-              uiLevel = 0;
-              if( iFloor == 1 )
+              const cost_t sigZero = rq_icost( P, fbSig[0] );
+              cost_t bestLvlCost = zeroCost[inGrp] + sigZero;
+              cost_t bestSig = sigZero;
+              cost_t costDown = bestLvlCost;
+              lvlPick = 0;
+              if( lvlDown == 1 )
               {
-                const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
-                iCostF = rq_dist( iErrF, iErrScale ) + iCostSig1 + rq_level_rate_cost( P, iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-                if( iCostF < iBestCost )
+                const cost_t errDown = scaledMag - ( lvlDown << qShift );
+                costDown = rq_dist( errDown, errScl ) + sigOne + rq_level_rate_cost( P, lvlDown, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+                if( costDown < bestLvlCost )
                 {
-                  uiLevel = iFloor; iBestCost = iCostF; iBestCostSig = iCostSig1;
-                  if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iBestCost - iCostF; piAddSBH[iScanPosinCG] = -1; }
+                  lvlPick = lvlDown; bestLvlCost = costDown; bestSig = sigOne;
+                  if( bSBH ) { flipDelta[inGrp] = bestLvlCost - costDown; flipStep[inGrp] = -1; }
                 }
                 else
                 {
-                  if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iBestCost; piAddSBH[iScanPosinCG] = 1; }
+                  if( bSBH ) { flipDelta[inGrp] = costDown - bestLvlCost; flipStep[inGrp] = 1; }
                 }
               }
-              const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
-              const cost_t iCostC = rq_dist( iErrC, iErrScale ) + iCostSig1 + rq_level_rate_cost( P, iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-              if( iCostC < iBestCost )
+              const cost_t errUp = scaledMag - ( lvlUp << qShift );
+              const cost_t costUp = rq_dist( errUp, errScl ) + sigOne + rq_level_rate_cost( P, lvlUp, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+              if( costUp < bestLvlCost )
               {
-                uiLevel = iCeil;
-                piCostCoeff[iScanPosinCG] = iCostC;
-                piCostSig[iScanPosinCG]   = iCostSig1;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iCostC; piAddSBH[iScanPosinCG] = -1; }
+                lvlPick = lvlUp;
+                keepCost[inGrp] = costUp;
+                sigCost[inGrp]   = sigOne;
+                if( bSBH ) { flipDelta[inGrp] = costDown - costUp; flipStep[inGrp] = -1; }
               }
               else
               {
-                piCostCoeff[iScanPosinCG] = iBestCost;
-                piCostSig[iScanPosinCG]   = iBestCostSig;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostC - iCostF; piAddSBH[iScanPosinCG] = 1; }
+                keepCost[inGrp] = bestLvlCost;
+                sigCost[inGrp]   = bestSig;
+                if( bSBH ) { flipDelta[inGrp] = costUp - costDown; flipStep[inGrp] = 1; }
               }
             }
             else                                                  // levels x, x + 1, :908-940
             {
-              const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
-              const cost_t iCostF = rq_dist( iErrF, iErrScale ) + iCostSig1 + rq_level_rate_cost( P, iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-              const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
-              const cost_t iCostC = rq_dist( iErrC, iErrScale ) + iCostSig1 + rq_level_rate_cost( P, iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-              piCostSig[iScanPosinCG] = iCostSig1;
-              if( iCostC < iCostF )
+              const cost_t errDown = scaledMag - ( lvlDown << qShift );
+              const cost_t costDown = rq_dist( errDown, errScl ) + sigOne + rq_level_rate_cost( P, lvlDown, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+              const cost_t errUp = scaledMag - ( lvlUp << qShift );
+              const cost_t costUp = rq_dist( errUp, errScl ) + sigOne + rq_level_rate_cost( P, lvlUp, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+              sigCost[inGrp] = sigOne;
+              if( costUp < costDown )
               {
-                uiLevel = iCeil;
-                piCostCoeff[iScanPosinCG] = iCostC;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iCostC; piAddSBH[iScanPosinCG] = -1; }
+                lvlPick = lvlUp;
+                keepCost[inGrp] = costUp;
+                if( bSBH ) { flipDelta[inGrp] = costDown - costUp; flipStep[inGrp] = -1; }
               }
               else
               {
-                uiLevel = iFloor;
-                piCostCoeff[iScanPosinCG] = iCostF;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostC - iCostF; piAddSBH[iScanPosinCG] = 1; }
+                lvlPick = lvlDown;
+                keepCost[inGrp] = costDown;
+                if( bSBH ) { flipDelta[inGrp] = costUp - costDown; flipStep[inGrp] = 1; }
               }
             }
           }
-          q[uiBlkPos] = (int16_t) uiLevel;                        // :942
-          if( uiLevel )
+          q[cpos] = (int16_t) lvlPick;                        // :942
+          if( lvlPick )
           {
-            uiAbsSumCG    += uiLevel;
-            iNZbeforePos0 += iScanPosinCG;
-            sigGroupFlags |= cgBit;                               // setSigGroup
+            sumGrp    += lvlPick;
+            nzWeight += inGrp;
+            grpFlags |= cgBit;                               // setSigGroup
           }
         }
 
-        if( ( ( iScanPos & iCGSizeM1 ) == 0 ) && ( iScanPos > 0 ) ) goRiceParam = 0;                      // :956-963
-        else if( remRegBins >= 4 ) remRegBins -= ( uiLevel < 2 ? (int) uiLevel : 3 ) + ( iScanPos != iLastScanPos );
+        if( ( ( spos & grpMask ) == 0 ) && ( spos > 0 ) ) rice = 0;                      // :956-963
+        else if( remRegBins >= 4 ) remRegBins -= ( lvlPick < 2 ? (int) lvlPick : 3 ) + ( spos != lastPosNow );
 
-        iUncodedCostCG += piCostCoeff0[iScanPosinCG];
-        iCodedCostCG   += piCostCoeff[iScanPosinCG];
+        uncodedGrp += zeroCost[inGrp];
+        codedGrp   += keepCost[inGrp];
       }
       if( !again ) break;
-      findLast = true;
+      seekLast = true;
     }
 
     //================== group significance flag, :971-1036 ===================
-    cost_t iCostCoeffGroupSig = 0;
-    if( lastSubSetId >= 0 )
+    cost_t grpFlagCost = 0;
+    if( lastGrp >= 0 )
     {
-      if( subSetId )
+      if( grp )
       {
-        const cost_t iCostCoeffGroupSig0 = rq_icost( P, R.sigGroupBits[sigGroupCtx][0] );
-        if( !( sigGroupFlags & cgBit ) )
+        const cost_t grpFlag0 = rq_icost( P, R.sigGroupBits[grpCtx][0] );
+        if( !( grpFlags & cgBit ) )
         {
-          iCodedCostCG = iUncodedCostCG + iCostCoeffGroupSig0;
-          iCostCoeffGroupSig = iCostCoeffGroupSig0;
+          codedGrp = uncodedGrp + grpFlag0;
+          grpFlagCost = grpFlag0;
         }
         else
         {
-          if( subSetId < lastSubSetId )
+          if( grp < lastGrp )
           {
-            const cost_t iCostCoeffGroupSig1 = rq_icost( P, R.sigGroupBits[sigGroupCtx][1] );
-            iCostCoeffGroupSig = iCostCoeffGroupSig1;
-            if( !iNZbeforePos0 ) iCodedCostCG -= piCostSig[0];
-            const cost_t iUncodedCostCGTmp = iUncodedCostCG + iCostCoeffGroupSig0;
-            iCodedCostCG += iCostCoeffGroupSig1;
-            if( iUncodedCostCGTmp < iCodedCostCG )                // cheaper as an all-zero group
+            const cost_t grpFlag1 = rq_icost( P, R.sigGroupBits[grpCtx][1] );
+            grpFlagCost = grpFlag1;
+            if( !nzWeight ) codedGrp -= sigCost[0];
+            const cost_t uncodedGrpAlt = uncodedGrp + grpFlag0;
+            codedGrp += grpFlag1;
+            if( uncodedGrpAlt < codedGrp )                // cheaper as an all-zero group
             {
-              sigGroupFlags &= ~cgBit;                            // resetSigGroup
-              iCodedCostCG = iUncodedCostCGTmp;
-              iCostCoeffGroupSig = iCostCoeffGroupSig0;
-              remRegBins = remRegBinsStartCG;
-              for( int p = iCGSize - 1; p >= 0; p-- ) q[RQ_BLKPOS( subSetId * iCGSize + p )] = 0;
-              uiAbsSumCG = 0;
-              if( lastSubSetId == subSetId ) { iCodedCostCG = 0; iUncodedCostCG = 0; iLastScanPos = -1; lastSubSetId = -1; }
+              grpFlags &= ~cgBit;                            // resetSigGroup
+              codedGrp = uncodedGrpAlt;
+              grpFlagCost = grpFlag0;
+              remRegBins = binsAtGrpStart;
+              for( int p = grpLen - 1; p >= 0; p-- ) q[RQ_BLKPOS( grp * grpLen + p )] = 0;
+              sumGrp = 0;
+              if( lastGrp == grp ) { codedGrp = 0; uncodedGrp = 0; lastPosNow = -1; lastGrp = -1; }
             }
           }
-          else sigGroupFlags |= cgBit;
+          else grpFlags |= cgBit;
         }
       }
     }
 
     //===== last position cost, :1038-1095 =====
-    bestTotalCost += iCodedCostCG;
-    if( !lastOptFinished )
+    bestTuCost += codedGrp;
+    if( !lastSearchDone )
     {
-      if( sigGroupFlags & cgBit )
+      if( grpFlags & cgBit )
       {
-        cost_t codedCostBlockTmp = iUncodedCostBlock + iCodedCostCG - iCostCoeffGroupSig;
-        const int startPosInCG = subSetId == lastSubSetId ? iLastScanPos % iCGSize : iCGSizeM1;
-        int newAbsSumCG = uiAbsSumCG;
-        int bestLastIdxP1 = iLastScanPos + 1;
-        for( int pc = startPosInCG; pc >= 0; pc-- )
+        cost_t runningCost = uncodedTu + codedGrp - grpFlagCost;
+        const int startIn = grp == lastGrp ? lastPosNow % grpLen : grpMask;
+        int runningSum = sumGrp;
+        int bestEnd = lastPosNow + 1;
+        for( int pc = startIn; pc >= 0; pc-- )
         {
-          const int sp = ( subSetId << log2CGSize ) + pc;
+          const int sp = ( grp << lgGrpLen ) + pc;
           const int raster = scan[sp], px = raster & ( P.regionW - 1 ), py = raster >> lrw;
           const int bp = ( py << lw ) + px;
           if( q[bp] )
           {
             // xiGetCostLast, :445-461
             const uint32_t ctxX = c_rqGroupIdx[px], ctxY = c_rqGroupIdx[py];
-            uint32_t uiCost = (uint32_t) R.lastBitsX[ctxX] + (uint32_t) R.lastBitsY[ctxY];
-            if( ctxX > 3 ) uiCost += ( 1u << RQ_SCALE_BITS ) * ( ( ctxX - 2 ) >> 1 );
-            if( ctxY > 3 ) uiCost += ( 1u << RQ_SCALE_BITS ) * ( ( ctxY - 2 ) >> 1 );
-            const cost_t iCostLast = rq_icost( P, (int) uiCost );
-            const cost_t totalCost = codedCostBlockTmp + iCostLast - piCostSig[pc];
-            if( totalCost < bestTotalCost )
+            uint32_t lastBits = (uint32_t) R.lastBitsX[ctxX] + (uint32_t) R.lastBitsY[ctxY];
+            if( ctxX > 3 ) lastBits += ( 1u << RQ_SCALE_BITS ) * ( ( ctxX - 2 ) >> 1 );
+            if( ctxY > 3 ) lastBits += ( 1u << RQ_SCALE_BITS ) * ( ( ctxY - 2 ) >> 1 );
+            const cost_t lastCost = rq_icost( P, (int) lastBits );
+            const cost_t candCost = runningCost + lastCost - sigCost[pc];
+            if( candCost < bestTuCost )
             {
-              bestLastIdxP1 = sp + 1; bestTotalCost = totalCost; lastSubSetId = subSetId; uiAbsSumCG = newAbsSumCG; uiAbsSum = 0;
+              bestEnd = sp + 1; bestTuCost = candCost; lastGrp = grp; sumGrp = runningSum; sumTu = 0;
             }
-            if( q[bp] > 1 ) { lastOptFinished = true; break; }
-            newAbsSumCG -= 1;
-            codedCostBlockTmp -= piCostCoeff[pc];
-            codedCostBlockTmp += piCostCoeff0[pc];
+            if( q[bp] > 1 ) { lastSearchDone = true; break; }
+            runningSum -= 1;
+            runningCost -= keepCost[pc];
+            runningCost += zeroCost[pc];
           }
-          else codedCostBlockTmp -= piCostSig[pc];
+          else runningCost -= sigCost[pc];
         }
-        for( int sp = bestLastIdxP1; sp <= iLastScanPos; sp++ ) q[RQ_BLKPOS( sp )] = 0;
-        iLastScanPos = bestLastIdxP1 - 1;
+        for( int sp = bestEnd; sp <= lastPosNow; sp++ ) q[RQ_BLKPOS( sp )] = 0;
+        lastPosNow = bestEnd - 1;
       }
     }
 
     //=============== sign bit hiding, :1097-1167 ================
     if( bSBH )
     {
-      if( uiAbsSumCG >= 2 )
+      if( sumGrp >= 2 )
       {
-        const int iSubPos = subSetId * iCGSize;
-        int iLastNZPosInCG = -1, iFirstNZPosInCG = iCGSize;
-        for( int n = 0; n < iCGSize; n++ ) if( q[RQ_BLKPOS( n + iSubPos )] ) { iFirstNZPosInCG = n; break; }
-        if( lastSubSetId == subSetId )
+        const int grpBase = grp * grpLen;
+        int lastNz = -1, firstNz = grpLen;
+        for( int n = 0; n < grpLen; n++ ) if( q[RQ_BLKPOS( n + grpBase )] ) { firstNz = n; break; }
+        if( lastGrp == grp )
         {
-          iLastNZPosInCG = iLastScanPos % iCGSize;
-          if( q[RQ_BLKPOS( iLastScanPos )] == 1 && piAddSBH[iLastNZPosInCG] == -1 ) piCostDeltaSBH[iLastNZPosInCG] -= ( 4 << RQ_SCALE_BITS );
+          lastNz = lastPosNow % grpLen;
+          if( q[RQ_BLKPOS( lastPosNow )] == 1 && flipStep[lastNz] == -1 ) flipDelta[lastNz] -= ( 4 << RQ_SCALE_BITS );
         }
         else
         {
-          for( int n = iCGSize - 1; n >= 0; n-- ) if( q[RQ_BLKPOS( n + iSubPos )] ) { iLastNZPosInCG = n; break; }
+          for( int n = grpLen - 1; n >= 0; n-- ) if( q[RQ_BLKPOS( n + grpBase )] ) { lastNz = n; break; }
         }
-        if( iLastNZPosInCG - iFirstNZPosInCG >= RQ_SBH_THRESHOLD )
+        if( lastNz - firstNz >= RQ_SBH_THRESHOLD )
         {
-          iCodedCostCG -= rq_icost( P, 1 << RQ_SCALE_BITS );
-          const bool bSign = coef[RQ_BLKPOS( iSubPos + iFirstNZPosInCG )] < 0;
-          if( (int) bSign != ( uiAbsSumCG & 0x1 ) )
+          codedGrp -= rq_icost( P, 1 << RQ_SCALE_BITS );
+          const bool negFirst = coef[RQ_BLKPOS( grpBase + firstNz )] < 0;
+          if( (int) negFirst != ( sumGrp & 0x1 ) )
           {
-            const int iLastPosInCG = ( lastSubSetId == subSetId ) ? iLastNZPosInCG : iCGSize - 1;
-            int64_t iMinCostDelta = INT64_MAX;
-            int iMinCostPos = -1;
-            if( q[RQ_BLKPOS( iFirstNZPosInCG + iSubPos )] > 1 ) { iMinCostDelta = piCostDeltaSBH[iFirstNZPosInCG]; iMinCostPos = iFirstNZPosInCG; }
-            for( int n = 0; n < iFirstNZPosInCG; n++ )
-              if( ( coef[RQ_BLKPOS( iSubPos + n )] < 0 ) == bSign )
-                if( piCostDeltaSBH[n] < iMinCostDelta ) { iMinCostDelta = piCostDeltaSBH[n]; iMinCostPos = n; }
-            for( int n = iFirstNZPosInCG + 1; n <= iLastPosInCG; n++ )
-              if( piCostDeltaSBH[n] < iMinCostDelta ) { iMinCostDelta = piCostDeltaSBH[n]; iMinCostPos = n; }
-            const int bp = RQ_BLKPOS( iMinCostPos + iSubPos );
-            q[bp] = (int16_t)( q[bp] + piAddSBH[iMinCostPos] );
-            uiAbsSumCG   += piAddSBH[iMinCostPos];
-            iCodedCostCG += iMinCostDelta;
+            const int lastIn = ( lastGrp == grp ) ? lastNz : grpLen - 1;
+            int64_t minDelta = INT64_MAX;
+            int minAt = -1;
+            if( q[RQ_BLKPOS( firstNz + grpBase )] > 1 ) { minDelta = flipDelta[firstNz]; minAt = firstNz; }
+            for( int n = 0; n < firstNz; n++ )
+              if( ( coef[RQ_BLKPOS( grpBase + n )] < 0 ) == negFirst )
+                if( flipDelta[n] < minDelta ) { minDelta = flipDelta[n]; minAt = n; }
+            for( int n = firstNz + 1; n <= lastIn; n++ )
+              if( flipDelta[n] < minDelta ) { minDelta = flipDelta[n]; minAt = n; }
+            const int bp = RQ_BLKPOS( minAt + grpBase );
+            q[bp] = (int16_t)( q[bp] + flipStep[minAt] );
+            sumGrp   += flipStep[minAt];
+            codedGrp += minDelta;
           }
         }
       }
     }
 
-    iCodedCostBlock   += iCodedCostCG;
-    iUncodedCostBlock += iUncodedCostCG;
-    uiAbsSum += uiAbsSumCG;
+    codedTu   += codedGrp;
+    uncodedTu += uncodedGrp;
+    sumTu += sumGrp;
   }
 
-  iCodedCostBlock = bestTotalCost;                                // :1177
+  codedTu = bestTuCost;                                // :1177
 
-  if( iLastScanPos < 0 ) { *absSumOut = uiAbsSum; *lastPosOut = -1; return; }         // :1179-1183 (uiAbsSum is 0 there)
+  if( lastPosNow < 0 ) { *absSumOut = sumTu; *lastPosOut = -1; return; }         // :1179-1183 (sumTu is 0 there)
 
-  iUncodedCostBlock += rq_icost( P, R.cbfBits[0] );               // :1185-1226 (the caller resolved which context applies; zeros when the flag is inferred)
-  iCodedCostBlock   += rq_icost( P, R.cbfBits[1] );
+  uncodedTu += rq_icost( P, R.cbfBits[0] );               // :1185-1226 (the caller resolved which context applies; zeros when the flag is inferred)
+  codedTu   += rq_icost( P, R.cbfBits[1] );
 
-  if( iUncodedCostBlock <= iCodedCostBlock )                      // :1228-1233
+  if( uncodedTu <= codedTu )                      // :1228-1233
   {
     for( int i = 0; i < W * H; i++ ) q[i] = 0;
     *absSumOut = 0; *lastPosOut = -1;
     return;
   }
-  if( bSBH && q[RQ_BLKPOS( iLastScanPos )] == 0 )                 // :1237-1249
+  if( bSBH && q[RQ_BLKPOS( lastPosNow )] == 0 )                 // :1237-1249
   {
-    int sp = iLastScanPos - 1;
+    int sp = lastPosNow - 1;
     for( ; sp >= 0; sp-- ) if( q[RQ_BLKPOS( sp )] ) break;
-    iLastScanPos = sp;
+    lastPosNow = sp;
   }
-  for( int sp = 0; sp <= iLastScanPos; sp++ )                     // signs, :1251-1257
+  for( int sp = 0; sp <= lastPosNow; sp++ )                     // signs, :1251-1257
   {
     const int bp = RQ_BLKPOS( sp );
     const int level = q[bp];
     const int iSign = coef[bp] >> 31;
     q[bp] = (int16_t)( ( iSign ^ level ) - iSign );
   }
-  *absSumOut = uiAbsSum; *lastPosOut = iLastScanPos;
+  *absSumOut = sumTu; *lastPosOut = lastPosNow;
 #undef RQ_BLKPOS
 }
 
@@ -578,101 +578,101 @@ VVB_HD void rq_quant_tu_v2( const RqPar& P, const RqRates& R, const RqCost& C, c
   const int W = P.width, H = P.height, lw = P.log2W;
   const int lrw = ( P.regionW == 32 ? 5 : P.regionW == 16 ? 4 : P.regionW == 8 ? 3 : 2 );
   const bool bSBH = P.signHiding != 0, luma = P.isChroma == 0;
-  const int iQBits = P.qBits, quantScale = P.quantScale;
-  const int iQOffset = 1 << ( iQBits - 1 );
-  const cost_t iErrScale = P.errScale;
+  const int qShift = P.qBits, quantScale = P.quantScale;
+  const int qHalf = 1 << ( qShift - 1 );
+  const cost_t errScl = P.errScale;
   const int widthInGroups = rq_min( 32, W ) >> 2, heightInGroups = rq_min( 32, H ) >> 2;
 #define RQ_BLKPOS( sp ) ( ( ( scan[sp] >> lrw ) << lw ) + ( scan[sp] & ( P.regionW - 1 ) ) )
 
   for( int i = 0; i < W * H; i++ ) q[i] = 0;                      // :513
 
 #define RQ_LVL_COST( L, par_, gt1_, gt2_, rrb_, grz_, grp_ ) ( ( ( rrb_ ) >= 4 && (uint32_t)( L ) - 1u < 3u ) ? C.lvl[ctxOffset][(uint32_t)( L ) - 1u] : rq_level_rate_cost( P, ( L ), par_, gt1_, gt2_, rrb_, grz_, grp_ ) )
-  cost_t piCostCoeff[16], piCostSig[16], piCostCoeff0[16], piCostDeltaSBH[16];
-  int    piAddSBH[16];
-  for( int i = 0; i < 16; i++ ) { piCostCoeff[i] = 0; piCostSig[i] = 0; piCostCoeff0[i] = 0; piCostDeltaSBH[i] = 0; piAddSBH[i] = 0; }
+  cost_t keepCost[16], sigCost[16], zeroCost[16], flipDelta[16];
+  int    flipStep[16];
+  for( int i = 0; i < 16; i++ ) { keepCost[i] = 0; sigCost[i] = 0; zeroCost[i] = 0; flipDelta[i] = 0; flipStep[i] = 0; }
 
-  cost_t iCodedCostBlock = 0, iUncodedCostBlock = 0;
-  int    iLastScanPos = -1, lastSubSetId = -1;
-  bool   lastOptFinished = false;
-  cost_t bestTotalCost = INT64_MAX / 2;
+  cost_t codedTu = 0, uncodedTu = 0;
+  int    lastPosNow = -1, lastGrp = -1;
+  bool   lastSearchDone = false;
+  cost_t bestTuCost = INT64_MAX / 2;
   int    remRegBins = P.remRegBins;
-  uint32_t goRiceParam = 0;
-  int    uiAbsSum = 0;
-  const int iCGSize = 16, iCGSizeM1 = 15, log2CGSize = 4;
-  uint64_t sigGroupFlags = 0;                                     // m_sigCoeffGroupFlag, indexed by the raster position of the group
-  int    tmplCpDiag = -1, tmplCpSum1 = -1;                        // CoeffCodingContext::m_tmplCpDiag / m_tmplCpSum1 (persist from position to position)
+  uint32_t rice = 0;
+  int    sumTu = 0;
+  const int grpLen = 16, grpMask = 15, lgGrpLen = 4;
+  uint64_t grpFlags = 0;                                     // m_sigCoeffGroupFlag, indexed by the raster position of the group
+  int    tplDiag = -1, tplSum1 = -1;                        // CoeffCodingContext::m_tmplCpDiag / m_tmplCpSum1 (persist from position to position)
 
-  int iScanPos = P.firstScanPos;
-  for( ; iScanPos > 0; iScanPos-- ) if( coef[RQ_BLKPOS( iScanPos )] ) break;        // :561-567
+  int spos = P.firstScanPos;
+  for( ; spos > 0; spos-- ) if( coef[RQ_BLKPOS( spos )] ) break;        // :561-567
 
-  int subSetId = iScanPos >> log2CGSize;
-  for( ; subSetId >= 0; subSetId-- )
+  int grp = spos >> lgGrpLen;
+  for( ; grp >= 0; grp-- )
   {
-    int    iNZbeforePos0 = 0, uiAbsSumCG = 0;
-    cost_t iCodedCostCG = 0, iUncodedCostCG = 0;
-    int    iScanPosinCG = iScanPos & ( iCGSize - 1 );
+    int    nzWeight = 0, sumGrp = 0;
+    cost_t codedGrp = 0, uncodedGrp = 0;
+    int    inGrp = spos & ( grpLen - 1 );
 
-    if( iLastScanPos < 0 && iScanPos >= 16 )                      // :599-656 (the SIMD and the scalar form test the same positions: everything above iScanPos is zero)
+    if( lastPosNow < 0 && spos >= 16 )                      // :599-656 (the SIMD and the scalar form test the same positions: everything above spos is zero)
     {
-      bool allSmaller = true;
-      for( int xp = iScanPosinCG, xs = iScanPos; allSmaller && xp >= 0; xp--, xs-- ) allSmaller &= rq_abs( coef[RQ_BLKPOS( xs )] ) <= P.useThres;
-      if( allSmaller ) { iScanPos -= iScanPosinCG + 1; continue; }
+      bool allBelow = true;
+      for( int xp = inGrp, xs = spos; allBelow && xp >= 0; xp--, xs-- ) allBelow &= rq_abs( coef[RQ_BLKPOS( xs )] ) <= P.useThres;
+      if( allBelow ) { spos -= inGrp + 1; continue; }
     }
 
     // group position and the context of its significant-group flag (initSubblock, ContextModelling.cpp:113-133)
-    const int cgRaster = scan[subSetId << 4], cgX = ( cgRaster & ( P.regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
-    const int subSetPos = cgY * widthInGroups + cgX;
-    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
-    int remRegBinsStartCG = remRegBins;
-    int sigGroupCtx = 0;
+    const int cgRaster = scan[grp << 4], cgX = ( cgRaster & ( P.regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int grpRaster = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << grpRaster;
+    int binsAtGrpStart = remRegBins;
+    int grpCtx = 0;
 
-    bool findLast = iLastScanPos < 0;
+    bool seekLast = lastPosNow < 0;
     for( ;; )
     {
-      if( findLast )                                              // findlast2, :658-686
+      if( seekLast )                                              // findlast2, :658-686
       {
-        for( ; iScanPosinCG >= 0; iScanPosinCG--, iScanPos-- )
+        for( ; inGrp >= 0; inGrp--, spos-- )
         {
-          const uint32_t maxAbsLevel = (uint32_t)( ( rq_abs( coef[RQ_BLKPOS( iScanPos )] ) * quantScale + iQOffset ) >> iQBits );
-          if( maxAbsLevel ) { iLastScanPos = iScanPos; lastSubSetId = subSetId; break; }
+          const uint32_t maxAbsLevel = (uint32_t)( ( rq_abs( coef[RQ_BLKPOS( spos )] ) * quantScale + qHalf ) >> qShift );
+          if( maxAbsLevel ) { lastPosNow = spos; lastGrp = grp; break; }
         }
-        findLast = false;
+        seekLast = false;
       }
       {
-        const unsigned sigRight = ( cgX + 1 ) < widthInGroups  ? (unsigned)( ( sigGroupFlags >> ( subSetPos + 1 ) ) & 1 ) : 0u;
-        const unsigned sigLower = ( cgY + 1 ) < heightInGroups ? (unsigned)( ( sigGroupFlags >> ( subSetPos + widthInGroups ) ) & 1 ) : 0u;
-        sigGroupCtx = (int)( sigRight | sigLower );
+        const unsigned sigRight = ( cgX + 1 ) < widthInGroups  ? (unsigned)( ( grpFlags >> ( grpRaster + 1 ) ) & 1 ) : 0u;
+        const unsigned sigLower = ( cgY + 1 ) < heightInGroups ? (unsigned)( ( grpFlags >> ( grpRaster + widthInGroups ) ) & 1 ) : 0u;
+        grpCtx = (int)( sigRight | sigLower );
       }
-      remRegBinsStartCG = remRegBins;
+      binsAtGrpStart = remRegBins;
 
       bool again = false;
-      for( ; iScanPosinCG >= 0; iScanPosinCG--, iScanPos-- )      // :697-969
+      for( ; inGrp >= 0; inGrp--, spos-- )      // :697-969
       {
-        const int raster = scan[iScanPos], posX = raster & ( P.regionW - 1 ), posY = raster >> lrw;
-        const int uiBlkPos = ( posY << lw ) + posX;
-        const int iScaledLevel = rq_abs( coef[uiBlkPos] ) * quantScale;
-        const int iAbsLevel = ( iScaledLevel + iQOffset ) >> iQBits;
+        const int raster = scan[spos], posX = raster & ( P.regionW - 1 ), posY = raster >> lrw;
+        const int cpos = ( posY << lw ) + posX;
+        const int scaledMag = rq_abs( coef[cpos] ) * quantScale;
+        const int roundedLvl = ( scaledMag + qHalf ) >> qShift;
 
-        int ctxIdSig = 0;
-        if( iScanPos != iLastScanPos )                            // sigCtxIdAbsWithAcc( iScanPos, 0 ), ContextModelling.h:158-178
+        int sigCtx = 0;
+        if( spos != lastPosNow )                            // sigCtxIdAbsWithAcc( iScanPos, 0 ), ContextModelling.h:158-178
         {
-          const int acc = q[uiBlkPos];                                // the accumulator the decided neighbours left in this (still unvisited) slot
+          const int acc = q[cpos];                                // the accumulator the decided neighbours left in this (still unvisited) slot
           const int numPos = acc >> 5, sumAbs = acc & 31;
           const int diag = posX + posY;
-          ctxIdSig = rq_min( ( sumAbs + 1 ) >> 1, 3 ) + ( diag < 2 ? 4 : 0 );
-          if( luma ) ctxIdSig += diag < 5 ? 4 : 0;
-          tmplCpDiag = diag; tmplCpSum1 = sumAbs - numPos;
+          sigCtx = rq_min( ( sumAbs + 1 ) >> 1, 3 ) + ( diag < 2 ? 4 : 0 );
+          if( luma ) sigCtx += diag < 5 ? 4 : 0;
+          tplDiag = diag; tplSum1 = sumAbs - numPos;
         }
         int ctxOffset = 0;                                        // ctxOffsetAbs, ContextModelling.h:227-236
-        if( tmplCpDiag != -1 )
+        if( tplDiag != -1 )
         {
-          ctxOffset  = rq_min( tmplCpSum1, 4 ) + 1;
-          ctxOffset += ( !tmplCpDiag ? ( luma ? 15 : 5 ) : luma ? ( tmplCpDiag < 3 ? 10 : ( tmplCpDiag < 10 ? 5 : 0 ) ) : 0 );
+          ctxOffset  = rq_min( tplSum1, 4 ) + 1;
+          ctxOffset += ( !tplDiag ? ( luma ? 15 : 5 ) : luma ? ( tplDiag < 3 ? 10 : ( tplDiag < 10 ? 5 : 0 ) ) : 0 );
         }
         const int32_t* fbPar = R.parBits[ctxOffset];
         const int32_t* fbGt1 = R.gt1Bits[ctxOffset];
         const int32_t* fbGt2 = R.gt2Bits[ctxOffset];
-        uint32_t goRiceZero = 0;
+        uint32_t riceZero = 0;
 
         if( remRegBins < 4 )                                      // :731-736
         {
@@ -681,320 +681,320 @@ VVB_HD void rq_quant_tu_v2( const RqPar& P, const RqRates& R, const RqCost& C, c
           VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_SUM )
 #undef RQ_SUM
           const int sumAbs = rq_max( rq_min( sum, 31 ), 0 );      // templateAbsSum( ., ., 0 )
-          goRiceParam = c_rqGoRicePars[sumAbs];
-          goRiceZero  = 1u << goRiceParam;                        // g_auiGoRicePosCoeff0( 0, . ), Rom.h:137-140
+          rice = c_rqGoRicePars[sumAbs];
+          riceZero  = 1u << rice;                        // g_auiGoRicePosCoeff0( 0, . ), Rom.h:137-140
         }
 
-        piCostCoeff0[iScanPosinCG] = rq_dist( iScaledLevel, iErrScale );
+        zeroCost[inGrp] = rq_dist( scaledMag, errScl );
 
-        uint32_t uiLevel = 0;
-        if( iAbsLevel == 0 )                                      // :748-770
+        uint32_t lvlPick = 0;
+        if( roundedLvl == 0 )                                      // :748-770
         {
-          piCostSig  [iScanPosinCG] = C.sig[ctxIdSig][0];
-          piCostCoeff[iScanPosinCG] = piCostCoeff0[iScanPosinCG] + piCostSig[iScanPosinCG];
+          sigCost  [inGrp] = C.sig[sigCtx][0];
+          keepCost[inGrp] = zeroCost[inGrp] + sigCost[inGrp];
           if( bSBH )
           {
-            const cost_t iErr1  = iScaledLevel - ( (int64_t) 1 << iQBits );
-            const cost_t iDist1 = rq_dist( iErr1, iErrScale );
-            const cost_t iRate1 = remRegBins < 4 ? RQ_LVL_COST( 1, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam ) -
-                                                   RQ_LVL_COST( 0, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam )
+            const cost_t errOne  = scaledMag - ( (int64_t) 1 << qShift );
+            const cost_t distOne = rq_dist( errOne, errScl );
+            const cost_t rateOne = remRegBins < 4 ? RQ_LVL_COST( 1, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice ) -
+                                                   RQ_LVL_COST( 0, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice )
                                                  : (cost_t) fbGt1[0];
-            const cost_t iCost1 = iDist1 + iRate1 + C.sig[ctxIdSig][1];
-            piCostDeltaSBH[iScanPosinCG] = iCost1 - piCostCoeff[iScanPosinCG];
-            piAddSBH      [iScanPosinCG] = 1;
+            const cost_t costOne = distOne + rateOne + C.sig[sigCtx][1];
+            flipDelta[inGrp] = costOne - keepCost[inGrp];
+            flipStep      [inGrp] = 1;
           }
         }
         else
         {
-          const int iFloor = (int)( iScaledLevel >> iQBits );
-          const int iCeil  = iFloor + 1;
+          const int lvlDown = (int)( scaledMag >> qShift );
+          const int lvlUp  = lvlDown + 1;
 
-          if( remRegBins >= 4 && iScanPos != iLastScanPos && iCeil >= 4 )     // :777-781
+          if( remRegBins >= 4 && spos != lastPosNow && lvlUp >= 4 )     // :777-781
           {
             int sum = 0;
 #define RQ_SUM( v ) { sum += ( v ); }
             VVB_RQ_TEMPLATE( q, W, H, posX, posY, RQ_SUM )
 #undef RQ_SUM
-            goRiceParam = c_rqGoRicePars[rq_max( rq_min( sum - 5 * 4, 31 ), 0 )];
+            rice = c_rqGoRicePars[rq_max( rq_min( sum - 5 * 4, 31 ), 0 )];
           }
 
-          if( iScanPos == iLastScanPos )                          // last level, :783-835
+          if( spos == lastPosNow )                          // last level, :783-835
           {
-            piCostSig[iScanPosinCG] = 0;
-            cost_t iCurrCostF = piCostCoeff0[iScanPosinCG];
-            if( iFloor )
+            sigCost[inGrp] = 0;
+            cost_t lastDown = zeroCost[inGrp];
+            if( lvlDown )
             {
-              const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
-              iCurrCostF = rq_dist( iErrF, iErrScale ) + RQ_LVL_COST( iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+              const cost_t errDown = scaledMag - ( lvlDown << qShift );
+              lastDown = rq_dist( errDown, errScl ) + RQ_LVL_COST( lvlDown, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
             }
-            const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
-            const cost_t iCurrCostC = rq_dist( iErrC, iErrScale ) + RQ_LVL_COST( iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
+            const cost_t errUp = scaledMag - ( lvlUp << qShift );
+            const cost_t lastUp = rq_dist( errUp, errScl ) + RQ_LVL_COST( lvlUp, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
 
-            if( iCurrCostC < iCurrCostF )
+            if( lastUp < lastDown )
             {
-              uiLevel = iCeil;
-              piCostCoeff[iScanPosinCG] = iCurrCostC;
-              if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCurrCostF - iCurrCostC; piAddSBH[iScanPosinCG] = -1; }
+              lvlPick = lvlUp;
+              keepCost[inGrp] = lastUp;
+              if( bSBH ) { flipDelta[inGrp] = lastDown - lastUp; flipStep[inGrp] = -1; }
             }
             else
             {
-              if( iFloor == 0 )                                   // the candidate last position quantises to zero: look for the next one (goto findlast2, :816-827)
+              if( lvlDown == 0 )                                   // the candidate last position quantises to zero: look for the next one (goto findlast2, :816-827)
               {
-                iLastScanPos = -1; lastSubSetId = -1;
-                iScanPos--; iScanPosinCG--;
+                lastPosNow = -1; lastGrp = -1;
+                spos--; inGrp--;
                 again = true;
                 break;
               }
-              uiLevel = iFloor;
-              piCostCoeff[iScanPosinCG] = iCurrCostF;
-              if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCurrCostC - iCurrCostF; piAddSBH[iScanPosinCG] = 1; }
+              lvlPick = lvlDown;
+              keepCost[inGrp] = lastDown;
+              if( bSBH ) { flipDelta[inGrp] = lastUp - lastDown; flipStep[inGrp] = 1; }
             }
           }
           else
           {
-            const cost_t iCostSig1 = C.sig[ctxIdSig][1];
-            if( iCeil < 3 )                                       // levels 0, 1, 2, :840-907
+            const cost_t sigOne = C.sig[sigCtx][1];
+            if( lvlUp < 3 )                                       // levels 0, 1, 2, :840-907
             {
-              const cost_t iCostSig0 = C.sig[ctxIdSig][0];
-              cost_t iBestCost = piCostCoeff0[iScanPosinCG] + iCostSig0;
-              cost_t iBestCostSig = iCostSig0;
-              cost_t iCostF = iBestCost;
-              uiLevel = 0;
-              if( iFloor == 1 )
+              const cost_t sigZero = C.sig[sigCtx][0];
+              cost_t bestLvlCost = zeroCost[inGrp] + sigZero;
+              cost_t bestSig = sigZero;
+              cost_t costDown = bestLvlCost;
+              lvlPick = 0;
+              if( lvlDown == 1 )
               {
-                const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
-                iCostF = rq_dist( iErrF, iErrScale ) + iCostSig1 + RQ_LVL_COST( iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-                if( iCostF < iBestCost )
+                const cost_t errDown = scaledMag - ( lvlDown << qShift );
+                costDown = rq_dist( errDown, errScl ) + sigOne + RQ_LVL_COST( lvlDown, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+                if( costDown < bestLvlCost )
                 {
-                  uiLevel = iFloor; iBestCost = iCostF; iBestCostSig = iCostSig1;
-                  if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iBestCost - iCostF; piAddSBH[iScanPosinCG] = -1; }
+                  lvlPick = lvlDown; bestLvlCost = costDown; bestSig = sigOne;
+                  if( bSBH ) { flipDelta[inGrp] = bestLvlCost - costDown; flipStep[inGrp] = -1; }
                 }
                 else
                 {
-                  if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iBestCost; piAddSBH[iScanPosinCG] = 1; }
+                  if( bSBH ) { flipDelta[inGrp] = costDown - bestLvlCost; flipStep[inGrp] = 1; }
                 }
               }
-              const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
-              const cost_t iCostC = rq_dist( iErrC, iErrScale ) + iCostSig1 + RQ_LVL_COST( iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-              if( iCostC < iBestCost )
+              const cost_t errUp = scaledMag - ( lvlUp << qShift );
+              const cost_t costUp = rq_dist( errUp, errScl ) + sigOne + RQ_LVL_COST( lvlUp, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+              if( costUp < bestLvlCost )
               {
-                uiLevel = iCeil;
-                piCostCoeff[iScanPosinCG] = iCostC;
-                piCostSig[iScanPosinCG]   = iCostSig1;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iCostC; piAddSBH[iScanPosinCG] = -1; }
+                lvlPick = lvlUp;
+                keepCost[inGrp] = costUp;
+                sigCost[inGrp]   = sigOne;
+                if( bSBH ) { flipDelta[inGrp] = costDown - costUp; flipStep[inGrp] = -1; }
               }
               else
               {
-                piCostCoeff[iScanPosinCG] = iBestCost;
-                piCostSig[iScanPosinCG]   = iBestCostSig;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostC - iCostF; piAddSBH[iScanPosinCG] = 1; }
+                keepCost[inGrp] = bestLvlCost;
+                sigCost[inGrp]   = bestSig;
+                if( bSBH ) { flipDelta[inGrp] = costUp - costDown; flipStep[inGrp] = 1; }
               }
             }
             else                                                  // levels x, x + 1, :908-940
             {
-              const cost_t iErrF = iScaledLevel - ( iFloor << iQBits );
-              const cost_t iCostF = rq_dist( iErrF, iErrScale ) + iCostSig1 + RQ_LVL_COST( iFloor, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-              const cost_t iErrC = iScaledLevel - ( iCeil << iQBits );
-              const cost_t iCostC = rq_dist( iErrC, iErrScale ) + iCostSig1 + RQ_LVL_COST( iCeil, fbPar, fbGt1, fbGt2, remRegBins, goRiceZero, goRiceParam );
-              piCostSig[iScanPosinCG] = iCostSig1;
-              if( iCostC < iCostF )
+              const cost_t errDown = scaledMag - ( lvlDown << qShift );
+              const cost_t costDown = rq_dist( errDown, errScl ) + sigOne + RQ_LVL_COST( lvlDown, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+              const cost_t errUp = scaledMag - ( lvlUp << qShift );
+              const cost_t costUp = rq_dist( errUp, errScl ) + sigOne + RQ_LVL_COST( lvlUp, fbPar, fbGt1, fbGt2, remRegBins, riceZero, rice );
+              sigCost[inGrp] = sigOne;
+              if( costUp < costDown )
               {
-                uiLevel = iCeil;
-                piCostCoeff[iScanPosinCG] = iCostC;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostF - iCostC; piAddSBH[iScanPosinCG] = -1; }
+                lvlPick = lvlUp;
+                keepCost[inGrp] = costUp;
+                if( bSBH ) { flipDelta[inGrp] = costDown - costUp; flipStep[inGrp] = -1; }
               }
               else
               {
-                uiLevel = iFloor;
-                piCostCoeff[iScanPosinCG] = iCostF;
-                if( bSBH ) { piCostDeltaSBH[iScanPosinCG] = iCostC - iCostF; piAddSBH[iScanPosinCG] = 1; }
+                lvlPick = lvlDown;
+                keepCost[inGrp] = costDown;
+                if( bSBH ) { flipDelta[inGrp] = costUp - costDown; flipStep[inGrp] = 1; }
               }
             }
           }
-          if( uiLevel )
+          if( lvlPick )
           {
-            uiAbsSumCG    += uiLevel;
-            iNZbeforePos0 += iScanPosinCG;
-            sigGroupFlags |= cgBit;                               // setSigGroup
-            const int enc_ = VVB_RQ_ENC( (int) uiLevel );         // absVal1stPass
-            VVB_RQ_DEPS( q, W, posX, posY, enc_, true, cgIdx, widthInGroups, subSetId )
+            sumGrp    += lvlPick;
+            nzWeight += inGrp;
+            grpFlags |= cgBit;                               // setSigGroup
+            const int enc_ = VVB_RQ_ENC( (int) lvlPick );         // absVal1stPass
+            VVB_RQ_DEPS( q, W, posX, posY, enc_, true, cgIdx, widthInGroups, grp )
           }
         }
-        q[uiBlkPos] = (int16_t) uiLevel;                          // :942; also takes the accumulator out of a slot that stays zero
+        q[cpos] = (int16_t) lvlPick;                          // :942; also takes the accumulator out of a slot that stays zero
 
-        if( ( ( iScanPos & iCGSizeM1 ) == 0 ) && ( iScanPos > 0 ) ) goRiceParam = 0;                      // :956-963
-        else if( remRegBins >= 4 ) remRegBins -= ( uiLevel < 2 ? (int) uiLevel : 3 ) + ( iScanPos != iLastScanPos );
+        if( ( ( spos & grpMask ) == 0 ) && ( spos > 0 ) ) rice = 0;                      // :956-963
+        else if( remRegBins >= 4 ) remRegBins -= ( lvlPick < 2 ? (int) lvlPick : 3 ) + ( spos != lastPosNow );
 
-        iUncodedCostCG += piCostCoeff0[iScanPosinCG];
-        iCodedCostCG   += piCostCoeff[iScanPosinCG];
+        uncodedGrp += zeroCost[inGrp];
+        codedGrp   += keepCost[inGrp];
       }
       if( !again ) break;
-      findLast = true;
+      seekLast = true;
     }
 
     //================== group significance flag, :971-1036 ===================
-    cost_t iCostCoeffGroupSig = 0;
-    if( lastSubSetId >= 0 )
+    cost_t grpFlagCost = 0;
+    if( lastGrp >= 0 )
     {
-      if( subSetId )
+      if( grp )
       {
-        const cost_t iCostCoeffGroupSig0 = rq_icost( P, R.sigGroupBits[sigGroupCtx][0] );
-        if( !( sigGroupFlags & cgBit ) )
+        const cost_t grpFlag0 = rq_icost( P, R.sigGroupBits[grpCtx][0] );
+        if( !( grpFlags & cgBit ) )
         {
-          iCodedCostCG = iUncodedCostCG + iCostCoeffGroupSig0;
-          iCostCoeffGroupSig = iCostCoeffGroupSig0;
+          codedGrp = uncodedGrp + grpFlag0;
+          grpFlagCost = grpFlag0;
         }
         else
         {
-          if( subSetId < lastSubSetId )
+          if( grp < lastGrp )
           {
-            const cost_t iCostCoeffGroupSig1 = rq_icost( P, R.sigGroupBits[sigGroupCtx][1] );
-            iCostCoeffGroupSig = iCostCoeffGroupSig1;
-            if( !iNZbeforePos0 ) iCodedCostCG -= piCostSig[0];
-            const cost_t iUncodedCostCGTmp = iUncodedCostCG + iCostCoeffGroupSig0;
-            iCodedCostCG += iCostCoeffGroupSig1;
-            if( iUncodedCostCGTmp < iCodedCostCG )                // cheaper as an all-zero group
+            const cost_t grpFlag1 = rq_icost( P, R.sigGroupBits[grpCtx][1] );
+            grpFlagCost = grpFlag1;
+            if( !nzWeight ) codedGrp -= sigCost[0];
+            const cost_t uncodedGrpAlt = uncodedGrp + grpFlag0;
+            codedGrp += grpFlag1;
+            if( uncodedGrpAlt < codedGrp )                // cheaper as an all-zero group
             {
-              sigGroupFlags &= ~cgBit;                            // resetSigGroup
-              iCodedCostCG = iUncodedCostCGTmp;
-              iCostCoeffGroupSig = iCostCoeffGroupSig0;
-              remRegBins = remRegBinsStartCG;
-              for( int p = iCGSize - 1; p >= 0; p-- )
+              grpFlags &= ~cgBit;                            // resetSigGroup
+              codedGrp = uncodedGrpAlt;
+              grpFlagCost = grpFlag0;
+              remRegBins = binsAtGrpStart;
+              for( int p = grpLen - 1; p >= 0; p-- )
               {
-                const int rs_ = scan[subSetId * iCGSize + p], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
+                const int rs_ = scan[grp * grpLen + p], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
                 const int bp_ = ( py_ << lw ) + px_;
-                if( q[bp_] ) { const int enc_ = -VVB_RQ_ENC( (int) q[bp_] ); VVB_RQ_DEPS( q, W, px_, py_, enc_, false, cgIdx, widthInGroups, subSetId ) q[bp_] = 0; }      // remAbsVal1stPass
+                if( q[bp_] ) { const int enc_ = -VVB_RQ_ENC( (int) q[bp_] ); VVB_RQ_DEPS( q, W, px_, py_, enc_, false, cgIdx, widthInGroups, grp ) q[bp_] = 0; }      // remAbsVal1stPass
               }
-              uiAbsSumCG = 0;
-              if( lastSubSetId == subSetId ) { iCodedCostCG = 0; iUncodedCostCG = 0; iLastScanPos = -1; lastSubSetId = -1; }
+              sumGrp = 0;
+              if( lastGrp == grp ) { codedGrp = 0; uncodedGrp = 0; lastPosNow = -1; lastGrp = -1; }
             }
           }
-          else sigGroupFlags |= cgBit;
+          else grpFlags |= cgBit;
         }
       }
     }
 
     //===== last position cost, :1038-1095 =====
-    bestTotalCost += iCodedCostCG;
-    if( !lastOptFinished )
+    bestTuCost += codedGrp;
+    if( !lastSearchDone )
     {
-      if( sigGroupFlags & cgBit )
+      if( grpFlags & cgBit )
       {
-        cost_t codedCostBlockTmp = iUncodedCostBlock + iCodedCostCG - iCostCoeffGroupSig;
-        const int startPosInCG = subSetId == lastSubSetId ? iLastScanPos % iCGSize : iCGSizeM1;
-        int newAbsSumCG = uiAbsSumCG;
-        int bestLastIdxP1 = iLastScanPos + 1;
-        for( int pc = startPosInCG; pc >= 0; pc-- )
+        cost_t runningCost = uncodedTu + codedGrp - grpFlagCost;
+        const int startIn = grp == lastGrp ? lastPosNow % grpLen : grpMask;
+        int runningSum = sumGrp;
+        int bestEnd = lastPosNow + 1;
+        for( int pc = startIn; pc >= 0; pc-- )
         {
-          const int sp = ( subSetId << log2CGSize ) + pc;
+          const int sp = ( grp << lgGrpLen ) + pc;
           const int raster = scan[sp], px = raster & ( P.regionW - 1 ), py = raster >> lrw;
           const int bp = ( py << lw ) + px;
           if( q[bp] )
           {
             // xiGetCostLast, :445-461
             const uint32_t ctxX = c_rqGroupIdx[px], ctxY = c_rqGroupIdx[py];
-            uint32_t uiCost = (uint32_t) R.lastBitsX[ctxX] + (uint32_t) R.lastBitsY[ctxY];
-            if( ctxX > 3 ) uiCost += ( 1u << RQ_SCALE_BITS ) * ( ( ctxX - 2 ) >> 1 );
-            if( ctxY > 3 ) uiCost += ( 1u << RQ_SCALE_BITS ) * ( ( ctxY - 2 ) >> 1 );
-            const cost_t iCostLast = rq_icost( P, (int) uiCost );
-            const cost_t totalCost = codedCostBlockTmp + iCostLast - piCostSig[pc];
-            if( totalCost < bestTotalCost )
+            uint32_t lastBits = (uint32_t) R.lastBitsX[ctxX] + (uint32_t) R.lastBitsY[ctxY];
+            if( ctxX > 3 ) lastBits += ( 1u << RQ_SCALE_BITS ) * ( ( ctxX - 2 ) >> 1 );
+            if( ctxY > 3 ) lastBits += ( 1u << RQ_SCALE_BITS ) * ( ( ctxY - 2 ) >> 1 );
+            const cost_t lastCost = rq_icost( P, (int) lastBits );
+            const cost_t candCost = runningCost + lastCost - sigCost[pc];
+            if( candCost < bestTuCost )
             {
-              bestLastIdxP1 = sp + 1; bestTotalCost = totalCost; lastSubSetId = subSetId; uiAbsSumCG = newAbsSumCG; uiAbsSum = 0;
+              bestEnd = sp + 1; bestTuCost = candCost; lastGrp = grp; sumGrp = runningSum; sumTu = 0;
             }
-            if( q[bp] > 1 ) { lastOptFinished = true; break; }
-            newAbsSumCG -= 1;
-            codedCostBlockTmp -= piCostCoeff[pc];
-            codedCostBlockTmp += piCostCoeff0[pc];
+            if( q[bp] > 1 ) { lastSearchDone = true; break; }
+            runningSum -= 1;
+            runningCost -= keepCost[pc];
+            runningCost += zeroCost[pc];
           }
-          else codedCostBlockTmp -= piCostSig[pc];
+          else runningCost -= sigCost[pc];
         }
-        for( int sp = bestLastIdxP1; sp <= iLastScanPos; sp++ )
+        for( int sp = bestEnd; sp <= lastPosNow; sp++ )
         {
           const int rs_ = scan[sp], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
           const int bp_ = ( py_ << lw ) + px_;
-          if( q[bp_] ) { const int enc_ = -VVB_RQ_ENC( (int) q[bp_] ); VVB_RQ_DEPS( q, W, px_, py_, enc_, false, cgIdx, widthInGroups, subSetId ) q[bp_] = 0; }
+          if( q[bp_] ) { const int enc_ = -VVB_RQ_ENC( (int) q[bp_] ); VVB_RQ_DEPS( q, W, px_, py_, enc_, false, cgIdx, widthInGroups, grp ) q[bp_] = 0; }
         }
-        iLastScanPos = bestLastIdxP1 - 1;
+        lastPosNow = bestEnd - 1;
       }
     }
 
     //=============== sign bit hiding, :1097-1167 ================
     if( bSBH )
     {
-      if( uiAbsSumCG >= 2 )
+      if( sumGrp >= 2 )
       {
-        const int iSubPos = subSetId * iCGSize;
-        int iLastNZPosInCG = -1, iFirstNZPosInCG = iCGSize;
-        for( int n = 0; n < iCGSize; n++ ) if( q[RQ_BLKPOS( n + iSubPos )] ) { iFirstNZPosInCG = n; break; }
-        if( lastSubSetId == subSetId )
+        const int grpBase = grp * grpLen;
+        int lastNz = -1, firstNz = grpLen;
+        for( int n = 0; n < grpLen; n++ ) if( q[RQ_BLKPOS( n + grpBase )] ) { firstNz = n; break; }
+        if( lastGrp == grp )
         {
-          iLastNZPosInCG = iLastScanPos % iCGSize;
-          if( q[RQ_BLKPOS( iLastScanPos )] == 1 && piAddSBH[iLastNZPosInCG] == -1 ) piCostDeltaSBH[iLastNZPosInCG] -= ( 4 << RQ_SCALE_BITS );
+          lastNz = lastPosNow % grpLen;
+          if( q[RQ_BLKPOS( lastPosNow )] == 1 && flipStep[lastNz] == -1 ) flipDelta[lastNz] -= ( 4 << RQ_SCALE_BITS );
         }
         else
         {
-          for( int n = iCGSize - 1; n >= 0; n-- ) if( q[RQ_BLKPOS( n + iSubPos )] ) { iLastNZPosInCG = n; break; }
+          for( int n = grpLen - 1; n >= 0; n-- ) if( q[RQ_BLKPOS( n + grpBase )] ) { lastNz = n; break; }
         }
-        if( iLastNZPosInCG - iFirstNZPosInCG >= RQ_SBH_THRESHOLD )
+        if( lastNz - firstNz >= RQ_SBH_THRESHOLD )
         {
-          iCodedCostCG -= rq_icost( P, 1 << RQ_SCALE_BITS );
-          const bool bSign = coef[RQ_BLKPOS( iSubPos + iFirstNZPosInCG )] < 0;
-          if( (int) bSign != ( uiAbsSumCG & 0x1 ) )
+          codedGrp -= rq_icost( P, 1 << RQ_SCALE_BITS );
+          const bool negFirst = coef[RQ_BLKPOS( grpBase + firstNz )] < 0;
+          if( (int) negFirst != ( sumGrp & 0x1 ) )
           {
-            const int iLastPosInCG = ( lastSubSetId == subSetId ) ? iLastNZPosInCG : iCGSize - 1;
-            int64_t iMinCostDelta = INT64_MAX;
-            int iMinCostPos = -1;
-            if( q[RQ_BLKPOS( iFirstNZPosInCG + iSubPos )] > 1 ) { iMinCostDelta = piCostDeltaSBH[iFirstNZPosInCG]; iMinCostPos = iFirstNZPosInCG; }
-            for( int n = 0; n < iFirstNZPosInCG; n++ )
-              if( ( coef[RQ_BLKPOS( iSubPos + n )] < 0 ) == bSign )
-                if( piCostDeltaSBH[n] < iMinCostDelta ) { iMinCostDelta = piCostDeltaSBH[n]; iMinCostPos = n; }
-            for( int n = iFirstNZPosInCG + 1; n <= iLastPosInCG; n++ )
-              if( piCostDeltaSBH[n] < iMinCostDelta ) { iMinCostDelta = piCostDeltaSBH[n]; iMinCostPos = n; }
-            const int rs_ = scan[iMinCostPos + iSubPos], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
+            const int lastIn = ( lastGrp == grp ) ? lastNz : grpLen - 1;
+            int64_t minDelta = INT64_MAX;
+            int minAt = -1;
+            if( q[RQ_BLKPOS( firstNz + grpBase )] > 1 ) { minDelta = flipDelta[firstNz]; minAt = firstNz; }
+            for( int n = 0; n < firstNz; n++ )
+              if( ( coef[RQ_BLKPOS( grpBase + n )] < 0 ) == negFirst )
+                if( flipDelta[n] < minDelta ) { minDelta = flipDelta[n]; minAt = n; }
+            for( int n = firstNz + 1; n <= lastIn; n++ )
+              if( flipDelta[n] < minDelta ) { minDelta = flipDelta[n]; minAt = n; }
+            const int rs_ = scan[minAt + grpBase], px_ = rs_ & ( P.regionW - 1 ), py_ = rs_ >> lrw;
             const int bp = ( py_ << lw ) + px_;
-            const int encDelta_ = VVB_RQ_ENC( (int) q[bp] + piAddSBH[iMinCostPos] ) - VVB_RQ_ENC( (int) q[bp] );
-            if( encDelta_ ) VVB_RQ_DEPS( q, W, px_, py_, encDelta_, false, cgIdx, widthInGroups, subSetId )
-            q[bp] = (int16_t)( q[bp] + piAddSBH[iMinCostPos] );
-            uiAbsSumCG   += piAddSBH[iMinCostPos];
-            iCodedCostCG += iMinCostDelta;
+            const int encDelta_ = VVB_RQ_ENC( (int) q[bp] + flipStep[minAt] ) - VVB_RQ_ENC( (int) q[bp] );
+            if( encDelta_ ) VVB_RQ_DEPS( q, W, px_, py_, encDelta_, false, cgIdx, widthInGroups, grp )
+            q[bp] = (int16_t)( q[bp] + flipStep[minAt] );
+            sumGrp   += flipStep[minAt];
+            codedGrp += minDelta;
           }
         }
       }
     }
 
-    iCodedCostBlock   += iCodedCostCG;
-    iUncodedCostBlock += iUncodedCostCG;
-    uiAbsSum += uiAbsSumCG;
+    codedTu   += codedGrp;
+    uncodedTu += uncodedGrp;
+    sumTu += sumGrp;
   }
 
-  iCodedCostBlock = bestTotalCost;                                // :1177
+  codedTu = bestTuCost;                                // :1177
 
-  if( iLastScanPos < 0 ) { *absSumOut = uiAbsSum; *lastPosOut = -1; return; }         // :1179-1183 (uiAbsSum is 0 there)
+  if( lastPosNow < 0 ) { *absSumOut = sumTu; *lastPosOut = -1; return; }         // :1179-1183 (sumTu is 0 there)
 
-  iUncodedCostBlock += rq_icost( P, R.cbfBits[0] );               // :1185-1226 (the caller resolved which context applies; zeros when the flag is inferred)
-  iCodedCostBlock   += rq_icost( P, R.cbfBits[1] );
+  uncodedTu += rq_icost( P, R.cbfBits[0] );               // :1185-1226 (the caller resolved which context applies; zeros when the flag is inferred)
+  codedTu   += rq_icost( P, R.cbfBits[1] );
 
-  if( iUncodedCostBlock <= iCodedCostBlock )                      // :1228-1233
+  if( uncodedTu <= codedTu )                      // :1228-1233
   {
     for( int i = 0; i < W * H; i++ ) q[i] = 0;
     *absSumOut = 0; *lastPosOut = -1;
     return;
   }
-  if( bSBH && q[RQ_BLKPOS( iLastScanPos )] == 0 )                 // :1237-1249
+  if( bSBH && q[RQ_BLKPOS( lastPosNow )] == 0 )                 // :1237-1249
   {
-    int sp = iLastScanPos - 1;
+    int sp = lastPosNow - 1;
     for( ; sp >= 0; sp-- ) if( q[RQ_BLKPOS( sp )] ) break;
-    iLastScanPos = sp;
+    lastPosNow = sp;
   }
-  for( int sp = 0; sp <= iLastScanPos; sp++ )                     // signs, :1251-1257
+  for( int sp = 0; sp <= lastPosNow; sp++ )                     // signs, :1251-1257
   {
     const int bp = RQ_BLKPOS( sp );
     const int level = q[bp];
     const int iSign = coef[bp] >> 31;
     q[bp] = (int16_t)( ( iSign ^ level ) - iSign );
   }
-  *absSumOut = uiAbsSum; *lastPosOut = iLastScanPos;
+  *absSumOut = sumTu; *lastPosOut = lastPosNow;
 #undef RQ_BLKPOS
 #undef RQ_LVL_COST
 }
@@ -1039,58 +1039,58 @@ VVB_HD int rq_golomb_bits( uint32_t symbol, uint32_t ricePar )            // the
 }
 
 // xGetICRateTS, :1663-1807
-VVB_HD int rq_ts_level_rate( const RqTsRates& R, uint32_t absLevel, int remRegBins, const int32_t* fbSign, const int32_t* fbGt1, int& numCtxBins, int sign, uint32_t ricePar )
+VVB_HD int rq_ts_level_rate( const RqTsRates& R, uint32_t lv, int remRegBins, const int32_t* fbSign, const int32_t* fbGt1, int& binsOfCand, int sign, uint32_t ricePar )
 {
   if( remRegBins < 4 )                                            // everything by-pass coded
   {
-    int rate = absLevel ? ( 1 << RQ_SCALE_BITS ) : 0;
-    rate += rq_golomb_bits( absLevel, ricePar ) << RQ_SCALE_BITS;
+    int rate = lv ? ( 1 << RQ_SCALE_BITS ) : 0;
+    rate += rq_golomb_bits( lv, ricePar ) << RQ_SCALE_BITS;
     return rate;
   }
   else if( remRegBins < 8 )                                       // first pass context coded, the rest by-pass
   {
     int rate = fbSign[sign];
-    if( absLevel ) numCtxBins++;
-    if( absLevel > 1 )
+    if( lv ) binsOfCand++;
+    if( lv > 1 )
     {
       rate += fbGt1[1];
-      rate += R.parBits[( absLevel - 2 ) & 1];
-      numCtxBins += 2;
-      rate += rq_golomb_bits( ( absLevel - 2 ) >> 1, ricePar ) << RQ_SCALE_BITS;
+      rate += R.parBits[( lv - 2 ) & 1];
+      binsOfCand += 2;
+      rate += rq_golomb_bits( ( lv - 2 ) >> 1, ricePar ) << RQ_SCALE_BITS;
     }
-    else if( absLevel == 1 ) { rate += fbGt1[0]; numCtxBins++; }
+    else if( lv == 1 ) { rate += fbGt1[0]; binsOfCand++; }
     else rate = 0;
     return rate;
   }
   int rate = fbSign[sign];
-  if( absLevel ) numCtxBins++;
-  if( absLevel > 1 )
+  if( lv ) binsOfCand++;
+  if( lv > 1 )
   {
     rate += fbGt1[1];
-    rate += R.parBits[( absLevel - 2 ) & 1];
-    numCtxBins += 2;
+    rate += R.parBits[( lv - 2 ) & 1];
+    binsOfCand += 2;
     uint32_t cutoffVal = 2;
     for( int i = 0; i < 4; i++ )
     {
-      if( absLevel >= cutoffVal )
+      if( lv >= cutoffVal )
       {
-        rate += R.gtxBits[cutoffVal >> 1][absLevel >= ( cutoffVal + 2 ) ? 1 : 0];
-        numCtxBins++;
+        rate += R.gtxBits[cutoffVal >> 1][lv >= ( cutoffVal + 2 ) ? 1 : 0];
+        binsOfCand++;
       }
       cutoffVal += 2;
     }
-    if( absLevel >= cutoffVal ) rate += rq_golomb_bits( ( absLevel - cutoffVal ) >> 1, ricePar ) << RQ_SCALE_BITS;
+    if( lv >= cutoffVal ) rate += rq_golomb_bits( ( lv - cutoffVal ) >> 1, ricePar ) << RQ_SCALE_BITS;
   }
-  else if( absLevel == 1 ) { rate += fbGt1[0]; numCtxBins++; }
+  else if( lv == 1 ) { rate += fbGt1[0]; binsOfCand++; }
   else rate = 0;
   return rate;
 }
 
 // deriveModCoeff( right, below, absCoeff, 0 ), ContextModelling.h:363-386
-VVB_HD int rq_ts_mod_coeff( int rightPixel, int belowPixel, int absCoeff )
+VVB_HD int rq_ts_mod_coeff( int leftLvl, int upLvl, int absCoeff )
 {
   if( absCoeff == 0 ) return 0;
-  const int pred1 = rq_max( rq_abs( belowPixel ), rq_abs( rightPixel ) );
+  const int pred1 = rq_max( rq_abs( upLvl ), rq_abs( leftLvl ) );
   if( absCoeff == pred1 ) return 1;
   return absCoeff < pred1 ? absCoeff + 1 : absCoeff;
 }
@@ -1103,153 +1103,153 @@ VVB_HD void rq_ts_quant_tu( const RqTsPar& P, const RqTsRates& R, const int32_t*
   const int lrw = ( regionW == 32 ? 5 : regionW == 16 ? 4 : regionW == 8 ? 3 : 2 );
   const int qBits = P.qBits;
   const int widthInGroups = W >> 2, heightInGroups = H >> 2;
-  const int sbNum = ( W * H ) >> 4;
+  const int numGrp = ( W * H ) >> 4;
   const uint32_t entropyCodingMaximum = ( 1u << 15 ) - 1;
-  uint64_t sigGroupFlags = 0;
-  bool anySigCG = false;
+  uint64_t grpFlags = 0;
+  bool anyCodedGrp = false;
   int remRegBins = P.maxCtxBins;
   int absSum = 0;
 
   for( int i = 0; i < W * H; i++ ) q[i] = 0;                      // the caller's level buffer starts cleared (TrQuant::transformNxN works on a cleared TU, and neighbours ahead in the scan read as zero)
 
-  for( int sbId = 0; sbId < sbNum; sbId++ )
+  for( int grpTs = 0; grpTs < numGrp; grpTs++ )
   {
     // initSubblock: group position, the context of its significant-group flag from the left and upper groups (ContextModelling.cpp:113-133)
-    const int cgRaster = scan[sbId << 4], cgX = ( cgRaster & ( regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
-    const int subSetPos = cgY * widthInGroups + cgX;
-    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
-    const int sigLeft  = cgX > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - 1 ) ) & 1 ) : 0;
-    const int sigAbove = cgY > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - widthInGroups ) ) & 1 ) : 0;
-    const int32_t* fbSigGroup = R.sigGroupBits[sigLeft + sigAbove];
+    const int cgRaster = scan[grpTs << 4], cgX = ( cgRaster & ( regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int grpRaster = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << grpRaster;
+    const int sigLeft  = cgX > 0 ? (int)( ( grpFlags >> ( grpRaster - 1 ) ) & 1 ) : 0;
+    const int sigAbove = cgY > 0 ? (int)( ( grpFlags >> ( grpRaster - widthInGroups ) ) & 1 ) : 0;
+    const int32_t* grpBitsTs = R.sigGroupBits[sigLeft + sigAbove];
     (void) heightInGroups;
 
-    int noCoeffCoded = 0;
-    double baseCost = 0.0;
-    double d64CodedLevelandDist = 0.0, d64UncodedDist = 0.0, d64SigCost = 0.0;      // coeffGroupRDStats
-    int iNumSbbCtxBins = 0;
+    int codedInGrp = 0;
+    double grpCost = 0.0;
+    double keptSum = 0.0, zeroSum = 0.0, sigSum = 0.0;      // coeffGroupRDStats
+    int grpBins = 0;
 
-    for( int scanPosInSB = 0; scanPosInSB <= 15; scanPosInSB++ )
+    for( int inGrpTs = 0; inGrpTs <= 15; inGrpTs++ )
     {
-      const int scanPos = ( sbId << 4 ) + scanPosInSB;
+      const int scanPos = ( grpTs << 4 ) + inGrpTs;
       const int raster = scan[scanPos], posX = raster & ( regionW - 1 ), posY = raster >> lrw;
       const int blkPos = ( posY << lw ) + posX;
 
-      const int64_t tmpLevel = (int64_t) rq_abs( coef[blkPos] ) * P.quantScale;
+      const int64_t wide = (int64_t) rq_abs( coef[blkPos] ) * P.quantScale;
       const int64_t cap = (int64_t) INT32_MAX - ( (int64_t) 1 << ( qBits - 1 ) );
-      const int32_t levelDouble = (int32_t)( tmpLevel < cap ? tmpLevel : cap );
+      const int32_t mag = (int32_t)( wide < cap ? wide : cap );
 
-      const uint32_t roundAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( (uint32_t)( levelDouble + ( (int32_t) 1 << ( qBits - 1 ) ) ) >> qBits ) );
-      const uint32_t minAbsLevel = roundAbsLevel > 1 ? roundAbsLevel - 1 : 1;
-      const uint32_t downAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( levelDouble >> qBits ) );
-      const uint32_t upAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( downAbsLevel + 1 ) );
+      const uint32_t lvlNear = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( (uint32_t)( mag + ( (int32_t) 1 << ( qBits - 1 ) ) ) >> qBits ) );
+      const uint32_t lvlBelow = lvlNear > 1 ? lvlNear - 1 : 1;
+      const uint32_t lvlFloor = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( mag >> qBits ) );
+      const uint32_t lvlAbove = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( lvlFloor + 1 ) );
 
-      uint32_t coeffLevels[3];
-      int testedLevels = 0;
-      coeffLevels[testedLevels++] = roundAbsLevel;
-      if( minAbsLevel != roundAbsLevel ) coeffLevels[testedLevels++] = minAbsLevel;
+      uint32_t cand[3];
+      int numCand = 0;
+      cand[numCand++] = lvlNear;
+      if( lvlBelow != lvlNear ) cand[numCand++] = lvlBelow;
 
-      const int rightPixel = posX > 0 ? q[blkPos - 1] : 0;        // neighTS: the left and the upper neighbour (named as in the reference)
-      const int belowPixel = posY > 0 ? q[blkPos - W] : 0;
-      const int predPixel = rq_ts_mod_coeff( rightPixel, belowPixel, (int) upAbsLevel );
-      if( upAbsLevel != roundAbsLevel && upAbsLevel != minAbsLevel && predPixel == 1 ) coeffLevels[testedLevels++] = upAbsLevel;
+      const int leftLvl = posX > 0 ? q[blkPos - 1] : 0;        // neighTS: the left and the upper neighbour (named as in the reference)
+      const int upLvl = posY > 0 ? q[blkPos - W] : 0;
+      const int mappedUp = rq_ts_mod_coeff( leftLvl, upLvl, (int) lvlAbove );
+      if( lvlAbove != lvlNear && lvlAbove != lvlBelow && mappedUp == 1 ) cand[numCand++] = lvlAbove;
 
-      const double dErr0 = (double) levelDouble;
-      const double costCoeff0 = dErr0 * dErr0 * P.errorScale;
+      const double e0 = (double) mag;
+      const double zeroCostTs = e0 * e0 * P.errorScale;
 
       // contexts from the two neighbours: significance and greater-1 count the non-zero ones, the sign context looks at their signs (ContextModelling.h:271-357)
-      const int numPos = ( rightPixel != 0 ) + ( belowPixel != 0 );
+      const int numPos = ( leftLvl != 0 ) + ( upLvl != 0 );
       const int32_t* fbSig = R.sigBits[numPos];
       const int32_t* fbGt1 = R.lrg1Bits[numPos];
       int signCtx;
-      if( ( rightPixel == 0 && belowPixel == 0 ) || ( rightPixel * belowPixel ) < 0 ) signCtx = 0;
-      else if( rightPixel >= 0 && belowPixel >= 0 ) signCtx = 1;
+      if( ( leftLvl == 0 && upLvl == 0 ) || ( leftLvl * upLvl ) < 0 ) signCtx = 0;
+      else if( leftLvl >= 0 && upLvl >= 0 ) signCtx = 1;
       else signCtx = 2;
       const int32_t* fbSign = R.signBits[signCtx];
       const int sign = coef[blkPos] < 0 ? 1 : 0;
-      const uint32_t goRiceParam = 1;
-      const bool lastCoeff = scanPosInSB == 15 && noCoeffCoded == 0;
+      const uint32_t rice = 1;
+      const bool soleCand = inGrpTs == 15 && codedInGrp == 0;
 
       // xGetCodedLevelTSPred, :1578-1661
-      double costCoeff, costSig = 0.0;
-      uint32_t cLevel = 0;
-      int numUsedCtxBins = 0;
+      double lvlCostTs, sigCostTs = 0.0;
+      uint32_t pickTs = 0;
+      int binsUsed = 0;
       {
-        double currCostSig = 0;
-        int numBestCtxBin = 0;
+        double sigOneTs = 0;
+        int binsOfBest = 0;
         bool done = false;
-        if( !lastCoeff && coeffLevels[0] < 3 )
+        if( !soleCand && cand[0] < 3 )
         {
-          if( remRegBins >= 4 ) costSig = P.lambda * (double) fbSig[0];
-          else                  costSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
-          costCoeff = costCoeff0 + costSig;
-          if( remRegBins >= 4 ) numUsedCtxBins++;
-          if( coeffLevels[0] == 0 ) done = true;
+          if( remRegBins >= 4 ) sigCostTs = P.lambda * (double) fbSig[0];
+          else                  sigCostTs = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+          lvlCostTs = zeroCostTs + sigCostTs;
+          if( remRegBins >= 4 ) binsUsed++;
+          if( cand[0] == 0 ) done = true;
         }
-        else costCoeff = 1.7e+308;                                // MAX_DOUBLE (CommonDef.h)
+        else lvlCostTs = 1.7e+308;                                // MAX_DOUBLE (CommonDef.h)
         if( !done )
         {
-          if( !lastCoeff )
+          if( !soleCand )
           {
-            if( remRegBins >= 4 ) currCostSig = P.lambda * (double) fbSig[1];
-            else                  currCostSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
-            if( coeffLevels[0] >= 3 && remRegBins >= 4 ) numUsedCtxBins++;
+            if( remRegBins >= 4 ) sigOneTs = P.lambda * (double) fbSig[1];
+            else                  sigOneTs = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+            if( cand[0] >= 3 && remRegBins >= 4 ) binsUsed++;
           }
-          for( int errorInd = 1; errorInd <= testedLevels; errorInd++ )
+          for( int ci = 1; ci <= numCand; ci++ )
           {
-            const int absLevel = (int) coeffLevels[errorInd - 1];
-            const double dErr = (double)( levelDouble - ( (int32_t) absLevel << qBits ) );
-            const double levelError = dErr * dErr * P.errorScale;
-            int modAbsLevel = absLevel;
-            if( remRegBins >= 4 ) modAbsLevel = rq_ts_mod_coeff( rightPixel, belowPixel, absLevel );
-            int numCtxBins = 0;
-            double dCurrCost = levelError + P.lambda * (double) rq_ts_level_rate( R, (uint32_t) modAbsLevel, remRegBins, fbSign, fbGt1, numCtxBins, sign, goRiceParam );
-            if( remRegBins >= 4 ) dCurrCost += currCostSig;
-            if( dCurrCost < costCoeff ) { cLevel = (uint32_t) absLevel; costCoeff = dCurrCost; costSig = currCostSig; numBestCtxBin = numCtxBins; }
+            const int lv = (int) cand[ci - 1];
+            const double eCand = (double)( mag - ( (int32_t) lv << qBits ) );
+            const double candErr = eCand * eCand * P.errorScale;
+            int mappedLvl = lv;
+            if( remRegBins >= 4 ) mappedLvl = rq_ts_mod_coeff( leftLvl, upLvl, lv );
+            int binsOfCand = 0;
+            double candCostTs = candErr + P.lambda * (double) rq_ts_level_rate( R, (uint32_t) mappedLvl, remRegBins, fbSign, fbGt1, binsOfCand, sign, rice );
+            if( remRegBins >= 4 ) candCostTs += sigOneTs;
+            if( candCostTs < lvlCostTs ) { pickTs = (uint32_t) lv; lvlCostTs = candCostTs; sigCostTs = sigOneTs; binsOfBest = binsOfCand; }
           }
-          numUsedCtxBins += numBestCtxBin;
+          binsUsed += binsOfBest;
         }
       }
 
-      remRegBins -= numUsedCtxBins;
-      iNumSbbCtxBins += numUsedCtxBins;
-      if( cLevel > 0 ) noCoeffCoded++;
-      const int level = (int) cLevel;
+      remRegBins -= binsUsed;
+      grpBins += binsUsed;
+      if( pickTs > 0 ) codedInGrp++;
+      const int level = (int) pickTs;
       q[blkPos] = (int16_t)( ( level != 0 && coef[blkPos] < 0 ) ? -level : level );
-      baseCost   += costCoeff;
-      d64SigCost += costSig;
+      grpCost   += lvlCostTs;
+      sigSum += sigCostTs;
       if( q[blkPos] )
       {
-        sigGroupFlags |= cgBit;
-        d64CodedLevelandDist += costCoeff - costSig;
-        d64UncodedDist       += costCoeff0;
+        grpFlags |= cgBit;
+        keptSum += lvlCostTs - sigCostTs;
+        zeroSum       += zeroCostTs;
       }
     }
 
-    if( !( sigGroupFlags & cgBit ) )                              // :1271-1277
+    if( !( grpFlags & cgBit ) )                              // :1271-1277
     {
-      baseCost += P.lambda * (double) fbSigGroup[0] - d64SigCost;
-      remRegBins += iNumSbbCtxBins;
+      grpCost += P.lambda * (double) grpBitsTs[0] - sigSum;
+      remRegBins += grpBins;
     }
-    else if( sbId != sbNum - 1 || anySigCG )                      // :1278-1322
+    else if( grpTs != numGrp - 1 || anyCodedGrp )                      // :1278-1322
     {
-      double costZeroSB = baseCost;
-      baseCost   += P.lambda * (double) fbSigGroup[1];
-      costZeroSB += P.lambda * (double) fbSigGroup[0];
-      costZeroSB += d64UncodedDist;
-      costZeroSB -= d64CodedLevelandDist;
-      costZeroSB -= d64SigCost;
-      if( costZeroSB < baseCost )
+      double zeroGrpCost = grpCost;
+      grpCost   += P.lambda * (double) grpBitsTs[1];
+      zeroGrpCost += P.lambda * (double) grpBitsTs[0];
+      zeroGrpCost += zeroSum;
+      zeroGrpCost -= keptSum;
+      zeroGrpCost -= sigSum;
+      if( zeroGrpCost < grpCost )
       {
-        sigGroupFlags &= ~cgBit;
-        baseCost = costZeroSB;
-        remRegBins += iNumSbbCtxBins;
+        grpFlags &= ~cgBit;
+        grpCost = zeroGrpCost;
+        remRegBins += grpBins;
         for( int p = 0; p <= 15; p++ )
         {
-          const int raster = scan[( sbId << 4 ) + p];
+          const int raster = scan[( grpTs << 4 ) + p];
           q[( ( raster >> lrw ) << lw ) + ( raster & ( regionW - 1 ) )] = 0;
         }
       }
-      else anySigCG = true;
+      else anyCodedGrp = true;
     }
   }
 
@@ -1261,8 +1261,8 @@ VVB_HD void rq_ts_quant_tu( const RqTsPar& P, const RqTsRates& R, const int32_t*
 // ------------------------------------------------------------------------------------------------------------------------------------------------------------------
 // BDPCM: QuantRDOQ::forwardRDPCM (CommonLib/QuantRDOQ.cpp:1338-1562), the quantiser of a transform-skipped TU whose CU carries a block-DPCM direction (1 horizontal, 2 vertical).
 // The routine of rq_ts_quant_tu with three differences: what is quantised is the residual minus the RECONSTRUCTED left / upper neighbour (xDequantSample :1564-1576 of the level
-// just chosen plus its own prediction, kept in fullCoeff), the contexts take their BDPCM variants (greater-1: numPos 3; sign: + 3; no neighbour-based level mapping), and only
-// the rounded level and the one below are tried.  fullCoeff: w * h int32 of scratch per TU.  One quirk is kept on purpose: when a group is zeroed out, the member refreshes
+// just chosen plus its own prediction, kept in recon), the contexts take their BDPCM variants (greater-1: numPos 3; sign: + 3; no neighbour-based level mapping), and only
+// the rounded level and the one below are tried.  recon: w * h int32 of scratch per TU.  One quirk is kept on purpose: when a group is zeroed out, the member refreshes
 // m_fullCoeff at index scanPos instead of blkPos (:1539) -- the reconstruction other positions predict from is the one the member has.
 struct RqBdpcmPar
 {
@@ -1282,156 +1282,156 @@ VVB_HD int32_t rq_dequant_sample( int level, const RqBdpcmPar& B )          // x
   return (int32_t)( ( (int32_t) level * B.dqScale ) * ( 1 << -B.dqRightShift ) );
 }
 
-VVB_HD void rq_bdpcm_quant_tu( const RqTsPar& P, const RqBdpcmPar& B, const RqTsRates& R, const int32_t* scan, const int32_t* coef, int16_t* q, int32_t* fullCoeff, int32_t* absSumOut )
+VVB_HD void rq_bdpcm_quant_tu( const RqTsPar& P, const RqBdpcmPar& B, const RqTsRates& R, const int32_t* scan, const int32_t* coef, int16_t* q, int32_t* recon, int32_t* absSumOut )
 {
   const int W = P.width, H = P.height, lw = P.log2W;
   const int regionW = rq_min( 32, W );
   const int lrw = ( regionW == 32 ? 5 : regionW == 16 ? 4 : regionW == 8 ? 3 : 2 );
   const int qBits = P.qBits;
   const int widthInGroups = W >> 2;
-  const int sbNum = ( W * H ) >> 4;
+  const int numGrp = ( W * H ) >> 4;
   const uint32_t entropyCodingMaximum = ( 1u << 15 ) - 1;
   const int dirMode = B.dirMode;
-  uint64_t sigGroupFlags = 0;
-  bool anySigCG = false;
+  uint64_t grpFlags = 0;
+  bool anyCodedGrp = false;
   int remRegBins = P.maxCtxBins;
   int absSum = 0;
 
-  for( int i = 0; i < W * H; i++ ) { q[i] = 0; fullCoeff[i] = 0; }       // :1368-1370
+  for( int i = 0; i < W * H; i++ ) { q[i] = 0; recon[i] = 0; }       // :1368-1370
 
-  for( int sbId = 0; sbId < sbNum; sbId++ )
+  for( int grpTs = 0; grpTs < numGrp; grpTs++ )
   {
-    const int cgRaster = scan[sbId << 4], cgX = ( cgRaster & ( regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
-    const int subSetPos = cgY * widthInGroups + cgX;
-    const uint64_t cgBit = (uint64_t) 1 << subSetPos;
-    const int sigLeft  = cgX > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - 1 ) ) & 1 ) : 0;
-    const int sigAbove = cgY > 0 ? (int)( ( sigGroupFlags >> ( subSetPos - widthInGroups ) ) & 1 ) : 0;
-    const int32_t* fbSigGroup = R.sigGroupBits[sigLeft + sigAbove];
+    const int cgRaster = scan[grpTs << 4], cgX = ( cgRaster & ( regionW - 1 ) ) >> 2, cgY = ( cgRaster >> lrw ) >> 2;
+    const int grpRaster = cgY * widthInGroups + cgX;
+    const uint64_t cgBit = (uint64_t) 1 << grpRaster;
+    const int sigLeft  = cgX > 0 ? (int)( ( grpFlags >> ( grpRaster - 1 ) ) & 1 ) : 0;
+    const int sigAbove = cgY > 0 ? (int)( ( grpFlags >> ( grpRaster - widthInGroups ) ) & 1 ) : 0;
+    const int32_t* grpBitsTs = R.sigGroupBits[sigLeft + sigAbove];
 
-    int noCoeffCoded = 0;
-    double baseCost = 0.0;
-    double d64CodedLevelandDist = 0.0, d64UncodedDist = 0.0, d64SigCost = 0.0;
-    int iNumSbbCtxBins = 0;
+    int codedInGrp = 0;
+    double grpCost = 0.0;
+    double keptSum = 0.0, zeroSum = 0.0, sigSum = 0.0;
+    int grpBins = 0;
 
-    for( int scanPosInSB = 0; scanPosInSB <= 15; scanPosInSB++ )
+    for( int inGrpTs = 0; inGrpTs <= 15; inGrpTs++ )
     {
-      const int scanPos = ( sbId << 4 ) + scanPosInSB;
+      const int scanPos = ( grpTs << 4 ) + inGrpTs;
       const int raster = scan[scanPos], posX = raster & ( regionW - 1 ), posY = raster >> lrw;
       const int blkPos = ( posY << lw ) + posX;
       const int posS = ( 1 == dirMode ) ? posX : posY;
       const int posNb = ( 1 == dirMode ) ? ( posX - 1 ) + posY * W : posX + ( posY - 1 ) * W;
-      const int32_t predCoeff = ( 0 != posS ) ? fullCoeff[posNb] : 0;
+      const int32_t pred = ( 0 != posS ) ? recon[posNb] : 0;
 
-      const int64_t tmpLevel = (int64_t) rq_abs( coef[blkPos] - predCoeff ) * P.quantScale;
+      const int64_t wide = (int64_t) rq_abs( coef[blkPos] - pred ) * P.quantScale;
       const int64_t cap = (int64_t) INT32_MAX - ( (int64_t) 1 << ( qBits - 1 ) );
-      const int32_t levelDouble = (int32_t)( tmpLevel < cap ? tmpLevel : cap );
-      const uint32_t roundAbsLevel = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( (uint32_t)( levelDouble + ( (int32_t) 1 << ( qBits - 1 ) ) ) >> qBits ) );
-      const uint32_t minAbsLevel = roundAbsLevel > 1 ? roundAbsLevel - 1 : 1;
-      uint32_t coeffLevels[3];
-      int testedLevels = 0;
-      coeffLevels[testedLevels++] = roundAbsLevel;
-      if( minAbsLevel != roundAbsLevel ) coeffLevels[testedLevels++] = minAbsLevel;
+      const int32_t mag = (int32_t)( wide < cap ? wide : cap );
+      const uint32_t lvlNear = (uint32_t) rq_min( (int) entropyCodingMaximum, (int)( (uint32_t)( mag + ( (int32_t) 1 << ( qBits - 1 ) ) ) >> qBits ) );
+      const uint32_t lvlBelow = lvlNear > 1 ? lvlNear - 1 : 1;
+      uint32_t cand[3];
+      int numCand = 0;
+      cand[numCand++] = lvlNear;
+      if( lvlBelow != lvlNear ) cand[numCand++] = lvlBelow;
 
-      const double dErr0 = (double) levelDouble;
-      const double costCoeff0 = dErr0 * dErr0 * P.errorScale;
+      const double e0 = (double) mag;
+      const double zeroCostTs = e0 * e0 * P.errorScale;
 
-      const int rightPixel = posX > 0 ? q[blkPos - 1] : 0;
-      const int belowPixel = posY > 0 ? q[blkPos - W] : 0;
-      const int numPos = ( rightPixel != 0 ) + ( belowPixel != 0 );
+      const int leftLvl = posX > 0 ? q[blkPos - 1] : 0;
+      const int upLvl = posY > 0 ? q[blkPos - W] : 0;
+      const int numPos = ( leftLvl != 0 ) + ( upLvl != 0 );
       const int32_t* fbSig = R.sigBits[numPos];                  // sigCtxIdAbsTS has no BDPCM variant
       const int32_t* fbGt1 = R.lrg1Bits[3];                      // lrg1CtxIdAbsTS( ., ., bdpcm ): numPos = 3
       int signCtx;
-      if( ( rightPixel == 0 && belowPixel == 0 ) || ( rightPixel * belowPixel ) < 0 ) signCtx = 0;
-      else if( rightPixel >= 0 && belowPixel >= 0 ) signCtx = 1;
+      if( ( leftLvl == 0 && upLvl == 0 ) || ( leftLvl * upLvl ) < 0 ) signCtx = 0;
+      else if( leftLvl >= 0 && upLvl >= 0 ) signCtx = 1;
       else signCtx = 2;
       const int32_t* fbSign = R.signBits[signCtx + 3];           // signCtxIdAbsTS( ., ., bdpcm ): + 3
-      const int sign = coef[blkPos] - predCoeff < 0 ? 1 : 0;
-      const uint32_t goRiceParam = 1;
-      const bool lastCoeff = scanPosInSB == 15 && noCoeffCoded == 0;
+      const int sign = coef[blkPos] - pred < 0 ? 1 : 0;
+      const uint32_t rice = 1;
+      const bool soleCand = inGrpTs == 15 && codedInGrp == 0;
 
-      double costCoeff, costSig = 0.0;
-      uint32_t cLevel = 0;
-      int numUsedCtxBins = 0;
+      double lvlCostTs, sigCostTs = 0.0;
+      uint32_t pickTs = 0;
+      int binsUsed = 0;
       {
-        double currCostSig = 0;
-        int numBestCtxBin = 0;
+        double sigOneTs = 0;
+        int binsOfBest = 0;
         bool done = false;
-        if( !lastCoeff && coeffLevels[0] < 3 )
+        if( !soleCand && cand[0] < 3 )
         {
-          if( remRegBins >= 4 ) costSig = P.lambda * (double) fbSig[0];
-          else                  costSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
-          costCoeff = costCoeff0 + costSig;
-          if( remRegBins >= 4 ) numUsedCtxBins++;
-          if( coeffLevels[0] == 0 ) done = true;
+          if( remRegBins >= 4 ) sigCostTs = P.lambda * (double) fbSig[0];
+          else                  sigCostTs = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+          lvlCostTs = zeroCostTs + sigCostTs;
+          if( remRegBins >= 4 ) binsUsed++;
+          if( cand[0] == 0 ) done = true;
         }
-        else costCoeff = 1.7e+308;
+        else lvlCostTs = 1.7e+308;
         if( !done )
         {
-          if( !lastCoeff )
+          if( !soleCand )
           {
-            if( remRegBins >= 4 ) currCostSig = P.lambda * (double) fbSig[1];
-            else                  currCostSig = P.lambda * (double)( 1 << RQ_SCALE_BITS );
-            if( coeffLevels[0] >= 3 && remRegBins >= 4 ) numUsedCtxBins++;
+            if( remRegBins >= 4 ) sigOneTs = P.lambda * (double) fbSig[1];
+            else                  sigOneTs = P.lambda * (double)( 1 << RQ_SCALE_BITS );
+            if( cand[0] >= 3 && remRegBins >= 4 ) binsUsed++;
           }
-          for( int errorInd = 1; errorInd <= testedLevels; errorInd++ )
+          for( int ci = 1; ci <= numCand; ci++ )
           {
-            const int absLevel = (int) coeffLevels[errorInd - 1];
-            const double dErr = (double)( levelDouble - ( (int32_t) absLevel << qBits ) );
-            const double levelError = dErr * dErr * P.errorScale;
-            int numCtxBins = 0;                                   // deriveModCoeff( ., ., absLevel, bdpcm != 0 ) leaves the level as it is
-            double dCurrCost = levelError + P.lambda * (double) rq_ts_level_rate( R, (uint32_t) absLevel, remRegBins, fbSign, fbGt1, numCtxBins, sign, goRiceParam );
-            if( remRegBins >= 4 ) dCurrCost += currCostSig;
-            if( dCurrCost < costCoeff ) { cLevel = (uint32_t) absLevel; costCoeff = dCurrCost; costSig = currCostSig; numBestCtxBin = numCtxBins; }
+            const int lv = (int) cand[ci - 1];
+            const double eCand = (double)( mag - ( (int32_t) lv << qBits ) );
+            const double candErr = eCand * eCand * P.errorScale;
+            int binsOfCand = 0;                                   // deriveModCoeff( ., ., lv, bdpcm != 0 ) leaves the level as it is
+            double candCostTs = candErr + P.lambda * (double) rq_ts_level_rate( R, (uint32_t) lv, remRegBins, fbSign, fbGt1, binsOfCand, sign, rice );
+            if( remRegBins >= 4 ) candCostTs += sigOneTs;
+            if( candCostTs < lvlCostTs ) { pickTs = (uint32_t) lv; lvlCostTs = candCostTs; sigCostTs = sigOneTs; binsOfBest = binsOfCand; }
           }
-          numUsedCtxBins += numBestCtxBin;
+          binsUsed += binsOfBest;
         }
       }
 
-      remRegBins -= numUsedCtxBins;
-      iNumSbbCtxBins += numUsedCtxBins;
-      if( cLevel > 0 ) noCoeffCoded++;
-      q[blkPos] = (int16_t)( sign ? -(int) cLevel : (int) cLevel );
-      fullCoeff[blkPos] = rq_dequant_sample( q[blkPos], B ) + predCoeff;          // :1491-1492
-      baseCost   += costCoeff;
-      d64SigCost += costSig;
+      remRegBins -= binsUsed;
+      grpBins += binsUsed;
+      if( pickTs > 0 ) codedInGrp++;
+      q[blkPos] = (int16_t)( sign ? -(int) pickTs : (int) pickTs );
+      recon[blkPos] = rq_dequant_sample( q[blkPos], B ) + pred;          // :1491-1492
+      grpCost   += lvlCostTs;
+      sigSum += sigCostTs;
       if( q[blkPos] )
       {
-        sigGroupFlags |= cgBit;
-        d64CodedLevelandDist += costCoeff - costSig;
-        d64UncodedDist       += costCoeff0;
+        grpFlags |= cgBit;
+        keptSum += lvlCostTs - sigCostTs;
+        zeroSum       += zeroCostTs;
       }
     }
 
-    if( !( sigGroupFlags & cgBit ) )
+    if( !( grpFlags & cgBit ) )
     {
-      baseCost += P.lambda * (double) fbSigGroup[0] - d64SigCost;
-      remRegBins += iNumSbbCtxBins;
+      grpCost += P.lambda * (double) grpBitsTs[0] - sigSum;
+      remRegBins += grpBins;
     }
-    else if( sbId != sbNum - 1 || anySigCG )
+    else if( grpTs != numGrp - 1 || anyCodedGrp )
     {
-      double costZeroSB = baseCost;
-      baseCost   += P.lambda * (double) fbSigGroup[1];
-      costZeroSB += P.lambda * (double) fbSigGroup[0];
-      costZeroSB += d64UncodedDist;
-      costZeroSB -= d64CodedLevelandDist;
-      costZeroSB -= d64SigCost;
-      if( costZeroSB < baseCost )
+      double zeroGrpCost = grpCost;
+      grpCost   += P.lambda * (double) grpBitsTs[1];
+      zeroGrpCost += P.lambda * (double) grpBitsTs[0];
+      zeroGrpCost += zeroSum;
+      zeroGrpCost -= keptSum;
+      zeroGrpCost -= sigSum;
+      if( zeroGrpCost < grpCost )
       {
-        sigGroupFlags &= ~cgBit;
-        baseCost = costZeroSB;
-        remRegBins += iNumSbbCtxBins;
+        grpFlags &= ~cgBit;
+        grpCost = zeroGrpCost;
+        remRegBins += grpBins;
         for( int p = 0; p <= 15; p++ )
         {
-          const int scanPos = ( sbId << 4 ) + p;
+          const int scanPos = ( grpTs << 4 ) + p;
           const int raster = scan[scanPos], posX = raster & ( regionW - 1 ), posY = raster >> lrw;
           const int blkPos = ( posY << lw ) + posX;
           const int posS = ( 1 == dirMode ) ? posX : posY;
           const int posNb = ( 1 == dirMode ) ? ( posX - 1 ) + posY * W : posX + ( posY - 1 ) * W;
-          fullCoeff[scanPos] = ( 0 != posS ) ? fullCoeff[posNb] : 0;              // the member indexes by scanPos here (:1539)
+          recon[scanPos] = ( 0 != posS ) ? recon[posNb] : 0;              // the member indexes by scanPos here (:1539)
           q[blkPos] = 0;
         }
       }
-      else anySigCG = true;
+      else anyCodedGrp = true;
     }
   }
 
